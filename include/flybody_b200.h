@@ -1,0 +1,241 @@
+/* flybody_b200.h -- C ABI of the B200-native batched fruit-fly physics stepper.
+ *
+ * The reference (TuragaLab/flybody) has no FFI of its own: the hot path sits behind
+ * dm_control's `Physics.step()` which `composer.Environment.step()` calls n_sub_steps times per
+ * control step (reference flybody/fly_envs.py:152-155).  These entry
+ * points are what a ctypes binding replacing that `physics.step()` loop binds to; each one
+ * names the reference-side call it stands in for.
+ *
+ * Conventions: plain C, no torch types.  Return 0 on success, negative code on error
+ * (message via fb_last_error).  Caller owns host buffers; the library owns device buffers.
+ * One handle = one device + one stream; calls on a handle are not re-entrant.
+ * All per-env device arrays are SoA, [component][env] with env fastest, fp32.
+ * Host-side buffers passed to fb_* are AoS [env][component] (what numpy/dm_env code holds).
+ */
+#ifndef FLYBODY_B200_H_
+#define FLYBODY_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* enums shared by compiler (Python), oracle (C) and kernels (CUDA) */
+enum { FB_GEOM_PLANE = 0, FB_GEOM_SPHERE = 2, FB_GEOM_CAPSULE = 3, FB_GEOM_ELLIPSOID = 4,
+       FB_GEOM_CYLINDER = 5, FB_GEOM_BOX = 6 };
+enum { FB_JNT_FREE = 0, FB_JNT_HINGE = 3 };
+enum { FB_TRN_JOINT = 0, FB_TRN_TENDON = 1, FB_TRN_BODY = 2 };
+enum { FB_DYN_NONE = 0, FB_DYN_FILTER = 2, FB_DYN_FILTEREXACT = 3 };
+enum { FB_SENS_TOUCH = 0, FB_SENS_ACCELEROMETER = 1, FB_SENS_VELOCIMETER = 2, FB_SENS_GYRO = 3,
+       FB_SENS_FORCE = 4 };
+
+/* Flat model = the subset of mjModel the fly's mj_step touches (generated from
+ * flybody_b200/flymodel.py:FIELDS; tests/test_model.py keeps the two in sync). */
+/*@FBMODEL_BEGIN*/
+typedef struct FbModel {
+  int32_t nq;
+  int32_t nv;
+  int32_t nu;
+  int32_t na;
+  int32_t nbody;
+  int32_t njnt;
+  int32_t ngeom;
+  int32_t npair;
+  int32_t nsite;
+  int32_t ntendon;
+  int32_t nwrap;
+  int32_t nsensor;
+  int32_t nsensordata;
+  int32_t nM;
+  int32_t nfluid;
+  int32_t opt_iterations;
+  int32_t opt_ls_iterations;
+  int32_t opt_noslip_iterations;
+  int32_t opt_cone_elliptic;
+  double opt_timestep;
+  double opt_gravity[3];
+  double opt_density;
+  double opt_viscosity;
+  double opt_wind[3];
+  double opt_impratio;
+  double opt_tolerance;
+  double opt_ls_tolerance;
+  double opt_noslip_tolerance;
+  double stat_meaninertia;
+  const int32_t* body_parentid;
+  const int32_t* body_rootid;
+  const int32_t* body_jntadr;
+  const int32_t* body_jntnum;
+  const int32_t* body_dofadr;
+  const int32_t* body_dofnum;
+  const int32_t* body_lastdof;
+  const int32_t* body_fluid_ellipsoid;
+  const double* body_pos;
+  const double* body_quat;
+  const double* body_ipos;
+  const double* body_iquat;
+  const double* body_mass;
+  const double* body_inertia;
+  const double* body_invweight0;
+  const double* body_subtreemass;
+  const int32_t* jnt_type;
+  const int32_t* jnt_qposadr;
+  const int32_t* jnt_dofadr;
+  const int32_t* jnt_bodyid;
+  const int32_t* jnt_limited;
+  const double* jnt_pos;
+  const double* jnt_axis;
+  const double* jnt_stiffness;
+  const double* jnt_range;
+  const double* jnt_solref;
+  const double* jnt_solimp;
+  const double* jnt_margin;
+  const double* qpos0;
+  const double* qpos_spring;
+  const int32_t* dof_bodyid;
+  const int32_t* dof_jntid;
+  const int32_t* dof_parentid;
+  const int32_t* dof_Madr;
+  const double* dof_armature;
+  const double* dof_damping;
+  const double* dof_invweight0;
+  const int32_t* geom_type;
+  const int32_t* geom_bodyid;
+  const int32_t* geom_condim;
+  const int32_t* geom_priority;
+  const double* geom_size;
+  const double* geom_pos;
+  const double* geom_quat;
+  const double* geom_rbound;
+  const double* geom_friction;
+  const double* geom_solmix;
+  const double* geom_solref;
+  const double* geom_solimp;
+  const double* geom_margin;
+  const double* geom_gap;
+  const int32_t* pair_geom1;
+  const int32_t* pair_geom2;
+  const int32_t* fluid_bodyid;
+  const double* fluid_pos;
+  const double* fluid_quat;
+  const double* fluid_size;
+  const double* fluid_coef;
+  const int32_t* site_bodyid;
+  const int32_t* site_type;
+  const double* site_pos;
+  const double* site_quat;
+  const double* site_size;
+  const int32_t* tendon_adr;
+  const int32_t* tendon_num;
+  const int32_t* wrap_dofid;
+  const int32_t* wrap_qposadr;
+  const double* wrap_coef;
+  const int32_t* actuator_trntype;
+  const int32_t* actuator_trnid;
+  const int32_t* actuator_dyntype;
+  const int32_t* actuator_biastype;
+  const int32_t* actuator_ctrllimited;
+  const int32_t* actuator_forcelimited;
+  const int32_t* actuator_actadr;
+  const double* actuator_dynprm;
+  const double* actuator_gainprm;
+  const double* actuator_biasprm;
+  const double* actuator_ctrlrange;
+  const double* actuator_forcerange;
+  const int32_t* sensor_type;
+  const int32_t* sensor_objid;
+  const int32_t* sensor_adr;
+  const int32_t* sensor_dim;
+} FbModel;
+/*@FBMODEL_END*/
+
+/* fields for fb_get / fb_set (per-env arrays; n = floats per env) */
+enum FbField {
+  FB_QPOS = 0,        /* nq   : physics.data.qpos                                   */
+  FB_QVEL = 1,        /* nv   : physics.data.qvel                                   */
+  FB_ACT = 2,         /* na   : physics.data.act                                    */
+  FB_CTRL = 3,        /* nu   : physics.data.ctrl (physics.set_control)             */
+  FB_QACC = 4,        /* nv   : physics.data.qacc (tasks/base.py:224)               */
+  FB_QACC_WARMSTART = 5,
+  FB_SENSORDATA = 6,  /* nsensordata : last-substep sensordata                      */
+  FB_SENSOR_MEAN = 7, /* nsensordata : mean over the substeps of the last fb_step
+                         (observable buffer_size + aggregator='mean', fruitfly.py:626-665) */
+  FB_XPOS = 8,        /* nbody*3  : physics.bind(bodies).xpos                       */
+  FB_XMAT = 9,        /* nbody*9  : physics.bind(bodies).xmat                       */
+  FB_SITE_XPOS = 10,  /* nsite*3                                                    */
+  FB_SITE_XMAT = 11,  /* nsite*9                                                    */
+  FB_SUBTREE_COM = 12,/* nbody*3  : physics.data.subtree_com                        */
+  FB_NCON = 13,       /* 1 (as float): number of detected contacts                  */
+  FB_NEFC = 14,       /* 1 (as float): number of constraint rows                    */
+  FB_TIME = 15,       /* 1 : physics.data.time                                      */
+  FB_QFRC_SMOOTH = 16,/* nv : passive - bias + actuator                             */
+  FB_QM_DENSE = 17,   /* nv*nv : dense joint-space inertia (debug / parity)         */
+  FB_QFRC_CONSTRAINT = 18, /* nv                                                    */
+  FB_SOLVER_NITER = 19,    /* 1                                                     */
+  FB_QFRC_PASSIVE = 20,    /* nv                                                    */
+  FB_QFRC_BIAS = 21,       /* nv                                                    */
+  FB_QFRC_ACTUATOR = 22,   /* nv                                                    */
+  FB_CONTACT = 23,    /* FB_MAXCON * 16: per contact [dist, pos3, normal3, geom1, geom2, dim, incl, mu, efc_adr, pad3] */
+  FB_EFC_FORCE = 24,  /* FB_MAXEFC                                                  */
+  FB_FLAGS = 25,      /* 1 (as float): bit0 bad state (nan/inf or |qacc|>1e14), bit1 contact overflow, bit2 efc overflow */
+  FB_NFIELDS = 26
+};
+
+#define FB_MAXCON 64     /* contact slots per env   */
+#define FB_MAXEFC 160    /* constraint rows per env */
+
+typedef struct FbSim* FbHandle;
+
+/* mjcf.Physics.from_mjcf_model + mj_makeData, batched: uploads the model, allocates SoA state
+ * for n_envs environments on `device`, all envs at qpos0 / zero velocity.                     */
+int fb_create(const FbModel* m, int n_envs, int device, FbHandle* out);
+int fb_destroy(FbHandle h);
+
+/* physics.reset_context()/bind(...).qpos = ... (walk_imitation.py:112-136): overwrite qpos/qvel
+ * of the listed envs (AoS host arrays [n][nq], [n][nv]; NULL = model defaults), zero act /
+ * warm start / time, then mj_forward for those envs.  env_ids == NULL means all envs.        */
+int fb_reset(FbHandle h, const int32_t* env_ids, int n, const float* qpos, const float* qvel);
+
+/* physics.set_control(ctrl) (fruitfly.py:540-544).  ctrl: [N][nu] AoS host (is_device=0) or
+ * [nu][N] SoA device pointer (is_device=1).                                                    */
+int fb_set_ctrl(FbHandle h, const float* ctrl, int is_device);
+
+/* walker.set_pose / set_velocity on a subset of coordinates (walk_imitation.py:141-145):
+ * field in {FB_QPOS, FB_QVEL, FB_ACT}; vals is [N][k] AoS host, written to coordinates idx[k]
+ * of every env.  No forward pass is run (dm_control does not run one either).               */
+int fb_write_state(FbHandle h, int field, const int32_t* idx, int k, const float* vals);
+
+/* n_substeps x physics.step() with legacy_step=True, i.e. (mj_step2; mj_step1) per substep
+ * (SURVEY.md App. A), accumulating the per-substep sensor mean.  Asynchronous on the handle's
+ * stream.                                                                                     */
+int fb_step(FbHandle h, int n_substeps);
+
+/* mj_forward on all envs (after external state writes).                                       */
+int fb_forward(FbHandle h);
+
+/* Read a per-env field.  is_device=0: dst is host [N][n] AoS float32, synchronises.
+ * is_device=1: *(void**)dst receives the borrowed device pointer ([n][Npad] SoA).           */
+int fb_get(FbHandle h, int field, void* dst, int is_device);
+int fb_field_size(FbHandle h, int field);   /* floats per env, <0 on error */
+int fb_set(FbHandle h, int field, const float* src);  /* host [N][n] AoS -> device, all envs */
+
+/* Packed observation buffer of the last control step, [N][floats_per_env] AoS on device, for the
+ * NCCL gather to rank 0.  Layout: qpos, qvel, act, sensor_mean, xpos/xmat of
+ * root, site_xpos.                                                                            */
+int fb_obs_ptr(FbHandle h, void** dev_ptr, int* floats_per_env);
+
+int fb_n_envs(FbHandle h);
+int fb_n_envs_padded(FbHandle h);
+void* fb_stream(FbHandle h);                 /* cudaStream_t the handle launches on */
+int fb_sync(FbHandle h);
+long long fb_launch_count(FbHandle h);       /* kernels launched by this handle so far */
+/* device time (ms) of the last fb_step measured with CUDA events on the handle's stream */
+float fb_last_step_ms(FbHandle h);
+/* solver configuration: tolerance and iteration cap of the constraint solver */
+int fb_set_solver(FbHandle h, float tolerance, int max_iter);
+const char* fb_last_error(FbHandle h);
+const char* fb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,159 @@
+"""Physics invariants that pin the CPU oracle in the absence of a live MuJoCo."""
+import numpy as np
+import pytest
+
+from flybody_b200.flymodel import load_model
+from oracle import fly_oracle as fo
+from conftest import walk_reset_qpos
+
+
+def free_model(gravity=True):
+    """walk model with everything dissipative / external switched off."""
+    m = load_model('walk').copy()
+    a = m.a
+    a['opt_density'] = 0.0
+    a['opt_viscosity'] = 0.0
+    a['dof_damping'] = np.zeros_like(a['dof_damping'])
+    a['jnt_stiffness'] = np.zeros_like(a['jnt_stiffness'])
+    a['jnt_limited'] = np.zeros_like(a['jnt_limited'])
+    a['npair'] = 0
+    a['actuator_gainprm'] = np.zeros_like(a['actuator_gainprm'])
+    a['actuator_biasprm'] = np.zeros_like(a['actuator_biasprm'])
+    if not gravity:
+        a['opt_gravity'] = np.zeros(3)
+    a['opt_timestep'] = 2e-5
+    return m.rebuild()
+
+
+def energy(m, o):
+    M = o.get(fo.QM_DENSE).reshape(m.nv, m.nv)
+    v = o.qvel
+    com = o.get(fo.SUBTREE_COM).reshape(-1, 3)
+    # ghost (last body) and walker root are the two children of world
+    xipos_w = com[1]
+    pe = -m.body_subtreemass[1] * np.dot(m.opt_gravity, xipos_w) \
+         - m.body_subtreemass[m.nbody - 1] * np.dot(m.opt_gravity, com[m.nbody - 1])
+    return 0.5 * v @ M @ v, pe
+
+
+def test_mass_matrix_spd_and_matches_compiler():
+    from flybody_b200.compiler.compile_model import dense_mass_matrix
+    m = load_model('walk')
+    o = fo.Oracle(m)
+    rs = np.random.RandomState(1)
+    q = walk_reset_qpos(m)
+    q[7:109] += rs.uniform(-0.2, 0.2, 102)
+    o.reset(q)
+    M = o.get(fo.QM_DENSE).reshape(m.nv, m.nv)
+    Mc, _ = dense_mass_matrix(m.a, q)
+    assert np.abs(M - M.T).max() == 0
+    assert np.linalg.eigvalsh(M).min() > 0
+    assert np.abs(M - Mc).max() <= 1e-12 * np.abs(Mc).max()
+
+
+def test_energy_conservation_free_fall_tumbling():
+    m = free_model()
+    o = fo.Oracle(m)
+    rs = np.random.RandomState(2)
+    q = walk_reset_qpos(m)
+    q[2] = 5.0
+    v = np.zeros(m.nv)
+    v[:3] = rs.uniform(-5, 5, 3)
+    v[3:6] = rs.uniform(-20, 20, 3)
+    v[6:108] = rs.uniform(-30, 30, 102)
+    o.reset(q, v)
+    ke0, pe0 = energy(m, o)
+    for _ in range(400):
+        o.step()
+    ke1, pe1 = energy(m, o)
+    e0, e1 = ke0 + pe0, ke1 + pe1
+    # semi-implicit Euler: drift is O(h); the fall exchanged a sizeable part of KE
+    assert abs(e1 - e0) < 2e-3 * max(abs(ke0), abs(ke1)), (e0, e1, ke0, ke1)
+
+
+def test_momentum_conservation_no_gravity():
+    m = free_model(gravity=False)
+    o = fo.Oracle(m)
+    rs = np.random.RandomState(3)
+    q = walk_reset_qpos(m)
+    v = np.zeros(m.nv)
+    v[:3] = [1.0, -2.0, 0.5]
+    v[3:6] = rs.uniform(-10, 10, 3)
+    v[6:108] = rs.uniform(-30, 30, 102)
+    o.reset(q, v)
+    c0 = o.get(fo.SUBTREE_COM).reshape(-1, 3)[1].copy()
+    o.control_step(1)
+    c1 = o.get(fo.SUBTREE_COM).reshape(-1, 3)[1].copy()
+    o.control_step(300)
+    c2 = o.get(fo.SUBTREE_COM).reshape(-1, 3)[1].copy()
+    o.control_step(1)
+    c3 = o.get(fo.SUBTREE_COM).reshape(-1, 3)[1].copy()
+    vel_a, vel_b = (c1 - c0), (c3 - c2)
+    assert np.abs(vel_a - vel_b).max() < 2e-5 * np.abs(vel_a).max()   # O(h^2) per step drift of semi-implicit Euler
+
+
+def test_gravity_bias_matches_potential_gradient():
+    m = free_model()
+    o = fo.Oracle(m)
+    q = walk_reset_qpos(m)
+    rs = np.random.RandomState(4)
+    q[7:109] += rs.uniform(-0.3, 0.3, 102)
+    o.reset(q)
+    bias = o.get(fo.QFRC_BIAS)
+
+    def pe(qq):
+        o.reset(qq)
+        return energy(m, o)[1]
+    eps = 1e-6
+    for dof in (6, 20, 40, 60, 100):         # hinge dofs: qpos index = dof + 1
+        qp, qm = q.copy(), q.copy()
+        qp[dof + 1] += eps
+        qm[dof + 1] -= eps
+        g = (pe(qp) - pe(qm)) / (2 * eps)
+        assert abs(g - bias[dof]) < 1e-6 * max(1e-6, np.abs(bias).max()), (dof, g, bias[dof])
+
+
+def test_standing_contact_force_supports_weight():
+    m = load_model('walk')
+    o = fo.Oracle(m)
+    o.reset(walk_reset_qpos(m))
+    # hold the reset pose with the position servos (ctrl = current joint angle)
+    ctrl = np.zeros(m.nu)
+    for i in range(m.nu):
+        if m.actuator_trntype[i] == 0:
+            ctrl[i] = o.qpos[m.jnt_qposadr[m.actuator_trnid[i]]]
+    o.set(fo.CTRL, ctrl)
+    fz = []
+    for k in range(150):
+        o.control_step(10)
+        con = o.get(fo.CONTACT).reshape(-1, 16)
+        f = o.get(fo.EFC_FORCE)
+        tot = 0.0
+        for c in con:
+            if c[12] >= 0 and c[7] == 0:
+                tot += f[int(c[12])] * c[6]
+        fz.append(tot)
+    weight = m.body_subtreemass[1] * 981.0
+    assert o.get(fo.FLAGS)[0] == 0
+    assert abs(np.mean(fz[-50:]) - weight) < 0.05 * weight, (np.mean(fz[-50:]), weight)
+
+
+def test_solver_kkt_residual_small():
+    m = load_model('walk')
+    o = fo.Oracle(m, tolerance=1e-12)
+    o.reset(walk_reset_qpos(m))
+    rs = np.random.RandomState(5)
+    for k in range(20):
+        o.set(fo.CTRL, rs.uniform(-0.5, 0.5, m.nu))
+        o.control_step(10)
+    o.forward()
+    # at the solution: M (qacc - qacc_smooth) = J^T f  (before noslip this is exact; noslip keeps it by construction)
+    M = o.get(fo.QM_DENSE).reshape(m.nv, m.nv)
+    r = M @ o.qacc - o.get(fo.QFRC_SMOOTH) - o.get(fo.QFRC_CONSTRAINT)
+    assert np.abs(r).max() < 1e-6 * max(1.0, np.abs(o.get(fo.QFRC_SMOOTH)).max())
+    e = o.efc()
+    f = o.get(fo.EFC_FORCE)
+    # unilateral rows push only
+    for i, tp in enumerate(e['type']):
+        if tp in (0, 1):
+            assert f[i] >= 0
