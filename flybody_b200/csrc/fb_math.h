@@ -1,0 +1,84 @@
+// fb_math.h -- small fp32 vector / quaternion / spatial helpers used by every stage.
+#pragma once
+#include <math.h>
+#include "fb_types.h"
+
+struct V3 { float x, y, z; };
+struct Q4 { float w, x, y, z; };
+struct M3 { float m[9]; };       // row-major
+
+FB_DEV V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+FB_DEV V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+FB_DEV V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+FB_DEV V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+FB_DEV V3 operator*(float s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
+FB_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+FB_DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+FB_DEV float norm(V3 a) { return sqrtf(dot(a, a)); }
+FB_DEV V3 normalized(V3 a) { float n = norm(a); if (n < 1e-30f) return v3(1, 0, 0); float s = 1.0f / n; return a * s; }
+FB_DEV float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+FB_DEV Q4 q4(float w, float x, float y, float z) { Q4 q; q.w = w; q.x = x; q.y = y; q.z = z; return q; }
+FB_DEV Q4 qmul(Q4 a, Q4 b) {
+  return q4(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+            a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
+}
+FB_DEV Q4 qnormalize(Q4 q) {
+  float n = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  if (n < 1e-30f) return q4(1, 0, 0, 0);
+  float s = 1.0f / n; return q4(q.w * s, q.x * s, q.y * s, q.z * s);
+}
+FB_DEV M3 q2m(Q4 q) {
+  M3 R; float w = q.w, x = q.x, y = q.y, z = q.z;
+  R.m[0] = w * w + x * x - y * y - z * z; R.m[1] = 2 * (x * y - w * z); R.m[2] = 2 * (x * z + w * y);
+  R.m[3] = 2 * (x * y + w * z); R.m[4] = w * w - x * x + y * y - z * z; R.m[5] = 2 * (y * z - w * x);
+  R.m[6] = 2 * (x * z - w * y); R.m[7] = 2 * (y * z + w * x); R.m[8] = w * w - x * x - y * y + z * z;
+  return R;
+}
+FB_DEV V3 mul(const M3& R, V3 v) {
+  return v3(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z, R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z,
+            R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
+}
+FB_DEV V3 mulT(const M3& R, V3 v) {
+  return v3(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z, R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z,
+            R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
+}
+FB_DEV V3 col(const M3& R, int i) { return v3(R.m[i], R.m[3 + i], R.m[6 + i]); }
+FB_DEV Q4 axisangle(V3 axis, float ang) {
+  float s, c;
+#ifdef __CUDACC__
+  sincosf(0.5f * ang, &s, &c);
+#else
+  s = sinf(0.5f * ang); c = cosf(0.5f * ang);
+#endif
+  return q4(c, axis.x * s, axis.y * s, axis.z * s);
+}
+FB_DEV float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// SoA accessors: component i of env e
+#define AT(arr, i) (arr)[(size_t)(i) * (size_t)d.Np + (size_t)e]
+
+FB_DEV V3 ld3(const float* arr, int i, const DevData& d, int e) { return v3(AT(arr, 3 * i), AT(arr, 3 * i + 1), AT(arr, 3 * i + 2)); }
+FB_DEV void st3(float* arr, int i, const DevData& d, int e, V3 v) { AT(arr, 3 * i) = v.x; AT(arr, 3 * i + 1) = v.y; AT(arr, 3 * i + 2) = v.z; }
+FB_DEV Q4 ld4(const float* arr, int i, const DevData& d, int e) { return q4(AT(arr, 4 * i), AT(arr, 4 * i + 1), AT(arr, 4 * i + 2), AT(arr, 4 * i + 3)); }
+FB_DEV void st4(float* arr, int i, const DevData& d, int e, Q4 q) { AT(arr, 4 * i) = q.w; AT(arr, 4 * i + 1) = q.x; AT(arr, 4 * i + 2) = q.y; AT(arr, 4 * i + 3) = q.z; }
+FB_DEV M3 ld9(const float* arr, int i, const DevData& d, int e) { M3 R; for (int k = 0; k < 9; k++) R.m[k] = AT(arr, 9 * i + k); return R; }
+FB_DEV void st9(float* arr, int i, const DevData& d, int e, const M3& R) { for (int k = 0; k < 9; k++) AT(arr, 9 * i + k) = R.m[k]; }
+FB_DEV V3 mld3(const float* a, int i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+FB_DEV Q4 mld4(const float* a, int i) { return q4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]); }
+
+// 10-parameter spatial inertia about the reference point: m, h[3], Ixx Iyy Izz Ixy Ixz Iyz
+struct I10 { float v[10]; };
+FB_DEV void inert_mul(const I10& I, V3 w, V3 v, V3& L, V3& p) {
+  V3 h = v3(I.v[1], I.v[2], I.v[3]);
+  V3 hv = cross(h, v), wh = cross(w, h);
+  L = v3(I.v[4] * w.x + I.v[7] * w.y + I.v[8] * w.z + hv.x, I.v[7] * w.x + I.v[5] * w.y + I.v[9] * w.z + hv.y,
+         I.v[8] * w.x + I.v[9] * w.y + I.v[6] * w.z + hv.z);
+  p = v3(I.v[0] * v.x + wh.x, I.v[0] * v.y + wh.y, I.v[0] * v.z + wh.z);
+}
+FB_DEV I10 ld10(const float* arr, int b, const DevData& d, int e) { I10 I; for (int k = 0; k < 10; k++) I.v[k] = AT(arr, 10 * b + k); return I; }
+
+// spatial 6-vector [angular; linear]
+struct S6 { V3 a, l; };
+FB_DEV S6 ld6(const float* arr, int b, const DevData& d, int e) { S6 s; s.a = ld3(arr, 2 * b, d, e); s.l = ld3(arr, 2 * b + 1, d, e); return s; }
+FB_DEV void st6(float* arr, int b, const DevData& d, int e, const S6& s) { st3(arr, 2 * b, d, e, s.a); st3(arr, 2 * b + 1, d, e, s.l); }

@@ -1,0 +1,476 @@
+// fb_tree.h -- tree-structured stages: kinematics, composite inertia, sparse L^T D L factorisation
+// and solve, body velocities, RNE bias, passive (spring/damper/fluid) forces.
+//
+// Thread mapping of every "tree kernel": blockDim = (32 envs, nlist branch lists).  lane == env
+// (coalesced SoA access); threadIdx.y walks one branch list of the kinematic tree (a leg, the
+// abdomen chain, the head sub-tree ...) in topological order.  The root bodies (free joints) are
+// handled by y == 0; the lists exchange their contributions to the root through shared memory.
+// Each kernel is a sequence of *phases* separated by block barriers (see fb_run in fb_kernels.cu).
+#pragma once
+#include "fb_math.h"
+
+struct ShTree {
+  float part[FB_NLMAX][24][32];    // per-list partial sums towards the root (crb:10, factor:21, solve:6, rne:12)
+};
+
+#define FB_PHASE_ARGS const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y
+#define FB_LIST_LOOP_FWD for (int li_ = 0, b = 0; li_ < m.list_num[y] && ((b = m.list_body[m.list_adr[y] + li_]), true); li_++)
+#define FB_LIST_LOOP_REV for (int li_ = m.list_num[y] - 1, b = 0; li_ >= 0 && ((b = m.list_body[m.list_adr[y] + li_]), true); li_--)
+
+// ---------------------------------------------------------------------------------------------
+// K1 kinematics (MuJoCo mj_kinematics + mj_comPos; reference model fruitfly.xml:307-731)
+FB_DEV void body_kinematics(const DevModel& m, const DevData& d, int e, int b) {
+  int p = m.body_parentid[b];
+  V3 ppos = ld3(d.xpos, p, d, e);
+  Q4 pq = ld4(d.xquat, p, d, e);
+  M3 pR = q2m(pq);
+  V3 pos = ppos + mul(pR, mld3(m.body_pos, b));
+  Q4 quat = qmul(pq, mld4(m.body_quat, b));
+  V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
+  int jn = m.body_jntnum[b];
+  for (int k = 0; k < jn; k++) {
+    int j = m.body_jntadr[b] + k, qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
+    if (m.jnt_type[j] == FB_JNT_FREE) {
+      pos = v3(AT(d.qpos, qa), AT(d.qpos, qa + 1), AT(d.qpos, qa + 2)) - ref;
+      quat = qnormalize(q4(AT(d.qpos, qa + 3), AT(d.qpos, qa + 4), AT(d.qpos, qa + 5), AT(d.qpos, qa + 6)));
+      M3 R = q2m(quat);
+      for (int i = 0; i < 3; i++) {
+        V3 ei = v3(i == 0, i == 1, i == 2);
+        st3(d.Sang, da + i, d, e, v3(0, 0, 0));
+        st3(d.Slin, da + i, d, e, ei);
+        V3 ax = col(R, i);
+        st3(d.Sang, da + 3 + i, d, e, ax);
+        st3(d.Slin, da + 3 + i, d, e, cross(pos, ax));
+      }
+    } else {
+      M3 R = q2m(quat);
+      V3 jp = mld3(m.jnt_pos, j), ja = mld3(m.jnt_axis, j);
+      V3 anchor = pos + mul(R, jp);
+      V3 axis = mul(R, ja);
+      quat = qmul(quat, axisangle(ja, AT(d.qpos, qa) - m.qpos0[qa]));
+      R = q2m(quat);
+      pos = anchor - mul(R, jp);
+      st3(d.Sang, da, d, e, axis);
+      st3(d.Slin, da, d, e, cross(anchor, axis));
+    }
+  }
+  quat = qnormalize(quat);
+  M3 R = q2m(quat);
+  st3(d.xpos, b, d, e, pos); st4(d.xquat, b, d, e, quat); st9(d.xmat, b, d, e, R);
+  V3 ipos = pos + mul(R, mld3(m.body_ipos, b));
+  M3 iR = q2m(qmul(quat, mld4(m.body_iquat, b)));
+  st3(d.xipos, b, d, e, ipos); st9(d.ximat, b, d, e, iR);
+  // spatial inertia about ref
+  float mass = m.body_mass[b];
+  V3 di = mld3(m.body_inertia, b);
+  float Ic[6];   // xx yy zz xy xz yz of R diag(di) R^T
+  Ic[0] = iR.m[0] * iR.m[0] * di.x + iR.m[1] * iR.m[1] * di.y + iR.m[2] * iR.m[2] * di.z;
+  Ic[1] = iR.m[3] * iR.m[3] * di.x + iR.m[4] * iR.m[4] * di.y + iR.m[5] * iR.m[5] * di.z;
+  Ic[2] = iR.m[6] * iR.m[6] * di.x + iR.m[7] * iR.m[7] * di.y + iR.m[8] * iR.m[8] * di.z;
+  Ic[3] = iR.m[0] * iR.m[3] * di.x + iR.m[1] * iR.m[4] * di.y + iR.m[2] * iR.m[5] * di.z;
+  Ic[4] = iR.m[0] * iR.m[6] * di.x + iR.m[1] * iR.m[7] * di.y + iR.m[2] * iR.m[8] * di.z;
+  Ic[5] = iR.m[3] * iR.m[6] * di.x + iR.m[4] * iR.m[7] * di.y + iR.m[5] * iR.m[8] * di.z;
+  float cc = dot(ipos, ipos);
+  float I[10];
+  I[0] = mass; I[1] = mass * ipos.x; I[2] = mass * ipos.y; I[3] = mass * ipos.z;
+  I[4] = Ic[0] + mass * (cc - ipos.x * ipos.x); I[5] = Ic[1] + mass * (cc - ipos.y * ipos.y); I[6] = Ic[2] + mass * (cc - ipos.z * ipos.z);
+  I[7] = Ic[3] - mass * ipos.x * ipos.y; I[8] = Ic[4] - mass * ipos.x * ipos.z; I[9] = Ic[5] - mass * ipos.y * ipos.z;
+  for (int k = 0; k < 10; k++) { AT(d.inert10, 10 * b + k) = I[k]; AT(d.crb10, 10 * b + k) = I[k]; }
+  // geoms and sites rigidly attached to this body
+  for (int g = m.body_geomadr[b], ge = g + m.body_geomnum[b]; g < ge; g++) {
+    st3(d.geom_xpos, g, d, e, pos + mul(R, mld3(m.geom_pos, g)));
+    st9(d.geom_xmat, g, d, e, q2m(qmul(quat, mld4(m.geom_quat, g))));
+  }
+  for (int s = m.body_siteadr[b], se = s + m.body_sitenum[b]; s < se; s++) {
+    st3(d.site_xpos, s, d, e, pos + mul(R, mld3(m.site_pos, s)));
+    st9(d.site_xmat, s, d, e, q2m(qmul(quat, mld4(m.site_quat, s))));
+  }
+}
+
+FB_DEV void kpos_p0(FB_PHASE_ARGS) {
+  if (y != 0) return;
+  // reference point = position of the first root's free joint
+  int rb = m.root_body[0];
+  V3 ref = v3(0, 0, 0);
+  if (m.body_jntnum[rb] > 0 && m.jnt_type[m.body_jntadr[rb]] == FB_JNT_FREE) {
+    int qa = m.jnt_qposadr[m.body_jntadr[rb]];
+    ref = v3(AT(d.qpos, qa), AT(d.qpos, qa + 1), AT(d.qpos, qa + 2));
+  }
+  AT(d.ref, 0) = ref.x; AT(d.ref, 1) = ref.y; AT(d.ref, 2) = ref.z;
+  // world body
+  st3(d.xpos, 0, d, e, v3(0, 0, 0) - ref); st4(d.xquat, 0, d, e, q4(1, 0, 0, 0));
+  M3 I; for (int k = 0; k < 9; k++) I.m[k] = (k % 4 == 0) ? 1.f : 0.f;
+  st9(d.xmat, 0, d, e, I); st3(d.xipos, 0, d, e, v3(0, 0, 0) - ref); st9(d.ximat, 0, d, e, I);
+  for (int k = 0; k < 10; k++) { AT(d.inert10, k) = 0; AT(d.crb10, k) = 0; }
+  for (int g = m.body_geomadr[0], ge = g + m.body_geomnum[0]; g < ge; g++) {
+    st3(d.geom_xpos, g, d, e, mld3(m.geom_pos, g) - ref);
+    st9(d.geom_xmat, g, d, e, q2m(mld4(m.geom_quat, g)));
+  }
+  for (int r = 0; r < m.nroot; r++) body_kinematics(m, d, e, m.root_body[r]);
+}
+FB_DEV void kpos_p1(FB_PHASE_ARGS) {
+  if (y >= m.nlist) return;
+  FB_LIST_LOOP_FWD body_kinematics(m, d, e, b);
+}
+// K2 composite inertia, backward accumulation (MuJoCo mj_crb)
+FB_DEV void kpos_p2(FB_PHASE_ARGS) {
+  if (y >= m.nlist) return;
+  float acc[10];
+  for (int k = 0; k < 10; k++) acc[k] = 0;
+  FB_LIST_LOOP_REV {
+    int p = m.body_parentid[b];
+    if (m.body_isroot[p]) { for (int k = 0; k < 10; k++) acc[k] += AT(d.crb10, 10 * b + k); }
+    else { for (int k = 0; k < 10; k++) AT(d.crb10, 10 * p + k) += AT(d.crb10, 10 * b + k); }
+  }
+  for (int k = 0; k < 10; k++) sh.part[y][k][lane] = acc[k];
+}
+FB_DEV void kpos_p3(FB_PHASE_ARGS) {
+  if (y != 0) return;
+  for (int r = 0; r < m.nroot; r++) {
+    int b = m.root_body[r];
+    for (int k = 0; k < 10; k++) {
+      float s = AT(d.inert10, 10 * b + k);
+      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) s += sh.part[l][k][lane];
+      AT(d.crb10, 10 * b + k) = s;
+    }
+  }
+}
+// joint-space inertia entries of dof i (row of the sparse lower triangle along the ancestor chain)
+FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int i) {
+  int b = m.dof_bodyid[i];
+  I10 I = ld10(d.crb10, b, d, e);
+  V3 L, p;
+  inert_mul(I, ld3(d.Sang, i, d, e), ld3(d.Slin, i, d, e), L, p);
+  int adr = m.dof_Madr[i];
+  float hd = m.timestep * m.dof_damping[i];
+  int t = 0;
+  for (int j = i; j >= 0; j = m.dof_parentid[j], t++) {
+    float v = dot(ld3(d.Sang, j, d, e), L) + dot(ld3(d.Slin, j, d, e), p);
+    if (t == 0) v += m.dof_armature[i];
+    AT(d.qM, adr + t) = v; AT(d.qLD, adr + t) = v; AT(d.qLDe, adr + t) = (t == 0) ? v + hd : v;
+  }
+}
+FB_DEV void kpos_p4(FB_PHASE_ARGS) {
+  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) mass_row(m, d, e, m.body_dofadr[b] + k); }
+  if (y >= m.nlist) return;
+  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) mass_row(m, d, e, m.body_dofadr[b] + k); }
+}
+
+// sparse L^T D L factorisation (Featherstone; MuJoCo mj_factorM), list part.  Row k of LD holds
+// (k,k), (k,parent(k)), ... at dof_Madr[k] + t.  Updates that land in the root block are summed
+// into sh.part (21 entries) and applied by the root thread.
+FB_DEV void factor_lists(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* LD) {
+  if (y >= m.nlist) return;
+  for (int k = 0; k < 21; k++) sh.part[y][k][lane] = 0;
+  FB_LIST_LOOP_REV {
+    for (int kk = m.body_dofnum[b] - 1; kk >= 0; kk--) {
+      int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
+      float Dk = AT(LD, adrk);
+      float invD = 1.0f / Dk;
+      int t = 1;
+      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) {
+        float a = AT(LD, adrk + t) * invD;
+        if (!m.dof_isroot[i]) {
+          int adri = m.dof_Madr[i], len = m.dof_chainlen[i];
+          for (int s = 0; s < len; s++) AT(LD, adri + s) -= a * AT(LD, adrk + t + s);
+        } else {
+          int il = m.dof_depth[i];        // for root dofs depth == local index
+          int base = il * (il + 1) / 2;
+          for (int s = 0; s <= il; s++) sh.part[y][base + s][lane] += a * AT(LD, adrk + t + s);
+        }
+        AT(LD, adrk + t) = a;
+      }
+    }
+  }
+}
+FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* LD) {
+  if (y != 0) return;
+  for (int r = 0; r < m.nroot; r++) {
+    int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
+    if (nd == 0) continue;
+    for (int il = 0; il < nd; il++) {
+      int adri = m.dof_Madr[d0 + il], base = il * (il + 1) / 2;
+      for (int s = 0; s <= il; s++) {
+        float acc = 0;
+        for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc += sh.part[l][base + s][lane];
+        AT(LD, adri + s) -= acc;
+      }
+    }
+    for (int kl = nd - 1; kl >= 0; kl--) {
+      int adrk = m.dof_Madr[d0 + kl];
+      float invD = 1.0f / AT(LD, adrk);
+      for (int t = 1; t <= kl; t++) {
+        int il = kl - t, adri = m.dof_Madr[d0 + il];
+        float a = AT(LD, adrk + t) * invD;
+        for (int s = 0; s <= il; s++) AT(LD, adri + s) -= a * AT(LD, adrk + t + s);
+        AT(LD, adrk + t) = a;
+      }
+    }
+  }
+}
+FB_DEV void kpos_p5(FB_PHASE_ARGS) { factor_lists(m, d, sh, e, lane, y, d.qLD); }
+FB_DEV void kpos_p6(FB_PHASE_ARGS) { factor_root(m, d, sh, e, lane, y, d.qLD); }
+FB_DEV void kpos_p7(FB_PHASE_ARGS) { factor_lists(m, d, sh, e, lane, y, d.qLDe); }
+FB_DEV void kpos_p8(FB_PHASE_ARGS) { factor_root(m, d, sh, e, lane, y, d.qLDe); }
+
+// ---------------------------------------------------------------------------------------------
+// x <- (L^T D L)^-1 x in three phases (MuJoCo mj_solveLD)
+FB_DEV void solve_a(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, float* x) {
+  if (y >= m.nlist) return;
+  for (int k = 0; k < 6; k++) sh.part[y][k][lane] = 0;
+  FB_LIST_LOOP_REV {
+    for (int kk = m.body_dofnum[b] - 1; kk >= 0; kk--) {
+      int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
+      float xk = AT(x, k);
+      int t = 1;
+      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) {
+        float l = AT(LD, adrk + t);
+        if (!m.dof_isroot[i]) AT(x, i) -= l * xk; else sh.part[y][m.dof_depth[i]][lane] += l * xk;
+      }
+    }
+  }
+}
+FB_DEV void solve_b(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, float* x) {
+  if (y != 0) return;
+  for (int r = 0; r < m.nroot; r++) {
+    int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
+    for (int il = 0; il < nd; il++) {
+      float acc = 0;
+      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc += sh.part[l][il][lane];
+      AT(x, d0 + il) -= acc;
+    }
+    for (int kl = nd - 1; kl >= 0; kl--) {
+      float xk = AT(x, d0 + kl); int adrk = m.dof_Madr[d0 + kl];
+      for (int t = 1; t <= kl; t++) AT(x, d0 + kl - t) -= AT(LD, adrk + t) * xk;
+    }
+    for (int kl = 0; kl < nd; kl++) {
+      int adrk = m.dof_Madr[d0 + kl];
+      float v = AT(x, d0 + kl) / AT(LD, adrk);
+      for (int t = 1; t <= kl; t++) v -= AT(LD, adrk + t) * AT(x, d0 + kl - t);
+      AT(x, d0 + kl) = v;
+    }
+  }
+}
+FB_DEV void solve_c(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, float* x) {
+  if (y >= m.nlist) return;
+  FB_LIST_LOOP_FWD {
+    for (int kk = 0; kk < m.body_dofnum[b]; kk++) {
+      int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
+      float v = AT(x, k) / AT(LD, adrk);
+      int t = 1;
+      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) v -= AT(LD, adrk + t) * AT(x, i);
+      AT(x, k) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 velocities + RNE bias, K5-K7 passive forces (MuJoCo mj_comVel, mj_rne, mj_passive)
+FB_DEV S6 motion_cross(const S6& v, V3 Sa, V3 Sl) { S6 r; r.a = cross(v.a, Sa); r.l = cross(v.a, Sl) + cross(v.l, Sa); return r; }
+
+// forward recursion for one body; qacc == nullptr -> bias acceleration only
+FB_DEV void body_vel_acc(const DevModel& m, const DevData& d, int e, int b, const float* qacc, float* bvel, float* bacc) {
+  int p = m.body_parentid[b];
+  S6 v = ld6(bvel, p, d, e), a = ld6(bacc, p, d, e);
+  int jn = m.body_jntnum[b];
+  for (int k = 0; k < jn; k++) {
+    int j = m.body_jntadr[b] + k, da = m.jnt_dofadr[j];
+    if (m.jnt_type[j] == FB_JNT_FREE) {
+      V3 vlin = v3(AT(d.qvel, da), AT(d.qvel, da + 1), AT(d.qvel, da + 2)), w = v3(0, 0, 0);
+      for (int i = 0; i < 6; i++) {
+        float qd = AT(d.qvel, da + i);
+        V3 Sa = ld3(d.Sang, da + i, d, e), Sl = ld3(d.Slin, da + i, d, e);
+        v.a = v.a + Sa * qd; v.l = v.l + Sl * qd;
+        if (i >= 3) w = w + Sa * qd;
+        if (qacc) { float qa = AT(qacc, da + i); a.a = a.a + Sa * qa; a.l = a.l + Sl * qa; }
+      }
+      a.l = a.l + cross(vlin, w);
+    } else {
+      float qd = AT(d.qvel, da);
+      V3 Sa = ld3(d.Sang, da, d, e), Sl = ld3(d.Slin, da, d, e);
+      S6 r = motion_cross(v, Sa, Sl);
+      a.a = a.a + r.a * qd; a.l = a.l + r.l * qd;
+      v.a = v.a + Sa * qd; v.l = v.l + Sl * qd;
+      if (qacc) { float qa = AT(qacc, da); a.a = a.a + Sa * qa; a.l = a.l + Sl * qa; }
+    }
+  }
+  st6(bvel, b, d, e, v); st6(bacc, b, d, e, a);
+}
+// inertial force of body b: I a + v x* (I v), [torque about ref; force]
+FB_DEV S6 body_inertial_force(const DevModel& m, const DevData& d, int e, int b, const float* bvel, const float* bacc) {
+  I10 I = ld10(d.inert10, b, d, e);
+  S6 v = ld6(bvel, b, d, e), a = ld6(bacc, b, d, e);
+  V3 L, p, La, pa;
+  inert_mul(I, v.a, v.l, L, p); inert_mul(I, a.a, a.l, La, pa);
+  S6 f;
+  f.a = La + cross(v.a, L) + cross(v.l, p);
+  f.l = pa + cross(v.a, p);
+  return f;
+}
+FB_DEV float pow4(float x) { float y = x * x; return y * y; }
+// fluid wrench on body b about ref (inertia-box model, or ellipsoid model for flagged bodies)
+FB_DEV S6 body_fluid_wrench(const DevModel& m, const DevData& d, int e, int b) {
+  S6 out; out.a = v3(0, 0, 0); out.l = v3(0, 0, 0);
+  float rho = m.density, eta = m.viscosity;
+  float mass = m.body_mass[b];
+  if ((rho <= 0 && eta <= 0) || mass < FB_MINVAL) return out;
+  S6 bv = ld6(d.bvel, b, d, e);
+  V3 wind = v3(m.wind[0], m.wind[1], m.wind[2]);
+  const float PI = 3.14159265358979f;
+  if (!m.body_fluid_ellipsoid[b]) {
+    V3 I = mld3(m.body_inertia, b);
+    float bx = sqrtf(fmaxf(FB_MINVAL, I.y + I.z - I.x) / mass * 6.0f);
+    float by = sqrtf(fmaxf(FB_MINVAL, I.x + I.z - I.y) / mass * 6.0f);
+    float bz = sqrtf(fmaxf(FB_MINVAL, I.x + I.y - I.z) / mass * 6.0f);
+    V3 c = ld3(d.xipos, b, d, e);
+    M3 R = ld9(d.ximat, b, d, e);
+    V3 lw = mulT(R, bv.a), lv = mulT(R, bv.l + cross(bv.a, c) - wind);
+    V3 tq = v3(0, 0, 0), fr = v3(0, 0, 0);
+    if (eta > 0) {
+      float diam = (bx + by + bz) / 3.0f;
+      tq = lw * (-PI * diam * diam * diam * eta);
+      fr = lv * (-3.0f * PI * diam * eta);
+    }
+    if (rho > 0) {
+      fr.x -= 0.5f * rho * by * bz * fabsf(lv.x) * lv.x;
+      fr.y -= 0.5f * rho * bx * bz * fabsf(lv.y) * lv.y;
+      fr.z -= 0.5f * rho * bx * by * fabsf(lv.z) * lv.z;
+      tq.x -= rho * bx * (pow4(by) + pow4(bz)) * fabsf(lw.x) * lw.x / 64.0f;
+      tq.y -= rho * by * (pow4(bx) + pow4(bz)) * fabsf(lw.y) * lw.y / 64.0f;
+      tq.z -= rho * bz * (pow4(bx) + pow4(by)) * fabsf(lw.z) * lw.z / 64.0f;
+    }
+    V3 F = mul(R, fr), T = mul(R, tq);
+    out.l = F; out.a = T + cross(c, F);
+    return out;
+  }
+  // ellipsoid model (reference flybody/ellipsoid_fluid_model.py:88-310) for every fluid geom of this body
+  for (int g = 0; g < m.nfluid; g++) {
+    if (m.fluid_bodyid[g] != b) continue;
+    const float* coef = m.fluid_coef + 12 * g;
+    if (coef[0] == 0.0f) continue;
+    V3 size = mld3(m.fluid_size, g);
+    V3 bpos = ld3(d.xpos, b, d, e); Q4 bq = ld4(d.xquat, b, d, e);
+    M3 bR = q2m(bq);
+    V3 gpos = bpos + mul(bR, mld3(m.fluid_pos, g));
+    M3 gR = q2m(qmul(bq, mld4(m.fluid_quat, g)));
+    V3 lw = mulT(gR, bv.a), lv = mulT(gR, bv.l + cross(bv.a, gpos) - wind);
+    float blunt = coef[1], slender = coef[2], angc = coef[3], kutta = coef[4], magnus = coef[5];
+    V3 vmass = v3(coef[6], coef[7], coef[8]), vin = v3(coef[9], coef[10], coef[11]);
+    V3 vlm = v3(rho * vmass.x * lv.x, rho * vmass.y * lv.y, rho * vmass.z * lv.z);
+    V3 vam = v3(rho * vin.x * lw.x, rho * vin.y * lw.y, rho * vin.z * lw.z);
+    V3 tq = cross(vlm, lv) + cross(vam, lw);
+    V3 fr = cross(vlm, lw);
+    float volume = 4.0f / 3.0f * PI * size.x * size.y * size.z;
+    float dmax = fmaxf(size.x, fmaxf(size.y, size.z)), dmin = fminf(size.x, fminf(size.y, size.z));
+    float dmid = size.x + size.y + size.z - dmax - dmin;
+    float A_max = PI * dmax * dmid;
+    V3 magf = cross(lw, lv) * (magnus * rho * volume);
+    float s12 = size.y * size.z, s20 = size.z * size.x, s01 = size.x * size.y;
+    float proj_denom = pow4(s12) * lv.x * lv.x + pow4(s20) * lv.y * lv.y + pow4(s01) * lv.z * lv.z;
+    float proj_num = (s12 * lv.x) * (s12 * lv.x) + (s20 * lv.y) * (s20 * lv.y) + (s01 * lv.z) * (s01 * lv.z);
+    // the products of 1e-3 .. 1e-1 cm semi-axes underflow fp32 MINVAL=1e-15; use a scaled guard
+    float A_proj = PI * sqrtf(proj_denom / fmaxf(1e-37f, proj_num));
+    V3 nrm = v3(s12 * s12 * lv.x, s20 * s20 * lv.y, s01 * s01 * lv.z);
+    float speed = norm(lv);
+    float cos_alpha = proj_num / fmaxf(1e-37f, speed * proj_denom);
+    V3 kc = cross(nrm, lv) * (kutta * rho * cos_alpha * A_proj);
+    V3 kf = cross(kc, lv);
+    float eqD = 2.0f / 3.0f * (size.x + size.y + size.z);
+    float lin_coef = 3.0f * PI * eqD, ang_coef = PI * eqD * eqD * eqD;
+    float I_max = 8.0f / 15.0f * PI * dmid * pow4(dmax);
+    float II0 = 8.0f / 15.0f * PI * size.x * pow4(fmaxf(size.y, size.z));
+    float II1 = 8.0f / 15.0f * PI * size.y * pow4(fmaxf(size.z, size.x));
+    float II2 = 8.0f / 15.0f * PI * size.z * pow4(fmaxf(size.x, size.y));
+    V3 mom = v3(lw.x * (angc * II0 + slender * (I_max - II0)), lw.y * (angc * II1 + slender * (I_max - II1)),
+                lw.z * (angc * II2 + slender * (I_max - II2)));
+    float drag_lin = eta * lin_coef + rho * speed * (A_proj * blunt + slender * (A_max - A_proj));
+    float drag_ang = eta * ang_coef + rho * norm(mom);
+    tq = tq - lw * drag_ang;
+    fr = fr + magf + kf - lv * drag_lin;
+    tq = tq * coef[0]; fr = fr * coef[0];
+    V3 F = mul(gR, fr), T = mul(gR, tq);
+    out.l = out.l + F; out.a = out.a + T + cross(gpos, F);
+  }
+  return out;
+}
+
+FB_DEV void kvel_p0(FB_PHASE_ARGS) {
+  if (y != 0) return;
+  S6 z; z.a = v3(0, 0, 0); z.l = v3(0, 0, 0);
+  st6(d.bvel, 0, d, e, z);
+  z.l = v3(-m.gravity[0], -m.gravity[1], -m.gravity[2]);
+  st6(d.bacc, 0, d, e, z);
+  for (int r = 0; r < m.nroot; r++) {
+    int b = m.root_body[r];
+    body_vel_acc(m, d, e, b, nullptr, d.bvel, d.bacc);
+    st6(d.bfrc, b, d, e, body_inertial_force(m, d, e, b, d.bvel, d.bacc));
+    st6(d.bfl, b, d, e, body_fluid_wrench(m, d, e, b));
+  }
+}
+FB_DEV void kvel_p1(FB_PHASE_ARGS) {
+  if (y >= m.nlist) return;
+  FB_LIST_LOOP_FWD {
+    body_vel_acc(m, d, e, b, nullptr, d.bvel, d.bacc);
+    st6(d.bfrc, b, d, e, body_inertial_force(m, d, e, b, d.bvel, d.bacc));
+    st6(d.bfl, b, d, e, body_fluid_wrench(m, d, e, b));
+  }
+}
+FB_DEV void project_body_forces(const DevModel& m, const DevData& d, int e, int b, const S6& f, const S6& fl) {
+  for (int kk = 0; kk < m.body_dofnum[b]; kk++) {
+    int k = m.body_dofadr[b] + kk;
+    V3 Sa = ld3(d.Sang, k, d, e), Sl = ld3(d.Slin, k, d, e);
+    AT(d.qfrc_bias, k) = dot(Sa, f.a) + dot(Sl, f.l);
+    float pas = dot(Sa, fl.a) + dot(Sl, fl.l) - m.dof_damping[k] * AT(d.qvel, k);
+    int j = m.dof_jntid[k];
+    if (m.jnt_type[j] == FB_JNT_HINGE) { int qa = m.jnt_qposadr[j]; pas -= m.jnt_stiffness[j] * (AT(d.qpos, qa) - m.qpos_spring[qa]); }
+    AT(d.qfrc_passive, k) = pas;
+  }
+}
+FB_DEV void kvel_p2(FB_PHASE_ARGS) {
+  if (y >= m.nlist) return;
+  float acc[12];
+  for (int k = 0; k < 12; k++) acc[k] = 0;
+  FB_LIST_LOOP_REV {
+    S6 f = ld6(d.bfrc, b, d, e), fl = ld6(d.bfl, b, d, e);
+    project_body_forces(m, d, e, b, f, fl);
+    int p = m.body_parentid[b];
+    if (m.body_isroot[p]) {
+      acc[0] += f.a.x; acc[1] += f.a.y; acc[2] += f.a.z; acc[3] += f.l.x; acc[4] += f.l.y; acc[5] += f.l.z;
+      acc[6] += fl.a.x; acc[7] += fl.a.y; acc[8] += fl.a.z; acc[9] += fl.l.x; acc[10] += fl.l.y; acc[11] += fl.l.z;
+    } else {
+      S6 pf = ld6(d.bfrc, p, d, e), pfl = ld6(d.bfl, p, d, e);
+      pf.a = pf.a + f.a; pf.l = pf.l + f.l; pfl.a = pfl.a + fl.a; pfl.l = pfl.l + fl.l;
+      st6(d.bfrc, p, d, e, pf); st6(d.bfl, p, d, e, pfl);
+    }
+  }
+  for (int k = 0; k < 12; k++) sh.part[y][k][lane] = acc[k];
+}
+FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e);
+FB_DEV void kvel_p3(FB_PHASE_ARGS) {
+  if (y != 0) return;
+  for (int r = 0; r < m.nroot; r++) {
+    int b = m.root_body[r];
+    float acc[12];
+    for (int k = 0; k < 12; k++) { acc[k] = 0; for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc[k] += sh.part[l][k][lane]; }
+    S6 f = ld6(d.bfrc, b, d, e), fl = ld6(d.bfl, b, d, e);
+    f.a = f.a + v3(acc[0], acc[1], acc[2]); f.l = f.l + v3(acc[3], acc[4], acc[5]);
+    fl.a = fl.a + v3(acc[6], acc[7], acc[8]); fl.l = fl.l + v3(acc[9], acc[10], acc[11]);
+    st6(d.bfrc, b, d, e, f); st6(d.bfl, b, d, e, fl);
+    project_body_forces(m, d, e, b, f, fl);
+  }
+  sensors_vel(m, d, e);
+}
+// gyro / velocimeter (MuJoCo mj_sensorVel; sensors fruitfly.xml:900-903)
+FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e) {
+  for (int s = 0; s < m.nsensor; s++) {
+    int tp = m.sensor_type[s];
+    if (tp != FB_SENS_GYRO && tp != FB_SENS_VELOCIMETER) continue;
+    int site = m.sensor_objid[s], adr = m.sensor_adr[s], b = m.site_bodyid[site];
+    S6 v = ld6(d.bvel, b, d, e);
+    M3 R = ld9(d.site_xmat, site, d, e);
+    V3 out;
+    if (tp == FB_SENS_GYRO) out = mulT(R, v.a);
+    else out = mulT(R, v.l + cross(v.a, ld3(d.site_xpos, site, d, e)));
+    AT(d.sensordata, adr) = out.x; AT(d.sensordata, adr + 1) = out.y; AT(d.sensordata, adr + 2) = out.z;
+  }
+}

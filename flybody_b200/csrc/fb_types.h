@@ -1,0 +1,103 @@
+// fb_types.h -- device-side model / state layout of the batched fly stepper.
+//
+// Layout rule (DESIGN.md "Data layout in HBM"): every per-env array is SoA [component][env], env
+// fastest, fp32, env count padded to a multiple of 32, so that lane == env gives one coalesced
+// 128-byte transaction per component.  Model constants are small read-only arrays that every lane
+// reads at the same address (broadcast, L1-resident).
+#pragma once
+#include <stdint.h>
+#include "../../include/flybody_b200.h"
+
+#ifdef __CUDACC__
+#define FB_DEV __device__ __forceinline__
+#define FB_DEVN __device__ __noinline__
+#define FB_HD __host__ __device__
+#else
+#define FB_DEV static inline
+#define FB_DEVN static
+#define FB_HD
+#endif
+
+#define FB_NLMAX 12          // branch lists (threadIdx.y of tree kernels)
+#define FB_MAXCHUNK 32       // collision chunks (threadIdx.y of the collision kernel)
+#define FB_CHUNKCAP 16       // contacts one chunk may emit
+#define FB_ROWPAR 8          // rows processed in parallel by the projection kernel
+#define FB_MINVAL 1e-15f
+
+struct DevModel {
+  // sizes / options
+  int nq, nv, nu, na, nbody, njnt, ngeom, npair, nsite, ntendon, nwrap, nsensor, nsensordata, nM, nfluid;
+  int noslip_iterations, cone_elliptic, max_iter, ls_iter;
+  float timestep, gravity[3], density, viscosity, wind[3], impratio, tolerance, noslip_tolerance, meaninertia;
+  // tree partition
+  int nroot, nlist;
+  const int *root_body;                    // [nroot]
+  const int *list_adr, *list_num, *list_body, *list_root;   // bodies of each branch list in topological order
+  // bodies
+  const int *body_parentid, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_lastdof,
+      *body_fluid_ellipsoid, *body_isroot, *body_geomadr, *body_geomnum, *body_siteadr, *body_sitenum;
+  const float *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
+  // joints / dofs
+  const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
+  const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen;
+  const float *dof_armature, *dof_damping, *dof_invweight0;
+  // geoms
+  const int *geom_type, *geom_bodyid, *geom_condim;
+  const float *geom_size, *geom_pos, *geom_quat, *geom_rbound, *geom_friction, *geom_solmix, *geom_solref, *geom_solimp,
+      *geom_margin, *geom_gap;
+  const int *pair_geom1, *pair_geom2;
+  int nchunk; const int* chunk_start;   // [nchunk+1] pair ranges, balanced by expected contact count
+  // fluid geoms, sites, tendons, actuators, sensors
+  const int *fluid_bodyid; const float *fluid_pos, *fluid_quat, *fluid_size, *fluid_coef;
+  const int *site_bodyid, *site_type; const float *site_pos, *site_quat, *site_size;
+  const int *tendon_adr, *tendon_num, *wrap_dofid, *wrap_qposadr; const float *wrap_coef;
+  const int *actuator_trntype, *actuator_trnid, *actuator_dyntype, *actuator_biastype, *actuator_ctrllimited,
+      *actuator_forcelimited, *actuator_actadr;
+  const float *actuator_dynprm, *actuator_gainprm, *actuator_biasprm, *actuator_ctrlrange, *actuator_forcerange;
+  const int *sensor_type, *sensor_objid, *sensor_adr, *sensor_dim;
+};
+
+// efc row types
+enum { FB_CT_LIMIT = 0, FB_CT_FRICTIONLESS = 1, FB_CT_ELLIPTIC = 2 };
+
+struct DevData {
+  int N, Np;                   // envs, padded envs (stride of every array)
+  int nsub_done;
+  // integrated state
+  float *qpos, *qvel, *act, *ctrl, *qacc, *qacc_warmstart, *time;
+  // position stage
+  float *ref;                  // [3] reference point (root position) all spatial quantities are taken about
+  float *xpos, *xquat, *xmat, *xipos, *ximat;          // body frames (positions relative to ref)
+  float *geom_xpos, *geom_xmat, *site_xpos, *site_xmat, *subtree_com;
+  float *Sang, *Slin;          // [nv*3] motion subspaces about ref
+  float *inert10, *crb10;      // [nbody*10]
+  float *qM, *qLD, *qLDe;      // [nM] inertia, its L^T D L factor, factor of M + h*diag(damping)
+  // velocity stage
+  float *bvel, *bacc, *bfrc, *bfl;   // [nbody*6] spatial velocity, bias accel, bias force, fluid wrench accum
+  float *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qacc_smooth, *qfrc_constraint, *qtmp;
+  float *act_dot, *actuator_force;
+  // contacts
+  int *ncon; float *con_dist, *con_pos, *con_frame; int *con_geom1, *con_geom2, *con_efcadr, *con_dim;
+  float *con_mu, *con_fric;    // mu, friction[2]
+  float *tmp_con; int *tmp_geom;   // chunk staging
+  // constraints
+  int *nefc; int *efc_type, *efc_id;
+  float *efc_pos, *efc_margin, *efc_D, *efc_R, *efc_K, *efc_B, *efc_imp, *efc_aref, *efc_b, *efc_force, *efc_jarws;
+  float *efc_J, *efc_Z;        // [MAXEFC*nv] dense-by-dof (only the row's dof set is touched)
+  float *efc_A, *efc_G;        // [MAXEFC*MAXEFC]
+  float *efc_w;                // [8*MAXEFC] solver work vectors
+  int *efc_ecol; float *efc_eval;   // E columns of the solver Hessian factor: base row, 3 values
+  // sensors / outputs
+  float *sensordata, *sensor_sum;
+  int *flags, *niter;
+  float *obs;                  // packed AoS observation [N][obs_dim]
+  int obs_dim;
+};
+
+#ifdef __CUDACC__
+#define FB_FLAG_OR(bit) atomicOr(&AT(d.flags, 0), (bit))
+#else
+#define FB_FLAG_OR(bit) (AT(d.flags, 0) |= (bit))
+#endif
+static inline int fb_pad32(int n) { return (n + 31) & ~31; }

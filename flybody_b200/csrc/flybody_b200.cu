@@ -1,0 +1,551 @@
+// flybody_b200.cu -- C ABI (include/flybody_b200.h) + kernel launch sequence of the batched fly
+// stepper for sm_100a.
+//
+// One control step = n_substeps x [ step2 ; step1 ] exactly as dm_control's legacy Physics.step()
+// (SURVEY.md App. A), each substep being the staged kernel pipeline
+//   step2: k_act -> k_smooth(solve) -> k_ref -> k_solve -> k_finish(qacc, sensors, Euler)
+//   step1: k_pos(kinematics, CRB, factor) -> k_col -> k_con -> k_proj(J, Z, A) -> k_vel(RNE, passive)
+// with all intermediates in SoA device arrays (fb_types.h).
+//
+// The same translation unit compiles as plain C++ with -DFB_EMU (tests/_emu): phases run in
+// nested host loops.  That build exists ONLY so CPU tests can exercise the kernel source; the
+// Python package never loads it (flybody_b200/stepper.py refuses to run without the CUDA library).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#ifndef FB_EMU
+#include <cuda_runtime.h>
+#endif
+#include "fb_constraint.h"
+
+#ifdef FB_EMU
+typedef int cudaStream_t_;
+#endif
+
+// -------------------------------------------------------------------------------------------
+// memory / launch abstraction
+#ifndef FB_EMU
+#define FB_CUDA_OK(call) do { cudaError_t err_ = (call); if (err_ != cudaSuccess) { s->err = std::string(#call) + ": " + cudaGetErrorString(err_); return -2; } } while (0)
+static void* dev_alloc(size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) return nullptr; cudaMemset(p, 0, bytes ? bytes : 4); return p; }
+static void dev_free(void* p) { cudaFree(p); }
+static void h2d(void* dst, const void* src, size_t n) { cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); }
+static void d2h(void* dst, const void* src, size_t n) { cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost); }
+#else
+#define FB_CUDA_OK(call) do { } while (0)
+static void* dev_alloc(size_t bytes) { return calloc(bytes ? bytes : 4, 1); }
+static void dev_free(void* p) { free(p); }
+static void h2d(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
+static void d2h(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
+#endif
+
+struct FbSim {
+  DevModel m; DevData d;
+  FbModel hm;                       // host copy of scalar fields (pointers invalid after create)
+  std::vector<void*> allocs;
+  std::vector<int> h_dof_parent, h_dof_Madr, h_body_lastdof, h_geom_bodyid;
+  std::vector<double> h_qpos0;
+  int device; long long launches; float last_ms; std::string err;
+  int first_substep;
+#ifndef FB_EMU
+  cudaStream_t stream; cudaEvent_t ev0, ev1;
+#endif
+};
+
+#ifndef FB_EMU
+template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
+__global__ void fb_run(DevModel m, DevData d) {
+  __shared__ Sh sh;
+  int lane = threadIdx.x, y = threadIdx.y, e = blockIdx.x * 32 + lane;
+  ((Ph(m, d, sh, e, lane, y), __syncthreads()), ...);
+}
+template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
+static void fb_launch(FbSim* s, int ny) {
+  dim3 block(32, ny), grid(s->d.Np / 32);
+  fb_run<Sh, Ph...><<<grid, block, 0, s->stream>>>(s->m, s->d);
+  s->launches++;
+}
+#else
+template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
+static void fb_launch(FbSim* s, int ny) {
+  static Sh sh;
+  for (int blk = 0; blk < s->d.Np / 32; blk++) {
+    auto run = [&](void (*ph)(const DevModel&, const DevData&, Sh&, int, int, int)) {
+      for (int y = 0; y < ny; y++) for (int lane = 0; lane < 32; lane++) ph(s->m, s->d, sh, blk * 32 + lane, lane, y);
+    };
+    (run(Ph), ...);
+  }
+  s->launches++;
+}
+#endif
+
+// lane == env kernels wrapped as single-phase functions
+FB_DEV void ph_act(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kact(m, d, e); }
+FB_DEV void ph_con(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kcon(m, d, e); }
+FB_DEV void ph_solve(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksolve(m, d, e); }
+FB_DEV void ph_sens_first(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksens_accum(m, d, e, 1); }
+FB_DEV void ph_sens_next(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksens_accum(m, d, e, 0); }
+// qacc_smooth = M^-1 qfrc_smooth (qacc_smooth already holds the rhs)
+FB_DEV void ph_smooth_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD, d.qacc_smooth); }
+FB_DEV void ph_smooth_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD, d.qacc_smooth); }
+FB_DEV void ph_smooth_c(FB_PHASE_ARGS) { solve_c(m, d, sh, e, lane, y, d.qLD, d.qacc_smooth); }
+
+static void launch_step1(FbSim* s) {
+  int nl = s->m.nlist;
+  fb_launch<ShTree, kpos_p0, kpos_p1, kpos_p2, kpos_p3, kpos_p4, kpos_p5, kpos_p6, kpos_p7, kpos_p8>(s, nl);
+  fb_launch<ShCol, kcol_p0, kcol_p1>(s, s->m.nchunk);
+  fb_launch<ShNone, ph_con>(s, 1);
+  fb_launch<ShNone, kproj_p0, kproj_p1>(s, FB_ROWPAR);
+  fb_launch<ShTree, kvel_p0, kvel_p1, kvel_p2, kvel_p3>(s, nl);
+}
+static void launch_step2(FbSim* s, bool integrate) {
+  int nl = s->m.nlist;
+  fb_launch<ShNone, ph_act>(s, 1);
+  fb_launch<ShTree, ph_smooth_a, ph_smooth_b, ph_smooth_c>(s, nl);
+  fb_launch<ShNone, kref>(s, FB_ROWPAR);
+  fb_launch<ShNone, ph_solve>(s, 1);
+  if (integrate)
+    fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
+              kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl);
+  else
+    fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
+              kfin_sens_out>(s, nl);
+}
+
+// -------------------------------------------------------------------------------------------
+// model upload
+template <typename T> static const T* up(FbSim* s, const std::vector<T>& v) {
+  void* p = dev_alloc(sizeof(T) * std::max<size_t>(v.size(), 1));
+  if (v.size()) h2d(p, v.data(), sizeof(T) * v.size());
+  s->allocs.push_back(p);
+  return (const T*)p;
+}
+static const float* upf(FbSim* s, const double* src, size_t n) { std::vector<float> v(n); for (size_t i = 0; i < n; i++) v[i] = (float)src[i]; return up(s, v); }
+static const int* upi(FbSim* s, const int32_t* src, size_t n) { std::vector<int> v(src, src + n); return up(s, v); }
+template <typename T> static T* dalloc(FbSim* s, size_t n) { void* p = dev_alloc(sizeof(T) * n); s->allocs.push_back(p); return (T*)p; }
+
+static int build_model(FbSim* s, const FbModel* h) {
+  DevModel& m = s->m;
+  memset(&m, 0, sizeof(m));
+  m.nq = h->nq; m.nv = h->nv; m.nu = h->nu; m.na = h->na; m.nbody = h->nbody; m.njnt = h->njnt; m.ngeom = h->ngeom;
+  m.npair = h->npair; m.nsite = h->nsite; m.ntendon = h->ntendon; m.nwrap = h->nwrap; m.nsensor = h->nsensor;
+  m.nsensordata = h->nsensordata; m.nM = h->nM; m.nfluid = h->nfluid;
+  m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.max_iter = 30; m.ls_iter = 20;
+  m.timestep = (float)h->opt_timestep; m.density = (float)h->opt_density; m.viscosity = (float)h->opt_viscosity;
+  for (int i = 0; i < 3; i++) { m.gravity[i] = (float)h->opt_gravity[i]; m.wind[i] = (float)h->opt_wind[i]; }
+  m.impratio = (float)h->opt_impratio; m.tolerance = (float)h->opt_tolerance; m.noslip_tolerance = (float)h->opt_noslip_tolerance;
+  m.meaninertia = (float)h->stat_meaninertia;
+  int nb = m.nbody, nv = m.nv;
+  // ---- tree partition: roots = children of world; each root's child sub-trees are packed into lists
+  std::vector<int> roots, isroot(nb, 0);
+  for (int b = 1; b < nb; b++) if (h->body_parentid[b] == 0) { roots.push_back(b); isroot[b] = 1; }
+  isroot[0] = 1;   // the world behaves like a root for "parent is root" tests (never accumulated into)
+  for (int r : roots) {
+    if (!(h->body_jntnum[r] == 0 || (h->body_jntnum[r] == 1 && h->jnt_type[h->body_jntadr[r]] == FB_JNT_FREE))) { s->err = "root bodies must carry a single free joint or none"; return -3; }
+  }
+  std::vector<std::vector<int>> subtrees; std::vector<int> sub_root;
+  for (size_t ri = 0; ri < roots.size(); ri++) {
+    for (int b = 1; b < nb; b++) if (h->body_parentid[b] == roots[ri]) {
+      std::vector<int> st; std::vector<char> in(nb, 0); in[b] = 1; st.push_back(b);
+      for (int c = b + 1; c < nb; c++) if (in[h->body_parentid[c]]) { in[c] = 1; st.push_back(c); }
+      subtrees.push_back(st); sub_root.push_back((int)ri);
+    }
+  }
+  size_t maxsz = 1, total = 0; for (auto& st : subtrees) { maxsz = std::max(maxsz, st.size()); total += st.size(); }
+  int nlist = (int)std::min<size_t>(FB_NLMAX, std::max<size_t>(1, (total + maxsz - 1) / maxsz + 1));
+  std::vector<std::vector<int>> lists(nlist); std::vector<int> lroot(nlist, -1);
+  std::vector<size_t> order(subtrees.size()); for (size_t i = 0; i < order.size(); i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return subtrees[a].size() > subtrees[b].size(); });
+  for (size_t oi : order) {
+    int best = -1;
+    for (int l = 0; l < nlist; l++) { if (lroot[l] != -1 && lroot[l] != sub_root[oi]) continue; if (best < 0 || lists[l].size() < lists[best].size()) best = l; }
+    if (best < 0) { s->err = "tree partition: more roots with children than lists"; return -3; }
+    lroot[best] = sub_root[oi];
+    lists[best].insert(lists[best].end(), subtrees[oi].begin(), subtrees[oi].end());
+  }
+  std::vector<int> ladr, lnum, lbody, lr;
+  for (int l = 0; l < nlist; l++) { ladr.push_back((int)lbody.size()); lnum.push_back((int)lists[l].size()); lbody.insert(lbody.end(), lists[l].begin(), lists[l].end()); lr.push_back(lroot[l] < 0 ? 0 : lroot[l]); }
+  m.nroot = (int)roots.size(); m.nlist = nlist;
+  m.root_body = up(s, roots); m.list_adr = up(s, ladr); m.list_num = up(s, lnum); m.list_body = up(s, lbody); m.list_root = up(s, lr);
+  m.body_isroot = up(s, isroot);
+  // geoms / sites per body (both are stored in body order by the compiler)
+  std::vector<int> gadr(nb, 0), gnum(nb, 0), sadr(nb, 0), snum(nb, 0);
+  for (int g = 0; g < m.ngeom; g++) { int b = h->geom_bodyid[g]; if (gnum[b] == 0) gadr[b] = g; gnum[b]++; if (g > 0 && h->geom_bodyid[g] < h->geom_bodyid[g - 1]) { s->err = "geoms not in body order"; return -3; } }
+  for (int t = 0; t < m.nsite; t++) { int b = h->site_bodyid[t]; if (snum[b] == 0) sadr[b] = t; snum[b]++; if (t > 0 && h->site_bodyid[t] < h->site_bodyid[t - 1]) { s->err = "sites not in body order"; return -3; } }
+  m.body_geomadr = up(s, gadr); m.body_geomnum = up(s, gnum); m.body_siteadr = up(s, sadr); m.body_sitenum = up(s, snum);
+  // dof helpers
+  std::vector<int> subend(nv), depth(nv), disroot(nv), chainlen(nv);
+  for (int i = 0; i < nv; i++) subend[i] = i;
+  for (int i = nv - 1; i >= 0; i--) { int p = h->dof_parentid[i]; if (p >= 0) subend[p] = std::max(subend[p], subend[i]); }
+  for (int i = 0; i < nv; i++) {
+    disroot[i] = isroot[h->dof_bodyid[i]] && h->dof_bodyid[i] != 0;
+    int len = 0, nonroot = 0;
+    for (int j = i; j >= 0; j = h->dof_parentid[j]) { len++; if (j != i && !(isroot[h->dof_bodyid[j]] && h->dof_bodyid[j] != 0)) nonroot++; }
+    chainlen[i] = len;
+    depth[i] = disroot[i] ? (i - h->body_dofadr[h->dof_bodyid[i]]) : nonroot;
+  }
+  m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);
+  // plain copies
+  m.body_parentid = upi(s, h->body_parentid, nb); m.body_rootid = upi(s, h->body_rootid, nb);
+  m.body_jntadr = upi(s, h->body_jntadr, nb); m.body_jntnum = upi(s, h->body_jntnum, nb);
+  m.body_dofadr = upi(s, h->body_dofadr, nb); m.body_dofnum = upi(s, h->body_dofnum, nb);
+  m.body_lastdof = upi(s, h->body_lastdof, nb); m.body_fluid_ellipsoid = upi(s, h->body_fluid_ellipsoid, nb);
+  m.body_pos = upf(s, h->body_pos, 3 * nb); m.body_quat = upf(s, h->body_quat, 4 * nb); m.body_ipos = upf(s, h->body_ipos, 3 * nb);
+  m.body_iquat = upf(s, h->body_iquat, 4 * nb); m.body_mass = upf(s, h->body_mass, nb); m.body_inertia = upf(s, h->body_inertia, 3 * nb);
+  m.body_invweight0 = upf(s, h->body_invweight0, 2 * nb);
+  int nj = m.njnt;
+  m.jnt_type = upi(s, h->jnt_type, nj); m.jnt_qposadr = upi(s, h->jnt_qposadr, nj); m.jnt_dofadr = upi(s, h->jnt_dofadr, nj);
+  m.jnt_bodyid = upi(s, h->jnt_bodyid, nj); m.jnt_limited = upi(s, h->jnt_limited, nj);
+  m.jnt_pos = upf(s, h->jnt_pos, 3 * nj); m.jnt_axis = upf(s, h->jnt_axis, 3 * nj); m.jnt_stiffness = upf(s, h->jnt_stiffness, nj);
+  m.jnt_range = upf(s, h->jnt_range, 2 * nj); m.jnt_solref = upf(s, h->jnt_solref, 2 * nj); m.jnt_solimp = upf(s, h->jnt_solimp, 5 * nj);
+  m.jnt_margin = upf(s, h->jnt_margin, nj); m.qpos0 = upf(s, h->qpos0, m.nq); m.qpos_spring = upf(s, h->qpos_spring, m.nq);
+  m.dof_bodyid = upi(s, h->dof_bodyid, nv); m.dof_jntid = upi(s, h->dof_jntid, nv); m.dof_parentid = upi(s, h->dof_parentid, nv);
+  m.dof_Madr = upi(s, h->dof_Madr, nv); m.dof_armature = upf(s, h->dof_armature, nv); m.dof_damping = upf(s, h->dof_damping, nv);
+  m.dof_invweight0 = upf(s, h->dof_invweight0, nv);
+  int ng = m.ngeom;
+  m.geom_type = upi(s, h->geom_type, ng); m.geom_bodyid = upi(s, h->geom_bodyid, ng); m.geom_condim = upi(s, h->geom_condim, ng);
+  m.geom_size = upf(s, h->geom_size, 3 * ng); m.geom_pos = upf(s, h->geom_pos, 3 * ng); m.geom_quat = upf(s, h->geom_quat, 4 * ng);
+  m.geom_rbound = upf(s, h->geom_rbound, ng); m.geom_friction = upf(s, h->geom_friction, 3 * ng); m.geom_solmix = upf(s, h->geom_solmix, ng);
+  m.geom_solref = upf(s, h->geom_solref, 2 * ng); m.geom_solimp = upf(s, h->geom_solimp, 5 * ng);
+  m.geom_margin = upf(s, h->geom_margin, ng); m.geom_gap = upf(s, h->geom_gap, ng);
+  m.pair_geom1 = upi(s, h->pair_geom1, m.npair); m.pair_geom2 = upi(s, h->pair_geom2, m.npair);
+  {  // chunk boundaries: plane pairs produce most contacts (up to 4 each), weight them 16x
+    m.nchunk = FB_MAXCHUNK;
+    std::vector<int> w(m.npair); long tot = 0;
+    for (int k = 0; k < m.npair; k++) { w[k] = (h->geom_type[h->pair_geom1[k]] == FB_GEOM_PLANE) ? 16 : 1; tot += w[k]; }
+    std::vector<int> cs(m.nchunk + 1, m.npair); cs[0] = 0;
+    long acc = 0; int c = 1;
+    for (int k = 0; k < m.npair && c < m.nchunk; k++) { acc += w[k]; if (acc * m.nchunk >= tot * c) { cs[c++] = k + 1; } }
+    for (; c <= m.nchunk; c++) cs[c] = m.npair;
+    m.chunk_start = up(s, cs);
+  }
+  m.fluid_bodyid = upi(s, h->fluid_bodyid, m.nfluid); m.fluid_pos = upf(s, h->fluid_pos, 3 * m.nfluid);
+  m.fluid_quat = upf(s, h->fluid_quat, 4 * m.nfluid); m.fluid_size = upf(s, h->fluid_size, 3 * m.nfluid); m.fluid_coef = upf(s, h->fluid_coef, 12 * m.nfluid);
+  m.site_bodyid = upi(s, h->site_bodyid, m.nsite); m.site_type = upi(s, h->site_type, m.nsite);
+  m.site_pos = upf(s, h->site_pos, 3 * m.nsite); m.site_quat = upf(s, h->site_quat, 4 * m.nsite); m.site_size = upf(s, h->site_size, 3 * m.nsite);
+  m.tendon_adr = upi(s, h->tendon_adr, m.ntendon); m.tendon_num = upi(s, h->tendon_num, m.ntendon);
+  m.wrap_dofid = upi(s, h->wrap_dofid, m.nwrap); m.wrap_qposadr = upi(s, h->wrap_qposadr, m.nwrap); m.wrap_coef = upf(s, h->wrap_coef, m.nwrap);
+  int nu = m.nu;
+  m.actuator_trntype = upi(s, h->actuator_trntype, nu); m.actuator_trnid = upi(s, h->actuator_trnid, nu); m.actuator_dyntype = upi(s, h->actuator_dyntype, nu);
+  m.actuator_biastype = upi(s, h->actuator_biastype, nu); m.actuator_ctrllimited = upi(s, h->actuator_ctrllimited, nu);
+  m.actuator_forcelimited = upi(s, h->actuator_forcelimited, nu); m.actuator_actadr = upi(s, h->actuator_actadr, nu);
+  m.actuator_dynprm = upf(s, h->actuator_dynprm, 3 * nu); m.actuator_gainprm = upf(s, h->actuator_gainprm, 3 * nu); m.actuator_biasprm = upf(s, h->actuator_biasprm, 3 * nu);
+  m.actuator_ctrlrange = upf(s, h->actuator_ctrlrange, 2 * nu); m.actuator_forcerange = upf(s, h->actuator_forcerange, 2 * nu);
+  m.sensor_type = upi(s, h->sensor_type, m.nsensor); m.sensor_objid = upi(s, h->sensor_objid, m.nsensor);
+  m.sensor_adr = upi(s, h->sensor_adr, m.nsensor); m.sensor_dim = upi(s, h->sensor_dim, m.nsensor);
+  s->h_dof_parent.assign(h->dof_parentid, h->dof_parentid + nv); s->h_dof_Madr.assign(h->dof_Madr, h->dof_Madr + nv);
+  s->h_qpos0.assign(h->qpos0, h->qpos0 + m.nq);
+  s->h_body_lastdof.assign(h->body_lastdof, h->body_lastdof + nb); s->h_geom_bodyid.assign(h->geom_bodyid, h->geom_bodyid + ng);
+  return 0;
+}
+
+static int alloc_data(FbSim* s, int N) {
+  DevData& d = s->d; const DevModel& m = s->m;
+  memset(&d, 0, sizeof(d));
+  d.N = N; d.Np = fb_pad32(N);
+  size_t Np = d.Np;
+#define FA(field, n) d.field = dalloc<float>(s, (size_t)(n) * Np); if (!d.field) { s->err = "out of device memory (" #field ")"; return -4; }
+#define IA(field, n) d.field = dalloc<int>(s, (size_t)(n) * Np); if (!d.field) { s->err = "out of device memory (" #field ")"; return -4; }
+  FA(qpos, m.nq) FA(qvel, m.nv) FA(act, m.na + 1) FA(ctrl, m.nu + 1) FA(qacc, m.nv) FA(qacc_warmstart, m.nv) FA(time, 1)
+  FA(ref, 3) FA(xpos, 3 * m.nbody) FA(xquat, 4 * m.nbody) FA(xmat, 9 * m.nbody) FA(xipos, 3 * m.nbody) FA(ximat, 9 * m.nbody)
+  FA(geom_xpos, 3 * m.ngeom) FA(geom_xmat, 9 * m.ngeom) FA(site_xpos, 3 * m.nsite + 3) FA(site_xmat, 9 * m.nsite + 9)
+  FA(Sang, 3 * m.nv) FA(Slin, 3 * m.nv) FA(inert10, 10 * m.nbody) FA(crb10, 10 * m.nbody)
+  FA(qM, m.nM) FA(qLD, m.nM) FA(qLDe, m.nM)
+  FA(bvel, 6 * m.nbody) FA(bacc, 6 * m.nbody) FA(bfrc, 6 * m.nbody) FA(bfl, 6 * m.nbody)
+  FA(qfrc_bias, m.nv) FA(qfrc_passive, m.nv) FA(qfrc_actuator, m.nv) FA(qfrc_smooth, m.nv) FA(qacc_smooth, m.nv) FA(qfrc_constraint, m.nv) FA(qtmp, m.nv)
+  FA(act_dot, m.na + 1) FA(actuator_force, m.nu + 1)
+  IA(ncon, 1) FA(con_dist, FB_MAXCON) FA(con_pos, 3 * FB_MAXCON) FA(con_frame, 9 * FB_MAXCON) IA(con_geom1, FB_MAXCON) IA(con_geom2, FB_MAXCON)
+  IA(con_efcadr, FB_MAXCON) IA(con_dim, FB_MAXCON) FA(con_mu, FB_MAXCON) FA(con_fric, 2 * FB_MAXCON)
+  FA(tmp_con, 13 * FB_MAXCHUNK * FB_CHUNKCAP) IA(tmp_geom, 2 * FB_MAXCHUNK * FB_CHUNKCAP)
+  IA(nefc, 1) IA(efc_type, FB_MAXEFC) IA(efc_id, FB_MAXEFC)
+  FA(efc_pos, FB_MAXEFC) FA(efc_margin, FB_MAXEFC) FA(efc_D, FB_MAXEFC) FA(efc_R, FB_MAXEFC) FA(efc_K, FB_MAXEFC) FA(efc_B, FB_MAXEFC)
+  FA(efc_imp, FB_MAXEFC) FA(efc_aref, FB_MAXEFC) FA(efc_b, FB_MAXEFC) FA(efc_force, FB_MAXEFC) FA(efc_jarws, FB_MAXEFC)
+  FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv) FA(efc_A, (size_t)FB_MAXEFC * FB_MAXEFC) FA(efc_G, (size_t)FB_MAXEFC * FB_MAXEFC)
+  FA(efc_w, 8 * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) FA(efc_eval, 3 * FB_MAXEFC)
+  FA(sensordata, m.nsensordata + 1) FA(sensor_sum, m.nsensordata + 1) IA(flags, 1) IA(niter, 1)
+#undef FA
+#undef IA
+  d.obs_dim = m.nq + m.nv + m.na + m.nsensordata + 12 + 3 * m.nsite;
+  d.obs = dalloc<float>(s, (size_t)d.obs_dim * Np);
+  return 0;
+}
+
+// SoA <-> AoS host transfers
+static void field_to_host(FbSim* s, const float* dev, int n, float* dst_aos) {
+  size_t Np = s->d.Np; std::vector<float> tmp((size_t)n * Np);
+  d2h(tmp.data(), dev, sizeof(float) * n * Np);
+  for (int e = 0; e < s->d.N; e++) for (int i = 0; i < n; i++) dst_aos[(size_t)e * n + i] = tmp[(size_t)i * Np + e];
+}
+static void ifield_to_host(FbSim* s, const int* dev, int n, std::vector<int>& out) {
+  size_t Np = s->d.Np; out.resize((size_t)n * Np);
+  d2h(out.data(), dev, sizeof(int) * n * Np);
+}
+static void field_from_host(FbSim* s, float* dev, int n, const float* src_aos) {
+  size_t Np = s->d.Np; std::vector<float> tmp((size_t)n * Np);
+  for (size_t e = 0; e < Np; e++) { size_t se = e < (size_t)s->d.N ? e : 0; for (int i = 0; i < n; i++) tmp[(size_t)i * Np + e] = src_aos[se * n + i]; }
+  h2d(dev, tmp.data(), sizeof(float) * n * Np);
+}
+
+static int sync_stream(FbSim* s) {
+#ifndef FB_EMU
+  FB_CUDA_OK(cudaStreamSynchronize(s->stream));
+  FB_CUDA_OK(cudaGetLastError());
+#endif
+  return 0;
+}
+
+extern "C" {
+
+const char* fb_version(void) {
+#ifdef FB_EMU
+  return "flybody_b200 0.1 (host emulation build: tests only)";
+#else
+  return "flybody_b200 0.1 (sm_100a)";
+#endif
+}
+
+int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
+  if (!hm || !out || n_envs <= 0) return -1;
+  FbSim* s = new FbSim();
+  s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1;
+#ifndef FB_EMU
+  if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
+  cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
+#endif
+  int rc = build_model(s, hm);
+  if (rc == 0) rc = alloc_data(s, n_envs);
+  *out = s;
+  if (rc != 0) return rc;
+  std::vector<float> q0((size_t)n_envs * hm->nq);
+  for (int e = 0; e < n_envs; e++) for (int i = 0; i < hm->nq; i++) q0[(size_t)e * hm->nq + i] = (float)hm->qpos0[i];
+  field_from_host(s, s->d.qpos, hm->nq, q0.data());
+  return fb_forward(s);
+}
+
+int fb_destroy(FbHandle s) {
+  if (!s) return -1;
+#ifndef FB_EMU
+  cudaSetDevice(s->device); cudaStreamSynchronize(s->stream);
+  cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1); cudaStreamDestroy(s->stream);
+#endif
+  for (void* p : s->allocs) dev_free(p);
+  delete s;
+  return 0;
+}
+
+const char* fb_last_error(FbHandle s) { return s ? s->err.c_str() : "null handle"; }
+int fb_n_envs(FbHandle s) { return s ? s->d.N : -1; }
+int fb_n_envs_padded(FbHandle s) { return s ? s->d.Np : -1; }
+long long fb_launch_count(FbHandle s) { return s ? s->launches : -1; }
+float fb_last_step_ms(FbHandle s) {
+#ifndef FB_EMU
+  if (!s) return -1; float ms = 0; cudaEventSynchronize(s->ev1); cudaEventElapsedTime(&ms, s->ev0, s->ev1); return ms;
+#else
+  return 0;
+#endif
+}
+void* fb_stream(FbHandle s) {
+#ifndef FB_EMU
+  return s ? (void*)s->stream : nullptr;
+#else
+  return nullptr;
+#endif
+}
+int fb_sync(FbHandle s) { if (!s) return -1; return sync_stream(s); }
+int fb_set_solver(FbHandle s, float tolerance, int max_iter) {
+  if (!s) return -1;
+  if (tolerance > 0) s->m.tolerance = tolerance;
+  if (max_iter > 0) s->m.max_iter = max_iter;
+  return 0;
+}
+
+int fb_forward(FbHandle s) {
+  if (!s) return -1;
+#ifndef FB_EMU
+  cudaSetDevice(s->device);
+#endif
+  launch_step1(s);
+  launch_step2(s, false);
+  return sync_stream(s);
+}
+
+int fb_step(FbHandle s, int n_substeps) {
+  if (!s || n_substeps <= 0) return -1;
+#ifndef FB_EMU
+  cudaSetDevice(s->device);
+  cudaEventRecord(s->ev0, s->stream);
+#endif
+  for (int k = 0; k < n_substeps; k++) {
+    launch_step2(s, true);
+    launch_step1(s);
+    if (k == 0) fb_launch<ShNone, ph_sens_first>(s, 1); else fb_launch<ShNone, ph_sens_next>(s, 1);
+  }
+  s->d.nsub_done = n_substeps;
+#ifndef FB_EMU
+  cudaEventRecord(s->ev1, s->stream);
+  if (cudaGetLastError() != cudaSuccess) { s->err = "kernel launch failed"; return -2; }
+#endif
+  return 0;
+}
+
+static float* field_ptr(FbSim* s, int field, int* n) {
+  const DevModel& m = s->m; DevData& d = s->d;
+  switch (field) {
+    case FB_QPOS: *n = m.nq; return d.qpos;
+    case FB_QVEL: *n = m.nv; return d.qvel;
+    case FB_ACT: *n = m.na; return d.act;
+    case FB_CTRL: *n = m.nu; return d.ctrl;
+    case FB_QACC: *n = m.nv; return d.qacc;
+    case FB_QACC_WARMSTART: *n = m.nv; return d.qacc_warmstart;
+    case FB_SENSORDATA: *n = m.nsensordata; return d.sensordata;
+    case FB_SENSOR_MEAN: *n = m.nsensordata; return d.sensor_sum;
+    case FB_XPOS: *n = 3 * m.nbody; return d.xpos;
+    case FB_XMAT: *n = 9 * m.nbody; return d.xmat;
+    case FB_SITE_XPOS: *n = 3 * m.nsite; return d.site_xpos;
+    case FB_SITE_XMAT: *n = 9 * m.nsite; return d.site_xmat;
+    case FB_TIME: *n = 1; return d.time;
+    case FB_QFRC_SMOOTH: *n = m.nv; return d.qfrc_smooth;
+    case FB_QFRC_CONSTRAINT: *n = m.nv; return d.qfrc_constraint;
+    case FB_QFRC_PASSIVE: *n = m.nv; return d.qfrc_passive;
+    case FB_QFRC_BIAS: *n = m.nv; return d.qfrc_bias;
+    case FB_QFRC_ACTUATOR: *n = m.nv; return d.qfrc_actuator;
+    case FB_EFC_FORCE: *n = FB_MAXEFC; return d.efc_force;
+    default: *n = -1; return nullptr;
+  }
+}
+
+int fb_field_size(FbHandle s, int field) {
+  if (!s) return -1;
+  int n; if (field_ptr(s, field, &n)) return n;
+  switch (field) {
+    case FB_SUBTREE_COM: return 3 * s->m.nbody;
+    case FB_NCON: case FB_NEFC: case FB_SOLVER_NITER: case FB_FLAGS: return 1;
+    case FB_QM_DENSE: return s->m.nv * s->m.nv;
+    case FB_CONTACT: return 16 * FB_MAXCON;
+    default: return -1;
+  }
+}
+
+int fb_get(FbHandle s, int field, void* dst, int is_device) {
+  if (!s || !dst) return -1;
+  if (sync_stream(s) != 0) return -2;
+  int n; float* p = field_ptr(s, field, &n);
+  const DevModel& m = s->m; int N = s->d.N; size_t Np = s->d.Np;
+  if (is_device) { if (!p) { s->err = "field has no device array"; return -1; } *(void**)dst = p; return 0; }
+  float* out = (float*)dst;
+  if (p) {
+    field_to_host(s, p, n, out);
+    if (field == FB_XPOS || field == FB_SITE_XPOS) {     // stored relative to ref
+      std::vector<float> ref((size_t)3 * N); field_to_host(s, s->d.ref, 3, ref.data());
+      for (int e = 0; e < N; e++) for (int i = 0; i < n; i++) out[(size_t)e * n + i] += ref[(size_t)e * 3 + i % 3];
+    }
+    if (field == FB_SENSOR_MEAN && s->d.nsub_done > 0) for (size_t i = 0; i < (size_t)N * n; i++) out[i] /= (float)s->d.nsub_done;
+    return 0;
+  }
+  std::vector<int> iv;
+  switch (field) {
+    case FB_NCON: ifield_to_host(s, s->d.ncon, 1, iv); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
+    case FB_NEFC: ifield_to_host(s, s->d.nefc, 1, iv); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
+    case FB_SOLVER_NITER: ifield_to_host(s, s->d.niter, 1, iv); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
+    case FB_FLAGS: ifield_to_host(s, s->d.flags, 1, iv); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
+    case FB_SUBTREE_COM: {
+      std::vector<float> crb((size_t)10 * m.nbody * N), ref((size_t)3 * N);
+      field_to_host(s, s->d.crb10, 10 * m.nbody, crb.data()); field_to_host(s, s->d.ref, 3, ref.data());
+      for (int e = 0; e < N; e++) for (int b = 0; b < m.nbody; b++) { const float* c = &crb[((size_t)e * m.nbody + b) * 10];
+        for (int i = 0; i < 3; i++) out[((size_t)e * m.nbody + b) * 3 + i] = (c[0] > 0 ? c[1 + i] / c[0] : 0.0f) + ref[(size_t)e * 3 + i]; }
+      return 0; }
+    case FB_QM_DENSE: {
+      std::vector<float> qm((size_t)m.nM * N); field_to_host(s, s->d.qM, m.nM, qm.data());
+      int nv = m.nv; memset(out, 0, sizeof(float) * (size_t)N * nv * nv);
+      for (int e = 0; e < N; e++) for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = s->h_dof_parent[j], t++) {
+        float v = qm[(size_t)e * m.nM + s->h_dof_Madr[i] + t]; out[((size_t)e * nv + i) * nv + j] = v; out[((size_t)e * nv + j) * nv + i] = v; } }
+      return 0; }
+    case FB_CONTACT: {
+      std::vector<float> dist((size_t)FB_MAXCON * N), pos((size_t)3 * FB_MAXCON * N), frame((size_t)9 * FB_MAXCON * N), mu((size_t)FB_MAXCON * N), ref((size_t)3 * N);
+      std::vector<int> g1, g2, ea, dm, nc;
+      field_to_host(s, s->d.con_dist, FB_MAXCON, dist.data()); field_to_host(s, s->d.con_pos, 3 * FB_MAXCON, pos.data());
+      field_to_host(s, s->d.con_frame, 9 * FB_MAXCON, frame.data()); field_to_host(s, s->d.con_mu, FB_MAXCON, mu.data()); field_to_host(s, s->d.ref, 3, ref.data());
+      ifield_to_host(s, s->d.con_geom1, FB_MAXCON, g1); ifield_to_host(s, s->d.con_geom2, FB_MAXCON, g2);
+      ifield_to_host(s, s->d.con_efcadr, FB_MAXCON, ea); ifield_to_host(s, s->d.con_dim, FB_MAXCON, dm); ifield_to_host(s, s->d.ncon, 1, nc);
+      memset(out, 0, sizeof(float) * (size_t)N * 16 * FB_MAXCON);
+      for (int e = 0; e < N; e++) for (int c = 0; c < nc[e] && c < FB_MAXCON; c++) {
+        float* o = out + ((size_t)e * FB_MAXCON + c) * 16;
+        o[0] = dist[(size_t)e * FB_MAXCON + c];
+        for (int i = 0; i < 3; i++) { o[1 + i] = pos[((size_t)e * FB_MAXCON + c) * 3 + i] + ref[(size_t)e * 3 + i]; o[4 + i] = frame[((size_t)e * FB_MAXCON + c) * 9 + i]; }
+        o[7] = (float)g1[(size_t)c * Np + e]; o[8] = (float)g2[(size_t)c * Np + e]; o[9] = (float)dm[(size_t)c * Np + e];
+        o[12] = (float)ea[(size_t)c * Np + e]; o[10] = o[12] >= 0 ? 1.0f : 0.0f; o[11] = mu[(size_t)e * FB_MAXCON + c];
+      }
+      return 0; }
+    default: s->err = "unknown field"; return -1;
+  }
+}
+
+int fb_set(FbHandle s, int field, const float* src) {
+  if (!s || !src) return -1;
+  if (sync_stream(s) != 0) return -2;
+  int n; float* p = field_ptr(s, field, &n);
+  if (!p || !(field == FB_QPOS || field == FB_QVEL || field == FB_ACT || field == FB_CTRL || field == FB_QACC_WARMSTART || field == FB_QACC || field == FB_TIME)) { s->err = "field is not writable"; return -1; }
+  if (n > 0) field_from_host(s, p, n, src);
+  return 0;
+}
+
+int fb_set_ctrl(FbHandle s, const float* ctrl, int is_device) {
+  if (!s || !ctrl) return -1;
+  if (!is_device) return fb_set(s, FB_CTRL, ctrl);
+#ifndef FB_EMU
+  FB_CUDA_OK(cudaMemcpyAsync(s->d.ctrl, ctrl, sizeof(float) * s->m.nu * s->d.Np, cudaMemcpyDeviceToDevice, s->stream));
+#else
+  memcpy(s->d.ctrl, ctrl, sizeof(float) * s->m.nu * s->d.Np);
+#endif
+  return 0;
+}
+
+int fb_write_state(FbHandle s, int field, const int32_t* idx, int k, const float* vals) {
+  if (!s || !idx || !vals || k <= 0) return -1;
+  if (sync_stream(s) != 0) return -2;
+  int n; float* p = field_ptr(s, field, &n);
+  if (!p || !(field == FB_QPOS || field == FB_QVEL || field == FB_ACT)) { s->err = "fb_write_state: field must be qpos, qvel or act"; return -1; }
+  size_t Np = s->d.Np; std::vector<float> row(Np);
+  for (int c = 0; c < k; c++) {
+    if (idx[c] < 0 || idx[c] >= n) { s->err = "fb_write_state: index out of range"; return -1; }
+    for (size_t e = 0; e < Np; e++) row[e] = vals[(e < (size_t)s->d.N ? e : 0) * k + c];
+    h2d(p + (size_t)idx[c] * Np, row.data(), sizeof(float) * Np);
+  }
+  return 0;
+}
+
+int fb_reset(FbHandle s, const int32_t* env_ids, int n, const float* qpos, const float* qvel) {
+  if (!s) return -1;
+  if (sync_stream(s) != 0) return -2;
+  const DevModel& m = s->m; int N = s->d.N; size_t Np = s->d.Np;
+  std::vector<int> ids;
+  if (env_ids) ids.assign(env_ids, env_ids + n); else { ids.resize(N); for (int e = 0; e < N; e++) ids[e] = e; n = N; }
+  for (int e : ids) if (e < 0 || e >= N) { s->err = "fb_reset: env id out of range"; return -1; }
+  auto patch = [&](float* dev, int nf, const float* src, const double* dflt) {
+    std::vector<float> tmp((size_t)nf * Np);
+    d2h(tmp.data(), dev, sizeof(float) * nf * Np);
+    for (int k = 0; k < n; k++) for (int i = 0; i < nf; i++) tmp[(size_t)i * Np + ids[k]] = src ? src[(size_t)k * nf + i] : (dflt ? (float)dflt[i] : 0.0f);
+    if (n == N) for (size_t e = N; e < Np; e++) for (int i = 0; i < nf; i++) tmp[(size_t)i * Np + e] = tmp[(size_t)i * Np];
+    h2d(dev, tmp.data(), sizeof(float) * nf * Np);
+  };
+  patch(s->d.qpos, m.nq, qpos, s->h_qpos0.data());
+  patch(s->d.qvel, m.nv, qvel, nullptr);
+  if (m.na) patch(s->d.act, m.na, nullptr, nullptr);
+  patch(s->d.qacc_warmstart, m.nv, nullptr, nullptr);
+  patch(s->d.qacc, m.nv, nullptr, nullptr);
+  patch(s->d.time, 1, nullptr, nullptr);
+  { std::vector<int> fl(Np); d2h(fl.data(), s->d.flags, sizeof(int) * Np); for (int k = 0; k < n; k++) fl[ids[k]] = 0; if (n == N) for (size_t e = N; e < Np; e++) fl[e] = 0; h2d(s->d.flags, fl.data(), sizeof(int) * Np); }
+  return fb_forward(s);
+}
+
+int fb_obs_ptr(FbHandle s, void** dev_ptr, int* floats_per_env) {
+  if (!s || !dev_ptr || !floats_per_env) return -1;
+  *dev_ptr = s->d.obs; *floats_per_env = s->d.obs_dim;
+  return 0;
+}
+
+}  // extern "C"

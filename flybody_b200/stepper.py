@@ -1,0 +1,157 @@
+"""ctypes binding of the CUDA stepper's C ABI (`include/flybody_b200.h`).
+
+`BatchedStepper` is the batched stand-in for the `physics` object that dm_control hands to the
+reference's task hooks: `set_control`, `step`, state reads.  It fails loudly
+when the CUDA library is missing -- there is no CPU fallback in the product path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .flymodel import FbModel, FlyModel
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libflybody_b200.so')
+
+# enum FbField
+(QPOS, QVEL, ACT, CTRL, QACC, QACC_WARMSTART, SENSORDATA, SENSOR_MEAN, XPOS, XMAT, SITE_XPOS, SITE_XMAT,
+ SUBTREE_COM, NCON, NEFC, TIME, QFRC_SMOOTH, QM_DENSE, QFRC_CONSTRAINT, SOLVER_NITER, QFRC_PASSIVE,
+ QFRC_BIAS, QFRC_ACTUATOR, CONTACT, EFC_FORCE, FLAGS) = range(26)
+MAXCON, MAXEFC = 64, 160
+
+EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_set_ctrl', 'fb_write_state', 'fb_step', 'fb_forward',
+           'fb_get', 'fb_field_size', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
+           'fb_sync', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+
+
+class StepperError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise StepperError(
+            f'CUDA stepper library not found at {path}. Build it with `python -c "import __graft_entry__ as g; '
+            f'g.build()"` (nvcc, sm_100a). There is no CPU fallback.')
+    lib = C.CDLL(path)
+    lib.fb_create.argtypes = [C.POINTER(FbModel), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.fb_destroy.argtypes = [C.c_void_p]
+    lib.fb_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.fb_set_ctrl.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.fb_write_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.fb_step.argtypes = [C.c_void_p, C.c_int]
+    lib.fb_forward.argtypes = [C.c_void_p]
+    lib.fb_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.fb_field_size.argtypes = [C.c_void_p, C.c_int]
+    lib.fb_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.fb_obs_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    lib.fb_n_envs.argtypes = [C.c_void_p]
+    lib.fb_n_envs_padded.argtypes = [C.c_void_p]
+    lib.fb_stream.argtypes = [C.c_void_p]
+    lib.fb_stream.restype = C.c_void_p
+    lib.fb_sync.argtypes = [C.c_void_p]
+    lib.fb_launch_count.argtypes = [C.c_void_p]
+    lib.fb_launch_count.restype = C.c_longlong
+    lib.fb_last_step_ms.argtypes = [C.c_void_p]
+    lib.fb_last_step_ms.restype = C.c_float
+    lib.fb_set_solver.argtypes = [C.c_void_p, C.c_float, C.c_int]
+    lib.fb_last_error.argtypes = [C.c_void_p]
+    lib.fb_last_error.restype = C.c_char_p
+    lib.fb_version.restype = C.c_char_p
+    return lib
+
+
+class BatchedStepper:
+    """N fly environments stepped in lock-step on one device."""
+
+    def __init__(self, model: FlyModel, n_envs: int, device: int = 0, lib_path: str | None = None):
+        self.model = model
+        self.n_envs = int(n_envs)
+        self._lib = load_library(lib_path)
+        h = C.c_void_p()
+        rc = self._lib.fb_create(C.byref(model.c), self.n_envs, int(device), C.byref(h))
+        self._h = h
+        if rc != 0:
+            msg = self._lib.fb_last_error(h).decode() if h else 'no handle'
+            raise StepperError(f'fb_create failed ({rc}): {msg}')
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.fb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise StepperError(f'{what} failed ({rc}): {self._lib.fb_last_error(self._h).decode()}')
+
+    # -- state access ---------------------------------------------------------------------
+    def get(self, field):
+        n = self._lib.fb_field_size(self._h, field)
+        if n < 0:
+            raise KeyError(field)
+        out = np.zeros((self.n_envs, max(n, 1)), np.float32)
+        self._check(self._lib.fb_get(self._h, field, out.ctypes.data, 0), 'fb_get')
+        return out[:, :n]
+
+    def set(self, field, values):
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(values, np.float32), (self.n_envs, np.asarray(values).shape[-1])))
+        self._check(self._lib.fb_set(self._h, field, v.ctypes.data), 'fb_set')
+
+    def set_control(self, ctrl):
+        """physics.set_control (reference fruitfly.py:540-544), ctrl [N, nu] (or [nu], broadcast)."""
+        c = np.ascontiguousarray(np.broadcast_to(np.asarray(ctrl, np.float32), (self.n_envs, self.model.nu)))
+        self._check(self._lib.fb_set_ctrl(self._h, c.ctypes.data, 0), 'fb_set_ctrl')
+
+    def write_state(self, field, idx, vals):
+        idx = np.ascontiguousarray(idx, np.int32)
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(vals, np.float32), (self.n_envs, len(idx))))
+        self._check(self._lib.fb_write_state(self._h, field, idx.ctypes.data, len(idx), v.ctypes.data), 'fb_write_state')
+
+    def reset(self, qpos=None, qvel=None, env_ids=None):
+        n = self.n_envs if env_ids is None else len(env_ids)
+        ids = None if env_ids is None else np.ascontiguousarray(env_ids, np.int32)
+        qp = None if qpos is None else np.ascontiguousarray(np.broadcast_to(np.asarray(qpos, np.float32), (n, self.model.nq)))
+        qv = None if qvel is None else np.ascontiguousarray(np.broadcast_to(np.asarray(qvel, np.float32), (n, self.model.nv)))
+        self._check(self._lib.fb_reset(self._h, None if ids is None else ids.ctypes.data, n,
+                                       None if qp is None else qp.ctypes.data, None if qv is None else qv.ctypes.data), 'fb_reset')
+
+    def step(self, n_substeps):
+        self._check(self._lib.fb_step(self._h, int(n_substeps)), 'fb_step')
+
+    def forward(self):
+        self._check(self._lib.fb_forward(self._h), 'fb_forward')
+
+    def sync(self):
+        self._check(self._lib.fb_sync(self._h), 'fb_sync')
+
+    def set_solver(self, tolerance=0.0, max_iter=0):
+        self._lib.fb_set_solver(self._h, float(tolerance), int(max_iter))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.fb_launch_count(self._h))
+
+    @property
+    def last_step_ms(self):
+        return float(self._lib.fb_last_step_ms(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.fb_stream(self._h)
+
+    def obs_ptr(self):
+        p = C.c_void_p()
+        n = C.c_int()
+        self._check(self._lib.fb_obs_ptr(self._h, C.byref(p), C.byref(n)), 'fb_obs_ptr')
+        return p.value, n.value
+
+    def version(self):
+        return self._lib.fb_version().decode()
