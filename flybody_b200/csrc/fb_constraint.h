@@ -771,6 +771,7 @@ FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int b) {
 }
 FB_DEV void keul_solve_c_integrate(FB_PHASE_ARGS) {
   solve_c(m, d, sh, e, lane, y, d.qLDe, d.qtmp);
+  if (AT(d.hold, 0)) return;          // env staged for reset: recompute (forward) but do not integrate
   if (y == 0) {
     for (int r = 0; r < m.nroot; r++) integrate_body(m, d, e, m.root_body[r]);
     for (int i = 0; i < m.na; i++) AT(d.act, i) += m.timestep * AT(d.act_dot, i);
@@ -783,3 +784,37 @@ FB_DEV void keul_solve_c_integrate(FB_PHASE_ARGS) {
 FB_DEV void ksens_accum(const DevModel& m, const DevData& d, int e, int first) {
   for (int i = 0; i < m.nsensordata; i++) AT(d.sensor_sum, i) = (first ? 0.0f : AT(d.sensor_sum, i)) + AT(d.sensordata, i);
 }
+
+// ---------------------------------------------------------------------------------------------
+// packed per-env observation record (AoS, one row per env) for the host task code / NCCL gather:
+//   qpos[nq] qvel[nv] act[na] sensor_mean[nsd] sensordata[nsd] root_xpos[3] root_xmat[9] site_xpos[3*nsite]
+//   flags[1] qacc_sq[1] time[1]
+FB_DEV void kpack(const DevModel& m, const DevData& d, int e, float inv_nsub) {
+  float* o = d.obs + (size_t)e * d.obs_dim;
+  int k = 0;
+  for (int i = 0; i < m.nq; i++) o[k++] = AT(d.qpos, i);
+  for (int i = 0; i < m.nv; i++) o[k++] = AT(d.qvel, i);
+  for (int i = 0; i < m.na; i++) o[k++] = AT(d.act, i);
+  for (int i = 0; i < m.nsensordata; i++) o[k++] = AT(d.sensor_sum, i) * inv_nsub;
+  for (int i = 0; i < m.nsensordata; i++) o[k++] = AT(d.sensordata, i);
+  int rb = m.root_body[0];
+  V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
+  V3 rp = ld3(d.xpos, rb, d, e) + ref;
+  o[k++] = rp.x; o[k++] = rp.y; o[k++] = rp.z;
+  for (int i = 0; i < 9; i++) o[k++] = AT(d.xmat, 9 * rb + i);
+  for (int s = 0; s < m.nsite; s++) { V3 p = ld3(d.site_xpos, s, d, e) + ref; o[k++] = p.x; o[k++] = p.y; o[k++] = p.z; }
+  o[k++] = (float)AT(d.flags, 0);
+  float s2 = 0; for (int i = 0; i < m.nv; i++) { float a = AT(d.qacc, i); s2 += a * a; }
+  o[k++] = s2; o[k++] = AT(d.time, 0);
+}
+
+// partial reset staged by fb_reset_hold: thread k (global index) rewrites env rst_ids[k]
+FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int k) {
+  if (k >= d.rst_n) return;
+  int e = d.rst_ids[k];
+  for (int i = 0; i < m.nq; i++) AT(d.qpos, i) = d.rst_qpos[(size_t)k * m.nq + i];
+  for (int i = 0; i < m.nv; i++) { AT(d.qvel, i) = d.rst_has_qvel ? d.rst_qvel[(size_t)k * m.nv + i] : 0.0f; AT(d.qacc, i) = 0; AT(d.qacc_warmstart, i) = 0; }
+  for (int i = 0; i < m.na; i++) AT(d.act, i) = 0;
+  AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = 1;
+}
+FB_DEV void kclear_hold(const DevModel& m, const DevData& d, int e) { AT(d.hold, 0) = 0; }

@@ -90,7 +90,8 @@ struct DevData {
   int *efc_ecol; float *efc_eval;   // E columns of the solver Hessian factor: base row, 3 values
   // sensors / outputs
   float *sensordata, *sensor_sum;
-  int *flags, *niter;
+  int *flags, *niter, *hold;   // hold != 0: env is not integrated by the next fb_step (pending reset)
+  const int* rst_ids; const float* rst_qpos; const float* rst_qvel; int rst_n, rst_has_qvel;   // staged partial reset
   float *obs;                  // packed AoS observation [N][obs_dim]
   int obs_dim;
 };

@@ -42,14 +42,24 @@ static void h2d(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 static void d2h(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 #endif
 
+enum { K_ACT = 0, K_SMOOTH, K_REF, K_SOLVE, K_FINISH, K_POS, K_COL, K_CON, K_PROJ, K_VEL, K_SENS, K_PACK, K_MISC, K_NKIND };
+static const char* const kKindNames[K_NKIND] = {"act", "smooth", "ref", "solve", "finish", "pos", "col", "con", "proj", "vel", "sens", "pack", "misc"};
+#ifndef FB_EMU
+struct ProfEvent { int kind; cudaEvent_t a, b; };
+#endif
 struct FbSim {
   DevModel m; DevData d;
+  int prof_on; double prof_ms[K_NKIND]; long long prof_n[K_NKIND];
+#ifndef FB_EMU
+  std::vector<ProfEvent> prof_events;
+#endif
   FbModel hm;                       // host copy of scalar fields (pointers invalid after create)
   std::vector<void*> allocs;
   std::vector<int> h_dof_parent, h_dof_Madr, h_body_lastdof, h_geom_bodyid;
   std::vector<double> h_qpos0;
   int device; long long launches; float last_ms; std::string err;
-  int first_substep;
+  int first_substep; int hold_pending;
+  int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
 #ifndef FB_EMU
   cudaStream_t stream; cudaEvent_t ev0, ev1;
 #endif
@@ -63,14 +73,23 @@ __global__ void fb_run(DevModel m, DevData d) {
   ((Ph(m, d, sh, e, lane, y), __syncthreads()), ...);
 }
 template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
-static void fb_launch(FbSim* s, int ny) {
+static void fb_launch(FbSim* s, int ny, int kind) {
   dim3 block(32, ny), grid(s->d.Np / 32);
-  fb_run<Sh, Ph...><<<grid, block, 0, s->stream>>>(s->m, s->d);
+  if (s->prof_on) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s->stream);
+    fb_run<Sh, Ph...><<<grid, block, 0, s->stream>>>(s->m, s->d);
+    cudaEventRecord(b, s->stream);
+    s->prof_events.push_back({kind, a, b});
+  } else {
+    fb_run<Sh, Ph...><<<grid, block, 0, s->stream>>>(s->m, s->d);
+  }
   s->launches++;
 }
 #else
 template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
-static void fb_launch(FbSim* s, int ny) {
+static void fb_launch(FbSim* s, int ny, int kind) {
+  (void)kind;
   static Sh sh;
   for (int blk = 0; blk < s->d.Np / 32; blk++) {
     auto run = [&](void (*ph)(const DevModel&, const DevData&, Sh&, int, int, int)) {
@@ -87,6 +106,9 @@ FB_DEV void ph_act(const DevModel& m, const DevData& d, ShNone&, int e, int, int
 FB_DEV void ph_con(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kcon(m, d, e); }
 FB_DEV void ph_solve(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksolve(m, d, e); }
 FB_DEV void ph_sens_first(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksens_accum(m, d, e, 1); }
+FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kreset_scatter(m, d, e); }
+FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kclear_hold(m, d, e); }
+FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kpack(m, d, e, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); }
 FB_DEV void ph_sens_next(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksens_accum(m, d, e, 0); }
 // qacc_smooth = M^-1 qfrc_smooth (qacc_smooth already holds the rhs)
 FB_DEV void ph_smooth_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD, d.qacc_smooth); }
@@ -95,24 +117,24 @@ FB_DEV void ph_smooth_c(FB_PHASE_ARGS) { solve_c(m, d, sh, e, lane, y, d.qLD, d.
 
 static void launch_step1(FbSim* s) {
   int nl = s->m.nlist;
-  fb_launch<ShTree, kpos_p0, kpos_p1, kpos_p2, kpos_p3, kpos_p4, kpos_p5, kpos_p6, kpos_p7, kpos_p8>(s, nl);
-  fb_launch<ShCol, kcol_p0, kcol_p1>(s, s->m.nchunk);
-  fb_launch<ShNone, ph_con>(s, 1);
-  fb_launch<ShNone, kproj_p0, kproj_p1>(s, FB_ROWPAR);
-  fb_launch<ShTree, kvel_p0, kvel_p1, kvel_p2, kvel_p3>(s, nl);
+  fb_launch<ShTree, kpos_p0, kpos_p1, kpos_p2, kpos_p3, kpos_p4, kpos_p5, kpos_p6, kpos_p7, kpos_p8>(s, nl, K_POS);
+  fb_launch<ShCol, kcol_p0, kcol_p1>(s, s->m.nchunk, K_COL);
+  fb_launch<ShNone, ph_con>(s, 1, K_CON);
+  fb_launch<ShNone, kproj_p0, kproj_p1>(s, FB_ROWPAR, K_PROJ);
+  fb_launch<ShTree, kvel_p0, kvel_p1, kvel_p2, kvel_p3>(s, nl, K_VEL);
 }
 static void launch_step2(FbSim* s, bool integrate) {
   int nl = s->m.nlist;
-  fb_launch<ShNone, ph_act>(s, 1);
-  fb_launch<ShTree, ph_smooth_a, ph_smooth_b, ph_smooth_c>(s, nl);
-  fb_launch<ShNone, kref>(s, FB_ROWPAR);
-  fb_launch<ShNone, ph_solve>(s, 1);
+  fb_launch<ShNone, ph_act>(s, 1, K_ACT);
+  fb_launch<ShTree, ph_smooth_a, ph_smooth_b, ph_smooth_c>(s, nl, K_SMOOTH);
+  fb_launch<ShNone, kref>(s, FB_ROWPAR, K_REF);
+  fb_launch<ShNone, ph_solve>(s, 1, K_SOLVE);
   if (integrate)
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
-              kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl);
+              kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl, K_FINISH);
   else
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
-              kfin_sens_out>(s, nl);
+              kfin_sens_out>(s, nl, K_FINISH);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -265,10 +287,10 @@ static int alloc_data(FbSim* s, int N) {
   FA(efc_imp, FB_MAXEFC) FA(efc_aref, FB_MAXEFC) FA(efc_b, FB_MAXEFC) FA(efc_force, FB_MAXEFC) FA(efc_jarws, FB_MAXEFC)
   FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv) FA(efc_A, (size_t)FB_MAXEFC * FB_MAXEFC) FA(efc_G, (size_t)FB_MAXEFC * FB_MAXEFC)
   FA(efc_w, 8 * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) FA(efc_eval, 3 * FB_MAXEFC)
-  FA(sensordata, m.nsensordata + 1) FA(sensor_sum, m.nsensordata + 1) IA(flags, 1) IA(niter, 1)
+  FA(sensordata, m.nsensordata + 1) FA(sensor_sum, m.nsensordata + 1) IA(flags, 1) IA(niter, 1) IA(hold, 1)
 #undef FA
 #undef IA
-  d.obs_dim = m.nq + m.nv + m.na + m.nsensordata + 12 + 3 * m.nsite;
+  d.obs_dim = m.nq + m.nv + m.na + 2 * m.nsensordata + 12 + 3 * m.nsite + 3;
   d.obs = dalloc<float>(s, (size_t)d.obs_dim * Np);
   return 0;
 }
@@ -310,7 +332,8 @@ const char* fb_version(void) {
 int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   if (!hm || !out || n_envs <= 0) return -1;
   FbSim* s = new FbSim();
-  s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1;
+  s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
+  s->rst_ids_dev = nullptr; s->rst_qpos_dev = nullptr; s->rst_qvel_dev = nullptr; s->rst_cap = 0;
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -382,9 +405,10 @@ int fb_step(FbHandle s, int n_substeps) {
   for (int k = 0; k < n_substeps; k++) {
     launch_step2(s, true);
     launch_step1(s);
-    if (k == 0) fb_launch<ShNone, ph_sens_first>(s, 1); else fb_launch<ShNone, ph_sens_next>(s, 1);
+    if (k == 0) fb_launch<ShNone, ph_sens_first>(s, 1, K_SENS); else fb_launch<ShNone, ph_sens_next>(s, 1, K_SENS);
   }
   s->d.nsub_done = n_substeps;
+  if (s->hold_pending) { fb_launch<ShNone, ph_clear_hold>(s, 1, K_MISC); s->hold_pending = 0; }
 #ifndef FB_EMU
   cudaEventRecord(s->ev1, s->stream);
   if (cudaGetLastError() != cudaSuccess) { s->err = "kernel launch failed"; return -2; }
@@ -542,6 +566,59 @@ int fb_reset(FbHandle s, const int32_t* env_ids, int n, const float* qpos, const
   return fb_forward(s);
 }
 
+int fb_reset_hold(FbHandle s, const int32_t* env_ids, int n, const float* qpos, const float* qvel) {
+  if (!s || !env_ids || !qpos || n <= 0) return -1;
+  const DevModel& m = s->m;
+  for (int k = 0; k < n; k++) if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_reset_hold: env id out of range"; return -1; }
+  if (sync_stream(s) != 0) return -2;
+  if (n > s->rst_cap) {
+    s->rst_cap = std::max(n, s->d.N);
+    s->rst_ids_dev = dalloc<int>(s, s->rst_cap); s->rst_qpos_dev = dalloc<float>(s, (size_t)s->rst_cap * m.nq); s->rst_qvel_dev = dalloc<float>(s, (size_t)s->rst_cap * m.nv);
+  }
+  h2d(s->rst_ids_dev, env_ids, sizeof(int) * n);
+  h2d(s->rst_qpos_dev, qpos, sizeof(float) * (size_t)n * m.nq);
+  if (qvel) h2d(s->rst_qvel_dev, qvel, sizeof(float) * (size_t)n * m.nv);
+  s->d.rst_ids = s->rst_ids_dev; s->d.rst_qpos = s->rst_qpos_dev; s->d.rst_qvel = s->rst_qvel_dev; s->d.rst_n = n; s->d.rst_has_qvel = qvel ? 1 : 0;
+  fb_launch<ShNone, ph_reset_scatter>(s, 1, K_MISC);
+  s->d.rst_n = 0;
+  s->hold_pending = 1;
+  return 0;
+}
+int fb_profile(FbHandle s, int enable) {
+  if (!s) return -1;
+  s->prof_on = enable ? 1 : 0;
+  if (enable) { memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n)); }
+  return 0;
+}
+int fb_profile_read(FbHandle s, double* ms, long long* counts, int n) {
+  if (!s || !ms || !counts) return -1;
+#ifndef FB_EMU
+  if (sync_stream(s) != 0) return -2;
+  for (auto& ev : s->prof_events) { float t = 0; cudaEventElapsedTime(&t, ev.a, ev.b); s->prof_ms[ev.kind] += t; s->prof_n[ev.kind]++; cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  s->prof_events.clear();
+#endif
+  for (int k = 0; k < n && k < K_NKIND; k++) { ms[k] = s->prof_ms[k]; counts[k] = s->prof_n[k]; }
+  return K_NKIND;
+}
+const char* fb_profile_name(int kind) { return (kind >= 0 && kind < K_NKIND) ? kKindNames[kind] : ""; }
+int fb_pack_obs(FbHandle s) {
+  if (!s) return -1;
+#ifndef FB_EMU
+  cudaSetDevice(s->device);
+#endif
+  fb_launch<ShNone, ph_pack>(s, 1, K_PACK);
+  return 0;
+}
+int fb_read_obs(FbHandle s, float* host_dst) {
+  if (!s || !host_dst) return -1;
+#ifndef FB_EMU
+  FB_CUDA_OK(cudaMemcpyAsync(host_dst, s->d.obs, sizeof(float) * (size_t)s->d.N * s->d.obs_dim, cudaMemcpyDeviceToHost, s->stream));
+  return sync_stream(s);
+#else
+  memcpy(host_dst, s->d.obs, sizeof(float) * (size_t)s->d.N * s->d.obs_dim);
+  return 0;
+#endif
+}
 int fb_obs_ptr(FbHandle s, void** dev_ptr, int* floats_per_env) {
   if (!s || !dev_ptr || !floats_per_env) return -1;
   *dev_ptr = s->d.obs; *floats_per_env = s->d.obs_dim;

@@ -20,9 +20,9 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libflybody_b200.so')
  QFRC_BIAS, QFRC_ACTUATOR, CONTACT, EFC_FORCE, FLAGS) = range(26)
 MAXCON, MAXEFC = 64, 160
 
-EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_set_ctrl', 'fb_write_state', 'fb_step', 'fb_forward',
+EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
-           'fb_sync', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
 
 class StepperError(RuntimeError):
@@ -39,6 +39,7 @@ def load_library(path=None):
     lib.fb_create.argtypes = [C.POINTER(FbModel), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.fb_destroy.argtypes = [C.c_void_p]
     lib.fb_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.fb_reset_hold.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.fb_set_ctrl.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.fb_write_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_step.argtypes = [C.c_void_p, C.c_int]
@@ -47,6 +48,12 @@ def load_library(path=None):
     lib.fb_field_size.argtypes = [C.c_void_p, C.c_int]
     lib.fb_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_obs_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    lib.fb_pack_obs.argtypes = [C.c_void_p]
+    lib.fb_read_obs.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fb_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.fb_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.fb_profile_name.argtypes = [C.c_int]
+    lib.fb_profile_name.restype = C.c_char_p
     lib.fb_n_envs.argtypes = [C.c_void_p]
     lib.fb_n_envs_padded.argtypes = [C.c_void_p]
     lib.fb_stream.argtypes = [C.c_void_p]
@@ -123,6 +130,13 @@ class BatchedStepper:
         self._check(self._lib.fb_reset(self._h, None if ids is None else ids.ctypes.data, n,
                                        None if qp is None else qp.ctypes.data, None if qv is None else qv.ctypes.data), 'fb_reset')
 
+    def reset_hold(self, env_ids, qpos, qvel=None):
+        ids = np.ascontiguousarray(env_ids, np.int32)
+        qp = np.ascontiguousarray(np.broadcast_to(np.asarray(qpos, np.float32), (len(ids), self.model.nq)))
+        qv = None if qvel is None else np.ascontiguousarray(np.broadcast_to(np.asarray(qvel, np.float32), (len(ids), self.model.nv)))
+        self._check(self._lib.fb_reset_hold(self._h, ids.ctypes.data, len(ids), qp.ctypes.data,
+                                            None if qv is None else qv.ctypes.data), 'fb_reset_hold')
+
     def step(self, n_substeps):
         self._check(self._lib.fb_step(self._h, int(n_substeps)), 'fb_step')
 
@@ -152,6 +166,45 @@ class BatchedStepper:
         n = C.c_int()
         self._check(self._lib.fb_obs_ptr(self._h, C.byref(p), C.byref(n)), 'fb_obs_ptr')
         return p.value, n.value
+
+    def profile(self, enable=True):
+        self._lib.fb_profile(self._h, 1 if enable else 0)
+
+    def profile_read(self):
+        ms = np.zeros(16, np.float64)
+        cnt = np.zeros(16, np.int64)
+        n = self._lib.fb_profile_read(self._h, ms.ctypes.data, cnt.ctypes.data, 16)
+        return {self._lib.fb_profile_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
+
+    def set_control_device(self, dev_ptr):
+        """ctrl already resident on the device as SoA [nu][n_envs_padded] fp32."""
+        self._check(self._lib.fb_set_ctrl(self._h, C.c_void_p(dev_ptr), 1), 'fb_set_ctrl')
+
+    def pack_obs(self):
+        self._check(self._lib.fb_pack_obs(self._h), 'fb_pack_obs')
+
+    @property
+    def n_envs_padded(self):
+        return int(self._lib.fb_n_envs_padded(self._h))
+
+    def read_obs(self, out=None):
+        """Pack + copy the per-env observation record [N, obs_dim] (see fb_pack_obs in the header)."""
+        _, dim = self.obs_ptr()
+        if out is None:
+            out = np.empty((self.n_envs, dim), np.float32)
+        self._check(self._lib.fb_pack_obs(self._h), 'fb_pack_obs')
+        self._check(self._lib.fb_read_obs(self._h, out.ctypes.data), 'fb_read_obs')
+        return out
+
+    def obs_layout(self):
+        m = self.model
+        off, lay = 0, {}
+        for name, n in (('qpos', m.nq), ('qvel', m.nv), ('act', m.na), ('sensor_mean', m.nsensordata),
+                        ('sensordata', m.nsensordata), ('root_xpos', 3), ('root_xmat', 9),
+                        ('site_xpos', 3 * m.nsite), ('flags', 1), ('qacc_sq', 1), ('time', 1)):
+            lay[name] = slice(off, off + n)
+            off += n
+        return lay
 
     def version(self):
         return self._lib.fb_version().decode()

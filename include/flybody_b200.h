@@ -195,6 +195,12 @@ int fb_destroy(FbHandle h);
  * warm start / time, then mj_forward for those envs.  env_ids == NULL means all envs.        */
 int fb_reset(FbHandle h, const int32_t* env_ids, int n, const float* qpos, const float* qvel);
 
+/* Auto-reset of a subset of envs inside a batched rollout (composer.Environment resets an env on the step()
+ * after a LAST timestep and returns the reset observation without stepping): writes the reset state of the
+ * listed envs on the device and marks them "held" -- the next fb_step recomputes their forward quantities
+ * every substep but does not integrate them; the hold is cleared when that fb_step completes.            */
+int fb_reset_hold(FbHandle h, const int32_t* env_ids, int n, const float* qpos, const float* qvel);
+
 /* physics.set_control(ctrl) (fruitfly.py:540-544).  ctrl: [N][nu] AoS host (is_device=0) or
  * [nu][N] SoA device pointer (is_device=1).                                                    */
 int fb_set_ctrl(FbHandle h, const float* ctrl, int is_device);
@@ -222,6 +228,11 @@ int fb_set(FbHandle h, int field, const float* src);  /* host [N][n] AoS -> devi
  * NCCL gather to rank 0.  Layout: qpos, qvel, act, sensor_mean, xpos/xmat of
  * root, site_xpos.                                                                            */
 int fb_obs_ptr(FbHandle h, void** dev_ptr, int* floats_per_env);
+/* Launch the pack kernel (after fb_step) / copy the packed rows to a (pinned) host buffer [N][floats_per_env]:
+ * qpos, qvel, act, sensor_mean, sensordata, root xpos[3], root xmat[9], site_xpos[3*nsite], flags, |qacc|^2, time.
+ * Stands in for the observation_updater reads of composer.Environment.step.        */
+int fb_pack_obs(FbHandle h);
+int fb_read_obs(FbHandle h, float* host_dst);
 
 int fb_n_envs(FbHandle h);
 int fb_n_envs_padded(FbHandle h);
@@ -231,6 +242,11 @@ long long fb_launch_count(FbHandle h);       /* kernels launched by this handle 
 /* device time (ms) of the last fb_step measured with CUDA events on the handle's stream */
 float fb_last_step_ms(FbHandle h);
 /* solver configuration: tolerance and iteration cap of the constraint solver */
+/* per-kernel device timing (CUDA events around every launch while enabled): cumulative ms and launch
+ * counts per pipeline stage; fb_profile_name(kind) names the stage.  Used by bench.py's roofline block. */
+int fb_profile(FbHandle h, int enable);
+int fb_profile_read(FbHandle h, double* ms, long long* counts, int n);
+const char* fb_profile_name(int kind);
 int fb_set_solver(FbHandle h, float tolerance, int max_iter);
 const char* fb_last_error(FbHandle h);
 const char* fb_version(void);

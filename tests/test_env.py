@@ -1,0 +1,85 @@
+"""dm_env surface of the batched walk_imitation env (contracts of reference tests/test_walking_env.py),
+run on the host-emulation build (no GPU here); tests/test_gpu_parity.py repeats the smoke on the B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+from flybody_b200 import fly_envs
+from flybody_b200.dm_env_shim import StepType
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'reference_goldens.json')))
+
+# trajectory of reference tests/test_walking_env.py:27-35
+n_steps, ctrl_timestep = 200, 0.002
+qpos = np.zeros((n_steps, 7))
+qpos[:, 0] = np.arange(0, n_steps * ctrl_timestep, ctrl_timestep)
+qpos[:, [2, 3]] = [0.14355, 1.]
+qvel = np.zeros((n_steps, 6))
+qvel[:, 0] = 1.
+
+
+@pytest.fixture(scope='module')
+def emu():
+    ge.build()
+    return ge.EMU
+
+
+def test_can_create_env_inference_mode(emu):
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), lib_path=emu)
+    assert list(env.observation_spec()) == G['walk_obs_names']
+    assert env.action_spec().shape == (G['walk_num_act'],)
+    assert env.action_spec().name.split('\t') == G['action_names']
+    env.task._traj_generator.set_next_trajectory(qpos, qvel)
+    ts = env.reset()
+    assert ts.step_type == StepType.FIRST
+    for name in G['walk_obs_names']:
+        assert isinstance(ts.observation[name], (float, np.ndarray))
+        assert ts.observation[name].shape == env.observation_spec()[name].shape
+    assert np.isclose(env.control_timestep(), 2e-3)
+    assert np.isclose(env.physics.timestep(), 2e-4)
+
+
+def test_can_step_env_inference_mode(emu):
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), lib_path=emu)
+    env.task._traj_generator.set_next_trajectory(qpos, qvel)
+    env.reset()
+    rs = np.random.RandomState(0)
+    for _ in range(30):
+        ts = env.step(rs.uniform(-0.5, 0.5, 59))
+        assert ts.reward == 1.
+        assert all(np.all(np.isfinite(v)) for v in ts.observation.values())
+
+
+def test_batched_env_autoreset_semantics(emu):
+    env = fly_envs.walk_imitation(terminal_com_dist=0.05, n_envs=3, lib_path=emu)    # ghost leaves 0.05 cm after ~13 steps
+    ts = env.reset()
+    assert ts.observation['walker/joints_pos'].shape == (3, 85)
+    rs = np.random.RandomState(1)
+    seen_last = seen_first = False
+    prev_last = np.zeros(3, bool)
+    for _ in range(40):
+        ts = env.step(rs.uniform(-0.3, 0.3, (3, 59)))
+        # the step after LAST is FIRST with the reset observation (composer.Environment semantics)
+        assert np.all(ts.step_type[prev_last] == StepType.FIRST)
+        if prev_last.any():
+            seen_first = True
+            d0 = np.linalg.norm(ts.observation['walker/ref_displacement'][prev_last, 0], axis=1)
+            assert np.all(d0 < 1e-6)
+        prev_last = ts.step_type == StepType.LAST
+        if prev_last.any():
+            seen_last = True
+            assert np.all(ts.discount[prev_last] == 0.0)       # fatal termination (com distance)
+    assert seen_last and seen_first
+
+
+def test_nan_action_is_zeroed(emu):
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=2, lib_path=emu)
+    env.reset()
+    a = np.zeros((2, 59))
+    a[0, 5] = np.nan                                           # walk_imitation.py:147-148
+    ts = env.step(a)
+    assert np.all(np.isfinite(ts.observation['walker/joints_pos']))

@@ -1,0 +1,121 @@
+"""Parity tests proper: the CUDA stepper on a B200, through the C ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+
+from flybody_b200 import stepper as st
+from flybody_b200.flymodel import load_model
+from oracle import fly_oracle as fo
+from parity_common import compare_stage_fields, teacher_forced_errors, reset_qpos
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_the_cuda_build():
+    m = load_model('walk')
+    s = st.BatchedStepper(m, 32)
+    assert 'sm_100a' in s.version()
+    assert s.launch_count > 0
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2, 3])
+def test_stage_parity_walk(seed):
+    m = load_model('walk')
+    compare_stage_fields(m, st.BatchedStepper(m, 64), seed=seed, env=17)
+
+
+@pytest.mark.parametrize('seed', [0, 1])
+def test_stage_parity_flight(seed):
+    m = load_model('flight')
+    compare_stage_fields(m, st.BatchedStepper(m, 64), seed=seed, vel_scale=20.0, env=5)
+
+
+def test_teacher_forced_200_control_steps_walk():
+    """BASELINE.json config 1: 200 random-action control steps, error measured one step ahead."""
+    m = load_model('walk')
+    eq, ev = teacher_forced_errors(m, st.BatchedStepper(m, 32), n_steps=200, n_sub=10)
+    print(f'teacher-forced walk: max|dqpos|={eq:.2e} max|dqvel|={ev:.2e}')
+    assert eq < 2e-6 and ev < 5e-3
+
+
+def test_teacher_forced_flight():
+    m = load_model('flight')
+    eq, ev = teacher_forced_errors(m, st.BatchedStepper(m, 32), n_steps=50, n_sub=4, ctrl_scale=0.2)
+    print(f'teacher-forced flight: max|dqpos|={eq:.2e} max|dqvel|={ev:.2e}')
+    assert eq < 2e-6 and ev < 5e-2
+
+
+def test_free_running_drift_walk_reported():
+    """Free-running divergence over 50 control steps (chaotic contact dynamics: reported, loosely gated)."""
+    m = load_model('walk')
+    s = st.BatchedStepper(m, 32)
+    o = fo.Oracle(m, tolerance=1e-12)
+    q0 = reset_qpos(m)
+    s.reset(q0)
+    o.reset(q0)
+    rs = np.random.RandomState(0)
+    for k in range(50):
+        c = rs.uniform(-0.5, 0.5, m.nu)
+        s.set_control(c)
+        o.set(fo.CTRL, c)
+        s.step(10)
+        o.control_step(10)
+    e = np.abs(s.get(st.QPOS)[0][:109] - o.qpos[:109]).max()
+    print(f'free-running 50 steps: max|dqpos|={e:.2e}')
+    assert e < 5e-2
+
+
+def test_batch_consistency_and_size_independent_properties():
+    """4096 envs: identical envs give bit-identical results; padding / env index do not matter;
+    quaternions stay normalised; the fly stays on the floor (no tunnelling) under random actions."""
+    m = load_model('walk')
+    N = 4096
+    s = st.BatchedStepper(m, N)
+    q0 = reset_qpos(m)
+    s.reset(q0)
+    rs = np.random.RandomState(0)
+    for k in range(5):
+        s.set_control(rs.uniform(-0.5, 0.5, m.nu))
+        s.step(10)
+    q = s.get(st.QPOS)
+    assert np.all(q == q[0])                       # bit-exact across lanes / blocks
+    assert np.all(s.get(st.FLAGS) == 0)
+    # decorrelated envs
+    qq = np.tile(q0, (N, 1))
+    hinge = np.arange(7, 109)
+    qq[:, hinge] += rs.uniform(-0.05, 0.05, (N, 102))
+    s.reset(qq)
+    for k in range(10):
+        s.set_control(rs.uniform(-0.5, 0.5, (N, m.nu)))
+        s.step(10)
+    q = s.get(st.QPOS)
+    assert np.all(np.isfinite(q))
+    assert np.abs(np.linalg.norm(q[:, 3:7], axis=1) - 1).max() < 1e-5
+    assert q[:, 2].min() > 0.02 and q[:, 2].max() < 0.3
+    assert (s.get(st.FLAGS)[:, 0] != 0).mean() < 0.01
+    # a shuffled copy of the batch gives the shuffled result (env order independence)
+    perm = rs.permutation(N)
+    s2 = st.BatchedStepper(m, N)
+    s2.reset(qq[perm])
+    s.reset(qq)
+    c = rs.uniform(-0.5, 0.5, (N, m.nu)).astype(np.float32)
+    s.set_control(c)
+    s2.set_control(c[perm])
+    s.step(10)
+    s2.step(10)
+    assert np.array_equal(s.get(st.QPOS)[perm], s2.get(st.QPOS))
+
+
+def test_env_facade_on_gpu():
+    from flybody_b200 import fly_envs
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=256)
+    ts = env.reset()
+    rs = np.random.RandomState(0)
+    for _ in range(20):
+        ts = env.step(rs.uniform(-0.5, 0.5, (256, 59)))
+        assert np.all(ts.reward == 1.0)
+    assert all(np.all(np.isfinite(v)) for v in ts.observation.values())
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()
