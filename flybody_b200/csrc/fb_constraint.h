@@ -284,6 +284,7 @@ FB_DEV void kproj_p0(FB_ROW_ARGS) {
   for (int r = y; r < n; r += FB_ROWPAR) {
     int ci, frow; float sign;
     RowChains rc = row_chains(m, d, e, r, ci, frow, sign);
+    AT(d.efc_la, r) = rc.la; AT(d.efc_lb, r) = rc.lb;
     V3 f = v3(0, 0, 0), pos = v3(0, 0, 0);
     if (ci >= 0) { f = v3(CON_F(d.con_frame, ci, 3 * frow, 9), CON_F(d.con_frame, ci, 3 * frow + 1, 9), CON_F(d.con_frame, ci, 3 * frow + 2, 9));
                    pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3)); }
@@ -402,81 +403,6 @@ FB_DEV void kact(const DevModel& m, const DevData& d, int e) {
 // solved through the small SPD system G = I + E^T A E (Cholesky), followed by the same exact line
 // search.  The minimiser is the one MuJoCo's primal Newton converges to (strictly convex problem).
 enum { W_LAM = 0, W_JAR = 1, W_F = 2, W_R = 3, W_U = 4, W_DL = 5, W_ADL = 6, W_P = 7 };
-// E columns: col c has entries on rows row..row+n-1 with values val[0..n-1]
-#define ECOL_ROW(c) AT(d.efc_ecol, (c))
-#define ECOL_VAL(c, k) AT(d.efc_eval, 3 * (c) + (k))
-
-struct ConeInfo { float mu, f1, f2; };
-
-// per-row cost/force evaluation at jar (W_JAR) -> W_F; optionally builds E columns.  returns cost.
-FB_DEV float constraint_update(const DevModel& m, const DevData& d, int e, int n, bool build, int* ncol_out) {
-  float cost = 0; int nc = 0;
-  for (int i = 0; i < n; i++) {
-    int tp = EFC(d.efc_type, i);
-    float jar = EW(W_JAR, i), D = EFC(d.efc_D, i);
-    if (tp != FB_CT_ELLIPTIC) {
-      if (jar < 0) { EW(W_F, i) = -D * jar; cost += 0.5f * D * jar * jar; if (build) { ECOL_ROW(nc) = i; ECOL_VAL(nc, 0) = sqrtf(D); ECOL_VAL(nc, 1) = 0; ECOL_VAL(nc, 2) = 0; nc++; } }
-      else EW(W_F, i) = 0;
-    } else {
-      int ci = EFC(d.efc_id, i);
-      float mu = AT(d.con_mu, ci), f1 = CON_F(d.con_fric, ci, 0, 2), f2 = CON_F(d.con_fric, ci, 1, 2);
-      float j1 = EW(W_JAR, i + 1), j2 = EW(W_JAR, i + 2), D1 = EFC(d.efc_D, i + 1), D2 = EFC(d.efc_D, i + 2);
-      float U0 = jar * mu, U1 = j1 * f1, U2 = j2 * f2, N = U0, T = sqrtf(U1 * U1 + U2 * U2);
-      if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-        EW(W_F, i) = -D * jar; EW(W_F, i + 1) = -D1 * j1; EW(W_F, i + 2) = -D2 * j2;
-        cost += 0.5f * (D * jar * jar + D1 * j1 * j1 + D2 * j2 * j2);
-        if (build) { for (int r = 0; r < 3; r++) { ECOL_ROW(nc) = i + r; ECOL_VAL(nc, 0) = sqrtf(EFC(d.efc_D, i + r)); ECOL_VAL(nc, 1) = 0; ECOL_VAL(nc, 2) = 0; nc++; } }
-      } else if (N >= mu * T || (T <= 0 && N >= 0)) {
-        EW(W_F, i) = 0; EW(W_F, i + 1) = 0; EW(W_F, i + 2) = 0;
-      } else {
-        float Dm = D / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
-        cost += 0.5f * Dm * NmT * NmT;
-        float f0 = -Dm * NmT * mu;
-        EW(W_F, i) = f0; EW(W_F, i + 1) = -f0 / T * U1 * f1; EW(W_F, i + 2) = -f0 / T * U2 * f2;
-        if (build) {
-          // C = Dm [ (S g)(S g)^T + (-f mu / T)(S t)(S t)^T ],  g = (1, -mu U1/T, -mu U2/T), t = (0, -U2, U1)/T
-          float sD = sqrtf(Dm);
-          ECOL_ROW(nc) = -(i + 1);            // negative: 3-row column starting at row i
-          ECOL_VAL(nc, 0) = sD * mu; ECOL_VAL(nc, 1) = -sD * f1 * mu * U1 / T; ECOL_VAL(nc, 2) = -sD * f2 * mu * U2 / T; nc++;
-          float k2 = sqrtf(fmaxf(0.0f, Dm * (-NmT) * mu / T));
-          ECOL_ROW(nc) = -(i + 1);
-          ECOL_VAL(nc, 0) = 0; ECOL_VAL(nc, 1) = -k2 * f1 * U2 / T; ECOL_VAL(nc, 2) = k2 * f2 * U1 / T; nc++;
-        }
-      }
-      i += 2;
-    }
-  }
-  if (ncol_out) *ncol_out = nc;
-  return cost;
-}
-// 1-D cost along lam + alpha*dlam: constraint part only (value, first and second derivative)
-FB_DEV void ls_eval(const DevModel& m, const DevData& d, int e, int n, float alpha, float& c, float& g, float& h) {
-  for (int i = 0; i < n; i++) {
-    int tp = EFC(d.efc_type, i);
-    float jv = EW(W_ADL, i), x = EW(W_JAR, i) + alpha * jv, D = EFC(d.efc_D, i);
-    if (tp != FB_CT_ELLIPTIC) { if (x < 0) { c += 0.5f * D * x * x; g += D * x * jv; h += D * jv * jv; } }
-    else {
-      int ci = EFC(d.efc_id, i);
-      float mu = AT(d.con_mu, ci), f1 = CON_F(d.con_fric, ci, 0, 2), f2 = CON_F(d.con_fric, ci, 1, 2);
-      float jv1 = EW(W_ADL, i + 1), jv2 = EW(W_ADL, i + 2);
-      float x1 = EW(W_JAR, i + 1) + alpha * jv1, x2 = EW(W_JAR, i + 2) + alpha * jv2;
-      float D1 = EFC(d.efc_D, i + 1), D2 = EFC(d.efc_D, i + 2);
-      float U0 = x * mu, U1 = x1 * f1, U2 = x2 * f2, dU0 = jv * mu, dU1 = jv1 * f1, dU2 = jv2 * f2;
-      float N = U0, T = sqrtf(U1 * U1 + U2 * U2);
-      if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-        c += 0.5f * (D * x * x + D1 * x1 * x1 + D2 * x2 * x2); g += D * x * jv + D1 * x1 * jv1 + D2 * x2 * jv2;
-        h += D * jv * jv + D1 * jv1 * jv1 + D2 * jv2 * jv2;
-      } else if (N >= mu * T || (T <= 0 && N >= 0)) {
-      } else {
-        float Dm = D / (mu * mu * (1 + mu * mu)), f = N - mu * T;
-        float dT = (U1 * dU1 + U2 * dU2) / T, ddT = (dU1 * dU1 + dU2 * dU2 - dT * dT) / T;
-        float fp = dU0 - mu * dT, fpp = -mu * ddT;
-        c += 0.5f * Dm * f * f; g += Dm * f * fp; h += Dm * (fp * fp + f * fpp);
-      }
-      i += 2;
-    }
-  }
-}
 FB_DEV int qcqp2(float* res, const float* A, const float* b, float d0, float d1, float r) {   // mju_QCQP2
   float A11 = A[0] * d0 * d0, A22 = A[3] * d1 * d1, A12 = A[1] * d0 * d1, b1 = b[0] * d0, b2 = b[1] * d1;
   float la = 0, v1 = 0, v2 = 0;
@@ -494,138 +420,6 @@ FB_DEV int qcqp2(float* res, const float* A, const float* b, float d0, float d1,
   }
   res[0] = v1 * d0; res[1] = v2 * d1;
   return la != 0;
-}
-
-FB_DEV void ksolve(const DevModel& m, const DevData& d, int e) {
-  int n = AT(d.nefc, 0);
-  AT(d.niter, 0) = 0;
-  if (n == 0) { for (int k = 0; k < m.nv; k++) AT(d.qfrc_constraint, k) = 0; return; }
-  float scale = 1.0f / (m.meaninertia * (m.nv > 1 ? m.nv : 1));
-  // ---- warm start: forces implied by the previous qacc, kept if cheaper than lam = 0
-  for (int i = 0; i < n; i++) EW(W_JAR, i) = EFC(d.efc_jarws, i);
-  constraint_update(m, d, e, n, false, nullptr);
-  for (int i = 0; i < n; i++) EW(W_LAM, i) = EW(W_F, i);
-  float cost_ws, cost0;
-  {
-    float q = 0;
-    for (int i = 0; i < n; i++) { float s = EFC(d.efc_b, i); for (int j = 0; j < n; j++) s += EA(d.efc_A, i, j) * EW(W_LAM, j); EW(W_JAR, i) = s; q += 0.5f * EW(W_LAM, i) * (s - EFC(d.efc_b, i)); }
-    cost_ws = q + constraint_update(m, d, e, n, false, nullptr);
-    for (int i = 0; i < n; i++) EW(W_JAR, i) = EFC(d.efc_b, i);
-    cost0 = constraint_update(m, d, e, n, false, nullptr);
-    if (!(cost_ws < cost0)) for (int i = 0; i < n; i++) EW(W_LAM, i) = 0;
-  }
-  int iter = 0;
-  for (; iter < m.max_iter; iter++) {
-    // jar = b + A lam, forces, E columns
-    float quad = 0;
-    for (int i = 0; i < n; i++) { float s = EFC(d.efc_b, i); for (int j = 0; j < n; j++) s += EA(d.efc_A, i, j) * EW(W_LAM, j); EW(W_JAR, i) = s; quad += 0.5f * EW(W_LAM, i) * (s - EFC(d.efc_b, i)); }
-    int nc = 0;
-    float cost = quad + constraint_update(m, d, e, n, true, &nc);
-    float rr = 0, ll = 0;
-    for (int i = 0; i < n; i++) { float r = EW(W_LAM, i) - EW(W_F, i); EW(W_R, i) = r; rr += r * r; ll += EW(W_F, i) * EW(W_F, i); }
-    if (rr <= 1e-12f * (ll + 1e-30f)) break;
-    // u = A r
-    for (int i = 0; i < n; i++) { float s = 0; for (int j = 0; j < n; j++) s += EA(d.efc_A, i, j) * EW(W_R, j); EW(W_U, i) = s; }
-    // G = I + E^T A E (lower triangle), p = E^T u
-    for (int p = 0; p < nc; p++) {
-      int rp = ECOL_ROW(p), np = 1; if (rp < 0) { rp = -rp - 1; np = 3; }
-      float pv = 0; for (int a = 0; a < np; a++) pv += ECOL_VAL(p, a) * EW(W_U, rp + a);
-      EW(W_P, p) = pv;
-      for (int q = 0; q <= p; q++) {
-        int rq = ECOL_ROW(q), nq = 1; if (rq < 0) { rq = -rq - 1; nq = 3; }
-        float s = (p == q) ? 1.0f : 0.0f;
-        for (int a = 0; a < np; a++) { float va = ECOL_VAL(p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * EA(d.efc_A, rp + a, rq + bb) * ECOL_VAL(q, bb); }
-        EA(d.efc_G, p, q) = s;
-      }
-    }
-    // Cholesky G = L L^T in place, solve G q = p
-    for (int j = 0; j < nc; j++) {
-      float s = EA(d.efc_G, j, j);
-      for (int k = 0; k < j; k++) { float l = EA(d.efc_G, j, k); s -= l * l; }
-      s = sqrtf(fmaxf(s, 1e-12f)); EA(d.efc_G, j, j) = s; float inv = 1.0f / s;
-      for (int i = j + 1; i < nc; i++) { float t = EA(d.efc_G, i, j); for (int k = 0; k < j; k++) t -= EA(d.efc_G, i, k) * EA(d.efc_G, j, k); EA(d.efc_G, i, j) = t * inv; }
-    }
-    for (int i = 0; i < nc; i++) { float s = EW(W_P, i); for (int k = 0; k < i; k++) s -= EA(d.efc_G, i, k) * EW(W_P, k); EW(W_P, i) = s / EA(d.efc_G, i, i); }
-    for (int i = nc - 1; i >= 0; i--) { float s = EW(W_P, i); for (int k = i + 1; k < nc; k++) s -= EA(d.efc_G, k, i) * EW(W_P, k); EW(W_P, i) = s / EA(d.efc_G, i, i); }
-    // dlam = -r + E q
-    for (int i = 0; i < n; i++) EW(W_DL, i) = -EW(W_R, i);
-    for (int p = 0; p < nc; p++) { int rp = ECOL_ROW(p), np = 1; if (rp < 0) { rp = -rp - 1; np = 3; } float qv = EW(W_P, p); for (int a = 0; a < np; a++) EW(W_DL, rp + a) += ECOL_VAL(p, a) * qv; }
-    // A dlam, quadratic coefficients of the Gauss term
-    float q1 = 0, q2 = 0;
-    for (int i = 0; i < n; i++) { float s = 0; for (int j = 0; j < n; j++) s += EA(d.efc_A, i, j) * EW(W_DL, j); EW(W_ADL, i) = s; q1 += EW(W_DL, i) * (EW(W_JAR, i) - EFC(d.efc_b, i)); q2 += 0.5f * EW(W_DL, i) * s; }
-    // exact line search (safeguarded Newton on the derivative)
-    float c0 = quad, g0 = q1, h0 = 2 * q2;
-    ls_eval(m, d, e, n, 0.0f, c0, g0, h0);
-    if (!(g0 < 0) || !(h0 > 0)) break;
-    float alpha = -g0 / h0, lo = 0, hi = -1, cbest = c0;
-    for (int ls = 0; ls < m.ls_iter; ls++) {
-      float c = quad + alpha * q1 + alpha * alpha * q2, g = q1 + 2 * alpha * q2, h = 2 * q2;
-      ls_eval(m, d, e, n, alpha, c, g, h);
-      cbest = c;
-      if (fabsf(g) < 1e-6f * fabsf(g0)) break;
-      if (g < 0) lo = alpha; else hi = alpha;
-      float na = alpha - g / h;
-      if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
-      else if (hi < 0 && na <= lo) na = 2 * alpha;
-      if (fabsf(na - alpha) <= 1e-7f * fabsf(alpha)) { alpha = na; break; }
-      alpha = na;
-    }
-    for (int i = 0; i < n; i++) EW(W_LAM, i) += alpha * EW(W_DL, i);
-    float improvement = scale * (cost - cbest);
-    if (improvement < m.tolerance) { iter++; break; }
-  }
-  AT(d.niter, 0) = iter;
-  // final forces at the solution: lam = f(b + A lam)
-  for (int i = 0; i < n; i++) { float s = EFC(d.efc_b, i); for (int j = 0; j < n; j++) s += EA(d.efc_A, i, j) * EW(W_LAM, j); EW(W_JAR, i) = s; }
-  constraint_update(m, d, e, n, false, nullptr);
-  for (int i = 0; i < n; i++) EFC(d.efc_force, i) = EW(W_F, i);
-  // ---- noslip (MuJoCo mj_solNoSlip): Gauss-Seidel on the friction rows with the unregularised A
-  if (m.noslip_iterations > 0) {
-    for (int it = 0; it < m.noslip_iterations; it++) {
-      float improvement = 0;
-      if (it == 0) for (int i = 0; i < n; i++) improvement += 0.5f * EFC(d.efc_force, i) * EFC(d.efc_force, i) * EFC(d.efc_R, i);
-      bool any = false;
-      for (int i = 0; i < n; i++) {
-        if (EFC(d.efc_type, i) != FB_CT_ELLIPTIC) continue;
-        any = true;
-        int ci = EFC(d.efc_id, i);
-        float fn = EFC(d.efc_force, i), old0 = EFC(d.efc_force, i + 1), old1 = EFC(d.efc_force, i + 2);
-        float res[2], Ac[4], bc[2], v[2];
-        for (int r = 0; r < 2; r++) { float s = EFC(d.efc_b, i + 1 + r); for (int j = 0; j < n; j++) s += EA(d.efc_A, i + 1 + r, j) * EFC(d.efc_force, j); res[r] = s; }
-        Ac[0] = EA(d.efc_A, i + 1, i + 1); Ac[1] = EA(d.efc_A, i + 1, i + 2); Ac[2] = EA(d.efc_A, i + 2, i + 1); Ac[3] = EA(d.efc_A, i + 2, i + 2);
-        bc[0] = res[0] - Ac[0] * old0 - Ac[1] * old1; bc[1] = res[1] - Ac[2] * old0 - Ac[3] * old1;
-        float fr0 = CON_F(d.con_fric, ci, 0, 2), fr1 = CON_F(d.con_fric, ci, 1, 2);
-        if (fn < FB_MINVAL) { v[0] = 0; v[1] = 0; }
-        else {
-          int active = qcqp2(v, Ac, bc, fr0, fr1, fn);
-          if (active) { float s = (v[0] / fr0) * (v[0] / fr0) + (v[1] / fr1) * (v[1] / fr1); s = sqrtf(fn * fn / fmaxf(FB_MINVAL, s)); v[0] *= s; v[1] *= s; }
-        }
-        float d0 = v[0] - old0, d1 = v[1] - old1;
-        float change = 0.5f * (d0 * (Ac[0] * d0 + Ac[1] * d1) + d1 * (Ac[2] * d0 + Ac[3] * d1)) + d0 * res[0] + d1 * res[1];
-        if (change > 1e-10f) { v[0] = old0; v[1] = old1; change = 0; }
-        EFC(d.efc_force, i + 1) = v[0]; EFC(d.efc_force, i + 2) = v[1];
-        improvement -= change;
-        i += 2;
-      }
-      if (!any) break;
-      if (improvement * scale < m.noslip_tolerance) break;
-    }
-  }
-  // qfrc_constraint = J^T f
-  for (int k = 0; k < m.nv; k++) AT(d.qfrc_constraint, k) = 0;
-  for (int r = 0; r < n; r++) {
-    float f = EFC(d.efc_force, r);
-    if (f == 0.0f) continue;
-    int ci, frow; float sign;
-    RowChains rc = row_chains(m, d, e, r, ci, frow, sign);
-    int la = rc.la, lb = rc.lb;
-    while (la >= 0 || lb >= 0) {
-      int k = la > lb ? la : lb;
-      if (la == k) la = m.dof_parentid[la];
-      if (lb == k) lb = m.dof_parentid[lb];
-      AT(d.qfrc_constraint, k) += EJ(d.efc_J, r, k) * f;
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------

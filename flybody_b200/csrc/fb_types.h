@@ -87,7 +87,8 @@ struct DevData {
   float *efc_J, *efc_Z;        // [MAXEFC*nv] dense-by-dof (only the row's dof set is touched)
   float *efc_A, *efc_G;        // [MAXEFC*MAXEFC]
   float *efc_w;                // [8*MAXEFC] solver work vectors
-  int *efc_ecol; float *efc_eval;   // E columns of the solver Hessian factor: base row, 3 values
+  int *efc_ecol, *efc_ekind, *efc_state, *efc_colidx, *efc_la, *efc_lb;   // solver bookkeeping: E columns, row zones, row dof chains
+  float *efc_w2;               // [4*MAXEFC] more solver vectors
   // sensors / outputs
   float *sensordata, *sensor_sum;
   int *flags, *niter, *hold;   // hold != 0: env is not integrated by the next fb_step (pending reset)

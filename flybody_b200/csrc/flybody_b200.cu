@@ -20,7 +20,7 @@
 #ifndef FB_EMU
 #include <cuda_runtime.h>
 #endif
-#include "fb_constraint.h"
+#include "fb_solver.h"
 
 #ifdef FB_EMU
 typedef int cudaStream_t_;
@@ -101,10 +101,39 @@ static void fb_launch(FbSim* s, int ny, int kind) {
 }
 #endif
 
+#ifndef FB_EMU
+template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
+__global__ void fb_run_block(DevModel m, DevData d) {
+  __shared__ Sh sh;
+  F(m, d, sh, blockIdx.x);
+}
+template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
+static void fb_launch_block(FbSim* s, int ny, int kind) {
+  dim3 block(32, ny), grid(s->d.Np / 32);
+  if (s->prof_on) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s->stream);
+    fb_run_block<Sh, F><<<grid, block, 0, s->stream>>>(s->m, s->d);
+    cudaEventRecord(b, s->stream);
+    s->prof_events.push_back({kind, a, b});
+  } else {
+    fb_run_block<Sh, F><<<grid, block, 0, s->stream>>>(s->m, s->d);
+  }
+  s->launches++;
+}
+#else
+template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
+static void fb_launch_block(FbSim* s, int ny, int kind) {
+  (void)ny; (void)kind;
+  static Sh sh;
+  for (int blk = 0; blk < s->d.Np / 32; blk++) F(s->m, s->d, sh, blk);
+  s->launches++;
+}
+#endif
+
 // lane == env kernels wrapped as single-phase functions
 FB_DEV void ph_act(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kact(m, d, e); }
 FB_DEV void ph_con(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kcon(m, d, e); }
-FB_DEV void ph_solve(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksolve(m, d, e); }
 FB_DEV void ph_sens_first(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksens_accum(m, d, e, 1); }
 FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kreset_scatter(m, d, e); }
 FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kclear_hold(m, d, e); }
@@ -128,7 +157,7 @@ static void launch_step2(FbSim* s, bool integrate) {
   fb_launch<ShNone, ph_act>(s, 1, K_ACT);
   fb_launch<ShTree, ph_smooth_a, ph_smooth_b, ph_smooth_c>(s, nl, K_SMOOTH);
   fb_launch<ShNone, kref>(s, FB_ROWPAR, K_REF);
-  fb_launch<ShNone, ph_solve>(s, 1, K_SOLVE);
+  fb_launch_block<ShSolve, ksolve_block>(s, FB_SOLVE_Y, K_SOLVE);
   if (integrate)
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
               kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl, K_FINISH);
@@ -286,7 +315,7 @@ static int alloc_data(FbSim* s, int N) {
   FA(efc_pos, FB_MAXEFC) FA(efc_margin, FB_MAXEFC) FA(efc_D, FB_MAXEFC) FA(efc_R, FB_MAXEFC) FA(efc_K, FB_MAXEFC) FA(efc_B, FB_MAXEFC)
   FA(efc_imp, FB_MAXEFC) FA(efc_aref, FB_MAXEFC) FA(efc_b, FB_MAXEFC) FA(efc_force, FB_MAXEFC) FA(efc_jarws, FB_MAXEFC)
   FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv) FA(efc_A, (size_t)FB_MAXEFC * FB_MAXEFC) FA(efc_G, (size_t)FB_MAXEFC * FB_MAXEFC)
-  FA(efc_w, 8 * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) FA(efc_eval, 3 * FB_MAXEFC)
+  FA(efc_w, 8 * FB_MAXEFC) FA(efc_w2, 4 * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) IA(efc_ekind, FB_MAXEFC) IA(efc_state, FB_MAXEFC) IA(efc_colidx, FB_MAXEFC) IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC)
   FA(sensordata, m.nsensordata + 1) FA(sensor_sum, m.nsensordata + 1) IA(flags, 1) IA(niter, 1) IA(hold, 1)
 #undef FA
 #undef IA

