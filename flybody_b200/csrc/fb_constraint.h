@@ -197,34 +197,64 @@ FB_DEV void row_params(const DevModel& m, const DevData& d, int e, int r, const 
   if (isfric) K = 0;
   EFC(d.efc_R, r) = R; EFC(d.efc_D, r) = 1.0f / R; EFC(d.efc_K, r) = K; EFC(d.efc_B, r) = B; EFC(d.efc_imp, r) = imp;
 }
-FB_DEV void kcon(const DevModel& m, const DevData& d, int e) {
-  int n = 0;
-  for (int j = 0; j < m.njnt; j++) {
+struct ShCon { int cnt[FB_ROWPAR][32]; int base[32]; };
+#define FB_CON_ARGS const DevModel& m, const DevData& d, ShCon& sh, int e, int lane, int y
+FB_DEV bool limit_active(const DevModel& m, const DevData& d, int e, int j, int side, float& dist) {
+  float value = AT(d.qpos, m.jnt_qposadr[j]);
+  dist = side * (m.jnt_range[2 * j + (side + 1) / 2] - value);
+  return dist < m.jnt_margin[j];
+}
+// phase 0/1: joint-limit rows (joints split into contiguous ranges over y so that rows stay in joint order)
+FB_DEV void kcon_p0(FB_CON_ARGS) {
+  int j0 = (int)((long)y * m.njnt / FB_ROWPAR), j1 = (int)((long)(y + 1) * m.njnt / FB_ROWPAR), c = 0; float dist;
+  for (int j = j0; j < j1; j++) { if (!m.jnt_limited[j] || m.jnt_type[j] != FB_JNT_HINGE) continue; for (int side = -1; side <= 1; side += 2) c += limit_active(m, d, e, j, side, dist) ? 1 : 0; }
+  sh.cnt[y][lane] = c;
+}
+FB_DEV void kcon_p1(FB_CON_ARGS) {
+  int n = 0; for (int yy = 0; yy < y; yy++) n += sh.cnt[yy][lane];
+  int j0 = (int)((long)y * m.njnt / FB_ROWPAR), j1 = (int)((long)(y + 1) * m.njnt / FB_ROWPAR); float dist;
+  for (int j = j0; j < j1; j++) {
     if (!m.jnt_limited[j] || m.jnt_type[j] != FB_JNT_HINGE) continue;
-    float value = AT(d.qpos, m.jnt_qposadr[j]), margin = m.jnt_margin[j];
     for (int side = -1; side <= 1; side += 2) {
-      float dist = side * (m.jnt_range[2 * j + (side + 1) / 2] - value);
-      if (dist < margin && n < FB_MAXEFC) {
+      if (limit_active(m, d, e, j, side, dist) && n < FB_MAXEFC) {
         EFC(d.efc_type, n) = FB_CT_LIMIT; EFC(d.efc_id, n) = (side < 0) ? j : -(j + 1);   // sign encodes the side
-        EFC(d.efc_pos, n) = dist; EFC(d.efc_margin, n) = margin;
-        row_params(m, d, e, n, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist, margin, m.dof_invweight0[m.jnt_dofadr[j]], false);
+        EFC(d.efc_pos, n) = dist; EFC(d.efc_margin, n) = m.jnt_margin[j];
+        row_params(m, d, e, n, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist, m.jnt_margin[j], m.dof_invweight0[m.jnt_dofadr[j]], false);
         n++;
       }
     }
   }
+  if (y == FB_ROWPAR - 1) sh.base[lane] = n < FB_MAXEFC ? n : FB_MAXEFC;
+}
+// contact -> (dim, included)
+FB_DEV int contact_dim(const DevModel& m, const DevData& d, int e, int ci, float& includemargin, bool& incl) {
+  int g1 = AT(d.con_geom1, ci), g2 = AT(d.con_geom2, ci);
+  float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]), gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
+  includemargin = margin - gap;
+  int dim = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
+  incl = AT(d.con_dist, ci) < includemargin;
+  return dim >= 3 ? 3 : 1;
+}
+FB_DEV void kcon_p2(FB_CON_ARGS) {
   int ncon = AT(d.ncon, 0);
-  for (int ci = 0; ci < ncon; ci++) {
+  int c0 = y * ncon / FB_ROWPAR, c1 = (y + 1) * ncon / FB_ROWPAR, rows = 0;
+  for (int ci = c0; ci < c1; ci++) { float im; bool incl; int dim = contact_dim(m, d, e, ci, im, incl); if (incl) rows += dim; }
+  sh.cnt[y][lane] = rows;
+}
+FB_DEV void kcon_p3(FB_CON_ARGS) {
+  int ncon = AT(d.ncon, 0);
+  int n = sh.base[lane]; for (int yy = 0; yy < y; yy++) n += sh.cnt[yy][lane];
+  int c0 = y * ncon / FB_ROWPAR, c1 = (y + 1) * ncon / FB_ROWPAR;
+  for (int ci = c0; ci < c1; ci++) {
+    float includemargin; bool incl; int dim = contact_dim(m, d, e, ci, includemargin, incl);
     int g1 = AT(d.con_geom1, ci), g2 = AT(d.con_geom2, ci);
-    float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]), gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
-    float includemargin = margin - gap, dist = AT(d.con_dist, ci);
-    int dim = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
-    dim = dim >= 3 ? 3 : 1;
+    float dist = AT(d.con_dist, ci);
     float fr0 = fmaxf(m.geom_friction[3 * g1], m.geom_friction[3 * g2]);
     AT(d.con_dim, ci) = dim; AT(d.con_mu, ci) = fr0 * sqrtf(1.0f / m.impratio);
     CON_F(d.con_fric, ci, 0, 2) = fr0; CON_F(d.con_fric, ci, 1, 2) = fr0;
     AT(d.con_efcadr, ci) = -1;
-    if (!(dist < includemargin)) continue;          // detected, but inside the gap: adhesion only
-    if (n + dim > FB_MAXEFC) { FB_FLAG_OR(4); continue; }
+    if (!incl) continue;                            // detected, but inside the gap: adhesion only
+    if (n + dim > FB_MAXEFC) { FB_FLAG_OR(4); n += dim; continue; }
     float mix1 = m.geom_solmix[g1], mix2 = m.geom_solmix[g2], mix;
     if (mix1 >= FB_MINVAL && mix2 >= FB_MINVAL) mix = mix1 / (mix1 + mix2);
     else if (mix1 < FB_MINVAL && mix2 < FB_MINVAL) mix = 0.5f; else mix = (mix1 < FB_MINVAL) ? 0.0f : 1.0f;
@@ -246,7 +276,12 @@ FB_DEV void kcon(const DevModel& m, const DevData& d, int e) {
     }
     n += dim;
   }
-  AT(d.nefc, 0) = n;
+  if (y == FB_ROWPAR - 1) {
+    // rows are contiguous up to the first overflowing contact; later ones were all dropped
+    int tot = n;
+    if (tot > FB_MAXEFC) { tot = sh.base[lane]; for (int ci = 0; ci < ncon; ci++) { int a = AT(d.con_efcadr, ci); if (a >= 0 && a + AT(d.con_dim, ci) > tot) tot = a + AT(d.con_dim, ci); } }
+    AT(d.nefc, 0) = tot;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -278,7 +313,7 @@ FB_DEV float contact_J(const DevModel& m, const DevData& d, int e, V3 f, V3 pos,
 //   phase 0: J (dense-by-dof storage), Z = D^-1/2 L^-T J^T restricted to the row's dof set
 //   phase 1: A = Z Z^T  (= J M^-1 J^T, the unregularised Delassus matrix)
 struct ShNone { int dummy; };
-#define FB_ROW_ARGS const DevModel& m, const DevData& d, ShNone& sh, int e, int lane, int y
+#define FB_ROW_ARGS const DevModel& m, const DevData& d, ShCon& sh, int e, int lane, int y
 FB_DEV void kproj_p0(FB_ROW_ARGS) {
   int n = AT(d.nefc, 0);
   for (int r = y; r < n; r += FB_ROWPAR) {
@@ -288,13 +323,14 @@ FB_DEV void kproj_p0(FB_ROW_ARGS) {
     V3 f = v3(0, 0, 0), pos = v3(0, 0, 0);
     if (ci >= 0) { f = v3(CON_F(d.con_frame, ci, 3 * frow, 9), CON_F(d.con_frame, ci, 3 * frow + 1, 9), CON_F(d.con_frame, ci, 3 * frow + 2, 9));
                    pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3)); }
-    // J over the dof set
+    // J over the dof set; the sweep scratch z lives in shared memory, indexed by dof: zs[y][dof][lane]
+    float* zs = sh_dyn(sh) + (size_t)y * m.nv * 32;
     int la = rc.la, lb = rc.lb;
     while (la >= 0 || lb >= 0) {
       int k = la > lb ? la : lb; float v = 0;
       if (ci < 0) v = (k == rc.la) ? sign : 0.0f;
       else { if (la == k) v += contact_J(m, d, e, f, pos, k); if (lb == k) v -= contact_J(m, d, e, f, pos, k); }
-      EJ(d.efc_J, r, k) = v; EJ(d.efc_Z, r, k) = v;
+      EJ(d.efc_J, r, k) = v; zs[k * 32 + lane] = v;
       if (la == k) la = m.dof_parentid[la];
       if (lb == k) lb = m.dof_parentid[lb];
     }
@@ -304,9 +340,9 @@ FB_DEV void kproj_p0(FB_ROW_ARGS) {
       int k = la > lb ? la : lb;
       if (la == k) la = m.dof_parentid[la];
       if (lb == k) lb = m.dof_parentid[lb];
-      float zk = EJ(d.efc_Z, r, k);
+      float zk = zs[k * 32 + lane];
       int adrk = m.dof_Madr[k], t = 1;
-      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) EJ(d.efc_Z, r, i) -= AT(d.qLD, adrk + t) * zk;
+      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) zs[i * 32 + lane] -= AT(d.qLD, adrk + t) * zk;
       EJ(d.efc_Z, r, k) = zk / sqrtf(AT(d.qLD, adrk));
     }
   }
@@ -330,9 +366,9 @@ FB_DEV void kproj_p1(FB_ROW_ARGS) {
   }
 }
 // J . x for every row (x: qvel, qacc_smooth, qacc_warmstart): aref, b, jar at the warm start
-FB_DEV void kref(FB_ROW_ARGS) {
+FB_DEV void kref(FB_PHASE_ARGS) {
   int n = AT(d.nefc, 0);
-  for (int r = y; r < n; r += FB_ROWPAR) {
+  for (int r = y; r < n; r += m.nlist) {
     int ci, frow; float sign;
     RowChains rc = row_chains(m, d, e, r, ci, frow, sign);
     float vel = 0, as = 0, ws = 0; int la = rc.la, lb = rc.lb;
@@ -350,10 +386,9 @@ FB_DEV void kref(FB_ROW_ARGS) {
 
 // ---------------------------------------------------------------------------------------------
 // K3 + K8 transmission and actuation (MuJoCo mj_transmission, mj_fwdActuation), lane = env
-FB_DEV void kact(const DevModel& m, const DevData& d, int e) {
-  for (int k = 0; k < m.nv; k++) AT(d.qfrc_actuator, k) = 0;
-  int ncon = AT(d.ncon, 0);
-  for (int i = 0; i < m.nu; i++) {
+FB_DEV void kact_p0(FB_PHASE_ARGS) { for (int k = y; k < m.nv; k += m.nlist) AT(d.qfrc_actuator, k) = 0; }
+FB_DEV void kact_p1(FB_PHASE_ARGS) {
+  for (int i = y; i < m.nu; i += m.nlist) {
     float ctrl = AT(d.ctrl, i);
     if (m.actuator_ctrllimited[i]) ctrl = clampf(ctrl, m.actuator_ctrlrange[2 * i], m.actuator_ctrlrange[2 * i + 1]);
     int id = m.actuator_trnid[i], tt = m.actuator_trntype[i];
@@ -368,30 +403,43 @@ FB_DEV void kact(const DevModel& m, const DevData& d, int e) {
     if (m.actuator_biastype[i] == 1) force += m.actuator_biasprm[3 * i] + m.actuator_biasprm[3 * i + 1] * len + m.actuator_biasprm[3 * i + 2] * vel;
     if (m.actuator_forcelimited[i]) force = clampf(force, m.actuator_forcerange[2 * i], m.actuator_forcerange[2 * i + 1]);
     AT(d.actuator_force, i) = force;
+    // joint / tendon transmissions touch disjoint dofs (one actuator per joint or tendon in the fly model)
     if (tt == FB_TRN_JOINT) AT(d.qfrc_actuator, m.jnt_dofadr[id]) += force;
     else if (tt == FB_TRN_TENDON) { for (int w = m.tendon_adr[id]; w < m.tendon_adr[id] + m.tendon_num[id]; w++) AT(d.qfrc_actuator, m.wrap_dofid[w]) += m.wrap_coef[w] * force; }
-    else {
-      // adhesion: moment = - mean of the contact-normal Jacobians of all detected contacts of the body
-      int cnt = 0;
-      for (int ci = 0; ci < ncon; ci++) { if (m.geom_bodyid[AT(d.con_geom1, ci)] == id || m.geom_bodyid[AT(d.con_geom2, ci)] == id) cnt++; }
-      if (cnt == 0 || force == 0.0f) continue;
-      float sc = -force / cnt;
-      for (int ci = 0; ci < ncon; ci++) {
-        int b1 = m.geom_bodyid[AT(d.con_geom1, ci)], b2 = m.geom_bodyid[AT(d.con_geom2, ci)];
-        if (b1 != id && b2 != id) continue;
-        V3 f = v3(CON_F(d.con_frame, ci, 0, 9), CON_F(d.con_frame, ci, 1, 9), CON_F(d.con_frame, ci, 2, 9));
-        V3 pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3));
-        for (int k = m.body_lastdof[b2]; k >= 0; k = m.dof_parentid[k]) AT(d.qfrc_actuator, k) += sc * contact_J(m, d, e, f, pos, k);
-        for (int k = m.body_lastdof[b1]; k >= 0; k = m.dof_parentid[k]) AT(d.qfrc_actuator, k) -= sc * contact_J(m, d, e, f, pos, k);
-      }
-    }
-  }
-  for (int k = 0; k < m.nv; k++) {
-    float s = AT(d.qfrc_passive, k) - AT(d.qfrc_bias, k) + AT(d.qfrc_actuator, k);
-    AT(d.qfrc_smooth, k) = s; AT(d.qacc_smooth, k) = s;
   }
 }
-
+// adhesion (body transmission): moment = - mean of the contact-normal Jacobians of all detected contacts of the
+// body (incl. those inside the gap).  Chains share the root dofs, so this part runs on one thread.
+FB_DEV void kact_p2(FB_PHASE_ARGS) {
+  if (y != 0) return;
+  int ncon = AT(d.ncon, 0);
+  if (ncon == 0) return;
+  for (int i = 0; i < m.nu; i++) {
+    if (m.actuator_trntype[i] != FB_TRN_BODY) continue;
+    float force = AT(d.actuator_force, i); int id = m.actuator_trnid[i];
+    if (force == 0.0f) continue;
+    int cnt = 0;
+    for (int ci = 0; ci < ncon; ci++) { if (m.geom_bodyid[AT(d.con_geom1, ci)] == id || m.geom_bodyid[AT(d.con_geom2, ci)] == id) cnt++; }
+    if (cnt == 0) continue;
+    float sc = -force / cnt;
+    for (int ci = 0; ci < ncon; ci++) {
+      int b1 = m.geom_bodyid[AT(d.con_geom1, ci)], b2 = m.geom_bodyid[AT(d.con_geom2, ci)];
+      if (b1 != id && b2 != id) continue;
+      V3 f = v3(CON_F(d.con_frame, ci, 0, 9), CON_F(d.con_frame, ci, 1, 9), CON_F(d.con_frame, ci, 2, 9));
+      V3 pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3));
+      for (int k = m.body_lastdof[b2]; k >= 0; k = m.dof_parentid[k]) AT(d.qfrc_actuator, k) += sc * contact_J(m, d, e, f, pos, k);
+      for (int k = m.body_lastdof[b1]; k >= 0; k = m.dof_parentid[k]) AT(d.qfrc_actuator, k) -= sc * contact_J(m, d, e, f, pos, k);
+    }
+  }
+}
+// qfrc_smooth = passive - bias + actuator, staged into shared memory as the rhs of M x = qfrc_smooth
+FB_DEV void kact_p3(FB_PHASE_ARGS) {
+  float* xs = sh_dyn(sh);
+  for (int k = y; k < m.nv; k += m.nlist) {
+    float s = AT(d.qfrc_passive, k) - AT(d.qfrc_bias, k) + AT(d.qfrc_actuator, k);
+    AT(d.qfrc_smooth, k) = s; XS(k) = s;
+  }
+}
 // ---------------------------------------------------------------------------------------------
 // K11 constraint solve in the dual (force) space, lane = env.
 //
@@ -426,18 +474,20 @@ FB_DEV int qcqp2(float* res, const float* A, const float* b, float d0, float d1,
 // K12 acceleration-stage sensors + K13 Euler (tree kernel phases, see fb_kernels.cu for the order)
 // phase: qtmp <- qfrc_constraint (rhs of M x = J^T f)
 FB_DEV void kfin_copy(FB_PHASE_ARGS) {
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qtmp, i) = AT(d.qfrc_constraint, i); } }
+  float* xs = sh_dyn(sh);
+  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; XS(i) = AT(d.qfrc_constraint, i); } }
   if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qtmp, i) = AT(d.qfrc_constraint, i); } }
+  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; XS(i) = AT(d.qfrc_constraint, i); } }
 }
-FB_DEV void kfin_solve_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD, d.qtmp); }
-FB_DEV void kfin_solve_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD, d.qtmp); }
+FB_DEV void kfin_solve_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD); }
+FB_DEV void kfin_solve_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD); }
 FB_DEV void kfin_solve_c(FB_PHASE_ARGS) {
-  solve_c(m, d, sh, e, lane, y, d.qLD, d.qtmp);
+  float* xs = sh_dyn(sh);
+  solve_c(m, d, sh, e, lane, y, d.qLD);
   // qacc = qacc_smooth + M^-1 J^T f for own dofs (root dofs by y == 0 were finalised in phase b)
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc, i) = AT(d.qacc_smooth, i) + AT(d.qtmp, i); } }
+  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc, i) = AT(d.qacc_smooth, i) + XS(i); } }
   if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc, i) = AT(d.qacc_smooth, i) + AT(d.qtmp, i); } }
+  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc, i) = AT(d.qacc_smooth, i) + XS(i); } }
 }
 // sensors: full RNE with qacc, minus contact forces -> cfrc_int (MuJoCo mj_rnePostConstraint)
 FB_DEV void kfin_sens_root(FB_PHASE_ARGS) {
@@ -538,18 +588,19 @@ FB_DEV void kfin_sens_out(FB_PHASE_ARGS) {
 }
 // Euler: qtmp <- qfrc_smooth + qfrc_constraint, solve with the (M + h D) factor, integrate
 FB_DEV void keul_rhs(FB_PHASE_ARGS) {
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qtmp, i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); } }
+  float* xs = sh_dyn(sh);
+  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); } }
   if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qtmp, i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); } }
+  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); } }
 }
-FB_DEV void keul_solve_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLDe, d.qtmp); }
-FB_DEV void keul_solve_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLDe, d.qtmp); }
-FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int b) {
+FB_DEV void keul_solve_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLDe); }
+FB_DEV void keul_solve_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLDe); }
+FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int lane, const float* xs, int b) {
   float h = m.timestep;
   for (int k = 0; k < m.body_jntnum[b]; k++) {
     int j = m.body_jntadr[b] + k, qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
     if (m.jnt_type[j] == FB_JNT_FREE) {
-      for (int i = 0; i < 6; i++) { AT(d.qvel, da + i) += h * AT(d.qtmp, da + i); AT(d.qacc_warmstart, da + i) = AT(d.qacc, da + i); }
+      for (int i = 0; i < 6; i++) { AT(d.qvel, da + i) += h * XS(da + i); AT(d.qacc_warmstart, da + i) = AT(d.qacc, da + i); }
       for (int i = 0; i < 3; i++) AT(d.qpos, qa + i) += h * AT(d.qvel, da + i);
       V3 w = v3(AT(d.qvel, da + 3), AT(d.qvel, da + 4), AT(d.qvel, da + 5));
       float ang = norm(w) * h;
@@ -558,26 +609,29 @@ FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int b) {
       q = qnormalize(q);
       AT(d.qpos, qa + 3) = q.w; AT(d.qpos, qa + 4) = q.x; AT(d.qpos, qa + 5) = q.y; AT(d.qpos, qa + 6) = q.z;
     } else {
-      AT(d.qvel, da) += h * AT(d.qtmp, da); AT(d.qacc_warmstart, da) = AT(d.qacc, da);
+      AT(d.qvel, da) += h * XS(da); AT(d.qacc_warmstart, da) = AT(d.qacc, da);
       AT(d.qpos, qa) += h * AT(d.qvel, da);
     }
   }
 }
 FB_DEV void keul_solve_c_integrate(FB_PHASE_ARGS) {
-  solve_c(m, d, sh, e, lane, y, d.qLDe, d.qtmp);
+  float* xs = sh_dyn(sh);
+  solve_c(m, d, sh, e, lane, y, d.qLDe);
   if (AT(d.hold, 0)) return;          // env staged for reset: recompute (forward) but do not integrate
   if (y == 0) {
-    for (int r = 0; r < m.nroot; r++) integrate_body(m, d, e, m.root_body[r]);
+    for (int r = 0; r < m.nroot; r++) integrate_body(m, d, e, lane, xs, m.root_body[r]);
     for (int i = 0; i < m.na; i++) AT(d.act, i) += m.timestep * AT(d.act_dot, i);
     AT(d.time, 0) += m.timestep;
   }
   if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD integrate_body(m, d, e, b);
+  FB_LIST_LOOP_FWD integrate_body(m, d, e, lane, xs, b);
 }
 // accumulate sensor sums (after step1 of the substep: vel sensors are from the new state)
 FB_DEV void ksens_accum(const DevModel& m, const DevData& d, int e, int first) {
   for (int i = 0; i < m.nsensordata; i++) AT(d.sensor_sum, i) = (first ? 0.0f : AT(d.sensor_sum, i)) + AT(d.sensordata, i);
 }
+// last phase of the velocity kernel: per-substep sensor accumulation (d.sens_mode: 1 first substep, 0 next, -1 off)
+FB_DEV void kvel_p4(FB_PHASE_ARGS) { if (y == 0 && d.sens_mode >= 0) ksens_accum(m, d, e, d.sens_mode); }
 
 // ---------------------------------------------------------------------------------------------
 // packed per-env observation record (AoS, one row per env) for the host task code / NCCL gather:

@@ -22,8 +22,14 @@ struct ShSolve {
 enum { SC_COST = 0, SC_QUAD, SC_Q1, SC_Q2, SC_ALPHA, SC_LO, SC_HI, SC_G0, SC_CBEST, SC_DIAG, SC_COSTWS, SC_COST0, SC_RR, SC_LL, SC_CPREV };
 enum { I_N = 0, I_NC, I_DONE, I_ITER, I_LSDONE };
 // extra solver vectors (beyond W_LAM..W_P of fb_constraint.h) live in efc_w2
-enum { X_E0 = 0, X_E1, X_XQ, X_OUT, X_NW2 };
-#define EW2(slot, r) AT(d.efc_w2, (slot) * FB_MAXEFC + (r))
+enum { X_E0 = 8, X_E1, X_XQ, X_OUT, X_NW2 };
+// solver vectors: 12 slots (W_LAM..W_P = 0..7, X_* = 8..11).  When they fit, they live in shared memory
+// ([slot][row][lane], row stride = block-wide max nefc); otherwise in the global efc_w / efc_w2 arrays.
+struct SolveCtx { float* vsh; int vstride; float* gsh; int gcap; int gmode; };
+#define FB_SOLVE_DYN_FLOATS (190 * 256)
+#define SWG(slot, r) ((slot) < 8 ? &AT(d.efc_w, (slot) * FB_MAXEFC + (r)) : &AT(d.efc_w2, ((slot) - 8) * FB_MAXEFC + (r)))
+#define SW(slot, r) (*(cx.vsh ? &cx.vsh[((slot) * cx.vstride + (r)) * 32 + lane] : SWG(slot, r)))
+#define GM(p, q) (*(cx.gmode ? &cx.gsh[((p) * cx.gcap + (q)) * 32 + lane] : &EA(d.efc_G, p, q)))
 #define ESTATE(r) AT(d.efc_state, (r))
 #define ECOLIDX(r) AT(d.efc_colidx, (r))
 #define ECROW(p) AT(d.efc_ecol, (p))
@@ -49,35 +55,35 @@ FB_DEV int blk_any_ls(const ShSolve& sh) { int v = 0; for (int l = 0; l < 32; l+
 
 // forces / cost of the rows headed at r (a non-elliptic row, or the first row of an elliptic contact).
 // Returns the cost; writes W_F; with build: state + E values.
-FB_DEV float head_update(const DevModel& m, const DevData& d, int e, int r, bool build) {
+FB_DEV float head_update(const DevModel& m, const DevData& d, const SolveCtx& cx, int lane, int e, int r, bool build) {
   int tp = EFC(d.efc_type, r);
-  float jar = EW(W_JAR, r), D = EFC(d.efc_D, r), cost = 0;
+  float jar = SW(W_JAR, r), D = EFC(d.efc_D, r), cost = 0;
   if (tp != FB_CT_ELLIPTIC) {
-    if (jar < 0) { EW(W_F, r) = -D * jar; cost = 0.5f * D * jar * jar; if (build) { ESTATE(r) = 1; EW2(X_E0, r) = sqrtf(D); } }
-    else { EW(W_F, r) = 0; if (build) ESTATE(r) = 0; }
+    if (jar < 0) { SW(W_F, r) = -D * jar; cost = 0.5f * D * jar * jar; if (build) { ESTATE(r) = 1; SW(X_E0, r) = sqrtf(D); } }
+    else { SW(W_F, r) = 0; if (build) ESTATE(r) = 0; }
     return cost;
   }
   int ci = EFC(d.efc_id, r);
   float mu = AT(d.con_mu, ci), f1 = CON_F(d.con_fric, ci, 0, 2), f2 = CON_F(d.con_fric, ci, 1, 2);
-  float j1 = EW(W_JAR, r + 1), j2 = EW(W_JAR, r + 2), D1 = EFC(d.efc_D, r + 1), D2 = EFC(d.efc_D, r + 2);
+  float j1 = SW(W_JAR, r + 1), j2 = SW(W_JAR, r + 2), D1 = EFC(d.efc_D, r + 1), D2 = EFC(d.efc_D, r + 2);
   float U0 = jar * mu, U1 = j1 * f1, U2 = j2 * f2, N = U0, T = sqrtf(U1 * U1 + U2 * U2);
   if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-    EW(W_F, r) = -D * jar; EW(W_F, r + 1) = -D1 * j1; EW(W_F, r + 2) = -D2 * j2;
+    SW(W_F, r) = -D * jar; SW(W_F, r + 1) = -D1 * j1; SW(W_F, r + 2) = -D2 * j2;
     cost = 0.5f * (D * jar * jar + D1 * j1 * j1 + D2 * j2 * j2);
-    if (build) { ESTATE(r) = 1; ESTATE(r + 1) = 1; ESTATE(r + 2) = 1; EW2(X_E0, r) = sqrtf(D); EW2(X_E0, r + 1) = sqrtf(D1); EW2(X_E0, r + 2) = sqrtf(D2); }
+    if (build) { ESTATE(r) = 1; ESTATE(r + 1) = 1; ESTATE(r + 2) = 1; SW(X_E0, r) = sqrtf(D); SW(X_E0, r + 1) = sqrtf(D1); SW(X_E0, r + 2) = sqrtf(D2); }
   } else if (N >= mu * T || (T <= 0 && N >= 0)) {
-    EW(W_F, r) = 0; EW(W_F, r + 1) = 0; EW(W_F, r + 2) = 0;
+    SW(W_F, r) = 0; SW(W_F, r + 1) = 0; SW(W_F, r + 2) = 0;
     if (build) { ESTATE(r) = 0; ESTATE(r + 1) = 0; ESTATE(r + 2) = 0; }
   } else {
     float Dm = D / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
     cost = 0.5f * Dm * NmT * NmT;
     float f0 = -Dm * NmT * mu;
-    EW(W_F, r) = f0; EW(W_F, r + 1) = -f0 / T * U1 * f1; EW(W_F, r + 2) = -f0 / T * U2 * f2;
+    SW(W_F, r) = f0; SW(W_F, r + 1) = -f0 / T * U1 * f1; SW(W_F, r + 2) = -f0 / T * U2 * f2;
     if (build) {
       float sD = sqrtf(Dm), k2 = sqrtf(fmaxf(0.0f, Dm * (-NmT) * mu / T));
       ESTATE(r) = 2; ESTATE(r + 1) = 3; ESTATE(r + 2) = 3;
-      EW2(X_E0, r) = sD * mu; EW2(X_E0, r + 1) = -sD * f1 * mu * U1 / T; EW2(X_E0, r + 2) = -sD * f2 * mu * U2 / T;
-      EW2(X_E1, r) = 0; EW2(X_E1, r + 1) = -k2 * f1 * U2 / T; EW2(X_E1, r + 2) = k2 * f2 * U1 / T;
+      SW(X_E0, r) = sD * mu; SW(X_E0, r + 1) = -sD * f1 * mu * U1 / T; SW(X_E0, r + 2) = -sD * f2 * mu * U2 / T;
+      SW(X_E1, r) = 0; SW(X_E1, r + 1) = -k2 * f1 * U2 / T; SW(X_E1, r + 2) = k2 * f2 * U1 / T;
     }
   }
   return cost;
@@ -86,14 +92,14 @@ FB_DEV bool is_head(const DevData& d, int e, int r) {
   return EFC(d.efc_type, r) != FB_CT_ELLIPTIC || AT(d.con_efcadr, EFC(d.efc_id, r)) == r;
 }
 // line-search contribution of the rows headed at r
-FB_DEV void head_ls(const DevModel& m, const DevData& d, int e, int r, float alpha, float& c, float& g, float& h) {
+FB_DEV void head_ls(const DevModel& m, const DevData& d, const SolveCtx& cx, int lane, int e, int r, float alpha, float& c, float& g, float& h) {
   int tp = EFC(d.efc_type, r);
-  float jv = EW(W_ADL, r), x = EW(W_JAR, r) + alpha * jv, D = EFC(d.efc_D, r);
+  float jv = SW(W_ADL, r), x = SW(W_JAR, r) + alpha * jv, D = EFC(d.efc_D, r);
   if (tp != FB_CT_ELLIPTIC) { if (x < 0) { c += 0.5f * D * x * x; g += D * x * jv; h += D * jv * jv; } return; }
   int ci = EFC(d.efc_id, r);
   float mu = AT(d.con_mu, ci), f1 = CON_F(d.con_fric, ci, 0, 2), f2 = CON_F(d.con_fric, ci, 1, 2);
-  float jv1 = EW(W_ADL, r + 1), jv2 = EW(W_ADL, r + 2);
-  float x1 = EW(W_JAR, r + 1) + alpha * jv1, x2 = EW(W_JAR, r + 2) + alpha * jv2;
+  float jv1 = SW(W_ADL, r + 1), jv2 = SW(W_ADL, r + 2);
+  float x1 = SW(W_JAR, r + 1) + alpha * jv1, x2 = SW(W_JAR, r + 2) + alpha * jv2;
   float D1 = EFC(d.efc_D, r + 1), D2 = EFC(d.efc_D, r + 2);
   float U0 = x * mu, U1 = x1 * f1, U2 = x2 * f2, dU0 = jv * mu, dU1 = jv1 * f1, dU2 = jv2 * f2;
   float N = U0, T = sqrtf(U1 * U1 + U2 * U2);
@@ -109,9 +115,9 @@ FB_DEV void head_ls(const DevModel& m, const DevData& d, int e, int r, float alp
   }
 }
 // column p of E: value on row `row` (0 if the column does not touch it)
-FB_DEV float ecol_val(const DevData& d, int e, int p, int a) {   // a-th entry of column p
+FB_DEV float ecol_val(const DevData& d, const SolveCtx& cx, int lane, int e, int p, int a) {   // a-th entry of column p
   int kind = ECKIND(p), r = ECROW(p);
-  return kind == 2 ? EW2(X_E1, r + a) : EW2(X_E0, r + a);
+  return kind == 2 ? SW(X_E1, r + a) : SW(X_E0, r + a);
 }
 
 #define ROWS_BEGIN for (int r = y; r < MY_N; r += FB_SOLVE_Y) {
@@ -124,30 +130,41 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
   PAR_BEGIN
     if (y == 0) { int n = AT(d.nefc, 0); sh.isc[I_N][lane] = n; sh.isc[I_DONE][lane] = (n == 0); sh.isc[I_ITER][lane] = 0; sh.isc[I_NC][lane] = 0; sh.isc[I_LSDONE][lane] = 1; }
   PAR_END
+  SolveCtx cx; cx.vsh = nullptr; cx.vstride = 0; cx.gsh = nullptr; cx.gcap = 0; cx.gmode = 0;
   if (blk_max_i(sh, I_N) > 0) {
+    {
+      int nmaxb = blk_max_i(sh, I_N);
+      float* dyn = sh_dyn(sh);
+      if (12 * nmaxb * 32 <= FB_SOLVE_DYN_FLOATS) {
+        cx.vsh = dyn; cx.vstride = nmaxb; cx.gsh = dyn + (size_t)12 * nmaxb * 32;
+        int rem = FB_SOLVE_DYN_FLOATS / 32 - 12 * nmaxb, g = 0;
+        while ((g + 1) * (g + 1) <= rem) g++;
+        cx.gcap = g;
+      }
+    }
     // ---------------- warm start
-    PAR_BEGIN float c = 0; ROWS_BEGIN EW(W_JAR, r) = EFC(d.efc_jarws, r); ROWS_END sh.red[y][0][lane] = c; PAR_END
-    PAR_BEGIN ROWS_BEGIN if (is_head(d, e, r)) head_update(m, d, e, r, false); ROWS_END PAR_END
-    PAR_BEGIN ROWS_BEGIN EW(W_LAM, r) = EW(W_F, r); ROWS_END PAR_END
+    PAR_BEGIN float c = 0; ROWS_BEGIN SW(W_JAR, r) = EFC(d.efc_jarws, r); ROWS_END sh.red[y][0][lane] = c; PAR_END
+    PAR_BEGIN ROWS_BEGIN if (is_head(d, e, r)) head_update(m, d, cx, lane, e, r, false); ROWS_END PAR_END
+    PAR_BEGIN ROWS_BEGIN SW(W_LAM, r) = SW(W_F, r); ROWS_END PAR_END
     PAR_BEGIN float q = 0; int n = MY_N;
-      ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * EW(W_LAM, j); EW(W_JAR, r) = s; q += 0.5f * EW(W_LAM, r) * (s - EFC(d.efc_b, r)); ROWS_END
+      ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; q += 0.5f * SW(W_LAM, r) * (s - EFC(d.efc_b, r)); ROWS_END
       sh.red[y][0][lane] = q; PAR_END
-    PAR_BEGIN float c = 0; ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, e, r, false); ROWS_END sh.red[y][1][lane] = c; PAR_END
-    PAR_BEGIN if (y == 0) sh.sc[SC_COSTWS][lane] = RED_SUM(0) + RED_SUM(1); ROWS_BEGIN EW(W_JAR, r) = EFC(d.efc_b, r); ROWS_END PAR_END
-    PAR_BEGIN float c = 0; ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, e, r, false); ROWS_END sh.red[y][0][lane] = c; PAR_END
+    PAR_BEGIN float c = 0; ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, cx, lane, e, r, false); ROWS_END sh.red[y][1][lane] = c; PAR_END
+    PAR_BEGIN if (y == 0) sh.sc[SC_COSTWS][lane] = RED_SUM(0) + RED_SUM(1); ROWS_BEGIN SW(W_JAR, r) = EFC(d.efc_b, r); ROWS_END PAR_END
+    PAR_BEGIN float c = 0; ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, cx, lane, e, r, false); ROWS_END sh.red[y][0][lane] = c; PAR_END
     PAR_BEGIN if (y == 0) sh.sc[SC_COST0][lane] = RED_SUM(0); PAR_END
-    PAR_BEGIN if (!(sh.sc[SC_COSTWS][lane] < sh.sc[SC_COST0][lane])) { ROWS_BEGIN EW(W_LAM, r) = 0; ROWS_END } PAR_END
+    PAR_BEGIN if (!(sh.sc[SC_COSTWS][lane] < sh.sc[SC_COST0][lane])) { ROWS_BEGIN SW(W_LAM, r) = 0; ROWS_END } PAR_END
     // ---------------- Newton iterations
     for (int iter = 0; iter < m.max_iter; iter++) {
       if (!blk_any_active(sh)) break;
       // jar = b + A lam
       PAR_BEGIN float q = 0; int n = MY_N;
-        if (ACTIVE) { ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * EW(W_LAM, j); EW(W_JAR, r) = s; q += 0.5f * EW(W_LAM, r) * (s - EFC(d.efc_b, r)); ROWS_END }
+        if (ACTIVE) { ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; q += 0.5f * SW(W_LAM, r) * (s - EFC(d.efc_b, r)); ROWS_END }
         sh.red[y][0][lane] = q; PAR_END
-      PAR_BEGIN float c = 0; if (ACTIVE) { ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, e, r, true); ROWS_END } sh.red[y][1][lane] = c; PAR_END
+      PAR_BEGIN float c = 0; if (ACTIVE) { ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, cx, lane, e, r, true); ROWS_END } sh.red[y][1][lane] = c; PAR_END
       // residual r = lam - f, column bookkeeping (sequential prefix over rows by y == 0)
       PAR_BEGIN float rr = 0, ll = 0;
-        if (ACTIVE) { ROWS_BEGIN float f = EW(W_F, r), rv = EW(W_LAM, r) - f; EW(W_R, r) = rv; rr += rv * rv; ll += f * f; ROWS_END }
+        if (ACTIVE) { ROWS_BEGIN float f = SW(W_F, r), rv = SW(W_LAM, r) - f; SW(W_R, r) = rv; rr += rv * rv; ll += f * f; ROWS_END }
         sh.red[y][2][lane] = rr; sh.red[y][3][lane] = ll;
         if (y == 0 && ACTIVE) {
           sh.sc[SC_QUAD][lane] = RED_SUM(0); sh.sc[SC_COST][lane] = RED_SUM(0) + RED_SUM(1);
@@ -164,66 +181,67 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
       PAR_BEGIN if (y == 0 && ACTIVE) { float rr = RED_SUM(2), ll = RED_SUM(3); if (rr <= 1e-12f * (ll + 1e-30f)) sh.isc[I_DONE][lane] = 1; } PAR_END
       if (!blk_any_active(sh)) break;
       // u = A r
-      PAR_BEGIN int n = MY_N; if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * EW(W_R, j); EW(W_U, r) = s; ROWS_END } PAR_END
+      PAR_BEGIN int n = MY_N; if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_R, j); SW(W_U, r) = s; ROWS_END } PAR_END
+      int ncmax = 0; for (int l = 0; l < 32; l++) if (!sh.isc[I_DONE][l] && sh.isc[I_NC][l] > ncmax) ncmax = sh.isc[I_NC][l];
+      cx.gmode = (cx.gsh != nullptr && ncmax <= cx.gcap) ? 1 : 0;
       // p = E^T u ; G = I + E^T A E (lower triangle)
       PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
         for (int p = y; p < nc; p += FB_SOLVE_Y) {
           int rp = ECROW(p), np = ECKIND(p) == 0 ? 1 : 3;
-          float pv = 0; for (int a = 0; a < np; a++) pv += ecol_val(d, e, p, a) * EW(W_U, rp + a);
-          EW(W_P, p) = pv;
+          float pv = 0; for (int a = 0; a < np; a++) pv += ecol_val(d, cx, lane, e, p, a) * SW(W_U, rp + a);
+          SW(W_P, p) = pv;
           for (int q = 0; q <= p; q++) {
             int rq = ECROW(q), nq = ECKIND(q) == 0 ? 1 : 3;
             float s = (p == q) ? 1.0f : 0.0f;
-            for (int a = 0; a < np; a++) { float va = ecol_val(d, e, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * EA(d.efc_A, rp + a, rq + bb) * ecol_val(d, e, q, bb); }
-            EA(d.efc_G, p, q) = s;
+            for (int a = 0; a < np; a++) { float va = ecol_val(d, cx, lane, e, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * EA(d.efc_A, rp + a, rq + bb) * ecol_val(d, cx, lane, e, q, bb); }
+            GM(p, q) = s;
           }
         } }
       PAR_END
       // Cholesky G = L L^T (left-looking, two barriers per column), then the two triangular solves
-      int ncmax = 0; for (int l = 0; l < 32; l++) if (!sh.isc[I_DONE][l] && sh.isc[I_NC][l] > ncmax) ncmax = sh.isc[I_NC][l];
       for (int j = 0; j < ncmax; j++) {
         PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
           if (j < nc) for (int i = j + ((y - j % FB_SOLVE_Y + FB_SOLVE_Y) % FB_SOLVE_Y); i < nc; i += FB_SOLVE_Y) {
-            float t = EA(d.efc_G, i, j); for (int k = 0; k < j; k++) t -= EA(d.efc_G, i, k) * EA(d.efc_G, j, k);
-            EA(d.efc_G, i, j) = t; if (i == j) sh.sc[SC_DIAG][lane] = sqrtf(fmaxf(t, 1e-12f));
+            float t = GM(i, j); for (int k = 0; k < j; k++) t -= GM(i, k) * GM(j, k);
+            GM(i, j) = t; if (i == j) sh.sc[SC_DIAG][lane] = sqrtf(fmaxf(t, 1e-12f));
           } }
         PAR_END
         PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane]; float dg = sh.sc[SC_DIAG][lane];
-          if (j < nc) for (int i = j + ((y - j % FB_SOLVE_Y + FB_SOLVE_Y) % FB_SOLVE_Y); i < nc; i += FB_SOLVE_Y) EA(d.efc_G, i, j) = (i == j) ? dg : EA(d.efc_G, i, j) / dg; }
+          if (j < nc) for (int i = j + ((y - j % FB_SOLVE_Y + FB_SOLVE_Y) % FB_SOLVE_Y); i < nc; i += FB_SOLVE_Y) GM(i, j) = (i == j) ? dg : GM(i, j) / dg; }
         PAR_END
       }
       for (int j = 0; j < ncmax; j++) {     // forward: L xq = p
         PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
-          if (j < nc) { float xj = EW(W_P, j) / EA(d.efc_G, j, j);
-            for (int i = j + 1 + ((y - (j + 1) % FB_SOLVE_Y + FB_SOLVE_Y) % FB_SOLVE_Y); i < nc; i += FB_SOLVE_Y) EW(W_P, i) -= EA(d.efc_G, i, j) * xj;
-            if (y == 0) EW2(X_XQ, j) = xj; } }
+          if (j < nc) { float xj = SW(W_P, j) / GM(j, j);
+            for (int i = j + 1 + ((y - (j + 1) % FB_SOLVE_Y + FB_SOLVE_Y) % FB_SOLVE_Y); i < nc; i += FB_SOLVE_Y) SW(W_P, i) -= GM(i, j) * xj;
+            if (y == 0) SW(X_XQ, j) = xj; } }
         PAR_END
       }
       for (int j = ncmax - 1; j >= 0; j--) {   // backward: L^T out = xq
         PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
-          if (j < nc) { float xj = EW2(X_XQ, j) / EA(d.efc_G, j, j);
-            for (int i = y; i < j; i += FB_SOLVE_Y) EW2(X_XQ, i) -= EA(d.efc_G, j, i) * xj;
-            if (y == 0) EW2(X_OUT, j) = xj; } }
+          if (j < nc) { float xj = SW(X_XQ, j) / GM(j, j);
+            for (int i = y; i < j; i += FB_SOLVE_Y) SW(X_XQ, i) -= GM(j, i) * xj;
+            if (y == 0) SW(X_OUT, j) = xj; } }
         PAR_END
       }
       // dlam = -r + E q
       PAR_BEGIN if (ACTIVE) { ROWS_BEGIN
-          float v = -EW(W_R, r); int stt = ESTATE(r), c0 = ECOLIDX(r);
-          if (stt == 1) v += EW2(X_E0, r) * EW2(X_OUT, c0);
-          else if (stt >= 2) v += EW2(X_E0, r) * EW2(X_OUT, c0) + EW2(X_E1, r) * EW2(X_OUT, c0 + 1);
-          EW(W_DL, r) = v;
+          float v = -SW(W_R, r); int stt = ESTATE(r), c0 = ECOLIDX(r);
+          if (stt == 1) v += SW(X_E0, r) * SW(X_OUT, c0);
+          else if (stt >= 2) v += SW(X_E0, r) * SW(X_OUT, c0) + SW(X_E1, r) * SW(X_OUT, c0 + 1);
+          SW(W_DL, r) = v;
         ROWS_END } PAR_END
       // A dlam, q1, q2
       PAR_BEGIN float q1 = 0, q2 = 0; int n = MY_N;
-        if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * EW(W_DL, j); EW(W_ADL, r) = s;
-          q1 += EW(W_DL, r) * (EW(W_JAR, r) - EFC(d.efc_b, r)); q2 += 0.5f * EW(W_DL, r) * s; ROWS_END }
+        if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_DL, j); SW(W_ADL, r) = s;
+          q1 += SW(W_DL, r) * (SW(W_JAR, r) - EFC(d.efc_b, r)); q2 += 0.5f * SW(W_DL, r) * s; ROWS_END }
         sh.red[y][0][lane] = q1; sh.red[y][1][lane] = q2; PAR_END
       PAR_BEGIN if (y == 0 && ACTIVE) { sh.sc[SC_Q1][lane] = RED_SUM(0); sh.sc[SC_Q2][lane] = RED_SUM(1); sh.sc[SC_ALPHA][lane] = 0; sh.sc[SC_LO][lane] = 0; sh.sc[SC_HI][lane] = -1; sh.isc[I_LSDONE][lane] = 0; } PAR_END
       // exact line search: evaluation 0 at alpha = 0, then safeguarded Newton on the derivative
       for (int ls = 0; ls <= m.ls_iter; ls++) {
         if (!blk_any_ls(sh)) break;
         PAR_BEGIN float c = 0, g = 0, h = 0;
-          if (ACTIVE && !sh.isc[I_LSDONE][lane]) { float alpha = sh.sc[SC_ALPHA][lane]; ROWS_BEGIN if (is_head(d, e, r)) head_ls(m, d, e, r, alpha, c, g, h); ROWS_END }
+          if (ACTIVE && !sh.isc[I_LSDONE][lane]) { float alpha = sh.sc[SC_ALPHA][lane]; ROWS_BEGIN if (is_head(d, e, r)) head_ls(m, d, cx, lane, e, r, alpha, c, g, h); ROWS_END }
           sh.red[y][0][lane] = c; sh.red[y][1][lane] = g; sh.red[y][2][lane] = h; PAR_END
         PAR_BEGIN if (y == 0 && ACTIVE && !sh.isc[I_LSDONE][lane]) {
           float alpha = sh.sc[SC_ALPHA][lane], quad = sh.sc[SC_QUAD][lane], q1 = sh.sc[SC_Q1][lane], q2 = sh.sc[SC_Q2][lane];
@@ -247,13 +265,13 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
           } }
         PAR_END
       }
-      PAR_BEGIN if (ACTIVE) { float alpha = sh.sc[SC_ALPHA][lane]; ROWS_BEGIN EW(W_LAM, r) += alpha * EW(W_DL, r); ROWS_END } PAR_END
+      PAR_BEGIN if (ACTIVE) { float alpha = sh.sc[SC_ALPHA][lane]; ROWS_BEGIN SW(W_LAM, r) += alpha * SW(W_DL, r); ROWS_END } PAR_END
       PAR_BEGIN if (y == 0 && ACTIVE) { sh.isc[I_ITER][lane] = iter + 1; float imp = scale * (sh.sc[SC_COST][lane] - sh.sc[SC_CBEST][lane]); if (imp < m.tolerance) sh.isc[I_DONE][lane] = 1; } PAR_END
     }
     // ---------------- forces at the solution
-    PAR_BEGIN int n = MY_N; ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * EW(W_LAM, j); EW(W_JAR, r) = s; ROWS_END PAR_END
-    PAR_BEGIN ROWS_BEGIN if (is_head(d, e, r)) head_update(m, d, e, r, false); ROWS_END PAR_END
-    PAR_BEGIN ROWS_BEGIN EFC(d.efc_force, r) = EW(W_F, r); ROWS_END if (y == 0) AT(d.niter, 0) = sh.isc[I_ITER][lane]; PAR_END
+    PAR_BEGIN int n = MY_N; ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; ROWS_END PAR_END
+    PAR_BEGIN ROWS_BEGIN if (is_head(d, e, r)) head_update(m, d, cx, lane, e, r, false); ROWS_END PAR_END
+    PAR_BEGIN ROWS_BEGIN EFC(d.efc_force, r) = SW(W_F, r); ROWS_END if (y == 0) AT(d.niter, 0) = sh.isc[I_ITER][lane]; PAR_END
     // ---------------- noslip: inherently sequential Gauss-Seidel over the friction rows (y == 0)
     if (m.noslip_iterations > 0) {
       PAR_BEGIN if (y == 0) { int n = MY_N;

@@ -13,6 +13,12 @@ struct ShTree {
   float part[FB_NLMAX][24][32];    // per-list partial sums towards the root (crb:10, factor:21, solve:6, rne:12)
 };
 
+// dynamic shared memory that follows the fixed struct (per-kernel scratch: the L^T D L rows during the
+// factorisation, the right-hand side during tree solves), laid out [entry][lane]
+template <typename Sh> FB_DEV float* sh_dyn(Sh& sh) { return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&sh) + ((sizeof(Sh) + 15) & ~(size_t)15)); }
+#define LS(k) ldsh[(k) * 32 + lane]
+#define XS(k) xs[(k) * 32 + lane]
+
 #define FB_PHASE_ARGS const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y
 #define FB_LIST_LOOP_FWD for (int li_ = 0, b = 0; li_ < m.list_num[y] && ((b = m.list_body[m.list_adr[y] + li_]), true); li_++)
 #define FB_LIST_LOOP_REV for (int li_ = m.list_num[y] - 1, b = 0; li_ >= 0 && ((b = m.list_body[m.list_adr[y] + li_]), true); li_--)
@@ -136,7 +142,7 @@ FB_DEV void kpos_p3(FB_PHASE_ARGS) {
   }
 }
 // joint-space inertia entries of dof i (row of the sparse lower triangle along the ancestor chain)
-FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int i) {
+FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int lane, float* ldsh, int i) {
   int b = m.dof_bodyid[i];
   I10 I = ld10(d.crb10, b, d, e);
   V3 L, p;
@@ -147,43 +153,57 @@ FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int i) {
   for (int j = i; j >= 0; j = m.dof_parentid[j], t++) {
     float v = dot(ld3(d.Sang, j, d, e), L) + dot(ld3(d.Slin, j, d, e), p);
     if (t == 0) v += m.dof_armature[i];
-    AT(d.qM, adr + t) = v; AT(d.qLD, adr + t) = v; AT(d.qLDe, adr + t) = (t == 0) ? v + hd : v;
+    AT(d.qM, adr + t) = v; LS(adr + t) = v;
   }
+  (void)hd;
 }
 FB_DEV void kpos_p4(FB_PHASE_ARGS) {
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) mass_row(m, d, e, m.body_dofadr[b] + k); }
+  float* ldsh = sh_dyn(sh);
+  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) mass_row(m, d, e, lane, ldsh, m.body_dofadr[b] + k); }
   if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) mass_row(m, d, e, m.body_dofadr[b] + k); }
+  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) mass_row(m, d, e, lane, ldsh, m.body_dofadr[b] + k); }
+}
+// copy the factor held in shared memory out to `dst`; optionally re-initialise the shared rows with
+// M + h*diag(damping) for the second factorisation (entries are split over all threads of the block)
+FB_DEV void ld_writeout(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* dst, bool reinit) {
+  float* ldsh = sh_dyn(sh);
+  for (int k = y; k < m.nM; k += m.nlist) { AT(dst, k) = LS(k); if (reinit) LS(k) = AT(d.qM, k); }
+}
+FB_DEV void ld_add_damping(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
+  float* ldsh = sh_dyn(sh);
+  for (int i = y; i < m.nv; i += m.nlist) LS(m.dof_Madr[i]) += m.timestep * m.dof_damping[i];
 }
 
 // sparse L^T D L factorisation (Featherstone; MuJoCo mj_factorM), list part.  Row k of LD holds
 // (k,k), (k,parent(k)), ... at dof_Madr[k] + t.  Updates that land in the root block are summed
 // into sh.part (21 entries) and applied by the root thread.
-FB_DEV void factor_lists(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* LD) {
+FB_DEV void factor_lists(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
+  float* ldsh = sh_dyn(sh);
   if (y >= m.nlist) return;
   for (int k = 0; k < 21; k++) sh.part[y][k][lane] = 0;
   FB_LIST_LOOP_REV {
     for (int kk = m.body_dofnum[b] - 1; kk >= 0; kk--) {
       int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
-      float Dk = AT(LD, adrk);
+      float Dk = LS(adrk);
       float invD = 1.0f / Dk;
       int t = 1;
       for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) {
-        float a = AT(LD, adrk + t) * invD;
+        float a = LS(adrk + t) * invD;
         if (!m.dof_isroot[i]) {
           int adri = m.dof_Madr[i], len = m.dof_chainlen[i];
-          for (int s = 0; s < len; s++) AT(LD, adri + s) -= a * AT(LD, adrk + t + s);
+          for (int s = 0; s < len; s++) LS(adri + s) -= a * LS(adrk + t + s);
         } else {
           int il = m.dof_depth[i];        // for root dofs depth == local index
           int base = il * (il + 1) / 2;
-          for (int s = 0; s <= il; s++) sh.part[y][base + s][lane] += a * AT(LD, adrk + t + s);
+          for (int s = 0; s <= il; s++) sh.part[y][base + s][lane] += a * LS(adrk + t + s);
         }
-        AT(LD, adrk + t) = a;
+        LS(adrk + t) = a;
       }
     }
   }
 }
-FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* LD) {
+FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
+  float* ldsh = sh_dyn(sh);
   if (y != 0) return;
   for (int r = 0; r < m.nroot; r++) {
     int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
@@ -193,73 +213,80 @@ FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, 
       for (int s = 0; s <= il; s++) {
         float acc = 0;
         for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc += sh.part[l][base + s][lane];
-        AT(LD, adri + s) -= acc;
+        LS(adri + s) -= acc;
       }
     }
     for (int kl = nd - 1; kl >= 0; kl--) {
       int adrk = m.dof_Madr[d0 + kl];
-      float invD = 1.0f / AT(LD, adrk);
+      float invD = 1.0f / LS(adrk);
       for (int t = 1; t <= kl; t++) {
         int il = kl - t, adri = m.dof_Madr[d0 + il];
-        float a = AT(LD, adrk + t) * invD;
-        for (int s = 0; s <= il; s++) AT(LD, adri + s) -= a * AT(LD, adrk + t + s);
-        AT(LD, adrk + t) = a;
+        float a = LS(adrk + t) * invD;
+        for (int s = 0; s <= il; s++) LS(adri + s) -= a * LS(adrk + t + s);
+        LS(adrk + t) = a;
       }
     }
   }
 }
-FB_DEV void kpos_p5(FB_PHASE_ARGS) { factor_lists(m, d, sh, e, lane, y, d.qLD); }
-FB_DEV void kpos_p6(FB_PHASE_ARGS) { factor_root(m, d, sh, e, lane, y, d.qLD); }
-FB_DEV void kpos_p7(FB_PHASE_ARGS) { factor_lists(m, d, sh, e, lane, y, d.qLDe); }
-FB_DEV void kpos_p8(FB_PHASE_ARGS) { factor_root(m, d, sh, e, lane, y, d.qLDe); }
+FB_DEV void kpos_p5(FB_PHASE_ARGS) { factor_lists(m, d, sh, e, lane, y); }
+FB_DEV void kpos_p6(FB_PHASE_ARGS) { factor_root(m, d, sh, e, lane, y); }
+FB_DEV void kpos_p6w(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLD, true); }
+FB_DEV void kpos_p6d(FB_PHASE_ARGS) { ld_add_damping(m, d, sh, e, lane, y); }
+FB_DEV void kpos_p7(FB_PHASE_ARGS) { factor_lists(m, d, sh, e, lane, y); }
+FB_DEV void kpos_p8(FB_PHASE_ARGS) { factor_root(m, d, sh, e, lane, y); }
+FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe, false); }
 
 // ---------------------------------------------------------------------------------------------
-// x <- (L^T D L)^-1 x in three phases (MuJoCo mj_solveLD)
-FB_DEV void solve_a(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, float* x) {
+// x <- (L^T D L)^-1 x in three phases (MuJoCo mj_solveLD); x lives in shared memory (XS), LD is read-only
+// own_dofs_* helpers move a list's / the root's entries between global vectors and XS
+FB_DEV void solve_a(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
+  float* xs = sh_dyn(sh);
   if (y >= m.nlist) return;
   for (int k = 0; k < 6; k++) sh.part[y][k][lane] = 0;
   FB_LIST_LOOP_REV {
     for (int kk = m.body_dofnum[b] - 1; kk >= 0; kk--) {
       int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
-      float xk = AT(x, k);
+      float xk = XS(k);
       int t = 1;
       for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) {
         float l = AT(LD, adrk + t);
-        if (!m.dof_isroot[i]) AT(x, i) -= l * xk; else sh.part[y][m.dof_depth[i]][lane] += l * xk;
+        if (!m.dof_isroot[i]) XS(i) -= l * xk; else sh.part[y][m.dof_depth[i]][lane] += l * xk;
       }
     }
   }
 }
-FB_DEV void solve_b(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, float* x) {
+FB_DEV void solve_b(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
+  float* xs = sh_dyn(sh);
   if (y != 0) return;
   for (int r = 0; r < m.nroot; r++) {
     int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
     for (int il = 0; il < nd; il++) {
       float acc = 0;
       for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc += sh.part[l][il][lane];
-      AT(x, d0 + il) -= acc;
+      XS(d0 + il) -= acc;
     }
     for (int kl = nd - 1; kl >= 0; kl--) {
-      float xk = AT(x, d0 + kl); int adrk = m.dof_Madr[d0 + kl];
-      for (int t = 1; t <= kl; t++) AT(x, d0 + kl - t) -= AT(LD, adrk + t) * xk;
+      float xk = XS(d0 + kl); int adrk = m.dof_Madr[d0 + kl];
+      for (int t = 1; t <= kl; t++) XS(d0 + kl - t) -= AT(LD, adrk + t) * xk;
     }
     for (int kl = 0; kl < nd; kl++) {
       int adrk = m.dof_Madr[d0 + kl];
-      float v = AT(x, d0 + kl) / AT(LD, adrk);
-      for (int t = 1; t <= kl; t++) v -= AT(LD, adrk + t) * AT(x, d0 + kl - t);
-      AT(x, d0 + kl) = v;
+      float v = XS(d0 + kl) / AT(LD, adrk);
+      for (int t = 1; t <= kl; t++) v -= AT(LD, adrk + t) * XS(d0 + kl - t);
+      XS(d0 + kl) = v;
     }
   }
 }
-FB_DEV void solve_c(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, float* x) {
+FB_DEV void solve_c(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
+  float* xs = sh_dyn(sh);
   if (y >= m.nlist) return;
   FB_LIST_LOOP_FWD {
     for (int kk = 0; kk < m.body_dofnum[b]; kk++) {
       int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
-      float v = AT(x, k) / AT(LD, adrk);
+      float v = XS(k) / AT(LD, adrk);
       int t = 1;
-      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) v -= AT(LD, adrk + t) * AT(x, i);
-      AT(x, k) = v;
+      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) v -= AT(LD, adrk + t) * XS(i);
+      XS(k) = v;
     }
   }
 }

@@ -63,7 +63,7 @@ enum { FB_CT_LIMIT = 0, FB_CT_FRICTIONLESS = 1, FB_CT_ELLIPTIC = 2 };
 
 struct DevData {
   int N, Np;                   // envs, padded envs (stride of every array)
-  int nsub_done;
+  int nsub_done, sens_mode;
   // integrated state
   float *qpos, *qvel, *act, *ctrl, *qacc, *qacc_warmstart, *time;
   // position stage

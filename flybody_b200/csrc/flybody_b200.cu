@@ -68,29 +68,37 @@ struct FbSim {
 #ifndef FB_EMU
 template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
 __global__ void fb_run(DevModel m, DevData d) {
-  __shared__ Sh sh;
+  extern __shared__ __align__(16) unsigned char fb_smem[];
+  Sh& sh = *reinterpret_cast<Sh*>(fb_smem);
   int lane = threadIdx.x, y = threadIdx.y, e = blockIdx.x * 32 + lane;
   ((Ph(m, d, sh, e, lane, y), __syncthreads()), ...);
 }
+static size_t smem_bytes(size_t fixed, size_t dyn_floats) { return ((fixed + 15) & ~(size_t)15) + dyn_floats * sizeof(float); }
 template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
-static void fb_launch(FbSim* s, int ny, int kind) {
+static void fb_launch(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
   dim3 block(32, ny), grid(s->d.Np / 32);
+  size_t bytes = smem_bytes(sizeof(Sh), dyn_floats);
+  static size_t configured = 0;
+  if (bytes > configured) { cudaFuncSetAttribute(fb_run<Sh, Ph...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, s->stream);
-    fb_run<Sh, Ph...><<<grid, block, 0, s->stream>>>(s->m, s->d);
+    fb_run<Sh, Ph...><<<grid, block, bytes, s->stream>>>(s->m, s->d);
     cudaEventRecord(b, s->stream);
     s->prof_events.push_back({kind, a, b});
   } else {
-    fb_run<Sh, Ph...><<<grid, block, 0, s->stream>>>(s->m, s->d);
+    fb_run<Sh, Ph...><<<grid, block, bytes, s->stream>>>(s->m, s->d);
   }
   s->launches++;
 }
 #else
 template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
-static void fb_launch(FbSim* s, int ny, int kind) {
+static void fb_launch(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
   (void)kind;
-  static Sh sh;
+  static std::vector<unsigned char> buf;
+  size_t need = ((sizeof(Sh) + 15) & ~(size_t)15) + dyn_floats * sizeof(float) + 64;
+  if (buf.size() < need) buf.resize(need);
+  Sh& sh = *reinterpret_cast<Sh*>(buf.data());
   for (int blk = 0; blk < s->d.Np / 32; blk++) {
     auto run = [&](void (*ph)(const DevModel&, const DevData&, Sh&, int, int, int)) {
       for (int y = 0; y < ny; y++) for (int lane = 0; lane < 32; lane++) ph(s->m, s->d, sh, blk * 32 + lane, lane, y);
@@ -104,66 +112,71 @@ static void fb_launch(FbSim* s, int ny, int kind) {
 #ifndef FB_EMU
 template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
 __global__ void fb_run_block(DevModel m, DevData d) {
-  __shared__ Sh sh;
-  F(m, d, sh, blockIdx.x);
+  extern __shared__ __align__(16) unsigned char fb_smem_b[];
+  F(m, d, *reinterpret_cast<Sh*>(fb_smem_b), blockIdx.x);
 }
 template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
-static void fb_launch_block(FbSim* s, int ny, int kind) {
+static void fb_launch_block(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
   dim3 block(32, ny), grid(s->d.Np / 32);
+  size_t bytes = smem_bytes(sizeof(Sh), dyn_floats);
+  static size_t configured = 0;
+  if (bytes > configured) { cudaFuncSetAttribute(fb_run_block<Sh, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, s->stream);
-    fb_run_block<Sh, F><<<grid, block, 0, s->stream>>>(s->m, s->d);
+    fb_run_block<Sh, F><<<grid, block, bytes, s->stream>>>(s->m, s->d);
     cudaEventRecord(b, s->stream);
     s->prof_events.push_back({kind, a, b});
   } else {
-    fb_run_block<Sh, F><<<grid, block, 0, s->stream>>>(s->m, s->d);
+    fb_run_block<Sh, F><<<grid, block, bytes, s->stream>>>(s->m, s->d);
   }
   s->launches++;
 }
 #else
 template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
-static void fb_launch_block(FbSim* s, int ny, int kind) {
+static void fb_launch_block(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
   (void)ny; (void)kind;
-  static Sh sh;
+  static std::vector<unsigned char> buf;
+  size_t need = ((sizeof(Sh) + 15) & ~(size_t)15) + dyn_floats * sizeof(float) + 64;
+  if (buf.size() < need) buf.resize(need);
+  Sh& sh = *reinterpret_cast<Sh*>(buf.data());
   for (int blk = 0; blk < s->d.Np / 32; blk++) F(s->m, s->d, sh, blk);
   s->launches++;
 }
 #endif
 
 // lane == env kernels wrapped as single-phase functions
-FB_DEV void ph_act(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kact(m, d, e); }
-FB_DEV void ph_con(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kcon(m, d, e); }
-FB_DEV void ph_sens_first(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksens_accum(m, d, e, 1); }
 FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kreset_scatter(m, d, e); }
 FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kclear_hold(m, d, e); }
 FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kpack(m, d, e, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); }
-FB_DEV void ph_sens_next(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { ksens_accum(m, d, e, 0); }
 // qacc_smooth = M^-1 qfrc_smooth (qacc_smooth already holds the rhs)
-FB_DEV void ph_smooth_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD, d.qacc_smooth); }
-FB_DEV void ph_smooth_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD, d.qacc_smooth); }
-FB_DEV void ph_smooth_c(FB_PHASE_ARGS) { solve_c(m, d, sh, e, lane, y, d.qLD, d.qacc_smooth); }
+FB_DEV void ph_smooth_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD); }
+FB_DEV void ph_smooth_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD); }
+FB_DEV void ph_smooth_c(FB_PHASE_ARGS) {
+  float* xs = sh_dyn(sh);
+  solve_c(m, d, sh, e, lane, y, d.qLD);
+  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc_smooth, i) = XS(i); } }
+  if (y >= m.nlist) return;
+  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc_smooth, i) = XS(i); } }
+}
 
 static void launch_step1(FbSim* s) {
   int nl = s->m.nlist;
-  fb_launch<ShTree, kpos_p0, kpos_p1, kpos_p2, kpos_p3, kpos_p4, kpos_p5, kpos_p6, kpos_p7, kpos_p8>(s, nl, K_POS);
+  fb_launch<ShTree, kpos_p0, kpos_p1, kpos_p2, kpos_p3, kpos_p4, kpos_p5, kpos_p6, kpos_p6w, kpos_p6d, kpos_p7, kpos_p8, kpos_p9>(s, nl, K_POS, (size_t)s->m.nM * 32);
   fb_launch<ShCol, kcol_p0, kcol_p1>(s, s->m.nchunk, K_COL);
-  fb_launch<ShNone, ph_con>(s, 1, K_CON);
-  fb_launch<ShNone, kproj_p0, kproj_p1>(s, FB_ROWPAR, K_PROJ);
-  fb_launch<ShTree, kvel_p0, kvel_p1, kvel_p2, kvel_p3>(s, nl, K_VEL);
+  fb_launch<ShCon, kcon_p0, kcon_p1, kcon_p2, kcon_p3, kproj_p0, kproj_p1>(s, FB_ROWPAR, K_PROJ, (size_t)FB_ROWPAR * s->m.nv * 32);
+  fb_launch<ShTree, kvel_p0, kvel_p1, kvel_p2, kvel_p3, kvel_p4>(s, nl, K_VEL);
 }
 static void launch_step2(FbSim* s, bool integrate) {
   int nl = s->m.nlist;
-  fb_launch<ShNone, ph_act>(s, 1, K_ACT);
-  fb_launch<ShTree, ph_smooth_a, ph_smooth_b, ph_smooth_c>(s, nl, K_SMOOTH);
-  fb_launch<ShNone, kref>(s, FB_ROWPAR, K_REF);
-  fb_launch_block<ShSolve, ksolve_block>(s, FB_SOLVE_Y, K_SOLVE);
+  fb_launch<ShTree, kact_p0, kact_p1, kact_p2, kact_p3, ph_smooth_a, ph_smooth_b, ph_smooth_c, kref>(s, nl, K_SMOOTH, (size_t)s->m.nv * 32);
+  fb_launch_block<ShSolve, ksolve_block>(s, FB_SOLVE_Y, K_SOLVE, FB_SOLVE_DYN_FLOATS);
   if (integrate)
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
-              kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl, K_FINISH);
+              kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl, K_FINISH, (size_t)s->m.nv * 32);
   else
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
-              kfin_sens_out>(s, nl, K_FINISH);
+              kfin_sens_out>(s, nl, K_FINISH, (size_t)s->m.nv * 32);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -296,7 +309,7 @@ static int build_model(FbSim* s, const FbModel* h) {
 static int alloc_data(FbSim* s, int N) {
   DevData& d = s->d; const DevModel& m = s->m;
   memset(&d, 0, sizeof(d));
-  d.N = N; d.Np = fb_pad32(N);
+  d.N = N; d.Np = fb_pad32(N); d.sens_mode = -1;
   size_t Np = d.Np;
 #define FA(field, n) d.field = dalloc<float>(s, (size_t)(n) * Np); if (!d.field) { s->err = "out of device memory (" #field ")"; return -4; }
 #define IA(field, n) d.field = dalloc<int>(s, (size_t)(n) * Np); if (!d.field) { s->err = "out of device memory (" #field ")"; return -4; }
@@ -433,8 +446,9 @@ int fb_step(FbHandle s, int n_substeps) {
 #endif
   for (int k = 0; k < n_substeps; k++) {
     launch_step2(s, true);
+    s->d.sens_mode = (k == 0) ? 1 : 0;
     launch_step1(s);
-    if (k == 0) fb_launch<ShNone, ph_sens_first>(s, 1, K_SENS); else fb_launch<ShNone, ph_sens_next>(s, 1, K_SENS);
+    s->d.sens_mode = -1;
   }
   s->d.nsub_done = n_substeps;
   if (s->hold_pending) { fb_launch<ShNone, ph_clear_hold>(s, 1, K_MISC); s->hold_pending = 0; }
