@@ -135,9 +135,9 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
     {
       int nmaxb = blk_max_i(sh, I_N);
       float* dyn = sh_dyn(sh);
-      if (12 * nmaxb * 32 <= FB_SOLVE_DYN_FLOATS) {
+      if (12 * nmaxb * 32 <= m.solve_dyn_floats) {
         cx.vsh = dyn; cx.vstride = nmaxb; cx.gsh = dyn + (size_t)12 * nmaxb * 32;
-        int rem = FB_SOLVE_DYN_FLOATS / 32 - 12 * nmaxb, g = 0;
+        int rem = m.solve_dyn_floats / 32 - 12 * nmaxb, g = 0;
         while ((g + 1) * (g + 1) <= rem) g++;
         cx.gcap = g;
       }

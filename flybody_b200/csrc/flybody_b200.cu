@@ -170,7 +170,7 @@ static void launch_step1(FbSim* s) {
 static void launch_step2(FbSim* s, bool integrate) {
   int nl = s->m.nlist;
   fb_launch<ShTree, kact_p0, kact_p1, kact_p2, kact_p3, ph_smooth_a, ph_smooth_b, ph_smooth_c, kref>(s, nl, K_SMOOTH, (size_t)s->m.nv * 32);
-  fb_launch_block<ShSolve, ksolve_block>(s, FB_SOLVE_Y, K_SOLVE, FB_SOLVE_DYN_FLOATS);
+  fb_launch_block<ShSolve, ksolve_block>(s, FB_SOLVE_Y, K_SOLVE, (size_t)s->m.solve_dyn_floats);
   if (integrate)
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
               kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl, K_FINISH, (size_t)s->m.nv * 32);
@@ -198,6 +198,7 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.npair = h->npair; m.nsite = h->nsite; m.ntendon = h->ntendon; m.nwrap = h->nwrap; m.nsensor = h->nsensor;
   m.nsensordata = h->nsensordata; m.nM = h->nM; m.nfluid = h->nfluid;
   m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.max_iter = 30; m.ls_iter = 20;
+  { const char* kb = getenv("FB_SOLVE_SMEM_KB"); m.solve_dyn_floats = kb ? atoi(kb) * 256 : FB_SOLVE_DYN_FLOATS; if (m.solve_dyn_floats > FB_SOLVE_DYN_FLOATS) m.solve_dyn_floats = FB_SOLVE_DYN_FLOATS; }
   m.timestep = (float)h->opt_timestep; m.density = (float)h->opt_density; m.viscosity = (float)h->opt_viscosity;
   for (int i = 0; i < 3; i++) { m.gravity[i] = (float)h->opt_gravity[i]; m.wind[i] = (float)h->opt_wind[i]; }
   m.impratio = (float)h->opt_impratio; m.tolerance = (float)h->opt_tolerance; m.noslip_tolerance = (float)h->opt_noslip_tolerance;
