@@ -666,3 +666,48 @@ FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int k) {
   AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = 1;
 }
 FB_DEV void kclear_hold(const DevModel& m, const DevData& d, int e) { AT(d.hold, 0) = 0; }
+
+// ---------------------------------------------------------------------------------------------
+// task observation program: evaluates the reference task's observables (FruitFlyObservables,
+// fruitfly.py:585-756; ref_displacement / ref_root_quat, tasks/base.py:245-268) on the device.
+FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e) {
+  if (!d.tobs || e >= d.N) return;
+  float* o = d.tobs + (size_t)e * d.tobs_dim;
+  int k = 0;
+  int rb = d.op_root_body;
+  V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
+  V3 rpos = ld3(d.xpos, rb, d, e);
+  M3 R = ld9(d.xmat, rb, d, e);
+  bool first = d.op_first ? d.op_first[e] != 0 : false;
+  float inv = d.op_nsub > 0 ? 1.0f / d.op_nsub : 1.0f;
+  int step = d.op_step ? d.op_step[e] : 0;
+  int rj = m.body_jntadr[rb], rq = rj >= 0 ? m.jnt_qposadr[rj] : 0;
+  for (int it = 0; it < d.op_n; it++) {
+    int kind = d.op_kind[it], a = d.op_a[it], b = d.op_b[it];
+    switch (kind) {
+      case FB_OBS_SENSOR_MEAN: for (int i = 0; i < b; i++) o[k++] = first ? AT(d.sensordata, a + i) * inv : AT(d.sensor_sum, a + i) * inv; break;
+      case FB_OBS_SENSOR_NOW: for (int i = 0; i < b; i++) o[k++] = AT(d.sensordata, a + i); break;
+      case FB_OBS_ACT: for (int i = 0; i < b; i++) o[k++] = AT(d.act, a + i); break;
+      case FB_OBS_QPOS: for (int i = 0; i < b; i++) o[k++] = AT(d.qpos, d.op_list[a + i]); break;
+      case FB_OBS_QVEL: for (int i = 0; i < b; i++) o[k++] = AT(d.qvel, d.op_list[a + i]); break;
+      case FB_OBS_SITES_EGO: for (int i = 0; i < b; i++) { V3 v = mulT(R, ld3(d.site_xpos, d.op_list[a + i], d, e) - rpos); o[k++] = v.x; o[k++] = v.y; o[k++] = v.z; } break;
+      case FB_OBS_ROOT_ZAXIS: o[k++] = R.m[6]; o[k++] = R.m[7]; o[k++] = R.m[8]; break;
+      case FB_OBS_REF_DISP: {
+        V3 fly = v3(AT(d.qpos, rq), AT(d.qpos, rq + 1), AT(d.qpos, rq + 2));
+        for (int i = 0; i < b; i++) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = d.op_ref + 7 * t;
+          V3 v = mulT(R, v3(rr[0], rr[1], rr[2]) - fly); o[k++] = v.x; o[k++] = v.y; o[k++] = v.z; }
+      } break;
+      case FB_OBS_REF_QUAT: {
+        Q4 q = q4(AT(d.qpos, rq + 3), AT(d.qpos, rq + 4), AT(d.qpos, rq + 5), AT(d.qpos, rq + 6));
+        float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z; float s = 1.0f / n2;
+        Q4 qi = q4(q.w * s, -q.x * s, -q.y * s, -q.z * s);
+        for (int i = 0; i < b; i++) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = d.op_ref + 7 * t;
+          Q4 r4 = qmul(qi, q4(rr[3], rr[4], rr[5], rr[6])); o[k++] = r4.w; o[k++] = r4.x; o[k++] = r4.y; o[k++] = r4.z; }
+      } break;
+      case FB_OBS_SCALARS: { o[k++] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; } o[k++] = s2; o[k++] = AT(d.time, 0); } break;
+      case FB_OBS_ROOT_POSE: { V3 p = rpos + ref; o[k++] = p.x; o[k++] = p.y; o[k++] = p.z; for (int i = 0; i < 4; i++) o[k++] = AT(d.qpos, rq + 3 + i); } break;
+      case FB_OBS_SUBTREE_COM: { float mass = AT(d.crb10, 10 * a); for (int i = 0; i < 3; i++) o[k++] = (mass > 0 ? AT(d.crb10, 10 * a + 1 + i) / mass : 0.0f) + AT(d.ref, i); } break;
+      default: break;
+    }
+  }
+}

@@ -22,18 +22,24 @@ struct ShSolve {
 enum { SC_COST = 0, SC_QUAD, SC_Q1, SC_Q2, SC_ALPHA, SC_LO, SC_HI, SC_G0, SC_CBEST, SC_DIAG, SC_COSTWS, SC_COST0, SC_RR, SC_LL, SC_CPREV };
 enum { I_N = 0, I_NC, I_DONE, I_ITER, I_LSDONE };
 // extra solver vectors (beyond W_LAM..W_P of fb_constraint.h) live in efc_w2
-enum { X_E0 = 8, X_E1, X_XQ, X_OUT, X_NW2 };
+enum { X_E0 = 8, X_E1, X_XQ, X_OUT,
+       // row constants staged once per solve (so the Newton phases never chase global metadata)
+       S_D, S_B, S_R, S_TYPE /* 0 plain, 1 elliptic head, 2 elliptic tail */, S_MU, S_F1, S_F2, S_LA, S_LB,
+       S_STATE, S_COLIDX, S_ECROW, S_ECKIND, S_NSLOT };
 // solver vectors: 12 slots (W_LAM..W_P = 0..7, X_* = 8..11).  When they fit, they live in shared memory
 // ([slot][row][lane], row stride = block-wide max nefc); otherwise in the global efc_w / efc_w2 arrays.
-struct SolveCtx { float* vsh; int vstride; float* gsh; int gcap; int gmode; };
+struct SolveCtx { float* vsh; int vstride; float* gsh; int gcap; int gmode; float* ash; int amode; };
 #define FB_SOLVE_DYN_FLOATS (190 * 256)
 #define SWG(slot, r) ((slot) < 8 ? &AT(d.efc_w, (slot) * FB_MAXEFC + (r)) : &AT(d.efc_w2, ((slot) - 8) * FB_MAXEFC + (r)))
 #define SW(slot, r) (*(cx.vsh ? &cx.vsh[((slot) * cx.vstride + (r)) * 32 + lane] : SWG(slot, r)))
+// Delassus matrix: packed lower triangle in shared memory when it fits, else the global array
+#define TRI(r, c) ((r) * ((r) + 1) / 2 + (c))
+#define AM(r, c) (cx.amode ? cx.ash[((r) >= (c) ? TRI(r, c) : TRI(c, r)) * 32 + lane] : EA(d.efc_A, r, c))
 #define GM(p, q) (*(cx.gmode ? &cx.gsh[((p) * cx.gcap + (q)) * 32 + lane] : &EA(d.efc_G, p, q)))
-#define ESTATE(r) AT(d.efc_state, (r))
-#define ECOLIDX(r) AT(d.efc_colidx, (r))
-#define ECROW(p) AT(d.efc_ecol, (p))
-#define ECKIND(p) AT(d.efc_ekind, (p))
+#define ESTATE(r) SW(S_STATE, r)
+#define ECOLIDX(r) SW(S_COLIDX, r)
+#define ECROW(p) SW(S_ECROW, p)
+#define ECKIND(p) SW(S_ECKIND, p)
 
 #ifdef __CUDACC__
 #define PAR_BEGIN { const int lane = threadIdx.x, y = threadIdx.y; const int e = blk * 32 + lane; (void)y; (void)e; (void)lane;
@@ -56,16 +62,15 @@ FB_DEV int blk_any_ls(const ShSolve& sh) { int v = 0; for (int l = 0; l < 32; l+
 // forces / cost of the rows headed at r (a non-elliptic row, or the first row of an elliptic contact).
 // Returns the cost; writes W_F; with build: state + E values.
 FB_DEV float head_update(const DevModel& m, const DevData& d, const SolveCtx& cx, int lane, int e, int r, bool build) {
-  int tp = EFC(d.efc_type, r);
-  float jar = SW(W_JAR, r), D = EFC(d.efc_D, r), cost = 0;
-  if (tp != FB_CT_ELLIPTIC) {
+  int tp = (int)SW(S_TYPE, r);
+  float jar = SW(W_JAR, r), D = SW(S_D, r), cost = 0;
+  if (tp == 0) {
     if (jar < 0) { SW(W_F, r) = -D * jar; cost = 0.5f * D * jar * jar; if (build) { ESTATE(r) = 1; SW(X_E0, r) = sqrtf(D); } }
     else { SW(W_F, r) = 0; if (build) ESTATE(r) = 0; }
     return cost;
   }
-  int ci = EFC(d.efc_id, r);
-  float mu = AT(d.con_mu, ci), f1 = CON_F(d.con_fric, ci, 0, 2), f2 = CON_F(d.con_fric, ci, 1, 2);
-  float j1 = SW(W_JAR, r + 1), j2 = SW(W_JAR, r + 2), D1 = EFC(d.efc_D, r + 1), D2 = EFC(d.efc_D, r + 2);
+  float mu = SW(S_MU, r), f1 = SW(S_F1, r), f2 = SW(S_F2, r);
+  float j1 = SW(W_JAR, r + 1), j2 = SW(W_JAR, r + 2), D1 = SW(S_D, r + 1), D2 = SW(S_D, r + 2);
   float U0 = jar * mu, U1 = j1 * f1, U2 = j2 * f2, N = U0, T = sqrtf(U1 * U1 + U2 * U2);
   if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
     SW(W_F, r) = -D * jar; SW(W_F, r + 1) = -D1 * j1; SW(W_F, r + 2) = -D2 * j2;
@@ -88,19 +93,16 @@ FB_DEV float head_update(const DevModel& m, const DevData& d, const SolveCtx& cx
   }
   return cost;
 }
-FB_DEV bool is_head(const DevData& d, int e, int r) {
-  return EFC(d.efc_type, r) != FB_CT_ELLIPTIC || AT(d.con_efcadr, EFC(d.efc_id, r)) == r;
-}
+#define IS_HEAD(r) (SW(S_TYPE, r) < 1.5f)
 // line-search contribution of the rows headed at r
 FB_DEV void head_ls(const DevModel& m, const DevData& d, const SolveCtx& cx, int lane, int e, int r, float alpha, float& c, float& g, float& h) {
-  int tp = EFC(d.efc_type, r);
-  float jv = SW(W_ADL, r), x = SW(W_JAR, r) + alpha * jv, D = EFC(d.efc_D, r);
-  if (tp != FB_CT_ELLIPTIC) { if (x < 0) { c += 0.5f * D * x * x; g += D * x * jv; h += D * jv * jv; } return; }
-  int ci = EFC(d.efc_id, r);
-  float mu = AT(d.con_mu, ci), f1 = CON_F(d.con_fric, ci, 0, 2), f2 = CON_F(d.con_fric, ci, 1, 2);
+  int tp = (int)SW(S_TYPE, r);
+  float jv = SW(W_ADL, r), x = SW(W_JAR, r) + alpha * jv, D = SW(S_D, r);
+  if (tp == 0) { if (x < 0) { c += 0.5f * D * x * x; g += D * x * jv; h += D * jv * jv; } return; }
+  float mu = SW(S_MU, r), f1 = SW(S_F1, r), f2 = SW(S_F2, r);
   float jv1 = SW(W_ADL, r + 1), jv2 = SW(W_ADL, r + 2);
   float x1 = SW(W_JAR, r + 1) + alpha * jv1, x2 = SW(W_JAR, r + 2) + alpha * jv2;
-  float D1 = EFC(d.efc_D, r + 1), D2 = EFC(d.efc_D, r + 2);
+  float D1 = SW(S_D, r + 1), D2 = SW(S_D, r + 2);
   float U0 = x * mu, U1 = x1 * f1, U2 = x2 * f2, dU0 = jv * mu, dU1 = jv1 * f1, dU2 = jv2 * f2;
   float N = U0, T = sqrtf(U1 * U1 + U2 * U2);
   if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
@@ -116,7 +118,7 @@ FB_DEV void head_ls(const DevModel& m, const DevData& d, const SolveCtx& cx, int
 }
 // column p of E: value on row `row` (0 if the column does not touch it)
 FB_DEV float ecol_val(const DevData& d, const SolveCtx& cx, int lane, int e, int p, int a) {   // a-th entry of column p
-  int kind = ECKIND(p), r = ECROW(p);
+  int kind = (int)ECKIND(p), r = (int)ECROW(p);
   return kind == 2 ? SW(X_E1, r + a) : SW(X_E0, r + a);
 }
 
@@ -130,28 +132,39 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
   PAR_BEGIN
     if (y == 0) { int n = AT(d.nefc, 0); sh.isc[I_N][lane] = n; sh.isc[I_DONE][lane] = (n == 0); sh.isc[I_ITER][lane] = 0; sh.isc[I_NC][lane] = 0; sh.isc[I_LSDONE][lane] = 1; }
   PAR_END
-  SolveCtx cx; cx.vsh = nullptr; cx.vstride = 0; cx.gsh = nullptr; cx.gcap = 0; cx.gmode = 0;
+  SolveCtx cx; cx.vsh = nullptr; cx.vstride = 0; cx.gsh = nullptr; cx.gcap = 0; cx.gmode = 0; cx.ash = nullptr; cx.amode = 0;
   if (blk_max_i(sh, I_N) > 0) {
     {
       int nmaxb = blk_max_i(sh, I_N);
       float* dyn = sh_dyn(sh);
-      if (12 * nmaxb * 32 <= m.solve_dyn_floats) {
-        cx.vsh = dyn; cx.vstride = nmaxb; cx.gsh = dyn + (size_t)12 * nmaxb * 32;
-        int rem = m.solve_dyn_floats / 32 - 12 * nmaxb, g = 0;
-        while ((g + 1) * (g + 1) <= rem) g++;
-        cx.gcap = g;
+      int rem = m.solve_dyn_floats / 32;          // floats per lane: vectors first, then A (packed), then G
+      if (S_NSLOT * nmaxb <= rem) {
+        cx.vsh = dyn; cx.vstride = nmaxb; rem -= S_NSLOT * nmaxb; dyn += (size_t)S_NSLOT * nmaxb * 32;
+        int tri = nmaxb * (nmaxb + 1) / 2;
+        if (tri <= rem) { cx.ash = dyn; cx.amode = 1; rem -= tri; dyn += (size_t)tri * 32; }
+        int g = 0; while ((g + 1) * (g + 1) <= rem) g++;
+        cx.gsh = dyn; cx.gcap = g;
       }
     }
+    // ---------------- stage row constants (and A) into shared memory
+    PAR_BEGIN ROWS_BEGIN
+      int tp = EFC(d.efc_type, r), tcode = 0; float mu = 0, f1 = 0, f2 = 0;
+      if (tp == FB_CT_ELLIPTIC) { int ci = EFC(d.efc_id, r); tcode = (AT(d.con_efcadr, ci) == r) ? 1 : 2; mu = AT(d.con_mu, ci); f1 = CON_F(d.con_fric, ci, 0, 2); f2 = CON_F(d.con_fric, ci, 1, 2); }
+      SW(S_TYPE, r) = (float)tcode; SW(S_MU, r) = mu; SW(S_F1, r) = f1; SW(S_F2, r) = f2;
+      SW(S_D, r) = EFC(d.efc_D, r); SW(S_B, r) = EFC(d.efc_b, r); SW(S_R, r) = EFC(d.efc_R, r);
+      SW(S_LA, r) = (float)AT(d.efc_la, r); SW(S_LB, r) = (float)AT(d.efc_lb, r);
+      if (cx.amode) for (int c = 0; c <= r; c++) cx.ash[TRI(r, c) * 32 + lane] = EA(d.efc_A, r, c);
+    ROWS_END PAR_END
     // ---------------- warm start
     PAR_BEGIN float c = 0; ROWS_BEGIN SW(W_JAR, r) = EFC(d.efc_jarws, r); ROWS_END sh.red[y][0][lane] = c; PAR_END
-    PAR_BEGIN ROWS_BEGIN if (is_head(d, e, r)) head_update(m, d, cx, lane, e, r, false); ROWS_END PAR_END
+    PAR_BEGIN ROWS_BEGIN if (IS_HEAD(r)) head_update(m, d, cx, lane, e, r, false); ROWS_END PAR_END
     PAR_BEGIN ROWS_BEGIN SW(W_LAM, r) = SW(W_F, r); ROWS_END PAR_END
     PAR_BEGIN float q = 0; int n = MY_N;
-      ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; q += 0.5f * SW(W_LAM, r) * (s - EFC(d.efc_b, r)); ROWS_END
+      ROWS_BEGIN float s = SW(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; q += 0.5f * SW(W_LAM, r) * (s - SW(S_B, r)); ROWS_END
       sh.red[y][0][lane] = q; PAR_END
-    PAR_BEGIN float c = 0; ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, cx, lane, e, r, false); ROWS_END sh.red[y][1][lane] = c; PAR_END
-    PAR_BEGIN if (y == 0) sh.sc[SC_COSTWS][lane] = RED_SUM(0) + RED_SUM(1); ROWS_BEGIN SW(W_JAR, r) = EFC(d.efc_b, r); ROWS_END PAR_END
-    PAR_BEGIN float c = 0; ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, cx, lane, e, r, false); ROWS_END sh.red[y][0][lane] = c; PAR_END
+    PAR_BEGIN float c = 0; ROWS_BEGIN if (IS_HEAD(r)) c += head_update(m, d, cx, lane, e, r, false); ROWS_END sh.red[y][1][lane] = c; PAR_END
+    PAR_BEGIN if (y == 0) sh.sc[SC_COSTWS][lane] = RED_SUM(0) + RED_SUM(1); ROWS_BEGIN SW(W_JAR, r) = SW(S_B, r); ROWS_END PAR_END
+    PAR_BEGIN float c = 0; ROWS_BEGIN if (IS_HEAD(r)) c += head_update(m, d, cx, lane, e, r, false); ROWS_END sh.red[y][0][lane] = c; PAR_END
     PAR_BEGIN if (y == 0) sh.sc[SC_COST0][lane] = RED_SUM(0); PAR_END
     PAR_BEGIN if (!(sh.sc[SC_COSTWS][lane] < sh.sc[SC_COST0][lane])) { ROWS_BEGIN SW(W_LAM, r) = 0; ROWS_END } PAR_END
     // ---------------- Newton iterations
@@ -159,9 +172,9 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
       if (!blk_any_active(sh)) break;
       // jar = b + A lam
       PAR_BEGIN float q = 0; int n = MY_N;
-        if (ACTIVE) { ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; q += 0.5f * SW(W_LAM, r) * (s - EFC(d.efc_b, r)); ROWS_END }
+        if (ACTIVE) { ROWS_BEGIN float s = SW(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; q += 0.5f * SW(W_LAM, r) * (s - SW(S_B, r)); ROWS_END }
         sh.red[y][0][lane] = q; PAR_END
-      PAR_BEGIN float c = 0; if (ACTIVE) { ROWS_BEGIN if (is_head(d, e, r)) c += head_update(m, d, cx, lane, e, r, true); ROWS_END } sh.red[y][1][lane] = c; PAR_END
+      PAR_BEGIN float c = 0; if (ACTIVE) { ROWS_BEGIN if (IS_HEAD(r)) c += head_update(m, d, cx, lane, e, r, true); ROWS_END } sh.red[y][1][lane] = c; PAR_END
       // residual r = lam - f, column bookkeeping (sequential prefix over rows by y == 0)
       PAR_BEGIN float rr = 0, ll = 0;
         if (ACTIVE) { ROWS_BEGIN float f = SW(W_F, r), rv = SW(W_LAM, r) - f; SW(W_R, r) = rv; rr += rv * rv; ll += f * f; ROWS_END }
@@ -170,7 +183,7 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
           sh.sc[SC_QUAD][lane] = RED_SUM(0); sh.sc[SC_COST][lane] = RED_SUM(0) + RED_SUM(1);
           int n = MY_N, nc = 0;
           for (int r = 0; r < n; r++) {
-            int stt = ESTATE(r);
+            int stt = (int)ESTATE(r);
             if (stt == 1) { ECOLIDX(r) = nc; ECROW(nc) = r; ECKIND(nc) = 0; nc++; }
             else if (stt == 2) { ECOLIDX(r) = nc; ECOLIDX(r + 1) = nc; ECOLIDX(r + 2) = nc; ECROW(nc) = r; ECKIND(nc) = 1; ECROW(nc + 1) = r; ECKIND(nc + 1) = 2; nc += 2; }
             else if (stt == 0) ECOLIDX(r) = -1;
@@ -181,19 +194,19 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
       PAR_BEGIN if (y == 0 && ACTIVE) { float rr = RED_SUM(2), ll = RED_SUM(3); if (rr <= 1e-12f * (ll + 1e-30f)) sh.isc[I_DONE][lane] = 1; } PAR_END
       if (!blk_any_active(sh)) break;
       // u = A r
-      PAR_BEGIN int n = MY_N; if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_R, j); SW(W_U, r) = s; ROWS_END } PAR_END
+      PAR_BEGIN int n = MY_N; if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_R, j); SW(W_U, r) = s; ROWS_END } PAR_END
       int ncmax = 0; for (int l = 0; l < 32; l++) if (!sh.isc[I_DONE][l] && sh.isc[I_NC][l] > ncmax) ncmax = sh.isc[I_NC][l];
       cx.gmode = (cx.gsh != nullptr && ncmax <= cx.gcap) ? 1 : 0;
       // p = E^T u ; G = I + E^T A E (lower triangle)
       PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
         for (int p = y; p < nc; p += FB_SOLVE_Y) {
-          int rp = ECROW(p), np = ECKIND(p) == 0 ? 1 : 3;
+          int rp = (int)ECROW(p), np = ECKIND(p) == 0 ? 1 : 3;
           float pv = 0; for (int a = 0; a < np; a++) pv += ecol_val(d, cx, lane, e, p, a) * SW(W_U, rp + a);
           SW(W_P, p) = pv;
           for (int q = 0; q <= p; q++) {
-            int rq = ECROW(q), nq = ECKIND(q) == 0 ? 1 : 3;
+            int rq = (int)ECROW(q), nq = ECKIND(q) == 0 ? 1 : 3;
             float s = (p == q) ? 1.0f : 0.0f;
-            for (int a = 0; a < np; a++) { float va = ecol_val(d, cx, lane, e, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * EA(d.efc_A, rp + a, rq + bb) * ecol_val(d, cx, lane, e, q, bb); }
+            for (int a = 0; a < np; a++) { float va = ecol_val(d, cx, lane, e, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * AM(rp + a, rq + bb) * ecol_val(d, cx, lane, e, q, bb); }
             GM(p, q) = s;
           }
         } }
@@ -226,22 +239,22 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
       }
       // dlam = -r + E q
       PAR_BEGIN if (ACTIVE) { ROWS_BEGIN
-          float v = -SW(W_R, r); int stt = ESTATE(r), c0 = ECOLIDX(r);
+          float v = -SW(W_R, r); int stt = (int)ESTATE(r), c0 = (int)ECOLIDX(r);
           if (stt == 1) v += SW(X_E0, r) * SW(X_OUT, c0);
           else if (stt >= 2) v += SW(X_E0, r) * SW(X_OUT, c0) + SW(X_E1, r) * SW(X_OUT, c0 + 1);
           SW(W_DL, r) = v;
         ROWS_END } PAR_END
       // A dlam, q1, q2
       PAR_BEGIN float q1 = 0, q2 = 0; int n = MY_N;
-        if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_DL, j); SW(W_ADL, r) = s;
-          q1 += SW(W_DL, r) * (SW(W_JAR, r) - EFC(d.efc_b, r)); q2 += 0.5f * SW(W_DL, r) * s; ROWS_END }
+        if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_DL, j); SW(W_ADL, r) = s;
+          q1 += SW(W_DL, r) * (SW(W_JAR, r) - SW(S_B, r)); q2 += 0.5f * SW(W_DL, r) * s; ROWS_END }
         sh.red[y][0][lane] = q1; sh.red[y][1][lane] = q2; PAR_END
       PAR_BEGIN if (y == 0 && ACTIVE) { sh.sc[SC_Q1][lane] = RED_SUM(0); sh.sc[SC_Q2][lane] = RED_SUM(1); sh.sc[SC_ALPHA][lane] = 0; sh.sc[SC_LO][lane] = 0; sh.sc[SC_HI][lane] = -1; sh.isc[I_LSDONE][lane] = 0; } PAR_END
       // exact line search: evaluation 0 at alpha = 0, then safeguarded Newton on the derivative
       for (int ls = 0; ls <= m.ls_iter; ls++) {
         if (!blk_any_ls(sh)) break;
         PAR_BEGIN float c = 0, g = 0, h = 0;
-          if (ACTIVE && !sh.isc[I_LSDONE][lane]) { float alpha = sh.sc[SC_ALPHA][lane]; ROWS_BEGIN if (is_head(d, e, r)) head_ls(m, d, cx, lane, e, r, alpha, c, g, h); ROWS_END }
+          if (ACTIVE && !sh.isc[I_LSDONE][lane]) { float alpha = sh.sc[SC_ALPHA][lane]; ROWS_BEGIN if (IS_HEAD(r)) head_ls(m, d, cx, lane, e, r, alpha, c, g, h); ROWS_END }
           sh.red[y][0][lane] = c; sh.red[y][1][lane] = g; sh.red[y][2][lane] = h; PAR_END
         PAR_BEGIN if (y == 0 && ACTIVE && !sh.isc[I_LSDONE][lane]) {
           float alpha = sh.sc[SC_ALPHA][lane], quad = sh.sc[SC_QUAD][lane], q1 = sh.sc[SC_Q1][lane], q2 = sh.sc[SC_Q2][lane];
@@ -269,26 +282,24 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
       PAR_BEGIN if (y == 0 && ACTIVE) { sh.isc[I_ITER][lane] = iter + 1; float imp = scale * (sh.sc[SC_COST][lane] - sh.sc[SC_CBEST][lane]); if (imp < m.tolerance) sh.isc[I_DONE][lane] = 1; } PAR_END
     }
     // ---------------- forces at the solution
-    PAR_BEGIN int n = MY_N; ROWS_BEGIN float s = EFC(d.efc_b, r); for (int j = 0; j < n; j++) s += EA(d.efc_A, r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; ROWS_END PAR_END
-    PAR_BEGIN ROWS_BEGIN if (is_head(d, e, r)) head_update(m, d, cx, lane, e, r, false); ROWS_END PAR_END
-    PAR_BEGIN ROWS_BEGIN EFC(d.efc_force, r) = SW(W_F, r); ROWS_END if (y == 0) AT(d.niter, 0) = sh.isc[I_ITER][lane]; PAR_END
-    // ---------------- noslip: inherently sequential Gauss-Seidel over the friction rows (y == 0)
+    PAR_BEGIN int n = MY_N; ROWS_BEGIN float s = SW(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; ROWS_END PAR_END
+    PAR_BEGIN ROWS_BEGIN if (IS_HEAD(r)) head_update(m, d, cx, lane, e, r, false); ROWS_END PAR_END
+    // ---------------- noslip: inherently sequential Gauss-Seidel over the friction rows (y == 0), on W_F
     if (m.noslip_iterations > 0) {
-      PAR_BEGIN if (y == 0) { int n = MY_N;
+      PAR_BEGIN if (y == 0) { int n = MY_N; AT(d.niter, 0) = sh.isc[I_ITER][lane];
         for (int it = 0; it < m.noslip_iterations && n > 0; it++) {
           float improvement = 0;
-          if (it == 0) for (int i = 0; i < n; i++) improvement += 0.5f * EFC(d.efc_force, i) * EFC(d.efc_force, i) * EFC(d.efc_R, i);
+          if (it == 0) for (int i = 0; i < n; i++) improvement += 0.5f * SW(W_F, i) * SW(W_F, i) * SW(S_R, i);
           bool any = false;
           for (int i = 0; i < n; i++) {
-            if (EFC(d.efc_type, i) != FB_CT_ELLIPTIC) continue;
+            if (SW(S_TYPE, i) < 0.5f) continue;
             any = true;
-            int ci = EFC(d.efc_id, i);
-            float fn = EFC(d.efc_force, i), old0 = EFC(d.efc_force, i + 1), old1 = EFC(d.efc_force, i + 2);
+            float fn = SW(W_F, i), old0 = SW(W_F, i + 1), old1 = SW(W_F, i + 2);
             float res[2], Ac[4], bc[2], v[2];
-            for (int rr = 0; rr < 2; rr++) { float s = EFC(d.efc_b, i + 1 + rr); for (int j = 0; j < n; j++) s += EA(d.efc_A, i + 1 + rr, j) * EFC(d.efc_force, j); res[rr] = s; }
-            Ac[0] = EA(d.efc_A, i + 1, i + 1); Ac[1] = EA(d.efc_A, i + 1, i + 2); Ac[2] = EA(d.efc_A, i + 2, i + 1); Ac[3] = EA(d.efc_A, i + 2, i + 2);
+            for (int rr = 0; rr < 2; rr++) { float s = SW(S_B, i + 1 + rr); for (int j = 0; j < n; j++) s += AM(i + 1 + rr, j) * SW(W_F, j); res[rr] = s; }
+            Ac[0] = AM(i + 1, i + 1); Ac[1] = AM(i + 1, i + 2); Ac[2] = Ac[1]; Ac[3] = AM(i + 2, i + 2);
             bc[0] = res[0] - Ac[0] * old0 - Ac[1] * old1; bc[1] = res[1] - Ac[2] * old0 - Ac[3] * old1;
-            float fr0 = CON_F(d.con_fric, ci, 0, 2), fr1 = CON_F(d.con_fric, ci, 1, 2);
+            float fr0 = SW(S_F1, i), fr1 = SW(S_F2, i);
             if (fn < FB_MINVAL) { v[0] = 0; v[1] = 0; }
             else {
               int active = qcqp2(v, Ac, bc, fr0, fr1, fn);
@@ -297,7 +308,7 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
             float d0 = v[0] - old0, d1 = v[1] - old1;
             float change = 0.5f * (d0 * (Ac[0] * d0 + Ac[1] * d1) + d1 * (Ac[2] * d0 + Ac[3] * d1)) + d0 * res[0] + d1 * res[1];
             if (change > 1e-10f) { v[0] = old0; v[1] = old1; change = 0; }
-            EFC(d.efc_force, i + 1) = v[0]; EFC(d.efc_force, i + 2) = v[1];
+            SW(W_F, i + 1) = v[0]; SW(W_F, i + 2) = v[1];
             improvement -= change;
             i += 2;
           }
@@ -306,15 +317,16 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
         } }
       PAR_END
     }
+    PAR_BEGIN ROWS_BEGIN EFC(d.efc_force, r) = SW(W_F, r); ROWS_END if (y == 0) AT(d.niter, 0) = sh.isc[I_ITER][lane]; PAR_END
   }
   // ---------------- qfrc_constraint = J^T f, gathered per dof (race free)
   PAR_BEGIN int n = MY_N;
     for (int k = y; k < m.nv; k += FB_SOLVE_Y) {
       float s = 0;
       for (int r = 0; r < n; r++) {
-        float f = EFC(d.efc_force, r);
+        float f = SW(W_F, r);
         if (f == 0.0f) continue;
-        if (in_chain(m, k, AT(d.efc_la, r)) || in_chain(m, k, AT(d.efc_lb, r))) s += EJ(d.efc_J, r, k) * f;
+        if (in_chain(m, k, (int)SW(S_LA, r)) || in_chain(m, k, (int)SW(S_LB, r))) s += EJ(d.efc_J, r, k) * f;
       }
       AT(d.qfrc_constraint, k) = s;
     }

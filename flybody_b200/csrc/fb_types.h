@@ -95,6 +95,9 @@ struct DevData {
   const int* rst_ids; const float* rst_qpos; const float* rst_qvel; int rst_n, rst_has_qvel;   // staged partial reset
   float *obs;                  // packed AoS observation [N][obs_dim]
   int obs_dim;
+  // task observation program (fb_obs_program): final observation rows [N][tobs_dim]
+  float *tobs; int tobs_dim, op_n, op_root_body, op_ref_len, op_nsub;
+  const int *op_kind, *op_a, *op_b, *op_list; const float* op_ref; const int* op_step; const unsigned char* op_first;
 };
 
 #ifdef __CUDACC__

@@ -60,6 +60,7 @@ struct FbSim {
   int device; long long launches; float last_ms; std::string err;
   int first_substep; int hold_pending;
   int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
+  int* op_step_dev; unsigned char* op_first_dev;
 #ifndef FB_EMU
   cudaStream_t stream; cudaEvent_t ev0, ev1;
 #endif
@@ -148,7 +149,7 @@ static void fb_launch_block(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
 // lane == env kernels wrapped as single-phase functions
 FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kreset_scatter(m, d, e); }
 FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kclear_hold(m, d, e); }
-FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kpack(m, d, e, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); }
+FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kpack(m, d, e, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); ktaskobs(m, d, e); }
 // qacc_smooth = M^-1 qfrc_smooth (qacc_smooth already holds the rhs)
 FB_DEV void ph_smooth_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD); }
 FB_DEV void ph_smooth_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD); }
@@ -329,7 +330,7 @@ static int alloc_data(FbSim* s, int N) {
   FA(efc_pos, FB_MAXEFC) FA(efc_margin, FB_MAXEFC) FA(efc_D, FB_MAXEFC) FA(efc_R, FB_MAXEFC) FA(efc_K, FB_MAXEFC) FA(efc_B, FB_MAXEFC)
   FA(efc_imp, FB_MAXEFC) FA(efc_aref, FB_MAXEFC) FA(efc_b, FB_MAXEFC) FA(efc_force, FB_MAXEFC) FA(efc_jarws, FB_MAXEFC)
   FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv) FA(efc_A, (size_t)FB_MAXEFC * FB_MAXEFC) FA(efc_G, (size_t)FB_MAXEFC * FB_MAXEFC)
-  FA(efc_w, 8 * FB_MAXEFC) FA(efc_w2, 4 * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) IA(efc_ekind, FB_MAXEFC) IA(efc_state, FB_MAXEFC) IA(efc_colidx, FB_MAXEFC) IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC)
+  FA(efc_w, 8 * FB_MAXEFC) FA(efc_w2, 20 * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) IA(efc_ekind, FB_MAXEFC) IA(efc_state, FB_MAXEFC) IA(efc_colidx, FB_MAXEFC) IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC)
   FA(sensordata, m.nsensordata + 1) FA(sensor_sum, m.nsensordata + 1) IA(flags, 1) IA(niter, 1) IA(hold, 1)
 #undef FA
 #undef IA
@@ -376,6 +377,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   if (!hm || !out || n_envs <= 0) return -1;
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
+  s->op_step_dev = nullptr; s->op_first_dev = nullptr;
   s->rst_ids_dev = nullptr; s->rst_qpos_dev = nullptr; s->rst_qvel_dev = nullptr; s->rst_cap = 0;
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
@@ -645,6 +647,54 @@ int fb_profile_read(FbHandle s, double* ms, long long* counts, int n) {
   return K_NKIND;
 }
 const char* fb_profile_name(int kind) { return (kind >= 0 && kind < K_NKIND) ? kKindNames[kind] : ""; }
+int fb_obs_program(FbHandle s, const FbObsProgram* p) {
+  if (!s || !p || p->n_items <= 0) return -1;
+  if (sync_stream(s) != 0) return -2;
+  const DevModel& m = s->m;
+  int dim = 0;
+  for (int i = 0; i < p->n_items; i++) {
+    int k = p->kind[i], b = p->b[i];
+    switch (k) {
+      case FB_OBS_SENSOR_MEAN: case FB_OBS_SENSOR_NOW: case FB_OBS_ACT: case FB_OBS_QPOS: case FB_OBS_QVEL: dim += b; break;
+      case FB_OBS_SITES_EGO: case FB_OBS_REF_DISP: dim += 3 * b; break;
+      case FB_OBS_REF_QUAT: dim += 4 * b; break;
+      case FB_OBS_ROOT_ZAXIS: case FB_OBS_SCALARS: case FB_OBS_SUBTREE_COM: dim += 3; break;
+      case FB_OBS_ROOT_POSE: dim += 7; break;
+      default: s->err = "fb_obs_program: unknown item kind"; return -1;
+    }
+    if ((k == FB_OBS_REF_DISP || k == FB_OBS_REF_QUAT) && (!p->ref_qpos || p->ref_len <= 0)) { s->err = "fb_obs_program: reference table missing"; return -1; }
+    if ((k == FB_OBS_QPOS || k == FB_OBS_QVEL || k == FB_OBS_SITES_EGO) && (p->a[i] < 0 || p->a[i] + b > p->n_list)) { s->err = "fb_obs_program: list range"; return -1; }
+  }
+  if (p->root_body <= 0 || p->root_body >= m.nbody) { s->err = "fb_obs_program: root body"; return -1; }
+  std::vector<int> kind(p->kind, p->kind + p->n_items), a(p->a, p->a + p->n_items), b(p->b, p->b + p->n_items), list(p->list, p->list + std::max(p->n_list, 0));
+  s->d.op_kind = up(s, kind); s->d.op_a = up(s, a); s->d.op_b = up(s, b); s->d.op_list = up(s, list);
+  s->d.op_n = p->n_items; s->d.op_root_body = p->root_body; s->d.op_nsub = p->n_sub; s->d.op_ref_len = p->ref_len;
+  if (p->ref_qpos && p->ref_len > 0) { std::vector<float> r(p->ref_qpos, p->ref_qpos + (size_t)7 * p->ref_len); s->d.op_ref = up(s, r); } else s->d.op_ref = nullptr;
+  s->d.tobs_dim = dim; s->d.tobs = dalloc<float>(s, (size_t)dim * s->d.Np);
+  s->op_step_dev = dalloc<int>(s, s->d.Np); s->op_first_dev = (unsigned char*)dalloc<int>(s, s->d.Np);
+  s->d.op_step = s->op_step_dev; s->d.op_first = s->op_first_dev;
+  return dim;
+}
+int fb_task_inputs(FbHandle s, const int32_t* step_idx, const uint8_t* first) {
+  if (!s || !s->d.tobs || !step_idx || !first) return -1;
+#ifndef FB_EMU
+  FB_CUDA_OK(cudaMemcpyAsync(s->op_step_dev, step_idx, sizeof(int) * s->d.N, cudaMemcpyHostToDevice, s->stream));
+  FB_CUDA_OK(cudaMemcpyAsync(s->op_first_dev, first, s->d.N, cudaMemcpyHostToDevice, s->stream));
+#else
+  memcpy(s->op_step_dev, step_idx, sizeof(int) * s->d.N); memcpy(s->op_first_dev, first, s->d.N);
+#endif
+  return 0;
+}
+int fb_read_task_obs(FbHandle s, float* host_dst) {
+  if (!s || !host_dst || !s->d.tobs) return -1;
+#ifndef FB_EMU
+  FB_CUDA_OK(cudaMemcpyAsync(host_dst, s->d.tobs, sizeof(float) * (size_t)s->d.N * s->d.tobs_dim, cudaMemcpyDeviceToHost, s->stream));
+  return sync_stream(s);
+#else
+  memcpy(host_dst, s->d.tobs, sizeof(float) * (size_t)s->d.N * s->d.tobs_dim);
+  return 0;
+#endif
+}
 int fb_pack_obs(FbHandle s) {
   if (!s) return -1;
 #ifndef FB_EMU

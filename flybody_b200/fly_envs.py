@@ -182,14 +182,9 @@ class BatchedFlyEnv:
                         force=sd([f'force_tarsus_{l}' for l in legs]), touch=sd([f'touch_claw_{l}' for l in legs]))
         self._leg_act_qadr = np.array([m.jnt_qposadr[m.actuator_trnid[i]] for i in range(m.nu)
                                        if m.actuator_trntype[i] == 0 and any(t in m.meta['actuator_names'][i] for t in ('T1', 'T2', 'T3'))])
-        self._lay = self._sim.obs_layout()
-        _, self._rec_dim = self._sim.obs_ptr()
-        try:
-            import torch
-            self._rec = torch.empty((N, self._rec_dim), dtype=torch.float32).pin_memory().numpy() if torch.cuda.is_available() \
-                else np.empty((N, self._rec_dim), np.float32)
-        except Exception:
-            self._rec = np.empty((N, self._rec_dim), np.float32)
+        self._future = future_steps + 1
+        self._rec = None
+        self._program_ref_id = None
         # --- per-env episode state
         self._step_counter = np.zeros(N, np.int64)
         self._time = np.zeros(N)
@@ -213,7 +208,7 @@ class BatchedFlyEnv:
             ('walker/touch', (6,)), ('walker/velocimeter', (3,)), ('walker/world_zaxis', (3,)),
             ('walker/ref_displacement', (f, 3)), ('walker/ref_root_quat', (f, 4))])
         lead = (self.n_envs,) if self._batched else ()
-        return collections.OrderedDict((k, Array(lead + v, np.float64, name=k)) for k, v in shapes.items())
+        return collections.OrderedDict((k, Array(lead + v, np.float32, name=k)) for k, v in shapes.items())
 
     def reward_spec(self):
         return Array((self.n_envs,) if self._batched else (), np.float64, name='reward')
@@ -225,10 +220,43 @@ class BatchedFlyEnv:
         return self._control_timestep
 
     # -------------------------------------------------------------------------------- episode
+    def _upload_program(self):
+        """Observation program = the task's observables in spec order, evaluated on the device (fb_obs_program)."""
+        m = self.model
+        sd = self._sd
+        lists = list(self._app_sites) + list(self._obs_qadr) + list(self._obs_vadr)
+        o_app, o_q, o_v = 0, len(self._app_sites), len(self._app_sites) + len(self._obs_qadr)
+        f = self._future
+        items = [(st.OBS_SENSOR_MEAN, sd['accelerometer'][0], 3), (st.OBS_ACT, 0, m.na), (st.OBS_SITES_EGO, o_app, len(self._app_sites)),
+                 (st.OBS_SENSOR_MEAN, sd['force'][0], len(sd['force'])), (st.OBS_SENSOR_MEAN, sd['gyro'][0], 3),
+                 (st.OBS_QPOS, o_q, len(self._obs_qadr)), (st.OBS_QVEL, o_v, len(self._obs_vadr)),
+                 (st.OBS_SENSOR_MEAN, sd['touch'][0], len(sd['touch'])), (st.OBS_SENSOR_MEAN, sd['velocimeter'][0], 3),
+                 (st.OBS_ROOT_ZAXIS, 0, 3), (st.OBS_REF_DISP, 0, f), (st.OBS_REF_QUAT, 0, f),
+                 (st.OBS_SENSOR_NOW, sd['velocimeter'][0], 3), (st.OBS_SENSOR_NOW, sd['gyro'][0], 3), (st.OBS_SCALARS, 0, 3)]
+        dim = self._sim.obs_program(items, lists, m.body_id('walker/thorax'), self._n_sub, self._ref_qpos[:, :7])
+        names = ['walker/accelerometer', 'walker/actuator_activation', 'walker/appendages_pos', 'walker/force', 'walker/gyro',
+                 'walker/joints_pos', 'walker/joints_vel', 'walker/touch', 'walker/velocimeter', 'walker/world_zaxis',
+                 'walker/ref_displacement', 'walker/ref_root_quat', '_velocimeter_now', '_gyro_now', '_scalars']
+        widths = [3, m.na, 3 * len(self._app_sites), len(sd['force']), 3, len(self._obs_qadr), len(self._obs_vadr),
+                  len(sd['touch']), 3, 3, 3 * f, 4 * f, 3, 3, 3]
+        assert sum(widths) == dim
+        off = np.concatenate([[0], np.cumsum(widths)])
+        self._obs_slices = {n_: slice(int(off[i]), int(off[i + 1])) for i, n_ in enumerate(names)}
+        N = self.n_envs
+        try:
+            import torch
+            self._rec = torch.empty((N, dim), dtype=torch.float32).pin_memory().numpy() if torch.cuda.is_available() \
+                else np.empty((N, dim), np.float32)
+        except Exception:
+            self._rec = np.empty((N, dim), np.float32)
+
     def _load_snippet(self):
         snip = self.task._traj_generator.get_trajectory(traj_idx=None)
         self._ref_qpos = snip['qpos']
         self._ref_qvel = snip['qvel']
+        if self._program_ref_id is not self._ref_qpos:
+            self._program_ref_id = self._ref_qpos
+            self._upload_program()
         snippet_steps = self._ref_qpos.shape[0] - self.task._future_steps - 1
         self._episode_steps = min(self.task._max_episode_steps, snippet_steps)      # walk_imitation.py:104-105
 
@@ -254,8 +282,9 @@ class BatchedFlyEnv:
 
     def reset(self):
         self._reset_envs(np.arange(self.n_envs))
-        rec = self._sim.read_obs(self._rec)
-        obs = self._observation(rec, first=np.ones(self.n_envs, bool))
+        self._sim.task_inputs(self._step_counter, np.ones(self.n_envs, np.uint8))
+        rec = self._sim.read_task_obs(self._rec)
+        obs = self._observation(rec)
         N = self.n_envs
         ts = TimeStep(np.full(N, StepType.FIRST), np.zeros(N), np.ones(N), obs)
         return self._unbatch(ts, first=True)
@@ -283,20 +312,21 @@ class BatchedFlyEnv:
         self._sim.set_control(ctrl)
         self.h2d_bytes_per_step = ctrl.nbytes + ghost.nbytes
         # n_sub_steps x physics.step()
+        self._sim.task_inputs(self._step_counter, resetting)
         self._sim.step(self._n_sub)
-        rec = self._sim.read_obs(self._rec)
+        rec = self._sim.read_task_obs(self._rec)
         self.d2h_bytes_per_step = rec.nbytes
         self._time = np.where(resetting, 0.0, self._time + self._control_timestep)
-        lay = self._lay
-        obs = self._observation(rec, first=resetting)
+        obs = self._observation(rec)
+        sl = self._obs_slices
         # check_termination / reward / discount (walk_imitation.py:152-203, base.py:203-225)
-        sdn = rec[:, lay['sensordata']]
-        linvel = np.linalg.norm(sdn[:, self._sd['velocimeter']], axis=1)
-        angvel = np.linalg.norm(sdn[:, self._sd['gyro']], axis=1)
+        linvel = np.linalg.norm(rec[:, sl['_velocimeter_now']], axis=1)
+        angvel = np.linalg.norm(rec[:, sl['_gyro_now']], axis=1)
         step_now = np.round(self._time / self._control_timestep).astype(np.int64)
         com_dist = np.linalg.norm(obs['walker/ref_displacement'][:, 0], axis=1)
         reached_end = step_now == self._episode_steps
-        bad = (rec[:, lay['flags']][:, 0] != 0) | ~(np.sqrt(rec[:, lay['qacc_sq']][:, 0].astype(np.float64)) <= _TERMINAL_QACC)
+        scal = rec[:, sl['_scalars']]
+        bad = (scal[:, 0] != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
         terminate = (linvel > _TERMINAL_LINVEL) | (angvel > _TERMINAL_ANGVEL) | reached_end | \
                     (com_dist > self.task._terminal_com_dist) | bad
         reward = np.ones(N)                                   # inference mode: reward factors == (1,)
@@ -311,40 +341,19 @@ class BatchedFlyEnv:
         return self._unbatch(TimeStep(step_type, reward, discount, obs))
 
     # ---------------------------------------------------------------------------- observations
-    def _observation(self, rec, first):
-        lay = self._lay
-        N = self.n_envs
-        qpos = rec[:, lay['qpos']].astype(np.float64)
-        qvel = rec[:, lay['qvel']].astype(np.float64)
-        sm = rec[:, lay['sensor_mean']].astype(np.float64)
-        if first.any():
-            # observation buffers hold one sample after reset; the updater pads with zeros [3P-memory]
-            sm = np.where(first[:, None], rec[:, lay['sensordata']].astype(np.float64) / self._n_sub, sm)
-        xpos = rec[:, lay['root_xpos']].astype(np.float64)
-        xmat = rec[:, lay['root_xmat']].astype(np.float64).reshape(N, 3, 3)
-        sites = rec[:, lay['site_xpos']].astype(np.float64).reshape(N, -1, 3)
-        app = np.einsum('nsi,nij->nsj', sites[:, self._app_sites] - xpos[:, None], xmat).reshape(N, -1)   # fruitfly.py:674-684
-        f = self.task._future_steps + 1
-        idx = self._step_counter[:, None] + np.arange(f)[None]
-        idx = np.minimum(idx, self._ref_qpos.shape[0] - 1)
-        ref = self._ref_qpos[idx]                                          # [N, f, 7]
-        fly_pos = qpos[:, self._root_q:self._root_q + 3]
-        fly_quat = qpos[:, self._root_q + 3:self._root_q + 7]
-        disp = np.einsum('nfi,nij->nfj', ref[:, :, :3] - fly_pos[:, None], xmat)          # base.py:245-256
-        rq = mult_quat(np.broadcast_to(reciprocal_quat(fly_quat)[:, None], (N, f, 4)), ref[:, :, 3:7])   # base.py:258-268
+    def _observation(self, rec):
+        """Views into the device-evaluated observation rows (fp32; the reference returns float64 copies)."""
+        N, f = self.n_envs, self._future
         obs = collections.OrderedDict()
-        obs['walker/accelerometer'] = sm[:, self._sd['accelerometer']]
-        obs['walker/actuator_activation'] = rec[:, lay['act']].astype(np.float64)
-        obs['walker/appendages_pos'] = app
-        obs['walker/force'] = sm[:, self._sd['force']]
-        obs['walker/gyro'] = sm[:, self._sd['gyro']]
-        obs['walker/joints_pos'] = qpos[:, self._obs_qadr]
-        obs['walker/joints_vel'] = qvel[:, self._obs_vadr]
-        obs['walker/touch'] = sm[:, self._sd['touch']]
-        obs['walker/velocimeter'] = sm[:, self._sd['velocimeter']]
-        obs['walker/world_zaxis'] = xmat[:, 2, :].copy()                  # xmat[6:]
-        obs['walker/ref_displacement'] = disp
-        obs['walker/ref_root_quat'] = rq
+        for k, sl in self._obs_slices.items():
+            if k.startswith('_'):
+                continue
+            v = rec[:, sl]
+            if k == 'walker/ref_displacement':
+                v = v.reshape(N, f, 3)
+            elif k == 'walker/ref_root_quat':
+                v = v.reshape(N, f, 4)
+            obs[k] = v
         return obs
 
     def _unbatch(self, ts, first=False):

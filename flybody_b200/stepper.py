@@ -22,7 +22,19 @@ MAXCON, MAXEFC = 64, 160
 
 EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
-           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+
+
+# enum FbObsItem
+(OBS_SENSOR_MEAN, OBS_SENSOR_NOW, OBS_ACT, OBS_QPOS, OBS_QVEL, OBS_SITES_EGO, OBS_ROOT_ZAXIS, OBS_REF_DISP,
+ OBS_REF_QUAT, OBS_SCALARS, OBS_ROOT_POSE, OBS_SUBTREE_COM) = range(12)
+
+
+class FbObsProgram(C.Structure):
+    _fields_ = [('n_items', C.c_int32), ('kind', C.POINTER(C.c_int32)), ('a', C.POINTER(C.c_int32)),
+                ('b', C.POINTER(C.c_int32)), ('n_list', C.c_int32), ('list', C.POINTER(C.c_int32)),
+                ('root_body', C.c_int32), ('n_sub', C.c_int32), ('ref_len', C.c_int32),
+                ('ref_qpos', C.POINTER(C.c_float))]
 
 
 class StepperError(RuntimeError):
@@ -48,6 +60,9 @@ def load_library(path=None):
     lib.fb_field_size.argtypes = [C.c_void_p, C.c_int]
     lib.fb_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_obs_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    lib.fb_obs_program.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fb_task_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fb_read_task_obs.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_pack_obs.argtypes = [C.c_void_p]
     lib.fb_read_obs.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_profile.argtypes = [C.c_void_p, C.c_int]
@@ -166,6 +181,33 @@ class BatchedStepper:
         n = C.c_int()
         self._check(self._lib.fb_obs_ptr(self._h, C.byref(p), C.byref(n)), 'fb_obs_ptr')
         return p.value, n.value
+
+    def obs_program(self, items, lists, root_body, n_sub, ref_qpos=None):
+        """items: [(kind, a, b)], lists: flat int list referenced by QPOS/QVEL/SITES items. Returns row length."""
+        kind = np.ascontiguousarray([i[0] for i in items], np.int32)
+        a = np.ascontiguousarray([i[1] for i in items], np.int32)
+        b = np.ascontiguousarray([i[2] for i in items], np.int32)
+        lst = np.ascontiguousarray(lists if len(lists) else [0], np.int32)
+        ref = None if ref_qpos is None else np.ascontiguousarray(ref_qpos, np.float32)
+        p = FbObsProgram(len(items), kind.ctypes.data_as(C.POINTER(C.c_int32)), a.ctypes.data_as(C.POINTER(C.c_int32)),
+                         b.ctypes.data_as(C.POINTER(C.c_int32)), len(lists), lst.ctypes.data_as(C.POINTER(C.c_int32)),
+                         int(root_body), int(n_sub), 0 if ref is None else ref.shape[0],
+                         None if ref is None else ref.ctypes.data_as(C.POINTER(C.c_float)))
+        dim = self._lib.fb_obs_program(self._h, C.byref(p))
+        if dim < 0:
+            raise StepperError(f'fb_obs_program failed ({dim}): {self._lib.fb_last_error(self._h).decode()}')
+        self._tobs_dim = dim
+        return dim
+
+    def task_inputs(self, step_idx, first):
+        si = np.ascontiguousarray(step_idx, np.int32)
+        fi = np.ascontiguousarray(first, np.uint8)
+        self._check(self._lib.fb_task_inputs(self._h, si.ctypes.data, fi.ctypes.data), 'fb_task_inputs')
+
+    def read_task_obs(self, out):
+        self._check(self._lib.fb_pack_obs(self._h), 'fb_pack_obs')
+        self._check(self._lib.fb_read_task_obs(self._h, out.ctypes.data), 'fb_read_task_obs')
+        return out
 
     def profile(self, enable=True):
         self._lib.fb_profile(self._h, 1 if enable else 0)

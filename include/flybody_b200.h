@@ -228,6 +228,35 @@ int fb_set(FbHandle h, int field, const float* src);  /* host [N][n] AoS -> devi
  * NCCL gather to rank 0.  Layout: qpos, qvel, act, sensor_mean, xpos/xmat of
  * root, site_xpos.                                                                            */
 int fb_obs_ptr(FbHandle h, void** dev_ptr, int* floats_per_env);
+/* Task observation program: the observables of the reference task (FruitFlyObservables, fruitfly.py:585-756;
+ * ref_displacement / ref_root_quat, tasks/base.py:245-268) evaluated on the device right after fb_step, one
+ * fp32 row per env in the task's final observation layout.  Items are concatenated in order.           */
+enum FbObsItem {
+  FB_OBS_SENSOR_MEAN = 0, /* a = sensordata adr, b = len : per-substep mean (first[e]: single sample / n_sub) */
+  FB_OBS_SENSOR_NOW = 1,  /* a = adr, b = len           : last sample (termination checks)                   */
+  FB_OBS_ACT = 2,         /* a = first act, b = len                                                          */
+  FB_OBS_QPOS = 3,        /* a = offset into list, b = len : qpos[list[a..a+b)]                              */
+  FB_OBS_QVEL = 4,
+  FB_OBS_SITES_EGO = 5,   /* a = offset into list (site ids), b = count : (site_xpos - root_xpos) @ root_xmat */
+  FB_OBS_ROOT_ZAXIS = 6,  /* root xmat[6:9]                                                                  */
+  FB_OBS_REF_DISP = 7,    /* b = future_steps+1 : (ref_pos[step+i] - root_pos) @ root_xmat                   */
+  FB_OBS_REF_QUAT = 8,    /* b = future_steps+1 : root_quat^-1 * ref_quat[step+i]                            */
+  FB_OBS_SCALARS = 9,     /* flags, |qacc|^2, time                                                           */
+  FB_OBS_ROOT_POSE = 10,  /* root xpos[3] + quat[4]                                                          */
+  FB_OBS_SUBTREE_COM = 11 /* a = body id : physics.data.subtree_com[body]                                    */
+};
+typedef struct FbObsProgram {
+  int32_t n_items; const int32_t* kind; const int32_t* a; const int32_t* b;
+  int32_t n_list; const int32_t* list;
+  int32_t root_body, n_sub;
+  int32_t ref_len; const float* ref_qpos;      /* [ref_len][7] reference root trajectory */
+} FbObsProgram;
+/* Upload the program (and reference table); returns the row length in floats (<0 on error).             */
+int fb_obs_program(FbHandle h, const FbObsProgram* p);
+/* Per control step: index into the reference table and "first step after reset" flag of every env.      */
+int fb_task_inputs(FbHandle h, const int32_t* step_idx, const uint8_t* first);
+/* Copy the task observation rows [N][row_len] to a (pinned) host buffer (fb_pack_obs must have run).    */
+int fb_read_task_obs(FbHandle h, float* host_dst);
 /* Launch the pack kernel (after fb_step) / copy the packed rows to a (pinned) host buffer [N][floats_per_env]:
  * qpos, qvel, act, sensor_mean, sensordata, root xpos[3], root xmat[9], site_xpos[3*nsite], flags, |qacc|^2, time.
  * Stands in for the observation_updater reads of composer.Environment.step.        */

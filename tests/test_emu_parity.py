@@ -33,3 +33,12 @@ def test_teacher_forced_control_steps_walk(emu):
     m = load_model('walk')
     r = summarize_tf(*teacher_forced_errors(m, st.BatchedStepper(m, 1, lib_path=emu), n_steps=8, n_sub=10))
     assert r['p90_q'] < 2e-6 and r['p90_v'] < 5e-3 and r['events'] <= 1, r
+
+
+@pytest.mark.parametrize('kb', ['0', '24'])
+def test_solver_global_memory_fallback_paths(emu, kb, monkeypatch):
+    """The solver keeps its vectors / Delassus matrix / Hessian factor in shared memory when they fit and
+    falls back to the global arrays otherwise; both placements must give the same answer."""
+    monkeypatch.setenv('FB_SOLVE_SMEM_KB', kb)
+    m = load_model('walk')
+    compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=emu), seed=0)

@@ -83,3 +83,38 @@ def test_nan_action_is_zeroed(emu):
     a[0, 5] = np.nan                                           # walk_imitation.py:147-148
     ts = env.step(a)
     assert np.all(np.isfinite(ts.observation['walker/joints_pos']))
+
+
+def test_device_observation_program_matches_numpy_formulas(emu):
+    """The device-evaluated observables equal the reference's formulas (fruitfly.py:674-684, base.py:245-268)
+    evaluated in numpy on the raw state record."""
+    from flybody_b200.fly_envs import mult_quat, reciprocal_quat
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=3, lib_path=emu)
+    env.reset()
+    rs = np.random.RandomState(3)
+    for _ in range(4):
+        ts = env.step(rs.uniform(-0.5, 0.5, (3, 59)))
+    sim, m = env._sim, env.model
+    raw = sim.read_obs()
+    lay = sim.obs_layout()
+    qpos, qvel = raw[:, lay['qpos']].astype(np.float64), raw[:, lay['qvel']].astype(np.float64)
+    xpos = raw[:, lay['root_xpos']].astype(np.float64)
+    xmat = raw[:, lay['root_xmat']].astype(np.float64).reshape(3, 3, 3)
+    sites = raw[:, lay['site_xpos']].astype(np.float64).reshape(3, -1, 3)
+    app = np.einsum('nsi,nij->nsj', sites[:, env._app_sites] - xpos[:, None], xmat).reshape(3, -1)
+    f = 65
+    idx = np.minimum(env._step_counter[:, None] + np.arange(f)[None], env._ref_qpos.shape[0] - 1)
+    ref = env._ref_qpos[idx]
+    disp = np.einsum('nfi,nij->nfj', ref[:, :, :3] - qpos[:, None, :3], xmat)
+    rq = mult_quat(np.broadcast_to(reciprocal_quat(qpos[:, 3:7])[:, None], (3, f, 4)), ref[:, :, 3:7])
+    o = ts.observation
+    assert np.allclose(o['walker/appendages_pos'], app, atol=2e-6)
+    assert np.allclose(o['walker/ref_displacement'], disp, atol=2e-6)
+    assert np.allclose(o['walker/ref_root_quat'], rq, atol=2e-6)
+    assert np.allclose(o['walker/joints_pos'], qpos[:, env._obs_qadr], atol=0)
+    assert np.allclose(o['walker/joints_vel'], qvel[:, env._obs_vadr], atol=0)
+    assert np.allclose(o['walker/world_zaxis'], xmat[:, 2, :], atol=1e-7)
+    sm = raw[:, lay['sensor_mean']]
+    assert np.allclose(o['walker/accelerometer'], sm[:, env._sd['accelerometer']], rtol=1e-6)
+    assert np.allclose(o['walker/force'], sm[:, env._sd['force']], rtol=1e-6, atol=1e-9)
+    assert np.allclose(o['walker/touch'], sm[:, env._sd['touch']], rtol=1e-6, atol=1e-9)
