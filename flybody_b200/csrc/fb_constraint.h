@@ -361,7 +361,7 @@ FB_DEV void kproj_p1(FB_ROW_ARGS) {
         if (lb == k) lb = m.dof_parentid[lb];
         if (in_chain(m, k, rr.la) || in_chain(m, k, rr.lb)) s += EJ(d.efc_Z, r, k) * EJ(d.efc_Z, c, k);
       }
-      EA(d.efc_A, r, c) = s; EA(d.efc_A, c, r) = s;
+      AT(d.efc_A, (size_t)r * (r + 1) / 2 + c) = s;      // packed lower triangle
     }
   }
 }
@@ -450,7 +450,6 @@ FB_DEV void kact_p3(FB_PHASE_ARGS) {
 //   dlam = -(I + C A)^-1 (lam - f(lam)),   C = Hessian of s = E E^T,
 // solved through the small SPD system G = I + E^T A E (Cholesky), followed by the same exact line
 // search.  The minimiser is the one MuJoCo's primal Newton converges to (strictly convex problem).
-enum { W_LAM = 0, W_JAR = 1, W_F = 2, W_R = 3, W_U = 4, W_DL = 5, W_ADL = 6, W_P = 7 };
 FB_DEV int qcqp2(float* res, const float* A, const float* b, float d0, float d1, float r) {   // mju_QCQP2
   float A11 = A[0] * d0 * d0, A22 = A[3] * d1 * d1, A12 = A[1] * d0 * d1, b1 = b[0] * d0, b2 = b[1] * d1;
   float la = 0, v1 = 0, v2 = 0;

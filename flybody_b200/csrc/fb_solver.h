@@ -1,108 +1,96 @@
-// fb_solver.h -- block-cooperative version of the constraint solve (K11).
+// fb_solver.h -- K11 constraint solve, one WARP per environment.
 //
-// blockDim = (32 envs, FB_SOLVE_Y).  lane == env as everywhere else; the FB_SOLVE_Y threads that
-// share a lane split the rows of that env's dual problem (matrix-vector products with the Delassus
-// matrix, the Hessian-factor assembly, Cholesky columns, line-search partial sums) and meet at block
-// barriers.  Control flow is block-uniform: loops run to the block-wide maximum trip count and envs
-// that are already converged idle through the barriers.
+// Thread mapping: blockDim = (32, FB_SOLVE_WPB); warp (threadIdx.y) owns one env, its 32 lanes split the
+// rows of that env's dual problem (rows of the Delassus matrix-vector products, columns of the Hessian
+// factor, line-search partial sums).  Every env therefore runs exactly its own number of Newton
+// iterations on its own problem size -- no divergence between envs -- and synchronisation is
+// __syncwarp only.  The working set of an env (row constants, 12 work vectors, the packed Delassus
+// matrix A and the packed Hessian factor G) lives in the warp's slice of shared memory when
+// nefc <= FB_SOLVE_NCAP (the common case); larger problems run the same code on the global arrays.
 //
-// The code is written as a sequence of PAR sections (each ends in a barrier); on the GPU every thread
-// executes the uniform code between sections redundantly, in the host emulation a PAR section is a
-// loop over (y, lane).  Per-env scalars therefore live in shared memory (sh.sc / sh.isc).
+// Math (see DESIGN.md "Solver"): with a = qacc_smooth + M^-1 J^T lam the primal cost of MuJoCo's Newton
+// solver becomes  c(lam) = 1/2 lam^T A lam + s(b + A lam),  A = J M^-1 J^T,  b = J qacc_smooth - aref,
+// s = per-row cost (half-quadratic for limits / frictionless contacts, three-zone elliptic cone for
+// frictional contacts).  Primal Newton steps map to  dlam = -(I + C A)^-1 (lam - f(lam)),  C = Hess s =
+// E E^T, solved through the SPD system G = I + E^T A E (Cholesky) + the same exact line search.
+//
+// Written as WPAR sections (each ends in a warp barrier); code between sections is warp-uniform and is
+// executed redundantly by all lanes on the GPU / once by the host emulation, where a WPAR section is a
+// loop over the 32 lanes.
 #pragma once
 #include "fb_constraint.h"
 
-#define FB_SOLVE_Y 16
+#define FB_SOLVE_WPB 8          // warps (envs) per block
+#define FB_SOLVE_NCAP 32        // rows that fit the shared-memory slice
 
-struct ShSolve {
-  float red[FB_SOLVE_Y][4][32];
-  float sc[20][32];
-  int isc[8][32];
-};
-enum { SC_COST = 0, SC_QUAD, SC_Q1, SC_Q2, SC_ALPHA, SC_LO, SC_HI, SC_G0, SC_CBEST, SC_DIAG, SC_COSTWS, SC_COST0, SC_RR, SC_LL, SC_CPREV };
-enum { I_N = 0, I_NC, I_DONE, I_ITER, I_LSDONE };
-// extra solver vectors (beyond W_LAM..W_P of fb_constraint.h) live in efc_w2
-enum { X_E0 = 8, X_E1, X_XQ, X_OUT,
+enum { W_LAM = 0, W_JAR, W_F, W_R, W_U, W_DL, W_ADL, W_P, X_E0, X_E1, X_XQ, X_OUT,
        // row constants staged once per solve (so the Newton phases never chase global metadata)
        S_D, S_B, S_R, S_TYPE /* 0 plain, 1 elliptic head, 2 elliptic tail */, S_MU, S_F1, S_F2, S_LA, S_LB,
        S_STATE, S_COLIDX, S_ECROW, S_ECKIND, S_NSLOT };
-// solver vectors: 12 slots (W_LAM..W_P = 0..7, X_* = 8..11).  When they fit, they live in shared memory
-// ([slot][row][lane], row stride = block-wide max nefc); otherwise in the global efc_w / efc_w2 arrays.
-struct SolveCtx { float* vsh; int vstride; float* gsh; int gcap; int gmode; float* ash; int amode; };
-#define FB_SOLVE_DYN_FLOATS (190 * 256)
-#define SWG(slot, r) ((slot) < 8 ? &AT(d.efc_w, (slot) * FB_MAXEFC + (r)) : &AT(d.efc_w2, ((slot) - 8) * FB_MAXEFC + (r)))
-#define SW(slot, r) (*(cx.vsh ? &cx.vsh[((slot) * cx.vstride + (r)) * 32 + lane] : SWG(slot, r)))
-// Delassus matrix: packed lower triangle in shared memory when it fits, else the global array
 #define TRI(r, c) ((r) * ((r) + 1) / 2 + (c))
-#define AM(r, c) (cx.amode ? cx.ash[((r) >= (c) ? TRI(r, c) : TRI(c, r)) * 32 + lane] : EA(d.efc_A, r, c))
-#define GM(p, q) (*(cx.gmode ? &cx.gsh[((p) * cx.gcap + (q)) * 32 + lane] : &EA(d.efc_G, p, q)))
-#define ESTATE(r) SW(S_STATE, r)
-#define ECOLIDX(r) SW(S_COLIDX, r)
-#define ECROW(p) SW(S_ECROW, p)
-#define ECKIND(p) SW(S_ECKIND, p)
+#define FB_SOLVE_WARP_FLOATS (S_NSLOT * FB_SOLVE_NCAP + 2 * TRI(FB_SOLVE_NCAP, 0) + 4 * 32)
+
+// memory of one env's problem: base pointers + element strides (1 in shared memory, Np in global memory)
+struct SolveMem { float* v; int vcap, vs; float* A; int as; float* G; int gs; float* red; };
+#define SV(slot, r) sm.v[(size_t)((slot) * sm.vcap + (r)) * sm.vs]
+#define AM(r, c) sm.A[(size_t)((r) >= (c) ? TRI(r, c) : TRI(c, r)) * sm.as]
+#define GM(p, q) sm.G[(size_t)TRI(p, q) * sm.gs]        // p >= q
+#define RED(k, l) sm.red[(k) * 32 + (l)]
 
 #ifdef __CUDACC__
-#define PAR_BEGIN { const int lane = threadIdx.x, y = threadIdx.y; const int e = blk * 32 + lane; (void)y; (void)e; (void)lane;
-#define PAR_END } __syncthreads();
-#define FB_BLOCKFN __device__ __noinline__
+#define WPAR_BEGIN { const int lane = threadIdx.x;
+#define WPAR_END } __syncwarp();
 #else
-#define PAR_BEGIN for (int y = 0; y < FB_SOLVE_Y; y++) for (int lane = 0; lane < 32; lane++) { const int e = blk * 32 + lane; (void)e;
-#define PAR_END }
-#define FB_BLOCKFN static
+#define WPAR_BEGIN for (int lane = 0; lane < 32; lane++) {
+#define WPAR_END }
 #endif
-#define MY_N (sh.isc[I_N][lane])
-#define ACTIVE (!sh.isc[I_DONE][lane])
+#define WROWS for (int r = lane; r < n; r += 32)
+FB_DEV float red_total(const SolveMem& sm, int k) { float s = 0; for (int l = 0; l < 32; l++) s += RED(k, l); return s; }
+#define IS_HEAD(r) (SV(S_TYPE, r) < 1.5f)
 
-FB_DEV float red_sum(const ShSolve& sh, int k, int lane) { float s_ = 0; for (int yy = 0; yy < FB_SOLVE_Y; yy++) s_ += sh.red[yy][k][lane]; return s_; }
-// block-uniform helpers (read shared after a barrier)
-FB_DEV int blk_max_i(const ShSolve& sh, int slot) { int v = 0; for (int l = 0; l < 32; l++) v = sh.isc[slot][l] > v ? sh.isc[slot][l] : v; return v; }
-FB_DEV int blk_any_active(const ShSolve& sh) { int v = 0; for (int l = 0; l < 32; l++) v |= !sh.isc[I_DONE][l]; return v; }
-FB_DEV int blk_any_ls(const ShSolve& sh) { int v = 0; for (int l = 0; l < 32; l++) v |= (!sh.isc[I_DONE][l] && !sh.isc[I_LSDONE][l]); return v; }
-
-// forces / cost of the rows headed at r (a non-elliptic row, or the first row of an elliptic contact).
-// Returns the cost; writes W_F; with build: state + E values.
-FB_DEV float head_update(const DevModel& m, const DevData& d, const SolveCtx& cx, int lane, int e, int r, bool build) {
-  int tp = (int)SW(S_TYPE, r);
-  float jar = SW(W_JAR, r), D = SW(S_D, r), cost = 0;
+// forces / cost of the rows headed at r (a plain row, or the first row of an elliptic contact)
+FB_DEV float head_update(const SolveMem& sm, int r, bool build) {
+  int tp = (int)SV(S_TYPE, r);
+  float jar = SV(W_JAR, r), D = SV(S_D, r), cost = 0;
   if (tp == 0) {
-    if (jar < 0) { SW(W_F, r) = -D * jar; cost = 0.5f * D * jar * jar; if (build) { ESTATE(r) = 1; SW(X_E0, r) = sqrtf(D); } }
-    else { SW(W_F, r) = 0; if (build) ESTATE(r) = 0; }
+    if (jar < 0) { SV(W_F, r) = -D * jar; cost = 0.5f * D * jar * jar; if (build) { SV(S_STATE, r) = 1; SV(X_E0, r) = sqrtf(D); } }
+    else { SV(W_F, r) = 0; if (build) SV(S_STATE, r) = 0; }
     return cost;
   }
-  float mu = SW(S_MU, r), f1 = SW(S_F1, r), f2 = SW(S_F2, r);
-  float j1 = SW(W_JAR, r + 1), j2 = SW(W_JAR, r + 2), D1 = SW(S_D, r + 1), D2 = SW(S_D, r + 2);
+  float mu = SV(S_MU, r), f1 = SV(S_F1, r), f2 = SV(S_F2, r);
+  float j1 = SV(W_JAR, r + 1), j2 = SV(W_JAR, r + 2), D1 = SV(S_D, r + 1), D2 = SV(S_D, r + 2);
   float U0 = jar * mu, U1 = j1 * f1, U2 = j2 * f2, N = U0, T = sqrtf(U1 * U1 + U2 * U2);
-  if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-    SW(W_F, r) = -D * jar; SW(W_F, r + 1) = -D1 * j1; SW(W_F, r + 2) = -D2 * j2;
+  if (mu * N + T <= 0 || (T <= 0 && N < 0)) {             // bottom zone: quadratic
+    SV(W_F, r) = -D * jar; SV(W_F, r + 1) = -D1 * j1; SV(W_F, r + 2) = -D2 * j2;
     cost = 0.5f * (D * jar * jar + D1 * j1 * j1 + D2 * j2 * j2);
-    if (build) { ESTATE(r) = 1; ESTATE(r + 1) = 1; ESTATE(r + 2) = 1; SW(X_E0, r) = sqrtf(D); SW(X_E0, r + 1) = sqrtf(D1); SW(X_E0, r + 2) = sqrtf(D2); }
-  } else if (N >= mu * T || (T <= 0 && N >= 0)) {
-    SW(W_F, r) = 0; SW(W_F, r + 1) = 0; SW(W_F, r + 2) = 0;
-    if (build) { ESTATE(r) = 0; ESTATE(r + 1) = 0; ESTATE(r + 2) = 0; }
-  } else {
+    if (build) { SV(S_STATE, r) = 1; SV(S_STATE, r + 1) = 1; SV(S_STATE, r + 2) = 1; SV(X_E0, r) = sqrtf(D); SV(X_E0, r + 1) = sqrtf(D1); SV(X_E0, r + 2) = sqrtf(D2); }
+  } else if (N >= mu * T || (T <= 0 && N >= 0)) {          // top zone: satisfied
+    SV(W_F, r) = 0; SV(W_F, r + 1) = 0; SV(W_F, r + 2) = 0;
+    if (build) { SV(S_STATE, r) = 0; SV(S_STATE, r + 1) = 0; SV(S_STATE, r + 2) = 0; }
+  } else {                                                  // middle zone: cone
     float Dm = D / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
     cost = 0.5f * Dm * NmT * NmT;
     float f0 = -Dm * NmT * mu;
-    SW(W_F, r) = f0; SW(W_F, r + 1) = -f0 / T * U1 * f1; SW(W_F, r + 2) = -f0 / T * U2 * f2;
+    SV(W_F, r) = f0; SV(W_F, r + 1) = -f0 / T * U1 * f1; SV(W_F, r + 2) = -f0 / T * U2 * f2;
     if (build) {
+      // C = Dm [ (S g)(S g)^T + (-f mu / T)(S t)(S t)^T ],  g = (1, -mu U1/T, -mu U2/T), t = (0, -U2, U1)/T
       float sD = sqrtf(Dm), k2 = sqrtf(fmaxf(0.0f, Dm * (-NmT) * mu / T));
-      ESTATE(r) = 2; ESTATE(r + 1) = 3; ESTATE(r + 2) = 3;
-      SW(X_E0, r) = sD * mu; SW(X_E0, r + 1) = -sD * f1 * mu * U1 / T; SW(X_E0, r + 2) = -sD * f2 * mu * U2 / T;
-      SW(X_E1, r) = 0; SW(X_E1, r + 1) = -k2 * f1 * U2 / T; SW(X_E1, r + 2) = k2 * f2 * U1 / T;
+      SV(S_STATE, r) = 2; SV(S_STATE, r + 1) = 3; SV(S_STATE, r + 2) = 3;
+      SV(X_E0, r) = sD * mu; SV(X_E0, r + 1) = -sD * f1 * mu * U1 / T; SV(X_E0, r + 2) = -sD * f2 * mu * U2 / T;
+      SV(X_E1, r) = 0; SV(X_E1, r + 1) = -k2 * f1 * U2 / T; SV(X_E1, r + 2) = k2 * f2 * U1 / T;
     }
   }
   return cost;
 }
-#define IS_HEAD(r) (SW(S_TYPE, r) < 1.5f)
-// line-search contribution of the rows headed at r
-FB_DEV void head_ls(const DevModel& m, const DevData& d, const SolveCtx& cx, int lane, int e, int r, float alpha, float& c, float& g, float& h) {
-  int tp = (int)SW(S_TYPE, r);
-  float jv = SW(W_ADL, r), x = SW(W_JAR, r) + alpha * jv, D = SW(S_D, r);
+// line-search contribution (value, 1st, 2nd derivative) of the rows headed at r
+FB_DEV void head_ls(const SolveMem& sm, int r, float alpha, float& c, float& g, float& h) {
+  int tp = (int)SV(S_TYPE, r);
+  float jv = SV(W_ADL, r), x = SV(W_JAR, r) + alpha * jv, D = SV(S_D, r);
   if (tp == 0) { if (x < 0) { c += 0.5f * D * x * x; g += D * x * jv; h += D * jv * jv; } return; }
-  float mu = SW(S_MU, r), f1 = SW(S_F1, r), f2 = SW(S_F2, r);
-  float jv1 = SW(W_ADL, r + 1), jv2 = SW(W_ADL, r + 2);
-  float x1 = SW(W_JAR, r + 1) + alpha * jv1, x2 = SW(W_JAR, r + 2) + alpha * jv2;
-  float D1 = SW(S_D, r + 1), D2 = SW(S_D, r + 2);
+  float mu = SV(S_MU, r), f1 = SV(S_F1, r), f2 = SV(S_F2, r);
+  float jv1 = SV(W_ADL, r + 1), jv2 = SV(W_ADL, r + 2);
+  float x1 = SV(W_JAR, r + 1) + alpha * jv1, x2 = SV(W_JAR, r + 2) + alpha * jv2;
+  float D1 = SV(S_D, r + 1), D2 = SV(S_D, r + 2);
   float U0 = x * mu, U1 = x1 * f1, U2 = x2 * f2, dU0 = jv * mu, dU1 = jv1 * f1, dU2 = jv2 * f2;
   float N = U0, T = sqrtf(U1 * U1 + U2 * U2);
   if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
@@ -116,190 +104,162 @@ FB_DEV void head_ls(const DevModel& m, const DevData& d, const SolveCtx& cx, int
     c += 0.5f * Dm * f * f; g += Dm * f * fp; h += Dm * (fp * fp + f * fpp);
   }
 }
-// column p of E: value on row `row` (0 if the column does not touch it)
-FB_DEV float ecol_val(const DevData& d, const SolveCtx& cx, int lane, int e, int p, int a) {   // a-th entry of column p
-  int kind = (int)ECKIND(p), r = (int)ECROW(p);
-  return kind == 2 ? SW(X_E1, r + a) : SW(X_E0, r + a);
+FB_DEV float ecol_val(const SolveMem& sm, int p, int a) {   // a-th entry of column p of E
+  int kind = (int)SV(S_ECKIND, p), r = (int)SV(S_ECROW, p);
+  return kind == 2 ? SV(X_E1, r + a) : SV(X_E0, r + a);
 }
 
-#define ROWS_BEGIN for (int r = y; r < MY_N; r += FB_SOLVE_Y) {
-#define ROWS_END }
-// sum the per-thread partials of slot k into per-env scalar `dst` (call inside a y==0 guard)
-#define RED_SUM(k) red_sum(sh, k, lane)
+#ifdef __CUDACC__
+#define FB_WARPFN __device__ __noinline__
+#else
+#define FB_WARPFN static
+#endif
 
-FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, int blk) {
+// one env; `wsm` = this warp's shared-memory slice (FB_SOLVE_WARP_FLOATS floats)
+FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int e) {
+  const int n = AT(d.nefc, 0);
   const float scale = 1.0f / (m.meaninertia * (m.nv > 1 ? m.nv : 1));
-  PAR_BEGIN
-    if (y == 0) { int n = AT(d.nefc, 0); sh.isc[I_N][lane] = n; sh.isc[I_DONE][lane] = (n == 0); sh.isc[I_ITER][lane] = 0; sh.isc[I_NC][lane] = 0; sh.isc[I_LSDONE][lane] = 1; }
-  PAR_END
-  SolveCtx cx; cx.vsh = nullptr; cx.vstride = 0; cx.gsh = nullptr; cx.gcap = 0; cx.gmode = 0; cx.ash = nullptr; cx.amode = 0;
-  if (blk_max_i(sh, I_N) > 0) {
-    {
-      int nmaxb = blk_max_i(sh, I_N);
-      float* dyn = sh_dyn(sh);
-      int rem = m.solve_dyn_floats / 32;          // floats per lane: vectors first, then A (packed), then G
-      if (S_NSLOT * nmaxb <= rem) {
-        cx.vsh = dyn; cx.vstride = nmaxb; rem -= S_NSLOT * nmaxb; dyn += (size_t)S_NSLOT * nmaxb * 32;
-        int tri = nmaxb * (nmaxb + 1) / 2;
-        if (tri <= rem) { cx.ash = dyn; cx.amode = 1; rem -= tri; dyn += (size_t)tri * 32; }
-        int g = 0; while ((g + 1) * (g + 1) <= rem) g++;
-        cx.gsh = dyn; cx.gcap = g;
-      }
-    }
-    // ---------------- stage row constants (and A) into shared memory
-    PAR_BEGIN ROWS_BEGIN
+  SolveMem sm;
+  sm.red = wsm;
+  if (n <= m.solve_ncap) {
+    sm.v = wsm + 4 * 32; sm.vcap = FB_SOLVE_NCAP; sm.vs = 1;
+    sm.A = sm.v + S_NSLOT * FB_SOLVE_NCAP; sm.as = 1;
+    sm.G = sm.A + TRI(FB_SOLVE_NCAP, 0); sm.gs = 1;
+  } else {   // large problem: same code on the global arrays (element stride = padded env count)
+    sm.v = d.efc_w + e; sm.vcap = FB_MAXEFC; sm.vs = d.Np;
+    sm.A = d.efc_A + e; sm.as = d.Np;
+    sm.G = d.efc_G + e; sm.gs = d.Np;
+  }
+  int niter = 0;
+  if (n > 0) {
+    // ---- stage row constants (and A) next to the work vectors
+    WPAR_BEGIN WROWS {
       int tp = EFC(d.efc_type, r), tcode = 0; float mu = 0, f1 = 0, f2 = 0;
       if (tp == FB_CT_ELLIPTIC) { int ci = EFC(d.efc_id, r); tcode = (AT(d.con_efcadr, ci) == r) ? 1 : 2; mu = AT(d.con_mu, ci); f1 = CON_F(d.con_fric, ci, 0, 2); f2 = CON_F(d.con_fric, ci, 1, 2); }
-      SW(S_TYPE, r) = (float)tcode; SW(S_MU, r) = mu; SW(S_F1, r) = f1; SW(S_F2, r) = f2;
-      SW(S_D, r) = EFC(d.efc_D, r); SW(S_B, r) = EFC(d.efc_b, r); SW(S_R, r) = EFC(d.efc_R, r);
-      SW(S_LA, r) = (float)AT(d.efc_la, r); SW(S_LB, r) = (float)AT(d.efc_lb, r);
-      if (cx.amode) for (int c = 0; c <= r; c++) cx.ash[TRI(r, c) * 32 + lane] = EA(d.efc_A, r, c);
-    ROWS_END PAR_END
-    // ---------------- warm start
-    PAR_BEGIN float c = 0; ROWS_BEGIN SW(W_JAR, r) = EFC(d.efc_jarws, r); ROWS_END sh.red[y][0][lane] = c; PAR_END
-    PAR_BEGIN ROWS_BEGIN if (IS_HEAD(r)) head_update(m, d, cx, lane, e, r, false); ROWS_END PAR_END
-    PAR_BEGIN ROWS_BEGIN SW(W_LAM, r) = SW(W_F, r); ROWS_END PAR_END
-    PAR_BEGIN float q = 0; int n = MY_N;
-      ROWS_BEGIN float s = SW(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; q += 0.5f * SW(W_LAM, r) * (s - SW(S_B, r)); ROWS_END
-      sh.red[y][0][lane] = q; PAR_END
-    PAR_BEGIN float c = 0; ROWS_BEGIN if (IS_HEAD(r)) c += head_update(m, d, cx, lane, e, r, false); ROWS_END sh.red[y][1][lane] = c; PAR_END
-    PAR_BEGIN if (y == 0) sh.sc[SC_COSTWS][lane] = RED_SUM(0) + RED_SUM(1); ROWS_BEGIN SW(W_JAR, r) = SW(S_B, r); ROWS_END PAR_END
-    PAR_BEGIN float c = 0; ROWS_BEGIN if (IS_HEAD(r)) c += head_update(m, d, cx, lane, e, r, false); ROWS_END sh.red[y][0][lane] = c; PAR_END
-    PAR_BEGIN if (y == 0) sh.sc[SC_COST0][lane] = RED_SUM(0); PAR_END
-    PAR_BEGIN if (!(sh.sc[SC_COSTWS][lane] < sh.sc[SC_COST0][lane])) { ROWS_BEGIN SW(W_LAM, r) = 0; ROWS_END } PAR_END
-    // ---------------- Newton iterations
-    for (int iter = 0; iter < m.max_iter; iter++) {
-      if (!blk_any_active(sh)) break;
-      // jar = b + A lam
-      PAR_BEGIN float q = 0; int n = MY_N;
-        if (ACTIVE) { ROWS_BEGIN float s = SW(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; q += 0.5f * SW(W_LAM, r) * (s - SW(S_B, r)); ROWS_END }
-        sh.red[y][0][lane] = q; PAR_END
-      PAR_BEGIN float c = 0; if (ACTIVE) { ROWS_BEGIN if (IS_HEAD(r)) c += head_update(m, d, cx, lane, e, r, true); ROWS_END } sh.red[y][1][lane] = c; PAR_END
-      // residual r = lam - f, column bookkeeping (sequential prefix over rows by y == 0)
-      PAR_BEGIN float rr = 0, ll = 0;
-        if (ACTIVE) { ROWS_BEGIN float f = SW(W_F, r), rv = SW(W_LAM, r) - f; SW(W_R, r) = rv; rr += rv * rv; ll += f * f; ROWS_END }
-        sh.red[y][2][lane] = rr; sh.red[y][3][lane] = ll;
-        if (y == 0 && ACTIVE) {
-          sh.sc[SC_QUAD][lane] = RED_SUM(0); sh.sc[SC_COST][lane] = RED_SUM(0) + RED_SUM(1);
-          int n = MY_N, nc = 0;
-          for (int r = 0; r < n; r++) {
-            int stt = (int)ESTATE(r);
-            if (stt == 1) { ECOLIDX(r) = nc; ECROW(nc) = r; ECKIND(nc) = 0; nc++; }
-            else if (stt == 2) { ECOLIDX(r) = nc; ECOLIDX(r + 1) = nc; ECOLIDX(r + 2) = nc; ECROW(nc) = r; ECKIND(nc) = 1; ECROW(nc + 1) = r; ECKIND(nc + 1) = 2; nc += 2; }
-            else if (stt == 0) ECOLIDX(r) = -1;
-          }
-          sh.isc[I_NC][lane] = nc;
-        }
-      PAR_END
-      PAR_BEGIN if (y == 0 && ACTIVE) { float rr = RED_SUM(2), ll = RED_SUM(3); if (rr <= 1e-12f * (ll + 1e-30f)) sh.isc[I_DONE][lane] = 1; } PAR_END
-      if (!blk_any_active(sh)) break;
-      // u = A r
-      PAR_BEGIN int n = MY_N; if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_R, j); SW(W_U, r) = s; ROWS_END } PAR_END
-      int ncmax = 0; for (int l = 0; l < 32; l++) if (!sh.isc[I_DONE][l] && sh.isc[I_NC][l] > ncmax) ncmax = sh.isc[I_NC][l];
-      cx.gmode = (cx.gsh != nullptr && ncmax <= cx.gcap) ? 1 : 0;
-      // p = E^T u ; G = I + E^T A E (lower triangle)
-      PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
-        for (int p = y; p < nc; p += FB_SOLVE_Y) {
-          int rp = (int)ECROW(p), np = ECKIND(p) == 0 ? 1 : 3;
-          float pv = 0; for (int a = 0; a < np; a++) pv += ecol_val(d, cx, lane, e, p, a) * SW(W_U, rp + a);
-          SW(W_P, p) = pv;
-          for (int q = 0; q <= p; q++) {
-            int rq = (int)ECROW(q), nq = ECKIND(q) == 0 ? 1 : 3;
-            float s = (p == q) ? 1.0f : 0.0f;
-            for (int a = 0; a < np; a++) { float va = ecol_val(d, cx, lane, e, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * AM(rp + a, rq + bb) * ecol_val(d, cx, lane, e, q, bb); }
-            GM(p, q) = s;
-          }
-        } }
-      PAR_END
-      // Cholesky G = L L^T (left-looking, two barriers per column), then the two triangular solves
-      for (int j = 0; j < ncmax; j++) {
-        PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
-          if (j < nc) for (int i = j + ((y - j % FB_SOLVE_Y + FB_SOLVE_Y) % FB_SOLVE_Y); i < nc; i += FB_SOLVE_Y) {
-            float t = GM(i, j); for (int k = 0; k < j; k++) t -= GM(i, k) * GM(j, k);
-            GM(i, j) = t; if (i == j) sh.sc[SC_DIAG][lane] = sqrtf(fmaxf(t, 1e-12f));
-          } }
-        PAR_END
-        PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane]; float dg = sh.sc[SC_DIAG][lane];
-          if (j < nc) for (int i = j + ((y - j % FB_SOLVE_Y + FB_SOLVE_Y) % FB_SOLVE_Y); i < nc; i += FB_SOLVE_Y) GM(i, j) = (i == j) ? dg : GM(i, j) / dg; }
-        PAR_END
-      }
-      for (int j = 0; j < ncmax; j++) {     // forward: L xq = p
-        PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
-          if (j < nc) { float xj = SW(W_P, j) / GM(j, j);
-            for (int i = j + 1 + ((y - (j + 1) % FB_SOLVE_Y + FB_SOLVE_Y) % FB_SOLVE_Y); i < nc; i += FB_SOLVE_Y) SW(W_P, i) -= GM(i, j) * xj;
-            if (y == 0) SW(X_XQ, j) = xj; } }
-        PAR_END
-      }
-      for (int j = ncmax - 1; j >= 0; j--) {   // backward: L^T out = xq
-        PAR_BEGIN if (ACTIVE) { int nc = sh.isc[I_NC][lane];
-          if (j < nc) { float xj = SW(X_XQ, j) / GM(j, j);
-            for (int i = y; i < j; i += FB_SOLVE_Y) SW(X_XQ, i) -= GM(j, i) * xj;
-            if (y == 0) SW(X_OUT, j) = xj; } }
-        PAR_END
-      }
-      // dlam = -r + E q
-      PAR_BEGIN if (ACTIVE) { ROWS_BEGIN
-          float v = -SW(W_R, r); int stt = (int)ESTATE(r), c0 = (int)ECOLIDX(r);
-          if (stt == 1) v += SW(X_E0, r) * SW(X_OUT, c0);
-          else if (stt >= 2) v += SW(X_E0, r) * SW(X_OUT, c0) + SW(X_E1, r) * SW(X_OUT, c0 + 1);
-          SW(W_DL, r) = v;
-        ROWS_END } PAR_END
-      // A dlam, q1, q2
-      PAR_BEGIN float q1 = 0, q2 = 0; int n = MY_N;
-        if (ACTIVE) { ROWS_BEGIN float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_DL, j); SW(W_ADL, r) = s;
-          q1 += SW(W_DL, r) * (SW(W_JAR, r) - SW(S_B, r)); q2 += 0.5f * SW(W_DL, r) * s; ROWS_END }
-        sh.red[y][0][lane] = q1; sh.red[y][1][lane] = q2; PAR_END
-      PAR_BEGIN if (y == 0 && ACTIVE) { sh.sc[SC_Q1][lane] = RED_SUM(0); sh.sc[SC_Q2][lane] = RED_SUM(1); sh.sc[SC_ALPHA][lane] = 0; sh.sc[SC_LO][lane] = 0; sh.sc[SC_HI][lane] = -1; sh.isc[I_LSDONE][lane] = 0; } PAR_END
-      // exact line search: evaluation 0 at alpha = 0, then safeguarded Newton on the derivative
-      for (int ls = 0; ls <= m.ls_iter; ls++) {
-        if (!blk_any_ls(sh)) break;
-        PAR_BEGIN float c = 0, g = 0, h = 0;
-          if (ACTIVE && !sh.isc[I_LSDONE][lane]) { float alpha = sh.sc[SC_ALPHA][lane]; ROWS_BEGIN if (IS_HEAD(r)) head_ls(m, d, cx, lane, e, r, alpha, c, g, h); ROWS_END }
-          sh.red[y][0][lane] = c; sh.red[y][1][lane] = g; sh.red[y][2][lane] = h; PAR_END
-        PAR_BEGIN if (y == 0 && ACTIVE && !sh.isc[I_LSDONE][lane]) {
-          float alpha = sh.sc[SC_ALPHA][lane], quad = sh.sc[SC_QUAD][lane], q1 = sh.sc[SC_Q1][lane], q2 = sh.sc[SC_Q2][lane];
-          float c = quad + alpha * q1 + alpha * alpha * q2 + RED_SUM(0), g = q1 + 2 * alpha * q2 + RED_SUM(1), h = 2 * q2 + RED_SUM(2);
-          if (ls == 0) {
-            sh.sc[SC_G0][lane] = g; sh.sc[SC_CBEST][lane] = c;
-            if (!(g < 0) || !(h > 0)) { sh.isc[I_LSDONE][lane] = 1; sh.isc[I_DONE][lane] = 1; sh.sc[SC_ALPHA][lane] = 0; }
-            else sh.sc[SC_ALPHA][lane] = -g / h;
-          } else {
-            sh.sc[SC_CBEST][lane] = c;
-            float g0 = sh.sc[SC_G0][lane], lo = sh.sc[SC_LO][lane], hi = sh.sc[SC_HI][lane];
-            if (fabsf(g) < 1e-6f * fabsf(g0) || ls == m.ls_iter) sh.isc[I_LSDONE][lane] = 1;
-            else {
-              if (g < 0) lo = alpha; else hi = alpha;
-              float na = alpha - g / h;
-              if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
-              else if (hi < 0 && na <= lo) na = 2 * alpha;
-              if (fabsf(na - alpha) <= 1e-7f * fabsf(alpha)) sh.isc[I_LSDONE][lane] = 1;
-              sh.sc[SC_ALPHA][lane] = na; sh.sc[SC_LO][lane] = lo; sh.sc[SC_HI][lane] = hi;
-            }
-          } }
-        PAR_END
-      }
-      PAR_BEGIN if (ACTIVE) { float alpha = sh.sc[SC_ALPHA][lane]; ROWS_BEGIN SW(W_LAM, r) += alpha * SW(W_DL, r); ROWS_END } PAR_END
-      PAR_BEGIN if (y == 0 && ACTIVE) { sh.isc[I_ITER][lane] = iter + 1; float imp = scale * (sh.sc[SC_COST][lane] - sh.sc[SC_CBEST][lane]); if (imp < m.tolerance) sh.isc[I_DONE][lane] = 1; } PAR_END
+      SV(S_TYPE, r) = (float)tcode; SV(S_MU, r) = mu; SV(S_F1, r) = f1; SV(S_F2, r) = f2;
+      SV(S_D, r) = EFC(d.efc_D, r); SV(S_B, r) = EFC(d.efc_b, r); SV(S_R, r) = EFC(d.efc_R, r);
+      SV(S_LA, r) = (float)AT(d.efc_la, r); SV(S_LB, r) = (float)AT(d.efc_lb, r);
+      SV(W_JAR, r) = EFC(d.efc_jarws, r);
     }
-    // ---------------- forces at the solution
-    PAR_BEGIN int n = MY_N; ROWS_BEGIN float s = SW(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SW(W_LAM, j); SW(W_JAR, r) = s; ROWS_END PAR_END
-    PAR_BEGIN ROWS_BEGIN if (IS_HEAD(r)) head_update(m, d, cx, lane, e, r, false); ROWS_END PAR_END
-    // ---------------- noslip: inherently sequential Gauss-Seidel over the friction rows (y == 0), on W_F
+    if (sm.as == 1) { int nt = TRI(n, 0); for (int k = lane; k < nt; k += 32) sm.A[k] = AT(d.efc_A, k); }
+    WPAR_END
+    // ---- warm start: forces implied by the previous qacc, kept if cheaper than lam = 0
+    WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update(sm, r, false); WPAR_END
+    WPAR_BEGIN WROWS SV(W_LAM, r) = SV(W_F, r); WPAR_END
+    WPAR_BEGIN float q = 0; WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; q += 0.5f * SV(W_LAM, r) * (s - SV(S_B, r)); } RED(0, lane) = q; WPAR_END
+    WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update(sm, r, false); RED(1, lane) = c; WPAR_END
+    float cost_ws = red_total(sm, 0) + red_total(sm, 1);
+    WPAR_BEGIN WROWS SV(W_JAR, r) = SV(S_B, r); WPAR_END
+    WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update(sm, r, false); RED(0, lane) = c; WPAR_END
+    float cost0 = red_total(sm, 0);
+    WPAR_BEGIN WPAR_END
+    if (!(cost_ws < cost0)) { WPAR_BEGIN WROWS SV(W_LAM, r) = 0; WPAR_END }
+    // ---- Newton iterations
+    for (int iter = 0; iter < m.max_iter; iter++) {
+      WPAR_BEGIN float q = 0; WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; q += 0.5f * SV(W_LAM, r) * (s - SV(S_B, r)); } RED(0, lane) = q; WPAR_END
+      WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update(sm, r, true); RED(1, lane) = c; WPAR_END
+      WPAR_BEGIN float rr = 0, ll = 0; WROWS { float f = SV(W_F, r), rv = SV(W_LAM, r) - f; SV(W_R, r) = rv; rr += rv * rv; ll += f * f; } RED(2, lane) = rr; RED(3, lane) = ll; WPAR_END
+      float quad = red_total(sm, 0), cost = quad + red_total(sm, 1);
+      float rr = red_total(sm, 2), ll = red_total(sm, 3);
+      WPAR_BEGIN WPAR_END              // all lanes have read RED before it is reused
+      if (rr <= 1e-12f * (ll + 1e-30f)) break;
+      // column bookkeeping (prefix over rows) by lane 0; nc is left in RED(0, 0)
+      WPAR_BEGIN if (lane == 0) { int nc = 0;
+        for (int r = 0; r < n; r++) { int stt = (int)SV(S_STATE, r);
+          if (stt == 1) { SV(S_COLIDX, r) = (float)nc; SV(S_ECROW, nc) = (float)r; SV(S_ECKIND, nc) = 0; nc++; }
+          else if (stt == 2) { SV(S_COLIDX, r) = (float)nc; SV(S_COLIDX, r + 1) = (float)nc; SV(S_COLIDX, r + 2) = (float)nc; SV(S_ECROW, nc) = (float)r; SV(S_ECKIND, nc) = 1; SV(S_ECROW, nc + 1) = (float)r; SV(S_ECKIND, nc + 1) = 2; nc += 2; }
+          else if (stt == 0) SV(S_COLIDX, r) = -1.0f; }
+        RED(0, 0) = (float)nc; }
+      WPAR_END
+      const int nc = (int)RED(0, 0);
+      // u = A r
+      WPAR_BEGIN WROWS { float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_R, j); SV(W_U, r) = s; } WPAR_END
+      // p = E^T u ; G = I + E^T A E (packed lower triangle)
+      WPAR_BEGIN for (int p = lane; p < nc; p += 32) {
+          int rp = (int)SV(S_ECROW, p), np = SV(S_ECKIND, p) == 0 ? 1 : 3;
+          float pv = 0; for (int a = 0; a < np; a++) pv += ecol_val(sm, p, a) * SV(W_U, rp + a);
+          SV(W_P, p) = pv;
+          for (int q = 0; q <= p; q++) {
+            int rq = (int)SV(S_ECROW, q), nq = SV(S_ECKIND, q) == 0 ? 1 : 3;
+            float s = (p == q) ? 1.0f : 0.0f;
+            for (int a = 0; a < np; a++) { float va = ecol_val(sm, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * AM(rp + a, rq + bb) * ecol_val(sm, q, bb); }
+            GM(p, q) = s;
+          } }
+      WPAR_END
+      // Cholesky G = L L^T, column by column; the forward substitution L y = p rides along (lane 0)
+      for (int j = 0; j < nc; j++) {
+        WPAR_BEGIN for (int i = j + lane; i < nc; i += 32) {
+            float t = GM(i, j); for (int k = 0; k < j; k++) t -= GM(i, k) * GM(j, k);
+            GM(i, j) = t; if (i == j) RED(1, 0) = sqrtf(fmaxf(t, 1e-12f)); }
+        WPAR_END
+        WPAR_BEGIN float dg = RED(1, 0);
+          for (int i = j + lane; i < nc; i += 32) GM(i, j) = (i == j) ? dg : GM(i, j) / dg;
+          if (lane == 0) { float yv = SV(W_P, j); for (int k = 0; k < j; k++) yv -= GM(j, k) * SV(X_XQ, k); SV(X_XQ, j) = yv / dg; }
+        WPAR_END
+      }
+      for (int j = nc - 1; j >= 0; j--) {     // backward: L^T out = y
+        WPAR_BEGIN float xj = SV(X_XQ, j) / GM(j, j);
+          for (int i = lane; i < j; i += 32) SV(X_XQ, i) -= GM(j, i) * xj;
+          if (lane == 0) SV(X_OUT, j) = xj;
+        WPAR_END
+      }
+      // dlam = -r + E q ;  A dlam ; quadratic coefficients of the Gauss term along dlam
+      WPAR_BEGIN WROWS { float v = -SV(W_R, r); int stt = (int)SV(S_STATE, r), c0 = (int)SV(S_COLIDX, r);
+          if (stt == 1) v += SV(X_E0, r) * SV(X_OUT, c0);
+          else if (stt >= 2) v += SV(X_E0, r) * SV(X_OUT, c0) + SV(X_E1, r) * SV(X_OUT, c0 + 1);
+          SV(W_DL, r) = v; }
+      WPAR_END
+      WPAR_BEGIN float q1 = 0, q2 = 0; WROWS { float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_DL, j); SV(W_ADL, r) = s;
+          q1 += SV(W_DL, r) * (SV(W_JAR, r) - SV(S_B, r)); q2 += 0.5f * SV(W_DL, r) * s; } RED(0, lane) = q1; RED(1, lane) = q2; WPAR_END
+      const float q1 = red_total(sm, 0), q2 = red_total(sm, 1);
+      WPAR_BEGIN WPAR_END
+      // exact line search: safeguarded Newton on the derivative of the 1-D cost
+      float alpha = 0, lo = 0, hi = -1, g0 = 0, cbest = cost; bool stop = false, nodescent = false;
+      for (int ls = 0; ls <= m.ls_iter && !stop; ls++) {
+        WPAR_BEGIN float c = 0, g = 0, h = 0; WROWS if (IS_HEAD(r)) head_ls(sm, r, alpha, c, g, h); RED(0, lane) = c; RED(1, lane) = g; RED(2, lane) = h; WPAR_END
+        float c = quad + alpha * q1 + alpha * alpha * q2 + red_total(sm, 0), g = q1 + 2 * alpha * q2 + red_total(sm, 1), h = 2 * q2 + red_total(sm, 2);
+        WPAR_BEGIN WPAR_END          // keep RED reads of all lanes ahead of the next section's writes
+        if (ls == 0) {
+          g0 = g;
+          if (!(g < 0) || !(h > 0)) { alpha = 0; stop = true; nodescent = true; }
+          else alpha = -g / h;
+        } else {
+          cbest = c;
+          if (fabsf(g) < 1e-6f * fabsf(g0) || ls == m.ls_iter) stop = true;
+          else {
+            if (g < 0) lo = alpha; else hi = alpha;
+            float na = alpha - g / h;
+            if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
+            else if (hi < 0 && na <= lo) na = 2 * alpha;
+            if (fabsf(na - alpha) <= 1e-7f * fabsf(alpha)) stop = true;
+            alpha = na;
+          }
+        }
+      }
+      if (nodescent) break;                               // converged to fp32 resolution
+      WPAR_BEGIN WROWS SV(W_LAM, r) += alpha * SV(W_DL, r); WPAR_END
+      niter = iter + 1;
+      if (scale * (cost - cbest) < m.tolerance) break;
+    }
+    // ---- forces at the solution: lam = f(b + A lam)
+    WPAR_BEGIN WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; } WPAR_END
+    WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update(sm, r, false); WPAR_END
+    // ---- noslip (MuJoCo mj_solNoSlip): sequential Gauss-Seidel over the friction rows with the unregularised A
     if (m.noslip_iterations > 0) {
-      PAR_BEGIN if (y == 0) { int n = MY_N; AT(d.niter, 0) = sh.isc[I_ITER][lane];
-        for (int it = 0; it < m.noslip_iterations && n > 0; it++) {
+      WPAR_BEGIN if (lane == 0) {
+        for (int it = 0; it < m.noslip_iterations; it++) {
           float improvement = 0;
-          if (it == 0) for (int i = 0; i < n; i++) improvement += 0.5f * SW(W_F, i) * SW(W_F, i) * SW(S_R, i);
+          if (it == 0) for (int i = 0; i < n; i++) improvement += 0.5f * SV(W_F, i) * SV(W_F, i) * SV(S_R, i);
           bool any = false;
           for (int i = 0; i < n; i++) {
-            if (SW(S_TYPE, i) < 0.5f) continue;
+            if (SV(S_TYPE, i) < 0.5f) continue;
             any = true;
-            float fn = SW(W_F, i), old0 = SW(W_F, i + 1), old1 = SW(W_F, i + 2);
+            float fn = SV(W_F, i), old0 = SV(W_F, i + 1), old1 = SV(W_F, i + 2);
             float res[2], Ac[4], bc[2], v[2];
-            for (int rr = 0; rr < 2; rr++) { float s = SW(S_B, i + 1 + rr); for (int j = 0; j < n; j++) s += AM(i + 1 + rr, j) * SW(W_F, j); res[rr] = s; }
-            Ac[0] = AM(i + 1, i + 1); Ac[1] = AM(i + 1, i + 2); Ac[2] = Ac[1]; Ac[3] = AM(i + 2, i + 2);
+            for (int rr2 = 0; rr2 < 2; rr2++) { float s = SV(S_B, i + 1 + rr2); for (int j = 0; j < n; j++) s += AM(i + 1 + rr2, j) * SV(W_F, j); res[rr2] = s; }
+            Ac[0] = AM(i + 1, i + 1); Ac[1] = AM(i + 2, i + 1); Ac[2] = Ac[1]; Ac[3] = AM(i + 2, i + 2);
             bc[0] = res[0] - Ac[0] * old0 - Ac[1] * old1; bc[1] = res[1] - Ac[2] * old0 - Ac[3] * old1;
-            float fr0 = SW(S_F1, i), fr1 = SW(S_F2, i);
+            float fr0 = SV(S_F1, i), fr1 = SV(S_F2, i);
             if (fn < FB_MINVAL) { v[0] = 0; v[1] = 0; }
             else {
               int active = qcqp2(v, Ac, bc, fr0, fr1, fn);
@@ -308,27 +268,28 @@ FB_BLOCKFN void ksolve_block(const DevModel& m, const DevData& d, ShSolve& sh, i
             float d0 = v[0] - old0, d1 = v[1] - old1;
             float change = 0.5f * (d0 * (Ac[0] * d0 + Ac[1] * d1) + d1 * (Ac[2] * d0 + Ac[3] * d1)) + d0 * res[0] + d1 * res[1];
             if (change > 1e-10f) { v[0] = old0; v[1] = old1; change = 0; }
-            SW(W_F, i + 1) = v[0]; SW(W_F, i + 2) = v[1];
+            SV(W_F, i + 1) = v[0]; SV(W_F, i + 2) = v[1];
             improvement -= change;
             i += 2;
           }
           if (!any) break;
           if (improvement * scale < m.noslip_tolerance) break;
         } }
-      PAR_END
+      WPAR_END
     }
-    PAR_BEGIN ROWS_BEGIN EFC(d.efc_force, r) = SW(W_F, r); ROWS_END if (y == 0) AT(d.niter, 0) = sh.isc[I_ITER][lane]; PAR_END
+    WPAR_BEGIN WROWS EFC(d.efc_force, r) = SV(W_F, r); WPAR_END
   }
-  // ---------------- qfrc_constraint = J^T f, gathered per dof (race free)
-  PAR_BEGIN int n = MY_N;
-    for (int k = y; k < m.nv; k += FB_SOLVE_Y) {
+  // ---- qfrc_constraint = J^T f, gathered per dof (race free)
+  WPAR_BEGIN
+    if (lane == 0) AT(d.niter, 0) = niter;
+    for (int k = lane; k < m.nv; k += 32) {
       float s = 0;
       for (int r = 0; r < n; r++) {
-        float f = SW(W_F, r);
+        float f = SV(W_F, r);
         if (f == 0.0f) continue;
-        if (in_chain(m, k, (int)SW(S_LA, r)) || in_chain(m, k, (int)SW(S_LB, r))) s += EJ(d.efc_J, r, k) * f;
+        if (in_chain(m, k, (int)SV(S_LA, r)) || in_chain(m, k, (int)SV(S_LB, r))) s += EJ(d.efc_J, r, k) * f;
       }
       AT(d.qfrc_constraint, k) = s;
     }
-  PAR_END
+  WPAR_END
 }

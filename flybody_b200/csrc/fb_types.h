@@ -27,7 +27,7 @@
 struct DevModel {
   // sizes / options
   int nq, nv, nu, na, nbody, njnt, ngeom, npair, nsite, ntendon, nwrap, nsensor, nsensordata, nM, nfluid;
-  int noslip_iterations, cone_elliptic, max_iter, ls_iter, solve_dyn_floats;
+  int noslip_iterations, cone_elliptic, max_iter, ls_iter, solve_ncap;
   float timestep, gravity[3], density, viscosity, wind[3], impratio, tolerance, noslip_tolerance, meaninertia;
   // tree partition
   int nroot, nlist;
@@ -88,7 +88,6 @@ struct DevData {
   float *efc_A, *efc_G;        // [MAXEFC*MAXEFC]
   float *efc_w;                // [8*MAXEFC] solver work vectors
   int *efc_ecol, *efc_ekind, *efc_state, *efc_colidx, *efc_la, *efc_lb;   // solver bookkeeping: E columns, row zones, row dof chains
-  float *efc_w2;               // [4*MAXEFC] more solver vectors
   // sensors / outputs
   float *sensordata, *sensor_sum;
   int *flags, *niter, *hold;   // hold != 0: env is not integrated by the next fb_step (pending reset)

@@ -111,37 +111,33 @@ static void fb_launch(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
 #endif
 
 #ifndef FB_EMU
-template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
-__global__ void fb_run_block(DevModel m, DevData d) {
-  extern __shared__ __align__(16) unsigned char fb_smem_b[];
-  F(m, d, *reinterpret_cast<Sh*>(fb_smem_b), blockIdx.x);
+__global__ void fb_run_solve(DevModel m, DevData d) {
+  extern __shared__ __align__(16) float fb_smem_w[];
+  int e = blockIdx.x * FB_SOLVE_WPB + threadIdx.y;
+  if (e >= d.Np) return;
+  ksolve_warp(m, d, fb_smem_w + (size_t)threadIdx.y * FB_SOLVE_WARP_FLOATS, e);
 }
-template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
-static void fb_launch_block(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
-  dim3 block(32, ny), grid(s->d.Np / 32);
-  size_t bytes = smem_bytes(sizeof(Sh), dyn_floats);
-  static size_t configured = 0;
-  if (bytes > configured) { cudaFuncSetAttribute(fb_run_block<Sh, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
+static void fb_launch_warp(FbSim* s, int kind) {
+  dim3 block(32, FB_SOLVE_WPB), grid((s->d.Np + FB_SOLVE_WPB - 1) / FB_SOLVE_WPB);
+  size_t bytes = sizeof(float) * FB_SOLVE_WARP_FLOATS * FB_SOLVE_WPB;
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(fb_run_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = true; }
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, s->stream);
-    fb_run_block<Sh, F><<<grid, block, bytes, s->stream>>>(s->m, s->d);
+    fb_run_solve<<<grid, block, bytes, s->stream>>>(s->m, s->d);
     cudaEventRecord(b, s->stream);
     s->prof_events.push_back({kind, a, b});
   } else {
-    fb_run_block<Sh, F><<<grid, block, bytes, s->stream>>>(s->m, s->d);
+    fb_run_solve<<<grid, block, bytes, s->stream>>>(s->m, s->d);
   }
   s->launches++;
 }
 #else
-template <typename Sh, void (*F)(const DevModel&, const DevData&, Sh&, int)>
-static void fb_launch_block(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
-  (void)ny; (void)kind;
-  static std::vector<unsigned char> buf;
-  size_t need = ((sizeof(Sh) + 15) & ~(size_t)15) + dyn_floats * sizeof(float) + 64;
-  if (buf.size() < need) buf.resize(need);
-  Sh& sh = *reinterpret_cast<Sh*>(buf.data());
-  for (int blk = 0; blk < s->d.Np / 32; blk++) F(s->m, s->d, sh, blk);
+static void fb_launch_warp(FbSim* s, int kind) {
+  (void)kind;
+  static std::vector<float> buf(FB_SOLVE_WARP_FLOATS);
+  for (int e = 0; e < s->d.Np; e++) ksolve_warp(s->m, s->d, buf.data(), e);
   s->launches++;
 }
 #endif
@@ -171,7 +167,7 @@ static void launch_step1(FbSim* s) {
 static void launch_step2(FbSim* s, bool integrate) {
   int nl = s->m.nlist;
   fb_launch<ShTree, kact_p0, kact_p1, kact_p2, kact_p3, ph_smooth_a, ph_smooth_b, ph_smooth_c, kref>(s, nl, K_SMOOTH, (size_t)s->m.nv * 32);
-  fb_launch_block<ShSolve, ksolve_block>(s, FB_SOLVE_Y, K_SOLVE, (size_t)s->m.solve_dyn_floats);
+  fb_launch_warp(s, K_SOLVE);
   if (integrate)
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
               kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl, K_FINISH, (size_t)s->m.nv * 32);
@@ -199,7 +195,7 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.npair = h->npair; m.nsite = h->nsite; m.ntendon = h->ntendon; m.nwrap = h->nwrap; m.nsensor = h->nsensor;
   m.nsensordata = h->nsensordata; m.nM = h->nM; m.nfluid = h->nfluid;
   m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.max_iter = 30; m.ls_iter = 20;
-  { const char* kb = getenv("FB_SOLVE_SMEM_KB"); m.solve_dyn_floats = kb ? atoi(kb) * 256 : FB_SOLVE_DYN_FLOATS; if (m.solve_dyn_floats > FB_SOLVE_DYN_FLOATS) m.solve_dyn_floats = FB_SOLVE_DYN_FLOATS; }
+  { const char* nc = getenv("FB_SOLVE_NCAP"); m.solve_ncap = nc ? atoi(nc) : FB_SOLVE_NCAP; if (m.solve_ncap > FB_SOLVE_NCAP) m.solve_ncap = FB_SOLVE_NCAP; }   // test hook: smaller cap -> global-memory path
   m.timestep = (float)h->opt_timestep; m.density = (float)h->opt_density; m.viscosity = (float)h->opt_viscosity;
   for (int i = 0; i < 3; i++) { m.gravity[i] = (float)h->opt_gravity[i]; m.wind[i] = (float)h->opt_wind[i]; }
   m.impratio = (float)h->opt_impratio; m.tolerance = (float)h->opt_tolerance; m.noslip_tolerance = (float)h->opt_noslip_tolerance;
@@ -329,8 +325,8 @@ static int alloc_data(FbSim* s, int N) {
   IA(nefc, 1) IA(efc_type, FB_MAXEFC) IA(efc_id, FB_MAXEFC)
   FA(efc_pos, FB_MAXEFC) FA(efc_margin, FB_MAXEFC) FA(efc_D, FB_MAXEFC) FA(efc_R, FB_MAXEFC) FA(efc_K, FB_MAXEFC) FA(efc_B, FB_MAXEFC)
   FA(efc_imp, FB_MAXEFC) FA(efc_aref, FB_MAXEFC) FA(efc_b, FB_MAXEFC) FA(efc_force, FB_MAXEFC) FA(efc_jarws, FB_MAXEFC)
-  FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv) FA(efc_A, (size_t)FB_MAXEFC * FB_MAXEFC) FA(efc_G, (size_t)FB_MAXEFC * FB_MAXEFC)
-  FA(efc_w, 8 * FB_MAXEFC) FA(efc_w2, 20 * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) IA(efc_ekind, FB_MAXEFC) IA(efc_state, FB_MAXEFC) IA(efc_colidx, FB_MAXEFC) IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC)
+  FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv) FA(efc_A, (size_t)FB_MAXEFC * (FB_MAXEFC + 1) / 2) FA(efc_G, (size_t)FB_MAXEFC * (FB_MAXEFC + 1) / 2)
+  FA(efc_w, (size_t)S_NSLOT * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) IA(efc_ekind, FB_MAXEFC) IA(efc_state, FB_MAXEFC) IA(efc_colidx, FB_MAXEFC) IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC)
   FA(sensordata, m.nsensordata + 1) FA(sensor_sum, m.nsensordata + 1) IA(flags, 1) IA(niter, 1) IA(hold, 1)
 #undef FA
 #undef IA

@@ -35,10 +35,11 @@ def test_teacher_forced_control_steps_walk(emu):
     assert r['p90_q'] < 2e-6 and r['p90_v'] < 5e-3 and r['events'] <= 1, r
 
 
-@pytest.mark.parametrize('kb', ['0', '24'])
-def test_solver_global_memory_fallback_paths(emu, kb, monkeypatch):
-    """The solver keeps its vectors / Delassus matrix / Hessian factor in shared memory when they fit and
-    falls back to the global arrays otherwise; both placements must give the same answer."""
-    monkeypatch.setenv('FB_SOLVE_SMEM_KB', kb)
+@pytest.mark.parametrize('ncap,seed', [('0', 0), ('32', 4)])
+def test_solver_shared_and_global_memory_paths(emu, ncap, seed, monkeypatch):
+    """The solver keeps an env's working set in its warp's shared-memory slice when nefc <= 32 and runs the
+    same code on the global arrays otherwise; both placements must agree with the oracle.
+    (seed 0 has nefc = 53 -> global path even with the default cap; seed 4 with pos_scale 0 has nefc = 18.)"""
+    monkeypatch.setenv('FB_SOLVE_NCAP', ncap)
     m = load_model('walk')
-    compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=emu), seed=0)
+    compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=emu), seed=seed, pos_scale=0.1 if seed == 0 else 0.0)
