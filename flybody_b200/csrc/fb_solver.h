@@ -31,10 +31,11 @@ enum { W_LAM = 0, W_JAR, W_F, W_R, W_U, W_DL, W_ADL, W_P, X_E0, X_E1, X_XQ, X_OU
 #define FB_SOLVE_WARP_FLOATS (S_NSLOT * FB_SOLVE_NCAP + 2 * TRI(FB_SOLVE_NCAP, 0) + 4 * 32)
 
 // memory of one env's problem: base pointers + element strides (1 in shared memory, Np in global memory)
-struct SolveMem { float* v; int vcap, vs; float* A; int as; float* G; int gs; float* red; };
-#define SV(slot, r) sm.v[(size_t)((slot) * sm.vcap + (r)) * sm.vs]
-#define AM(r, c) sm.A[(size_t)((r) >= (c) ? TRI(r, c) : TRI(c, r)) * sm.as]
-#define GM(p, q) sm.G[(size_t)TRI(p, q) * sm.gs]        // p >= q
+struct SolveMem { float* v; float* A; float* G; float* red; int st; };
+// SM == true: the env's slice of shared memory (unit stride); false: global arrays (stride = padded env count)
+#define SV(slot, r) sm.v[SM ? ((slot) * FB_SOLVE_NCAP + (r)) : ((slot) * FB_MAXEFC + (r)) * sm.st]
+#define AM(r, c) sm.A[SM ? ((r) >= (c) ? TRI(r, c) : TRI(c, r)) : ((r) >= (c) ? TRI(r, c) : TRI(c, r)) * sm.st]
+#define GM(p, q) sm.G[SM ? TRI(p, q) : TRI(p, q) * sm.st]        // p >= q
 #define RED(k, l) sm.red[(k) * 32 + (l)]
 
 #ifdef __CUDACC__
@@ -46,10 +47,20 @@ struct SolveMem { float* v; int vcap, vs; float* A; int as; float* G; int gs; fl
 #endif
 #define WROWS for (int r = lane; r < n; r += 32)
 FB_DEV float red_total(const SolveMem& sm, int k) { float s = 0; for (int l = 0; l < 32; l++) s += RED(k, l); return s; }
+// warp sums: butterfly shuffles on the GPU (every lane gets the total, no shared-memory round trip);
+// the host emulation runs lanes one after the other, so it stages partials in RED and sums afterwards
+#ifdef __CUDACC__
+FB_DEV float wsum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+#define WSUM_PUT(k, v) tot[k] = wsum(v)
+#define WSUM_GET(k) (tot[k])
+#else
+#define WSUM_PUT(k, v) RED(k, lane) = (v)
+#define WSUM_GET(k) red_total(sm, k)
+#endif
 #define IS_HEAD(r) (SV(S_TYPE, r) < 1.5f)
 
 // forces / cost of the rows headed at r (a plain row, or the first row of an elliptic contact)
-FB_DEV float head_update(const SolveMem& sm, int r, bool build) {
+template <bool SM> FB_DEV float head_update(const SolveMem& sm, int r, bool build) {
   int tp = (int)SV(S_TYPE, r);
   float jar = SV(W_JAR, r), D = SV(S_D, r), cost = 0;
   if (tp == 0) {
@@ -83,7 +94,7 @@ FB_DEV float head_update(const SolveMem& sm, int r, bool build) {
   return cost;
 }
 // line-search contribution (value, 1st, 2nd derivative) of the rows headed at r
-FB_DEV void head_ls(const SolveMem& sm, int r, float alpha, float& c, float& g, float& h) {
+template <bool SM> FB_DEV void head_ls(const SolveMem& sm, int r, float alpha, float& c, float& g, float& h) {
   int tp = (int)SV(S_TYPE, r);
   float jv = SV(W_ADL, r), x = SV(W_JAR, r) + alpha * jv, D = SV(S_D, r);
   if (tp == 0) { if (x < 0) { c += 0.5f * D * x * x; g += D * x * jv; h += D * jv * jv; } return; }
@@ -104,7 +115,7 @@ FB_DEV void head_ls(const SolveMem& sm, int r, float alpha, float& c, float& g, 
     c += 0.5f * Dm * f * f; g += Dm * f * fp; h += Dm * (fp * fp + f * fpp);
   }
 }
-FB_DEV float ecol_val(const SolveMem& sm, int p, int a) {   // a-th entry of column p of E
+template <bool SM> FB_DEV float ecol_val(const SolveMem& sm, int p, int a) {   // a-th entry of column p of E
   int kind = (int)SV(S_ECKIND, p), r = (int)SV(S_ECROW, p);
   return kind == 2 ? SV(X_E1, r + a) : SV(X_E0, r + a);
 }
@@ -115,21 +126,10 @@ FB_DEV float ecol_val(const SolveMem& sm, int p, int a) {   // a-th entry of col
 #define FB_WARPFN static
 #endif
 
-// one env; `wsm` = this warp's shared-memory slice (FB_SOLVE_WARP_FLOATS floats)
-FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int e) {
-  const int n = AT(d.nefc, 0);
+template <bool SM>
+FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& sm, int e, int n) {
   const float scale = 1.0f / (m.meaninertia * (m.nv > 1 ? m.nv : 1));
-  SolveMem sm;
-  sm.red = wsm;
-  if (n <= m.solve_ncap) {
-    sm.v = wsm + 4 * 32; sm.vcap = FB_SOLVE_NCAP; sm.vs = 1;
-    sm.A = sm.v + S_NSLOT * FB_SOLVE_NCAP; sm.as = 1;
-    sm.G = sm.A + TRI(FB_SOLVE_NCAP, 0); sm.gs = 1;
-  } else {   // large problem: same code on the global arrays (element stride = padded env count)
-    sm.v = d.efc_w + e; sm.vcap = FB_MAXEFC; sm.vs = d.Np;
-    sm.A = d.efc_A + e; sm.as = d.Np;
-    sm.G = d.efc_G + e; sm.gs = d.Np;
-  }
+  float tot[4] = {0, 0, 0, 0}; (void)tot;
   int niter = 0;
   if (n > 0) {
     // ---- stage row constants (and A) next to the work vectors
@@ -141,26 +141,26 @@ FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int 
       SV(S_LA, r) = (float)AT(d.efc_la, r); SV(S_LB, r) = (float)AT(d.efc_lb, r);
       SV(W_JAR, r) = EFC(d.efc_jarws, r);
     }
-    if (sm.as == 1) { int nt = TRI(n, 0); for (int k = lane; k < nt; k += 32) sm.A[k] = AT(d.efc_A, k); }
+    if (SM) { int nt = TRI(n, 0); for (int k = lane; k < nt; k += 32) sm.A[k] = AT(d.efc_A, k); }
     WPAR_END
     // ---- warm start: forces implied by the previous qacc, kept if cheaper than lam = 0
-    WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update(sm, r, false); WPAR_END
+    WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update<SM>(sm, r, false); WPAR_END
     WPAR_BEGIN WROWS SV(W_LAM, r) = SV(W_F, r); WPAR_END
-    WPAR_BEGIN float q = 0; WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; q += 0.5f * SV(W_LAM, r) * (s - SV(S_B, r)); } RED(0, lane) = q; WPAR_END
-    WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update(sm, r, false); RED(1, lane) = c; WPAR_END
-    float cost_ws = red_total(sm, 0) + red_total(sm, 1);
+    WPAR_BEGIN float q = 0; WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; q += 0.5f * SV(W_LAM, r) * (s - SV(S_B, r)); } WSUM_PUT(0, q); WPAR_END
+    WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, false); WSUM_PUT(1, c); WPAR_END
+    float cost_ws = WSUM_GET(0) + WSUM_GET(1);
     WPAR_BEGIN WROWS SV(W_JAR, r) = SV(S_B, r); WPAR_END
-    WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update(sm, r, false); RED(0, lane) = c; WPAR_END
-    float cost0 = red_total(sm, 0);
+    WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, false); WSUM_PUT(0, c); WPAR_END
+    float cost0 = WSUM_GET(0);
     WPAR_BEGIN WPAR_END
     if (!(cost_ws < cost0)) { WPAR_BEGIN WROWS SV(W_LAM, r) = 0; WPAR_END }
     // ---- Newton iterations
     for (int iter = 0; iter < m.max_iter; iter++) {
-      WPAR_BEGIN float q = 0; WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; q += 0.5f * SV(W_LAM, r) * (s - SV(S_B, r)); } RED(0, lane) = q; WPAR_END
-      WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update(sm, r, true); RED(1, lane) = c; WPAR_END
-      WPAR_BEGIN float rr = 0, ll = 0; WROWS { float f = SV(W_F, r), rv = SV(W_LAM, r) - f; SV(W_R, r) = rv; rr += rv * rv; ll += f * f; } RED(2, lane) = rr; RED(3, lane) = ll; WPAR_END
-      float quad = red_total(sm, 0), cost = quad + red_total(sm, 1);
-      float rr = red_total(sm, 2), ll = red_total(sm, 3);
+      WPAR_BEGIN float q = 0; WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; q += 0.5f * SV(W_LAM, r) * (s - SV(S_B, r)); } WSUM_PUT(0, q); WPAR_END
+      WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, true); WSUM_PUT(1, c); WPAR_END
+      WPAR_BEGIN float rr = 0, ll = 0; WROWS { float f = SV(W_F, r), rv = SV(W_LAM, r) - f; SV(W_R, r) = rv; rr += rv * rv; ll += f * f; } WSUM_PUT(2, rr); WSUM_PUT(3, ll); WPAR_END
+      float quad = WSUM_GET(0), cost = quad + WSUM_GET(1);
+      float rr = WSUM_GET(2), ll = WSUM_GET(3);
       WPAR_BEGIN WPAR_END              // all lanes have read RED before it is reused
       if (rr <= 1e-12f * (ll + 1e-30f)) break;
       // column bookkeeping (prefix over rows) by lane 0; nc is left in RED(0, 0)
@@ -177,12 +177,12 @@ FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int 
       // p = E^T u ; G = I + E^T A E (packed lower triangle)
       WPAR_BEGIN for (int p = lane; p < nc; p += 32) {
           int rp = (int)SV(S_ECROW, p), np = SV(S_ECKIND, p) == 0 ? 1 : 3;
-          float pv = 0; for (int a = 0; a < np; a++) pv += ecol_val(sm, p, a) * SV(W_U, rp + a);
+          float pv = 0; for (int a = 0; a < np; a++) pv += ecol_val<SM>(sm, p, a) * SV(W_U, rp + a);
           SV(W_P, p) = pv;
           for (int q = 0; q <= p; q++) {
             int rq = (int)SV(S_ECROW, q), nq = SV(S_ECKIND, q) == 0 ? 1 : 3;
             float s = (p == q) ? 1.0f : 0.0f;
-            for (int a = 0; a < np; a++) { float va = ecol_val(sm, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * AM(rp + a, rq + bb) * ecol_val(sm, q, bb); }
+            for (int a = 0; a < np; a++) { float va = ecol_val<SM>(sm, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * AM(rp + a, rq + bb) * ecol_val<SM>(sm, q, bb); }
             GM(p, q) = s;
           } }
       WPAR_END
@@ -210,14 +210,14 @@ FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int 
           SV(W_DL, r) = v; }
       WPAR_END
       WPAR_BEGIN float q1 = 0, q2 = 0; WROWS { float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_DL, j); SV(W_ADL, r) = s;
-          q1 += SV(W_DL, r) * (SV(W_JAR, r) - SV(S_B, r)); q2 += 0.5f * SV(W_DL, r) * s; } RED(0, lane) = q1; RED(1, lane) = q2; WPAR_END
-      const float q1 = red_total(sm, 0), q2 = red_total(sm, 1);
+          q1 += SV(W_DL, r) * (SV(W_JAR, r) - SV(S_B, r)); q2 += 0.5f * SV(W_DL, r) * s; } WSUM_PUT(0, q1); WSUM_PUT(1, q2); WPAR_END
+      const float q1 = WSUM_GET(0), q2 = WSUM_GET(1);
       WPAR_BEGIN WPAR_END
       // exact line search: safeguarded Newton on the derivative of the 1-D cost
       float alpha = 0, lo = 0, hi = -1, g0 = 0, cbest = cost; bool stop = false, nodescent = false;
       for (int ls = 0; ls <= m.ls_iter && !stop; ls++) {
-        WPAR_BEGIN float c = 0, g = 0, h = 0; WROWS if (IS_HEAD(r)) head_ls(sm, r, alpha, c, g, h); RED(0, lane) = c; RED(1, lane) = g; RED(2, lane) = h; WPAR_END
-        float c = quad + alpha * q1 + alpha * alpha * q2 + red_total(sm, 0), g = q1 + 2 * alpha * q2 + red_total(sm, 1), h = 2 * q2 + red_total(sm, 2);
+        WPAR_BEGIN float c = 0, g = 0, h = 0; WROWS if (IS_HEAD(r)) head_ls<SM>(sm, r, alpha, c, g, h); WSUM_PUT(0, c); WSUM_PUT(1, g); WSUM_PUT(2, h); WPAR_END
+        float c = quad + alpha * q1 + alpha * alpha * q2 + WSUM_GET(0), g = q1 + 2 * alpha * q2 + WSUM_GET(1), h = 2 * q2 + WSUM_GET(2);
         WPAR_BEGIN WPAR_END          // keep RED reads of all lanes ahead of the next section's writes
         if (ls == 0) {
           g0 = g;
@@ -225,7 +225,7 @@ FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int 
           else alpha = -g / h;
         } else {
           cbest = c;
-          if (fabsf(g) < 1e-6f * fabsf(g0) || ls == m.ls_iter) stop = true;
+          if (fabsf(g) < m.ls_tolerance * fabsf(g0) || ls == m.ls_iter) stop = true;
           else {
             if (g < 0) lo = alpha; else hi = alpha;
             float na = alpha - g / h;
@@ -243,7 +243,7 @@ FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int 
     }
     // ---- forces at the solution: lam = f(b + A lam)
     WPAR_BEGIN WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; } WPAR_END
-    WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update(sm, r, false); WPAR_END
+    WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update<SM>(sm, r, false); WPAR_END
     // ---- noslip (MuJoCo mj_solNoSlip): sequential Gauss-Seidel over the friction rows with the unregularised A
     if (m.noslip_iterations > 0) {
       WPAR_BEGIN if (lane == 0) {
@@ -292,4 +292,18 @@ FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int 
       AT(d.qfrc_constraint, k) = s;
     }
   WPAR_END
+}
+
+// one env; `wsm` = this warp's shared-memory slice (FB_SOLVE_WARP_FLOATS floats)
+FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int e) {
+  const int n = AT(d.nefc, 0);
+  SolveMem sm;
+  sm.red = wsm;
+  if (n <= m.solve_ncap) {
+    sm.v = wsm + 4 * 32; sm.A = sm.v + S_NSLOT * FB_SOLVE_NCAP; sm.G = sm.A + TRI(FB_SOLVE_NCAP, 0); sm.st = 1;
+    ksolve_impl<true>(m, d, sm, e, n);
+  } else {   // large problem: same code on the global arrays (element stride = padded env count)
+    sm.v = d.efc_w + e; sm.A = d.efc_A + e; sm.G = d.efc_G + e; sm.st = d.Np;
+    ksolve_impl<false>(m, d, sm, e, n);
+  }
 }

@@ -194,7 +194,7 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.nq = h->nq; m.nv = h->nv; m.nu = h->nu; m.na = h->na; m.nbody = h->nbody; m.njnt = h->njnt; m.ngeom = h->ngeom;
   m.npair = h->npair; m.nsite = h->nsite; m.ntendon = h->ntendon; m.nwrap = h->nwrap; m.nsensor = h->nsensor;
   m.nsensordata = h->nsensordata; m.nM = h->nM; m.nfluid = h->nfluid;
-  m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.max_iter = 30; m.ls_iter = 20;
+  m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.max_iter = 30; m.ls_iter = 12; m.ls_tolerance = 1e-3f;
   { const char* nc = getenv("FB_SOLVE_NCAP"); m.solve_ncap = nc ? atoi(nc) : FB_SOLVE_NCAP; if (m.solve_ncap > FB_SOLVE_NCAP) m.solve_ncap = FB_SOLVE_NCAP; }   // test hook: smaller cap -> global-memory path
   m.timestep = (float)h->opt_timestep; m.density = (float)h->opt_density; m.viscosity = (float)h->opt_viscosity;
   for (int i = 0; i < 3; i++) { m.gravity[i] = (float)h->opt_gravity[i]; m.wind[i] = (float)h->opt_wind[i]; }
