@@ -6,8 +6,8 @@
 // contact record: con_pos[3], con_frame[9] per slot (positions relative to ref)
 #define CON_F(arr, slot, k, K) AT(arr, (slot) * (K) + (k))
 #define EFC(arr, r) AT(arr, r)
-#define EJ(arr, r, dof) AT(arr, (size_t)(r) * m.nv + (dof))
-#define EA(arr, r, c) AT(arr, (size_t)(r) * FB_MAXEFC + (c))
+#define EJ(arr, r, dof) AT(arr, (r) * m.nv + (dof))
+#define EA(arr, r, c) AT(arr, (r) * FB_MAXEFC + (c))
 #define EW(slot, r) AT(d.efc_w, (slot) * FB_MAXEFC + (r))
 
 // ---------------------------------------------------------------------------------------------
@@ -361,7 +361,7 @@ FB_DEV void kproj_p1(FB_ROW_ARGS) {
         if (lb == k) lb = m.dof_parentid[lb];
         if (in_chain(m, k, rr.la) || in_chain(m, k, rr.lb)) s += EJ(d.efc_Z, r, k) * EJ(d.efc_Z, c, k);
       }
-      AT(d.efc_A, (size_t)r * (r + 1) / 2 + c) = s;      // packed lower triangle
+      AT(d.efc_A, r * (r + 1) / 2 + c) = s;      // packed lower triangle
     }
   }
 }

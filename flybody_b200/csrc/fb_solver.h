@@ -60,7 +60,7 @@ FB_DEV float wsum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sy
 #define IS_HEAD(r) (SV(S_TYPE, r) < 1.5f)
 
 // forces / cost of the rows headed at r (a plain row, or the first row of an elliptic contact)
-template <bool SM> FB_DEV float head_update(const SolveMem& sm, int r, bool build) {
+template <bool SM> FB_DEVN float head_update(const SolveMem sm, int r, bool build) {
   int tp = (int)SV(S_TYPE, r);
   float jar = SV(W_JAR, r), D = SV(S_D, r), cost = 0;
   if (tp == 0) {
@@ -94,7 +94,7 @@ template <bool SM> FB_DEV float head_update(const SolveMem& sm, int r, bool buil
   return cost;
 }
 // line-search contribution (value, 1st, 2nd derivative) of the rows headed at r
-template <bool SM> FB_DEV void head_ls(const SolveMem& sm, int r, float alpha, float& c, float& g, float& h) {
+template <bool SM> FB_DEVN void head_ls(const SolveMem sm, int r, float alpha, float& c, float& g, float& h) {
   int tp = (int)SV(S_TYPE, r);
   float jv = SV(W_ADL, r), x = SV(W_JAR, r) + alpha * jv, D = SV(S_D, r);
   if (tp == 0) { if (x < 0) { c += 0.5f * D * x * x; g += D * x * jv; h += D * jv * jv; } return; }
@@ -120,10 +120,22 @@ template <bool SM> FB_DEV float ecol_val(const SolveMem& sm, int p, int a) {   /
   return kind == 2 ? SV(X_E1, r + a) : SV(X_E0, r + a);
 }
 
+// dst[r] = (addb ? b[r] : 0) + sum_j A[r][j] src[j] for this lane's rows; returns sum_r src[r]*(dst[r]-b[r]) partial
+template <bool SM> FB_DEVN float matvec_rows(const SolveMem sm, int n, int lane, int src, int dst, bool addb) {
+  float acc = 0;
+  for (int r = lane; r < n; r += 32) {
+    float s = 0;
+#pragma unroll 2
+    for (int j = 0; j < n; j++) s += AM(r, j) * SV(src, j);
+    acc += SV(src, r) * s;
+    SV(dst, r) = addb ? s + SV(S_B, r) : s;
+  }
+  return acc;
+}
 #ifdef __CUDACC__
-#define FB_WARPFN __device__ __noinline__
+#define FB_WARPFN __device__ __forceinline__
 #else
-#define FB_WARPFN static
+#define FB_WARPFN static inline
 #endif
 
 template <bool SM>
@@ -146,7 +158,7 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
     // ---- warm start: forces implied by the previous qacc, kept if cheaper than lam = 0
     WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update<SM>(sm, r, false); WPAR_END
     WPAR_BEGIN WROWS SV(W_LAM, r) = SV(W_F, r); WPAR_END
-    WPAR_BEGIN float q = 0; WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; q += 0.5f * SV(W_LAM, r) * (s - SV(S_B, r)); } WSUM_PUT(0, q); WPAR_END
+    WPAR_BEGIN float q = 0.5f * matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WSUM_PUT(0, q); WPAR_END
     WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, false); WSUM_PUT(1, c); WPAR_END
     float cost_ws = WSUM_GET(0) + WSUM_GET(1);
     WPAR_BEGIN WROWS SV(W_JAR, r) = SV(S_B, r); WPAR_END
@@ -156,7 +168,7 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
     if (!(cost_ws < cost0)) { WPAR_BEGIN WROWS SV(W_LAM, r) = 0; WPAR_END }
     // ---- Newton iterations
     for (int iter = 0; iter < m.max_iter; iter++) {
-      WPAR_BEGIN float q = 0; WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; q += 0.5f * SV(W_LAM, r) * (s - SV(S_B, r)); } WSUM_PUT(0, q); WPAR_END
+      WPAR_BEGIN float q = 0.5f * matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WSUM_PUT(0, q); WPAR_END
       WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, true); WSUM_PUT(1, c); WPAR_END
       WPAR_BEGIN float rr = 0, ll = 0; WROWS { float f = SV(W_F, r), rv = SV(W_LAM, r) - f; SV(W_R, r) = rv; rr += rv * rv; ll += f * f; } WSUM_PUT(2, rr); WSUM_PUT(3, ll); WPAR_END
       float quad = WSUM_GET(0), cost = quad + WSUM_GET(1);
@@ -173,7 +185,7 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
       WPAR_END
       const int nc = (int)RED(0, 0);
       // u = A r
-      WPAR_BEGIN WROWS { float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_R, j); SV(W_U, r) = s; } WPAR_END
+      WPAR_BEGIN matvec_rows<SM>(sm, n, lane, W_R, W_U, false); WPAR_END
       // p = E^T u ; G = I + E^T A E (packed lower triangle)
       WPAR_BEGIN for (int p = lane; p < nc; p += 32) {
           int rp = (int)SV(S_ECROW, p), np = SV(S_ECKIND, p) == 0 ? 1 : 3;
@@ -209,8 +221,8 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
           else if (stt >= 2) v += SV(X_E0, r) * SV(X_OUT, c0) + SV(X_E1, r) * SV(X_OUT, c0 + 1);
           SV(W_DL, r) = v; }
       WPAR_END
-      WPAR_BEGIN float q1 = 0, q2 = 0; WROWS { float s = 0; for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_DL, j); SV(W_ADL, r) = s;
-          q1 += SV(W_DL, r) * (SV(W_JAR, r) - SV(S_B, r)); q2 += 0.5f * SV(W_DL, r) * s; } WSUM_PUT(0, q1); WSUM_PUT(1, q2); WPAR_END
+      WPAR_BEGIN float q2 = 0.5f * matvec_rows<SM>(sm, n, lane, W_DL, W_ADL, false), q1 = 0;
+          WROWS q1 += SV(W_DL, r) * (SV(W_JAR, r) - SV(S_B, r)); WSUM_PUT(0, q1); WSUM_PUT(1, q2); WPAR_END
       const float q1 = WSUM_GET(0), q2 = WSUM_GET(1);
       WPAR_BEGIN WPAR_END
       // exact line search: safeguarded Newton on the derivative of the 1-D cost
@@ -242,7 +254,7 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
       if (scale * (cost - cbest) < m.tolerance) break;
     }
     // ---- forces at the solution: lam = f(b + A lam)
-    WPAR_BEGIN WROWS { float s = SV(S_B, r); for (int j = 0; j < n; j++) s += AM(r, j) * SV(W_LAM, j); SV(W_JAR, r) = s; } WPAR_END
+    WPAR_BEGIN matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WPAR_END
     WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update<SM>(sm, r, false); WPAR_END
     // ---- noslip (MuJoCo mj_solNoSlip): sequential Gauss-Seidel over the friction rows with the unregularised A
     if (m.noslip_iterations > 0) {

@@ -371,6 +371,7 @@ const char* fb_version(void) {
 
 int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   if (!hm || !out || n_envs <= 0) return -1;
+  if ((double)fb_pad32(n_envs) * FB_MAXEFC * (hm->nv > 0 ? hm->nv : 1) >= 4.0e9) return -5;   // 32-bit SoA indexing limit
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
   s->op_step_dev = nullptr; s->op_first_dev = nullptr;
