@@ -172,7 +172,7 @@ def run_ours(args):
     obs = torch.as_tensor(CudaView(obs_ptr, (N, obs_dim)), device=f'cuda:{local}')
     K, W = args.steps, args.warmup
     gen = torch.Generator(device=f'cuda:{local}'); gen.manual_seed(1234 + rank)
-    acts = (torch.rand((K + W, m.nu, Np), device=f'cuda:{local}', generator=gen) - 0.5)      # SoA ctrl, resident in HBM
+    acts = (torch.rand((K + W, N, m.nu), device=f'cuda:{local}', generator=gen) - 0.5)      # ctrl rows [N][nu], resident in HBM
     # identity permutation between action and ctrl order is irrelevant for a random policy
     gather_list = [torch.empty((N, obs_dim), device=f'cuda:{local}') for _ in range(world)] if (world > 1 and rank == 0) else None
     bad_total = 0
@@ -253,7 +253,7 @@ def run_ours(args):
             'config': {'workload': f'walk_imitation {N} envs per GPU, random policy U(-0.5,0.5), 10 substeps x 2e-4 s '
                                    f'(BASELINE.json configs[1]; N>1: configs[3] sharding + NCCL obs gather to rank 0)',
                        'envs_per_gpu': N, 'total_envs': total_envs, 'n_substeps': N_SUB,
-                       'l2': 'inputs larger than L2: ~50 KB of SoA intermediates per env-substep x 4096 envs ~ 200 MB touched per substep (> 126 MB L2); no explicit flush',
+                       'l2': 'inputs larger than L2: ~50 KB of intermediates touched per env-substep x 4096 env records ~ 200 MB per substep (> 126 MB L2); no explicit flush',
                        'parallelism': f'env-sharded x{world}' + (', torch.distributed NCCL gather of packed obs per control step' if world > 1 else ''),
                        'unstable_envs_flagged': bad_total},
             'clocks': clocks, 'gpu_launches': int(launches),

@@ -15,7 +15,7 @@
 // candidate pair list (bounding-sphere broadphase, then the analytic narrowphase) into a private
 // staging area; a prefix sum over the chunk counts makes the final contact order deterministic
 // (pair-list order), which the Gauss-Seidel noslip sweeps depend on.
-struct ShCol { int cnt[FB_MAXCHUNK][32]; };
+struct ShCol { int cnt[FB_MAXCHUNK][FB_LANES]; };
 struct RawCon { float dist; V3 pos, n, t; };
 
 FB_DEV int raw_sphere_sphere(RawCon* c, float margin, V3 p1, float r1, V3 p2, float r2) {
@@ -197,7 +197,7 @@ FB_DEV void row_params(const DevModel& m, const DevData& d, int e, int r, const 
   if (isfric) K = 0;
   EFC(d.efc_R, r) = R; EFC(d.efc_D, r) = 1.0f / R; EFC(d.efc_K, r) = K; EFC(d.efc_B, r) = B; EFC(d.efc_imp, r) = imp;
 }
-struct ShCon { int cnt[FB_ROWPAR][32]; int base[32]; };
+struct ShCon { int cnt[FB_ROWPAR][FB_LANES]; int base[FB_LANES]; };
 #define FB_CON_ARGS const DevModel& m, const DevData& d, ShCon& sh, int e, int lane, int y
 FB_DEV bool limit_active(const DevModel& m, const DevData& d, int e, int j, int side, float& dist) {
   float value = AT(d.qpos, m.jnt_qposadr[j]);
@@ -206,11 +206,13 @@ FB_DEV bool limit_active(const DevModel& m, const DevData& d, int e, int j, int 
 }
 // phase 0/1: joint-limit rows (joints split into contiguous ranges over y so that rows stay in joint order)
 FB_DEV void kcon_p0(FB_CON_ARGS) {
+  if (y >= FB_ROWPAR) return;
   int j0 = (int)((long)y * m.njnt / FB_ROWPAR), j1 = (int)((long)(y + 1) * m.njnt / FB_ROWPAR), c = 0; float dist;
   for (int j = j0; j < j1; j++) { if (!m.jnt_limited[j] || m.jnt_type[j] != FB_JNT_HINGE) continue; for (int side = -1; side <= 1; side += 2) c += limit_active(m, d, e, j, side, dist) ? 1 : 0; }
   sh.cnt[y][lane] = c;
 }
 FB_DEV void kcon_p1(FB_CON_ARGS) {
+  if (y >= FB_ROWPAR) return;
   int n = 0; for (int yy = 0; yy < y; yy++) n += sh.cnt[yy][lane];
   int j0 = (int)((long)y * m.njnt / FB_ROWPAR), j1 = (int)((long)(y + 1) * m.njnt / FB_ROWPAR); float dist;
   for (int j = j0; j < j1; j++) {
@@ -236,12 +238,14 @@ FB_DEV int contact_dim(const DevModel& m, const DevData& d, int e, int ci, float
   return dim >= 3 ? 3 : 1;
 }
 FB_DEV void kcon_p2(FB_CON_ARGS) {
+  if (y >= FB_ROWPAR) return;
   int ncon = AT(d.ncon, 0);
   int c0 = y * ncon / FB_ROWPAR, c1 = (y + 1) * ncon / FB_ROWPAR, rows = 0;
   for (int ci = c0; ci < c1; ci++) { float im; bool incl; int dim = contact_dim(m, d, e, ci, im, incl); if (incl) rows += dim; }
   sh.cnt[y][lane] = rows;
 }
 FB_DEV void kcon_p3(FB_CON_ARGS) {
+  if (y >= FB_ROWPAR) return;
   int ncon = AT(d.ncon, 0);
   int n = sh.base[lane]; for (int yy = 0; yy < y; yy++) n += sh.cnt[yy][lane];
   int c0 = y * ncon / FB_ROWPAR, c1 = (y + 1) * ncon / FB_ROWPAR;
@@ -315,6 +319,7 @@ FB_DEV float contact_J(const DevModel& m, const DevData& d, int e, V3 f, V3 pos,
 struct ShNone { int dummy; };
 #define FB_ROW_ARGS const DevModel& m, const DevData& d, ShCon& sh, int e, int lane, int y
 FB_DEV void kproj_p0(FB_ROW_ARGS) {
+  if (y >= FB_ROWPAR) return;
   int n = AT(d.nefc, 0);
   for (int r = y; r < n; r += FB_ROWPAR) {
     int ci, frow; float sign;
@@ -324,13 +329,13 @@ FB_DEV void kproj_p0(FB_ROW_ARGS) {
     if (ci >= 0) { f = v3(CON_F(d.con_frame, ci, 3 * frow, 9), CON_F(d.con_frame, ci, 3 * frow + 1, 9), CON_F(d.con_frame, ci, 3 * frow + 2, 9));
                    pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3)); }
     // J over the dof set; the sweep scratch z lives in shared memory, indexed by dof: zs[y][dof][lane]
-    float* zs = sh_dyn(sh) + (size_t)y * m.nv * 32;
+    float* zs = sh_dyn(sh) + (size_t)y * m.nv * FB_LANES;
     int la = rc.la, lb = rc.lb;
     while (la >= 0 || lb >= 0) {
       int k = la > lb ? la : lb; float v = 0;
       if (ci < 0) v = (k == rc.la) ? sign : 0.0f;
       else { if (la == k) v += contact_J(m, d, e, f, pos, k); if (lb == k) v -= contact_J(m, d, e, f, pos, k); }
-      EJ(d.efc_J, r, k) = v; zs[k * 32 + lane] = v;
+      EJ(d.efc_J, r, k) = v; zs[k * FB_LANES + lane] = v;
       if (la == k) la = m.dof_parentid[la];
       if (lb == k) lb = m.dof_parentid[lb];
     }
@@ -340,14 +345,15 @@ FB_DEV void kproj_p0(FB_ROW_ARGS) {
       int k = la > lb ? la : lb;
       if (la == k) la = m.dof_parentid[la];
       if (lb == k) lb = m.dof_parentid[lb];
-      float zk = zs[k * 32 + lane];
+      float zk = zs[k * FB_LANES + lane];
       int adrk = m.dof_Madr[k], t = 1;
-      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) zs[i * 32 + lane] -= AT(d.qLD, adrk + t) * zk;
+      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) zs[i * FB_LANES + lane] -= AT(d.qLD, adrk + t) * zk;
       EJ(d.efc_Z, r, k) = zk / sqrtf(AT(d.qLD, adrk));
     }
   }
 }
 FB_DEV void kproj_p1(FB_ROW_ARGS) {
+  if (y >= FB_ROWPAR) return;
   int n = AT(d.nefc, 0);
   for (int r = y; r < n; r += FB_ROWPAR) {
     int ci, frow; float sign;
@@ -368,7 +374,7 @@ FB_DEV void kproj_p1(FB_ROW_ARGS) {
 // J . x for every row (x: qvel, qacc_smooth, qacc_warmstart): aref, b, jar at the warm start
 FB_DEV void kref(FB_PHASE_ARGS) {
   int n = AT(d.nefc, 0);
-  for (int r = y; r < n; r += m.nlist) {
+  for (int r = y; r < n; r += FB_NY) {
     int ci, frow; float sign;
     RowChains rc = row_chains(m, d, e, r, ci, frow, sign);
     float vel = 0, as = 0, ws = 0; int la = rc.la, lb = rc.lb;
@@ -386,9 +392,9 @@ FB_DEV void kref(FB_PHASE_ARGS) {
 
 // ---------------------------------------------------------------------------------------------
 // K3 + K8 transmission and actuation (MuJoCo mj_transmission, mj_fwdActuation), lane = env
-FB_DEV void kact_p0(FB_PHASE_ARGS) { for (int k = y; k < m.nv; k += m.nlist) AT(d.qfrc_actuator, k) = 0; }
+FB_DEV void kact_p0(FB_PHASE_ARGS) { for (int k = y; k < m.nv; k += FB_NY) AT(d.qfrc_actuator, k) = 0; }
 FB_DEV void kact_p1(FB_PHASE_ARGS) {
-  for (int i = y; i < m.nu; i += m.nlist) {
+  for (int i = y; i < m.nu; i += FB_NY) {
     float ctrl = AT(d.ctrl, i);
     if (m.actuator_ctrllimited[i]) ctrl = clampf(ctrl, m.actuator_ctrlrange[2 * i], m.actuator_ctrlrange[2 * i + 1]);
     int id = m.actuator_trnid[i], tt = m.actuator_trntype[i];
@@ -435,7 +441,7 @@ FB_DEV void kact_p2(FB_PHASE_ARGS) {
 // qfrc_smooth = passive - bias + actuator, staged into shared memory as the rhs of M x = qfrc_smooth
 FB_DEV void kact_p3(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
-  for (int k = y; k < m.nv; k += m.nlist) {
+  for (int k = y; k < m.nv; k += FB_NY) {
     float s = AT(d.qfrc_passive, k) - AT(d.qfrc_bias, k) + AT(d.qfrc_actuator, k);
     AT(d.qfrc_smooth, k) = s; XS(k) = s;
   }
@@ -630,49 +636,42 @@ FB_DEV void ksens_accum(const DevModel& m, const DevData& d, int e, int first) {
   for (int i = 0; i < m.nsensordata; i++) AT(d.sensor_sum, i) = (first ? 0.0f : AT(d.sensor_sum, i)) + AT(d.sensordata, i);
 }
 // last phase of the velocity kernel: per-substep sensor accumulation (d.sens_mode: 1 first substep, 0 next, -1 off)
-FB_DEV void kvel_p4(FB_PHASE_ARGS) { if (y == 0 && d.sens_mode >= 0) ksens_accum(m, d, e, d.sens_mode); }
+FB_DEV void kvel_p4(FB_PHASE_ARGS) {
+  if (d.sens_mode < 0) return;
+  for (int i = y; i < m.nsensordata; i += FB_NY) AT(d.sensor_sum, i) = (d.sens_mode ? 0.0f : AT(d.sensor_sum, i)) + AT(d.sensordata, i);
+}
 
 // ---------------------------------------------------------------------------------------------
 // packed per-env observation record (AoS, one row per env) for the host task code / NCCL gather:
 //   qpos[nq] qvel[nv] act[na] sensor_mean[nsd] sensordata[nsd] root_xpos[3] root_xmat[9] site_xpos[3*nsite]
 //   flags[1] qacc_sq[1] time[1]
-FB_DEV void kpack(const DevModel& m, const DevData& d, int e, float inv_nsub) {
+FB_DEV void kpack(const DevModel& m, const DevData& d, int e, int y, float inv_nsub) {
+  if (e >= d.N) return;
   float* o = d.obs + (size_t)e * d.obs_dim;
   int k = 0;
-  for (int i = 0; i < m.nq; i++) o[k++] = AT(d.qpos, i);
-  for (int i = 0; i < m.nv; i++) o[k++] = AT(d.qvel, i);
-  for (int i = 0; i < m.na; i++) o[k++] = AT(d.act, i);
-  for (int i = 0; i < m.nsensordata; i++) o[k++] = AT(d.sensor_sum, i) * inv_nsub;
-  for (int i = 0; i < m.nsensordata; i++) o[k++] = AT(d.sensordata, i);
+  for (int i = y; i < m.nq; i += FB_NY) o[k + i] = AT(d.qpos, i);
+  k += m.nq;
+  for (int i = y; i < m.nv; i += FB_NY) o[k + i] = AT(d.qvel, i);
+  k += m.nv;
+  for (int i = y; i < m.na; i += FB_NY) o[k + i] = AT(d.act, i);
+  k += m.na;
+  for (int i = y; i < m.nsensordata; i += FB_NY) { o[k + i] = AT(d.sensor_sum, i) * inv_nsub; o[k + m.nsensordata + i] = AT(d.sensordata, i); }
+  k += 2 * m.nsensordata;
   int rb = m.root_body[0];
-  V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
-  V3 rp = ld3(d.xpos, rb, d, e) + ref;
-  o[k++] = rp.x; o[k++] = rp.y; o[k++] = rp.z;
-  for (int i = 0; i < 9; i++) o[k++] = AT(d.xmat, 9 * rb + i);
-  for (int s = 0; s < m.nsite; s++) { V3 p = ld3(d.site_xpos, s, d, e) + ref; o[k++] = p.x; o[k++] = p.y; o[k++] = p.z; }
-  o[k++] = (float)AT(d.flags, 0);
-  float s2 = 0; for (int i = 0; i < m.nv; i++) { float a = AT(d.qacc, i); s2 += a * a; }
-  o[k++] = s2; o[k++] = AT(d.time, 0);
+  if (y < 3) o[k + y] = AT(d.xpos, 3 * rb + y) + AT(d.ref, y);
+  k += 3;
+  if (y < 9) o[k + y] = AT(d.xmat, 9 * rb + y);
+  k += 9;
+  for (int i = y; i < 3 * m.nsite; i += FB_NY) o[k + i] = AT(d.site_xpos, i) + AT(d.ref, i % 3);
+  k += 3 * m.nsite;
+  if (y == 0) { o[k] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float a = AT(d.qacc, i); s2 += a * a; } o[k + 1] = s2; o[k + 2] = AT(d.time, 0); }
 }
-
-// partial reset staged by fb_reset_hold: thread k (global index) rewrites env rst_ids[k]
-FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int k) {
-  if (k >= d.rst_n) return;
-  int e = d.rst_ids[k];
-  for (int i = 0; i < m.nq; i++) AT(d.qpos, i) = d.rst_qpos[(size_t)k * m.nq + i];
-  for (int i = 0; i < m.nv; i++) { AT(d.qvel, i) = d.rst_has_qvel ? d.rst_qvel[(size_t)k * m.nv + i] : 0.0f; AT(d.qacc, i) = 0; AT(d.qacc_warmstart, i) = 0; }
-  for (int i = 0; i < m.na; i++) AT(d.act, i) = 0;
-  AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = 1;
-}
-FB_DEV void kclear_hold(const DevModel& m, const DevData& d, int e) { AT(d.hold, 0) = 0; }
-
 // ---------------------------------------------------------------------------------------------
 // task observation program: evaluates the reference task's observables (FruitFlyObservables,
 // fruitfly.py:585-756; ref_displacement / ref_root_quat, tasks/base.py:245-268) on the device.
-FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e) {
+FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e, int y) {
   if (!d.tobs || e >= d.N) return;
   float* o = d.tobs + (size_t)e * d.tobs_dim;
-  int k = 0;
   int rb = d.op_root_body;
   V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
   V3 rpos = ld3(d.xpos, rb, d, e);
@@ -682,31 +681,47 @@ FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e) {
   int step = d.op_step ? d.op_step[e] : 0;
   int rj = m.body_jntadr[rb], rq = rj >= 0 ? m.jnt_qposadr[rj] : 0;
   for (int it = 0; it < d.op_n; it++) {
-    int kind = d.op_kind[it], a = d.op_a[it], b = d.op_b[it];
+    int kind = d.op_kind[it], a = d.op_a[it], b = d.op_b[it], k = d.op_off[it];
     switch (kind) {
-      case FB_OBS_SENSOR_MEAN: for (int i = 0; i < b; i++) o[k++] = first ? AT(d.sensordata, a + i) * inv : AT(d.sensor_sum, a + i) * inv; break;
-      case FB_OBS_SENSOR_NOW: for (int i = 0; i < b; i++) o[k++] = AT(d.sensordata, a + i); break;
-      case FB_OBS_ACT: for (int i = 0; i < b; i++) o[k++] = AT(d.act, a + i); break;
-      case FB_OBS_QPOS: for (int i = 0; i < b; i++) o[k++] = AT(d.qpos, d.op_list[a + i]); break;
-      case FB_OBS_QVEL: for (int i = 0; i < b; i++) o[k++] = AT(d.qvel, d.op_list[a + i]); break;
-      case FB_OBS_SITES_EGO: for (int i = 0; i < b; i++) { V3 v = mulT(R, ld3(d.site_xpos, d.op_list[a + i], d, e) - rpos); o[k++] = v.x; o[k++] = v.y; o[k++] = v.z; } break;
-      case FB_OBS_ROOT_ZAXIS: o[k++] = R.m[6]; o[k++] = R.m[7]; o[k++] = R.m[8]; break;
+      case FB_OBS_SENSOR_MEAN: for (int i = y; i < b; i += FB_NY) o[k + i] = first ? AT(d.sensordata, a + i) * inv : AT(d.sensor_sum, a + i) * inv; break;
+      case FB_OBS_SENSOR_NOW: for (int i = y; i < b; i += FB_NY) o[k + i] = AT(d.sensordata, a + i); break;
+      case FB_OBS_ACT: for (int i = y; i < b; i += FB_NY) o[k + i] = AT(d.act, a + i); break;
+      case FB_OBS_QPOS: for (int i = y; i < b; i += FB_NY) o[k + i] = AT(d.qpos, d.op_list[a + i]); break;
+      case FB_OBS_QVEL: for (int i = y; i < b; i += FB_NY) o[k + i] = AT(d.qvel, d.op_list[a + i]); break;
+      case FB_OBS_SITES_EGO: for (int i = y; i < b; i += FB_NY) { V3 v = mulT(R, ld3(d.site_xpos, d.op_list[a + i], d, e) - rpos); o[k + 3 * i] = v.x; o[k + 3 * i + 1] = v.y; o[k + 3 * i + 2] = v.z; } break;
+      case FB_OBS_ROOT_ZAXIS: if (y < 3) o[k + y] = R.m[6 + y]; break;
       case FB_OBS_REF_DISP: {
         V3 fly = v3(AT(d.qpos, rq), AT(d.qpos, rq + 1), AT(d.qpos, rq + 2));
-        for (int i = 0; i < b; i++) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = d.op_ref + 7 * t;
-          V3 v = mulT(R, v3(rr[0], rr[1], rr[2]) - fly); o[k++] = v.x; o[k++] = v.y; o[k++] = v.z; }
+        for (int i = y; i < b; i += FB_NY) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = d.op_ref + 7 * t;
+          V3 v = mulT(R, v3(rr[0], rr[1], rr[2]) - fly); o[k + 3 * i] = v.x; o[k + 3 * i + 1] = v.y; o[k + 3 * i + 2] = v.z; }
       } break;
       case FB_OBS_REF_QUAT: {
         Q4 q = q4(AT(d.qpos, rq + 3), AT(d.qpos, rq + 4), AT(d.qpos, rq + 5), AT(d.qpos, rq + 6));
         float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z; float s = 1.0f / n2;
         Q4 qi = q4(q.w * s, -q.x * s, -q.y * s, -q.z * s);
-        for (int i = 0; i < b; i++) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = d.op_ref + 7 * t;
-          Q4 r4 = qmul(qi, q4(rr[3], rr[4], rr[5], rr[6])); o[k++] = r4.w; o[k++] = r4.x; o[k++] = r4.y; o[k++] = r4.z; }
+        for (int i = y; i < b; i += FB_NY) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = d.op_ref + 7 * t;
+          Q4 r4 = qmul(qi, q4(rr[3], rr[4], rr[5], rr[6])); o[k + 4 * i] = r4.w; o[k + 4 * i + 1] = r4.x; o[k + 4 * i + 2] = r4.y; o[k + 4 * i + 3] = r4.z; }
       } break;
-      case FB_OBS_SCALARS: { o[k++] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; } o[k++] = s2; o[k++] = AT(d.time, 0); } break;
-      case FB_OBS_ROOT_POSE: { V3 p = rpos + ref; o[k++] = p.x; o[k++] = p.y; o[k++] = p.z; for (int i = 0; i < 4; i++) o[k++] = AT(d.qpos, rq + 3 + i); } break;
-      case FB_OBS_SUBTREE_COM: { float mass = AT(d.crb10, 10 * a); for (int i = 0; i < 3; i++) o[k++] = (mass > 0 ? AT(d.crb10, 10 * a + 1 + i) / mass : 0.0f) + AT(d.ref, i); } break;
+      case FB_OBS_SCALARS: if (y == 0) { o[k] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; } o[k + 1] = s2; o[k + 2] = AT(d.time, 0); } break;
+      case FB_OBS_ROOT_POSE: if (y < 3) o[k + y] = comp(rpos + ref, y); else if (y < 7) o[k + y] = AT(d.qpos, rq + y); break;
+      case FB_OBS_SUBTREE_COM: if (y < 3) { float mass = AT(d.crb10, 10 * a); o[k + y] = (mass > 0 ? AT(d.crb10, 10 * a + 1 + y) / mass : 0.0f) + AT(d.ref, y); } break;
       default: break;
     }
   }
+}
+// partial reset staged by fb_reset / fb_reset_hold: warp w of the launch rewrites env rst_ids[w]
+FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int w, int y) {
+  if (w >= d.rst_n) return;
+  int e = d.rst_ids[w];
+  for (int i = y; i < m.nq; i += FB_NY) AT(d.qpos, i) = d.rst_qpos[(size_t)w * m.nq + i];
+  for (int i = y; i < m.nv; i += FB_NY) { AT(d.qvel, i) = d.rst_has_qvel ? d.rst_qvel[(size_t)w * m.nv + i] : 0.0f; AT(d.qacc, i) = 0; AT(d.qacc_warmstart, i) = 0; }
+  for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) = 0;
+  if (y == 0) { AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = d.rst_hold; }
+}
+FB_DEV void kclear_hold(const DevModel& m, const DevData& d, int e, int y) { if (y == 0) AT(d.hold, 0) = 0; }
+// generic column scatter (fb_write_state / fb_set_ctrl): field[idx[c]] of env e <- vals[e][c]
+FB_DEV void kscatter(const DevModel& m, const DevData& d, int e, int y) {
+  if (e >= d.N && e < d.Np) { for (int c = y; c < d.sc_k; c += FB_NY) AT(d.sc_field, d.sc_idx ? d.sc_idx[c] : c) = d.sc_vals[c]; return; }   // pad envs mirror env 0
+  if (e >= d.Np) return;
+  for (int c = y; c < d.sc_k; c += FB_NY) AT(d.sc_field, d.sc_idx ? d.sc_idx[c] : c) = d.sc_vals[(size_t)e * d.sc_k + c];
 }

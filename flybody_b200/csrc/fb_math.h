@@ -55,10 +55,9 @@ FB_DEV Q4 axisangle(V3 axis, float ang) {
 }
 FB_DEV float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-// SoA accessors: component i of env e
-// 32-bit index arithmetic: the largest per-env array (efc_J, 160*nv entries) stays below 2^32 elements for
-// up to ~230k padded envs per device (checked in fb_create)
-#define AT(arr, i) (arr)[(unsigned)(i) * (unsigned)d.Np + (unsigned)e]
+// record accessor: slot i of array `arr` of env e (arr = record base + array offset).  32-bit index
+// arithmetic: rec * Np stays below 2^32 (checked in fb_create).
+#define AT(arr, i) (arr)[(unsigned)e * d.rec + (unsigned)(i)]
 
 FB_DEV V3 ld3(const float* arr, int i, const DevData& d, int e) { return v3(AT(arr, 3 * i), AT(arr, 3 * i + 1), AT(arr, 3 * i + 2)); }
 FB_DEV void st3(float* arr, int i, const DevData& d, int e, V3 v) { AT(arr, 3 * i) = v.x; AT(arr, 3 * i + 1) = v.y; AT(arr, 3 * i + 2) = v.z; }

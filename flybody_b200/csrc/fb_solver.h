@@ -32,7 +32,8 @@ enum { W_LAM = 0, W_JAR, W_F, W_R, W_U, W_DL, W_ADL, W_P, X_E0, X_E1, X_XQ, X_OU
 
 // memory of one env's problem: base pointers + element strides (1 in shared memory, Np in global memory)
 struct SolveMem { float* v; float* A; float* G; float* red; int st; };
-// SM == true: the env's slice of shared memory (unit stride); false: global arrays (stride = padded env count)
+// SM == true: the env's slice of shared memory (row capacity FB_SOLVE_NCAP); false: the env's global record
+// (row capacity FB_MAXEFC)
 #define SV(slot, r) sm.v[SM ? ((slot) * FB_SOLVE_NCAP + (r)) : ((slot) * FB_MAXEFC + (r)) * sm.st]
 #define AM(r, c) sm.A[SM ? ((r) >= (c) ? TRI(r, c) : TRI(c, r)) : ((r) >= (c) ? TRI(r, c) : TRI(c, r)) * sm.st]
 #define GM(p, q) sm.G[SM ? TRI(p, q) : TRI(p, q) * sm.st]        // p >= q
@@ -314,8 +315,8 @@ FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int 
   if (n <= m.solve_ncap) {
     sm.v = wsm + 4 * 32; sm.A = sm.v + S_NSLOT * FB_SOLVE_NCAP; sm.G = sm.A + TRI(FB_SOLVE_NCAP, 0); sm.st = 1;
     ksolve_impl<true>(m, d, sm, e, n);
-  } else {   // large problem: same code on the global arrays (element stride = padded env count)
-    sm.v = d.efc_w + e; sm.A = d.efc_A + e; sm.G = d.efc_G + e; sm.st = d.Np;
+  } else {   // large problem: same code on the env's global record (row capacity FB_MAXEFC)
+    sm.v = &AT(d.efc_w, 0); sm.A = &AT(d.efc_A, 0); sm.G = &AT(d.efc_G, 0); sm.st = 1;
     ksolve_impl<false>(m, d, sm, e, n);
   }
 }

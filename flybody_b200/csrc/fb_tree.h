@@ -1,23 +1,23 @@
 // fb_tree.h -- tree-structured stages: kinematics, composite inertia, sparse L^T D L factorisation
 // and solve, body velocities, RNE bias, passive (spring/damper/fluid) forces.
 //
-// Thread mapping of every "tree kernel": blockDim = (32 envs, nlist branch lists).  lane == env
-// (coalesced SoA access); threadIdx.y walks one branch list of the kinematic tree (a leg, the
-// abdomen chain, the head sub-tree ...) in topological order.  The root bodies (free joints) are
-// handled by y == 0; the lists exchange their contributions to the root through shared memory.
-// Each kernel is a sequence of *phases* separated by block barriers (see fb_run in fb_kernels.cu).
+// Thread mapping of every "tree kernel": one warp per env; lane y < nlist walks one branch list of the
+// kinematic tree (a leg, the abdomen chain, the head sub-tree ...) in topological order.  The root
+// bodies (free joints) are handled by y == 0; the lists exchange their contributions to the root through
+// the env's shared-memory slice.  Each kernel is a sequence of *phases* separated by warp barriers (see
+// fb_run in flybody_b200.cu).  (`lane` in the phase signatures indexes FB_LANES == 1 shared slices.)
 #pragma once
 #include "fb_math.h"
 
 struct ShTree {
-  float part[FB_NLMAX][24][32];    // per-list partial sums towards the root (crb:10, factor:21, solve:6, rne:12)
+  float part[FB_NLMAX][24][FB_LANES];    // per-list partial sums towards the root (crb:10, factor:21, solve:6, rne:12)
 };
 
 // dynamic shared memory that follows the fixed struct (per-kernel scratch: the L^T D L rows during the
 // factorisation, the right-hand side during tree solves), laid out [entry][lane]
 template <typename Sh> FB_DEV float* sh_dyn(Sh& sh) { return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&sh) + ((sizeof(Sh) + 15) & ~(size_t)15)); }
-#define LS(k) ldsh[(k) * 32 + lane]
-#define XS(k) xs[(k) * 32 + lane]
+#define LS(k) ldsh[(k) * FB_LANES + lane]
+#define XS(k) xs[(k) * FB_LANES + lane]
 
 #define FB_PHASE_ARGS const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y
 #define FB_LIST_LOOP_FWD for (int li_ = 0, b = 0; li_ < m.list_num[y] && ((b = m.list_body[m.list_adr[y] + li_]), true); li_++)
@@ -167,11 +167,11 @@ FB_DEV void kpos_p4(FB_PHASE_ARGS) {
 // M + h*diag(damping) for the second factorisation (entries are split over all threads of the block)
 FB_DEV void ld_writeout(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* dst, bool reinit) {
   float* ldsh = sh_dyn(sh);
-  for (int k = y; k < m.nM; k += m.nlist) { AT(dst, k) = LS(k); if (reinit) LS(k) = AT(d.qM, k); }
+  for (int k = y; k < m.nM; k += FB_NY) { AT(dst, k) = LS(k); if (reinit) LS(k) = AT(d.qM, k); }
 }
 FB_DEV void ld_add_damping(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
   float* ldsh = sh_dyn(sh);
-  for (int i = y; i < m.nv; i += m.nlist) LS(m.dof_Madr[i]) += m.timestep * m.dof_damping[i];
+  for (int i = y; i < m.nv; i += FB_NY) LS(m.dof_Madr[i]) += m.timestep * m.dof_damping[i];
 }
 
 // sparse L^T D L factorisation (Featherstone; MuJoCo mj_factorM), list part.  Row k of LD holds

@@ -1,9 +1,12 @@
 // fb_types.h -- device-side model / state layout of the batched fly stepper.
 //
-// Layout rule (DESIGN.md "Data layout in HBM"): every per-env array is SoA [component][env], env
-// fastest, fp32, env count padded to a multiple of 32, so that lane == env gives one coalesced
-// 128-byte transaction per component.  Model constants are small read-only arrays that every lane
-// reads at the same address (broadcast, L1-resident).
+// Thread mapping / layout rule (DESIGN.md "Data layout in HBM"): ONE WARP OWNS ONE ENVIRONMENT.  The 32
+// lanes of the warp split the env's intra-step parallelism (branch lists of the kinematic tree, pair
+// chunks of the collision list, constraint rows, dofs); synchronisation is __syncwarp only and every env
+// runs its own data-dependent trip counts.  All per-env state and intermediates live in one fp32/int32
+// RECORD per env (array-of-records, `rec` 4-byte slots apart), so the lanes of a warp touch neighbouring
+// addresses of the same record.  Model constants are small read-only arrays read through the constant
+// bank / L1.
 #pragma once
 #include <stdint.h>
 #include "../../include/flybody_b200.h"
@@ -18,8 +21,11 @@
 #define FB_HD
 #endif
 
-#define FB_NLMAX 12          // branch lists (threadIdx.y of tree kernels)
-#define FB_MAXCHUNK 32       // collision chunks (threadIdx.y of the collision kernel)
+#define FB_NY 32             // lanes per env (threadIdx.x); every kernel runs 32 lanes per env
+#define FB_WPB 8             // envs (warps) per block
+#define FB_LANES 1           // shared-memory slices are per env
+#define FB_NLMAX 12          // branch lists of the tree kernels (lanes 0..nlist-1 active)
+#define FB_MAXCHUNK 32       // collision chunks (one per lane)
 #define FB_CHUNKCAP 16       // contacts one chunk may emit
 #define FB_ROWPAR 8          // rows processed in parallel by the projection kernel
 #define FB_MINVAL 1e-15f
@@ -62,7 +68,8 @@ struct DevModel {
 enum { FB_CT_LIMIT = 0, FB_CT_FRICTIONLESS = 1, FB_CT_ELLIPTIC = 2 };
 
 struct DevData {
-  int N, Np;                   // envs, padded envs (stride of every array)
+  int N, Np;                   // envs, padded envs
+  unsigned rec;                // record stride (4-byte slots) between consecutive envs
   int nsub_done, sens_mode;
   // integrated state
   float *qpos, *qvel, *act, *ctrl, *qacc, *qacc_warmstart, *time;
@@ -91,12 +98,13 @@ struct DevData {
   // sensors / outputs
   float *sensordata, *sensor_sum;
   int *flags, *niter, *hold;   // hold != 0: env is not integrated by the next fb_step (pending reset)
-  const int* rst_ids; const float* rst_qpos; const float* rst_qvel; int rst_n, rst_has_qvel;   // staged partial reset
+  const int* rst_ids; const float* rst_qpos; const float* rst_qvel; int rst_n, rst_has_qvel, rst_hold;   // staged partial reset
+  float* sc_field; const int* sc_idx; const float* sc_vals; int sc_k;                                 // staged column scatter
   float *obs;                  // packed AoS observation [N][obs_dim]
   int obs_dim;
   // task observation program (fb_obs_program): final observation rows [N][tobs_dim]
   float *tobs; int tobs_dim, op_n, op_root_body, op_ref_len, op_nsub;
-  const int *op_kind, *op_a, *op_b, *op_list; const float* op_ref; const int* op_step; const unsigned char* op_first;
+  const int *op_kind, *op_a, *op_b, *op_off, *op_list; const float* op_ref; const int* op_step; const unsigned char* op_first;
 };
 
 #ifdef __CUDACC__

@@ -5,7 +5,7 @@
 // (SURVEY.md App. A), each substep being the staged kernel pipeline
 //   step2: k_act -> k_smooth(solve) -> k_ref -> k_solve -> k_finish(qacc, sensors, Euler)
 //   step1: k_pos(kinematics, CRB, factor) -> k_col -> k_con -> k_proj(J, Z, A) -> k_vel(RNE, passive)
-// with all intermediates in SoA device arrays (fb_types.h).
+// One warp per env, all per-env data in one record per env (fb_types.h).
 //
 // The same translation unit compiles as plain C++ with -DFB_EMU (tests/_emu): phases run in
 // nested host loops.  That build exists ONLY so CPU tests can exercise the kernel source; the
@@ -61,57 +61,43 @@ struct FbSim {
   int first_substep; int hold_pending;
   int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
   int* op_step_dev; unsigned char* op_first_dev;
+  float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
 #ifndef FB_EMU
   cudaStream_t stream; cudaEvent_t ev0, ev1;
 #endif
 };
 
+static size_t slice_bytes(size_t fixed, size_t dyn_floats) { return ((((fixed + 15) & ~(size_t)15) + dyn_floats * sizeof(float)) + 15) & ~(size_t)15; }
 #ifndef FB_EMU
+// one warp per env: threadIdx.x = lane ("y" of the phase functions), threadIdx.y = env within the block
 template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
-__global__ void fb_run(DevModel m, DevData d) {
+__global__ void __launch_bounds__(32 * FB_WPB) fb_run(DevModel m, DevData d, int slice, int nwarps) {
   extern __shared__ __align__(16) unsigned char fb_smem[];
-  Sh& sh = *reinterpret_cast<Sh*>(fb_smem);
-  int lane = threadIdx.x, y = threadIdx.y, e = blockIdx.x * 32 + lane;
-  ((Ph(m, d, sh, e, lane, y), __syncthreads()), ...);
+  int e = blockIdx.x * FB_WPB + threadIdx.y;
+  if (e >= nwarps) return;
+  Sh& sh = *reinterpret_cast<Sh*>(fb_smem + (size_t)threadIdx.y * slice);
+  int y = threadIdx.x;
+  ((Ph(m, d, sh, e, 0, y), __syncwarp()), ...);
 }
-static size_t smem_bytes(size_t fixed, size_t dyn_floats) { return ((fixed + 15) & ~(size_t)15) + dyn_floats * sizeof(float); }
 template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
-static void fb_launch(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
-  dim3 block(32, ny), grid(s->d.Np / 32);
-  size_t bytes = smem_bytes(sizeof(Sh), dyn_floats);
+static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1) {
+  if (nwarps < 0) nwarps = s->d.Np;
+  dim3 block(32, FB_WPB), grid((nwarps + FB_WPB - 1) / FB_WPB);
+  size_t slice = slice_bytes(sizeof(Sh), dyn_floats), bytes = slice * FB_WPB;
   static size_t configured = 0;
   if (bytes > configured) { cudaFuncSetAttribute(fb_run<Sh, Ph...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, s->stream);
-    fb_run<Sh, Ph...><<<grid, block, bytes, s->stream>>>(s->m, s->d);
+    fb_run<Sh, Ph...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps);
     cudaEventRecord(b, s->stream);
     s->prof_events.push_back({kind, a, b});
   } else {
-    fb_run<Sh, Ph...><<<grid, block, bytes, s->stream>>>(s->m, s->d);
+    fb_run<Sh, Ph...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps);
   }
   s->launches++;
 }
-#else
-template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
-static void fb_launch(FbSim* s, int ny, int kind, size_t dyn_floats = 0) {
-  (void)kind;
-  static std::vector<unsigned char> buf;
-  size_t need = ((sizeof(Sh) + 15) & ~(size_t)15) + dyn_floats * sizeof(float) + 64;
-  if (buf.size() < need) buf.resize(need);
-  Sh& sh = *reinterpret_cast<Sh*>(buf.data());
-  for (int blk = 0; blk < s->d.Np / 32; blk++) {
-    auto run = [&](void (*ph)(const DevModel&, const DevData&, Sh&, int, int, int)) {
-      for (int y = 0; y < ny; y++) for (int lane = 0; lane < 32; lane++) ph(s->m, s->d, sh, blk * 32 + lane, lane, y);
-    };
-    (run(Ph), ...);
-  }
-  s->launches++;
-}
-#endif
-
-#ifndef FB_EMU
-__global__ void fb_run_solve(DevModel m, DevData d) {
+__global__ void __launch_bounds__(32 * FB_SOLVE_WPB) fb_run_solve(DevModel m, DevData d) {
   extern __shared__ __align__(16) float fb_smem_w[];
   int e = blockIdx.x * FB_SOLVE_WPB + threadIdx.y;
   if (e >= d.Np) return;
@@ -134,6 +120,20 @@ static void fb_launch_warp(FbSim* s, int kind) {
   s->launches++;
 }
 #else
+template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
+static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1) {
+  (void)kind;
+  if (nwarps < 0) nwarps = s->d.Np;
+  static std::vector<unsigned char> buf;
+  size_t need = slice_bytes(sizeof(Sh), dyn_floats) + 64;
+  if (buf.size() < need) buf.resize(need);
+  Sh& sh = *reinterpret_cast<Sh*>(buf.data());
+  for (int e = 0; e < nwarps; e++) {
+    auto run = [&](void (*ph)(const DevModel&, const DevData&, Sh&, int, int, int)) { for (int y = 0; y < FB_NY; y++) ph(s->m, s->d, sh, e, 0, y); };
+    (run(Ph), ...);
+  }
+  s->launches++;
+}
 static void fb_launch_warp(FbSim* s, int kind) {
   (void)kind;
   static std::vector<float> buf(FB_SOLVE_WARP_FLOATS);
@@ -143,9 +143,10 @@ static void fb_launch_warp(FbSim* s, int kind) {
 #endif
 
 // lane == env kernels wrapped as single-phase functions
-FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kreset_scatter(m, d, e); }
-FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kclear_hold(m, d, e); }
-FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int) { kpack(m, d, e, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); ktaskobs(m, d, e); }
+FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kreset_scatter(m, d, e, y); }
+FB_DEV void ph_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kscatter(m, d, e, y); }
+FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kclear_hold(m, d, e, y); }
+FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kpack(m, d, e, y, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); ktaskobs(m, d, e, y); }
 // qacc_smooth = M^-1 qfrc_smooth (qacc_smooth already holds the rhs)
 FB_DEV void ph_smooth_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD); }
 FB_DEV void ph_smooth_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD); }
@@ -158,22 +159,20 @@ FB_DEV void ph_smooth_c(FB_PHASE_ARGS) {
 }
 
 static void launch_step1(FbSim* s) {
-  int nl = s->m.nlist;
-  fb_launch<ShTree, kpos_p0, kpos_p1, kpos_p2, kpos_p3, kpos_p4, kpos_p5, kpos_p6, kpos_p6w, kpos_p6d, kpos_p7, kpos_p8, kpos_p9>(s, nl, K_POS, (size_t)s->m.nM * 32);
-  fb_launch<ShCol, kcol_p0, kcol_p1>(s, s->m.nchunk, K_COL);
-  fb_launch<ShCon, kcon_p0, kcon_p1, kcon_p2, kcon_p3, kproj_p0, kproj_p1>(s, FB_ROWPAR, K_PROJ, (size_t)FB_ROWPAR * s->m.nv * 32);
-  fb_launch<ShTree, kvel_p0, kvel_p1, kvel_p2, kvel_p3, kvel_p4>(s, nl, K_VEL);
+  fb_launch<ShTree, kpos_p0, kpos_p1, kpos_p2, kpos_p3, kpos_p4, kpos_p5, kpos_p6, kpos_p6w, kpos_p6d, kpos_p7, kpos_p8, kpos_p9>(s, K_POS, (size_t)s->m.nM);
+  fb_launch<ShCol, kcol_p0, kcol_p1>(s, K_COL);
+  fb_launch<ShCon, kcon_p0, kcon_p1, kcon_p2, kcon_p3, kproj_p0, kproj_p1>(s, K_PROJ, (size_t)FB_ROWPAR * s->m.nv);
+  fb_launch<ShTree, kvel_p0, kvel_p1, kvel_p2, kvel_p3, kvel_p4>(s, K_VEL);
 }
 static void launch_step2(FbSim* s, bool integrate) {
-  int nl = s->m.nlist;
-  fb_launch<ShTree, kact_p0, kact_p1, kact_p2, kact_p3, ph_smooth_a, ph_smooth_b, ph_smooth_c, kref>(s, nl, K_SMOOTH, (size_t)s->m.nv * 32);
+  fb_launch<ShTree, kact_p0, kact_p1, kact_p2, kact_p3, ph_smooth_a, ph_smooth_b, ph_smooth_c, kref>(s, K_SMOOTH, (size_t)s->m.nv);
   fb_launch_warp(s, K_SOLVE);
   if (integrate)
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
-              kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, nl, K_FINISH, (size_t)s->m.nv * 32);
+              kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, K_FINISH, (size_t)s->m.nv);
   else
     fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
-              kfin_sens_out>(s, nl, K_FINISH, (size_t)s->m.nv * 32);
+              kfin_sens_out>(s, K_FINISH, (size_t)s->m.nv);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -307,10 +306,12 @@ static int build_model(FbSim* s, const FbModel* h) {
 static int alloc_data(FbSim* s, int N) {
   DevData& d = s->d; const DevModel& m = s->m;
   memset(&d, 0, sizeof(d));
-  d.N = N; d.Np = fb_pad32(N); d.sens_mode = -1;
-  size_t Np = d.Np;
-#define FA(field, n) d.field = dalloc<float>(s, (size_t)(n) * Np); if (!d.field) { s->err = "out of device memory (" #field ")"; return -4; }
-#define IA(field, n) d.field = dalloc<int>(s, (size_t)(n) * Np); if (!d.field) { s->err = "out of device memory (" #field ")"; return -4; }
+  d.N = N; d.Np = (N + FB_WPB - 1) / FB_WPB * FB_WPB; d.sens_mode = -1;
+  // pass 1: lay the per-env record out (offsets in 4-byte slots); pass 2: one allocation, rebase the pointers
+  std::vector<std::pair<void**, size_t>> fields;
+  size_t off = 0;
+#define FA(field, n) { fields.push_back({(void**)&d.field, off}); off += (size_t)(n); }
+#define IA(field, n) FA(field, n)
   FA(qpos, m.nq) FA(qvel, m.nv) FA(act, m.na + 1) FA(ctrl, m.nu + 1) FA(qacc, m.nv) FA(qacc_warmstart, m.nv) FA(time, 1)
   FA(ref, 3) FA(xpos, 3 * m.nbody) FA(xquat, 4 * m.nbody) FA(xmat, 9 * m.nbody) FA(xipos, 3 * m.nbody) FA(ximat, 9 * m.nbody)
   FA(geom_xpos, 3 * m.ngeom) FA(geom_xmat, 9 * m.ngeom) FA(site_xpos, 3 * m.nsite + 3) FA(site_xmat, 9 * m.nsite + 9)
@@ -325,30 +326,56 @@ static int alloc_data(FbSim* s, int N) {
   IA(nefc, 1) IA(efc_type, FB_MAXEFC) IA(efc_id, FB_MAXEFC)
   FA(efc_pos, FB_MAXEFC) FA(efc_margin, FB_MAXEFC) FA(efc_D, FB_MAXEFC) FA(efc_R, FB_MAXEFC) FA(efc_K, FB_MAXEFC) FA(efc_B, FB_MAXEFC)
   FA(efc_imp, FB_MAXEFC) FA(efc_aref, FB_MAXEFC) FA(efc_b, FB_MAXEFC) FA(efc_force, FB_MAXEFC) FA(efc_jarws, FB_MAXEFC)
-  FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv) FA(efc_A, (size_t)FB_MAXEFC * (FB_MAXEFC + 1) / 2) FA(efc_G, (size_t)FB_MAXEFC * (FB_MAXEFC + 1) / 2)
-  FA(efc_w, (size_t)S_NSLOT * FB_MAXEFC) IA(efc_ecol, FB_MAXEFC) IA(efc_ekind, FB_MAXEFC) IA(efc_state, FB_MAXEFC) IA(efc_colidx, FB_MAXEFC) IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC)
+  IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC)
   FA(sensordata, m.nsensordata + 1) FA(sensor_sum, m.nsensordata + 1) IA(flags, 1) IA(niter, 1) IA(hold, 1)
+  // large, sparsely touched arrays last
+  FA(efc_w, (size_t)S_NSLOT * FB_MAXEFC)
+  FA(efc_A, (size_t)FB_MAXEFC * (FB_MAXEFC + 1) / 2) FA(efc_G, (size_t)FB_MAXEFC * (FB_MAXEFC + 1) / 2)
+  FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv)
 #undef FA
 #undef IA
+  off = (off + 31) & ~(size_t)31;              // records start on 128-byte boundaries
+  if ((double)off * d.Np >= 4.0e9) { s->err = "too many envs for 32-bit record indexing"; return -5; }
+  d.rec = (unsigned)off;
+  float* base = dalloc<float>(s, (size_t)d.Np * off);
+  if (!base) { s->err = "out of device memory (env records)"; return -4; }
+  for (auto& f : fields) *f.first = (void*)(base + f.second);
   d.obs_dim = m.nq + m.nv + m.na + 2 * m.nsensordata + 12 + 3 * m.nsite + 3;
-  d.obs = dalloc<float>(s, (size_t)d.obs_dim * Np);
+  d.obs = dalloc<float>(s, (size_t)d.obs_dim * d.Np);
+  s->stage_cap = 0; s->stage = nullptr; s->stage_i = nullptr;
   return 0;
 }
 
-// SoA <-> AoS host transfers
-static void field_to_host(FbSim* s, const float* dev, int n, float* dst_aos) {
-  size_t Np = s->d.Np; std::vector<float> tmp((size_t)n * Np);
-  d2h(tmp.data(), dev, sizeof(float) * n * Np);
-  for (int e = 0; e < s->d.N; e++) for (int i = 0; i < n; i++) dst_aos[(size_t)e * n + i] = tmp[(size_t)i * Np + e];
+// host <-> device transfers of one field: host side is AoS [N][n]; device side is n slots of every record
+static void field_to_host(FbSim* s, const void* dev, int n, void* dst) {
+  if (n <= 0) return;
+#ifndef FB_EMU
+  cudaMemcpy2D(dst, (size_t)n * 4, dev, (size_t)s->d.rec * 4, (size_t)n * 4, s->d.N, cudaMemcpyDeviceToHost);
+#else
+  for (int e = 0; e < s->d.N; e++) memcpy((char*)dst + (size_t)e * n * 4, (const char*)dev + (size_t)e * s->d.rec * 4, (size_t)n * 4);
+#endif
 }
-static void ifield_to_host(FbSim* s, const int* dev, int n, std::vector<int>& out) {
-  size_t Np = s->d.Np; out.resize((size_t)n * Np);
-  d2h(out.data(), dev, sizeof(int) * n * Np);
+static void field_from_host(FbSim* s, void* dev, int n, const void* src) {
+  if (n <= 0) return;
+#ifndef FB_EMU
+  cudaMemcpy2D(dev, (size_t)s->d.rec * 4, src, (size_t)n * 4, (size_t)n * 4, s->d.N, cudaMemcpyHostToDevice);
+  for (int e = s->d.N; e < s->d.Np; e++) cudaMemcpy((char*)dev + (size_t)e * s->d.rec * 4, src, (size_t)n * 4, cudaMemcpyHostToDevice);   // pad envs mirror env 0
+#else
+  for (int e = 0; e < s->d.Np; e++) memcpy((char*)dev + (size_t)e * s->d.rec * 4, (const char*)src + (size_t)(e < s->d.N ? e : 0) * n * 4, (size_t)n * 4);
+#endif
 }
-static void field_from_host(FbSim* s, float* dev, int n, const float* src_aos) {
-  size_t Np = s->d.Np; std::vector<float> tmp((size_t)n * Np);
-  for (size_t e = 0; e < Np; e++) { size_t se = e < (size_t)s->d.N ? e : 0; for (int i = 0; i < n; i++) tmp[(size_t)i * Np + e] = src_aos[se * n + i]; }
-  h2d(dev, tmp.data(), sizeof(float) * n * Np);
+// device staging buffer for scatter-style uploads (ctrl, ghost pose, partial resets)
+static int ensure_stage(FbSim* s, size_t floats, size_t ints) {
+  if (floats > s->stage_cap) { s->stage = dalloc<float>(s, floats); s->stage_cap = floats; if (!s->stage) return -4; }
+  if (ints > s->stage_icap) { s->stage_i = dalloc<int>(s, ints); s->stage_icap = ints; if (!s->stage_i) return -4; }
+  return 0;
+}
+static void upload_async(FbSim* s, void* dst, const void* src, size_t bytes) {
+#ifndef FB_EMU
+  cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->stream);
+#else
+  memcpy(dst, src, bytes);
+#endif
 }
 
 static int sync_stream(FbSim* s) {
@@ -363,19 +390,17 @@ extern "C" {
 
 const char* fb_version(void) {
 #ifdef FB_EMU
-  return "flybody_b200 0.1 (host emulation build: tests only)";
+  return "flybody_b200 0.2 (host emulation build: tests only)";
 #else
-  return "flybody_b200 0.1 (sm_100a)";
+  return "flybody_b200 0.2 (sm_100a)";
 #endif
 }
 
 int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   if (!hm || !out || n_envs <= 0) return -1;
-  if ((double)fb_pad32(n_envs) * FB_MAXEFC * (hm->nv > 0 ? hm->nv : 1) >= 4.0e9) return -5;   // 32-bit SoA indexing limit
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
-  s->op_step_dev = nullptr; s->op_first_dev = nullptr;
-  s->rst_ids_dev = nullptr; s->rst_qpos_dev = nullptr; s->rst_qvel_dev = nullptr; s->rst_cap = 0;
+  s->op_step_dev = nullptr; s->op_first_dev = nullptr; s->stage_cap = 0; s->stage_icap = 0; s->stage = nullptr; s->stage_i = nullptr;
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -405,6 +430,7 @@ int fb_destroy(FbHandle s) {
 const char* fb_last_error(FbHandle s) { return s ? s->err.c_str() : "null handle"; }
 int fb_n_envs(FbHandle s) { return s ? s->d.N : -1; }
 int fb_n_envs_padded(FbHandle s) { return s ? s->d.Np : -1; }
+int fb_record_stride(FbHandle s) { return s ? (int)s->d.rec : -1; }
 long long fb_launch_count(FbHandle s) { return s ? s->launches : -1; }
 float fb_last_step_ms(FbHandle s) {
 #ifndef FB_EMU
@@ -451,7 +477,7 @@ int fb_step(FbHandle s, int n_substeps) {
     s->d.sens_mode = -1;
   }
   s->d.nsub_done = n_substeps;
-  if (s->hold_pending) { fb_launch<ShNone, ph_clear_hold>(s, 1, K_MISC); s->hold_pending = 0; }
+  if (s->hold_pending) { fb_launch<ShNone, ph_clear_hold>(s, K_MISC); s->hold_pending = 0; }
 #ifndef FB_EMU
   cudaEventRecord(s->ev1, s->stream);
   if (cudaGetLastError() != cudaSuccess) { s->err = "kernel launch failed"; return -2; }
@@ -459,7 +485,7 @@ int fb_step(FbHandle s, int n_substeps) {
   return 0;
 }
 
-static float* field_ptr(FbSim* s, int field, int* n) {
+static void* field_ptr(FbSim* s, int field, int* n) {
   const DevModel& m = s->m; DevData& d = s->d;
   switch (field) {
     case FB_QPOS: *n = m.nq; return d.qpos;
@@ -500,8 +526,8 @@ int fb_field_size(FbHandle s, int field) {
 int fb_get(FbHandle s, int field, void* dst, int is_device) {
   if (!s || !dst) return -1;
   if (sync_stream(s) != 0) return -2;
-  int n; float* p = field_ptr(s, field, &n);
-  const DevModel& m = s->m; int N = s->d.N; size_t Np = s->d.Np;
+  int n; void* p = field_ptr(s, field, &n);
+  const DevModel& m = s->m; int N = s->d.N;
   if (is_device) { if (!p) { s->err = "field has no device array"; return -1; } *(void**)dst = p; return 0; }
   float* out = (float*)dst;
   if (p) {
@@ -513,12 +539,12 @@ int fb_get(FbHandle s, int field, void* dst, int is_device) {
     if (field == FB_SENSOR_MEAN && s->d.nsub_done > 0) for (size_t i = 0; i < (size_t)N * n; i++) out[i] /= (float)s->d.nsub_done;
     return 0;
   }
-  std::vector<int> iv;
+  std::vector<int> iv(N);
   switch (field) {
-    case FB_NCON: ifield_to_host(s, s->d.ncon, 1, iv); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
-    case FB_NEFC: ifield_to_host(s, s->d.nefc, 1, iv); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
-    case FB_SOLVER_NITER: ifield_to_host(s, s->d.niter, 1, iv); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
-    case FB_FLAGS: ifield_to_host(s, s->d.flags, 1, iv); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
+    case FB_NCON: field_to_host(s, s->d.ncon, 1, iv.data()); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
+    case FB_NEFC: field_to_host(s, s->d.nefc, 1, iv.data()); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
+    case FB_SOLVER_NITER: field_to_host(s, s->d.niter, 1, iv.data()); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
+    case FB_FLAGS: field_to_host(s, s->d.flags, 1, iv.data()); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
     case FB_SUBTREE_COM: {
       std::vector<float> crb((size_t)10 * m.nbody * N), ref((size_t)3 * N);
       field_to_host(s, s->d.crb10, 10 * m.nbody, crb.data()); field_to_host(s, s->d.ref, 3, ref.data());
@@ -533,18 +559,18 @@ int fb_get(FbHandle s, int field, void* dst, int is_device) {
       return 0; }
     case FB_CONTACT: {
       std::vector<float> dist((size_t)FB_MAXCON * N), pos((size_t)3 * FB_MAXCON * N), frame((size_t)9 * FB_MAXCON * N), mu((size_t)FB_MAXCON * N), ref((size_t)3 * N);
-      std::vector<int> g1, g2, ea, dm, nc;
+      std::vector<int> g1((size_t)FB_MAXCON * N), g2((size_t)FB_MAXCON * N), ea((size_t)FB_MAXCON * N), dm((size_t)FB_MAXCON * N), nc(N);
       field_to_host(s, s->d.con_dist, FB_MAXCON, dist.data()); field_to_host(s, s->d.con_pos, 3 * FB_MAXCON, pos.data());
       field_to_host(s, s->d.con_frame, 9 * FB_MAXCON, frame.data()); field_to_host(s, s->d.con_mu, FB_MAXCON, mu.data()); field_to_host(s, s->d.ref, 3, ref.data());
-      ifield_to_host(s, s->d.con_geom1, FB_MAXCON, g1); ifield_to_host(s, s->d.con_geom2, FB_MAXCON, g2);
-      ifield_to_host(s, s->d.con_efcadr, FB_MAXCON, ea); ifield_to_host(s, s->d.con_dim, FB_MAXCON, dm); ifield_to_host(s, s->d.ncon, 1, nc);
+      field_to_host(s, s->d.con_geom1, FB_MAXCON, g1.data()); field_to_host(s, s->d.con_geom2, FB_MAXCON, g2.data());
+      field_to_host(s, s->d.con_efcadr, FB_MAXCON, ea.data()); field_to_host(s, s->d.con_dim, FB_MAXCON, dm.data()); field_to_host(s, s->d.ncon, 1, nc.data());
       memset(out, 0, sizeof(float) * (size_t)N * 16 * FB_MAXCON);
       for (int e = 0; e < N; e++) for (int c = 0; c < nc[e] && c < FB_MAXCON; c++) {
-        float* o = out + ((size_t)e * FB_MAXCON + c) * 16;
-        o[0] = dist[(size_t)e * FB_MAXCON + c];
-        for (int i = 0; i < 3; i++) { o[1 + i] = pos[((size_t)e * FB_MAXCON + c) * 3 + i] + ref[(size_t)e * 3 + i]; o[4 + i] = frame[((size_t)e * FB_MAXCON + c) * 9 + i]; }
-        o[7] = (float)g1[(size_t)c * Np + e]; o[8] = (float)g2[(size_t)c * Np + e]; o[9] = (float)dm[(size_t)c * Np + e];
-        o[12] = (float)ea[(size_t)c * Np + e]; o[10] = o[12] >= 0 ? 1.0f : 0.0f; o[11] = mu[(size_t)e * FB_MAXCON + c];
+        float* o = out + ((size_t)e * FB_MAXCON + c) * 16; size_t ec = (size_t)e * FB_MAXCON + c;
+        o[0] = dist[ec];
+        for (int i = 0; i < 3; i++) { o[1 + i] = pos[ec * 3 + i] + ref[(size_t)e * 3 + i]; o[4 + i] = frame[ec * 9 + i]; }
+        o[7] = (float)g1[ec]; o[8] = (float)g2[ec]; o[9] = (float)dm[ec];
+        o[12] = (float)ea[ec]; o[10] = o[12] >= 0 ? 1.0f : 0.0f; o[11] = mu[ec];
       }
       return 0; }
     default: s->err = "unknown field"; return -1;
@@ -554,79 +580,86 @@ int fb_get(FbHandle s, int field, void* dst, int is_device) {
 int fb_set(FbHandle s, int field, const float* src) {
   if (!s || !src) return -1;
   if (sync_stream(s) != 0) return -2;
-  int n; float* p = field_ptr(s, field, &n);
+  int n; void* p = field_ptr(s, field, &n);
   if (!p || !(field == FB_QPOS || field == FB_QVEL || field == FB_ACT || field == FB_CTRL || field == FB_QACC_WARMSTART || field == FB_QACC || field == FB_TIME)) { s->err = "field is not writable"; return -1; }
   if (n > 0) field_from_host(s, p, n, src);
   return 0;
 }
 
+// scatter vals[N][k] (already on the device, row-major) into columns idx[k] (device ints, or NULL = 0..k-1) of `field`
+static void launch_scatter(FbSim* s, float* field, const int* idx_dev, const float* vals_dev, int k) {
+  s->d.sc_field = field; s->d.sc_idx = idx_dev; s->d.sc_vals = vals_dev; s->d.sc_k = k;
+  fb_launch<ShNone, ph_scatter>(s, K_MISC);
+}
+
 int fb_set_ctrl(FbHandle s, const float* ctrl, int is_device) {
   if (!s || !ctrl) return -1;
-  if (!is_device) return fb_set(s, FB_CTRL, ctrl);
-#ifndef FB_EMU
-  FB_CUDA_OK(cudaMemcpyAsync(s->d.ctrl, ctrl, sizeof(float) * s->m.nu * s->d.Np, cudaMemcpyDeviceToDevice, s->stream));
-#else
-  memcpy(s->d.ctrl, ctrl, sizeof(float) * s->m.nu * s->d.Np);
-#endif
+  const float* src = ctrl;
+  if (!is_device) {
+    if (ensure_stage(s, (size_t)s->d.N * s->m.nu, 0) != 0) { s->err = "out of device memory (staging)"; return -4; }
+    upload_async(s, s->stage, ctrl, sizeof(float) * (size_t)s->d.N * s->m.nu);
+    src = s->stage;
+  }
+  launch_scatter(s, s->d.ctrl, nullptr, src, s->m.nu);
   return 0;
 }
 
 int fb_write_state(FbHandle s, int field, const int32_t* idx, int k, const float* vals) {
   if (!s || !idx || !vals || k <= 0) return -1;
-  if (sync_stream(s) != 0) return -2;
-  int n; float* p = field_ptr(s, field, &n);
+  int n; float* p = (float*)field_ptr(s, field, &n);
   if (!p || !(field == FB_QPOS || field == FB_QVEL || field == FB_ACT)) { s->err = "fb_write_state: field must be qpos, qvel or act"; return -1; }
-  size_t Np = s->d.Np; std::vector<float> row(Np);
-  for (int c = 0; c < k; c++) {
-    if (idx[c] < 0 || idx[c] >= n) { s->err = "fb_write_state: index out of range"; return -1; }
-    for (size_t e = 0; e < Np; e++) row[e] = vals[(e < (size_t)s->d.N ? e : 0) * k + c];
-    h2d(p + (size_t)idx[c] * Np, row.data(), sizeof(float) * Np);
-  }
+  for (int c = 0; c < k; c++) if (idx[c] < 0 || idx[c] >= n) { s->err = "fb_write_state: index out of range"; return -1; }
+  // separate staging regions so that several writes can be in flight before the next sync
+  size_t need = (size_t)s->d.N * s->m.nu + (size_t)4 * s->d.N * 16;
+  if (k > 16) return -1;
+  if (ensure_stage(s, need, 64) != 0) { s->err = "out of device memory (staging)"; return -4; }
+  int slot = s->ws_slot++ & 3;
+  float* vdev = s->stage + (size_t)s->d.N * s->m.nu + (size_t)slot * s->d.N * 16;
+  int* idev = s->stage_i + slot * 16;
+  upload_async(s, idev, idx, sizeof(int) * k);
+  upload_async(s, vdev, vals, sizeof(float) * (size_t)s->d.N * k);
+  launch_scatter(s, p, idev, vdev, k);
   return 0;
 }
 
-int fb_reset(FbHandle s, const int32_t* env_ids, int n, const float* qpos, const float* qvel) {
-  if (!s) return -1;
+static int do_reset(FbSim* s, const int32_t* env_ids, int n, const float* qpos, const float* qvel, int hold) {
+  const DevModel& m = s->m; int N = s->d.N, Np = s->d.Np;
   if (sync_stream(s) != 0) return -2;
-  const DevModel& m = s->m; int N = s->d.N; size_t Np = s->d.Np;
-  std::vector<int> ids;
-  if (env_ids) ids.assign(env_ids, env_ids + n); else { ids.resize(N); for (int e = 0; e < N; e++) ids[e] = e; n = N; }
-  for (int e : ids) if (e < 0 || e >= N) { s->err = "fb_reset: env id out of range"; return -1; }
-  auto patch = [&](float* dev, int nf, const float* src, const double* dflt) {
-    std::vector<float> tmp((size_t)nf * Np);
-    d2h(tmp.data(), dev, sizeof(float) * nf * Np);
-    for (int k = 0; k < n; k++) for (int i = 0; i < nf; i++) tmp[(size_t)i * Np + ids[k]] = src ? src[(size_t)k * nf + i] : (dflt ? (float)dflt[i] : 0.0f);
-    if (n == N) for (size_t e = N; e < Np; e++) for (int i = 0; i < nf; i++) tmp[(size_t)i * Np + e] = tmp[(size_t)i * Np];
-    h2d(dev, tmp.data(), sizeof(float) * nf * Np);
-  };
-  patch(s->d.qpos, m.nq, qpos, s->h_qpos0.data());
-  patch(s->d.qvel, m.nv, qvel, nullptr);
-  if (m.na) patch(s->d.act, m.na, nullptr, nullptr);
-  patch(s->d.qacc_warmstart, m.nv, nullptr, nullptr);
-  patch(s->d.qacc, m.nv, nullptr, nullptr);
-  patch(s->d.time, 1, nullptr, nullptr);
-  { std::vector<int> fl(Np); d2h(fl.data(), s->d.flags, sizeof(int) * Np); for (int k = 0; k < n; k++) fl[ids[k]] = 0; if (n == N) for (size_t e = N; e < Np; e++) fl[e] = 0; h2d(s->d.flags, fl.data(), sizeof(int) * Np); }
-  return fb_forward(s);
-}
-
-int fb_reset_hold(FbHandle s, const int32_t* env_ids, int n, const float* qpos, const float* qvel) {
-  if (!s || !env_ids || !qpos || n <= 0) return -1;
-  const DevModel& m = s->m;
-  for (int k = 0; k < n; k++) if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_reset_hold: env id out of range"; return -1; }
-  if (sync_stream(s) != 0) return -2;
-  if (n > s->rst_cap) {
-    s->rst_cap = std::max(n, s->d.N);
+  std::vector<int> ids; std::vector<float> qp, qv;
+  bool all = (env_ids == nullptr);
+  if (all) n = N;
+  for (int k = 0; k < n; k++) { int e = all ? k : env_ids[k]; if (e < 0 || e >= N) { s->err = "reset: env id out of range"; return -1; } ids.push_back(e); }
+  qp.resize((size_t)ids.size() * m.nq);
+  for (size_t k = 0; k < ids.size(); k++) for (int i = 0; i < m.nq; i++) qp[k * m.nq + i] = qpos ? qpos[k * m.nq + i] : (float)s->h_qpos0[i];
+  if (qvel) qv.assign(qvel, qvel + (size_t)ids.size() * m.nv);
+  if (all) for (int e = N; e < Np; e++) {          // pad envs mirror env 0
+    ids.push_back(e); qp.insert(qp.end(), qp.begin(), qp.begin() + m.nq); if (qvel) qv.insert(qv.end(), qv.begin(), qv.begin() + m.nv);
+  }
+  int cnt = (int)ids.size();
+  if (cnt > s->rst_cap) {
+    s->rst_cap = std::max(cnt, Np);
     s->rst_ids_dev = dalloc<int>(s, s->rst_cap); s->rst_qpos_dev = dalloc<float>(s, (size_t)s->rst_cap * m.nq); s->rst_qvel_dev = dalloc<float>(s, (size_t)s->rst_cap * m.nv);
   }
-  h2d(s->rst_ids_dev, env_ids, sizeof(int) * n);
-  h2d(s->rst_qpos_dev, qpos, sizeof(float) * (size_t)n * m.nq);
-  if (qvel) h2d(s->rst_qvel_dev, qvel, sizeof(float) * (size_t)n * m.nv);
-  s->d.rst_ids = s->rst_ids_dev; s->d.rst_qpos = s->rst_qpos_dev; s->d.rst_qvel = s->rst_qvel_dev; s->d.rst_n = n; s->d.rst_has_qvel = qvel ? 1 : 0;
-  fb_launch<ShNone, ph_reset_scatter>(s, 1, K_MISC);
+  h2d(s->rst_ids_dev, ids.data(), sizeof(int) * cnt);
+  h2d(s->rst_qpos_dev, qp.data(), sizeof(float) * qp.size());
+  if (qvel) h2d(s->rst_qvel_dev, qv.data(), sizeof(float) * qv.size());
+  s->d.rst_ids = s->rst_ids_dev; s->d.rst_qpos = s->rst_qpos_dev; s->d.rst_qvel = s->rst_qvel_dev; s->d.rst_n = cnt; s->d.rst_has_qvel = qvel ? 1 : 0; s->d.rst_hold = hold;
+  fb_launch<ShNone, ph_reset_scatter>(s, K_MISC, 0, cnt);
   s->d.rst_n = 0;
-  s->hold_pending = 1;
   return 0;
 }
+int fb_reset(FbHandle s, const int32_t* env_ids, int n, const float* qpos, const float* qvel) {
+  if (!s) return -1;
+  int rc = do_reset(s, env_ids, n, qpos, qvel, 0);
+  return rc != 0 ? rc : fb_forward(s);
+}
+int fb_reset_hold(FbHandle s, const int32_t* env_ids, int n, const float* qpos, const float* qvel) {
+  if (!s || !env_ids || !qpos || n <= 0) return -1;
+  int rc = do_reset(s, env_ids, n, qpos, qvel, 1);
+  if (rc == 0) s->hold_pending = 1;
+  return rc;
+}
+
 int fb_profile(FbHandle s, int enable) {
   if (!s) return -1;
   s->prof_on = enable ? 1 : 0;
@@ -644,13 +677,15 @@ int fb_profile_read(FbHandle s, double* ms, long long* counts, int n) {
   return K_NKIND;
 }
 const char* fb_profile_name(int kind) { return (kind >= 0 && kind < K_NKIND) ? kKindNames[kind] : ""; }
+
 int fb_obs_program(FbHandle s, const FbObsProgram* p) {
   if (!s || !p || p->n_items <= 0) return -1;
   if (sync_stream(s) != 0) return -2;
   const DevModel& m = s->m;
-  int dim = 0;
+  int dim = 0; std::vector<int> offs;
   for (int i = 0; i < p->n_items; i++) {
     int k = p->kind[i], b = p->b[i];
+    offs.push_back(dim);
     switch (k) {
       case FB_OBS_SENSOR_MEAN: case FB_OBS_SENSOR_NOW: case FB_OBS_ACT: case FB_OBS_QPOS: case FB_OBS_QVEL: dim += b; break;
       case FB_OBS_SITES_EGO: case FB_OBS_REF_DISP: dim += 3 * b; break;
@@ -664,7 +699,7 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
   }
   if (p->root_body <= 0 || p->root_body >= m.nbody) { s->err = "fb_obs_program: root body"; return -1; }
   std::vector<int> kind(p->kind, p->kind + p->n_items), a(p->a, p->a + p->n_items), b(p->b, p->b + p->n_items), list(p->list, p->list + std::max(p->n_list, 0));
-  s->d.op_kind = up(s, kind); s->d.op_a = up(s, a); s->d.op_b = up(s, b); s->d.op_list = up(s, list);
+  s->d.op_kind = up(s, kind); s->d.op_a = up(s, a); s->d.op_b = up(s, b); s->d.op_off = up(s, offs); s->d.op_list = up(s, list);
   s->d.op_n = p->n_items; s->d.op_root_body = p->root_body; s->d.op_nsub = p->n_sub; s->d.op_ref_len = p->ref_len;
   if (p->ref_qpos && p->ref_len > 0) { std::vector<float> r(p->ref_qpos, p->ref_qpos + (size_t)7 * p->ref_len); s->d.op_ref = up(s, r); } else s->d.op_ref = nullptr;
   s->d.tobs_dim = dim; s->d.tobs = dalloc<float>(s, (size_t)dim * s->d.Np);
@@ -674,12 +709,8 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
 }
 int fb_task_inputs(FbHandle s, const int32_t* step_idx, const uint8_t* first) {
   if (!s || !s->d.tobs || !step_idx || !first) return -1;
-#ifndef FB_EMU
-  FB_CUDA_OK(cudaMemcpyAsync(s->op_step_dev, step_idx, sizeof(int) * s->d.N, cudaMemcpyHostToDevice, s->stream));
-  FB_CUDA_OK(cudaMemcpyAsync(s->op_first_dev, first, s->d.N, cudaMemcpyHostToDevice, s->stream));
-#else
-  memcpy(s->op_step_dev, step_idx, sizeof(int) * s->d.N); memcpy(s->op_first_dev, first, s->d.N);
-#endif
+  upload_async(s, s->op_step_dev, step_idx, sizeof(int) * s->d.N);
+  upload_async(s, s->op_first_dev, first, s->d.N);
   return 0;
 }
 int fb_read_task_obs(FbHandle s, float* host_dst) {
@@ -697,7 +728,7 @@ int fb_pack_obs(FbHandle s) {
 #ifndef FB_EMU
   cudaSetDevice(s->device);
 #endif
-  fb_launch<ShNone, ph_pack>(s, 1, K_PACK);
+  fb_launch<ShNone, ph_pack>(s, K_PACK);
   return 0;
 }
 int fb_read_obs(FbHandle s, float* host_dst) {

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libflybody_b200.so')
 MAXCON, MAXEFC = 64, 160
 
 EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_write_state', 'fb_step', 'fb_forward',
-           'fb_get', 'fb_field_size', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
+           'fb_get', 'fb_field_size', 'fb_record_stride', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
            'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
 
@@ -58,6 +58,7 @@ def load_library(path=None):
     lib.fb_forward.argtypes = [C.c_void_p]
     lib.fb_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.fb_field_size.argtypes = [C.c_void_p, C.c_int]
+    lib.fb_record_stride.argtypes = [C.c_void_p]
     lib.fb_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_obs_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     lib.fb_obs_program.argtypes = [C.c_void_p, C.c_void_p]
@@ -219,7 +220,7 @@ class BatchedStepper:
         return {self._lib.fb_profile_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
 
     def set_control_device(self, dev_ptr):
-        """ctrl already resident on the device as SoA [nu][n_envs_padded] fp32."""
+        """ctrl already resident on the device as contiguous rows [n_envs][nu] fp32."""
         self._check(self._lib.fb_set_ctrl(self._h, C.c_void_p(dev_ptr), 1), 'fb_set_ctrl')
 
     def pack_obs(self):

@@ -9,8 +9,8 @@
  * Conventions: plain C, no torch types.  Return 0 on success, negative code on error
  * (message via fb_last_error).  Caller owns host buffers; the library owns device buffers.
  * One handle = one device + one stream; calls on a handle are not re-entrant.
- * All per-env device arrays are SoA, [component][env] with env fastest, fp32.
- * Host-side buffers passed to fb_* are AoS [env][component] (what numpy/dm_env code holds).
+ * Device side: one fp32/int32 record per env (one warp steps one env); host-side buffers passed to fb_*
+ * are rows [env][component] (what numpy/dm_env code holds).
  */
 #ifndef FLYBODY_B200_H_
 #define FLYBODY_B200_H_
@@ -201,8 +201,8 @@ int fb_reset(FbHandle h, const int32_t* env_ids, int n, const float* qpos, const
  * every substep but does not integrate them; the hold is cleared when that fb_step completes.            */
 int fb_reset_hold(FbHandle h, const int32_t* env_ids, int n, const float* qpos, const float* qvel);
 
-/* physics.set_control(ctrl) (fruitfly.py:540-544).  ctrl: [N][nu] AoS host (is_device=0) or
- * [nu][N] SoA device pointer (is_device=1).                                                    */
+/* physics.set_control(ctrl) (fruitfly.py:540-544).  ctrl: contiguous rows [N][nu], on the host
+ * (is_device=0, copied asynchronously on the handle's stream) or already on the device (is_device=1). */
 int fb_set_ctrl(FbHandle h, const float* ctrl, int is_device);
 
 /* walker.set_pose / set_velocity on a subset of coordinates (walk_imitation.py:141-145):
@@ -219,9 +219,11 @@ int fb_step(FbHandle h, int n_substeps);
 int fb_forward(FbHandle h);
 
 /* Read a per-env field.  is_device=0: dst is host [N][n] AoS float32, synchronises.
- * is_device=1: *(void**)dst receives the borrowed device pointer ([n][Npad] SoA).           */
+ * is_device=1: *(void**)dst receives the borrowed device pointer of env 0's slots; consecutive envs
+ * are fb_record_stride() 4-byte slots apart.                                                  */
 int fb_get(FbHandle h, int field, void* dst, int is_device);
 int fb_field_size(FbHandle h, int field);   /* floats per env, <0 on error */
+int fb_record_stride(FbHandle h);           /* 4-byte slots between the records of consecutive envs */
 int fb_set(FbHandle h, int field, const float* src);  /* host [N][n] AoS -> device, all envs */
 
 /* Packed observation buffer of the last control step, [N][floats_per_env] AoS on device, for the
