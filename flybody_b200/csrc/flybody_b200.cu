@@ -30,9 +30,10 @@ typedef int cudaStream_t_;
 // memory / launch abstraction
 #ifndef FB_EMU
 #define FB_CUDA_OK(call) do { cudaError_t err_ = (call); if (err_ != cudaSuccess) { s->err = std::string(#call) + ": " + cudaGetErrorString(err_); return -2; } } while (0)
-static void* dev_alloc(size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) return nullptr; cudaMemset(p, 0, bytes ? bytes : 4); return p; }
+static void* dev_alloc(size_t bytes) {   // rare (create / first use): zero-fill and make it visible to every stream
+  void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) return nullptr; cudaMemset(p, 0, bytes ? bytes : 4); cudaDeviceSynchronize(); return p; }
 static void dev_free(void* p) { cudaFree(p); }
-static void h2d(void* dst, const void* src, size_t n) { cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); }
+static void h2d(void* dst, const void* src, size_t n) { cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); cudaDeviceSynchronize(); }
 static void d2h(void* dst, const void* src, size_t n) { cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost); }
 #else
 #define FB_CUDA_OK(call) do { } while (0)
@@ -350,7 +351,8 @@ static int alloc_data(FbSim* s, int N) {
 static void field_to_host(FbSim* s, const void* dev, int n, void* dst) {
   if (n <= 0) return;
 #ifndef FB_EMU
-  cudaMemcpy2D(dst, (size_t)n * 4, dev, (size_t)s->d.rec * 4, (size_t)n * 4, s->d.N, cudaMemcpyDeviceToHost);
+  cudaMemcpy2DAsync(dst, (size_t)n * 4, dev, (size_t)s->d.rec * 4, (size_t)n * 4, s->d.N, cudaMemcpyDeviceToHost, s->stream);
+  cudaStreamSynchronize(s->stream);
 #else
   for (int e = 0; e < s->d.N; e++) memcpy((char*)dst + (size_t)e * n * 4, (const char*)dev + (size_t)e * s->d.rec * 4, (size_t)n * 4);
 #endif
@@ -358,14 +360,19 @@ static void field_to_host(FbSim* s, const void* dev, int n, void* dst) {
 static void field_from_host(FbSim* s, void* dev, int n, const void* src) {
   if (n <= 0) return;
 #ifndef FB_EMU
-  cudaMemcpy2D(dev, (size_t)s->d.rec * 4, src, (size_t)n * 4, (size_t)n * 4, s->d.N, cudaMemcpyHostToDevice);
-  for (int e = s->d.N; e < s->d.Np; e++) cudaMemcpy((char*)dev + (size_t)e * s->d.rec * 4, src, (size_t)n * 4, cudaMemcpyHostToDevice);   // pad envs mirror env 0
+  // stream-ordered (the handle's stream is non-blocking: legacy default-stream copies would not order with its kernels)
+  cudaMemcpy2DAsync(dev, (size_t)s->d.rec * 4, src, (size_t)n * 4, (size_t)n * 4, s->d.N, cudaMemcpyHostToDevice, s->stream);
+  for (int e = s->d.N; e < s->d.Np; e++) cudaMemcpyAsync((char*)dev + (size_t)e * s->d.rec * 4, src, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream);   // pad envs mirror env 0
+  cudaStreamSynchronize(s->stream);
 #else
   for (int e = 0; e < s->d.Np; e++) memcpy((char*)dev + (size_t)e * s->d.rec * 4, (const char*)src + (size_t)(e < s->d.N ? e : 0) * n * 4, (size_t)n * 4);
 #endif
 }
 // device staging buffer for scatter-style uploads (ctrl, ghost pose, partial resets)
 static int ensure_stage(FbSim* s, size_t floats, size_t ints) {
+#ifndef FB_EMU
+  if (floats > s->stage_cap || ints > s->stage_icap) cudaDeviceSynchronize();
+#endif
   if (floats > s->stage_cap) { s->stage = dalloc<float>(s, floats); s->stage_cap = floats; if (!s->stage) return -4; }
   if (ints > s->stage_icap) { s->stage_i = dalloc<int>(s, ints); s->stage_icap = ints; if (!s->stage_i) return -4; }
   return 0;
@@ -410,6 +417,9 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   if (rc == 0) rc = alloc_data(s, n_envs);
   *out = s;
   if (rc != 0) return rc;
+#ifndef FB_EMU
+  cudaDeviceSynchronize();                 // model uploads / memsets ran on the legacy stream
+#endif
   std::vector<float> q0((size_t)n_envs * hm->nq);
   for (int e = 0; e < n_envs; e++) for (int i = 0; i < hm->nq; i++) q0[(size_t)e * hm->nq + i] = (float)hm->qpos0[i];
   field_from_host(s, s->d.qpos, hm->nq, q0.data());
@@ -640,9 +650,12 @@ static int do_reset(FbSim* s, const int32_t* env_ids, int n, const float* qpos, 
     s->rst_cap = std::max(cnt, Np);
     s->rst_ids_dev = dalloc<int>(s, s->rst_cap); s->rst_qpos_dev = dalloc<float>(s, (size_t)s->rst_cap * m.nq); s->rst_qvel_dev = dalloc<float>(s, (size_t)s->rst_cap * m.nv);
   }
-  h2d(s->rst_ids_dev, ids.data(), sizeof(int) * cnt);
-  h2d(s->rst_qpos_dev, qp.data(), sizeof(float) * qp.size());
-  if (qvel) h2d(s->rst_qvel_dev, qv.data(), sizeof(float) * qv.size());
+  upload_async(s, s->rst_ids_dev, ids.data(), sizeof(int) * cnt);
+  upload_async(s, s->rst_qpos_dev, qp.data(), sizeof(float) * qp.size());
+  if (qvel) upload_async(s, s->rst_qvel_dev, qv.data(), sizeof(float) * qv.size());
+#ifndef FB_EMU
+  cudaStreamSynchronize(s->stream);       // the host vectors go out of scope below
+#endif
   s->d.rst_ids = s->rst_ids_dev; s->d.rst_qpos = s->rst_qpos_dev; s->d.rst_qvel = s->rst_qvel_dev; s->d.rst_n = cnt; s->d.rst_has_qvel = qvel ? 1 : 0; s->d.rst_hold = hold;
   fb_launch<ShNone, ph_reset_scatter>(s, K_MISC, 0, cnt);
   s->d.rst_n = 0;
@@ -705,6 +718,9 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
   s->d.tobs_dim = dim; s->d.tobs = dalloc<float>(s, (size_t)dim * s->d.Np);
   s->op_step_dev = dalloc<int>(s, s->d.Np); s->op_first_dev = (unsigned char*)dalloc<int>(s, s->d.Np);
   s->d.op_step = s->op_step_dev; s->d.op_first = s->op_first_dev;
+#ifndef FB_EMU
+  cudaDeviceSynchronize();
+#endif
   return dim;
 }
 int fb_task_inputs(FbHandle s, const int32_t* step_idx, const uint8_t* first) {
