@@ -39,13 +39,6 @@ struct SolveMem { float* v; float* A; float* G; float* red; int st; };
 #define GM(p, q) sm.G[SM ? TRI(p, q) : TRI(p, q) * sm.st]        // p >= q
 #define RED(k, l) sm.red[(k) * 32 + (l)]
 
-#ifdef __CUDACC__
-#define WPAR_BEGIN { const int lane = threadIdx.x;
-#define WPAR_END } __syncwarp();
-#else
-#define WPAR_BEGIN for (int lane = 0; lane < 32; lane++) {
-#define WPAR_END }
-#endif
 #define WROWS for (int r = lane; r < n; r += 32)
 FB_DEV float red_total(const SolveMem& sm, int k) { float s = 0; for (int l = 0; l < 32; l++) s += RED(k, l); return s; }
 // warp sums: butterfly shuffles on the GPU (every lane gets the total, no shared-memory round trip);
@@ -133,11 +126,7 @@ template <bool SM> FB_DEVN float matvec_rows(const SolveMem sm, int n, int lane,
   }
   return acc;
 }
-#ifdef __CUDACC__
-#define FB_WARPFN __device__ __forceinline__
-#else
-#define FB_WARPFN static inline
-#endif
+
 
 template <bool SM>
 FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& sm, int e, int n) {

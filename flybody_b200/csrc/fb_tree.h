@@ -10,7 +10,7 @@
 #include "fb_math.h"
 
 struct ShTree {
-  float part[FB_NLMAX][24][FB_LANES];    // per-list partial sums towards the root (crb:10, factor:21, solve:6, rne:12)
+  float part[FB_NY][24][FB_LANES];    // per-list partial sums towards the root (crb:10, factor:21, solve:6, rne:12)
 };
 
 // dynamic shared memory that follows the fixed struct (per-kernel scratch: the L^T D L rows during the
@@ -25,14 +25,12 @@ template <typename Sh> FB_DEV float* sh_dyn(Sh& sh) { return reinterpret_cast<fl
 
 // ---------------------------------------------------------------------------------------------
 // K1 kinematics (MuJoCo mj_kinematics + mj_comPos; reference model fruitfly.xml:307-731)
-FB_DEV void body_kinematics(const DevModel& m, const DevData& d, int e, int b) {
-  int p = m.body_parentid[b];
-  V3 ppos = ld3(d.xpos, p, d, e);
-  Q4 pq = ld4(d.xquat, p, d, e);
+// chain part: pose of body b from its parent's pose (pp, pq) and the joint coordinates; writes xpos, xquat
+// and the motion subspaces of the body's dofs.  Returns the body's pose for the next link of the chain.
+FB_DEV void body_pose(const DevModel& m, const DevData& d, int e, int b, V3 ppos, Q4 pq, V3 ref, V3& pos, Q4& quat) {
   M3 pR = q2m(pq);
-  V3 pos = ppos + mul(pR, mld3(m.body_pos, b));
-  Q4 quat = qmul(pq, mld4(m.body_quat, b));
-  V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
+  pos = ppos + mul(pR, mld3(m.body_pos, b));
+  quat = qmul(pq, mld4(m.body_quat, b));
   int jn = m.body_jntnum[b];
   for (int k = 0; k < jn; k++) {
     int j = m.body_jntadr[b] + k, qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
@@ -61,12 +59,16 @@ FB_DEV void body_kinematics(const DevModel& m, const DevData& d, int e, int b) {
     }
   }
   quat = qnormalize(quat);
+  st3(d.xpos, b, d, e, pos); st4(d.xquat, b, d, e, quat);
+}
+// per-body part (no dependence between bodies): rotation matrix, inertial frame, spatial inertia about ref
+FB_DEV void body_derived(const DevModel& m, const DevData& d, int e, int b) {
+  V3 pos = ld3(d.xpos, b, d, e); Q4 quat = ld4(d.xquat, b, d, e);
   M3 R = q2m(quat);
-  st3(d.xpos, b, d, e, pos); st4(d.xquat, b, d, e, quat); st9(d.xmat, b, d, e, R);
+  st9(d.xmat, b, d, e, R);
   V3 ipos = pos + mul(R, mld3(m.body_ipos, b));
   M3 iR = q2m(qmul(quat, mld4(m.body_iquat, b)));
   st3(d.xipos, b, d, e, ipos); st9(d.ximat, b, d, e, iR);
-  // spatial inertia about ref
   float mass = m.body_mass[b];
   V3 di = mld3(m.body_inertia, b);
   float Ic[6];   // xx yy zz xy xz yz of R diag(di) R^T
@@ -82,15 +84,6 @@ FB_DEV void body_kinematics(const DevModel& m, const DevData& d, int e, int b) {
   I[4] = Ic[0] + mass * (cc - ipos.x * ipos.x); I[5] = Ic[1] + mass * (cc - ipos.y * ipos.y); I[6] = Ic[2] + mass * (cc - ipos.z * ipos.z);
   I[7] = Ic[3] - mass * ipos.x * ipos.y; I[8] = Ic[4] - mass * ipos.x * ipos.z; I[9] = Ic[5] - mass * ipos.y * ipos.z;
   for (int k = 0; k < 10; k++) { AT(d.inert10, 10 * b + k) = I[k]; AT(d.crb10, 10 * b + k) = I[k]; }
-  // geoms and sites rigidly attached to this body
-  for (int g = m.body_geomadr[b], ge = g + m.body_geomnum[b]; g < ge; g++) {
-    st3(d.geom_xpos, g, d, e, pos + mul(R, mld3(m.geom_pos, g)));
-    st9(d.geom_xmat, g, d, e, q2m(qmul(quat, mld4(m.geom_quat, g))));
-  }
-  for (int s = m.body_siteadr[b], se = s + m.body_sitenum[b]; s < se; s++) {
-    st3(d.site_xpos, s, d, e, pos + mul(R, mld3(m.site_pos, s)));
-    st9(d.site_xmat, s, d, e, q2m(qmul(quat, mld4(m.site_quat, s))));
-  }
 }
 
 FB_DEV void kpos_p0(FB_PHASE_ARGS) {
@@ -105,29 +98,56 @@ FB_DEV void kpos_p0(FB_PHASE_ARGS) {
   AT(d.ref, 0) = ref.x; AT(d.ref, 1) = ref.y; AT(d.ref, 2) = ref.z;
   // world body
   st3(d.xpos, 0, d, e, v3(0, 0, 0) - ref); st4(d.xquat, 0, d, e, q4(1, 0, 0, 0));
-  M3 I; for (int k = 0; k < 9; k++) I.m[k] = (k % 4 == 0) ? 1.f : 0.f;
-  st9(d.xmat, 0, d, e, I); st3(d.xipos, 0, d, e, v3(0, 0, 0) - ref); st9(d.ximat, 0, d, e, I);
-  for (int k = 0; k < 10; k++) { AT(d.inert10, k) = 0; AT(d.crb10, k) = 0; }
-  for (int g = m.body_geomadr[0], ge = g + m.body_geomnum[0]; g < ge; g++) {
-    st3(d.geom_xpos, g, d, e, mld3(m.geom_pos, g) - ref);
-    st9(d.geom_xmat, g, d, e, q2m(mld4(m.geom_quat, g)));
-  }
-  for (int r = 0; r < m.nroot; r++) body_kinematics(m, d, e, m.root_body[r]);
+  for (int r = 0; r < m.nroot; r++) { V3 pos; Q4 q; body_pose(m, d, e, m.root_body[r], v3(0, 0, 0) - ref, q4(1, 0, 0, 0), ref, pos, q); }
 }
+// chains: a list is walked in topological order; the parent pose is carried in registers when the parent is the
+// body visited just before (the usual case along a leg / the abdomen), otherwise re-read from the record
 FB_DEV void kpos_p1(FB_PHASE_ARGS) {
   if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD body_kinematics(m, d, e, b);
+  V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
+  int prev = -1; V3 cpos = v3(0, 0, 0); Q4 cq = q4(1, 0, 0, 0);
+  FB_LIST_LOOP_FWD {
+    int p = m.body_parentid[b];
+    V3 ppos; Q4 pq;
+    if (p == prev) { ppos = cpos; pq = cq; } else { ppos = ld3(d.xpos, p, d, e); pq = ld4(d.xquat, p, d, e); }
+    body_pose(m, d, e, b, ppos, pq, ref, cpos, cq);
+    prev = b;
+  }
 }
-// K2 composite inertia, backward accumulation (MuJoCo mj_crb)
+// all 32 lanes: per-body derived quantities, geom and site frames
+FB_DEV void kpos_p1b(FB_PHASE_ARGS) {
+  for (int b = y; b < m.nbody; b += FB_NY) {
+    if (b == 0) { M3 I; for (int k = 0; k < 9; k++) I.m[k] = (k % 4 == 0) ? 1.f : 0.f;
+      st9(d.xmat, 0, d, e, I); st3(d.xipos, 0, d, e, ld3(d.xpos, 0, d, e)); st9(d.ximat, 0, d, e, I);
+      for (int k = 0; k < 10; k++) { AT(d.inert10, k) = 0; AT(d.crb10, k) = 0; }
+    } else body_derived(m, d, e, b);
+  }
+  for (int g = y; g < m.ngeom; g += FB_NY) {
+    int b = m.geom_bodyid[g]; V3 pos = ld3(d.xpos, b, d, e); Q4 quat = ld4(d.xquat, b, d, e);
+    st3(d.geom_xpos, g, d, e, pos + mul(q2m(quat), mld3(m.geom_pos, g)));
+    st9(d.geom_xmat, g, d, e, q2m(qmul(quat, mld4(m.geom_quat, g))));
+  }
+  for (int t = y; t < m.nsite; t += FB_NY) {
+    int b = m.site_bodyid[t]; V3 pos = ld3(d.xpos, b, d, e); Q4 quat = ld4(d.xquat, b, d, e);
+    st3(d.site_xpos, t, d, e, pos + mul(q2m(quat), mld3(m.site_pos, t)));
+    st9(d.site_xmat, t, d, e, q2m(qmul(quat, mld4(m.site_quat, t))));
+  }
+}
+// K2 composite inertia, backward accumulation (MuJoCo mj_crb); the running sum of a chain stays in registers
 FB_DEV void kpos_p2(FB_PHASE_ARGS) {
   if (y >= m.nlist) return;
-  float acc[10];
-  for (int k = 0; k < 10; k++) acc[k] = 0;
+  float acc[10], carry[10]; int carry_to = -1;
+  for (int k = 0; k < 10; k++) { acc[k] = 0; carry[k] = 0; }
   FB_LIST_LOOP_REV {
+    float cur[10];
+    for (int k = 0; k < 10; k++) cur[k] = AT(d.crb10, 10 * b + k);
+    if (carry_to == b) { for (int k = 0; k < 10; k++) cur[k] += carry[k]; for (int k = 0; k < 10; k++) AT(d.crb10, 10 * b + k) = cur[k]; }
+    else if (carry_to >= 0) { for (int k = 0; k < 10; k++) AT(d.crb10, 10 * carry_to + k) += carry[k]; }   // branch point: flush
     int p = m.body_parentid[b];
-    if (m.body_isroot[p]) { for (int k = 0; k < 10; k++) acc[k] += AT(d.crb10, 10 * b + k); }
-    else { for (int k = 0; k < 10; k++) AT(d.crb10, 10 * p + k) += AT(d.crb10, 10 * b + k); }
+    if (m.body_isroot[p]) { for (int k = 0; k < 10; k++) acc[k] += cur[k]; carry_to = -1; }
+    else { for (int k = 0; k < 10; k++) carry[k] = cur[k]; carry_to = p; }
   }
+  if (carry_to >= 0) for (int k = 0; k < 10; k++) AT(d.crb10, 10 * carry_to + k) += carry[k];
   for (int k = 0; k < 10; k++) sh.part[y][k][lane] = acc[k];
 }
 FB_DEV void kpos_p3(FB_PHASE_ARGS) {
@@ -148,23 +168,19 @@ FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int lane, float
   V3 L, p;
   inert_mul(I, ld3(d.Sang, i, d, e), ld3(d.Slin, i, d, e), L, p);
   int adr = m.dof_Madr[i];
-  float hd = m.timestep * m.dof_damping[i];
   int t = 0;
   for (int j = i; j >= 0; j = m.dof_parentid[j], t++) {
     float v = dot(ld3(d.Sang, j, d, e), L) + dot(ld3(d.Slin, j, d, e), p);
     if (t == 0) v += m.dof_armature[i];
     AT(d.qM, adr + t) = v; LS(adr + t) = v;
   }
-  (void)hd;
 }
-FB_DEV void kpos_p4(FB_PHASE_ARGS) {
+FB_DEV void kpos_p4(FB_PHASE_ARGS) {      // all 32 lanes over the dofs
   float* ldsh = sh_dyn(sh);
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) mass_row(m, d, e, lane, ldsh, m.body_dofadr[b] + k); }
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) mass_row(m, d, e, lane, ldsh, m.body_dofadr[b] + k); }
+  for (int i = y; i < m.nv; i += FB_NY) mass_row(m, d, e, lane, ldsh, i);
 }
 // copy the factor held in shared memory out to `dst`; optionally re-initialise the shared rows with
-// M + h*diag(damping) for the second factorisation (entries are split over all threads of the block)
+// M + h*diag(damping) for the second factorisation (entries are split over all lanes)
 FB_DEV void ld_writeout(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* dst, bool reinit) {
   float* ldsh = sh_dyn(sh);
   for (int k = y; k < m.nM; k += FB_NY) { AT(dst, k) = LS(k); if (reinit) LS(k) = AT(d.qM, k); }
@@ -174,33 +190,38 @@ FB_DEV void ld_add_damping(const DevModel& m, const DevData& d, ShTree& sh, int 
   for (int i = y; i < m.nv; i += FB_NY) LS(m.dof_Madr[i]) += m.timestep * m.dof_damping[i];
 }
 
-// sparse L^T D L factorisation (Featherstone; MuJoCo mj_factorM), list part.  Row k of LD holds
-// (k,k), (k,parent(k)), ... at dof_Madr[k] + t.  Updates that land in the root block are summed
-// into sh.part (21 entries) and applied by the root thread.
-FB_DEV void factor_lists(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
+// sparse L^T D L factorisation (Featherstone; MuJoCo mj_factorM).  Row k of LD holds (k,k), (k,parent(k)), ...
+// at dof_Madr[k] + t.  The lists advance in lock-step, one dof per step (deepest first); FB_FSUB lanes share a
+// list and split the rank-1 update of the ancestor rows of that dof.  Updates that land in the root block are
+// summed into sh.part (21 entries per lane) and applied by the root lane afterwards.
+#define FB_FSUB 3
+FB_DEV void factor_clear(FB_PHASE_ARGS) { for (int k = 0; k < 21; k++) sh.part[y][k][lane] = 0; }
+FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* ldsh = sh_dyn(sh);
-  if (y >= m.nlist) return;
-  for (int k = 0; k < 21; k++) sh.part[y][k][lane] = 0;
-  FB_LIST_LOOP_REV {
-    for (int kk = m.body_dofnum[b] - 1; kk >= 0; kk--) {
-      int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
-      float Dk = LS(adrk);
-      float invD = 1.0f / Dk;
-      int t = 1;
-      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) {
-        float a = LS(adrk + t) * invD;
-        if (!m.dof_isroot[i]) {
-          int adri = m.dof_Madr[i], len = m.dof_chainlen[i];
-          for (int s = 0; s < len; s++) LS(adri + s) -= a * LS(adrk + t + s);
-        } else {
-          int il = m.dof_depth[i];        // for root dofs depth == local index
-          int base = il * (il + 1) / 2;
-          for (int s = 0; s <= il; s++) sh.part[y][base + s][lane] += a * LS(adrk + t + s);
-        }
-        LS(adrk + t) = a;
-      }
+  int l = y / FB_FSUB, sub = y % FB_FSUB;
+  if (l >= m.nlist || step >= m.list_ndof[l]) return;
+  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k];
+  float invD = 1.0f / LS(adrk);
+  int t = 1, cnt = 0;
+  for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) {
+    float a = LS(adrk + t) * invD;
+    if (!m.dof_isroot[i]) {
+      int adri = m.dof_Madr[i], len = m.dof_chainlen[i];
+      for (int s2 = 0; s2 < len; s2++, cnt++) if (cnt % FB_FSUB == sub) LS(adri + s2) -= a * LS(adrk + t + s2);
+    } else {
+      int il = m.dof_depth[i], base = il * (il + 1) / 2;       // for root dofs depth == local index
+      for (int s2 = 0; s2 <= il; s2++, cnt++) if (cnt % FB_FSUB == sub) sh.part[y][base + s2][lane] += a * LS(adrk + t + s2);
     }
   }
+}
+FB_DEV void factor_step_scale(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+  float* ldsh = sh_dyn(sh);
+  int l = y / FB_FSUB, sub = y % FB_FSUB;
+  if (l >= m.nlist || step >= m.list_ndof[l] || sub != 0) return;
+  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k];
+  float invD = 1.0f / LS(adrk);
+  int len = m.dof_chainlen[k];
+  for (int t = 1; t < len; t++) LS(adrk + t) *= invD;
 }
 FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
   float* ldsh = sh_dyn(sh);
@@ -212,7 +233,7 @@ FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, 
       int adri = m.dof_Madr[d0 + il], base = il * (il + 1) / 2;
       for (int s = 0; s <= il; s++) {
         float acc = 0;
-        for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc += sh.part[l][base + s][lane];
+        for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) for (int u = 0; u < FB_FSUB; u++) acc += sh.part[l * FB_FSUB + u][base + s][lane];
         LS(adri + s) -= acc;
       }
     }
@@ -228,12 +249,17 @@ FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, 
     }
   }
 }
-FB_DEV void kpos_p5(FB_PHASE_ARGS) { factor_lists(m, d, sh, e, lane, y); }
-FB_DEV void kpos_p6(FB_PHASE_ARGS) { factor_root(m, d, sh, e, lane, y); }
+// warp function: the whole factorisation of the rows currently held in shared memory
+FB_WARPFN void kpos_factor(const DevModel& m, const DevData& d, ShTree& sh, int e) {
+  WPAR_BEGIN factor_clear(m, d, sh, e, 0, lane); WPAR_END
+  for (int step = 0; step < m.max_list_ndof; step++) {
+    WPAR_BEGIN factor_step_update(m, d, sh, e, 0, lane, step); WPAR_END
+    WPAR_BEGIN factor_step_scale(m, d, sh, e, 0, lane, step); WPAR_END
+  }
+  WPAR_BEGIN factor_root(m, d, sh, e, 0, lane); WPAR_END
+}
 FB_DEV void kpos_p6w(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLD, true); }
 FB_DEV void kpos_p6d(FB_PHASE_ARGS) { ld_add_damping(m, d, sh, e, lane, y); }
-FB_DEV void kpos_p7(FB_PHASE_ARGS) { factor_lists(m, d, sh, e, lane, y); }
-FB_DEV void kpos_p8(FB_PHASE_ARGS) { factor_root(m, d, sh, e, lane, y); }
 FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe, false); }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,11 +24,24 @@
 #define FB_NY 32             // lanes per env (threadIdx.x); every kernel runs 32 lanes per env
 #define FB_WPB 8             // envs (warps) per block
 #define FB_LANES 1           // shared-memory slices are per env
-#define FB_NLMAX 12          // branch lists of the tree kernels (lanes 0..nlist-1 active)
+#define FB_NLMAX 10          // branch lists of the tree kernels (lanes 0..nlist-1 active; 3 lanes per list in the factorisation)
 #define FB_MAXCHUNK 32       // collision chunks (one per lane)
 #define FB_CHUNKCAP 16       // contacts one chunk may emit
 #define FB_ROWPAR 8          // rows processed in parallel by the projection kernel
 #define FB_MINVAL 1e-15f
+
+// Warp-cooperative code is written as WPAR sections: on the GPU every lane runs the section body and the
+// section ends in a warp barrier; the host emulation (tests only) runs the 32 lanes one after the other.
+// Code between sections is warp-uniform.
+#ifdef __CUDACC__
+#define WPAR_BEGIN { const int lane = threadIdx.x;
+#define WPAR_END } __syncwarp();
+#define FB_WARPFN __device__ __forceinline__
+#else
+#define WPAR_BEGIN for (int lane = 0; lane < 32; lane++) {
+#define WPAR_END }
+#define FB_WARPFN static inline
+#endif
 
 struct DevModel {
   // sizes / options
@@ -39,6 +52,7 @@ struct DevModel {
   int nroot, nlist;
   const int *root_body;                    // [nroot]
   const int *list_adr, *list_num, *list_body, *list_root;   // bodies of each branch list in topological order
+  const int *list_dofadr, *list_ndof, *list_dof; int max_list_ndof;   // dofs of each list, deepest first (factorisation order)
   // bodies
   const int *body_parentid, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_lastdof,
       *body_fluid_ellipsoid, *body_isroot, *body_geomadr, *body_geomnum, *body_siteadr, *body_sitenum;

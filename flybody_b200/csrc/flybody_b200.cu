@@ -69,32 +69,46 @@ struct FbSim {
 };
 
 static size_t slice_bytes(size_t fixed, size_t dyn_floats) { return ((((fixed + 15) & ~(size_t)15) + dyn_floats * sizeof(float)) + 15) & ~(size_t)15; }
+// kernel = sequence of stages for one env.  Ph<f>: per-lane phase f(m, d, sh, e, 0, y), a warp barrier follows;
+// Wf<f>: warp function f(m, d, sh, e) written with WPAR sections (its own barriers inside).
+template <auto F> struct Ph {
+#ifdef __CUDACC__
+  template <typename Sh> static __device__ __forceinline__ void run(const DevModel& m, const DevData& d, Sh& sh, int e, int y) { F(m, d, sh, e, 0, y); }
+#endif
+  template <typename Sh> static void emu(const DevModel& m, const DevData& d, Sh& sh, int e) { for (int y = 0; y < FB_NY; y++) F(m, d, sh, e, 0, y); }
+};
+template <auto F> struct Wf {
+#ifdef __CUDACC__
+  template <typename Sh> static __device__ __forceinline__ void run(const DevModel& m, const DevData& d, Sh& sh, int e, int) { F(m, d, sh, e); }
+#endif
+  template <typename Sh> static void emu(const DevModel& m, const DevData& d, Sh& sh, int e) { F(m, d, sh, e); }
+};
 #ifndef FB_EMU
 // one warp per env: threadIdx.x = lane ("y" of the phase functions), threadIdx.y = env within the block
-template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
+template <typename Sh, typename... St>
 __global__ void __launch_bounds__(32 * FB_WPB) fb_run(DevModel m, DevData d, int slice, int nwarps) {
   extern __shared__ __align__(16) unsigned char fb_smem[];
   int e = blockIdx.x * FB_WPB + threadIdx.y;
   if (e >= nwarps) return;
   Sh& sh = *reinterpret_cast<Sh*>(fb_smem + (size_t)threadIdx.y * slice);
   int y = threadIdx.x;
-  ((Ph(m, d, sh, e, 0, y), __syncwarp()), ...);
+  ((St::run(m, d, sh, e, y), __syncwarp()), ...);
 }
-template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
+template <typename Sh, typename... St>
 static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1) {
   if (nwarps < 0) nwarps = s->d.Np;
   dim3 block(32, FB_WPB), grid((nwarps + FB_WPB - 1) / FB_WPB);
   size_t slice = slice_bytes(sizeof(Sh), dyn_floats), bytes = slice * FB_WPB;
   static size_t configured = 0;
-  if (bytes > configured) { cudaFuncSetAttribute(fb_run<Sh, Ph...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
+  if (bytes > configured) { cudaFuncSetAttribute(fb_run<Sh, St...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, s->stream);
-    fb_run<Sh, Ph...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps);
+    fb_run<Sh, St...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps);
     cudaEventRecord(b, s->stream);
     s->prof_events.push_back({kind, a, b});
   } else {
-    fb_run<Sh, Ph...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps);
+    fb_run<Sh, St...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps);
   }
   s->launches++;
 }
@@ -121,7 +135,7 @@ static void fb_launch_warp(FbSim* s, int kind) {
   s->launches++;
 }
 #else
-template <typename Sh, void (*... Ph)(const DevModel&, const DevData&, Sh&, int, int, int)>
+template <typename Sh, typename... St>
 static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1) {
   (void)kind;
   if (nwarps < 0) nwarps = s->d.Np;
@@ -129,10 +143,7 @@ static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1
   size_t need = slice_bytes(sizeof(Sh), dyn_floats) + 64;
   if (buf.size() < need) buf.resize(need);
   Sh& sh = *reinterpret_cast<Sh*>(buf.data());
-  for (int e = 0; e < nwarps; e++) {
-    auto run = [&](void (*ph)(const DevModel&, const DevData&, Sh&, int, int, int)) { for (int y = 0; y < FB_NY; y++) ph(s->m, s->d, sh, e, 0, y); };
-    (run(Ph), ...);
-  }
+  for (int e = 0; e < nwarps; e++) (St::emu(s->m, s->d, sh, e), ...);
   s->launches++;
 }
 static void fb_launch_warp(FbSim* s, int kind) {
@@ -160,20 +171,18 @@ FB_DEV void ph_smooth_c(FB_PHASE_ARGS) {
 }
 
 static void launch_step1(FbSim* s) {
-  fb_launch<ShTree, kpos_p0, kpos_p1, kpos_p2, kpos_p3, kpos_p4, kpos_p5, kpos_p6, kpos_p6w, kpos_p6d, kpos_p7, kpos_p8, kpos_p9>(s, K_POS, (size_t)s->m.nM);
-  fb_launch<ShCol, kcol_p0, kcol_p1>(s, K_COL);
-  fb_launch<ShCon, kcon_p0, kcon_p1, kcon_p2, kcon_p3, kproj_p0, kproj_p1>(s, K_PROJ, (size_t)FB_ROWPAR * s->m.nv);
-  fb_launch<ShTree, kvel_p0, kvel_p1, kvel_p2, kvel_p3, kvel_p4>(s, K_VEL);
+  fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, (size_t)s->m.nM);
+  fb_launch<ShCol, Ph<kcol_p0>, Ph<kcol_p1>>(s, K_COL);
+  fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_ROWPAR * s->m.nv);
+  fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p4>>(s, K_VEL);
 }
 static void launch_step2(FbSim* s, bool integrate) {
-  fb_launch<ShTree, kact_p0, kact_p1, kact_p2, kact_p3, ph_smooth_a, ph_smooth_b, ph_smooth_c, kref>(s, K_SMOOTH, (size_t)s->m.nv);
+  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p3>, Ph<ph_smooth_a>, Ph<ph_smooth_b>, Ph<ph_smooth_c>, Ph<kref>>(s, K_SMOOTH, (size_t)s->m.nv);
   fb_launch_warp(s, K_SOLVE);
   if (integrate)
-    fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
-              kfin_sens_out, keul_rhs, keul_solve_a, keul_solve_b, keul_solve_c_integrate>(s, K_FINISH, (size_t)s->m.nv);
+    fb_launch<ShTree, Ph<kfin_copy>, Ph<kfin_solve_a>, Ph<kfin_solve_b>, Ph<kfin_solve_c>, Ph<kfin_sens_root>, Ph<kfin_sens_fwd>, Ph<kfin_sens_bwd>, Ph<kfin_sens_out>, Ph<keul_rhs>, Ph<keul_solve_a>, Ph<keul_solve_b>, Ph<keul_solve_c_integrate>>(s, K_FINISH, (size_t)s->m.nv);
   else
-    fb_launch<ShTree, kfin_copy, kfin_solve_a, kfin_solve_b, kfin_solve_c, kfin_sens_root, kfin_sens_fwd, kfin_sens_bwd,
-              kfin_sens_out>(s, K_FINISH, (size_t)s->m.nv);
+    fb_launch<ShTree, Ph<kfin_copy>, Ph<kfin_solve_a>, Ph<kfin_solve_b>, Ph<kfin_solve_c>, Ph<kfin_sens_root>, Ph<kfin_sens_fwd>, Ph<kfin_sens_bwd>, Ph<kfin_sens_out>>(s, K_FINISH, (size_t)s->m.nv);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -231,6 +240,13 @@ static int build_model(FbSim* s, const FbModel* h) {
   std::vector<int> ladr, lnum, lbody, lr;
   for (int l = 0; l < nlist; l++) { ladr.push_back((int)lbody.size()); lnum.push_back((int)lists[l].size()); lbody.insert(lbody.end(), lists[l].begin(), lists[l].end()); lr.push_back(lroot[l] < 0 ? 0 : lroot[l]); }
   m.nroot = (int)roots.size(); m.nlist = nlist;
+  { // factorisation order of each list: bodies in reverse, dofs in reverse
+    std::vector<int> dadr, dnum, dl; int mx = 0;
+    for (int l = 0; l < nlist; l++) { dadr.push_back((int)dl.size()); int c = 0;
+      for (int bi = (int)lists[l].size() - 1; bi >= 0; bi--) { int bb = lists[l][bi]; for (int kk = h->body_dofnum[bb] - 1; kk >= 0; kk--) { dl.push_back(h->body_dofadr[bb] + kk); c++; } }
+      dnum.push_back(c); mx = std::max(mx, c); }
+    m.list_dofadr = up(s, dadr); m.list_ndof = up(s, dnum); m.list_dof = up(s, dl); m.max_list_ndof = mx;
+  }
   m.root_body = up(s, roots); m.list_adr = up(s, ladr); m.list_num = up(s, lnum); m.list_body = up(s, lbody); m.list_root = up(s, lr);
   m.body_isroot = up(s, isroot);
   // geoms / sites per body (both are stored in body order by the compiler)
@@ -487,7 +503,7 @@ int fb_step(FbHandle s, int n_substeps) {
     s->d.sens_mode = -1;
   }
   s->d.nsub_done = n_substeps;
-  if (s->hold_pending) { fb_launch<ShNone, ph_clear_hold>(s, K_MISC); s->hold_pending = 0; }
+  if (s->hold_pending) { fb_launch<ShNone, Ph<ph_clear_hold>>(s, K_MISC); s->hold_pending = 0; }
 #ifndef FB_EMU
   cudaEventRecord(s->ev1, s->stream);
   if (cudaGetLastError() != cudaSuccess) { s->err = "kernel launch failed"; return -2; }
@@ -599,7 +615,7 @@ int fb_set(FbHandle s, int field, const float* src) {
 // scatter vals[N][k] (already on the device, row-major) into columns idx[k] (device ints, or NULL = 0..k-1) of `field`
 static void launch_scatter(FbSim* s, float* field, const int* idx_dev, const float* vals_dev, int k) {
   s->d.sc_field = field; s->d.sc_idx = idx_dev; s->d.sc_vals = vals_dev; s->d.sc_k = k;
-  fb_launch<ShNone, ph_scatter>(s, K_MISC);
+  fb_launch<ShNone, Ph<ph_scatter>>(s, K_MISC);
 }
 
 int fb_set_ctrl(FbHandle s, const float* ctrl, int is_device) {
@@ -657,7 +673,7 @@ static int do_reset(FbSim* s, const int32_t* env_ids, int n, const float* qpos, 
   cudaStreamSynchronize(s->stream);       // the host vectors go out of scope below
 #endif
   s->d.rst_ids = s->rst_ids_dev; s->d.rst_qpos = s->rst_qpos_dev; s->d.rst_qvel = s->rst_qvel_dev; s->d.rst_n = cnt; s->d.rst_has_qvel = qvel ? 1 : 0; s->d.rst_hold = hold;
-  fb_launch<ShNone, ph_reset_scatter>(s, K_MISC, 0, cnt);
+  fb_launch<ShNone, Ph<ph_reset_scatter>>(s, K_MISC, 0, cnt);
   s->d.rst_n = 0;
   return 0;
 }
@@ -744,7 +760,7 @@ int fb_pack_obs(FbHandle s) {
 #ifndef FB_EMU
   cudaSetDevice(s->device);
 #endif
-  fb_launch<ShNone, ph_pack>(s, K_PACK);
+  fb_launch<ShNone, Ph<ph_pack>>(s, K_PACK);
   return 0;
 }
 int fb_read_obs(FbHandle s, float* host_dst) {
