@@ -476,29 +476,30 @@ FB_DEV int qcqp2(float* res, const float* A, const float* b, float d0, float d1,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K12 acceleration-stage sensors + K13 Euler (tree kernel phases, see fb_kernels.cu for the order)
-// phase: qtmp <- qfrc_constraint (rhs of M x = J^T f)
-FB_DEV void kfin_copy(FB_PHASE_ARGS) {
+// K12 acceleration-stage sensors + K13 Euler: the "finish" kernel of step2.
+//   F1 all lanes : XS <- qfrc_constraint ; ext wrench array cleared
+//   F2..F4       : tree solve  XS <- M^-1 J^T f
+//   F5 all lanes : qacc = qacc_smooth + XS ; XS <- qfrc_smooth + qfrc_constraint (Euler rhs) ; lane 0: contact wrenches
+//   F6 lists     : Euler solve phase a (M + hD factor)       | root: delta-acceleration of the roots
+//   F7 lists     : delta-acceleration chains + body forces    | root: Euler solve phase b
+//   F8 lists     : subtree force sums ; Euler solve phase c ; integrate
+//   F9 all lanes : sensors (accelerometer, force, touch), state check
+// The sensor pass reuses the velocity stage: with the bias accelerations a0_b (bacc) and per-body bias forces
+// f0_b (bfrc0) of the same state, the full quantities are a_b = a0_b + delta_b, f_b = f0_b + I_b delta_b with
+// delta_b = delta_parent + sum_d S_d qacc_d (MuJoCo mj_rnePostConstraint restated).
+FB_DEV void kfin_f1(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; XS(i) = AT(d.qfrc_constraint, i); } }
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; XS(i) = AT(d.qfrc_constraint, i); } }
+  for (int i = y; i < m.nv; i += FB_NY) XS(i) = AT(d.qfrc_constraint, i);
+  for (int k = y; k < 6 * m.nbody; k += FB_NY) AT(d.bfl, k) = 0;
 }
 FB_DEV void kfin_solve_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD); }
 FB_DEV void kfin_solve_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD); }
-FB_DEV void kfin_solve_c(FB_PHASE_ARGS) {
+FB_DEV void kfin_solve_c(FB_PHASE_ARGS) { solve_c(m, d, sh, e, lane, y, d.qLD); }
+FB_DEV void kfin_f5(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
-  solve_c(m, d, sh, e, lane, y, d.qLD);
-  // qacc = qacc_smooth + M^-1 J^T f for own dofs (root dofs by y == 0 were finalised in phase b)
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc, i) = AT(d.qacc_smooth, i) + XS(i); } }
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc, i) = AT(d.qacc_smooth, i) + XS(i); } }
-}
-// sensors: full RNE with qacc, minus contact forces -> cfrc_int (MuJoCo mj_rnePostConstraint)
-FB_DEV void kfin_sens_root(FB_PHASE_ARGS) {
+  for (int i = y; i < m.nv; i += FB_NY) { AT(d.qacc, i) = AT(d.qacc_smooth, i) + XS(i); XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); }
   if (y != 0) return;
-  // external (contact) wrench per body into bfl (about ref), scattered sequentially
-  for (int b = 0; b < m.nbody; b++) { S6 z; z.a = v3(0, 0, 0); z.l = v3(0, 0, 0); st6(d.bfl, b, d, e, z); }
+  // external (contact) wrench per body into bfl (about ref)
   int ncon = AT(d.ncon, 0);
   for (int ci = 0; ci < ncon; ci++) {
     int adr = AT(d.con_efcadr, ci); if (adr < 0) continue;
@@ -511,25 +512,58 @@ FB_DEV void kfin_sens_root(FB_PHASE_ARGS) {
     S6 w2 = ld6(d.bfl, b2, d, e); w2.a = w2.a + tq; w2.l = w2.l + F; st6(d.bfl, b2, d, e, w2);
     S6 w1 = ld6(d.bfl, b1, d, e); w1.a = w1.a - tq; w1.l = w1.l - F; st6(d.bfl, b1, d, e, w1);
   }
-  for (int r = 0; r < m.nroot; r++) body_vel_acc(m, d, e, m.root_body[r], d.qacc, d.bvel, d.bacc);
 }
-FB_DEV void kfin_sens_fwd(FB_PHASE_ARGS) {
+// delta acceleration of body b from its parent's delta: dl += sum_d S_d qacc_d
+FB_DEV void delta_from_parent(const DevModel& m, const DevData& d, int e, int b, S6& dl) {
+  for (int kk = 0; kk < m.body_dofnum[b]; kk++) {
+    int k = m.body_dofadr[b] + kk; float qa = AT(d.qacc, k);
+    dl.a = dl.a + ld3(d.Sang, k, d, e) * qa; dl.l = dl.l + ld3(d.Slin, k, d, e) * qa;
+  }
+}
+FB_DEV void kfin_f6(FB_PHASE_ARGS) {
+  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; S6 dl; dl.a = dl.l = v3(0, 0, 0); delta_from_parent(m, d, e, b, dl); st6(d.bdel, b, d, e, dl); }
+  solve_a(m, d, sh, e, lane, y, d.qLDe);
+}
+FB_DEV void kfin_f7(FB_PHASE_ARGS) {
+  solve_b(m, d, sh, e, lane, y, d.qLDe);
   if (y >= m.nlist) return;
+  int prev = -1; S6 cd; cd.a = cd.l = v3(0, 0, 0);
   FB_LIST_LOOP_FWD {
-    body_vel_acc(m, d, e, b, d.qacc, d.bvel, d.bacc);
-    S6 f = body_inertial_force(m, d, e, b, d.bvel, d.bacc), x = ld6(d.bfl, b, d, e);
-    f.a = f.a - x.a; f.l = f.l - x.l;
-    st6(d.bfrc, b, d, e, f);
+    if (!m.body_sensacc[b]) { prev = -1; continue; }
+    int p = m.body_parentid[b];
+    if (p != prev) cd = ld6(d.bdel, p, d, e);
+    delta_from_parent(m, d, e, b, cd);
+    st6(d.bdel, b, d, e, cd);
+    prev = b;
+    if (m.body_sensfrc[b]) {   // f_b = f0_b + I_b delta_b - ext_b
+      I10 I = ld10(d.inert10, b, d, e); V3 L, pm; inert_mul(I, cd.a, cd.l, L, pm);
+      S6 f = ld6(d.bfrc0, b, d, e), x = ld6(d.bfl, b, d, e);
+      f.a = f.a + L - x.a; f.l = f.l + pm - x.l;
+      st6(d.bfrc, b, d, e, f);
+    }
   }
 }
-FB_DEV void kfin_sens_bwd(FB_PHASE_ARGS) {
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_REV {
-    int p = m.body_parentid[b];
-    if (m.body_isroot[p]) continue;       // cfrc_int of root bodies is not read by any fly sensor
-    S6 f = ld6(d.bfrc, b, d, e), pf = ld6(d.bfrc, p, d, e);
-    pf.a = pf.a + f.a; pf.l = pf.l + f.l; st6(d.bfrc, p, d, e, pf);
+FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int lane, const float* xs, int b);
+FB_DEV void kfin_f8(FB_PHASE_ARGS) {
+  float* xs = sh_dyn(sh);
+  if (y < m.nlist) {
+    FB_LIST_LOOP_REV {      // cfrc_int of the force-sensor bodies: sums over their subtrees
+      if (!m.body_sensfrc[b]) continue;
+      int p = m.body_parentid[b];
+      if (!m.body_sensfrc[p]) continue;
+      S6 f = ld6(d.bfrc, b, d, e), pf = ld6(d.bfrc, p, d, e);
+      pf.a = pf.a + f.a; pf.l = pf.l + f.l; st6(d.bfrc, p, d, e, pf);
+    }
   }
+  if (!d.do_integrate) return;
+  solve_c(m, d, sh, e, lane, y, d.qLDe);
+  if (AT(d.hold, 0)) return;          // env staged for reset: recompute (forward) but do not integrate
+  if (y == 0) {
+    for (int r = 0; r < m.nroot; r++) integrate_body(m, d, e, lane, xs, m.root_body[r]);
+    AT(d.time, 0) += m.timestep;
+  }
+  if (y >= m.nlist) return;
+  FB_LIST_LOOP_FWD integrate_body(m, d, e, lane, xs, b);
 }
 FB_DEV float ray_quad(float a, float b, float c, float* x) {
   float det = b * b - a * c;
@@ -552,13 +586,13 @@ FB_DEV float ray_capsule(V3 pos, const M3& mat, V3 size, V3 pnt, V3 vec) {
   for (int i = 0; i < 2; i++) if (xx[i] >= 0 && lp.z + xx[i] * lv.z <= -size.y) { if (x < 0 || xx[i] < x) x = xx[i]; }
   return x;
 }
-FB_DEV void kfin_sens_out(FB_PHASE_ARGS) {
-  if (y != 0) return;
+FB_DEV void kfin_f9(FB_PHASE_ARGS) {
   int ncon = AT(d.ncon, 0);
-  for (int s = 0; s < m.nsensor; s++) {
+  for (int s = y; s < m.nsensor; s += FB_NY) {
     int tp = m.sensor_type[s], site = m.sensor_objid[s], adr = m.sensor_adr[s], b = m.site_bodyid[site];
     if (tp == FB_SENS_ACCELEROMETER) {
-      S6 a = ld6(d.bacc, b, d, e), v = ld6(d.bvel, b, d, e);
+      S6 a = ld6(d.bacc, b, d, e), dl = ld6(d.bdel, b, d, e), v = ld6(d.bvel, b, d, e);
+      a.a = a.a + dl.a; a.l = a.l + dl.l;
       V3 p = ld3(d.site_xpos, site, d, e);
       V3 vp = v.l + cross(v.a, p);
       V3 acc = a.l + cross(a.a, p) + cross(v.a, vp);
@@ -586,20 +620,12 @@ FB_DEV void kfin_sens_out(FB_PHASE_ARGS) {
       AT(d.sensordata, adr) = sum;
     }
   }
-  // per-substep sensor accumulation + state check (|qacc| > 1e14 or non-finite: reference tasks/base.py:222-225)
+  // state check (|qacc| > 1e14 or non-finite: reference tasks/base.py:222-225); each lane tests its dofs
   float s2 = 0; bool bad = false;
-  for (int k = 0; k < m.nv; k++) { float a = AT(d.qacc, k); s2 += a * a; if (!isfinite(a) || !isfinite(AT(d.qvel, k))) bad = true; }
+  for (int k = y; k < m.nv; k += FB_NY) { float a = AT(d.qacc, k); s2 += a * a; if (!isfinite(a) || !isfinite(AT(d.qvel, k))) bad = true; }
   if (bad || !(s2 < 1e28f)) FB_FLAG_OR(1);
+  if (d.do_integrate && !AT(d.hold, 0)) for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) += m.timestep * AT(d.act_dot, i);
 }
-// Euler: qtmp <- qfrc_smooth + qfrc_constraint, solve with the (M + h D) factor, integrate
-FB_DEV void keul_rhs(FB_PHASE_ARGS) {
-  float* xs = sh_dyn(sh);
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); } }
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); } }
-}
-FB_DEV void keul_solve_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLDe); }
-FB_DEV void keul_solve_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLDe); }
 FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int lane, const float* xs, int b) {
   float h = m.timestep;
   for (int k = 0; k < m.body_jntnum[b]; k++) {
@@ -618,18 +644,6 @@ FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int lane,
       AT(d.qpos, qa) += h * AT(d.qvel, da);
     }
   }
-}
-FB_DEV void keul_solve_c_integrate(FB_PHASE_ARGS) {
-  float* xs = sh_dyn(sh);
-  solve_c(m, d, sh, e, lane, y, d.qLDe);
-  if (AT(d.hold, 0)) return;          // env staged for reset: recompute (forward) but do not integrate
-  if (y == 0) {
-    for (int r = 0; r < m.nroot; r++) integrate_body(m, d, e, lane, xs, m.root_body[r]);
-    for (int i = 0; i < m.na; i++) AT(d.act, i) += m.timestep * AT(d.act_dot, i);
-    AT(d.time, 0) += m.timestep;
-  }
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD integrate_body(m, d, e, lane, xs, b);
 }
 // accumulate sensor sums (after step1 of the substep: vel sensors are from the new state)
 FB_DEV void ksens_accum(const DevModel& m, const DevData& d, int e, int first) {

@@ -200,28 +200,28 @@ FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, 
   float* ldsh = sh_dyn(sh);
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (l >= m.nlist || step >= m.list_ndof[l]) return;
-  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k];
+  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
   float invD = 1.0f / LS(adrk);
-  int t = 1, cnt = 0;
-  for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) {
+  // ancestor rows are dealt round-robin to the FB_FSUB lanes of the list (dof_anc[adrk + t] = t-th ancestor of k)
+  for (int t = 1 + sub; t < len; t += FB_FSUB) {
+    int i = m.dof_anc[adrk + t];
     float a = LS(adrk + t) * invD;
     if (!m.dof_isroot[i]) {
-      int adri = m.dof_Madr[i], len = m.dof_chainlen[i];
-      for (int s2 = 0; s2 < len; s2++, cnt++) if (cnt % FB_FSUB == sub) LS(adri + s2) -= a * LS(adrk + t + s2);
+      int adri = m.dof_Madr[i], li = len - t;                 // chain of i = tail of the chain of k
+      for (int s2 = 0; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
     } else {
       int il = m.dof_depth[i], base = il * (il + 1) / 2;       // for root dofs depth == local index
-      for (int s2 = 0; s2 <= il; s2++, cnt++) if (cnt % FB_FSUB == sub) sh.part[y][base + s2][lane] += a * LS(adrk + t + s2);
+      for (int s2 = 0; s2 <= il; s2++) sh.part[y][base + s2][lane] += a * LS(adrk + t + s2);
     }
   }
 }
 FB_DEV void factor_step_scale(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* ldsh = sh_dyn(sh);
   int l = y / FB_FSUB, sub = y % FB_FSUB;
-  if (l >= m.nlist || step >= m.list_ndof[l] || sub != 0) return;
-  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k];
+  if (l >= m.nlist || step >= m.list_ndof[l]) return;
+  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
   float invD = 1.0f / LS(adrk);
-  int len = m.dof_chainlen[k];
-  for (int t = 1; t < len; t++) LS(adrk + t) *= invD;
+  for (int t = 1 + sub; t < len; t += FB_FSUB) LS(adrk + t) *= invD;
 }
 FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
   float* ldsh = sh_dyn(sh);
@@ -447,31 +447,93 @@ FB_DEV S6 body_fluid_wrench(const DevModel& m, const DevData& d, int e, int b) {
   return out;
 }
 
+// velocity stage.  Chain part (lists): body velocities and bias accelerations, the parent's values carried in
+// registers along a chain.  Per-body part (all lanes): inertial bias force and fluid wrench.  Backward part
+// (lists): subtree sums, carried in registers.  Per-dof part (all lanes): projections onto the dofs.
+FB_DEV void vel_acc_from_parent(const DevModel& m, const DevData& d, int e, int b, S6& v, S6& a) {
+  int jn = m.body_jntnum[b];
+  for (int k = 0; k < jn; k++) {
+    int j = m.body_jntadr[b] + k, da = m.jnt_dofadr[j];
+    if (m.jnt_type[j] == FB_JNT_FREE) {
+      V3 vlin = v3(AT(d.qvel, da), AT(d.qvel, da + 1), AT(d.qvel, da + 2)), w = v3(0, 0, 0);
+      for (int i = 0; i < 6; i++) {
+        float qd = AT(d.qvel, da + i);
+        V3 Sa = ld3(d.Sang, da + i, d, e), Sl = ld3(d.Slin, da + i, d, e);
+        v.a = v.a + Sa * qd; v.l = v.l + Sl * qd;
+        if (i >= 3) w = w + Sa * qd;
+      }
+      a.l = a.l + cross(vlin, w);
+    } else {
+      float qd = AT(d.qvel, da);
+      V3 Sa = ld3(d.Sang, da, d, e), Sl = ld3(d.Slin, da, d, e);
+      S6 r = motion_cross(v, Sa, Sl);
+      a.a = a.a + r.a * qd; a.l = a.l + r.l * qd;
+      v.a = v.a + Sa * qd; v.l = v.l + Sl * qd;
+    }
+  }
+  st6(d.bvel, b, d, e, v); st6(d.bacc, b, d, e, a);
+}
 FB_DEV void kvel_p0(FB_PHASE_ARGS) {
   if (y != 0) return;
   S6 z; z.a = v3(0, 0, 0); z.l = v3(0, 0, 0);
   st6(d.bvel, 0, d, e, z);
-  z.l = v3(-m.gravity[0], -m.gravity[1], -m.gravity[2]);
-  st6(d.bacc, 0, d, e, z);
-  for (int r = 0; r < m.nroot; r++) {
-    int b = m.root_body[r];
-    body_vel_acc(m, d, e, b, nullptr, d.bvel, d.bacc);
-    st6(d.bfrc, b, d, e, body_inertial_force(m, d, e, b, d.bvel, d.bacc));
-    st6(d.bfl, b, d, e, body_fluid_wrench(m, d, e, b));
-  }
+  S6 g = z; g.l = v3(-m.gravity[0], -m.gravity[1], -m.gravity[2]);
+  st6(d.bacc, 0, d, e, g);
+  for (int r = 0; r < m.nroot; r++) { S6 v = z, a = g; vel_acc_from_parent(m, d, e, m.root_body[r], v, a); }
 }
 FB_DEV void kvel_p1(FB_PHASE_ARGS) {
   if (y >= m.nlist) return;
+  int prev = -1; S6 cv, ca; cv.a = cv.l = ca.a = ca.l = v3(0, 0, 0);
   FB_LIST_LOOP_FWD {
-    body_vel_acc(m, d, e, b, nullptr, d.bvel, d.bacc);
-    st6(d.bfrc, b, d, e, body_inertial_force(m, d, e, b, d.bvel, d.bacc));
-    st6(d.bfl, b, d, e, body_fluid_wrench(m, d, e, b));
+    int p = m.body_parentid[b];
+    if (p != prev) { cv = ld6(d.bvel, p, d, e); ca = ld6(d.bacc, p, d, e); }
+    vel_acc_from_parent(m, d, e, b, cv, ca);
+    prev = b;
   }
 }
-FB_DEV void project_body_forces(const DevModel& m, const DevData& d, int e, int b, const S6& f, const S6& fl) {
-  for (int kk = 0; kk < m.body_dofnum[b]; kk++) {
-    int k = m.body_dofadr[b] + kk;
+// all lanes over bodies: bias force (kept un-accumulated in bfrc0 for the sensor pass) and fluid wrench
+FB_DEV void kvel_p1b(FB_PHASE_ARGS) {
+  for (int b = y; b < m.nbody; b += FB_NY) {
+    S6 f; f.a = f.l = v3(0, 0, 0); S6 fl = f;
+    if (b > 0) { f = body_inertial_force(m, d, e, b, d.bvel, d.bacc); fl = body_fluid_wrench(m, d, e, b); }
+    st6(d.bfrc, b, d, e, f); st6(d.bfrc0, b, d, e, f); st6(d.bfl, b, d, e, fl);
+  }
+}
+// subtree sums of (bias force, fluid wrench): child -> parent along the lists
+FB_DEV void kvel_p2(FB_PHASE_ARGS) {
+  if (y >= m.nlist) return;
+  float acc[12], carry[12]; int carry_to = -1;
+  for (int k = 0; k < 12; k++) { acc[k] = 0; carry[k] = 0; }
+  FB_LIST_LOOP_REV {
+    float cur[12];
+    for (int k = 0; k < 6; k++) { cur[k] = AT(d.bfrc, 6 * b + k); cur[6 + k] = AT(d.bfl, 6 * b + k); }
+    if (carry_to == b) { for (int k = 0; k < 12; k++) cur[k] += carry[k]; for (int k = 0; k < 6; k++) { AT(d.bfrc, 6 * b + k) = cur[k]; AT(d.bfl, 6 * b + k) = cur[6 + k]; } }
+    else if (carry_to >= 0) { for (int k = 0; k < 6; k++) { AT(d.bfrc, 6 * carry_to + k) += carry[k]; AT(d.bfl, 6 * carry_to + k) += carry[6 + k]; } }
+    int p = m.body_parentid[b];
+    if (m.body_isroot[p]) { for (int k = 0; k < 12; k++) acc[k] += cur[k]; carry_to = -1; }
+    else { for (int k = 0; k < 12; k++) carry[k] = cur[k]; carry_to = p; }
+  }
+  if (carry_to >= 0) for (int k = 0; k < 6; k++) { AT(d.bfrc, 6 * carry_to + k) += carry[k]; AT(d.bfl, 6 * carry_to + k) += carry[6 + k]; }
+  for (int k = 0; k < 12; k++) sh.part[y][k][lane] = acc[k];
+}
+FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e, int y);
+FB_DEV void kvel_p3(FB_PHASE_ARGS) {
+  if (y < m.nroot) {
+    int r = y, b = m.root_body[r];
+    for (int k = 0; k < 6; k++) {
+      float a1 = 0, a2 = 0;
+      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) { a1 += sh.part[l][k][lane]; a2 += sh.part[l][6 + k][lane]; }
+      AT(d.bfrc, 6 * b + k) += a1; AT(d.bfl, 6 * b + k) += a2;
+    }
+  }
+  sensors_vel(m, d, e, y);
+}
+// all lanes over dofs: qfrc_bias = S . f_subtree ; qfrc_passive = S . fluid_subtree + springs + dampers
+FB_DEV void kvel_p3b(FB_PHASE_ARGS) {
+  for (int k = y; k < m.nv; k += FB_NY) {
+    int b = m.dof_bodyid[k];
     V3 Sa = ld3(d.Sang, k, d, e), Sl = ld3(d.Slin, k, d, e);
+    S6 f = ld6(d.bfrc, b, d, e), fl = ld6(d.bfl, b, d, e);
     AT(d.qfrc_bias, k) = dot(Sa, f.a) + dot(Sl, f.l);
     float pas = dot(Sa, fl.a) + dot(Sl, fl.l) - m.dof_damping[k] * AT(d.qvel, k);
     int j = m.dof_jntid[k];
@@ -479,43 +541,9 @@ FB_DEV void project_body_forces(const DevModel& m, const DevData& d, int e, int 
     AT(d.qfrc_passive, k) = pas;
   }
 }
-FB_DEV void kvel_p2(FB_PHASE_ARGS) {
-  if (y >= m.nlist) return;
-  float acc[12];
-  for (int k = 0; k < 12; k++) acc[k] = 0;
-  FB_LIST_LOOP_REV {
-    S6 f = ld6(d.bfrc, b, d, e), fl = ld6(d.bfl, b, d, e);
-    project_body_forces(m, d, e, b, f, fl);
-    int p = m.body_parentid[b];
-    if (m.body_isroot[p]) {
-      acc[0] += f.a.x; acc[1] += f.a.y; acc[2] += f.a.z; acc[3] += f.l.x; acc[4] += f.l.y; acc[5] += f.l.z;
-      acc[6] += fl.a.x; acc[7] += fl.a.y; acc[8] += fl.a.z; acc[9] += fl.l.x; acc[10] += fl.l.y; acc[11] += fl.l.z;
-    } else {
-      S6 pf = ld6(d.bfrc, p, d, e), pfl = ld6(d.bfl, p, d, e);
-      pf.a = pf.a + f.a; pf.l = pf.l + f.l; pfl.a = pfl.a + fl.a; pfl.l = pfl.l + fl.l;
-      st6(d.bfrc, p, d, e, pf); st6(d.bfl, p, d, e, pfl);
-    }
-  }
-  for (int k = 0; k < 12; k++) sh.part[y][k][lane] = acc[k];
-}
-FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e);
-FB_DEV void kvel_p3(FB_PHASE_ARGS) {
-  if (y != 0) return;
-  for (int r = 0; r < m.nroot; r++) {
-    int b = m.root_body[r];
-    float acc[12];
-    for (int k = 0; k < 12; k++) { acc[k] = 0; for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc[k] += sh.part[l][k][lane]; }
-    S6 f = ld6(d.bfrc, b, d, e), fl = ld6(d.bfl, b, d, e);
-    f.a = f.a + v3(acc[0], acc[1], acc[2]); f.l = f.l + v3(acc[3], acc[4], acc[5]);
-    fl.a = fl.a + v3(acc[6], acc[7], acc[8]); fl.l = fl.l + v3(acc[9], acc[10], acc[11]);
-    st6(d.bfrc, b, d, e, f); st6(d.bfl, b, d, e, fl);
-    project_body_forces(m, d, e, b, f, fl);
-  }
-  sensors_vel(m, d, e);
-}
 // gyro / velocimeter (MuJoCo mj_sensorVel; sensors fruitfly.xml:900-903)
-FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e) {
-  for (int s = 0; s < m.nsensor; s++) {
+FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e, int y) {
+  for (int s = y; s < m.nsensor; s += FB_NY) {
     int tp = m.sensor_type[s];
     if (tp != FB_SENS_GYRO && tp != FB_SENS_VELOCIMETER) continue;
     int site = m.sensor_objid[s], adr = m.sensor_adr[s], b = m.site_bodyid[site];

@@ -55,12 +55,12 @@ struct DevModel {
   const int *list_dofadr, *list_ndof, *list_dof; int max_list_ndof;   // dofs of each list, deepest first (factorisation order)
   // bodies
   const int *body_parentid, *body_rootid, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_lastdof,
-      *body_fluid_ellipsoid, *body_isroot, *body_geomadr, *body_geomnum, *body_siteadr, *body_sitenum;
+      *body_fluid_ellipsoid, *body_isroot, *body_sensacc, *body_sensfrc, *body_geomadr, *body_geomnum, *body_siteadr, *body_sitenum;
   const float *body_pos, *body_quat, *body_ipos, *body_iquat, *body_mass, *body_inertia, *body_invweight0;
   // joints / dofs
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
-  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen, *dof_anc /* [nM] t-th ancestor of the row's dof */;
   const float *dof_armature, *dof_damping, *dof_invweight0;
   // geoms
   const int *geom_type, *geom_bodyid, *geom_condim;
@@ -84,7 +84,7 @@ enum { FB_CT_LIMIT = 0, FB_CT_FRICTIONLESS = 1, FB_CT_ELLIPTIC = 2 };
 struct DevData {
   int N, Np;                   // envs, padded envs
   unsigned rec;                // record stride (4-byte slots) between consecutive envs
-  int nsub_done, sens_mode;
+  int nsub_done, sens_mode, do_integrate;
   // integrated state
   float *qpos, *qvel, *act, *ctrl, *qacc, *qacc_warmstart, *time;
   // position stage
@@ -95,7 +95,7 @@ struct DevData {
   float *inert10, *crb10;      // [nbody*10]
   float *qM, *qLD, *qLDe;      // [nM] inertia, its L^T D L factor, factor of M + h*diag(damping)
   // velocity stage
-  float *bvel, *bacc, *bfrc, *bfl;   // [nbody*6] spatial velocity, bias accel, bias force, fluid wrench accum
+  float *bvel, *bacc, *bfrc, *bfl, *bfrc0, *bdel;   // [nbody*6] spatial velocity, bias accel, bias force (subtree sums), fluid wrench, per-body bias force
   float *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qacc_smooth, *qfrc_constraint, *qtmp;
   float *act_dot, *actuator_force;
   // contacts

@@ -174,15 +174,13 @@ static void launch_step1(FbSim* s) {
   fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, (size_t)s->m.nM);
   fb_launch<ShCol, Ph<kcol_p0>, Ph<kcol_p1>>(s, K_COL);
   fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_ROWPAR * s->m.nv);
-  fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p4>>(s, K_VEL);
+  fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL);
 }
 static void launch_step2(FbSim* s, bool integrate) {
   fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p3>, Ph<ph_smooth_a>, Ph<ph_smooth_b>, Ph<ph_smooth_c>, Ph<kref>>(s, K_SMOOTH, (size_t)s->m.nv);
   fb_launch_warp(s, K_SOLVE);
-  if (integrate)
-    fb_launch<ShTree, Ph<kfin_copy>, Ph<kfin_solve_a>, Ph<kfin_solve_b>, Ph<kfin_solve_c>, Ph<kfin_sens_root>, Ph<kfin_sens_fwd>, Ph<kfin_sens_bwd>, Ph<kfin_sens_out>, Ph<keul_rhs>, Ph<keul_solve_a>, Ph<keul_solve_b>, Ph<keul_solve_c_integrate>>(s, K_FINISH, (size_t)s->m.nv);
-  else
-    fb_launch<ShTree, Ph<kfin_copy>, Ph<kfin_solve_a>, Ph<kfin_solve_b>, Ph<kfin_solve_c>, Ph<kfin_sens_root>, Ph<kfin_sens_fwd>, Ph<kfin_sens_bwd>, Ph<kfin_sens_out>>(s, K_FINISH, (size_t)s->m.nv);
+  s->d.do_integrate = integrate ? 1 : 0;
+  fb_launch<ShTree, Ph<kfin_f1>, Ph<kfin_solve_a>, Ph<kfin_solve_b>, Ph<kfin_solve_c>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)s->m.nv);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -249,6 +247,16 @@ static int build_model(FbSim* s, const FbModel* h) {
   }
   m.root_body = up(s, roots); m.list_adr = up(s, ladr); m.list_num = up(s, lnum); m.list_body = up(s, lbody); m.list_root = up(s, lr);
   m.body_isroot = up(s, isroot);
+  { // bodies the acceleration-stage sensors need: force sensors read the subtree sum at the site's body;
+    // accelerometers need the (delta) acceleration of the site's body; both need their ancestors' deltas
+    std::vector<int> sfrc(nb, 0), sacc(nb, 0), frcroot(nb, 0);
+    for (int t = 0; t < h->nsensor; t++) { int b = h->site_bodyid[h->sensor_objid[t]]; if (h->sensor_type[t] == FB_SENS_FORCE) frcroot[b] = 1; if (h->sensor_type[t] == FB_SENS_FORCE || h->sensor_type[t] == FB_SENS_ACCELEROMETER) sacc[b] = 1; }
+    for (int b = 1; b < nb; b++) if (frcroot[b] || sfrc[h->body_parentid[b]]) sfrc[b] = 1;
+    for (int b = 1; b < nb; b++) if (sfrc[b]) sacc[b] = 1;
+    for (int b = nb - 1; b > 0; b--) if (sacc[b]) sacc[h->body_parentid[b]] = 1;
+    sacc[0] = 0;
+    m.body_sensacc = up(s, sacc); m.body_sensfrc = up(s, sfrc);
+  }
   // geoms / sites per body (both are stored in body order by the compiler)
   std::vector<int> gadr(nb, 0), gnum(nb, 0), sadr(nb, 0), snum(nb, 0);
   for (int g = 0; g < m.ngeom; g++) { int b = h->geom_bodyid[g]; if (gnum[b] == 0) gadr[b] = g; gnum[b]++; if (g > 0 && h->geom_bodyid[g] < h->geom_bodyid[g - 1]) { s->err = "geoms not in body order"; return -3; } }
@@ -265,6 +273,7 @@ static int build_model(FbSim* s, const FbModel* h) {
     chainlen[i] = len;
     depth[i] = disroot[i] ? (i - h->body_dofadr[h->dof_bodyid[i]]) : nonroot;
   }
+  { std::vector<int> anc(h->nM, -1); for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) anc[h->dof_Madr[i] + t] = j; } m.dof_anc = up(s, anc); }
   m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);
   // plain copies
   m.body_parentid = upi(s, h->body_parentid, nb); m.body_rootid = upi(s, h->body_rootid, nb);
@@ -334,7 +343,7 @@ static int alloc_data(FbSim* s, int N) {
   FA(geom_xpos, 3 * m.ngeom) FA(geom_xmat, 9 * m.ngeom) FA(site_xpos, 3 * m.nsite + 3) FA(site_xmat, 9 * m.nsite + 9)
   FA(Sang, 3 * m.nv) FA(Slin, 3 * m.nv) FA(inert10, 10 * m.nbody) FA(crb10, 10 * m.nbody)
   FA(qM, m.nM) FA(qLD, m.nM) FA(qLDe, m.nM)
-  FA(bvel, 6 * m.nbody) FA(bacc, 6 * m.nbody) FA(bfrc, 6 * m.nbody) FA(bfl, 6 * m.nbody)
+  FA(bvel, 6 * m.nbody) FA(bacc, 6 * m.nbody) FA(bfrc, 6 * m.nbody) FA(bfl, 6 * m.nbody) FA(bfrc0, 6 * m.nbody) FA(bdel, 6 * m.nbody)
   FA(qfrc_bias, m.nv) FA(qfrc_passive, m.nv) FA(qfrc_actuator, m.nv) FA(qfrc_smooth, m.nv) FA(qacc_smooth, m.nv) FA(qfrc_constraint, m.nv) FA(qtmp, m.nv)
   FA(act_dot, m.na + 1) FA(actuator_force, m.nu + 1)
   IA(ncon, 1) FA(con_dist, FB_MAXCON) FA(con_pos, 3 * FB_MAXCON) FA(con_frame, 9 * FB_MAXCON) IA(con_geom1, FB_MAXCON) IA(con_geom2, FB_MAXCON)
