@@ -318,57 +318,61 @@ FB_DEV float contact_J(const DevModel& m, const DevData& d, int e, V3 f, V3 pos,
 //   phase 1: A = Z Z^T  (= J M^-1 J^T, the unregularised Delassus matrix)
 struct ShNone { int dummy; };
 #define FB_ROW_ARGS const DevModel& m, const DevData& d, ShCon& sh, int e, int lane, int y
+#define FB_ZCAP 24      // longest dof chain the projection scratch holds (fly: 20)
+// one dof chain of a row: Jacobian entries along the chain, then z = D^-1/2 L^-T j by a dense back-sweep over the
+// chain (the ancestors of the p-th chain element are the elements p+1.. and L[k_p][k_q] sits at qLD[Madr[k_p] + q - p])
+FB_DEV void proj_chain(const DevModel& m, const DevData& d, int e, int r, int last, float sgn, bool contact, V3 f, V3 pos, float* zc,
+                       int other_last, bool accumulate) {
+  if (last < 0) return;
+  int adr0 = m.dof_Madr[last], L = m.dof_chainlen[last];
+  if (L > FB_ZCAP) { FB_FLAG_OR(4); L = FB_ZCAP; }
+  for (int p = 0; p < L; p++) {
+    int k = m.dof_anc[adr0 + p];
+    float v = contact ? sgn * contact_J(m, d, e, f, pos, k) : (p == 0 ? sgn : 0.0f);
+    zc[p] = v;
+    if (accumulate && in_chain(m, k, other_last)) EJ(d.efc_J, r, k) += v; else EJ(d.efc_J, r, k) = v;
+  }
+  for (int p = 0; p < L; p++) {
+    int k = m.dof_anc[adr0 + p], row = m.dof_Madr[k];
+    float zk = zc[p];
+    for (int q = p + 1; q < L; q++) zc[q] -= AT(d.qLD, row + (q - p)) * zk;
+    float zf = zk / sqrtf(AT(d.qLD, row));
+    if (accumulate && in_chain(m, k, other_last)) EJ(d.efc_Z, r, k) += zf; else EJ(d.efc_Z, r, k) = zf;
+  }
+}
+// all 32 lanes over rows: J (dense-by-dof storage) and Z = D^-1/2 L^-T J^T, chain by chain (a contact row is the
+// difference of two single-chain rows; the sweep is linear)
 FB_DEV void kproj_p0(FB_ROW_ARGS) {
-  if (y >= FB_ROWPAR) return;
   int n = AT(d.nefc, 0);
-  for (int r = y; r < n; r += FB_ROWPAR) {
+  float* zc = sh_dyn(sh) + (size_t)y * FB_ZCAP;
+  for (int r = y; r < n; r += FB_NY) {
     int ci, frow; float sign;
     RowChains rc = row_chains(m, d, e, r, ci, frow, sign);
     AT(d.efc_la, r) = rc.la; AT(d.efc_lb, r) = rc.lb;
     V3 f = v3(0, 0, 0), pos = v3(0, 0, 0);
     if (ci >= 0) { f = v3(CON_F(d.con_frame, ci, 3 * frow, 9), CON_F(d.con_frame, ci, 3 * frow + 1, 9), CON_F(d.con_frame, ci, 3 * frow + 2, 9));
                    pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3)); }
-    // J over the dof set; the sweep scratch z lives in shared memory, indexed by dof: zs[y][dof][lane]
-    float* zs = sh_dyn(sh) + (size_t)y * m.nv * FB_LANES;
-    int la = rc.la, lb = rc.lb;
-    while (la >= 0 || lb >= 0) {
-      int k = la > lb ? la : lb; float v = 0;
-      if (ci < 0) v = (k == rc.la) ? sign : 0.0f;
-      else { if (la == k) v += contact_J(m, d, e, f, pos, k); if (lb == k) v -= contact_J(m, d, e, f, pos, k); }
-      EJ(d.efc_J, r, k) = v; zs[k * FB_LANES + lane] = v;
-      if (la == k) la = m.dof_parentid[la];
-      if (lb == k) lb = m.dof_parentid[lb];
-    }
-    // Z <- L^-T sweep (descending dofs), then scale by D^-1/2
-    la = rc.la; lb = rc.lb;
+    proj_chain(m, d, e, r, rc.la, ci >= 0 ? 1.0f : sign, ci >= 0, f, pos, zc, -1, false);
+    if (ci >= 0) proj_chain(m, d, e, r, rc.lb, -1.0f, true, f, pos, zc, rc.la, true);
+  }
+}
+// A = Z Z^T (= J M^-1 J^T, the unregularised Delassus matrix), packed lower triangle; pairs dealt to all lanes
+FB_DEV void kproj_p1(FB_ROW_ARGS) {
+  int n = AT(d.nefc, 0), npair = n * (n + 1) / 2;
+  for (int idx = y; idx < npair; idx += FB_NY) {
+    int r = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+    while (r * (r + 1) / 2 > idx) r--;
+    while ((r + 1) * (r + 2) / 2 <= idx) r++;
+    int c = idx - r * (r + 1) / 2;
+    int rla = AT(d.efc_la, r), rlb = AT(d.efc_lb, r);
+    float sacc = 0; int la = AT(d.efc_la, c), lb = AT(d.efc_lb, c);
     while (la >= 0 || lb >= 0) {
       int k = la > lb ? la : lb;
       if (la == k) la = m.dof_parentid[la];
       if (lb == k) lb = m.dof_parentid[lb];
-      float zk = zs[k * FB_LANES + lane];
-      int adrk = m.dof_Madr[k], t = 1;
-      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) zs[i * FB_LANES + lane] -= AT(d.qLD, adrk + t) * zk;
-      EJ(d.efc_Z, r, k) = zk / sqrtf(AT(d.qLD, adrk));
+      if (in_chain(m, k, rla) || in_chain(m, k, rlb)) sacc += EJ(d.efc_Z, r, k) * EJ(d.efc_Z, c, k);
     }
-  }
-}
-FB_DEV void kproj_p1(FB_ROW_ARGS) {
-  if (y >= FB_ROWPAR) return;
-  int n = AT(d.nefc, 0);
-  for (int r = y; r < n; r += FB_ROWPAR) {
-    int ci, frow; float sign;
-    RowChains rr = row_chains(m, d, e, r, ci, frow, sign);
-    for (int c = 0; c <= r; c++) {
-      RowChains rc = row_chains(m, d, e, c, ci, frow, sign);
-      float s = 0; int la = rc.la, lb = rc.lb;
-      while (la >= 0 || lb >= 0) {
-        int k = la > lb ? la : lb;
-        if (la == k) la = m.dof_parentid[la];
-        if (lb == k) lb = m.dof_parentid[lb];
-        if (in_chain(m, k, rr.la) || in_chain(m, k, rr.lb)) s += EJ(d.efc_Z, r, k) * EJ(d.efc_Z, c, k);
-      }
-      AT(d.efc_A, r * (r + 1) / 2 + c) = s;      // packed lower triangle
-    }
+    AT(d.efc_A, idx) = sacc;
   }
 }
 // J . x for every row (x: qvel, qacc_smooth, qacc_warmstart): aref, b, jar at the warm start

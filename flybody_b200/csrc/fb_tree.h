@@ -208,7 +208,13 @@ FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, 
     float a = LS(adrk + t) * invD;
     if (!m.dof_isroot[i]) {
       int adri = m.dof_Madr[i], li = len - t;                 // chain of i = tail of the chain of k
-      for (int s2 = 0; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
+      int s2 = 0;
+      for (; s2 + 4 <= li; s2 += 4) {                          // batched so that the loads are in flight together
+        float r0 = LS(adrk + t + s2), r1 = LS(adrk + t + s2 + 1), r2 = LS(adrk + t + s2 + 2), r3 = LS(adrk + t + s2 + 3);
+        float x0 = LS(adri + s2), x1 = LS(adri + s2 + 1), x2 = LS(adri + s2 + 2), x3 = LS(adri + s2 + 3);
+        LS(adri + s2) = x0 - a * r0; LS(adri + s2 + 1) = x1 - a * r1; LS(adri + s2 + 2) = x2 - a * r2; LS(adri + s2 + 3) = x3 - a * r3;
+      }
+      for (; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
     } else {
       int il = m.dof_depth[i], base = il * (il + 1) / 2;       // for root dofs depth == local index
       for (int s2 = 0; s2 <= il; s2++) sh.part[y][base + s2][lane] += a * LS(adrk + t + s2);
