@@ -349,6 +349,14 @@ FB_DEV void kproj_p0(FB_ROW_ARGS) {
     int ci, frow; float sign;
     RowChains rc = row_chains(m, d, e, r, ci, frow, sign);
     AT(d.efc_la, r) = rc.la; AT(d.efc_lb, r) = rc.lb;
+    {   // row identity for the warm start: limit -> (joint, side); contact -> (geom pair, ordinal within the pair, frame row)
+      int key;
+      if (ci < 0) key = 0x40000000 | (EFC(d.efc_id, r) + FB_MAXEFC * 4);
+      else { int g1 = AT(d.con_geom1, ci), g2 = AT(d.con_geom2, ci), ord = 0;
+        while (ci - ord - 1 >= 0 && AT(d.con_geom1, ci - ord - 1) == g1 && AT(d.con_geom2, ci - ord - 1) == g2) ord++;
+        key = (((g1 * m.ngeom + g2) * 4 + (ord & 3)) * 3 + frow); }
+      AT(d.efc_key, r) = key;
+    }
     V3 f = v3(0, 0, 0), pos = v3(0, 0, 0);
     if (ci >= 0) { f = v3(CON_F(d.con_frame, ci, 3 * frow, 9), CON_F(d.con_frame, ci, 3 * frow + 1, 9), CON_F(d.con_frame, ci, 3 * frow + 2, 9));
                    pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3)); }
@@ -734,7 +742,7 @@ FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int w, int y) {
   for (int i = y; i < m.nq; i += FB_NY) AT(d.qpos, i) = d.rst_qpos[(size_t)w * m.nq + i];
   for (int i = y; i < m.nv; i += FB_NY) { AT(d.qvel, i) = d.rst_has_qvel ? d.rst_qvel[(size_t)w * m.nv + i] : 0.0f; AT(d.qacc, i) = 0; AT(d.qacc_warmstart, i) = 0; }
   for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) = 0;
-  if (y == 0) { AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = d.rst_hold; }
+  if (y == 0) { AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = d.rst_hold; AT(d.prev_n, 0) = 0; }
 }
 FB_DEV void kclear_hold(const DevModel& m, const DevData& d, int e, int y) { if (y == 0) AT(d.hold, 0) = 0; }
 // generic column scatter (fb_write_state / fb_set_ctrl): field[idx[c]] of env e <- vals[e][c]

@@ -141,13 +141,14 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
       SV(S_TYPE, r) = (float)tcode; SV(S_MU, r) = mu; SV(S_F1, r) = f1; SV(S_F2, r) = f2;
       SV(S_D, r) = EFC(d.efc_D, r); SV(S_B, r) = EFC(d.efc_b, r); SV(S_R, r) = EFC(d.efc_R, r);
       SV(S_LA, r) = (float)AT(d.efc_la, r); SV(S_LB, r) = (float)AT(d.efc_lb, r);
-      SV(W_JAR, r) = EFC(d.efc_jarws, r);
+      // warm start: force of the same row in the previous solve (0 for new rows)
+      { int key = AT(d.efc_key, r), pn = AT(d.prev_n, 0); float l0 = 0;
+        for (int q = 0; q < pn; q++) if (AT(d.prev_key, q) == key) { l0 = AT(d.prev_lam, q); break; }
+        SV(W_LAM, r) = l0; }
     }
     if (SM) { int nt = TRI(n, 0); for (int k = lane; k < nt; k += 32) sm.A[k] = AT(d.efc_A, k); }
     WPAR_END
-    // ---- warm start: forces implied by the previous qacc, kept if cheaper than lam = 0
-    WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update<SM>(sm, r, false); WPAR_END
-    WPAR_BEGIN WROWS SV(W_LAM, r) = SV(W_F, r); WPAR_END
+    // ---- warm start: the previous solve's forces (matched by row identity), kept if cheaper than lam = 0
     WPAR_BEGIN float q = 0.5f * matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WSUM_PUT(0, q); WPAR_END
     WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, false); WSUM_PUT(1, c); WPAR_END
     float cost_ws = WSUM_GET(0) + WSUM_GET(1);
@@ -241,7 +242,9 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
       if (nodescent) break;                               // converged to fp32 resolution
       WPAR_BEGIN WROWS SV(W_LAM, r) += alpha * SV(W_DL, r); WPAR_END
       niter = iter + 1;
-      if (scale * (cost - cbest) < m.tolerance) break;
+      // MuJoCo's absolute criterion, plus a relative one: Newton converges quadratically, so a step whose
+      // improvement is below 1e-7 of the cost has already landed within fp32 resolution of the minimiser
+      if (scale * (cost - cbest) < m.tolerance || (cost - cbest) < 1e-7f * fabsf(cost)) break;
     }
     // ---- forces at the solution: lam = f(b + A lam)
     WPAR_BEGIN matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WPAR_END
@@ -279,11 +282,11 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
         } }
       WPAR_END
     }
-    WPAR_BEGIN WROWS EFC(d.efc_force, r) = SV(W_F, r); WPAR_END
+    WPAR_BEGIN WROWS { EFC(d.efc_force, r) = SV(W_F, r); AT(d.prev_lam, r) = SV(W_LAM, r); AT(d.prev_key, r) = AT(d.efc_key, r); } WPAR_END
   }
   // ---- qfrc_constraint = J^T f, gathered per dof (race free)
   WPAR_BEGIN
-    if (lane == 0) AT(d.niter, 0) = niter;
+    if (lane == 0) { AT(d.niter, 0) = niter; if (d.do_integrate) AT(d.prev_n, 0) = n; }
     for (int k = lane; k < m.nv; k += 32) {
       float s = 0;
       for (int r = 0; r < n; r++) {

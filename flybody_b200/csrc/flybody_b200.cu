@@ -362,7 +362,7 @@ static int alloc_data(FbSim* s, int N) {
   IA(nefc, 1) IA(efc_type, FB_MAXEFC) IA(efc_id, FB_MAXEFC)
   FA(efc_pos, FB_MAXEFC) FA(efc_margin, FB_MAXEFC) FA(efc_D, FB_MAXEFC) FA(efc_R, FB_MAXEFC) FA(efc_K, FB_MAXEFC) FA(efc_B, FB_MAXEFC)
   FA(efc_imp, FB_MAXEFC) FA(efc_aref, FB_MAXEFC) FA(efc_b, FB_MAXEFC) FA(efc_force, FB_MAXEFC) FA(efc_jarws, FB_MAXEFC)
-  IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC)
+  IA(efc_la, FB_MAXEFC) IA(efc_lb, FB_MAXEFC) IA(efc_key, FB_MAXEFC) IA(prev_key, FB_MAXEFC) IA(prev_n, 1) FA(prev_lam, FB_MAXEFC)
   FA(sensordata, m.nsensordata + 1) FA(sensor_sum, m.nsensordata + 1) IA(flags, 1) IA(niter, 1) IA(hold, 1)
   // large, sparsely touched arrays last
   FA(efc_w, (size_t)S_NSLOT * FB_MAXEFC)
