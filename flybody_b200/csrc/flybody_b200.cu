@@ -187,9 +187,9 @@ static void launch_step1(FbSim* s) {
   fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL);
 }
 static void launch_step2(FbSim* s, bool integrate) {
+  s->d.do_integrate = integrate ? 1 : 0;     // read by the solve (warm-start bookkeeping) and the finish kernel
   fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p3>, Ph<ph_smooth_a>, Ph<ph_smooth_b>, Ph<ph_smooth_c>, Ph<kref>>(s, K_SMOOTH, (size_t)s->m.nv);
   fb_launch_warp(s, K_SOLVE);
-  s->d.do_integrate = integrate ? 1 : 0;
   fb_launch<ShTree, Ph<kfin_f1>, Ph<kfin_solve_a>, Ph<kfin_solve_b>, Ph<kfin_solve_c>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)s->m.nv);
 }
 

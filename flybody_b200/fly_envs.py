@@ -39,6 +39,18 @@ def reciprocal_quat(q):
     return q * np.array([1.0, -1, -1, -1]) / np.sum(q * q, -1, keepdims=True)
 
 
+def quat_dist_short_arc(q1, q2):
+    """geodesic angle between unit quaternions, in [0, pi) (reference `quaternions.py:285-307`)."""
+    q1 = q1 / np.linalg.norm(q1, axis=-1, keepdims=True)
+    q2 = q2 / np.linalg.norm(q2, axis=-1, keepdims=True)
+    return np.arccos(np.minimum(1.0, 2 * np.sum(q1 * q2, -1) ** 2 - 1))
+
+
+def linear_tolerance(x, margin):
+    """`dm_control.utils.rewards.tolerance(x, bounds=(0, 0), sigmoid='linear', margin, value_at_margin=0)`."""
+    return np.clip(1.0 - np.abs(x) / margin, 0.0, 1.0)
+
+
 def constant_speed_trajectory(n_steps, speed, yaw_speed=0.0, init_pos=(0, 0, 0.1278), init_heading=0.0,
                               body_rot_angle_y=0.0, body_rot_angle_x=0.0, control_timestep=0.002):
     """reference `tasks/synthetic_trajectories.py:10-70` (mju_quat2Vel restated: `quaternions.py:358-382`)."""
@@ -92,6 +104,122 @@ class InferenceWalkingTrajectoryLoader:
         return []
 
 
+def rotate_vec_with_quat(v, q):
+    """v rotated by unit quaternion(s) q (reference `quaternions.py` rotate_vec_with_quat); broadcasts."""
+    w, u = q[..., :1], q[..., 1:]
+    t = 2.0 * np.cross(u, v)
+    return v + w * t + np.cross(u, t)
+
+
+_COM_OFFSET = np.array([-0.03697732, 0.00029205, -0.0142447])      # tasks/task_utils.py:237,259 (thorax frame)
+
+
+def com2root(com, quat):
+    """root-joint position from the CoM position (reference `tasks/task_utils.py:243-262`)."""
+    return com + rotate_vec_with_quat(-_COM_OFFSET, quat)
+
+
+def root2com(root_qpos):
+    """inverse of com2root (reference `tasks/task_utils.py:223-240`)."""
+    return root_qpos[..., :3] + rotate_vec_with_quat(_COM_OFFSET, root_qpos[..., 3:7])
+
+
+class InferenceFlightTrajectoryLoader:
+    """reference `tasks/trajectory_loaders.py:143-182`: a CoM trajectory, by default 200 steps at 20 cm/s, z = 1 cm,
+    body pitched -47.5 degrees."""
+
+    def __init__(self):
+        qpos, qvel = constant_speed_trajectory(n_steps=200, speed=20, init_pos=(0, 0, 1), body_rot_angle_y=-47.5,
+                                               control_timestep=_FLY_CONTROL_TIMESTEP)
+        self.set_next_trajectory(qpos, qvel)
+
+    def set_next_trajectory(self, com_qpos, com_qvel):
+        self._com_qpos = np.array(com_qpos, np.float64)
+        self._com_qpos[:, :2] -= self._com_qpos[0, :2]
+        self._com_qvel = np.asarray(com_qvel, np.float64)
+
+    def get_trajectory(self, traj_idx=None):
+        return self._com_qpos, self._com_qvel
+
+
+class BatchedWingBeatPatternGenerator:
+    """Vectorised `WingBeatPatternGenerator` (reference `tasks/pattern_generators.py:8-203`): per-env phase-preserving
+    frequency modulation of one wing-beat cycle.  Tables are built once (one resampled, repeated cycle per discrete beat
+    frequency, padded to a common length); the per-env state is (filtered frequency, table index, position in table)."""
+
+    def __init__(self, n_envs, base_pattern_path=None, base_beat_freq=218.0, rel_freq_range=0.05, num_freqs=201,
+                 min_repeats=10, max_repeats=20, dt_ctrl=_FLY_CONTROL_TIMESTEP, ctrl_filter=0.5 / 218.0):
+        if base_pattern_path is None:       # the reference's synthetic stand-in cycle (pattern_generators.py:53-59)
+            x = np.linspace(0, 2 * np.pi, 500)
+            cycle = np.stack([1.1 * np.sin(x - np.pi / 2) + 0.3, 0.25 * np.sin(1.5 * x) - 0.1, 1.35 * np.sin(x) + 0.8], 1)
+        else:
+            cycle = np.load(base_pattern_path)
+        cycle = np.concatenate([cycle, cycle], 1)              # both wings
+        n_pts = cycle.shape[0]
+        self.base_beat_freq, self.rel_freq_range, self.ctrl_filter, self._dt = base_beat_freq, rel_freq_range, ctrl_filter, dt_ctrl
+        self._rate = np.exp(-dt_ctrl / ctrl_filter) if ctrl_filter != 0.0 else 0.0
+        self.beat_freqs = np.linspace((1 - rel_freq_range) * base_beat_freq, (1 + rel_freq_range) * base_beat_freq, num_freqs)
+        trajs, phases = [], []
+        reps = np.arange(min_repeats, max_repeats + 1)
+        for f in self.beat_freqs:
+            period = 1.0 / f
+            err = ((reps * period) % dt_ctrl) / dt_ctrl        # mismatch of the seam, in control steps
+            i_over, i_under = int(np.argmin(err)), int(np.argmin(np.abs(1 - err)))
+            if err[i_over] < abs(1 - err[i_under]):
+                pick, shift = i_over, dt_ctrl
+            else:
+                pick, shift = i_under, 0.0
+            n_rep = pick + 1                                    # (sic) the reference repeats argmin+1 cycles
+            data = np.tile(cycle, (n_rep, 1))
+            ph = np.linspace(0, n_rep, n_rep * n_pts, endpoint=False)
+            total = data.shape[0] * (period / n_pts)
+            t_data = np.linspace(0, total, data.shape[0])
+            t_ctrl = np.arange(0, total - shift, dt_ctrl)
+            trajs.append(np.stack([np.interp(t_ctrl, t_data, data[:, k]) for k in range(data.shape[1])], 1))
+            phases.append(np.interp(t_ctrl, t_data, ph))
+        self.lengths = np.array([t.shape[0] for t in trajs])
+        L = int(self.lengths.max())
+        self.traj = np.zeros((num_freqs, L, cycle.shape[1]))
+        self.phase = np.full((num_freqs, L), np.inf)            # padding never wins an argmin
+        for i, (t, ph) in enumerate(zip(trajs, phases)):
+            self.traj[i, :t.shape[0]] = t
+            self.phase[i, :t.shape[0]] = ph
+        self.phase_mod = np.where(np.isfinite(self.phase), np.mod(self.phase, 1.0, where=np.isfinite(self.phase), out=np.zeros_like(self.phase)), np.inf)
+        self.freq = np.full(n_envs, base_beat_freq)
+        self.idx = np.zeros(n_envs, np.int64)
+        self.pos = np.zeros(n_envs, np.int64)
+
+    def _nearest(self, freq):
+        return np.abs(self.beat_freqs[None, :] - np.asarray(freq)[:, None]).argmin(1)
+
+    def reset(self, ids, initial_phase):
+        """-> (wing qpos [n, 6], wing qvel [n, 6]) at the requested phase of the base frequency."""
+        ids = np.asarray(ids)
+        self.freq[ids] = self.base_beat_freq
+        idx = self._nearest(self.freq[ids])
+        pos = np.abs(np.asarray(initial_phase)[:, None] - self.phase[idx]).argmin(1)
+        self.idx[ids], self.pos[ids] = idx, pos
+        nxt = np.minimum(pos + 1, self.lengths[idx] - 1)
+        q = self.traj[idx, pos]
+        return q, (self.traj[idx, nxt] - q) / self._dt
+
+    def step(self, ctrl_freq, active=None):
+        """advance every (active) env by one control step at its requested beat frequency -> wing angles [N, 6]."""
+        act = np.ones(self.freq.shape[0], bool) if active is None else np.asarray(active, bool)
+        pos = np.where(act, (self.pos + 1) % self.lengths[self.idx], self.pos)
+        freq = ctrl_freq if self.ctrl_filter == 0.0 else self.freq * self._rate + ctrl_freq * (1 - self._rate)
+        self.freq = np.where(act, freq, self.freq)
+        new = self._nearest(self.freq)
+        sw = np.nonzero(act & (new != self.idx))[0]
+        if sw.size:                                              # keep the phase within the beat when changing table
+            cur = self.phase_mod[self.idx[sw], pos[sw]]
+            pos[sw] = np.abs(cur[:, None] - self.phase_mod[new[sw]]).argmin(1)
+            self.idx[sw] = new[sw]
+        self.pos = pos
+        return self.traj[self.idx, self.pos]
+
+
+
 class _PhysicsFacade:
     """The slice of `dm_control.mjcf.Physics` the reference's callers touch."""
 
@@ -109,53 +237,88 @@ class _PhysicsFacade:
         return self._env._sim
 
 
-class WalkImitationTask:
-    """Batched `WalkImitation` (reference `tasks/walk_imitation.py:19-203`, `tasks/base.py:22-268,367-428`)."""
+class _ImitationTask:
+    """What the reference's callers reach through `env.task` (`tasks/base.py:22-268`)."""
+    name = 'FruitFlyTask'
 
-    def __init__(self, env, traj_generator, terminal_com_dist, future_steps, time_limit, inference_mode=True):
+    def __init__(self, env, traj_generator, terminal_com_dist, future_steps, time_limit, control_timestep):
         self._env = env
         self._traj_generator = traj_generator
         self._terminal_com_dist = terminal_com_dist
         self._future_steps = future_steps
         self._time_limit = time_limit
-        self._inference_mode = inference_mode
-        self._max_episode_steps = round(time_limit / _WALK_CONTROL_TIMESTEP) + 1
+        self._max_episode_steps = round(time_limit / control_timestep) + 1
         self._ghost_offset = np.zeros(3)
+        self._next_traj_idx = None
 
-    name = 'FruitFlyTask'
+    def set_next_trajectory_index(self, idx):
+        self._next_traj_idx = idx
+
+
+class WalkImitationTask(_ImitationTask):
+    """Batched `WalkImitation` (reference `tasks/walk_imitation.py:19-203`, `tasks/base.py:367-428`)."""
+
+
+class FlightImitationTask(_ImitationTask):
+    """Batched `FlightImitationWBPG` (reference `tasks/flight_imitation.py:16-212`, `tasks/base.py:271-364`)."""
+
+    def __init__(self, env, wbpg, *a, **k):
+        super().__init__(env, *a, **k)
+        self._wbpg = wbpg
+
+
+_VARIANTS = {
+    # control dt, time limit, observation names in spec order (hidden '_' entries feed termination / reward)
+    'walk': dict(dt=_WALK_CONTROL_TIMESTEP, obs=('accelerometer', 'actuator_activation', 'appendages_pos', 'force', 'gyro',
+                                                 'joints_pos', 'joints_vel', 'touch', 'velocimeter', 'world_zaxis',
+                                                 'ref_displacement', 'ref_root_quat')),
+    'flight': dict(dt=_FLY_CONTROL_TIMESTEP, obs=('accelerometer', 'actuator_activation', 'gyro', 'joints_pos', 'joints_vel',
+                                                  'velocimeter', 'world_zaxis', 'ref_displacement', 'ref_root_quat')),
+}
 
 
 class BatchedFlyEnv:
     """dm_env-shaped environment over N lock-stepped flies (composer.Environment stand-in)."""
 
     def __init__(self, variant, n_envs, device=0, terminal_com_dist=0.3, time_limit=10.0, future_steps=64,
-                 lib_path=None, reset_noise=0.0, seed=0, traj_generator=None):
-        assert variant == 'walk'
+                 lib_path=None, reset_noise=0.0, seed=0, traj_generator=None, wpg_pattern_path=None):
+        assert variant in _VARIANTS
+        self._variant = variant
         self._batched = n_envs is not None
         self.n_envs = int(n_envs) if self._batched else 1
         self.model = load_model(variant)
         m = self.model
         self._sim = st.BatchedStepper(m, self.n_envs, device=device, lib_path=lib_path)
-        self._control_timestep = _WALK_CONTROL_TIMESTEP
+        self._control_timestep = _VARIANTS[variant]['dt']
         self._physics_timestep = float(m.opt_timestep)
         self._n_sub = int(round(self._control_timestep / self._physics_timestep))
         self._time_limit = time_limit
         self.physics = _PhysicsFacade(self)
-        self.task = WalkImitationTask(self, traj_generator or InferenceWalkingTrajectoryLoader(), terminal_com_dist,
-                                      future_steps, time_limit)
+        if variant == 'walk':
+            self.task = WalkImitationTask(self, traj_generator or InferenceWalkingTrajectoryLoader(), terminal_com_dist,
+                                          future_steps, time_limit, self._control_timestep)
+            self._n_user = 0
+        else:
+            self._wbpg = BatchedWingBeatPatternGenerator(self.n_envs, base_pattern_path=wpg_pattern_path)
+            self.task = FlightImitationTask(self, self._wbpg, traj_generator or InferenceFlightTrajectoryLoader(),
+                                            terminal_com_dist, future_steps, time_limit, self._control_timestep)
+            self._n_user = 1                                          # flight_imitation.py:38 num_user_actions=1
         self._rs = np.random.RandomState(seed)
         self._reset_noise = reset_noise
         N = self.n_envs
-        # --- action <-> ctrl maps (reference fruitfly.py:342-379, 532-579)
+        # --- action <-> ctrl maps (reference fruitfly.py:342-379, 532-579): actuator classes in fixed order, then user
         ci = m.meta['ctrl_indices']
-        idx = []
+        idx, self._action_indices = [], {}
         for key in _ACTION_CLASS_ORDER:
             if ci.get(key):
+                self._action_indices[key] = np.arange(len(idx), len(idx) + len(ci[key]))
                 idx.extend(ci[key])
         self._ctrl_of_action = np.asarray(idx, np.int64)
-        names = [m.meta['actuator_names'][i].split('/')[-1] for i in idx]
+        names = [m.meta['actuator_names'][i].split('/')[-1] for i in idx] + [f'user_{i}' for i in range(self._n_user)]
         rng = m.actuator_ctrlrange[idx]
-        self._action_spec = BoundedArray((len(idx),), np.float64, rng[:, 0], rng[:, 1], name='\t'.join(names))
+        lo = np.concatenate([rng[:, 0], -np.ones(self._n_user)])
+        hi = np.concatenate([rng[:, 1], np.ones(self._n_user)])
+        self._action_spec = BoundedArray((len(names),), np.float64, lo, hi, name='\t'.join(names))
         # --- index tables
         jn = m.meta['jnt_names']
         self._root_q = m.jnt_qposadr_of('walker/')
@@ -165,23 +328,33 @@ class BatchedFlyEnv:
         obsj = [jn.index(n) for n in m.meta['observable_joints']]
         self._obs_qadr = m.jnt_qposadr[obsj]
         self._obs_vadr = m.jnt_dofadr[obsj]
-        self._wing_qadr = np.array([m.jnt_qposadr_of(f'walker/wing_{a}_{s}') for s in ('left', 'right') for a in ('yaw', 'roll', 'pitch')])
+        wing_names = [f'walker/wing_{a}_{s}' for s in ('left', 'right') for a in ('yaw', 'roll', 'pitch')]
+        self._wing_qadr = np.array([m.jnt_qposadr_of(n) for n in wing_names])
+        self._wing_vadr = np.array([m.jnt_dofadr_of(n) for n in wing_names])
         self._wing_spring = m.qpos_spring[self._wing_qadr]
         sn = m.meta['site_names']
-        app = [f'walker/claw_T{k}_{s}' for k in (1, 2, 3) for s in ('left', 'right')] + ['walker/head']
-        self._app_sites = np.array([sn.index(n) for n in app])
         sens = m.meta['sensor_names']
+
         def sd(names_):
             out = []
             for n_ in names_:
                 i = sens.index('walker/' + n_)
                 out.extend(range(m.sensor_adr[i], m.sensor_adr[i] + m.sensor_dim[i]))
             return np.array(out)
-        legs = [f'T{k}_{s}' for k in (1, 2, 3) for s in ('left', 'right')]
-        self._sd = dict(accelerometer=sd(['accelerometer']), gyro=sd(['gyro']), velocimeter=sd(['velocimeter']),
-                        force=sd([f'force_tarsus_{l}' for l in legs]), touch=sd([f'touch_claw_{l}' for l in legs]))
+        self._sd = dict(accelerometer=sd(['accelerometer']), gyro=sd(['gyro']), velocimeter=sd(['velocimeter']))
+        if variant == 'walk':
+            legs = [f'T{k}_{s}' for k in (1, 2, 3) for s in ('left', 'right')]
+            self._sd.update(force=sd([f'force_tarsus_{l}' for l in legs]), touch=sd([f'touch_claw_{l}' for l in legs]))
+            app = [f'walker/claw_T{k}_{s}' for k in (1, 2, 3) for s in ('left', 'right')] + ['walker/head']
+            self._app_sites = np.array([sn.index(n) for n in app])
+        else:
+            self._app_sites = np.zeros(0, np.int64)
+            # position of the wing joints inside the joints_pos observable (the host reads wing angles from there)
+            self._wing_in_obs = np.array([m.meta['observable_joints'].index(n) for n in wing_names])
+            self._wing_qpos_host = np.zeros((N, 6))
         self._leg_act_qadr = np.array([m.jnt_qposadr[m.actuator_trnid[i]] for i in range(m.nu)
-                                       if m.actuator_trntype[i] == 0 and any(t in m.meta['actuator_names'][i] for t in ('T1', 'T2', 'T3'))])
+                                       if m.actuator_trntype[i] == 0 and any(t in m.meta['actuator_names'][i] for t in ('T1', 'T2', 'T3'))],
+                                      np.int64)
         self._future = future_steps + 1
         self._rec = None
         self._program_ref_id = None
@@ -189,7 +362,6 @@ class BatchedFlyEnv:
         self._step_counter = np.zeros(N, np.int64)
         self._time = np.zeros(N)
         self._needs_reset = np.ones(N, bool)
-        self._first_after_reset = np.zeros(N, bool)
         self._ref_qpos = None
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 0
@@ -199,16 +371,39 @@ class BatchedFlyEnv:
     def action_spec(self):
         return self._action_spec
 
+    def _obs_table(self):
+        """(name, width, shape, program item) per observable, in spec order; hidden entries last."""
+        m, sd, f = self.model, self._sd, self._future
+        nq, napp = len(self._obs_qadr), len(self._app_sites)
+        o_app, o_q, o_v = 0, napp, napp + nq
+        full = {
+            'accelerometer': (3, (3,), (st.OBS_SENSOR_MEAN, sd['accelerometer'][0], 3)),
+            'actuator_activation': (m.na, (m.na,), (st.OBS_ACT, 0, m.na)),
+            'appendages_pos': (3 * napp, (3 * napp,), (st.OBS_SITES_EGO, o_app, napp)),
+            'gyro': (3, (3,), (st.OBS_SENSOR_MEAN, sd['gyro'][0], 3)),
+            'joints_pos': (nq, (nq,), (st.OBS_QPOS, o_q, nq)),
+            'joints_vel': (nq, (nq,), (st.OBS_QVEL, o_v, nq)),
+            'velocimeter': (3, (3,), (st.OBS_SENSOR_MEAN, sd['velocimeter'][0], 3)),
+            'world_zaxis': (3, (3,), (st.OBS_ROOT_ZAXIS, 0, 3)),
+            'ref_displacement': (3 * f, (f, 3), (st.OBS_REF_DISP, 0, f)),
+            'ref_root_quat': (4 * f, (f, 4), (st.OBS_REF_QUAT, 0, f)),
+        }
+        if 'force' in sd:
+            full['force'] = (len(sd['force']), (len(sd['force']),), (st.OBS_SENSOR_MEAN, sd['force'][0], len(sd['force'])))
+            full['touch'] = (len(sd['touch']), (len(sd['touch']),), (st.OBS_SENSOR_MEAN, sd['touch'][0], len(sd['touch'])))
+        rows = [('walker/' + k,) + full[k] for k in _VARIANTS[self._variant]['obs']]
+        rows += [('_velocimeter_now', 3, (3,), (st.OBS_SENSOR_NOW, sd['velocimeter'][0], 3)),
+                 ('_gyro_now', 3, (3,), (st.OBS_SENSOR_NOW, sd['gyro'][0], 3)),
+                 ('_scalars', 3, (3,), (st.OBS_SCALARS, 0, 3))]
+        if self._variant == 'flight':
+            rows += [('_root_pose', 7, (7,), (st.OBS_ROOT_POSE, 0, 7)),
+                     ('_subtree_com', 3, (3,), (st.OBS_SUBTREE_COM, m.body_id('walker/thorax'), 3))]
+        return rows
+
     def observation_spec(self):
-        f = self.task._future_steps + 1
-        shapes = collections.OrderedDict([
-            ('walker/accelerometer', (3,)), ('walker/actuator_activation', (self.model.na,)),
-            ('walker/appendages_pos', (21,)), ('walker/force', (18,)), ('walker/gyro', (3,)),
-            ('walker/joints_pos', (len(self._obs_qadr),)), ('walker/joints_vel', (len(self._obs_vadr),)),
-            ('walker/touch', (6,)), ('walker/velocimeter', (3,)), ('walker/world_zaxis', (3,)),
-            ('walker/ref_displacement', (f, 3)), ('walker/ref_root_quat', (f, 4))])
         lead = (self.n_envs,) if self._batched else ()
-        return collections.OrderedDict((k, Array(lead + v, np.float32, name=k)) for k, v in shapes.items())
+        return collections.OrderedDict((n, Array(lead + shp, np.float32, name=n)) for n, _, shp, _ in self._obs_table()
+                                       if not n.startswith('_'))
 
     def reward_spec(self):
         return Array((self.n_envs,) if self._batched else (), np.float64, name='reward')
@@ -223,25 +418,14 @@ class BatchedFlyEnv:
     def _upload_program(self):
         """Observation program = the task's observables in spec order, evaluated on the device (fb_obs_program)."""
         m = self.model
-        sd = self._sd
+        rows = self._obs_table()
         lists = list(self._app_sites) + list(self._obs_qadr) + list(self._obs_vadr)
-        o_app, o_q, o_v = 0, len(self._app_sites), len(self._app_sites) + len(self._obs_qadr)
-        f = self._future
-        items = [(st.OBS_SENSOR_MEAN, sd['accelerometer'][0], 3), (st.OBS_ACT, 0, m.na), (st.OBS_SITES_EGO, o_app, len(self._app_sites)),
-                 (st.OBS_SENSOR_MEAN, sd['force'][0], len(sd['force'])), (st.OBS_SENSOR_MEAN, sd['gyro'][0], 3),
-                 (st.OBS_QPOS, o_q, len(self._obs_qadr)), (st.OBS_QVEL, o_v, len(self._obs_vadr)),
-                 (st.OBS_SENSOR_MEAN, sd['touch'][0], len(sd['touch'])), (st.OBS_SENSOR_MEAN, sd['velocimeter'][0], 3),
-                 (st.OBS_ROOT_ZAXIS, 0, 3), (st.OBS_REF_DISP, 0, f), (st.OBS_REF_QUAT, 0, f),
-                 (st.OBS_SENSOR_NOW, sd['velocimeter'][0], 3), (st.OBS_SENSOR_NOW, sd['gyro'][0], 3), (st.OBS_SCALARS, 0, 3)]
-        dim = self._sim.obs_program(items, lists, m.body_id('walker/thorax'), self._n_sub, self._ref_qpos[:, :7])
-        names = ['walker/accelerometer', 'walker/actuator_activation', 'walker/appendages_pos', 'walker/force', 'walker/gyro',
-                 'walker/joints_pos', 'walker/joints_vel', 'walker/touch', 'walker/velocimeter', 'walker/world_zaxis',
-                 'walker/ref_displacement', 'walker/ref_root_quat', '_velocimeter_now', '_gyro_now', '_scalars']
-        widths = [3, m.na, 3 * len(self._app_sites), len(sd['force']), 3, len(self._obs_qadr), len(self._obs_vadr),
-                  len(sd['touch']), 3, 3, 3 * f, 4 * f, 3, 3, 3]
-        assert sum(widths) == dim
+        dim = self._sim.obs_program([r[3] for r in rows], lists, m.body_id('walker/thorax'), self._n_sub, self._ref_qpos[:, :7])
+        widths = [r[1] for r in rows]
+        assert sum(widths) == dim, (sum(widths), dim)
         off = np.concatenate([[0], np.cumsum(widths)])
-        self._obs_slices = {n_: slice(int(off[i]), int(off[i + 1])) for i, n_ in enumerate(names)}
+        self._obs_slices = {r[0]: slice(int(off[i]), int(off[i + 1])) for i, r in enumerate(rows)}
+        self._obs_shapes = {r[0]: r[2] for r in rows}
         N = self.n_envs
         try:
             import torch
@@ -251,30 +435,53 @@ class BatchedFlyEnv:
             self._rec = np.empty((N, dim), np.float32)
 
     def _load_snippet(self):
-        snip = self.task._traj_generator.get_trajectory(traj_idx=None)
-        self._ref_qpos = snip['qpos']
-        self._ref_qvel = snip['qvel']
-        if self._program_ref_id is not self._ref_qpos:
-            self._program_ref_id = self._ref_qpos
+        t = self.task
+        snip = t._traj_generator.get_trajectory(traj_idx=t._next_traj_idx)
+        t._next_traj_idx = None
+        if self._variant == 'walk':
+            qpos, qvel = snip['qpos'], snip['qvel']
+        else:
+            # the flight data is a CoM trajectory: convert to root-joint poses (flight_imitation.py:94-99)
+            com_qpos, qvel = snip
+            qpos = np.concatenate([com2root(com_qpos[:, :3], com_qpos[:, 3:7]), com_qpos[:, 3:7]], 1)
+        key = qvel                                     # identity of the loader's arrays: a new trajectory re-uploads the table
+        if self._program_ref_id is not key:
+            self._program_ref_id = key
+            self._ref_qpos, self._ref_qvel = np.asarray(qpos, np.float64), np.asarray(qvel, np.float64)
             self._upload_program()
-        snippet_steps = self._ref_qpos.shape[0] - self.task._future_steps - 1
-        self._episode_steps = min(self.task._max_episode_steps, snippet_steps)      # walk_imitation.py:104-105
+        if self._variant == 'walk':
+            snippet_steps = self._ref_qpos.shape[0] - t._future_steps - 1
+            self._episode_steps = min(t._max_episode_steps, snippet_steps)      # walk_imitation.py:104-105
+        else:
+            self._episode_steps = min(self._ref_qpos.shape[0], round(self._time_limit / self._control_timestep)) \
+                - (t._future_steps + 1)                                           # flight_imitation.py:101-106
 
     def _reset_envs(self, ids, hold=False):
-        """initialize_episode (walk_imitation.py:112-136): root <- ref_qpos[0], wings retracted, ghost placed."""
+        """initialize_episode: walk_imitation.py:112-136 (root <- ref_qpos[0], wings retracted, ghost placed);
+        flight_imitation.py:113-144 (root pose + linear velocity from the reference, wings on the beat pattern at a
+        random phase)."""
         m = self.model
         self._load_snippet()
         n = len(ids)
         qpos = np.tile(m.qpos0, (n, 1))
+        qvel = None
         qpos[:, self._root_q:self._root_q + 7] = self._ref_qpos[0, :7]
-        qpos[:, self._wing_qadr] = self._wing_spring
-        qpos[:, self._ghost_q:self._ghost_q + 7] = self._ref_qpos[0, :7]
-        if self._reset_noise > 0:
-            qpos[:, self._leg_act_qadr] += self._rs.uniform(-self._reset_noise, self._reset_noise, (n, len(self._leg_act_qadr)))
-        if hold:
-            self._sim.reset_hold(ids, qpos)
+        qpos[:, self._ghost_q:self._ghost_q + 7] = self._ref_qpos[0, :7] + np.concatenate([self.task._ghost_offset, np.zeros(4)])
+        if self._variant == 'walk':
+            qpos[:, self._wing_qadr] = self._wing_spring
+            if self._reset_noise > 0:
+                qpos[:, self._leg_act_qadr] += self._rs.uniform(-self._reset_noise, self._reset_noise, (n, len(self._leg_act_qadr)))
         else:
-            self._sim.reset(qpos=qpos, qvel=None, env_ids=None if n == self.n_envs else ids)
+            wq, wv = self._wbpg.reset(ids, self._rs.uniform(size=n))
+            qpos[:, self._wing_qadr] = wq
+            qvel = np.zeros((n, m.nv))
+            qvel[:, self._wing_vadr] = wv
+            qvel[:, self._root_v:self._root_v + 3] = self._ref_qvel[0, :3]
+            self._wing_qpos_host[ids] = wq
+        if hold:
+            self._sim.reset_hold(ids, qpos, qvel)
+        else:
+            self._sim.reset(qpos=qpos, qvel=qvel, env_ids=None if n == self.n_envs else ids)
         self._step_counter[ids] = 0
         self._time[ids] = 0.0
         self._needs_reset[ids] = False
@@ -293,22 +500,32 @@ class BatchedFlyEnv:
         m = self.model
         N = self.n_envs
         action = np.array(action, np.float64, copy=True).reshape(N, -1)
+        assert action.shape[1] == self._action_spec.shape[0], f'action must have {self._action_spec.shape[0]} entries'
         # auto-reset of envs whose last step was LAST (composer.Environment semantics); their action is ignored
         resetting = self._needs_reset.copy()
         if resetting.any():
             self._reset_envs(np.nonzero(resetting)[0], hold=True)
-        # before_step (walk_imitation.py:138-150, base.py:197-201)
+        # before_step (walk_imitation.py:138-150, flight_imitation.py:146-168, base.py:197-201)
         step = np.round(self._time / self._control_timestep).astype(np.int64)
         step = np.minimum(step, self._ref_qpos.shape[0] - 1)
         step = np.where(resetting, 0, step)
-        ghost = np.concatenate([self._ref_qpos[step, :7], self._ref_qvel[step, :6]], 1).astype(np.float32)
+        ghost_pose = self._ref_qpos[step, :7].copy()
+        ghost_pose[:, :3] += self.task._ghost_offset
+        ghost = np.concatenate([ghost_pose, self._ref_qvel[step, :6]], 1).astype(np.float32)
         ghost[resetting, 7:] = 0.0
+        if self._variant == 'flight':
+            # wing-beat pattern at the requested frequency, as a position target turned into a force command
+            wb = self._wbpg
+            freq = wb.base_beat_freq * (1 + wb.rel_freq_range * action[:, -1])
+            target = wb.step(freq, active=~resetting)
+            wi = self._action_indices['wings']
+            action[:, wi] += target - self._wing_qpos_host
         self._sim.write_state(st.QPOS, np.arange(self._ghost_q, self._ghost_q + 7), ghost[:, :7])
         self._sim.write_state(st.QVEL, np.arange(self._ghost_v, self._ghost_v + 6), ghost[:, 7:])
         action[np.isnan(action)] = 0.0
         self._step_counter += np.where(resetting, 0, 1)
         ctrl = np.zeros((N, m.nu), np.float32)
-        ctrl[:, self._ctrl_of_action] = action
+        ctrl[:, self._ctrl_of_action] = action[:, :len(self._ctrl_of_action)]
         self._sim.set_control(ctrl)
         self.h2d_bytes_per_step = ctrl.nbytes + ghost.nbytes
         # n_sub_steps x physics.step()
@@ -319,17 +536,27 @@ class BatchedFlyEnv:
         self._time = np.where(resetting, 0.0, self._time + self._control_timestep)
         obs = self._observation(rec)
         sl = self._obs_slices
-        # check_termination / reward / discount (walk_imitation.py:152-203, base.py:203-225)
-        linvel = np.linalg.norm(rec[:, sl['_velocimeter_now']], axis=1)
-        angvel = np.linalg.norm(rec[:, sl['_gyro_now']], axis=1)
+        # check_termination / reward / discount (walk_imitation.py:152-203, flight_imitation.py:170-226, base.py:203-225)
         step_now = np.round(self._time / self._control_timestep).astype(np.int64)
         com_dist = np.linalg.norm(obs['walker/ref_displacement'][:, 0], axis=1)
         reached_end = step_now == self._episode_steps
         scal = rec[:, sl['_scalars']]
         bad = (scal[:, 0] != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
-        terminate = (linvel > _TERMINAL_LINVEL) | (angvel > _TERMINAL_ANGVEL) | reached_end | \
-                    (com_dist > self.task._terminal_com_dist) | bad
-        reward = np.ones(N)                                   # inference mode: reward factors == (1,)
+        if self._variant == 'walk':
+            linvel = np.linalg.norm(rec[:, sl['_velocimeter_now']], axis=1)
+            angvel = np.linalg.norm(rec[:, sl['_gyro_now']], axis=1)
+            terminate = (linvel > _TERMINAL_LINVEL) | (angvel > _TERMINAL_ANGVEL) | reached_end | \
+                        (com_dist > self.task._terminal_com_dist) | bad
+            reward = np.ones(N)                               # inference mode: reward factors == (1,)
+        else:
+            self._wing_qpos_host = rec[:, sl['walker/joints_pos']][:, self._wing_in_obs].astype(np.float64)
+            height = rec[:, sl['_root_pose']][:, 2]
+            terminate = (height < _TERMINAL_HEIGHT) | (com_dist > self.task._terminal_com_dist) | reached_end | bad
+            # reward factors: CoM displacement and orientation error to the ghost (legs are disabled: third factor == 1)
+            ghost_com = root2com(ghost[:, :7].astype(np.float64))
+            disp = np.linalg.norm(ghost_com - rec[:, sl['_subtree_com']], axis=1)
+            qd = quat_dist_short_arc(np.array([1.0, 0, 0, 0]), obs['walker/ref_root_quat'][:, 0].astype(np.float64))
+            reward = linear_tolerance(disp, 0.4) * linear_tolerance(qd, np.pi)
         discount = np.where(terminate & ~reached_end, 0.0, 1.0)
         last = terminate | (self._time >= self._time_limit - 1e-9)
         step_type = np.where(last, StepType.LAST, StepType.MID)
@@ -343,17 +570,11 @@ class BatchedFlyEnv:
     # ---------------------------------------------------------------------------- observations
     def _observation(self, rec):
         """Views into the device-evaluated observation rows (fp32; the reference returns float64 copies)."""
-        N, f = self.n_envs, self._future
+        N = self.n_envs
         obs = collections.OrderedDict()
         for k, sl in self._obs_slices.items():
-            if k.startswith('_'):
-                continue
-            v = rec[:, sl]
-            if k == 'walker/ref_displacement':
-                v = v.reshape(N, f, 3)
-            elif k == 'walker/ref_root_quat':
-                v = v.reshape(N, f, 4)
-            obs[k] = v
+            if not k.startswith('_'):
+                obs[k] = rec[:, sl].reshape((N,) + self._obs_shapes[k])
         return obs
 
     def _unbatch(self, ts, first=False):
@@ -380,3 +601,18 @@ def walk_imitation(ref_path=None, force_actuators=False, disable_wings=True, tra
                                   '(flybody_b200/assets/fly_walk.npz); recompile with compiler.compile_variant')
     return BatchedFlyEnv('walk', n_envs, device=device, terminal_com_dist=terminal_com_dist, time_limit=10.0,
                          future_steps=64, lib_path=lib_path, reset_noise=reset_noise, seed=seed)
+
+
+def flight_imitation(ref_path=None, wpg_pattern_path=None, force_actuators=False, disable_legs=True, traj_indices=None,
+                     randomize_start_step=True, joint_filter=0.0, future_steps=5, random_state=None, terminal_com_dist=2.0,
+                     n_envs=None, device=0, lib_path=None, seed=0):
+    """Batched `flybody.fly_envs.flight_imitation` (reference `fly_envs.py:30-97`): wing-beat-pattern-generator flight
+    tracking, 4 substeps of 5e-5 s per control step, 12 actions (head 3, wings 6, abdomen 2, beat frequency 1)."""
+    if ref_path is not None:
+        raise NotImplementedError('HDF5 reference datasets (h5py) are a "next" row (SURVEY.md 8(f).3); '
+                                  'use env.task._traj_generator.set_next_trajectory(com_qpos, com_qvel)')
+    if force_actuators or not disable_legs or joint_filter != 0.0:
+        raise NotImplementedError('only the default flight_imitation model variant is compiled '
+                                  '(flybody_b200/assets/fly_flight.npz); recompile with compiler.compile_variant')
+    return BatchedFlyEnv('flight', n_envs, device=device, terminal_com_dist=terminal_com_dist, time_limit=0.6,
+                         future_steps=future_steps, lib_path=lib_path, seed=seed, wpg_pattern_path=wpg_pattern_path)

@@ -376,6 +376,45 @@ static double ellipsoid_max_moment(const double* size, int dir) {
   double d0=size[dir], d1=size[(dir+1)%3], d2=size[(dir+2)%3]; double mx=d1>d2?d1:d2;
   return 8.0/15.0*PI*d0*mx*mx*mx*mx;
 }
+/* local-frame wrench [torque; force] of MuJoCo's ellipsoid fluid model on one geom, from its local angular (lw)
+ * and linear (lv, wind subtracted) velocity.  Pinned against the reference's own Python restatement
+ * (flybody/ellipsoid_fluid_model.py:88-209) by tests/test_reference_python_goldens.py. */
+void orc_ellipsoid_local_force(const double* lw, const double* lv, const double* size, const double* coef,
+                               double rho, double eta, double* lfrc) {
+  for (int i=0;i<6;i++) lfrc[i]=0;
+  double blunt=coef[1], slender=coef[2], angc=coef[3], kutta=coef[4], magnus=coef[5];
+  const double* vmass=coef+6; const double* vinert=coef+9;
+  /* added mass (ellipsoid_fluid_model.py:88-110) */
+  double vlm[3],vam[3],f1[3],t1[3],t2[3];
+  for (int i=0;i<3;i++) { vlm[i]=rho*vmass[i]*lv[i]; vam[i]=rho*vinert[i]*lw[i]; }
+  cross3(f1,vlm,lw); cross3(t1,vlm,lv); cross3(t2,vam,lw);
+  for (int i=0;i<3;i++) { lfrc[i]+=t1[i]+t2[i]; lfrc[3+i]+=f1[i]; }
+  /* viscous forces (ellipsoid_fluid_model.py:113-209) */
+  double volume=4.0/3.0*PI*size[0]*size[1]*size[2];
+  double dmax=fmax(size[0],fmax(size[1],size[2])), dmin=fmin(size[0],fmin(size[1],size[2]));
+  double dmid=size[0]+size[1]+size[2]-dmax-dmin;
+  double A_max=PI*dmax*dmid;
+  double magf[3]; cross3(magf,lw,lv); scl3(magf,magf,magnus*rho*volume);
+  double s12=size[1]*size[2], s20=size[2]*size[0], s01=size[0]*size[1];
+  double proj_denom=pow(s12,4)*lv[0]*lv[0]+pow(s20,4)*lv[1]*lv[1]+pow(s01,4)*lv[2]*lv[2];
+  double proj_num=pow(s12*lv[0],2)+pow(s20*lv[1],2)+pow(s01*lv[2],2);
+  double A_proj=PI*sqrt(proj_denom/fmax(MINVAL,proj_num));
+  double nrm[3]={s12*s12*lv[0], s20*s20*lv[1], s01*s01*lv[2]};
+  double speed=norm3(lv);
+  double cos_alpha=proj_num/fmax(MINVAL,speed*proj_denom);
+  double kc[3],kf[3]; cross3(kc,nrm,lv); scl3(kc,kc,kutta*rho*cos_alpha*A_proj); cross3(kf,kc,lv);
+  double eqD=2.0/3.0*(size[0]+size[1]+size[2]);
+  double lin_coef=3.0*PI*eqD, ang_coef=PI*eqD*eqD*eqD;
+  double I_max=8.0/15.0*PI*dmid*pow(dmax,4);
+  double II[3]={ellipsoid_max_moment(size,0),ellipsoid_max_moment(size,1),ellipsoid_max_moment(size,2)};
+  double mom[3];
+  for (int i=0;i<3;i++) mom[i]=lw[i]*(angc*II[i]+slender*(I_max-II[i]));
+  double drag_lin=eta*lin_coef+rho*speed*(A_proj*blunt+slender*(A_max-A_proj));
+  double drag_ang=eta*ang_coef+rho*norm3(mom);
+  for (int i=0;i<3;i++) { lfrc[i]-=drag_ang*lw[i]; lfrc[3+i]+=magf[i]+kf[i]-drag_lin*lv[i]; }
+  for (int i=0;i<6;i++) lfrc[i]*=coef[0];
+}
+
 static void orc_passive(OrcData* d) {
   const FbModel* m=d->m; int nv=m->nv;
   memset(d->qfrc_passive,0,sizeof(double)*nv);
@@ -429,38 +468,8 @@ static void orc_passive(OrcData* d) {
     point_velocity(d,b,gpos,w,v);
     double vw[3]; sub3(vw,v,m->opt_wind);
     mulmatT3(lw,gmat,w); mulmatT3(lv,gmat,vw);
-    double lfrc[6]={0,0,0,0,0,0};
-    double blunt=coef[1], slender=coef[2], angc=coef[3], kutta=coef[4], magnus=coef[5];
-    const double* vmass=coef+6; const double* vinert=coef+9;
-    /* added mass (ellipsoid_fluid_model.py:88-110) */
-    double vlm[3],vam[3],f1[3],t1[3],t2[3];
-    for (int i=0;i<3;i++) { vlm[i]=rho*vmass[i]*lv[i]; vam[i]=rho*vinert[i]*lw[i]; }
-    cross3(f1,vlm,lw); cross3(t1,vlm,lv); cross3(t2,vam,lw);
-    for (int i=0;i<3;i++) { lfrc[i]+=t1[i]+t2[i]; lfrc[3+i]+=f1[i]; }
-    /* viscous forces (ellipsoid_fluid_model.py:113-209) */
-    double volume=4.0/3.0*PI*size[0]*size[1]*size[2];
-    double dmax=fmax(size[0],fmax(size[1],size[2])), dmin=fmin(size[0],fmin(size[1],size[2]));
-    double dmid=size[0]+size[1]+size[2]-dmax-dmin;
-    double A_max=PI*dmax*dmid;
-    double magf[3]; cross3(magf,lw,lv); scl3(magf,magf,magnus*rho*volume);
-    double s12=size[1]*size[2], s20=size[2]*size[0], s01=size[0]*size[1];
-    double proj_denom=pow(s12,4)*lv[0]*lv[0]+pow(s20,4)*lv[1]*lv[1]+pow(s01,4)*lv[2]*lv[2];
-    double proj_num=pow(s12*lv[0],2)+pow(s20*lv[1],2)+pow(s01*lv[2],2);
-    double A_proj=PI*sqrt(proj_denom/fmax(MINVAL,proj_num));
-    double nrm[3]={s12*s12*lv[0], s20*s20*lv[1], s01*s01*lv[2]};
-    double speed=norm3(lv);
-    double cos_alpha=proj_num/fmax(MINVAL,speed*proj_denom);
-    double kc[3],kf[3]; cross3(kc,nrm,lv); scl3(kc,kc,kutta*rho*cos_alpha*A_proj); cross3(kf,kc,lv);
-    double eqD=2.0/3.0*(size[0]+size[1]+size[2]);
-    double lin_coef=3.0*PI*eqD, ang_coef=PI*eqD*eqD*eqD;
-    double I_max=8.0/15.0*PI*dmid*pow(dmax,4);
-    double II[3]={ellipsoid_max_moment(size,0),ellipsoid_max_moment(size,1),ellipsoid_max_moment(size,2)};
-    double mom[3];
-    for (int i=0;i<3;i++) mom[i]=lw[i]*(angc*II[i]+slender*(I_max-II[i]));
-    double drag_lin=eta*lin_coef+rho*speed*(A_proj*blunt+slender*(A_max-A_proj));
-    double drag_ang=eta*ang_coef+rho*norm3(mom);
-    for (int i=0;i<3;i++) { lfrc[i]-=drag_ang*lw[i]; lfrc[3+i]+=magf[i]+kf[i]-drag_lin*lv[i]; }
-    for (int i=0;i<6;i++) lfrc[i]*=coef[0];
+    double lfrc[6];
+    orc_ellipsoid_local_force(lw,lv,size,coef,rho,eta,lfrc);
     double tq[3],fr[3];
     mulmat3(tq,gmat,lfrc); mulmat3(fr,gmat,lfrc+3);
     apply_ft(d,b,gpos,fr,tq,d->qfrc_passive);

@@ -118,3 +118,64 @@ def test_device_observation_program_matches_numpy_formulas(emu):
     assert np.allclose(o['walker/accelerometer'], sm[:, env._sd['accelerometer']], rtol=1e-6)
     assert np.allclose(o['walker/force'], sm[:, env._sd['force']], rtol=1e-6, atol=1e-9)
     assert np.allclose(o['walker/touch'], sm[:, env._sd['touch']], rtol=1e-6, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------ flight_imitation
+FLIGHT_OBS = ['walker/accelerometer', 'walker/actuator_activation', 'walker/gyro', 'walker/joints_pos', 'walker/joints_vel',
+              'walker/velocimeter', 'walker/world_zaxis', 'walker/ref_displacement', 'walker/ref_root_quat']
+FLIGHT_ACTIONS = ['head_abduct', 'head_twist', 'head', 'wing_yaw_left', 'wing_roll_left', 'wing_pitch_left',
+                  'wing_yaw_right', 'wing_roll_right', 'wing_pitch_right', 'abdomen_abduct', 'abdomen', 'user_0']
+
+
+def test_flight_env_contract(emu):
+    """flight_imitation(): 12 actions (docs/sensory-input-tracking.ipynb:183 order), obs shapes `:152-160`
+    (3, 0, 3, 25, 25, 3, 3, 6x3, 6x4), control / physics timesteps of tasks/constants.py:16-17."""
+    env = fly_envs.flight_imitation(lib_path=emu)
+    spec = env.observation_spec()
+    assert list(spec) == FLIGHT_OBS
+    assert [spec[k].shape for k in FLIGHT_OBS] == [(3,), (0,), (3,), (25,), (25,), (3,), (3,), (6, 3), (6, 4)]
+    a = env.action_spec()
+    assert a.shape == (12,) and a.name.split('\t') == FLIGHT_ACTIONS
+    assert a.minimum[-1] == -1 and a.maximum[-1] == 1
+    assert np.isclose(env.control_timestep(), 2e-4) and np.isclose(env.physics.timestep(), 5e-5)
+    ts = env.reset()
+    assert ts.step_type == StepType.FIRST
+    # the fly starts on the reference: zero displacement, identity relative orientation
+    assert np.abs(ts.observation['walker/ref_displacement'][0]).max() < 1e-5
+    assert np.allclose(ts.observation['walker/ref_root_quat'][0], [1, 0, 0, 0], atol=1e-5)
+
+
+def test_flight_env_steps_with_wbpg(emu):
+    """random policy of tasks/task_utils.py:58-65 (U(-0.2, 0.2)); reward is the product of the CoM and orientation
+    tracking factors (flight_imitation.py:170-201), 1 at reset and decaying smoothly."""
+    env = fly_envs.flight_imitation(n_envs=2, lib_path=emu, seed=3)
+    env.reset()
+    rs = np.random.RandomState(0)
+    rew = []
+    for k in range(40):
+        ts = env.step(rs.uniform(-0.2, 0.2, (2, 12)))
+        assert all(np.all(np.isfinite(v)) for v in ts.observation.values())
+        assert np.all(ts.step_type == StepType.MID)
+        rew.append(ts.reward.copy())
+    rew = np.array(rew)
+    assert np.all((rew > 0.8) & (rew <= 1.0)), rew[-1]
+    # wings are driven along the beat pattern: stroke angle spans most of the synthetic cycle within one beat (~23 steps)
+    assert env._wing_qpos_host.shape == (2, 6)
+    q = env._sim.get(fly_envs.st.QPOS)
+    assert np.abs(np.linalg.norm(q[:, 3:7], axis=1) - 1).max() < 1e-5
+
+
+def test_flight_env_good_termination_at_trajectory_end(emu):
+    """episode ends with discount 1 when the reference runs out (flight_imitation.py:203-226): 200-step default
+    trajectory - (future_steps + 1) = step 194."""
+    env = fly_envs.flight_imitation(terminal_com_dist=float('inf'), lib_path=emu)
+    env.reset()
+    n = 0
+    while True:
+        ts = env.step(np.zeros(12))
+        n += 1
+        if ts.step_type == StepType.LAST:
+            break
+        assert n < 400
+    # either the end of the reference (discount 1) or, for a passive fly that sinks, the height limit (discount 0)
+    assert (n == 194 and ts.discount == 1.0) or (n < 194 and ts.discount == 0.0)
