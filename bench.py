@@ -151,7 +151,7 @@ def run_ours(args):
     import torch.distributed as dist
     from flybody_b200.flymodel import load_model
     from flybody_b200 import stepper as st
-    from flybody_b200 import fly_envs
+    from flybody_b200 import fly_envs, sharding
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -163,7 +163,7 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     N = args.envs
     m = load_model('walk')
-    rs = np.random.RandomState(1234 + rank)
+    rs = np.random.RandomState(sharding.rank_seed(1234, rank))
     sim = st.BatchedStepper(m, N, device=local)
     Np = sim.n_envs_padded
     sim.reset(walk_reset_batch(m, N, rs))
@@ -183,7 +183,7 @@ def run_ours(args):
             sim.step(N_SUB)
             sim.pack_obs()
             if world > 1:
-                dist.gather(obs, gather_list, dst=0)
+                sharding.gather_observations(obs, world, rank, gather_list)
 
     for k in range(W):
         one_step(k)
@@ -253,7 +253,7 @@ def run_ours(args):
             'config': {'workload': f'walk_imitation {N} envs per GPU, random policy U(-0.5,0.5), 10 substeps x 2e-4 s '
                                    f'(BASELINE.json configs[1]; N>1: configs[3] sharding + NCCL obs gather to rank 0)',
                        'envs_per_gpu': N, 'total_envs': total_envs, 'n_substeps': N_SUB,
-                       'l2': 'inputs larger than L2: ~50 KB of intermediates touched per env-substep x 4096 env records ~ 200 MB per substep (> 126 MB L2); no explicit flush',
+                       'l2': f'inputs larger than L2: every launch streams the env records ({sim.record_bytes / 1e6:.2f} MB each, {sim.record_bytes * N / 1e9:.2f} GB per GPU vs 126 MB L2); no explicit flush',
                        'parallelism': f'env-sharded x{world}' + (', torch.distributed NCCL gather of packed obs per control step' if world > 1 else ''),
                        'unstable_envs_flagged': bad_total},
             'clocks': clocks, 'gpu_launches': int(launches),

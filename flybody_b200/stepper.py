@@ -227,6 +227,11 @@ class BatchedStepper:
         self._check(self._lib.fb_pack_obs(self._h), 'fb_pack_obs')
 
     @property
+    def record_bytes(self):
+        """bytes of device state per env (one record: persistent state + per-substep intermediates)."""
+        return 4 * int(self._lib.fb_record_stride(self._h))
+
+    @property
     def n_envs_padded(self):
         return int(self._lib.fb_n_envs_padded(self._h))
 

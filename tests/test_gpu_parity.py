@@ -118,6 +118,17 @@ def test_env_facade_on_gpu():
     assert all(np.all(np.isfinite(v)) for v in ts.observation.values())
 
 
+def test_flight_env_facade_on_gpu():
+    from flybody_b200 import fly_envs
+    env = fly_envs.flight_imitation(n_envs=128, seed=1)
+    env.reset()
+    rs = np.random.RandomState(0)
+    for _ in range(30):
+        ts = env.step(rs.uniform(-0.2, 0.2, (128, 12)))
+    assert all(np.all(np.isfinite(v)) for v in ts.observation.values())
+    assert np.all((ts.reward > 0.8) & (ts.reward <= 1.0))
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
