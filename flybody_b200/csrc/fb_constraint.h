@@ -504,9 +504,9 @@ FB_DEV void kfin_f1(FB_PHASE_ARGS) {
   for (int i = y; i < m.nv; i += FB_NY) XS(i) = AT(d.qfrc_constraint, i);
   for (int k = y; k < 6 * m.nbody; k += FB_NY) AT(d.bfl, k) = 0;
 }
-FB_DEV void kfin_solve_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD); }
-FB_DEV void kfin_solve_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD); }
-FB_DEV void kfin_solve_c(FB_PHASE_ARGS) { solve_c(m, d, sh, e, lane, y, d.qLD); }
+FB_WARPFN void kfin_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e, d.qLD); }
+// Euler with implicit joint damping: qacc' = (M + h D)^-1 (qfrc_smooth + qfrc_constraint), second factor qLDe
+FB_WARPFN void kfin_solve_euler(const DevModel& m, const DevData& d, ShTree& sh, int e) { if (d.do_integrate) tri_solve(m, d, sh, e, d.qLDe); }
 FB_DEV void kfin_f5(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
   for (int i = y; i < m.nv; i += FB_NY) { AT(d.qacc, i) = AT(d.qacc_smooth, i) + XS(i); XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); }
@@ -534,10 +534,8 @@ FB_DEV void delta_from_parent(const DevModel& m, const DevData& d, int e, int b,
 }
 FB_DEV void kfin_f6(FB_PHASE_ARGS) {
   if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; S6 dl; dl.a = dl.l = v3(0, 0, 0); delta_from_parent(m, d, e, b, dl); st6(d.bdel, b, d, e, dl); }
-  solve_a(m, d, sh, e, lane, y, d.qLDe);
 }
 FB_DEV void kfin_f7(FB_PHASE_ARGS) {
-  solve_b(m, d, sh, e, lane, y, d.qLDe);
   if (y >= m.nlist) return;
   int prev = -1; S6 cd; cd.a = cd.l = v3(0, 0, 0);
   FB_LIST_LOOP_FWD {
@@ -568,7 +566,6 @@ FB_DEV void kfin_f8(FB_PHASE_ARGS) {
     }
   }
   if (!d.do_integrate) return;
-  solve_c(m, d, sh, e, lane, y, d.qLDe);
   if (AT(d.hold, 0)) return;          // env staged for reset: recompute (forward) but do not integrate
   if (y == 0) {
     for (int r = 0; r < m.nroot; r++) integrate_body(m, d, e, lane, xs, m.root_body[r]);

@@ -229,29 +229,33 @@ FB_DEV void factor_step_scale(const DevModel& m, const DevData& d, ShTree& sh, i
   float invD = 1.0f / LS(adrk);
   for (int t = 1 + sub; t < len; t += FB_FSUB) LS(adrk + t) *= invD;
 }
-FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
+// root blocks: 21 lanes add up the lists' partial updates (one packed lower-triangle entry each) ...
+FB_DEV void factor_root_gather(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
   float* ldsh = sh_dyn(sh);
-  if (y != 0) return;
+  if (y >= 21) return;
+  int il = 0; while ((il + 1) * (il + 2) / 2 <= y) il++;
+  int s = y - il * (il + 1) / 2;
   for (int r = 0; r < m.nroot; r++) {
     int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
-    if (nd == 0) continue;
-    for (int il = 0; il < nd; il++) {
-      int adri = m.dof_Madr[d0 + il], base = il * (il + 1) / 2;
-      for (int s = 0; s <= il; s++) {
-        float acc = 0;
-        for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) for (int u = 0; u < FB_FSUB; u++) acc += sh.part[l * FB_FSUB + u][base + s][lane];
-        LS(adri + s) -= acc;
-      }
-    }
-    for (int kl = nd - 1; kl >= 0; kl--) {
-      int adrk = m.dof_Madr[d0 + kl];
-      float invD = 1.0f / LS(adrk);
-      for (int t = 1; t <= kl; t++) {
-        int il = kl - t, adri = m.dof_Madr[d0 + il];
-        float a = LS(adrk + t) * invD;
-        for (int s = 0; s <= il; s++) LS(adri + s) -= a * LS(adrk + t + s);
-        LS(adrk + t) = a;
-      }
+    if (il >= nd) continue;
+    float acc = 0;
+    for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) for (int u = 0; u < FB_FSUB; u++) acc += sh.part[l * FB_FSUB + u][y][lane];
+    LS(m.dof_Madr[d0 + il] + s) -= acc;
+  }
+}
+// ... then one lane per root body factors its dense (<= 6x6) block
+FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
+  float* ldsh = sh_dyn(sh);
+  if (y >= m.nroot) return;
+  int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
+  for (int kl = nd - 1; kl >= 0; kl--) {
+    int adrk = m.dof_Madr[d0 + kl];
+    float invD = 1.0f / LS(adrk);
+    for (int t = 1; t <= kl; t++) {
+      int il = kl - t, adri = m.dof_Madr[d0 + il];
+      float a = LS(adrk + t) * invD;
+      for (int s = 0; s <= il; s++) LS(adri + s) -= a * LS(adrk + t + s);
+      LS(adrk + t) = a;
     }
   }
 }
@@ -262,6 +266,7 @@ FB_WARPFN void kpos_factor(const DevModel& m, const DevData& d, ShTree& sh, int 
     WPAR_BEGIN factor_step_update(m, d, sh, e, 0, lane, step); WPAR_END
     WPAR_BEGIN factor_step_scale(m, d, sh, e, 0, lane, step); WPAR_END
   }
+  WPAR_BEGIN factor_root_gather(m, d, sh, e, 0, lane); WPAR_END
   WPAR_BEGIN factor_root(m, d, sh, e, 0, lane); WPAR_END
 }
 FB_DEV void kpos_p6w(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLD, true); }
@@ -269,57 +274,77 @@ FB_DEV void kpos_p6d(FB_PHASE_ARGS) { ld_add_damping(m, d, sh, e, lane, y); }
 FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe, false); }
 
 // ---------------------------------------------------------------------------------------------
-// x <- (L^T D L)^-1 x in three phases (MuJoCo mj_solveLD); x lives in shared memory (XS), LD is read-only
-// own_dofs_* helpers move a list's / the root's entries between global vectors and XS
-FB_DEV void solve_a(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
+// x <- (L^T D L)^-1 x (MuJoCo mj_solveLD).  x lives in shared memory: XS(0..nv) plus FB_ROOTD private accumulators per
+// list at XS(nv + FB_ROOTD*l + il) for the updates that land on the root's dofs.  The lists advance in lock-step, one
+// dof per step; the FB_FSUB lanes of a list split that dof's ancestor chain (dof_ancslot / dof_anc give the shared slot
+// of the t-th ancestor without pointer chasing).
+#define FB_ROOTD 6
+FB_DEV void tsolve_clear(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
-  if (y >= m.nlist) return;
-  for (int k = 0; k < 6; k++) sh.part[y][k][lane] = 0;
-  FB_LIST_LOOP_REV {
-    for (int kk = m.body_dofnum[b] - 1; kk >= 0; kk--) {
-      int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
-      float xk = XS(k);
-      int t = 1;
-      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) {
-        float l = AT(LD, adrk + t);
-        if (!m.dof_isroot[i]) XS(i) -= l * xk; else sh.part[y][m.dof_depth[i]][lane] += l * xk;
-      }
-    }
-  }
+  for (int k = y; k < FB_ROOTD * m.nlist; k += FB_NY) XS(m.nv + k) = 0;
 }
-FB_DEV void solve_b(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
+// x <- L^-T x restricted to the list dofs, deepest first: x[anc] -= L[k][anc] x[k]
+FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, int step) {
   float* xs = sh_dyn(sh);
-  if (y != 0) return;
+  int l = y / FB_FSUB, sub = y % FB_FSUB;
+  if (l >= m.nlist || step >= m.list_ndof[l]) return;
+  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
+  float xk = XS(k);
+  for (int t = 1 + sub; t < len; t += FB_FSUB) XS(m.dof_ancslot[adrk + t]) -= AT(LD, adrk + t) * xk;
+}
+// root blocks: collect the lists' contributions, then the dense (<= 6x6) back / scale / forward substitution
+FB_DEV void tsolve_b_gather(FB_PHASE_ARGS) {
+  float* xs = sh_dyn(sh);
   for (int r = 0; r < m.nroot; r++) {
     int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
-    for (int il = 0; il < nd; il++) {
-      float acc = 0;
-      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc += sh.part[l][il][lane];
-      XS(d0 + il) -= acc;
-    }
-    for (int kl = nd - 1; kl >= 0; kl--) {
-      float xk = XS(d0 + kl); int adrk = m.dof_Madr[d0 + kl];
-      for (int t = 1; t <= kl; t++) XS(d0 + kl - t) -= AT(LD, adrk + t) * xk;
-    }
-    for (int kl = 0; kl < nd; kl++) {
-      int adrk = m.dof_Madr[d0 + kl];
-      float v = XS(d0 + kl) / AT(LD, adrk);
-      for (int t = 1; t <= kl; t++) v -= AT(LD, adrk + t) * XS(d0 + kl - t);
-      XS(d0 + kl) = v;
-    }
+    if (y >= nd) continue;
+    float acc = 0;
+    for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) acc += XS(m.nv + FB_ROOTD * l + y);
+    XS(d0 + y) += acc;
   }
 }
-FB_DEV void solve_c(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
+FB_DEV void tsolve_b_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
   float* xs = sh_dyn(sh);
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD {
-    for (int kk = 0; kk < m.body_dofnum[b]; kk++) {
-      int k = m.body_dofadr[b] + kk, adrk = m.dof_Madr[k];
-      float v = XS(k) / AT(LD, adrk);
-      int t = 1;
-      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i], t++) v -= AT(LD, adrk + t) * XS(i);
-      XS(k) = v;
-    }
+  if (y >= m.nroot) return;                      // one lane per root body
+  int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
+  for (int kl = nd - 1; kl >= 0; kl--) {
+    float xk = XS(d0 + kl); int adrk = m.dof_Madr[d0 + kl];
+    for (int t = 1; t <= kl; t++) XS(d0 + kl - t) -= AT(LD, adrk + t) * xk;
+  }
+  for (int kl = 0; kl < nd; kl++) {
+    int adrk = m.dof_Madr[d0 + kl];
+    float v = XS(d0 + kl) / AT(LD, adrk);
+    for (int t = 1; t <= kl; t++) v -= AT(LD, adrk + t) * XS(d0 + kl - t);
+    XS(d0 + kl) = v;
+  }
+}
+// x <- L^-1 D^-1 x on the list dofs, shallowest first: x[k] = x[k] / D[k] - sum_t L[k][anc_t] x[anc_t]
+FB_DEV void tsolve_c_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, int step) {
+  float* xs = sh_dyn(sh);
+  int l = y / FB_FSUB, sub = y % FB_FSUB;
+  if (l >= m.nlist || step >= m.list_ndof[l]) return;
+  int k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
+  float p = 0;
+  for (int t = 1 + sub; t < len; t += FB_FSUB) p += AT(LD, adrk + t) * XS(m.dof_anc[adrk + t]);
+  sh.part[y][0][lane] = p;
+}
+FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, int step) {
+  float* xs = sh_dyn(sh);
+  int l = y / FB_FSUB, sub = y % FB_FSUB;
+  if (sub != 0 || l >= m.nlist || step >= m.list_ndof[l]) return;
+  int k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step];
+  float p = 0;
+  for (int u = 0; u < FB_FSUB; u++) p += sh.part[y + u][0][lane];
+  XS(k) = XS(k) / AT(LD, m.dof_Madr[k]) - p;
+}
+FB_WARPFN void tri_solve(const DevModel& m, const DevData& d, ShTree& sh, int e, const float* LD) {
+  WPAR_BEGIN tsolve_clear(m, d, sh, e, 0, lane); WPAR_END
+  for (int step = 0; step < m.max_list_ndof; step++) { WPAR_BEGIN tsolve_a_step(m, d, sh, e, 0, lane, LD, step); WPAR_END }
+  WPAR_BEGIN tsolve_b_gather(m, d, sh, e, 0, lane); WPAR_END
+  WPAR_BEGIN tsolve_b_root(m, d, sh, e, 0, lane, LD); WPAR_END
+  for (int step = 0; step < m.max_list_ndof; step++) {
+    WPAR_BEGIN tsolve_c_step(m, d, sh, e, 0, lane, LD, step); WPAR_END
+    WPAR_BEGIN tsolve_c_fin(m, d, sh, e, 0, lane, LD, step); WPAR_END
   }
 }
 

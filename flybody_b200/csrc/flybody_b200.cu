@@ -160,14 +160,10 @@ FB_DEV void ph_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int,
 FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kclear_hold(m, d, e, y); }
 FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kpack(m, d, e, y, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); ktaskobs(m, d, e, y); }
 // qacc_smooth = M^-1 qfrc_smooth (qacc_smooth already holds the rhs)
-FB_DEV void ph_smooth_a(FB_PHASE_ARGS) { solve_a(m, d, sh, e, lane, y, d.qLD); }
-FB_DEV void ph_smooth_b(FB_PHASE_ARGS) { solve_b(m, d, sh, e, lane, y, d.qLD); }
-FB_DEV void ph_smooth_c(FB_PHASE_ARGS) {
+FB_WARPFN void wf_smooth_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e, d.qLD); }
+FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
-  solve_c(m, d, sh, e, lane, y, d.qLD);
-  if (y == 0) for (int r = 0; r < m.nroot; r++) { int b = m.root_body[r]; for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc_smooth, i) = XS(i); } }
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD { for (int k = 0; k < m.body_dofnum[b]; k++) { int i = m.body_dofadr[b] + k; AT(d.qacc_smooth, i) = XS(i); } }
+  for (int i = y; i < m.nv; i += FB_NY) AT(d.qacc_smooth, i) = XS(i);
 }
 
 static void launch_step1(FbSim* s) {
@@ -188,9 +184,9 @@ static void launch_step1(FbSim* s) {
 }
 static void launch_step2(FbSim* s, bool integrate) {
   s->d.do_integrate = integrate ? 1 : 0;     // read by the solve (warm-start bookkeeping) and the finish kernel
-  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p3>, Ph<ph_smooth_a>, Ph<ph_smooth_b>, Ph<ph_smooth_c>, Ph<kref>>(s, K_SMOOTH, (size_t)s->m.nv);
+  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(s->m.nv + FB_ROOTD * s->m.nlist));
   fb_launch_warp(s, K_SOLVE);
-  fb_launch<ShTree, Ph<kfin_f1>, Ph<kfin_solve_a>, Ph<kfin_solve_b>, Ph<kfin_solve_c>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)s->m.nv);
+  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(s->m.nv + FB_ROOTD * s->m.nlist));
 }
 
 // -------------------------------------------------------------------------------------------
@@ -284,6 +280,13 @@ static int build_model(FbSim* s, const FbModel* h) {
     depth[i] = disroot[i] ? (i - h->body_dofadr[h->dof_bodyid[i]]) : nonroot;
   }
   { std::vector<int> anc(h->nM, -1); for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) anc[h->dof_Madr[i] + t] = j; } m.dof_anc = up(s, anc); }
+  { // shared-memory slot of the t-th ancestor for the triangular solves: root dofs map to the list's private accumulators
+    std::vector<int> dof_list(nv, -1);
+    for (int l = 0; l < nlist; l++) for (int bb : lists[l]) for (int kk = 0; kk < h->body_dofnum[bb]; kk++) dof_list[h->body_dofadr[bb] + kk] = l;
+    std::vector<int> slot(h->nM, 0);
+    for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) slot[h->dof_Madr[i] + t] = (disroot[j] && dof_list[i] >= 0) ? nv + FB_ROOTD * dof_list[i] + depth[j] : j; }
+    m.dof_ancslot = up(s, slot);
+  }
   m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);
   // plain copies
   m.body_parentid = upi(s, h->body_parentid, nb); m.body_rootid = upi(s, h->body_rootid, nb);
