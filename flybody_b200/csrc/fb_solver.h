@@ -20,7 +20,7 @@
 #pragma once
 #include "fb_constraint.h"
 
-#define FB_SOLVE_WPB 8          // warps (envs) per block
+#define FB_SOLVE_WPB 4          // warps (envs) per block
 #define FB_SOLVE_NCAP 32        // rows that fit the shared-memory slice
 
 enum { W_LAM = 0, W_JAR, W_F, W_R, W_U, W_DL, W_ADL, W_P, X_E0, X_E1, X_XQ, X_OUT,

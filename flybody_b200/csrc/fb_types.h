@@ -22,7 +22,8 @@
 #endif
 
 #define FB_NY 32             // lanes per env (threadIdx.x); every kernel runs 32 lanes per env
-#define FB_WPB 8             // envs (warps) per block
+#define FB_MINB 7            // resident blocks per SM the kernels are compiled for: 7 x 4 warps >= 4096 envs / 148 SMs, one wave
+#define FB_WPB 4             // envs (warps) per block
 #define FB_LANES 1           // shared-memory slices are per env
 #define FB_NLMAX 10          // branch lists of the tree kernels (lanes 0..nlist-1 active; 3 lanes per list in the factorisation)
 #define FB_MAXCHUNK 32       // collision chunks (one per lane)

@@ -86,7 +86,7 @@ template <auto F> struct Wf {
 #ifndef FB_EMU
 // one warp per env: threadIdx.x = lane ("y" of the phase functions), threadIdx.y = env within the block
 template <typename Sh, typename... St>
-__global__ void __launch_bounds__(32 * FB_WPB) fb_run(DevModel m, DevData d, int slice, int nwarps) {
+__global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevData d, int slice, int nwarps) {
   extern __shared__ __align__(16) unsigned char fb_smem[];
   int e = blockIdx.x * FB_WPB + threadIdx.y;
   if (e >= nwarps) return;
@@ -112,7 +112,7 @@ static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1
   }
   s->launches++;
 }
-__global__ void __launch_bounds__(32 * FB_SOLVE_WPB) fb_run_solve(DevModel m, DevData d) {
+__global__ void __launch_bounds__(32 * FB_SOLVE_WPB, FB_MINB) fb_run_solve(DevModel m, DevData d) {
   extern __shared__ __align__(16) float fb_smem_w[];
   int e = blockIdx.x * FB_SOLVE_WPB + threadIdx.y;
   if (e >= d.Np) return;
