@@ -39,7 +39,8 @@ struct SolveMem { float* v; float* A; float* G; float* red; int st; };
 #define GM(p, q) sm.G[SM ? TRI(p, q) : TRI(p, q) * sm.st]        // p >= q
 #define RED(k, l) sm.red[(k) * 32 + (l)]
 
-#define WROWS for (int r = lane; r < n; r += 32)
+#define NOUNROLL _Pragma("unroll 1")
+#define WROWS NOUNROLL for (int r = lane; r < n; r += 32)
 FB_DEV float red_total(const SolveMem& sm, int k) { float s = 0; for (int l = 0; l < 32; l++) s += RED(k, l); return s; }
 // warp sums: butterfly shuffles on the GPU (every lane gets the total, no shared-memory round trip);
 // the host emulation runs lanes one after the other, so it stages partials in RED and sums afterwards
@@ -143,10 +144,10 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
       SV(S_LA, r) = (float)AT(d.efc_la, r); SV(S_LB, r) = (float)AT(d.efc_lb, r);
       // warm start: force of the same row in the previous solve (0 for new rows)
       { int key = AT(d.efc_key, r), pn = AT(d.prev_n, 0); float l0 = 0;
-        for (int q = 0; q < pn; q++) if (AT(d.prev_key, q) == key) { l0 = AT(d.prev_lam, q); break; }
+        NOUNROLL for (int q = 0; q < pn; q++) if (AT(d.prev_key, q) == key) { l0 = AT(d.prev_lam, q); break; }
         SV(W_LAM, r) = l0; }
     }
-    if (SM) { int nt = TRI(n, 0); for (int k = lane; k < nt; k += 32) sm.A[k] = AT(d.efc_A, k); }
+    if (SM) { int nt = TRI(n, 0); NOUNROLL for (int k = lane; k < nt; k += 32) sm.A[k] = AT(d.efc_A, k); }
     WPAR_END
     // ---- warm start: the previous solve's forces (matched by row identity), kept if cheaper than lam = 0
     WPAR_BEGIN float q = 0.5f * matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WSUM_PUT(0, q); WPAR_END
@@ -158,7 +159,7 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
     WPAR_BEGIN WPAR_END
     if (!(cost_ws < cost0)) { WPAR_BEGIN WROWS SV(W_LAM, r) = 0; WPAR_END }
     // ---- Newton iterations
-    for (int iter = 0; iter < m.max_iter; iter++) {
+    NOUNROLL for (int iter = 0; iter < m.max_iter; iter++) {
       WPAR_BEGIN float q = 0.5f * matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WSUM_PUT(0, q); WPAR_END
       WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, true); WSUM_PUT(1, c); WPAR_END
       WPAR_BEGIN float rr = 0, ll = 0; WROWS { float f = SV(W_F, r), rv = SV(W_LAM, r) - f; SV(W_R, r) = rv; rr += rv * rv; ll += f * f; } WSUM_PUT(2, rr); WSUM_PUT(3, ll); WPAR_END
@@ -168,7 +169,7 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
       if (rr <= 1e-12f * (ll + 1e-30f)) break;
       // column bookkeeping (prefix over rows) by lane 0; nc is left in RED(0, 0)
       WPAR_BEGIN if (lane == 0) { int nc = 0;
-        for (int r = 0; r < n; r++) { int stt = (int)SV(S_STATE, r);
+        NOUNROLL for (int r = 0; r < n; r++) { int stt = (int)SV(S_STATE, r);
           if (stt == 1) { SV(S_COLIDX, r) = (float)nc; SV(S_ECROW, nc) = (float)r; SV(S_ECKIND, nc) = 0; nc++; }
           else if (stt == 2) { SV(S_COLIDX, r) = (float)nc; SV(S_COLIDX, r + 1) = (float)nc; SV(S_COLIDX, r + 2) = (float)nc; SV(S_ECROW, nc) = (float)r; SV(S_ECKIND, nc) = 1; SV(S_ECROW, nc + 1) = (float)r; SV(S_ECKIND, nc + 1) = 2; nc += 2; }
           else if (stt == 0) SV(S_COLIDX, r) = -1.0f; }
@@ -178,31 +179,39 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
       // u = A r
       WPAR_BEGIN matvec_rows<SM>(sm, n, lane, W_R, W_U, false); WPAR_END
       // p = E^T u ; G = I + E^T A E (packed lower triangle)
-      WPAR_BEGIN for (int p = lane; p < nc; p += 32) {
+      WPAR_BEGIN
+        NOUNROLL for (int p = lane; p < nc; p += 32) {
           int rp = (int)SV(S_ECROW, p), np = SV(S_ECKIND, p) == 0 ? 1 : 3;
-          float pv = 0; for (int a = 0; a < np; a++) pv += ecol_val<SM>(sm, p, a) * SV(W_U, rp + a);
+          float pv = 0; NOUNROLL for (int a = 0; a < np; a++) pv += ecol_val<SM>(sm, p, a) * SV(W_U, rp + a);
           SV(W_P, p) = pv;
-          for (int q = 0; q <= p; q++) {
-            int rq = (int)SV(S_ECROW, q), nq = SV(S_ECKIND, q) == 0 ? 1 : 3;
-            float s = (p == q) ? 1.0f : 0.0f;
-            for (int a = 0; a < np; a++) { float va = ecol_val<SM>(sm, p, a); if (va == 0.0f) continue; for (int bb = 0; bb < nq; bb++) s += va * AM(rp + a, rq + bb) * ecol_val<SM>(sm, q, bb); }
-            GM(p, q) = s;
-          } }
+        }
+        const int npairs = nc * (nc + 1) / 2;                 // lanes over the entries (p >= q) of the packed triangle
+        NOUNROLL for (int t = lane; t < npairs; t += 32) {
+          int p = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+          while ((p + 1) * (p + 2) / 2 <= t) p++;
+          while (p * (p + 1) / 2 > t) p--;
+          int q = t - p * (p + 1) / 2;
+          int rp = (int)SV(S_ECROW, p), np = SV(S_ECKIND, p) == 0 ? 1 : 3;
+          int rq = (int)SV(S_ECROW, q), nq = SV(S_ECKIND, q) == 0 ? 1 : 3;
+          float s = (p == q) ? 1.0f : 0.0f;
+          NOUNROLL for (int a = 0; a < np; a++) { float va = ecol_val<SM>(sm, p, a); if (va == 0.0f) continue; NOUNROLL for (int bb = 0; bb < nq; bb++) s += va * AM(rp + a, rq + bb) * ecol_val<SM>(sm, q, bb); }
+          GM(p, q) = s;
+        }
       WPAR_END
       // Cholesky G = L L^T, column by column; the forward substitution L y = p rides along (lane 0)
-      for (int j = 0; j < nc; j++) {
-        WPAR_BEGIN for (int i = j + lane; i < nc; i += 32) {
-            float t = GM(i, j); for (int k = 0; k < j; k++) t -= GM(i, k) * GM(j, k);
+      NOUNROLL for (int j = 0; j < nc; j++) {
+        WPAR_BEGIN NOUNROLL for (int i = j + lane; i < nc; i += 32) {
+            float t = GM(i, j); NOUNROLL for (int k = 0; k < j; k++) t -= GM(i, k) * GM(j, k);
             GM(i, j) = t; if (i == j) RED(1, 0) = sqrtf(fmaxf(t, 1e-12f)); }
         WPAR_END
         WPAR_BEGIN float dg = RED(1, 0);
-          for (int i = j + lane; i < nc; i += 32) GM(i, j) = (i == j) ? dg : GM(i, j) / dg;
-          if (lane == 0) { float yv = SV(W_P, j); for (int k = 0; k < j; k++) yv -= GM(j, k) * SV(X_XQ, k); SV(X_XQ, j) = yv / dg; }
+          NOUNROLL for (int i = j + lane; i < nc; i += 32) GM(i, j) = (i == j) ? dg : GM(i, j) / dg;
+          if (lane == 0) { float yv = SV(W_P, j); NOUNROLL for (int k = 0; k < j; k++) yv -= GM(j, k) * SV(X_XQ, k); SV(X_XQ, j) = yv / dg; }
         WPAR_END
       }
-      for (int j = nc - 1; j >= 0; j--) {     // backward: L^T out = y
+      NOUNROLL for (int j = nc - 1; j >= 0; j--) {     // backward: L^T out = y
         WPAR_BEGIN float xj = SV(X_XQ, j) / GM(j, j);
-          for (int i = lane; i < j; i += 32) SV(X_XQ, i) -= GM(j, i) * xj;
+          NOUNROLL for (int i = lane; i < j; i += 32) SV(X_XQ, i) -= GM(j, i) * xj;
           if (lane == 0) SV(X_OUT, j) = xj;
         WPAR_END
       }
@@ -218,7 +227,7 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
       WPAR_BEGIN WPAR_END
       // exact line search: safeguarded Newton on the derivative of the 1-D cost
       float alpha = 0, lo = 0, hi = -1, g0 = 0, cbest = cost; bool stop = false, nodescent = false;
-      for (int ls = 0; ls <= m.ls_iter && !stop; ls++) {
+      NOUNROLL for (int ls = 0; ls <= m.ls_iter && !stop; ls++) {
         WPAR_BEGIN float c = 0, g = 0, h = 0; WROWS if (IS_HEAD(r)) head_ls<SM>(sm, r, alpha, c, g, h); WSUM_PUT(0, c); WSUM_PUT(1, g); WSUM_PUT(2, h); WPAR_END
         float c = quad + alpha * q1 + alpha * alpha * q2 + WSUM_GET(0), g = q1 + 2 * alpha * q2 + WSUM_GET(1), h = 2 * q2 + WSUM_GET(2);
         WPAR_BEGIN WPAR_END          // keep RED reads of all lanes ahead of the next section's writes
@@ -251,19 +260,20 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
     WPAR_BEGIN WROWS if (IS_HEAD(r)) head_update<SM>(sm, r, false); WPAR_END
     // ---- noslip (MuJoCo mj_solNoSlip): sequential Gauss-Seidel over the friction rows with the unregularised A
     if (m.noslip_iterations > 0) {
-      WPAR_BEGIN if (lane == 0) {
-        for (int it = 0; it < m.noslip_iterations; it++) {
-          float improvement = 0;
-          if (it == 0) for (int i = 0; i < n; i++) improvement += 0.5f * SV(W_F, i) * SV(W_F, i) * SV(S_R, i);
-          bool any = false;
-          for (int i = 0; i < n; i++) {
-            if (SV(S_TYPE, i) < 0.5f) continue;
-            any = true;
+      // residual res = b + A f of every row, kept current in W_U: the contact being updated reads its two friction
+      // entries, then all lanes apply the rank-2 change -- no O(n) dot products on a single lane
+      WPAR_BEGIN matvec_rows<SM>(sm, n, lane, W_F, W_U, true); WPAR_END
+      WPAR_BEGIN if (lane == 0) { float imp = 0; NOUNROLL for (int i = 0; i < n; i++) imp += 0.5f * SV(W_F, i) * SV(W_F, i) * SV(S_R, i); RED(1, 0) = imp; } WPAR_END
+      NOUNROLL for (int it = 0; it < m.noslip_iterations; it++) {
+        bool any = false;
+        NOUNROLL for (int i = 0; i < n; i++) {
+          if (SV(S_TYPE, i) < 0.5f || SV(S_TYPE, i) > 1.5f) continue;        // heads of frictional contacts only
+          any = true;
+          WPAR_BEGIN if (lane == 0) {
             float fn = SV(W_F, i), old0 = SV(W_F, i + 1), old1 = SV(W_F, i + 2);
-            float res[2], Ac[4], bc[2], v[2];
-            for (int rr2 = 0; rr2 < 2; rr2++) { float s = SV(S_B, i + 1 + rr2); for (int j = 0; j < n; j++) s += AM(i + 1 + rr2, j) * SV(W_F, j); res[rr2] = s; }
+            float res0 = SV(W_U, i + 1), res1 = SV(W_U, i + 2), Ac[4], bc[2], v[2];
             Ac[0] = AM(i + 1, i + 1); Ac[1] = AM(i + 2, i + 1); Ac[2] = Ac[1]; Ac[3] = AM(i + 2, i + 2);
-            bc[0] = res[0] - Ac[0] * old0 - Ac[1] * old1; bc[1] = res[1] - Ac[2] * old0 - Ac[3] * old1;
+            bc[0] = res0 - Ac[0] * old0 - Ac[1] * old1; bc[1] = res1 - Ac[2] * old0 - Ac[3] * old1;
             float fr0 = SV(S_F1, i), fr1 = SV(S_F2, i);
             if (fn < FB_MINVAL) { v[0] = 0; v[1] = 0; }
             else {
@@ -271,28 +281,36 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
               if (active) { float s = (v[0] / fr0) * (v[0] / fr0) + (v[1] / fr1) * (v[1] / fr1); s = sqrtf(fn * fn / fmaxf(FB_MINVAL, s)); v[0] *= s; v[1] *= s; }
             }
             float d0 = v[0] - old0, d1 = v[1] - old1;
-            float change = 0.5f * (d0 * (Ac[0] * d0 + Ac[1] * d1) + d1 * (Ac[2] * d0 + Ac[3] * d1)) + d0 * res[0] + d1 * res[1];
-            if (change > 1e-10f) { v[0] = old0; v[1] = old1; change = 0; }
+            float change = 0.5f * (d0 * (Ac[0] * d0 + Ac[1] * d1) + d1 * (Ac[2] * d0 + Ac[3] * d1)) + d0 * res0 + d1 * res1;
+            if (change > 1e-10f) { v[0] = old0; v[1] = old1; change = 0; d0 = 0; d1 = 0; }
             SV(W_F, i + 1) = v[0]; SV(W_F, i + 2) = v[1];
-            improvement -= change;
-            i += 2;
-          }
-          if (!any) break;
-          if (improvement * scale < m.noslip_tolerance) break;
-        } }
-      WPAR_END
+            RED(1, 0) -= change; RED(0, 0) = d0; RED(0, 1) = d1;
+          } WPAR_END
+          const float d0 = RED(0, 0), d1 = RED(0, 1);
+          if (d0 != 0.0f || d1 != 0.0f) { WPAR_BEGIN WROWS SV(W_U, r) += AM(r, i + 1) * d0 + AM(r, i + 2) * d1; WPAR_END }
+        }
+        const float improvement = RED(1, 0);
+        WPAR_BEGIN if (lane == 0) RED(1, 0) = 0; WPAR_END
+        if (!any) break;
+        if (improvement * scale < m.noslip_tolerance) break;
+      }
     }
     WPAR_BEGIN WROWS { EFC(d.efc_force, r) = SV(W_F, r); AT(d.prev_lam, r) = SV(W_LAM, r); AT(d.prev_key, r) = AT(d.efc_key, r); } WPAR_END
   }
   // ---- qfrc_constraint = J^T f, gathered per dof (race free)
   WPAR_BEGIN
     if (lane == 0) { AT(d.niter, 0) = niter; if (d.do_integrate) AT(d.prev_n, 0) = n; }
-    for (int k = lane; k < m.nv; k += 32) {
+    NOUNROLL for (int k = lane; k < m.nv; k += 32) {
+      const int se = m.dof_subend[k];
       float s = 0;
+      // a row touches dof k iff k is on the ancestor chain of one of its two end dofs; the loads are predicated, not
+      // branched around, so that several rows are in flight
+#pragma unroll 4
       for (int r = 0; r < n; r++) {
-        float f = SV(W_F, r);
-        if (f == 0.0f) continue;
-        if (in_chain(m, k, (int)SV(S_LA, r)) || in_chain(m, k, (int)SV(S_LB, r))) s += EJ(d.efc_J, r, k) * f;
+        int la = (int)SV(S_LA, r), lb = (int)SV(S_LB, r);
+        bool in = (k <= la && la <= se) || (k <= lb && lb <= se);
+        float jv = in ? EJ(d.efc_J, r, k) : 0.0f;
+        s += jv * SV(W_F, r);
       }
       AT(d.qfrc_constraint, k) = s;
     }

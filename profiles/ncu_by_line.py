@@ -4,7 +4,7 @@ ncu's CSV export of the source page is SASS-only; this joins it (by instruction 
 of the cubin embedded in the shipped library, then sums executed instructions and stall samples per source line and per
 enclosing function.
 
-    python profiles/ncu_by_line.py gpurun_out/prof.ncu-rep <kernel substring> [launch ordinal] [--top 25]
+    python profiles/ncu_by_line.py gpurun_out/prof.ncu-rep <kernel substring> [launch ordinal] [--top 25] [--lib path/to/lib.so]
 """
 import csv
 import io
@@ -43,8 +43,8 @@ def sass_page(rep, ksub, ordinal):
     return b['name'], rows
 
 
-def mangled_candidates(cubin_text, n_instr):
-    """functions in the cubin with exactly n_instr instructions -> {name: [(file, line) per instruction]}"""
+def cubin_functions(cubin_text):
+    """{function: [((file, line), normalised sass text) per instruction]} for every function in the cubin"""
     funcs, cur, loc = {}, None, ('?', 0)
     for line in cubin_text.splitlines():
         m = re.match(r'^\.text\.(\S+):', line)
@@ -55,9 +55,32 @@ def mangled_candidates(cubin_text, n_instr):
         m = re.search(r'//## File "([^"]+)", line (\d+)', line)
         if m:
             loc = (os.path.basename(m.group(1)), int(m.group(2))); continue
-        if re.match(r'^\s+/\*[0-9a-f]{4,}\*/\s', line):
-            funcs[cur].append(loc)
-    return {k: v for k, v in funcs.items() if len(v) == n_instr}
+        m = re.match(r'^\s+/\*[0-9a-f]{4,}\*/\s+(.*?);', line)
+        if m:
+            funcs[cur].append((loc, norm(m.group(1))))
+    return funcs
+
+
+def norm(t):
+    return re.sub(r'\s+', ' ', t.replace('`', '').strip().rstrip(';')).split(' ')[0:2].__str__()
+
+
+def align(rows, funcs):
+    """ncu lists the kernel followed by the device functions it calls; align each run of rows with the cubin function
+    whose instruction texts match (opcode + first operand of the first instructions)."""
+    locs, i = [], 0
+    names = list(funcs)
+    while i < len(rows):
+        best = None
+        for n in names:
+            f = funcs[n]
+            if len(f) <= len(rows) - i and all(norm(rows[i + j][4]) == f[j][1] for j in range(min(len(f), 12))):
+                if best is None or len(f) > len(funcs[best]):
+                    best = n
+        if best is None:
+            locs.append(('?', 0)); i += 1; continue
+        locs.extend(l for l, _ in funcs[best]); i += len(funcs[best])
+    return locs
 
 
 def function_table():
@@ -76,17 +99,18 @@ def function_table():
 
 def main():
     rep, ksub = sys.argv[1], sys.argv[2]
+    lib = sys.argv[sys.argv.index('--lib') + 1] if '--lib' in sys.argv else LIB
     ordinal = int(sys.argv[3]) if len(sys.argv) > 3 and not sys.argv[3].startswith('--') else 0
     top = int(sys.argv[sys.argv.index('--top') + 1]) if '--top' in sys.argv else 25
     name, rows = sass_page(rep, ksub, ordinal)
     with tempfile.TemporaryDirectory() as td:
-        subprocess.run(['cuobjdump', '-xelf', 'all', LIB], cwd=td, capture_output=True)
+        subprocess.run(['cuobjdump', '-xelf', 'all', lib], cwd=td, capture_output=True)
         cub = [os.path.join(td, f) for f in os.listdir(td) if f.endswith('.cubin')][0]
         text = subprocess.run(['nvdisasm', '--print-line-info', cub], capture_output=True, text=True).stdout
-    cands = mangled_candidates(text, len(rows))
-    if len(cands) != 1:
-        print(f'warning: {len(cands)} cubin functions with {len(rows)} instructions; using the first', file=sys.stderr)
-    locs = next(iter(cands.values()))
+    locs = align(rows, cubin_functions(text))
+    unmatched = sum(1 for l in locs if l[0] == '?')
+    if unmatched:
+        print(f'warning: {unmatched} of {len(rows)} instructions not matched to the cubin', file=sys.stderr)
     ftab = function_table()
 
     def func_of(loc):
