@@ -383,22 +383,30 @@ FB_DEV void kproj_p1(FB_ROW_ARGS) {
     AT(d.efc_A, idx) = sacc;
   }
 }
-// J . x for every row (x: qvel, qacc_smooth, qacc_warmstart): aref, b, jar at the warm start
+// J . x for every row (x: qvel, qacc_smooth): aref and b = J qacc_smooth - aref.  qacc_smooth is still in shared
+// memory (XS) from the solve; the chains are walked through dof_anc (no pointer chasing), chain b stops where it
+// joins chain a.
 FB_DEV void kref(FB_PHASE_ARGS) {
+  const float* xs = sh_dyn(sh);
   int n = AT(d.nefc, 0);
   for (int r = y; r < n; r += FB_NY) {
     int ci, frow; float sign;
     RowChains rc = row_chains(m, d, e, r, ci, frow, sign);
-    float vel = 0, as = 0, ws = 0; int la = rc.la, lb = rc.lb;
-    while (la >= 0 || lb >= 0) {
-      int k = la > lb ? la : lb;
-      if (la == k) la = m.dof_parentid[la];
-      if (lb == k) lb = m.dof_parentid[lb];
-      float J = EJ(d.efc_J, r, k);
-      vel += J * AT(d.qvel, k); as += J * AT(d.qacc_smooth, k); ws += J * AT(d.qacc_warmstart, k);
+    float vel = 0, as = 0; const int la = rc.la, lb = rc.lb;
+    if (la >= 0) {
+      int adr = m.dof_Madr[la], len = m.dof_chainlen[la];
+      for (int t = 0; t < len; t++) { int k = m.dof_anc[adr + t]; float J = EJ(d.efc_J, r, k); vel += J * AT(d.qvel, k); as += J * XS(k); }
+    }
+    if (lb >= 0) {
+      int adr = m.dof_Madr[lb], len = m.dof_chainlen[lb];
+      for (int t = 0; t < len; t++) {
+        int k = m.dof_anc[adr + t];
+        if (la >= 0 && k <= la && la <= m.dof_subend[k]) break;      // common ancestors were counted with chain a
+        float J = EJ(d.efc_J, r, k); vel += J * AT(d.qvel, k); as += J * XS(k);
+      }
     }
     float aref = -EFC(d.efc_B, r) * vel - EFC(d.efc_K, r) * EFC(d.efc_imp, r) * (EFC(d.efc_pos, r) - EFC(d.efc_margin, r));
-    EFC(d.efc_aref, r) = aref; EFC(d.efc_b, r) = as - aref; EFC(d.efc_jarws, r) = ws - aref;
+    EFC(d.efc_aref, r) = aref; EFC(d.efc_b, r) = as - aref;
   }
 }
 
@@ -428,29 +436,41 @@ FB_DEV void kact_p1(FB_PHASE_ARGS) {
 }
 // adhesion (body transmission): moment = - mean of the contact-normal Jacobians of all detected contacts of the
 // body (incl. those inside the gap).  Chains share the root dofs, so this part runs on one thread.
-FB_DEV void kact_p2(FB_PHASE_ARGS) {
-  if (y != 0) return;
+FB_DEV void kact_p2(FB_PHASE_ARGS) {       // force per contact of every adhesion body: -force / (number of its contacts)
+  float* xs = sh_dyn(sh);
   int ncon = AT(d.ncon, 0);
-  if (ncon == 0) return;
-  for (int i = 0; i < m.nu; i++) {
-    if (m.actuator_trntype[i] != FB_TRN_BODY) continue;
-    float force = AT(d.actuator_force, i); int id = m.actuator_trnid[i];
-    if (force == 0.0f) continue;
-    int cnt = 0;
-    for (int ci = 0; ci < ncon; ci++) { if (m.geom_bodyid[AT(d.con_geom1, ci)] == id || m.geom_bodyid[AT(d.con_geom2, ci)] == id) cnt++; }
-    if (cnt == 0) continue;
-    float sc = -force / cnt;
-    for (int ci = 0; ci < ncon; ci++) {
-      int b1 = m.geom_bodyid[AT(d.con_geom1, ci)], b2 = m.geom_bodyid[AT(d.con_geom2, ci)];
-      if (b1 != id && b2 != id) continue;
-      V3 f = v3(CON_F(d.con_frame, ci, 0, 9), CON_F(d.con_frame, ci, 1, 9), CON_F(d.con_frame, ci, 2, 9));
-      V3 pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3));
-      for (int k = m.body_lastdof[b2]; k >= 0; k = m.dof_parentid[k]) AT(d.qfrc_actuator, k) += sc * contact_J(m, d, e, f, pos, k);
-      for (int k = m.body_lastdof[b1]; k >= 0; k = m.dof_parentid[k]) AT(d.qfrc_actuator, k) -= sc * contact_J(m, d, e, f, pos, k);
+  for (int b = y; b < m.nbody; b += FB_NY) {
+    int i = m.body_adhesion[b]; float sc = 0;
+    if (i >= 0 && ncon > 0) {
+      float force = AT(d.actuator_force, i); int cnt = 0;
+      if (force != 0.0f) for (int ci = 0; ci < ncon; ci++) { if (m.geom_bodyid[AT(d.con_geom1, ci)] == b || m.geom_bodyid[AT(d.con_geom2, ci)] == b) cnt++; }
+      if (cnt > 0) sc = -force / cnt;
     }
+    XS(b) = sc;
   }
 }
-// qfrc_smooth = passive - bias + actuator, staged into shared memory as the rhs of M x = qfrc_smooth
+// ... applied along the chains of the two bodies of each such contact; lanes over the dofs (a dof on both chains gets
+// +J - J = 0, as in the sequential formulation)
+FB_DEV void kact_p2b(FB_PHASE_ARGS) {
+  const float* xs = sh_dyn(sh);
+  int ncon = AT(d.ncon, 0);
+  if (ncon == 0) return;
+  for (int k = y; k < m.nv; k += FB_NY) {
+    const int se = m.dof_subend[k]; float s = 0;
+    for (int ci = 0; ci < ncon; ci++) {
+      int b1 = m.geom_bodyid[AT(d.con_geom1, ci)], b2 = m.geom_bodyid[AT(d.con_geom2, ci)];
+      float sc = XS(b1) + XS(b2);
+      if (sc == 0.0f) continue;
+      int l1 = m.body_lastdof[b1], l2 = m.body_lastdof[b2];
+      int sgn = ((l2 >= 0 && k <= l2 && l2 <= se) ? 1 : 0) - ((l1 >= 0 && k <= l1 && l1 <= se) ? 1 : 0);
+      if (sgn == 0) continue;
+      V3 f = v3(CON_F(d.con_frame, ci, 0, 9), CON_F(d.con_frame, ci, 1, 9), CON_F(d.con_frame, ci, 2, 9));
+      V3 pos = v3(CON_F(d.con_pos, ci, 0, 3), CON_F(d.con_pos, ci, 1, 3), CON_F(d.con_pos, ci, 2, 3));
+      s += sgn * sc * contact_J(m, d, e, f, pos, k);
+    }
+    if (s != 0.0f) AT(d.qfrc_actuator, k) += s;
+  }
+}
 FB_DEV void kact_p3(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
   for (int k = y; k < m.nv; k += FB_NY) {
@@ -503,6 +523,7 @@ FB_DEV void kfin_f1(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
   for (int i = y; i < m.nv; i += FB_NY) XS(i) = AT(d.qfrc_constraint, i);
   for (int k = y; k < 6 * m.nbody; k += FB_NY) AT(d.bfl, k) = 0;
+  if (d.do_integrate) for (int k = 32 * y; k < m.nM; k += 32 * FB_NY) prefetch_l2(&AT(d.qLDe, k));   // second factor, used after the sensor sweeps
 }
 FB_WARPFN void kfin_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e, d.qLD); }
 // Euler with implicit joint damping: qacc' = (M + h D)^-1 (qfrc_smooth + qfrc_constraint), second factor qLDe

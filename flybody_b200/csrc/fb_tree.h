@@ -9,9 +9,15 @@
 #pragma once
 #include "fb_math.h"
 
-struct ShTree {
-  float part[FB_NY][24][FB_LANES];    // per-list partial sums towards the root (crb:10, factor:21, solve:6, rne:12)
-};
+// Shared memory of one warp (= one env) in the tree kernels.  Fixed part: one float per lane for small reductions.
+// Dynamic part (sized per launch), in this order where present:
+//   PART  [FB_NY][FB_PARTK]  per-list partial sums towards the root (crb: 10, factor: 21, rne: 12)   -- pos, vel
+//   LS    [nM]               the joint-space inertia / its factor                                     -- pos
+//   XS    [nv + FB_ROOTD*nlist], LDS [nM]   right-hand side and staged factor of the triangular solves -- smooth, finish
+struct ShTree { float red[FB_NY][FB_LANES]; };
+#define FB_PARTK 24
+#define FB_PARTF (FB_NY * FB_PARTK * FB_LANES)
+#define PART(yy, k) part_[((yy) * FB_PARTK + (k)) * FB_LANES + lane]
 
 // dynamic shared memory that follows the fixed struct (per-kernel scratch: the L^T D L rows during the
 // factorisation, the right-hand side during tree solves), laid out [entry][lane]
@@ -135,6 +141,7 @@ FB_DEV void kpos_p1b(FB_PHASE_ARGS) {
 }
 // K2 composite inertia, backward accumulation (MuJoCo mj_crb); the running sum of a chain stays in registers
 FB_DEV void kpos_p2(FB_PHASE_ARGS) {
+  float* part_ = sh_dyn(sh);
   if (y >= m.nlist) return;
   float acc[10], carry[10]; int carry_to = -1;
   for (int k = 0; k < 10; k++) { acc[k] = 0; carry[k] = 0; }
@@ -148,15 +155,16 @@ FB_DEV void kpos_p2(FB_PHASE_ARGS) {
     else { for (int k = 0; k < 10; k++) carry[k] = cur[k]; carry_to = p; }
   }
   if (carry_to >= 0) for (int k = 0; k < 10; k++) AT(d.crb10, 10 * carry_to + k) += carry[k];
-  for (int k = 0; k < 10; k++) sh.part[y][k][lane] = acc[k];
+  for (int k = 0; k < 10; k++) PART(y, k) = acc[k];
 }
 FB_DEV void kpos_p3(FB_PHASE_ARGS) {
+  float* part_ = sh_dyn(sh);
   if (y != 0) return;
   for (int r = 0; r < m.nroot; r++) {
     int b = m.root_body[r];
     for (int k = 0; k < 10; k++) {
       float s = AT(d.inert10, 10 * b + k);
-      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) s += sh.part[l][k][lane];
+      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) s += PART(l, k);
       AT(d.crb10, 10 * b + k) = s;
     }
   }
@@ -176,17 +184,17 @@ FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int lane, float
   }
 }
 FB_DEV void kpos_p4(FB_PHASE_ARGS) {      // all 32 lanes over the dofs
-  float* ldsh = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   for (int i = y; i < m.nv; i += FB_NY) mass_row(m, d, e, lane, ldsh, i);
 }
 // copy the factor held in shared memory out to `dst`; optionally re-initialise the shared rows with
 // M + h*diag(damping) for the second factorisation (entries are split over all lanes)
 FB_DEV void ld_writeout(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* dst, bool reinit) {
-  float* ldsh = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   for (int k = y; k < m.nM; k += FB_NY) { AT(dst, k) = LS(k); if (reinit) LS(k) = AT(d.qM, k); }
 }
 FB_DEV void ld_add_damping(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
-  float* ldsh = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   for (int i = y; i < m.nv; i += FB_NY) LS(m.dof_Madr[i]) += m.timestep * m.dof_damping[i];
 }
 
@@ -195,9 +203,9 @@ FB_DEV void ld_add_damping(const DevModel& m, const DevData& d, ShTree& sh, int 
 // list and split the rank-1 update of the ancestor rows of that dof.  Updates that land in the root block are
 // summed into sh.part (21 entries per lane) and applied by the root lane afterwards.
 #define FB_FSUB 3
-FB_DEV void factor_clear(FB_PHASE_ARGS) { for (int k = 0; k < 21; k++) sh.part[y][k][lane] = 0; }
+FB_DEV void factor_clear(FB_PHASE_ARGS) { float* part_ = sh_dyn(sh); for (int k = 0; k < 21; k++) PART(y, k) = 0; }
 FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
-  float* ldsh = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (l >= m.nlist || step >= m.list_ndof[l]) return;
   int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
@@ -217,12 +225,12 @@ FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, 
       for (; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
     } else {
       int il = m.dof_depth[i], base = il * (il + 1) / 2;       // for root dofs depth == local index
-      for (int s2 = 0; s2 <= il; s2++) sh.part[y][base + s2][lane] += a * LS(adrk + t + s2);
+      for (int s2 = 0; s2 <= il; s2++) PART(y, base + s2) += a * LS(adrk + t + s2);
     }
   }
 }
 FB_DEV void factor_step_scale(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
-  float* ldsh = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (l >= m.nlist || step >= m.list_ndof[l]) return;
   int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
@@ -231,7 +239,7 @@ FB_DEV void factor_step_scale(const DevModel& m, const DevData& d, ShTree& sh, i
 }
 // root blocks: 21 lanes add up the lists' partial updates (one packed lower-triangle entry each) ...
 FB_DEV void factor_root_gather(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
-  float* ldsh = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   if (y >= 21) return;
   int il = 0; while ((il + 1) * (il + 2) / 2 <= y) il++;
   int s = y - il * (il + 1) / 2;
@@ -239,13 +247,13 @@ FB_DEV void factor_root_gather(const DevModel& m, const DevData& d, ShTree& sh, 
     int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
     if (il >= nd) continue;
     float acc = 0;
-    for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) for (int u = 0; u < FB_FSUB; u++) acc += sh.part[l * FB_FSUB + u][y][lane];
+    for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) for (int u = 0; u < FB_FSUB; u++) acc += PART(l * FB_FSUB + u, y);
     LS(m.dof_Madr[d0 + il] + s) -= acc;
   }
 }
 // ... then one lane per root body factors its dense (<= 6x6) block
 FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
-  float* ldsh = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   if (y >= m.nroot) return;
   int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
   for (int kl = nd - 1; kl >= 0; kl--) {
@@ -279,18 +287,30 @@ FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe, f
 // dof per step; the FB_FSUB lanes of a list split that dof's ancestor chain (dof_ancslot / dof_anc give the shared slot
 // of the t-th ancestor without pointer chasing).
 #define FB_ROOTD 6
-FB_DEV void tsolve_clear(FB_PHASE_ARGS) {
-  float* xs = sh_dyn(sh);
+#define FB_NXS(m) ((m).nv + FB_ROOTD * (m).nlist)
+#define LDS(k) lds[(k) * FB_LANES + lane]
+FB_DEV void prefetch_l2(const void* p) {
+#ifdef __CUDACC__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// stage the factor into shared memory with coalesced, independent loads (one exposed memory latency instead of one
+// per step of the sweeps) and clear the lists' private root accumulators
+FB_DEV void tsolve_stage(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
+  float* xs = sh_dyn(sh); float* lds = xs + FB_NXS(m);
+  for (int k = y; k < m.nM; k += FB_NY) LDS(k) = AT(LD, k);
   for (int k = y; k < FB_ROOTD * m.nlist; k += FB_NY) XS(m.nv + k) = 0;
 }
 // x <- L^-T x restricted to the list dofs, deepest first: x[anc] -= L[k][anc] x[k]
-FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, int step) {
-  float* xs = sh_dyn(sh);
+FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+  float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (l >= m.nlist || step >= m.list_ndof[l]) return;
   int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
   float xk = XS(k);
-  for (int t = 1 + sub; t < len; t += FB_FSUB) XS(m.dof_ancslot[adrk + t]) -= AT(LD, adrk + t) * xk;
+  for (int t = 1 + sub; t < len; t += FB_FSUB) XS(m.dof_ancslot[adrk + t]) -= LDS(adrk + t) * xk;
 }
 // root blocks: collect the lists' contributions, then the dense (<= 6x6) back / scale / forward substitution
 FB_DEV void tsolve_b_gather(FB_PHASE_ARGS) {
@@ -303,48 +323,48 @@ FB_DEV void tsolve_b_gather(FB_PHASE_ARGS) {
     XS(d0 + y) += acc;
   }
 }
-FB_DEV void tsolve_b_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
-  float* xs = sh_dyn(sh);
+FB_DEV void tsolve_b_root(FB_PHASE_ARGS) {
+  float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
   if (y >= m.nroot) return;                      // one lane per root body
   int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
   for (int kl = nd - 1; kl >= 0; kl--) {
     float xk = XS(d0 + kl); int adrk = m.dof_Madr[d0 + kl];
-    for (int t = 1; t <= kl; t++) XS(d0 + kl - t) -= AT(LD, adrk + t) * xk;
+    for (int t = 1; t <= kl; t++) XS(d0 + kl - t) -= LDS(adrk + t) * xk;
   }
   for (int kl = 0; kl < nd; kl++) {
     int adrk = m.dof_Madr[d0 + kl];
-    float v = XS(d0 + kl) / AT(LD, adrk);
-    for (int t = 1; t <= kl; t++) v -= AT(LD, adrk + t) * XS(d0 + kl - t);
+    float v = XS(d0 + kl) / LDS(adrk);
+    for (int t = 1; t <= kl; t++) v -= LDS(adrk + t) * XS(d0 + kl - t);
     XS(d0 + kl) = v;
   }
 }
 // x <- L^-1 D^-1 x on the list dofs, shallowest first: x[k] = x[k] / D[k] - sum_t L[k][anc_t] x[anc_t]
-FB_DEV void tsolve_c_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, int step) {
-  float* xs = sh_dyn(sh);
+FB_DEV void tsolve_c_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+  float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (l >= m.nlist || step >= m.list_ndof[l]) return;
   int k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
   float p = 0;
-  for (int t = 1 + sub; t < len; t += FB_FSUB) p += AT(LD, adrk + t) * XS(m.dof_anc[adrk + t]);
-  sh.part[y][0][lane] = p;
+  for (int t = 1 + sub; t < len; t += FB_FSUB) p += LDS(adrk + t) * XS(m.dof_anc[adrk + t]);
+  sh.red[y][lane] = p;
 }
-FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD, int step) {
-  float* xs = sh_dyn(sh);
+FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+  float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (sub != 0 || l >= m.nlist || step >= m.list_ndof[l]) return;
   int k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step];
   float p = 0;
-  for (int u = 0; u < FB_FSUB; u++) p += sh.part[y + u][0][lane];
-  XS(k) = XS(k) / AT(LD, m.dof_Madr[k]) - p;
+  for (int u = 0; u < FB_FSUB; u++) p += sh.red[y + u][lane];
+  XS(k) = XS(k) / LDS(m.dof_Madr[k]) - p;
 }
 FB_WARPFN void tri_solve(const DevModel& m, const DevData& d, ShTree& sh, int e, const float* LD) {
-  WPAR_BEGIN tsolve_clear(m, d, sh, e, 0, lane); WPAR_END
-  for (int step = 0; step < m.max_list_ndof; step++) { WPAR_BEGIN tsolve_a_step(m, d, sh, e, 0, lane, LD, step); WPAR_END }
+  WPAR_BEGIN tsolve_stage(m, d, sh, e, 0, lane, LD); WPAR_END
+  for (int step = 0; step < m.max_list_ndof; step++) { WPAR_BEGIN tsolve_a_step(m, d, sh, e, 0, lane, step); WPAR_END }
   WPAR_BEGIN tsolve_b_gather(m, d, sh, e, 0, lane); WPAR_END
-  WPAR_BEGIN tsolve_b_root(m, d, sh, e, 0, lane, LD); WPAR_END
+  WPAR_BEGIN tsolve_b_root(m, d, sh, e, 0, lane); WPAR_END
   for (int step = 0; step < m.max_list_ndof; step++) {
-    WPAR_BEGIN tsolve_c_step(m, d, sh, e, 0, lane, LD, step); WPAR_END
-    WPAR_BEGIN tsolve_c_fin(m, d, sh, e, 0, lane, LD, step); WPAR_END
+    WPAR_BEGIN tsolve_c_step(m, d, sh, e, 0, lane, step); WPAR_END
+    WPAR_BEGIN tsolve_c_fin(m, d, sh, e, 0, lane, step); WPAR_END
   }
 }
 
@@ -532,6 +552,7 @@ FB_DEV void kvel_p1b(FB_PHASE_ARGS) {
 }
 // subtree sums of (bias force, fluid wrench): child -> parent along the lists
 FB_DEV void kvel_p2(FB_PHASE_ARGS) {
+  float* part_ = sh_dyn(sh);
   if (y >= m.nlist) return;
   float acc[12], carry[12]; int carry_to = -1;
   for (int k = 0; k < 12; k++) { acc[k] = 0; carry[k] = 0; }
@@ -545,15 +566,16 @@ FB_DEV void kvel_p2(FB_PHASE_ARGS) {
     else { for (int k = 0; k < 12; k++) carry[k] = cur[k]; carry_to = p; }
   }
   if (carry_to >= 0) for (int k = 0; k < 6; k++) { AT(d.bfrc, 6 * carry_to + k) += carry[k]; AT(d.bfl, 6 * carry_to + k) += carry[6 + k]; }
-  for (int k = 0; k < 12; k++) sh.part[y][k][lane] = acc[k];
+  for (int k = 0; k < 12; k++) PART(y, k) = acc[k];
 }
 FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e, int y);
 FB_DEV void kvel_p3(FB_PHASE_ARGS) {
+  float* part_ = sh_dyn(sh);
   if (y < m.nroot) {
     int r = y, b = m.root_body[r];
     for (int k = 0; k < 6; k++) {
       float a1 = 0, a2 = 0;
-      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) { a1 += sh.part[l][k][lane]; a2 += sh.part[l][6 + k][lane]; }
+      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) { a1 += PART(l, k); a2 += PART(l, 6 + k); }
       AT(d.bfrc, 6 * b + k) += a1; AT(d.bfl, 6 * b + k) += a2;
     }
   }

@@ -62,6 +62,7 @@ struct DevModel {
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
   const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen, *dof_anc /* [nM] t-th ancestor of the row's dof */, *dof_ancslot /* same, as shared-memory slot of tri_solve */;
+  const int* body_adhesion;    // adhesion actuator acting on the body, or -1
   const float *dof_armature, *dof_damping, *dof_invweight0;
   // geoms
   const int *geom_type, *geom_bodyid, *geom_condim;

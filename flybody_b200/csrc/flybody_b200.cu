@@ -168,7 +168,7 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 
 static void launch_step1(FbSim* s) {
   static int pos_trunc = getenv("FB_POS_TRUNC") ? atoi(getenv("FB_POS_TRUNC")) : 0;     // profiling aid: run only a prefix of the phases
-  size_t nm = (size_t)s->m.nM;
+  size_t nm = (size_t)FB_PARTF + (size_t)s->m.nM;
   switch (pos_trunc) {
     case 1: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>>(s, K_POS, nm); break;
     case 2: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>>(s, K_POS, nm); break;
@@ -180,13 +180,13 @@ static void launch_step1(FbSim* s) {
   }
   fb_launch<ShCol, Ph<kcol_p0>, Ph<kcol_p1>>(s, K_COL);
   fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_NY * FB_ZCAP);
-  fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL);
+  fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL, (size_t)FB_PARTF);
 }
 static void launch_step2(FbSim* s, bool integrate) {
   s->d.do_integrate = integrate ? 1 : 0;     // read by the solve (warm-start bookkeeping) and the finish kernel
-  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(s->m.nv + FB_ROOTD * s->m.nlist));
+  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(FB_NXS(s->m) + s->m.nM));
   fb_launch_warp(s, K_SOLVE);
-  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(s->m.nv + FB_ROOTD * s->m.nlist));
+  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(FB_NXS(s->m) + s->m.nM));
 }
 
 // -------------------------------------------------------------------------------------------
@@ -287,6 +287,7 @@ static int build_model(FbSim* s, const FbModel* h) {
     for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) slot[h->dof_Madr[i] + t] = (disroot[j] && dof_list[i] >= 0) ? nv + FB_ROOTD * dof_list[i] + depth[j] : j; }
     m.dof_ancslot = up(s, slot);
   }
+  { std::vector<int> adh(nb, -1); for (int i = 0; i < h->nu; i++) if (h->actuator_trntype[i] == FB_TRN_BODY) adh[h->actuator_trnid[i]] = i; m.body_adhesion = up(s, adh); }
   m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);
   // plain copies
   m.body_parentid = upi(s, h->body_parentid, nb); m.body_rootid = upi(s, h->body_rootid, nb);
