@@ -412,7 +412,7 @@ FB_DEV void kref(FB_PHASE_ARGS) {
 
 // ---------------------------------------------------------------------------------------------
 // K3 + K8 transmission and actuation (MuJoCo mj_transmission, mj_fwdActuation), lane = env
-FB_DEV void kact_p0(FB_PHASE_ARGS) { for (int k = y; k < m.nv; k += FB_NY) AT(d.qfrc_actuator, k) = 0; }
+FB_DEV void kact_p0(FB_PHASE_ARGS) { tsolve_stage_issue(m, d, sh, e, lane, y, d.qLD); for (int k = y; k < m.nv; k += FB_NY) AT(d.qfrc_actuator, k) = 0; }
 FB_DEV void kact_p1(FB_PHASE_ARGS) {
   for (int i = y; i < m.nu; i += FB_NY) {
     float ctrl = AT(d.ctrl, i);
@@ -523,13 +523,15 @@ FB_DEV void kfin_f1(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
   for (int i = y; i < m.nv; i += FB_NY) XS(i) = AT(d.qfrc_constraint, i);
   for (int k = y; k < 6 * m.nbody; k += FB_NY) AT(d.bfl, k) = 0;
-  if (d.do_integrate) for (int k = 32 * y; k < m.nM; k += 32 * FB_NY) prefetch_l2(&AT(d.qLDe, k));   // second factor, used after the sensor sweeps
+  tsolve_stage_issue(m, d, sh, e, lane, y, d.qLD);
+  if (d.do_integrate) for (int k = 32 * y; k < m.nM; k += 32 * FB_NY) prefetch_l2(&AT(d.qLDe, k));   // second factor, staged after the first solve
 }
-FB_WARPFN void kfin_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e, d.qLD); }
+FB_WARPFN void kfin_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e); }
 // Euler with implicit joint damping: qacc' = (M + h D)^-1 (qfrc_smooth + qfrc_constraint), second factor qLDe
-FB_WARPFN void kfin_solve_euler(const DevModel& m, const DevData& d, ShTree& sh, int e) { if (d.do_integrate) tri_solve(m, d, sh, e, d.qLDe); }
+FB_WARPFN void kfin_solve_euler(const DevModel& m, const DevData& d, ShTree& sh, int e) { if (d.do_integrate) tri_solve(m, d, sh, e); }
 FB_DEV void kfin_f5(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
+  if (d.do_integrate) tsolve_stage_issue(m, d, sh, e, lane, y, d.qLDe);      // overlaps the sensor sweeps below
   for (int i = y; i < m.nv; i += FB_NY) { AT(d.qacc, i) = AT(d.qacc_smooth, i) + XS(i); XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); }
   if (y != 0) return;
   // external (contact) wrench per body into bfl (about ref)

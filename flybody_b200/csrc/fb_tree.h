@@ -15,7 +15,7 @@
 //   LS    [nM]               the joint-space inertia / its factor                                     -- pos
 //   XS    [nv + FB_ROOTD*nlist], LDS [nM]   right-hand side and staged factor of the triangular solves -- smooth, finish
 struct ShTree { float red[FB_NY][FB_LANES]; };
-#define FB_PARTK 24
+#define FB_PARTK 21
 #define FB_PARTF (FB_NY * FB_PARTK * FB_LANES)
 #define PART(yy, k) part_[((yy) * FB_PARTK + (k)) * FB_LANES + lane]
 
@@ -287,7 +287,7 @@ FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe, f
 // dof per step; the FB_FSUB lanes of a list split that dof's ancestor chain (dof_ancslot / dof_anc give the shared slot
 // of the t-th ancestor without pointer chasing).
 #define FB_ROOTD 6
-#define FB_NXS(m) ((m).nv + FB_ROOTD * (m).nlist)
+#define FB_NXS(m) (((m).nv + FB_ROOTD * (m).nlist + 3) & ~3)      // multiple of 4: the staged factor behind it stays 16-byte aligned
 #define LDS(k) lds[(k) * FB_LANES + lane]
 FB_DEV void prefetch_l2(const void* p) {
 #ifdef __CUDACC__
@@ -296,12 +296,25 @@ FB_DEV void prefetch_l2(const void* p) {
   (void)p;
 #endif
 }
-// stage the factor into shared memory with coalesced, independent loads (one exposed memory latency instead of one
-// per step of the sweeps) and clear the lists' private root accumulators
-FB_DEV void tsolve_stage(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
+// Stage a factor into the warp's shared slice with asynchronous 16-byte copies (cp.async): issued early (first phase
+// of the kernel / right after the previous solve), waited for at the start of tri_solve, so the DRAM latency overlaps
+// the phases in between and the sweeps only touch shared memory.  Record arrays start on 16-byte boundaries.
+FB_DEV void tsolve_stage_issue(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, const float* LD) {
   float* xs = sh_dyn(sh); float* lds = xs + FB_NXS(m);
+#ifdef __CUDACC__
+  unsigned sa = (unsigned)__cvta_generic_to_shared(lds);
+  for (int k = 4 * y; k < m.nM; k += 4 * FB_NY) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 4u * k), "l"(&AT(LD, k)) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#else
   for (int k = y; k < m.nM; k += FB_NY) LDS(k) = AT(LD, k);
-  for (int k = y; k < FB_ROOTD * m.nlist; k += FB_NY) XS(m.nv + k) = 0;
+#endif
+}
+FB_DEV void tsolve_stage_wait(FB_PHASE_ARGS) {
+  float* xs = sh_dyn(sh);
+#ifdef __CUDACC__
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+  for (int k = y; k < FB_ROOTD * m.nlist; k += FB_NY) XS(m.nv + k) = 0;      // the lists' private root accumulators
 }
 // x <- L^-T x restricted to the list dofs, deepest first: x[anc] -= L[k][anc] x[k]
 FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
@@ -357,8 +370,9 @@ FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e,
   for (int u = 0; u < FB_FSUB; u++) p += sh.red[y + u][lane];
   XS(k) = XS(k) / LDS(m.dof_Madr[k]) - p;
 }
-FB_WARPFN void tri_solve(const DevModel& m, const DevData& d, ShTree& sh, int e, const float* LD) {
-  WPAR_BEGIN tsolve_stage(m, d, sh, e, 0, lane, LD); WPAR_END
+// the factor must have been issued with tsolve_stage_issue by this warp
+FB_WARPFN void tri_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) {
+  WPAR_BEGIN tsolve_stage_wait(m, d, sh, e, 0, lane); WPAR_END
   for (int step = 0; step < m.max_list_ndof; step++) { WPAR_BEGIN tsolve_a_step(m, d, sh, e, 0, lane, step); WPAR_END }
   WPAR_BEGIN tsolve_b_gather(m, d, sh, e, 0, lane); WPAR_END
   WPAR_BEGIN tsolve_b_root(m, d, sh, e, 0, lane); WPAR_END

@@ -160,7 +160,7 @@ FB_DEV void ph_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int,
 FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kclear_hold(m, d, e, y); }
 FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kpack(m, d, e, y, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); ktaskobs(m, d, e, y); }
 // qacc_smooth = M^-1 qfrc_smooth (qacc_smooth already holds the rhs)
-FB_WARPFN void wf_smooth_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e, d.qLD); }
+FB_WARPFN void wf_smooth_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e); }
 FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
   for (int i = y; i < m.nv; i += FB_NY) AT(d.qacc_smooth, i) = XS(i);
@@ -184,9 +184,9 @@ static void launch_step1(FbSim* s) {
 }
 static void launch_step2(FbSim* s, bool integrate) {
   s->d.do_integrate = integrate ? 1 : 0;     // read by the solve (warm-start bookkeeping) and the finish kernel
-  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(FB_NXS(s->m) + s->m.nM));
+  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)));
   fb_launch_warp(s, K_SOLVE);
-  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(FB_NXS(s->m) + s->m.nM));
+  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)));
 }
 
 // -------------------------------------------------------------------------------------------
@@ -350,7 +350,7 @@ static int alloc_data(FbSim* s, int N) {
   // pass 1: lay the per-env record out (offsets in 4-byte slots); pass 2: one allocation, rebase the pointers
   std::vector<std::pair<void**, size_t>> fields;
   size_t off = 0;
-#define FA(field, n) { fields.push_back({(void**)&d.field, off}); off += (size_t)(n); }
+#define FA(field, n) { off = (off + 3) & ~(size_t)3; fields.push_back({(void**)&d.field, off}); off += (size_t)(n); }   // arrays start on 16-byte boundaries
 #define IA(field, n) FA(field, n)
   FA(qpos, m.nq) FA(qvel, m.nv) FA(act, m.na + 1) FA(ctrl, m.nu + 1) FA(qacc, m.nv) FA(qacc_warmstart, m.nv) FA(time, 1)
   FA(ref, 3) FA(xpos, 3 * m.nbody) FA(xquat, 4 * m.nbody) FA(xmat, 9 * m.nbody) FA(xipos, 3 * m.nbody) FA(ximat, 9 * m.nbody)
