@@ -383,8 +383,8 @@ FB_DEV void kproj_p1(FB_ROW_ARGS) {
     AT(d.efc_A, idx) = sacc;
   }
 }
-// J . x for every row (x: qvel, qacc_smooth): aref and b = J qacc_smooth - aref.  qacc_smooth is still in shared
-// memory (XS) from the solve; the chains are walked through dof_anc (no pointer chasing), chain b stops where it
+// aref and b = J qacc_smooth - aref for every row.  J qacc_smooth = Z (D^-1/2 L^-T qfrc_smooth); that vector is
+// in shared memory (XS) from the half solve; the chains are walked through dof_anc (no pointer chasing), chain b stops where it
 // joins chain a.
 FB_DEV void kref(FB_PHASE_ARGS) {
   const float* xs = sh_dyn(sh);
@@ -395,14 +395,14 @@ FB_DEV void kref(FB_PHASE_ARGS) {
     float vel = 0, as = 0; const int la = rc.la, lb = rc.lb;
     if (la >= 0) {
       int adr = m.dof_Madr[la], len = m.dof_chainlen[la];
-      for (int t = 0; t < len; t++) { int k = m.dof_anc[adr + t]; float J = EJ(d.efc_J, r, k); vel += J * AT(d.qvel, k); as += J * XS(k); }
+      for (int t = 0; t < len; t++) { int k = m.dof_anc[adr + t]; vel += EJ(d.efc_J, r, k) * AT(d.qvel, k); as += EJ(d.efc_Z, r, k) * XS(k); }
     }
     if (lb >= 0) {
       int adr = m.dof_Madr[lb], len = m.dof_chainlen[lb];
       for (int t = 0; t < len; t++) {
         int k = m.dof_anc[adr + t];
         if (la >= 0 && k <= la && la <= m.dof_subend[k]) break;      // common ancestors were counted with chain a
-        float J = EJ(d.efc_J, r, k); vel += J * AT(d.qvel, k); as += J * XS(k);
+        vel += EJ(d.efc_J, r, k) * AT(d.qvel, k); as += EJ(d.efc_Z, r, k) * XS(k);
       }
     }
     float aref = -EFC(d.efc_B, r) * vel - EFC(d.efc_K, r) * EFC(d.efc_imp, r) * (EFC(d.efc_pos, r) - EFC(d.efc_margin, r));
@@ -521,18 +521,21 @@ FB_DEV int qcqp2(float* res, const float* A, const float* b, float d0, float d1,
 // delta_b = delta_parent + sum_d S_d qacc_d (MuJoCo mj_rnePostConstraint restated).
 FB_DEV void kfin_f1(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
-  for (int i = y; i < m.nv; i += FB_NY) XS(i) = AT(d.qfrc_constraint, i);
+  for (int i = y; i < m.nv; i += FB_NY) XS(i) = AT(d.qtmp, i) + AT(d.dof_isd, i) * AT(d.qfrc_zf, i);      // D^-1 u + D^-1/2 Z^T f
   for (int k = y; k < 6 * m.nbody; k += FB_NY) AT(d.bfl, k) = 0;
   tsolve_stage_issue(m, d, sh, e, lane, y, d.qLD);
   if (d.do_integrate) for (int k = 32 * y; k < m.nM; k += 32 * FB_NY) prefetch_l2(&AT(d.qLDe, k));   // second factor, staged after the first solve
 }
-FB_WARPFN void kfin_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e); }
+FB_WARPFN void kfin_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) {      // qacc = L^-1 (...)
+  WPAR_BEGIN tsolve_stage_wait(m, d, sh, e, 0, lane); WPAR_END
+  tsolve_c(m, d, sh, e);
+}
 // Euler with implicit joint damping: qacc' = (M + h D)^-1 (qfrc_smooth + qfrc_constraint), second factor qLDe
 FB_WARPFN void kfin_solve_euler(const DevModel& m, const DevData& d, ShTree& sh, int e) { if (d.do_integrate) tri_solve(m, d, sh, e); }
 FB_DEV void kfin_f5(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
   if (d.do_integrate) tsolve_stage_issue(m, d, sh, e, lane, y, d.qLDe);      // overlaps the sensor sweeps below
-  for (int i = y; i < m.nv; i += FB_NY) { AT(d.qacc, i) = AT(d.qacc_smooth, i) + XS(i); XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); }
+  for (int i = y; i < m.nv; i += FB_NY) { AT(d.qacc, i) = XS(i); XS(i) = AT(d.qfrc_smooth, i) + AT(d.qfrc_constraint, i); }
   if (y != 0) return;
   // external (contact) wrench per body into bfl (about ref)
   int ncon = AT(d.ncon, 0);
@@ -663,7 +666,7 @@ FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int lane,
   for (int k = 0; k < m.body_jntnum[b]; k++) {
     int j = m.body_jntadr[b] + k, qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
     if (m.jnt_type[j] == FB_JNT_FREE) {
-      for (int i = 0; i < 6; i++) { AT(d.qvel, da + i) += h * XS(da + i); AT(d.qacc_warmstart, da + i) = AT(d.qacc, da + i); }
+      for (int i = 0; i < 6; i++) { AT(d.qvel, da + i) += h * XS(da + i); }
       for (int i = 0; i < 3; i++) AT(d.qpos, qa + i) += h * AT(d.qvel, da + i);
       V3 w = v3(AT(d.qvel, da + 3), AT(d.qvel, da + 4), AT(d.qvel, da + 5));
       float ang = norm(w) * h;
@@ -672,7 +675,7 @@ FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int lane,
       q = qnormalize(q);
       AT(d.qpos, qa + 3) = q.w; AT(d.qpos, qa + 4) = q.x; AT(d.qpos, qa + 5) = q.y; AT(d.qpos, qa + 6) = q.z;
     } else {
-      AT(d.qvel, da) += h * XS(da); AT(d.qacc_warmstart, da) = AT(d.qacc, da);
+      AT(d.qvel, da) += h * XS(da);
       AT(d.qpos, qa) += h * AT(d.qvel, da);
     }
   }
@@ -760,7 +763,7 @@ FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int w, int y) {
   if (w >= d.rst_n) return;
   int e = d.rst_ids[w];
   for (int i = y; i < m.nq; i += FB_NY) AT(d.qpos, i) = d.rst_qpos[(size_t)w * m.nq + i];
-  for (int i = y; i < m.nv; i += FB_NY) { AT(d.qvel, i) = d.rst_has_qvel ? d.rst_qvel[(size_t)w * m.nv + i] : 0.0f; AT(d.qacc, i) = 0; AT(d.qacc_warmstart, i) = 0; }
+  for (int i = y; i < m.nv; i += FB_NY) { AT(d.qvel, i) = d.rst_has_qvel ? d.rst_qvel[(size_t)w * m.nv + i] : 0.0f; AT(d.qacc, i) = 0; }
   for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) = 0;
   if (y == 0) { AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = d.rst_hold; AT(d.prev_n, 0) = 0; }
 }

@@ -302,16 +302,17 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
     if (lane == 0) { AT(d.niter, 0) = niter; if (d.do_integrate) AT(d.prev_n, 0) = n; }
     NOUNROLL for (int k = lane; k < m.nv; k += 32) {
       const int se = m.dof_subend[k];
-      float s = 0;
+      float s = 0, sz = 0;
       // a row touches dof k iff k is on the ancestor chain of one of its two end dofs; the loads are predicated, not
       // branched around, so that several rows are in flight
 #pragma unroll 4
       for (int r = 0; r < n; r++) {
         int la = (int)SV(S_LA, r), lb = (int)SV(S_LB, r);
         bool in = (k <= la && la <= se) || (k <= lb && lb <= se);
-        float jv = in ? EJ(d.efc_J, r, k) : 0.0f;
-        s += jv * SV(W_F, r);
+        float jv = in ? EJ(d.efc_J, r, k) : 0.0f, zv = in ? EJ(d.efc_Z, r, k) : 0.0f, f = SV(W_F, r);
+        s += jv * f; sz += zv * f;
       }
+      AT(d.qfrc_zf, k) = sz;                      // Z^T f: the constraint part of qacc before the L^-1 sweep (finish kernel)
       AT(d.qfrc_constraint, k) = s;
     }
   WPAR_END

@@ -187,15 +187,17 @@ FB_DEV void kpos_p4(FB_PHASE_ARGS) {      // all 32 lanes over the dofs
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   for (int i = y; i < m.nv; i += FB_NY) mass_row(m, d, e, lane, ldsh, i);
 }
-// copy the factor held in shared memory out to `dst`; optionally re-initialise the shared rows with
-// M + h*diag(damping) for the second factorisation (entries are split over all lanes)
-FB_DEV void ld_writeout(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* dst, bool reinit) {
+// Copy the factor held in shared memory out to `dst`.  The elimination leaves row k's off-diagonal entries unscaled
+// (M'[k][anc]); L[k][anc] = M'[k][anc] / D[k] is applied here, spread over all lanes, instead of in a per-step pass
+// (M_diag[k] = index of the row's diagonal, -1 for diagonals and for the root rows, which factor_root scales itself).
+FB_DEV void ld_writeout(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* dst) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  for (int k = y; k < m.nM; k += FB_NY) { AT(dst, k) = LS(k); if (reinit) LS(k) = AT(d.qM, k); }
+  for (int k = y; k < m.nM; k += FB_NY) { int dk = m.M_diag[k]; float v = LS(k); AT(dst, k) = dk < 0 ? v : v / LS(dk); }
 }
-FB_DEV void ld_add_damping(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
+// re-initialise the shared rows with M + h*diag(damping) for the second factorisation (Euler with implicit damping)
+FB_DEV void ld_reinit_damped(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  for (int i = y; i < m.nv; i += FB_NY) LS(m.dof_Madr[i]) += m.timestep * m.dof_damping[i];
+  for (int k = y; k < m.nM; k += FB_NY) LS(k) = AT(d.qM, k) + m.timestep * m.M_damp[k];
 }
 
 // sparse L^T D L factorisation (Featherstone; MuJoCo mj_factorM).  Row k of LD holds (k,k), (k,parent(k)), ...
@@ -228,14 +230,6 @@ FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, 
       for (int s2 = 0; s2 <= il; s2++) PART(y, base + s2) += a * LS(adrk + t + s2);
     }
   }
-}
-FB_DEV void factor_step_scale(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
-  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  int l = y / FB_FSUB, sub = y % FB_FSUB;
-  if (l >= m.nlist || step >= m.list_ndof[l]) return;
-  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
-  float invD = 1.0f / LS(adrk);
-  for (int t = 1 + sub; t < len; t += FB_FSUB) LS(adrk + t) *= invD;
 }
 // root blocks: 21 lanes add up the lists' partial updates (one packed lower-triangle entry each) ...
 FB_DEV void factor_root_gather(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
@@ -272,14 +266,13 @@ FB_WARPFN void kpos_factor(const DevModel& m, const DevData& d, ShTree& sh, int 
   WPAR_BEGIN factor_clear(m, d, sh, e, 0, lane); WPAR_END
   for (int step = 0; step < m.max_list_ndof; step++) {
     WPAR_BEGIN factor_step_update(m, d, sh, e, 0, lane, step); WPAR_END
-    WPAR_BEGIN factor_step_scale(m, d, sh, e, 0, lane, step); WPAR_END
   }
   WPAR_BEGIN factor_root_gather(m, d, sh, e, 0, lane); WPAR_END
   WPAR_BEGIN factor_root(m, d, sh, e, 0, lane); WPAR_END
 }
-FB_DEV void kpos_p6w(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLD, true); }
-FB_DEV void kpos_p6d(FB_PHASE_ARGS) { ld_add_damping(m, d, sh, e, lane, y); }
-FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe, false); }
+FB_DEV void kpos_p6w(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLD); }
+FB_DEV void kpos_p6d(FB_PHASE_ARGS) { ld_reinit_damped(m, d, sh, e, lane, y); }
+FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe); }
 
 // ---------------------------------------------------------------------------------------------
 // x <- (L^T D L)^-1 x (MuJoCo mj_solveLD).  x lives in shared memory: XS(0..nv) plus FB_ROOTD private accumulators per
@@ -336,22 +329,31 @@ FB_DEV void tsolve_b_gather(FB_PHASE_ARGS) {
     XS(d0 + y) += acc;
   }
 }
-FB_DEV void tsolve_b_root(FB_PHASE_ARGS) {
+FB_DEV void tsolve_root_a(FB_PHASE_ARGS) {       // x <- L^-T x inside the root block, one lane per root body
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  if (y >= m.nroot) return;                      // one lane per root body
+  if (y >= m.nroot) return;
   int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
   for (int kl = nd - 1; kl >= 0; kl--) {
     float xk = XS(d0 + kl); int adrk = m.dof_Madr[d0 + kl];
     for (int t = 1; t <= kl; t++) XS(d0 + kl - t) -= LDS(adrk + t) * xk;
   }
+}
+FB_DEV void tsolve_root_c(FB_PHASE_ARGS) {       // x <- L^-1 x inside the root block
+  float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
+  if (y >= m.nroot) return;
+  int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
   for (int kl = 0; kl < nd; kl++) {
     int adrk = m.dof_Madr[d0 + kl];
-    float v = XS(d0 + kl) / LDS(adrk);
+    float v = XS(d0 + kl);
     for (int t = 1; t <= kl; t++) v -= LDS(adrk + t) * XS(d0 + kl - t);
     XS(d0 + kl) = v;
   }
 }
-// x <- L^-1 D^-1 x on the list dofs, shallowest first: x[k] = x[k] / D[k] - sum_t L[k][anc_t] x[anc_t]
+FB_DEV void tsolve_scale(FB_PHASE_ARGS) {        // x <- D^-1 x
+  float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
+  for (int k = y; k < m.nv; k += FB_NY) XS(k) /= LDS(m.dof_Madr[k]);
+}
+// x <- L^-1 x on the list dofs, shallowest first: x[k] -= sum_t L[k][anc_t] x[anc_t]
 FB_DEV void tsolve_c_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
   int l = y / FB_FSUB, sub = y % FB_FSUB;
@@ -368,18 +370,29 @@ FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e,
   int k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step];
   float p = 0;
   for (int u = 0; u < FB_FSUB; u++) p += sh.red[y + u][lane];
-  XS(k) = XS(k) / LDS(m.dof_Madr[k]) - p;
+  XS(k) -= p;
 }
-// the factor must have been issued with tsolve_stage_issue by this warp
-FB_WARPFN void tri_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) {
+// M^-1 = L^-1 D^-1 L^-T is applied in halves so that callers can work between them (the factor must have been issued
+// with tsolve_stage_issue by this warp):
+//   tsolve_a : wait for the staged factor, x <- L^-T x
+//   tsolve_c : x <- L^-1 x
+FB_WARPFN void tsolve_a(const DevModel& m, const DevData& d, ShTree& sh, int e) {
   WPAR_BEGIN tsolve_stage_wait(m, d, sh, e, 0, lane); WPAR_END
   for (int step = 0; step < m.max_list_ndof; step++) { WPAR_BEGIN tsolve_a_step(m, d, sh, e, 0, lane, step); WPAR_END }
   WPAR_BEGIN tsolve_b_gather(m, d, sh, e, 0, lane); WPAR_END
-  WPAR_BEGIN tsolve_b_root(m, d, sh, e, 0, lane); WPAR_END
+  WPAR_BEGIN tsolve_root_a(m, d, sh, e, 0, lane); WPAR_END
+}
+FB_WARPFN void tsolve_c(const DevModel& m, const DevData& d, ShTree& sh, int e) {
+  WPAR_BEGIN tsolve_root_c(m, d, sh, e, 0, lane); WPAR_END
   for (int step = 0; step < m.max_list_ndof; step++) {
     WPAR_BEGIN tsolve_c_step(m, d, sh, e, 0, lane, step); WPAR_END
     WPAR_BEGIN tsolve_c_fin(m, d, sh, e, 0, lane, step); WPAR_END
   }
+}
+FB_WARPFN void tri_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) {
+  tsolve_a(m, d, sh, e);
+  WPAR_BEGIN tsolve_scale(m, d, sh, e, 0, lane); WPAR_END
+  tsolve_c(m, d, sh, e);
 }
 
 // ---------------------------------------------------------------------------------------------

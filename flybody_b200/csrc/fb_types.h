@@ -62,6 +62,7 @@ struct DevModel {
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
   const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen, *dof_anc /* [nM] t-th ancestor of the row's dof */, *dof_ancslot /* same, as shared-memory slot of tri_solve */;
+  const int* M_diag; const float* M_damp;      // per entry of the packed inertia: its row's diagonal (or -1), joint damping on diagonals
   const int* body_adhesion;    // adhesion actuator acting on the body, or -1
   const float *dof_armature, *dof_damping, *dof_invweight0;
   // geoms
@@ -88,7 +89,7 @@ struct DevData {
   unsigned rec;                // record stride (4-byte slots) between consecutive envs
   int nsub_done, sens_mode, do_integrate;
   // integrated state
-  float *qpos, *qvel, *act, *ctrl, *qacc, *qacc_warmstart, *time;
+  float *qpos, *qvel, *act, *ctrl, *qacc, *dof_isd /* D^-1/2 of the current factor */, *time;
   // position stage
   float *ref;                  // [3] reference point (root position) all spatial quantities are taken about
   float *xpos, *xquat, *xmat, *xipos, *ximat;          // body frames (positions relative to ref)
@@ -98,7 +99,7 @@ struct DevData {
   float *qM, *qLD, *qLDe;      // [nM] inertia, its L^T D L factor, factor of M + h*diag(damping)
   // velocity stage
   float *bvel, *bacc, *bfrc, *bfl, *bfrc0, *bdel;   // [nbody*6] spatial velocity, bias accel, bias force (subtree sums), fluid wrench, per-body bias force
-  float *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qacc_smooth, *qfrc_constraint, *qtmp;
+  float *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qfrc_zf /* Z^T f */, *qfrc_constraint, *qtmp /* D^-1 L^-T qfrc_smooth */;
   float *act_dot, *actuator_force;
   // contacts
   int *ncon; float *con_dist, *con_pos, *con_frame; int *con_geom1, *con_geom2, *con_efcadr, *con_dim;

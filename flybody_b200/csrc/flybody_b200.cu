@@ -159,11 +159,18 @@ FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e
 FB_DEV void ph_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kscatter(m, d, e, y); }
 FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kclear_hold(m, d, e, y); }
 FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kpack(m, d, e, y, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); ktaskobs(m, d, e, y); }
-// qacc_smooth = M^-1 qfrc_smooth (qacc_smooth already holds the rhs)
-FB_WARPFN void wf_smooth_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tri_solve(m, d, sh, e); }
+// Smooth dynamics in half-solve form: with M = L^T D L and u = L^-T qfrc_smooth,
+//   J qacc_smooth = Z (D^-1/2 u)          (Z = D^-1/2 L^-T J^T, rows written by the projection kernel)
+//   qacc          = L^-1 (D^-1 u + D^-1/2 Z^T f)
+// so the step needs L^-T once (here) and L^-1 once (finish kernel) instead of two full solves.  qtmp <- D^-1 u,
+// dof_isd <- D^-1/2, XS <- D^-1/2 u for kref.
+FB_WARPFN void wf_smooth_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) { tsolve_a(m, d, sh, e); }
 FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
-  float* xs = sh_dyn(sh);
-  for (int i = y; i < m.nv; i += FB_NY) AT(d.qacc_smooth, i) = XS(i);
+  float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
+  for (int i = y; i < m.nv; i += FB_NY) {
+    float D = LDS(m.dof_Madr[i]), u = XS(i), isd = 1.0f / sqrtf(D);
+    AT(d.qtmp, i) = u / D; AT(d.dof_isd, i) = isd; XS(i) = u * isd;
+  }
 }
 
 static void launch_step1(FbSim* s) {
@@ -288,6 +295,9 @@ static int build_model(FbSim* s, const FbModel* h) {
     m.dof_ancslot = up(s, slot);
   }
   { std::vector<int> adh(nb, -1); for (int i = 0; i < h->nu; i++) if (h->actuator_trntype[i] == FB_TRN_BODY) adh[h->actuator_trnid[i]] = i; m.body_adhesion = up(s, adh); }
+  { std::vector<int> mdiag(h->nM, -1); std::vector<float> mdamp(h->nM, 0.0f);
+    for (int i = 0; i < nv; i++) { int adr = h->dof_Madr[i]; mdamp[adr] = (float)h->dof_damping[i]; if (!disroot[i]) for (int t = 1; t < chainlen[i]; t++) mdiag[adr + t] = adr; }
+    m.M_diag = up(s, mdiag); m.M_damp = up(s, mdamp); }
   m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);
   // plain copies
   m.body_parentid = upi(s, h->body_parentid, nb); m.body_rootid = upi(s, h->body_rootid, nb);
@@ -352,13 +362,13 @@ static int alloc_data(FbSim* s, int N) {
   size_t off = 0;
 #define FA(field, n) { off = (off + 3) & ~(size_t)3; fields.push_back({(void**)&d.field, off}); off += (size_t)(n); }   // arrays start on 16-byte boundaries
 #define IA(field, n) FA(field, n)
-  FA(qpos, m.nq) FA(qvel, m.nv) FA(act, m.na + 1) FA(ctrl, m.nu + 1) FA(qacc, m.nv) FA(qacc_warmstart, m.nv) FA(time, 1)
+  FA(qpos, m.nq) FA(qvel, m.nv) FA(act, m.na + 1) FA(ctrl, m.nu + 1) FA(qacc, m.nv) FA(dof_isd, m.nv) FA(time, 1)
   FA(ref, 3) FA(xpos, 3 * m.nbody) FA(xquat, 4 * m.nbody) FA(xmat, 9 * m.nbody) FA(xipos, 3 * m.nbody) FA(ximat, 9 * m.nbody)
   FA(geom_xpos, 3 * m.ngeom) FA(geom_xmat, 9 * m.ngeom) FA(site_xpos, 3 * m.nsite + 3) FA(site_xmat, 9 * m.nsite + 9)
   FA(Sang, 3 * m.nv) FA(Slin, 3 * m.nv) FA(inert10, 10 * m.nbody) FA(crb10, 10 * m.nbody)
   FA(qM, m.nM) FA(qLD, m.nM) FA(qLDe, m.nM)
   FA(bvel, 6 * m.nbody) FA(bacc, 6 * m.nbody) FA(bfrc, 6 * m.nbody) FA(bfl, 6 * m.nbody) FA(bfrc0, 6 * m.nbody) FA(bdel, 6 * m.nbody)
-  FA(qfrc_bias, m.nv) FA(qfrc_passive, m.nv) FA(qfrc_actuator, m.nv) FA(qfrc_smooth, m.nv) FA(qacc_smooth, m.nv) FA(qfrc_constraint, m.nv) FA(qtmp, m.nv)
+  FA(qfrc_bias, m.nv) FA(qfrc_passive, m.nv) FA(qfrc_actuator, m.nv) FA(qfrc_smooth, m.nv) FA(qfrc_zf, m.nv) FA(qfrc_constraint, m.nv) FA(qtmp, m.nv)
   FA(act_dot, m.na + 1) FA(actuator_force, m.nu + 1)
   IA(ncon, 1) FA(con_dist, FB_MAXCON) FA(con_pos, 3 * FB_MAXCON) FA(con_frame, 9 * FB_MAXCON) IA(con_geom1, FB_MAXCON) IA(con_geom2, FB_MAXCON)
   IA(con_efcadr, FB_MAXCON) IA(con_dim, FB_MAXCON) FA(con_mu, FB_MAXCON) FA(con_fric, 2 * FB_MAXCON)
@@ -542,7 +552,7 @@ static void* field_ptr(FbSim* s, int field, int* n) {
     case FB_ACT: *n = m.na; return d.act;
     case FB_CTRL: *n = m.nu; return d.ctrl;
     case FB_QACC: *n = m.nv; return d.qacc;
-    case FB_QACC_WARMSTART: *n = m.nv; return d.qacc_warmstart;
+    case FB_QACC_WARMSTART: *n = m.nv; return d.qacc;        /* the dual solver warm-starts from forces; kept for ABI compatibility */
     case FB_SENSORDATA: *n = m.nsensordata; return d.sensordata;
     case FB_SENSOR_MEAN: *n = m.nsensordata; return d.sensor_sum;
     case FB_XPOS: *n = 3 * m.nbody; return d.xpos;
