@@ -206,6 +206,7 @@ FB_DEV bool limit_active(const DevModel& m, const DevData& d, int e, int j, int 
 }
 // phase 0/1: joint-limit rows (joints split into contiguous ranges over y so that rows stay in joint order)
 FB_DEV void kcon_p0(FB_CON_ARGS) {
+  prefetch_rec(d.qLD, m.nM, d, e, y); prefetch_rec(d.Sang, 3 * m.nv, d, e, y); prefetch_rec(d.Slin, 3 * m.nv, d, e, y);   // for the projection phases
   if (y >= FB_ROWPAR) return;
   int j0 = (int)((long)y * m.njnt / FB_ROWPAR), j1 = (int)((long)(y + 1) * m.njnt / FB_ROWPAR), c = 0; float dist;
   for (int j = j0; j < j1; j++) { if (!m.jnt_limited[j] || m.jnt_type[j] != FB_JNT_HINGE) continue; for (int side = -1; side <= 1; side += 2) c += limit_active(m, d, e, j, side, dist) ? 1 : 0; }
@@ -521,10 +522,11 @@ FB_DEV int qcqp2(float* res, const float* A, const float* b, float d0, float d1,
 // delta_b = delta_parent + sum_d S_d qacc_d (MuJoCo mj_rnePostConstraint restated).
 FB_DEV void kfin_f1(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
+  tsolve_stage_issue(m, d, sh, e, lane, y, d.qLD);
+  prefetch_rec(d.Sang, 3 * m.nv, d, e, y); prefetch_rec(d.Slin, 3 * m.nv, d, e, y); prefetch_rec(d.inert10, 10 * m.nbody, d, e, y); prefetch_rec(d.bfrc0, 6 * m.nbody, d, e, y);
+  if (d.do_integrate) prefetch_rec(d.qLDe, m.nM, d, e, y);   // second factor, staged after the first solve
   for (int i = y; i < m.nv; i += FB_NY) XS(i) = AT(d.qtmp, i) + AT(d.dof_isd, i) * AT(d.qfrc_zf, i);      // D^-1 u + D^-1/2 Z^T f
   for (int k = y; k < 6 * m.nbody; k += FB_NY) AT(d.bfl, k) = 0;
-  tsolve_stage_issue(m, d, sh, e, lane, y, d.qLD);
-  if (d.do_integrate) for (int k = 32 * y; k < m.nM; k += 32 * FB_NY) prefetch_l2(&AT(d.qLDe, k));   // second factor, staged after the first solve
 }
 FB_WARPFN void kfin_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) {      // qacc = L^-1 (...)
   WPAR_BEGIN tsolve_stage_wait(m, d, sh, e, 0, lane); WPAR_END

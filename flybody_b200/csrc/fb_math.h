@@ -83,3 +83,16 @@ FB_DEV I10 ld10(const float* arr, int b, const DevData& d, int e) { I10 I; for (
 struct S6 { V3 a, l; };
 FB_DEV S6 ld6(const float* arr, int b, const DevData& d, int e) { S6 s; s.a = ld3(arr, 2 * b, d, e); s.l = ld3(arr, 2 * b + 1, d, e); return s; }
 FB_DEV void st6(float* arr, int b, const DevData& d, int e, const S6& s) { st3(arr, 2 * b, d, e, s.a); st3(arr, 2 * b + 1, d, e, s.l); }
+
+// L2 prefetch of a record array (one request per 128-byte line, lanes take consecutive lines): used in the first phase of
+// a kernel for arrays it will read later through dependent, scattered loads
+FB_DEV void prefetch_l2(const void* p) {
+#ifdef __CUDACC__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+FB_DEV void prefetch_rec(const float* arr, int n, const DevData& d, int e, int y) {
+  for (int k = 32 * y; k < n; k += 32 * FB_NY) prefetch_l2(&AT(arr, k));
+}

@@ -321,6 +321,8 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
 // one env; `wsm` = this warp's shared-memory slice (FB_SOLVE_WARP_FLOATS floats)
 FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int e) {
   const int n = AT(d.nefc, 0);
+  // the Jacobian / Z rows are only needed by the J^T f gather at the very end: request them now
+  WPAR_BEGIN for (int k = 32 * lane; k < n * m.nv; k += 32 * 32) { prefetch_l2(&AT(d.efc_J, k)); prefetch_l2(&AT(d.efc_Z, k)); } WPAR_END
   SolveMem sm;
   sm.red = wsm;
   if (n <= m.solve_ncap) {

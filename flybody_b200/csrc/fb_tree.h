@@ -205,45 +205,64 @@ FB_DEV void ld_reinit_damped(const DevModel& m, const DevData& d, ShTree& sh, in
 // list and split the rank-1 update of the ancestor rows of that dof.  Updates that land in the root block are
 // summed into sh.part (21 entries per lane) and applied by the root lane afterwards.
 #define FB_FSUB 3
-FB_DEV void factor_clear(FB_PHASE_ARGS) { float* part_ = sh_dyn(sh); for (int k = 0; k < 21; k++) PART(y, k) = 0; }
+#define FB_ROOTD6 6            // dofs of a root body (free joint)
 FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (l >= m.nlist || step >= m.list_ndof[l]) return;
   int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
   float invD = 1.0f / LS(adrk);
-  // ancestor rows are dealt round-robin to the FB_FSUB lanes of the list (dof_anc[adrk + t] = t-th ancestor of k)
-  for (int t = 1 + sub; t < len; t += FB_FSUB) {
+  // non-root ancestor rows are dealt round-robin to the FB_FSUB lanes of the list (dof_anc[adrk + t] = t-th ancestor
+  // of k; the root's dofs are the tail of every chain and are handled by factor_root_accum)
+  const int tend = 1 + m.dof_depth[k];
+  for (int t = 1 + sub; t < tend; t += FB_FSUB) {
     int i = m.dof_anc[adrk + t];
     float a = LS(adrk + t) * invD;
-    if (!m.dof_isroot[i]) {
-      int adri = m.dof_Madr[i], li = len - t;                 // chain of i = tail of the chain of k
-      int s2 = 0;
-      for (; s2 + 4 <= li; s2 += 4) {                          // batched so that the loads are in flight together
-        float r0 = LS(adrk + t + s2), r1 = LS(adrk + t + s2 + 1), r2 = LS(adrk + t + s2 + 2), r3 = LS(adrk + t + s2 + 3);
-        float x0 = LS(adri + s2), x1 = LS(adri + s2 + 1), x2 = LS(adri + s2 + 2), x3 = LS(adri + s2 + 3);
-        LS(adri + s2) = x0 - a * r0; LS(adri + s2 + 1) = x1 - a * r1; LS(adri + s2 + 2) = x2 - a * r2; LS(adri + s2 + 3) = x3 - a * r3;
-      }
-      for (; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
-    } else {
-      int il = m.dof_depth[i], base = il * (il + 1) / 2;       // for root dofs depth == local index
-      for (int s2 = 0; s2 <= il; s2++) PART(y, base + s2) += a * LS(adrk + t + s2);
+    int adri = m.dof_Madr[i], li = len - t;                 // chain of i = tail of the chain of k
+    int s2 = 0;
+    for (; s2 + 4 <= li; s2 += 4) {                          // batched so that the loads are in flight together
+      float r0 = LS(adrk + t + s2), r1 = LS(adrk + t + s2 + 1), r2 = LS(adrk + t + s2 + 2), r3 = LS(adrk + t + s2 + 3);
+      float x0 = LS(adri + s2), x1 = LS(adri + s2 + 1), x2 = LS(adri + s2 + 2), x3 = LS(adri + s2 + 3);
+      LS(adri + s2) = x0 - a * r0; LS(adri + s2 + 1) = x1 - a * r1; LS(adri + s2 + 2) = x2 - a * r2; LS(adri + s2 + 3) = x3 - a * r3;
     }
+    for (; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
   }
 }
-// root blocks: 21 lanes add up the lists' partial updates (one packed lower-triangle entry each) ...
-FB_DEV void factor_root_gather(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
-  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
+// Root blocks.  Once the lists are eliminated, row k of a non-root dof holds its final (unscaled) coupling r_k to the
+// root's dofs and D_k; the Schur update of the root block is sum_k r_k r_k^T / D_k.  32 lanes split the dofs, each
+// accumulates the 21 packed lower-triangle entries in registers ...
+FB_DEV void factor_root_accum(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int r) {
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF;
+  float acc[21];
+#pragma unroll
+  for (int j = 0; j < 21; j++) acc[j] = 0;
+  for (int k = y; k < m.nv; k += FB_NY) {
+    if (m.dof_rootidx[k] != r) continue;
+    int adrk = m.dof_Madr[k], len = m.dof_chainlen[k], nr = len - 1 - m.dof_depth[k];
+    float invD = 1.0f / LS(adrk), rr[FB_ROOTD6];
+#pragma unroll
+    for (int il = 0; il < FB_ROOTD6; il++) rr[il] = il < nr ? LS(adrk + len - 1 - il) : 0.0f;     // coupling to root dof il
+#pragma unroll
+    for (int i = 0; i < FB_ROOTD6; i++) {
+      float a = rr[i] * invD;
+#pragma unroll
+      for (int j = 0; j <= i; j++) acc[i * (i + 1) / 2 + (i - j)] += a * rr[j];                   // row i, (i-j)-th ancestor
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 21; j++) PART(y, j) = acc[j];
+}
+// ... 21 lanes add the partials up (one packed entry each) ...
+FB_DEV void factor_root_gather(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int r) {
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF;
   if (y >= 21) return;
   int il = 0; while ((il + 1) * (il + 2) / 2 <= y) il++;
   int s = y - il * (il + 1) / 2;
-  for (int r = 0; r < m.nroot; r++) {
-    int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
-    if (il >= nd) continue;
-    float acc = 0;
-    for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) for (int u = 0; u < FB_FSUB; u++) acc += PART(l * FB_FSUB + u, y);
-    LS(m.dof_Madr[d0 + il] + s) -= acc;
-  }
+  int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
+  if (il >= nd) return;
+  float acc = 0;
+  for (int l = 0; l < FB_NY; l++) acc += PART(l, y);
+  LS(m.dof_Madr[d0 + il] + s) -= acc;
 }
 // ... then one lane per root body factors its dense (<= 6x6) block
 FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
@@ -263,11 +282,14 @@ FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, 
 }
 // warp function: the whole factorisation of the rows currently held in shared memory
 FB_WARPFN void kpos_factor(const DevModel& m, const DevData& d, ShTree& sh, int e) {
-  WPAR_BEGIN factor_clear(m, d, sh, e, 0, lane); WPAR_END
   for (int step = 0; step < m.max_list_ndof; step++) {
     WPAR_BEGIN factor_step_update(m, d, sh, e, 0, lane, step); WPAR_END
   }
-  WPAR_BEGIN factor_root_gather(m, d, sh, e, 0, lane); WPAR_END
+  for (int r = 0; r < m.nroot; r++) {
+    if (!m.root_haslists[r]) continue;
+    WPAR_BEGIN factor_root_accum(m, d, sh, e, 0, lane, r); WPAR_END
+    WPAR_BEGIN factor_root_gather(m, d, sh, e, 0, lane, r); WPAR_END
+  }
   WPAR_BEGIN factor_root(m, d, sh, e, 0, lane); WPAR_END
 }
 FB_DEV void kpos_p6w(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLD); }
@@ -282,13 +304,6 @@ FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe); 
 #define FB_ROOTD 6
 #define FB_NXS(m) (((m).nv + FB_ROOTD * (m).nlist + 3) & ~3)      // multiple of 4: the staged factor behind it stays 16-byte aligned
 #define LDS(k) lds[(k) * FB_LANES + lane]
-FB_DEV void prefetch_l2(const void* p) {
-#ifdef __CUDACC__
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
 // Stage a factor into the warp's shared slice with asynchronous 16-byte copies (cp.async): issued early (first phase
 // of the kernel / right after the previous solve), waited for at the start of tri_solve, so the DRAM latency overlaps
 // the phases in between and the sweeps only touch shared memory.  Record arrays start on 16-byte boundaries.
@@ -552,6 +567,9 @@ FB_DEV void vel_acc_from_parent(const DevModel& m, const DevData& d, int e, int 
   st6(d.bvel, b, d, e, v); st6(d.bacc, b, d, e, a);
 }
 FB_DEV void kvel_p0(FB_PHASE_ARGS) {
+  // inputs written by the position kernel three launches ago: ask for them now, all lines at once
+  prefetch_rec(d.Sang, 3 * m.nv, d, e, y); prefetch_rec(d.Slin, 3 * m.nv, d, e, y); prefetch_rec(d.inert10, 10 * m.nbody, d, e, y);
+  prefetch_rec(d.xipos, 3 * m.nbody, d, e, y); prefetch_rec(d.ximat, 9 * m.nbody, d, e, y);
   if (y != 0) return;
   S6 z; z.a = v3(0, 0, 0); z.l = v3(0, 0, 0);
   st6(d.bvel, 0, d, e, z);

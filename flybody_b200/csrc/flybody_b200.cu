@@ -293,6 +293,9 @@ static int build_model(FbSim* s, const FbModel* h) {
     std::vector<int> slot(h->nM, 0);
     for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) slot[h->dof_Madr[i] + t] = (disroot[j] && dof_list[i] >= 0) ? nv + FB_ROOTD * dof_list[i] + depth[j] : j; }
     m.dof_ancslot = up(s, slot);
+    std::vector<int> rootidx(nv, -1), haslists(roots.size(), 0);
+    for (int i = 0; i < nv; i++) if (dof_list[i] >= 0) { rootidx[i] = lr[dof_list[i]]; haslists[lr[dof_list[i]]] = 1; }
+    m.dof_rootidx = up(s, rootidx); m.root_haslists = up(s, haslists);
   }
   { std::vector<int> adh(nb, -1); for (int i = 0; i < h->nu; i++) if (h->actuator_trntype[i] == FB_TRN_BODY) adh[h->actuator_trnid[i]] = i; m.body_adhesion = up(s, adh); }
   { std::vector<int> mdiag(h->nM, -1); std::vector<float> mdamp(h->nM, 0.0f);
