@@ -114,20 +114,33 @@ FB_DEV void make_frame(V3 n, V3 t, V3& f1, V3& f2) {   // mju_makeFrame
 }
 
 #define FB_COL_ARGS const DevModel& m, const DevData& d, ShCol& sh, int e, int lane, int y
+// geom positions of this env into shared memory (coalesced), so that the pair loop does not touch the record
+FB_DEV void kcol_stage(FB_COL_ARGS) {
+  float* gx = sh_dyn(sh);
+  for (int i = y; i < 3 * m.ngeom; i += FB_NY) gx[i * FB_LANES + lane] = AT(d.geom_xpos, i);
+}
 FB_DEV void kcol_p0(FB_COL_ARGS) {
+  const float* gx = sh_dyn(sh);
   int cnt = 0;
   int p0 = m.chunk_start[y], p1 = m.chunk_start[y + 1];
-  V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
-  (void)ref;
   for (int k = p0; k < p1; k++) {
-    int g1 = m.pair_geom1[k], g2 = m.pair_geom2[k];
-    int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-    float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
-    V3 x1 = ld3(d.geom_xpos, g1, d, e), x2 = ld3(d.geom_xpos, g2, d, e);
+    // broadphase on the packed static pair record: geoms, plane flag, margin + bounding radii
+    const int pw = m.pair_info[k]; const float rsum = m.pair_rsum[k];
+    const int g1 = pw & 0x7fff, g2 = (pw >> 15) & 0x7fff; const bool plane = (pw >> 30) & 1;
+    V3 x1 = v3(gx[(3 * g1) * FB_LANES + lane], gx[(3 * g1 + 1) * FB_LANES + lane], gx[(3 * g1 + 2) * FB_LANES + lane]);
+    V3 x2 = v3(gx[(3 * g2) * FB_LANES + lane], gx[(3 * g2 + 1) * FB_LANES + lane], gx[(3 * g2 + 2) * FB_LANES + lane]);
+    V3 pn = v3(0, 0, 1);
+    if (plane) {
+      pn = v3(AT(d.geom_xmat, 9 * g1 + 2), AT(d.geom_xmat, 9 * g1 + 5), AT(d.geom_xmat, 9 * g1 + 8));
+      if (dot(x2 - x1, pn) > rsum) continue;
+    } else {
+      V3 df = x2 - x1;
+      if (dot(df, df) > rsum * rsum) continue;
+    }
+    const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+    const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
     RawCon rc[4]; int n = 0;
-    if (t1 == FB_GEOM_PLANE) {
-      V3 pn = v3(AT(d.geom_xmat, 9 * g1 + 2), AT(d.geom_xmat, 9 * g1 + 5), AT(d.geom_xmat, 9 * g1 + 8));
-      if (dot(x2 - x1, pn) > margin + m.geom_rbound[g2]) continue;
+    if (plane) {
       V3 s2 = mld3(m.geom_size, g2);
       if (t2 == FB_GEOM_SPHERE) n = raw_plane_sphere(rc, margin, x1, pn, x2, s2.x);
       else { M3 R2 = ld9(d.geom_xmat, g2, d, e);
@@ -135,8 +148,6 @@ FB_DEV void kcol_p0(FB_COL_ARGS) {
         else if (t2 == FB_GEOM_CYLINDER) n = col_plane_cylinder(rc, margin, x1, pn, x2, R2, s2);
         else if (t2 == FB_GEOM_ELLIPSOID) n = col_plane_ellipsoid(rc, margin, x1, pn, x2, R2, s2); }
     } else {
-      V3 df = x2 - x1; float r = margin + m.geom_rbound[g1] + m.geom_rbound[g2];
-      if (dot(df, df) > r * r) continue;
       V3 s1 = mld3(m.geom_size, g1), s2 = mld3(m.geom_size, g2);
       if (t1 == FB_GEOM_SPHERE && t2 == FB_GEOM_SPHERE) n = raw_sphere_sphere(rc, margin, x1, s1.x, x2, s2.x);
       else if (t1 == FB_GEOM_SPHERE && t2 == FB_GEOM_CAPSULE) { M3 R2 = ld9(d.geom_xmat, g2, d, e); n = col_sphere_capsule(rc, margin, x1, s1.x, x2, R2, s2); }

@@ -115,13 +115,19 @@ template <bool SM> FB_DEV float ecol_val(const SolveMem& sm, int p, int a) {   /
   return kind == 2 ? SV(X_E1, r + a) : SV(X_E0, r + a);
 }
 
-// dst[r] = (addb ? b[r] : 0) + sum_j A[r][j] src[j] for this lane's rows; returns sum_r src[r]*(dst[r]-b[r]) partial
+// dst[r] = (addb ? b[r] : 0) + sum_j A[r][j] src[j] for this lane's rows; returns sum_r src[r]*(dst[r]-b[r]) partial.
+// A is the packed lower triangle: row r is contiguous up to the diagonal, below it the column is walked with a growing
+// stride (no index multiply / compare per element).
 template <bool SM> FB_DEVN float matvec_rows(const SolveMem sm, int n, int lane, int src, int dst, bool addb) {
   float acc = 0;
-  for (int r = lane; r < n; r += 32) {
+  const int st = SM ? 1 : sm.st;
+  NOUNROLL for (int r = lane; r < n; r += 32) {
     float s = 0;
-#pragma unroll 2
-    for (int j = 0; j < n; j++) s += AM(r, j) * SV(src, j);
+    const float* a = sm.A + TRI(r, 0) * st;
+    const float* x = &SV(src, 0);
+    for (int j = 0; j <= r; j++) s += a[j * st] * x[j * st];
+    int idx = TRI(r + 1, r);
+    for (int j = r + 1; j < n; j++) { s += sm.A[idx * st] * x[j * st]; idx += j + 1; }
     acc += SV(src, r) * s;
     SV(dst, r) = addb ? s + SV(S_B, r) : s;
   }
@@ -297,25 +303,30 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
     }
     WPAR_BEGIN WROWS { EFC(d.efc_force, r) = SV(W_F, r); AT(d.prev_lam, r) = SV(W_LAM, r); AT(d.prev_key, r) = AT(d.efc_key, r); } WPAR_END
   }
-  // ---- qfrc_constraint = J^T f, gathered per dof (race free)
+  // ---- qfrc_constraint = J^T f and Z^T f (the constraint part of qacc before the L^-1 sweep of the finish kernel).
+  // Row by row: the lanes take the dofs of the row's two ancestor chains (chain b without the part it shares with
+  // chain a), all distinct, and add into per-dof accumulators held in the work-vector slots that are free by now.
+  float* accj = &SV(W_R, 0);                     // slots W_R .. W_ADL  (4 * NCAP >= nv floats)
+  float* accz = &SV(W_P, 0);                     // slots W_P .. X_XQ
   WPAR_BEGIN
     if (lane == 0) { AT(d.niter, 0) = niter; if (d.do_integrate) AT(d.prev_n, 0) = n; }
-    NOUNROLL for (int k = lane; k < m.nv; k += 32) {
-      const int se = m.dof_subend[k];
-      float s = 0, sz = 0;
-      // a row touches dof k iff k is on the ancestor chain of one of its two end dofs; the loads are predicated, not
-      // branched around, so that several rows are in flight
-#pragma unroll 4
-      for (int r = 0; r < n; r++) {
-        int la = (int)SV(S_LA, r), lb = (int)SV(S_LB, r);
-        bool in = (k <= la && la <= se) || (k <= lb && lb <= se);
-        float jv = in ? EJ(d.efc_J, r, k) : 0.0f, zv = in ? EJ(d.efc_Z, r, k) : 0.0f, f = SV(W_F, r);
-        s += jv * f; sz += zv * f;
-      }
-      AT(d.qfrc_zf, k) = sz;                      // Z^T f: the constraint part of qacc before the L^-1 sweep (finish kernel)
-      AT(d.qfrc_constraint, k) = s;
-    }
+    NOUNROLL for (int k = lane; k < m.nv; k += 32) { accj[k] = 0; accz[k] = 0; }
   WPAR_END
+  NOUNROLL for (int r = 0; r < n; r++) {
+    const float f = SV(W_F, r);
+    if (f == 0.0f) continue;
+    const int la = (int)SV(S_LA, r), lb = (int)SV(S_LB, r);
+    const int na = la >= 0 ? m.dof_chainlen[la] : 0, nb = lb >= 0 ? m.dof_chainlen[lb] : 0;
+    WPAR_BEGIN
+      NOUNROLL for (int t = lane; t < na + nb; t += 32) {
+        int k;
+        if (t < na) k = m.dof_anc[m.dof_Madr[la] + t];
+        else { k = m.dof_anc[m.dof_Madr[lb] + t - na]; if (la >= 0 && k <= la && la <= m.dof_subend[k]) continue; }
+        accj[k] += EJ(d.efc_J, r, k) * f; accz[k] += EJ(d.efc_Z, r, k) * f;
+      }
+    WPAR_END
+  }
+  WPAR_BEGIN NOUNROLL for (int k = lane; k < m.nv; k += 32) { AT(d.qfrc_constraint, k) = accj[k]; AT(d.qfrc_zf, k) = accz[k]; } WPAR_END
 }
 
 // one env; `wsm` = this warp's shared-memory slice (FB_SOLVE_WARP_FLOATS floats)

@@ -71,6 +71,7 @@ struct DevModel {
   const float *geom_size, *geom_pos, *geom_quat, *geom_rbound, *geom_friction, *geom_solmix, *geom_solref, *geom_solimp,
       *geom_margin, *geom_gap;
   const int *pair_geom1, *pair_geom2;
+  const int* pair_info; const float* pair_rsum;   // packed broadphase record: g1 | g2 << 15 | plane << 30, margin + bounding radii
   int nchunk; const int* chunk_start;   // [nchunk+1] pair ranges, balanced by expected contact count
   // fluid geoms, sites, tendons, actuators, sensors
   const int *fluid_bodyid; const float *fluid_pos, *fluid_quat, *fluid_size, *fluid_coef;

@@ -185,7 +185,7 @@ static void launch_step1(FbSim* s) {
     case 6: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>>(s, K_POS, nm); break;
     default: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, nm);
   }
-  fb_launch<ShCol, Ph<kcol_p0>, Ph<kcol_p1>>(s, K_COL);
+  fb_launch<ShCol, Ph<kcol_stage>, Ph<kcol_p0>, Ph<kcol_p1>>(s, K_COL, (size_t)3 * s->m.ngeom);
   fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_NY * FB_ZCAP);
   fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL, (size_t)FB_PARTF);
 }
@@ -215,6 +215,7 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.npair = h->npair; m.nsite = h->nsite; m.ntendon = h->ntendon; m.nwrap = h->nwrap; m.nsensor = h->nsensor;
   m.nsensordata = h->nsensordata; m.nM = h->nM; m.nfluid = h->nfluid;
   m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.max_iter = 30; m.ls_iter = 12; m.ls_tolerance = 1e-3f;
+  if (h->nv > 4 * FB_SOLVE_NCAP) { s->err = "nv exceeds the solver's per-dof accumulator window (4 * FB_SOLVE_NCAP)"; return -3; }
   { const char* nc = getenv("FB_SOLVE_NCAP"); m.solve_ncap = nc ? atoi(nc) : FB_SOLVE_NCAP; if (m.solve_ncap > FB_SOLVE_NCAP) m.solve_ncap = FB_SOLVE_NCAP; }   // test hook: smaller cap -> global-memory path
   m.timestep = (float)h->opt_timestep; m.density = (float)h->opt_density; m.viscosity = (float)h->opt_viscosity;
   for (int i = 0; i < 3; i++) { m.gravity[i] = (float)h->opt_gravity[i]; m.wind[i] = (float)h->opt_wind[i]; }
@@ -326,6 +327,17 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.geom_solref = upf(s, h->geom_solref, 2 * ng); m.geom_solimp = upf(s, h->geom_solimp, 5 * ng);
   m.geom_margin = upf(s, h->geom_margin, ng); m.geom_gap = upf(s, h->geom_gap, ng);
   m.pair_geom1 = upi(s, h->pair_geom1, m.npair); m.pair_geom2 = upi(s, h->pair_geom2, m.npair);
+  { // packed broadphase record per pair: geoms + plane flag, and margin + bounding radii (plane pairs: of geom 2 only)
+    std::vector<int> pi((size_t)std::max(m.npair, 1), 0); std::vector<float> rs(std::max(m.npair, 1), 0.0f);
+    for (int k = 0; k < m.npair; k++) {
+      int g1 = h->pair_geom1[k], g2 = h->pair_geom2[k]; bool plane = h->geom_type[g1] == FB_GEOM_PLANE;
+      if (g1 >= 32768 || g2 >= 32768) { s->err = "too many geoms for the packed pair record"; return -3; }
+      pi[k] = g1 | (g2 << 15) | (plane ? (1 << 30) : 0);
+      double margin = std::max(h->geom_margin[g1], h->geom_margin[g2]);
+      rs[k] = (float)(margin + h->geom_rbound[g2] + (plane ? 0.0 : h->geom_rbound[g1]));
+    }
+    m.pair_info = up(s, pi); m.pair_rsum = up(s, rs);
+  }
   {  // chunk boundaries: plane pairs produce most contacts (up to 4 each), weight them 16x
     m.nchunk = FB_MAXCHUNK;
     std::vector<int> w(m.npair); long tot = 0;
