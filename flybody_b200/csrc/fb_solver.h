@@ -304,29 +304,29 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
     WPAR_BEGIN WROWS { EFC(d.efc_force, r) = SV(W_F, r); AT(d.prev_lam, r) = SV(W_LAM, r); AT(d.prev_key, r) = AT(d.efc_key, r); } WPAR_END
   }
   // ---- qfrc_constraint = J^T f and Z^T f (the constraint part of qacc before the L^-1 sweep of the finish kernel).
-  // Row by row: the lanes take the dofs of the row's two ancestor chains (chain b without the part it shares with
-  // chain a), all distinct, and add into per-dof accumulators held in the work-vector slots that are free by now.
-  float* accj = &SV(W_R, 0);                     // slots W_R .. W_ADL  (4 * NCAP >= nv floats)
-  float* accz = &SV(W_P, 0);                     // slots W_P .. X_XQ
+  // Lane l owns the dofs l, l + 32, l + 64, l + 96 (nv <= 128, checked in fb_create).  A row touches dof k iff k lies on
+  // the ancestor chain of one of its two end dofs.  The loads are unconditional (rows not touching k read row 0, always a
+  // valid address, and are discarded by a select), so two rows x four dofs x {J, Z} are in flight together.
   WPAR_BEGIN
     if (lane == 0) { AT(d.niter, 0) = niter; if (d.do_integrate) AT(d.prev_n, 0) = n; }
-    NOUNROLL for (int k = lane; k < m.nv; k += 32) { accj[k] = 0; accz[k] = 0; }
-  WPAR_END
-  NOUNROLL for (int r = 0; r < n; r++) {
-    const float f = SV(W_F, r);
-    if (f == 0.0f) continue;
-    const int la = (int)SV(S_LA, r), lb = (int)SV(S_LB, r);
-    const int na = la >= 0 ? m.dof_chainlen[la] : 0, nb = lb >= 0 ? m.dof_chainlen[lb] : 0;
-    WPAR_BEGIN
-      NOUNROLL for (int t = lane; t < na + nb; t += 32) {
-        int k;
-        if (t < na) k = m.dof_anc[m.dof_Madr[la] + t];
-        else { k = m.dof_anc[m.dof_Madr[lb] + t - na]; if (la >= 0 && k <= la && la <= m.dof_subend[k]) continue; }
-        accj[k] += EJ(d.efc_J, r, k) * f; accz[k] += EJ(d.efc_Z, r, k) * f;
+    float sj[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0}; int se[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; se[i] = k < m.nv ? m.dof_subend[k] : -1; }
+#pragma unroll 2
+    for (int r = 0; r < n; r++) {
+      const int la = (int)SV(S_LA, r), lb = (int)SV(S_LB, r); const float f = SV(W_F, r);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int k = lane + 32 * i;
+        const bool in = (k <= la && la <= se[i]) || (k <= lb && lb <= se[i]);
+        const int idx = in ? r * m.nv + k : 0;
+        const float vj = AT(d.efc_J, idx), vz = AT(d.efc_Z, idx);
+        sj[i] += in ? vj * f : 0.0f; sz[i] += in ? vz * f : 0.0f;
       }
-    WPAR_END
-  }
-  WPAR_BEGIN NOUNROLL for (int k = lane; k < m.nv; k += 32) { AT(d.qfrc_constraint, k) = accj[k]; AT(d.qfrc_zf, k) = accz[k]; } WPAR_END
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; if (k < m.nv) { AT(d.qfrc_constraint, k) = sj[i]; AT(d.qfrc_zf, k) = sz[i]; } }
+  WPAR_END
 }
 
 // one env; `wsm` = this warp's shared-memory slice (FB_SOLVE_WARP_FLOATS floats)
