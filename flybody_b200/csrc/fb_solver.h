@@ -115,19 +115,14 @@ template <bool SM> FB_DEV float ecol_val(const SolveMem& sm, int p, int a) {   /
   return kind == 2 ? SV(X_E1, r + a) : SV(X_E0, r + a);
 }
 
-// dst[r] = (addb ? b[r] : 0) + sum_j A[r][j] src[j] for this lane's rows; returns sum_r src[r]*(dst[r]-b[r]) partial.
-// A is the packed lower triangle: row r is contiguous up to the diagonal, below it the column is walked with a growing
-// stride (no index multiply / compare per element).
+// dst[r] = (addb ? b[r] : 0) + sum_j A[r][j] src[j] for this lane's rows; returns sum_r src[r]*(dst[r]-b[r]) partial
+// (one loop over j with a select for the packed index: splitting it at the diagonal makes the lanes diverge)
 template <bool SM> FB_DEVN float matvec_rows(const SolveMem sm, int n, int lane, int src, int dst, bool addb) {
   float acc = 0;
-  const int st = SM ? 1 : sm.st;
   NOUNROLL for (int r = lane; r < n; r += 32) {
     float s = 0;
-    const float* a = sm.A + TRI(r, 0) * st;
-    const float* x = &SV(src, 0);
-    for (int j = 0; j <= r; j++) s += a[j * st] * x[j * st];
-    int idx = TRI(r + 1, r);
-    for (int j = r + 1; j < n; j++) { s += sm.A[idx * st] * x[j * st]; idx += j + 1; }
+#pragma unroll 2
+    for (int j = 0; j < n; j++) s += AM(r, j) * SV(src, j);
     acc += SV(src, r) * s;
     SV(dst, r) = addb ? s + SV(S_B, r) : s;
   }
@@ -155,21 +150,25 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
     }
     if (SM) { int nt = TRI(n, 0); NOUNROLL for (int k = lane; k < nt; k += 32) sm.A[k] = AT(d.efc_A, k); }
     WPAR_END
-    // ---- warm start: the previous solve's forces (matched by row identity), kept if cheaper than lam = 0
-    WPAR_BEGIN float q = 0.5f * matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WSUM_PUT(0, q); WPAR_END
-    WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, false); WSUM_PUT(1, c); WPAR_END
-    float cost_ws = WSUM_GET(0) + WSUM_GET(1);
+    // ---- warm start: the previous solve's forces (matched by row identity), kept if cheaper than lam = 0.
+    // jar = b + A lam and quad = 1/2 lam^T A lam are carried along the iterations: a step lam += alpha dlam changes them by
+    // alpha * (A dlam) and alpha q1 + alpha^2 q2, both already known from the line search (the forces at the solution are
+    // recomputed from scratch after the loop)
     WPAR_BEGIN WROWS SV(W_JAR, r) = SV(S_B, r); WPAR_END
     WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, false); WSUM_PUT(0, c); WPAR_END
-    float cost0 = WSUM_GET(0);
+    const float cost0 = WSUM_GET(0);
     WPAR_BEGIN WPAR_END
-    if (!(cost_ws < cost0)) { WPAR_BEGIN WROWS SV(W_LAM, r) = 0; WPAR_END }
+    WPAR_BEGIN float q = 0.5f * matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WSUM_PUT(0, q); WPAR_END
+    WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, false); WSUM_PUT(1, c); WPAR_END
+    float quad = WSUM_GET(0);
+    const float cost_ws = quad + WSUM_GET(1);
+    WPAR_BEGIN WPAR_END
+    if (!(cost_ws < cost0)) { WPAR_BEGIN WROWS { SV(W_LAM, r) = 0; SV(W_JAR, r) = SV(S_B, r); } WPAR_END quad = 0; }
     // ---- Newton iterations
     NOUNROLL for (int iter = 0; iter < m.max_iter; iter++) {
-      WPAR_BEGIN float q = 0.5f * matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WSUM_PUT(0, q); WPAR_END
       WPAR_BEGIN float c = 0; WROWS if (IS_HEAD(r)) c += head_update<SM>(sm, r, true); WSUM_PUT(1, c); WPAR_END
       WPAR_BEGIN float rr = 0, ll = 0; WROWS { float f = SV(W_F, r), rv = SV(W_LAM, r) - f; SV(W_R, r) = rv; rr += rv * rv; ll += f * f; } WSUM_PUT(2, rr); WSUM_PUT(3, ll); WPAR_END
-      float quad = WSUM_GET(0), cost = quad + WSUM_GET(1);
+      float cost = quad + WSUM_GET(1);
       float rr = WSUM_GET(2), ll = WSUM_GET(3);
       WPAR_BEGIN WPAR_END              // all lanes have read RED before it is reused
       if (rr <= 1e-12f * (ll + 1e-30f)) break;
@@ -255,11 +254,12 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
         }
       }
       if (nodescent) break;                               // converged to fp32 resolution
-      WPAR_BEGIN WROWS SV(W_LAM, r) += alpha * SV(W_DL, r); WPAR_END
+      WPAR_BEGIN WROWS { SV(W_LAM, r) += alpha * SV(W_DL, r); SV(W_JAR, r) += alpha * SV(W_ADL, r); } WPAR_END
+      quad += alpha * q1 + alpha * alpha * q2;
       niter = iter + 1;
       // MuJoCo's absolute criterion, plus a relative one: Newton converges quadratically, so a step whose
       // improvement is below 1e-7 of the cost has already landed within fp32 resolution of the minimiser
-      if (scale * (cost - cbest) < m.tolerance || (cost - cbest) < 1e-7f * fabsf(cost)) break;
+      if (scale * (cost - cbest) < m.tolerance || (cost - cbest) < m.solve_rtol * fabsf(cost)) break;
     }
     // ---- forces at the solution: lam = f(b + A lam)
     WPAR_BEGIN matvec_rows<SM>(sm, n, lane, W_LAM, W_JAR, true); WPAR_END

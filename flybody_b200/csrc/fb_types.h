@@ -47,7 +47,7 @@
 struct DevModel {
   // sizes / options
   int nq, nv, nu, na, nbody, njnt, ngeom, npair, nsite, ntendon, nwrap, nsensor, nsensordata, nM, nfluid;
-  int noslip_iterations, cone_elliptic, max_iter, ls_iter, solve_ncap;
+  int noslip_iterations, cone_elliptic, max_iter, ls_iter, solve_ncap; float solve_rtol;
   float timestep, gravity[3], density, viscosity, wind[3], impratio, tolerance, noslip_tolerance, meaninertia, ls_tolerance;
   // tree partition
   int nroot, nlist;

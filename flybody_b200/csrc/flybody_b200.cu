@@ -216,6 +216,7 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.nsensordata = h->nsensordata; m.nM = h->nM; m.nfluid = h->nfluid;
   m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.max_iter = 30; m.ls_iter = 12; m.ls_tolerance = 1e-3f;
   if (h->nv > 4 * FB_SOLVE_NCAP) { s->err = "nv exceeds the solver's per-dof accumulator window (4 * FB_SOLVE_NCAP)"; return -3; }
+  { const char* rt = getenv("FB_SOLVE_RTOL"); m.solve_rtol = rt ? (float)atof(rt) : 1e-6f; }     // relative improvement that ends the Newton iteration (test hook)
   { const char* nc = getenv("FB_SOLVE_NCAP"); m.solve_ncap = nc ? atoi(nc) : FB_SOLVE_NCAP; if (m.solve_ncap > FB_SOLVE_NCAP) m.solve_ncap = FB_SOLVE_NCAP; }   // test hook: smaller cap -> global-memory path
   m.timestep = (float)h->opt_timestep; m.density = (float)h->opt_density; m.viscosity = (float)h->opt_viscosity;
   for (int i = 0; i < 3; i++) { m.gravity[i] = (float)h->opt_gravity[i]; m.wind[i] = (float)h->opt_wind[i]; }
