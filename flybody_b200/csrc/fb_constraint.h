@@ -346,9 +346,9 @@ FB_DEV void proj_chain(const DevModel& m, const DevData& d, int e, int r, int la
   }
   for (int p = 0; p < L; p++) {
     int k = m.dof_anc[adr0 + p], row = m.dof_Madr[k];
-    float zk = zc[p];
-    for (int q = p + 1; q < L; q++) zc[q] -= AT(d.qLD, row + (q - p)) * zk;
-    float zf = zk / sqrtf(AT(d.qLD, row));
+    float zk = zc[p], D = AT(d.qLD, row), zs = zk / D;          // unscaled rows: L[k][anc] z[k] = M'[k][anc] (z[k] / D[k])
+    for (int q = p + 1; q < L; q++) zc[q] -= AT(d.qLD, row + (q - p)) * zs;
+    float zf = zk / sqrtf(D);
     if (accumulate && in_chain(m, k, other_last)) EJ(d.efc_Z, r, k) += zf; else EJ(d.efc_Z, r, k) = zf;
   }
 }

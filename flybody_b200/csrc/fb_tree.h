@@ -157,16 +157,13 @@ FB_DEV void kpos_p2(FB_PHASE_ARGS) {
   if (carry_to >= 0) for (int k = 0; k < 10; k++) AT(d.crb10, 10 * carry_to + k) += carry[k];
   for (int k = 0; k < 10; k++) PART(y, k) = acc[k];
 }
-FB_DEV void kpos_p3(FB_PHASE_ARGS) {
+FB_DEV void kpos_p3(FB_PHASE_ARGS) {       // composite inertia of the root bodies: lanes over (root, component)
   float* part_ = sh_dyn(sh);
-  if (y != 0) return;
-  for (int r = 0; r < m.nroot; r++) {
-    int b = m.root_body[r];
-    for (int k = 0; k < 10; k++) {
-      float s = AT(d.inert10, 10 * b + k);
-      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) s += PART(l, k);
-      AT(d.crb10, 10 * b + k) = s;
-    }
+  for (int t = y; t < 10 * m.nroot; t += FB_NY) {
+    int r = t / 10, k = t - 10 * r, b = m.root_body[r];
+    float s = AT(d.inert10, 10 * b + k);
+    for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) s += PART(l, k);
+    AT(d.crb10, 10 * b + k) = s;
   }
 }
 // joint-space inertia entries of dof i (row of the sparse lower triangle along the ancestor chain)
@@ -187,12 +184,12 @@ FB_DEV void kpos_p4(FB_PHASE_ARGS) {      // all 32 lanes over the dofs
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   for (int i = y; i < m.nv; i += FB_NY) mass_row(m, d, e, lane, ldsh, i);
 }
-// Copy the factor held in shared memory out to `dst`.  The elimination leaves row k's off-diagonal entries unscaled
-// (M'[k][anc]); L[k][anc] = M'[k][anc] / D[k] is applied here, spread over all lanes, instead of in a per-step pass
-// (M_diag[k] = index of the row's diagonal, -1 for diagonals and for the root rows, which factor_root scales itself).
+// Copy the factor held in shared memory out to `dst`.  Convention of qLD / qLDe: the diagonal holds D[k], the off-diagonal
+// entries stay UNSCALED, M'[k][anc] = D[k] L[k][anc] -- every consumer multiplies a whole row by one 1/D[k] instead of
+// scaling each entry here.
 FB_DEV void ld_writeout(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* dst) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  for (int k = y; k < m.nM; k += FB_NY) { int dk = m.M_diag[k]; float v = LS(k); AT(dst, k) = dk < 0 ? v : v / LS(dk); }
+  for (int k = y; k < m.nM; k += FB_NY) AT(dst, k) = LS(k);
 }
 // re-initialise the shared rows with M + h*diag(damping) for the second factorisation (Euler with implicit damping)
 FB_DEV void ld_reinit_damped(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
@@ -276,7 +273,6 @@ FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, 
       int il = kl - t, adri = m.dof_Madr[d0 + il];
       float a = LS(adrk + t) * invD;
       for (int s = 0; s <= il; s++) LS(adri + s) -= a * LS(adrk + t + s);
-      LS(adrk + t) = a;
     }
   }
 }
@@ -330,7 +326,7 @@ FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (l >= m.nlist || step >= m.list_ndof[l]) return;
   int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
-  float xk = XS(k);
+  float xk = XS(k) / LDS(adrk);                    // rows are stored unscaled: L[k][anc] x[k] = M'[k][anc] (x[k] / D[k])
   for (int t = 1 + sub; t < len; t += FB_FSUB) XS(m.dof_ancslot[adrk + t]) -= LDS(adrk + t) * xk;
 }
 // root blocks: collect the lists' contributions, then the dense (<= 6x6) back / scale / forward substitution
@@ -349,7 +345,7 @@ FB_DEV void tsolve_root_a(FB_PHASE_ARGS) {       // x <- L^-T x inside the root 
   if (y >= m.nroot) return;
   int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
   for (int kl = nd - 1; kl >= 0; kl--) {
-    float xk = XS(d0 + kl); int adrk = m.dof_Madr[d0 + kl];
+    int adrk = m.dof_Madr[d0 + kl]; float xk = XS(d0 + kl) / LDS(adrk);
     for (int t = 1; t <= kl; t++) XS(d0 + kl - t) -= LDS(adrk + t) * xk;
   }
 }
@@ -359,9 +355,9 @@ FB_DEV void tsolve_root_c(FB_PHASE_ARGS) {       // x <- L^-1 x inside the root 
   int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
   for (int kl = 0; kl < nd; kl++) {
     int adrk = m.dof_Madr[d0 + kl];
-    float v = XS(d0 + kl);
-    for (int t = 1; t <= kl; t++) v -= LDS(adrk + t) * XS(d0 + kl - t);
-    XS(d0 + kl) = v;
+    float p = 0;
+    for (int t = 1; t <= kl; t++) p += LDS(adrk + t) * XS(d0 + kl - t);
+    XS(d0 + kl) -= p / LDS(adrk);
   }
 }
 FB_DEV void tsolve_scale(FB_PHASE_ARGS) {        // x <- D^-1 x
@@ -385,7 +381,7 @@ FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e,
   int k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step];
   float p = 0;
   for (int u = 0; u < FB_FSUB; u++) p += sh.red[y + u][lane];
-  XS(k) -= p;
+  XS(k) -= p / LDS(m.dof_Madr[k]);
 }
 // M^-1 = L^-1 D^-1 L^-T is applied in halves so that callers can work between them (the factor must have been issued
 // with tsolve_stage_issue by this warp):

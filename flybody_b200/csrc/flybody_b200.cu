@@ -300,9 +300,7 @@ static int build_model(FbSim* s, const FbModel* h) {
     m.dof_rootidx = up(s, rootidx); m.root_haslists = up(s, haslists);
   }
   { std::vector<int> adh(nb, -1); for (int i = 0; i < h->nu; i++) if (h->actuator_trntype[i] == FB_TRN_BODY) adh[h->actuator_trnid[i]] = i; m.body_adhesion = up(s, adh); }
-  { std::vector<int> mdiag(h->nM, -1); std::vector<float> mdamp(h->nM, 0.0f);
-    for (int i = 0; i < nv; i++) { int adr = h->dof_Madr[i]; mdamp[adr] = (float)h->dof_damping[i]; if (!disroot[i]) for (int t = 1; t < chainlen[i]; t++) mdiag[adr + t] = adr; }
-    m.M_diag = up(s, mdiag); m.M_damp = up(s, mdamp); }
+  { std::vector<float> mdamp(h->nM, 0.0f); for (int i = 0; i < nv; i++) mdamp[h->dof_Madr[i]] = (float)h->dof_damping[i]; m.M_damp = up(s, mdamp); }
   m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);
   // plain copies
   m.body_parentid = upi(s, h->body_parentid, nb); m.body_rootid = upi(s, h->body_rootid, nb);
