@@ -329,18 +329,3 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
   WPAR_END
 }
 
-// one env; `wsm` = this warp's shared-memory slice (FB_SOLVE_WARP_FLOATS floats)
-FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int e) {
-  const int n = AT(d.nefc, 0);
-  // the Jacobian / Z rows are only needed by the J^T f gather at the very end: request them now
-  WPAR_BEGIN for (int k = 32 * lane; k < n * m.nv; k += 32 * 32) { prefetch_l2(&AT(d.efc_J, k)); prefetch_l2(&AT(d.efc_Z, k)); } WPAR_END
-  SolveMem sm;
-  sm.red = wsm;
-  if (n <= m.solve_ncap) {
-    sm.v = wsm + 4 * 32; sm.A = sm.v + S_NSLOT * FB_SOLVE_NCAP; sm.G = sm.A + TRI(FB_SOLVE_NCAP, 0); sm.st = 1;
-    ksolve_impl<true>(m, d, sm, e, n);
-  } else {   // large problem: same code on the env's global record (row capacity FB_MAXEFC)
-    sm.v = &AT(d.efc_w, 0); sm.A = &AT(d.efc_A, 0); sm.G = &AT(d.efc_G, 0); sm.st = 1;
-    ksolve_impl<false>(m, d, sm, e, n);
-  }
-}

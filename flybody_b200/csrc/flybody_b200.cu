@@ -20,7 +20,7 @@
 #ifndef FB_EMU
 #include <cuda_runtime.h>
 #endif
-#include "fb_solver.h"
+#include "fb_solver_reg.h"
 
 #ifdef FB_EMU
 typedef int cudaStream_t_;
