@@ -105,7 +105,6 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
   LREG(float, lam); LREG(float, jar); LREG(float, f); LREG(float, res); LREG(float, dl); LREG(float, adl); LREG(float, e0); LREG(float, e1);
   LREG(float, j1); LREG(float, j2); LREG(float, hf1); LREG(float, hf2); LREG(float, he01); LREG(float, he02); LREG(float, he11); LREG(float, he12);
   LREG(float, ja1); LREG(float, ja2); LREG(float, jv1); LREG(float, jv2); LREG(float, tmp); LREG(float, tmp2); LREG(float, chg);
-  LREG(int, en0); LREG(int, en1); LREG(int, en2); LREG(int, en3);
   LREG(int, kind); LREG(int, state); LREG(int, hst); LREG(int, colx); LREG(int, la); LREG(int, lb);
   int niter = 0;
   if (n > 0) {
@@ -161,7 +160,7 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
           if (L(state) == 1) { ECR[c0] = lane; ECK[c0] = 0; }
           else if (L(state) == 2) { ECR[c0] = lane; ECK[c0] = 1; ECR[c0 + 1] = lane; ECK[c0 + 1] = 2; } } WPAR_END
       WPAR_BEGIN { int c1_ = SHF(colx, lane - 1), c2_ = SHF(colx, lane - 2); if (L(state) == 3) L(colx) = (L(kind) == 2) ? c1_ : c2_; } WPAR_END
-      // u = A r ; p = E^T u
+      // u = A r ; p = E^T u ; G = I + E^T A E (packed lower triangle)
       WPAR_BEGIN { float s; REG_MATVEC(s, res) Us[lane] = s; } WPAR_END
       WPAR_BEGIN
         NOUNROLL for (int p = lane; p < nc; p += 32) {
@@ -169,48 +168,30 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
           float pv = 0; NOUNROLL for (int a = 0; a < np; a++) pv += Ep[rp + a] * Us[rp + a];
           P[p] = pv;
         }
+        const int npairs = nc * (nc + 1) / 2;
+        NOUNROLL for (int t = lane; t < npairs; t += 32) {
+          int p = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+          while ((p + 1) * (p + 2) / 2 <= t) p++;
+          while (p * (p + 1) / 2 > t) p--;
+          int q = t - p * (p + 1) / 2;
+          int rp = ECR[p], np = ECK[p] == 0 ? 1 : 3, rq = ECR[q], nq = ECK[q] == 0 ? 1 : 3;
+          const float* Ep = ECK[p] == 2 ? E1s : E0s; const float* Eq = ECK[q] == 2 ? E1s : E0s;
+          float s = (p == q) ? 1.0f : 0.0f;
+          NOUNROLL for (int a = 0; a < np; a++) { float va = Ep[rp + a]; if (va == 0.0f) continue; NOUNROLL for (int bb = 0; bb < nq; bb++) s += va * A_(rp + a, rq + bb) * Eq[rq + bb]; }
+          GP(p, q) = s;
+        }
       WPAR_END
-      // G = I + E^T A E (packed lower triangle), one column of E at a time: w = A E_q over the rows (one value per lane,
-      // mirrored in shared memory), then G[p][q] = delta_pq + E_p . w for the lanes p >= q
-      NOUNROLL for (int q = 0; q < nc; q++) {
-        const int rq = ECR[q], kq = ECK[q], nq = kq == 0 ? 1 : 3;
-        WPAR_BEGIN { const float* Eq = kq == 2 ? E1s : E0s; float w = 0;
-            NOUNROLL for (int a = 0; a < nq; a++) w += A_(lane, rq + a) * Eq[rq + a];
-            Us[lane] = lane < n ? w : 0.0f; } WPAR_END
-        WPAR_BEGIN { const int p = q + lane;
-            if (p < nc) { int rp = ECR[p], kd = ECK[p], np = kd == 0 ? 1 : 3; const float* Ep = kd == 2 ? E1s : E0s;
-              float s = (p == q) ? 1.0f : 0.0f; NOUNROLL for (int a = 0; a < np; a++) s += Ep[rp + a] * Us[rp + a];
-              GP(p, q) = s; } } WPAR_END
-      }
-      // Cholesky G = L L^T with the forward substitution L y = p riding along.  Right-looking: after column j is scaled,
-      // every remaining entry takes its rank-1 update.  Each lane owns up to four entries of the packed triangle (decoded
-      // once), so a column costs O(1) per lane; more than 128 entries (nc > 15) fall back to the left-looking loop.
-      const int npairs = nc * (nc + 1) / 2;
-      if (npairs <= 128) {
-#define CH_DECODE(slot, var) { int t = lane + 32 * slot, v = -1; if (t < npairs) { int p = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f); \
-          while ((p + 1) * (p + 2) / 2 <= t) p++; while (p * (p + 1) / 2 > t) p--; v = (p << 8) | (t - p * (p + 1) / 2); } L(var) = v; }
-#define CH_SCALE(slot, var) { int v = L(var); if (v >= 0 && (v & 255) == j && (v >> 8) > j) G[lane + 32 * slot] /= dg; }
-#define CH_UPDATE(slot, var) { int v = L(var); if (v >= 0 && (v & 255) > j) G[lane + 32 * slot] -= GP(v >> 8, j) * GP(v & 255, j); }
-        WPAR_BEGIN { CH_DECODE(0, en0) CH_DECODE(1, en1) CH_DECODE(2, en2) CH_DECODE(3, en3) } WPAR_END
-        NOUNROLL for (int j = 0; j < nc; j++) {
-          const float dg = sqrtf(fmaxf(GP(j, j), 1e-12f)), yj = P[j] / dg;
-          WPAR_BEGIN { CH_SCALE(0, en0) if (npairs > 32) { CH_SCALE(1, en1) if (npairs > 64) { CH_SCALE(2, en2) CH_SCALE(3, en3) } } } WPAR_END
-          WPAR_BEGIN { CH_UPDATE(0, en0) if (npairs > 32) { CH_UPDATE(1, en1) if (npairs > 64) { CH_UPDATE(2, en2) CH_UPDATE(3, en3) } }
-            if (lane > j && lane < nc) P[lane] -= GP(lane, j) * yj;
-            if (lane == 0) { GP(j, j) = dg; XQ[j] = yj; } } WPAR_END
-        }
-      } else {
-        NOUNROLL for (int j = 0; j < nc; j++) {
-          WPAR_BEGIN NOUNROLL for (int i = j + lane; i < nc; i += 32) {
-              float t = GP(i, j); NOUNROLL for (int k = 0; k < j; k++) t -= GP(i, k) * GP(j, k);
-              GP(i, j) = t; }
-          WPAR_END
-          WPAR_BEGIN float dg = sqrtf(fmaxf(GP(j, j), 1e-12f));
-            NOUNROLL for (int i = j + 1 + lane; i < nc; i += 32) GP(i, j) = GP(i, j) / dg;
-            if (lane == 0) { float yv = P[j]; NOUNROLL for (int k = 0; k < j; k++) yv -= GP(j, k) * XQ[k]; XQ[j] = yv / dg; }
-          WPAR_END
-          WPAR_BEGIN if (lane == 0) GP(j, j) = sqrtf(fmaxf(GP(j, j), 1e-12f)); WPAR_END
-        }
+      // Cholesky G = L L^T, column by column; the forward substitution L y = p rides along (lane 0)
+      NOUNROLL for (int j = 0; j < nc; j++) {
+        WPAR_BEGIN NOUNROLL for (int i = j + lane; i < nc; i += 32) {
+            float t = GP(i, j); NOUNROLL for (int k = 0; k < j; k++) t -= GP(i, k) * GP(j, k);
+            GP(i, j) = t; }
+        WPAR_END
+        WPAR_BEGIN float dg = sqrtf(fmaxf(GP(j, j), 1e-12f));
+          NOUNROLL for (int i = j + 1 + lane; i < nc; i += 32) GP(i, j) = GP(i, j) / dg;
+          if (lane == 0) { float yv = P[j]; NOUNROLL for (int k = 0; k < j; k++) yv -= GP(j, k) * XQ[k]; XQ[j] = yv / dg; }
+        WPAR_END
+        WPAR_BEGIN if (lane == 0) GP(j, j) = sqrtf(fmaxf(GP(j, j), 1e-12f)); WPAR_END
       }
       NOUNROLL for (int j = nc - 1; j >= 0; j--) {     // backward: L^T out = y
         WPAR_BEGIN float xj = XQ[j] / GP(j, j);

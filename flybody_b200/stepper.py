@@ -42,7 +42,7 @@ class StepperError(RuntimeError):
 
 
 def load_library(path=None):
-    path = path or LIB_PATH
+    path = path or os.environ.get('FLYBODY_B200_LIB') or LIB_PATH      # the env override is for A/B timing of kernel variants
     if not os.path.exists(path):
         raise StepperError(
             f'CUDA stepper library not found at {path}. Build it with `python -c "import __graft_entry__ as g; '
