@@ -181,17 +181,17 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
           GP(p, q) = s;
         }
       WPAR_END
-      // Cholesky G = L L^T, column by column; the forward substitution L y = p rides along (lane 0)
+      // Cholesky G = L L^T, column by column (two warp barriers per column); the forward substitution L y = p rides
+      // along on lane 0
       NOUNROLL for (int j = 0; j < nc; j++) {
         WPAR_BEGIN NOUNROLL for (int i = j + lane; i < nc; i += 32) {
             float t = GP(i, j); NOUNROLL for (int k = 0; k < j; k++) t -= GP(i, k) * GP(j, k);
-            GP(i, j) = t; }
+            GP(i, j) = (i == j) ? sqrtf(fmaxf(t, 1e-12f)) : t; }
         WPAR_END
-        WPAR_BEGIN float dg = sqrtf(fmaxf(GP(j, j), 1e-12f));
+        WPAR_BEGIN const float dg = GP(j, j);
           NOUNROLL for (int i = j + 1 + lane; i < nc; i += 32) GP(i, j) = GP(i, j) / dg;
           if (lane == 0) { float yv = P[j]; NOUNROLL for (int k = 0; k < j; k++) yv -= GP(j, k) * XQ[k]; XQ[j] = yv / dg; }
         WPAR_END
-        WPAR_BEGIN if (lane == 0) GP(j, j) = sqrtf(fmaxf(GP(j, j), 1e-12f)); WPAR_END
       }
       NOUNROLL for (int j = nc - 1; j >= 0; j--) {     // backward: L^T out = y
         WPAR_BEGIN float xj = XQ[j] / GP(j, j);

@@ -393,11 +393,32 @@ FB_WARPFN void tsolve_a(const DevModel& m, const DevData& d, ShTree& sh, int e) 
   WPAR_BEGIN tsolve_b_gather(m, d, sh, e, 0, lane); WPAR_END
   WPAR_BEGIN tsolve_root_a(m, d, sh, e, 0, lane); WPAR_END
 }
+#ifdef __CUDACC__
+// GPU: the three partial dot products of a list are combined with two shuffles instead of a trip through shared memory
+// and a second barrier (the host emulation runs the lanes one after the other and keeps the two-section form)
+FB_DEV void tsolve_c_step_shfl(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+  float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
+  int l = y / FB_FSUB, sub = y % FB_FSUB;
+  const bool active = l < m.nlist && step < m.list_ndof[l];
+  float p = 0; int k = 0, adrk = 0;
+  if (active) {
+    k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step]; adrk = m.dof_Madr[k];
+    int len = m.dof_chainlen[k];
+    for (int t = 1 + sub; t < len; t += FB_FSUB) p += LDS(adrk + t) * XS(m.dof_anc[adrk + t]);
+  }
+  float p1 = __shfl_down_sync(0xffffffffu, p, 1), p2 = __shfl_down_sync(0xffffffffu, p, 2);
+  if (active && sub == 0) XS(k) -= (p + p1 + p2) / LDS(adrk);
+}
+#endif
 FB_WARPFN void tsolve_c(const DevModel& m, const DevData& d, ShTree& sh, int e) {
   WPAR_BEGIN tsolve_root_c(m, d, sh, e, 0, lane); WPAR_END
   for (int step = 0; step < m.max_list_ndof; step++) {
+#ifdef __CUDACC__
+    WPAR_BEGIN tsolve_c_step_shfl(m, d, sh, e, 0, lane, step); WPAR_END
+#else
     WPAR_BEGIN tsolve_c_step(m, d, sh, e, 0, lane, step); WPAR_END
     WPAR_BEGIN tsolve_c_fin(m, d, sh, e, 0, lane, step); WPAR_END
+#endif
   }
 }
 FB_WARPFN void tri_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) {
