@@ -783,7 +783,13 @@ FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int w, int y) {
 FB_DEV void kclear_hold(const DevModel& m, const DevData& d, int e, int y) { if (y == 0) AT(d.hold, 0) = 0; }
 // generic column scatter (fb_write_state / fb_set_ctrl): field[idx[c]] of env e <- vals[e][c]
 FB_DEV void kscatter(const DevModel& m, const DevData& d, int e, int y) {
-  if (e >= d.N && e < d.Np) { for (int c = y; c < d.sc_k; c += FB_NY) AT(d.sc_field, d.sc_idx ? d.sc_idx[c] : c) = d.sc_vals[c]; return; }   // pad envs mirror env 0
   if (e >= d.Np) return;
-  for (int c = y; c < d.sc_k; c += FB_NY) AT(d.sc_field, d.sc_idx ? d.sc_idx[c] : c) = d.sc_vals[(size_t)e * d.sc_k + c];
+  const int src = (e >= d.N) ? 0 : e;                  // pad envs mirror env 0
+  for (int c = y; c < d.sc_k; c += FB_NY) {
+    int t = d.sc_idx ? d.sc_idx[c] : c;
+    if (t < 0) continue;                                 // column without a target (e.g. a user action)
+    float v = d.sc_vals[(size_t)src * d.sc_k + c];
+    if (d.sc_nan0 && !(v == v)) v = 0.0f;                // NaN actions act as 0 (reference tasks/base.py:199)
+    AT(d.sc_field, t) = v;
+  }
 }

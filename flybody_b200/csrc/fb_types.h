@@ -119,7 +119,7 @@ struct DevData {
   float *sensordata, *sensor_sum;
   int *flags, *niter, *hold;   // hold != 0: env is not integrated by the next fb_step (pending reset)
   const int* rst_ids; const float* rst_qpos; const float* rst_qvel; int rst_n, rst_has_qvel, rst_hold;   // staged partial reset
-  float* sc_field; const int* sc_idx; const float* sc_vals; int sc_k;                                 // staged column scatter
+  float* sc_field; const int* sc_idx; const float* sc_vals; int sc_k, sc_nan0;                                 // staged column scatter
   float *obs;                  // packed AoS observation [N][obs_dim]
   int obs_dim;
   // task observation program (fb_obs_program): final observation rows [N][tobs_dim]

@@ -61,10 +61,14 @@ struct FbSim {
   int device; long long launches; float last_ms; std::string err;
   int first_substep; int hold_pending;
   int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
+  const int* act_map_dev; int n_action;
   int* op_step_dev; unsigned char* op_first_dev;
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
 #ifndef FB_EMU
   cudaStream_t stream; cudaEvent_t ev0, ev1;
+  struct StepGraph { cudaGraphExec_t exec; bool seen, failed; int n_sub; long long launches; DevData d; DevModel m; };
+  StepGraph graph[2];          // [hold pending?]
+  bool graphs_on;
 #endif
 };
 
@@ -475,6 +479,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
+  s->graphs_on = getenv("FB_NO_GRAPH") == nullptr;
 #endif
   int rc = build_model(s, hm);
   if (rc == 0) rc = alloc_data(s, n_envs);
@@ -493,6 +498,7 @@ int fb_destroy(FbHandle s) {
   if (!s) return -1;
 #ifndef FB_EMU
   cudaSetDevice(s->device); cudaStreamSynchronize(s->stream);
+  for (auto& g : s->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1); cudaStreamDestroy(s->stream);
 #endif
   for (void* p : s->allocs) dev_free(p);
@@ -537,12 +543,8 @@ int fb_forward(FbHandle s) {
   return sync_stream(s);
 }
 
-int fb_step(FbHandle s, int n_substeps) {
-  if (!s || n_substeps <= 0) return -1;
-#ifndef FB_EMU
-  cudaSetDevice(s->device);
-  cudaEventRecord(s->ev0, s->stream);
-#endif
+// the launch sequence of one control step: n x [ step2 ; step1 ], sensor accumulation restarted at the first substep
+static void step_sequence(FbSim* s, int n_substeps) {
   for (int k = 0; k < n_substeps; k++) {
     launch_step2(s, true);
     s->d.sens_mode = (k == 0) ? 1 : 0;
@@ -551,9 +553,56 @@ int fb_step(FbHandle s, int n_substeps) {
   }
   s->d.nsub_done = n_substeps;
   if (s->hold_pending) { fb_launch<ShNone, Ph<ph_clear_hold>>(s, K_MISC); s->hold_pending = 0; }
+}
 #ifndef FB_EMU
+// Kernel parameters (DevModel, DevData by value) are frozen into a captured graph, so a graph is reused only while the
+// parts of the handle state that the step kernels read are unchanged; staging pointers of scatter / reset launches are not
+// read by them and are masked out of the comparison.
+static DevData canonical(const DevData& d) {
+  DevData c = d;
+  c.sc_field = nullptr; c.sc_idx = nullptr; c.sc_vals = nullptr; c.sc_k = 0; c.sc_nan0 = 0;
+  c.rst_ids = nullptr; c.rst_qpos = nullptr; c.rst_qvel = nullptr; c.rst_n = 0; c.rst_has_qvel = 0; c.rst_hold = 0;
+  return c;
+}
+#endif
+int fb_step(FbHandle s, int n_substeps) {
+  if (!s || n_substeps <= 0) return -1;
+#ifndef FB_EMU
+  cudaSetDevice(s->device);
+  cudaEventRecord(s->ev0, s->stream);
+  // The 7 n launches of a control step are replayed from a CUDA graph: captured the second time the same (n_substeps,
+  // hold) signature is stepped with unchanged handle state, so the first call still runs (and configures) plain launches.
+  const int hold = s->hold_pending ? 1 : 0;
+  bool done = false;
+  if (s->graphs_on && !s->prof_on) {
+    DevData c = canonical(s->d);
+    FbSim::StepGraph& g = s->graph[hold];
+    const bool same = g.seen && g.n_sub == n_substeps && memcmp(&c, &g.d, sizeof(DevData)) == 0 && memcmp(&s->m, &g.m, sizeof(DevModel)) == 0;
+    if (same && g.exec) {
+      if (cudaGraphLaunch(g.exec, s->stream) == cudaSuccess) {
+        s->d.do_integrate = 1; s->d.sens_mode = -1; s->d.nsub_done = n_substeps; s->hold_pending = 0; s->launches += g.launches;
+        done = true;
+      } else { cudaGetLastError(); cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = false; }
+    } else if (same && !g.failed) {
+      long long l0 = s->launches; cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        step_sequence(s, n_substeps);
+        cudaError_t e1 = cudaStreamEndCapture(s->stream, &graph);
+        if (e1 == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess && cudaGraphLaunch(g.exec, s->stream) == cudaSuccess) {
+          g.launches = s->launches - l0; done = true;
+        } else { cudaGetLastError(); g.exec = nullptr; g.failed = true; s->launches = l0; s->hold_pending = hold; }
+        if (graph) cudaGraphDestroy(graph);
+      } else { cudaGetLastError(); g.failed = true; }
+    } else {
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+      g.seen = true; g.n_sub = n_substeps; g.d = c; g.m = s->m;
+    }
+  }
+  if (!done) step_sequence(s, n_substeps);
   cudaEventRecord(s->ev1, s->stream);
   if (cudaGetLastError() != cudaSuccess) { s->err = "kernel launch failed"; return -2; }
+#else
+  step_sequence(s, n_substeps);
 #endif
   return 0;
 }
@@ -660,20 +709,30 @@ int fb_set(FbHandle s, int field, const float* src) {
 }
 
 // scatter vals[N][k] (already on the device, row-major) into columns idx[k] (device ints, or NULL = 0..k-1) of `field`
-static void launch_scatter(FbSim* s, float* field, const int* idx_dev, const float* vals_dev, int k) {
-  s->d.sc_field = field; s->d.sc_idx = idx_dev; s->d.sc_vals = vals_dev; s->d.sc_k = k;
+static void launch_scatter(FbSim* s, float* field, const int* idx_dev, const float* vals_dev, int k, int nan_to_zero = 0) {
+  s->d.sc_field = field; s->d.sc_idx = idx_dev; s->d.sc_vals = vals_dev; s->d.sc_k = k; s->d.sc_nan0 = nan_to_zero;
   fb_launch<ShNone, Ph<ph_scatter>>(s, K_MISC);
 }
 
 int fb_set_ctrl(FbHandle s, const float* ctrl, int is_device) {
   if (!s || !ctrl) return -1;
   const float* src = ctrl;
+  const int k = s->act_map_dev ? s->n_action : s->m.nu;     // row length: actions (mapped on the device) or ctrl
   if (!is_device) {
-    if (ensure_stage(s, (size_t)s->d.N * s->m.nu, 0) != 0) { s->err = "out of device memory (staging)"; return -4; }
-    upload_async(s, s->stage, ctrl, sizeof(float) * (size_t)s->d.N * s->m.nu);
+    if (ensure_stage(s, (size_t)s->d.N * std::max(k, s->m.nu), 0) != 0) { s->err = "out of device memory (staging)"; return -4; }
+    upload_async(s, s->stage, ctrl, sizeof(float) * (size_t)s->d.N * k);
     src = s->stage;
   }
-  launch_scatter(s, s->d.ctrl, nullptr, src, s->m.nu);
+  launch_scatter(s, s->d.ctrl, s->act_map_dev, src, k, s->act_map_dev ? 1 : 0);
+  return 0;
+}
+int fb_set_action_map(FbHandle s, const int32_t* ctrl_index, int n_action) {
+  if (!s) return -1;
+  if (!ctrl_index || n_action <= 0) { s->act_map_dev = nullptr; s->n_action = 0; return 0; }      // back to plain ctrl rows
+  for (int c = 0; c < n_action; c++) if (ctrl_index[c] >= s->m.nu) { s->err = "fb_set_action_map: ctrl index out of range"; return -1; }
+  if (sync_stream(s) != 0) return -2;
+  std::vector<int> v(ctrl_index, ctrl_index + n_action);
+  s->act_map_dev = up(s, v); s->n_action = n_action;
   return 0;
 }
 

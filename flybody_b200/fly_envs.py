@@ -314,6 +314,11 @@ class BatchedFlyEnv:
                 self._action_indices[key] = np.arange(len(idx), len(idx) + len(ci[key]))
                 idx.extend(ci[key])
         self._ctrl_of_action = np.asarray(idx, np.int64)
+        # walking: actions go to the device as they are, the action -> ctrl permutation and NaN -> 0 run in the scatter
+        # kernel (fb_set_action_map); flight keeps the host path because the wing actions are modified by the WBPG first
+        self._device_action_map = variant == 'walk'
+        if self._device_action_map:
+            self._sim.set_action_map(self._ctrl_of_action)
         names = [m.meta['actuator_names'][i].split('/')[-1] for i in idx] + [f'user_{i}' for i in range(self._n_user)]
         rng = m.actuator_ctrlrange[idx]
         lo = np.concatenate([rng[:, 0], -np.ones(self._n_user)])
@@ -499,7 +504,10 @@ class BatchedFlyEnv:
     def step(self, action):
         m = self.model
         N = self.n_envs
-        action = np.array(action, np.float64, copy=True).reshape(N, -1)
+        if self._device_action_map:
+            action = np.asarray(action, np.float32).reshape(N, -1)          # not modified on the host
+        else:
+            action = np.array(action, np.float64, copy=True).reshape(N, -1)
         assert action.shape[1] == self._action_spec.shape[0], f'action must have {self._action_spec.shape[0]} entries'
         # auto-reset of envs whose last step was LAST (composer.Environment semantics); their action is ignored
         resetting = self._needs_reset.copy()
@@ -522,12 +530,16 @@ class BatchedFlyEnv:
             action[:, wi] += target - self._wing_qpos_host
         self._sim.write_state(st.QPOS, np.arange(self._ghost_q, self._ghost_q + 7), ghost[:, :7])
         self._sim.write_state(st.QVEL, np.arange(self._ghost_v, self._ghost_v + 6), ghost[:, 7:])
-        action[np.isnan(action)] = 0.0
         self._step_counter += np.where(resetting, 0, 1)
-        ctrl = np.zeros((N, m.nu), np.float32)
-        ctrl[:, self._ctrl_of_action] = action[:, :len(self._ctrl_of_action)]
-        self._sim.set_control(ctrl)
-        self.h2d_bytes_per_step = ctrl.nbytes + ghost.nbytes
+        if self._device_action_map:
+            self._sim.set_control(action)
+            self.h2d_bytes_per_step = action.nbytes + ghost.nbytes
+        else:
+            action[np.isnan(action)] = 0.0
+            ctrl = np.zeros((N, m.nu), np.float32)
+            ctrl[:, self._ctrl_of_action] = action[:, :len(self._ctrl_of_action)]
+            self._sim.set_control(ctrl)
+            self.h2d_bytes_per_step = ctrl.nbytes + ghost.nbytes
         # n_sub_steps x physics.step()
         self._sim.task_inputs(self._step_counter, resetting)
         self._sim.step(self._n_sub)

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libflybody_b200.so')
  QFRC_BIAS, QFRC_ACTUATOR, CONTACT, EFC_FORCE, FLAGS) = range(26)
 MAXCON, MAXEFC = 64, 160
 
-EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_write_state', 'fb_step', 'fb_forward',
+EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_set_action_map', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_record_stride', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
            'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
@@ -53,6 +53,7 @@ def load_library(path=None):
     lib.fb_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.fb_reset_hold.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.fb_set_ctrl.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.fb_set_action_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.fb_write_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_step.argtypes = [C.c_void_p, C.c_int]
     lib.fb_forward.argtypes = [C.c_void_p]
@@ -130,7 +131,8 @@ class BatchedStepper:
 
     def set_control(self, ctrl):
         """physics.set_control (reference fruitfly.py:540-544), ctrl [N, nu] (or [nu], broadcast)."""
-        c = np.ascontiguousarray(np.broadcast_to(np.asarray(ctrl, np.float32), (self.n_envs, self.model.nu)))
+        k = getattr(self, '_n_ctrl_cols', self.model.nu)      # action columns after set_action_map, else nu
+        c = np.ascontiguousarray(np.broadcast_to(np.asarray(ctrl, np.float32), (self.n_envs, k)))
         self._check(self._lib.fb_set_ctrl(self._h, c.ctypes.data, 0), 'fb_set_ctrl')
 
     def write_state(self, field, idx, vals):
@@ -152,6 +154,16 @@ class BatchedStepper:
         qv = None if qvel is None else np.ascontiguousarray(np.broadcast_to(np.asarray(qvel, np.float32), (len(ids), self.model.nv)))
         self._check(self._lib.fb_reset_hold(self._h, ids.ctypes.data, len(ids), qp.ctypes.data,
                                             None if qv is None else qv.ctypes.data), 'fb_reset_hold')
+
+    def set_action_map(self, ctrl_index):
+        """fb_set_action_map: afterwards set_control takes rows in action order (see the header)."""
+        if ctrl_index is None:
+            self._n_ctrl_cols = self.model.nu
+            self._check(self._lib.fb_set_action_map(self._h, None, 0), 'fb_set_action_map')
+            return
+        idx = np.ascontiguousarray(ctrl_index, np.int32)
+        self._check(self._lib.fb_set_action_map(self._h, idx.ctypes.data, len(idx)), 'fb_set_action_map')
+        self._n_ctrl_cols = len(idx)
 
     def step(self, n_substeps):
         self._check(self._lib.fb_step(self._h, int(n_substeps)), 'fb_step')

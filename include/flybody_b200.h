@@ -204,6 +204,10 @@ int fb_reset_hold(FbHandle h, const int32_t* env_ids, int n, const float* qpos, 
 /* physics.set_control(ctrl) (fruitfly.py:540-544).  ctrl: contiguous rows [N][nu], on the host
  * (is_device=0, copied asynchronously on the handle's stream) or already on the device (is_device=1). */
 int fb_set_ctrl(FbHandle h, const float* ctrl, int is_device);
+/* FruitFly.apply_action (fruitfly.py:532-544) on the device: after this call fb_set_ctrl takes rows [N][n_action] in the
+ * environment's ACTION order; ctrl_index[c] is the ctrl slot of action c (-1: no actuator, e.g. a user action), NaN
+ * actions are applied as 0 (tasks/base.py:197-201).  ctrl_index == NULL restores plain ctrl rows.                  */
+int fb_set_action_map(FbHandle h, const int32_t* ctrl_index, int n_action);
 
 /* walker.set_pose / set_velocity on a subset of coordinates (walk_imitation.py:141-145):
  * field in {FB_QPOS, FB_QVEL, FB_ACT}; vals is [N][k] AoS host, written to coordinates idx[k]

@@ -179,3 +179,23 @@ def test_flight_env_good_termination_at_trajectory_end(emu):
         assert n < 400
     # either the end of the reference (discount 1) or, for a passive fly that sinks, the height limit (discount 0)
     assert (n == 194 and ts.discount == 1.0) or (n < 194 and ts.discount == 0.0)
+
+
+def test_action_map_on_device_matches_host_permutation(emu):
+    """fb_set_action_map (FruitFly.apply_action on the device): actions in action order + NaN -> 0 give the same ctrl as
+    the host-side permutation (fruitfly.py:532-544, tasks/base.py:197-201)."""
+    from flybody_b200 import stepper as st
+    from flybody_b200.flymodel import load_model
+    m = load_model('walk')
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=3, lib_path=emu)
+    env.reset()
+    rs = np.random.RandomState(1)
+    a = rs.uniform(-0.5, 0.5, (3, 59))
+    a[1, 7] = np.nan
+    env.step(a)
+    ctrl = env._sim.get(st.CTRL)
+    want = np.zeros((3, m.nu), np.float32)
+    want[:, env._ctrl_of_action] = np.nan_to_num(a, nan=0.0)
+    rng = m.actuator_ctrlrange
+    assert np.allclose(ctrl, want, atol=1e-7)
+    assert want[1, env._ctrl_of_action[7]] == 0.0
