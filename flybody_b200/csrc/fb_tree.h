@@ -15,7 +15,7 @@
 //   LS    [nM]               the joint-space inertia / its factor                                     -- pos
 //   XS    [nv + FB_ROOTD*nlist], LDS [nM]   right-hand side and staged factor of the triangular solves -- smooth, finish
 struct ShTree { float red[FB_NY][FB_LANES]; };
-#define FB_PARTK 12
+#define FB_PARTK 21
 #define FB_PARTF (FB_NY * FB_PARTK * FB_LANES)
 #define PART(yy, k) part_[((yy) * FB_PARTK + (k)) * FB_LANES + lane]
 
@@ -172,12 +172,12 @@ FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int lane, float
   I10 I = ld10(d.crb10, b, d, e);
   V3 L, p;
   inert_mul(I, ld3(d.Sang, i, d, e), ld3(d.Slin, i, d, e), L, p);
-  int adr = m.dof_Madr[i], lsadr = m.dof_LSadr[i];
+  int adr = m.dof_Madr[i];
   int t = 0;
   for (int j = i; j >= 0; j = m.dof_parentid[j], t++) {
     float v = dot(ld3(d.Sang, j, d, e), L) + dot(ld3(d.Slin, j, d, e), p);
     if (t == 0) v += m.dof_armature[i];
-    AT(d.qM, adr + t) = v; LS(lsadr + t) = v;
+    AT(d.qM, adr + t) = v; LS(adr + t) = v;
   }
 }
 FB_DEV void kpos_p4(FB_PHASE_ARGS) {      // all 32 lanes over the dofs
@@ -189,27 +189,16 @@ FB_DEV void kpos_p4(FB_PHASE_ARGS) {      // all 32 lanes over the dofs
 // scaling each entry here.
 FB_DEV void ld_writeout(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, float* dst) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  for (int k = y; k < m.nM; k += FB_NY) AT(dst, k) = LS(m.M_ls[k]);
+  for (int k = y; k < m.nM; k += FB_NY) AT(dst, k) = LS(k);
 }
 // re-initialise the shared rows with M + h*diag(damping) for the second factorisation (Euler with implicit damping)
 FB_DEV void ld_reinit_damped(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  for (int k = y; k < m.nM; k += FB_NY) LS(m.M_ls[k]) = AT(d.qM, k) + m.timestep * m.M_damp[k];
+  for (int k = y; k < m.nM; k += FB_NY) LS(k) = AT(d.qM, k) + m.timestep * m.M_damp[k];
 }
 
-// x[0..3] -= a * y[0..3] on 16-byte aligned shared memory
-FB_DEV void ls_axpy4(float* x, const float* y, float a) {
-#if defined(__CUDACC__) && FB_LANES == 1
-  float4 xv = *reinterpret_cast<float4*>(x); const float4 yv = *reinterpret_cast<const float4*>(y);
-  xv.x -= a * yv.x; xv.y -= a * yv.y; xv.z -= a * yv.z; xv.w -= a * yv.w;
-  *reinterpret_cast<float4*>(x) = xv;
-#else
-  for (int i = 0; i < 4; i++) x[i * FB_LANES] -= a * y[i * FB_LANES];
-#endif
-}
 // sparse L^T D L factorisation (Featherstone; MuJoCo mj_factorM).  Row k of LD holds (k,k), (k,parent(k)), ...
-// at dof_Madr[k] + t in the record and at dof_LSadr[k] + t in shared memory (rows padded in front so that they END on
-// 16-byte boundaries: the tail of row k and the whole row of an ancestor are then aligned alike).  The lists advance in lock-step, one dof per step (deepest first); FB_FSUB lanes share a
+// at dof_Madr[k] + t.  The lists advance in lock-step, one dof per step (deepest first); FB_FSUB lanes share a
 // list and split the rank-1 update of the ancestor rows of that dof.  Updates that land in the root block are
 // summed into sh.part (21 entries per lane) and applied by the root lane afterwards.
 #define FB_FSUB 3
@@ -218,33 +207,35 @@ FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, 
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   int l = y / FB_FSUB, sub = y % FB_FSUB;
   if (l >= m.nlist || step >= m.list_ndof[l]) return;
-  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_LSadr[k], madrk = m.dof_Madr[k], len = m.dof_chainlen[k];
+  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
   float invD = 1.0f / LS(adrk);
   // non-root ancestor rows are dealt round-robin to the FB_FSUB lanes of the list (dof_anc[adrk + t] = t-th ancestor
   // of k; the root's dofs are the tail of every chain and are handled by factor_root_accum)
   const int tend = 1 + m.dof_depth[k];
   for (int t = 1 + sub; t < tend; t += FB_FSUB) {
-    int i = m.dof_anc[madrk + t];
+    int i = m.dof_anc[adrk + t];
     float a = LS(adrk + t) * invD;
-    int adri = m.dof_LSadr[i], li = len - t;                 // chain of i = tail of the chain of k
-    // the rows end on 16-byte boundaries in shared memory (dof_LSadr), so source and target have the same alignment:
-    // up to three leading scalars, then float4 AXPYs
+    int adri = m.dof_Madr[i], li = len - t;                 // chain of i = tail of the chain of k
     int s2 = 0;
-    for (; s2 < (li & 3); s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
-    for (; s2 < li; s2 += 4) ls_axpy4(&LS(adri + s2), &LS(adrk + t + s2), a);
+    for (; s2 + 4 <= li; s2 += 4) {                          // batched so that the loads are in flight together
+      float r0 = LS(adrk + t + s2), r1 = LS(adrk + t + s2 + 1), r2 = LS(adrk + t + s2 + 2), r3 = LS(adrk + t + s2 + 3);
+      float x0 = LS(adri + s2), x1 = LS(adri + s2 + 1), x2 = LS(adri + s2 + 2), x3 = LS(adri + s2 + 3);
+      LS(adri + s2) = x0 - a * r0; LS(adri + s2 + 1) = x1 - a * r1; LS(adri + s2 + 2) = x2 - a * r2; LS(adri + s2 + 3) = x3 - a * r3;
+    }
+    for (; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
   }
 }
 // Root blocks.  Once the lists are eliminated, row k of a non-root dof holds its final (unscaled) coupling r_k to the
 // root's dofs and D_k; the Schur update of the root block is sum_k r_k r_k^T / D_k.  32 lanes split the dofs, each
 // accumulates the 21 packed lower-triangle entries in registers ...
-FB_DEV void factor_root_accum(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int r, int pass) {
+FB_DEV void factor_root_accum(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int r) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF;
   float acc[21];
 #pragma unroll
   for (int j = 0; j < 21; j++) acc[j] = 0;
   for (int k = y; k < m.nv; k += FB_NY) {
     if (m.dof_rootidx[k] != r) continue;
-    int adrk = m.dof_LSadr[k], len = m.dof_chainlen[k], nr = len - 1 - m.dof_depth[k];
+    int adrk = m.dof_Madr[k], len = m.dof_chainlen[k], nr = len - 1 - m.dof_depth[k];
     float invD = 1.0f / LS(adrk), rr[FB_ROOTD6];
 #pragma unroll
     for (int il = 0; il < FB_ROOTD6; il++) rr[il] = il < nr ? LS(adrk + len - 1 - il) : 0.0f;     // coupling to root dof il
@@ -255,22 +246,20 @@ FB_DEV void factor_root_accum(const DevModel& m, const DevData& d, ShTree& sh, i
       for (int j = 0; j <= i; j++) acc[i * (i + 1) / 2 + (i - j)] += a * rr[j];                   // row i, (i-j)-th ancestor
     }
   }
-  // the 21 sums leave through FB_PARTK = 12 slots per lane in two passes (entries 0..11, then 12..20)
 #pragma unroll
-  for (int j = 0; j < 21; j++) if (j / FB_PARTK == pass) PART(y, j % FB_PARTK) = acc[j];
+  for (int j = 0; j < 21; j++) PART(y, j) = acc[j];
 }
-// ... the lanes add the partials up (one packed entry each) ...
-FB_DEV void factor_root_gather(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int r, int pass) {
+// ... 21 lanes add the partials up (one packed entry each) ...
+FB_DEV void factor_root_gather(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int r) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF;
-  const int ent = pass * FB_PARTK + y;
-  if (y >= FB_PARTK || ent >= 21) return;
-  int il = 0; while ((il + 1) * (il + 2) / 2 <= ent) il++;
-  int s = ent - il * (il + 1) / 2;
+  if (y >= 21) return;
+  int il = 0; while ((il + 1) * (il + 2) / 2 <= y) il++;
+  int s = y - il * (il + 1) / 2;
   int b = m.root_body[r], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
   if (il >= nd) return;
   float acc = 0;
   for (int l = 0; l < FB_NY; l++) acc += PART(l, y);
-  LS(m.dof_LSadr[d0 + il] + s) -= acc;
+  LS(m.dof_Madr[d0 + il] + s) -= acc;
 }
 // ... then one lane per root body factors its dense (<= 6x6) block
 FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y) {
@@ -278,10 +267,10 @@ FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, 
   if (y >= m.nroot) return;
   int b = m.root_body[y], nd = m.body_dofnum[b], d0 = m.body_dofadr[b];
   for (int kl = nd - 1; kl >= 0; kl--) {
-    int adrk = m.dof_LSadr[d0 + kl];
+    int adrk = m.dof_Madr[d0 + kl];
     float invD = 1.0f / LS(adrk);
     for (int t = 1; t <= kl; t++) {
-      int il = kl - t, adri = m.dof_LSadr[d0 + il];
+      int il = kl - t, adri = m.dof_Madr[d0 + il];
       float a = LS(adrk + t) * invD;
       for (int s = 0; s <= il; s++) LS(adri + s) -= a * LS(adrk + t + s);
     }
@@ -294,10 +283,8 @@ FB_WARPFN void kpos_factor(const DevModel& m, const DevData& d, ShTree& sh, int 
   }
   for (int r = 0; r < m.nroot; r++) {
     if (!m.root_haslists[r]) continue;
-    for (int pass = 0; pass < 2; pass++) {
-      WPAR_BEGIN factor_root_accum(m, d, sh, e, 0, lane, r, pass); WPAR_END
-      WPAR_BEGIN factor_root_gather(m, d, sh, e, 0, lane, r, pass); WPAR_END
-    }
+    WPAR_BEGIN factor_root_accum(m, d, sh, e, 0, lane, r); WPAR_END
+    WPAR_BEGIN factor_root_gather(m, d, sh, e, 0, lane, r); WPAR_END
   }
   WPAR_BEGIN factor_root(m, d, sh, e, 0, lane); WPAR_END
 }

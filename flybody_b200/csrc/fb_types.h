@@ -63,7 +63,6 @@ struct DevModel {
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
   const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen, *dof_anc /* [nM] t-th ancestor of the row's dof */, *dof_ancslot /* same, as shared-memory slot of tri_solve */;
   const int *dof_rootidx /* root (index into root_body) a list dof hangs off, -1 for root dofs */, *root_haslists;
-  const int *dof_LSadr, *M_ls; int nLS;     // rows of the inertia in shared memory during the factorisation (rows end 16-byte aligned)
   const float* M_damp;         // per entry of the packed inertia: joint damping on the diagonals, 0 elsewhere
   const int* body_adhesion;    // adhesion actuator acting on the body, or -1
   const float *dof_armature, *dof_damping, *dof_invweight0;

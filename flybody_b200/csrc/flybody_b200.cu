@@ -179,7 +179,7 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 
 static void launch_step1(FbSim* s) {
   static int pos_trunc = getenv("FB_POS_TRUNC") ? atoi(getenv("FB_POS_TRUNC")) : 0;     // profiling aid: run only a prefix of the phases
-  size_t nm = (size_t)FB_PARTF + (size_t)s->m.nLS;
+  size_t nm = (size_t)FB_PARTF + (size_t)s->m.nM;
   switch (pos_trunc) {
     case 1: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>>(s, K_POS, nm); break;
     case 2: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>>(s, K_POS, nm); break;
@@ -304,12 +304,6 @@ static int build_model(FbSim* s, const FbModel* h) {
     m.dof_rootidx = up(s, rootidx); m.root_haslists = up(s, haslists);
   }
   { std::vector<int> adh(nb, -1); for (int i = 0; i < h->nu; i++) if (h->actuator_trntype[i] == FB_TRN_BODY) adh[h->actuator_trnid[i]] = i; m.body_adhesion = up(s, adh); }
-  { // shared-memory placement of the inertia rows during the factorisation: padded in front so that every row ends on a
-    // 16-byte boundary; M_ls maps a packed index to its shared slot
-    std::vector<int> lsadr(nv), mls(h->nM); int off = 0;
-    for (int i = 0; i < nv; i++) { int len = chainlen[i]; off += (4 - (off + len) % 4) % 4; lsadr[i] = off; for (int t = 0; t < len; t++) mls[h->dof_Madr[i] + t] = off + t; off += len; }
-    m.dof_LSadr = up(s, lsadr); m.M_ls = up(s, mls); m.nLS = off;
-  }
   { std::vector<float> mdamp(h->nM, 0.0f); for (int i = 0; i < nv; i++) mdamp[h->dof_Madr[i]] = (float)h->dof_damping[i]; m.M_damp = up(s, mdamp); }
   m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);
   // plain copies
