@@ -178,17 +178,8 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 }
 
 static void launch_step1(FbSim* s) {
-  static int pos_trunc = getenv("FB_POS_TRUNC") ? atoi(getenv("FB_POS_TRUNC")) : 0;     // profiling aid: run only a prefix of the phases
   size_t nm = (size_t)FB_PARTF + (size_t)s->m.nM;
-  switch (pos_trunc) {
-    case 1: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>>(s, K_POS, nm); break;
-    case 2: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>>(s, K_POS, nm); break;
-    case 3: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>>(s, K_POS, nm); break;
-    case 4: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>>(s, K_POS, nm); break;
-    case 5: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>>(s, K_POS, nm); break;
-    case 6: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>>(s, K_POS, nm); break;
-    default: fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, nm);
-  }
+  fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, nm);
   fb_launch<ShCol, Ph<kcol_stage>, Ph<kcol_p0>, Ph<kcol_p1>>(s, K_COL, (size_t)3 * s->m.ngeom);
   fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_NY * FB_ZCAP);
   fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL, (size_t)FB_PARTF);
