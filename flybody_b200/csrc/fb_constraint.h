@@ -119,28 +119,60 @@ FB_DEV void kcol_stage(FB_COL_ARGS) {
   float* gx = sh_dyn(sh);
   for (int i = y; i < 3 * m.ngeom; i += FB_NY) gx[i * FB_LANES + lane] = AT(d.geom_xpos, i);
 }
-FB_DEV void kcol_p0(FB_COL_ARGS) {
-  const float* gx = sh_dyn(sh);
+// Collision in four converged phases.  Broadphase and narrowphase are separated on purpose: in a fused pair loop the
+// whole warp pays for the narrowphase whenever ANY lane has a candidate in that iteration (68 iterations x ~1300 cycles);
+// here the lanes first only filter their pairs, and the candidates are then narrow-phased one per lane.
+#define FB_CANDL 32                    // candidates a lane can hold from its chunk of pairs
+#define FB_MAXCAND 192                 // candidates per env (4 contact slots each in tmp_con)
+#define COL_CAND(l, c) cand[((l) * FB_CANDL + (c)) * FB_LANES + lane]
+#define COL_FLAT(j) flat[(j) * FB_LANES + lane]
+#define COL_NCON(j) ccnt[(j) * FB_LANES + lane]
+#define FB_COL_DYN(m) (3 * (m).ngeom + FB_NY * FB_CANDL + 2 * FB_MAXCAND)
+#define FB_COL_PTRS float* gx = sh_dyn(sh); int* cand = reinterpret_cast<int*>(gx + 3 * m.ngeom * FB_LANES); \
+  int* flat = cand + FB_NY * FB_CANDL * FB_LANES; int* ccnt = flat + FB_MAXCAND * FB_LANES; (void)gx; (void)cand; (void)flat; (void)ccnt;
+// 1. broadphase: each lane filters its chunk of the static pair list (packed record: geoms, plane flag, margin + radii)
+FB_DEV void kcol_broad(FB_COL_ARGS) {
+  FB_COL_PTRS
   int cnt = 0;
   int p0 = m.chunk_start[y], p1 = m.chunk_start[y + 1];
   for (int k = p0; k < p1; k++) {
-    // broadphase on the packed static pair record: geoms, plane flag, margin + bounding radii
     const int pw = m.pair_info[k]; const float rsum = m.pair_rsum[k];
     const int g1 = pw & 0x7fff, g2 = (pw >> 15) & 0x7fff; const bool plane = (pw >> 30) & 1;
     V3 x1 = v3(gx[(3 * g1) * FB_LANES + lane], gx[(3 * g1 + 1) * FB_LANES + lane], gx[(3 * g1 + 2) * FB_LANES + lane]);
     V3 x2 = v3(gx[(3 * g2) * FB_LANES + lane], gx[(3 * g2 + 1) * FB_LANES + lane], gx[(3 * g2 + 2) * FB_LANES + lane]);
-    V3 pn = v3(0, 0, 1);
-    if (plane) {
-      pn = v3(AT(d.geom_xmat, 9 * g1 + 2), AT(d.geom_xmat, 9 * g1 + 5), AT(d.geom_xmat, 9 * g1 + 8));
-      if (dot(x2 - x1, pn) > rsum) continue;
-    } else {
-      V3 df = x2 - x1;
-      if (dot(df, df) > rsum * rsum) continue;
-    }
+    bool hit;
+    if (plane) { V3 pn = v3(AT(d.geom_xmat, 9 * g1 + 2), AT(d.geom_xmat, 9 * g1 + 5), AT(d.geom_xmat, 9 * g1 + 8)); hit = dot(x2 - x1, pn) <= rsum; }
+    else { V3 df = x2 - x1; hit = dot(df, df) <= rsum * rsum; }
+    if (!hit) continue;
+    if (cnt >= FB_CANDL) { FB_FLAG_OR(2); break; }
+    COL_CAND(y, cnt) = k; cnt++;
+  }
+  sh.cnt[y][lane] = cnt;
+}
+// 2. the lanes' candidate lists, concatenated in lane order (= pair order)
+FB_DEV void kcol_flatten(FB_COL_ARGS) {
+  FB_COL_PTRS
+  int off = 0;
+  for (int yy = 0; yy < y; yy++) off += sh.cnt[yy][lane];
+  int cnt = sh.cnt[y][lane];
+  for (int c = 0; c < cnt; c++) { if (off + c >= FB_MAXCAND) { FB_FLAG_OR(2); break; } COL_FLAT(off + c) = COL_CAND(y, c); }
+}
+// 3. narrowphase: one candidate per lane, up to 4 contacts each into tmp_con[4 j + i]
+FB_DEV void kcol_narrow(FB_COL_ARGS) {
+  FB_COL_PTRS
+  int T = 0;
+  for (int yy = 0; yy < m.nchunk; yy++) T += sh.cnt[yy][lane];
+  if (T > FB_MAXCAND) T = FB_MAXCAND;
+  for (int j = y; j < T; j += FB_NY) {
+    const int k = COL_FLAT(j), pw = m.pair_info[k];
+    const int g1 = pw & 0x7fff, g2 = (pw >> 15) & 0x7fff; const bool plane = (pw >> 30) & 1;
+    V3 x1 = v3(gx[(3 * g1) * FB_LANES + lane], gx[(3 * g1 + 1) * FB_LANES + lane], gx[(3 * g1 + 2) * FB_LANES + lane]);
+    V3 x2 = v3(gx[(3 * g2) * FB_LANES + lane], gx[(3 * g2 + 1) * FB_LANES + lane], gx[(3 * g2 + 2) * FB_LANES + lane]);
     const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
     const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
     RawCon rc[4]; int n = 0;
     if (plane) {
+      V3 pn = v3(AT(d.geom_xmat, 9 * g1 + 2), AT(d.geom_xmat, 9 * g1 + 5), AT(d.geom_xmat, 9 * g1 + 8));
       V3 s2 = mld3(m.geom_size, g2);
       if (t2 == FB_GEOM_SPHERE) n = raw_plane_sphere(rc, margin, x1, pn, x2, s2.x);
       else { M3 R2 = ld9(d.geom_xmat, g2, d, e);
@@ -155,8 +187,7 @@ FB_DEV void kcol_p0(FB_COL_ARGS) {
       else n = 0;    // generic convex pairs (ellipsoid / cylinder vs non-plane): next row, DESIGN.md
     }
     for (int i = 0; i < n; i++) {
-      if (cnt >= FB_CHUNKCAP) { FB_FLAG_OR(2); break; }
-      int slot = y * FB_CHUNKCAP + cnt;
+      int slot = 4 * j + i;
       V3 f1, f2; make_frame(rc[i].n, rc[i].t, f1, f2);
       CON_F(d.tmp_con, slot, 0, 13) = rc[i].dist;
       CON_F(d.tmp_con, slot, 1, 13) = rc[i].pos.x; CON_F(d.tmp_con, slot, 2, 13) = rc[i].pos.y; CON_F(d.tmp_con, slot, 3, 13) = rc[i].pos.z;
@@ -164,24 +195,30 @@ FB_DEV void kcol_p0(FB_COL_ARGS) {
       CON_F(d.tmp_con, slot, 7, 13) = f1.x; CON_F(d.tmp_con, slot, 8, 13) = f1.y; CON_F(d.tmp_con, slot, 9, 13) = f1.z;
       CON_F(d.tmp_con, slot, 10, 13) = f2.x; CON_F(d.tmp_con, slot, 11, 13) = f2.y; CON_F(d.tmp_con, slot, 12, 13) = f2.z;
       AT(d.tmp_geom, 2 * slot) = g1; AT(d.tmp_geom, 2 * slot + 1) = g2;
-      cnt++;
+    }
+    COL_NCON(j) = n;
+  }
+}
+// 4. compaction into the contact list, in candidate order
+FB_DEV void kcol_compact(FB_COL_ARGS) {
+  FB_COL_PTRS
+  int T = 0;
+  for (int yy = 0; yy < m.nchunk; yy++) T += sh.cnt[yy][lane];
+  if (T > FB_MAXCAND) T = FB_MAXCAND;
+  int off = 0, jj = 0;
+  for (int j = y; j < T; j += FB_NY) {
+    for (; jj < j; jj++) off += COL_NCON(jj);
+    int cnt = COL_NCON(j);
+    for (int i = 0; i < cnt; i++) {
+      int dst = off + i, src = 4 * j + i;
+      if (dst >= FB_MAXCON) { FB_FLAG_OR(2); break; }
+      AT(d.con_dist, dst) = CON_F(d.tmp_con, src, 0, 13);
+      for (int k = 0; k < 3; k++) CON_F(d.con_pos, dst, k, 3) = CON_F(d.tmp_con, src, 1 + k, 13);
+      for (int k = 0; k < 9; k++) CON_F(d.con_frame, dst, k, 9) = CON_F(d.tmp_con, src, 4 + k, 13);
+      AT(d.con_geom1, dst) = AT(d.tmp_geom, 2 * src); AT(d.con_geom2, dst) = AT(d.tmp_geom, 2 * src + 1);
     }
   }
-  sh.cnt[y][lane] = cnt;
-}
-FB_DEV void kcol_p1(FB_COL_ARGS) {
-  int off = 0;
-  for (int yy = 0; yy < y; yy++) off += sh.cnt[yy][lane];
-  int cnt = sh.cnt[y][lane];
-  for (int i = 0; i < cnt; i++) {
-    int dst = off + i, src = y * FB_CHUNKCAP + i;
-    if (dst >= FB_MAXCON) { FB_FLAG_OR(2); break; }
-    AT(d.con_dist, dst) = CON_F(d.tmp_con, src, 0, 13);
-    for (int k = 0; k < 3; k++) CON_F(d.con_pos, dst, k, 3) = CON_F(d.tmp_con, src, 1 + k, 13);
-    for (int k = 0; k < 9; k++) CON_F(d.con_frame, dst, k, 9) = CON_F(d.tmp_con, src, 4 + k, 13);
-    AT(d.con_geom1, dst) = AT(d.tmp_geom, 2 * src); AT(d.con_geom2, dst) = AT(d.tmp_geom, 2 * src + 1);
-  }
-  if (y == m.nchunk - 1) { int tot = off + cnt; AT(d.ncon, 0) = tot > FB_MAXCON ? FB_MAXCON : tot; }
+  if (y == 0) { int tot = 0; for (int j = 0; j < T; j++) tot += COL_NCON(j); AT(d.ncon, 0) = tot > FB_MAXCON ? FB_MAXCON : tot; }
 }
 
 // ---------------------------------------------------------------------------------------------

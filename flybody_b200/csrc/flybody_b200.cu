@@ -96,11 +96,21 @@ __global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevDa
   if (e >= nwarps) return;
   Sh& sh = *reinterpret_cast<Sh*>(fb_smem + (size_t)threadIdx.y * slice);
   int y = threadIdx.x;
+#ifdef FB_CLK
+  // latency profile: stage boundaries of env 0's warp, 32 slots per launch (slot 0 = kernel entry)
+  int ci = 0; long long* ck = d.clk + 32 * d.clk_launch;
+  if (e == 0 && y == 0) ck[ci] = clock64();
+  ((St::run(m, d, sh, e, y), __syncwarp(), (e == 0 && y == 0 ? (void)(ck[++ci] = clock64()) : (void)0)), ...);
+#else
   ((St::run(m, d, sh, e, y), __syncwarp()), ...);
+#endif
 }
 template <typename Sh, typename... St>
 static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1) {
   if (nwarps < 0) nwarps = s->d.Np;
+#ifdef FB_CLK
+  s->d.clk_launch = (int)(s->launches % 4096);
+#endif
   dim3 block(32, FB_WPB), grid((nwarps + FB_WPB - 1) / FB_WPB);
   size_t slice = slice_bytes(sizeof(Sh), dyn_floats), bytes = slice * FB_WPB;
   static size_t configured = 0;
@@ -120,9 +130,18 @@ __global__ void __launch_bounds__(32 * FB_SOLVE_WPB, FB_MINB) fb_run_solve(DevMo
   extern __shared__ __align__(16) float fb_smem_w[];
   int e = blockIdx.x * FB_SOLVE_WPB + threadIdx.y;
   if (e >= d.Np) return;
+#ifdef FB_CLK
+  if (e == 0 && threadIdx.x == 0) d.clk[32 * d.clk_launch] = clock64();
+#endif
   ksolve_warp(m, d, fb_smem_w + (size_t)threadIdx.y * FB_SOLVE_WARP_FLOATS, e);
+#ifdef FB_CLK
+  if (e == 0 && threadIdx.x == 0) d.clk[32 * d.clk_launch + 1] = clock64();
+#endif
 }
 static void fb_launch_warp(FbSim* s, int kind) {
+#ifdef FB_CLK
+  s->d.clk_launch = (int)(s->launches % 4096);
+#endif
   dim3 block(32, FB_SOLVE_WPB), grid((s->d.Np + FB_SOLVE_WPB - 1) / FB_SOLVE_WPB);
   size_t bytes = sizeof(float) * FB_SOLVE_WARP_FLOATS * FB_SOLVE_WPB;
   static bool configured = false;
@@ -180,7 +199,7 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 static void launch_step1(FbSim* s) {
   size_t nm = (size_t)FB_PARTF + (size_t)s->m.nM;
   fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, nm);
-  fb_launch<ShCol, Ph<kcol_stage>, Ph<kcol_p0>, Ph<kcol_p1>>(s, K_COL, (size_t)3 * s->m.ngeom);
+  fb_launch<ShCol, Ph<kcol_stage>, Ph<kcol_broad>, Ph<kcol_flatten>, Ph<kcol_narrow>, Ph<kcol_compact>>(s, K_COL, (size_t)FB_COL_DYN(s->m));
   fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_NY * FB_ZCAP);
   fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL, (size_t)FB_PARTF);
 }
@@ -381,7 +400,7 @@ static int alloc_data(FbSim* s, int N) {
   FA(act_dot, m.na + 1) FA(actuator_force, m.nu + 1)
   IA(ncon, 1) FA(con_dist, FB_MAXCON) FA(con_pos, 3 * FB_MAXCON) FA(con_frame, 9 * FB_MAXCON) IA(con_geom1, FB_MAXCON) IA(con_geom2, FB_MAXCON)
   IA(con_efcadr, FB_MAXCON) IA(con_dim, FB_MAXCON) FA(con_mu, FB_MAXCON) FA(con_fric, 2 * FB_MAXCON)
-  FA(tmp_con, 13 * FB_MAXCHUNK * FB_CHUNKCAP) IA(tmp_geom, 2 * FB_MAXCHUNK * FB_CHUNKCAP)
+  FA(tmp_con, 13 * 4 * FB_MAXCAND) IA(tmp_geom, 2 * 4 * FB_MAXCAND)
   IA(nefc, 1) IA(efc_type, FB_MAXEFC) IA(efc_id, FB_MAXEFC)
   FA(efc_pos, FB_MAXEFC) FA(efc_margin, FB_MAXEFC) FA(efc_D, FB_MAXEFC) FA(efc_R, FB_MAXEFC) FA(efc_K, FB_MAXEFC) FA(efc_B, FB_MAXEFC)
   FA(efc_imp, FB_MAXEFC) FA(efc_aref, FB_MAXEFC) FA(efc_b, FB_MAXEFC) FA(efc_force, FB_MAXEFC) FA(efc_jarws, FB_MAXEFC)
@@ -399,6 +418,9 @@ static int alloc_data(FbSim* s, int N) {
   float* base = dalloc<float>(s, (size_t)d.Np * off);
   if (!base) { s->err = "out of device memory (env records)"; return -4; }
   for (auto& f : fields) *f.first = (void*)(base + f.second);
+#ifdef FB_CLK
+  d.clk = (long long*)dalloc<long long>(s, 32 * 4096);
+#endif
   d.obs_dim = m.nq + m.nv + m.na + 2 * m.nsensordata + 12 + 3 * m.nsite + 3;
   d.obs = dalloc<float>(s, (size_t)d.obs_dim * d.Np);
   s->stage_cap = 0; s->stage = nullptr; s->stage_i = nullptr;
@@ -497,6 +519,9 @@ int fb_destroy(FbHandle s) {
   return 0;
 }
 
+#ifdef FB_CLK
+extern "C" int fb_clk_read(FbHandle s, long long* dst) { if (!s) return -1; cudaStreamSynchronize(s->stream); cudaMemcpy(dst, s->d.clk, sizeof(long long) * 32 * 4096, cudaMemcpyDeviceToHost); return (int)(s->launches % 4096); }
+#endif
 const char* fb_last_error(FbHandle s) { return s ? s->err.c_str() : "null handle"; }
 int fb_n_envs(FbHandle s) { return s ? s->d.N : -1; }
 int fb_n_envs_padded(FbHandle s) { return s ? s->d.Np : -1; }
