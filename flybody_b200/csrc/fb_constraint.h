@@ -116,53 +116,60 @@ FB_DEV void make_frame(V3 n, V3 t, V3& f1, V3& f2) {   // mju_makeFrame
 #define FB_COL_ARGS const DevModel& m, const DevData& d, ShCol& sh, int e, int lane, int y
 // geom positions of this env into shared memory (coalesced), so that the pair loop does not touch the record
 FB_DEV void kcol_stage(FB_COL_ARGS) {
-  float* gx = sh_dyn(sh);
+  float* gx = sh_dyn(sh); float* gn = gx + 3 * m.ngeom * FB_LANES;      // positions; normals (z axes) of the plane geoms
   for (int i = y; i < 3 * m.ngeom; i += FB_NY) gx[i * FB_LANES + lane] = AT(d.geom_xpos, i);
+  for (int g = y; g < m.ngeom; g += FB_NY) if (m.geom_type[g] == FB_GEOM_PLANE) for (int c = 0; c < 3; c++) gn[(3 * g + c) * FB_LANES + lane] = AT(d.geom_xmat, 9 * g + 3 * c + 2);
 }
-// Collision in four converged phases.  Broadphase and narrowphase are separated on purpose: in a fused pair loop the
+// Collision in three converged phases.  Broadphase and narrowphase are separated on purpose: in a fused pair loop the
 // whole warp pays for the narrowphase whenever ANY lane has a candidate in that iteration (68 iterations x ~1300 cycles);
 // here the lanes first only filter their pairs, and the candidates are then narrow-phased one per lane.
-#define FB_CANDL 32                    // candidates a lane can hold from its chunk of pairs
 #define FB_MAXCAND 192                 // candidates per env (4 contact slots each in tmp_con)
-#define COL_CAND(l, c) cand[((l) * FB_CANDL + (c)) * FB_LANES + lane]
 #define COL_FLAT(j) flat[(j) * FB_LANES + lane]
 #define COL_NCON(j) ccnt[(j) * FB_LANES + lane]
-#define FB_COL_DYN(m) (3 * (m).ngeom + FB_NY * FB_CANDL + 2 * FB_MAXCAND)
-#define FB_COL_PTRS float* gx = sh_dyn(sh); int* cand = reinterpret_cast<int*>(gx + 3 * m.ngeom * FB_LANES); \
-  int* flat = cand + FB_NY * FB_CANDL * FB_LANES; int* ccnt = flat + FB_MAXCAND * FB_LANES; (void)gx; (void)cand; (void)flat; (void)ccnt;
-// 1. broadphase: each lane filters its chunk of the static pair list (packed record: geoms, plane flag, margin + radii)
-FB_DEV void kcol_broad(FB_COL_ARGS) {
-  FB_COL_PTRS
-  int cnt = 0;
-  int p0 = m.chunk_start[y], p1 = m.chunk_start[y + 1];
-  for (int k = p0; k < p1; k++) {
-    const int pw = m.pair_info[k]; const float rsum = m.pair_rsum[k];
-    const int g1 = pw & 0x7fff, g2 = (pw >> 15) & 0x7fff; const bool plane = (pw >> 30) & 1;
-    V3 x1 = v3(gx[(3 * g1) * FB_LANES + lane], gx[(3 * g1 + 1) * FB_LANES + lane], gx[(3 * g1 + 2) * FB_LANES + lane]);
-    V3 x2 = v3(gx[(3 * g2) * FB_LANES + lane], gx[(3 * g2 + 1) * FB_LANES + lane], gx[(3 * g2 + 2) * FB_LANES + lane]);
-    bool hit;
-    if (plane) { V3 pn = v3(AT(d.geom_xmat, 9 * g1 + 2), AT(d.geom_xmat, 9 * g1 + 5), AT(d.geom_xmat, 9 * g1 + 8)); hit = dot(x2 - x1, pn) <= rsum; }
-    else { V3 df = x2 - x1; hit = dot(df, df) <= rsum * rsum; }
-    if (!hit) continue;
-    if (cnt >= FB_CANDL) { FB_FLAG_OR(2); break; }
-    COL_CAND(y, cnt) = k; cnt++;
+#define FB_COL_DYN(m) (6 * (m).ngeom + 2 * FB_MAXCAND)
+#define FB_COL_PTRS float* gx = sh_dyn(sh); float* gn = gx + 3 * m.ngeom * FB_LANES; int* flat = reinterpret_cast<int*>(gn + 3 * m.ngeom * FB_LANES); \
+  int* ccnt = flat + FB_MAXCAND * FB_LANES; (void)gx; (void)gn; (void)flat; (void)ccnt;
+// 1. broadphase: lane l tests the pairs l, l + 32, ... of the static pair list (packed record: geoms, plane flag; margin +
+// bounding radii -- one coalesced line per step), four steps loaded ahead of the tests.  The hits are ranked with ballots,
+// so the candidate list comes out in pair order without per-lane lists.
+FB_WARPFN void kcol_broad(const DevModel& m, const DevData& d, ShCol& sh, int e) {
+  LREG(int, h0); LREG(int, h1); LREG(int, h2); LREG(int, h3);
+  int base = 0;
+  const int nstep = (m.npair + 31) / 32;
+  for (int i0 = 0; i0 < nstep; i0 += 4) {
+    WPAR_BEGIN { FB_COL_PTRS
+      int pw[4]; float rs[4]; int hit[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { int k = 32 * (i0 + u) + lane; bool ok = k < m.npair; pw[u] = ok ? m.pair_info[k] : -1; rs[u] = ok ? m.pair_rsum[k] : 0.0f; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        hit[u] = 0;
+        if (pw[u] < 0) continue;
+        const int g1 = pw[u] & 0x7fff, g2 = (pw[u] >> 15) & 0x7fff; const bool plane = (pw[u] >> 30) & 1;
+        V3 x1 = v3(gx[3 * g1], gx[3 * g1 + 1], gx[3 * g1 + 2]), x2 = v3(gx[3 * g2], gx[3 * g2 + 1], gx[3 * g2 + 2]);
+        V3 df = x2 - x1;
+        if (plane) hit[u] = dot(df, v3(gn[3 * g1], gn[3 * g1 + 1], gn[3 * g1 + 2])) <= rs[u];
+        else hit[u] = dot(df, df) <= rs[u] * rs[u];
+      }
+      L(h0) = hit[0]; L(h1) = hit[1]; L(h2) = hit[2]; L(h3) = hit[3];
+    } WPAR_END
+    unsigned m0, m1, m2, m3;
+    BALLOT(m0, h0, != 0); BALLOT(m1, h1, != 0); BALLOT(m2, h2, != 0); BALLOT(m3, h3, != 0);
+    WPAR_BEGIN { FB_COL_PTRS
+      const unsigned lt = (1u << lane) - 1u; int b = base, pos;
+      if (L(h0)) { pos = b + POPC(m0 & lt); if (pos < FB_MAXCAND) flat[pos] = 32 * i0 + lane; } b += POPC(m0);
+      if (L(h1)) { pos = b + POPC(m1 & lt); if (pos < FB_MAXCAND) flat[pos] = 32 * (i0 + 1) + lane; } b += POPC(m1);
+      if (L(h2)) { pos = b + POPC(m2 & lt); if (pos < FB_MAXCAND) flat[pos] = 32 * (i0 + 2) + lane; } b += POPC(m2);
+      if (L(h3)) { pos = b + POPC(m3 & lt); if (pos < FB_MAXCAND) flat[pos] = 32 * (i0 + 3) + lane; }
+    } WPAR_END
+    base += POPC(m0) + POPC(m1) + POPC(m2) + POPC(m3);
   }
-  sh.cnt[y][lane] = cnt;
+  WPAR_BEGIN { if (lane == 0) { sh.cnt[0][0] = base > FB_MAXCAND ? FB_MAXCAND : base; if (base > FB_MAXCAND) FB_FLAG_OR(2); } } WPAR_END
 }
-// 2. the lanes' candidate lists, concatenated in lane order (= pair order)
-FB_DEV void kcol_flatten(FB_COL_ARGS) {
-  FB_COL_PTRS
-  int off = 0;
-  for (int yy = 0; yy < y; yy++) off += sh.cnt[yy][lane];
-  int cnt = sh.cnt[y][lane];
-  for (int c = 0; c < cnt; c++) { if (off + c >= FB_MAXCAND) { FB_FLAG_OR(2); break; } COL_FLAT(off + c) = COL_CAND(y, c); }
-}
-// 3. narrowphase: one candidate per lane, up to 4 contacts each into tmp_con[4 j + i]
+// 2. narrowphase: one candidate per lane, up to 4 contacts each into tmp_con[4 j + i]
 FB_DEV void kcol_narrow(FB_COL_ARGS) {
   FB_COL_PTRS
-  int T = 0;
-  for (int yy = 0; yy < m.nchunk; yy++) T += sh.cnt[yy][lane];
-  if (T > FB_MAXCAND) T = FB_MAXCAND;
+  const int T = sh.cnt[0][lane];
   for (int j = y; j < T; j += FB_NY) {
     const int k = COL_FLAT(j), pw = m.pair_info[k];
     const int g1 = pw & 0x7fff, g2 = (pw >> 15) & 0x7fff; const bool plane = (pw >> 30) & 1;
@@ -172,7 +179,7 @@ FB_DEV void kcol_narrow(FB_COL_ARGS) {
     const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
     RawCon rc[4]; int n = 0;
     if (plane) {
-      V3 pn = v3(AT(d.geom_xmat, 9 * g1 + 2), AT(d.geom_xmat, 9 * g1 + 5), AT(d.geom_xmat, 9 * g1 + 8));
+      V3 pn = v3(gn[(3 * g1) * FB_LANES + lane], gn[(3 * g1 + 1) * FB_LANES + lane], gn[(3 * g1 + 2) * FB_LANES + lane]);
       V3 s2 = mld3(m.geom_size, g2);
       if (t2 == FB_GEOM_SPHERE) n = raw_plane_sphere(rc, margin, x1, pn, x2, s2.x);
       else { M3 R2 = ld9(d.geom_xmat, g2, d, e);
@@ -199,12 +206,10 @@ FB_DEV void kcol_narrow(FB_COL_ARGS) {
     COL_NCON(j) = n;
   }
 }
-// 4. compaction into the contact list, in candidate order
+// 3. compaction into the contact list, in candidate order
 FB_DEV void kcol_compact(FB_COL_ARGS) {
   FB_COL_PTRS
-  int T = 0;
-  for (int yy = 0; yy < m.nchunk; yy++) T += sh.cnt[yy][lane];
-  if (T > FB_MAXCAND) T = FB_MAXCAND;
+  const int T = sh.cnt[0][lane];
   int off = 0, jj = 0;
   for (int j = y; j < T; j += FB_NY) {
     for (; jj < j; jj++) off += COL_NCON(jj);

@@ -14,21 +14,6 @@
 #pragma once
 #include "fb_solver.h"
 
-#ifdef __CUDACC__
-#define LREG(type, name) type name
-#define L(name) name
-#define SHF(name, src) __shfl_sync(0xffffffffu, name, (src) & 31)
-#define BALLOT(out, name, cmp) out = __ballot_sync(0xffffffffu, (name)cmp)
-#define POPC(x) __popc(x)
-#define FFS(x) __ffs((int)(x))
-#else
-#define LREG(type, name) type name[32] = {}
-#define L(name) name[lane]
-#define SHF(name, src) name[(src) & 31]
-#define BALLOT(out, name, cmp) { out = 0; for (int l_ = 0; l_ < 32; l_++) if ((name[l_])cmp) out |= 1u << l_; }
-#define POPC(x) __builtin_popcount(x)
-#define FFS(x) __builtin_ffs((int)(x))
-#endif
 #define A_(r, c) A[(r) * 33 + (c)]
 #define GP(p, q) G[TRI(p, q)]                    // p >= q
 

@@ -43,6 +43,24 @@
 #define WPAR_END }
 #define FB_WARPFN static inline
 #endif
+// Lane registers of warp functions: a register per lane on the GPU, an array over the 32 lanes in the host emulation
+// (where a WPAR section runs lane after lane: a value read through SHF / BALLOT must have been written in an EARLIER section).
+#ifdef __CUDACC__
+#define LREG(type, name) type name
+#define L(name) name
+#define SHF(name, src) __shfl_sync(0xffffffffu, name, (src) & 31)
+#define BALLOT(out, name, cmp) out = __ballot_sync(0xffffffffu, (name)cmp)
+#define POPC(x) __popc(x)
+#define FFS(x) __ffs((int)(x))
+#else
+#define LREG(type, name) type name[32] = {}
+#define L(name) name[lane]
+#define SHF(name, src) name[(src) & 31]
+#define BALLOT(out, name, cmp) { out = 0; for (int l_ = 0; l_ < 32; l_++) if ((name[l_])cmp) out |= 1u << l_; }
+#define POPC(x) __builtin_popcount(x)
+#define FFS(x) __builtin_ffs((int)(x))
+#endif
+
 
 struct DevModel {
   // sizes / options

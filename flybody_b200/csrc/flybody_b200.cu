@@ -199,7 +199,7 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 static void launch_step1(FbSim* s) {
   size_t nm = (size_t)FB_PARTF + (size_t)s->m.nM;
   fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, nm);
-  fb_launch<ShCol, Ph<kcol_stage>, Ph<kcol_broad>, Ph<kcol_flatten>, Ph<kcol_narrow>, Ph<kcol_compact>>(s, K_COL, (size_t)FB_COL_DYN(s->m));
+  fb_launch<ShCol, Ph<kcol_stage>, Wf<kcol_broad>, Ph<kcol_narrow>, Ph<kcol_compact>>(s, K_COL, (size_t)FB_COL_DYN(s->m));
   fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_NY * FB_ZCAP);
   fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL, (size_t)FB_PARTF);
 }
@@ -360,6 +360,7 @@ static int build_model(FbSim* s, const FbModel* h) {
     for (int k = 0; k < m.npair && c < m.nchunk; k++) { acc += w[k]; if (acc * m.nchunk >= tot * c) { cs[c++] = k + 1; } }
     for (; c <= m.nchunk; c++) cs[c] = m.npair;
     m.chunk_start = up(s, cs);
+
   }
   m.fluid_bodyid = upi(s, h->fluid_bodyid, m.nfluid); m.fluid_pos = upf(s, h->fluid_pos, 3 * m.nfluid);
   m.fluid_quat = upf(s, h->fluid_quat, 4 * m.nfluid); m.fluid_size = upf(s, h->fluid_size, 3 * m.nfluid); m.fluid_coef = upf(s, h->fluid_coef, 12 * m.nfluid);
