@@ -202,20 +202,26 @@ FB_DEV void ld_reinit_damped(const DevModel& m, const DevData& d, ShTree& sh, in
 // list and split the rank-1 update of the ancestor rows of that dof.  Updates that land in the root block are
 // summed into sh.part (21 entries per lane) and applied by the root lane afterwards.
 #define FB_FSUB 3
+// packed per-(step, lane) header of the lock-step sweeps: one coalesced load instead of the dependent chain
+// list_dofadr -> list_dof -> dof_Madr / dof_chainlen / dof_depth.  adr | len << 12 | depth << 18 | dof << 24, ~0 = idle
+#define FB_HDR_IDLE 0xffffffffu
+#define HDR_ADR(h) ((int)((h) & 4095u))
+#define HDR_LEN(h) ((int)(((h) >> 12) & 63u))
+#define HDR_DEPTH(h) ((int)(((h) >> 18) & 63u))
+#define HDR_DOF(h) ((int)((h) >> 24))
 #define FB_ROOTD6 6            // dofs of a root body (free joint)
 FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  int l = y / FB_FSUB, sub = y % FB_FSUB;
-  if (l >= m.nlist || step >= m.list_ndof[l]) return;
-  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
+  const unsigned hd = m.step_hdr_a[step * FB_NY + y];
+  if (hd == FB_HDR_IDLE) return;
+  const int sub = y % FB_FSUB, adrk = HDR_ADR(hd), len = HDR_LEN(hd);
   float invD = 1.0f / LS(adrk);
-  // non-root ancestor rows are dealt round-robin to the FB_FSUB lanes of the list (dof_anc[adrk + t] = t-th ancestor
-  // of k; the root's dofs are the tail of every chain and are handled by factor_root_accum)
-  const int tend = 1 + m.dof_depth[k];
+  // non-root ancestor rows are dealt round-robin to the FB_FSUB lanes of the list (M_ancadr[adrk + t] = row address of
+  // the t-th ancestor; the root's dofs are the tail of every chain and are handled by factor_root_accum)
+  const int tend = 1 + HDR_DEPTH(hd);
   for (int t = 1 + sub; t < tend; t += FB_FSUB) {
-    int i = m.dof_anc[adrk + t];
     float a = LS(adrk + t) * invD;
-    int adri = m.dof_Madr[i], li = len - t;                 // chain of i = tail of the chain of k
+    int adri = m.M_ancadr[adrk + t], li = len - t;          // chain of the ancestor = tail of the chain of k
     int s2 = 0;
     for (; s2 + 4 <= li; s2 += 4) {                          // batched so that the loads are in flight together
       float r0 = LS(adrk + t + s2), r1 = LS(adrk + t + s2 + 1), r2 = LS(adrk + t + s2 + 2), r3 = LS(adrk + t + s2 + 3);
@@ -323,9 +329,9 @@ FB_DEV void tsolve_stage_wait(FB_PHASE_ARGS) {
 // x <- L^-T x restricted to the list dofs, deepest first: x[anc] -= L[k][anc] x[k]
 FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  int l = y / FB_FSUB, sub = y % FB_FSUB;
-  if (l >= m.nlist || step >= m.list_ndof[l]) return;
-  int k = m.list_dof[m.list_dofadr[l] + step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
+  const unsigned hd = m.step_hdr_a[step * FB_NY + y];
+  if (hd == FB_HDR_IDLE) return;
+  const int sub = y % FB_FSUB, k = HDR_DOF(hd), adrk = HDR_ADR(hd), len = HDR_LEN(hd);
   float xk = XS(k) / LDS(adrk);                    // rows are stored unscaled: L[k][anc] x[k] = M'[k][anc] (x[k] / D[k])
   for (int t = 1 + sub; t < len; t += FB_FSUB) XS(m.dof_ancslot[adrk + t]) -= LDS(adrk + t) * xk;
 }
@@ -367,21 +373,20 @@ FB_DEV void tsolve_scale(FB_PHASE_ARGS) {        // x <- D^-1 x
 // x <- L^-1 x on the list dofs, shallowest first: x[k] -= sum_t L[k][anc_t] x[anc_t]
 FB_DEV void tsolve_c_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  int l = y / FB_FSUB, sub = y % FB_FSUB;
-  if (l >= m.nlist || step >= m.list_ndof[l]) return;
-  int k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step], adrk = m.dof_Madr[k], len = m.dof_chainlen[k];
+  const unsigned hd = m.step_hdr_c[step * FB_NY + y];
+  if (hd == FB_HDR_IDLE) return;
+  const int sub = y % FB_FSUB, adrk = HDR_ADR(hd), len = HDR_LEN(hd);
   float p = 0;
   for (int t = 1 + sub; t < len; t += FB_FSUB) p += LDS(adrk + t) * XS(m.dof_anc[adrk + t]);
   sh.red[y][lane] = p;
 }
 FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  int l = y / FB_FSUB, sub = y % FB_FSUB;
-  if (sub != 0 || l >= m.nlist || step >= m.list_ndof[l]) return;
-  int k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step];
+  const unsigned hd = m.step_hdr_c[step * FB_NY + y];
+  if (hd == FB_HDR_IDLE || y % FB_FSUB != 0) return;
   float p = 0;
   for (int u = 0; u < FB_FSUB; u++) p += sh.red[y + u][lane];
-  XS(k) -= p / LDS(m.dof_Madr[k]);
+  XS(HDR_DOF(hd)) -= p / LDS(HDR_ADR(hd));
 }
 // M^-1 = L^-1 D^-1 L^-T is applied in halves so that callers can work between them (the factor must have been issued
 // with tsolve_stage_issue by this warp):
@@ -398,12 +403,12 @@ FB_WARPFN void tsolve_a(const DevModel& m, const DevData& d, ShTree& sh, int e) 
 // and a second barrier (the host emulation runs the lanes one after the other and keeps the two-section form)
 FB_DEV void tsolve_c_step_shfl(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  int l = y / FB_FSUB, sub = y % FB_FSUB;
-  const bool active = l < m.nlist && step < m.list_ndof[l];
-  float p = 0; int k = 0, adrk = 0;
+  const unsigned hd = m.step_hdr_c[step * FB_NY + y];
+  const bool active = hd != FB_HDR_IDLE;
+  const int sub = y % FB_FSUB, k = HDR_DOF(hd), adrk = HDR_ADR(hd);
+  float p = 0;
   if (active) {
-    k = m.list_dof[m.list_dofadr[l] + m.list_ndof[l] - 1 - step]; adrk = m.dof_Madr[k];
-    int len = m.dof_chainlen[k];
+    const int len = HDR_LEN(hd);
     for (int t = 1 + sub; t < len; t += FB_FSUB) p += LDS(adrk + t) * XS(m.dof_anc[adrk + t]);
   }
   float p1 = __shfl_down_sync(0xffffffffu, p, 1), p2 = __shfl_down_sync(0xffffffffu, p, 2);

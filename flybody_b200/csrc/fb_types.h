@@ -81,6 +81,8 @@ struct DevModel {
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
   const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen, *dof_anc /* [nM] t-th ancestor of the row's dof */, *dof_ancslot /* same, as shared-memory slot of tri_solve */;
   const int *dof_rootidx /* root (index into root_body) a list dof hangs off, -1 for root dofs */, *root_haslists;
+  const unsigned *step_hdr_a, *step_hdr_c;   // [max_list_ndof][32] packed sweep headers, deepest-first / shallowest-first
+  const int* M_ancadr;         // [nM] row address (dof_Madr) of the ancestor an entry belongs to
   const float* M_damp;         // per entry of the packed inertia: joint damping on the diagonals, 0 elsewhere
   const int* body_adhesion;    // adhesion actuator acting on the body, or -1
   const float *dof_armature, *dof_damping, *dof_invweight0;

@@ -314,6 +314,26 @@ static int build_model(FbSim* s, const FbModel* h) {
     m.dof_rootidx = up(s, rootidx); m.root_haslists = up(s, haslists);
   }
   { std::vector<int> adh(nb, -1); for (int i = 0; i < h->nu; i++) if (h->actuator_trntype[i] == FB_TRN_BODY) adh[h->actuator_trnid[i]] = i; m.body_adhesion = up(s, adh); }
+  { // packed headers of the lock-step sweeps (see fb_tree.h) and the row address of every ancestor entry
+    if (h->nM >= 4096 || nv >= 256) { s->err = "model too large for the packed sweep headers (nM < 4096, nv < 256)"; return -3; }
+    const int* ldadr = nullptr; (void)ldadr;
+    std::vector<unsigned> ha((size_t)FB_NY * std::max(m.max_list_ndof, 1), 0xffffffffu), hc(ha);
+    std::vector<int> dadr_h, dnum_h, dl_h;      // rebuild the per-list dof order exactly as above
+    for (int l = 0; l < nlist; l++) { dadr_h.push_back((int)dl_h.size()); int c = 0;
+      for (int bi = (int)lists[l].size() - 1; bi >= 0; bi--) { int bb = lists[l][bi]; for (int kk = h->body_dofnum[bb] - 1; kk >= 0; kk--) { dl_h.push_back(h->body_dofadr[bb] + kk); c++; } }
+      dnum_h.push_back(c); }
+    auto pack = [&](int k) -> unsigned {
+      if (chainlen[k] >= 64 || depth[k] >= 64) return 0xfffffffeu;
+      return (unsigned)h->dof_Madr[k] | ((unsigned)chainlen[k] << 12) | ((unsigned)depth[k] << 18) | ((unsigned)k << 24); };
+    for (int l = 0; l < nlist && FB_FSUB * l + FB_FSUB <= FB_NY; l++) for (int st = 0; st < dnum_h[l]; st++) for (int u = 0; u < FB_FSUB; u++) {
+      unsigned a = pack(dl_h[dadr_h[l] + st]), c = pack(dl_h[dadr_h[l] + dnum_h[l] - 1 - st]);
+      if (a == 0xfffffffeu || c == 0xfffffffeu) { s->err = "chain too long for the packed sweep headers"; return -3; }
+      ha[(size_t)st * FB_NY + FB_FSUB * l + u] = a; hc[(size_t)st * FB_NY + FB_FSUB * l + u] = c; }
+    m.step_hdr_a = up(s, ha); m.step_hdr_c = up(s, hc);
+    std::vector<int> ancadr(h->nM, 0);
+    for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) ancadr[h->dof_Madr[i] + t] = h->dof_Madr[j]; }
+    m.M_ancadr = up(s, ancadr);
+  }
   { std::vector<float> mdamp(h->nM, 0.0f); for (int i = 0; i < nv; i++) mdamp[h->dof_Madr[i]] = (float)h->dof_damping[i]; m.M_damp = up(s, mdamp); }
   m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);
   // plain copies
