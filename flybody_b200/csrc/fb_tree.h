@@ -14,7 +14,7 @@
 //   PART  [FB_NY][FB_PARTK]  per-list partial sums towards the root (crb: 10, factor: 21, rne: 12)   -- pos, vel
 //   LS    [nM]               the joint-space inertia / its factor                                     -- pos
 //   XS    [nv + FB_ROOTD*nlist], LDS [nM]   right-hand side and staged factor of the triangular solves -- smooth, finish
-struct ShTree { float red[FB_NY][FB_LANES]; };
+struct ShTree { float red[FB_NY][FB_LANES]; const unsigned* prog; const unsigned* pad_; };   // prog: the CTA's copy of the sweep program (smooth / finish kernels)
 #define FB_PARTK 21
 #define FB_PARTF (FB_NY * FB_PARTK * FB_LANES)
 #define PART(yy, k) part_[((yy) * FB_PARTK + (k)) * FB_LANES + lane]
@@ -304,6 +304,13 @@ FB_DEV void kpos_p9(FB_PHASE_ARGS) { ld_writeout(m, d, sh, e, lane, y, d.qLDe); 
 // dof per step; the FB_FSUB lanes of a list split that dof's ancestor chain (dof_ancslot / dof_anc give the shared slot
 // of the t-th ancestor without pointer chasing).
 #define FB_ROOTD 6
+// Sweep program of the triangular solves, copied once per CTA into shared memory (DevModel::tsolve_blob): the packed step
+// headers of both directions and, per entry of the packed factor, the shared slot of its ancestor (L^-T sweep: the lists'
+// private root accumulators; L^-1 sweep: the dof itself) as bytes.  The sweeps then touch no global table at all.
+#define TS_HDR_A(sh, m) ((sh).prog)
+#define TS_HDR_C(sh, m) ((sh).prog + (m).ts_hdr_words)
+#define TS_SLOT8(sh, m) (reinterpret_cast<const unsigned char*>((sh).prog + 2 * (m).ts_hdr_words))
+#define TS_ANC8(sh, m) (TS_SLOT8(sh, m) + (m).ts_nm_pad)
 #define FB_NXS(m) (((m).nv + FB_ROOTD * (m).nlist + 3) & ~3)      // multiple of 4: the staged factor behind it stays 16-byte aligned
 #define LDS(k) lds[(k) * FB_LANES + lane]
 // Stage a factor into the warp's shared slice with asynchronous 16-byte copies (cp.async): issued early (first phase
@@ -329,11 +336,12 @@ FB_DEV void tsolve_stage_wait(FB_PHASE_ARGS) {
 // x <- L^-T x restricted to the list dofs, deepest first: x[anc] -= L[k][anc] x[k]
 FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  const unsigned hd = m.step_hdr_a[step * FB_NY + y];
+  const unsigned hd = TS_HDR_A(sh, m)[step * FB_NY + y];
   if (hd == FB_HDR_IDLE) return;
   const int sub = y % FB_FSUB, k = HDR_DOF(hd), adrk = HDR_ADR(hd), len = HDR_LEN(hd);
+  const unsigned char* slot8 = TS_SLOT8(sh, m);
   float xk = XS(k) / LDS(adrk);                    // rows are stored unscaled: L[k][anc] x[k] = M'[k][anc] (x[k] / D[k])
-  for (int t = 1 + sub; t < len; t += FB_FSUB) XS(m.dof_ancslot[adrk + t]) -= LDS(adrk + t) * xk;
+  for (int t = 1 + sub; t < len; t += FB_FSUB) XS(slot8[adrk + t]) -= LDS(adrk + t) * xk;
 }
 // root blocks: collect the lists' contributions, then the dense (<= 6x6) back / scale / forward substitution
 FB_DEV void tsolve_b_gather(FB_PHASE_ARGS) {
@@ -373,16 +381,17 @@ FB_DEV void tsolve_scale(FB_PHASE_ARGS) {        // x <- D^-1 x
 // x <- L^-1 x on the list dofs, shallowest first: x[k] -= sum_t L[k][anc_t] x[anc_t]
 FB_DEV void tsolve_c_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  const unsigned hd = m.step_hdr_c[step * FB_NY + y];
+  const unsigned hd = TS_HDR_C(sh, m)[step * FB_NY + y];
   if (hd == FB_HDR_IDLE) return;
   const int sub = y % FB_FSUB, adrk = HDR_ADR(hd), len = HDR_LEN(hd);
+  const unsigned char* anc8 = TS_ANC8(sh, m);
   float p = 0;
-  for (int t = 1 + sub; t < len; t += FB_FSUB) p += LDS(adrk + t) * XS(m.dof_anc[adrk + t]);
+  for (int t = 1 + sub; t < len; t += FB_FSUB) p += LDS(adrk + t) * XS(anc8[adrk + t]);
   sh.red[y][lane] = p;
 }
 FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  const unsigned hd = m.step_hdr_c[step * FB_NY + y];
+  const unsigned hd = TS_HDR_C(sh, m)[step * FB_NY + y];
   if (hd == FB_HDR_IDLE || y % FB_FSUB != 0) return;
   float p = 0;
   for (int u = 0; u < FB_FSUB; u++) p += sh.red[y + u][lane];
@@ -403,13 +412,14 @@ FB_WARPFN void tsolve_a(const DevModel& m, const DevData& d, ShTree& sh, int e) 
 // and a second barrier (the host emulation runs the lanes one after the other and keeps the two-section form)
 FB_DEV void tsolve_c_step_shfl(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  const unsigned hd = m.step_hdr_c[step * FB_NY + y];
+  const unsigned hd = TS_HDR_C(sh, m)[step * FB_NY + y];
   const bool active = hd != FB_HDR_IDLE;
   const int sub = y % FB_FSUB, k = HDR_DOF(hd), adrk = HDR_ADR(hd);
+  const unsigned char* anc8 = TS_ANC8(sh, m);
   float p = 0;
   if (active) {
     const int len = HDR_LEN(hd);
-    for (int t = 1 + sub; t < len; t += FB_FSUB) p += LDS(adrk + t) * XS(m.dof_anc[adrk + t]);
+    for (int t = 1 + sub; t < len; t += FB_FSUB) p += LDS(adrk + t) * XS(anc8[adrk + t]);
   }
   float p1 = __shfl_down_sync(0xffffffffu, p, 1), p2 = __shfl_down_sync(0xffffffffu, p, 2);
   if (active && sub == 0) XS(k) -= (p + p1 + p2) / LDS(adrk);

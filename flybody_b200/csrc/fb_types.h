@@ -82,6 +82,7 @@ struct DevModel {
   const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen, *dof_anc /* [nM] t-th ancestor of the row's dof */, *dof_ancslot /* same, as shared-memory slot of tri_solve */;
   const int *dof_rootidx /* root (index into root_body) a list dof hangs off, -1 for root dofs */, *root_haslists;
   const unsigned *step_hdr_a, *step_hdr_c;   // [max_list_ndof][32] packed sweep headers, deepest-first / shallowest-first
+  const unsigned* tsolve_blob; int ts_hdr_words, ts_nm_pad, ts_blob_words;    // sweep program copied per CTA into shared memory (fb_tree.h)
   const int* M_ancadr;         // [nM] row address (dof_Madr) of the ancestor an entry belongs to
   const float* M_damp;         // per entry of the packed inertia: joint damping on the diagonals, 0 elsewhere
   const int* body_adhesion;    // adhesion actuator acting on the body, or -1

@@ -89,13 +89,22 @@ template <auto F> struct Wf {
 };
 #ifndef FB_EMU
 // one warp per env: threadIdx.x = lane ("y" of the phase functions), threadIdx.y = env within the block
+template <typename Sh> __device__ __forceinline__ void set_prog(Sh&, const unsigned*) {}
+__device__ __forceinline__ void set_prog(ShTree& sh, const unsigned* p) { sh.prog = p; }
 template <typename Sh, typename... St>
-__global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevData d, int slice, int nwarps) {
+__global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevData d, int slice, int nwarps, int blob_words) {
   extern __shared__ __align__(16) unsigned char fb_smem[];
+  // optional CTA-wide copy of the sweep program in front of the warps' slices (the only block-level barrier of the step)
+  unsigned* blob = reinterpret_cast<unsigned*>(fb_smem);
+  if (blob_words) {
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < blob_words; i += 32 * FB_WPB) blob[i] = m.tsolve_blob[i];
+    __syncthreads();
+  }
   int e = blockIdx.x * FB_WPB + threadIdx.y;
   if (e >= nwarps) return;
-  Sh& sh = *reinterpret_cast<Sh*>(fb_smem + (size_t)threadIdx.y * slice);
+  Sh& sh = *reinterpret_cast<Sh*>(fb_smem + (size_t)blob_words * 4 + (size_t)threadIdx.y * slice);
   int y = threadIdx.x;
+  if (blob_words) { set_prog(sh, blob); __syncwarp(); }
 #ifdef FB_CLK
   // latency profile: stage boundaries of env 0's warp, 32 slots per launch (slot 0 = kernel entry)
   int ci = 0; long long* ck = d.clk + 32 * d.clk_launch;
@@ -106,23 +115,23 @@ __global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevDa
 #endif
 }
 template <typename Sh, typename... St>
-static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1) {
+static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1, int blob_words = 0) {
   if (nwarps < 0) nwarps = s->d.Np;
 #ifdef FB_CLK
   s->d.clk_launch = (int)(s->launches % 4096);
 #endif
   dim3 block(32, FB_WPB), grid((nwarps + FB_WPB - 1) / FB_WPB);
-  size_t slice = slice_bytes(sizeof(Sh), dyn_floats), bytes = slice * FB_WPB;
+  size_t slice = slice_bytes(sizeof(Sh), dyn_floats), bytes = slice * FB_WPB + (size_t)blob_words * 4;
   static size_t configured = 0;
   if (bytes > configured) { cudaFuncSetAttribute(fb_run<Sh, St...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, s->stream);
-    fb_run<Sh, St...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps);
+    fb_run<Sh, St...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps, blob_words);
     cudaEventRecord(b, s->stream);
     s->prof_events.push_back({kind, a, b});
   } else {
-    fb_run<Sh, St...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps);
+    fb_run<Sh, St...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps, blob_words);
   }
   s->launches++;
 }
@@ -158,14 +167,17 @@ static void fb_launch_warp(FbSim* s, int kind) {
   s->launches++;
 }
 #else
+template <typename Sh> static void set_prog(Sh&, const unsigned*) {}
+static void set_prog(ShTree& sh, const unsigned* p) { sh.prog = p; }
 template <typename Sh, typename... St>
-static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1) {
+static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1, int blob_words = 0) {
   (void)kind;
   if (nwarps < 0) nwarps = s->d.Np;
   static std::vector<unsigned char> buf;
   size_t need = slice_bytes(sizeof(Sh), dyn_floats) + 64;
   if (buf.size() < need) buf.resize(need);
   Sh& sh = *reinterpret_cast<Sh*>(buf.data());
+  if (blob_words) set_prog(sh, s->m.tsolve_blob);        // host emulation: the program is read in place
   for (int e = 0; e < nwarps; e++) (St::emu(s->m, s->d, sh, e), ...);
   s->launches++;
 }
@@ -205,9 +217,9 @@ static void launch_step1(FbSim* s) {
 }
 static void launch_step2(FbSim* s, bool integrate) {
   s->d.do_integrate = integrate ? 1 : 0;     // read by the solve (warm-start bookkeeping) and the finish kernel
-  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)));
+  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)), -1, s->m.ts_blob_words);
   fb_launch_warp(s, K_SOLVE);
-  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)));
+  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)), -1, s->m.ts_blob_words);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -330,6 +342,19 @@ static int build_model(FbSim* s, const FbModel* h) {
       if (a == 0xfffffffeu || c == 0xfffffffeu) { s->err = "chain too long for the packed sweep headers"; return -3; }
       ha[(size_t)st * FB_NY + FB_FSUB * l + u] = a; hc[(size_t)st * FB_NY + FB_FSUB * l + u] = c; }
     m.step_hdr_a = up(s, ha); m.step_hdr_c = up(s, hc);
+    { // the same headers + ancestor slots as bytes, in one blob that the smooth / finish kernels copy into shared memory
+      if (nv + FB_ROOTD * nlist >= 256) { s->err = "too many dofs for byte-sized sweep slots"; return -3; }
+      const int H = (int)ha.size(), nmp = (h->nM + 3) & ~3;
+      std::vector<unsigned> blob((((size_t)2 * H + 2 * nmp / 4) + 3) & ~(size_t)3, 0u);       // whole 16-byte units: the warps' slices follow
+      for (int i = 0; i < H; i++) { blob[i] = ha[i]; blob[H + i] = hc[i]; }
+      unsigned char* b8 = reinterpret_cast<unsigned char*>(blob.data() + 2 * H);
+      std::vector<int> dof_list2(nv, -1);
+      for (int l = 0; l < nlist; l++) for (int bb : lists[l]) for (int kk = 0; kk < h->body_dofnum[bb]; kk++) dof_list2[h->body_dofadr[bb] + kk] = l;
+      for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) {
+          int slot = (disroot[j] && dof_list2[i] >= 0) ? nv + FB_ROOTD * dof_list2[i] + depth[j] : j;
+          b8[h->dof_Madr[i] + t] = (unsigned char)slot; b8[nmp + h->dof_Madr[i] + t] = (unsigned char)j; } }
+      m.tsolve_blob = up(s, blob); m.ts_hdr_words = H; m.ts_nm_pad = nmp; m.ts_blob_words = (int)blob.size();
+    }
     std::vector<int> ancadr(h->nM, 0);
     for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) ancadr[h->dof_Madr[i] + t] = h->dof_Madr[j]; }
     m.M_ancadr = up(s, ancadr);
