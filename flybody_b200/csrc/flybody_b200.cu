@@ -62,6 +62,7 @@ struct FbSim {
   int first_substep; int hold_pending;
   int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
   const int* act_map_dev; int n_action;
+  int blob_in_smem;            // copy the sweep program of the triangular solves into shared memory per CTA (FB_NO_BLOB=1: read it in place)
   int* op_step_dev; unsigned char* op_first_dev;
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
 #ifndef FB_EMU
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevDa
   if (e >= nwarps) return;
   Sh& sh = *reinterpret_cast<Sh*>(fb_smem + (size_t)blob_words * 4 + (size_t)threadIdx.y * slice);
   int y = threadIdx.x;
-  if (blob_words) { set_prog(sh, blob); __syncwarp(); }
+  if (blob_words) { set_prog(sh, blob); __syncwarp(); } else { set_prog(sh, m.tsolve_blob); __syncwarp(); }   // no CTA copy: read the program in place
 #ifdef FB_CLK
   // latency profile: stage boundaries of env 0's warp, 32 slots per launch (slot 0 = kernel entry)
   int ci = 0; long long* ck = d.clk + 32 * d.clk_launch;
@@ -177,7 +178,7 @@ static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1
   size_t need = slice_bytes(sizeof(Sh), dyn_floats) + 64;
   if (buf.size() < need) buf.resize(need);
   Sh& sh = *reinterpret_cast<Sh*>(buf.data());
-  if (blob_words) set_prog(sh, s->m.tsolve_blob);        // host emulation: the program is read in place
+  (void)blob_words; set_prog(sh, s->m.tsolve_blob);        // host emulation: the program is read in place
   for (int e = 0; e < nwarps; e++) (St::emu(s->m, s->d, sh, e), ...);
   s->launches++;
 }
@@ -217,9 +218,9 @@ static void launch_step1(FbSim* s) {
 }
 static void launch_step2(FbSim* s, bool integrate) {
   s->d.do_integrate = integrate ? 1 : 0;     // read by the solve (warm-start bookkeeping) and the finish kernel
-  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)), -1, s->m.ts_blob_words);
+  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)), -1, s->blob_in_smem ? s->m.ts_blob_words : 0);
   fb_launch_warp(s, K_SOLVE);
-  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)), -1, s->m.ts_blob_words);
+  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)), -1, s->blob_in_smem ? s->m.ts_blob_words : 0);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -539,6 +540,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
   s->graphs_on = getenv("FB_NO_GRAPH") == nullptr;
+  s->blob_in_smem = getenv("FB_NO_BLOB") == nullptr;
 #endif
   int rc = build_model(s, hm);
   if (rc == 0) rc = alloc_data(s, n_envs);
