@@ -62,7 +62,7 @@ struct FbSim {
   int first_substep; int hold_pending;
   int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
   const int* act_map_dev; int n_action;
-  int blob_in_smem;            // copy the sweep program of the triangular solves into shared memory per CTA (FB_NO_BLOB=1: read it in place)
+  int blob_in_smem;            // copy the sweep program of the triangular solves into shared memory per CTA (default: for batches <= 1024 envs; FB_BLOB=0/1 overrides)
   int* op_step_dev; unsigned char* op_first_dev;
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
 #ifndef FB_EMU
@@ -540,7 +540,9 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
   s->graphs_on = getenv("FB_NO_GRAPH") == nullptr;
-  s->blob_in_smem = getenv("FB_NO_BLOB") == nullptr;
+  // small batches are latency-bound (a per-CTA copy of the sweep program in shared memory halves the sweeps' latency);
+  // at full occupancy the copy costs more than it saves and the compact program is read in place.  FB_BLOB=0/1 overrides.
+  s->blob_in_smem = getenv("FB_BLOB") ? atoi(getenv("FB_BLOB")) : (n_envs <= 1024);
 #endif
   int rc = build_model(s, hm);
   if (rc == 0) rc = alloc_data(s, n_envs);
