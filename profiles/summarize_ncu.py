@@ -12,7 +12,7 @@ import re
 import subprocess
 import sys
 
-STAGES = [('kpos_p0', 'pos'), ('kcol_p0', 'col'), ('kcon_p0', 'proj'), ('kvel_p0', 'vel'), ('kact_p0', 'smooth'),
+STAGES = [('kpos_p0', 'pos'), ('kcol_', 'col'), ('kcon_p0', 'proj'), ('kvel_p0', 'vel'), ('kact_p0', 'smooth'),
           ('fb_run_solve', 'solve'), ('kfin_f1', 'finish'), ('ph_scatter', 'misc'), ('ph_pack', 'pack'), ('ph_reset', 'misc')]
 
 
