@@ -107,6 +107,172 @@ FB_DEV int col_capsule_capsule(RawCon* c, float margin, V3 p1, const M3& m1, V3 
   x = clampf((u + mb * s2.y) / ma, -s1.y, s1.y); k += raw_sphere_sphere(c + k, margin, p1 + a1 * x, s1.x, p2 - a2 * s2.y, s2.x);
   return k;
 }
+// ---------------------------------------------------------------------------------------------
+// Generic convex pairs (MuJoCo mjc_Convex): Minkowski Portal Refinement as in libccd (mpr.c: discoverPortal /
+// refinePortal / findPenetr / findPos, vec3.c: point-triangle distance), with MuJoCo's support functions (each geom
+// inflated by margin / 2), tolerance 1e-6, 50 iterations, dist = margin - depth.
+// This routine runs in DOUBLE precision: libccd's portal logic is built on exact-zero tests scaled by the machine epsilon and
+// loses 6 % of shallow contacts (depth off by 10x) when compiled in fp32; the bounding-capsule test in col_convex leaves only a
+// handful of pairs per env for it.
+#define MPR_EPS 2.220446049250313e-16
+struct D3 { double x, y, z; };
+FB_DEV D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+FB_DEV D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+FB_DEV D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+FB_DEV D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
+FB_DEV double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+FB_DEV D3 dcross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+FB_DEV double dnorm(D3 a) { return sqrt(ddot(a, a)); }
+FB_DEV D3 dnormalized(D3 a) { double n = dnorm(a); if (n < 1e-300) return d3(1, 0, 0); return a * (1.0 / n); }
+struct MprPt { D3 v, v1, v2; };
+struct MprObj { D3 pos; double mat[9]; D3 size; int type; double margin; };
+FB_DEV bool mpr_zero(double x) { return fabs(x) < MPR_EPS; }
+FB_DEV bool mpr_eq(double a, double b) { double ab = fabs(a - b); if (ab < MPR_EPS) return true; a = fabs(a); b = fabs(b); return (b > a) ? ab < MPR_EPS * b : ab < MPR_EPS * a; }
+FB_DEV double mpr_sgn(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
+FB_DEV D3 mpr_support1(const MprObj& o, D3 dir) {     // mjccd_support
+  const double* R = o.mat;
+  D3 ld = d3(R[0] * dir.x + R[3] * dir.y + R[6] * dir.z, R[1] * dir.x + R[4] * dir.y + R[7] * dir.z, R[2] * dir.x + R[5] * dir.y + R[8] * dir.z), r = d3(0, 0, 0);
+  if (o.type == FB_GEOM_SPHERE) r = ld * o.size.x;
+  else if (o.type == FB_GEOM_CAPSULE) { r = ld * o.size.x; r.z += mpr_sgn(ld.z) * o.size.y; }
+  else if (o.type == FB_GEOM_ELLIPSOID) {
+    D3 t = d3(ld.x * o.size.x, ld.y * o.size.y, ld.z * o.size.z); double n = dnorm(t);
+    if (n >= 1e-15) r = d3(t.x / n * o.size.x, t.y / n * o.size.y, t.z / n * o.size.z);
+  } else if (o.type == FB_GEOM_CYLINDER) {
+    double n = sqrt(ld.x * ld.x + ld.y * ld.y);
+    if (n > 1e-15) { r.x = ld.x / n * o.size.x; r.y = ld.y / n * o.size.x; }
+    r.z = mpr_sgn(ld.z) * o.size.y;
+  }
+  r = r + ld * (0.5 * o.margin);
+  return d3(R[0] * r.x + R[1] * r.y + R[2] * r.z, R[3] * r.x + R[4] * r.y + R[5] * r.z, R[6] * r.x + R[7] * r.y + R[8] * r.z) + o.pos;
+}
+FB_DEV MprPt mpr_support(const MprObj& a, const MprObj& b, D3 dir) { MprPt p; p.v1 = mpr_support1(a, dir); p.v2 = mpr_support1(b, d3(0, 0, 0) - dir); p.v = p.v1 - p.v2; return p; }
+FB_DEV double mpr_seg_dist2(D3 P, D3 x0, D3 b, D3& w) {
+  D3 dd = b - x0, a = x0 - P; double t = -ddot(a, dd) / ddot(dd, dd);
+  if (t < 0 || mpr_zero(t)) w = x0; else if (t > 1 || mpr_eq(t, 1)) w = b; else w = x0 + dd * t;
+  D3 ee = w - P; return ddot(ee, ee);
+}
+FB_DEV double mpr_tri_dist2(D3 P, D3 x0, D3 B, D3 C, D3& w) {
+  D3 d1 = B - x0, d2 = C - x0, a = x0 - P;
+  double v = ddot(d1, d1), ww = ddot(d2, d2), pp = ddot(a, d1), q = ddot(a, d2), r = ddot(d1, d2);
+  double s = (q * r - ww * pp) / (ww * v - r * r), t = (-s * r - q) / ww;
+  if ((mpr_zero(s) || s > 0) && (mpr_eq(s, 1) || s < 1) && (mpr_zero(t) || t > 0) && (mpr_eq(t, 1) || t < 1) && (mpr_eq(t + s, 1) || t + s < 1)) {
+    w = x0 + d1 * s + d2 * t; D3 ee = w - P; return ddot(ee, ee);
+  }
+  D3 w2; double dist = mpr_seg_dist2(P, x0, B, w), dd = mpr_seg_dist2(P, x0, C, w2);
+  if (dd < dist) { dist = dd; w = w2; }
+  dd = mpr_seg_dist2(P, B, C, w2);
+  if (dd < dist) { dist = dd; w = w2; }
+  return dist;
+}
+FB_DEV D3 mpr_portal_dir(const MprPt* s) { return dnormalized(dcross(s[2].v - s[1].v, s[3].v - s[1].v)); }
+FB_DEV bool mpr_reach_tol(const MprPt* s, const MprPt& v4, D3 dir, double tol) {
+  double dv4 = ddot(v4.v, dir), dmin = fmin(dv4 - ddot(s[1].v, dir), fmin(dv4 - ddot(s[2].v, dir), dv4 - ddot(s[3].v, dir)));
+  return mpr_eq(dmin, tol) || dmin < tol;
+}
+FB_DEV void mpr_expand(MprPt* s, const MprPt& v4) {
+  D3 v4v0 = dcross(v4.v, s[0].v);
+  if (ddot(s[1].v, v4v0) > 0) { if (ddot(s[2].v, v4v0) > 0) s[1] = v4; else s[3] = v4; }
+  else { if (ddot(s[3].v, v4v0) > 0) s[2] = v4; else s[1] = v4; }
+}
+// 0 and depth / dir / pos when the inflated shapes intersect, -1 otherwise
+FB_DEVN int mpr_penetration(const MprObj& o1, const MprObj& o2, double tol, int max_iter, double& depth, D3& pdir, D3& pos) {
+  MprPt s[4]; D3 dir; double dt;
+  s[0].v1 = o1.pos; s[0].v2 = o2.pos; s[0].v = s[0].v1 - s[0].v2;
+  if (mpr_eq(s[0].v.x, 0) && mpr_eq(s[0].v.y, 0) && mpr_eq(s[0].v.z, 0)) s[0].v = d3(MPR_EPS * 10, 0, 0);
+  dir = dnormalized(d3(0, 0, 0) - s[0].v);
+  s[1] = mpr_support(o1, o2, dir);
+  dt = ddot(s[1].v, dir);
+  if (mpr_zero(dt) || dt < 0) return -1;
+  dir = dcross(s[0].v, s[1].v);
+  int res = 0;
+  if (mpr_zero(ddot(dir, dir))) res = (mpr_eq(s[1].v.x, 0) && mpr_eq(s[1].v.y, 0) && mpr_eq(s[1].v.z, 0)) ? 1 : 2;
+  if (res == 0) {
+    dir = dnormalized(dir);
+    s[2] = mpr_support(o1, o2, dir);
+    dt = ddot(s[2].v, dir);
+    if (mpr_zero(dt) || dt < 0) return -1;
+    dir = dnormalized(dcross(s[1].v - s[0].v, s[2].v - s[0].v));
+    if (ddot(dir, s[0].v) > 0) { MprPt t = s[1]; s[1] = s[2]; s[2] = t; dir = d3(0, 0, 0) - dir; }
+    for (int guard = 0;; guard++) {
+      s[3] = mpr_support(o1, o2, dir);
+      dt = ddot(s[3].v, dir);
+      if (mpr_zero(dt) || dt < 0) return -1;
+      bool cont = false;
+      dt = ddot(dcross(s[1].v, s[3].v), s[0].v);
+      if (dt < 0 && !mpr_zero(dt)) { s[2] = s[3]; cont = true; }
+      if (!cont) { dt = ddot(dcross(s[3].v, s[2].v), s[0].v); if (dt < 0 && !mpr_zero(dt)) { s[1] = s[3]; cont = true; } }
+      if (!cont) break;
+      dir = dnormalized(dcross(s[1].v - s[0].v, s[2].v - s[0].v));
+      if (guard > 1000) return -1;                 // (libccd loops without a bound here)
+    }
+  }
+  if (res == 1) { depth = 0; pdir = d3(0, 0, 0); pos = (s[1].v1 + s[1].v2) * 0.5; return 0; }
+  if (res == 2) { pos = (s[1].v1 + s[1].v2) * 0.5; depth = dnorm(s[1].v); pdir = dnormalized(s[1].v); return 0; }
+  MprPt v4;
+  for (int guard = 0;; guard++) {                // refinePortal
+    dir = mpr_portal_dir(s);
+    dt = ddot(dir, s[1].v);
+    if (mpr_zero(dt) || dt > 0) break;
+    v4 = mpr_support(o1, o2, dir);
+    dt = ddot(v4.v, dir);
+    if (!(mpr_zero(dt) || dt > 0) || mpr_reach_tol(s, v4, dir, tol) || guard > 1000) return -1;
+    mpr_expand(s, v4);
+  }
+  for (int it = 0;; it++) {                      // findPenetr
+    dir = mpr_portal_dir(s);
+    v4 = mpr_support(o1, o2, dir);
+    if (mpr_reach_tol(s, v4, dir, tol) || it > max_iter) {
+      depth = sqrt(mpr_tri_dist2(d3(0, 0, 0), s[1].v, s[2].v, s[3].v, pdir));
+      if (mpr_zero(pdir.x) && mpr_zero(pdir.y) && mpr_zero(pdir.z)) pdir = dir;
+      pdir = dnormalized(pdir);
+      double b0 = ddot(dcross(s[1].v, s[2].v), s[3].v), b1 = ddot(dcross(s[3].v, s[2].v), s[0].v);
+      double b2 = ddot(dcross(s[0].v, s[1].v), s[3].v), b3 = ddot(dcross(s[2].v, s[1].v), s[0].v);
+      double sum = b0 + b1 + b2 + b3;
+      if (mpr_zero(sum) || sum < 0) {
+        b0 = 0; b1 = ddot(dcross(s[2].v, s[3].v), dir); b2 = ddot(dcross(s[3].v, s[1].v), dir); b3 = ddot(dcross(s[1].v, s[2].v), dir);
+        sum = b1 + b2 + b3;
+      }
+      double inv = 0.5 / sum;
+      pos = (s[0].v1 * b0 + s[1].v1 * b1 + s[2].v1 * b2 + s[3].v1 * b3 + s[0].v2 * b0 + s[1].v2 * b1 + s[2].v2 * b2 + s[3].v2 * b3) * inv;
+      return 0;
+    }
+    mpr_expand(s, v4);
+  }
+}
+// bounding capsule (axis index, half length, radius) of a convex geom: contains the shape, so that disjoint bounding capsules
+// (segment-segment distance > radii + margin) mean "no contact" without running MPR
+FB_DEV void bound_capsule(int type, V3 size, int& axis, float& h, float& r) {
+  axis = 2; h = 0; r = size.x;
+  if (type == FB_GEOM_CAPSULE || type == FB_GEOM_CYLINDER) { h = size.y; }
+  else if (type == FB_GEOM_ELLIPSOID) {
+    axis = (size.x >= size.y && size.x >= size.z) ? 0 : (size.y >= size.z ? 1 : 2);
+    float L = comp(size, axis); r = fmaxf(comp(size, (axis + 1) % 3), comp(size, (axis + 2) % 3)); h = fmaxf(L - r, 0.0f);
+  }
+}
+FB_DEV float seg_seg_dist2(V3 p1, V3 a1, float h1, V3 p2, V3 a2, float h2) {       // distance^2 between two centred segments
+  V3 dif = p1 - p2;
+  float mb = -dot(a1, a2), u = -dot(a1, dif), v = dot(a2, dif), det = 1.0f - mb * mb, x1, x2;
+  if (det > 1e-6f) { x1 = clampf((u - mb * v) / det, -h1, h1); } else x1 = 0;
+  x2 = clampf(v - mb * x1, -h2, h2);
+  x1 = clampf(u - mb * x2, -h1, h1);
+  x2 = clampf(v - mb * x1, -h2, h2);
+  V3 dd = (p1 + a1 * x1) - (p2 + a2 * x2); return dot(dd, dd);
+}
+FB_DEV int col_convex(RawCon* c, float margin, int t1, V3 p1, const M3& m1, V3 s1, int t2, V3 p2, const M3& m2, V3 s2) {
+  int ax1, ax2; float h1, r1, h2, r2;
+  bound_capsule(t1, s1, ax1, h1, r1); bound_capsule(t2, s2, ax2, h2, r2);
+  float lim = r1 + r2 + margin; lim *= 1.0001f;
+  if (seg_seg_dist2(p1, col(m1, ax1), h1, p2, col(m2, ax2), h2) > lim * lim) return 0;
+  MprObj a, b;
+  a.pos = d3(p1.x, p1.y, p1.z); a.size = d3(s1.x, s1.y, s1.z); a.type = t1; a.margin = margin;
+  b.pos = d3(p2.x, p2.y, p2.z); b.size = d3(s2.x, s2.y, s2.z); b.type = t2; b.margin = margin;
+  for (int k = 0; k < 9; k++) { a.mat[k] = m1.m[k]; b.mat[k] = m2.m[k]; }
+  double depth; D3 dir, pos;
+  if (mpr_penetration(a, b, 1e-6, 50, depth, dir, pos) != 0) return 0;
+  if (mpr_eq(dir.x, 0) && mpr_eq(dir.y, 0) && mpr_eq(dir.z, 0)) return 0;
+  c->dist = (float)(margin - depth); c->pos = v3((float)pos.x, (float)pos.y, (float)pos.z); c->n = v3((float)dir.x, (float)dir.y, (float)dir.z); c->t = v3(0, 0, 0);
+  return 1;
+}
 FB_DEV void make_frame(V3 n, V3 t, V3& f1, V3& f2) {   // mju_makeFrame
   if (norm(t) < 0.5f) { t = (n.y < 0.5f && n.y > -0.5f) ? v3(0, 1, 0) : v3(0, 0, 1); }
   t = normalized(t - n * dot(n, t));
@@ -191,7 +357,7 @@ FB_DEV void kcol_narrow(FB_COL_ARGS) {
       if (t1 == FB_GEOM_SPHERE && t2 == FB_GEOM_SPHERE) n = raw_sphere_sphere(rc, margin, x1, s1.x, x2, s2.x);
       else if (t1 == FB_GEOM_SPHERE && t2 == FB_GEOM_CAPSULE) { M3 R2 = ld9(d.geom_xmat, g2, d, e); n = col_sphere_capsule(rc, margin, x1, s1.x, x2, R2, s2); }
       else if (t1 == FB_GEOM_CAPSULE && t2 == FB_GEOM_CAPSULE) { M3 R1 = ld9(d.geom_xmat, g1, d, e), R2 = ld9(d.geom_xmat, g2, d, e); n = col_capsule_capsule(rc, margin, x1, R1, s1, x2, R2, s2); }
-      else n = 0;    // generic convex pairs (ellipsoid / cylinder vs non-plane): next row, DESIGN.md
+      else { M3 R1 = ld9(d.geom_xmat, g1, d, e), R2 = ld9(d.geom_xmat, g2, d, e); n = col_convex(rc, margin, t1, x1, R1, s1, t2, x2, R2, s2); }    // generic convex pairs: MPR
     }
     for (int i = 0; i < n; i++) {
       int slot = 4 * j + i;

@@ -572,6 +572,16 @@ int fb_destroy(FbHandle s) {
 #ifdef FB_CLK
 extern "C" int fb_clk_read(FbHandle s, long long* dst) { if (!s) return -1; cudaStreamSynchronize(s->stream); cudaMemcpy(dst, s->d.clk, sizeof(long long) * 32 * 4096, cudaMemcpyDeviceToHost); return (int)(s->launches % 4096); }
 #endif
+#ifdef FB_EMU
+// host-emulation build only (tests): the fp32 generic-convex narrowphase on one pair; out = dist, pos[3], normal[3]
+extern "C" int fb_emu_convex_pair(int t1, const float* p1, const float* m1, const float* s1, int t2, const float* p2, const float* m2, const float* s2,
+                                  float margin, float* out) {
+  M3 R1, R2; for (int k = 0; k < 9; k++) { R1.m[k] = m1[k]; R2.m[k] = m2[k]; }
+  RawCon c; int n = col_convex(&c, margin, t1, v3(p1[0], p1[1], p1[2]), R1, v3(s1[0], s1[1], s1[2]), t2, v3(p2[0], p2[1], p2[2]), R2, v3(s2[0], s2[1], s2[2]));
+  if (n) { out[0] = c.dist; out[1] = c.pos.x; out[2] = c.pos.y; out[3] = c.pos.z; out[4] = c.n.x; out[5] = c.n.y; out[6] = c.n.z; }
+  return n;
+}
+#endif
 const char* fb_last_error(FbHandle s) { return s ? s->err.c_str() : "null handle"; }
 int fb_n_envs(FbHandle s) { return s ? s->d.N : -1; }
 int fb_n_envs_padded(FbHandle s) { return s ? s->d.Np : -1; }

@@ -599,6 +599,182 @@ static int col_capsule_capsule(RawCon* c, double margin, const double* p1, const
   return n;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Generic convex pairs (MuJoCo mjc_Convex, engine_collision_convex.c): Minkowski Portal Refinement as published in
+ * libccd (src/mpr.c: ccdMPRPenetration -> discoverPortal / refinePortal / findPenetr / findPos, src/vec3.c:
+ * ccdVec3PointTriDist2), which MuJoCo links for every pair without an analytic routine, with MuJoCo's support functions
+ * (mjccd_support: each geom inflated by margin / 2), mpr_tolerance 1e-6, mpr_iterations 50, contact dist = margin - depth.
+ * Restated from memory of libccd 2.1 / MuJoCo 2.3-3.1; mjc_fixNormal and multiccd are not restated.        */
+#define CCD_EPS 2.220446049250313e-16
+typedef struct { double v[3], v1[3], v2[3]; } MprPt;
+typedef struct { const double *pos, *mat, *size; int type; double margin; } MprObj;
+static int ccd_zero(double x) { return fabs(x)<CCD_EPS; }
+static int ccd_eq(double a, double b) {
+  double ab=fabs(a-b); if (ab<CCD_EPS) return 1;
+  a=fabs(a); b=fabs(b); return (b>a) ? ab<CCD_EPS*b : ab<CCD_EPS*a;
+}
+static double sgn(double x) { return x>0 ? 1.0 : (x<0 ? -1.0 : 0.0); }
+static void mpr_support1(const MprObj* o, const double* dir, double* out) {   /* mjccd_support */
+  double ld[3], r[3]={0,0,0};
+  mulmatT3(ld,o->mat,dir);
+  if (o->type==FB_GEOM_SPHERE) { for (int i=0;i<3;i++) r[i]=ld[i]*o->size[0]; }
+  else if (o->type==FB_GEOM_CAPSULE) { for (int i=0;i<3;i++) r[i]=ld[i]*o->size[0]; r[2]+=sgn(ld[2])*o->size[1]; }
+  else if (o->type==FB_GEOM_ELLIPSOID) {
+    double t[3]={ld[0]*o->size[0],ld[1]*o->size[1],ld[2]*o->size[2]}; double n=norm3(t);
+    if (n>=MINVAL) for (int i=0;i<3;i++) r[i]=t[i]/n*o->size[i];
+  } else if (o->type==FB_GEOM_CYLINDER) {
+    double n=sqrt(ld[0]*ld[0]+ld[1]*ld[1]);
+    if (n>MINVAL) { r[0]=ld[0]/n*o->size[0]; r[1]=ld[1]/n*o->size[0]; }
+    r[2]=sgn(ld[2])*o->size[1];
+  }
+  for (int i=0;i<3;i++) r[i]+=ld[i]*0.5*o->margin;
+  mulmat3(out,o->mat,r); add3(out,out,o->pos);
+}
+static void mpr_support(const MprObj* a, const MprObj* b, const double* dir, MprPt* p) {   /* __ccdSupport */
+  double nd[3]={-dir[0],-dir[1],-dir[2]};
+  mpr_support1(a,dir,p->v1); mpr_support1(b,nd,p->v2); sub3(p->v,p->v1,p->v2);
+}
+static double seg_dist2(const double* P, const double* x0, const double* b, double* w) {     /* ccdVec3PointSegmentDist2 */
+  double d[3],a[3],t; sub3(d,b,x0); sub3(a,x0,P);
+  t=-dot3(a,d)/dot3(d,d);
+  if (t<0 || ccd_zero(t)) { copy3(w,x0); }
+  else if (t>1 || ccd_eq(t,1)) { copy3(w,b); }
+  else { for (int i=0;i<3;i++) w[i]=x0[i]+t*d[i]; }
+  double e[3]; sub3(e,w,P); return dot3(e,e);
+}
+static double tri_dist2(const double* P, const double* x0, const double* B, const double* C, double* w) {   /* ccdVec3PointTriDist2 */
+  double d1[3],d2[3],a[3]; sub3(d1,B,x0); sub3(d2,C,x0); sub3(a,x0,P);
+  double v=dot3(d1,d1), ww=dot3(d2,d2), pp=dot3(a,d1), q=dot3(a,d2), r=dot3(d1,d2);
+  double s=(q*r-ww*pp)/(ww*v-r*r), t=(-s*r-q)/ww;
+  if ((ccd_zero(s)||s>0) && (ccd_eq(s,1)||s<1) && (ccd_zero(t)||t>0) && (ccd_eq(t,1)||t<1) && (ccd_eq(t+s,1)||t+s<1)) {
+    for (int i=0;i<3;i++) w[i]=x0[i]+s*d1[i]+t*d2[i];
+    double e[3]; sub3(e,w,P); return dot3(e,e);
+  }
+  double w2[3], dist=seg_dist2(P,x0,B,w), d2_=seg_dist2(P,x0,C,w2);
+  if (d2_<dist) { dist=d2_; copy3(w,w2); }
+  d2_=seg_dist2(P,B,C,w2);
+  if (d2_<dist) { dist=d2_; copy3(w,w2); }
+  return dist;
+}
+static void portal_dir(const MprPt* s, double* dir) {
+  double a[3],b[3]; sub3(a,s[2].v,s[1].v); sub3(b,s[3].v,s[1].v); cross3(dir,a,b); normalize3(dir);
+}
+static int portal_reach_tol(const MprPt* s, const MprPt* v4, const double* dir, double tol) {
+  double dv1=dot3(s[1].v,dir), dv2=dot3(s[2].v,dir), dv3=dot3(s[3].v,dir), dv4=dot3(v4->v,dir);
+  double d=fmin(dv4-dv1,fmin(dv4-dv2,dv4-dv3));
+  return ccd_eq(d,tol) || d<tol;
+}
+static void expand_portal(MprPt* s, const MprPt* v4) {
+  double v4v0[3]; cross3(v4v0,v4->v,s[0].v);
+  double dot=dot3(s[1].v,v4v0);
+  if (dot>0) { dot=dot3(s[2].v,v4v0); if (dot>0) s[1]=*v4; else s[3]=*v4; }
+  else { dot=dot3(s[3].v,v4v0); if (dot>0) s[2]=*v4; else s[1]=*v4; }
+}
+/* returns 0 and depth / dir / pos when the (inflated) shapes intersect, -1 otherwise */
+static int mpr_penetration(const MprObj* o1, const MprObj* o2, double tol, int max_iter, double* depth, double* pdir, double* pos) {
+  MprPt s[4]; int size; double dir[3],va[3],vb[3],dot; MprPt v4;
+  const double origin[3]={0,0,0};
+  /* --- discoverPortal */
+  copy3(s[0].v1,o1->pos); copy3(s[0].v2,o2->pos); sub3(s[0].v,s[0].v1,s[0].v2); size=1;
+  if (ccd_eq(s[0].v[0],0)&&ccd_eq(s[0].v[1],0)&&ccd_eq(s[0].v[2],0)) { s[0].v[0]=CCD_EPS*10; s[0].v[1]=0; s[0].v[2]=0; }
+  scl3(dir,s[0].v,-1); normalize3(dir);
+  mpr_support(o1,o2,dir,&s[1]); size=2;
+  dot=dot3(s[1].v,dir);
+  if (ccd_zero(dot)||dot<0) return -1;
+  cross3(dir,s[0].v,s[1].v);
+  int res=0;
+  if (ccd_zero(dot3(dir,dir))) res = (ccd_eq(s[1].v[0],0)&&ccd_eq(s[1].v[1],0)&&ccd_eq(s[1].v[2],0)) ? 1 : 2;
+  if (res==0) {
+    normalize3(dir);
+    mpr_support(o1,o2,dir,&s[2]);
+    dot=dot3(s[2].v,dir);
+    if (ccd_zero(dot)||dot<0) return -1;
+    size=3;
+    sub3(va,s[1].v,s[0].v); sub3(vb,s[2].v,s[0].v); cross3(dir,va,vb); normalize3(dir);
+    dot=dot3(dir,s[0].v);
+    if (dot>0) { MprPt t=s[1]; s[1]=s[2]; s[2]=t; scl3(dir,dir,-1); }
+    while (size<4) {
+      mpr_support(o1,o2,dir,&s[3]);
+      dot=dot3(s[3].v,dir);
+      if (ccd_zero(dot)||dot<0) return -1;
+      int cont=0;
+      cross3(va,s[1].v,s[3].v); dot=dot3(va,s[0].v);
+      if (dot<0 && !ccd_zero(dot)) { s[2]=s[3]; cont=1; }
+      if (!cont) {
+        cross3(va,s[3].v,s[2].v); dot=dot3(va,s[0].v);
+        if (dot<0 && !ccd_zero(dot)) { s[1]=s[3]; cont=1; }
+      }
+      if (cont) { sub3(va,s[1].v,s[0].v); sub3(vb,s[2].v,s[0].v); cross3(dir,va,vb); normalize3(dir); }
+      else size=4;
+    }
+  }
+  if (res==1) {          /* findPenetrTouch: origin on v1 */
+    *depth=0; copy3(pdir,origin);
+    for (int i=0;i<3;i++) pos[i]=0.5*(s[1].v1[i]+s[1].v2[i]);
+    return 0;
+  }
+  if (res==2) {          /* findPenetrSegment: origin on the segment v0-v1 */
+    for (int i=0;i<3;i++) pos[i]=0.5*(s[1].v1[i]+s[1].v2[i]);
+    copy3(pdir,s[1].v); *depth=norm3(pdir); normalize3(pdir);
+    return 0;
+  }
+  /* --- refinePortal */
+  for (;;) {
+    portal_dir(s,dir);
+    dot=dot3(dir,s[1].v);
+    if (ccd_zero(dot)||dot>0) break;                 /* portalEncapsulesOrigin */
+    mpr_support(o1,o2,dir,&v4);
+    dot=dot3(v4.v,dir);
+    if (!(ccd_zero(dot)||dot>0) || portal_reach_tol(s,&v4,dir,tol)) return -1;     /* portalCanEncapsuleOrigin */
+    expand_portal(s,&v4);
+  }
+  /* --- findPenetr */
+  for (int it=0;;it++) {
+    portal_dir(s,dir);
+    mpr_support(o1,o2,dir,&v4);
+    if (portal_reach_tol(s,&v4,dir,tol) || it>max_iter) {
+      *depth=sqrt(tri_dist2(origin,s[1].v,s[2].v,s[3].v,pdir));
+      if (ccd_zero(pdir[0])&&ccd_zero(pdir[1])&&ccd_zero(pdir[2])) copy3(pdir,dir);
+      normalize3(pdir);
+      /* findPos: barycentric coordinates of the origin in the portal tetrahedron */
+      double b[4],t[3],sum;
+      cross3(t,s[1].v,s[2].v); b[0]=dot3(t,s[3].v);
+      cross3(t,s[3].v,s[2].v); b[1]=dot3(t,s[0].v);
+      cross3(t,s[0].v,s[1].v); b[2]=dot3(t,s[3].v);
+      cross3(t,s[2].v,s[1].v); b[3]=dot3(t,s[0].v);
+      sum=b[0]+b[1]+b[2]+b[3];
+      if (ccd_zero(sum)||sum<0) {
+        b[0]=0;
+        cross3(t,s[2].v,s[3].v); b[1]=dot3(t,dir);
+        cross3(t,s[3].v,s[1].v); b[2]=dot3(t,dir);
+        cross3(t,s[1].v,s[2].v); b[3]=dot3(t,dir);
+        sum=b[1]+b[2]+b[3];
+      }
+      double inv=1.0/sum, p1[3]={0,0,0}, p2[3]={0,0,0};
+      for (int k=0;k<4;k++) for (int i=0;i<3;i++) { p1[i]+=b[k]*s[k].v1[i]; p2[i]+=b[k]*s[k].v2[i]; }
+      for (int i=0;i<3;i++) pos[i]=0.5*inv*(p1[i]+p2[i]);
+      return 0;
+    }
+    expand_portal(s,&v4);
+  }
+}
+static int col_convex(RawCon* c, double margin, int t1, const double* p1, const double* m1, const double* s1,
+                      int t2, const double* p2, const double* m2, const double* s2) {
+  MprObj a={p1,m1,s1,t1,margin}, b={p2,m2,s2,t2,margin};
+  double depth,dir[3],pos[3];
+  if (mpr_penetration(&a,&b,1e-6,50,&depth,dir,pos)!=0) return 0;
+  if (ccd_eq(dir[0],0)&&ccd_eq(dir[1],0)&&ccd_eq(dir[2],0)) return 0;      /* normal undefined */
+  c->dist=margin-depth; copy3(c->pos,pos); copy3(c->normal,dir); c->tangent[0]=c->tangent[1]=c->tangent[2]=0;
+  return 1;
+}
+/* exported for the tests: one generic pair */
+int orc_convex_pair(int t1, const double* p1, const double* m1, const double* s1, int t2, const double* p2, const double* m2, const double* s2,
+                    double margin, double* out /* dist, pos[3], normal[3] */) {
+  RawCon c; int n=col_convex(&c,margin,t1,p1,m1,s1,t2,p2,m2,s2);
+  if (n) { out[0]=c.dist; copy3(out+1,c.pos); copy3(out+4,c.normal); }
+  return n;
+}
+
 static void orc_collision(OrcData* d) {
   const FbModel* m=d->m;
   d->ncon=0;
@@ -626,7 +802,7 @@ static void orc_collision(OrcData* d) {
     } else if (t1==FB_GEOM_SPHERE && t2==FB_GEOM_SPHERE) n=raw_sphere_sphere(rc,margin,p1,s1[0],p2,s2[0]);
     else if (t1==FB_GEOM_SPHERE && t2==FB_GEOM_CAPSULE) n=col_sphere_capsule(rc,margin,p1,s1[0],p2,m2,s2);
     else if (t1==FB_GEOM_CAPSULE && t2==FB_GEOM_CAPSULE) n=col_capsule_capsule(rc,margin,p1,m1,s1,p2,m2,s2);
-    else n=0;   /* generic convex pairs (ellipsoid / cylinder vs non-plane): not built yet, DESIGN.md */
+    else n=col_convex(rc,margin,t1,p1,m1,s1,t2,p2,m2,s2);   /* generic convex pairs: MPR */
     for (int i=0;i<n && d->ncon<ORC_MAXCON;i++) {
       OrcContact* c=&d->con[d->ncon++];
       c->dist=rc[i].dist; copy3(c->pos,rc[i].pos); copy3(c->frame,rc[i].normal); copy3(c->frame+3,rc[i].tangent);

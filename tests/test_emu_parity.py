@@ -43,3 +43,48 @@ def test_solver_shared_and_global_memory_paths(emu, ncap, seed, monkeypatch):
     monkeypatch.setenv('FB_SOLVE_NCAP', ncap)
     m = load_model('walk')
     compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=emu), seed=seed, pos_scale=0.1 if seed == 0 else 0.0)
+
+
+def test_generic_convex_narrowphase_matches_the_oracle_on_shallow_contacts():
+    """device MPR (double precision inside, fp32 inputs) vs the fp64 oracle on random sphere / capsule / ellipsoid /
+    cylinder pairs brought to a 3e-4 cm overlap: same contact decision, depth within 2e-5 in >= 98 % of the cases (MPR is
+    discontinuous where a support point jumps, e.g. across a cylinder rim)."""
+    import ctypes as C
+    from test_oracle_invariants import _convex, _rot, SPH, CAP, ELL, CYL
+    ge.build()
+    emu = C.CDLL(ge.EMU)
+    fp = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(C.POINTER(C.c_float))
+    emu.fb_emu_convex_pair.argtypes = [C.c_int] + [C.POINTER(C.c_float)] * 3 + [C.c_int] + [C.POINTER(C.c_float)] * 3 + [C.c_float, C.POINTER(C.c_float)]
+
+    def dev(t1, p1, R1, s1, t2, p2, R2, s2):
+        out = np.zeros(7, np.float32)
+        n = emu.fb_emu_convex_pair(t1, fp(p1), fp(np.asarray(R1).reshape(9)), fp(s1), t2, fp(p2), fp(np.asarray(R2).reshape(9)), fp(s2), 0.0,
+                                   out.ctypes.data_as(C.POINTER(C.c_float)))
+        return n, float(out[0]), out[4:7].astype(np.float64)
+    rs = np.random.RandomState(0)
+
+    def size(t):
+        if t == SPH:
+            return [rs.uniform(0.01, 0.05), 0, 0]
+        if t in (CAP, CYL):
+            return [rs.uniform(0.005, 0.03), rs.uniform(0.01, 0.06), 0]
+        return list(rs.uniform(0.005, 0.06, 3))
+    tot = ok = 0
+    for _ in range(200):
+        t1, t2 = rs.choice([SPH, CAP, ELL, CYL], 2)
+        s1, s2, R1, R2 = size(t1), size(t2), _rot(rs), _rot(rs)
+        p1 = rs.normal(size=3) * 0.05
+        u = rs.normal(size=3); u /= np.linalg.norm(u)
+        lo, hi = 0.0, 0.3
+        for _k in range(40):                      # bisect the separation to a 3e-4 overlap (oracle)
+            mid = 0.5 * (lo + hi)
+            n, dist, _, _ = _convex(t1, p1, R1, s1, t2, p1 + u * mid, R2, s2)
+            lo, hi = (mid, hi) if (n and dist < -3e-4) else (lo, mid)
+        p2 = p1 + u * lo
+        n, dist, _, nrm = _convex(t1, p1, R1, s1, t2, p2, R2, s2)
+        if not n:
+            continue
+        tot += 1
+        nd, dd, nn = dev(t1, p1, R1, s1, t2, p2, R2, s2)
+        ok += int(nd == 1 and abs(dd - dist) < 2e-5 and np.abs(nn - nrm).max() < 5e-2)
+    assert tot > 150 and ok >= 0.98 * tot, (ok, tot)

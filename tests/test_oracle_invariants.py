@@ -157,3 +157,68 @@ def test_solver_kkt_residual_small():
     for i, tp in enumerate(e['type']):
         if tp in (0, 1):
             assert f[i] >= 0
+
+
+# ------------------------------------------------------------------------------------------ generic convex pairs (MPR)
+def _convex(t1, p1, R1, s1, t2, p2, R2, s2, margin=0.0):
+    import ctypes as C
+    lib = fo.lib()
+    dp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.POINTER(C.c_double))
+    lib.orc_convex_pair.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3 + [C.c_int] + [C.POINTER(C.c_double)] * 3 + [C.c_double, C.POINTER(C.c_double)]
+    out = np.zeros(7)
+    n = lib.orc_convex_pair(t1, dp(p1), dp(np.asarray(R1).reshape(9)), dp(s1), t2, dp(p2), dp(np.asarray(R2).reshape(9)), dp(s2), margin,
+                            out.ctypes.data_as(C.POINTER(C.c_double)))
+    return n, out[0], out[1:4], out[4:7]
+
+
+SPH, CAP, ELL, CYL = 2, 3, 4, 5
+
+
+def _rot(rs):
+    q = rs.normal(size=4); q /= np.linalg.norm(q); w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def test_mpr_round_ellipsoids_match_the_sphere_formula():
+    """two ellipsoids with equal semi-axes are spheres: dist = d - r1 - r2, normal along the centres, position mid-way
+    (libccd MPR as linked by MuJoCo's mjc_Convex, tolerance 1e-6)"""
+    rs = np.random.RandomState(0)
+    for _ in range(20):
+        r1, r2 = rs.uniform(0.01, 0.05, 2)
+        u = rs.normal(size=3); u /= np.linalg.norm(u)
+        d = (r1 + r2) * rs.uniform(0.5, 0.98)
+        p1 = rs.normal(size=3) * 0.1; p2 = p1 + u * d
+        n, dist, pos, nrm = _convex(ELL, p1, _rot(rs), [r1] * 3, ELL, p2, _rot(rs), [r2] * 3)
+        assert n == 1
+        assert abs(dist - (d - r1 - r2)) < 5e-6
+        assert np.allclose(nrm, u, atol=2e-3)
+        assert np.allclose(pos, p1 + u * (r1 + (d - r1 - r2) / 2), atol=2e-3 * (r1 + r2))
+
+
+def test_mpr_separated_shapes_give_no_contact_and_margin_inflates():
+    rs = np.random.RandomState(1)
+    R = _rot(rs)
+    n, *_ = _convex(ELL, [0, 0, 0], R, [0.02, 0.03, 0.05], CYL, [0.2, 0, 0], _rot(rs), [0.02, 0.03, 0])
+    assert n == 0
+    # just out of touch along x, brought into range by the margin (each shape is inflated by margin / 2)
+    n0, *_ = _convex(ELL, [0, 0, 0], np.eye(3), [0.02, 0.03, 0.05], ELL, [0.0405, 0, 0], np.eye(3), [0.02, 0.03, 0.05])
+    n1, dist, pos, nrm = _convex(ELL, [0, 0, 0], np.eye(3), [0.02, 0.03, 0.05], ELL, [0.0405, 0, 0], np.eye(3), [0.02, 0.03, 0.05], margin=0.001)
+    assert n0 == 0 and n1 == 1
+    assert abs(dist - 0.0005) < 5e-6 and np.allclose(nrm, [1, 0, 0], atol=1e-3)
+
+
+def test_mpr_capsule_against_round_ellipsoid_matches_the_analytic_sphere_capsule():
+    rs = np.random.RandomState(2)
+    for _ in range(10):
+        r, cr, ch = rs.uniform(0.01, 0.03), rs.uniform(0.005, 0.02), rs.uniform(0.02, 0.06)
+        Rc = _rot(rs); axis = Rc[:, 2]
+        pc = rs.normal(size=3) * 0.05
+        t = rs.uniform(-0.8, 0.8) * ch
+        side = np.cross(axis, rs.normal(size=3)); side /= np.linalg.norm(side)
+        gap = (r + cr) * rs.uniform(0.6, 0.95)
+        ps = pc + axis * t + side * gap
+        n, dist, pos, nrm = _convex(CAP, pc, Rc, [cr, ch, 0], ELL, ps, _rot(rs), [r] * 3)
+        assert n == 1 and abs(dist - (gap - r - cr)) < 5e-6
+        assert np.allclose(nrm, side, atol=1e-2)          # the portal normal is only as good as the 1e-6 support tolerance
