@@ -123,7 +123,11 @@ FB_DEV D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
 FB_DEV double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 FB_DEV D3 dcross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 FB_DEV double dnorm(D3 a) { return sqrt(ddot(a, a)); }
-FB_DEV D3 dnormalized(D3 a) { double n = dnorm(a); if (n < 1e-300) return d3(1, 0, 0); return a * (1.0 / n); }
+// 1/sqrt(x) and 1/x to ~1e-15: single-precision seed + two Newton steps in double (the double-precision sqrt / divide of the
+// GPU are long software sequences; these sit in the inner loop of MPR)
+FB_DEV double fast_rsqrt(double x) { double y = (double)(1.0f / sqrtf((float)x)); y = y * (1.5 - 0.5 * x * y * y); return y * (1.5 - 0.5 * x * y * y); }
+FB_DEV double fast_rcp(double x) { double y = (double)(1.0f / (float)x); y = y * (2.0 - x * y); return y * (2.0 - x * y); }
+FB_DEV D3 dnormalized(D3 a) { double n2 = ddot(a, a); if (n2 < 1e-36) { double n = sqrt(n2); if (n < 1e-300) return d3(1, 0, 0); return a * (1.0 / n); } return a * fast_rsqrt(n2); }
 struct MprPt { D3 v, v1, v2; };
 struct MprObj { D3 pos; double mat[9]; D3 size; int type; double margin; };
 FB_DEV bool mpr_zero(double x) { return fabs(x) < MPR_EPS; }
@@ -135,11 +139,11 @@ FB_DEV D3 mpr_support1(const MprObj& o, D3 dir) {     // mjccd_support
   if (o.type == FB_GEOM_SPHERE) r = ld * o.size.x;
   else if (o.type == FB_GEOM_CAPSULE) { r = ld * o.size.x; r.z += mpr_sgn(ld.z) * o.size.y; }
   else if (o.type == FB_GEOM_ELLIPSOID) {
-    D3 t = d3(ld.x * o.size.x, ld.y * o.size.y, ld.z * o.size.z); double n = dnorm(t);
-    if (n >= 1e-15) r = d3(t.x / n * o.size.x, t.y / n * o.size.y, t.z / n * o.size.z);
+    D3 t = d3(ld.x * o.size.x, ld.y * o.size.y, ld.z * o.size.z); double n2 = ddot(t, t);
+    if (n2 >= 1e-30) { double in = fast_rsqrt(n2); r = d3(t.x * in * o.size.x, t.y * in * o.size.y, t.z * in * o.size.z); }
   } else if (o.type == FB_GEOM_CYLINDER) {
-    double n = sqrt(ld.x * ld.x + ld.y * ld.y);
-    if (n > 1e-15) { r.x = ld.x / n * o.size.x; r.y = ld.y / n * o.size.x; }
+    double n2 = ld.x * ld.x + ld.y * ld.y;
+    if (n2 > 1e-30) { double in = fast_rsqrt(n2); r.x = ld.x * in * o.size.x; r.y = ld.y * in * o.size.x; }
     r.z = mpr_sgn(ld.z) * o.size.y;
   }
   r = r + ld * (0.5 * o.margin);
@@ -258,11 +262,40 @@ FB_DEV float seg_seg_dist2(V3 p1, V3 a1, float h1, V3 p2, V3 a2, float h2) {    
   x2 = clampf(v - mb * x1, -h2, h2);
   V3 dd = (p1 + a1 * x1) - (p2 + a2 * x2); return dot(dd, dd);
 }
+#ifdef FB_EMU
+static long g_convex_stats[3];     // host emulation only: candidates, past the bounding-capsule test, contacts
+#define CONVEX_STAT(i) g_convex_stats[i]++
+#else
+#define CONVEX_STAT(i)
+#endif
+// half width of a convex geom along the unit direction d (its support function measured from the centre)
+FB_DEV float support_width(int type, V3 size, const M3& R, V3 d) {
+  V3 ld = mulT(R, d);
+  if (type == FB_GEOM_SPHERE) return size.x;
+  if (type == FB_GEOM_CAPSULE) return size.x + fabsf(ld.z) * size.y;
+  if (type == FB_GEOM_ELLIPSOID) return sqrtf(ld.x * ld.x * size.x * size.x + ld.y * ld.y * size.y * size.y + ld.z * ld.z * size.z * size.z);
+  return size.x * sqrtf(fmaxf(0.0f, 1.0f - ld.z * ld.z)) + fabsf(ld.z) * size.y;      // cylinder
+}
+// true if the plane orthogonal to d separates the two geoms by more than the margin (conservative, fp32 with a safety band)
+FB_DEV bool separated_along(V3 d, V3 dc, float margin, int t1, V3 s1, const M3& m1, int t2, V3 s2, const M3& m2) {
+  float gap = fabsf(dot(dc, d)) - support_width(t1, s1, m1, d) - support_width(t2, s2, m2, d);
+  return gap > margin + 1e-5f;
+}
 FB_DEV int col_convex(RawCon* c, float margin, int t1, V3 p1, const M3& m1, V3 s1, int t2, V3 p2, const M3& m2, V3 s2) {
+  CONVEX_STAT(0);
   int ax1, ax2; float h1, r1, h2, r2;
   bound_capsule(t1, s1, ax1, h1, r1); bound_capsule(t2, s2, ax2, h2, r2);
   float lim = r1 + r2 + margin; lim *= 1.0001f;
   if (seg_seg_dist2(p1, col(m1, ax1), h1, p2, col(m2, ax2), h2) > lim * lim) return 0;
+  // cheap separating-axis tests before the double-precision MPR: the centre line and the principal axes of both geoms.
+  // A separating plane proves that MPR would report no intersection, so pruning here does not change any result.
+  { V3 dc = p2 - p1; float n = norm(dc);
+    if (n > 1e-9f && separated_along(dc * (1.0f / n), dc, margin, t1, s1, m1, t2, s2, m2)) return 0;
+    for (int k = 0; k < 3; k++) {
+      if (separated_along(col(m1, k), dc, margin, t1, s1, m1, t2, s2, m2)) return 0;
+      if (separated_along(col(m2, k), dc, margin, t1, s1, m1, t2, s2, m2)) return 0;
+    } }
+  CONVEX_STAT(1);
   MprObj a, b;
   a.pos = d3(p1.x, p1.y, p1.z); a.size = d3(s1.x, s1.y, s1.z); a.type = t1; a.margin = margin;
   b.pos = d3(p2.x, p2.y, p2.z); b.size = d3(s2.x, s2.y, s2.z); b.type = t2; b.margin = margin;
@@ -270,6 +303,7 @@ FB_DEV int col_convex(RawCon* c, float margin, int t1, V3 p1, const M3& m1, V3 s
   double depth; D3 dir, pos;
   if (mpr_penetration(a, b, 1e-6, 50, depth, dir, pos) != 0) return 0;
   if (mpr_eq(dir.x, 0) && mpr_eq(dir.y, 0) && mpr_eq(dir.z, 0)) return 0;
+  CONVEX_STAT(2);
   c->dist = (float)(margin - depth); c->pos = v3((float)pos.x, (float)pos.y, (float)pos.z); c->n = v3((float)dir.x, (float)dir.y, (float)dir.z); c->t = v3(0, 0, 0);
   return 1;
 }

@@ -573,6 +573,7 @@ int fb_destroy(FbHandle s) {
 extern "C" int fb_clk_read(FbHandle s, long long* dst) { if (!s) return -1; cudaStreamSynchronize(s->stream); cudaMemcpy(dst, s->d.clk, sizeof(long long) * 32 * 4096, cudaMemcpyDeviceToHost); return (int)(s->launches % 4096); }
 #endif
 #ifdef FB_EMU
+extern "C" void fb_emu_convex_stats(long* out) { for (int i = 0; i < 3; i++) { out[i] = g_convex_stats[i]; g_convex_stats[i] = 0; } }
 // host-emulation build only (tests): the fp32 generic-convex narrowphase on one pair; out = dist, pos[3], normal[3]
 extern "C" int fb_emu_convex_pair(int t1, const float* p1, const float* m1, const float* s1, int t2, const float* p2, const float* m2, const float* s2,
                                   float margin, float* out) {
