@@ -111,66 +111,91 @@ FB_DEV int col_capsule_capsule(RawCon* c, float margin, V3 p1, const M3& m1, V3 
 // Generic convex pairs (MuJoCo mjc_Convex): Minkowski Portal Refinement as in libccd (mpr.c: discoverPortal /
 // refinePortal / findPenetr / findPos, vec3.c: point-triangle distance), with MuJoCo's support functions (each geom
 // inflated by margin / 2), tolerance 1e-6, 50 iterations, dist = margin - depth.
-// This routine runs in DOUBLE precision: libccd's portal logic is built on exact-zero tests scaled by the machine epsilon and
-// loses 6 % of shallow contacts (depth off by 10x) when compiled in fp32; the bounding-capsule test in col_convex leaves only a
-// handful of pairs per env for it.
+#ifdef FB_EMU
+static long g_convex_stats[4];     // host emulation only: generic candidates, past the pre-tests, contacts, support evaluations
+#define CONVEX_STAT(i) g_convex_stats[i]++
+#else
+#define CONVEX_STAT(i)
+#endif
+// Scalar type of MPR.  libccd's zero tests compare against an ABSOLUTE machine epsilon, which in double (1e-16) is far below
+// any geometric quantity but in single precision (1e-7) is not: with centimetre-scale geometry |v0 x v1|^2 ~ 1e-7 sin^2 and
+// the portal discovery mis-classifies ordinary configurations as degenerate (6 % of shallow contacts came out 10x too deep).
+// The fp32 variant therefore keeps the RELATIVE comparisons at FLT_EPSILON and makes the absolute zero test scale-free
+// (1e-30); with that it agrees with the fp64 oracle as often as a double-precision copy fed with the same fp32 inputs does
+// (tests/test_emu_parity.py).  -DFB_MPR_DOUBLE selects double (3x slower: the FP64 pipe is narrow).
+#ifndef FB_MPR_DOUBLE
+typedef float mreal;
+#define MPR_EPS 1.1920929e-7f
+#define MPR_ZERO 1e-30f
+#define MSQRT(x) sqrtf(x)
+#define MFABS(x) fabsf(x)
+#define MFMIN(a, b) fminf(a, b)
+#else
+typedef double mreal;
 #define MPR_EPS 2.220446049250313e-16
-struct D3 { double x, y, z; };
-FB_DEV D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+#define MPR_ZERO 2.220446049250313e-16
+#define MSQRT(x) sqrt(x)
+#define MFABS(x) fabs(x)
+#define MFMIN(a, b) fmin(a, b)
+#endif
+struct D3 { mreal x, y, z; };
+FB_DEV D3 d3(mreal x, mreal y, mreal z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
 FB_DEV D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
 FB_DEV D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
-FB_DEV D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
-FB_DEV double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+FB_DEV D3 operator*(D3 a, mreal s) { return d3(a.x * s, a.y * s, a.z * s); }
+FB_DEV mreal ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 FB_DEV D3 dcross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-FB_DEV double dnorm(D3 a) { return sqrt(ddot(a, a)); }
-// 1/sqrt(x) and 1/x to ~1e-15: single-precision seed + two Newton steps in double (the double-precision sqrt / divide of the
+FB_DEV mreal dnorm(D3 a) { return MSQRT(ddot(a, a)); }
+// 1/MSQRT(x) and 1/x to ~1e-15: single-precision seed + two Newton steps in mreal (the mreal-precision sqrt / divide of the
 // GPU are long software sequences; these sit in the inner loop of MPR)
-FB_DEV double fast_rsqrt(double x) { double y = (double)(1.0f / sqrtf((float)x)); y = y * (1.5 - 0.5 * x * y * y); return y * (1.5 - 0.5 * x * y * y); }
-FB_DEV double fast_rcp(double x) { double y = (double)(1.0f / (float)x); y = y * (2.0 - x * y); return y * (2.0 - x * y); }
-FB_DEV D3 dnormalized(D3 a) { double n2 = ddot(a, a); if (n2 < 1e-36) { double n = sqrt(n2); if (n < 1e-300) return d3(1, 0, 0); return a * (1.0 / n); } return a * fast_rsqrt(n2); }
+FB_DEV mreal fast_rsqrt(mreal x) { mreal y = (mreal)(1.0f / sqrtf((float)x)); y = y * ((mreal)1.5 - (mreal)0.5 * x * y * y); return y * ((mreal)1.5 - (mreal)0.5 * x * y * y); }
+FB_DEV mreal fast_rcp(mreal x) { mreal y = (mreal)(1.0f / (float)x); y = y * ((mreal)2.0 - x * y); return y * ((mreal)2.0 - x * y); }
+FB_DEV D3 dnormalized(D3 a) { mreal n2 = ddot(a, a); if (n2 < 1e-36) { mreal n = MSQRT(n2); if (n < 1e-300) return d3(1, 0, 0); return a * (1.0 / n); } return a * fast_rsqrt(n2); }
 struct MprPt { D3 v, v1, v2; };
-struct MprObj { D3 pos; double mat[9]; D3 size; int type; double margin; };
-FB_DEV bool mpr_zero(double x) { return fabs(x) < MPR_EPS; }
-FB_DEV bool mpr_eq(double a, double b) { double ab = fabs(a - b); if (ab < MPR_EPS) return true; a = fabs(a); b = fabs(b); return (b > a) ? ab < MPR_EPS * b : ab < MPR_EPS * a; }
-FB_DEV double mpr_sgn(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
+struct MprObj { D3 pos; mreal mat[9]; D3 size; int type; mreal margin; };
+FB_DEV bool mpr_zero(mreal x) { return MFABS(x) < MPR_ZERO; }
+FB_DEV bool mpr_eq(mreal a, mreal b) { mreal ab = MFABS(a - b); if (ab < MPR_ZERO) return true; a = MFABS(a); b = MFABS(b); return (b > a) ? ab < MPR_EPS * b : ab < MPR_EPS * a; }
+FB_DEV mreal mpr_sgn(mreal x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
 FB_DEV D3 mpr_support1(const MprObj& o, D3 dir) {     // mjccd_support
-  const double* R = o.mat;
+  const mreal* R = o.mat;
   D3 ld = d3(R[0] * dir.x + R[3] * dir.y + R[6] * dir.z, R[1] * dir.x + R[4] * dir.y + R[7] * dir.z, R[2] * dir.x + R[5] * dir.y + R[8] * dir.z), r = d3(0, 0, 0);
   if (o.type == FB_GEOM_SPHERE) r = ld * o.size.x;
   else if (o.type == FB_GEOM_CAPSULE) { r = ld * o.size.x; r.z += mpr_sgn(ld.z) * o.size.y; }
   else if (o.type == FB_GEOM_ELLIPSOID) {
-    D3 t = d3(ld.x * o.size.x, ld.y * o.size.y, ld.z * o.size.z); double n2 = ddot(t, t);
-    if (n2 >= 1e-30) { double in = fast_rsqrt(n2); r = d3(t.x * in * o.size.x, t.y * in * o.size.y, t.z * in * o.size.z); }
+    D3 t = d3(ld.x * o.size.x, ld.y * o.size.y, ld.z * o.size.z); mreal n2 = ddot(t, t);
+    if (n2 >= 1e-30) { mreal in = fast_rsqrt(n2); r = d3(t.x * in * o.size.x, t.y * in * o.size.y, t.z * in * o.size.z); }
   } else if (o.type == FB_GEOM_CYLINDER) {
-    double n2 = ld.x * ld.x + ld.y * ld.y;
-    if (n2 > 1e-30) { double in = fast_rsqrt(n2); r.x = ld.x * in * o.size.x; r.y = ld.y * in * o.size.x; }
+    mreal n2 = ld.x * ld.x + ld.y * ld.y;
+    if (n2 > 1e-30) { mreal in = fast_rsqrt(n2); r.x = ld.x * in * o.size.x; r.y = ld.y * in * o.size.x; }
     r.z = mpr_sgn(ld.z) * o.size.y;
   }
   r = r + ld * (0.5 * o.margin);
   return d3(R[0] * r.x + R[1] * r.y + R[2] * r.z, R[3] * r.x + R[4] * r.y + R[5] * r.z, R[6] * r.x + R[7] * r.y + R[8] * r.z) + o.pos;
 }
-FB_DEV MprPt mpr_support(const MprObj& a, const MprObj& b, D3 dir) { MprPt p; p.v1 = mpr_support1(a, dir); p.v2 = mpr_support1(b, d3(0, 0, 0) - dir); p.v = p.v1 - p.v2; return p; }
-FB_DEV double mpr_seg_dist2(D3 P, D3 x0, D3 b, D3& w) {
-  D3 dd = b - x0, a = x0 - P; double t = -ddot(a, dd) / ddot(dd, dd);
+FB_DEV MprPt mpr_support(const MprObj& a, const MprObj& b, D3 dir) { MprPt p;
+  CONVEX_STAT(3);
+ p.v1 = mpr_support1(a, dir); p.v2 = mpr_support1(b, d3(0, 0, 0) - dir); p.v = p.v1 - p.v2; return p; }
+FB_DEV mreal mpr_seg_dist2(D3 P, D3 x0, D3 b, D3& w) {
+  D3 dd = b - x0, a = x0 - P; mreal t = -ddot(a, dd) / ddot(dd, dd);
   if (t < 0 || mpr_zero(t)) w = x0; else if (t > 1 || mpr_eq(t, 1)) w = b; else w = x0 + dd * t;
   D3 ee = w - P; return ddot(ee, ee);
 }
-FB_DEV double mpr_tri_dist2(D3 P, D3 x0, D3 B, D3 C, D3& w) {
+FB_DEV mreal mpr_tri_dist2(D3 P, D3 x0, D3 B, D3 C, D3& w) {
   D3 d1 = B - x0, d2 = C - x0, a = x0 - P;
-  double v = ddot(d1, d1), ww = ddot(d2, d2), pp = ddot(a, d1), q = ddot(a, d2), r = ddot(d1, d2);
-  double s = (q * r - ww * pp) / (ww * v - r * r), t = (-s * r - q) / ww;
+  mreal v = ddot(d1, d1), ww = ddot(d2, d2), pp = ddot(a, d1), q = ddot(a, d2), r = ddot(d1, d2);
+  mreal s = (q * r - ww * pp) / (ww * v - r * r), t = (-s * r - q) / ww;
   if ((mpr_zero(s) || s > 0) && (mpr_eq(s, 1) || s < 1) && (mpr_zero(t) || t > 0) && (mpr_eq(t, 1) || t < 1) && (mpr_eq(t + s, 1) || t + s < 1)) {
     w = x0 + d1 * s + d2 * t; D3 ee = w - P; return ddot(ee, ee);
   }
-  D3 w2; double dist = mpr_seg_dist2(P, x0, B, w), dd = mpr_seg_dist2(P, x0, C, w2);
+  D3 w2; mreal dist = mpr_seg_dist2(P, x0, B, w), dd = mpr_seg_dist2(P, x0, C, w2);
   if (dd < dist) { dist = dd; w = w2; }
   dd = mpr_seg_dist2(P, B, C, w2);
   if (dd < dist) { dist = dd; w = w2; }
   return dist;
 }
 FB_DEV D3 mpr_portal_dir(const MprPt* s) { return dnormalized(dcross(s[2].v - s[1].v, s[3].v - s[1].v)); }
-FB_DEV bool mpr_reach_tol(const MprPt* s, const MprPt& v4, D3 dir, double tol) {
-  double dv4 = ddot(v4.v, dir), dmin = fmin(dv4 - ddot(s[1].v, dir), fmin(dv4 - ddot(s[2].v, dir), dv4 - ddot(s[3].v, dir)));
+FB_DEV bool mpr_reach_tol(const MprPt* s, const MprPt& v4, D3 dir, mreal tol) {
+  mreal dv4 = ddot(v4.v, dir), dmin = MFMIN(dv4 - ddot(s[1].v, dir), MFMIN(dv4 - ddot(s[2].v, dir), dv4 - ddot(s[3].v, dir)));
   return mpr_eq(dmin, tol) || dmin < tol;
 }
 FB_DEV void mpr_expand(MprPt* s, const MprPt& v4) {
@@ -179,8 +204,8 @@ FB_DEV void mpr_expand(MprPt* s, const MprPt& v4) {
   else { if (ddot(s[3].v, v4v0) > 0) s[2] = v4; else s[1] = v4; }
 }
 // 0 and depth / dir / pos when the inflated shapes intersect, -1 otherwise
-FB_DEVN int mpr_penetration(const MprObj& o1, const MprObj& o2, double tol, int max_iter, double& depth, D3& pdir, D3& pos) {
-  MprPt s[4]; D3 dir; double dt;
+FB_DEVN int mpr_penetration(const MprObj& o1, const MprObj& o2, mreal tol, int max_iter, mreal& depth, D3& pdir, D3& pos) {
+  MprPt s[4]; D3 dir; mreal dt;
   s[0].v1 = o1.pos; s[0].v2 = o2.pos; s[0].v = s[0].v1 - s[0].v2;
   if (mpr_eq(s[0].v.x, 0) && mpr_eq(s[0].v.y, 0) && mpr_eq(s[0].v.z, 0)) s[0].v = d3(MPR_EPS * 10, 0, 0);
   dir = dnormalized(d3(0, 0, 0) - s[0].v);
@@ -226,17 +251,17 @@ FB_DEVN int mpr_penetration(const MprObj& o1, const MprObj& o2, double tol, int 
     dir = mpr_portal_dir(s);
     v4 = mpr_support(o1, o2, dir);
     if (mpr_reach_tol(s, v4, dir, tol) || it > max_iter) {
-      depth = sqrt(mpr_tri_dist2(d3(0, 0, 0), s[1].v, s[2].v, s[3].v, pdir));
+      depth = MSQRT(mpr_tri_dist2(d3(0, 0, 0), s[1].v, s[2].v, s[3].v, pdir));
       if (mpr_zero(pdir.x) && mpr_zero(pdir.y) && mpr_zero(pdir.z)) pdir = dir;
       pdir = dnormalized(pdir);
-      double b0 = ddot(dcross(s[1].v, s[2].v), s[3].v), b1 = ddot(dcross(s[3].v, s[2].v), s[0].v);
-      double b2 = ddot(dcross(s[0].v, s[1].v), s[3].v), b3 = ddot(dcross(s[2].v, s[1].v), s[0].v);
-      double sum = b0 + b1 + b2 + b3;
+      mreal b0 = ddot(dcross(s[1].v, s[2].v), s[3].v), b1 = ddot(dcross(s[3].v, s[2].v), s[0].v);
+      mreal b2 = ddot(dcross(s[0].v, s[1].v), s[3].v), b3 = ddot(dcross(s[2].v, s[1].v), s[0].v);
+      mreal sum = b0 + b1 + b2 + b3;
       if (mpr_zero(sum) || sum < 0) {
         b0 = 0; b1 = ddot(dcross(s[2].v, s[3].v), dir); b2 = ddot(dcross(s[3].v, s[1].v), dir); b3 = ddot(dcross(s[1].v, s[2].v), dir);
         sum = b1 + b2 + b3;
       }
-      double inv = 0.5 / sum;
+      mreal inv = 0.5 / sum;
       pos = (s[0].v1 * b0 + s[1].v1 * b1 + s[2].v1 * b2 + s[3].v1 * b3 + s[0].v2 * b0 + s[1].v2 * b1 + s[2].v2 * b2 + s[3].v2 * b3) * inv;
       return 0;
     }
@@ -262,12 +287,21 @@ FB_DEV float seg_seg_dist2(V3 p1, V3 a1, float h1, V3 p2, V3 a2, float h2) {    
   x2 = clampf(v - mb * x1, -h2, h2);
   V3 dd = (p1 + a1 * x1) - (p2 + a2 * x2); return dot(dd, dd);
 }
-#ifdef FB_EMU
-static long g_convex_stats[3];     // host emulation only: candidates, past the bounding-capsule test, contacts
-#define CONVEX_STAT(i) g_convex_stats[i]++
-#else
-#define CONVEX_STAT(i)
-#endif
+// mjc_fixNormal: the portal normal is replaced by the geometric surface normals at the contact point (see the oracle)
+FB_DEV bool surface_normal(int type, V3 pos, const M3& mat, V3 size, V3 p, V3& n) {
+  V3 l = mulT(mat, p - pos), nl = v3(0, 0, 0);
+  if (type == FB_GEOM_SPHERE) nl = l;
+  else if (type == FB_GEOM_CAPSULE) { float z = clampf(l.z, -size.y, size.y); nl = v3(l.x, l.y, l.z - z); }
+  else if (type == FB_GEOM_ELLIPSOID) nl = v3(l.x / (size.x * size.x), l.y / (size.y * size.y), l.z / (size.z * size.z));
+  else if (type == FB_GEOM_CYLINDER) {
+    float rad = sqrtf(l.x * l.x + l.y * l.y);
+    if (size.x - rad < size.y - fabsf(l.z)) nl = v3(l.x, l.y, 0); else nl = v3(0, 0, l.z > 0 ? 1.0f : -1.0f);
+  } else return false;
+  float nn = norm(nl);
+  if (nn < FB_MINVAL) return false;
+  n = mul(mat, nl * (1.0f / nn));
+  return true;
+}
 // half width of a convex geom along the unit direction d (its support function measured from the centre)
 FB_DEV float support_width(int type, V3 size, const M3& R, V3 d) {
   V3 ld = mulT(R, d);
@@ -281,31 +315,44 @@ FB_DEV bool separated_along(V3 d, V3 dc, float margin, int t1, V3 s1, const M3& 
   float gap = fabsf(dot(dc, d)) - support_width(t1, s1, m1, d) - support_width(t2, s2, m2, d);
   return gap > margin + 1e-5f;
 }
-FB_DEV int col_convex(RawCon* c, float margin, int t1, V3 p1, const M3& m1, V3 s1, int t2, V3 p2, const M3& m2, V3 s2) {
+// cheap tests that prove "no contact" for a generic convex pair: disjoint bounding capsules, or a separating plane along
+// the centre line / a principal axis of either geom.  MPR would report no intersection in these cases, so pruning here does
+// not change any result; it leaves ~4 of ~77 generic candidates per env-substep for MPR.
+FB_DEV bool convex_prefilter(float margin, int t1, V3 p1, const M3& m1, V3 s1, int t2, V3 p2, const M3& m2, V3 s2) {
   CONVEX_STAT(0);
   int ax1, ax2; float h1, r1, h2, r2;
   bound_capsule(t1, s1, ax1, h1, r1); bound_capsule(t2, s2, ax2, h2, r2);
   float lim = r1 + r2 + margin; lim *= 1.0001f;
-  if (seg_seg_dist2(p1, col(m1, ax1), h1, p2, col(m2, ax2), h2) > lim * lim) return 0;
-  // cheap separating-axis tests before the double-precision MPR: the centre line and the principal axes of both geoms.
-  // A separating plane proves that MPR would report no intersection, so pruning here does not change any result.
-  { V3 dc = p2 - p1; float n = norm(dc);
-    if (n > 1e-9f && separated_along(dc * (1.0f / n), dc, margin, t1, s1, m1, t2, s2, m2)) return 0;
-    for (int k = 0; k < 3; k++) {
-      if (separated_along(col(m1, k), dc, margin, t1, s1, m1, t2, s2, m2)) return 0;
-      if (separated_along(col(m2, k), dc, margin, t1, s1, m1, t2, s2, m2)) return 0;
-    } }
+  if (seg_seg_dist2(p1, col(m1, ax1), h1, p2, col(m2, ax2), h2) > lim * lim) return false;
+  V3 dc = p2 - p1; float n = norm(dc);
+  if (n > 1e-9f && separated_along(dc * (1.0f / n), dc, margin, t1, s1, m1, t2, s2, m2)) return false;
+  for (int k = 0; k < 3; k++) {
+    if (separated_along(col(m1, k), dc, margin, t1, s1, m1, t2, s2, m2)) return false;
+    if (separated_along(col(m2, k), dc, margin, t1, s1, m1, t2, s2, m2)) return false;
+  }
+  return true;
+}
+FB_DEV int convex_mpr(RawCon* c, float margin, int t1, V3 p1, const M3& m1, V3 s1, int t2, V3 p2, const M3& m2, V3 s2) {
   CONVEX_STAT(1);
+  // MPR works on differences of support points: move the origin to the middle of the two centres first, so that the
+  // coordinates are of the size of the geoms (fp32 resolution) rather than of their distance to the env's reference point
+  const V3 mid = (p1 + p2) * 0.5f;
   MprObj a, b;
-  a.pos = d3(p1.x, p1.y, p1.z); a.size = d3(s1.x, s1.y, s1.z); a.type = t1; a.margin = margin;
-  b.pos = d3(p2.x, p2.y, p2.z); b.size = d3(s2.x, s2.y, s2.z); b.type = t2; b.margin = margin;
+  a.pos = d3(p1.x - mid.x, p1.y - mid.y, p1.z - mid.z); a.size = d3(s1.x, s1.y, s1.z); a.type = t1; a.margin = margin;
+  b.pos = d3(p2.x - mid.x, p2.y - mid.y, p2.z - mid.z); b.size = d3(s2.x, s2.y, s2.z); b.type = t2; b.margin = margin;
   for (int k = 0; k < 9; k++) { a.mat[k] = m1.m[k]; b.mat[k] = m2.m[k]; }
-  double depth; D3 dir, pos;
-  if (mpr_penetration(a, b, 1e-6, 50, depth, dir, pos) != 0) return 0;
+  mreal depth; D3 dir, pos;
+  if (mpr_penetration(a, b, (mreal)1e-6, 50, depth, dir, pos) != 0) return 0;
   if (mpr_eq(dir.x, 0) && mpr_eq(dir.y, 0) && mpr_eq(dir.z, 0)) return 0;
   CONVEX_STAT(2);
-  c->dist = (float)(margin - depth); c->pos = v3((float)pos.x, (float)pos.y, (float)pos.z); c->n = v3((float)dir.x, (float)dir.y, (float)dir.z); c->t = v3(0, 0, 0);
+  c->dist = (float)(margin - depth); c->pos = v3((float)pos.x, (float)pos.y, (float)pos.z) + mid; c->n = v3((float)dir.x, (float)dir.y, (float)dir.z); c->t = v3(0, 0, 0);
+  { V3 n1, n2, nf; bool h1 = surface_normal(t1, p1, m1, s1, c->pos, n1), h2 = surface_normal(t2, p2, m2, s2, c->pos, n2);
+    if (h1 || h2) { nf = (h1 && h2) ? n1 - n2 : (h1 ? n1 : v3(0, 0, 0) - n2); float nn = norm(nf); if (nn >= FB_MINVAL) c->n = nf * (1.0f / nn); } }
   return 1;
+}
+FB_DEV int col_convex(RawCon* c, float margin, int t1, V3 p1, const M3& m1, V3 s1, int t2, V3 p2, const M3& m2, V3 s2) {
+  if (!convex_prefilter(margin, t1, p1, m1, s1, t2, p2, m2, s2)) return 0;
+  return convex_mpr(c, margin, t1, p1, m1, s1, t2, p2, m2, s2);
 }
 FB_DEV void make_frame(V3 n, V3 t, V3& f1, V3& f2) {   // mju_makeFrame
   if (norm(t) < 0.5f) { t = (n.y < 0.5f && n.y > -0.5f) ? v3(0, 1, 0) : v3(0, 0, 1); }
@@ -326,9 +373,9 @@ FB_DEV void kcol_stage(FB_COL_ARGS) {
 #define FB_MAXCAND 192                 // candidates per env (4 contact slots each in tmp_con)
 #define COL_FLAT(j) flat[(j) * FB_LANES + lane]
 #define COL_NCON(j) ccnt[(j) * FB_LANES + lane]
-#define FB_COL_DYN(m) (6 * (m).ngeom + 2 * FB_MAXCAND)
+#define FB_COL_DYN(m) (6 * (m).ngeom + 3 * FB_MAXCAND)
 #define FB_COL_PTRS float* gx = sh_dyn(sh); float* gn = gx + 3 * m.ngeom * FB_LANES; int* flat = reinterpret_cast<int*>(gn + 3 * m.ngeom * FB_LANES); \
-  int* ccnt = flat + FB_MAXCAND * FB_LANES; (void)gx; (void)gn; (void)flat; (void)ccnt;
+  int* ccnt = flat + FB_MAXCAND * FB_LANES; int* jobs = ccnt + FB_MAXCAND * FB_LANES; (void)gx; (void)gn; (void)flat; (void)ccnt; (void)jobs;
 // 1. broadphase: lane l tests the pairs l, l + 32, ... of the static pair list (packed record: geoms, plane flag; margin +
 // bounding radii -- one coalesced line per step), four steps loaded ahead of the tests.  The hits are ranked with ballots,
 // so the candidate list comes out in pair order without per-lane lists.
@@ -366,6 +413,18 @@ FB_WARPFN void kcol_broad(const DevModel& m, const DevData& d, ShCol& sh, int e)
   }
   WPAR_BEGIN { if (lane == 0) { sh.cnt[0][0] = base > FB_MAXCAND ? FB_MAXCAND : base; if (base > FB_MAXCAND) FB_FLAG_OR(2); } } WPAR_END
 }
+FB_DEV void col_store(const DevModel& m, const DevData& d, int e, int j, const RawCon* rc, int n, int g1, int g2) {
+  for (int i = 0; i < n; i++) {
+    int slot = 4 * j + i;
+    V3 f1, f2; make_frame(rc[i].n, rc[i].t, f1, f2);
+    CON_F(d.tmp_con, slot, 0, 13) = rc[i].dist;
+    CON_F(d.tmp_con, slot, 1, 13) = rc[i].pos.x; CON_F(d.tmp_con, slot, 2, 13) = rc[i].pos.y; CON_F(d.tmp_con, slot, 3, 13) = rc[i].pos.z;
+    CON_F(d.tmp_con, slot, 4, 13) = rc[i].n.x; CON_F(d.tmp_con, slot, 5, 13) = rc[i].n.y; CON_F(d.tmp_con, slot, 6, 13) = rc[i].n.z;
+    CON_F(d.tmp_con, slot, 7, 13) = f1.x; CON_F(d.tmp_con, slot, 8, 13) = f1.y; CON_F(d.tmp_con, slot, 9, 13) = f1.z;
+    CON_F(d.tmp_con, slot, 10, 13) = f2.x; CON_F(d.tmp_con, slot, 11, 13) = f2.y; CON_F(d.tmp_con, slot, 12, 13) = f2.z;
+    AT(d.tmp_geom, 2 * slot) = g1; AT(d.tmp_geom, 2 * slot + 1) = g2;
+  }
+}
 // 2. narrowphase: one candidate per lane, up to 4 contacts each into tmp_con[4 j + i]
 FB_DEV void kcol_narrow(FB_COL_ARGS) {
   FB_COL_PTRS
@@ -391,20 +450,36 @@ FB_DEV void kcol_narrow(FB_COL_ARGS) {
       if (t1 == FB_GEOM_SPHERE && t2 == FB_GEOM_SPHERE) n = raw_sphere_sphere(rc, margin, x1, s1.x, x2, s2.x);
       else if (t1 == FB_GEOM_SPHERE && t2 == FB_GEOM_CAPSULE) { M3 R2 = ld9(d.geom_xmat, g2, d, e); n = col_sphere_capsule(rc, margin, x1, s1.x, x2, R2, s2); }
       else if (t1 == FB_GEOM_CAPSULE && t2 == FB_GEOM_CAPSULE) { M3 R1 = ld9(d.geom_xmat, g1, d, e), R2 = ld9(d.geom_xmat, g2, d, e); n = col_capsule_capsule(rc, margin, x1, R1, s1, x2, R2, s2); }
-      else { M3 R1 = ld9(d.geom_xmat, g1, d, e), R2 = ld9(d.geom_xmat, g2, d, e); n = col_convex(rc, margin, t1, x1, R1, s1, t2, x2, R2, s2); }    // generic convex pairs: MPR
+      else { M3 R1 = ld9(d.geom_xmat, g1, d, e), R2 = ld9(d.geom_xmat, g2, d, e);      // generic convex pair: MPR job if the cheap tests cannot rule it out
+        n = convex_prefilter(margin, t1, x1, R1, s1, t2, x2, R2, s2) ? -1 : 0; }
     }
-    for (int i = 0; i < n; i++) {
-      int slot = 4 * j + i;
-      V3 f1, f2; make_frame(rc[i].n, rc[i].t, f1, f2);
-      CON_F(d.tmp_con, slot, 0, 13) = rc[i].dist;
-      CON_F(d.tmp_con, slot, 1, 13) = rc[i].pos.x; CON_F(d.tmp_con, slot, 2, 13) = rc[i].pos.y; CON_F(d.tmp_con, slot, 3, 13) = rc[i].pos.z;
-      CON_F(d.tmp_con, slot, 4, 13) = rc[i].n.x; CON_F(d.tmp_con, slot, 5, 13) = rc[i].n.y; CON_F(d.tmp_con, slot, 6, 13) = rc[i].n.z;
-      CON_F(d.tmp_con, slot, 7, 13) = f1.x; CON_F(d.tmp_con, slot, 8, 13) = f1.y; CON_F(d.tmp_con, slot, 9, 13) = f1.z;
-      CON_F(d.tmp_con, slot, 10, 13) = f2.x; CON_F(d.tmp_con, slot, 11, 13) = f2.y; CON_F(d.tmp_con, slot, 12, 13) = f2.z;
-      AT(d.tmp_geom, 2 * slot) = g1; AT(d.tmp_geom, 2 * slot + 1) = g2;
-    }
+    col_store(m, d, e, j, rc, n, g1, g2);
     COL_NCON(j) = n;
   }
+}
+// 2b. the generic pairs that survived the cheap tests, compacted with ballots and run through MPR one per lane: in the
+// candidate loop above a single such pair would stall the other 31 lanes of its round
+FB_WARPFN void kcol_mpr(const DevModel& m, const DevData& d, ShCol& sh, int e) {      // (`lane` is the real lane here: index the lists directly, not through the per-phase macros)
+  LREG(int, pend);
+  const int T = sh.cnt[0][0];
+  int njobs = 0;
+  for (int base = 0; base < T; base += 32) {
+    WPAR_BEGIN { FB_COL_PTRS L(pend) = (base + lane < T && ccnt[base + lane] < 0) ? 1 : 0; } WPAR_END
+    unsigned mk; BALLOT(mk, pend, != 0);
+    WPAR_BEGIN { FB_COL_PTRS if (L(pend)) jobs[njobs + POPC(mk & ((1u << lane) - 1u))] = base + lane; } WPAR_END
+    njobs += POPC(mk);
+  }
+  WPAR_BEGIN { FB_COL_PTRS
+    for (int q = lane; q < njobs; q += 32) {
+      const int j = jobs[q], k = flat[j], pw = m.pair_info[k];
+      const int g1 = pw & 0x7fff, g2 = (pw >> 15) & 0x7fff;
+      V3 x1 = v3(gx[3 * g1], gx[3 * g1 + 1], gx[3 * g1 + 2]), x2 = v3(gx[3 * g2], gx[3 * g2 + 1], gx[3 * g2 + 2]);
+      M3 R1 = ld9(d.geom_xmat, g1, d, e), R2 = ld9(d.geom_xmat, g2, d, e);
+      RawCon rc[1];
+      int n = convex_mpr(rc, fmaxf(m.geom_margin[g1], m.geom_margin[g2]), m.geom_type[g1], x1, R1, mld3(m.geom_size, g1), m.geom_type[g2], x2, R2, mld3(m.geom_size, g2));
+      col_store(m, d, e, j, rc, n, g1, g2);
+      ccnt[j] = n;
+    } } WPAR_END
 }
 // 3. compaction into the contact list, in candidate order
 FB_DEV void kcol_compact(FB_COL_ARGS) {

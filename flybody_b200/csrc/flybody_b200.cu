@@ -212,7 +212,7 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 static void launch_step1(FbSim* s) {
   size_t nm = (size_t)FB_PARTF + (size_t)s->m.nM;
   fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, nm);
-  fb_launch<ShCol, Ph<kcol_stage>, Wf<kcol_broad>, Ph<kcol_narrow>, Ph<kcol_compact>>(s, K_COL, (size_t)FB_COL_DYN(s->m));
+  fb_launch<ShCol, Ph<kcol_stage>, Wf<kcol_broad>, Ph<kcol_narrow>, Wf<kcol_mpr>, Ph<kcol_compact>>(s, K_COL, (size_t)FB_COL_DYN(s->m));
   fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_NY * FB_ZCAP);
   fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL, (size_t)FB_PARTF);
 }
@@ -573,7 +573,7 @@ int fb_destroy(FbHandle s) {
 extern "C" int fb_clk_read(FbHandle s, long long* dst) { if (!s) return -1; cudaStreamSynchronize(s->stream); cudaMemcpy(dst, s->d.clk, sizeof(long long) * 32 * 4096, cudaMemcpyDeviceToHost); return (int)(s->launches % 4096); }
 #endif
 #ifdef FB_EMU
-extern "C" void fb_emu_convex_stats(long* out) { for (int i = 0; i < 3; i++) { out[i] = g_convex_stats[i]; g_convex_stats[i] = 0; } }
+extern "C" void fb_emu_convex_stats(long* out) { for (int i = 0; i < 4; i++) { out[i] = g_convex_stats[i]; g_convex_stats[i] = 0; } }
 // host-emulation build only (tests): the fp32 generic-convex narrowphase on one pair; out = dist, pos[3], normal[3]
 extern "C" int fb_emu_convex_pair(int t1, const float* p1, const float* m1, const float* s1, int t2, const float* p2, const float* m2, const float* s2,
                                   float margin, float* out) {

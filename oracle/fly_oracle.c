@@ -604,7 +604,7 @@ static int col_capsule_capsule(RawCon* c, double margin, const double* p1, const
  * libccd (src/mpr.c: ccdMPRPenetration -> discoverPortal / refinePortal / findPenetr / findPos, src/vec3.c:
  * ccdVec3PointTriDist2), which MuJoCo links for every pair without an analytic routine, with MuJoCo's support functions
  * (mjccd_support: each geom inflated by margin / 2), mpr_tolerance 1e-6, mpr_iterations 50, contact dist = margin - depth.
- * Restated from memory of libccd 2.1 / MuJoCo 2.3-3.1; mjc_fixNormal and multiccd are not restated.        */
+ * Restated from memory of libccd 2.1 / MuJoCo 2.3-3.1; multiccd is not restated.        */
 #define CCD_EPS 2.220446049250313e-16
 typedef struct { double v[3], v1[3], v2[3]; } MprPt;
 typedef struct { const double *pos, *mat, *size; int type; double margin; } MprObj;
@@ -758,6 +758,32 @@ static int mpr_penetration(const MprObj* o1, const MprObj* o2, double tol, int m
     expand_portal(s,&v4);
   }
 }
+/* mjc_fixNormal (engine_collision_convex.c): MPR's portal normal is only as good as its 1e-6 tolerance (~1e-2 rad); for the
+ * smooth primitives MuJoCo replaces it by the geometric surface normals at the contact point: n = normalize(n1 - n2) with
+ * n_i the outward normal of geom i there (sphere: from the centre; capsule: from the axis segment; ellipsoid: gradient of the
+ * implicit function; cylinder: side or cap, whichever the point is nearer to).  Restated from memory, see DESIGN.md.      */
+static int surface_normal(int type, const double* pos, const double* mat, const double* size, const double* p, double* n) {
+  double d[3], l[3]; sub3(d,p,pos); mulmatT3(l,mat,d);
+  double nl[3]={0,0,0};
+  if (type==FB_GEOM_SPHERE) { copy3(nl,l); }
+  else if (type==FB_GEOM_CAPSULE) { double z=l[2]<-size[1]?-size[1]:(l[2]>size[1]?size[1]:l[2]); nl[0]=l[0]; nl[1]=l[1]; nl[2]=l[2]-z; }
+  else if (type==FB_GEOM_ELLIPSOID) { for (int i=0;i<3;i++) nl[i]=l[i]/(size[i]*size[i]); }
+  else if (type==FB_GEOM_CYLINDER) {
+    double rad=sqrt(l[0]*l[0]+l[1]*l[1]);
+    if (size[0]-rad < size[1]-fabs(l[2])) { nl[0]=l[0]; nl[1]=l[1]; }      /* nearer to the side */
+    else nl[2]=l[2]>0?1.0:-1.0;                                            /* nearer to a cap */
+  } else return 0;
+  if (normalize3(nl)<MINVAL) return 0;
+  mulmat3(n,mat,nl);
+  return 1;
+}
+static void fix_normal(RawCon* c, int t1, const double* p1, const double* m1, const double* s1, int t2, const double* p2, const double* m2, const double* s2) {
+  double n1[3], n2[3]; int h1=surface_normal(t1,p1,m1,s1,c->pos,n1), h2=surface_normal(t2,p2,m2,s2,c->pos,n2);
+  double n[3];
+  if (h1&&h2) sub3(n,n1,n2); else if (h1) copy3(n,n1); else if (h2) scl3(n,n2,-1); else return;
+  if (normalize3(n)<MINVAL) return;
+  copy3(c->normal,n);
+}
 static int col_convex(RawCon* c, double margin, int t1, const double* p1, const double* m1, const double* s1,
                       int t2, const double* p2, const double* m2, const double* s2) {
   MprObj a={p1,m1,s1,t1,margin}, b={p2,m2,s2,t2,margin};
@@ -765,6 +791,7 @@ static int col_convex(RawCon* c, double margin, int t1, const double* p1, const 
   if (mpr_penetration(&a,&b,1e-6,50,&depth,dir,pos)!=0) return 0;
   if (ccd_eq(dir[0],0)&&ccd_eq(dir[1],0)&&ccd_eq(dir[2],0)) return 0;      /* normal undefined */
   c->dist=margin-depth; copy3(c->pos,pos); copy3(c->normal,dir); c->tangent[0]=c->tangent[1]=c->tangent[2]=0;
+  fix_normal(c,t1,p1,m1,s1,t2,p2,m2,s2);
   return 1;
 }
 /* exported for the tests: one generic pair */

