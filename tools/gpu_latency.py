@@ -22,7 +22,7 @@ buf = buf.reshape(4096, 32)
 names = ['smooth', 'solve', 'finish', 'pos', 'col', 'proj', 'vel']
 stages = {'smooth': ['act0', 'act1', 'adh', 'adh_b', 'qfrc', 'L^-T', 'out', 'kref'], 'solve': ['solve'],
           'finish': ['f1', 'L^-1', 'f5', 'f6', 'f7', 'euler', 'f8', 'f9'], 'pos': ['p0', 'p1 kin', 'p1b', 'p2 crb', 'p3', 'p4 M', 'factor', 'wr', 'reinit', 'factor2', 'wr2'],
-          'col': ['stage', 'broad', 'narrow', 'compact'], 'proj': ['c0', 'c1', 'c2', 'c3', 'J,Z', 'A'], 'vel': ['v0', 'v1', 'v1b', 'v2', 'v3', 'v3b', 'v4']}
+          'col': ['stage', 'broad', 'narrow', 'mpr', 'compact'], 'proj': ['c0', 'c1', 'c2', 'c3', 'J,Z', 'A'], 'vel': ['v0', 'v1', 'v1b', 'v2', 'v3', 'v3b', 'v4']}
 tot = 0
 for j in range(7):                       # second substep of the step(2) call: launches l0+7 .. l0+13
     row = buf[(l0 + 7 + j) % 4096]
