@@ -240,7 +240,10 @@ def run_ours(args):
         dom_name, (dom_ms, dom_n) = dom
         step_ms_sum = sum(v[0] for v in prof.values())
         avg_launch_s = dom_ms / max(dom_n, 1) * 1e-3
-        alg_bytes_per_launch = BYTES_PER_ENV_SUBSTEP * N          # one launch = one substep stage over N envs
+        # one launch of a stage kernel = one substep over N envs; fused launch groupings (FB_FUSE) run 1 or N_SUB whole
+        # substeps per launch: the substeps a launch of the dominant kernel covers = timed substeps / its launch count
+        substeps_per_launch = max(1, round(K * N_SUB / max(dom_n, 1)))
+        alg_bytes_per_launch = BYTES_PER_ENV_SUBSTEP * N * substeps_per_launch
         achieved = alg_bytes_per_launch / avg_launch_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
@@ -261,7 +264,7 @@ def run_ours(args):
                     'd2h_bytes_per_step': int(env.d2h_bytes_per_step), 'api': 'flybody_b200.fly_envs.walk_imitation(n_envs).step(action)'},
             'roofline': {'bound': 'hbm', 'kernel': dom_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
-                         'how': f'algorithmic bytes = {BYTES_PER_ENV_SUBSTEP} B/env-substep x {N} envs per launch / mean CUDA-event duration of the '
+                         'how': f'algorithmic bytes = {BYTES_PER_ENV_SUBSTEP} B/env-substep x {N} envs x {substeps_per_launch} substep(s) per launch / mean CUDA-event duration of the '
                                 f'"{dom_name}" kernel over the timed region ({dom_n} launches); whole-step algorithmic GB/s = '
                                 f'{BYTES_PER_ENV_STEP * total_envs * K / (ms * 1e-3) / 1e9:.2f}',
                          'kernel_share': dom_ms / max(step_ms_sum, 1e-9),

@@ -43,8 +43,11 @@ static void h2d(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 static void d2h(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 #endif
 
-enum { K_ACT = 0, K_SMOOTH, K_REF, K_SOLVE, K_FINISH, K_POS, K_COL, K_CON, K_PROJ, K_VEL, K_SENS, K_PACK, K_MISC, K_NKIND };
-static const char* const kKindNames[K_NKIND] = {"act", "smooth", "ref", "solve", "finish", "pos", "col", "con", "proj", "vel", "sens", "pack", "misc"};
+#ifndef FB_FUSE_DEFAULT
+#define FB_FUSE_DEFAULT 0
+#endif
+enum { K_ACT = 0, K_SMOOTH, K_REF, K_SOLVE, K_FINISH, K_POS, K_COL, K_CON, K_PROJ, K_VEL, K_SENS, K_PACK, K_MISC, K_STEP2, K_STEP1, K_STEP, K_NKIND };
+static const char* const kKindNames[K_NKIND] = {"act", "smooth", "ref", "solve", "finish", "pos", "col", "con", "proj", "vel", "sens", "pack", "misc", "step2", "step1", "step"};
 #ifndef FB_EMU
 struct ProfEvent { int kind; cudaEvent_t a, b; };
 #endif
@@ -62,6 +65,7 @@ struct FbSim {
   int first_substep; int hold_pending;
   int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
   const int* act_map_dev; int n_action;
+  int fuse;                    // FB_FUSE: how the stage kernels of a step are grouped into launches (see fb_launch_fused)
   int blob_in_smem;            // copy the sweep program of the triangular solves into shared memory per CTA (default: for batches <= 1024 envs; FB_BLOB=0/1 overrides)
   int* op_step_dev; unsigned char* op_first_dev;
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
@@ -209,18 +213,122 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
   }
 }
 
+// the stage lists of the seven step kernels (shared by the one-kernel-per-stage launches and the fused launches below)
+#define FB_ST_POS Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>
+#define FB_ST_COL Ph<kcol_stage>, Wf<kcol_broad>, Ph<kcol_narrow>, Wf<kcol_mpr>, Ph<kcol_compact>
+#define FB_ST_PROJ Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>
+#define FB_ST_VEL Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>
+#define FB_ST_SMOOTH Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>
+#define FB_ST_FINISH Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>
+static size_t dyn_pos(const DevModel& m) { return (size_t)FB_PARTF + (size_t)m.nM; }
+static size_t dyn_col(const DevModel& m) { return (size_t)FB_COL_DYN(m); }
+static size_t dyn_proj(const DevModel&) { return (size_t)FB_NY * FB_ZCAP; }
+static size_t dyn_vel(const DevModel&) { return (size_t)FB_PARTF; }
+static size_t dyn_tsolve(const DevModel& m) { return (size_t)(FB_NXS(m) + ((m.nM + 3) & ~3)); }
+
 static void launch_step1(FbSim* s) {
-  size_t nm = (size_t)FB_PARTF + (size_t)s->m.nM;
-  fb_launch<ShTree, Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>>(s, K_POS, nm);
-  fb_launch<ShCol, Ph<kcol_stage>, Wf<kcol_broad>, Ph<kcol_narrow>, Wf<kcol_mpr>, Ph<kcol_compact>>(s, K_COL, (size_t)FB_COL_DYN(s->m));
-  fb_launch<ShCon, Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>>(s, K_PROJ, (size_t)FB_NY * FB_ZCAP);
-  fb_launch<ShTree, Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>>(s, K_VEL, (size_t)FB_PARTF);
+  fb_launch<ShTree, FB_ST_POS>(s, K_POS, dyn_pos(s->m));
+  fb_launch<ShCol, FB_ST_COL>(s, K_COL, dyn_col(s->m));
+  fb_launch<ShCon, FB_ST_PROJ>(s, K_PROJ, dyn_proj(s->m));
+  fb_launch<ShTree, FB_ST_VEL>(s, K_VEL, dyn_vel(s->m));
 }
 static void launch_step2(FbSim* s, bool integrate) {
   s->d.do_integrate = integrate ? 1 : 0;     // read by the solve (warm-start bookkeeping) and the finish kernel
-  fb_launch<ShTree, Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>>(s, K_SMOOTH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)), -1, s->blob_in_smem ? s->m.ts_blob_words : 0);
+  fb_launch<ShTree, FB_ST_SMOOTH>(s, K_SMOOTH, dyn_tsolve(s->m), -1, s->blob_in_smem ? s->m.ts_blob_words : 0);
   fb_launch_warp(s, K_SOLVE);
-  fb_launch<ShTree, Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>>(s, K_FINISH, (size_t)(FB_NXS(s->m) + ((s->m.nM + 3) & ~3)), -1, s->blob_in_smem ? s->m.ts_blob_words : 0);
+  fb_launch<ShTree, FB_ST_FINISH>(s, K_FINISH, dyn_tsolve(s->m), -1, s->blob_in_smem ? s->m.ts_blob_words : 0);
+}
+
+// -------------------------------------------------------------------------------------------
+// Fused launches.  An env is owned by one warp from the first to the last stage of a step and no stage looks at another
+// env, so consecutive stage kernels can run back to back inside one launch: a *group* is one of the kernels above (its
+// shared-memory struct re-interpreted on the warp's slice, sized for the largest group), a fused kernel is a list of groups,
+// optionally looped over the substeps of a control step.  What it buys: no grid-wide drain between stages (the envs of a
+// batch differ in contact count and Newton iterations, so every stage boundary otherwise waits for its slowest warp), the
+// warps of an SM drift apart and stop competing for the same unit at the same time, and an env's intermediates are re-read
+// from the L1/L2 of the SM that wrote them.  FB_FUSE selects: 0 one kernel per stage (7 per substep), 1 two kernels per
+// substep ([smooth solve finish] [pos col proj vel]), 2 one kernel per substep, 3 one kernel per control step.
+template <typename Sh, typename... St> struct Grp {
+#ifdef __CUDACC__
+  static __device__ __forceinline__ void run(const DevModel& m, const DevData& d, unsigned char* slice, const unsigned* prog, int e, int y) {
+    Sh& sh = *reinterpret_cast<Sh*>(slice);
+    set_prog(sh, prog); __syncwarp();
+    ((St::run(m, d, sh, e, y), __syncwarp()), ...);
+  }
+#endif
+  static void emu(const DevModel& m, const DevData& d, unsigned char* slice, int e) {
+    Sh& sh = *reinterpret_cast<Sh*>(slice);
+    set_prog(sh, m.tsolve_blob);
+    (St::emu(m, d, sh, e), ...);
+  }
+};
+struct GrpSolve {
+#ifdef __CUDACC__
+  static __device__ __forceinline__ void run(const DevModel& m, const DevData& d, unsigned char* slice, const unsigned*, int e, int) {
+    ksolve_warp(m, d, reinterpret_cast<float*>(slice), e); __syncwarp();
+  }
+#else
+  static void emu(const DevModel& m, const DevData& d, unsigned char* slice, int e) { ksolve_warp(m, d, reinterpret_cast<float*>(slice), e); }
+#endif
+};
+using GSmooth = Grp<ShTree, FB_ST_SMOOTH>; using GFinish = Grp<ShTree, FB_ST_FINISH>; using GPos = Grp<ShTree, FB_ST_POS>;
+using GCol = Grp<ShCol, FB_ST_COL>; using GProj = Grp<ShCon, FB_ST_PROJ>; using GVel = Grp<ShTree, FB_ST_VEL>;
+FB_DEV void fused_sens_accum(const DevModel& m, const DevData& d, int e, int y, int first) {
+  for (int i = y; i < m.nsensordata; i += FB_NY) AT(d.sensor_sum, i) = (first ? 0.0f : AT(d.sensor_sum, i)) + AT(d.sensordata, i);
+}
+static size_t fused_slice_bytes(const DevModel& m) {
+  size_t b = slice_bytes(sizeof(ShTree), std::max(std::max(dyn_pos(m), dyn_tsolve(m)), dyn_vel(m)));
+  b = std::max(b, slice_bytes(sizeof(ShCol), dyn_col(m)));
+  b = std::max(b, slice_bytes(sizeof(ShCon), dyn_proj(m)));
+  b = std::max(b, slice_bytes(0, (size_t)FB_SOLVE_WARP_FLOATS));
+  return b;
+}
+#ifndef FB_EMU
+// loop_sens: the kernel runs n_sub whole substeps and restarts / continues the sensor sums itself (d.sens_mode is -1 then)
+template <typename... G>
+__global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run_fused(DevModel m, DevData d, int slice, int nwarps, int blob_words, int n_sub, int loop_sens) {
+  extern __shared__ __align__(16) unsigned char fb_smem[];
+  unsigned* blob = reinterpret_cast<unsigned*>(fb_smem);
+  if (blob_words) {
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < blob_words; i += 32 * FB_WPB) blob[i] = m.tsolve_blob[i];
+    __syncthreads();
+  }
+  int e = blockIdx.x * FB_WPB + threadIdx.y;
+  if (e >= nwarps) return;
+  unsigned char* sl = fb_smem + (size_t)blob_words * 4 + (size_t)threadIdx.y * slice;
+  const unsigned* prog = blob_words ? blob : m.tsolve_blob;
+  const int y = threadIdx.x;
+  for (int k = 0; k < n_sub; k++) {
+    (G::run(m, d, sl, prog, e, y), ...);
+    if (loop_sens) { fused_sens_accum(m, d, e, y, k == 0); __syncwarp(); }
+  }
+}
+#endif
+template <typename... G>
+static void fb_launch_fused(FbSim* s, int kind, int n_sub, int loop_sens) {
+  const int nwarps = s->d.Np;
+  size_t slice = fused_slice_bytes(s->m);
+#ifndef FB_EMU
+  const int blob_words = s->blob_in_smem ? s->m.ts_blob_words : 0;
+  dim3 block(32, FB_WPB), grid((nwarps + FB_WPB - 1) / FB_WPB);
+  size_t bytes = slice * FB_WPB + (size_t)blob_words * 4;
+  static size_t configured = 0;
+  if (bytes > configured) { cudaFuncSetAttribute(fb_run_fused<G...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
+  cudaEvent_t a = nullptr, b = nullptr;
+  if (s->prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s->stream); }
+  fb_run_fused<G...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps, blob_words, n_sub, loop_sens);
+  if (s->prof_on) { cudaEventRecord(b, s->stream); s->prof_events.push_back({kind, a, b}); }
+#else
+  (void)kind;
+  static std::vector<unsigned char> buf;
+  if (buf.size() < slice + 64) buf.resize(slice + 64);
+  for (int e = 0; e < nwarps; e++)
+    for (int k = 0; k < n_sub; k++) {
+      (G::emu(s->m, s->d, buf.data(), e), ...);
+      if (loop_sens) for (int y = 0; y < FB_NY; y++) fused_sens_accum(s->m, s->d, e, y, k == 0);
+    }
+#endif
+  s->launches++;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -534,6 +642,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   if (!hm || !out || n_envs <= 0) return -1;
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
+  s->fuse = getenv("FB_FUSE") ? atoi(getenv("FB_FUSE")) : FB_FUSE_DEFAULT; if (s->fuse < 0 || s->fuse > 3) s->fuse = FB_FUSE_DEFAULT;
   s->op_step_dev = nullptr; s->op_first_dev = nullptr; s->stage_cap = 0; s->stage_icap = 0; s->stage = nullptr; s->stage_i = nullptr;
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
@@ -622,10 +731,23 @@ int fb_forward(FbHandle s) {
 
 // the launch sequence of one control step: n x [ step2 ; step1 ], sensor accumulation restarted at the first substep
 static void step_sequence(FbSim* s, int n_substeps) {
-  for (int k = 0; k < n_substeps; k++) {
-    launch_step2(s, true);
-    s->d.sens_mode = (k == 0) ? 1 : 0;
-    launch_step1(s);
+  if (s->fuse == 3) {                       // the whole control step in one launch
+    s->d.do_integrate = 1; s->d.sens_mode = -1;
+    fb_launch_fused<GSmooth, GrpSolve, GFinish, GPos, GCol, GProj, GVel>(s, K_STEP, n_substeps, 1);
+  } else for (int k = 0; k < n_substeps; k++) {
+    if (s->fuse == 0) {
+      launch_step2(s, true);
+      s->d.sens_mode = (k == 0) ? 1 : 0;
+      launch_step1(s);
+    } else if (s->fuse == 1) {
+      s->d.do_integrate = 1;
+      fb_launch_fused<GSmooth, GrpSolve, GFinish>(s, K_STEP2, 1, 0);
+      s->d.sens_mode = (k == 0) ? 1 : 0;
+      fb_launch_fused<GPos, GCol, GProj, GVel>(s, K_STEP1, 1, 0);
+    } else {
+      s->d.do_integrate = 1; s->d.sens_mode = (k == 0) ? 1 : 0;       // only the last group (vel) reads sens_mode
+      fb_launch_fused<GSmooth, GrpSolve, GFinish, GPos, GCol, GProj, GVel>(s, K_STEP, 1, 0);
+    }
     s->d.sens_mode = -1;
   }
   s->d.nsub_done = n_substeps;
