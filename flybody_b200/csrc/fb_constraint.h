@@ -1059,6 +1059,7 @@ FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e, int y) {
   float inv = d.op_nsub > 0 ? 1.0f / d.op_nsub : 1.0f;
   int step = d.op_step ? d.op_step[e] : 0;
   int rj = m.body_jntadr[rb], rq = rj >= 0 ? m.jnt_qposadr[rj] : 0;
+  const float* rtab = d.op_ref_slot ? d.op_ref + (size_t)e * 7 * d.op_ref_len : d.op_ref;      // the env's own reference snippet, or the shared one
   for (int it = 0; it < d.op_n; it++) {
     int kind = d.op_kind[it], a = d.op_a[it], b = d.op_b[it], k = d.op_off[it];
     switch (kind) {
@@ -1068,17 +1069,18 @@ FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e, int y) {
       case FB_OBS_QPOS: for (int i = y; i < b; i += FB_NY) o[k + i] = AT(d.qpos, d.op_list[a + i]); break;
       case FB_OBS_QVEL: for (int i = y; i < b; i += FB_NY) o[k + i] = AT(d.qvel, d.op_list[a + i]); break;
       case FB_OBS_SITES_EGO: for (int i = y; i < b; i += FB_NY) { V3 v = mulT(R, ld3(d.site_xpos, d.op_list[a + i], d, e) - rpos); o[k + 3 * i] = v.x; o[k + 3 * i + 1] = v.y; o[k + 3 * i + 2] = v.z; } break;
+      case FB_OBS_DOF_AXIS_EGO: for (int i = y; i < b; i += FB_NY) { V3 v = mulT(R, ld3(d.Sang, d.op_list[a + i], d, e)); o[k + 3 * i] = v.x; o[k + 3 * i + 1] = v.y; o[k + 3 * i + 2] = v.z; } break;
       case FB_OBS_ROOT_ZAXIS: if (y < 3) o[k + y] = R.m[6 + y]; break;
       case FB_OBS_REF_DISP: {
         V3 fly = v3(AT(d.qpos, rq), AT(d.qpos, rq + 1), AT(d.qpos, rq + 2));
-        for (int i = y; i < b; i += FB_NY) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = d.op_ref + 7 * t;
+        for (int i = y; i < b; i += FB_NY) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = rtab + 7 * t;
           V3 v = mulT(R, v3(rr[0], rr[1], rr[2]) - fly); o[k + 3 * i] = v.x; o[k + 3 * i + 1] = v.y; o[k + 3 * i + 2] = v.z; }
       } break;
       case FB_OBS_REF_QUAT: {
         Q4 q = q4(AT(d.qpos, rq + 3), AT(d.qpos, rq + 4), AT(d.qpos, rq + 5), AT(d.qpos, rq + 6));
         float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z; float s = 1.0f / n2;
         Q4 qi = q4(q.w * s, -q.x * s, -q.y * s, -q.z * s);
-        for (int i = y; i < b; i += FB_NY) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = d.op_ref + 7 * t;
+        for (int i = y; i < b; i += FB_NY) { int t = step + i; if (t > d.op_ref_len - 1) t = d.op_ref_len - 1; const float* rr = rtab + 7 * t;
           Q4 r4 = qmul(qi, q4(rr[3], rr[4], rr[5], rr[6])); o[k + 4 * i] = r4.w; o[k + 4 * i + 1] = r4.x; o[k + 4 * i + 2] = r4.y; o[k + 4 * i + 3] = r4.z; }
       } break;
       case FB_OBS_SCALARS: if (y == 0) { o[k] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; } o[k + 1] = s2; o[k + 2] = AT(d.time, 0); } break;

@@ -145,7 +145,7 @@ struct DevData {
   float *obs;                  // packed AoS observation [N][obs_dim]
   int obs_dim;
   // task observation program (fb_obs_program): final observation rows [N][tobs_dim]
-  float *tobs; int tobs_dim, op_n, op_root_body, op_ref_len, op_nsub;
+  float *tobs; int tobs_dim, op_n, op_root_body, op_ref_len, op_nsub, op_ref_slot /* 1: op_ref is [N][op_ref_len][7], one table per env */;
   const int *op_kind, *op_a, *op_b, *op_off, *op_list; const float* op_ref; const int* op_step; const unsigned char* op_first;
 };
 

@@ -68,6 +68,7 @@ struct FbSim {
   int fuse;                    // FB_FUSE: how the stage kernels of a step are grouped into launches (see fb_launch_fused)
   int blob_in_smem;            // copy the sweep program of the triangular solves into shared memory per CTA (default: for batches <= 1024 envs; FB_BLOB=0/1 overrides)
   int* op_step_dev; unsigned char* op_first_dev;
+  float* ref_slots; int ref_slot_len;      // per-env reference tables (fb_ref_slots)
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
 #ifndef FB_EMU
   cudaStream_t stream; cudaEvent_t ev0, ev1;
@@ -643,6 +644,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
   s->fuse = getenv("FB_FUSE") ? atoi(getenv("FB_FUSE")) : FB_FUSE_DEFAULT; if (s->fuse < 0 || s->fuse > 3) s->fuse = FB_FUSE_DEFAULT;
+  s->ref_slots = nullptr; s->ref_slot_len = 0;
   s->op_step_dev = nullptr; s->op_first_dev = nullptr; s->stage_cap = 0; s->stage_icap = 0; s->stage = nullptr; s->stage_i = nullptr;
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
@@ -1022,19 +1024,19 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
     offs.push_back(dim);
     switch (k) {
       case FB_OBS_SENSOR_MEAN: case FB_OBS_SENSOR_NOW: case FB_OBS_ACT: case FB_OBS_QPOS: case FB_OBS_QVEL: dim += b; break;
-      case FB_OBS_SITES_EGO: case FB_OBS_REF_DISP: dim += 3 * b; break;
+      case FB_OBS_SITES_EGO: case FB_OBS_REF_DISP: case FB_OBS_DOF_AXIS_EGO: dim += 3 * b; break;
       case FB_OBS_REF_QUAT: dim += 4 * b; break;
       case FB_OBS_ROOT_ZAXIS: case FB_OBS_SCALARS: case FB_OBS_SUBTREE_COM: dim += 3; break;
       case FB_OBS_ROOT_POSE: dim += 7; break;
       default: s->err = "fb_obs_program: unknown item kind"; return -1;
     }
     if ((k == FB_OBS_REF_DISP || k == FB_OBS_REF_QUAT) && (!p->ref_qpos || p->ref_len <= 0)) { s->err = "fb_obs_program: reference table missing"; return -1; }
-    if ((k == FB_OBS_QPOS || k == FB_OBS_QVEL || k == FB_OBS_SITES_EGO) && (p->a[i] < 0 || p->a[i] + b > p->n_list)) { s->err = "fb_obs_program: list range"; return -1; }
+    if ((k == FB_OBS_QPOS || k == FB_OBS_QVEL || k == FB_OBS_SITES_EGO || k == FB_OBS_DOF_AXIS_EGO) && (p->a[i] < 0 || p->a[i] + b > p->n_list)) { s->err = "fb_obs_program: list range"; return -1; }
   }
   if (p->root_body <= 0 || p->root_body >= m.nbody) { s->err = "fb_obs_program: root body"; return -1; }
   std::vector<int> kind(p->kind, p->kind + p->n_items), a(p->a, p->a + p->n_items), b(p->b, p->b + p->n_items), list(p->list, p->list + std::max(p->n_list, 0));
   s->d.op_kind = up(s, kind); s->d.op_a = up(s, a); s->d.op_b = up(s, b); s->d.op_off = up(s, offs); s->d.op_list = up(s, list);
-  s->d.op_n = p->n_items; s->d.op_root_body = p->root_body; s->d.op_nsub = p->n_sub; s->d.op_ref_len = p->ref_len;
+  s->d.op_n = p->n_items; s->d.op_root_body = p->root_body; s->d.op_nsub = p->n_sub; s->d.op_ref_len = p->ref_len; s->d.op_ref_slot = 0;
   if (p->ref_qpos && p->ref_len > 0) { std::vector<float> r(p->ref_qpos, p->ref_qpos + (size_t)7 * p->ref_len); s->d.op_ref = up(s, r); } else s->d.op_ref = nullptr;
   s->d.tobs_dim = dim; s->d.tobs = dalloc<float>(s, (size_t)dim * s->d.Np);
   s->op_step_dev = dalloc<int>(s, s->d.Np); s->op_first_dev = (unsigned char*)dalloc<int>(s, s->d.Np);
@@ -1043,6 +1045,28 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
   cudaDeviceSynchronize();
 #endif
   return dim;
+}
+int fb_ref_slots(FbHandle s, int slot_len) {
+  if (!s || !s->d.tobs || slot_len <= 0) return -1;
+  if (sync_stream(s) != 0) return -2;
+  if (!s->ref_slots || s->ref_slot_len != slot_len) {          // (re)allocate: one [slot_len][7] table per env
+    if (s->ref_slots) {
+      for (auto& a : s->allocs) if (a == s->ref_slots) { a = nullptr; break; }
+      dev_free(s->ref_slots);
+    }
+    s->ref_slots = dalloc<float>(s, (size_t)s->d.Np * 7 * slot_len); s->ref_slot_len = slot_len;
+  }
+  s->d.op_ref = s->ref_slots; s->d.op_ref_len = slot_len; s->d.op_ref_slot = 1;
+  return 0;
+}
+int fb_ref_slot_write(FbHandle s, const int32_t* env_ids, int n, const float* rows) {
+  if (!s || !s->ref_slots || !s->d.op_ref_slot || !env_ids || !rows || n < 0) return -1;
+  const size_t per = (size_t)7 * s->ref_slot_len;
+  for (int k = 0; k < n; k++) {
+    if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_ref_slot_write: env id out of range"; return -1; }
+    upload_async(s, s->ref_slots + per * env_ids[k], rows + per * k, sizeof(float) * per);
+  }
+  return sync_stream(s);                                        // the caller's rows may be reused right away
 }
 int fb_task_inputs(FbHandle s, const int32_t* step_idx, const uint8_t* first) {
   if (!s || !s->d.tobs || !step_idx || !first) return -1;

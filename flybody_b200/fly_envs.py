@@ -12,134 +12,17 @@ import collections
 
 import numpy as np
 
+from . import rewards as rw
 from . import stepper as st
 from .dm_env_shim import Array, BoundedArray, StepType, TimeStep
 from .flymodel import load_model
 
-_WALK_CONTROL_TIMESTEP = 2e-3      # reference tasks/constants.py:10-13
-_WALK_PHYSICS_TIMESTEP = 2e-4
-_TERMINAL_LINVEL = 50.0
-_TERMINAL_ANGVEL = 200.0
-_FLY_CONTROL_TIMESTEP = 2e-4       # tasks/constants.py:16-19
-_FLY_PHYSICS_TIMESTEP = 5e-5
-_TERMINAL_HEIGHT = 0.2
-_TERMINAL_QACC = 1e14              # tasks/constants.py:21
-_ACTION_CLASS_ORDER = ('adhesion', 'head', 'mouth', 'antennae', 'wings', 'abdomen', 'legs', 'user')  # fruitfly.py:25-32
-
-
-# --- quaternion helpers on [..., 4] arrays (reference flybody/quaternions.py:13-76) -----------
-def mult_quat(a, b):
-    aw, ax, ay, az = np.moveaxis(a, -1, 0)
-    bw, bx, by, bz = np.moveaxis(b, -1, 0)
-    return np.stack([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
-                     aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw], -1)
-
-
-def reciprocal_quat(q):
-    return q * np.array([1.0, -1, -1, -1]) / np.sum(q * q, -1, keepdims=True)
-
-
-def quat_dist_short_arc(q1, q2):
-    """geodesic angle between unit quaternions, in [0, pi) (reference `quaternions.py:285-307`)."""
-    q1 = q1 / np.linalg.norm(q1, axis=-1, keepdims=True)
-    q2 = q2 / np.linalg.norm(q2, axis=-1, keepdims=True)
-    return np.arccos(np.minimum(1.0, 2 * np.sum(q1 * q2, -1) ** 2 - 1))
-
-
-def linear_tolerance(x, margin):
-    """`dm_control.utils.rewards.tolerance(x, bounds=(0, 0), sigmoid='linear', margin, value_at_margin=0)`."""
-    return np.clip(1.0 - np.abs(x) / margin, 0.0, 1.0)
-
-
-def constant_speed_trajectory(n_steps, speed, yaw_speed=0.0, init_pos=(0, 0, 0.1278), init_heading=0.0,
-                              body_rot_angle_y=0.0, body_rot_angle_x=0.0, control_timestep=0.002):
-    """reference `tasks/synthetic_trajectories.py:10-70` (mju_quat2Vel restated: `quaternions.py:358-382`)."""
-    qpos = np.zeros((n_steps, 7))
-    qvel = np.zeros((n_steps, 6))
-    qpos[0, :3] = init_pos
-    qpos[:, 2] = init_pos[2]
-    ya, xa = np.deg2rad(body_rot_angle_y), np.deg2rad(body_rot_angle_x)
-    qpos[0, 3:] = [np.cos(ya / 2), 0.0, np.sin(ya / 2), 0.0]
-    qpos[0, 3:] = mult_quat(np.array([np.cos(xa / 2), np.sin(xa / 2), 0.0, 0]), qpos[0, 3:])
-    dq = np.array([np.cos(init_heading / 2), 0, 0, np.sin(init_heading / 2)])
-    qpos[0, 3:] = mult_quat(dq, qpos[0, 3:])
-    qvel[0, :2] = speed * np.array([np.cos(init_heading), np.sin(init_heading)])
-    dtheta = yaw_speed * control_timestep
-    dq = np.array([np.cos(dtheta / 2), 0, 0, np.sin(dtheta / 2)])
-    axis = dq[1:]
-    sin_a_2 = np.linalg.norm(axis)
-    vel = np.zeros(3)
-    if sin_a_2 > 0:
-        speed_ang = 2 * np.arctan2(sin_a_2, dq[0])
-        if speed_ang > np.pi:
-            speed_ang -= 2 * np.pi
-        vel = axis / sin_a_2 * speed_ang / 1.0
-    qvel[:, 3:] = vel
-    M = np.array([[np.cos(dtheta), -np.sin(dtheta)], [np.sin(dtheta), np.cos(dtheta)]])
-    for i in range(1, n_steps):
-        qvel[i, :2] = M @ qvel[i - 1, :2]
-        qpos[i, :2] = qpos[i - 1, :2] + qvel[i, :2] * control_timestep
-        qpos[i, 3:] = mult_quat(dq, qpos[i - 1, 3:])
-    return qpos, qvel
-
-
-class InferenceWalkingTrajectoryLoader:
-    """reference `tasks/trajectory_loaders.py:267-309`."""
-
-    def __init__(self):
-        qpos, qvel = constant_speed_trajectory(n_steps=300, speed=2, init_pos=(0, 0, 0.1278),
-                                               control_timestep=_WALK_CONTROL_TIMESTEP)
-        self.set_next_trajectory(qpos, qvel)
-
-    def set_next_trajectory(self, qpos, qvel):
-        self._snippet = {'qpos': np.asarray(qpos, np.float64), 'qvel': np.asarray(qvel, np.float64)}
-
-    def get_trajectory(self, traj_idx=None):
-        return self._snippet
-
-    def get_joint_names(self):
-        return []
-
-    def get_site_names(self):
-        return []
-
-
-def rotate_vec_with_quat(v, q):
-    """v rotated by unit quaternion(s) q (reference `quaternions.py` rotate_vec_with_quat); broadcasts."""
-    w, u = q[..., :1], q[..., 1:]
-    t = 2.0 * np.cross(u, v)
-    return v + w * t + np.cross(u, t)
-
-
-_COM_OFFSET = np.array([-0.03697732, 0.00029205, -0.0142447])      # tasks/task_utils.py:237,259 (thorax frame)
-
-
-def com2root(com, quat):
-    """root-joint position from the CoM position (reference `tasks/task_utils.py:243-262`)."""
-    return com + rotate_vec_with_quat(-_COM_OFFSET, quat)
-
-
-def root2com(root_qpos):
-    """inverse of com2root (reference `tasks/task_utils.py:223-240`)."""
-    return root_qpos[..., :3] + rotate_vec_with_quat(_COM_OFFSET, root_qpos[..., 3:7])
-
-
-class InferenceFlightTrajectoryLoader:
-    """reference `tasks/trajectory_loaders.py:143-182`: a CoM trajectory, by default 200 steps at 20 cm/s, z = 1 cm,
-    body pitched -47.5 degrees."""
-
-    def __init__(self):
-        qpos, qvel = constant_speed_trajectory(n_steps=200, speed=20, init_pos=(0, 0, 1), body_rot_angle_y=-47.5,
-                                               control_timestep=_FLY_CONTROL_TIMESTEP)
-        self.set_next_trajectory(qpos, qvel)
-
-    def set_next_trajectory(self, com_qpos, com_qvel):
-        self._com_qpos = np.array(com_qpos, np.float64)
-        self._com_qpos[:, :2] -= self._com_qpos[0, :2]
-        self._com_qvel = np.asarray(com_qvel, np.float64)
-
-    def get_trajectory(self, traj_idx=None):
-        return self._com_qpos, self._com_qvel
+from .synthetic import (_WALK_CONTROL_TIMESTEP, _WALK_PHYSICS_TIMESTEP, _TERMINAL_LINVEL, _TERMINAL_ANGVEL,  # noqa: F401
+                        _FLY_CONTROL_TIMESTEP, _FLY_PHYSICS_TIMESTEP, _TERMINAL_HEIGHT, _TERMINAL_QACC, _ACTION_CLASS_ORDER,
+                        mult_quat, reciprocal_quat, quat_dist_short_arc, linear_tolerance, constant_speed_trajectory,
+                        rotate_vec_with_quat, com2root, root2com, _COM_OFFSET)
+from .trajectory_loaders import (HDF5FlightTrajectoryLoader, HDF5WalkingTrajectoryLoader,  # noqa: F401
+                                 InferenceFlightTrajectoryLoader, InferenceWalkingTrajectoryLoader)
 
 
 class BatchedWingBeatPatternGenerator:
@@ -220,6 +103,40 @@ class BatchedWingBeatPatternGenerator:
 
 
 
+class _FeatureBank:
+    """Full-body reference features of the walking snippets in use, concatenated row-wise (append-only, cached by
+    trajectory index) so that the per-env reward gathers are single fancy-index reads."""
+
+    def __init__(self):
+        self._off, self._n = {}, 0
+        self.qpos = self.qvel = self.root2site = self.joint_quat = None
+
+    @staticmethod
+    def _append(buf, n_used, new):
+        new = np.asarray(new, np.float64)
+        if buf is None:
+            buf = np.zeros((max(4 * new.shape[0], 1024),) + new.shape[1:])
+        while n_used + new.shape[0] > buf.shape[0]:
+            buf = np.concatenate([buf, np.zeros_like(buf)], 0)
+        buf[n_used:n_used + new.shape[0]] = new
+        return buf
+
+    def offset_of(self, idx, snip):
+        key = None if idx is None else int(idx)
+        if key is not None and key in self._off:
+            return self._off[key]
+        T = snip['qpos'].shape[0]
+        self.qpos = self._append(self.qpos, self._n, snip['qpos'])
+        self.qvel = self._append(self.qvel, self._n, snip['qvel'])
+        self.root2site = self._append(self.root2site, self._n, snip['root2site'])
+        self.joint_quat = self._append(self.joint_quat, self._n, snip['joint_quat'])
+        off = self._n
+        self._n += T
+        if key is not None:
+            self._off[key] = off
+        return off
+
+
 class _PhysicsFacade:
     """The slice of `dm_control.mjcf.Physics` the reference's callers touch."""
 
@@ -281,7 +198,8 @@ class BatchedFlyEnv:
     """dm_env-shaped environment over N lock-stepped flies (composer.Environment stand-in)."""
 
     def __init__(self, variant, n_envs, device=0, terminal_com_dist=0.3, time_limit=10.0, future_steps=64,
-                 lib_path=None, reset_noise=0.0, seed=0, traj_generator=None, wpg_pattern_path=None):
+                 lib_path=None, reset_noise=0.0, seed=0, traj_generator=None, wpg_pattern_path=None, inference_mode=True,
+                 max_reference_steps=None):
         assert variant in _VARIANTS
         self._variant = variant
         self._batched = n_envs is not None
@@ -363,6 +281,23 @@ class BatchedFlyEnv:
         self._future = future_steps + 1
         self._rec = None
         self._program_ref_id = None
+        # One reference per env (dataset loaders hand out a different snippet per episode) or one shared by all envs (the
+        # Inference* loaders hold a single trajectory): the shared case keeps one device table, the per-env case one slot per env.
+        tg = self.task._traj_generator
+        self._per_env_ref = not isinstance(tg, (InferenceWalkingTrajectoryLoader, InferenceFlightTrajectoryLoader))
+        self._max_reference_steps = max_reference_steps
+        self._ref_rows = None                       # per-env mode: [N, slot_len, 13] fp32 (root qpos 7, root qvel 6), padded with the last row
+        self._ref_len = np.zeros(N, np.int64)
+        self._episode_steps = np.zeros(N, np.int64)
+        # full-body imitation reward (reference walk_imitation.py:152-177): mocap joints / sites named by the dataset
+        self._inference_mode = bool(inference_mode) or variant != 'walk'
+        if not self._inference_mode:
+            jnames, snames = tg.get_joint_names(), tg.get_site_names()
+            mj = [jn.index('walker/' + n) for n in jnames]
+            self._mocap_qadr, self._mocap_vadr = m.jnt_qposadr[mj].astype(np.int64), m.jnt_dofadr[mj].astype(np.int64)
+            self._mocap_sites = np.array([sn.index('walker/' + n) for n in snames], np.int64)
+            self._bank = _FeatureBank()
+            self._env_bank_off = np.zeros(N, np.int64)
         # --- per-env episode state
         self._step_counter = np.zeros(N, np.int64)
         self._time = np.zeros(N)
@@ -403,6 +338,16 @@ class BatchedFlyEnv:
         if self._variant == 'flight':
             rows += [('_root_pose', 7, (7,), (st.OBS_ROOT_POSE, 0, 7)),
                      ('_subtree_com', 3, (3,), (st.OBS_SUBTREE_COM, m.body_id('walker/thorax'), 3))]
+        if not self._inference_mode:                 # what get_walker_features reads (tasks/rewards.py:37-63)
+            nj, ns = len(self._mocap_qadr), len(self._mocap_sites)
+            o = napp + 2 * nq
+            rows += [('_root_pose', 7, (7,), (st.OBS_ROOT_POSE, 0, 7)),
+                     ('_root_qvel', 6, (6,), (st.OBS_QVEL, o, 6)),
+                     ('_mocap_qpos', nj, (nj,), (st.OBS_QPOS, o + 6, nj)),
+                     ('_mocap_qvel', nj, (nj,), (st.OBS_QVEL, o + 6 + nj, nj)),
+                     ('_mocap_axes', 3 * nj, (nj, 3), (st.OBS_DOF_AXIS_EGO, o + 6 + nj, nj)),
+                     ('_mocap_sites', 3 * ns, (ns, 3), (st.OBS_SITES_EGO, o + 6 + 2 * nj, ns)),
+                     ('_wing_qpos', 6, (6,), (st.OBS_QPOS, o + 6 + 2 * nj + ns, 6))]
         return rows
 
     def observation_spec(self):
@@ -425,7 +370,13 @@ class BatchedFlyEnv:
         m = self.model
         rows = self._obs_table()
         lists = list(self._app_sites) + list(self._obs_qadr) + list(self._obs_vadr)
-        dim = self._sim.obs_program([r[3] for r in rows], lists, m.body_id('walker/thorax'), self._n_sub, self._ref_qpos[:, :7])
+        if not self._inference_mode:
+            lists += list(range(self._root_v, self._root_v + 6)) + list(self._mocap_qadr) + list(self._mocap_vadr) \
+                + list(self._mocap_sites) + list(self._wing_qadr)
+        shared = self._ref_qpos[:, :7] if not self._per_env_ref else np.zeros((self._future, 7))
+        dim = self._sim.obs_program([r[3] for r in rows], lists, m.body_id('walker/thorax'), self._n_sub, shared)
+        if self._per_env_ref:
+            self._sim.ref_slots(self._slot_len)
         widths = [r[1] for r in rows]
         assert sum(widths) == dim, (sum(widths), dim)
         off = np.concatenate([[0], np.cumsum(widths)])
@@ -439,40 +390,85 @@ class BatchedFlyEnv:
         except Exception:
             self._rec = np.empty((N, dim), np.float32)
 
-    def _load_snippet(self):
+    def _snippet_root(self, snip):
+        """root-joint reference (qpos [T,7], qvel [T,6]) of one loader snippet."""
+        if self._variant == 'walk':
+            return np.asarray(snip['qpos'])[:, :7], np.asarray(snip['qvel'])[:, :6]
+        com_qpos, qvel = snip                       # flight data is a CoM trajectory (flight_imitation.py:94-99)
+        com_qpos = np.asarray(com_qpos)
+        return np.concatenate([com2root(com_qpos[:, :3], com_qpos[:, 3:7]), com_qpos[:, 3:7]], 1), np.asarray(qvel)[:, :6]
+
+    def _steps_of(self, n_rows):
         t = self.task
-        snip = t._traj_generator.get_trajectory(traj_idx=t._next_traj_idx)
-        t._next_traj_idx = None
         if self._variant == 'walk':
-            qpos, qvel = snip['qpos'], snip['qvel']
-        else:
-            # the flight data is a CoM trajectory: convert to root-joint poses (flight_imitation.py:94-99)
-            com_qpos, qvel = snip
-            qpos = np.concatenate([com2root(com_qpos[:, :3], com_qpos[:, 3:7]), com_qpos[:, 3:7]], 1)
-        key = qvel                                     # identity of the loader's arrays: a new trajectory re-uploads the table
-        if self._program_ref_id is not key:
-            self._program_ref_id = key
-            self._ref_qpos, self._ref_qvel = np.asarray(qpos, np.float64), np.asarray(qvel, np.float64)
+            return min(t._max_episode_steps, n_rows - t._future_steps - 1)                               # walk_imitation.py:104-105
+        return min(n_rows, round(self._time_limit / self._control_timestep)) - (t._future_steps + 1)     # flight_imitation.py:101-106
+
+    def _load_snippet(self, ids):
+        """initialize_episode_mjcf: pick the reference of the episode that starts now (walk_imitation.py:93-110,
+        flight_imitation.py:88-111).  Shared mode: one trajectory for every env (re-uploaded only when the loader's arrays
+        change); per-env mode: each env of `ids` draws its own snippet and its device slot is rewritten."""
+        t = self.task
+        tg = t._traj_generator
+        if not self._per_env_ref:
+            snip = tg.get_trajectory(traj_idx=t._next_traj_idx)
+            t._next_traj_idx = None
+            key = snip['qvel'] if self._variant == 'walk' else snip[1]     # identity of the loader's arrays
+            if self._program_ref_id is not key:
+                self._program_ref_id = key
+                qpos, qvel = self._snippet_root(snip)
+                self._ref_qpos, self._ref_qvel = np.asarray(qpos, np.float64), np.asarray(qvel, np.float64)
+                self._upload_program()
+            self._ref_len[:] = self._ref_qpos.shape[0]
+            self._episode_steps[:] = self._steps_of(self._ref_qpos.shape[0])
+            return
+        if self._ref_rows is None:                   # slot length: the longest reference an episode can consume
+            cap = self._max_reference_steps or (t._max_episode_steps + t._future_steps + 1)
+            if hasattr(tg, 'trajectory_len') and hasattr(tg, 'num_trajectories'):
+                cap = min(cap, max(int(tg.trajectory_len(i)) for i in range(tg.num_trajectories)))
+            self._slot_len = int(cap)
+            self._ref_rows = np.zeros((self.n_envs, self._slot_len, 13), np.float32)
             self._upload_program()
-        if self._variant == 'walk':
-            snippet_steps = self._ref_qpos.shape[0] - t._future_steps - 1
-            self._episode_steps = min(t._max_episode_steps, snippet_steps)      # walk_imitation.py:104-105
-        else:
-            self._episode_steps = min(self._ref_qpos.shape[0], round(self._time_limit / self._control_timestep)) \
-                - (t._future_steps + 1)                                           # flight_imitation.py:101-106
+        L = self._slot_len
+        for e in ids:
+            idx = t._next_traj_idx
+            if idx is None and hasattr(tg, 'traj_indices') and hasattr(tg, '_random_state'):
+                idx = tg._random_state.choice(tg.traj_indices)             # the draw the loader itself would make
+            snip = tg.get_trajectory(traj_idx=idx)
+            qpos, qvel = self._snippet_root(snip)
+            n = min(qpos.shape[0], L)
+            self._ref_rows[e, :n, :7], self._ref_rows[e, :n, 7:] = qpos[:n], qvel[:n]
+            self._ref_rows[e, n:] = self._ref_rows[e, n - 1]
+            self._ref_len[e] = n
+            self._episode_steps[e] = self._steps_of(n)
+            if not self._inference_mode:
+                self._env_bank_off[e] = self._bank.offset_of(idx, snip)
+        t._next_traj_idx = None
+        self._sim.ref_slot_write(ids, self._ref_rows[ids, :, :7])
+
+    def _ref_at(self, step, ids=None):
+        """[n, 13] root reference (qpos 7, qvel 6) of the listed envs at their own steps."""
+        if not self._per_env_ref:
+            return np.concatenate([self._ref_qpos[step, :7], self._ref_qvel[step, :6]], 1)
+        ids = np.arange(self.n_envs) if ids is None else ids
+        return self._ref_rows[ids, step].astype(np.float64)
 
     def _reset_envs(self, ids, hold=False):
         """initialize_episode: walk_imitation.py:112-136 (root <- ref_qpos[0], wings retracted, ghost placed);
         flight_imitation.py:113-144 (root pose + linear velocity from the reference, wings on the beat pattern at a
         random phase)."""
         m = self.model
-        self._load_snippet()
+        ids = np.asarray(ids)
+        self._load_snippet(ids)
         n = len(ids)
         qpos = np.tile(m.qpos0, (n, 1))
         qvel = None
-        qpos[:, self._root_q:self._root_q + 7] = self._ref_qpos[0, :7]
-        qpos[:, self._ghost_q:self._ghost_q + 7] = self._ref_qpos[0, :7] + np.concatenate([self.task._ghost_offset, np.zeros(4)])
+        ref0 = self._ref_at(np.zeros(n, np.int64), ids)
+        qpos[:, self._root_q:self._root_q + 7] = ref0[:, :7]
+        qpos[:, self._ghost_q:self._ghost_q + 7] = ref0[:, :7] + np.concatenate([self.task._ghost_offset, np.zeros(4)])
         if self._variant == 'walk':
+            if not self._inference_mode:          # full-body start pose from the snippet (walk_imitation.py:117-118)
+                qpos[:, self._mocap_qadr] = self._bank.qpos[self._env_bank_off[ids], 7:]
             qpos[:, self._wing_qadr] = self._wing_spring
             if self._reset_noise > 0:
                 qpos[:, self._leg_act_qadr] += self._rs.uniform(-self._reset_noise, self._reset_noise, (n, len(self._leg_act_qadr)))
@@ -481,7 +477,7 @@ class BatchedFlyEnv:
             qpos[:, self._wing_qadr] = wq
             qvel = np.zeros((n, m.nv))
             qvel[:, self._wing_vadr] = wv
-            qvel[:, self._root_v:self._root_v + 3] = self._ref_qvel[0, :3]
+            qvel[:, self._root_v:self._root_v + 3] = ref0[:, 7:10]
             self._wing_qpos_host[ids] = wq
         if hold:
             self._sim.reset_hold(ids, qpos, qvel)
@@ -515,11 +511,11 @@ class BatchedFlyEnv:
             self._reset_envs(np.nonzero(resetting)[0], hold=True)
         # before_step (walk_imitation.py:138-150, flight_imitation.py:146-168, base.py:197-201)
         step = np.round(self._time / self._control_timestep).astype(np.int64)
-        step = np.minimum(step, self._ref_qpos.shape[0] - 1)
+        step = np.minimum(step, self._ref_len - 1)
         step = np.where(resetting, 0, step)
-        ghost_pose = self._ref_qpos[step, :7].copy()
-        ghost_pose[:, :3] += self.task._ghost_offset
-        ghost = np.concatenate([ghost_pose, self._ref_qvel[step, :6]], 1).astype(np.float32)
+        ghost = self._ref_at(step)
+        ghost[:, :3] += self.task._ghost_offset
+        ghost = ghost.astype(np.float32)
         ghost[resetting, 7:] = 0.0
         if self._variant == 'flight':
             # wing-beat pattern at the requested frequency, as a position target turned into a force command
@@ -559,7 +555,10 @@ class BatchedFlyEnv:
             angvel = np.linalg.norm(rec[:, sl['_gyro_now']], axis=1)
             terminate = (linvel > _TERMINAL_LINVEL) | (angvel > _TERMINAL_ANGVEL) | reached_end | \
                         (com_dist > self.task._terminal_com_dist) | bad
-            reward = np.ones(N)                               # inference mode: reward factors == (1,)
+            if self._inference_mode:
+                reward = np.ones(N)                           # reward factors == (1,)
+            else:
+                reward = np.prod(self._walk_reward_factors(rec, np.minimum(step_now, self._ref_len - 1)), axis=1)
         else:
             self._wing_qpos_host = rec[:, sl['walker/joints_pos']][:, self._wing_in_obs].astype(np.float64)
             height = rec[:, sl['_root_pose']][:, 2]
@@ -578,6 +577,22 @@ class BatchedFlyEnv:
         discount = np.where(resetting, 1.0, discount)
         self._needs_reset = last & ~resetting
         return self._unbatch(TimeStep(step_type, reward, discount, obs))
+
+    def _walk_reward_factors(self, rec, step):
+        """[N, 4 + 6]: DeepMimic factors (weights 20, 1, 1, 1) and one wing-retraction factor per wing joint
+        (reference walk_imitation.py:152-177)."""
+        sl = self._obs_slices
+        nj, ns = len(self._mocap_qadr), len(self._mocap_sites)
+        f64 = lambda k, shape=None: rec[:, sl[k]].astype(np.float64).reshape((self.n_envs,) + (shape or (-1,)))
+        wf = rw.get_walker_features(f64('_root_pose'), f64('_mocap_qpos'), f64('_root_qvel'), f64('_mocap_qvel'),
+                                    f64('_mocap_sites', (ns, 3)), f64('_mocap_axes', (nj, 3)))
+        rows = self._env_bank_off + step
+        b = self._bank
+        rf = {'com': b.qpos[rows, :3], 'qvel': b.qvel[rows], 'root2site': b.root2site[rows],
+              'joint_quat': np.concatenate([b.qpos[rows, None, 3:7], b.joint_quat[rows]], 1)}
+        factors = rw.reward_factors_deep_mimic(wf, rf, weights=(20, 1, 1, 1))
+        retract = linear_tolerance(f64('_wing_qpos') - self._wing_spring, 3.0)
+        return np.concatenate([factors, retract], 1)
 
     # ---------------------------------------------------------------------------- observations
     def _observation(self, rec):
@@ -603,28 +618,35 @@ class BatchedFlyEnv:
 
 def walk_imitation(ref_path=None, force_actuators=False, disable_wings=True, traj_indices=None, random_state=None,
                    terminal_com_dist=0.3, joint_filter=0.01, n_envs=None, device=0, lib_path=None, reset_noise=0.0,
-                   seed=0):
-    """Batched `flybody.fly_envs.walk_imitation` (reference `fly_envs.py:100-155`)."""
-    if ref_path is not None:
-        raise NotImplementedError('HDF5 reference datasets (h5py) are a "next" row (SURVEY.md 8(f).3); '
-                                  'use env.task._traj_generator.set_next_trajectory(qpos, qvel)')
+                   seed=0, max_reference_steps=None):
+    """Batched `flybody.fly_envs.walk_imitation` (reference `fly_envs.py:100-155`).  With `ref_path` (an HDF5 walking
+    dataset, or its `.npz` conversion, see `trajectory_loaders`) every env tracks its own snippet, starts from the
+    snippet's full-body pose and is rewarded with the DeepMimic factors; without it the task runs in inference mode on
+    the synthetic straight walk, reward 1 (`fly_envs.py:127-135`)."""
     if force_actuators or not disable_wings or joint_filter != 0.01:
         raise NotImplementedError('only the default walk_imitation model variant is compiled '
                                   '(flybody_b200/assets/fly_walk.npz); recompile with compiler.compile_variant')
+    tg = None
+    if ref_path is not None:
+        tg = HDF5WalkingTrajectoryLoader(path=ref_path, random_state=random_state, traj_indices=traj_indices)
     return BatchedFlyEnv('walk', n_envs, device=device, terminal_com_dist=terminal_com_dist, time_limit=10.0,
-                         future_steps=64, lib_path=lib_path, reset_noise=reset_noise, seed=seed)
+                         future_steps=64, lib_path=lib_path, reset_noise=reset_noise, seed=seed, traj_generator=tg,
+                         inference_mode=ref_path is None, max_reference_steps=max_reference_steps)
 
 
 def flight_imitation(ref_path=None, wpg_pattern_path=None, force_actuators=False, disable_legs=True, traj_indices=None,
                      randomize_start_step=True, joint_filter=0.0, future_steps=5, random_state=None, terminal_com_dist=2.0,
                      n_envs=None, device=0, lib_path=None, seed=0):
     """Batched `flybody.fly_envs.flight_imitation` (reference `fly_envs.py:30-97`): wing-beat-pattern-generator flight
-    tracking, 4 substeps of 5e-5 s per control step, 12 actions (head 3, wings 6, abdomen 2, beat frequency 1)."""
-    if ref_path is not None:
-        raise NotImplementedError('HDF5 reference datasets (h5py) are a "next" row (SURVEY.md 8(f).3); '
-                                  'use env.task._traj_generator.set_next_trajectory(com_qpos, com_qvel)')
+    tracking, 4 substeps of 5e-5 s per control step, 12 actions (head 3, wings 6, abdomen 2, beat frequency 1).  With
+    `ref_path` every env tracks its own (randomly cut) CoM trajectory of the flight dataset."""
     if force_actuators or not disable_legs or joint_filter != 0.0:
         raise NotImplementedError('only the default flight_imitation model variant is compiled '
                                   '(flybody_b200/assets/fly_flight.npz); recompile with compiler.compile_variant')
+    tg = None
+    if ref_path is not None:
+        tg = HDF5FlightTrajectoryLoader(path=ref_path, traj_indices=traj_indices, randomize_start_step=randomize_start_step,
+                                        random_state=random_state)
     return BatchedFlyEnv('flight', n_envs, device=device, terminal_com_dist=terminal_com_dist, time_limit=0.6,
-                         future_steps=future_steps, lib_path=lib_path, seed=seed, wpg_pattern_path=wpg_pattern_path)
+                         future_steps=future_steps, lib_path=lib_path, seed=seed, wpg_pattern_path=wpg_pattern_path,
+                         traj_generator=tg)

@@ -22,12 +22,12 @@ MAXCON, MAXEFC = 64, 160
 
 EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_set_action_map', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_record_stride', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
-           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
 
 # enum FbObsItem
 (OBS_SENSOR_MEAN, OBS_SENSOR_NOW, OBS_ACT, OBS_QPOS, OBS_QVEL, OBS_SITES_EGO, OBS_ROOT_ZAXIS, OBS_REF_DISP,
- OBS_REF_QUAT, OBS_SCALARS, OBS_ROOT_POSE, OBS_SUBTREE_COM) = range(12)
+ OBS_REF_QUAT, OBS_SCALARS, OBS_ROOT_POSE, OBS_SUBTREE_COM, OBS_DOF_AXIS_EGO) = range(13)
 
 
 class FbObsProgram(C.Structure):
@@ -64,6 +64,8 @@ def load_library(path=None):
     lib.fb_obs_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     lib.fb_obs_program.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_task_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fb_ref_slots.argtypes = [C.c_void_p, C.c_int]
+    lib.fb_ref_slot_write.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_read_task_obs.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_pack_obs.argtypes = [C.c_void_p]
     lib.fb_read_obs.argtypes = [C.c_void_p, C.c_void_p]
@@ -211,6 +213,17 @@ class BatchedStepper:
             raise StepperError(f'fb_obs_program failed ({dim}): {self._lib.fb_last_error(self._h).decode()}')
         self._tobs_dim = dim
         return dim
+
+    def ref_slots(self, slot_len):
+        """one reference table [slot_len][7] per env instead of the shared one (fb_ref_slots)."""
+        self._check(self._lib.fb_ref_slots(self._h, int(slot_len)), 'fb_ref_slots')
+        self._slot_len = int(slot_len)
+
+    def ref_slot_write(self, env_ids, rows):
+        ids = np.ascontiguousarray(env_ids, np.int32)
+        r = np.ascontiguousarray(rows, np.float32)
+        assert r.shape == (len(ids), self._slot_len, 7), r.shape
+        self._check(self._lib.fb_ref_slot_write(self._h, ids.ctypes.data, len(ids), r.ctypes.data), 'fb_ref_slot_write')
 
     def task_inputs(self, step_idx, first):
         si = np.ascontiguousarray(step_idx, np.int32)

@@ -249,7 +249,9 @@ enum FbObsItem {
   FB_OBS_REF_QUAT = 8,    /* b = future_steps+1 : root_quat^-1 * ref_quat[step+i]                            */
   FB_OBS_SCALARS = 9,     /* flags, |qacc|^2, time                                                           */
   FB_OBS_ROOT_POSE = 10,  /* root xpos[3] + quat[4]                                                          */
-  FB_OBS_SUBTREE_COM = 11 /* a = body id : physics.data.subtree_com[body]                                    */
+  FB_OBS_SUBTREE_COM = 11,/* a = body id : physics.data.subtree_com[body]                                    */
+  FB_OBS_DOF_AXIS_EGO = 12 /* a = offset into list (dof ids), b = count : world joint axis (physics.bind(joints).xaxis,
+                              tasks/rewards.py:48-50) rotated into the root frame                                */
 };
 typedef struct FbObsProgram {
   int32_t n_items; const int32_t* kind; const int32_t* a; const int32_t* b;
@@ -259,6 +261,13 @@ typedef struct FbObsProgram {
 } FbObsProgram;
 /* Upload the program (and reference table); returns the row length in floats (<0 on error).             */
 int fb_obs_program(FbHandle h, const FbObsProgram* p);
+/* Per-env reference tables: every env tracks its own reference trajectory (one dataset snippet per episode, reference
+ * tasks/walk_imitation.py:93-105, tasks/flight_imitation.py:88-106).  Called after fb_obs_program, fb_ref_slots switches
+ * FB_OBS_REF_DISP / FB_OBS_REF_QUAT to a device table [n_envs][slot_len][7]; fb_ref_slot_write fills the slots of the
+ * listed envs from rows [n][slot_len][7] (the caller pads a shorter snippet with its last row).  The step index given to
+ * fb_task_inputs then counts inside the env's own slot.                                                  */
+int fb_ref_slots(FbHandle h, int slot_len);
+int fb_ref_slot_write(FbHandle h, const int32_t* env_ids, int n, const float* rows);
 /* Per control step: index into the reference table and "first step after reset" flag of every env.      */
 int fb_task_inputs(FbHandle h, const int32_t* step_idx, const uint8_t* first);
 /* Copy the task observation rows [N][row_len] to a (pinned) host buffer (fb_pack_obs must have run).    */
