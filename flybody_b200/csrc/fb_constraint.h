@@ -15,7 +15,7 @@
 // candidate pair list (bounding-sphere broadphase, then the analytic narrowphase) into a private
 // staging area; a prefix sum over the chunk counts makes the final contact order deterministic
 // (pair-list order), which the Gauss-Seidel noslip sweeps depend on.
-struct ShCol { int cnt[FB_MAXCHUNK][FB_LANES]; };
+struct ShCol { int cnt[FB_MAXCHUNK][FB_LANES]; int njobs, slice; /* MPR jobs of this env; byte stride between the warps' slices (GPU) */ };
 struct RawCon { float dist; V3 pos, n, t; };
 
 FB_DEV int raw_sphere_sphere(RawCon* c, float margin, V3 p1, float r1, V3 p2, float r2) {
@@ -148,28 +148,37 @@ FB_DEV D3 dcross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x 
 FB_DEV mreal dnorm(D3 a) { return MSQRT(ddot(a, a)); }
 // 1/MSQRT(x) and 1/x to ~1e-15: single-precision seed + two Newton steps in mreal (the mreal-precision sqrt / divide of the
 // GPU are long software sequences; these sit in the inner loop of MPR)
+#if defined(__CUDACC__) && !defined(FB_MPR_DOUBLE)
+// fp32: hardware reciprocal square root + one Newton step (full single precision without the IEEE sqrt and divide sequences)
+FB_DEV mreal fast_rsqrt(mreal x) { float y = rsqrtf(x); return y * (1.5f - 0.5f * x * y * y); }
+#else
 FB_DEV mreal fast_rsqrt(mreal x) { mreal y = (mreal)(1.0f / sqrtf((float)x)); y = y * ((mreal)1.5 - (mreal)0.5 * x * y * y); return y * ((mreal)1.5 - (mreal)0.5 * x * y * y); }
+#endif
 FB_DEV mreal fast_rcp(mreal x) { mreal y = (mreal)(1.0f / (float)x); y = y * ((mreal)2.0 - x * y); return y * ((mreal)2.0 - x * y); }
 FB_DEV D3 dnormalized(D3 a) { mreal n2 = ddot(a, a); if (n2 < 1e-36) { mreal n = MSQRT(n2); if (n < 1e-300) return d3(1, 0, 0); return a * (1.0 / n); } return a * fast_rsqrt(n2); }
 struct MprPt { D3 v, v1, v2; };
-struct MprObj { D3 pos; mreal mat[9]; D3 size; int type; mreal margin; };
+// e / zoff: per-type coefficients of the branch-free support function below (set by mpr_obj_coefs)
+struct MprObj { D3 pos; mreal mat[9]; D3 size; int type; mreal margin; D3 e; mreal zoff; };
+FB_DEV void mpr_obj_coefs(MprObj& o) {
+  const bool round = o.type == FB_GEOM_SPHERE || o.type == FB_GEOM_CAPSULE, cyl = o.type == FB_GEOM_CYLINDER;
+  o.e = (round || cyl) ? d3(o.size.x, o.size.x, cyl ? 0 : o.size.x) : o.size;
+  o.zoff = (o.type == FB_GEOM_CAPSULE || cyl) ? o.size.y : 0;
+}
 FB_DEV bool mpr_zero(mreal x) { return MFABS(x) < MPR_ZERO; }
 FB_DEV bool mpr_eq(mreal a, mreal b) { mreal ab = MFABS(a - b); if (ab < MPR_ZERO) return true; a = MFABS(a); b = MFABS(b); return (b > a) ? ab < MPR_EPS * b : ab < MPR_EPS * a; }
 FB_DEV mreal mpr_sgn(mreal x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
-FB_DEV D3 mpr_support1(const MprObj& o, D3 dir) {     // mjccd_support
+// mjccd_support for sphere / capsule / ellipsoid / cylinder as ONE expression: in the geom frame the support point is
+//   e (.) normalize(e (.) d) + sgn(d_z) zoff e_z        e = (r, r, r) sphere, capsule; semi-axes ellipsoid; (r, r, 0) cylinder
+// (a sphere is an ellipsoid with equal axes, a capsule a sphere swept by +-zoff, a cylinder a disc swept by +-zoff).  The MPR
+// jobs of a warp's lanes are different geom pairs: with a switch over the type every lane pays for every type present.
+FB_DEV D3 mpr_support1(const MprObj& o, D3 dir) {
   const mreal* R = o.mat;
-  D3 ld = d3(R[0] * dir.x + R[3] * dir.y + R[6] * dir.z, R[1] * dir.x + R[4] * dir.y + R[7] * dir.z, R[2] * dir.x + R[5] * dir.y + R[8] * dir.z), r = d3(0, 0, 0);
-  if (o.type == FB_GEOM_SPHERE) r = ld * o.size.x;
-  else if (o.type == FB_GEOM_CAPSULE) { r = ld * o.size.x; r.z += mpr_sgn(ld.z) * o.size.y; }
-  else if (o.type == FB_GEOM_ELLIPSOID) {
-    D3 t = d3(ld.x * o.size.x, ld.y * o.size.y, ld.z * o.size.z); mreal n2 = ddot(t, t);
-    if (n2 >= 1e-30) { mreal in = fast_rsqrt(n2); r = d3(t.x * in * o.size.x, t.y * in * o.size.y, t.z * in * o.size.z); }
-  } else if (o.type == FB_GEOM_CYLINDER) {
-    mreal n2 = ld.x * ld.x + ld.y * ld.y;
-    if (n2 > 1e-30) { mreal in = fast_rsqrt(n2); r.x = ld.x * in * o.size.x; r.y = ld.y * in * o.size.x; }
-    r.z = mpr_sgn(ld.z) * o.size.y;
-  }
-  r = r + ld * (0.5 * o.margin);
+  D3 ld = d3(R[0] * dir.x + R[3] * dir.y + R[6] * dir.z, R[1] * dir.x + R[4] * dir.y + R[7] * dir.z, R[2] * dir.x + R[5] * dir.y + R[8] * dir.z);
+  D3 t = d3(ld.x * o.e.x, ld.y * o.e.y, ld.z * o.e.z);
+  mreal n2 = ddot(t, t), in = n2 >= (mreal)1e-30 ? fast_rsqrt(n2) : (mreal)0;
+  D3 r = d3(t.x * in * o.e.x, t.y * in * o.e.y, t.z * in * o.e.z);
+  r.z += mpr_sgn(ld.z) * o.zoff;
+  r = r + ld * ((mreal)0.5 * o.margin);
   return d3(R[0] * r.x + R[1] * r.y + R[2] * r.z, R[3] * r.x + R[4] * r.y + R[5] * r.z, R[6] * r.x + R[7] * r.y + R[8] * r.z) + o.pos;
 }
 FB_DEV MprPt mpr_support(const MprObj& a, const MprObj& b, D3 dir) { MprPt p;
@@ -193,79 +202,80 @@ FB_DEV mreal mpr_tri_dist2(D3 P, D3 x0, D3 B, D3 C, D3& w) {
   if (dd < dist) { dist = dd; w = w2; }
   return dist;
 }
-FB_DEV D3 mpr_portal_dir(const MprPt* s) { return dnormalized(dcross(s[2].v - s[1].v, s[3].v - s[1].v)); }
-FB_DEV bool mpr_reach_tol(const MprPt* s, const MprPt& v4, D3 dir, mreal tol) {
-  mreal dv4 = ddot(v4.v, dir), dmin = MFMIN(dv4 - ddot(s[1].v, dir), MFMIN(dv4 - ddot(s[2].v, dir), dv4 - ddot(s[3].v, dir)));
+// The portal lives in registers: v0..v3 are the Minkowski-difference vertices, p1[i] the first object's support point of
+// vertex i (the second's is p1[i] - v_i; only read for the contact position at the very end, so it may sit in local memory).
+// Vertex replacement is a chain of selects, not a branch per case: the lanes of a warp refine different pairs.
+FB_DEV D3 dsel(bool c, D3 a, D3 b) { return d3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
+FB_DEV D3 mpr_portal_dir3(D3 v1, D3 v2, D3 v3) { return dnormalized(dcross(v2 - v1, v3 - v1)); }
+FB_DEV bool mpr_reach_tol3(D3 v1, D3 v2, D3 v3, D3 v4, D3 dir, mreal tol) {
+  mreal dv4 = ddot(v4, dir), dmin = MFMIN(dv4 - ddot(v1, dir), MFMIN(dv4 - ddot(v2, dir), dv4 - ddot(v3, dir)));
   return mpr_eq(dmin, tol) || dmin < tol;
 }
-FB_DEV void mpr_expand(MprPt* s, const MprPt& v4) {
-  D3 v4v0 = dcross(v4.v, s[0].v);
-  if (ddot(s[1].v, v4v0) > 0) { if (ddot(s[2].v, v4v0) > 0) s[1] = v4; else s[3] = v4; }
-  else { if (ddot(s[3].v, v4v0) > 0) s[2] = v4; else s[1] = v4; }
-}
+#define MPR_EXPAND() { D3 v4v0 = dcross(n.v, v0); const bool c1 = ddot(v1, v4v0) > 0, c2 = ddot(v2, v4v0) > 0, c3 = ddot(v3, v4v0) > 0; \
+    const int k = c1 ? (c2 ? 1 : 3) : (c3 ? 2 : 1); v1 = dsel(k == 1, n.v, v1); v2 = dsel(k == 2, n.v, v2); v3 = dsel(k == 3, n.v, v3); p1[k] = n.v1; }
 // 0 and depth / dir / pos when the inflated shapes intersect, -1 otherwise
 FB_DEVN int mpr_penetration(const MprObj& o1, const MprObj& o2, mreal tol, int max_iter, mreal& depth, D3& pdir, D3& pos) {
-  MprPt s[4]; D3 dir; mreal dt;
-  s[0].v1 = o1.pos; s[0].v2 = o2.pos; s[0].v = s[0].v1 - s[0].v2;
-  if (mpr_eq(s[0].v.x, 0) && mpr_eq(s[0].v.y, 0) && mpr_eq(s[0].v.z, 0)) s[0].v = d3(MPR_EPS * 10, 0, 0);
-  dir = dnormalized(d3(0, 0, 0) - s[0].v);
-  s[1] = mpr_support(o1, o2, dir);
-  dt = ddot(s[1].v, dir);
+  D3 p1[4], v0, v1, v2, v3, dir; mreal dt; MprPt n;
+  v2 = v3 = d3(0, 0, 0); p1[2] = p1[3] = d3(0, 0, 0);
+  p1[0] = o1.pos; v0 = o1.pos - o2.pos;
+  if (mpr_eq(v0.x, 0) && mpr_eq(v0.y, 0) && mpr_eq(v0.z, 0)) v0 = d3(MPR_EPS * 10, 0, 0);
+  dir = dnormalized(d3(0, 0, 0) - v0);
+  n = mpr_support(o1, o2, dir); v1 = n.v; p1[1] = n.v1;
+  dt = ddot(v1, dir);
   if (mpr_zero(dt) || dt < 0) return -1;
-  dir = dcross(s[0].v, s[1].v);
+  dir = dcross(v0, v1);
   int res = 0;
-  if (mpr_zero(ddot(dir, dir))) res = (mpr_eq(s[1].v.x, 0) && mpr_eq(s[1].v.y, 0) && mpr_eq(s[1].v.z, 0)) ? 1 : 2;
-  if (res == 0) {
-    dir = dnormalized(dir);
-    s[2] = mpr_support(o1, o2, dir);
-    dt = ddot(s[2].v, dir);
+  if (mpr_zero(ddot(dir, dir))) res = (mpr_eq(v1.x, 0) && mpr_eq(v1.y, 0) && mpr_eq(v1.z, 0)) ? 1 : 2;
+  if (res == 1) { depth = 0; pdir = d3(0, 0, 0); pos = (p1[1] + p1[1] - v1) * 0.5; return 0; }
+  if (res == 2) { pos = (p1[1] + p1[1] - v1) * 0.5; depth = dnorm(v1); pdir = dnormalized(v1); return 0; }
+  dir = dnormalized(dir);
+  n = mpr_support(o1, o2, dir); v2 = n.v; p1[2] = n.v1;
+  dt = ddot(v2, dir);
+  if (mpr_zero(dt) || dt < 0) return -1;
+  dir = dnormalized(dcross(v1 - v0, v2 - v0));
+  if (ddot(dir, v0) > 0) { D3 tv = v1; v1 = v2; v2 = tv; tv = p1[1]; p1[1] = p1[2]; p1[2] = tv; dir = d3(0, 0, 0) - dir; }
+  for (int guard = 0;; guard++) {                // discoverPortal
+    n = mpr_support(o1, o2, dir); v3 = n.v; p1[3] = n.v1;
+    dt = ddot(v3, dir);
     if (mpr_zero(dt) || dt < 0) return -1;
-    dir = dnormalized(dcross(s[1].v - s[0].v, s[2].v - s[0].v));
-    if (ddot(dir, s[0].v) > 0) { MprPt t = s[1]; s[1] = s[2]; s[2] = t; dir = d3(0, 0, 0) - dir; }
-    for (int guard = 0;; guard++) {
-      s[3] = mpr_support(o1, o2, dir);
-      dt = ddot(s[3].v, dir);
-      if (mpr_zero(dt) || dt < 0) return -1;
-      bool cont = false;
-      dt = ddot(dcross(s[1].v, s[3].v), s[0].v);
-      if (dt < 0 && !mpr_zero(dt)) { s[2] = s[3]; cont = true; }
-      if (!cont) { dt = ddot(dcross(s[3].v, s[2].v), s[0].v); if (dt < 0 && !mpr_zero(dt)) { s[1] = s[3]; cont = true; } }
-      if (!cont) break;
-      dir = dnormalized(dcross(s[1].v - s[0].v, s[2].v - s[0].v));
-      if (guard > 1000) return -1;                 // (libccd loops without a bound here)
-    }
+    dt = ddot(dcross(v1, v3), v0);
+    const bool r2 = dt < 0 && !mpr_zero(dt);
+    dt = ddot(dcross(v3, v2), v0);
+    const bool r1 = !r2 && dt < 0 && !mpr_zero(dt);
+    if (!(r1 || r2)) break;
+    v2 = dsel(r2, v3, v2); v1 = dsel(r1, v3, v1); p1[r2 ? 2 : 1] = p1[3];
+    dir = dnormalized(dcross(v1 - v0, v2 - v0));
+    if (guard > 1000) return -1;                 // (libccd loops without a bound here)
   }
-  if (res == 1) { depth = 0; pdir = d3(0, 0, 0); pos = (s[1].v1 + s[1].v2) * 0.5; return 0; }
-  if (res == 2) { pos = (s[1].v1 + s[1].v2) * 0.5; depth = dnorm(s[1].v); pdir = dnormalized(s[1].v); return 0; }
-  MprPt v4;
   for (int guard = 0;; guard++) {                // refinePortal
-    dir = mpr_portal_dir(s);
-    dt = ddot(dir, s[1].v);
+    dir = mpr_portal_dir3(v1, v2, v3);
+    dt = ddot(dir, v1);
     if (mpr_zero(dt) || dt > 0) break;
-    v4 = mpr_support(o1, o2, dir);
-    dt = ddot(v4.v, dir);
-    if (!(mpr_zero(dt) || dt > 0) || mpr_reach_tol(s, v4, dir, tol) || guard > 1000) return -1;
-    mpr_expand(s, v4);
+    n = mpr_support(o1, o2, dir);
+    dt = ddot(n.v, dir);
+    if (!(mpr_zero(dt) || dt > 0) || mpr_reach_tol3(v1, v2, v3, n.v, dir, tol) || guard > 1000) return -1;
+    MPR_EXPAND()
   }
   for (int it = 0;; it++) {                      // findPenetr
-    dir = mpr_portal_dir(s);
-    v4 = mpr_support(o1, o2, dir);
-    if (mpr_reach_tol(s, v4, dir, tol) || it > max_iter) {
-      depth = MSQRT(mpr_tri_dist2(d3(0, 0, 0), s[1].v, s[2].v, s[3].v, pdir));
+    dir = mpr_portal_dir3(v1, v2, v3);
+    n = mpr_support(o1, o2, dir);
+    if (mpr_reach_tol3(v1, v2, v3, n.v, dir, tol) || it > max_iter) {
+      depth = MSQRT(mpr_tri_dist2(d3(0, 0, 0), v1, v2, v3, pdir));
       if (mpr_zero(pdir.x) && mpr_zero(pdir.y) && mpr_zero(pdir.z)) pdir = dir;
       pdir = dnormalized(pdir);
-      mreal b0 = ddot(dcross(s[1].v, s[2].v), s[3].v), b1 = ddot(dcross(s[3].v, s[2].v), s[0].v);
-      mreal b2 = ddot(dcross(s[0].v, s[1].v), s[3].v), b3 = ddot(dcross(s[2].v, s[1].v), s[0].v);
+      mreal b0 = ddot(dcross(v1, v2), v3), b1 = ddot(dcross(v3, v2), v0);
+      mreal b2 = ddot(dcross(v0, v1), v3), b3 = ddot(dcross(v2, v1), v0);
       mreal sum = b0 + b1 + b2 + b3;
       if (mpr_zero(sum) || sum < 0) {
-        b0 = 0; b1 = ddot(dcross(s[2].v, s[3].v), dir); b2 = ddot(dcross(s[3].v, s[1].v), dir); b3 = ddot(dcross(s[1].v, s[2].v), dir);
+        b0 = 0; b1 = ddot(dcross(v2, v3), dir); b2 = ddot(dcross(v3, v1), dir); b3 = ddot(dcross(v1, v2), dir);
         sum = b1 + b2 + b3;
       }
       mreal inv = 0.5 / sum;
-      pos = (s[0].v1 * b0 + s[1].v1 * b1 + s[2].v1 * b2 + s[3].v1 * b3 + s[0].v2 * b0 + s[1].v2 * b1 + s[2].v2 * b2 + s[3].v2 * b3) * inv;
+      // sum_i b_i (first_i + second_i): vertex 0 = the two centres, vertices 1..3 second_i = first_i - v_i
+      pos = ((o1.pos + o2.pos) * b0 + (p1[1] + p1[1] - v1) * b1 + (p1[2] + p1[2] - v2) * b2 + (p1[3] + p1[3] - v3) * b3) * inv;
       return 0;
     }
-    mpr_expand(s, v4);
+    MPR_EXPAND()
   }
 }
 // bounding capsule (axis index, half length, radius) of a convex geom: contains the shape, so that disjoint bounding capsules
@@ -341,6 +351,7 @@ FB_DEV int convex_mpr(RawCon* c, float margin, int t1, V3 p1, const M3& m1, V3 s
   a.pos = d3(p1.x - mid.x, p1.y - mid.y, p1.z - mid.z); a.size = d3(s1.x, s1.y, s1.z); a.type = t1; a.margin = margin;
   b.pos = d3(p2.x - mid.x, p2.y - mid.y, p2.z - mid.z); b.size = d3(s2.x, s2.y, s2.z); b.type = t2; b.margin = margin;
   for (int k = 0; k < 9; k++) { a.mat[k] = m1.m[k]; b.mat[k] = m2.m[k]; }
+  mpr_obj_coefs(a); mpr_obj_coefs(b);
   mreal depth; D3 dir, pos;
   if (mpr_penetration(a, b, (mreal)1e-6, 50, depth, dir, pos) != 0) return 0;
   if (mpr_eq(dir.x, 0) && mpr_eq(dir.y, 0) && mpr_eq(dir.z, 0)) return 0;
@@ -469,6 +480,38 @@ FB_WARPFN void kcol_mpr(const DevModel& m, const DevData& d, ShCol& sh, int e) {
     WPAR_BEGIN { FB_COL_PTRS if (L(pend)) jobs[njobs + POPC(mk & ((1u << lane) - 1u))] = base + lane; } WPAR_END
     njobs += POPC(mk);
   }
+#if defined(__CUDACC__) && !defined(FB_MPR_PER_WARP)
+  // The block's envs pool their jobs: an env has ~4 of them, so a warp working on its own list keeps 4 of 32 lanes busy
+  // through the longest MPR of the four.  Warp 0 takes the jobs of all FB_WPB envs of the block (one per lane, reading the
+  // other warps' lists and geom positions in their shared slices) while the other warps wait at the barrier and leave
+  // their issue slots to the rest of the SM.  (All warps of a block are live: env ranges are multiples of FB_WPB.)
+  if (threadIdx.x == 0) sh.njobs = njobs;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    const int lane = threadIdx.x, e_first = e;
+    unsigned char* base = reinterpret_cast<unsigned char*>(&sh);
+    int nj[FB_WPB], tot = 0;
+#pragma unroll
+    for (int w = 0; w < FB_WPB; w++) { nj[w] = reinterpret_cast<ShCol*>(base + (size_t)w * sh.slice)->njobs; tot += nj[w]; }
+    for (int q = lane; q < tot; q += 32) {
+      int w = 0, r = q;
+      while (r >= nj[w]) { r -= nj[w]; w++; }
+      ShCol& o = *reinterpret_cast<ShCol*>(base + (size_t)w * sh.slice);
+      const float* gx = sh_dyn(o); const int* flat = reinterpret_cast<const int*>(gx + 6 * m.ngeom); int* ccnt = const_cast<int*>(flat) + FB_MAXCAND; const int* jobs = ccnt + FB_MAXCAND;
+      const int e = e_first + w;                                  // env of that warp (AT() and the loads below index by `e`)
+      const int j = jobs[r], k = flat[j], pw = m.pair_info[k];
+      const int g1 = pw & 0x7fff, g2 = (pw >> 15) & 0x7fff;
+      V3 x1 = v3(gx[3 * g1], gx[3 * g1 + 1], gx[3 * g1 + 2]), x2 = v3(gx[3 * g2], gx[3 * g2 + 1], gx[3 * g2 + 2]);
+      M3 R1 = ld9(d.geom_xmat, g1, d, e), R2 = ld9(d.geom_xmat, g2, d, e);
+      RawCon rc[1];
+      int n = convex_mpr(rc, fmaxf(m.geom_margin[g1], m.geom_margin[g2]), m.geom_type[g1], x1, R1, mld3(m.geom_size, g1), m.geom_type[g2], x2, R2, mld3(m.geom_size, g2));
+      col_store(m, d, e, j, rc, n, g1, g2);
+      ccnt[j] = n;
+    }
+  }
+  __syncthreads();
+  return;
+#endif
   WPAR_BEGIN { FB_COL_PTRS
     for (int q = lane; q < njobs; q += 32) {
       const int j = jobs[q], k = flat[j], pw = m.pair_info[k];
@@ -1089,6 +1132,136 @@ FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e, int y) {
       default: break;
     }
   }
+}
+// ---------------------------------------------------------------------------------------------
+// Device-side task logic (fb_task_program / fb_task_step): the reference's task hooks around the physics step.
+//   ktask_reset  : composer auto-reset of envs whose last step was LAST -> initialize_episode (walk_imitation.py:112-136,
+//                  flight_imitation.py:113-144): template state, root / ghost on the first reference row, wings on the beat
+//                  pattern at a random phase (flight), optional U(-a, a) noise on listed joints; the env is held (not
+//                  integrated) through the coming step, exactly as fb_reset_hold does for the host-side task code
+//   ktask_before : before_step (walk_imitation.py:138-150, flight_imitation.py:146-168): ghost root pose / velocity from
+//                  the reference row of the current step; flight: one step of the wing-beat pattern generator at the requested
+//                  frequency, wing force commands += pattern angle - wing angle (pattern_generators.py:131-203)
+//   ktask_after  : check_termination, get_reward, get_discount (base.py:203-225, walk_imitation.py:179-203,
+//                  flight_imitation.py:170-226) -> out[e] = reward, discount, step_type
+// Scalar work runs on lane 0 (table scans of <= ~500 entries a few times per episode), array copies over the lanes.
+FB_DEV unsigned tk_mix(unsigned x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+FB_DEV float tk_u01(const DevTask& t, int e, int episode, int k) {
+  return (float)(tk_mix(t.seed ^ tk_mix((unsigned)e * 0x9e3779b9u + (unsigned)episode * 0x85ebca6bu + (unsigned)k * 0xc2b2ae35u)) >> 8) * (1.0f / 16777216.0f);
+}
+FB_DEV int wb_nearest(const DevTask& t, float f) {          // np.abs(beat_freqs - f).argmin(): first minimum
+  int best = 0; float bd = fabsf(t.wb_freqs[0] - f);
+  for (int i = 1; i < t.n_freq; i++) { float dd = fabsf(t.wb_freqs[i] - f); if (dd < bd) { bd = dd; best = i; } }
+  return best;
+}
+FB_DEV int wb_argmin_phase(const float* tab, int n, float target) {
+  int best = 0; float bd = fabsf(target - tab[0]);
+  for (int i = 1; i < n; i++) { float dd = fabsf(target - tab[i]); if (dd < bd) { bd = dd; best = i; } }
+  return best;
+}
+FB_DEV void ktask_reset(const DevModel& m, const DevData& d, int e, int y) {
+  if (!d.task || e >= d.N) return;
+  const DevTask& t = *d.task;
+  if (!t.needs_reset[e]) return;
+  const int episode = t.episode[e];
+  for (int i = y; i < m.nq; i += FB_NY) AT(d.qpos, i) = t.reset_qpos[i];
+  for (int i = y; i < m.nv; i += FB_NY) { AT(d.qvel, i) = 0.0f; AT(d.qacc, i) = 0.0f; }
+  for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) = 0.0f;
+}
+FB_DEV void ktask_reset2(const DevModel& m, const DevData& d, int e, int y) {      // after the template copy (other lanes wrote it)
+  if (!d.task || e >= d.N) return;
+  const DevTask& t = *d.task;
+  if (!t.needs_reset[e]) return;
+  const int episode = t.episode[e];
+  if (y < 7) { float r = t.ref_qpos[y]; AT(d.qpos, t.root_qadr + y) = r; if (t.ghost_qadr >= 0) AT(d.qpos, t.ghost_qadr + y) = r + (y < 3 ? t.ghost_offset[y] : 0.0f); }
+  for (int i = y; i < t.n_noise; i += FB_NY) AT(d.qpos, t.noise_qadr[i]) += t.noise_amp * (2.0f * tk_u01(t, e, episode, 1 + i) - 1.0f);
+  if (y == 0) {
+    if (t.kind == 1) {          // wings on the beat pattern of the base frequency at a random phase, root at the reference speed
+      float phase = t.has_uniform[e] ? t.uniform[e] : tk_u01(t, e, episode, 0);
+      int idx = wb_nearest(t, t.wb_base_freq), len = t.wb_len[idx];
+      int pos = wb_argmin_phase(t.wb_phase + (size_t)idx * t.tab_len, t.tab_len, phase);
+      int nxt = pos + 1 < len ? pos + 1 : len - 1;
+      const float* q0 = t.wb_traj + ((size_t)idx * t.tab_len + pos) * t.n_wing; const float* q1 = t.wb_traj + ((size_t)idx * t.tab_len + nxt) * t.n_wing;
+      for (int i = 0; i < t.n_wing; i++) { AT(d.qpos, t.wing_qadr[i]) = q0[i]; AT(d.qvel, t.wing_vadr[i]) = (q1[i] - q0[i]) / t.dt; }
+      for (int i = 0; i < 3; i++) AT(d.qvel, t.root_vadr + i) = t.ref_qvel[i];
+      t.wb_freq[e] = t.wb_base_freq; t.wb_idx[e] = idx; t.wb_pos[e] = pos;
+    }
+    AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = 1; AT(d.prev_n, 0) = 0;
+    t.step[e] = 0; t.episode[e] = episode + 1; t.has_uniform[e] = 0;
+  }
+}
+FB_DEV void ktask_before(const DevModel& m, const DevData& d, int e, int y) {
+  if (!d.task || e >= d.N) return;
+  const DevTask& t = *d.task;
+  const int resetting = t.needs_reset[e];
+  int step = resetting ? 0 : t.step[e];
+  if (step > t.ref_len - 1) step = t.ref_len - 1;
+  if (t.ghost_qadr >= 0) {
+    if (y < 7) AT(d.qpos, t.ghost_qadr + y) = t.ref_qpos[7 * step + y] + (y < 3 ? t.ghost_offset[y] : 0.0f);
+    else if (y < 13) AT(d.qvel, t.ghost_vadr + y - 7) = resetting ? 0.0f : t.ref_qvel[6 * step + y - 7];
+  }
+  if (y == 0) {
+    if (t.kind == 1 && !resetting) {
+      float a = t.user_col >= 0 ? d.sc_vals[(size_t)e * d.sc_k + t.user_col] : 0.0f;
+      if (!(a == a)) a = 0.0f;
+      float ctrl_freq = t.wb_base_freq * (1.0f + t.wb_rel_range * a);
+      int idx = t.wb_idx[e], pos = (t.wb_pos[e] + 1) % t.wb_len[idx];
+      float f = t.wb_rate != 0.0f ? t.wb_freq[e] * t.wb_rate + ctrl_freq * (1.0f - t.wb_rate) : ctrl_freq;
+      int nw = wb_nearest(t, f);
+      if (nw != idx) {          // keep the phase within the beat when changing table
+        float cur = t.wb_phase_mod[(size_t)idx * t.tab_len + pos];
+        pos = wb_argmin_phase(t.wb_phase_mod + (size_t)nw * t.tab_len, t.tab_len, cur);
+        idx = nw;
+      }
+      t.wb_freq[e] = f; t.wb_idx[e] = idx; t.wb_pos[e] = pos;
+      const float* tg = t.wb_traj + ((size_t)idx * t.tab_len + pos) * t.n_wing;
+      for (int i = 0; i < t.n_wing; i++) AT(d.ctrl, t.wing_ctrl[i]) += tg[i] - AT(d.qpos, t.wing_qadr[i]);
+    }
+    t.resetting[e] = resetting;
+    if (!resetting) t.step[e] = t.step[e] + 1;
+    t.op_step[e] = t.step[e]; t.op_first[e] = (unsigned char)resetting;
+  }
+}
+FB_DEV float tk_lin_tol(float x, float margin) { float v = 1.0f - fabsf(x) / margin; return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+FB_DEV void ktask_after(const DevModel& m, const DevData& d, int e, int y) {
+  if (!d.task || !d.tobs || e >= d.N || y != 0) return;
+  const DevTask& t = *d.task;
+  const float* o = d.tobs + (size_t)e * d.tobs_dim;
+  const int resetting = t.resetting[e], step_now = t.step[e];
+  const float* rd = o + t.obs_refdisp_off;
+  const float com_dist = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+  const bool reached_end = step_now == t.episode_steps;
+  float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; }
+  const bool bad = AT(d.flags, 0) != 0 || !(sqrtf(s2) <= t.term_qacc);
+  bool terminate; float reward;
+  if (t.kind == 0) {
+    const float* lv = &AT(d.sensordata, t.velocimeter_adr); const float* av = &AT(d.sensordata, t.gyro_adr);
+    float linvel = sqrtf(lv[0] * lv[0] + lv[1] * lv[1] + lv[2] * lv[2]), angvel = sqrtf(av[0] * av[0] + av[1] * av[1] + av[2] * av[2]);
+    terminate = linvel > t.term_linvel || angvel > t.term_angvel || reached_end || com_dist > t.term_com || bad;
+    reward = 1.0f;                                   // inference mode: reward factors == (1,)
+  } else {
+    const float height = AT(d.qpos, t.root_qadr + 2);
+    terminate = height < t.term_height || com_dist > t.term_com || reached_end || bad;
+    // reward: CoM displacement and orientation error to the ghost (flight_imitation.py:190-212; legs disabled: third factor 1)
+    V3 gp = v3(AT(d.qpos, t.ghost_qadr), AT(d.qpos, t.ghost_qadr + 1), AT(d.qpos, t.ghost_qadr + 2));      // the ghost as placed (offset included)
+    Q4 gq = q4(AT(d.qpos, t.ghost_qadr + 3), AT(d.qpos, t.ghost_qadr + 4), AT(d.qpos, t.ghost_qadr + 5), AT(d.qpos, t.ghost_qadr + 6));
+    V3 gcom = gp + mul(q2m(gq), v3(t.com_offset[0], t.com_offset[1], t.com_offset[2]));
+    float mass = AT(d.crb10, 10 * t.com_body);
+    V3 com = v3(AT(d.crb10, 10 * t.com_body + 1), AT(d.crb10, 10 * t.com_body + 2), AT(d.crb10, 10 * t.com_body + 3)) * (mass > 0 ? 1.0f / mass : 0.0f)
+             + v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
+    V3 dv = gcom - com; float disp = sqrtf(dot(dv, dv));
+    const float* rq = o + t.obs_refquat_off;
+    float n2 = rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3];
+    float x = 2.0f * (rq[0] * rq[0] / n2) - 1.0f; if (x > 1.0f) x = 1.0f;
+    reward = tk_lin_tol(disp, 0.4f) * tk_lin_tol(acosf(x), 3.14159265358979f);
+  }
+  const bool last = terminate || (double)step_now * (double)t.dt >= (double)t.time_limit - 1e-9;
+  float* out = t.out + 4 * (size_t)e;
+  out[0] = resetting ? 0.0f : reward;
+  out[1] = resetting ? 1.0f : ((terminate && !reached_end) ? 0.0f : 1.0f);
+  out[2] = resetting ? 0.0f : (last ? 2.0f : 1.0f);
+  out[3] = 0.0f;
+  t.needs_reset[e] = (last && !resetting) ? 1 : 0;
 }
 // partial reset staged by fb_reset / fb_reset_hold: warp w of the launch rewrites env rst_ids[w]
 FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int w, int y) {

@@ -107,6 +107,7 @@ struct DevModel {
 // efc row types
 enum { FB_CT_LIMIT = 0, FB_CT_FRICTIONLESS = 1, FB_CT_ELLIPTIC = 2 };
 
+struct DevTask;
 struct DevData {
   int N, Np;                   // envs, padded envs
   unsigned rec;                // record stride (4-byte slots) between consecutive envs
@@ -147,6 +148,26 @@ struct DevData {
   // task observation program (fb_obs_program): final observation rows [N][tobs_dim]
   float *tobs; int tobs_dim, op_n, op_root_body, op_ref_len, op_nsub, op_ref_slot /* 1: op_ref is [N][op_ref_len][7], one table per env */;
   const int *op_kind, *op_a, *op_b, *op_off, *op_list; const float* op_ref; const int* op_step; const unsigned char* op_first;
+  const struct DevTask* task;  // device-side task logic, or nullptr
+};
+
+// Device-side task logic (fb_task_program): what the reference's task hooks do around the physics step -- auto-reset,
+// ghost placement, wing-beat pattern generator, termination, reward, discount -- for the shared-reference (inference)
+// form of walk_imitation / flight_imitation.  Lives in device memory; DevData::task points at it.
+struct DevTask {
+  int kind;                                // 0 walk_imitation, 1 flight_imitation
+  int root_qadr, root_vadr, ghost_qadr, ghost_vadr, root_body, user_col /* action column of the beat-frequency action, -1: none */;
+  float ghost_offset[3], dt, time_limit, term_com, term_linvel, term_angvel, term_qacc, term_height;
+  int velocimeter_adr, gyro_adr, com_body, episode_steps, ref_len, obs_refdisp_off, obs_refquat_off;
+  const float *reset_qpos, *ref_qpos /*[ref_len][7]*/, *ref_qvel /*[ref_len][6]*/;
+  int n_noise; const int* noise_qadr; float noise_amp; unsigned seed;
+  int n_wing; const int *wing_qadr, *wing_vadr, *wing_ctrl;
+  int n_freq, tab_len; const float *wb_traj /*[n_freq][tab_len][n_wing]*/, *wb_phase, *wb_phase_mod /*[n_freq][tab_len], +inf padded*/, *wb_freqs; const int* wb_len;
+  float wb_base_freq, wb_rel_range, wb_rate, com_offset[3];
+  // per-env state
+  int *step, *needs_reset, *resetting, *episode, *wb_idx, *wb_pos, *has_uniform; float *uniform, *wb_freq;
+  int* op_step; unsigned char* op_first;   // the observation program's per-env inputs, maintained here instead of by fb_task_inputs
+  float* out;                              // [N][4] reward, discount, step_type (0 FIRST, 1 MID, 2 LAST), 0
 };
 
 #ifdef __CUDACC__

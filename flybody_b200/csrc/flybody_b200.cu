@@ -43,6 +43,9 @@ static void h2d(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 static void d2h(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 #endif
 
+#ifndef FB_SPLIT_DEFAULT
+#define FB_SPLIT_DEFAULT 1
+#endif
 #ifndef FB_FUSE_DEFAULT
 #define FB_FUSE_DEFAULT 0
 #endif
@@ -65,19 +68,31 @@ struct FbSim {
   int first_substep; int hold_pending;
   int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
   const int* act_map_dev; int n_action;
+  int cur_e0, cur_n;           // env range of the step kernels being issued (whole batch unless FB_SPLIT)
   int fuse;                    // FB_FUSE: how the stage kernels of a step are grouped into launches (see fb_launch_fused)
   int blob_in_smem;            // copy the sweep program of the triangular solves into shared memory per CTA (default: for batches <= 1024 envs; FB_BLOB=0/1 overrides)
   int* op_step_dev; unsigned char* op_first_dev;
   float* ref_slots; int ref_slot_len;      // per-env reference tables (fb_ref_slots)
+  DevTask task_host;                       // host copy of the device-side task program (its pointers are device pointers)
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
 #ifndef FB_EMU
   cudaStream_t stream; cudaEvent_t ev0, ev1;
+  // FB_SPLIT: the batch is stepped as `split` env ranges ("chains") on their own streams, each chain started a few kernels
+  // after the previous one, so that different stage kernels share the SMs and one chain's stragglers overlap the other's work
+  int split, chain_stagger, chain_count, chain_idx; cudaStream_t cur_stream, aux[3]; cudaEvent_t chain_ev[4], join_ev[4];
   struct StepGraph { cudaGraphExec_t exec; bool seen, failed; int n_sub; long long launches; DevData d; DevModel m; };
   StepGraph graph[2];          // [hold pending?]
   bool graphs_on;
 #endif
 };
 
+#ifndef FB_EMU
+// FB_SPLIT chains (step_sequence): after the `chain_stagger`-th step kernel of a chain an event lets the next chain start
+static void chain_mark(FbSim* s) {
+  if (s->chain_count < 0) return;
+  if (++s->chain_count == s->chain_stagger) cudaEventRecord(s->chain_ev[s->chain_idx], s->cur_stream);
+}
+#endif
 static size_t slice_bytes(size_t fixed, size_t dyn_floats) { return ((((fixed + 15) & ~(size_t)15) + dyn_floats * sizeof(float)) + 15) & ~(size_t)15; }
 // kernel = sequence of stages for one env.  Ph<f>: per-lane phase f(m, d, sh, e, 0, y), a warp barrier follows;
 // Wf<f>: warp function f(m, d, sh, e) written with WPAR sections (its own barriers inside).
@@ -97,8 +112,10 @@ template <auto F> struct Wf {
 // one warp per env: threadIdx.x = lane ("y" of the phase functions), threadIdx.y = env within the block
 template <typename Sh> __device__ __forceinline__ void set_prog(Sh&, const unsigned*) {}
 __device__ __forceinline__ void set_prog(ShTree& sh, const unsigned* p) { sh.prog = p; }
+template <typename Sh> __device__ __forceinline__ void set_slice(Sh&, int) {}
+__device__ __forceinline__ void set_slice(ShCol& sh, int slice) { sh.slice = slice; }
 template <typename Sh, typename... St>
-__global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevData d, int slice, int nwarps, int blob_words) {
+__global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevData d, int slice, int e0, int nwarps, int blob_words) {
   extern __shared__ __align__(16) unsigned char fb_smem[];
   // optional CTA-wide copy of the sweep program in front of the warps' slices (the only block-level barrier of the step)
   unsigned* blob = reinterpret_cast<unsigned*>(fb_smem);
@@ -106,10 +123,11 @@ __global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevDa
     for (int i = threadIdx.y * 32 + threadIdx.x; i < blob_words; i += 32 * FB_WPB) blob[i] = m.tsolve_blob[i];
     __syncthreads();
   }
-  int e = blockIdx.x * FB_WPB + threadIdx.y;
-  if (e >= nwarps) return;
+  int e = e0 + blockIdx.x * FB_WPB + threadIdx.y;
+  if (e >= e0 + nwarps) return;
   Sh& sh = *reinterpret_cast<Sh*>(fb_smem + (size_t)blob_words * 4 + (size_t)threadIdx.y * slice);
   int y = threadIdx.x;
+  set_slice(sh, slice);
   if (blob_words) { set_prog(sh, blob); __syncwarp(); } else { set_prog(sh, m.tsolve_blob); __syncwarp(); }   // no CTA copy: read the program in place
 #ifdef FB_CLK
   // latency profile: stage boundaries of env 0's warp, 32 slots per launch (slot 0 = kernel entry)
@@ -122,7 +140,9 @@ __global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run(DevModel m, DevDa
 }
 template <typename Sh, typename... St>
 static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1, int blob_words = 0) {
-  if (nwarps < 0) nwarps = s->d.Np;
+  // step kernels (nwarps < 0) cover the env range of the chain being issued (all envs unless FB_SPLIT, see step_sequence)
+  int e0 = 0;
+  if (nwarps < 0) { e0 = s->cur_e0; nwarps = s->cur_n; }
 #ifdef FB_CLK
   s->d.clk_launch = (int)(s->launches % 4096);
 #endif
@@ -130,21 +150,23 @@ static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1
   size_t slice = slice_bytes(sizeof(Sh), dyn_floats), bytes = slice * FB_WPB + (size_t)blob_words * 4;
   static size_t configured = 0;
   if (bytes > configured) { cudaFuncSetAttribute(fb_run<Sh, St...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
+  cudaStream_t st = s->cur_stream;
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, s->stream);
-    fb_run<Sh, St...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps, blob_words);
-    cudaEventRecord(b, s->stream);
+    cudaEventRecord(a, st);
+    fb_run<Sh, St...><<<grid, block, bytes, st>>>(s->m, s->d, (int)slice, e0, nwarps, blob_words);
+    cudaEventRecord(b, st);
     s->prof_events.push_back({kind, a, b});
   } else {
-    fb_run<Sh, St...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps, blob_words);
+    fb_run<Sh, St...><<<grid, block, bytes, st>>>(s->m, s->d, (int)slice, e0, nwarps, blob_words);
   }
   s->launches++;
+  chain_mark(s);
 }
-__global__ void __launch_bounds__(32 * FB_SOLVE_WPB, FB_MINB) fb_run_solve(DevModel m, DevData d) {
+__global__ void __launch_bounds__(32 * FB_SOLVE_WPB, FB_MINB) fb_run_solve(DevModel m, DevData d, int e0, int nwarps) {
   extern __shared__ __align__(16) float fb_smem_w[];
-  int e = blockIdx.x * FB_SOLVE_WPB + threadIdx.y;
-  if (e >= d.Np) return;
+  int e = e0 + blockIdx.x * FB_SOLVE_WPB + threadIdx.y;
+  if (e >= e0 + nwarps) return;
 #ifdef FB_CLK
   if (e == 0 && threadIdx.x == 0) d.clk[32 * d.clk_launch] = clock64();
 #endif
@@ -157,20 +179,22 @@ static void fb_launch_warp(FbSim* s, int kind) {
 #ifdef FB_CLK
   s->d.clk_launch = (int)(s->launches % 4096);
 #endif
-  dim3 block(32, FB_SOLVE_WPB), grid((s->d.Np + FB_SOLVE_WPB - 1) / FB_SOLVE_WPB);
+  dim3 block(32, FB_SOLVE_WPB), grid((s->cur_n + FB_SOLVE_WPB - 1) / FB_SOLVE_WPB);
   size_t bytes = sizeof(float) * FB_SOLVE_WARP_FLOATS * FB_SOLVE_WPB;
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(fb_run_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = true; }
+  cudaStream_t st = s->cur_stream;
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, s->stream);
-    fb_run_solve<<<grid, block, bytes, s->stream>>>(s->m, s->d);
-    cudaEventRecord(b, s->stream);
+    cudaEventRecord(a, st);
+    fb_run_solve<<<grid, block, bytes, st>>>(s->m, s->d, s->cur_e0, s->cur_n);
+    cudaEventRecord(b, st);
     s->prof_events.push_back({kind, a, b});
   } else {
-    fb_run_solve<<<grid, block, bytes, s->stream>>>(s->m, s->d);
+    fb_run_solve<<<grid, block, bytes, st>>>(s->m, s->d, s->cur_e0, s->cur_n);
   }
   s->launches++;
+  chain_mark(s);
 }
 #else
 template <typename Sh> static void set_prog(Sh&, const unsigned*) {}
@@ -178,19 +202,20 @@ static void set_prog(ShTree& sh, const unsigned* p) { sh.prog = p; }
 template <typename Sh, typename... St>
 static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1, int blob_words = 0) {
   (void)kind;
-  if (nwarps < 0) nwarps = s->d.Np;
+  int e0 = 0;
+  if (nwarps < 0) { e0 = s->cur_e0; nwarps = s->cur_n; }
   static std::vector<unsigned char> buf;
   size_t need = slice_bytes(sizeof(Sh), dyn_floats) + 64;
   if (buf.size() < need) buf.resize(need);
   Sh& sh = *reinterpret_cast<Sh*>(buf.data());
   (void)blob_words; set_prog(sh, s->m.tsolve_blob);        // host emulation: the program is read in place
-  for (int e = 0; e < nwarps; e++) (St::emu(s->m, s->d, sh, e), ...);
+  for (int e = e0; e < e0 + nwarps; e++) (St::emu(s->m, s->d, sh, e), ...);
   s->launches++;
 }
 static void fb_launch_warp(FbSim* s, int kind) {
   (void)kind;
   static std::vector<float> buf(FB_SOLVE_WARP_FLOATS);
-  for (int e = 0; e < s->d.Np; e++) ksolve_warp(s->m, s->d, buf.data(), e);
+  for (int e = s->cur_e0; e < s->cur_e0 + s->cur_n; e++) ksolve_warp(s->m, s->d, buf.data(), e);
   s->launches++;
 }
 #endif
@@ -199,6 +224,10 @@ static void fb_launch_warp(FbSim* s, int kind) {
 FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kreset_scatter(m, d, e, y); }
 FB_DEV void ph_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kscatter(m, d, e, y); }
 FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kclear_hold(m, d, e, y); }
+FB_DEV void ph_task_reset(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_reset(m, d, e, y); }
+FB_DEV void ph_task_reset2(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_reset2(m, d, e, y); }
+FB_DEV void ph_task_before(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_before(m, d, e, y); }
+FB_DEV void ph_task_after(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_after(m, d, e, y); }
 FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kpack(m, d, e, y, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); ktaskobs(m, d, e, y); }
 // Smooth dynamics in half-solve form: with M = L^T D L and u = L^-T qfrc_smooth,
 //   J qacc_smooth = Z (D^-1/2 u)          (Z = D^-1/2 L^-T J^T, rows written by the projection kernel)
@@ -251,9 +280,9 @@ static void launch_step2(FbSim* s, bool integrate) {
 // substep ([smooth solve finish] [pos col proj vel]), 2 one kernel per substep, 3 one kernel per control step.
 template <typename Sh, typename... St> struct Grp {
 #ifdef __CUDACC__
-  static __device__ __forceinline__ void run(const DevModel& m, const DevData& d, unsigned char* slice, const unsigned* prog, int e, int y) {
+  static __device__ __forceinline__ void run(const DevModel& m, const DevData& d, unsigned char* slice, int stride, const unsigned* prog, int e, int y) {
     Sh& sh = *reinterpret_cast<Sh*>(slice);
-    set_prog(sh, prog); __syncwarp();
+    set_slice(sh, stride); set_prog(sh, prog); __syncwarp();
     ((St::run(m, d, sh, e, y), __syncwarp()), ...);
   }
 #endif
@@ -265,7 +294,7 @@ template <typename Sh, typename... St> struct Grp {
 };
 struct GrpSolve {
 #ifdef __CUDACC__
-  static __device__ __forceinline__ void run(const DevModel& m, const DevData& d, unsigned char* slice, const unsigned*, int e, int) {
+  static __device__ __forceinline__ void run(const DevModel& m, const DevData& d, unsigned char* slice, int, const unsigned*, int e, int) {
     ksolve_warp(m, d, reinterpret_cast<float*>(slice), e); __syncwarp();
   }
 #else
@@ -300,7 +329,7 @@ __global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_run_fused(DevModel m,
   const unsigned* prog = blob_words ? blob : m.tsolve_blob;
   const int y = threadIdx.x;
   for (int k = 0; k < n_sub; k++) {
-    (G::run(m, d, sl, prog, e, y), ...);
+    (G::run(m, d, sl, slice, prog, e, y), ...);
     if (loop_sens) { fused_sens_accum(m, d, e, y, k == 0); __syncwarp(); }
   }
 }
@@ -316,9 +345,9 @@ static void fb_launch_fused(FbSim* s, int kind, int n_sub, int loop_sens) {
   static size_t configured = 0;
   if (bytes > configured) { cudaFuncSetAttribute(fb_run_fused<G...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = bytes; }
   cudaEvent_t a = nullptr, b = nullptr;
-  if (s->prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s->stream); }
-  fb_run_fused<G...><<<grid, block, bytes, s->stream>>>(s->m, s->d, (int)slice, nwarps, blob_words, n_sub, loop_sens);
-  if (s->prof_on) { cudaEventRecord(b, s->stream); s->prof_events.push_back({kind, a, b}); }
+  if (s->prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s->cur_stream); }
+  fb_run_fused<G...><<<grid, block, bytes, s->cur_stream>>>(s->m, s->d, (int)slice, nwarps, blob_words, n_sub, loop_sens);
+  if (s->prof_on) { cudaEventRecord(b, s->cur_stream); s->prof_events.push_back({kind, a, b}); }
 #else
   (void)kind;
   static std::vector<unsigned char> buf;
@@ -651,12 +680,18 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
   s->graphs_on = getenv("FB_NO_GRAPH") == nullptr;
+  s->split = getenv("FB_SPLIT") ? atoi(getenv("FB_SPLIT")) : FB_SPLIT_DEFAULT; if (s->split < 1 || s->split > 4) s->split = 1;
+  s->chain_stagger = getenv("FB_STAGGER") ? atoi(getenv("FB_STAGGER")) : (s->split == 2 ? 3 : 2);
+  s->chain_count = -1; s->chain_idx = 0; s->cur_stream = s->stream;
+  for (int i = 0; i < 3; i++) cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 4; i++) { cudaEventCreateWithFlags(&s->chain_ev[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&s->join_ev[i], cudaEventDisableTiming); }
   // small batches are latency-bound (a per-CTA copy of the sweep program in shared memory halves the sweeps' latency);
   // at full occupancy the copy costs more than it saves and the compact program is read in place.  FB_BLOB=0/1 overrides.
   s->blob_in_smem = getenv("FB_BLOB") ? atoi(getenv("FB_BLOB")) : (n_envs <= 1024);
 #endif
   int rc = build_model(s, hm);
   if (rc == 0) rc = alloc_data(s, n_envs);
+  s->cur_e0 = 0; s->cur_n = s->d.Np;
   *out = s;
   if (rc != 0) return rc;
 #ifndef FB_EMU
@@ -736,7 +771,30 @@ static void step_sequence(FbSim* s, int n_substeps) {
   if (s->fuse == 3) {                       // the whole control step in one launch
     s->d.do_integrate = 1; s->d.sens_mode = -1;
     fb_launch_fused<GSmooth, GrpSolve, GFinish, GPos, GCol, GProj, GVel>(s, K_STEP, n_substeps, 1);
-  } else for (int k = 0; k < n_substeps; k++) {
+  }
+#ifndef FB_EMU
+  else if (s->fuse == 0 && s->split > 1) {
+    // env ranges as staggered chains on their own streams (captured into the step graph as parallel branches)
+    const int S = s->split, per = ((s->d.Np / FB_WPB + S - 1) / S) * FB_WPB;
+    for (int h = 0; h < S; h++) {
+      s->cur_stream = h == 0 ? s->stream : s->aux[h - 1];
+      s->cur_e0 = h * per; s->cur_n = std::min(per, s->d.Np - h * per);
+      if (s->cur_n <= 0) { s->cur_n = 0; continue; }
+      if (h > 0) cudaStreamWaitEvent(s->cur_stream, s->chain_ev[h - 1], 0);
+      s->chain_idx = h; s->chain_count = 0;
+      for (int k = 0; k < n_substeps; k++) {
+        launch_step2(s, true);
+        s->d.sens_mode = (k == 0) ? 1 : 0;
+        launch_step1(s);
+        s->d.sens_mode = -1;
+      }
+      s->chain_count = -1;
+      if (h > 0) { cudaEventRecord(s->join_ev[h], s->cur_stream); cudaStreamWaitEvent(s->stream, s->join_ev[h], 0); }
+    }
+    s->cur_stream = s->stream; s->cur_e0 = 0; s->cur_n = s->d.Np;
+  }
+#endif
+  else for (int k = 0; k < n_substeps; k++) {
     if (s->fuse == 0) {
       launch_step2(s, true);
       s->d.sens_mode = (k == 0) ? 1 : 0;
@@ -1067,6 +1125,93 @@ int fb_ref_slot_write(FbHandle s, const int32_t* env_ids, int n, const float* ro
     upload_async(s, s->ref_slots + per * env_ids[k], rows + per * k, sizeof(float) * per);
   }
   return sync_stream(s);                                        // the caller's rows may be reused right away
+}
+int fb_task_program(FbHandle s, const FbTaskProgram* p) {
+  if (!s || !p) return -1;
+  if (!s->d.tobs || !s->act_map_dev) { s->err = "fb_task_program: call fb_set_action_map and fb_obs_program first"; return -1; }
+  if (s->d.op_ref_slot) { s->err = "fb_task_program: per-env reference slots keep the host-side task code"; return -1; }
+  if (p->ref_len <= 0 || !p->ref_qpos || !p->ref_qvel || !p->reset_qpos) { s->err = "fb_task_program: reference / reset tables missing"; return -1; }
+  if (p->kind == 1 && (p->n_wing <= 0 || p->n_freq <= 0 || p->tab_len <= 0 || !p->wb_traj || !p->wb_phase || !p->wb_phase_mod || !p->wb_freqs || !p->wb_len)) { s->err = "fb_task_program: wing-beat tables missing"; return -1; }
+  if (sync_stream(s) != 0) return -2;
+  const DevModel& m = s->m; const int Np = s->d.Np;
+  DevTask t; memset(&t, 0, sizeof(t));
+  t.kind = p->kind; t.root_qadr = p->root_qadr; t.root_vadr = p->root_vadr; t.ghost_qadr = p->ghost_qadr; t.ghost_vadr = p->ghost_vadr;
+  t.root_body = s->d.op_root_body; t.user_col = p->user_col;
+  for (int i = 0; i < 3; i++) { t.ghost_offset[i] = p->ghost_offset[i]; t.com_offset[i] = p->com_offset[i]; }
+  t.dt = p->control_timestep; t.time_limit = p->time_limit; t.term_com = p->terminal_com_dist; t.term_linvel = p->terminal_linvel;
+  t.term_angvel = p->terminal_angvel; t.term_qacc = p->terminal_qacc; t.term_height = p->terminal_height;
+  t.velocimeter_adr = p->velocimeter_adr; t.gyro_adr = p->gyro_adr; t.com_body = p->com_body; t.episode_steps = p->episode_steps;
+  t.ref_len = p->ref_len; t.obs_refdisp_off = p->obs_refdisp_off; t.obs_refquat_off = p->obs_refquat_off;
+  auto upf32 = [&](const float* src, size_t n) { std::vector<float> v(src, src + n); return up(s, v); };
+  auto upi32 = [&](const int32_t* src, size_t n) { std::vector<int> v(src, src + n); return up(s, v); };
+  t.reset_qpos = upf32(p->reset_qpos, m.nq); t.ref_qpos = upf32(p->ref_qpos, (size_t)7 * p->ref_len); t.ref_qvel = upf32(p->ref_qvel, (size_t)6 * p->ref_len);
+  t.n_noise = p->noise_qadr ? p->n_noise : 0; t.noise_qadr = t.n_noise ? upi32(p->noise_qadr, t.n_noise) : nullptr; t.noise_amp = p->noise_amp; t.seed = p->seed;
+  if (p->kind == 1) {
+    t.n_wing = p->n_wing; t.wing_qadr = upi32(p->wing_qadr, p->n_wing); t.wing_vadr = upi32(p->wing_vadr, p->n_wing); t.wing_ctrl = upi32(p->wing_ctrl, p->n_wing);
+    t.n_freq = p->n_freq; t.tab_len = p->tab_len; const size_t nt = (size_t)p->n_freq * p->tab_len;
+    t.wb_traj = upf32(p->wb_traj, nt * p->n_wing); t.wb_phase = upf32(p->wb_phase, nt); t.wb_phase_mod = upf32(p->wb_phase_mod, nt);
+    t.wb_freqs = upf32(p->wb_freqs, p->n_freq); t.wb_len = upi32(p->wb_len, p->n_freq);
+    t.wb_base_freq = p->wb_base_freq; t.wb_rel_range = p->wb_rel_range; t.wb_rate = p->wb_rate;
+  }
+  t.step = dalloc<int>(s, Np); t.needs_reset = dalloc<int>(s, Np); t.resetting = dalloc<int>(s, Np); t.episode = dalloc<int>(s, Np);
+  t.wb_idx = dalloc<int>(s, Np); t.wb_pos = dalloc<int>(s, Np); t.has_uniform = dalloc<int>(s, Np);
+  t.uniform = dalloc<float>(s, Np); t.wb_freq = dalloc<float>(s, Np); t.out = dalloc<float>(s, (size_t)4 * Np);
+  t.op_step = s->op_step_dev; t.op_first = s->op_first_dev;
+  DevTask* dev = (DevTask*)dalloc<unsigned char>(s, sizeof(DevTask));
+  h2d(dev, &t, sizeof(t));
+  s->task_host = t; s->d.task = dev;
+  return fb_task_reset_all(s);
+}
+int fb_task_reset_all(FbHandle s) {
+  if (!s || !s->d.task) return -1;
+  if (sync_stream(s) != 0) return -2;
+  std::vector<int> ones((size_t)s->d.Np, 1);
+  h2d(s->task_host.needs_reset, ones.data(), sizeof(int) * ones.size());
+  return 0;
+}
+int fb_task_uniforms(FbHandle s, const int32_t* env_ids, int n, const float* u) {
+  if (!s || !s->d.task || !env_ids || !u || n < 0) return -1;
+  if (sync_stream(s) != 0) return -2;
+  const int one = 1;
+  for (int k = 0; k < n; k++) {
+    if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_task_uniforms: env id out of range"; return -1; }
+    h2d(s->task_host.uniform + env_ids[k], u + k, sizeof(float)); h2d(s->task_host.has_uniform + env_ids[k], &one, sizeof(int));
+  }
+  return 0;
+}
+int fb_task_step(FbHandle s, const float* action, int is_device, int n_substeps) {
+  if (!s || !s->d.task || !action || n_substeps <= 0) return -1;
+#ifndef FB_EMU
+  cudaSetDevice(s->device);
+#endif
+  fb_launch<ShNone, Ph<ph_task_reset>, Ph<ph_task_reset2>>(s, K_MISC, 0, s->d.N);      // envs whose last step was LAST
+  int rc = fb_set_ctrl(s, action, is_device);                                           // action -> ctrl (NaN -> 0), staged rows stay readable
+  if (rc != 0) return rc;
+  fb_launch<ShNone, Ph<ph_task_before>>(s, K_MISC, 0, s->d.N);
+  s->hold_pending = 1;                                                                  // freshly reset envs are held through this step
+  rc = fb_step(s, n_substeps);
+  if (rc != 0) return rc;
+  fb_launch<ShNone, Ph<ph_pack>, Ph<ph_task_after>>(s, K_PACK, 0, s->d.N);
+  return 0;
+}
+int fb_task_ptrs(FbHandle s, void** obs_dev, int* obs_dim, void** out_dev) {
+  if (!s || !s->d.task) return -1;
+  if (obs_dev) *obs_dev = s->d.tobs;
+  if (obs_dim) *obs_dim = s->d.tobs_dim;
+  if (out_dev) *out_dev = s->task_host.out;
+  return 0;
+}
+int fb_task_read(FbHandle s, float* obs_host, float* out_host) {
+  if (!s || !s->d.task) return -1;
+#ifndef FB_EMU
+  if (obs_host) FB_CUDA_OK(cudaMemcpyAsync(obs_host, s->d.tobs, sizeof(float) * (size_t)s->d.N * s->d.tobs_dim, cudaMemcpyDeviceToHost, s->stream));
+  if (out_host) FB_CUDA_OK(cudaMemcpyAsync(out_host, s->task_host.out, sizeof(float) * (size_t)4 * s->d.N, cudaMemcpyDeviceToHost, s->stream));
+  return sync_stream(s);
+#else
+  if (obs_host) memcpy(obs_host, s->d.tobs, sizeof(float) * (size_t)s->d.N * s->d.tobs_dim);
+  if (out_host) memcpy(out_host, s->task_host.out, sizeof(float) * (size_t)4 * s->d.N);
+  return 0;
+#endif
 }
 int fb_task_inputs(FbHandle s, const int32_t* step_idx, const uint8_t* first) {
   if (!s || !s->d.tobs || !step_idx || !first) return -1;

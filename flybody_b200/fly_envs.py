@@ -199,7 +199,7 @@ class BatchedFlyEnv:
 
     def __init__(self, variant, n_envs, device=0, terminal_com_dist=0.3, time_limit=10.0, future_steps=64,
                  lib_path=None, reset_noise=0.0, seed=0, traj_generator=None, wpg_pattern_path=None, inference_mode=True,
-                 max_reference_steps=None):
+                 max_reference_steps=None, device_task=False):
         assert variant in _VARIANTS
         self._variant = variant
         self._batched = n_envs is not None
@@ -234,9 +234,12 @@ class BatchedFlyEnv:
         self._ctrl_of_action = np.asarray(idx, np.int64)
         # walking: actions go to the device as they are, the action -> ctrl permutation and NaN -> 0 run in the scatter
         # kernel (fb_set_action_map); flight keeps the host path because the wing actions are modified by the WBPG first
-        self._device_action_map = variant == 'walk'
+        self._device_task = bool(device_task)       # task hooks evaluated on the device (fb_task_*): no host logic in step()
+        self._device_action_map = variant == 'walk' or self._device_task
         if self._device_action_map:
-            self._sim.set_action_map(self._ctrl_of_action)
+            # user actions (flight: the beat frequency) have no ctrl slot: column -> -1, read by the device-side task code
+            self._sim.set_action_map(np.concatenate([self._ctrl_of_action, -np.ones(self._n_user, np.int64)]) if self._device_task
+                                     else self._ctrl_of_action)
         names = [m.meta['actuator_names'][i].split('/')[-1] for i in idx] + [f'user_{i}' for i in range(self._n_user)]
         rng = m.actuator_ctrlrange[idx]
         lo = np.concatenate([rng[:, 0], -np.ones(self._n_user)])
@@ -291,6 +294,10 @@ class BatchedFlyEnv:
         self._episode_steps = np.zeros(N, np.int64)
         # full-body imitation reward (reference walk_imitation.py:152-177): mocap joints / sites named by the dataset
         self._inference_mode = bool(inference_mode) or variant != 'walk'
+        if self._device_task and (self._per_env_ref or not self._inference_mode):
+            raise NotImplementedError('device_task covers the shared-reference (inference-mode) tasks; dataset mode keeps the '
+                                      'host-side task code')
+        self._seed = seed
         if not self._inference_mode:
             jnames, snames = tg.get_joint_names(), tg.get_site_names()
             mj = [jn.index('walker/' + n) for n in jnames]
@@ -337,7 +344,8 @@ class BatchedFlyEnv:
                  ('_scalars', 3, (3,), (st.OBS_SCALARS, 0, 3))]
         if self._variant == 'flight':
             rows += [('_root_pose', 7, (7,), (st.OBS_ROOT_POSE, 0, 7)),
-                     ('_subtree_com', 3, (3,), (st.OBS_SUBTREE_COM, m.body_id('walker/thorax'), 3))]
+                     ('_subtree_com', 3, (3,), (st.OBS_SUBTREE_COM, m.body_id('walker/thorax'), 3)),
+                     ('_ghost_pose', 7, (7,), (st.OBS_QPOS, napp + 2 * nq, 7))]     # the ghost where it is after the step
         if not self._inference_mode:                 # what get_walker_features reads (tasks/rewards.py:37-63)
             nj, ns = len(self._mocap_qadr), len(self._mocap_sites)
             o = napp + 2 * nq
@@ -370,6 +378,8 @@ class BatchedFlyEnv:
         m = self.model
         rows = self._obs_table()
         lists = list(self._app_sites) + list(self._obs_qadr) + list(self._obs_vadr)
+        if self._variant == 'flight':
+            lists += list(range(self._ghost_q, self._ghost_q + 7))
         if not self._inference_mode:
             lists += list(range(self._root_v, self._root_v + 6)) + list(self._mocap_qadr) + list(self._mocap_vadr) \
                 + list(self._mocap_sites) + list(self._wing_qadr)
@@ -389,6 +399,33 @@ class BatchedFlyEnv:
                 else np.empty((N, dim), np.float32)
         except Exception:
             self._rec = np.empty((N, dim), np.float32)
+        if self._device_task:
+            self._upload_task_program()
+
+    def _upload_task_program(self):
+        """fb_task_program: the task hooks of this env as a device-side program (same constants as the host path below)."""
+        m, t, sl = self.model, self.task, self._obs_slices
+        q0 = m.qpos0.copy()
+        if self._variant == 'walk':
+            q0[self._wing_qadr] = self._wing_spring
+        kw = dict(kind=0 if self._variant == 'walk' else 1, root_qadr=self._root_q, root_vadr=self._root_v, ghost_qadr=self._ghost_q,
+                  ghost_vadr=self._ghost_v, user_col=len(self._ctrl_of_action) if self._n_user else -1, ghost_offset=t._ghost_offset,
+                  control_timestep=self._control_timestep, time_limit=self._time_limit, terminal_com_dist=min(t._terminal_com_dist, 3e38),
+                  terminal_linvel=_TERMINAL_LINVEL, terminal_angvel=_TERMINAL_ANGVEL, terminal_qacc=_TERMINAL_QACC, terminal_height=_TERMINAL_HEIGHT,
+                  velocimeter_adr=int(self._sd['velocimeter'][0]), gyro_adr=int(self._sd['gyro'][0]), com_body=m.body_id('walker/thorax'),
+                  episode_steps=int(self._steps_of(self._ref_qpos.shape[0])), ref_len=self._ref_qpos.shape[0], ref_qpos=self._ref_qpos[:, :7],
+                  ref_qvel=self._ref_qvel[:, :6], obs_refdisp_off=sl['walker/ref_displacement'].start, obs_refquat_off=sl['walker/ref_root_quat'].start,
+                  reset_qpos=q0, n_noise=len(self._leg_act_qadr) if (self._variant == 'walk' and self._reset_noise > 0) else 0,
+                  noise_qadr=self._leg_act_qadr if (self._variant == 'walk' and self._reset_noise > 0) else None,
+                  noise_amp=self._reset_noise, seed=int(self._seed) & 0xffffffff, com_offset=_COM_OFFSET)
+        if self._variant == 'flight':
+            wb = self._wbpg
+            kw.update(n_wing=6, wing_qadr=self._wing_qadr, wing_vadr=self._wing_vadr, wing_ctrl=self._ctrl_of_action[self._action_indices['wings']],
+                      n_freq=wb.traj.shape[0], tab_len=wb.traj.shape[1], wb_traj=wb.traj, wb_phase=np.where(np.isfinite(wb.phase), wb.phase, 3e38),
+                      wb_phase_mod=np.where(np.isfinite(wb.phase_mod), wb.phase_mod, 3e38), wb_freqs=wb.beat_freqs, wb_len=wb.lengths,
+                      wb_base_freq=wb.base_beat_freq, wb_rel_range=wb.rel_freq_range, wb_rate=wb._rate)
+        self._sim.task_program(**kw)
+        self._out4 = np.zeros((self.n_envs, 4), np.float32)
 
     def _snippet_root(self, snip):
         """root-joint reference (qpos [T,7], qvel [T,6]) of one loader snippet."""
@@ -488,7 +525,33 @@ class BatchedFlyEnv:
         self._needs_reset[ids] = False
         self.n_resets += n
 
+    def _device_step(self, action):
+        """one control step with the task hooks on the device: actions in, observation rows + (reward, discount, step_type) out."""
+        resetting = self._needs_reset.copy()
+        if resetting.any():
+            self._load_snippet(np.nonzero(resetting)[0])            # a trajectory set since the last reset re-uploads the programs
+        if self._variant == 'flight' and resetting.any():           # the wing-beat phases the host path would draw at these resets
+            ids = np.nonzero(resetting)[0]
+            self._sim.task_uniforms(ids, self._rs.uniform(size=len(ids)))
+        self._sim.task_step(action, self._n_sub)
+        self._sim.task_read(self._rec, self._out4)
+        self.h2d_bytes_per_step = action.nbytes
+        self.d2h_bytes_per_step = self._rec.nbytes + self._out4.nbytes
+        self._step_counter = np.where(resetting, 0, self._step_counter + 1)
+        self._time = np.where(resetting, 0.0, self._time + self._control_timestep)
+        self.n_resets += int(resetting.sum())
+        step_type = self._out4[:, 2].astype(np.int64)
+        self._needs_reset = step_type == int(StepType.LAST)
+        return TimeStep(step_type,
+                        self._out4[:, 0].astype(np.float64), self._out4[:, 1].astype(np.float64), self._observation(self._rec))
+
     def reset(self):
+        if self._device_task:
+            self._load_snippet(np.arange(self.n_envs))
+            self._sim.task_reset_all()
+            self._needs_reset[:] = True
+            ts = self._device_step(np.zeros((self.n_envs, self._action_spec.shape[0]), np.float32))    # every env held: FIRST
+            return self._unbatch(ts, first=True)
         self._reset_envs(np.arange(self.n_envs))
         self._sim.task_inputs(self._step_counter, np.ones(self.n_envs, np.uint8))
         rec = self._sim.read_task_obs(self._rec)
@@ -505,6 +568,8 @@ class BatchedFlyEnv:
         else:
             action = np.array(action, np.float64, copy=True).reshape(N, -1)
         assert action.shape[1] == self._action_spec.shape[0], f'action must have {self._action_spec.shape[0]} entries'
+        if self._device_task:
+            return self._unbatch(self._device_step(action))
         # auto-reset of envs whose last step was LAST (composer.Environment semantics); their action is ignored
         resetting = self._needs_reset.copy()
         if resetting.any():
@@ -543,9 +608,16 @@ class BatchedFlyEnv:
         self.d2h_bytes_per_step = rec.nbytes
         self._time = np.where(resetting, 0.0, self._time + self._control_timestep)
         obs = self._observation(rec)
+        step_type, reward, discount, self._needs_reset = self._task_after(rec, obs, resetting, self._time, ghost)
+        return self._unbatch(TimeStep(step_type, reward, discount, obs))
+
+    def _task_after(self, rec, obs, resetting, time, ghost):
+        """check_termination / reward / discount on the observation record of the step just taken (walk_imitation.py:152-203,
+        flight_imitation.py:170-226, base.py:203-225) -> step_type, reward, discount, needs_reset.  (The device-side task
+        program `ktask_after` is the same logic; tests/test_device_task.py holds the two against each other.)"""
+        N = self.n_envs
         sl = self._obs_slices
-        # check_termination / reward / discount (walk_imitation.py:152-203, flight_imitation.py:170-226, base.py:203-225)
-        step_now = np.round(self._time / self._control_timestep).astype(np.int64)
+        step_now = np.round(time / self._control_timestep).astype(np.int64)
         com_dist = np.linalg.norm(obs['walker/ref_displacement'][:, 0], axis=1)
         reached_end = step_now == self._episode_steps
         scal = rec[:, sl['_scalars']]
@@ -564,19 +636,20 @@ class BatchedFlyEnv:
             height = rec[:, sl['_root_pose']][:, 2]
             terminate = (height < _TERMINAL_HEIGHT) | (com_dist > self.task._terminal_com_dist) | reached_end | bad
             # reward factors: CoM displacement and orientation error to the ghost (legs are disabled: third factor == 1)
-            ghost_com = root2com(ghost[:, :7].astype(np.float64))
+            # (the ghost is a free body that coasts with its reference velocity during the substeps; the reference reads its
+            # pose after the step, flight_imitation.py:174-176)
+            ghost_com = root2com(rec[:, sl['_ghost_pose']].astype(np.float64))
             disp = np.linalg.norm(ghost_com - rec[:, sl['_subtree_com']], axis=1)
             qd = quat_dist_short_arc(np.array([1.0, 0, 0, 0]), obs['walker/ref_root_quat'][:, 0].astype(np.float64))
             reward = linear_tolerance(disp, 0.4) * linear_tolerance(qd, np.pi)
         discount = np.where(terminate & ~reached_end, 0.0, 1.0)
-        last = terminate | (self._time >= self._time_limit - 1e-9)
+        last = terminate | (time >= self._time_limit - 1e-9)
         step_type = np.where(last, StepType.LAST, StepType.MID)
         # rows that were reset this call report FIRST (their action was ignored)
         step_type = np.where(resetting, StepType.FIRST, step_type)
         reward = np.where(resetting, 0.0, reward)
         discount = np.where(resetting, 1.0, discount)
-        self._needs_reset = last & ~resetting
-        return self._unbatch(TimeStep(step_type, reward, discount, obs))
+        return step_type, reward, discount, last & ~resetting
 
     def _walk_reward_factors(self, rec, step):
         """[N, 4 + 6]: DeepMimic factors (weights 20, 1, 1, 1) and one wing-retraction factor per wing joint
@@ -618,7 +691,7 @@ class BatchedFlyEnv:
 
 def walk_imitation(ref_path=None, force_actuators=False, disable_wings=True, traj_indices=None, random_state=None,
                    terminal_com_dist=0.3, joint_filter=0.01, n_envs=None, device=0, lib_path=None, reset_noise=0.0,
-                   seed=0, max_reference_steps=None):
+                   seed=0, max_reference_steps=None, device_task=False):
     """Batched `flybody.fly_envs.walk_imitation` (reference `fly_envs.py:100-155`).  With `ref_path` (an HDF5 walking
     dataset, or its `.npz` conversion, see `trajectory_loaders`) every env tracks its own snippet, starts from the
     snippet's full-body pose and is rewarded with the DeepMimic factors; without it the task runs in inference mode on
@@ -631,12 +704,12 @@ def walk_imitation(ref_path=None, force_actuators=False, disable_wings=True, tra
         tg = HDF5WalkingTrajectoryLoader(path=ref_path, random_state=random_state, traj_indices=traj_indices)
     return BatchedFlyEnv('walk', n_envs, device=device, terminal_com_dist=terminal_com_dist, time_limit=10.0,
                          future_steps=64, lib_path=lib_path, reset_noise=reset_noise, seed=seed, traj_generator=tg,
-                         inference_mode=ref_path is None, max_reference_steps=max_reference_steps)
+                         inference_mode=ref_path is None, max_reference_steps=max_reference_steps, device_task=device_task)
 
 
 def flight_imitation(ref_path=None, wpg_pattern_path=None, force_actuators=False, disable_legs=True, traj_indices=None,
                      randomize_start_step=True, joint_filter=0.0, future_steps=5, random_state=None, terminal_com_dist=2.0,
-                     n_envs=None, device=0, lib_path=None, seed=0):
+                     n_envs=None, device=0, lib_path=None, seed=0, device_task=False):
     """Batched `flybody.fly_envs.flight_imitation` (reference `fly_envs.py:30-97`): wing-beat-pattern-generator flight
     tracking, 4 substeps of 5e-5 s per control step, 12 actions (head 3, wings 6, abdomen 2, beat frequency 1).  With
     `ref_path` every env tracks its own (randomly cut) CoM trajectory of the flight dataset."""
@@ -649,4 +722,4 @@ def flight_imitation(ref_path=None, wpg_pattern_path=None, force_actuators=False
                                         random_state=random_state)
     return BatchedFlyEnv('flight', n_envs, device=device, terminal_com_dist=terminal_com_dist, time_limit=0.6,
                          future_steps=future_steps, lib_path=lib_path, seed=seed, wpg_pattern_path=wpg_pattern_path,
-                         traj_generator=tg)
+                         traj_generator=tg, device_task=device_task)

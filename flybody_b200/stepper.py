@@ -22,7 +22,7 @@ MAXCON, MAXEFC = 64, 160
 
 EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_set_action_map', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_record_stride', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
-           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_uniforms', 'fb_task_ptrs', 'fb_task_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
 
 # enum FbObsItem
@@ -35,6 +35,21 @@ class FbObsProgram(C.Structure):
                 ('b', C.POINTER(C.c_int32)), ('n_list', C.c_int32), ('list', C.POINTER(C.c_int32)),
                 ('root_body', C.c_int32), ('n_sub', C.c_int32), ('ref_len', C.c_int32),
                 ('ref_qpos', C.POINTER(C.c_float))]
+
+
+class FbTaskProgram(C.Structure):
+    """include/flybody_b200.h: FbTaskProgram (device-side task logic)."""
+    _fields_ = [('kind', C.c_int32), ('root_qadr', C.c_int32), ('root_vadr', C.c_int32), ('ghost_qadr', C.c_int32), ('ghost_vadr', C.c_int32),
+                ('user_col', C.c_int32), ('ghost_offset', C.c_float * 3), ('control_timestep', C.c_float), ('time_limit', C.c_float),
+                ('terminal_com_dist', C.c_float), ('terminal_linvel', C.c_float), ('terminal_angvel', C.c_float), ('terminal_qacc', C.c_float),
+                ('terminal_height', C.c_float), ('velocimeter_adr', C.c_int32), ('gyro_adr', C.c_int32), ('com_body', C.c_int32),
+                ('episode_steps', C.c_int32), ('ref_len', C.c_int32), ('ref_qpos', C.POINTER(C.c_float)), ('ref_qvel', C.POINTER(C.c_float)),
+                ('obs_refdisp_off', C.c_int32), ('obs_refquat_off', C.c_int32), ('reset_qpos', C.POINTER(C.c_float)),
+                ('n_noise', C.c_int32), ('noise_qadr', C.POINTER(C.c_int32)), ('noise_amp', C.c_float), ('seed', C.c_uint32),
+                ('n_wing', C.c_int32), ('wing_qadr', C.POINTER(C.c_int32)), ('wing_vadr', C.POINTER(C.c_int32)), ('wing_ctrl', C.POINTER(C.c_int32)),
+                ('n_freq', C.c_int32), ('tab_len', C.c_int32), ('wb_traj', C.POINTER(C.c_float)), ('wb_phase', C.POINTER(C.c_float)),
+                ('wb_phase_mod', C.POINTER(C.c_float)), ('wb_freqs', C.POINTER(C.c_float)), ('wb_len', C.POINTER(C.c_int32)),
+                ('wb_base_freq', C.c_float), ('wb_rel_range', C.c_float), ('wb_rate', C.c_float), ('com_offset', C.c_float * 3)]
 
 
 class StepperError(RuntimeError):
@@ -65,6 +80,12 @@ def load_library(path=None):
     lib.fb_obs_program.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_task_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fb_ref_slots.argtypes = [C.c_void_p, C.c_int]
+    lib.fb_task_program.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fb_task_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.fb_task_reset_all.argtypes = [C.c_void_p]
+    lib.fb_task_uniforms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.fb_task_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    lib.fb_task_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fb_ref_slot_write.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_read_task_obs.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_pack_obs.argtypes = [C.c_void_p]
@@ -224,6 +245,55 @@ class BatchedStepper:
         r = np.ascontiguousarray(rows, np.float32)
         assert r.shape == (len(ids), self._slot_len, 7), r.shape
         self._check(self._lib.fb_ref_slot_write(self._h, ids.ctypes.data, len(ids), r.ctypes.data), 'fb_ref_slot_write')
+
+    # ---- device-side task logic (fb_task_*)
+    def task_program(self, **kw):
+        """upload an FbTaskProgram; array arguments are numpy arrays (kept alive for the duration of the call)."""
+        keep = []
+
+        def fp(a):
+            a = np.ascontiguousarray(a, np.float32); keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_float))
+
+        def ip(a):
+            a = np.ascontiguousarray(a, np.int32); keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_int32))
+        p = FbTaskProgram()
+        for name, ctype in FbTaskProgram._fields_:
+            if name not in kw or kw[name] is None:
+                continue
+            v = kw[name]
+            if ctype is C.POINTER(C.c_float):
+                v = fp(v)
+            elif ctype is C.POINTER(C.c_int32):
+                v = ip(v)
+            elif ctype is C.c_float * 3:
+                v = (C.c_float * 3)(*[float(x) for x in v])
+            setattr(p, name, v)
+        self._check(self._lib.fb_task_program(self._h, C.byref(p)), 'fb_task_program')
+
+    def task_step(self, action, n_substeps, is_device=False):
+        if is_device:
+            self._check(self._lib.fb_task_step(self._h, C.c_void_p(int(action)), 1, int(n_substeps)), 'fb_task_step')
+        else:
+            a = np.ascontiguousarray(action, np.float32)
+            self._keep_action = a                  # the copy is asynchronous
+            self._check(self._lib.fb_task_step(self._h, a.ctypes.data, 0, int(n_substeps)), 'fb_task_step')
+
+    def task_reset_all(self):
+        self._check(self._lib.fb_task_reset_all(self._h), 'fb_task_reset_all')
+
+    def task_uniforms(self, env_ids, u):
+        ids = np.ascontiguousarray(env_ids, np.int32); uu = np.ascontiguousarray(u, np.float32)
+        self._check(self._lib.fb_task_uniforms(self._h, ids.ctypes.data, len(ids), uu.ctypes.data), 'fb_task_uniforms')
+
+    def task_ptrs(self):
+        o, n, r = C.c_void_p(), C.c_int(), C.c_void_p()
+        self._check(self._lib.fb_task_ptrs(self._h, C.byref(o), C.byref(n), C.byref(r)), 'fb_task_ptrs')
+        return o.value, n.value, r.value
+
+    def task_read(self, obs_out, out4):
+        self._check(self._lib.fb_task_read(self._h, obs_out.ctypes.data, out4.ctypes.data), 'fb_task_read')
 
     def task_inputs(self, step_idx, first):
         si = np.ascontiguousarray(step_idx, np.int32)

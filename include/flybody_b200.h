@@ -278,6 +278,47 @@ int fb_read_task_obs(FbHandle h, float* host_dst);
 int fb_pack_obs(FbHandle h);
 int fb_read_obs(FbHandle h, float* host_dst);
 
+/* Device-side task logic: everything the reference's task hooks do around the physics step -- composer
+ * auto-reset + initialize_episode (tasks/walk_imitation.py:112-136, tasks/flight_imitation.py:113-144), before_step (ghost
+ * placement walk_imitation.py:138-150; wing-beat pattern generator flight_imitation.py:146-168, pattern_generators.py:131-203),
+ * check_termination / get_reward / get_discount (tasks/base.py:203-225, walk_imitation.py:179-203,
+ * flight_imitation.py:170-226) -- evaluated on the device, so that a control step needs no host round trip: actions in
+ * (host or device pointer), observation rows + (reward, discount, step_type) out.  Covers the shared-reference (inference-mode)
+ * tasks; dataset mode keeps the host-side task code.  Requires fb_set_action_map and fb_obs_program first.          */
+typedef struct FbTaskProgram {
+  int32_t kind;                        /* 0 walk_imitation, 1 flight_imitation */
+  int32_t root_qadr, root_vadr, ghost_qadr, ghost_vadr;   /* free-joint slots of the walker root and of the ghost */
+  int32_t user_col;                    /* column of the beat-frequency action in the action row, -1 if none */
+  float ghost_offset[3];
+  float control_timestep, time_limit;
+  float terminal_com_dist, terminal_linvel, terminal_angvel, terminal_qacc, terminal_height;
+  int32_t velocimeter_adr, gyro_adr;   /* sensordata addresses */
+  int32_t com_body;                    /* body whose subtree CoM the flight reward tracks */
+  int32_t episode_steps;               /* step index that ends the episode (end of the reference) */
+  int32_t ref_len; const float* ref_qpos /* [ref_len][7] */; const float* ref_qvel /* [ref_len][6] */;
+  int32_t obs_refdisp_off, obs_refquat_off;   /* offsets of ref_displacement / ref_root_quat inside the observation row */
+  const float* reset_qpos;             /* [nq] episode start pose (root / ghost slots are overwritten from the reference) */
+  int32_t n_noise; const int32_t* noise_qadr; float noise_amp; uint32_t seed;   /* U(-amp, amp) on these qpos at reset */
+  int32_t n_wing; const int32_t* wing_qadr; const int32_t* wing_vadr; const int32_t* wing_ctrl;
+  int32_t n_freq, tab_len;             /* wing-beat tables: one resampled pattern per discrete beat frequency */
+  const float* wb_traj /* [n_freq][tab_len][n_wing] */; const float* wb_phase; const float* wb_phase_mod /* [n_freq][tab_len], +inf padded */;
+  const float* wb_freqs /* [n_freq] */; const int32_t* wb_len /* [n_freq] */;
+  float wb_base_freq, wb_rel_range, wb_rate;
+  float com_offset[3];                 /* root -> CoM offset in the root frame (tasks/task_utils.py:237) */
+} FbTaskProgram;
+int fb_task_program(FbHandle h, const FbTaskProgram* p);
+/* One control step with the task logic on the device: [auto-reset] -> action -> ctrl -> before_step -> n_substeps x physics ->
+ * observation program -> termination / reward.  `action` rows [n_envs][n_action] (fb_set_action_map), host or device.  */
+int fb_task_step(FbHandle h, const float* action, int is_device, int n_substeps);
+/* Mark every env for reset at the next fb_task_step (env.reset()).                                                    */
+int fb_task_reset_all(FbHandle h);
+/* Uniform numbers in [0,1) consumed by the listed envs' next reset (flight: wing-beat phase); without them the device
+ * draws from a counter hash of (seed, env, episode).                                                                 */
+int fb_task_uniforms(FbHandle h, const int32_t* env_ids, int n, const float* u);
+/* Results of the last fb_task_step: borrowed device pointers (obs rows [n_envs][obs_dim], out rows [n_envs][4] = reward,
+ * discount, step_type 0 FIRST / 1 MID / 2 LAST, 0) and the host copy (synchronises).                                  */
+int fb_task_ptrs(FbHandle h, void** obs_dev, int* obs_dim, void** out_dev);
+int fb_task_read(FbHandle h, float* obs_host, float* out_host);
 int fb_n_envs(FbHandle h);
 int fb_n_envs_padded(FbHandle h);
 void* fb_stream(FbHandle h);                 /* cudaStream_t the handle launches on */

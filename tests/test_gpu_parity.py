@@ -130,6 +130,39 @@ def test_flight_env_facade_on_gpu():
     assert np.all((ts.reward > 0.8) & (ts.reward <= 1.0))
 
 
+def test_dataset_mode_envs_on_gpu(tmp_path):
+    """per-env reference slots, full-body start pose, DeepMimic reward (tests/test_env_dataset.py) on the CUDA build."""
+    import test_env_dataset as ds
+    ds.test_dataset_mode_tracks_own_snippet_and_rewards(None, tmp_path)
+    ds.test_dataset_mode_replay_keeps_maximal_reward(None, tmp_path)
+    ds.test_flight_dataset_mode_per_env_trajectories(None, tmp_path)
+
+
+@pytest.mark.parametrize('var,mode', [('FB_FUSE', '1'), ('FB_FUSE', '3'), ('FB_SPLIT', '2'), ('FB_SPLIT', '3')])
+def test_launch_groupings_match_on_gpu(var, mode, monkeypatch):
+    """FB_FUSE regroups the stage kernels into fewer launches, FB_SPLIT steps env ranges as staggered chains on their own
+    streams; same stage code per env, so the states must agree bit for bit."""
+    m = load_model('walk')
+    rs = np.random.RandomState(2)
+    c = [rs.uniform(-0.5, 0.5, (64, m.nu)).astype(np.float32) for _ in range(3)]
+    out = []
+    for fuse in ('0' if var == 'FB_FUSE' else '1', mode):
+        monkeypatch.setenv(var, fuse)
+        s = st.BatchedStepper(m, 64)
+        q0 = np.tile(reset_qpos(m), (64, 1)); q0[:, 7:109] += np.random.RandomState(3).uniform(-0.05, 0.05, (64, 102)); s.reset(q0)
+        for k in range(3):
+            s.set_control(c[k]); s.step(10)
+        out.append((s.get(st.QPOS).copy(), s.get(st.QVEL).copy(), s.get(st.SENSOR_MEAN).copy()))
+        s.close()
+    for a, b in zip(*out):
+        if var == 'FB_SPLIT':
+            assert np.array_equal(a, b)          # same kernels on other streams / env ranges
+        else:
+            # the fused kernels are separate compilations of the same stage code (different FMA contraction across the
+            # inlined phases): last-bit differences, amplified over 30 substeps
+            assert np.allclose(a, b, rtol=1e-3, atol=1e-3)
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()

@@ -22,7 +22,7 @@ def one(n_envs, steps):
         s.set_control(ctrl[it % 4]); s.step(10); s.sync(); dev.append(s.last_step_ms)
     wall = (time.perf_counter() - t0) / steps * 1e3
     q = s.get(st.QPOS)
-    print(f"FB_FUSE={os.environ.get('FB_FUSE')} n={n_envs} device ms/step median {np.median(dev):.3f} min {np.min(dev):.3f} wall {wall:.3f} "
+    print(f"FB_FUSE={os.environ.get('FB_FUSE')} FB_SPLIT={os.environ.get('FB_SPLIT')} FB_STAGGER={os.environ.get('FB_STAGGER')} n={n_envs} device ms/step median {np.median(dev):.3f} min {np.min(dev):.3f} wall {wall:.3f} "
           f"env-steps/s {n_envs / np.median(dev) * 1e3:.0f} checksum {float(np.abs(q).sum()):.6f} finite {bool(np.isfinite(q).all())}", flush=True)
 
 
@@ -31,6 +31,10 @@ if __name__ == '__main__':
         one(int(sys.argv[1]), int(sys.argv[2]))
     else:
         n = sys.argv[1] if len(sys.argv) > 1 else '4096'; k = sys.argv[2] if len(sys.argv) > 2 else '20'
-        for mode in os.environ.get('FB_AB_MODES', '0 1 2 3').split():
-            env = dict(os.environ, FB_FUSE=mode, FB_AB_CHILD='1')
+        # variants: ';'-separated lists of VAR=VALUE settings, e.g. FB_AB_VARIANTS="FB_SPLIT=1;FB_SPLIT=2 FB_STAGGER=3"
+        variants = os.environ.get('FB_AB_VARIANTS')
+        variants = [v.split() for v in variants.split(';')] if variants else [[f'FB_FUSE={m}'] for m in '0123']
+        for v in variants:
+            env = dict(os.environ, FB_AB_CHILD='1', **dict(x.split('=') for x in v))
+            print('==', ' '.join(v), flush=True)
             subprocess.run([sys.executable, __file__, n, k], env=env, timeout=300)
