@@ -211,7 +211,8 @@ def run_ours(args):
     bad_total = int((flags != 0).sum())
 
     # ---- e2e through the public env API (host actions in pinned memory, observation record out)
-    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=N, device=local, reset_noise=0.05, seed=1234 + rank)
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=N, device=local, reset_noise=0.05, seed=1234 + rank,
+                                  device_task=not args.host_task)
     env.reset()
     host_act = torch.empty((K + W, N, 59), dtype=torch.float32).pin_memory()
     host_act.copy_(torch.from_numpy(rs.uniform(-0.5, 0.5, (K + W, N, 59)).astype(np.float32)))
@@ -261,7 +262,7 @@ def run_ours(args):
                        'unstable_envs_flagged': bad_total},
             'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': total_envs * K / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(env.h2d_bytes_per_step),
-                    'd2h_bytes_per_step': int(env.d2h_bytes_per_step), 'api': 'flybody_b200.fly_envs.walk_imitation(n_envs).step(action)'},
+                    'd2h_bytes_per_step': int(env.d2h_bytes_per_step), 'api': 'flybody_b200.fly_envs.walk_imitation(n_envs' + ('' if args.host_task else ', device_task=True') + ').step(action)'},
             'roofline': {'bound': 'hbm', 'kernel': dom_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
                          'how': f'algorithmic bytes = {BYTES_PER_ENV_SUBSTEP} B/env-substep x {N} envs x {substeps_per_launch} substep(s) per launch / mean CUDA-event duration of the '
@@ -286,6 +287,7 @@ def main():
     ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='envs per GPU')
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--host-task', action='store_true', help='e2e leg: task hooks in host numpy instead of on the device (fb_task_*)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':

@@ -149,18 +149,20 @@ FB_DEV mreal dnorm(D3 a) { return MSQRT(ddot(a, a)); }
 // 1/MSQRT(x) and 1/x to ~1e-15: single-precision seed + two Newton steps in mreal (the mreal-precision sqrt / divide of the
 // GPU are long software sequences; these sit in the inner loop of MPR)
 #if defined(__CUDACC__) && !defined(FB_MPR_DOUBLE)
-// fp32: hardware reciprocal square root + one Newton step (full single precision without the IEEE sqrt and divide sequences)
-FB_DEV mreal fast_rsqrt(mreal x) { float y = rsqrtf(x); return y * (1.5f - 0.5f * x * y * y); }
+// fp32: hardware reciprocal square root + two Newton steps (full single precision without the IEEE sqrt and divide sequences)
+FB_DEV mreal fast_rsqrt(mreal x) { float y = rsqrtf(x); y = y * (1.5f - 0.5f * x * y * y); return y * (1.5f - 0.5f * x * y * y); }
 #else
 FB_DEV mreal fast_rsqrt(mreal x) { mreal y = (mreal)(1.0f / sqrtf((float)x)); y = y * ((mreal)1.5 - (mreal)0.5 * x * y * y); return y * ((mreal)1.5 - (mreal)0.5 * x * y * y); }
 #endif
 FB_DEV mreal fast_rcp(mreal x) { mreal y = (mreal)(1.0f / (float)x); y = y * ((mreal)2.0 - x * y); return y * ((mreal)2.0 - x * y); }
 FB_DEV D3 dnormalized(D3 a) { mreal n2 = ddot(a, a); if (n2 < 1e-36) { mreal n = MSQRT(n2); if (n < 1e-300) return d3(1, 0, 0); return a * (1.0 / n); } return a * fast_rsqrt(n2); }
+FB_DEV D3 dsel(bool c, D3 a, D3 b) { return d3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
 struct MprPt { D3 v, v1, v2; };
 // e / zoff: per-type coefficients of the branch-free support function below (set by mpr_obj_coefs)
-struct MprObj { D3 pos; mreal mat[9]; D3 size; int type; mreal margin; D3 e; mreal zoff; };
+struct MprObj { D3 pos; mreal mat[9]; D3 size; int type; mreal margin; D3 e; mreal zoff; bool round; };
 FB_DEV void mpr_obj_coefs(MprObj& o) {
   const bool round = o.type == FB_GEOM_SPHERE || o.type == FB_GEOM_CAPSULE, cyl = o.type == FB_GEOM_CYLINDER;
+  o.round = round;
   o.e = (round || cyl) ? d3(o.size.x, o.size.x, cyl ? 0 : o.size.x) : o.size;
   o.zoff = (o.type == FB_GEOM_CAPSULE || cyl) ? o.size.y : 0;
 }
@@ -177,6 +179,7 @@ FB_DEV D3 mpr_support1(const MprObj& o, D3 dir) {
   D3 t = d3(ld.x * o.e.x, ld.y * o.e.y, ld.z * o.e.z);
   mreal n2 = ddot(t, t), in = n2 >= (mreal)1e-30 ? fast_rsqrt(n2) : (mreal)0;
   D3 r = d3(t.x * in * o.e.x, t.y * in * o.e.y, t.z * in * o.e.z);
+  r = dsel(o.round, ld * o.e.x, r);                 // spheres / capsule caps: radius * d exactly (no normalisation of the unit d)
   r.z += mpr_sgn(ld.z) * o.zoff;
   r = r + ld * ((mreal)0.5 * o.margin);
   return d3(R[0] * r.x + R[1] * r.y + R[2] * r.z, R[3] * r.x + R[4] * r.y + R[5] * r.z, R[6] * r.x + R[7] * r.y + R[8] * r.z) + o.pos;
@@ -205,7 +208,6 @@ FB_DEV mreal mpr_tri_dist2(D3 P, D3 x0, D3 B, D3 C, D3& w) {
 // The portal lives in registers: v0..v3 are the Minkowski-difference vertices, p1[i] the first object's support point of
 // vertex i (the second's is p1[i] - v_i; only read for the contact position at the very end, so it may sit in local memory).
 // Vertex replacement is a chain of selects, not a branch per case: the lanes of a warp refine different pairs.
-FB_DEV D3 dsel(bool c, D3 a, D3 b) { return d3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
 FB_DEV D3 mpr_portal_dir3(D3 v1, D3 v2, D3 v3) { return dnormalized(dcross(v2 - v1, v3 - v1)); }
 FB_DEV bool mpr_reach_tol3(D3 v1, D3 v2, D3 v3, D3 v4, D3 dir, mreal tol) {
   mreal dv4 = ddot(v4, dir), dmin = MFMIN(dv4 - ddot(v1, dir), MFMIN(dv4 - ddot(v2, dir), dv4 - ddot(v3, dir)));
