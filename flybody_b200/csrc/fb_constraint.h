@@ -483,10 +483,12 @@ FB_WARPFN void kcol_mpr(const DevModel& m, const DevData& d, ShCol& sh, int e) {
     njobs += POPC(mk);
   }
 #if defined(__CUDACC__) && !defined(FB_MPR_PER_WARP)
-  // The block's envs pool their jobs: an env has ~4 of them, so a warp working on its own list keeps 4 of 32 lanes busy
-  // through the longest MPR of the four.  Warp 0 takes the jobs of all FB_WPB envs of the block (one per lane, reading the
+  // The block's envs pool their jobs: an env has ~3 of them, so a warp working on its own list keeps 3 of 32 lanes busy
+  // through the longest MPR of the three.  Warp 0 takes the jobs of all FB_WPB envs of the block (one per lane, reading the
   // other warps' lists and geom positions in their shared slices) while the other warps wait at the barrier and leave
-  // their issue slots to the rest of the SM.  (All warps of a block are live: env ranges are multiples of FB_WPB.)
+  // their issue slots to the rest of the SM.  (Dealing the pooled jobs out to all four warps was measured too: 1.32 ms
+  // per control step against 1.03 ms -- four diverging instruction streams per block instead of one.)  All warps of a block
+  // are live: env ranges are multiples of FB_WPB.
   if (threadIdx.x == 0) sh.njobs = njobs;
   __syncthreads();
   if (threadIdx.y == 0) {
