@@ -672,7 +672,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   if (!hm || !out || n_envs <= 0) return -1;
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
-  s->fuse = getenv("FB_FUSE") ? atoi(getenv("FB_FUSE")) : FB_FUSE_DEFAULT; if (s->fuse < 0 || s->fuse > 3) s->fuse = FB_FUSE_DEFAULT;
+  s->fuse = getenv("FB_FUSE") ? atoi(getenv("FB_FUSE")) : FB_FUSE_DEFAULT; if (s->fuse < 0 || s->fuse > 6 || s->fuse == 5) s->fuse = FB_FUSE_DEFAULT;
   s->ref_slots = nullptr; s->ref_slot_len = 0;
   s->op_step_dev = nullptr; s->op_first_dev = nullptr; s->stage_cap = 0; s->stage_icap = 0; s->stage = nullptr; s->stage_i = nullptr;
 #ifndef FB_EMU
@@ -799,6 +799,17 @@ static void step_sequence(FbSim* s, int n_substeps) {
       launch_step2(s, true);
       s->d.sens_mode = (k == 0) ? 1 : 0;
       launch_step1(s);
+    } else if (s->fuse == 4 || s->fuse == 6) {
+      // only the straggler-prone stage pairs share a launch: the Newton solve (1-7 iterations per env) with the finish stage,
+      // and (6) collision (MPR tail on one warp per block) with the constraint rows
+      s->d.do_integrate = 1;
+      fb_launch<ShTree, FB_ST_SMOOTH>(s, K_SMOOTH, dyn_tsolve(s->m), -1, s->blob_in_smem ? s->m.ts_blob_words : 0);
+      fb_launch_fused<GrpSolve, GFinish>(s, K_STEP2, 1, 0);
+      s->d.sens_mode = (k == 0) ? 1 : 0;
+      fb_launch<ShTree, FB_ST_POS>(s, K_POS, dyn_pos(s->m));
+      if (s->fuse == 6) fb_launch_fused<GCol, GProj>(s, K_STEP1, 1, 0);
+      else { fb_launch<ShCol, FB_ST_COL>(s, K_COL, dyn_col(s->m)); fb_launch<ShCon, FB_ST_PROJ>(s, K_PROJ, dyn_proj(s->m)); }
+      fb_launch<ShTree, FB_ST_VEL>(s, K_VEL, dyn_vel(s->m));
     } else if (s->fuse == 1) {
       s->d.do_integrate = 1;
       fb_launch_fused<GSmooth, GrpSolve, GFinish>(s, K_STEP2, 1, 0);

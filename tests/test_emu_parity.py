@@ -96,7 +96,7 @@ def test_fused_launch_groupings_are_bit_identical(emu, monkeypatch):
     included."""
     m = load_model('walk')
     out = {}
-    for mode in ('0', '1', '2', '3'):
+    for mode in ('0', '1', '2', '3', '4', '6'):
         monkeypatch.setenv('FB_FUSE', mode)
         sim = st.BatchedStepper(m, 2, lib_path=emu)
         rs = np.random.RandomState(5)
@@ -106,7 +106,7 @@ def test_fused_launch_groupings_are_bit_identical(emu, monkeypatch):
             sim.step(10)
         out[mode] = (sim.get(st.QPOS).copy(), sim.get(st.QVEL).copy(), sim.get(st.SENSOR_MEAN).copy(), sim.launch_count - l0)
         sim.close()
-    assert out['0'][3] > out['1'][3] > out['2'][3] > out['3'][3]
-    for mode in ('1', '2', '3'):
+    assert out['0'][3] > out['4'][3] > out['6'][3] > out['1'][3] > out['2'][3] > out['3'][3]
+    for mode in ('1', '2', '3', '4', '6'):
         for a, b in zip(out['0'][:3], out[mode][:3]):
             assert np.array_equal(a, b)
