@@ -160,6 +160,7 @@ def run_ours(args):
         raise SystemExit('bench.py: no CUDA device; the stepper has no CPU path (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # stdout carries exactly one JSON line (NCCL prints its version banner otherwise)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     N = args.envs
     m = load_model('walk')
