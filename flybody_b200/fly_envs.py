@@ -206,6 +206,7 @@ class BatchedFlyEnv:
         self.n_envs = int(n_envs) if self._batched else 1
         self.model = load_model(variant)
         m = self.model
+        self._device = int(device)
         self._sim = st.BatchedStepper(m, self.n_envs, device=device, lib_path=lib_path)
         self._control_timestep = _VARIANTS[variant]['dt']
         self._physics_timestep = float(m.opt_timestep)
@@ -401,6 +402,7 @@ class BatchedFlyEnv:
             self._rec = np.empty((N, dim), np.float32)
         if self._device_task:
             self._upload_task_program()
+            self._dev_views = None
 
     def _upload_task_program(self):
         """fb_task_program: the task hooks of this env as a device-side program (same constants as the host path below)."""
@@ -544,6 +546,36 @@ class BatchedFlyEnv:
         self._needs_reset = step_type == int(StepType.LAST)
         return TimeStep(step_type,
                         self._out4[:, 0].astype(np.float64), self._out4[:, 1].astype(np.float64), self._observation(self._rec))
+
+    def step_device(self, action):
+        """Device-resident control step for a policy that lives on the GPU: `action` is a CUDA tensor / array exposing
+        `__cuda_array_interface__` (fp32, [n_envs, n_action], on this env's device); returns zero-copy torch views
+        (observation rows [n_envs, obs_dim], out [n_envs, 4] = reward, discount, step_type, 0) of the library's buffers, valid
+        until the next step.  Nothing is copied to the host and the call does not synchronise: work is ordered on
+        `env.physics.stepper.stream` (wrap it in `torch.cuda.ExternalStream` to order a policy after it).  Requires
+        `device_task=True`; `observation_layout()` names the columns."""
+        if not self._device_task:
+            raise RuntimeError('step_device needs device_task=True (task hooks on the device)')
+        import torch
+        if self._rec is None:
+            self._load_snippet(np.arange(self.n_envs))
+        cai = action.__cuda_array_interface__
+        assert tuple(cai['shape']) == (self.n_envs, self._action_spec.shape[0]) and cai['typestr'] == '<f4', cai
+        self._sim.task_step(cai['data'][0], self._n_sub, is_device=True)
+        if getattr(self, '_dev_views', None) is None:
+            obs_ptr, dim, out_ptr = self._sim.task_ptrs()
+
+            class _View:
+                def __init__(self, ptr, shape):
+                    self.__cuda_array_interface__ = {'shape': shape, 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+            dev = f'cuda:{self._device}'
+            self._dev_views = (torch.as_tensor(_View(obs_ptr, (self.n_envs, dim)), device=dev),
+                               torch.as_tensor(_View(out_ptr, (self.n_envs, 4)), device=dev))
+        return self._dev_views
+
+    def observation_layout(self):
+        """{observable name: (column slice, shape)} of the observation rows `step_device` returns."""
+        return {k: (sl, self._obs_shapes[k]) for k, sl in self._obs_slices.items() if not k.startswith('_')}
 
     def reset(self):
         if self._device_task:

@@ -147,6 +147,33 @@ def test_device_task_logic_on_gpu():
     dt.test_flight_device_task_matches_host_task_code(None)
 
 
+def test_device_resident_rollout_matches_host_api():
+    """step_device (CUDA action tensor in, zero-copy observation / reward views out, no host copy) against step() on a twin env."""
+    import torch
+    from flybody_b200 import fly_envs
+    n = 64
+    a_env = fly_envs.walk_imitation(terminal_com_dist=0.05, n_envs=n, device_task=True)
+    b_env = fly_envs.walk_imitation(terminal_com_dist=0.05, n_envs=n, device_task=True)
+    a_env.reset(); b_env.reset()
+    stream = torch.cuda.ExternalStream(a_env.physics.stepper.stream)
+    rs = np.random.RandomState(0)
+    lay = a_env.observation_layout()
+    saw_first = False
+    for k in range(20):
+        act = rs.uniform(-0.5, 0.5, (n, 59)).astype(np.float32)
+        ts = b_env.step(act)
+        with torch.cuda.stream(stream):
+            obs, out = a_env.step_device(torch.from_numpy(act).cuda())
+            stream.synchronize()
+            obs_h, out_h = obs.cpu().numpy(), out.cpu().numpy()
+        assert np.array_equal(out_h[:, 2].astype(np.int64), np.asarray(ts.step_type, np.int64)), k
+        assert np.array_equal(out_h[:, 0], np.asarray(ts.reward, np.float32)) and np.array_equal(out_h[:, 1], np.asarray(ts.discount, np.float32))
+        sl, shp = lay['walker/joints_pos']
+        assert np.array_equal(obs_h[:, sl].reshape((n,) + shp), ts.observation['walker/joints_pos'])   # two handles, same kernels, same inputs
+        saw_first |= bool((out_h[:, 2] == 0).any())
+    assert saw_first
+
+
 @pytest.mark.parametrize('var,mode', [('FB_FUSE', '1'), ('FB_FUSE', '3'), ('FB_SPLIT', '2'), ('FB_SPLIT', '3')])
 def test_launch_groupings_match_on_gpu(var, mode, monkeypatch):
     """FB_FUSE regroups the stage kernels into fewer launches, FB_SPLIT steps env ranges as staggered chains on their own

@@ -23,3 +23,22 @@ for variant, make, na, scale in (('walk', lambda dev: fly_envs.walk_imitation(te
         dt = (time.perf_counter() - t0) / K
         print(f'{variant:7s} N={N} device_task={dev!s:5s} {dt * 1e3:8.3f} ms/step {N / dt:12.0f} env-steps/s  terminations {n_last}  mean reward {float(np.mean(ts.reward)):.4f}', flush=True)
         env.close()
+
+# device-resident rollout: actions from a CUDA tensor, observation / reward views left on the device (a GPU policy's loop)
+import torch
+for variant, make, na, scale in (('walk', lambda: fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=N, reset_noise=0.05, device_task=True), 59, 0.5),
+                                 ('flight', lambda: fly_envs.flight_imitation(n_envs=N, device_task=True), 12, 0.2)):
+    env = make(); env.reset()
+    stream = torch.cuda.ExternalStream(env.physics.stepper.stream)
+    with torch.cuda.stream(stream):
+        acts = (torch.rand((K + 5, N, na), device='cuda') - 0.5) * 2 * scale
+        for k in range(5):
+            env.step_device(acts[k])
+        stream.synchronize()
+        t0 = time.perf_counter()
+        for k in range(5, K + 5):
+            obs, out = env.step_device(acts[k])
+        stream.synchronize()
+        dt = (time.perf_counter() - t0) / K
+        print(f'{variant:7s} N={N} step_device (no host copies) {dt * 1e3:8.3f} ms/step {N / dt:12.0f} env-steps/s  mean reward {float(out[:, 0].mean()):.4f}', flush=True)
+    env.close()
