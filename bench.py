@@ -31,6 +31,19 @@ ENVS_PER_GPU = 4096
 N_SUB = 10
 BYTES_PER_ENV_SUBSTEP = 3628          # fp32 state read+write per physics substep (W model)
 BYTES_PER_ENV_STEP = BYTES_PER_ENV_SUBSTEP * N_SUB
+# --workload: the headline is walk (BASELINE.json configs[1]); flight is configs[2], same contract, not the driver's default
+WORKLOADS = {'walk': dict(model='walk', n_sub=10, bytes_substep=3628, act_scale=0.5, n_action=59, dt='2e-4',
+                          config='BASELINE.json configs[1]; N>1: configs[3] sharding + NCCL obs gather to rank 0'),
+             'flight': dict(model='flight', n_sub=4, bytes_substep=1284, act_scale=0.2, n_action=12, dt='5e-5',
+                            config='BASELINE.json configs[2]: ellipsoid fluid / wing forces, wing-beat pattern generator')}
+WL = WORKLOADS['walk']
+
+
+def set_workload(name):
+    global WL, N_SUB, BYTES_PER_ENV_SUBSTEP, BYTES_PER_ENV_STEP
+    WL = WORKLOADS[name]
+    N_SUB, BYTES_PER_ENV_SUBSTEP = WL['n_sub'], WL['bytes_substep']
+    BYTES_PER_ENV_STEP = BYTES_PER_ENV_SUBSTEP * N_SUB
 
 
 def measured_peaks():
@@ -70,6 +83,9 @@ class ClockSampler(threading.Thread):
 
 
 def walk_reset_batch(m, n, rs):
+    if WL['model'] == 'flight':                      # hovering start 1 cm above the floor (flight_imitation's synthetic trajectory height)
+        qq = np.tile(m.qpos0, (n, 1)); qq[:, 2] = 1.0
+        return qq
     q0 = m.qpos0.copy()
     for side in ('left', 'right'):
         for dof, val in (('yaw', 1.5), ('roll', 0.7), ('pitch', -1.0)):
@@ -88,11 +104,11 @@ def cpu_oracle_worker(args):
     seed, budget_s, max_steps = args
     from flybody_b200.flymodel import load_model
     from oracle import fly_oracle as fo
-    m = load_model('walk')
+    m = load_model(WL['model'])
     o = fo.Oracle(m)                       # MuJoCo default tolerance (1e-8)
     rs = np.random.RandomState(seed)
     o.reset(walk_reset_batch(m, 1, rs)[0])
-    acts = rs.uniform(-0.5, 0.5, (max_steps, m.nu))
+    acts = rs.uniform(-WL['act_scale'], WL['act_scale'], (max_steps, m.nu))
     for k in range(3):
         o.set(fo.CTRL, acts[k]); o.control_step(N_SUB)
     t0 = time.perf_counter()
@@ -114,7 +130,7 @@ def cpu_baseline(budget_s=10.0, max_steps=4000, cores=None):
         res = pool.map(cpu_oracle_worker, [(1000 + i, budget_s, max_steps) for i in range(cores)])
     rate = sum(n / t for n, t in res)
     return {'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{cores} processes x ~{budget_s:.0f}s of walk_imitation control steps (10 substeps, random actions), '
+            'sample': f'{cores} processes x ~{budget_s:.0f}s of {WL["model"]}_imitation control steps ({N_SUB} substeps, random actions), '
                       f'oracle/fly_oracle.c (restated mj_step, fp64; NOT MuJoCo: mujoco is not installable here), '
                       f'{sum(n for n, _ in res)} env-steps total',
             'per_core': rate / cores}
@@ -128,11 +144,11 @@ def run_reference(args):
     per_step_budget = 4.0
     cb = cpu_baseline(budget_s=per_step_budget * max(1, min(args.steps, 5)), cores=os.cpu_count())
     wall = time.perf_counter() - t0
-    line = {'impl': 'reference', 'metric': 'env-steps/sec on walk_imitation (control steps of 10 substeps)', 'value': cb['value'],
+    line = {'impl': 'reference', 'metric': f'env-steps/sec on {WL["model"]}_imitation (control steps of {N_SUB} substeps)', 'value': cb['value'],
             'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 / cb['per_core'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'walk_imitation, random policy, one env per host core (reference scaling model: '
+            'config': {'workload': f'{WL["model"]}_imitation, random policy, one env per host core (reference scaling model: '
                                    'one env per actor process, train_dmpo_ray.py:206-227)', 'cores': cb['cores']},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -163,7 +179,7 @@ def run_ours(args):
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # stdout carries exactly one JSON line (NCCL prints its version banner otherwise)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     N = args.envs
-    m = load_model('walk')
+    m = load_model(WL['model'])
     rs = np.random.RandomState(sharding.rank_seed(1234, rank))
     sim = st.BatchedStepper(m, N, device=local)
     Np = sim.n_envs_padded
@@ -173,7 +189,7 @@ def run_ours(args):
     obs = torch.as_tensor(CudaView(obs_ptr, (N, obs_dim)), device=f'cuda:{local}')
     K, W = args.steps, args.warmup
     gen = torch.Generator(device=f'cuda:{local}'); gen.manual_seed(1234 + rank)
-    acts = (torch.rand((K + W, N, m.nu), device=f'cuda:{local}', generator=gen) - 0.5)      # ctrl rows [N][nu], resident in HBM
+    acts = (torch.rand((K + W, N, m.nu), device=f'cuda:{local}', generator=gen) - 0.5) * (2 * WL['act_scale'])      # ctrl rows [N][nu], resident in HBM
     # identity permutation between action and ctrl order is irrelevant for a random policy
     gather_list = [torch.empty((N, obs_dim), device=f'cuda:{local}') for _ in range(world)] if (world > 1 and rank == 0) else None
     bad_total = 0
@@ -222,11 +238,15 @@ def run_ours(args):
     bad_total = int((flags != 0).sum())
 
     # ---- e2e through the public env API (host actions in pinned memory, observation record out)
-    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=N, device=local, reset_noise=0.05, seed=1234 + rank,
-                                  device_task=not args.host_task)
+    if WL['model'] == 'walk':
+        env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=N, device=local, reset_noise=0.05, seed=1234 + rank,
+                                      device_task=not args.host_task)
+    else:
+        env = fly_envs.flight_imitation(n_envs=N, device=local, seed=1234 + rank, device_task=not args.host_task)
     env.reset()
-    host_act = torch.empty((K + W, N, 59), dtype=torch.float32).pin_memory()
-    host_act.copy_(torch.from_numpy(rs.uniform(-0.5, 0.5, (K + W, N, 59)).astype(np.float32)))
+    na = WL['n_action']
+    host_act = torch.empty((K + W, N, na), dtype=torch.float32).pin_memory()
+    host_act.copy_(torch.from_numpy(rs.uniform(-WL['act_scale'], WL['act_scale'], (K + W, N, na)).astype(np.float32)))
     a_np = host_act.numpy()
     for k in range(W):
         env.step(a_np[k])
@@ -259,21 +279,21 @@ def run_ours(args):
         achieved = alg_bytes_per_launch / avg_launch_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
-        if os.path.exists(tp):
+        if os.path.exists(tp) and WL['model'] == 'walk':        # the ncu capture is of the walk model's kernels
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')
         line = {
-            'metric': 'env-steps/sec on walk_imitation (control steps of 10 substeps)', 'value': value, 'unit': 'env-steps/s',
+            'metric': f'env-steps/sec on {WL["model"]}_imitation (control steps of {N_SUB} substeps)', 'value': value, 'unit': 'env-steps/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'walk_imitation {N} envs per GPU, random policy U(-0.5,0.5), 10 substeps x 2e-4 s '
-                                   f'(BASELINE.json configs[1]; N>1: configs[3] sharding + NCCL obs gather to rank 0)',
+            'config': {'workload': f'{WL["model"]}_imitation {N} envs per GPU, random policy U(-{WL["act_scale"]},{WL["act_scale"]}), {N_SUB} substeps x {WL["dt"]} s '
+                                   f'({WL["config"]})',
                        'envs_per_gpu': N, 'total_envs': total_envs, 'n_substeps': N_SUB,
                        'l2': f'inputs larger than L2: every launch streams the env records ({sim.record_bytes / 1e6:.2f} MB each, {sim.record_bytes * N / 1e9:.2f} GB per GPU vs 126 MB L2); no explicit flush',
                        'parallelism': f'env-sharded x{world}' + (', torch.distributed NCCL gather of packed obs per control step' if world > 1 else ''),
                        'unstable_envs_flagged': bad_total},
             'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': total_envs * K / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(env.h2d_bytes_per_step),
-                    'd2h_bytes_per_step': int(env.d2h_bytes_per_step), 'api': 'flybody_b200.fly_envs.walk_imitation(n_envs' + ('' if args.host_task else ', device_task=True') + ').step(action)'},
+                    'd2h_bytes_per_step': int(env.d2h_bytes_per_step), 'api': f'flybody_b200.fly_envs.{WL["model"]}_imitation(n_envs' + ('' if args.host_task else ', device_task=True') + ').step(action)'},
             'roofline': {'bound': 'hbm', 'kernel': dom_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
                          'how': f'algorithmic bytes = {BYTES_PER_ENV_SUBSTEP} B/env-substep x {N} envs x {substeps_per_launch} substep(s) per launch / mean CUDA-event duration of the '
@@ -299,9 +319,11 @@ def main():
     ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='envs per GPU')
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--workload', default='walk', choices=sorted(WORKLOADS), help='walk = the headline (BASELINE configs[1]); flight = configs[2]')
     ap.add_argument('--host-task', action='store_true', help='e2e leg: task hooks in host numpy instead of on the device (fb_task_*)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    set_workload(args.workload)
     if args.impl == 'reference':
         run_reference(args)
     else:
