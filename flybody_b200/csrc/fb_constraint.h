@@ -1191,7 +1191,7 @@ FB_DEV void ktask_reset2(const DevModel& m, const DevData& d, int e, int y) {   
       t.wb_freq[e] = t.wb_base_freq; t.wb_idx[e] = idx; t.wb_pos[e] = pos;
     }
     AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = 1; AT(d.prev_n, 0) = 0;
-    t.step[e] = 0; t.episode[e] = episode + 1; t.has_uniform[e] = 0;
+    t.step[e] = 0; t.has_uniform[e] = 0;          // (the episode counter, read by every lane above, advances in ktask_before)
   }
 }
 FB_DEV void ktask_before(const DevModel& m, const DevData& d, int e, int y) {
@@ -1221,10 +1221,16 @@ FB_DEV void ktask_before(const DevModel& m, const DevData& d, int e, int y) {
       const float* tg = t.wb_traj + ((size_t)idx * t.tab_len + pos) * t.n_wing;
       for (int i = 0; i < t.n_wing; i++) AT(d.ctrl, t.wing_ctrl[i]) += tg[i] - AT(d.qpos, t.wing_qadr[i]);
     }
-    t.resetting[e] = resetting;
-    if (!resetting) t.step[e] = t.step[e] + 1;
-    t.op_step[e] = t.step[e]; t.op_first[e] = (unsigned char)resetting;
   }
+}
+// counters advance in a phase of their own: every lane of ktask_before reads the step it is about to leave
+FB_DEV void ktask_commit(const DevModel& m, const DevData& d, int e, int y) {
+  if (!d.task || e >= d.N || y != 0) return;
+  const DevTask& t = *d.task;
+  const int resetting = t.needs_reset[e];
+  t.resetting[e] = resetting;
+  if (resetting) t.episode[e] = t.episode[e] + 1; else t.step[e] = t.step[e] + 1;
+  t.op_step[e] = t.step[e]; t.op_first[e] = (unsigned char)resetting;
 }
 FB_DEV float tk_lin_tol(float x, float margin) { float v = 1.0f - fabsf(x) / margin; return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 FB_DEV void ktask_after(const DevModel& m, const DevData& d, int e, int y) {

@@ -227,6 +227,7 @@ FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, i
 FB_DEV void ph_task_reset(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_reset(m, d, e, y); }
 FB_DEV void ph_task_reset2(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_reset2(m, d, e, y); }
 FB_DEV void ph_task_before(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_before(m, d, e, y); }
+FB_DEV void ph_task_commit(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_commit(m, d, e, y); }
 FB_DEV void ph_task_after(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_after(m, d, e, y); }
 FB_DEV void ph_pack(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kpack(m, d, e, y, d.nsub_done > 0 ? 1.0f / d.nsub_done : 1.0f); ktaskobs(m, d, e, y); }
 // Smooth dynamics in half-solve form: with M = L^T D L and u = L^-T qfrc_smooth,
@@ -1198,7 +1199,7 @@ int fb_task_step(FbHandle s, const float* action, int is_device, int n_substeps)
   fb_launch<ShNone, Ph<ph_task_reset>, Ph<ph_task_reset2>>(s, K_MISC, 0, s->d.N);      // envs whose last step was LAST
   int rc = fb_set_ctrl(s, action, is_device);                                           // action -> ctrl (NaN -> 0), staged rows stay readable
   if (rc != 0) return rc;
-  fb_launch<ShNone, Ph<ph_task_before>>(s, K_MISC, 0, s->d.N);
+  fb_launch<ShNone, Ph<ph_task_before>, Ph<ph_task_commit>>(s, K_MISC, 0, s->d.N);
   s->hold_pending = 1;                                                                  // freshly reset envs are held through this step
   rc = fb_step(s, n_substeps);
   if (rc != 0) return rc;

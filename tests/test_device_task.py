@@ -34,10 +34,13 @@ def drive(env, actions, wb_ref=None):
         ts = env.step(actions[k])
         # before_step: ghost on the reference row of the step, wing commands from the pattern generator
         q, v = sim.get(st.QPOS), sim.get(st.QVEL)
-        # (the ghost is a free body without gravity or contacts: over the control step it coasts with the velocity it was given)
-        coast = ghost[:, :3] + np.where(resetting[:, None], 0.0, ghost[:, 7:10] * env._control_timestep)
-        assert np.allclose(q[:, env._ghost_q:env._ghost_q + 3], coast, atol=2e-5), (k, q[:, env._ghost_q:env._ghost_q + 3], coast)
-        assert np.allclose(q[:, env._ghost_q + 3:env._ghost_q + 7], ghost[:, 3:7], atol=2e-3), k
+        # (the ghost is a free body without gravity or contacts: over the control step it coasts with the velocity it was given,
+        # which takes it to the next row of a self-consistent reference; a held env stays on row 0)
+        nxt = env._ref_at(np.minimum(step + 1, env._ref_len - 1)); nxt[:, :3] += env.task._ghost_offset
+        want = np.where(resetting[:, None], ghost[:, :7], nxt[:, :7])
+        assert np.allclose(q[:, env._ghost_q:env._ghost_q + 3], want[:, :3], atol=2e-4), (k, q[:, env._ghost_q:env._ghost_q + 3], want[:, :3])
+        # (the synthetic reference's angular velocity is per control step, synthetic_trajectories.py:58-60: the heading barely coasts)
+        assert np.allclose(q[:, env._ghost_q + 3:env._ghost_q + 7], ghost[:, 3:7], atol=5e-4), k
         assert np.allclose(v[:, env._ghost_v:env._ghost_v + 6], ghost[:, 7:], atol=1e-2), k
         if wb_ref is not None:
             if resetting.any():                                     # same phases as the device consumed
@@ -74,6 +77,10 @@ def test_walk_device_task_matches_host_task_code(emu):
     actions[3, 1, 5] = np.nan                                              # NaN actions act as 0 (tasks/base.py:199)
     actions[20:, 2] = 3.0                                                  # env 2 thrashes
     env = fly_envs.walk_imitation(terminal_com_dist=0.05, n_envs=n, lib_path=emu, device_task=True)   # ghost leaves 0.05 cm after ~13 steps
+    # a turning reference: every component of the ghost's pose and velocity changes from row to row
+    from flybody_b200.synthetic import constant_speed_trajectory
+    env.task._traj_generator.set_next_trajectory(*constant_speed_trajectory(n_steps=300, speed=2, yaw_speed=4.0, init_pos=(0, 0, 0.1278),
+                                                                            control_timestep=2e-3))
     seen = drive(env, actions)
     assert (seen == int(StepType.LAST)).any() and (seen[1:] == int(StepType.FIRST)).any()
     # the NaN action reached the actuators as 0
