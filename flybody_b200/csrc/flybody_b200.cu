@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #endif
 #include "fb_solver_reg.h"
+#include "fb_render.h"
 
 #ifdef FB_EMU
 typedef int cudaStream_t_;
@@ -73,6 +74,7 @@ struct FbSim {
   int blob_in_smem;            // copy the sweep program of the triangular solves into shared memory per CTA (default: for batches <= 1024 envs; FB_BLOB=0/1 overrides)
   int* op_step_dev; unsigned char* op_first_dev;
   float* ref_slots; int ref_slot_len;      // per-env reference tables (fb_ref_slots)
+  DevEye eye; float* hfield_dev; float* hmax_dev; unsigned char* eye_out; size_t eye_bytes;   // eye cameras (fb_eye_program)
   DevTask task_host;                       // host copy of the device-side task program (its pointers are device pointers)
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
 #ifndef FB_EMU
@@ -674,7 +676,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
   s->fuse = getenv("FB_FUSE") ? atoi(getenv("FB_FUSE")) : FB_FUSE_DEFAULT; if (s->fuse < 0 || s->fuse > 6 || s->fuse == 5) s->fuse = FB_FUSE_DEFAULT;
-  s->ref_slots = nullptr; s->ref_slot_len = 0;
+  s->ref_slots = nullptr; s->ref_slot_len = 0; s->eye_out = nullptr; s->hfield_dev = nullptr; s->hmax_dev = nullptr; s->eye_bytes = 0;
   s->op_step_dev = nullptr; s->op_first_dev = nullptr; s->stage_cap = 0; s->stage_icap = 0; s->stage = nullptr; s->stage_i = nullptr;
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
@@ -1222,6 +1224,70 @@ int fb_task_read(FbHandle s, float* obs_host, float* out_host) {
 #else
   if (obs_host) memcpy(obs_host, s->d.tobs, sizeof(float) * (size_t)s->d.N * s->d.tobs_dim);
   if (out_host) memcpy(out_host, s->task_host.out, sizeof(float) * (size_t)4 * s->d.N);
+  return 0;
+#endif
+}
+#ifndef FB_EMU
+__global__ void __launch_bounds__(128) fb_render_kernel(DevData d, DevEye p) {
+  const int e = blockIdx.x / p.n_cam, cam = blockIdx.x % p.n_cam;
+  for (int px = threadIdx.x; px < p.size * p.size; px += blockDim.x) eye_pixel(d, p, e, cam, px / p.size, px % p.size);
+}
+#endif
+int fb_eye_program(FbHandle s, const FbEyeProgram* p) {
+  if (!s || !p) return -1;
+  if (p->n_cam < 1 || p->n_cam > FB_MAXCAM || p->size < 1 || p->size > 512 || !(p->fovy_deg > 0 && p->fovy_deg < 180) || p->nrow < 0 || (p->nrow > 0 && (p->nrow < 2 || p->ncol < 2 || !(p->half_size > 0)))) { s->err = "fb_eye_program: bad camera / grid parameters"; return -1; }
+  for (int c = 0; c < p->n_cam; c++) if (p->body[c] <= 0 || p->body[c] >= s->m.nbody) { s->err = "fb_eye_program: camera body out of range"; return -1; }
+  if (sync_stream(s) != 0) return -2;
+  DevEye& y = s->eye; memset(&y, 0, sizeof(y));
+  y.n_cam = p->n_cam; y.size = p->size; y.nrow = p->nrow; y.ncol = p->nrow > 0 ? p->ncol : 0;
+  for (int c = 0; c < p->n_cam; c++) { y.body[c] = p->body[c]; for (int k = 0; k < 3; k++) y.pos[c][k] = p->pos[c][k]; for (int k = 0; k < 4; k++) y.quat[c][k] = p->quat[c][k]; }
+  y.tan_half = tanf(0.5f * p->fovy_deg * 3.14159265358979f / 180.0f); y.half_size = p->half_size; y.z_offset = p->z_offset; y.zfar = p->zfar > 0 ? p->zfar : 50.0f;
+  for (int k = 0; k < 3; k++) { y.sky_top[k] = p->sky_top[k]; y.sky_horizon[k] = p->sky_horizon[k]; y.ground[k] = p->ground[k]; }
+  y.ambient = p->ambient; y.diffuse = p->diffuse;
+  const size_t cells = (size_t)y.nrow * y.ncol;
+  s->hfield_dev = cells ? dalloc<float>(s, cells * s->d.Np) : nullptr; s->hmax_dev = dalloc<float>(s, s->d.Np);
+  s->eye_bytes = (size_t)y.n_cam * y.size * y.size * 3;
+  s->eye_out = dalloc<unsigned char>(s, s->eye_bytes * s->d.Np);
+  y.hfield = s->hfield_dev; y.hmax = s->hmax_dev; y.out = s->eye_out;
+  return 0;
+}
+int fb_hfield_write(FbHandle s, const int32_t* env_ids, int n, const float* heights) {
+  if (!s || !s->eye_out || !s->hfield_dev || !env_ids || !heights || n < 0) return -1;
+  const size_t cells = (size_t)s->eye.nrow * s->eye.ncol;
+  for (int k = 0; k < n; k++) {
+    if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_hfield_write: env id out of range"; return -1; }
+    float mx = heights[cells * k]; for (size_t i = 1; i < cells; i++) mx = std::max(mx, heights[cells * k + i]);
+    upload_async(s, s->hfield_dev + cells * env_ids[k], heights + cells * k, sizeof(float) * cells);
+    if (sync_stream(s) != 0) return -2;
+    h2d(s->hmax_dev + env_ids[k], &mx, sizeof(float));
+  }
+  return 0;
+}
+int fb_render_eyes(FbHandle s) {
+  if (!s || !s->eye_out) return -1;
+#ifndef FB_EMU
+  cudaSetDevice(s->device);
+  fb_render_kernel<<<s->d.N * s->eye.n_cam, 128, 0, s->stream>>>(s->d, s->eye);
+  if (cudaGetLastError() != cudaSuccess) { s->err = "fb_render_eyes: launch failed"; return -2; }
+#else
+  for (int e = 0; e < s->d.N; e++) for (int c = 0; c < s->eye.n_cam; c++) for (int px = 0; px < s->eye.size * s->eye.size; px++) eye_pixel(s->d, s->eye, e, c, px / s->eye.size, px % s->eye.size);
+#endif
+  s->launches++;
+  return 0;
+}
+int fb_eyes_ptr(FbHandle s, void** dev_ptr, int* bytes_per_env) {
+  if (!s || !s->eye_out) return -1;
+  if (dev_ptr) *dev_ptr = s->eye_out;
+  if (bytes_per_env) *bytes_per_env = (int)s->eye_bytes;
+  return 0;
+}
+int fb_eyes_read(FbHandle s, uint8_t* host_dst) {
+  if (!s || !s->eye_out || !host_dst) return -1;
+#ifndef FB_EMU
+  FB_CUDA_OK(cudaMemcpyAsync(host_dst, s->eye_out, s->eye_bytes * s->d.N, cudaMemcpyDeviceToHost, s->stream));
+  return sync_stream(s);
+#else
+  memcpy(host_dst, s->eye_out, s->eye_bytes * s->d.N);
   return 0;
 #endif
 }

@@ -573,6 +573,34 @@ class BatchedFlyEnv:
                                torch.as_tensor(_View(out_ptr, (self.n_envs, 4)), device=dev))
         return self._dev_views
 
+    # ---------------------------------------------------------------------------------- eyes
+    # cameras `eye_right` / `eye_left` on the head (reference fruitfly.xml:335-336; the head body keeps its XML frame)
+    _EYE_CAMERAS = (('walker/right_eye', (0.0219, 0.0131, 0.0), (0.474, 0.688, -0.344, -0.429)),
+                    ('walker/left_eye', (-0.0219, 0.0131, 0.0), (0.474, 0.688, 0.344, 0.429)))
+
+    def enable_eyes(self, size=32, fovy=150.0, terrain_shape=None, half_size=20.0, z_offset=0.0):
+        """Turn on the eye-camera observables `walker/right_eye`, `walker/left_eye` (reference `fruitfly.py:729-745`; 32 x 32,
+        fovy 150 in `tasks/vision_flight.py:23-24`), rendered on the device by a ray caster over an optional per-env
+        heightfield `terrain_shape = (nrow, ncol)` spanning [-half_size, half_size]^2 (`flybody_b200.arenas`), the ground plane
+        and a sky.  `render_eyes()` returns them for the current state; they are not part of `step()`'s observation dict."""
+        quats = [np.asarray(q, np.float64) / np.linalg.norm(q) for _, _, q in self._EYE_CAMERAS]
+        head = self.model.body_id('walker/head')
+        nrow, ncol = terrain_shape if terrain_shape is not None else (0, 0)
+        self._sim.eye_program([head, head], [p for _, p, _ in self._EYE_CAMERAS], quats, fovy_deg=fovy, size=size, nrow=nrow, ncol=ncol,
+                              half_size=half_size, z_offset=z_offset)
+        self._eyes_on = True
+
+    def set_terrain(self, env_ids, heights):
+        """heights [n, nrow, ncol] (world units; row = y, col = x) of the listed envs' terrains, as seen by the eyes."""
+        self._sim.hfield_write(env_ids, heights)
+
+    def render_eyes(self):
+        """OrderedDict {'walker/right_eye', 'walker/left_eye'}: uint8 [n_envs, size, size, 3] from the current poses."""
+        if not getattr(self, '_eyes_on', False):
+            raise RuntimeError('call enable_eyes() first')
+        img = self._sim.render_eyes()
+        return collections.OrderedDict((name, img[:, k]) for k, (name, _, _) in enumerate(self._EYE_CAMERAS))
+
     def observation_layout(self):
         """{observable name: (column slice, shape)} of the observation rows `step_device` returns."""
         return {k: (sl, self._obs_shapes[k]) for k, sl in self._obs_slices.items() if not k.startswith('_')}

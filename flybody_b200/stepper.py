@@ -22,7 +22,7 @@ MAXCON, MAXEFC = 64, 160
 
 EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_set_action_map', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_record_stride', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
-           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_uniforms', 'fb_task_ptrs', 'fb_task_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_uniforms', 'fb_task_ptrs', 'fb_task_read', 'fb_eye_program', 'fb_hfield_write', 'fb_render_eyes', 'fb_eyes_ptr', 'fb_eyes_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
 
 # enum FbObsItem
@@ -50,6 +50,14 @@ class FbTaskProgram(C.Structure):
                 ('n_freq', C.c_int32), ('tab_len', C.c_int32), ('wb_traj', C.POINTER(C.c_float)), ('wb_phase', C.POINTER(C.c_float)),
                 ('wb_phase_mod', C.POINTER(C.c_float)), ('wb_freqs', C.POINTER(C.c_float)), ('wb_len', C.POINTER(C.c_int32)),
                 ('wb_base_freq', C.c_float), ('wb_rel_range', C.c_float), ('wb_rate', C.c_float), ('com_offset', C.c_float * 3)]
+
+
+class FbEyeProgram(C.Structure):
+    """include/flybody_b200.h: FbEyeProgram (eye cameras)."""
+    _fields_ = [('n_cam', C.c_int32), ('body', C.c_int32 * 2), ('pos', (C.c_float * 3) * 2), ('quat', (C.c_float * 4) * 2),
+                ('fovy_deg', C.c_float), ('size', C.c_int32), ('nrow', C.c_int32), ('ncol', C.c_int32), ('half_size', C.c_float),
+                ('z_offset', C.c_float), ('zfar', C.c_float), ('sky_top', C.c_float * 3), ('sky_horizon', C.c_float * 3),
+                ('ground', C.c_float * 3), ('ambient', C.c_float), ('diffuse', C.c_float)]
 
 
 class StepperError(RuntimeError):
@@ -86,6 +94,11 @@ def load_library(path=None):
     lib.fb_task_uniforms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_task_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
     lib.fb_task_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.fb_eye_program.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fb_hfield_write.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.fb_render_eyes.argtypes = [C.c_void_p]
+    lib.fb_eyes_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    lib.fb_eyes_read.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_ref_slot_write.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_read_task_obs.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_pack_obs.argtypes = [C.c_void_p]
@@ -294,6 +307,38 @@ class BatchedStepper:
 
     def task_read(self, obs_out, out4):
         self._check(self._lib.fb_task_read(self._h, obs_out.ctypes.data, out4.ctypes.data), 'fb_task_read')
+
+    # ---- eye cameras (fb_eye_program / fb_render_eyes)
+    def eye_program(self, bodies, pos, quat, fovy_deg=150.0, size=32, nrow=0, ncol=0, half_size=20.0, z_offset=0.0, zfar=50.0,
+                    sky_top=(0.25, 0.45, 0.85), sky_horizon=(0.75, 0.85, 0.95), ground=(0.45, 0.40, 0.25), ambient=0.4, diffuse=0.8):
+        p = FbEyeProgram()
+        p.n_cam = len(bodies)
+        for c in range(p.n_cam):
+            p.body[c] = int(bodies[c])
+            for k in range(3):
+                p.pos[c][k] = float(pos[c][k])
+            for k in range(4):
+                p.quat[c][k] = float(quat[c][k])
+        p.fovy_deg, p.size, p.nrow, p.ncol, p.half_size, p.z_offset, p.zfar = fovy_deg, size, nrow, ncol, half_size, z_offset, zfar
+        for k in range(3):
+            p.sky_top[k], p.sky_horizon[k], p.ground[k] = sky_top[k], sky_horizon[k], ground[k]
+        p.ambient, p.diffuse = ambient, diffuse
+        self._check(self._lib.fb_eye_program(self._h, C.byref(p)), 'fb_eye_program')
+        self._eye_shape = (self.n_envs, p.n_cam, size, size, 3)
+        self._hfield_cells = nrow * ncol
+
+    def hfield_write(self, env_ids, heights):
+        ids = np.ascontiguousarray(env_ids, np.int32)
+        h = np.ascontiguousarray(heights, np.float32).reshape(len(ids), -1)
+        assert h.shape[1] == self._hfield_cells, (h.shape, self._hfield_cells)
+        self._check(self._lib.fb_hfield_write(self._h, ids.ctypes.data, len(ids), h.ctypes.data), 'fb_hfield_write')
+
+    def render_eyes(self, out=None):
+        """-> uint8 [n_envs, n_cam, size, size, 3] rendered from the current body poses."""
+        self._check(self._lib.fb_render_eyes(self._h), 'fb_render_eyes')
+        out = np.empty(self._eye_shape, np.uint8) if out is None else out
+        self._check(self._lib.fb_eyes_read(self._h, out.ctypes.data), 'fb_eyes_read')
+        return out
 
     def task_inputs(self, step_idx, first):
         si = np.ascontiguousarray(step_idx, np.int32)

@@ -319,6 +319,25 @@ int fb_task_uniforms(FbHandle h, const int32_t* env_ids, int n, const float* u);
  * discount, step_type 0 FIRST / 1 MID / 2 LAST, 0) and the host copy (synchronises).                                  */
 int fb_task_ptrs(FbHandle h, void** obs_dev, int* obs_dim, void** out_dev);
 int fb_task_read(FbHandle h, float* obs_host, float* out_host);
+/* Eye cameras (reference FruitFlyObservables.right_eye / left_eye, fruitfly/fruitfly.py:729-745; cameras fruitfly.xml:335-336;
+ * 32 x 32 RGB, fovy 150 deg in tasks/vision_flight.py:23-24): a ray caster over a per-env heightfield terrain
+ * (tasks/arenas/hills.py), the ground plane and a sky, from the current body poses.  MuJoCo's camera model (pinhole, -z forward,
+ * +y up, vertical fovy, row 0 at the top); not MuJoCo's OpenGL image.                                                  */
+typedef struct FbEyeProgram {
+  int32_t n_cam;                         /* 1 or 2 */
+  int32_t body[2]; float pos[2][3]; float quat[2][4];   /* camera frames in the frame of the body they are attached to */
+  float fovy_deg; int32_t size;          /* vertical field of view; images are size x size */
+  int32_t nrow, ncol; float half_size;   /* heightfield grid over [-half_size, half_size]^2 (row = y, col = x); nrow = 0: none */
+  float z_offset, zfar;                  /* height of the ground plane / terrain base (hills.py:210), far clipping distance */
+  float sky_top[3], sky_horizon[3], ground[3], ambient, diffuse;   /* colours in [0,1]; headlight terms (hills.py:248-250) */
+} FbEyeProgram;
+int fb_eye_program(FbHandle h, const FbEyeProgram* p);
+/* Heights (world units) of the listed envs' terrains, rows [n][nrow * ncol]; envs never written are flat.            */
+int fb_hfield_write(FbHandle h, const int32_t* env_ids, int n, const float* heights);
+/* Render every env's eyes from the current poses into the library's buffer [n_envs][n_cam][size][size][3] (uint8).   */
+int fb_render_eyes(FbHandle h);
+int fb_eyes_ptr(FbHandle h, void** dev_ptr, int* bytes_per_env);
+int fb_eyes_read(FbHandle h, uint8_t* host_dst);
 int fb_n_envs(FbHandle h);
 int fb_n_envs_padded(FbHandle h);
 void* fb_stream(FbHandle h);                 /* cudaStream_t the handle launches on */

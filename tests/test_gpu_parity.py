@@ -147,6 +147,31 @@ def test_device_task_logic_on_gpu():
     dt.test_flight_device_task_matches_host_task_code(None)
 
 
+def test_eye_renderer_on_gpu_matches_host_emulation():
+    """fb_render_eyes on the B200 against the same kernel source run by the host-emulation build (tests/test_eyes.py holds
+    that one against the camera model and a brute-force ray marcher)."""
+    import __graft_entry__ as ge
+    from flybody_b200 import arenas, fly_envs
+    ge.build()
+    dim, dens = 6, 5
+    nrow, ncol = arenas.grid_shape(dim, dens)
+    terr = arenas.SineBumps(dim=dim, grid_density=dens, wavelength_range=(2.0, 3.0), height_range=(0.6, 0.9)).generate(np.random.RandomState(2))
+    imgs = []
+    for lib in (None, ge.EMU):
+        env = fly_envs.flight_imitation(n_envs=3, lib_path=lib)
+        env.reset()
+        env.enable_eyes(size=32, fovy=150.0, terrain_shape=(nrow, ncol), half_size=float(dim), z_offset=-0.01)
+        env.set_terrain(np.array([1, 2]), np.stack([terr, terr[::-1].copy()]))
+        imgs.append(env.render_eyes())
+        env.close()
+    for name in imgs[0]:
+        a, b = imgs[0][name].astype(np.int64), imgs[1][name].astype(np.int64)
+        assert a.shape == (3, 32, 32, 3)
+        close = np.abs(a - b).max(-1) <= 2
+        assert close.mean() > 0.98, (name, close.mean())            # (fp32 contraction differs: a few horizon / checker-edge pixels may flip)
+        assert a.std() > 10                                          # an image, not a constant
+
+
 def test_device_resident_rollout_matches_host_api():
     """step_device (CUDA action tensor in, zero-copy observation / reward views out, no host copy) against step() on a twin env."""
     import torch
