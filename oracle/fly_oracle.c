@@ -630,9 +630,17 @@ static void mpr_support1(const MprObj* o, const double* dir, double* out) {   /*
   for (int i=0;i<3;i++) r[i]+=ld[i]*0.5*o->margin;
   mulmat3(out,o->mat,r); add3(out,out,o->pos);
 }
+/* heightfield prism (mjc_ConvexHField): `size` points at its 6 vertices, given in the frame the test runs in */
+#define FB_GEOM_PRISM 100
+static void prism_support(const MprObj* o, const double* dir, double* out) {
+  int best=0; double bd=dot3(o->size,dir);
+  for (int k=1;k<6;k++) { double dd=dot3(o->size+3*k,dir); if (dd>bd) { bd=dd; best=k; } }
+  copy3(out,o->size+3*best);
+}
 static void mpr_support(const MprObj* a, const MprObj* b, const double* dir, MprPt* p) {   /* __ccdSupport */
   double nd[3]={-dir[0],-dir[1],-dir[2]};
-  mpr_support1(a,dir,p->v1); mpr_support1(b,nd,p->v2); sub3(p->v,p->v1,p->v2);
+  if (a->type==FB_GEOM_PRISM) prism_support(a,dir,p->v1); else mpr_support1(a,dir,p->v1);
+  mpr_support1(b,nd,p->v2); sub3(p->v,p->v1,p->v2);
 }
 static double seg_dist2(const double* P, const double* x0, const double* b, double* w) {     /* ccdVec3PointSegmentDist2 */
   double d[3],a[3],t; sub3(d,b,x0); sub3(a,x0,P);
@@ -793,6 +801,53 @@ static int col_convex(RawCon* c, double margin, int t1, const double* p1, const 
   c->dist=margin-depth; copy3(c->pos,pos); copy3(c->normal,dir); c->tangent[0]=c->tangent[1]=c->tangent[2]=0;
   fix_normal(c,t1,p1,m1,s1,t2,p2,m2,s2);
   return 1;
+}
+/* Convex geom against a heightfield (MuJoCo mjc_ConvexHField, engine_collision_convex.c, restated from memory): in the
+ * heightfield's frame, the grid cells under the geom's bounding box are walked row by row as a triangle strip; every triangle is
+ * the top of a prism that reaches down to the base (-size[3]), its top raised by the margin, and each prism runs through the same
+ * MPR as any convex pair (the prism's support function is the farthest of its six vertices, its centre their mean).  Every
+ * intersecting prism yields one contact (MuJoCo caps them at mjMAXCONPAIR = 50): dist = margin - depth, normal from the
+ * heightfield into the geom.  GROUNDWORK for SURVEY.md 8(f).1 (vision_guided_flight): no compiled model carries a heightfield
+ * yet, so orc_collision does not call this; tests/test_hfield.py holds it against closed forms and the device code against it.
+ * hf_size = (x half extent, y half extent, elevation scale, base depth); data [nrow][ncol] in [0, 1], row = y, col = x.        */
+int orc_convex_hfield(int type, const double* gpos, const double* gmat, const double* gsize, double margin,
+                      const double* hf_pos, const double* hf_mat, const double* hf_size, int nrow, int ncol, const double* data,
+                      double* out /* [max][7]: dist, pos[3], normal[3] */, int max) {
+  double pos[3], mat[9], tmp[3];
+  sub3(tmp,gpos,hf_pos); mulmatT3(pos,hf_mat,tmp);
+  for (int c=0;c<3;c++) { double col[3]={gmat[c],gmat[3+c],gmat[6+c]}, r[3]; mulmatT3(r,hf_mat,col); mat[c]=r[0]; mat[3+c]=r[1]; mat[6+c]=r[2]; }
+  MprObj g={pos,mat,gsize,type,0.0};
+  /* bounding box of the geom in the heightfield frame, from its support function */
+  double lo[3], hi[3];
+  for (int k=0;k<3;k++) { double d[3]={0,0,0}, p[3]; d[k]=1; mpr_support1(&g,d,p); hi[k]=p[k]; d[k]=-1; mpr_support1(&g,d,p); lo[k]=p[k]; }
+  if (lo[0]>hf_size[0] || hi[0]<-hf_size[0] || lo[1]>hf_size[1] || hi[1]<-hf_size[1] || lo[2]>hf_size[2]+margin || hi[2]<-hf_size[3]) return 0;
+  int cmin=(int)floor((lo[0]+hf_size[0])/(2*hf_size[0])*(ncol-1)), cmax=(int)ceil((hi[0]+hf_size[0])/(2*hf_size[0])*(ncol-1));
+  int rmin=(int)floor((lo[1]+hf_size[1])/(2*hf_size[1])*(nrow-1)), rmax=(int)ceil((hi[1]+hf_size[1])/(2*hf_size[1])*(nrow-1));
+  if (cmin<0) cmin=0; if (rmin<0) rmin=0; if (cmax>ncol-1) cmax=ncol-1; if (rmax>nrow-1) rmax=nrow-1;
+  const double dx=2*hf_size[0]/(ncol-1), dy=2*hf_size[1]/(nrow-1);
+  int cnt=0;
+  for (int r=rmin;r<rmax;r++) {
+    double prism[18]={0}; int nvert=0;
+    for (int c=cmin;c<=cmax;c++) for (int i=0;i<2;i++) {
+      /* next vertex of the strip: bottom copies in 0..2, top copies in 3..5 */
+      for (int k=0;k<2;k++) { copy3(prism+3*k,prism+3*(k+1)); copy3(prism+3*(3+k),prism+3*(4+k)); }
+      double x=dx*c-hf_size[0], y=dy*(r+i)-hf_size[1];
+      prism[6]=x; prism[7]=y; prism[8]=-hf_size[3];
+      prism[15]=x; prism[16]=y; prism[17]=data[(size_t)(r+i)*ncol+c]*hf_size[2]+margin;
+      if (++nvert<3) continue;
+      if (prism[11]<lo[2] && prism[14]<lo[2] && prism[17]<lo[2]) continue;        /* the geom is above this prism */
+      double ctr[3]={0,0,0}; for (int k=0;k<6;k++) addscl3(ctr,prism+3*k,1.0/6.0);
+      static const double eye[9]={1,0,0,0,1,0,0,0,1};
+      MprObj pr={ctr,eye,prism,FB_GEOM_PRISM,0.0};
+      double depth,dir[3],cp[3];
+      if (mpr_penetration(&pr,&g,1e-6,50,&depth,dir,cp)!=0) continue;
+      if (ccd_eq(dir[0],0)&&ccd_eq(dir[1],0)&&ccd_eq(dir[2],0)) continue;
+      double* o=out+7*cnt;
+      o[0]=margin-depth; mulmat3(tmp,hf_mat,cp); add3(o+1,tmp,hf_pos); mulmat3(o+4,hf_mat,dir);
+      if (++cnt>=max) return cnt;
+    }
+  }
+  return cnt;
 }
 /* exported for the tests: one generic pair */
 int orc_convex_pair(int t1, const double* p1, const double* m1, const double* s1, int t2, const double* p2, const double* m2, const double* s2,
