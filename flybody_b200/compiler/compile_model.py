@@ -28,6 +28,7 @@ _SPAWN_POS = np.array((0, 0, 0.1278))    # reference fruitfly.py:23
 
 # enums shared with include/flybody_b200.h
 GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX = 0, 2, 3, 4, 5, 6
+GEOM_HFIELD = 1
 GEOM_TYPES = {'plane': 0, 'sphere': 2, 'capsule': 3, 'ellipsoid': 4, 'cylinder': 5, 'box': 6, 'mesh': 7}
 JNT_FREE, JNT_HINGE = 0, 3
 TRN_JOINT, TRN_TENDON, TRN_BODY = 0, 1, 2
@@ -309,6 +310,7 @@ def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mes
     mesh_cache = mesh_cache or load_mesh_cache(assets_dir)
 
     floor = None
+    hfield = None
     ghost = False
     if variant == 'bare':
         fx = _bare_xml(xml_path)
@@ -337,6 +339,29 @@ def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mes
         # Flying.__init__ (base.py:308-346): floor contacts off, wing gains, fluid model, wing joint params
         floor = dict(friction=np.array([1.0, 0.005, 0.0001]), solref=np.array([0.02, 1.0]),
                      solimp=np.array([0.9, 0.95, 0.001, 0.5, 2.0]), contype=0, conaffinity=0)
+        for i, dc in enumerate(['yaw', 'roll', 'pitch']):
+            fx.class_child(dc, 'general').set('gainprm', repr(float([18, 18, 18][i])))
+        for g in fx.all('geom'):
+            if 'fluid' in (g.get('name') or ''):
+                g.set('fluidshape', 'ellipsoid')
+                sset(g, 'fluidcoef', [1.0, 0.5, 1.5, 1.7, 1.0])
+        wj = fx.class_child('wing', 'joint')
+        wj.set('stiffness', repr(0.01))
+        wj.set('damping', repr(0.007769230))
+        _add_wing_leg_excludes(fx)
+    elif variant == 'vision':
+        # vision_guided_flight (reference fly_envs.py:194-246, tasks/vision_flight.py:20-79): the flight model without a ghost,
+        # ground contacts ON (floor_contacts=True -> the arena's geoms keep MuJoCo's defaults), and the arena of
+        # tasks/arenas/hills.py:143-251 ('outdoor_natural'): heightfield `terrain` at z = -0.01 over [-20, 20]^2, 401 x 401
+        # points, elevation scale 1, base 0.05, next to the ground plane at z = 0
+        fx = build_fly_xml(xml_path, name='walker', use_legs=False, use_wings=True, use_mouth=False,
+                           use_antennae=False, joint_filter=0.0 if joint_filter is None else joint_filter, adhesion_filter=0.007,
+                           body_pitch_angle=47.5, stroke_plane_angle=0.0)
+        timestep = 5e-5
+        spawn, prefix, ghost = _SPAWN_POS, 'walker/', False
+        floor = dict(friction=np.array([1.0, 0.005, 0.0001]), solref=np.array([0.02, 1.0]),
+                     solimp=np.array([0.9, 0.95, 0.001, 0.5, 2.0]), contype=1, conaffinity=1)
+        hfield = dict(size=np.array([20.0, 20.0, 1.0, 0.05]), nrow=401, ncol=401, pos=np.array([0.0, 0.0, -0.01]))
         for i, dc in enumerate(['yaw', 'roll', 'pitch']):
             fx.class_child(dc, 'general').set('gainprm', repr(float([18, 18, 18][i])))
         for g in fx.all('geom'):
@@ -389,7 +414,7 @@ def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mes
     tendons = fx.all('tendon')
     sensors = fx.all('sensor')
     model = _flatten(bodies, classes, fx, prefix, actuators, tendons, sensors, excludes, floor, timestep,
-                     variant)
+                     variant, hfield=hfield)
     model['ctrl_indices'] = {k: v for k, v in fx.ctrl_indices.items()}
     model['observable_joints'] = [prefix + n for n in fx.observable_joints]
     return model
@@ -414,7 +439,7 @@ def _add_wing_leg_excludes(fx):
     fx._reindex()
 
 
-def _flatten(bodies, classes, fx, prefix, actuators, tendons, sensors, excludes, floor, timestep, variant):
+def _flatten(bodies, classes, fx, prefix, actuators, tendons, sensors, excludes, floor, timestep, variant, hfield=None):
     opt = fx.root.find('option')
     m = {}
     nbody = len(bodies)
@@ -536,6 +561,14 @@ def _flatten(bodies, classes, fx, prefix, actuators, tendons, sensors, excludes,
                           condim=3, priority=0, friction=floor['friction'], solmix=1.0, solref=floor['solref'],
                           solimp=floor['solimp'], margin=0.0, gap=0.0))
         ngeom_all += 1
+    if hfield is not None:
+        # the terrain: a world geom of MuJoCo type hfield (1).  It sits in the geom arrays for the contact parameters; its pairs
+        # are kept out of the generic pair list (hf_pair_geom below) because the heightfield narrowphase is its own kernel
+        geoms.append(dict(name='terrain', type=GEOM_HFIELD, body=0, pos=hfield['pos'], quat=np.array([1.0, 0, 0, 0]),
+                          size=hfield['size'][:3], contype=floor['contype'], conaffinity=floor['conaffinity'],
+                          condim=3, priority=0, friction=floor['friction'], solmix=1.0, solref=floor['solref'],
+                          solimp=floor['solimp'], margin=0.0, gap=0.0))
+        ngeom_all += 1
     for bi, b in enumerate(bodies):
         for g in b.geoms:
             ngeom_all += 1
@@ -577,11 +610,15 @@ def _flatten(bodies, classes, fx, prefix, actuators, tendons, sensors, excludes,
     m['body_fluid_ellipsoid'] = body_fluid_ell
 
     # ---- collision pair list (filters: SURVEY.md App. A.7)
-    pairs = []
+    pairs, hf_pairs = [], []
     for a in range(ngeom):
         for b_ in range(a + 1, ngeom):
             ga, gb = geoms[a], geoms[b_]
             if not ((ga['contype'] & gb['conaffinity']) or (gb['contype'] & ga['conaffinity'])):
+                continue
+            if GEOM_HFIELD in (ga['type'], gb['type']):
+                if ga['body'] != gb['body'] and GEOM_PLANE not in (ga['type'], gb['type']):
+                    hf_pairs.append(b_ if ga['type'] == GEOM_HFIELD else a)
                 continue
             b1, b2 = ga['body'], gb['body']
             if b1 == b2:
@@ -600,6 +637,11 @@ def _flatten(bodies, classes, fx, prefix, actuators, tendons, sensors, excludes,
             else:
                 pairs.append((a, b_))
     m['npair'] = len(pairs)
+    if hfield is not None:
+        m['hf_geom'] = [g['type'] for g in geoms].index(GEOM_HFIELD)
+        m['hf_pair_geom'] = np.array(hf_pairs, np.int32)
+        m['hf_size'] = np.asarray(hfield['size'], np.float64)
+        m['hf_nrow'], m['hf_ncol'] = int(hfield['nrow']), int(hfield['ncol'])
     m['pair_geom1'] = np.array([p[0] for p in pairs], np.int32)
     m['pair_geom2'] = np.array([p[1] for p in pairs], np.int32)
 
@@ -869,7 +911,7 @@ def main():
     import sys
     mode = sys.argv[1] if len(sys.argv) > 1 else 'legacy2'
     os.makedirs(ASSET_OUT, exist_ok=True)
-    for variant in ('bare', 'walk', 'flight'):
+    for variant in (sys.argv[2:] or ('bare', 'walk', 'flight', 'vision')):
         m = compile_variant(variant, inertia_mode=mode)
         save_model(m, os.path.join(ASSET_OUT, f'fly_{variant}.npz'))
         print(variant, {k: m[k] for k in ('nq', 'nv', 'nu', 'na', 'nbody', 'njnt', 'ngeom', 'ngeom_all', 'npair',

@@ -125,3 +125,48 @@ FB_DEV int col_convex_hfield(HfCon* out, int max, float margin, int type, V3 gp,
   }
   return cnt;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Heightfield contacts of one env, appended to the contact list after the collision kernel (fb_hfield_collision).  Runs as
+// its own launch between `col` and `proj`, and only for models that carry a heightfield: the step kernels of the other
+// models are untouched.  Phase 0: lane l takes the pairs l, l + 32, ... (terrain, geom): bounding-sphere test against the
+// highest point of the env's terrain, then the prism walk; up to FB_HF_PER_GEOM contacts per geom go to the staging
+// slots 4 k + i of pair k (free again after the collision kernel's compaction).  Phase 1: lane 0 appends them in pair order.
+#define FB_HF_PER_GEOM 4
+#define FB_HF_CNT(k) AT(d.tmp_geom, 1000 + (k))
+struct DevHf { int geom, nrow, ncol, npair; float size[4]; const int* pair_geom; const float* data; const float* hmax; };
+FB_DEV void khf_narrow(const DevModel& m, const DevData& d, const DevHf& p, int e, int y) {
+  // (geom positions are stored relative to the env's reference point, like every spatial quantity of the step: only
+  // differences enter the test, and the contact positions come out in the same relative coordinates)
+  const V3 hp = ld3(d.geom_xpos, p.geom, d, e); const M3 hm = ld9(d.geom_xmat, p.geom, d, e);
+  const float* data = p.data + (size_t)e * p.nrow * p.ncol;
+  for (int k = y; k < p.npair; k += FB_NY) {
+    const int g = p.pair_geom[k];
+    const V3 gp = ld3(d.geom_xpos, g, d, e);
+    const float margin = fmaxf(m.geom_margin[p.geom], m.geom_margin[g]);
+    int n = 0;
+    if (gp.z - m.geom_rbound[g] <= hp.z + p.hmax[e] * p.size[2] + margin) {      // (the terrain frame is upright: hills.py:205-211)
+      HfCon c[FB_HF_PER_GEOM]; RawCon rc[FB_HF_PER_GEOM];
+      n = col_convex_hfield(c, FB_HF_PER_GEOM, margin, m.geom_type[g], gp, ld9(d.geom_xmat, g, d, e), mld3(m.geom_size, g), hp, hm, p.size, p.nrow, p.ncol, data);
+      for (int i = 0; i < n; i++) { rc[i].dist = c[i].dist; rc[i].pos = c[i].pos; rc[i].n = c[i].n; rc[i].t = v3(0, 0, 0); }
+      col_store(m, d, e, k, rc, n, p.geom, g);
+    }
+    FB_HF_CNT(k) = n;
+  }
+}
+FB_DEV void khf_append(const DevModel& m, const DevData& d, const DevHf& p, int e, int y) {
+  if (y != 0) return;
+  int dst = AT(d.ncon, 0);
+  for (int k = 0; k < p.npair; k++) {
+    const int cnt = FB_HF_CNT(k);
+    for (int i = 0; i < cnt; i++, dst++) {
+      const int src = 4 * k + i;
+      if (dst >= FB_MAXCON) { FB_FLAG_OR(2); AT(d.ncon, 0) = FB_MAXCON; return; }
+      AT(d.con_dist, dst) = CON_F(d.tmp_con, src, 0, 13);
+      for (int c = 0; c < 3; c++) CON_F(d.con_pos, dst, c, 3) = CON_F(d.tmp_con, src, 1 + c, 13);
+      for (int c = 0; c < 9; c++) CON_F(d.con_frame, dst, c, 9) = CON_F(d.tmp_con, src, 4 + c, 13);
+      AT(d.con_geom1, dst) = AT(d.tmp_geom, 2 * src); AT(d.con_geom2, dst) = AT(d.tmp_geom, 2 * src + 1);
+    }
+  }
+  AT(d.ncon, 0) = dst;
+}

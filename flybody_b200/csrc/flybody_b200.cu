@@ -75,6 +75,7 @@ struct FbSim {
   int blob_in_smem;            // copy the sweep program of the triangular solves into shared memory per CTA (default: for batches <= 1024 envs; FB_BLOB=0/1 overrides)
   int* op_step_dev; unsigned char* op_first_dev;
   float* ref_slots; int ref_slot_len;      // per-env reference tables (fb_ref_slots)
+  DevHf hf; bool hf_on; int hf_nrow, hf_ncol;      // heightfield collision (fb_hfield_collision)
   DevEye eye; float* hfield_dev; float* hmax_dev; unsigned char* eye_out; size_t eye_bytes;   // eye cameras (fb_eye_program)
   DevTask task_host;                       // host copy of the device-side task program (its pointers are device pointers)
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
@@ -227,6 +228,25 @@ static void fb_launch_warp(FbSim* s, int kind) {
 FB_DEV void ph_reset_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kreset_scatter(m, d, e, y); }
 FB_DEV void ph_scatter(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kscatter(m, d, e, y); }
 FB_DEV void ph_clear_hold(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { kclear_hold(m, d, e, y); }
+// heightfield contacts: DevHf travels in its own kernel (not in DevModel / DevData: the step kernels of models without a
+// heightfield keep their parameter layout)
+#ifndef FB_EMU
+__global__ void __launch_bounds__(32 * FB_WPB, FB_MINB) fb_hf_kernel(DevModel m, DevData d, DevHf p, int nwarps) {
+  const int e = blockIdx.x * FB_WPB + threadIdx.y;
+  if (e >= nwarps) return;
+  khf_narrow(m, d, p, e, threadIdx.x); __syncwarp();
+  khf_append(m, d, p, e, threadIdx.x);
+}
+#endif
+static void launch_hfield(FbSim* s) {
+#ifndef FB_EMU
+  dim3 block(32, FB_WPB), grid((s->d.N + FB_WPB - 1) / FB_WPB);
+  fb_hf_kernel<<<grid, block, 0, s->cur_stream>>>(s->m, s->d, s->hf, s->d.N);
+#else
+  for (int e = 0; e < s->d.N; e++) { for (int y = 0; y < FB_NY; y++) khf_narrow(s->m, s->d, s->hf, e, y); for (int y = 0; y < FB_NY; y++) khf_append(s->m, s->d, s->hf, e, y); }
+#endif
+  s->launches++;
+}
 FB_DEV void ph_task_reset(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_reset(m, d, e, y); }
 FB_DEV void ph_task_reset2(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_reset2(m, d, e, y); }
 FB_DEV void ph_task_before(const DevModel& m, const DevData& d, ShNone&, int e, int, int y) { ktask_before(m, d, e, y); }
@@ -263,6 +283,7 @@ static size_t dyn_tsolve(const DevModel& m) { return (size_t)(FB_NXS(m) + ((m.nM
 static void launch_step1(FbSim* s) {
   fb_launch<ShTree, FB_ST_POS>(s, K_POS, dyn_pos(s->m));
   fb_launch<ShCol, FB_ST_COL>(s, K_COL, dyn_col(s->m));
+  if (s->hf_on) launch_hfield(s);              // heightfield contacts join the contact list before the constraint rows are built
   fb_launch<ShCon, FB_ST_PROJ>(s, K_PROJ, dyn_proj(s->m));
   fb_launch<ShTree, FB_ST_VEL>(s, K_VEL, dyn_vel(s->m));
 }
@@ -677,7 +698,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
   s->fuse = getenv("FB_FUSE") ? atoi(getenv("FB_FUSE")) : FB_FUSE_DEFAULT; if (s->fuse < 0 || s->fuse > 6 || s->fuse == 5) s->fuse = FB_FUSE_DEFAULT;
-  s->ref_slots = nullptr; s->ref_slot_len = 0; s->eye_out = nullptr; s->hfield_dev = nullptr; s->hmax_dev = nullptr; s->eye_bytes = 0;
+  s->ref_slots = nullptr; s->ref_slot_len = 0; s->eye_out = nullptr; s->hfield_dev = nullptr; s->hmax_dev = nullptr; s->eye_bytes = 0; s->hf_on = false; s->hf_nrow = s->hf_ncol = 0;
   s->op_step_dev = nullptr; s->op_first_dev = nullptr; s->stage_cap = 0; s->stage_icap = 0; s->stage = nullptr; s->stage_i = nullptr;
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
@@ -1242,6 +1263,36 @@ __global__ void __launch_bounds__(128) fb_render_kernel(DevData d, DevEye p) {
   for (int px = threadIdx.x; px < p.size * p.size; px += blockDim.x) eye_pixel(d, p, e, cam, px / p.size, px % p.size);
 }
 #endif
+// per-env heightfield buffer [Np][nrow * ncol] + highest point per env, shared by the collision and the eye cameras
+static int ensure_hfield(FbSim* s, int nrow, int ncol) {
+  if (s->hfield_dev) {
+    if (s->hf_nrow != nrow || s->hf_ncol != ncol) { s->err = "heightfield grid differs from the one already allocated"; return -1; }
+    return 0;
+  }
+  s->hfield_dev = dalloc<float>(s, (size_t)nrow * ncol * s->d.Np); s->hmax_dev = dalloc<float>(s, s->d.Np);
+  s->hf_nrow = nrow; s->hf_ncol = ncol;
+  return 0;
+}
+int fb_hfield_collision(FbHandle s, int geom, const float* size, int nrow, int ncol, const int32_t* pair_geom, int npair) {
+  if (!s || !size || !pair_geom || npair <= 0 || npair > FB_MAXCAND || nrow < 2 || ncol < 2) return -1;
+  if (geom < 0 || geom >= s->m.ngeom) { s->err = "fb_hfield_collision: geom id out of range"; return -1; }
+  for (int k = 0; k < npair; k++) if (pair_geom[k] < 0 || pair_geom[k] >= s->m.ngeom) { s->err = "fb_hfield_collision: pair geom out of range"; return -1; }
+  if (s->fuse != 0) { s->err = "fb_hfield_collision: needs the one-kernel-per-stage launch sequence (FB_FUSE=0, FB_SPLIT=1)"; return -1; }
+#ifndef FB_EMU
+  if (s->split > 1) { s->err = "fb_hfield_collision: needs the one-kernel-per-stage launch sequence (FB_FUSE=0, FB_SPLIT=1)"; return -1; }
+#endif
+  if (sync_stream(s) != 0) return -2;
+  if (ensure_hfield(s, nrow, ncol) != 0) return -1;
+  DevHf& h = s->hf; h.geom = geom; h.nrow = nrow; h.ncol = ncol; h.npair = npair;
+  for (int k = 0; k < 4; k++) h.size[k] = size[k];
+  std::vector<int> pg(pair_geom, pair_geom + npair); h.pair_geom = up(s, pg);
+  h.data = s->hfield_dev; h.hmax = s->hmax_dev;
+  s->hf_on = true;
+#ifndef FB_EMU
+  for (auto& g : s->graph) { if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } g.seen = false; }      // the launch sequence changed
+#endif
+  return 0;
+}
 int fb_eye_program(FbHandle s, const FbEyeProgram* p) {
   if (!s || !p) return -1;
   if (p->n_cam < 1 || p->n_cam > FB_MAXCAM || p->size < 1 || p->size > 512 || !(p->fovy_deg > 0 && p->fovy_deg < 180) || p->nrow < 0 || (p->nrow > 0 && (p->nrow < 2 || p->ncol < 2 || !(p->half_size > 0)))) { s->err = "fb_eye_program: bad camera / grid parameters"; return -1; }
@@ -1253,16 +1304,15 @@ int fb_eye_program(FbHandle s, const FbEyeProgram* p) {
   y.tan_half = tanf(0.5f * p->fovy_deg * 3.14159265358979f / 180.0f); y.half_size = p->half_size; y.z_offset = p->z_offset; y.zfar = p->zfar > 0 ? p->zfar : 50.0f;
   for (int k = 0; k < 3; k++) { y.sky_top[k] = p->sky_top[k]; y.sky_horizon[k] = p->sky_horizon[k]; y.ground[k] = p->ground[k]; }
   y.ambient = p->ambient; y.diffuse = p->diffuse;
-  const size_t cells = (size_t)y.nrow * y.ncol;
-  s->hfield_dev = cells ? dalloc<float>(s, cells * s->d.Np) : nullptr; s->hmax_dev = dalloc<float>(s, s->d.Np);
+  if (y.nrow > 0 && ensure_hfield(s, y.nrow, y.ncol) != 0) return -1;
   s->eye_bytes = (size_t)y.n_cam * y.size * y.size * 3;
   s->eye_out = dalloc<unsigned char>(s, s->eye_bytes * s->d.Np);
   y.hfield = s->hfield_dev; y.hmax = s->hmax_dev; y.out = s->eye_out;
   return 0;
 }
 int fb_hfield_write(FbHandle s, const int32_t* env_ids, int n, const float* heights) {
-  if (!s || !s->eye_out || !s->hfield_dev || !env_ids || !heights || n < 0) return -1;
-  const size_t cells = (size_t)s->eye.nrow * s->eye.ncol;
+  if (!s || !s->hfield_dev || !env_ids || !heights || n < 0) return -1;
+  const size_t cells = (size_t)s->hf_nrow * s->hf_ncol;
   for (int k = 0; k < n; k++) {
     if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_hfield_write: env id out of range"; return -1; }
     float mx = heights[cells * k]; for (size_t i = 1; i < cells; i++) mx = std::max(mx, heights[cells * k + i]);

@@ -22,7 +22,7 @@ MAXCON, MAXEFC = 64, 160
 
 EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_set_action_map', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_record_stride', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
-           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_uniforms', 'fb_task_ptrs', 'fb_task_read', 'fb_eye_program', 'fb_hfield_write', 'fb_render_eyes', 'fb_eyes_ptr', 'fb_eyes_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_uniforms', 'fb_task_ptrs', 'fb_task_read', 'fb_eye_program', 'fb_hfield_collision', 'fb_hfield_write', 'fb_render_eyes', 'fb_eyes_ptr', 'fb_eyes_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
 
 # enum FbObsItem
@@ -96,6 +96,7 @@ def load_library(path=None):
     lib.fb_task_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fb_eye_program.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_hfield_write.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.fb_hfield_collision.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.fb_render_eyes.argtypes = [C.c_void_p]
     lib.fb_eyes_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     lib.fb_eyes_read.argtypes = [C.c_void_p, C.c_void_p]
@@ -326,6 +327,12 @@ class BatchedStepper:
         self._check(self._lib.fb_eye_program(self._h, C.byref(p)), 'fb_eye_program')
         self._eye_shape = (self.n_envs, p.n_cam, size, size, 3)
         self._hfield_cells = nrow * ncol
+
+    def hfield_collision(self, geom, size, nrow, ncol, pair_geom):
+        """turn on the heightfield narrowphase for the model's terrain geom (fb_hfield_collision)."""
+        sz = np.ascontiguousarray(size, np.float32); pg = np.ascontiguousarray(pair_geom, np.int32)
+        self._check(self._lib.fb_hfield_collision(self._h, int(geom), sz.ctypes.data, int(nrow), int(ncol), pg.ctypes.data, len(pg)), 'fb_hfield_collision')
+        self._hfield_cells = int(nrow) * int(ncol)
 
     def hfield_write(self, env_ids, heights):
         ids = np.ascontiguousarray(env_ids, np.int32)

@@ -332,6 +332,11 @@ typedef struct FbEyeProgram {
   float sky_top[3], sky_horizon[3], ground[3], ambient, diffuse;   /* colours in [0,1]; headlight terms (hills.py:248-250) */
 } FbEyeProgram;
 int fb_eye_program(FbHandle h, const FbEyeProgram* p);
+/* Heightfield collision (MuJoCo mjc_ConvexHField; the terrain of tasks/arenas/hills.py): `geom` is the model's heightfield geom
+ * (pose and contact parameters come from the model), size = (x half extent, y half extent, elevation scale, base depth), the grid
+ * is nrow x ncol, pair_geom lists the geoms that can touch it.  Adds one kernel between collision and constraint rows.  The
+ * per-env heights are the ones of fb_hfield_write (shared with the eye cameras), as fractions of the elevation scale.       */
+int fb_hfield_collision(FbHandle h, int geom, const float* size, int nrow, int ncol, const int32_t* pair_geom, int npair);
 /* Heights (world units) of the listed envs' terrains, rows [n][nrow * ncol]; envs never written are flat.            */
 int fb_hfield_write(FbHandle h, const int32_t* env_ids, int n, const float* heights);
 /* Render every env's eyes from the current poses into the library's buffer [n_envs][n_cam][size][size][3] (uint8).   */

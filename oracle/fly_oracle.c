@@ -65,6 +65,8 @@ typedef struct OrcData {
   int solver_niter, flags;
   double solver_tolerance;      /* <=0 -> use model opt_tolerance */
   double *wk;                   /* scratch nv*nv + ... */
+  /* optional heightfield terrain (orc_set_hfield): geom id, grid, heights as fractions of the elevation scale, geoms that can touch it */
+  int hf_geom, hf_nrow, hf_ncol, hf_npair; int* hf_pair; double hf_size[4]; double* hf_data;
 } OrcData;
 
 enum { CT_LIMIT = 0, CT_CONTACT_FRICTIONLESS = 1, CT_CONTACT_ELLIPTIC = 2 };
@@ -167,6 +169,7 @@ void orc_destroy(OrcData* d) {
     d->bvel,d->bacc,d->qfrc_bias,d->qfrc_passive,d->qfrc_actuator,d->qfrc_smooth,d->qacc_smooth,d->qfrc_constraint,
     d->act_dot,d->actuator_force,d->actuator_length,d->actuator_velocity,d->moment,d->efc_J,d->sensordata,d->sensor_sum,d->wk};
   for (size_t i=0;i<sizeof(ptrs)/sizeof(ptrs[0]);i++) free(ptrs[i]);
+  free(d->hf_data); free(d->hf_pair);
   free(d);
 }
 
@@ -857,6 +860,41 @@ int orc_convex_pair(int t1, const double* p1, const double* m1, const double* s1
   return n;
 }
 
+int orc_convex_hfield(int type, const double* gpos, const double* gmat, const double* gsize, double margin,
+                      const double* hf_pos, const double* hf_mat, const double* hf_size, int nrow, int ncol, const double* data,
+                      double* out, int max);
+/* contacts of one geom pair -> d->con with mj_contactParam mixing */
+static void add_contacts(OrcData* d, const RawCon* rc, int n, int g1, int g2, double margin, double gap) {
+  const FbModel* m=d->m;
+  for (int i=0;i<n && d->ncon<ORC_MAXCON;i++) {
+    OrcContact* c=&d->con[d->ncon++];
+    c->dist=rc[i].dist; copy3(c->pos,rc[i].pos); copy3(c->frame,rc[i].normal); copy3(c->frame+3,rc[i].tangent);
+    make_frame(c->frame);
+    c->geom1=g1; c->geom2=g2;
+    /* mj_contactParam: equal priority -> max condim/friction, solmix-weighted solref/solimp */
+    c->dim = m->geom_condim[g1]>m->geom_condim[g2]?m->geom_condim[g1]:m->geom_condim[g2];
+    double f[3]; for (int q=0;q<3;q++) f[q]=fmax(m->geom_friction[3*g1+q],m->geom_friction[3*g2+q]);
+    if (m->geom_priority[g1]!=m->geom_priority[g2]) {
+      int gp=m->geom_priority[g1]>m->geom_priority[g2]?g1:g2;
+      c->dim=m->geom_condim[gp]; for (int q=0;q<3;q++) f[q]=m->geom_friction[3*gp+q];
+      for (int q=0;q<2;q++) c->solref[q]=m->geom_solref[2*gp+q];
+      for (int q=0;q<5;q++) c->solimp[q]=m->geom_solimp[5*gp+q];
+    } else {
+      double mix1=m->geom_solmix[g1], mix2=m->geom_solmix[g2], mix;
+      if (mix1>=MINVAL && mix2>=MINVAL) mix=mix1/(mix1+mix2);
+      else if (mix1<MINVAL && mix2<MINVAL) mix=0.5; else if (mix1<MINVAL) mix=0.0; else mix=1.0;
+      if (m->geom_solref[2*g1]>0 && m->geom_solref[2*g2]>0)
+        for (int q=0;q<2;q++) c->solref[q]=mix*m->geom_solref[2*g1+q]+(1-mix)*m->geom_solref[2*g2+q];
+      else for (int q=0;q<2;q++) c->solref[q]=fmin(m->geom_solref[2*g1+q],m->geom_solref[2*g2+q]);
+      for (int q=0;q<5;q++) c->solimp[q]=mix*m->geom_solimp[5*g1+q]+(1-mix)*m->geom_solimp[5*g2+q];
+    }
+    c->friction[0]=c->friction[1]=f[0]; c->friction[2]=f[1]; c->friction[3]=c->friction[4]=f[2];
+    c->includemargin=margin-gap;
+    c->exclude = (c->dist<c->includemargin)?0:1;
+    c->efc_address=-1; c->mu=f[0];
+  }
+}
+
 static void orc_collision(OrcData* d) {
   const FbModel* m=d->m;
   d->ncon=0;
@@ -885,32 +923,19 @@ static void orc_collision(OrcData* d) {
     else if (t1==FB_GEOM_SPHERE && t2==FB_GEOM_CAPSULE) n=col_sphere_capsule(rc,margin,p1,s1[0],p2,m2,s2);
     else if (t1==FB_GEOM_CAPSULE && t2==FB_GEOM_CAPSULE) n=col_capsule_capsule(rc,margin,p1,m1,s1,p2,m2,s2);
     else n=col_convex(rc,margin,t1,p1,m1,s1,t2,p2,m2,s2);   /* generic convex pairs: MPR */
-    for (int i=0;i<n && d->ncon<ORC_MAXCON;i++) {
-      OrcContact* c=&d->con[d->ncon++];
-      c->dist=rc[i].dist; copy3(c->pos,rc[i].pos); copy3(c->frame,rc[i].normal); copy3(c->frame+3,rc[i].tangent);
-      make_frame(c->frame);
-      c->geom1=g1; c->geom2=g2;
-      /* mj_contactParam: equal priority -> max condim/friction, solmix-weighted solref/solimp */
-      c->dim = m->geom_condim[g1]>m->geom_condim[g2]?m->geom_condim[g1]:m->geom_condim[g2];
-      double f[3]; for (int q=0;q<3;q++) f[q]=fmax(m->geom_friction[3*g1+q],m->geom_friction[3*g2+q]);
-      if (m->geom_priority[g1]!=m->geom_priority[g2]) {
-        int gp=m->geom_priority[g1]>m->geom_priority[g2]?g1:g2;
-        c->dim=m->geom_condim[gp]; for (int q=0;q<3;q++) f[q]=m->geom_friction[3*gp+q];
-        for (int q=0;q<2;q++) c->solref[q]=m->geom_solref[2*gp+q];
-        for (int q=0;q<5;q++) c->solimp[q]=m->geom_solimp[5*gp+q];
-      } else {
-        double mix1=m->geom_solmix[g1], mix2=m->geom_solmix[g2], mix;
-        if (mix1>=MINVAL && mix2>=MINVAL) mix=mix1/(mix1+mix2);
-        else if (mix1<MINVAL && mix2<MINVAL) mix=0.5; else if (mix1<MINVAL) mix=0.0; else mix=1.0;
-        if (m->geom_solref[2*g1]>0 && m->geom_solref[2*g2]>0)
-          for (int q=0;q<2;q++) c->solref[q]=mix*m->geom_solref[2*g1+q]+(1-mix)*m->geom_solref[2*g2+q];
-        else for (int q=0;q<2;q++) c->solref[q]=fmin(m->geom_solref[2*g1+q],m->geom_solref[2*g2+q]);
-        for (int q=0;q<5;q++) c->solimp[q]=mix*m->geom_solimp[5*g1+q]+(1-mix)*m->geom_solimp[5*g2+q];
-      }
-      c->friction[0]=c->friction[1]=f[0]; c->friction[2]=f[1]; c->friction[3]=c->friction[4]=f[2];
-      c->includemargin=margin-gap;
-      c->exclude = (c->dist<c->includemargin)?0:1;
-      c->efc_address=-1; c->mu=f[0];
+    add_contacts(d,rc,n,g1,g2,margin,gap);
+  }
+  /* terrain: every listed geom against the heightfield (mjc_ConvexHField), up to 4 contacts per geom, in list order */
+  if (d->hf_data) {
+    const int g1=d->hf_geom;
+    for (int k=0;k<d->hf_npair;k++) {
+      const int g2=d->hf_pair[k];
+      const double margin=fmax(m->geom_margin[g1],m->geom_margin[g2]), gap=fmax(m->geom_gap[g1],m->geom_gap[g2]);
+      double out[4*7]; RawCon rc[4];
+      int n=orc_convex_hfield(m->geom_type[g2],d->geom_xpos+3*g2,d->geom_xmat+9*g2,m->geom_size+3*g2,margin,
+                              d->geom_xpos+3*g1,d->geom_xmat+9*g1,d->hf_size,d->hf_nrow,d->hf_ncol,d->hf_data,out,4);
+      for (int i=0;i<n;i++) { rc[i].dist=out[7*i]; copy3(rc[i].pos,out+7*i+1); copy3(rc[i].normal,out+7*i+4); rc[i].tangent[0]=rc[i].tangent[1]=rc[i].tangent[2]=0; }
+      add_contacts(d,rc,n,g1,g2,margin,gap);
     }
   }
   if (d->ncon>=ORC_MAXCON) d->flags|=2;
@@ -1536,6 +1561,14 @@ int orc_set(OrcData* d, int field, const double* in) {
     case FB_QACC: memcpy(d->qacc,in,sizeof(double)*m->nv); return 0;
     default: return -1;
   }
+}
+/* heightfield terrain for the collision stage (tests of the vision-flight groundwork); data is copied */
+void orc_set_hfield(OrcData* d, int geom, const double* size, int nrow, int ncol, const double* data, const int* pair_geom, int npair) {
+  free(d->hf_data); free(d->hf_pair);
+  d->hf_geom=geom; d->hf_nrow=nrow; d->hf_ncol=ncol; d->hf_npair=npair;
+  for (int k=0;k<4;k++) d->hf_size[k]=size[k];
+  d->hf_data=(double*)malloc(sizeof(double)*(size_t)nrow*ncol); memcpy(d->hf_data,data,sizeof(double)*(size_t)nrow*ncol);
+  d->hf_pair=(int*)malloc(sizeof(int)*npair); memcpy(d->hf_pair,pair_geom,sizeof(int)*npair);
 }
 void orc_set_tolerance(OrcData* d, double tol) { d->solver_tolerance=tol; }
 /* efc row data for tests: J (dense), aref, D, R ; returns nefc */

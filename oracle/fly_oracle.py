@@ -59,6 +59,13 @@ class Oracle:
         except Exception:
             pass
 
+    def set_hfield(self, geom, size, heights, pair_geom):
+        """terrain for the collision stage: heights [nrow, ncol] as fractions of the elevation scale size[2]."""
+        h = np.ascontiguousarray(heights, np.float64); sz = np.ascontiguousarray(size, np.float64); pg = np.ascontiguousarray(pair_geom, np.int32)
+        self._l.orc_set_hfield.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        self._l.orc_set_hfield.restype = None
+        self._l.orc_set_hfield(self._d, int(geom), sz.ctypes.data, h.shape[0], h.shape[1], h.ctypes.data, pg.ctypes.data, len(pg))
+
     def get(self, field):
         n = self._l.orc_get(self._d, field, self._buf.ctypes.data)
         if n < 0:

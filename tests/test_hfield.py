@@ -120,3 +120,44 @@ def test_device_matches_oracle_on_a_bumpy_terrain(libs):
     print("hfield parity: oracle hits", n_hit, "compared", n_cmp, "close", n_close)
     assert n_hit > 40 and n_cmp > 40
     assert n_close >= 0.95 * n_cmp, (n_close, n_cmp)
+
+
+def test_vision_model_terrain_contacts_match_the_oracle_through_the_step():
+    """the compiled `vision` variant (flight model, no ghost, ground contacts on, 401 x 401 terrain geom): stage parity of the whole
+    forward pass against the oracle with the fly dipped into a bumpy terrain -- heightfield contacts, their rows and forces."""
+    import __graft_entry__ as ge
+    from flybody_b200 import arenas, stepper as st
+    from flybody_b200.flymodel import load_model
+    from parity_common import rel_err
+    ge.build()
+    m = load_model('vision')
+    assert (m.nq, m.nv, m.nu) == (43, 42, 11) and m.meta['hf_nrow'] == 401 and len(m.hf_pair_geom) == 70
+    terr = arenas.SineBumps().generate(np.random.RandomState(4)).astype(np.float32)
+    rs = np.random.RandomState(0)
+    for trial, dz in enumerate((0.13, 0.17, 0.6)):
+        x, y = (-5.0, 0.0) if trial < 2 else (3.0, -2.0)
+        ground = float(arenas.hfield_height(terr, [x], [y], 20.0)[0]) - 0.01
+        q = m.qpos0.copy(); q[:3] = [x, y, ground + dz]
+        v = np.zeros(m.nv); v[0] = 20.0
+        sim = st.BatchedStepper(m, 2, lib_path=ge.EMU)
+        sim.hfield_collision(m.meta['hf_geom'], m.hf_size, 401, 401, m.hf_pair_geom)
+        sim.hfield_write(np.arange(2), np.stack([terr, terr]))
+        o = fo.Oracle(m, tolerance=1e-12)
+        o.set_hfield(m.meta['hf_geom'], m.hf_size, terr, m.hf_pair_geom)
+        ctrl = rs.uniform(-0.2, 0.2, m.nu)
+        o.reset(q, v); sim.reset(np.tile(q, (2, 1)), np.tile(v, (2, 1)))
+        o.set(fo.CTRL, ctrl); sim.set_control(np.tile(ctrl, (2, 1)).astype(np.float32))
+        o.forward(); sim.forward()
+        ncon_o, ncon_d = int(o.get(fo.NCON)[0]), int(sim.get(st.NCON)[1, 0])
+        co = o.get(fo.CONTACT).reshape(-1, 16)[:ncon_o]
+        terrain_contacts = int((co[:, 7] == m.meta['hf_geom']).sum())
+        assert (terrain_contacts > 0) == (dz < 0.3), (trial, terrain_contacts)
+        assert ncon_o == ncon_d and int(o.get(fo.NEFC)[0]) == int(sim.get(st.NEFC)[1, 0])
+        cd = sim.get(st.CONTACT)[1].reshape(-1, 16)[:ncon_d].astype(np.float64)
+        assert np.array_equal(co[:, 7:9], cd[:, 7:9])                                   # same geom pairs in the same order
+        assert np.abs(co[:, 0] - cd[:, 0]).max() < 5e-5                                 # distances
+        for f in (fo.EFC_FORCE, fo.QFRC_CONSTRAINT, fo.QACC):
+            a = o.get(f)
+            if np.abs(a).max() > 0:
+                assert rel_err(a, sim.get(f)[1]) < 2e-3, (trial, f)
+        sim.close()
