@@ -785,12 +785,17 @@ def flight_imitation(ref_path=None, wpg_pattern_path=None, force_actuators=False
                          traj_generator=tg, device_task=device_task)
 
 
-def vision_guided_flight(*args, **kwargs):
-    """`flybody.fly_envs.vision_guided_flight` (reference `fly_envs.py:194-246`) is the next row of the build
-    (SURVEY.md 8(f).1).  Its terrain generators (`flybody_b200.arenas.SineBumps / SineTrench`) and eye cameras
-    (`BatchedFlyEnv.enable_eyes / set_terrain / render_eyes`) exist; the heightfield collision (fatal floor contacts,
-    `tasks/vision_flight.py:235-254`) and the task's reward (`:140-233`) do not, so the environment is not offered yet."""
-    raise NotImplementedError(vision_guided_flight.__doc__)
+def vision_guided_flight(wpg_pattern_path=None, bumps_or_trench='bumps', force_actuators=False, disable_legs=True, random_state=None,
+                         joint_filter=0.0, n_envs=None, device=0, lib_path=None, seed=0, **kwargs_arena):
+    """Batched `flybody.fly_envs.vision_guided_flight` (reference `fly_envs.py:194-246`): 'bumps' or 'trench' terrain, eye
+    cameras, wing-beat pattern generator, fatal ground contacts -- `flybody_b200.vision_env.BatchedVisionFlightEnv`.  A first
+    cut of SURVEY.md 8(f).1: verified under host emulation (terrain contacts against the fp64 oracle, eyes against the camera
+    model), the heightfield kernel has not been run or timed on a B200 yet."""
+    if force_actuators or not disable_legs or joint_filter != 0.0:
+        raise NotImplementedError('only the default vision_guided_flight model variant is compiled (flybody_b200/assets/fly_vision.npz)')
+    from .vision_env import BatchedVisionFlightEnv
+    return BatchedVisionFlightEnv(n_envs, bumps_or_trench=bumps_or_trench, wpg_pattern_path=wpg_pattern_path, device=device, lib_path=lib_path,
+                                  seed=seed, **kwargs_arena)
 
 
 def walk_on_ball(*args, **kwargs):

@@ -1,0 +1,267 @@
+"""Batched `flybody.fly_envs.vision_guided_flight` (reference `fly_envs.py:194-246`, `tasks/vision_flight.py`,
+`tasks/base.py:271-364`, `tasks/arenas/hills.py`): flight over a per-episode heightfield terrain ('bumps' or 'trench') with
+a controllable wing-beat pattern generator, egocentric eye cameras, fatal ground contacts.
+
+FIRST CUT of SURVEY.md 8(f).1, verified under host emulation only (the heightfield kernel has not run on a B200 yet): the physics
+is the `vision` model variant (flight model without a ghost, ground contacts on, terrain geom), terrain contacts come from the
+heightfield narrowphase (`fb_hfield_collision`, MuJoCo's prism walk + MPR, restated from memory), the eyes from the device ray
+caster (`fb_render_eyes`: MuJoCo's camera model, not its OpenGL image).  The task logic -- episode initialisation, the
+wing-beat generator in `before_step`, the seven reward factors, termination -- mirrors the reference in vectorised numpy on
+the read-back record, like the host path of `BatchedFlyEnv`.
+"""
+import collections
+
+import numpy as np
+
+from . import arenas
+from . import stepper as st
+from .dm_env_shim import Array, BoundedArray, StepType, TimeStep
+from .fly_envs import BatchedFlyEnv, BatchedWingBeatPatternGenerator
+from .flymodel import load_model
+from .synthetic import _ACTION_CLASS_ORDER, _FLY_CONTROL_TIMESTEP, _TERMINAL_QACC
+
+_BODY_PITCH_ANGLE = 47.5          # reference tasks/constants.py: body pitch of the hover pose, degrees
+
+
+def _tolerance_linear(x, lo, hi, margin):
+    """`dm_control.utils.rewards.tolerance(x, bounds=(lo, hi), sigmoid='linear', margin, value_at_margin=0)`."""
+    x = np.asarray(x, np.float64)
+    d = np.where(x < lo, lo - x, np.where(x > hi, x - hi, 0.0)) / margin
+    return np.where(d <= 0, 1.0, np.clip(1.0 - d, 0.0, 1.0))
+
+
+class BatchedVisionFlightEnv:
+    """dm_env-shaped environment over N lock-stepped flies on their own terrains."""
+
+    _OBS = ('accelerometer', 'actuator_activation', 'gyro', 'joints_pos', 'joints_vel', 'left_eye', 'right_eye', 'velocimeter', 'world_zaxis',
+            'task_input')
+
+    def __init__(self, n_envs, bumps_or_trench='bumps', wpg_pattern_path=None, device=0, lib_path=None, seed=0, eye_camera_size=32,
+                 eye_camera_fovy=150.0, target_height_range=(0.5, 0.8), target_speed_range=(20, 40), init_pos_x_range=(-5, -5),
+                 init_pos_y_range=(0, 0), time_limit=0.4, floor_contacts_fatal=True, **kwargs_arena):
+        if bumps_or_trench not in ('bumps', 'trench'):
+            raise ValueError("Only 'bumps' and 'trench' terrains are supported.")
+        self._batched = n_envs is not None
+        self.n_envs = N = int(n_envs) if self._batched else 1
+        self.model = m = load_model('vision')
+        self._sim = st.BatchedStepper(m, N, device=device, lib_path=lib_path)
+        self._control_timestep, self._physics_timestep = _FLY_CONTROL_TIMESTEP, float(m.opt_timestep)
+        self._n_sub = int(round(self._control_timestep / self._physics_timestep))
+        self._time_limit, self._fatal = time_limit, floor_contacts_fatal
+        self._rs = np.random.RandomState(seed)
+        self._wbpg = BatchedWingBeatPatternGenerator(N, base_pattern_path=wpg_pattern_path)
+        cls = arenas.SineBumps if bumps_or_trench == 'bumps' else arenas.SineTrench
+        self._arenas = [cls(**kwargs_arena) for _ in range(N)]
+        a0 = self._arenas[0]
+        assert (a0.nrow, a0.ncol) == (m.meta['hf_nrow'], m.meta['hf_ncol']) and a0.size[0] == m.hf_size[0], 'arena grid differs from the compiled model'
+        self._half = float(a0.size[0])
+        self._terrain = np.zeros((N, a0.nrow, a0.ncol), np.float32)
+        self._sim.hfield_collision(m.meta['hf_geom'], m.hf_size, a0.nrow, a0.ncol, m.hf_pair_geom)
+        self._ranges = dict(h=target_height_range, v=target_speed_range, x=init_pos_x_range, y=init_pos_y_range)
+        # action <-> ctrl (reference fruitfly.py:342-379): head 3, wings 6, abdomen 2, + 1 user action (beat frequency)
+        ci, idx, self._action_indices = m.meta['ctrl_indices'], [], {}
+        for key in _ACTION_CLASS_ORDER:
+            if ci.get(key):
+                self._action_indices[key] = np.arange(len(idx), len(idx) + len(ci[key]))
+                idx.extend(ci[key])
+        self._ctrl_of_action = np.asarray(idx, np.int64)
+        names = [m.meta['actuator_names'][i].split('/')[-1] for i in idx] + ['user_0']
+        rng = m.actuator_ctrlrange[idx]
+        self._action_spec = BoundedArray((len(names),), np.float64, np.concatenate([rng[:, 0], [-1.0]]), np.concatenate([rng[:, 1], [1.0]]),
+                                         name='\t'.join(names))
+        # index tables
+        jn, sens = m.meta['jnt_names'], m.meta['sensor_names']
+        self._root_q, self._root_v = m.jnt_qposadr_of('walker/'), m.jnt_dofadr_of('walker/')
+        obsj = [jn.index(n) for n in m.meta['observable_joints']]
+        self._obs_qadr, self._obs_vadr = m.jnt_qposadr[obsj], m.jnt_dofadr[obsj]
+        wing = [f'walker/wing_{a}_{s}' for s in ('left', 'right') for a in ('yaw', 'roll', 'pitch')]
+        self._wing_qadr = np.array([m.jnt_qposadr_of(n) for n in wing])
+        self._wing_in_obs = np.array([m.meta['observable_joints'].index(n) for n in wing])
+        sd = lambda n: int(m.sensor_adr[sens.index('walker/' + n)])
+        up = m.site_quat[m.meta['site_names'].index('walker/hover_up_dir')].copy()
+        up[0] *= -1.0                                        # neg_quat(up_dir): the hover pose (vision_flight.py:124-126)
+        self._hover_quat = up
+        th = np.deg2rad(_BODY_PITCH_ANGLE)
+        self._target_zaxis = np.array([np.sin(th), 0.0, np.cos(th)])
+        # observation program (device): the walker observables + what reward / termination read
+        nq = len(self._obs_qadr)
+        rows = [('walker/accelerometer', 3, (st.OBS_SENSOR_MEAN, sd('accelerometer'), 3)), ('walker/gyro', 3, (st.OBS_SENSOR_MEAN, sd('gyro'), 3)),
+                ('walker/joints_pos', nq, (st.OBS_QPOS, 0, nq)), ('walker/joints_vel', nq, (st.OBS_QVEL, nq, nq)),
+                ('walker/velocimeter', 3, (st.OBS_SENSOR_MEAN, sd('velocimeter'), 3)), ('walker/world_zaxis', 3, (st.OBS_ROOT_ZAXIS, 0, 3)),
+                ('_velocimeter_now', 3, (st.OBS_SENSOR_NOW, sd('velocimeter'), 3)), ('_root_pose', 7, (st.OBS_ROOT_POSE, 0, 7)),
+                ('_root_qvel', 6, (st.OBS_QVEL, 2 * nq, 6)), ('_scalars', 3, (st.OBS_SCALARS, 0, 3))]
+        lists = list(self._obs_qadr) + list(self._obs_vadr) + list(range(self._root_v, self._root_v + 6))
+        dim = self._sim.obs_program([r[2] for r in rows], lists, m.body_id('walker/thorax'), self._n_sub, None)
+        off = np.concatenate([[0], np.cumsum([r[1] for r in rows])])
+        assert off[-1] == dim
+        self._sl = {r[0]: slice(int(off[i]), int(off[i + 1])) for i, r in enumerate(rows)}
+        self._rec = np.empty((N, dim), np.float32)
+        # eyes
+        quats = [np.asarray(q, np.float64) / np.linalg.norm(q) for _, _, q in BatchedFlyEnv._EYE_CAMERAS]
+        head = m.body_id('walker/head')
+        self._sim.eye_program([head, head], [p for _, p, _ in BatchedFlyEnv._EYE_CAMERAS], quats, fovy_deg=eye_camera_fovy, size=eye_camera_size,
+                              nrow=a0.nrow, ncol=a0.ncol, half_size=self._half, z_offset=float(m.geom_pos[m.meta['hf_geom']][2]))
+        self._eye_size = eye_camera_size
+        # per-env episode state
+        self._target_height, self._target_speed = np.zeros(N), np.zeros(N)
+        self._time = np.zeros(N)
+        self._needs_reset = np.ones(N, bool)
+        self._wing_qpos = np.zeros((N, 6))
+        self.n_resets = 0
+
+    # ---------------------------------------------------------------------------------- specs
+    def action_spec(self):
+        return self._action_spec
+
+    def observation_spec(self):
+        lead = (self.n_envs,) if self._batched else ()
+        nq, s = len(self._obs_qadr), self._eye_size
+        shapes = {'accelerometer': (3,), 'actuator_activation': (0,), 'gyro': (3,), 'joints_pos': (nq,), 'joints_vel': (nq,), 'left_eye': (s, s, 3),
+                  'right_eye': (s, s, 3), 'velocimeter': (3,), 'world_zaxis': (3,), 'task_input': (2,)}
+        return collections.OrderedDict(('walker/' + k, Array(lead + shapes[k], np.uint8 if 'eye' in k else np.float32, name='walker/' + k)) for k in self._OBS)
+
+    def reward_spec(self):
+        return Array((self.n_envs,) if self._batched else (), np.float64, name='reward')
+
+    def discount_spec(self):
+        return BoundedArray((self.n_envs,) if self._batched else (), np.float64, 0.0, 1.0, name='discount')
+
+    def control_timestep(self):
+        return self._control_timestep
+
+    @property
+    def target_height(self):
+        return self._target_height.copy()
+
+    @property
+    def target_speed(self):
+        return self._target_speed.copy()
+
+    def hfield_height(self, x, y):
+        """`VisionFlightImitationWBPG.get_hfield_height` per env: height at the grid point nearest to (x, y)."""
+        return arenas.hfield_height(self._terrain, x, y, self._half)
+
+    # -------------------------------------------------------------------------------- episode
+    def _reset_envs(self, ids, hold):
+        """initialize_episode_mjcf + initialize_episode (vision_flight.py:97-139): targets, start point, wing-beat phase, a new
+        terrain (hills.py:442-473 / 333-392), the fly in its hover pose `target_height` above the terrain at the target speed."""
+        m, r = self.model, self._ranges
+        n = len(ids)
+        qpos, qvel = np.tile(m.qpos0, (n, 1)), np.zeros((n, m.nv))
+        for k, e in enumerate(ids):
+            self._target_height[e] = self._rs.uniform(*r['h'])
+            self._target_speed[e] = self._rs.uniform(*r['v'])
+            x, y = self._rs.uniform(*r['x']), self._rs.uniform(*r['y'])
+            wq, _ = self._wbpg.reset(np.array([e]), np.array([self._rs.uniform()]))
+            self._terrain[e] = self._arenas[e].generate(self._rs)
+            z = float(arenas.hfield_height(self._terrain[e], [x], [y], self._half)[0]) + self._target_height[e]
+            qpos[k, self._root_q:self._root_q + 3] = (x, y, z)
+            qpos[k, self._root_q + 3:self._root_q + 7] = self._hover_quat
+            qpos[k, self._wing_qadr] = wq[0]
+            qvel[k, self._root_v] = self._target_speed[e]
+            self._wing_qpos[e] = wq[0]
+        self._sim.hfield_write(ids, self._terrain[ids])
+        if hold:
+            self._sim.reset_hold(ids, qpos, qvel)
+        else:
+            self._sim.reset(qpos=qpos, qvel=qvel, env_ids=None if n == self.n_envs else ids)
+        self._time[ids] = 0.0
+        self._needs_reset[ids] = False
+        self.n_resets += n
+
+    def _observation(self):
+        rec, sl, N = self._rec, self._sl, self.n_envs
+        eyes = self._sim.render_eyes()
+        obs = collections.OrderedDict()
+        for k in self._OBS:
+            name = 'walker/' + k
+            if k == 'actuator_activation':
+                obs[name] = np.zeros((N, 0), np.float32)
+            elif k == 'left_eye':
+                obs[name] = eyes[:, 1]
+            elif k == 'right_eye':
+                obs[name] = eyes[:, 0]
+            elif k == 'task_input':
+                obs[name] = np.stack([self._target_height, self._target_speed], 1).astype(np.float32)
+            else:
+                obs[name] = rec[:, sl[name]]
+        return obs
+
+    def reset(self):
+        N = self.n_envs
+        self._reset_envs(np.arange(N), hold=False)
+        self._sim.task_inputs(np.zeros(N, np.int32), np.ones(N, np.uint8))
+        self._sim.read_task_obs(self._rec)
+        return self._unbatch(TimeStep(np.full(N, StepType.FIRST), np.zeros(N), np.ones(N), self._observation()), first=True)
+
+    def step(self, action):
+        m, N = self.model, self.n_envs
+        action = np.array(action, np.float64, copy=True).reshape(N, -1)
+        assert action.shape[1] == self._action_spec.shape[0], f'action must have {self._action_spec.shape[0]} entries'
+        resetting = self._needs_reset.copy()
+        if resetting.any():
+            self._reset_envs(np.nonzero(resetting)[0], hold=True)
+        # before_step (vision_flight.py:141-155): wing-beat pattern at the requested frequency, position target -> force command
+        action[np.isnan(action)] = 0.0
+        wb = self._wbpg
+        target = wb.step(wb.base_beat_freq * (1 + wb.rel_freq_range * action[:, -1]), active=~resetting)
+        action[:, self._action_indices['wings']] += np.where(resetting[:, None], 0.0, target - self._wing_qpos)
+        ctrl = np.zeros((N, m.nu), np.float32)
+        ctrl[:, self._ctrl_of_action] = action[:, :len(self._ctrl_of_action)]
+        self._sim.set_control(ctrl)
+        self._sim.task_inputs(np.zeros(N, np.int32), resetting)
+        self._sim.step(self._n_sub)
+        rec = self._sim.read_task_obs(self._rec)
+        self._time = np.where(resetting, 0.0, self._time + self._control_timestep)
+        self._wing_qpos = rec[:, self._sl['walker/joints_pos']][:, self._wing_in_obs].astype(np.float64)
+        obs = self._observation()
+        reward = np.prod(self.reward_factors(rec), axis=1)
+        scal = rec[:, self._sl['_scalars']]
+        bad = (scal[:, 0] != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
+        terminate = bad | (self.floor_contact() if self._fatal else False)
+        discount = np.where(terminate, 0.0, 1.0)                      # base.py:208-212
+        last = terminate | (self._time >= self._time_limit - 1e-9)
+        step_type = np.where(resetting, StepType.FIRST, np.where(last, StepType.LAST, StepType.MID))
+        self._needs_reset = last & ~resetting
+        return self._unbatch(TimeStep(step_type, np.where(resetting, 0.0, reward), np.where(resetting, 1.0, discount), obs))
+
+    # -------------------------------------------------------------------------- task quantities
+    def floor_contact(self):
+        """`check_floor_contact` (vision_flight.py:235-247): an active contact with a geom of the world body (ground plane, terrain)."""
+        ncon = self._sim.get(st.NCON)[:, 0].astype(np.int64)
+        c = self._sim.get(st.CONTACT).reshape(self.n_envs, -1, 16)
+        world = self.model.geom_bodyid[np.clip(c[..., 7].astype(np.int64), 0, self.model.ngeom - 1)] == 0
+        live = np.arange(c.shape[1])[None, :] < ncon[:, None]
+        return (live & world & (c[..., 0] < 0)).any(1)
+
+    def reward_factors(self, rec):
+        """[N, 6] (vision_flight.py:157-233): height above the terrain, forward speed, speed, side speed, body axis, centre of
+        the trench; the leg-retraction factor is empty with disabled legs."""
+        sl = self._sl
+        pose, vel = rec[:, sl['_root_pose']].astype(np.float64), rec[:, sl['_root_qvel']].astype(np.float64)[:, :3]
+        ts, th = self._target_speed, self._target_height
+        height = _tolerance_linear(pose[:, 2] - self.hfield_height(pose[:, 0], pose[:, 1]), th, th, 0.15)
+        x_speed = _tolerance_linear(vel[:, 0], ts, np.inf, 1.1 * ts)
+        speed = _tolerance_linear(np.linalg.norm(vel, axis=1), ts, ts, 1.1 * ts)
+        side = _tolerance_linear(rec[:, sl['_velocimeter_now']][:, 1], 0.0, 0.0, 10.0)
+        zaxis = rec[:, sl['walker/world_zaxis']].astype(np.float64)
+        ang = np.arccos(np.clip(zaxis @ self._target_zaxis, -1.0, 1.0))
+        world_zaxis = _tolerance_linear(ang, 0.0, 0.0, np.pi)
+        centre = np.ones(self.n_envs)
+        for e, a in enumerate(self._arenas):
+            spec = a.trench_specs
+            if spec is not None and spec['x_coords'][0] <= pose[e, 0] <= spec['x_coords'][-1]:
+                yc = spec['y_coords'][np.abs(spec['x_coords'] - pose[e, 0]).argmin()]
+                centre[e] = _tolerance_linear(pose[e, 1], yc, yc, 0.15)
+        return np.stack([height, x_speed, speed, side, world_zaxis, centre], 1)
+
+    def _unbatch(self, ts, first=False):
+        if self._batched:
+            return ts
+        obs = collections.OrderedDict((k, v[0]) for k, v in ts.observation.items())
+        if first or ts.step_type[0] == StepType.FIRST:
+            return TimeStep(StepType.FIRST, None, None, obs)
+        return TimeStep(StepType(int(ts.step_type[0])), float(ts.reward[0]), float(ts.discount[0]), obs)
+
+    def close(self):
+        self._sim.close()

@@ -1,0 +1,107 @@
+"""vision_guided_flight, first cut, on the host-emulation build: the dm_env contract of the reference task
+(`tasks/vision_flight.py`), reward factors against their definitions, fatal terrain contacts, per-episode terrains, eyes."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+from flybody_b200 import arenas, fly_envs, stepper as st
+from flybody_b200.dm_env_shim import StepType
+
+
+@pytest.fixture(scope='module')
+def emu():
+    ge.build()
+    return ge.EMU
+
+
+def test_contract_and_first_steps(emu):
+    env = fly_envs.vision_guided_flight(n_envs=2, lib_path=emu, seed=1)
+    spec = env.observation_spec()
+    assert list(spec) == ['walker/accelerometer', 'walker/actuator_activation', 'walker/gyro', 'walker/joints_pos', 'walker/joints_vel',
+                          'walker/left_eye', 'walker/right_eye', 'walker/velocimeter', 'walker/world_zaxis', 'walker/task_input']
+    assert spec['walker/right_eye'].shape == (2, 32, 32, 3) and spec['walker/right_eye'].dtype == np.uint8      # vision_flight.py:23-24
+    assert spec['walker/joints_pos'].shape == (2, 25) and spec['walker/task_input'].shape == (2, 2)
+    assert env.action_spec().shape == (12,) and env.action_spec().name.split('\t')[-1] == 'user_0'
+    assert np.isclose(env.control_timestep(), 2e-4)
+    ts = env.reset()
+    assert np.all(ts.step_type == StepType.FIRST)
+    for k, v in ts.observation.items():
+        assert v.shape == spec[k].shape and v.dtype == spec[k].dtype, k
+    th, tv = ts.observation['walker/task_input'][:, 0], ts.observation['walker/task_input'][:, 1]
+    assert np.all((0.5 <= th) & (th <= 0.8) & (20 <= tv) & (tv <= 40))                                        # vision_flight.py:28-29
+    # start: x = -5, y = 0, target height above the terrain's nearest grid point, flying at the target speed (vision_flight.py:111-139)
+    q, v = env._sim.get(st.QPOS), env._sim.get(st.QVEL)
+    assert np.allclose(q[:, :2], [-5.0, 0.0], atol=1e-6) and np.allclose(v[:, 0], tv, atol=1e-4)
+    assert np.allclose(q[:, 2] - env.hfield_height(q[:, 0], q[:, 1]), th, atol=1e-5)
+    # every env flies over its own terrain, and sees it
+    assert not np.array_equal(env._terrain[0], env._terrain[1])
+    assert not np.array_equal(ts.observation['walker/left_eye'][0], ts.observation['walker/left_eye'][1])
+    assert ts.observation['walker/right_eye'].std() > 10
+    rs = np.random.RandomState(0)
+    for _ in range(15):
+        ts = env.step(rs.uniform(-0.2, 0.2, (2, 12)))
+        assert np.all(ts.step_type == StepType.MID) and np.all(ts.discount == 1.0)
+        assert np.all((ts.reward > 0) & (ts.reward <= 1.0)) and all(np.all(np.isfinite(v)) for v in ts.observation.values())
+    env.close()
+
+
+def test_reward_factors_follow_their_definitions(emu):
+    env = fly_envs.vision_guided_flight(n_envs=3, lib_path=emu, seed=2)
+    env.reset()
+    env.step(np.zeros((3, 12)))
+    f = env.reward_factors(env._rec)
+    assert f.shape == (3, 6) and np.all((f >= 0) & (f <= 1))
+    pose = env._rec[:, env._sl['_root_pose']].astype(np.float64)
+    vel = env._rec[:, env._sl['_root_qvel']].astype(np.float64)[:, :3]
+    h = pose[:, 2] - env.hfield_height(pose[:, 0], pose[:, 1])
+    assert np.allclose(f[:, 0], np.clip(1 - np.abs(h - env.target_height) / 0.15, 0, 1))
+    ts = env.target_speed
+    assert np.allclose(f[:, 1], np.where(vel[:, 0] >= ts, 1.0, np.clip(1 - (ts - vel[:, 0]) / (1.1 * ts), 0, 1)))
+    assert np.allclose(f[:, 2], np.clip(1 - np.abs(np.linalg.norm(vel, axis=1) - ts) / (1.1 * ts), 0, 1))
+    assert np.all(f[:, 5] == 1.0)                                      # no trench in the 'bumps' arena
+    # one step after the start the fly is still close to its targets
+    assert np.all(f[:, 0] > 0.9) and np.all(f[:, 2] > 0.9) and np.all(f[:, 4] > 0.9)
+    env.close()
+
+
+def test_terrain_contact_is_fatal_and_the_next_episode_gets_a_new_terrain(emu):
+    env = fly_envs.vision_guided_flight(n_envs=2, lib_path=emu, seed=3, target_height_range=(0.5, 0.5))
+    env.reset()
+    terr0 = env._terrain.copy()
+    # push env 1 into the ground: place it a hair above the terrain with a downward velocity
+    q, v = env._sim.get(st.QPOS), env._sim.get(st.QVEL)
+    q[1, 2] = env.hfield_height(q[:, 0], q[:, 1])[1] - 0.01 + 0.14
+    v[1, 2] = -300.0
+    env._sim.set(st.QPOS, q); env._sim.set(st.QVEL, v)
+    hit = None
+    for k in range(12):
+        ts = env.step(np.zeros((2, 12)))
+        if ts.step_type[1] == StepType.LAST:
+            hit = k
+            break
+    assert hit is not None and ts.discount[1] == 0.0 and ts.step_type[0] == StepType.MID and ts.discount[0] == 1.0
+    assert env.floor_contact()[1] and not env.floor_contact()[0]
+    ts = env.step(np.zeros((2, 12)))                                   # auto-reset of env 1 only
+    assert ts.step_type[1] == StepType.FIRST and ts.step_type[0] == StepType.MID
+    assert np.array_equal(env._terrain[0], terr0[0]) and not np.array_equal(env._terrain[1], terr0[1])
+    q = env._sim.get(st.QPOS)
+    assert np.allclose(q[1, 2] - env.hfield_height(q[:, 0], q[:, 1])[1], 0.5, atol=1e-5)
+    env.close()
+
+
+def test_trench_arena_reward_and_time_limit(emu):
+    env = fly_envs.vision_guided_flight(n_envs=1, bumps_or_trench='trench', lib_path=emu, seed=5, init_pos_x_range=(-2.5, -2.5))
+    ts = env.reset()
+    spec = env._arenas[0].trench_specs
+    assert spec is not None and spec['x_coords'][0] <= -3.0
+    env.step(np.zeros(12))
+    f = env.reward_factors(env._rec)
+    pose = env._rec[:, env._sl['_root_pose']]
+    yc = spec['y_coords'][np.abs(spec['x_coords'] - pose[0, 0]).argmin()]
+    assert np.isclose(f[0, 5], np.clip(1 - abs(pose[0, 1] - yc) / 0.15, 0, 1))
+    # time limit 0.4 s = 2000 control steps is a LAST with discount 1: shorten it for the test
+    env._time_limit = 5 * env.control_timestep()
+    for k in range(4):
+        ts = env.step(np.zeros(12))
+    assert ts.step_type == StepType.LAST and ts.discount == 1.0
+    env.close()
