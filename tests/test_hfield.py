@@ -161,3 +161,15 @@ def test_vision_model_terrain_contacts_match_the_oracle_through_the_step():
             if np.abs(a).max() > 0:
                 assert rel_err(a, sim.get(f)[1]) < 2e-3, (trial, f)
         sim.close()
+
+
+def test_vision_model_stage_parity_in_free_flight():
+    """the `vision` variant away from the ground: every stage of the forward pass against the oracle (as the flight variant)."""
+    import __graft_entry__ as ge
+    from flybody_b200 import stepper as st
+    from flybody_b200.flymodel import load_model
+    from parity_common import compare_stage_fields
+    ge.build()
+    m = load_model('vision')
+    res = compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=ge.EMU), seed=1, vel_scale=20.0)
+    assert 'qM' in res and 'qfrc_passive' in res
