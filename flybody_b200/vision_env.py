@@ -38,7 +38,7 @@ class BatchedVisionFlightEnv:
 
     def __init__(self, n_envs, bumps_or_trench='bumps', wpg_pattern_path=None, device=0, lib_path=None, seed=0, eye_camera_size=32,
                  eye_camera_fovy=150.0, target_height_range=(0.5, 0.8), target_speed_range=(20, 40), init_pos_x_range=(-5, -5),
-                 init_pos_y_range=(0, 0), time_limit=0.4, floor_contacts_fatal=True, **kwargs_arena):
+                 init_pos_y_range=(0, 0), time_limit=0.4, floor_contacts_fatal=True, terrain_bank=None, **kwargs_arena):
         if bumps_or_trench not in ('bumps', 'trench'):
             raise ValueError("Only 'bumps' and 'trench' terrains are supported.")
         self._batched = n_envs is not None
@@ -56,6 +56,14 @@ class BatchedVisionFlightEnv:
         assert (a0.nrow, a0.ncol) == (m.meta['hf_nrow'], m.meta['hf_ncol']) and a0.size[0] == m.hf_size[0], 'arena grid differs from the compiled model'
         self._half = float(a0.size[0])
         self._terrain = np.zeros((N, a0.nrow, a0.ncol), np.float32)
+        # The reference draws a new terrain every episode (16 ms of scipy per terrain here).  `terrain_bank=K` pre-generates K
+        # terrains and lets every episode pick one at random instead -- the same distribution over a finite bank, for large batches.
+        self._bank = None
+        if terrain_bank:
+            self._bank = []
+            for _ in range(int(terrain_bank)):
+                t = a0.generate(self._rs)
+                self._bank.append((t.astype(np.float32), a0.trench_specs))
         self._sim.hfield_collision(m.meta['hf_geom'], m.hf_size, a0.nrow, a0.ncol, m.hf_pair_geom)
         self._ranges = dict(h=target_height_range, v=target_speed_range, x=init_pos_x_range, y=init_pos_y_range)
         # action <-> ctrl (reference fruitfly.py:342-379): head 3, wings 6, abdomen 2, + 1 user action (beat frequency)
@@ -153,7 +161,10 @@ class BatchedVisionFlightEnv:
             self._target_speed[e] = self._rs.uniform(*r['v'])
             x, y = self._rs.uniform(*r['x']), self._rs.uniform(*r['y'])
             wq, _ = self._wbpg.reset(np.array([e]), np.array([self._rs.uniform()]))
-            self._terrain[e] = self._arenas[e].generate(self._rs)
+            if self._bank is None:
+                self._terrain[e] = self._arenas[e].generate(self._rs)
+            else:
+                self._terrain[e], self._arenas[e].trench_specs = self._bank[self._rs.randint(len(self._bank))]
             z = float(arenas.hfield_height(self._terrain[e], [x], [y], self._half)[0]) + self._target_height[e]
             qpos[k, self._root_q:self._root_q + 3] = (x, y, z)
             qpos[k, self._root_q + 3:self._root_q + 7] = self._hover_quat

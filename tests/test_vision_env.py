@@ -105,3 +105,13 @@ def test_trench_arena_reward_and_time_limit(emu):
         ts = env.step(np.zeros(12))
     assert ts.step_type == StepType.LAST and ts.discount == 1.0
     env.close()
+
+
+def test_terrain_bank_option(emu):
+    env = fly_envs.vision_guided_flight(n_envs=4, lib_path=emu, seed=7, terrain_bank=2)
+    env.reset()
+    bank = [t for t, _ in env._bank]
+    assert len(bank) == 2 and all(any(np.array_equal(env._terrain[e], b) for b in bank) for e in range(4))
+    ts = env.step(np.zeros((4, 12)))
+    assert np.all(np.isfinite(ts.reward))
+    env.close()

@@ -32,7 +32,7 @@ same = np.array_equal(out[0][0], out[1][0])
 print('contact counts equal:', same, ' max |d dist|:', float(np.abs(out[0][1] - out[1][1]).max()) if same else None,
       ' qacc rel err:', float(np.abs(out[0][2] - out[1][2]).max() / np.abs(out[1][2]).max()))
 # (2) env throughput
-env = fly_envs.vision_guided_flight(n_envs=N, seed=1)
+env = fly_envs.vision_guided_flight(n_envs=N, seed=1, terrain_bank=64)
 t0 = time.perf_counter(); env.reset(); print(f'reset of {N} envs (terrain generation on the host): {time.perf_counter() - t0:.1f} s')
 rs = np.random.RandomState(0)
 acts = rs.uniform(-0.2, 0.2, (K + 5, N, 12))
