@@ -145,7 +145,26 @@ FB_DEV void khf_narrow(const DevModel& m, const DevData& d, const DevHf& p, int 
     const V3 gp = ld3(d.geom_xpos, g, d, e);
     const float margin = fmaxf(m.geom_margin[p.geom], m.geom_margin[g]);
     int n = 0;
-    if (gp.z - m.geom_rbound[g] <= hp.z + p.hmax[e] * p.size[2] + margin) {      // (the terrain frame is upright: hills.py:205-211)
+    // bounding sphere against the highest grid point under its footprint (the arena's rim rises to "horizon mountains" of 4-5
+    // length units, so the terrain-wide maximum would never reject a fly cruising at 0.5-0.8; the terrain frame is upright,
+    // hills.py:205-211)
+    const float rb = m.geom_rbound[g] + margin;
+    const bool upright = hm.m[0] > 0.9999f && hm.m[4] > 0.9999f && hm.m[8] > 0.9999f;      // any other terrain frame: no pre-test
+    bool near = !upright || gp.z - rb <= hp.z + p.hmax[e] * p.size[2];
+    if (near && upright) {
+      const float fx0 = (gp.x - hp.x - rb + p.size[0]) / (2 * p.size[0]) * (p.ncol - 1), fx1 = (gp.x - hp.x + rb + p.size[0]) / (2 * p.size[0]) * (p.ncol - 1);
+      const float fy0 = (gp.y - hp.y - rb + p.size[1]) / (2 * p.size[1]) * (p.nrow - 1), fy1 = (gp.y - hp.y + rb + p.size[1]) / (2 * p.size[1]) * (p.nrow - 1);
+      int c0 = (int)floorf(fx0), c1 = (int)ceilf(fx1), r0 = (int)floorf(fy0), r1 = (int)ceilf(fy1);
+      if (c1 < 0 || r1 < 0 || c0 > p.ncol - 1 || r0 > p.nrow - 1) near = false;            // beside the terrain
+      else {
+        c0 = c0 < 0 ? 0 : c0; r0 = r0 < 0 ? 0 : r0; c1 = c1 > p.ncol - 1 ? p.ncol - 1 : c1; r1 = r1 > p.nrow - 1 ? p.nrow - 1 : r1;
+        float top = 0.0f;
+        if ((c1 - c0 + 1) * (r1 - r0 + 1) <= 64) { for (int r = r0; r <= r1; r++) for (int c = c0; c <= c1; c++) top = fmaxf(top, data[(size_t)r * p.ncol + c]); }
+        else top = p.hmax[e];
+        near = gp.z - rb <= hp.z + top * p.size[2];
+      }
+    }
+    if (near) {
       HfCon c[FB_HF_PER_GEOM]; RawCon rc[FB_HF_PER_GEOM];
       n = col_convex_hfield(c, FB_HF_PER_GEOM, margin, m.geom_type[g], gp, ld9(d.geom_xmat, g, d, e), mld3(m.geom_size, g), hp, hm, p.size, p.nrow, p.ncol, data);
       for (int i = 0; i < n; i++) { rc[i].dist = c[i].dist; rc[i].pos = c[i].pos; rc[i].n = c[i].n; rc[i].t = v3(0, 0, 0); }
