@@ -131,7 +131,8 @@ def cpu_baseline(budget_s=10.0, max_steps=4000, cores=None):
     rate = sum(n / t for n, t in res)
     return {'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
             'sample': f'{cores} processes x ~{budget_s:.0f}s of {WL["model"]}_imitation control steps ({N_SUB} substeps, random actions), '
-                      f'oracle/fly_oracle.c (restated mj_step, fp64; NOT MuJoCo: mujoco is not installable here), '
+                      f'oracle/fly_oracle.c (restated mj_step, fp64, dense; NOT MuJoCo, which is not installable here and would be an estimated '
+                      f'20-40x faster per core under load: DESIGN.md section 6), '
                       f'{sum(n for n, _ in res)} env-steps total',
             'per_core': rate / cores}
 
