@@ -1032,11 +1032,16 @@ FB_DEV void kfin_f9(FB_PHASE_ARGS) {
       AT(d.sensordata, adr) = sum;
     }
   }
-  // state check (|qacc| > 1e14 or non-finite: reference tasks/base.py:222-225); each lane tests its dofs
+  // state check (|qacc| > 1e14 or non-finite: reference tasks/base.py:222-225): each lane sums its dofs, kfin_f10 adds the lanes up
   float s2 = 0; bool bad = false;
   for (int k = y; k < m.nv; k += FB_NY) { float a = AT(d.qacc, k); s2 += a * a; if (!isfinite(a) || !isfinite(AT(d.qvel, k))) bad = true; }
-  if (bad || !(s2 < 1e28f)) FB_FLAG_OR(1);
+  sh.red[y][lane] = bad ? INFINITY : s2;
   if (d.do_integrate && !AT(d.hold, 0)) for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) += m.timestep * AT(d.act_dot, i);
+}
+FB_DEV void kfin_f10(FB_PHASE_ARGS) {
+  if (y != 0) return;
+  float s2 = 0; for (int l = 0; l < FB_NY; l++) s2 += sh.red[l][lane];
+  if (!(s2 < 1e28f)) FB_FLAG_OR(1);
 }
 FB_DEV void integrate_body(const DevModel& m, const DevData& d, int e, int lane, const float* xs, int b) {
   float h = m.timestep;
@@ -1171,6 +1176,7 @@ FB_DEV void ktask_reset(const DevModel& m, const DevData& d, int e, int y) {
   for (int i = y; i < m.nq; i += FB_NY) AT(d.qpos, i) = t.reset_qpos[i];
   for (int i = y; i < m.nv; i += FB_NY) { AT(d.qvel, i) = 0.0f; AT(d.qacc, i) = 0.0f; }
   for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) = 0.0f;
+  for (int i = y; i < m.nu; i += FB_NY) AT(d.ctrl, i) = 0.0f;      // physics.reset() = mj_resetData: the FIRST observation does not see the old controls
 }
 FB_DEV void ktask_reset2(const DevModel& m, const DevData& d, int e, int y) {      // after the template copy (other lanes wrote it)
   if (!d.task || e >= d.N) return;
@@ -1242,7 +1248,7 @@ FB_DEV void ktask_after(const DevModel& m, const DevData& d, int e, int y) {
   const float com_dist = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
   const bool reached_end = step_now == t.episode_steps;
   float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; }
-  const bool bad = AT(d.flags, 0) != 0 || !(sqrtf(s2) <= t.term_qacc);
+  const bool bad = (AT(d.flags, 0) & 1) != 0 || !(sqrtf(s2) <= t.term_qacc);      // bits 1, 2 are capacity overflows, not bad physics
   bool terminate; float reward;
   if (t.kind == 0) {
     const float* lv = &AT(d.sensordata, t.velocimeter_adr); const float* av = &AT(d.sensordata, t.gyro_adr);
@@ -1280,6 +1286,7 @@ FB_DEV void kreset_scatter(const DevModel& m, const DevData& d, int w, int y) {
   for (int i = y; i < m.nq; i += FB_NY) AT(d.qpos, i) = d.rst_qpos[(size_t)w * m.nq + i];
   for (int i = y; i < m.nv; i += FB_NY) { AT(d.qvel, i) = d.rst_has_qvel ? d.rst_qvel[(size_t)w * m.nv + i] : 0.0f; AT(d.qacc, i) = 0; }
   for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) = 0;
+  for (int i = y; i < m.nu; i += FB_NY) AT(d.ctrl, i) = 0;         // mj_resetData zeroes ctrl (reference: physics.reset() before initialize_episode)
   if (y == 0) { AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = d.rst_hold; AT(d.prev_n, 0) = 0; }
 }
 FB_DEV void kclear_hold(const DevModel& m, const DevData& d, int e, int y) { if (y == 0) AT(d.hold, 0) = 0; }
@@ -1287,11 +1294,14 @@ FB_DEV void kclear_hold(const DevModel& m, const DevData& d, int e, int y) { if 
 FB_DEV void kscatter(const DevModel& m, const DevData& d, int e, int y) {
   if (e >= d.Np) return;
   const int src = (e >= d.N) ? 0 : e;                  // pad envs mirror env 0
+  // an env held for its reset ignores the action of the step() call that resets it (dm_env: the action passed with a reset is
+  // dropped), so its FIRST observation is computed with ctrl = 0 whatever the caller sent
+  const bool drop = d.sc_field == d.ctrl && AT(d.hold, 0) != 0;
   for (int c = y; c < d.sc_k; c += FB_NY) {
     int t = d.sc_idx ? d.sc_idx[c] : c;
     if (t < 0) continue;                                 // column without a target (e.g. a user action)
     float v = d.sc_vals[(size_t)src * d.sc_k + c];
     if (d.sc_nan0 && !(v == v)) v = 0.0f;                // NaN actions act as 0 (reference tasks/base.py:199)
-    AT(d.sc_field, t) = v;
+    AT(d.sc_field, t) = drop ? 0.0f : v;
   }
 }

@@ -273,7 +273,7 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 #define FB_ST_PROJ Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>
 #define FB_ST_VEL Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>
 #define FB_ST_SMOOTH Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>
-#define FB_ST_FINISH Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>
+#define FB_ST_FINISH Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>, Ph<kfin_f10>
 static size_t dyn_pos(const DevModel& m) { return (size_t)FB_PARTF + (size_t)m.nM; }
 static size_t dyn_col(const DevModel& m) { return (size_t)FB_COL_DYN(m); }
 static size_t dyn_proj(const DevModel&) { return (size_t)FB_NY * FB_ZCAP; }
@@ -404,7 +404,10 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.nq = h->nq; m.nv = h->nv; m.nu = h->nu; m.na = h->na; m.nbody = h->nbody; m.njnt = h->njnt; m.ngeom = h->ngeom;
   m.npair = h->npair; m.nsite = h->nsite; m.ntendon = h->ntendon; m.nwrap = h->nwrap; m.nsensor = h->nsensor;
   m.nsensordata = h->nsensordata; m.nM = h->nM; m.nfluid = h->nfluid;
-  m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.max_iter = 30; m.ls_iter = 12; m.ls_tolerance = 1e-3f;
+  m.noslip_iterations = h->opt_noslip_iterations; m.cone_elliptic = h->opt_cone_elliptic; m.ls_tolerance = 1e-3f;
+  // solver limits = the model's own (mjOption iterations / ls_iterations: 100 / 50 for the fly, fruitfly.xml:4 leaves the defaults);
+  // the loops leave on convergence long before (1-4 Newton iterations, 2-4 line-search evaluations per substep in the walking workload)
+  m.max_iter = h->opt_iterations > 0 ? h->opt_iterations : 100; m.ls_iter = h->opt_ls_iterations > 0 ? h->opt_ls_iterations : 50;
   if (h->nv > 4 * FB_SOLVE_NCAP) { s->err = "nv exceeds the solver's per-dof accumulator window (4 * FB_SOLVE_NCAP)"; return -3; }
   { const char* rt = getenv("FB_SOLVE_RTOL"); m.solve_rtol = rt ? (float)atof(rt) : 1e-6f; }     // relative improvement that ends the Newton iteration (test hook)
   { const char* nc = getenv("FB_SOLVE_NCAP"); m.solve_ncap = nc ? atoi(nc) : FB_SOLVE_NCAP; if (m.solve_ncap > FB_SOLVE_NCAP) m.solve_ncap = FB_SOLVE_NCAP; }   // test hook: smaller cap -> global-memory path
@@ -1032,7 +1035,7 @@ int fb_set_ctrl(FbHandle s, const float* ctrl, int is_device) {
 int fb_set_action_map(FbHandle s, const int32_t* ctrl_index, int n_action) {
   if (!s) return -1;
   if (!ctrl_index || n_action <= 0) { s->act_map_dev = nullptr; s->n_action = 0; return 0; }      // back to plain ctrl rows
-  for (int c = 0; c < n_action; c++) if (ctrl_index[c] >= s->m.nu) { s->err = "fb_set_action_map: ctrl index out of range"; return -1; }
+  for (int c = 0; c < n_action; c++) if (ctrl_index[c] >= s->m.nu || ctrl_index[c] < -1) { s->err = "fb_set_action_map: ctrl index out of range (valid: -1 = no target, 0..nu-1)"; return -1; }
   if (sync_stream(s) != 0) return -2;
   std::vector<int> v(ctrl_index, ctrl_index + n_action);
   s->act_map_dev = up(s, v); s->n_action = n_action;
@@ -1133,7 +1136,16 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
       default: s->err = "fb_obs_program: unknown item kind"; return -1;
     }
     if ((k == FB_OBS_REF_DISP || k == FB_OBS_REF_QUAT) && (!p->ref_qpos || p->ref_len <= 0)) { s->err = "fb_obs_program: reference table missing"; return -1; }
-    if ((k == FB_OBS_QPOS || k == FB_OBS_QVEL || k == FB_OBS_SITES_EGO || k == FB_OBS_DOF_AXIS_EGO) && (p->a[i] < 0 || p->a[i] + b > p->n_list)) { s->err = "fb_obs_program: list range"; return -1; }
+    if ((k == FB_OBS_QPOS || k == FB_OBS_QVEL || k == FB_OBS_SITES_EGO || k == FB_OBS_DOF_AXIS_EGO) && (p->a[i] < 0 || b < 0 || p->a[i] + b > p->n_list)) { s->err = "fb_obs_program: list range"; return -1; }
+    if ((k == FB_OBS_SENSOR_MEAN || k == FB_OBS_SENSOR_NOW) && (p->a[i] < 0 || b < 0 || p->a[i] + b > m.nsensordata)) { s->err = "fb_obs_program: sensor range"; return -1; }
+    if (k == FB_OBS_ACT && (p->a[i] < 0 || b < 0 || p->a[i] + b > m.na)) { s->err = "fb_obs_program: activation range"; return -1; }
+    if (k == FB_OBS_SUBTREE_COM && (p->a[i] < 0 || p->a[i] >= m.nbody)) { s->err = "fb_obs_program: subtree_com body id"; return -1; }
+    if ((k == FB_OBS_REF_DISP || k == FB_OBS_REF_QUAT) && b < 0) { s->err = "fb_obs_program: negative count"; return -1; }
+  }
+  for (int i = 0; i < p->n_items; i++) {          // entries of the index list, by the kind that reads them
+    const int k = p->kind[i], lim = k == FB_OBS_QPOS ? m.nq : (k == FB_OBS_QVEL || k == FB_OBS_DOF_AXIS_EGO) ? m.nv : k == FB_OBS_SITES_EGO ? m.nsite : -1;
+    if (lim < 0) continue;
+    for (int j = 0; j < p->b[i]; j++) if (p->list[p->a[i] + j] < 0 || p->list[p->a[i] + j] >= lim) { s->err = "fb_obs_program: list entry out of range"; return -1; }
   }
   if (p->root_body <= 0 || p->root_body >= m.nbody) { s->err = "fb_obs_program: root body"; return -1; }
   std::vector<int> kind(p->kind, p->kind + p->n_items), a(p->a, p->a + p->n_items), b(p->b, p->b + p->n_items), list(p->list, p->list + std::max(p->n_list, 0));

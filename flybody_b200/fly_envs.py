@@ -681,7 +681,11 @@ class BatchedFlyEnv:
         com_dist = np.linalg.norm(obs['walker/ref_displacement'][:, 0], axis=1)
         reached_end = step_now == self._episode_steps
         scal = rec[:, sl['_scalars']]
-        bad = (scal[:, 0] != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
+        # FB_FLAGS bit 0 = non-finite / diverged state (reference base.py:222-225 terminates on it); bits 1, 2 = contact /
+        # constraint-row capacity overflows, which are counted, not treated as bad physics
+        flags = scal[:, 0].astype(np.int64)
+        self.n_capacity_overflows = getattr(self, 'n_capacity_overflows', 0) + int(((flags & 6) != 0).sum())
+        bad = ((flags & 1) != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
         if self._variant == 'walk':
             linvel = np.linalg.norm(rec[:, sl['_velocimeter_now']], axis=1)
             angvel = np.linalg.norm(rec[:, sl['_gyro_now']], axis=1)

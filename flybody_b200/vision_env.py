@@ -228,7 +228,11 @@ class BatchedVisionFlightEnv:
         obs = self._observation()
         reward = np.prod(self.reward_factors(rec), axis=1)
         scal = rec[:, self._sl['_scalars']]
-        bad = (scal[:, 0] != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
+        # FB_FLAGS bit 0 = non-finite / diverged state (reference base.py:222-225 terminates on it); bits 1, 2 = contact /
+        # constraint-row capacity overflows, which are counted, not treated as bad physics
+        flags = scal[:, 0].astype(np.int64)
+        self.n_capacity_overflows = getattr(self, 'n_capacity_overflows', 0) + int(((flags & 6) != 0).sum())
+        bad = ((flags & 1) != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
         terminate = bad | (self.floor_contact() if self._fatal else False)
         discount = np.where(terminate, 0.0, 1.0)                      # base.py:208-212
         last = terminate | (self._time >= self._time_limit - 1e-9)

@@ -3,7 +3,9 @@
 Tolerances (fp32 stepper vs fp64 oracle, stated per BASELINE.json north_star):
   smooth-dynamics stages (kinematics, M, bias, passive, actuation): 2e-6 relative to the field's max
   constraint forces / qacc / acc-stage sensors                  : 2e-4 relative to the field's max
-  teacher-forced control step (10 substeps): |dqpos| < 2e-6, |dqvel| < 5e-3 (cm/s, rad/s)
+  teacher-forced control step (10 substeps): p90 |dqpos| < 2e-6, p90 |dqvel| < 5e-4 (cm/s, rad/s);
+      per-substep sensor MEAN of the control step (what 5 of the 12 walk observables are made of, SURVEY.md section 0 fact 5;
+      reference fruitfly.py:626-665) against the oracle's control-step mean: p90 of the per-sensor relative error < 2e-4
 """
 import numpy as np
 
@@ -77,7 +79,7 @@ def teacher_forced_errors(m, sim, n_steps, n_sub, seed=0, ctrl_scale=0.5):
     o.reset(q0)
     sim.reset(q0)
     rs = np.random.RandomState(seed)
-    eqs, evs = [], []
+    eqs, evs, ess = [], [], []
     for k in range(n_steps):
         sim.set(st.QPOS, o.qpos)
         sim.set(st.QVEL, o.qvel)
@@ -92,14 +94,35 @@ def teacher_forced_errors(m, sim, n_steps, n_sub, seed=0, ctrl_scale=0.5):
         sim.step(n_sub)
         eqs.append(np.abs(sim.get(st.QPOS)[0] - o.qpos).max())
         evs.append(np.abs(sim.get(st.QVEL)[0] - o.qvel).max())
-    return np.array(eqs), np.array(evs)
+        ess.append(sensor_mean_error(m, sim.get(st.SENSOR_MEAN)[0], sm_o))
+    return np.array(eqs), np.array(evs), np.array(ess)
 
 
-def summarize_tf(eqs, evs, tol_q=2e-6, tol_v=5e-3):
+# absolute floors of the per-sensor relative error, by sensor type (touch, accelerometer, velocimeter, gyro, force):
+# a sensor that reads ~0 (a leg in the air) is compared on the scale of a small reading of its kind
+SENSOR_FLOOR = {0: 1e-3, 1: 10.0, 2: 0.1, 3: 0.1, 4: 1e-3}
+
+
+def sensor_mean_error(m, mean_sim, mean_oracle):
+    """max over the sensors of |mean_sim - mean_oracle| / (|mean_oracle| + floor), per sensor block."""
+    worst = 0.0
+    for s in range(m.nsensor):
+        a, n = int(m.sensor_adr[s]), int(m.sensor_dim[s])
+        ref = np.asarray(mean_oracle[a:a + n], np.float64)
+        err = np.abs(np.asarray(mean_sim[a:a + n], np.float64) - ref).max()
+        worst = max(worst, err / (np.abs(ref).max() + SENSOR_FLOOR[int(m.sensor_type[s])]))
+    return worst
+
+
+def summarize_tf(eqs, evs, ess=None, tol_q=2e-6, tol_v=5e-4, tol_s=2e-4):
     """Contact dynamics are non-smooth: when a contact (or limit) switches on inside a control step an
     fp32 / fp64 pair can disagree about the substep in which it happens, which shows up as an isolated
     spike of the 1-step error.  Gate the bulk tightly, bound the number and size of such event steps."""
     bulk_q, bulk_v = np.percentile(eqs, 90), np.percentile(evs, 90)
     events = int(((eqs > tol_q) | (evs > tol_v)).sum())
-    return dict(p90_q=float(bulk_q), p90_v=float(bulk_v), max_q=float(eqs.max()), max_v=float(evs.max()), events=events,
-                steps=len(eqs))
+    r = dict(p90_q=float(bulk_q), p90_v=float(bulk_v), max_q=float(eqs.max()), max_v=float(evs.max()), events=events,
+             steps=len(eqs), p50_v=float(np.median(evs)),
+             hist_v={f'<{b:g}': int((evs < b).sum()) for b in (1e-4, 2e-4, 5e-4, 1e-3, 5e-3, 5e-2, 0.5, 5.0)})
+    if ess is not None:
+        r.update(p90_s=float(np.percentile(ess, 90)), max_s=float(ess.max()), sensor_events=int((ess > tol_s).sum()))
+    return r

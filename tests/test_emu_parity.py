@@ -32,7 +32,8 @@ def test_stage_parity_flight(emu):
 def test_teacher_forced_control_steps_walk(emu):
     m = load_model('walk')
     r = summarize_tf(*teacher_forced_errors(m, st.BatchedStepper(m, 1, lib_path=emu), n_steps=8, n_sub=10))
-    assert r['p90_q'] < 2e-6 and r['p90_v'] < 5e-3 and r['events'] <= 1, r
+    assert r['p90_q'] < 2e-6 and r['p90_v'] < 2e-3 and r['hist_v']['<0.005'] >= 7, r
+    assert r['p90_s'] < 1e-3, r          # per-substep sensor mean vs the oracle's control-step mean (8 steps: loose)
 
 
 @pytest.mark.parametrize('ncap,seed', [('0', 0), ('32', 4)])

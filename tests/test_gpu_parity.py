@@ -34,17 +34,22 @@ def test_teacher_forced_200_control_steps_walk():
     m = load_model('walk')
     r = summarize_tf(*teacher_forced_errors(m, st.BatchedStepper(m, 32), n_steps=200, n_sub=10))
     print('teacher-forced walk:', r)
-    # bulk: fp32 tolerance; isolated contact-switch events (incl. generic convex contacts whose MPR depth carries its 1e-6
-    # support tolerance): at most 5% of the steps, bounded size
-    assert r['p90_q'] < 2e-6 and r['p90_v'] < 5e-3, r
-    assert r['events'] <= 10 and r['max_q'] < 2e-3 and r['max_v'] < 5.0, r
+    # bulk: fp32 tolerance (gate = what is measured, x2.5); isolated contact-switch events (incl. generic convex contacts
+    # whose MPR depth carries its 1e-6 support tolerance): histogram printed, at most 10 % of the steps above the bulk gate,
+    # at most 2 % above 10x the gate, bounded size
+    assert r['p90_q'] < 2e-6 and r['p90_v'] < 5e-4, r
+    assert r['events'] <= 20 and r['hist_v']['<0.005'] >= 196 and r['max_q'] < 2e-3 and r['max_v'] < 5.0, r
+    # per-substep sensor mean of every control step against the oracle's (force / touch / accelerometer / gyro / velocimeter
+    # observables are this mean: reference fruitfly.py:626-665)
+    assert r['p90_s'] < 2e-4 and r['sensor_events'] <= 20 and r['max_s'] < 0.5, r
 
 
 def test_teacher_forced_flight():
     m = load_model('flight')
-    r = summarize_tf(*teacher_forced_errors(m, st.BatchedStepper(m, 32), n_steps=50, n_sub=4, ctrl_scale=0.2), tol_v=5e-2)
+    r = summarize_tf(*teacher_forced_errors(m, st.BatchedStepper(m, 32), n_steps=50, n_sub=4, ctrl_scale=0.2), tol_v=2e-3)
     print('teacher-forced flight:', r)
-    assert r['p90_q'] < 2e-6 and r['p90_v'] < 5e-2 and r['events'] <= 2, r
+    assert r['p90_q'] < 2e-6 and r['p90_v'] < 1e-3 and r['events'] <= 2, r
+    assert r['p90_s'] < 2e-4 and r['max_s'] < 2e-3, r
 
 
 def test_free_running_drift_walk_reported():
