@@ -120,6 +120,52 @@ def test_device_observation_program_matches_numpy_formulas(emu):
     assert np.allclose(o['walker/touch'], sm[:, env._sd['touch']], rtol=1e-6, atol=1e-9)
 
 
+def check_sensor_observables_against_oracle(lib, device_task):
+    """The five buffered observables (accelerometer, gyro, velocimeter, force, touch: `buffer_size = n_sub, aggregator = mean`,
+    reference fruitfly.py:626-665) returned by env.reset() / env.step() against the fp64 oracle driven with the same controls:
+    at FIRST the buffer holds one sample (the forward pass after the reset) padded with zeros (dm_control `Buffer`, SURVEY.md
+    App. C), afterwards the mean over the control step's substeps.  Also the instantaneous observables that read the state."""
+    from oracle import fly_oracle as fo
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=2, lib_path=lib, device_task=device_task)
+    m = env.model
+    o = fo.Oracle(m, tolerance=1e-12)
+    ts = env.reset()
+    q0 = env._sim.get(fly_envs.st.QPOS)[0].astype(np.float64)
+    o.reset(q0)
+    n_sub = env._n_sub
+    names = ('accelerometer', 'gyro', 'velocimeter', 'force', 'touch')
+    sd = o.get(fo.SENSORDATA)
+    for k in names:
+        want = sd[env._sd[k]] / n_sub
+        got = np.asarray(ts.observation['walker/' + k], np.float64)[0]
+        assert np.allclose(got, want, rtol=2e-4, atol=2e-4 * (np.abs(want).max() + 1e-3)), ('FIRST', k, got, want)
+    rs = np.random.RandomState(5)
+    sim = env._sim
+    for step in range(4):                                   # teacher-forced: each control step starts from the oracle's state
+        sim.set(fly_envs.st.QPOS, np.tile(o.qpos, (2, 1))); sim.set(fly_envs.st.QVEL, np.tile(o.qvel, (2, 1)))
+        sim.set(fly_envs.st.ACT, np.tile(o.get(fo.ACT), (2, 1))); sim.forward()
+        a = rs.uniform(-0.5, 0.5, (2, 59))
+        a[1] = a[0]
+        ts = env.step(a)
+        ctrl = np.zeros(m.nu); ctrl[env._ctrl_of_action] = a[0]
+        o.set(fo.CTRL, ctrl)
+        mean = o.control_step(n_sub)
+        for k in names:
+            want = mean[env._sd[k]]
+            got = np.asarray(ts.observation['walker/' + k], np.float64)[0]
+            assert np.allclose(got, want, rtol=2e-3, atol=2e-3 * (np.abs(want).max() + 1e-3)), (step, k, got, want)
+        assert np.allclose(ts.observation['walker/joints_pos'][0], o.qpos[env._obs_qadr], atol=2e-5), step
+        assert np.allclose(ts.observation['walker/joints_vel'][0], o.qvel[env._obs_vadr], atol=5e-3), step
+        assert np.allclose(ts.observation['walker/actuator_activation'][0], o.get(fo.ACT), atol=2e-5), step
+        assert np.array_equal(ts.observation['walker/force'][0], ts.observation['walker/force'][1])
+    env.close()
+
+
+@pytest.mark.parametrize('device_task', [False, True])
+def test_sensor_observables_match_the_oracle_mean_incl_first_step(emu, device_task):
+    check_sensor_observables_against_oracle(emu, device_task)
+
+
 # ------------------------------------------------------------------------------------ flight_imitation
 FLIGHT_OBS = ['walker/accelerometer', 'walker/actuator_activation', 'walker/gyro', 'walker/joints_pos', 'walker/joints_vel',
               'walker/velocimeter', 'walker/world_zaxis', 'walker/ref_displacement', 'walker/ref_root_quat']

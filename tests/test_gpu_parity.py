@@ -152,6 +152,38 @@ def test_device_task_logic_on_gpu():
     dt.test_flight_device_task_matches_host_task_code(None)
 
 
+def test_vision_model_terrain_contacts_on_gpu():
+    """heightfield narrowphase kernel (fb_hf_kernel) inside the step of the `vision` model: contacts, rows and forces against the
+    oracle's terrain collision (tests/test_hfield.py, here on the CUDA build)."""
+    import test_hfield as th
+    th.check_vision_terrain_contacts(None)
+
+
+def test_vision_model_stage_parity_on_gpu():
+    import test_hfield as th
+    th.check_vision_free_flight(None)
+
+
+@pytest.mark.parametrize('device_task', [False, True])
+def test_sensor_observables_match_the_oracle_mean_on_gpu(device_task):
+    """the buffered observables of env.reset() / env.step() against the oracle's per-substep mean, incl. the FIRST step"""
+    import test_env as te
+    te.check_sensor_observables_against_oracle(None, device_task)
+
+
+def test_device_observation_program_matches_numpy_formulas_on_gpu():
+    import test_env as te
+    te.test_device_observation_program_matches_numpy_formulas(None)
+
+
+def test_first_observation_is_independent_of_history_on_gpu(monkeypatch):
+    import test_reset_first_obs as tr
+    for dt in (False, True):
+        tr.test_flight_first_observation_is_independent_of_the_previous_action(None, dt)
+        tr.test_walk_first_observation_is_independent_of_the_previous_action(None, dt)
+    tr.test_flight_first_accelerometer_with_a_fixed_wing_phase(None)
+
+
 def test_eye_renderer_on_gpu_matches_host_emulation():
     """fb_render_eyes on the B200 against the same kernel source run by the host-emulation build (tests/test_eyes.py holds
     that one against the camera model and a brute-force ray marcher)."""

@@ -123,6 +123,10 @@ def test_device_matches_oracle_on_a_bumpy_terrain(libs):
 
 
 def test_vision_model_terrain_contacts_match_the_oracle_through_the_step():
+    check_vision_terrain_contacts(ge.EMU)
+
+
+def check_vision_terrain_contacts(lib):
     """the compiled `vision` variant (flight model, no ghost, ground contacts on, 401 x 401 terrain geom): stage parity of the whole
     forward pass against the oracle with the fly dipped into a bumpy terrain -- heightfield contacts, their rows and forces."""
     import __graft_entry__ as ge
@@ -139,7 +143,7 @@ def test_vision_model_terrain_contacts_match_the_oracle_through_the_step():
         ground = float(arenas.hfield_height(terr, [x], [y], 20.0)[0]) - 0.01
         q = m.qpos0.copy(); q[:3] = [x, y, ground + dz]
         v = np.zeros(m.nv); v[0] = 20.0
-        sim = st.BatchedStepper(m, 2, lib_path=ge.EMU)
+        sim = st.BatchedStepper(m, 2, lib_path=lib)
         sim.hfield_collision(m.meta['hf_geom'], m.hf_size, 401, 401, m.hf_pair_geom)
         sim.hfield_write(np.arange(2), np.stack([terr, terr]))
         o = fo.Oracle(m, tolerance=1e-12)
@@ -164,6 +168,10 @@ def test_vision_model_terrain_contacts_match_the_oracle_through_the_step():
 
 
 def test_vision_model_stage_parity_in_free_flight():
+    check_vision_free_flight(ge.EMU)
+
+
+def check_vision_free_flight(lib):
     """the `vision` variant away from the ground: every stage of the forward pass against the oracle (as the flight variant)."""
     import __graft_entry__ as ge
     from flybody_b200 import stepper as st
@@ -171,5 +179,5 @@ def test_vision_model_stage_parity_in_free_flight():
     from parity_common import compare_stage_fields
     ge.build()
     m = load_model('vision')
-    res = compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=ge.EMU), seed=1, vel_scale=20.0)
+    res = compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=lib), seed=1, vel_scale=20.0)
     assert 'qM' in res and 'qfrc_passive' in res
