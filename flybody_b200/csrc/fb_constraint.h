@@ -6,7 +6,13 @@
 // contact record: con_pos[3], con_frame[9] per slot (positions relative to ref)
 #define CON_F(arr, slot, k, K) AT(arr, (slot) * (K) + (k))
 #define EFC(arr, r) AT(arr, r)
-#define EJ(arr, r, dof) AT(arr, (r) * m.nv + (dof))
+// efc_J / efc_Z rows are stored CHAIN-SPARSE: a row touches the ancestor chain of one dof (limit) or of two (contact: chain a
+// of body 2, chain b of body 1).  Slot p < FB_ZCAP holds the p-th element of chain a counted from its end dof upwards
+// (= chainlen[la] - chainlen[k] for dof k on the chain); slot FB_ZCAP + p the p-th element of chain b, used only below the point
+// where b joins a (the common ancestors carry the sum J_a - J_b in their chain-a slot).  48 floats per row instead of nv = 114.
+#define FB_ZCAP 24      // longest dof chain a row may have (fly: 20)
+#define FB_JROW (2 * FB_ZCAP)
+#define EJC(arr, r, slot) AT(arr, (r) * FB_JROW + (slot))
 #define EA(arr, r, c) AT(arr, (r) * FB_MAXEFC + (c))
 #define EW(slot, r) AT(d.efc_w, (slot) * FB_MAXEFC + (r))
 
@@ -694,7 +700,6 @@ FB_DEV float contact_J(const DevModel& m, const DevData& d, int e, V3 f, V3 pos,
 //   phase 1: A = Z Z^T  (= J M^-1 J^T, the unregularised Delassus matrix)
 struct ShNone { int dummy; };
 #define FB_ROW_ARGS const DevModel& m, const DevData& d, ShCon& sh, int e, int lane, int y
-#define FB_ZCAP 24      // longest dof chain the projection scratch holds (fly: 20)
 // one dof chain of a row: Jacobian entries along the chain, then z = D^-1/2 L^-T j by a dense back-sweep over the
 // chain (the ancestors of the p-th chain element are the elements p+1.. and L[k_p][k_q] sits at qLD[Madr[k_p] + q - p])
 FB_DEV void proj_chain(const DevModel& m, const DevData& d, int e, int r, int last, float sgn, bool contact, V3 f, V3 pos, float* zc,
@@ -702,21 +707,25 @@ FB_DEV void proj_chain(const DevModel& m, const DevData& d, int e, int r, int la
   if (last < 0) return;
   int adr0 = m.dof_Madr[last], L = m.dof_chainlen[last];
   if (L > FB_ZCAP) { FB_FLAG_OR(4); L = FB_ZCAP; }
+  const int Lo = other_last >= 0 ? m.dof_chainlen[other_last] : 0, base = accumulate ? FB_ZCAP : 0;
+  // chain b joins chain a at its first common ancestor: from there up the entries are added to chain a's slots
+  int join = L;
+  if (accumulate) for (int p = 0; p < L; p++) if (in_chain(m, m.dof_anc[adr0 + p], other_last)) { join = p; break; }
   for (int p = 0; p < L; p++) {
     int k = m.dof_anc[adr0 + p];
     float v = contact ? sgn * contact_J(m, d, e, f, pos, k) : (p == 0 ? sgn : 0.0f);
     zc[p] = v;
-    if (accumulate && in_chain(m, k, other_last)) EJ(d.efc_J, r, k) += v; else EJ(d.efc_J, r, k) = v;
+    if (p >= join) EJC(d.efc_J, r, Lo - (L - p)) += v; else EJC(d.efc_J, r, base + p) = v;      // chainlen[k] = L - p
   }
   for (int p = 0; p < L; p++) {
     int k = m.dof_anc[adr0 + p], row = m.dof_Madr[k];
     float zk = zc[p], D = AT(d.qLD, row), zs = zk / D;          // unscaled rows: L[k][anc] z[k] = M'[k][anc] (z[k] / D[k])
     for (int q = p + 1; q < L; q++) zc[q] -= AT(d.qLD, row + (q - p)) * zs;
     float zf = zk / sqrtf(D);
-    if (accumulate && in_chain(m, k, other_last)) EJ(d.efc_Z, r, k) += zf; else EJ(d.efc_Z, r, k) = zf;
+    if (p >= join) EJC(d.efc_Z, r, Lo - (L - p)) += zf; else EJC(d.efc_Z, r, base + p) = zf;
   }
 }
-// all 32 lanes over rows: J (dense-by-dof storage) and Z = D^-1/2 L^-T J^T, chain by chain (a contact row is the
+// all 32 lanes over rows: J (chain-sparse storage, see EJC) and Z = D^-1/2 L^-T J^T, chain by chain (a contact row is the
 // difference of two single-chain rows; the sweep is linear)
 FB_DEV void kproj_p0(FB_ROW_ARGS) {
   int n = AT(d.nefc, 0);
@@ -741,6 +750,19 @@ FB_DEV void kproj_p0(FB_ROW_ARGS) {
   }
 }
 // A = Z Z^T (= J M^-1 J^T, the unregularised Delassus matrix), packed lower triangle; pairs dealt to all lanes
+// Z[r] . Z[c] restricted to one chain of row c (`cl` = its end dof, `cbase` = its slot base); chain b stops where it joins chain a
+FB_DEV float zdot_chain(const DevModel& m, const DevData& d, int e, int r, int rla, int rlb, int Lra, int Lrb, int c, int cl, int cbase, int stop_at) {
+  if (cl < 0) return 0.0f;
+  const int adr = m.dof_Madr[cl]; int L = m.dof_chainlen[cl]; if (L > FB_ZCAP) L = FB_ZCAP;
+  float s = 0;
+  for (int p = 0; p < L; p++) {
+    const int k = m.dof_anc[adr + p], ck = L - p;
+    if (stop_at >= 0 && in_chain(m, k, stop_at)) break;          // from here up the entries live in (and were counted with) chain a
+    if (in_chain(m, k, rla)) s += EJC(d.efc_Z, r, Lra - ck) * EJC(d.efc_Z, c, cbase + p);
+    else if (in_chain(m, k, rlb)) s += EJC(d.efc_Z, r, FB_ZCAP + Lrb - ck) * EJC(d.efc_Z, c, cbase + p);
+  }
+  return s;
+}
 FB_DEV void kproj_p1(FB_ROW_ARGS) {
   int n = AT(d.nefc, 0), npair = n * (n + 1) / 2;
   for (int idx = y; idx < npair; idx += FB_NY) {
@@ -748,15 +770,9 @@ FB_DEV void kproj_p1(FB_ROW_ARGS) {
     while (r * (r + 1) / 2 > idx) r--;
     while ((r + 1) * (r + 2) / 2 <= idx) r++;
     int c = idx - r * (r + 1) / 2;
-    int rla = AT(d.efc_la, r), rlb = AT(d.efc_lb, r);
-    float sacc = 0; int la = AT(d.efc_la, c), lb = AT(d.efc_lb, c);
-    while (la >= 0 || lb >= 0) {
-      int k = la > lb ? la : lb;
-      if (la == k) la = m.dof_parentid[la];
-      if (lb == k) lb = m.dof_parentid[lb];
-      if (in_chain(m, k, rla) || in_chain(m, k, rlb)) sacc += EJ(d.efc_Z, r, k) * EJ(d.efc_Z, c, k);
-    }
-    AT(d.efc_A, idx) = sacc;
+    const int rla = AT(d.efc_la, r), rlb = AT(d.efc_lb, r), cla = AT(d.efc_la, c), clb = AT(d.efc_lb, c);
+    const int Lra = rla >= 0 ? m.dof_chainlen[rla] : 0, Lrb = rlb >= 0 ? m.dof_chainlen[rlb] : 0;
+    AT(d.efc_A, idx) = zdot_chain(m, d, e, r, rla, rlb, Lra, Lrb, c, cla, 0, -1) + zdot_chain(m, d, e, r, rla, rlb, Lra, Lrb, c, clb, FB_ZCAP, cla);
   }
 }
 // aref and b = J qacc_smooth - aref for every row.  J qacc_smooth = Z (D^-1/2 L^-T qfrc_smooth); that vector is
@@ -771,14 +787,14 @@ FB_DEV void kref(FB_PHASE_ARGS) {
     float vel = 0, as = 0; const int la = rc.la, lb = rc.lb;
     if (la >= 0) {
       int adr = m.dof_Madr[la], len = m.dof_chainlen[la];
-      for (int t = 0; t < len; t++) { int k = m.dof_anc[adr + t]; vel += EJ(d.efc_J, r, k) * AT(d.qvel, k); as += EJ(d.efc_Z, r, k) * XS(k); }
+      for (int t = 0; t < len; t++) { int k = m.dof_anc[adr + t]; vel += EJC(d.efc_J, r, t) * AT(d.qvel, k); as += EJC(d.efc_Z, r, t) * XS(k); }
     }
     if (lb >= 0) {
       int adr = m.dof_Madr[lb], len = m.dof_chainlen[lb];
       for (int t = 0; t < len; t++) {
         int k = m.dof_anc[adr + t];
         if (la >= 0 && k <= la && la <= m.dof_subend[k]) break;      // common ancestors were counted with chain a
-        vel += EJ(d.efc_J, r, k) * AT(d.qvel, k); as += EJ(d.efc_Z, r, k) * XS(k);
+        vel += EJC(d.efc_J, r, FB_ZCAP + t) * AT(d.qvel, k); as += EJC(d.efc_Z, r, FB_ZCAP + t) * XS(k);
       }
     }
     float aref = -EFC(d.efc_B, r) * vel - EFC(d.efc_K, r) * EFC(d.efc_imp, r) * (EFC(d.efc_pos, r) - EFC(d.efc_margin, r));

@@ -309,17 +309,18 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
   // valid address, and are discarded by a select), so two rows x four dofs x {J, Z} are in flight together.
   WPAR_BEGIN
     if (lane == 0) { AT(d.niter, 0) = niter; if (d.do_integrate) AT(d.prev_n, 0) = n; }
-    float sj[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0}; int se[4];
+    float sj[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0}; int se[4], ck[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; se[i] = k < m.nv ? m.dof_subend[k] : -1; }
+    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; se[i] = k < m.nv ? m.dof_subend[k] : -1; ck[i] = k < m.nv ? m.dof_chainlen[k] : 0; }
 #pragma unroll 2
     for (int r = 0; r < n; r++) {
       const int la = (int)SV(S_LA, r), lb = (int)SV(S_LB, r); const float f = SV(W_F, r);
+      const int La = la >= 0 ? m.dof_chainlen[la] : 0, Lb = lb >= 0 ? m.dof_chainlen[lb] : 0;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int k = lane + 32 * i;
-        const bool in = (k <= la && la <= se[i]) || (k <= lb && lb <= se[i]);
-        const int idx = in ? r * m.nv + k : 0;
+        const bool ina = (k <= la && la <= se[i]), in = ina || (k <= lb && lb <= se[i]);
+        const int idx = in ? r * FB_JROW + (ina ? La - ck[i] : FB_ZCAP + Lb - ck[i]) : 0;      // chain-sparse rows (fb_constraint.h: EJC)
         const float vj = AT(d.efc_J, idx), vz = AT(d.efc_Z, idx);
         sj[i] += in ? vj * f : 0.0f; sz[i] += in ? vz * f : 0.0f;
       }

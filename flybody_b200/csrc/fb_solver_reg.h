@@ -90,19 +90,20 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
   LREG(float, lam); LREG(float, jar); LREG(float, f); LREG(float, res); LREG(float, dl); LREG(float, adl); LREG(float, e0); LREG(float, e1);
   LREG(float, j1); LREG(float, j2); LREG(float, hf1); LREG(float, hf2); LREG(float, he01); LREG(float, he02); LREG(float, he11); LREG(float, he12);
   LREG(float, ja1); LREG(float, ja2); LREG(float, jv1); LREG(float, jv2); LREG(float, tmp); LREG(float, tmp2); LREG(float, chg);
-  LREG(int, kind); LREG(int, state); LREG(int, hst); LREG(int, colx); LREG(int, la); LREG(int, lb);
+  LREG(int, kind); LREG(int, state); LREG(int, hst); LREG(int, colx); LREG(int, la); LREG(int, lb); LREG(int, cla); LREG(int, clb);
   int niter = 0;
   if (n > 0) {
     // ---- stage: row constants into registers, A into shared memory (full, symmetric), warm start from the previous forces
     WPAR_BEGIN {
       const int r = lane;
-      L(kind) = 0; L(D) = 0; L(b) = 0; L(Rr) = 0; L(mu) = 0; L(c1) = 0; L(c2) = 0; L(lam) = 0; L(la) = -1; L(lb) = -1;
+      L(kind) = 0; L(D) = 0; L(b) = 0; L(Rr) = 0; L(mu) = 0; L(c1) = 0; L(c2) = 0; L(lam) = 0; L(la) = -1; L(lb) = -1; L(cla) = 0; L(clb) = 0;
       L(state) = 0; L(hst) = 0; L(f) = 0; L(hf1) = 0; L(hf2) = 0; L(e0) = 0; L(e1) = 0; L(he01) = 0; L(he02) = 0; L(he11) = 0; L(he12) = 0; L(chg) = 0;
       if (r < n) {
         int tp = EFC(d.efc_type, r);
         if (tp == FB_CT_ELLIPTIC) { int ci = EFC(d.efc_id, r); L(kind) = 1 + (r - AT(d.con_efcadr, ci)); L(mu) = AT(d.con_mu, ci); L(c1) = CON_F(d.con_fric, ci, 0, 2); L(c2) = CON_F(d.con_fric, ci, 1, 2); }
         L(D) = EFC(d.efc_D, r); L(b) = EFC(d.efc_b, r); L(Rr) = EFC(d.efc_R, r);
         L(la) = AT(d.efc_la, r); L(lb) = AT(d.efc_lb, r);
+        L(cla) = L(la) >= 0 ? m.dof_chainlen[L(la)] : 0; L(clb) = L(lb) >= 0 ? m.dof_chainlen[L(lb)] : 0;
         int key = AT(d.efc_key, r), pn = AT(d.prev_n, 0); float l0 = 0;
         NOUNROLL for (int q = 0; q < pn; q++) if (AT(d.prev_key, q) == key) { l0 = AT(d.prev_lam, q); break; }
         L(lam) = l0;
@@ -270,17 +271,17 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
   // ---- qfrc_constraint = J^T f and Z^T f, per dof (see ksolve_impl); row data comes from the lane registers
   WPAR_BEGIN
     if (lane == 0) { AT(d.niter, 0) = niter; if (d.do_integrate) AT(d.prev_n, 0) = n; }
-    float sj[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0}; int se[4];
+    float sj[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0}; int se[4], ck[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; se[i] = k < m.nv ? m.dof_subend[k] : -1; }
+    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; se[i] = k < m.nv ? m.dof_subend[k] : -1; ck[i] = k < m.nv ? m.dof_chainlen[k] : 0; }
 #pragma unroll 2
     for (int r = 0; r < n; r++) {
-      const int la_ = SHF(la, r), lb_ = SHF(lb, r); const float fr = SHF(f, r);
+      const int la_ = SHF(la, r), lb_ = SHF(lb, r), La_ = SHF(cla, r), Lb_ = SHF(clb, r); const float fr = SHF(f, r);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int k = lane + 32 * i;
-        const bool in = (k <= la_ && la_ <= se[i]) || (k <= lb_ && lb_ <= se[i]);
-        const int idx = in ? r * m.nv + k : 0;
+        const bool ina = (k <= la_ && la_ <= se[i]), in = ina || (k <= lb_ && lb_ <= se[i]);
+        const int idx = in ? r * FB_JROW + (ina ? La_ - ck[i] : FB_ZCAP + Lb_ - ck[i]) : 0;      // chain-sparse rows (fb_constraint.h: EJC)
         const float vj = AT(d.efc_J, idx), vz = AT(d.efc_Z, idx);
         sj[i] += in ? vj * fr : 0.0f; sz[i] += in ? vz * fr : 0.0f;
       }

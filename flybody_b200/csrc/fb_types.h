@@ -132,7 +132,7 @@ struct DevData {
   // constraints
   int *nefc; int *efc_type, *efc_id;
   float *efc_pos, *efc_margin, *efc_D, *efc_R, *efc_K, *efc_B, *efc_imp, *efc_aref, *efc_b, *efc_force, *efc_jarws;
-  float *efc_J, *efc_Z;        // [MAXEFC*nv] dense-by-dof (only the row's dof set is touched)
+  float *efc_J, *efc_Z;        // [MAXEFC][FB_JROW] chain-sparse rows (fb_constraint.h: EJC)
   float *efc_A, *efc_G;        // packed lower triangles
   int *efc_key, *prev_key, *prev_n; float *prev_lam;   // warm start: constraint forces of the previous solve, matched by row identity
   float *efc_w;                // [8*MAXEFC] solver work vectors

@@ -622,7 +622,7 @@ static int alloc_data(FbSim* s, int N) {
   // large, sparsely touched arrays last
   FA(efc_w, (size_t)S_NSLOT * FB_MAXEFC)
   FA(efc_A, (size_t)FB_MAXEFC * (FB_MAXEFC + 1) / 2) FA(efc_G, (size_t)FB_MAXEFC * (FB_MAXEFC + 1) / 2)
-  FA(efc_J, (size_t)FB_MAXEFC * m.nv) FA(efc_Z, (size_t)FB_MAXEFC * m.nv)
+  FA(efc_J, (size_t)FB_MAXEFC * FB_JROW) FA(efc_Z, (size_t)FB_MAXEFC * FB_JROW)
 #undef FA
 #undef IA
   off = (off + 31) & ~(size_t)31;              // records start on 128-byte boundaries
