@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- env-steps/sec of the batched walk_imitation physics step (BASELINE.json metric).
+"""bench.py -- env-steps/sec of the batched fly environments (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA arm
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the restated mj_step on the host cores
 
-One "step" = one control step (10 physics substeps of 2e-4 s) of every environment of the batch:
-workload `walk_imitation 4096 envs, random policy` per GPU (BASELINE.json configs[1]); N>1 shards
-envs across ranks (weak scaling, 4096 envs per GPU) and gathers the packed observations + rewards to
-rank 0 over NCCL every control step (configs[3]).
+One "step" = one control step of every environment of the batch (walk: 10 physics substeps of 2e-4 s): workload
+`walk_imitation 4096 envs, random policy` per GPU (BASELINE.json configs[1]).  N > 1 is configs[3]: envs sharded across ranks
+(weak scaling, 4096 per GPU) and, every control step INSIDE the timed region, the actor-loop exchange over NCCL: actions
+[N x 59] scattered from rank 0, task observations (741 floats) + reward + discount + step_type gathered to rank 0.
 
-  value : env-steps/s, whole job, actions already resident in HBM, device-timed (CUDA events on the
-          stepper's stream, max over ranks), gather included for N>1
-  e2e   : the same metric through the public API `flybody_b200.fly_envs.walk_imitation(n_envs).step(a)`
-          with pinned host actions in and the observation record out every step
+Steady state: the env runs with its task hooks on the device (auto-reset at termination / episode end,
+observation program, reward); before the warm-up a PRE-ROLL of one episode length (235 control steps) with random actions resets
+env e at step hash(e) % 235, so the timed window sees flies at every phase of an episode -- standing, falling, lying on the floor
+under random torques -- not the first 50 ms after a standing reset.  `--preroll 0` reproduces the old standing-start window.
+
+  value : env-steps/s, whole job, actions resident in HBM, `env.step_device(actions)` (task hooks + physics + observation
+          program, no host copies), device-timed with CUDA events on the stepper's stream, max over ranks; exchange included for N>1
+  e2e   : the same metric through the public API `fly_envs.walk_imitation(n_envs, device_task=True).step(host_actions)` with
+          pinned host actions in and the observation rows + (reward, discount, step_type) out every step (+ the exchange for N>1)
+  extra : (N = 1) the flight_imitation workload (BASELINE.json configs[2]) measured the same way, as a nested block
 """
 import argparse
 import json
@@ -28,22 +34,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 4096
-N_SUB = 10
-BYTES_PER_ENV_SUBSTEP = 3628          # fp32 state read+write per physics substep (W model)
-BYTES_PER_ENV_STEP = BYTES_PER_ENV_SUBSTEP * N_SUB
-# --workload: the headline is walk (BASELINE.json configs[1]); flight is configs[2], same contract, not the driver's default
-WORKLOADS = {'walk': dict(model='walk', n_sub=10, bytes_substep=3628, act_scale=0.5, n_action=59, dt='2e-4',
-                          config='BASELINE.json configs[1]; N>1: configs[3] sharding + NCCL obs gather to rank 0'),
-             'flight': dict(model='flight', n_sub=4, bytes_substep=1284, act_scale=0.2, n_action=12, dt='5e-5',
+# algorithmic bytes per env-substep: fp32 state read + written by one physics substep
+WORKLOADS = {'walk': dict(model='walk', n_sub=10, bytes_substep=3628, act_scale=0.5, n_action=59, dt='2e-4', episode=235,
+                          config='BASELINE.json configs[1]; N>1: configs[3] sharding + NCCL action scatter / observation gather with rank 0'),
+             'flight': dict(model='flight', n_sub=4, bytes_substep=1284, act_scale=0.2, n_action=12, dt='5e-5', episode=135,
                             config='BASELINE.json configs[2]: ellipsoid fluid / wing forces, wing-beat pattern generator')}
-WL = WORKLOADS['walk']
-
-
-def set_workload(name):
-    global WL, N_SUB, BYTES_PER_ENV_SUBSTEP, BYTES_PER_ENV_STEP
-    WL = WORKLOADS[name]
-    N_SUB, BYTES_PER_ENV_SUBSTEP = WL['n_sub'], WL['bytes_substep']
-    BYTES_PER_ENV_STEP = BYTES_PER_ENV_SUBSTEP * N_SUB
 
 
 def measured_peaks():
@@ -82,110 +77,89 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][2]), 'reasons': reasons, 'samples': len(sm)}
 
 
-def walk_reset_batch(m, n, rs):
-    if WL['model'] == 'flight':                      # hovering start 1 cm above the floor (flight_imitation's synthetic trajectory height)
-        qq = np.tile(m.qpos0, (n, 1)); qq[:, 2] = 1.0
-        return qq
+def start_state(m, wl, rs):
+    """the state the CPU arm's single env starts from: the task's reset pose + the bench's joint noise"""
+    if wl['model'] == 'flight':
+        q = m.qpos0.copy(); q[2] = 1.0
+        return q
     q0 = m.qpos0.copy()
     for side in ('left', 'right'):
         for dof, val in (('yaw', 1.5), ('roll', 0.7), ('pitch', -1.0)):
             q0[m.jnt_qposadr_of(f'walker/wing_{dof}_{side}')] = val
-    qq = np.tile(q0, (n, 1))
-    # config 2: U(-0.05, 0.05) rad on the 48 actuated leg joints decorrelates the envs
     leg = [m.jnt_qposadr[m.actuator_trnid[i]] for i in range(m.nu)
            if m.actuator_trntype[i] == 0 and any(t in m.meta['actuator_names'][i] for t in ('T1', 'T2', 'T3'))]
-    qq[:, leg] += rs.uniform(-0.05, 0.05, (n, len(leg)))
-    return qq
+    q0[leg] += rs.uniform(-0.05, 0.05, len(leg))
+    return q0
 
 
-# ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------ CPU arm
+def host_cores():
+    """cores this process may run on (cgroup / affinity aware; os.cpu_count() is the machine's)"""
+    try:
+        return sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+
+
 def cpu_oracle_worker(args):
-    """One host core: restated mj_step (oracle), `steps` control steps of walk_imitation, random actions."""
-    seed, budget_s, max_steps = args
+    """One host core: the restated mj_step (oracle, fp64, MuJoCo's tree-sparse factorisation), one env, random actions, with the
+    episode structure of the GPU arm (reset to the start pose every `episode` control steps or on a diverged state)."""
+    seed, budget_s, max_steps, core, wl = args
+    if core is not None:
+        try:
+            os.sched_setaffinity(0, {core})
+        except Exception:
+            pass
     from flybody_b200.flymodel import load_model
     from oracle import fly_oracle as fo
-    m = load_model(WL['model'])
-    o = fo.Oracle(m)                       # MuJoCo default tolerance (1e-8)
+    m = load_model(wl['model'])
+    o = fo.Oracle(m)                       # the model's own solver tolerance (1e-8), sparse mode
     rs = np.random.RandomState(seed)
-    o.reset(walk_reset_batch(m, 1, rs)[0])
-    acts = rs.uniform(-WL['act_scale'], WL['act_scale'], (max_steps, m.nu))
-    for k in range(3):
-        o.set(fo.CTRL, acts[k]); o.control_step(N_SUB)
+    o.reset(start_state(m, wl, rs))
+    acts = rs.uniform(-wl['act_scale'], wl['act_scale'], (256, m.nu))
+    phase = int(rs.randint(wl['episode']))         # envs are spread over the phases of an episode, like the GPU arm after its pre-roll
+    for k in range(3 + phase % 7):
+        o.set(fo.CTRL, acts[k]); o.control_step(wl['n_sub'])
     t0 = time.perf_counter()
     n = 0
     while n < max_steps and time.perf_counter() - t0 < budget_s:
-        o.set(fo.CTRL, acts[n]); o.control_step(N_SUB)
-        n += 1
-        if o.get(fo.FLAGS)[0] != 0:
-            o.reset(walk_reset_batch(m, 1, rs)[0])
+        o.set(fo.CTRL, acts[n % 256]); o.control_step(wl['n_sub'])
+        n += 1; phase += 1
+        if phase >= wl['episode'] or o.get(fo.FLAGS)[0] != 0:
+            o.reset(start_state(m, wl, rs)); phase = 0
     return n, time.perf_counter() - t0
 
 
-def cpu_baseline(budget_s=10.0, max_steps=4000, cores=None):
+def cpu_baseline(wl, budget_s=10.0, max_steps=100000):
     import multiprocessing as mp
     from oracle import fly_oracle as fo
     fo.build()
-    cores = cores or os.cpu_count()
-    with mp.get_context('fork').Pool(cores) as pool:
-        res = pool.map(cpu_oracle_worker, [(1000 + i, budget_s, max_steps) for i in range(cores)])
+    cores = host_cores()
+    n1, t1 = cpu_oracle_worker((999, min(2.0, budget_s), max_steps, cores[0], wl))      # one process alone on the box
+    with mp.get_context('fork').Pool(len(cores)) as pool:
+        res = pool.map(cpu_oracle_worker, [(1000 + i, budget_s, max_steps, c, wl) for i, c in enumerate(cores)])
     rate = sum(n / t for n, t in res)
-    return {'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{cores} processes x ~{budget_s:.0f}s of {WL["model"]}_imitation control steps ({N_SUB} substeps, random actions), '
-                      f'oracle/fly_oracle.c (restated mj_step, fp64, dense; NOT MuJoCo, which is not installable here and would be an estimated '
-                      f'20-40x faster per core under load: DESIGN.md section 6), '
-                      f'{sum(n for n, _ in res)} env-steps total',
-            'per_core': rate / cores}
+    return {'value': rate, 'unit': 'env-steps/s', 'cores': len(cores), 'kind': 'port',
+            'sample': f'{len(cores)} pinned processes (one per core of os.sched_getaffinity) x ~{budget_s:.0f} s of {wl["model"]}_imitation control steps '
+                      f'({wl["n_sub"]} substeps, random actions, reset every {wl["episode"]} steps), oracle/fly_oracle.c: restated mj_step, fp64, '
+                      f'gcc -O3 -mavx2, tree-sparse L^T D L + low-rank Newton Hessian as MuJoCo structures it; NOT MuJoCo itself (not installable '
+                      f'here); {sum(n for n, _ in res)} env-steps total',
+            'per_core': rate / len(cores), 'single_process_per_core': n1 / t1,
+            'machine_cpu_count': os.cpu_count()}
 
 
-def cpu_kernel_source_worker(args):
-    """One host core: the step kernels' own source compiled for the host (tests/_emu, g++ -O2, fp32, sparse factorisation, dual
-    Newton) stepping a few envs -- a measured stand-in for what an optimised CPU engine does per core, next to the dense oracle."""
-    seed, budget_s, emu = args
-    from flybody_b200.flymodel import load_model
-    from flybody_b200 import stepper as st
-    m = load_model(WL['model'])
-    n = 4
-    sim = st.BatchedStepper(m, n, lib_path=emu)
-    rs = np.random.RandomState(seed)
-    sim.reset(walk_reset_batch(m, n, rs))
-    acts = rs.uniform(-WL['act_scale'], WL['act_scale'], (64, n, m.nu)).astype(np.float32)
-    for k in range(2):
-        sim.set_control(acts[k]); sim.step(N_SUB)
-    t0 = time.perf_counter(); steps = 0
-    while time.perf_counter() - t0 < budget_s:
-        sim.set_control(acts[steps % 64]); sim.step(N_SUB); steps += 1
-    return steps * n, time.perf_counter() - t0
-
-
-def cpu_kernel_source_baseline(budget_s=5.0, cores=None):
-    """-> extra JSON block: env-steps/s of the host-emulation build of the kernel source on all host cores (None if it is absent)."""
-    import multiprocessing as mp
-    import __graft_entry__ as ge
-    if not os.path.exists(ge.EMU):
-        return None
-    cores = cores or os.cpu_count()
-    with mp.get_context('fork').Pool(cores) as pool:
-        res = pool.map(cpu_kernel_source_worker, [(2000 + i, budget_s, ge.EMU) for i in range(cores)])
-    rate = sum(n / t for n, t in res)
-    return {'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'per_core': rate / cores,
-            'what': 'the step kernels\' source compiled for the host (tests/_emu/libfb_emu.so: g++ -O2, fp32, sparse L^T D L, dual Newton), one '
-                    f'process per core x 4 envs x ~{budget_s:.0f}s; test artefact, never loaded by the product path -- reported as a measured, '
-                    'stronger CPU number than the dense fp64 oracle of cpu_baseline'}
-
-
-def run_reference(args):
+def run_reference(args, wl):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    per_step_budget = 4.0
-    cb = cpu_baseline(budget_s=per_step_budget * max(1, min(args.steps, 5)), cores=os.cpu_count())
+    cb = cpu_baseline(wl, budget_s=4.0 * max(1, min(args.steps, 5)))
     wall = time.perf_counter() - t0
-    line = {'impl': 'reference', 'metric': f'env-steps/sec on {WL["model"]}_imitation (control steps of {N_SUB} substeps)', 'value': cb['value'],
+    line = {'impl': 'reference', 'metric': f'env-steps/sec on {wl["model"]}_imitation (control steps of {wl["n_sub"]} substeps)', 'value': cb['value'],
             'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 / cb['per_core'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'{WL["model"]}_imitation, random policy, one env per host core (reference scaling model: '
+            'config': {'workload': f'{wl["model"]}_imitation, random policy, one env per host core (reference scaling model: '
                                    'one env per actor process, train_dmpo_ray.py:206-227)', 'cores': cb['cores']},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -193,97 +167,114 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-# ------------------------------------------------------------------------------------------------
-class CudaView:
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def make_env(wl, N, local, seed, device_task=True):
+    from flybody_b200 import fly_envs
+    if wl['model'] == 'walk':
+        return fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=N, device=local, reset_noise=0.05, seed=seed, device_task=device_task)
+    return fly_envs.flight_imitation(n_envs=N, device=local, seed=seed, device_task=device_task)
 
 
-def run_ours(args):
+def measure(wl, args, world, rank, local, with_exchange):
+    """-> dict of raw measurements of one workload on this rank (rank 0 aggregates)"""
     import torch
     import torch.distributed as dist
-    from flybody_b200.flymodel import load_model
     from flybody_b200 import stepper as st
-    from flybody_b200 import fly_envs, sharding
+    dev = torch.device('cuda', local)
+    N, K, W, A = args.envs, args.steps, args.warmup, wl['n_action']
+    env = make_env(wl, N, local, 1234 + rank, device_task=True)
+    env.reset()
+    sim = env.physics.stepper
+    stream = torch.cuda.ExternalStream(sim.stream, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    P = args.preroll if args.preroll >= 0 else wl['episode']
+    n_act_rows = 64                                                    # a ring of resident random action batches
+    acts = (torch.rand((n_act_rows, N, A), device=dev, generator=gen) - 0.5) * (2 * wl['act_scale'])
+    # config 4 exchange buffers: rank 0 is the actor (policy side)
+    obs_dim = None
+    xb = {}
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device; the stepper has no CPU path (use --impl reference for the CPU arm)')
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # stdout carries exactly one JSON line (NCCL prints its version banner otherwise)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    N = args.envs
-    m = load_model(WL['model'])
-    rs = np.random.RandomState(sharding.rank_seed(1234, rank))
-    sim = st.BatchedStepper(m, N, device=local)
-    Np = sim.n_envs_padded
-    sim.reset(walk_reset_batch(m, N, rs))
-    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device('cuda', local))
-    obs_ptr, obs_dim = sim.obs_ptr()
-    obs = torch.as_tensor(CudaView(obs_ptr, (N, obs_dim)), device=f'cuda:{local}')
-    K, W = args.steps, args.warmup
-    gen = torch.Generator(device=f'cuda:{local}'); gen.manual_seed(1234 + rank)
-    acts = (torch.rand((K + W, N, m.nu), device=f'cuda:{local}', generator=gen) - 0.5) * (2 * WL['act_scale'])      # ctrl rows [N][nu], resident in HBM
-    # identity permutation between action and ctrl order is irrelevant for a random policy
-    gather_list = [torch.empty((N, obs_dim), device=f'cuda:{local}') for _ in range(world)] if (world > 1 and rank == 0) else None
-    bad_total = 0
+    def exchange(obs, out, k):
+        """actions for every rank leave rank 0, observations + (reward, discount, step_type) of every rank arrive on rank 0"""
+        if not with_exchange:
+            return acts[k % n_act_rows]
+        if 'a_loc' not in xb:
+            xb['a_loc'] = torch.empty((N, A), device=dev)
+            if rank == 0:
+                xb['a_all'] = (torch.rand((world, N, A), device=dev, generator=gen) - 0.5) * (2 * wl['act_scale'])
+                xb['obs_all'] = [torch.empty_like(obs) for _ in range(world)]
+                xb['out_all'] = [torch.empty_like(out) for _ in range(world)]
+        if obs is not None:
+            dist.gather(obs, xb['obs_all'] if rank == 0 else None, dst=0)
+            dist.gather(out, xb['out_all'] if rank == 0 else None, dst=0)
+        dist.scatter(xb['a_loc'], [xb['a_all'][r] for r in range(world)] if rank == 0 else None, src=0)
+        return xb['a_loc']
+
+    state = {'obs': None, 'out': None}
 
     def one_step(k):
         with torch.cuda.stream(stream):
-            sim.set_control_device(acts[k].data_ptr())
-            sim.step(N_SUB)
-            sim.pack_obs()
-            if world > 1:
-                sharding.gather_observations(obs, world, rank, gather_list)
+            a = exchange(state['obs'], state['out'], k)
+            state['obs'], state['out'] = env.step_device(a)
 
+    # ---- pre-roll: one episode length with staggered forced resets -> envs at every phase of an episode
+    t_pre = time.perf_counter()
+    if P > 0:
+        ids = np.arange(N)
+        slot = ((ids.astype(np.uint64) * np.uint64(2654435761)) >> np.uint64(7)) % np.uint64(P)
+        for k in range(P):
+            env.request_reset(ids[slot == k])
+            one_step(k)
     for k in range(W):
         one_step(k)
     sim.sync(); torch.cuda.synchronize()
+    pre_s = time.perf_counter() - t_pre
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local); sampler.start()
     l0 = sim.launch_count
+    resets0 = int(env.device_reset_count())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        for k in range(W, W + K):
-            one_step(k)
+        for k in range(K):
+            one_step(W + k)
         ev1.record(stream)
     sim.sync(); torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     launches = sim.launch_count - l0
-    # the same K steps once more with a CUDA event pair around every kernel launch (this pass cannot replay the step graph,
-    # so it is kept out of `value`): per-kernel durations for the roofline block
+    resets = int(env.device_reset_count()) - resets0
+    nefc = sim.get(st.NEFC)[:, 0].astype(np.int64); ncon = sim.get(st.NCON)[:, 0].astype(np.int64)
+    flags = sim.get(st.FLAGS)[:, 0].astype(np.int64)
+    # exchange alone (same buffers, no physics): what the NCCL part costs per control step
+    xms = 0.0
+    if with_exchange:
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            for k in range(3):
+                exchange(state['obs'], state['out'], k)
+            x0.record(stream)
+            for k in range(K):
+                exchange(state['obs'], state['out'], k)
+            x1.record(stream)
+        torch.cuda.synchronize()
+        xms = x0.elapsed_time(x1) / K
+    # the same K steps with a CUDA event pair around every kernel launch (cannot replay the step graph -> kept out of `value`)
     sim.profile(True)
     pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         pv0.record(stream)
-        for k in range(W, W + K):
-            one_step(k)
+        for k in range(K):
+            one_step(W + K + k)
         pv1.record(stream)
     sim.sync(); torch.cuda.synchronize()
-    ms_profiled = pv0.elapsed_time(pv1)
+    ms_prof = pv0.elapsed_time(pv1)
     prof = sim.profile_read(); sim.profile(False)
-    if world > 1:
-        t = torch.tensor([ms], device=f'cuda:{local}'); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-        dist.barrier()
-    flags = sim.get(st.FLAGS)[:, 0]
-    bad_total = int((flags != 0).sum())
-
-    # ---- e2e through the public env API (host actions in pinned memory, observation record out)
-    if WL['model'] == 'walk':
-        env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=N, device=local, reset_noise=0.05, seed=1234 + rank,
-                                      device_task=not args.host_task)
-    else:
-        env = fly_envs.flight_imitation(n_envs=N, device=local, seed=1234 + rank, device_task=not args.host_task)
-    env.reset()
-    na = WL['n_action']
-    host_act = torch.empty((K + W, N, na), dtype=torch.float32).pin_memory()
-    host_act.copy_(torch.from_numpy(rs.uniform(-WL['act_scale'], WL['act_scale'], (K + W, N, na)).astype(np.float32)))
+    # ---- e2e through the public API: pinned host actions in, observation rows + (reward, discount, step_type) out, every step
+    rs = np.random.RandomState(4321 + rank)
+    host_act = torch.empty((K + W, N, A), dtype=torch.float32).pin_memory()
+    host_act.copy_(torch.from_numpy(rs.uniform(-wl['act_scale'], wl['act_scale'], (K + W, N, A)).astype(np.float32)))
     a_np = host_act.numpy()
     for k in range(W):
         env.step(a_np[k])
@@ -292,59 +283,103 @@ def run_ours(args):
         dist.barrier()
     t0 = time.perf_counter()
     for k in range(W, W + K):
-        ts = env.step(a_np[k])
+        env.step(a_np[k])
+        if with_exchange:
+            with torch.cuda.stream(stream):
+                exchange(state['obs'], state['out'], k)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=f'cuda:{local}'); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
     sampler.stop_flag = True; sampler.join(timeout=2)
-    clocks = sampler.summary()
+    if world > 1:
+        t = torch.tensor([ms, e2e_s, xms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms, e2e_s, xms = [float(x) for x in t.tolist()]
+        r = torch.tensor([resets, int((flags & 1).sum()), int((flags & 6 != 0).sum())], device=dev); dist.all_reduce(r); resets, bad, over = [int(x) for x in r.tolist()]
+    else:
+        bad, over = int((flags & 1).sum()), int(((flags & 6) != 0).sum())
+    res = dict(ms=ms, e2e_s=e2e_s, xms=xms, launches=int(launches), prof=prof, ms_prof=ms_prof, resets=resets, bad=bad, over=over, pre_s=pre_s, P=P,
+               clocks=sampler.summary(), h2d=int(env.h2d_bytes_per_step), d2h=int(env.d2h_bytes_per_step), record_bytes=int(sim.record_bytes),
+               obs_dim=int(state['obs'].shape[1]),
+               nefc_hist={f'<={b}': int((nefc <= b).sum()) for b in (8, 16, 24, 32, 48, 64, 96, 128, 160)}, nefc_mean=float(nefc.mean()), nefc_max=int(nefc.max()),
+               ncon_mean=float(ncon.mean()), ncon_max=int(ncon.max()), share_global_solver=float((nefc > 32).mean()))
+    env.close()
+    return res
 
+
+def line_of(wl, args, world, r):
+    N, K = args.envs, args.steps
+    peak, peak_src = measured_peaks()
+    total = N * world
+    prof = r['prof']
+    stage = {k: v for k, v in prof.items() if v[1] > 0}
+    dom_name, (dom_ms, dom_n) = max(stage.items(), key=lambda kv: kv[1][0])
+    step_ms_sum = sum(v[0] for v in stage.values())
+    avg_launch_s = dom_ms / max(dom_n, 1) * 1e-3
+    substeps_per_launch = max(1, round(K * wl['n_sub'] / max(dom_n, 1)))
+    achieved = wl['bytes_substep'] * N * substeps_per_launch / avg_launch_s / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        ent = t.get('kernels', {}).get(f'{wl["model"]}:{dom_name}')
+        if ent:
+            traffic, traffic_src = ent['dram_bytes_per_launch'], ent.get('source')
+    bytes_step = wl['bytes_substep'] * wl['n_sub']
+    return {
+        'metric': f'env-steps/sec on {wl["model"]}_imitation (control steps of {wl["n_sub"]} substeps)', 'value': total * K / (r['ms'] * 1e-3), 'unit': 'env-steps/s',
+        'n_gpus': world, 'steps': K, 'warmup': args.warmup, 'ms_per_step': r['ms'] / K, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{wl["model"]}_imitation {N} envs per GPU, random policy U(-{wl["act_scale"]},{wl["act_scale"]}), {wl["n_sub"]} substeps x {wl["dt"]} s ({wl["config"]})',
+                   'envs_per_gpu': N, 'total_envs': total, 'n_substeps': wl['n_sub'],
+                   'steady_state': f'pre-roll of {r["P"]} control steps with staggered forced resets (envs at every phase of a {wl["episode"]}-step episode), then {args.warmup} warm-up steps; '
+                                   f'{r["resets"]} auto-resets inside the timed window (counted in the work)' if r['P'] > 0 else 'no pre-roll: standing start',
+                   'constraint_rows': {'mean': r['nefc_mean'], 'max': r['nefc_max'], 'hist_envs': r['nefc_hist'], 'contacts_mean': r['ncon_mean'], 'contacts_max': r['ncon_max'],
+                                       'share_of_envs_on_global_memory_solver_path(nefc>32)': r['share_global_solver']},
+                   'l2': f'inputs larger than L2: every launch streams the env records ({r["record_bytes"] / 1e3:.0f} KB each, {r["record_bytes"] * N / 1e9:.2f} GB per GPU vs 126 MB L2); no explicit flush',
+                   'parallelism': f'env-sharded x{world}' + (f', per control step inside the timed region: NCCL scatter of actions [{total}x{wl["n_action"]}] from rank 0 + gather of task observations '
+                                                             f'[{total}x{r["obs_dim"]}] and (reward, discount, step_type) to rank 0; exchange alone {r["xms"]:.3f} ms/step '
+                                                             f'({100 * r["xms"] / (r["ms"] / K):.1f} % of the step), limiter: rank-0 NVLink ingest of the gather' if world > 1 else ''),
+                   'diverged_envs_flagged': r['bad'], 'capacity_overflow_envs_flagged': r['over'], 'preroll_wall_s': r['pre_s']},
+        'clocks': r['clocks'], 'gpu_launches': r['launches'],
+        'e2e': {'value': total * K / r['e2e_s'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h'],
+                'api': f'flybody_b200.fly_envs.{wl["model"]}_imitation(n_envs, device_task=True).step(action)' + (' on every rank + the rank-0 exchange' if world > 1 else '')},
+        'roofline': {'bound': 'hbm', 'kernel': dom_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+                     'how': f'algorithmic bytes = {wl["bytes_substep"]} B/env-substep x {N} envs x {substeps_per_launch} substep(s) per launch / mean CUDA-event duration of the '
+                            f'"{dom_name}" kernel over a second pass of the same {K} steps with an event pair around every launch ({dom_n} launches, '
+                            f'{r["ms_prof"] / K:.3f} ms per step in that pass; `value` is the pass without per-launch events, which replays the step graph); whole-step algorithmic GB/s = '
+                            f'{bytes_step * total * K / (r["ms"] * 1e-3) / 1e9:.2f}',
+                     'kernel_share': dom_ms / max(step_ms_sum, 1e-9),
+                     'stage_ms_per_step': {k: v[0] / K for k, v in stage.items()}},
+    }
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the stepper has no CPU path (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # stdout carries exactly one JSON line
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    r = measure(wl, args, world, rank, local, with_exchange=world > 1)
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        total_envs = N * world
-        value = total_envs * K / (ms * 1e-3)
-        # dominant kernel of the step
-        dom = max(prof.items(), key=lambda kv: kv[1][0])
-        dom_name, (dom_ms, dom_n) = dom
-        step_ms_sum = sum(v[0] for v in prof.values())
-        avg_launch_s = dom_ms / max(dom_n, 1) * 1e-3
-        # one launch of a stage kernel = one substep over N envs; fused launch groupings (FB_FUSE) run 1 or N_SUB whole
-        # substeps per launch: the substeps a launch of the dominant kernel covers = timed substeps / its launch count
-        substeps_per_launch = max(1, round(K * N_SUB / max(dom_n, 1)))
-        alg_bytes_per_launch = BYTES_PER_ENV_SUBSTEP * N * substeps_per_launch
-        achieved = alg_bytes_per_launch / avg_launch_s / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
-        if os.path.exists(tp) and WL['model'] == 'walk':        # the ncu capture is of the walk model's kernels
-            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
-        line = {
-            'metric': f'env-steps/sec on {WL["model"]}_imitation (control steps of {N_SUB} substeps)', 'value': value, 'unit': 'env-steps/s',
-            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{WL["model"]}_imitation {N} envs per GPU, random policy U(-{WL["act_scale"]},{WL["act_scale"]}), {N_SUB} substeps x {WL["dt"]} s '
-                                   f'({WL["config"]})',
-                       'envs_per_gpu': N, 'total_envs': total_envs, 'n_substeps': N_SUB,
-                       'l2': f'inputs larger than L2: every launch streams the env records ({sim.record_bytes / 1e6:.2f} MB each, {sim.record_bytes * N / 1e9:.2f} GB per GPU vs 126 MB L2); no explicit flush',
-                       'parallelism': f'env-sharded x{world}' + (', torch.distributed NCCL gather of packed obs per control step' if world > 1 else ''),
-                       'unstable_envs_flagged': bad_total},
-            'clocks': clocks, 'gpu_launches': int(launches),
-            'e2e': {'value': total_envs * K / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(env.h2d_bytes_per_step),
-                    'd2h_bytes_per_step': int(env.d2h_bytes_per_step), 'api': f'flybody_b200.fly_envs.{WL["model"]}_imitation(n_envs' + ('' if args.host_task else ', device_task=True') + ').step(action)'},
-            'roofline': {'bound': 'hbm', 'kernel': dom_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src,
-                         'how': f'algorithmic bytes = {BYTES_PER_ENV_SUBSTEP} B/env-substep x {N} envs x {substeps_per_launch} substep(s) per launch / mean CUDA-event duration of the '
-                                f'"{dom_name}" kernel over a second pass of the same {K} steps with an event pair around every launch ({dom_n} launches, '
-                                f'{ms_profiled / K:.3f} ms per step in that pass; `value` is the pass without per-launch events, which replays the step graph); whole-step algorithmic GB/s = '
-                                f'{BYTES_PER_ENV_STEP * total_envs * K / (ms * 1e-3) / 1e9:.2f}',
-                         'kernel_share': dom_ms / max(step_ms_sum, 1e-9),
-                         'stage_ms_per_step': {k: v[0] / K for k, v in prof.items() if v[1] > 0}},
-        }
+        line = line_of(wl, args, world, r)
+        if world == 1 and not args.no_extra and args.workload == 'walk':
+            wf = WORKLOADS['flight']
+            try:
+                rf = measure(wf, args, 1, 0, local, False)
+                lf = line_of(wf, args, 1, rf)
+                line['extra'] = {'flight_imitation': {k: lf[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'config', 'gpu_launches', 'e2e', 'roofline')}}
+            except Exception as e:                                   # the headline must not depend on the extra block
+                line['extra'] = {'flight_imitation': {'error': repr(e)}}
         if world == 1 and not args.no_cpu:
-            line['cpu_baseline'] = cpu_baseline(budget_s=args.cpu_seconds)
-            line['cpu_kernel_source'] = cpu_kernel_source_baseline(budget_s=min(args.cpu_seconds, 5.0))
+            line['cpu_baseline'] = cpu_baseline(wl, budget_s=args.cpu_seconds)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -357,15 +392,16 @@ def main():
     ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='envs per GPU')
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the nested flight_imitation block')
+    ap.add_argument('--preroll', type=int, default=-1, help='control steps of staggered-reset pre-roll before the warm-up (-1: one episode length; 0: standing start)')
     ap.add_argument('--workload', default='walk', choices=sorted(WORKLOADS), help='walk = the headline (BASELINE configs[1]); flight = configs[2]')
-    ap.add_argument('--host-task', action='store_true', help='e2e leg: task hooks in host numpy instead of on the device (fb_task_*)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    set_workload(args.workload)
+    wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_ours(args)
+        run_ours(args, wl)
 
 
 if __name__ == '__main__':

@@ -1225,6 +1225,23 @@ int fb_task_reset_all(FbHandle s) {
   h2d(s->task_host.needs_reset, ones.data(), sizeof(int) * ones.size());
   return 0;
 }
+int fb_task_request_reset(FbHandle s, const int32_t* env_ids, int n) {
+  if (!s || !s->d.task || (n > 0 && !env_ids) || n < 0) return -1;
+  if (n == 0) return 0;
+  if (sync_stream(s) != 0) return -2;
+  const int one = 1;
+  for (int k = 0; k < n; k++) {
+    if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_task_request_reset: env id out of range"; return -1; }
+    h2d(s->task_host.needs_reset + env_ids[k], &one, sizeof(int));
+  }
+  return 0;
+}
+int fb_task_episodes(FbHandle s, int32_t* dst) {
+  if (!s || !s->d.task || !dst) return -1;
+  if (sync_stream(s) != 0) return -2;
+  d2h(dst, s->task_host.episode, sizeof(int) * (size_t)s->d.N);
+  return 0;
+}
 int fb_task_uniforms(FbHandle s, const int32_t* env_ids, int n, const float* u) {
   if (!s || !s->d.task || !env_ids || !u || n < 0) return -1;
   if (sync_stream(s) != 0) return -2;

@@ -547,6 +547,20 @@ class BatchedFlyEnv:
         return TimeStep(step_type,
                         self._out4[:, 0].astype(np.float64), self._out4[:, 1].astype(np.float64), self._observation(self._rec))
 
+    def request_reset(self, env_ids):
+        """Restart the listed envs at the next step (their action of that step is dropped and they report FIRST), whatever their
+        episode state -- an actor restarting single environments."""
+        ids = np.asarray(env_ids, np.int64).reshape(-1)
+        if len(ids) == 0:
+            return
+        if self._device_task:
+            self._sim.task_request_reset(ids)
+        self._needs_reset[ids] = True
+
+    def device_reset_count(self):
+        """episodes started so far, summed over the envs (device-side task logic: read from the device's episode counters)"""
+        return int(self._sim.task_episodes().sum()) if self._device_task else int(self.n_resets)
+
     def step_device(self, action):
         """Device-resident control step for a policy that lives on the GPU: `action` is a CUDA tensor / array exposing
         `__cuda_array_interface__` (fp32, [n_envs, n_action], on this env's device); returns zero-copy torch views
@@ -562,6 +576,7 @@ class BatchedFlyEnv:
         cai = action.__cuda_array_interface__
         assert tuple(cai['shape']) == (self.n_envs, self._action_spec.shape[0]) and cai['typestr'] == '<f4', cai
         self._sim.task_step(cai['data'][0], self._n_sub, is_device=True)
+        self._needs_reset[:] = False            # (host mirror of the device's reset flags: not read back on this path)
         if getattr(self, '_dev_views', None) is None:
             obs_ptr, dim, out_ptr = self._sim.task_ptrs()
 

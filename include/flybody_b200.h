@@ -312,6 +312,11 @@ int fb_task_program(FbHandle h, const FbTaskProgram* p);
 int fb_task_step(FbHandle h, const float* action, int is_device, int n_substeps);
 /* Mark every env for reset at the next fb_task_step (env.reset()).                                                    */
 int fb_task_reset_all(FbHandle h);
+/* Mark the listed envs for reset at the next fb_task_step, whatever their episode state (an actor restarting single
+ * environments; bench.py's pre-roll uses it to spread the envs over the phases of an episode).                          */
+int fb_task_request_reset(FbHandle h, const int32_t* env_ids, int n);
+/* Per-env count of episodes started so far (resets done by the device-side task logic), int32 [n_envs] to the host.    */
+int fb_task_episodes(FbHandle h, int32_t* dst);
 /* Uniform numbers in [0,1) consumed by the listed envs' next reset (flight: wing-beat phase); without them the device
  * draws from a counter hash of (seed, env, episode).                                                                 */
 int fb_task_uniforms(FbHandle h, const int32_t* env_ids, int n, const float* u);

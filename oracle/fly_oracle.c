@@ -48,7 +48,10 @@ typedef struct OrcData {
   double *Sang, *Slin;          /* per dof motion subspace */
   double *inert10;              /* per body: m, h[3], I_O[6] (xx,yy,zz,xy,xz,yz) about world origin */
   double *crb10;
-  double *M, *L;                /* dense nv*nv, and its Cholesky factor */
+  double *M, *L;                /* dense nv*nv, and its Cholesky factor (dense mode) */
+  /* sparse mode (default; orc_set_dense(d, 1) selects the dense factor for the self-check tests): L^T D L of M in MuJoCo's
+   * qLD layout (mj_factorM: row i = (i,i), (i,parent(i)), ... at dof_Madr[i]) and of M + h diag(damping) for the Euler step */
+  int dense; int* chainlen; double *qLD, *qLDiagInv, *qLDe, *qLDeDiagInv;
   /* velocity stage */
   double *bvel, *bacc;          /* per body spatial velocity / bias acceleration */
   double *qfrc_bias, *qfrc_passive, *qfrc_actuator, *qfrc_smooth, *qacc_smooth, *qfrc_constraint;
@@ -150,6 +153,9 @@ OrcData* orc_create(const FbModel* m) {
   d->site_xpos=dalloc(3*m->nsite); d->site_xmat=dalloc(9*m->nsite); d->subtree_com=dalloc(3*nb);
   d->Sang=dalloc(3*nv); d->Slin=dalloc(3*nv); d->inert10=dalloc(10*nb); d->crb10=dalloc(10*nb);
   d->M=dalloc((size_t)nv*nv); d->L=dalloc((size_t)nv*nv);
+  d->qLD=dalloc(m->nM); d->qLDiagInv=dalloc(nv); d->qLDe=dalloc(m->nM); d->qLDeDiagInv=dalloc(nv);
+  d->chainlen=(int*)calloc(nv>0?nv:1,sizeof(int));
+  for (int i=0;i<nv;i++) { int c=0; for (int j=i;j>=0;j=m->dof_parentid[j]) c++; d->chainlen[i]=c; }
   d->bvel=dalloc(6*nb); d->bacc=dalloc(6*nb);
   d->qfrc_bias=dalloc(nv); d->qfrc_passive=dalloc(nv); d->qfrc_actuator=dalloc(nv); d->qfrc_smooth=dalloc(nv);
   d->qacc_smooth=dalloc(nv); d->qfrc_constraint=dalloc(nv);
@@ -169,7 +175,7 @@ void orc_destroy(OrcData* d) {
     d->bvel,d->bacc,d->qfrc_bias,d->qfrc_passive,d->qfrc_actuator,d->qfrc_smooth,d->qacc_smooth,d->qfrc_constraint,
     d->act_dot,d->actuator_force,d->actuator_length,d->actuator_velocity,d->moment,d->efc_J,d->sensordata,d->sensor_sum,d->wk};
   for (size_t i=0;i<sizeof(ptrs)/sizeof(ptrs[0]);i++) free(ptrs[i]);
-  free(d->hf_data); free(d->hf_pair);
+  free(d->hf_data); free(d->hf_pair); free(d->qLD); free(d->qLDiagInv); free(d->qLDe); free(d->qLDeDiagInv); free(d->chainlen);
   free(d);
 }
 
@@ -252,25 +258,51 @@ static void orc_kinematics(OrcData* d) {
 }
 
 /* K2: composite rigid body inertia -> dense M, Cholesky (MuJoCo mj_crb + mj_factorM; A.3)      */
+/* contiguous dot product; `omp simd` lets the compiler vectorise the reduction (-fopenmp-simd, no runtime) */
+static inline double dotn(const double* a, const double* b, int n) {
+  double s=0;
+#pragma omp simd reduction(+:s)
+  for (int k=0;k<n;k++) s+=a[k]*b[k];
+  return s;
+}
 static int cholesky(double* L, const double* A, int n) {
   memcpy(L, A, sizeof(double)*n*n);
   for (int j=0;j<n;j++) {
-    double s = L[j*n+j];
-    for (int k=0;k<j;k++) s -= L[j*n+k]*L[j*n+k];
+    double s = L[j*n+j] - dotn(L+j*n, L+j*n, j);
     if (s < MINVAL) return -1;
     s = sqrt(s); L[j*n+j]=s;
-    for (int i=j+1;i<n;i++) {
-      double t = L[i*n+j];
-      for (int k=0;k<j;k++) t -= L[i*n+k]*L[j*n+k];
-      L[i*n+j]=t/s;
-    }
+    for (int i=j+1;i<n;i++) L[i*n+j]=(L[i*n+j]-dotn(L+i*n, L+j*n, j))/s;
   }
   return 0;
 }
 static void chol_solve(const double* L, double* x, int n) {   /* in place: x = (L L^T)^-1 x */
-  for (int i=0;i<n;i++) { double s=x[i]; for (int k=0;k<i;k++) s-=L[i*n+k]*x[k]; x[i]=s/L[i*n+i]; }
-  for (int i=n-1;i>=0;i--) { double s=x[i]; for (int k=i+1;k<n;k++) s-=L[k*n+i]*x[k]; x[i]=s/L[i*n+i]; }
+  for (int i=0;i<n;i++) x[i]=(x[i]-dotn(L+i*n,x,i))/L[i*n+i];
+  for (int i=n-1;i>=0;i--) { double xi=x[i]/L[i*n+i]; x[i]=xi; const double* Li=L+i*n;     /* column sweep: rows of L stay contiguous */
+#pragma omp simd
+    for (int k=0;k<i;k++) x[k]-=Li[k]*xi; }
 }
+/* MuJoCo mj_factorI / mj_solveLD on the tree-sparse inertia (engine_core_smooth.c): qLD <- L^T D L of (M + diag(add)) */
+static void factor_sparse(const OrcData* d, double* qLD, double* diaginv, const double* add) {
+  const FbModel* m=d->m; int nv=m->nv;
+  for (int i=0;i<nv;i++) { int a=m->dof_Madr[i], t=0; for (int j=i;j>=0;j=m->dof_parentid[j],t++) qLD[a+t]=d->M[(size_t)i*nv+j]; if (add) qLD[a]+=add[i]; }
+  for (int k=nv-1;k>=0;k--) {
+    int ak=m->dof_Madr[k], aki=ak+1, i=m->dof_parentid[k];
+    while (i>=0) {
+      double tmp=qLD[aki]/qLD[ak]; int ai=m->dof_Madr[i], cnt=d->chainlen[i];
+      for (int c=0;c<cnt;c++) qLD[ai+c]-=tmp*qLD[aki+c];
+      qLD[aki]=tmp; i=m->dof_parentid[i]; aki++;
+    }
+    diaginv[k]=1.0/qLD[ak];
+  }
+}
+static void solve_sparse(const OrcData* d, const double* qLD, const double* diaginv, double* x) {
+  const FbModel* m=d->m; int nv=m->nv;
+  for (int i=nv-1;i>=0;i--) { double xi=x[i]; if (xi==0) continue; int a=m->dof_Madr[i]+1; for (int j=m->dof_parentid[i];j>=0;j=m->dof_parentid[j]) x[j]-=qLD[a++]*xi; }
+  for (int i=0;i<nv;i++) x[i]*=diaginv[i];
+  for (int i=0;i<nv;i++) { int a=m->dof_Madr[i]+1; double s=x[i]; for (int j=m->dof_parentid[i];j>=0;j=m->dof_parentid[j]) s-=qLD[a++]*x[j]; x[i]=s; }
+}
+/* x <- M^-1 x with whichever factor the mode keeps */
+static void solve_M(const OrcData* d, double* x) { if (d->dense) chol_solve(d->L,x,d->m->nv); else solve_sparse(d,d->qLD,d->qLDiagInv,x); }
 static void orc_crb(OrcData* d) {
   const FbModel* m=d->m; int nb=m->nbody, nv=m->nv;
   memcpy(d->crb10, d->inert10, sizeof(double)*10*nb);
@@ -285,7 +317,7 @@ static void orc_crb(OrcData* d) {
     }
     d->M[i*nv+i] += m->dof_armature[i];
   }
-  cholesky(d->L, d->M, nv);
+  if (d->dense) cholesky(d->L, d->M, nv); else factor_sparse(d, d->qLD, d->qLDiagInv, NULL);
 }
 
 /* Jacobian of world point `p` attached to body b: jacp/jacr are 3 x nv dense (may be NULL) */
@@ -1172,20 +1204,66 @@ static void ls_eval(const OrcData* d, double alpha, const double* jar, const dou
 
 static void mul_M(const OrcData* d, double* r, const double* x) {
   int nv=d->m->nv;
-  for (int i=0;i<nv;i++) { double s=0; const double* row=d->M+(size_t)i*nv; for (int k=0;k<nv;k++) s+=row[k]*x[k]; r[i]=s; }
+  for (int i=0;i<nv;i++) r[i]=dotn(d->M+(size_t)i*nv,x,nv);
+}
+
+/* Newton direction in sparse mode.  H = M + U U^T with one column of U per active constraint direction: sqrt(D_r) J_r for an
+ * active plain / bottom-zone row, and J_c^T G_c for a contact in the cone's middle zone, G_c G_c^T its 3x3 PSD Hessian block
+ * (pivoted Cholesky, rank <= 3).  Then  H^-1 g = M^-1 g - W (I + U^T W)^-1 U^T M^-1 g,  W = M^-1 U  (Woodbury), with M^-1 from the
+ * tree-sparse factor: nc sparse solves + an nc x nc Cholesky instead of an nv x nv one.  Same direction as the dense path to
+ * round-off (tests/test_oracle_invariants.py holds the two modes against each other); MuJoCo reaches the same H^-1 g with a
+ * Cholesky of H that it updates by rank-1 steps as constraint states change (engine_solver.c).  Returns -1 if nc > nv. */
+static int newton_direction_lowrank(OrcData* d, int n, const int* state, const double* hcone, const double* grad, double* search, double* work) {
+  const FbModel* m=d->m; int nv=m->nv, nc=0;
+  double* U=work;                                   /* [nc][nv], then W [nc][nv], then S [nc][nc], t[nc] */
+  int cap=nv;                                        /* work holds 2 nv^2 doubles */
+  for (int r=0;r<n;r++) {
+    if (state[r]==1) {
+      if (nc>=cap) return -1;
+      double e=sqrt(d->efc_D[r]); const double* J=d->efc_J+(size_t)r*nv; double* u=U+(size_t)nc*nv;
+      for (int k=0;k<nv;k++) u[k]=e*J[k];
+      nc++;
+    } else if (state[r]==2 && d->con[d->efc_id[r]].efc_address==r) {
+      const double* Hc=hcone+9*d->efc_id[r]; double G[9]={0}, A[9]; memcpy(A,Hc,sizeof(A));
+      double scale=fabs(A[0])+fabs(A[4])+fabs(A[8]);
+      for (int j=0;j<3;j++) {                         /* outer-product Cholesky; a vanishing pivot drops the column (PSD, rank-deficient) */
+        double piv=A[3*j+j];
+        if (piv<=1e-14*scale) continue;
+        double sq=sqrt(piv);
+        for (int i=j;i<3;i++) G[3*i+j]=A[3*i+j]/sq;
+        for (int i=j;i<3;i++) for (int k=j;k<3;k++) A[3*i+k]-=G[3*i+j]*G[3*k+j];
+        if (nc>=cap) return -1;
+        double* u=U+(size_t)nc*nv; memset(u,0,sizeof(double)*nv);
+        for (int p=j;p<3;p++) { double g=G[3*p+j]; if (g==0) continue; const double* J=d->efc_J+(size_t)(r+p)*nv; for (int k=0;k<nv;k++) u[k]+=g*J[k]; }
+        nc++;
+      }
+    }
+  }
+  double* W=U+(size_t)nc*nv; double* S=W+(size_t)nc*nv; double* t=S+(size_t)nc*nc; double* LS=t+nc;
+  if ((size_t)(LS-work)+(size_t)nc*nc > (size_t)2*nv*nv) return -1;
+  for (int c=0;c<nc;c++) { memcpy(W+(size_t)c*nv,U+(size_t)c*nv,sizeof(double)*nv); solve_sparse(d,d->qLD,d->qLDiagInv,W+(size_t)c*nv); }
+  for (int a=0;a<nc;a++) for (int b=0;b<=a;b++) { double v=dotn(U+(size_t)a*nv,W+(size_t)b*nv,nv); if (a==b) v+=1.0; S[a*nc+b]=v; S[b*nc+a]=v; }
+  for (int i=0;i<nv;i++) search[i]=-grad[i];
+  solve_sparse(d,d->qLD,d->qLDiagInv,search);
+  if (nc==0) return 0;
+  for (int c=0;c<nc;c++) t[c]=dotn(U+(size_t)c*nv,search,nv);
+  if (cholesky(LS,S,nc)!=0) return -1;
+  chol_solve(LS,t,nc);
+  for (int c=0;c<nc;c++) { double tc=t[c]; const double* w=W+(size_t)c*nv; for (int k=0;k<nv;k++) search[k]-=w[k]*tc; }
+  return 0;
 }
 
 static void orc_solve(OrcData* d) {
   const FbModel* m=d->m; int nv=m->nv, n=d->nefc;
   /* qacc_smooth */
   for (int i=0;i<nv;i++) { d->qfrc_smooth[i]=d->qfrc_passive[i]-d->qfrc_bias[i]+d->qfrc_actuator[i]; d->qacc_smooth[i]=d->qfrc_smooth[i]; }
-  chol_solve(d->L,d->qacc_smooth,nv);
+  solve_M(d,d->qacc_smooth);
   d->solver_niter=0;
   if (n==0) {
     memcpy(d->qacc,d->qacc_smooth,sizeof(double)*nv); memset(d->qfrc_constraint,0,sizeof(double)*nv);
     return;
   }
-  for (int i=0;i<n;i++) { double s=0; const double* J=d->efc_J+(size_t)i*nv; for (int k=0;k<nv;k++) s+=J[k]*d->qacc_smooth[k]; d->efc_b[i]=s-d->efc_aref[i]; }
+  for (int i=0;i<n;i++) { const double* J=d->efc_J+(size_t)i*nv; d->efc_b[i]=dotn(J,d->qacc_smooth,nv)-d->efc_aref[i]; }
   double* wk=d->wk; double *Ma=wk, *grad=wk+nv, *search=wk+2*nv, *Mv=wk+3*nv, *tmp=wk+4*nv, *H=wk+8*nv, *LH=H+(size_t)nv*nv;
   double jar[ORC_MAXEFC], jv[ORC_MAXEFC], force[ORC_MAXEFC]; int state[ORC_MAXEFC];
   double* hcone=(double*)malloc(sizeof(double)*9*(d->ncon+1));
@@ -1195,7 +1273,7 @@ static void orc_solve(OrcData* d) {
   double cost_ws, cost_sm;
   {
     double* a=d->qacc_warmstart;
-    for (int i=0;i<n;i++) { double s=0; const double* J=d->efc_J+(size_t)i*nv; for (int k=0;k<nv;k++) s+=J[k]*a[k]; jar[i]=s-d->efc_aref[i]; }
+    for (int i=0;i<n;i++) { const double* J=d->efc_J+(size_t)i*nv; jar[i]=dotn(J,a,nv)-d->efc_aref[i]; }
     cost_ws=constraint_update(d,jar,force,state,NULL);
     mul_M(d,Ma,a);
     double g=0; for (int i=0;i<nv;i++) g+=0.5*(Ma[i]-d->qfrc_smooth[i])*(a[i]-d->qacc_smooth[i]);
@@ -1206,7 +1284,7 @@ static void orc_solve(OrcData* d) {
   int maxiter=m->opt_iterations;
   double cost=0;
   for (int iter=0; iter<maxiter; iter++) {
-    for (int i=0;i<n;i++) { double s=0; const double* J=d->efc_J+(size_t)i*nv; for (int k=0;k<nv;k++) s+=J[k]*d->qacc[k]; jar[i]=s-d->efc_aref[i]; }
+    for (int i=0;i<n;i++) { const double* J=d->efc_J+(size_t)i*nv; jar[i]=dotn(J,d->qacc,nv)-d->efc_aref[i]; }
     cost=constraint_update(d,jar,force,state,hcone);
     mul_M(d,Ma,d->qacc);
     double gauss=0; for (int i=0;i<nv;i++) gauss+=0.5*(Ma[i]-d->qfrc_smooth[i])*(d->qacc[i]-d->qacc_smooth[i]);
@@ -1216,26 +1294,30 @@ static void orc_solve(OrcData* d) {
     for (int r=0;r<n;r++) { if (force[r]==0) continue; const double* J=d->efc_J+(size_t)r*nv; for (int k=0;k<nv;k++) grad[k]-=J[k]*force[r]; }
     double gnorm=0; for (int i=0;i<nv;i++) gnorm+=grad[i]*grad[i]; gnorm=sqrt(gnorm);
     if (scale*gnorm<tol) break;
+    if (!d->dense && newton_direction_lowrank(d,n,state,hcone,grad,search,H)==0) {
+      /* search = -H^-1 grad through the low-rank form of H (below); falls through to the dense factor when it does not apply */
+    } else {
     /* Hessian H = M + J^T D_active J + cone blocks */
-    memcpy(H,d->M,sizeof(double)*nv*nv);
-    for (int r=0;r<n;r++) {
-      if (state[r]==1) {
-        const double* J=d->efc_J+(size_t)r*nv; double D=d->efc_D[r];
-        for (int a=0;a<nv;a++) { if (J[a]==0) continue; double t=D*J[a]; for (int b=0;b<nv;b++) H[a*nv+b]+=t*J[b]; }
-      } else if (state[r]==2 && d->con[d->efc_id[r]].efc_address==r) {
-        const double* Hc=hcone+9*d->efc_id[r];
-        for (int p=0;p<3;p++) for (int q=0;q<3;q++) {
-          const double* Jp=d->efc_J+(size_t)(r+p)*nv; const double* Jq=d->efc_J+(size_t)(r+q)*nv; double hc=Hc[3*p+q];
-          if (hc==0) continue;
-          for (int a=0;a<nv;a++) { if (Jp[a]==0) continue; double t=hc*Jp[a]; for (int b=0;b<nv;b++) H[a*nv+b]+=t*Jq[b]; }
+      memcpy(H,d->M,sizeof(double)*nv*nv);
+      for (int r=0;r<n;r++) {
+        if (state[r]==1) {
+          const double* J=d->efc_J+(size_t)r*nv; double D=d->efc_D[r];
+          for (int a=0;a<nv;a++) { if (J[a]==0) continue; double t=D*J[a]; for (int b=0;b<nv;b++) H[a*nv+b]+=t*J[b]; }
+        } else if (state[r]==2 && d->con[d->efc_id[r]].efc_address==r) {
+          const double* Hc=hcone+9*d->efc_id[r];
+          for (int p=0;p<3;p++) for (int q=0;q<3;q++) {
+            const double* Jp=d->efc_J+(size_t)(r+p)*nv; const double* Jq=d->efc_J+(size_t)(r+q)*nv; double hc=Hc[3*p+q];
+            if (hc==0) continue;
+            for (int a=0;a<nv;a++) { if (Jp[a]==0) continue; double t=hc*Jp[a]; for (int b=0;b<nv;b++) H[a*nv+b]+=t*Jq[b]; }
+          }
         }
       }
+      if (cholesky(LH,H,nv)!=0) { d->flags|=1; break; }
+      for (int i=0;i<nv;i++) search[i]=-grad[i];
+      chol_solve(LH,search,nv);
     }
-    if (cholesky(LH,H,nv)!=0) { d->flags|=1; break; }
-    for (int i=0;i<nv;i++) search[i]=-grad[i];
-    chol_solve(LH,search,nv);
     /* exact line search on phi(alpha) = cost(qacc + alpha*search) */
-    for (int i=0;i<n;i++) { double s=0; const double* J=d->efc_J+(size_t)i*nv; for (int k=0;k<nv;k++) s+=J[k]*search[k]; jv[i]=s; }
+    for (int i=0;i<n;i++) { const double* J=d->efc_J+(size_t)i*nv; jv[i]=dotn(J,search,nv); }
     mul_M(d,Mv,search);
     double q1=0,q2=0; for (int i=0;i<nv;i++) { q1+=search[i]*(Ma[i]-d->qfrc_smooth[i]); q2+=0.5*search[i]*Mv[i]; }
     double v0,g0,h0; ls_eval(d,0.0,jar,jv,gauss,q1,q2,&v0,&g0,&h0);
@@ -1259,14 +1341,14 @@ static void orc_solve(OrcData* d) {
     double improvement=scale*(v0-v1);
     if (improvement<tol) {
       /* final gradient check happens at loop top on next pass only if iterations remain */
-      for (int i=0;i<n;i++) { double s=0; const double* J=d->efc_J+(size_t)i*nv; for (int k=0;k<nv;k++) s+=J[k]*d->qacc[k]; jar[i]=s-d->efc_aref[i]; }
+      for (int i=0;i<n;i++) { const double* J=d->efc_J+(size_t)i*nv; jar[i]=dotn(J,d->qacc,nv)-d->efc_aref[i]; }
       constraint_update(d,jar,force,state,NULL);
       break;
     }
     (void)tmp;
   }
   /* final forces at the solution */
-  for (int i=0;i<n;i++) { double s=0; const double* J=d->efc_J+(size_t)i*nv; for (int k=0;k<nv;k++) s+=J[k]*d->qacc[k]; jar[i]=s-d->efc_aref[i]; }
+  for (int i=0;i<n;i++) { const double* J=d->efc_J+(size_t)i*nv; jar[i]=dotn(J,d->qacc,nv)-d->efc_aref[i]; }
   constraint_update(d,jar,force,state,NULL);
   memcpy(d->efc_force,force,sizeof(double)*n); memcpy(d->efc_state,state,sizeof(int)*n);
   memset(d->qfrc_constraint,0,sizeof(double)*nv);
@@ -1308,8 +1390,8 @@ static void orc_noslip(OrcData* d) {
   for (int i=0;i<n;i++) {
     if (d->efc_type[i]!=CT_CONTACT_ELLIPTIC) continue;
     memcpy(MinvJT,d->efc_J+(size_t)i*nv,sizeof(double)*nv);
-    chol_solve(d->L,MinvJT,nv);
-    for (int j=0;j<n;j++) { double s=0; const double* J=d->efc_J+(size_t)j*nv; for (int k=0;k<nv;k++) s+=J[k]*MinvJT[k]; A[(size_t)i*n+j]=s; }
+    solve_M(d,MinvJT);
+    for (int j=0;j<n;j++) A[(size_t)i*n+j]=dotn(d->efc_J+(size_t)j*nv,MinvJT,nv);
   }
   double* f=d->efc_force;
   double scale=1.0/(m->stat_meaninertia*(nv>1?nv:1));
@@ -1347,7 +1429,7 @@ static void orc_noslip(OrcData* d) {
   memset(d->qfrc_constraint,0,sizeof(double)*nv);
   for (int r=0;r<n;r++) { if (f[r]==0) continue; const double* J=d->efc_J+(size_t)r*nv; for (int k=0;k<nv;k++) d->qfrc_constraint[k]+=J[k]*f[r]; }
   memcpy(MinvJT,d->qfrc_constraint,sizeof(double)*nv);
-  chol_solve(d->L,MinvJT,nv);
+  solve_M(d,MinvJT);
   for (int k=0;k<nv;k++) d->qacc[k]=d->qacc_smooth[k]+MinvJT[k];
   free(MinvJT); free(A);
 }
@@ -1447,7 +1529,12 @@ static void orc_euler(OrcData* d) {
   const FbModel* m=d->m; int nv=m->nv; double h=m->opt_timestep;
   double* qacc=d->wk; int anydamp=0;
   for (int i=0;i<nv;i++) if (m->dof_damping[i]>0) anydamp=1;
-  if (anydamp) {
+  if (anydamp && !d->dense) {          /* implicit joint damping: (M + h D) qacc' = f, tree-sparse factor */
+    double* hd=d->wk+nv; for (int i=0;i<nv;i++) hd[i]=h*m->dof_damping[i];
+    factor_sparse(d,d->qLDe,d->qLDeDiagInv,hd);
+    for (int i=0;i<nv;i++) qacc[i]=d->qfrc_smooth[i]+d->qfrc_constraint[i];
+    solve_sparse(d,d->qLDe,d->qLDeDiagInv,qacc);
+  } else if (anydamp) {
     double* H=d->wk+nv; double* LH=H+(size_t)nv*nv;
     memcpy(H,d->M,sizeof(double)*nv*nv);
     for (int i=0;i<nv;i++) H[i*nv+i]+=h*m->dof_damping[i];
@@ -1571,6 +1658,8 @@ void orc_set_hfield(OrcData* d, int geom, const double* size, int nrow, int ncol
   d->hf_pair=(int*)malloc(sizeof(int)*npair); memcpy(d->hf_pair,pair_geom,sizeof(int)*npair);
 }
 void orc_set_tolerance(OrcData* d, double tol) { d->solver_tolerance=tol; }
+/* 1: dense Cholesky of M and of M + h D (the original, simplest statement); 0 (default): MuJoCo's tree-sparse L^T D L */
+void orc_set_dense(OrcData* d, int dense) { d->dense=dense; }
 /* efc row data for tests: J (dense), aref, D, R ; returns nefc */
 int orc_get_efc(OrcData* d, double* J, double* aref, double* D, double* R, double* pos, int* type) {
   int nv=d->m->nv, n=d->nefc;

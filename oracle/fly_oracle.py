@@ -38,6 +38,7 @@ def lib():
         _LIB.orc_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _LIB.orc_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _LIB.orc_set_tolerance.argtypes = [C.c_void_p, C.c_double]
+        _LIB.orc_set_dense.argtypes = [C.c_void_p, C.c_int]
         _LIB.orc_get_efc.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     return _LIB
 
@@ -45,10 +46,13 @@ def lib():
 class Oracle:
     """One double-precision environment stepped by the restated pipeline."""
 
-    def __init__(self, model, tolerance=None):
+    def __init__(self, model, tolerance=None, dense=False):
+        """dense=True: the original dense statement (Cholesky of M, of M + hD and of the Newton Hessian); default: MuJoCo's
+        tree-sparse L^T D L for M and the low-rank form of the Newton Hessian -- same numbers to round-off, ~5x faster."""
         self.model = model
         self._l = lib()
         self._d = self._l.orc_create(C.byref(model.c))
+        self._l.orc_set_dense(self._d, 1 if dense else 0)
         if tolerance is not None:
             self._l.orc_set_tolerance(self._d, float(tolerance))
         self._buf = np.zeros(max(model.nv * model.nv, 16 * 64, 9 * model.nbody, 1024), np.float64)

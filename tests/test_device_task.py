@@ -133,3 +133,22 @@ def test_device_task_requires_shared_reference(emu, tmp_path):
     trl._write_walking_dataset(path, np.random.RandomState(0), nj=0, ns=0)
     with pytest.raises(NotImplementedError):
         fly_envs.walk_imitation(ref_path=path, n_envs=2, lib_path=emu, device_task=True)
+
+
+def test_request_reset_restarts_single_envs(emu):
+    """fb_task_request_reset: the listed envs restart at the next step (FIRST, action dropped), the others carry on; the device's
+    episode counters (fb_task_episodes) count it."""
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=4, lib_path=emu, device_task=True)
+    env.reset()
+    rs = np.random.RandomState(0)
+    for _ in range(3):
+        env.step(rs.uniform(-0.5, 0.5, (4, 59)).astype(np.float32))
+    ep0 = env._sim.task_episodes().copy()
+    env.request_reset([1, 3])
+    ts = env.step(rs.uniform(-0.5, 0.5, (4, 59)).astype(np.float32))
+    assert list(np.asarray(ts.step_type)) == [int(StepType.MID), int(StepType.FIRST), int(StepType.MID), int(StepType.FIRST)]
+    assert list(env._sim.task_episodes() - ep0) == [0, 1, 0, 1]
+    q = env._sim.get(st.QPOS)
+    assert np.allclose(q[1, :3], env._ref_qpos[0, :3], atol=1e-6) and not np.allclose(q[0, :3], env._ref_qpos[0, :3], atol=1e-6)
+    assert env.device_reset_count() == int(env._sim.task_episodes().sum())
+    env.close()

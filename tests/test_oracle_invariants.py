@@ -222,3 +222,30 @@ def test_mpr_capsule_against_round_ellipsoid_matches_the_analytic_sphere_capsule
         n, dist, pos, nrm = _convex(CAP, pc, Rc, [cr, ch, 0], ELL, ps, _rot(rs), [r] * 3)
         assert n == 1 and abs(dist - (gap - r - cr)) < 5e-6
         assert np.allclose(nrm, side, atol=1e-2)          # the portal normal is only as good as the 1e-6 support tolerance
+
+
+def test_sparse_and_dense_oracle_modes_agree():
+    """The oracle's default mode (MuJoCo's tree-sparse L^T D L of M and of M + hD, Newton direction through the low-rank form of
+    the Hessian) against its original dense statement (dense Cholesky everywhere): same forces / accelerations on hard random
+    states (30-70 constraint rows, cones in all three zones) and the same trajectory, to round-off."""
+    from flybody_b200.flymodel import load_model
+    from parity_common import random_state, reset_qpos
+    for variant, n_sub, scale in (('walk', 10, 0.5), ('flight', 4, 0.2)):
+        m = load_model(variant)
+        for seed in range(3):
+            q, v = random_state(m, seed, vel_scale=1.0 if variant == 'walk' else 20.0)
+            out = []
+            for dense in (True, False):
+                o = fo.Oracle(m, tolerance=1e-12, dense=dense)
+                o.reset(q, v); o.set(fo.CTRL, np.random.RandomState(seed).uniform(-scale, scale, m.nu)); o.forward()
+                out.append((o.get(fo.QACC), o.get(fo.EFC_FORCE), int(o.get(fo.NEFC)[0]), int(o.get(fo.SOLVER_NITER)[0])))
+            assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
+            assert np.abs(out[0][0] - out[1][0]).max() <= 1e-10 * np.abs(out[0][0]).max()
+            assert np.abs(out[0][1] - out[1][1]).max() <= 1e-10 * (np.abs(out[0][1]).max() + 1e-30)
+        traj = []
+        for dense in (True, False):
+            o = fo.Oracle(m, dense=dense); o.reset(reset_qpos(m)); rs = np.random.RandomState(1)
+            for k in range(15):
+                o.set(fo.CTRL, rs.uniform(-scale, scale, m.nu)); o.control_step(n_sub)
+            traj.append((o.qpos, o.qvel))
+        assert np.abs(traj[0][0] - traj[1][0]).max() < 1e-10 and np.abs(traj[0][1] - traj[1][1]).max() < 1e-8
