@@ -292,7 +292,7 @@ def measure(wl, args, world, rank, local, with_exchange):
     sampler.stop_flag = True; sampler.join(timeout=2)
     if world > 1:
         t = torch.tensor([ms, e2e_s, xms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms, e2e_s, xms = [float(x) for x in t.tolist()]
-        r = torch.tensor([resets, int((flags & 1).sum()), int((flags & 6 != 0).sum())], device=dev); dist.all_reduce(r); resets, bad, over = [int(x) for x in r.tolist()]
+        r = torch.tensor([resets, int((flags & 1).sum()), int(((flags & 6) != 0).sum())], device=dev); dist.all_reduce(r); resets, bad, over = [int(x) for x in r.tolist()]
     else:
         bad, over = int((flags & 1).sum()), int(((flags & 6) != 0).sum())
     res = dict(ms=ms, e2e_s=e2e_s, xms=xms, launches=int(launches), prof=prof, ms_prof=ms_prof, resets=resets, bad=bad, over=over, pre_s=pre_s, P=P,

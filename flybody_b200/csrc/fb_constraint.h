@@ -383,8 +383,10 @@ FB_DEV void make_frame(V3 n, V3 t, V3& f1, V3& f2) {   // mju_makeFrame
 // geom positions of this env into shared memory (coalesced), so that the pair loop does not touch the record
 FB_DEV void kcol_stage(FB_COL_ARGS) {
   float* gx = sh_dyn(sh); float* gn = gx + 3 * m.ngeom * FB_LANES;      // positions; normals (z axes) of the plane geoms
-  for (int i = y; i < 3 * m.ngeom; i += FB_NY) gx[i * FB_LANES + lane] = AT(d.geom_xpos, i);
-  for (int g = y; g < m.ngeom; g += FB_NY) if (m.geom_type[g] == FB_GEOM_PLANE) for (int c = 0; c < 3; c++) gn[(3 * g + c) * FB_LANES + lane] = AT(d.geom_xmat, 9 * g + 3 * c + 2);
+  for (int g = y; g < m.ngeom; g += FB_NY) {
+    V3 p = ld3(d.geom_xpos, g, d, e); gx[(3 * g) * FB_LANES + lane] = p.x; gx[(3 * g + 1) * FB_LANES + lane] = p.y; gx[(3 * g + 2) * FB_LANES + lane] = p.z;
+    if (m.geom_type[g] == FB_GEOM_PLANE) for (int c = 0; c < 3; c++) gn[(3 * g + c) * FB_LANES + lane] = AT(d.geom_xmat, FB_M3S * g + 3 * c + 2);
+  }
 }
 // Collision in three converged phases.  Broadphase and narrowphase are separated on purpose: in a fused pair loop the
 // whole warp pays for the narrowphase whenever ANY lane has a candidate in that iteration (68 iterations x ~1300 cycles);
@@ -587,7 +589,7 @@ FB_DEV bool limit_active(const DevModel& m, const DevData& d, int e, int j, int 
 }
 // phase 0/1: joint-limit rows (joints split into contiguous ranges over y so that rows stay in joint order)
 FB_DEV void kcon_p0(FB_CON_ARGS) {
-  prefetch_rec(d.qLD, m.nM, d, e, y); prefetch_rec(d.Sang, 3 * m.nv, d, e, y); prefetch_rec(d.Slin, 3 * m.nv, d, e, y);   // for the projection phases
+  prefetch_rec(d.qLD, m.nM, d, e, y); prefetch_rec(d.Sang, FB_V3S * m.nv, d, e, y); prefetch_rec(d.Slin, FB_V3S * m.nv, d, e, y);   // for the projection phases
   if (y >= FB_ROWPAR) return;
   int j0 = (int)((long)y * m.njnt / FB_ROWPAR), j1 = (int)((long)(y + 1) * m.njnt / FB_ROWPAR), c = 0; float dist;
   for (int j = j0; j < j1; j++) { if (!m.jnt_limited[j] || m.jnt_type[j] != FB_JNT_HINGE) continue; for (int side = -1; side <= 1; side += 2) c += limit_active(m, d, e, j, side, dist) ? 1 : 0; }
@@ -914,10 +916,10 @@ FB_DEV int qcqp2(float* res, const float* A, const float* b, float d0, float d1,
 FB_DEV void kfin_f1(FB_PHASE_ARGS) {
   float* xs = sh_dyn(sh);
   tsolve_stage_issue(m, d, sh, e, lane, y, d.qLD);
-  prefetch_rec(d.Sang, 3 * m.nv, d, e, y); prefetch_rec(d.Slin, 3 * m.nv, d, e, y); prefetch_rec(d.inert10, 10 * m.nbody, d, e, y); prefetch_rec(d.bfrc0, 6 * m.nbody, d, e, y);
+  prefetch_rec(d.Sang, FB_V3S * m.nv, d, e, y); prefetch_rec(d.Slin, FB_V3S * m.nv, d, e, y); prefetch_rec(d.inert10, FB_I10S * m.nbody, d, e, y); prefetch_rec(d.bfrc0, FB_S6S * m.nbody, d, e, y);
   if (d.do_integrate) prefetch_rec(d.qLDe, m.nM, d, e, y);   // second factor, staged after the first solve
   for (int i = y; i < m.nv; i += FB_NY) XS(i) = AT(d.qtmp, i) + AT(d.dof_isd, i) * AT(d.qfrc_zf, i);      // D^-1 u + D^-1/2 Z^T f
-  for (int k = y; k < 6 * m.nbody; k += FB_NY) AT(d.bfl, k) = 0;
+  for (int k = y; k < FB_S6S * m.nbody; k += FB_NY) AT(d.bfl, k) = 0;
 }
 FB_WARPFN void kfin_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) {      // qacc = L^-1 (...)
   WPAR_BEGIN tsolve_stage_wait(m, d, sh, e, 0, lane); WPAR_END
@@ -1105,11 +1107,11 @@ FB_DEV void kpack(const DevModel& m, const DevData& d, int e, int y, float inv_n
   for (int i = y; i < m.nsensordata; i += FB_NY) { o[k + i] = AT(d.sensor_sum, i) * inv_nsub; o[k + m.nsensordata + i] = AT(d.sensordata, i); }
   k += 2 * m.nsensordata;
   int rb = m.root_body[0];
-  if (y < 3) o[k + y] = AT(d.xpos, 3 * rb + y) + AT(d.ref, y);
+  if (y < 3) o[k + y] = AT(d.xpos, FB_V3S * rb + y) + AT(d.ref, y);
   k += 3;
-  if (y < 9) o[k + y] = AT(d.xmat, 9 * rb + y);
+  if (y < 9) o[k + y] = AT(d.xmat, FB_M3S * rb + y);
   k += 9;
-  for (int i = y; i < 3 * m.nsite; i += FB_NY) o[k + i] = AT(d.site_xpos, i) + AT(d.ref, i % 3);
+  for (int i = y; i < 3 * m.nsite; i += FB_NY) o[k + i] = AT(d.site_xpos, FB_V3S * (i / 3) + i % 3) + AT(d.ref, i % 3);
   k += 3 * m.nsite;
   if (y == 0) { o[k] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float a = AT(d.qacc, i); s2 += a * a; } o[k + 1] = s2; o[k + 2] = AT(d.time, 0); }
 }
@@ -1153,7 +1155,7 @@ FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e, int y) {
       } break;
       case FB_OBS_SCALARS: if (y == 0) { o[k] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; } o[k + 1] = s2; o[k + 2] = AT(d.time, 0); } break;
       case FB_OBS_ROOT_POSE: if (y < 3) o[k + y] = comp(rpos + ref, y); else if (y < 7) o[k + y] = AT(d.qpos, rq + y); break;
-      case FB_OBS_SUBTREE_COM: if (y < 3) { float mass = AT(d.crb10, 10 * a); o[k + y] = (mass > 0 ? AT(d.crb10, 10 * a + 1 + y) / mass : 0.0f) + AT(d.ref, y); } break;
+      case FB_OBS_SUBTREE_COM: if (y < 3) { float mass = AT(d.crb10, FB_I10S * a); o[k + y] = (mass > 0 ? AT(d.crb10, FB_I10S * a + 1 + y) / mass : 0.0f) + AT(d.ref, y); } break;
       default: break;
     }
   }
@@ -1278,8 +1280,8 @@ FB_DEV void ktask_after(const DevModel& m, const DevData& d, int e, int y) {
     V3 gp = v3(AT(d.qpos, t.ghost_qadr), AT(d.qpos, t.ghost_qadr + 1), AT(d.qpos, t.ghost_qadr + 2));      // the ghost as placed (offset included)
     Q4 gq = q4(AT(d.qpos, t.ghost_qadr + 3), AT(d.qpos, t.ghost_qadr + 4), AT(d.qpos, t.ghost_qadr + 5), AT(d.qpos, t.ghost_qadr + 6));
     V3 gcom = gp + mul(q2m(gq), v3(t.com_offset[0], t.com_offset[1], t.com_offset[2]));
-    float mass = AT(d.crb10, 10 * t.com_body);
-    V3 com = v3(AT(d.crb10, 10 * t.com_body + 1), AT(d.crb10, 10 * t.com_body + 2), AT(d.crb10, 10 * t.com_body + 3)) * (mass > 0 ? 1.0f / mass : 0.0f)
+    float mass = AT(d.crb10, FB_I10S * t.com_body);
+    V3 com = v3(AT(d.crb10, FB_I10S * t.com_body + 1), AT(d.crb10, FB_I10S * t.com_body + 2), AT(d.crb10, FB_I10S * t.com_body + 3)) * (mass > 0 ? 1.0f / mass : 0.0f)
              + v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
     V3 dv = gcom - com; float disp = sqrtf(dot(dv, dv));
     const float* rq = o + t.obs_refquat_off;

@@ -59,14 +59,39 @@ FB_DEV float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi 
 // arithmetic: rec * Np stays below 2^32 (checked in fb_create).
 #define AT(arr, i) (arr)[(unsigned)e * d.rec + (unsigned)(i)]
 
-FB_DEV V3 ld3(const float* arr, int i, const DevData& d, int e) { return v3(AT(arr, 3 * i), AT(arr, 3 * i + 1), AT(arr, 3 * i + 2)); }
-FB_DEV void st3(float* arr, int i, const DevData& d, int e, V3 v) { AT(arr, 3 * i) = v.x; AT(arr, 3 * i + 1) = v.y; AT(arr, 3 * i + 2) = v.z; }
-FB_DEV Q4 ld4(const float* arr, int i, const DevData& d, int e) { return q4(AT(arr, 4 * i), AT(arr, 4 * i + 1), AT(arr, 4 * i + 2), AT(arr, 4 * i + 3)); }
-FB_DEV void st4(float* arr, int i, const DevData& d, int e, Q4 q) { AT(arr, 4 * i) = q.w; AT(arr, 4 * i + 1) = q.x; AT(arr, 4 * i + 2) = q.y; AT(arr, 4 * i + 3) = q.z; }
-FB_DEV M3 ld9(const float* arr, int i, const DevData& d, int e) { M3 R; for (int k = 0; k < 9; k++) R.m[k] = AT(arr, 9 * i + k); return R; }
-FB_DEV void st9(float* arr, int i, const DevData& d, int e, const M3& R) { for (int k = 0; k < 9; k++) AT(arr, 9 * i + k) = R.m[k]; }
-FB_DEV V3 mld3(const float* a, int i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
-FB_DEV Q4 mld4(const float* a, int i) { return q4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]); }
+// Record arrays of 3-vectors, quaternions, 3x3 matrices, spatial 6-vectors and 10-parameter inertias are PADDED to multiples of
+// four floats (V3 -> 4, M3 -> 12, S6 -> 2 x 4, I10 -> 12) and start on 16-byte boundaries (alloc_data), so that every element is
+// read / written with 128-bit accesses: one LDG.128 instead of three or four LDG.32 -- the L1TEX / LSU pipe is the busiest unit of
+// the tree kernels (profiles/README.md).  FB_V3S / FB_M3S / FB_S6S / FB_I10S are the element strides for the few direct indexers.
+#define FB_V3S 4
+#define FB_M3S 12
+#define FB_S6S 8
+#define FB_I10S 12
+#define S6I(b, k) (FB_S6S * (b) + (k) + ((k) >= 3 ? 1 : 0))      // slot of component k (0..5: angular xyz, linear xyz) of body b
+#ifdef __CUDACC__
+struct __align__(16) F4 { float x, y, z, w; };
+FB_DEV F4 ldf4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+FB_DEV void stf4(float* p, float x, float y, float z, float w) { F4 v; v.x = x; v.y = y; v.z = z; v.w = w; *reinterpret_cast<F4*>(p) = v; }
+#else
+struct F4 { float x, y, z, w; };
+FB_DEV F4 ldf4(const float* p) { F4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v; }
+FB_DEV void stf4(float* p, float x, float y, float z, float w) { p[0] = x; p[1] = y; p[2] = z; p[3] = w; }
+#endif
+FB_DEV V3 ld3(const float* arr, int i, const DevData& d, int e) { F4 v = ldf4(&AT(arr, FB_V3S * i)); return v3(v.x, v.y, v.z); }
+FB_DEV void st3(float* arr, int i, const DevData& d, int e, V3 v) { stf4(&AT(arr, FB_V3S * i), v.x, v.y, v.z, 0.0f); }
+FB_DEV Q4 ld4(const float* arr, int i, const DevData& d, int e) { F4 v = ldf4(&AT(arr, 4 * i)); return q4(v.x, v.y, v.z, v.w); }
+FB_DEV void st4(float* arr, int i, const DevData& d, int e, Q4 q) { stf4(&AT(arr, 4 * i), q.w, q.x, q.y, q.z); }
+FB_DEV M3 ld9(const float* arr, int i, const DevData& d, int e) {
+  const float* p = &AT(arr, FB_M3S * i); F4 a = ldf4(p), b = ldf4(p + 4), c = ldf4(p + 8); M3 R;
+  R.m[0] = a.x; R.m[1] = a.y; R.m[2] = a.z; R.m[3] = a.w; R.m[4] = b.x; R.m[5] = b.y; R.m[6] = b.z; R.m[7] = b.w; R.m[8] = c.x; return R;
+}
+FB_DEV void st9(float* arr, int i, const DevData& d, int e, const M3& R) {
+  float* p = &AT(arr, FB_M3S * i);
+  stf4(p, R.m[0], R.m[1], R.m[2], R.m[3]); stf4(p + 4, R.m[4], R.m[5], R.m[6], R.m[7]); stf4(p + 8, R.m[8], 0.0f, 0.0f, 0.0f);
+}
+// model tables of 3-vectors are uploaded padded to four floats (build_model: upf3), quaternion tables are four wide anyway
+FB_DEV V3 mld3(const float* a, int i) { F4 v = ldf4(a + 4 * i); return v3(v.x, v.y, v.z); }
+FB_DEV Q4 mld4(const float* a, int i) { F4 v = ldf4(a + 4 * i); return q4(v.x, v.y, v.z, v.w); }
 
 // 10-parameter spatial inertia about the reference point: m, h[3], Ixx Iyy Izz Ixy Ixz Iyz
 struct I10 { float v[10]; };
@@ -77,7 +102,14 @@ FB_DEV void inert_mul(const I10& I, V3 w, V3 v, V3& L, V3& p) {
          I.v[8] * w.x + I.v[9] * w.y + I.v[6] * w.z + hv.z);
   p = v3(I.v[0] * v.x + wh.x, I.v[0] * v.y + wh.y, I.v[0] * v.z + wh.z);
 }
-FB_DEV I10 ld10(const float* arr, int b, const DevData& d, int e) { I10 I; for (int k = 0; k < 10; k++) I.v[k] = AT(arr, 10 * b + k); return I; }
+FB_DEV I10 ld10(const float* arr, int b, const DevData& d, int e) {
+  const float* p = &AT(arr, FB_I10S * b); F4 a = ldf4(p), q = ldf4(p + 4), c = ldf4(p + 8); I10 I;
+  I.v[0] = a.x; I.v[1] = a.y; I.v[2] = a.z; I.v[3] = a.w; I.v[4] = q.x; I.v[5] = q.y; I.v[6] = q.z; I.v[7] = q.w; I.v[8] = c.x; I.v[9] = c.y; return I;
+}
+FB_DEV void st10(float* arr, int b, const DevData& d, int e, const float* v) {
+  float* p = &AT(arr, FB_I10S * b);
+  stf4(p, v[0], v[1], v[2], v[3]); stf4(p + 4, v[4], v[5], v[6], v[7]); stf4(p + 8, v[8], v[9], 0.0f, 0.0f);
+}
 
 // spatial 6-vector [angular; linear]
 struct S6 { V3 a, l; };

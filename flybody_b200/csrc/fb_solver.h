@@ -293,9 +293,11 @@ FB_WARPFN void ksolve_impl(const DevModel& m, const DevData& d, const SolveMem& 
             RED(1, 0) -= change; RED(0, 0) = d0; RED(0, 1) = d1;
           } WPAR_END
           const float d0 = RED(0, 0), d1 = RED(0, 1);
+          WPAR_BEGIN WPAR_END          // every lane has read RED(0, .) before lane 0 writes it again for the next contact (racecheck, r2)
           if (d0 != 0.0f || d1 != 0.0f) { WPAR_BEGIN WROWS SV(W_U, r) += AM(r, i + 1) * d0 + AM(r, i + 2) * d1; WPAR_END }
         }
         const float improvement = RED(1, 0);
+        WPAR_BEGIN WPAR_END            // ... and RED(1, 0) before it is cleared (racecheck, r2)
         WPAR_BEGIN if (lane == 0) RED(1, 0) = 0; WPAR_END
         if (!any) break;
         if (improvement * scale < m.noslip_tolerance) break;

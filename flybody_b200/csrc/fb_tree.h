@@ -68,7 +68,11 @@ FB_DEV void body_pose(const DevModel& m, const DevData& d, int e, int b, V3 ppos
   st3(d.xpos, b, d, e, pos); st4(d.xquat, b, d, e, quat);
 }
 // per-body part (no dependence between bodies): rotation matrix, inertial frame, spatial inertia about ref
-FB_DEV void body_derived(const DevModel& m, const DevData& d, int e, int b) {
+// CRBS(b, k): the composite inertias while they are being accumulated (kpos_p1b .. kpos_p3b) live in the shared-memory region that
+// later holds the inertia matrix rows (LS): the backward accumulation along the lists is a chain of read-modify-writes, which as
+// global-memory traffic costs an L2 round trip per body (12.8 % of the position kernel's stall samples, profiles/README.md)
+#define CRBS(b, k) ldsh[((b) * 10 + (k)) * FB_LANES + lane]
+FB_DEV void body_derived(const DevModel& m, const DevData& d, int e, int b, float* ldsh, int lane) {
   V3 pos = ld3(d.xpos, b, d, e); Q4 quat = ld4(d.xquat, b, d, e);
   M3 R = q2m(quat);
   st9(d.xmat, b, d, e, R);
@@ -89,7 +93,8 @@ FB_DEV void body_derived(const DevModel& m, const DevData& d, int e, int b) {
   I[0] = mass; I[1] = mass * ipos.x; I[2] = mass * ipos.y; I[3] = mass * ipos.z;
   I[4] = Ic[0] + mass * (cc - ipos.x * ipos.x); I[5] = Ic[1] + mass * (cc - ipos.y * ipos.y); I[6] = Ic[2] + mass * (cc - ipos.z * ipos.z);
   I[7] = Ic[3] - mass * ipos.x * ipos.y; I[8] = Ic[4] - mass * ipos.x * ipos.z; I[9] = Ic[5] - mass * ipos.y * ipos.z;
-  for (int k = 0; k < 10; k++) { AT(d.inert10, 10 * b + k) = I[k]; AT(d.crb10, 10 * b + k) = I[k]; }
+  st10(d.inert10, b, d, e, I);
+  for (int k = 0; k < 10; k++) CRBS(b, k) = I[k];
 }
 
 FB_DEV void kpos_p0(FB_PHASE_ARGS) {
@@ -122,11 +127,12 @@ FB_DEV void kpos_p1(FB_PHASE_ARGS) {
 }
 // all 32 lanes: per-body derived quantities, geom and site frames
 FB_DEV void kpos_p1b(FB_PHASE_ARGS) {
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
   for (int b = y; b < m.nbody; b += FB_NY) {
     if (b == 0) { M3 I; for (int k = 0; k < 9; k++) I.m[k] = (k % 4 == 0) ? 1.f : 0.f;
       st9(d.xmat, 0, d, e, I); st3(d.xipos, 0, d, e, ld3(d.xpos, 0, d, e)); st9(d.ximat, 0, d, e, I);
-      for (int k = 0; k < 10; k++) { AT(d.inert10, k) = 0; AT(d.crb10, k) = 0; }
-    } else body_derived(m, d, e, b);
+      { float z10[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; st10(d.inert10, 0, d, e, z10); for (int k = 0; k < 10; k++) CRBS(0, k) = 0; }
+    } else body_derived(m, d, e, b, ldsh, lane);
   }
   for (int g = y; g < m.ngeom; g += FB_NY) {
     int b = m.geom_bodyid[g]; V3 pos = ld3(d.xpos, b, d, e); Q4 quat = ld4(d.xquat, b, d, e);
@@ -141,30 +147,36 @@ FB_DEV void kpos_p1b(FB_PHASE_ARGS) {
 }
 // K2 composite inertia, backward accumulation (MuJoCo mj_crb); the running sum of a chain stays in registers
 FB_DEV void kpos_p2(FB_PHASE_ARGS) {
-  float* part_ = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF;
   if (y >= m.nlist) return;
   float acc[10], carry[10]; int carry_to = -1;
   for (int k = 0; k < 10; k++) { acc[k] = 0; carry[k] = 0; }
   FB_LIST_LOOP_REV {
     float cur[10];
-    for (int k = 0; k < 10; k++) cur[k] = AT(d.crb10, 10 * b + k);
-    if (carry_to == b) { for (int k = 0; k < 10; k++) cur[k] += carry[k]; for (int k = 0; k < 10; k++) AT(d.crb10, 10 * b + k) = cur[k]; }
-    else if (carry_to >= 0) { for (int k = 0; k < 10; k++) AT(d.crb10, 10 * carry_to + k) += carry[k]; }   // branch point: flush
+    for (int k = 0; k < 10; k++) cur[k] = CRBS(b, k);
+    if (carry_to == b) { for (int k = 0; k < 10; k++) { cur[k] += carry[k]; CRBS(b, k) = cur[k]; } }
+    else if (carry_to >= 0) { for (int k = 0; k < 10; k++) CRBS(carry_to, k) += carry[k]; }   // branch point: flush
     int p = m.body_parentid[b];
     if (m.body_isroot[p]) { for (int k = 0; k < 10; k++) acc[k] += cur[k]; carry_to = -1; }
     else { for (int k = 0; k < 10; k++) carry[k] = cur[k]; carry_to = p; }
   }
-  if (carry_to >= 0) for (int k = 0; k < 10; k++) AT(d.crb10, 10 * carry_to + k) += carry[k];
+  if (carry_to >= 0) for (int k = 0; k < 10; k++) CRBS(carry_to, k) += carry[k];
   for (int k = 0; k < 10; k++) PART(y, k) = acc[k];
 }
 FB_DEV void kpos_p3(FB_PHASE_ARGS) {       // composite inertia of the root bodies: lanes over (root, component)
-  float* part_ = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF;
   for (int t = y; t < 10 * m.nroot; t += FB_NY) {
     int r = t / 10, k = t - 10 * r, b = m.root_body[r];
-    float s = AT(d.inert10, 10 * b + k);
+    float s = CRBS(b, k);
     for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) s += PART(l, k);
-    AT(d.crb10, 10 * b + k) = s;
+    CRBS(b, k) = s;
   }
+}
+// the finished composite inertias go to the record (mass_row, the subtree-CoM observable and the task hooks read them there;
+// the shared region is overwritten by the inertia matrix next)
+FB_DEV void kpos_p3b(FB_PHASE_ARGS) {
+  float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
+  for (int b = y; b < m.nbody; b += FB_NY) { float v[10]; for (int k = 0; k < 10; k++) v[k] = CRBS(b, k); st10(d.crb10, b, d, e, v); }
 }
 // joint-space inertia entries of dof i (row of the sparse lower triangle along the ancestor chain)
 FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int lane, float* ldsh, int i) {
@@ -598,10 +610,14 @@ FB_DEV void vel_acc_from_parent(const DevModel& m, const DevData& d, int e, int 
   }
   st6(d.bvel, b, d, e, v); st6(d.bacc, b, d, e, a);
 }
+FB_DEV void st6v(float* arr, int b, const DevData& d, int e, const float* v) { st3(arr, 2 * b, d, e, v3(v[0], v[1], v[2])); st3(arr, 2 * b + 1, d, e, v3(v[3], v[4], v[5])); }
+FB_DEV void add6v(float* arr, int b, const DevData& d, int e, const float* v) {
+  S6 s = ld6(arr, b, d, e); s.a = s.a + v3(v[0], v[1], v[2]); s.l = s.l + v3(v[3], v[4], v[5]); st6(arr, b, d, e, s);
+}
 FB_DEV void kvel_p0(FB_PHASE_ARGS) {
   // inputs written by the position kernel three launches ago: ask for them now, all lines at once
-  prefetch_rec(d.Sang, 3 * m.nv, d, e, y); prefetch_rec(d.Slin, 3 * m.nv, d, e, y); prefetch_rec(d.inert10, 10 * m.nbody, d, e, y);
-  prefetch_rec(d.xipos, 3 * m.nbody, d, e, y); prefetch_rec(d.ximat, 9 * m.nbody, d, e, y);
+  prefetch_rec(d.Sang, FB_V3S * m.nv, d, e, y); prefetch_rec(d.Slin, FB_V3S * m.nv, d, e, y); prefetch_rec(d.inert10, FB_I10S * m.nbody, d, e, y);
+  prefetch_rec(d.xipos, FB_V3S * m.nbody, d, e, y); prefetch_rec(d.ximat, FB_M3S * m.nbody, d, e, y);
   if (y != 0) return;
   S6 z; z.a = v3(0, 0, 0); z.l = v3(0, 0, 0);
   st6(d.bvel, 0, d, e, z);
@@ -620,50 +636,59 @@ FB_DEV void kvel_p1(FB_PHASE_ARGS) {
   }
 }
 // all lanes over bodies: bias force (kept un-accumulated in bfrc0 for the sensor pass) and fluid wrench
+// BFS(b, k): bias force (k < 6) and fluid wrench (k >= 6) of body b, summed over its subtree in shared memory (kvel_p2, kvel_p3)
+// and projected onto the dofs (kvel_p3b); only the per-body bias force bfrc0 is needed after this kernel (sensor pass of `finish`)
+#define BFS(b, k) bfs_[((b) * 12 + (k)) * FB_LANES + lane]
+#define FB_VEL_DYN(m) (FB_PARTF + 12 * (m).nbody)
 FB_DEV void kvel_p1b(FB_PHASE_ARGS) {
+  float* part_ = sh_dyn(sh); float* bfs_ = part_ + FB_PARTF; (void)part_;
   for (int b = y; b < m.nbody; b += FB_NY) {
     S6 f; f.a = f.l = v3(0, 0, 0); S6 fl = f;
     if (b > 0) { f = body_inertial_force(m, d, e, b, d.bvel, d.bacc); fl = body_fluid_wrench(m, d, e, b); }
-    st6(d.bfrc, b, d, e, f); st6(d.bfrc0, b, d, e, f); st6(d.bfl, b, d, e, fl);
+    st6(d.bfrc0, b, d, e, f);
+    BFS(b, 0) = f.a.x; BFS(b, 1) = f.a.y; BFS(b, 2) = f.a.z; BFS(b, 3) = f.l.x; BFS(b, 4) = f.l.y; BFS(b, 5) = f.l.z;
+    BFS(b, 6) = fl.a.x; BFS(b, 7) = fl.a.y; BFS(b, 8) = fl.a.z; BFS(b, 9) = fl.l.x; BFS(b, 10) = fl.l.y; BFS(b, 11) = fl.l.z;
   }
 }
 // subtree sums of (bias force, fluid wrench): child -> parent along the lists
 FB_DEV void kvel_p2(FB_PHASE_ARGS) {
-  float* part_ = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* bfs_ = part_ + FB_PARTF;
   if (y >= m.nlist) return;
   float acc[12], carry[12]; int carry_to = -1;
   for (int k = 0; k < 12; k++) { acc[k] = 0; carry[k] = 0; }
   FB_LIST_LOOP_REV {
     float cur[12];
-    for (int k = 0; k < 6; k++) { cur[k] = AT(d.bfrc, 6 * b + k); cur[6 + k] = AT(d.bfl, 6 * b + k); }
-    if (carry_to == b) { for (int k = 0; k < 12; k++) cur[k] += carry[k]; for (int k = 0; k < 6; k++) { AT(d.bfrc, 6 * b + k) = cur[k]; AT(d.bfl, 6 * b + k) = cur[6 + k]; } }
-    else if (carry_to >= 0) { for (int k = 0; k < 6; k++) { AT(d.bfrc, 6 * carry_to + k) += carry[k]; AT(d.bfl, 6 * carry_to + k) += carry[6 + k]; } }
+    for (int k = 0; k < 12; k++) cur[k] = BFS(b, k);
+    if (carry_to == b) { for (int k = 0; k < 12; k++) { cur[k] += carry[k]; BFS(b, k) = cur[k]; } }
+    else if (carry_to >= 0) { for (int k = 0; k < 12; k++) BFS(carry_to, k) += carry[k]; }
     int p = m.body_parentid[b];
     if (m.body_isroot[p]) { for (int k = 0; k < 12; k++) acc[k] += cur[k]; carry_to = -1; }
     else { for (int k = 0; k < 12; k++) carry[k] = cur[k]; carry_to = p; }
   }
-  if (carry_to >= 0) for (int k = 0; k < 6; k++) { AT(d.bfrc, 6 * carry_to + k) += carry[k]; AT(d.bfl, 6 * carry_to + k) += carry[6 + k]; }
+  if (carry_to >= 0) for (int k = 0; k < 12; k++) BFS(carry_to, k) += carry[k];
   for (int k = 0; k < 12; k++) PART(y, k) = acc[k];
 }
 FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e, int y);
 FB_DEV void kvel_p3(FB_PHASE_ARGS) {
-  float* part_ = sh_dyn(sh);
+  float* part_ = sh_dyn(sh); float* bfs_ = part_ + FB_PARTF;
   if (y < m.nroot) {
     int r = y, b = m.root_body[r];
-    for (int k = 0; k < 6; k++) {
-      float a1 = 0, a2 = 0;
-      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) { a1 += PART(l, k); a2 += PART(l, 6 + k); }
-      AT(d.bfrc, 6 * b + k) += a1; AT(d.bfl, 6 * b + k) += a2;
+    for (int k = 0; k < 12; k++) {
+      float a1 = 0;
+      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) a1 += PART(l, k);
+      BFS(b, k) += a1;
     }
   }
   sensors_vel(m, d, e, y);
 }
 // all lanes over dofs: qfrc_bias = S . f_subtree ; qfrc_passive = S . fluid_subtree + springs + dampers
 FB_DEV void kvel_p3b(FB_PHASE_ARGS) {
+  float* part_ = sh_dyn(sh); const float* bfs_ = part_ + FB_PARTF; (void)part_;
   for (int k = y; k < m.nv; k += FB_NY) {
     int b = m.dof_bodyid[k];
     V3 Sa = ld3(d.Sang, k, d, e), Sl = ld3(d.Slin, k, d, e);
-    S6 f = ld6(d.bfrc, b, d, e), fl = ld6(d.bfl, b, d, e);
+    S6 f, fl; f.a = v3(BFS(b, 0), BFS(b, 1), BFS(b, 2)); f.l = v3(BFS(b, 3), BFS(b, 4), BFS(b, 5));
+    fl.a = v3(BFS(b, 6), BFS(b, 7), BFS(b, 8)); fl.l = v3(BFS(b, 9), BFS(b, 10), BFS(b, 11));
     AT(d.qfrc_bias, k) = dot(Sa, f.a) + dot(Sl, f.l);
     float pas = dot(Sa, fl.a) + dot(Sl, fl.l) - m.dof_damping[k] * AT(d.qvel, k);
     int j = m.dof_jntid[k];

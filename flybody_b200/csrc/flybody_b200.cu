@@ -268,7 +268,7 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 }
 
 // the stage lists of the seven step kernels (shared by the one-kernel-per-stage launches and the fused launches below)
-#define FB_ST_POS Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>
+#define FB_ST_POS Ph<kpos_p0>, Ph<kpos_p1>, Ph<kpos_p1b>, Ph<kpos_p2>, Ph<kpos_p3>, Ph<kpos_p3b>, Ph<kpos_p4>, Wf<kpos_factor>, Ph<kpos_p6w>, Ph<kpos_p6d>, Wf<kpos_factor>, Ph<kpos_p9>
 #define FB_ST_COL Ph<kcol_stage>, Wf<kcol_broad>, Ph<kcol_narrow>, Wf<kcol_mpr>, Ph<kcol_compact>
 #define FB_ST_PROJ Ph<kcon_p0>, Ph<kcon_p1>, Ph<kcon_p2>, Ph<kcon_p3>, Ph<kproj_p0>, Ph<kproj_p1>
 #define FB_ST_VEL Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>
@@ -277,7 +277,7 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 static size_t dyn_pos(const DevModel& m) { return (size_t)FB_PARTF + (size_t)m.nM; }
 static size_t dyn_col(const DevModel& m) { return (size_t)FB_COL_DYN(m); }
 static size_t dyn_proj(const DevModel&) { return (size_t)FB_NY * FB_ZCAP; }
-static size_t dyn_vel(const DevModel&) { return (size_t)FB_PARTF; }
+static size_t dyn_vel(const DevModel& m) { return (size_t)FB_VEL_DYN(m); }
 static size_t dyn_tsolve(const DevModel& m) { return (size_t)(FB_NXS(m) + ((m.nM + 3) & ~3)); }
 
 static void launch_step1(FbSim* s) {
@@ -395,6 +395,11 @@ template <typename T> static const T* up(FbSim* s, const std::vector<T>& v) {
   return (const T*)p;
 }
 static const float* upf(FbSim* s, const double* src, size_t n) { std::vector<float> v(n); for (size_t i = 0; i < n; i++) v[i] = (float)src[i]; return up(s, v); }
+static const float* upf3(FbSim* s, const double* src, size_t n) {      // n 3-vectors, padded to four floats each (fb_math.h: mld3)
+  std::vector<float> v(4 * std::max<size_t>(n, 1), 0.0f);
+  for (size_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) v[4 * i + k] = (float)src[3 * i + k];
+  return up(s, v);
+}
 static const int* upi(FbSim* s, const int32_t* src, size_t n) { std::vector<int> v(src, src + n); return up(s, v); }
 template <typename T> static T* dalloc(FbSim* s, size_t n) { void* p = dev_alloc(sizeof(T) * n); s->allocs.push_back(p); return (T*)p; }
 
@@ -533,13 +538,13 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.body_jntadr = upi(s, h->body_jntadr, nb); m.body_jntnum = upi(s, h->body_jntnum, nb);
   m.body_dofadr = upi(s, h->body_dofadr, nb); m.body_dofnum = upi(s, h->body_dofnum, nb);
   m.body_lastdof = upi(s, h->body_lastdof, nb); m.body_fluid_ellipsoid = upi(s, h->body_fluid_ellipsoid, nb);
-  m.body_pos = upf(s, h->body_pos, 3 * nb); m.body_quat = upf(s, h->body_quat, 4 * nb); m.body_ipos = upf(s, h->body_ipos, 3 * nb);
-  m.body_iquat = upf(s, h->body_iquat, 4 * nb); m.body_mass = upf(s, h->body_mass, nb); m.body_inertia = upf(s, h->body_inertia, 3 * nb);
+  m.body_pos = upf3(s, h->body_pos, nb); m.body_quat = upf(s, h->body_quat, 4 * nb); m.body_ipos = upf3(s, h->body_ipos, nb);
+  m.body_iquat = upf(s, h->body_iquat, 4 * nb); m.body_mass = upf(s, h->body_mass, nb); m.body_inertia = upf3(s, h->body_inertia, nb);
   m.body_invweight0 = upf(s, h->body_invweight0, 2 * nb);
   int nj = m.njnt;
   m.jnt_type = upi(s, h->jnt_type, nj); m.jnt_qposadr = upi(s, h->jnt_qposadr, nj); m.jnt_dofadr = upi(s, h->jnt_dofadr, nj);
   m.jnt_bodyid = upi(s, h->jnt_bodyid, nj); m.jnt_limited = upi(s, h->jnt_limited, nj);
-  m.jnt_pos = upf(s, h->jnt_pos, 3 * nj); m.jnt_axis = upf(s, h->jnt_axis, 3 * nj); m.jnt_stiffness = upf(s, h->jnt_stiffness, nj);
+  m.jnt_pos = upf3(s, h->jnt_pos, nj); m.jnt_axis = upf3(s, h->jnt_axis, nj); m.jnt_stiffness = upf(s, h->jnt_stiffness, nj);
   m.jnt_range = upf(s, h->jnt_range, 2 * nj); m.jnt_solref = upf(s, h->jnt_solref, 2 * nj); m.jnt_solimp = upf(s, h->jnt_solimp, 5 * nj);
   m.jnt_margin = upf(s, h->jnt_margin, nj); m.qpos0 = upf(s, h->qpos0, m.nq); m.qpos_spring = upf(s, h->qpos_spring, m.nq);
   m.dof_bodyid = upi(s, h->dof_bodyid, nv); m.dof_jntid = upi(s, h->dof_jntid, nv); m.dof_parentid = upi(s, h->dof_parentid, nv);
@@ -547,7 +552,7 @@ static int build_model(FbSim* s, const FbModel* h) {
   m.dof_invweight0 = upf(s, h->dof_invweight0, nv);
   int ng = m.ngeom;
   m.geom_type = upi(s, h->geom_type, ng); m.geom_bodyid = upi(s, h->geom_bodyid, ng); m.geom_condim = upi(s, h->geom_condim, ng);
-  m.geom_size = upf(s, h->geom_size, 3 * ng); m.geom_pos = upf(s, h->geom_pos, 3 * ng); m.geom_quat = upf(s, h->geom_quat, 4 * ng);
+  m.geom_size = upf3(s, h->geom_size, ng); m.geom_pos = upf3(s, h->geom_pos, ng); m.geom_quat = upf(s, h->geom_quat, 4 * ng);
   m.geom_rbound = upf(s, h->geom_rbound, ng); m.geom_friction = upf(s, h->geom_friction, 3 * ng); m.geom_solmix = upf(s, h->geom_solmix, ng);
   m.geom_solref = upf(s, h->geom_solref, 2 * ng); m.geom_solimp = upf(s, h->geom_solimp, 5 * ng);
   m.geom_margin = upf(s, h->geom_margin, ng); m.geom_gap = upf(s, h->geom_gap, ng);
@@ -574,10 +579,10 @@ static int build_model(FbSim* s, const FbModel* h) {
     m.chunk_start = up(s, cs);
 
   }
-  m.fluid_bodyid = upi(s, h->fluid_bodyid, m.nfluid); m.fluid_pos = upf(s, h->fluid_pos, 3 * m.nfluid);
-  m.fluid_quat = upf(s, h->fluid_quat, 4 * m.nfluid); m.fluid_size = upf(s, h->fluid_size, 3 * m.nfluid); m.fluid_coef = upf(s, h->fluid_coef, 12 * m.nfluid);
+  m.fluid_bodyid = upi(s, h->fluid_bodyid, m.nfluid); m.fluid_pos = upf3(s, h->fluid_pos, m.nfluid);
+  m.fluid_quat = upf(s, h->fluid_quat, 4 * m.nfluid); m.fluid_size = upf3(s, h->fluid_size, m.nfluid); m.fluid_coef = upf(s, h->fluid_coef, 12 * m.nfluid);
   m.site_bodyid = upi(s, h->site_bodyid, m.nsite); m.site_type = upi(s, h->site_type, m.nsite);
-  m.site_pos = upf(s, h->site_pos, 3 * m.nsite); m.site_quat = upf(s, h->site_quat, 4 * m.nsite); m.site_size = upf(s, h->site_size, 3 * m.nsite);
+  m.site_pos = upf3(s, h->site_pos, m.nsite); m.site_quat = upf(s, h->site_quat, 4 * m.nsite); m.site_size = upf3(s, h->site_size, m.nsite);
   m.tendon_adr = upi(s, h->tendon_adr, m.ntendon); m.tendon_num = upi(s, h->tendon_num, m.ntendon);
   m.wrap_dofid = upi(s, h->wrap_dofid, m.nwrap); m.wrap_qposadr = upi(s, h->wrap_qposadr, m.nwrap); m.wrap_coef = upf(s, h->wrap_coef, m.nwrap);
   int nu = m.nu;
@@ -604,11 +609,12 @@ static int alloc_data(FbSim* s, int N) {
 #define FA(field, n) { off = (off + 3) & ~(size_t)3; fields.push_back({(void**)&d.field, off}); off += (size_t)(n); }   // arrays start on 16-byte boundaries
 #define IA(field, n) FA(field, n)
   FA(qpos, m.nq) FA(qvel, m.nv) FA(act, m.na + 1) FA(ctrl, m.nu + 1) FA(qacc, m.nv) FA(dof_isd, m.nv) FA(time, 1)
-  FA(ref, 3) FA(xpos, 3 * m.nbody) FA(xquat, 4 * m.nbody) FA(xmat, 9 * m.nbody) FA(xipos, 3 * m.nbody) FA(ximat, 9 * m.nbody)
-  FA(geom_xpos, 3 * m.ngeom) FA(geom_xmat, 9 * m.ngeom) FA(site_xpos, 3 * m.nsite + 3) FA(site_xmat, 9 * m.nsite + 9)
-  FA(Sang, 3 * m.nv) FA(Slin, 3 * m.nv) FA(inert10, 10 * m.nbody) FA(crb10, 10 * m.nbody)
+  // vectors / matrices / inertias padded to whole float4s (fb_math.h: FB_V3S ...)
+  FA(ref, 3) FA(xpos, FB_V3S * m.nbody) FA(xquat, 4 * m.nbody) FA(xmat, FB_M3S * m.nbody) FA(xipos, FB_V3S * m.nbody) FA(ximat, FB_M3S * m.nbody)
+  FA(geom_xpos, FB_V3S * m.ngeom) FA(geom_xmat, FB_M3S * m.ngeom) FA(site_xpos, FB_V3S * (m.nsite + 1)) FA(site_xmat, FB_M3S * (m.nsite + 1))
+  FA(Sang, FB_V3S * m.nv) FA(Slin, FB_V3S * m.nv) FA(inert10, FB_I10S * m.nbody) FA(crb10, FB_I10S * m.nbody)
   FA(qM, m.nM) FA(qLD, m.nM) FA(qLDe, m.nM)
-  FA(bvel, 6 * m.nbody) FA(bacc, 6 * m.nbody) FA(bfrc, 6 * m.nbody) FA(bfl, 6 * m.nbody) FA(bfrc0, 6 * m.nbody) FA(bdel, 6 * m.nbody)
+  FA(bvel, FB_S6S * m.nbody) FA(bacc, FB_S6S * m.nbody) FA(bfrc, FB_S6S * m.nbody) FA(bfl, FB_S6S * m.nbody) FA(bfrc0, FB_S6S * m.nbody) FA(bdel, FB_S6S * m.nbody)
   FA(qfrc_bias, m.nv) FA(qfrc_passive, m.nv) FA(qfrc_actuator, m.nv) FA(qfrc_smooth, m.nv) FA(qfrc_zf, m.nv) FA(qfrc_constraint, m.nv) FA(qtmp, m.nv)
   FA(act_dot, m.na + 1) FA(actuator_force, m.nu + 1)
   IA(ncon, 1) FA(con_dist, FB_MAXCON) FA(con_pos, 3 * FB_MAXCON) FA(con_frame, 9 * FB_MAXCON) IA(con_geom1, FB_MAXCON) IA(con_geom2, FB_MAXCON)
@@ -649,6 +655,13 @@ static void field_to_host(FbSim* s, const void* dev, int n, void* dst) {
 #else
   for (int e = 0; e < s->d.N; e++) memcpy((char*)dst + (size_t)e * n * 4, (const char*)dev + (size_t)e * s->d.rec * 4, (size_t)n * 4);
 #endif
+}
+// padded device array (count elements of `width` floats every `stride` slots) -> compact host array [N][count * width]
+static void field_to_host_strided(FbSim* s, const void* dev, int count, int width, int stride, float* dst) {
+  std::vector<float> tmp((size_t)s->d.N * count * stride);
+  field_to_host(s, dev, count * stride, tmp.data());
+  for (int e = 0; e < s->d.N; e++) for (int i = 0; i < count; i++) for (int k = 0; k < width; k++)
+    dst[((size_t)e * count + i) * width + k] = tmp[((size_t)e * count + i) * stride + k];
 }
 static void field_from_host(FbSim* s, void* dev, int n, const void* src) {
   if (n <= 0) return;
@@ -924,7 +937,7 @@ static void* field_ptr(FbSim* s, int field, int* n) {
     case FB_QACC_WARMSTART: *n = m.nv; return d.qacc;        /* the dual solver warm-starts from forces; kept for ABI compatibility */
     case FB_SENSORDATA: *n = m.nsensordata; return d.sensordata;
     case FB_SENSOR_MEAN: *n = m.nsensordata; return d.sensor_sum;
-    case FB_XPOS: *n = 3 * m.nbody; return d.xpos;
+    case FB_XPOS: *n = 3 * m.nbody; return d.xpos;            /* padded on the device (fb_math.h): host reads go through field_to_host_strided */
     case FB_XMAT: *n = 9 * m.nbody; return d.xmat;
     case FB_SITE_XPOS: *n = 3 * m.nsite; return d.site_xpos;
     case FB_SITE_XMAT: *n = 9 * m.nsite; return d.site_xmat;
@@ -959,7 +972,11 @@ int fb_get(FbHandle s, int field, void* dst, int is_device) {
   if (is_device) { if (!p) { s->err = "field has no device array"; return -1; } *(void**)dst = p; return 0; }
   float* out = (float*)dst;
   if (p) {
-    field_to_host(s, p, n, out);
+    if (field == FB_XPOS) field_to_host_strided(s, p, m.nbody, 3, FB_V3S, out);
+    else if (field == FB_XMAT) field_to_host_strided(s, p, m.nbody, 9, FB_M3S, out);
+    else if (field == FB_SITE_XPOS) field_to_host_strided(s, p, m.nsite, 3, FB_V3S, out);
+    else if (field == FB_SITE_XMAT) field_to_host_strided(s, p, m.nsite, 9, FB_M3S, out);
+    else field_to_host(s, p, n, out);
     if (field == FB_XPOS || field == FB_SITE_XPOS) {     // stored relative to ref
       std::vector<float> ref((size_t)3 * N); field_to_host(s, s->d.ref, 3, ref.data());
       for (int e = 0; e < N; e++) for (int i = 0; i < n; i++) out[(size_t)e * n + i] += ref[(size_t)e * 3 + i % 3];
@@ -975,7 +992,7 @@ int fb_get(FbHandle s, int field, void* dst, int is_device) {
     case FB_FLAGS: field_to_host(s, s->d.flags, 1, iv.data()); for (int e = 0; e < N; e++) out[e] = (float)iv[e]; return 0;
     case FB_SUBTREE_COM: {
       std::vector<float> crb((size_t)10 * m.nbody * N), ref((size_t)3 * N);
-      field_to_host(s, s->d.crb10, 10 * m.nbody, crb.data()); field_to_host(s, s->d.ref, 3, ref.data());
+      field_to_host_strided(s, s->d.crb10, m.nbody, 10, FB_I10S, crb.data()); field_to_host(s, s->d.ref, 3, ref.data());
       for (int e = 0; e < N; e++) for (int b = 0; b < m.nbody; b++) { const float* c = &crb[((size_t)e * m.nbody + b) * 10];
         for (int i = 0; i < 3; i++) out[((size_t)e * m.nbody + b) * 3 + i] = (c[0] > 0 ? c[1 + i] / c[0] : 0.0f) + ref[(size_t)e * 3 + i]; }
       return 0; }
