@@ -304,7 +304,10 @@ def load_mesh_cache(assets_dir=None, rebuild=False):
 
 
 def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mesh_cache=None,
-                    joint_filter=None, claw_friction=1.0, terminal=None):
+                    joint_filter=None, claw_friction=1.0, terminal=None, force_actuators=False, use_wings=None, use_legs=None):
+    """`variant` picks the task's model surgery (reference tasks/base.py `Walking` / `Flying`); `force_actuators`, `use_wings`,
+    `use_legs` and `joint_filter` are the `FruitFly` constructor switches the env factories expose (reference fly_envs.py:100-246:
+    force_actuators, disable_wings, disable_legs, joint_filter); None keeps the task's default."""
     assets_dir = assets_dir or REFERENCE_ASSETS
     xml_path = os.path.join(assets_dir, 'fruitfly.xml')
     mesh_cache = mesh_cache or load_mesh_cache(assets_dir)
@@ -319,8 +322,9 @@ def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mes
         prefix = ''
     elif variant == 'walk':
         jf = 0.01 if joint_filter is None else joint_filter
-        fx = build_fly_xml(xml_path, name='walker', use_legs=True, use_wings=False, use_mouth=False,
-                           use_antennae=False, joint_filter=jf, adhesion_filter=0.007)
+        fx = build_fly_xml(xml_path, name='walker', use_legs=True if use_legs is None else use_legs,
+                           use_wings=False if use_wings is None else use_wings, use_mouth=False,
+                           use_antennae=False, joint_filter=jf, adhesion_filter=0.007, force_actuators=force_actuators)
         timestep = 2e-4                                  # reference tasks/constants.py:11
         spawn, prefix, ghost = _SPAWN_POS, 'walker/', True
         # Walking.__init__: floor params (base.py:398-401)
@@ -331,8 +335,9 @@ def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mes
             fx.class_child('adhesion-collision', 'geom').set('friction', repr(float(claw_friction)))
     elif variant == 'flight':
         jf = 0.0 if joint_filter is None else joint_filter
-        fx = build_fly_xml(xml_path, name='walker', use_legs=False, use_wings=True, use_mouth=False,
-                           use_antennae=False, joint_filter=jf, adhesion_filter=0.007,
+        fx = build_fly_xml(xml_path, name='walker', use_legs=False if use_legs is None else use_legs,
+                           use_wings=True if use_wings is None else use_wings, use_mouth=False,
+                           use_antennae=False, joint_filter=jf, adhesion_filter=0.007, force_actuators=force_actuators,
                            body_pitch_angle=47.5, stroke_plane_angle=0.0)
         timestep = 5e-5                                  # reference tasks/constants.py:17
         spawn, prefix, ghost = _SPAWN_POS, 'walker/', True
@@ -354,9 +359,10 @@ def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mes
         # ground contacts ON (floor_contacts=True -> the arena's geoms keep MuJoCo's defaults), and the arena of
         # tasks/arenas/hills.py:143-251 ('outdoor_natural'): heightfield `terrain` at z = -0.01 over [-20, 20]^2, 401 x 401
         # points, elevation scale 1, base 0.05, next to the ground plane at z = 0
-        fx = build_fly_xml(xml_path, name='walker', use_legs=False, use_wings=True, use_mouth=False,
+        fx = build_fly_xml(xml_path, name='walker', use_legs=False if use_legs is None else use_legs,
+                           use_wings=True if use_wings is None else use_wings, use_mouth=False,
                            use_antennae=False, joint_filter=0.0 if joint_filter is None else joint_filter, adhesion_filter=0.007,
-                           body_pitch_angle=47.5, stroke_plane_angle=0.0)
+                           force_actuators=force_actuators, body_pitch_angle=47.5, stroke_plane_angle=0.0)
         timestep = 5e-5
         spawn, prefix, ghost = _SPAWN_POS, 'walker/', False
         floor = dict(friction=np.array([1.0, 0.005, 0.0001]), solref=np.array([0.02, 1.0]),

@@ -96,6 +96,9 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
     // ---- stage: row constants into registers, A into shared memory (full, symmetric), warm start from the previous forces
     WPAR_BEGIN {
       const int r = lane;
+      // the J / Z rows are read once, at the very end (J^T f gather); ask for them now: without this the gather sits on DRAM misses
+      // for a quarter of the kernel's stall samples (profiles/r02_ncu_full_v8_summary.json, by-line)
+      prefetch_rec(d.efc_J, n * FB_JROW, d, e, lane); prefetch_rec(d.efc_Z, n * FB_JROW, d, e, lane);
       L(kind) = 0; L(D) = 0; L(b) = 0; L(Rr) = 0; L(mu) = 0; L(c1) = 0; L(c2) = 0; L(lam) = 0; L(la) = -1; L(lb) = -1; L(cla) = 0; L(clb) = 0;
       L(state) = 0; L(hst) = 0; L(f) = 0; L(hf1) = 0; L(hf2) = 0; L(e0) = 0; L(e1) = 0; L(he01) = 0; L(he02) = 0; L(he11) = 0; L(he12) = 0; L(chg) = 0;
       if (r < n) {

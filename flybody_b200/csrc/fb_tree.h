@@ -222,9 +222,8 @@ FB_DEV void ld_reinit_damped(const DevModel& m, const DevData& d, ShTree& sh, in
 #define HDR_DEPTH(h) ((int)(((h) >> 18) & 63u))
 #define HDR_DOF(h) ((int)((h) >> 24))
 #define FB_ROOTD6 6            // dofs of a root body (free joint)
-FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+FB_DEV void factor_step_update_h(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, unsigned hd) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  const unsigned hd = m.step_hdr_a[step * FB_NY + y];
   if (hd == FB_HDR_IDLE) return;
   const int sub = y % FB_FSUB, adrk = HDR_ADR(hd), len = HDR_LEN(hd);
   float invD = 1.0f / LS(adrk);
@@ -242,6 +241,9 @@ FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, 
     }
     for (; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
   }
+}
+FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+  factor_step_update_h(m, d, sh, e, lane, y, m.step_hdr_a[step * FB_NY + y]);
 }
 // Root blocks.  Once the lists are eliminated, row k of a non-root dof holds its final (unscaled) coupling r_k to the
 // root's dofs and D_k; the Schur update of the root block is sum_k r_k r_k^T / D_k.  32 lanes split the dofs, each
@@ -296,9 +298,21 @@ FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, 
 }
 // warp function: the whole factorisation of the rows currently held in shared memory
 FB_WARPFN void kpos_factor(const DevModel& m, const DevData& d, ShTree& sh, int e) {
+#ifdef __CUDACC__
+  {   // the packed header of the NEXT step is loaded while this step's rank-1 updates run (one dependent global load less per step)
+    const int lane = threadIdx.x; const unsigned* hp = m.step_hdr_a + lane;
+    unsigned hd = m.max_list_ndof > 0 ? hp[0] : FB_HDR_IDLE;
+    for (int step = 0; step < m.max_list_ndof; step++) {
+      const unsigned nxt = step + 1 < m.max_list_ndof ? hp[(step + 1) * FB_NY] : FB_HDR_IDLE;
+      factor_step_update_h(m, d, sh, e, 0, lane, hd); __syncwarp();
+      hd = nxt;
+    }
+  }
+#else
   for (int step = 0; step < m.max_list_ndof; step++) {
     WPAR_BEGIN factor_step_update(m, d, sh, e, 0, lane, step); WPAR_END
   }
+#endif
   for (int r = 0; r < m.nroot; r++) {
     if (!m.root_haslists[r]) continue;
     WPAR_BEGIN factor_root_accum(m, d, sh, e, 0, lane, r); WPAR_END
@@ -346,14 +360,16 @@ FB_DEV void tsolve_stage_wait(FB_PHASE_ARGS) {
   for (int k = y; k < FB_ROOTD * m.nlist; k += FB_NY) XS(m.nv + k) = 0;      // the lists' private root accumulators
 }
 // x <- L^-T x restricted to the list dofs, deepest first: x[anc] -= L[k][anc] x[k]
-FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+FB_DEV void tsolve_a_step_h(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, unsigned hd) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  const unsigned hd = TS_HDR_A(sh, m)[step * FB_NY + y];
   if (hd == FB_HDR_IDLE) return;
   const int sub = y % FB_FSUB, k = HDR_DOF(hd), adrk = HDR_ADR(hd), len = HDR_LEN(hd);
   const unsigned char* slot8 = TS_SLOT8(sh, m);
   float xk = XS(k) / LDS(adrk);                    // rows are stored unscaled: L[k][anc] x[k] = M'[k][anc] (x[k] / D[k])
   for (int t = 1 + sub; t < len; t += FB_FSUB) XS(slot8[adrk + t]) -= LDS(adrk + t) * xk;
+}
+FB_DEV void tsolve_a_step(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+  tsolve_a_step_h(m, d, sh, e, lane, y, TS_HDR_A(sh, m)[step * FB_NY + y]);
 }
 // root blocks: collect the lists' contributions, then the dense (<= 6x6) back / scale / forward substitution
 FB_DEV void tsolve_b_gather(FB_PHASE_ARGS) {
@@ -415,16 +431,25 @@ FB_DEV void tsolve_c_fin(const DevModel& m, const DevData& d, ShTree& sh, int e,
 //   tsolve_c : x <- L^-1 x
 FB_WARPFN void tsolve_a(const DevModel& m, const DevData& d, ShTree& sh, int e) {
   WPAR_BEGIN tsolve_stage_wait(m, d, sh, e, 0, lane); WPAR_END
+#ifdef __CUDACC__
+  { const int lane = threadIdx.x; const unsigned* hp = TS_HDR_A(sh, m) + lane;
+    unsigned hd = m.max_list_ndof > 0 ? hp[0] : FB_HDR_IDLE;
+    for (int step = 0; step < m.max_list_ndof; step++) {
+      const unsigned nxt = step + 1 < m.max_list_ndof ? hp[(step + 1) * FB_NY] : FB_HDR_IDLE;      // next step's header in flight during this step
+      tsolve_a_step_h(m, d, sh, e, 0, lane, hd); __syncwarp();
+      hd = nxt;
+    } }
+#else
   for (int step = 0; step < m.max_list_ndof; step++) { WPAR_BEGIN tsolve_a_step(m, d, sh, e, 0, lane, step); WPAR_END }
+#endif
   WPAR_BEGIN tsolve_b_gather(m, d, sh, e, 0, lane); WPAR_END
   WPAR_BEGIN tsolve_root_a(m, d, sh, e, 0, lane); WPAR_END
 }
 #ifdef __CUDACC__
 // GPU: the three partial dot products of a list are combined with two shuffles instead of a trip through shared memory
 // and a second barrier (the host emulation runs the lanes one after the other and keeps the two-section form)
-FB_DEV void tsolve_c_step_shfl(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
+FB_DEV void tsolve_c_step_shfl(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, unsigned hd) {
   float* xs = sh_dyn(sh); const float* lds = xs + FB_NXS(m);
-  const unsigned hd = TS_HDR_C(sh, m)[step * FB_NY + y];
   const bool active = hd != FB_HDR_IDLE;
   const int sub = y % FB_FSUB, k = HDR_DOF(hd), adrk = HDR_ADR(hd);
   const unsigned char* anc8 = TS_ANC8(sh, m);
@@ -439,14 +464,20 @@ FB_DEV void tsolve_c_step_shfl(const DevModel& m, const DevData& d, ShTree& sh, 
 #endif
 FB_WARPFN void tsolve_c(const DevModel& m, const DevData& d, ShTree& sh, int e) {
   WPAR_BEGIN tsolve_root_c(m, d, sh, e, 0, lane); WPAR_END
-  for (int step = 0; step < m.max_list_ndof; step++) {
 #ifdef __CUDACC__
-    WPAR_BEGIN tsolve_c_step_shfl(m, d, sh, e, 0, lane, step); WPAR_END
+  { const int lane = threadIdx.x; const unsigned* hp = TS_HDR_C(sh, m) + lane;
+    unsigned hd = m.max_list_ndof > 0 ? hp[0] : FB_HDR_IDLE;
+    for (int step = 0; step < m.max_list_ndof; step++) {
+      const unsigned nxt = step + 1 < m.max_list_ndof ? hp[(step + 1) * FB_NY] : FB_HDR_IDLE;
+      tsolve_c_step_shfl(m, d, sh, e, 0, lane, hd); __syncwarp();
+      hd = nxt;
+    } }
 #else
+  for (int step = 0; step < m.max_list_ndof; step++) {
     WPAR_BEGIN tsolve_c_step(m, d, sh, e, 0, lane, step); WPAR_END
     WPAR_BEGIN tsolve_c_fin(m, d, sh, e, 0, lane, step); WPAR_END
-#endif
   }
+#endif
 }
 FB_WARPFN void tri_solve(const DevModel& m, const DevData& d, ShTree& sh, int e) {
   tsolve_a(m, d, sh, e);
@@ -635,60 +666,56 @@ FB_DEV void kvel_p1(FB_PHASE_ARGS) {
     prev = b;
   }
 }
+// (Subtree sums of the velocity stage stay in the record: moving them to shared memory as in the position kernel was measured on
+// the B200 and lost 15 % in this kernel -- 3.3 KB more shared memory per warp shrinks the L1 the scattered record loads live in.)
 // all lanes over bodies: bias force (kept un-accumulated in bfrc0 for the sensor pass) and fluid wrench
-// BFS(b, k): bias force (k < 6) and fluid wrench (k >= 6) of body b, summed over its subtree in shared memory (kvel_p2, kvel_p3)
-// and projected onto the dofs (kvel_p3b); only the per-body bias force bfrc0 is needed after this kernel (sensor pass of `finish`)
-#define BFS(b, k) bfs_[((b) * 12 + (k)) * FB_LANES + lane]
-#define FB_VEL_DYN(m) (FB_PARTF + 12 * (m).nbody)
+// all lanes over bodies: bias force (kept un-accumulated in bfrc0 for the sensor pass) and fluid wrench
 FB_DEV void kvel_p1b(FB_PHASE_ARGS) {
-  float* part_ = sh_dyn(sh); float* bfs_ = part_ + FB_PARTF; (void)part_;
   for (int b = y; b < m.nbody; b += FB_NY) {
     S6 f; f.a = f.l = v3(0, 0, 0); S6 fl = f;
     if (b > 0) { f = body_inertial_force(m, d, e, b, d.bvel, d.bacc); fl = body_fluid_wrench(m, d, e, b); }
-    st6(d.bfrc0, b, d, e, f);
-    BFS(b, 0) = f.a.x; BFS(b, 1) = f.a.y; BFS(b, 2) = f.a.z; BFS(b, 3) = f.l.x; BFS(b, 4) = f.l.y; BFS(b, 5) = f.l.z;
-    BFS(b, 6) = fl.a.x; BFS(b, 7) = fl.a.y; BFS(b, 8) = fl.a.z; BFS(b, 9) = fl.l.x; BFS(b, 10) = fl.l.y; BFS(b, 11) = fl.l.z;
+    st6(d.bfrc, b, d, e, f); st6(d.bfrc0, b, d, e, f); st6(d.bfl, b, d, e, fl);
   }
 }
 // subtree sums of (bias force, fluid wrench): child -> parent along the lists
 FB_DEV void kvel_p2(FB_PHASE_ARGS) {
-  float* part_ = sh_dyn(sh); float* bfs_ = part_ + FB_PARTF;
+  float* part_ = sh_dyn(sh);
   if (y >= m.nlist) return;
   float acc[12], carry[12]; int carry_to = -1;
   for (int k = 0; k < 12; k++) { acc[k] = 0; carry[k] = 0; }
   FB_LIST_LOOP_REV {
     float cur[12];
-    for (int k = 0; k < 12; k++) cur[k] = BFS(b, k);
-    if (carry_to == b) { for (int k = 0; k < 12; k++) { cur[k] += carry[k]; BFS(b, k) = cur[k]; } }
-    else if (carry_to >= 0) { for (int k = 0; k < 12; k++) BFS(carry_to, k) += carry[k]; }
+    { S6 f_ = ld6(d.bfrc, b, d, e), g_ = ld6(d.bfl, b, d, e);
+      cur[0] = f_.a.x; cur[1] = f_.a.y; cur[2] = f_.a.z; cur[3] = f_.l.x; cur[4] = f_.l.y; cur[5] = f_.l.z;
+      cur[6] = g_.a.x; cur[7] = g_.a.y; cur[8] = g_.a.z; cur[9] = g_.l.x; cur[10] = g_.l.y; cur[11] = g_.l.z; }
+    if (carry_to == b) { for (int k = 0; k < 12; k++) cur[k] += carry[k]; st6v(d.bfrc, b, d, e, cur); st6v(d.bfl, b, d, e, cur + 6); }
+    else if (carry_to >= 0) { add6v(d.bfrc, carry_to, d, e, carry); add6v(d.bfl, carry_to, d, e, carry + 6); }
     int p = m.body_parentid[b];
     if (m.body_isroot[p]) { for (int k = 0; k < 12; k++) acc[k] += cur[k]; carry_to = -1; }
     else { for (int k = 0; k < 12; k++) carry[k] = cur[k]; carry_to = p; }
   }
-  if (carry_to >= 0) for (int k = 0; k < 12; k++) BFS(carry_to, k) += carry[k];
+  if (carry_to >= 0) { add6v(d.bfrc, carry_to, d, e, carry); add6v(d.bfl, carry_to, d, e, carry + 6); }
   for (int k = 0; k < 12; k++) PART(y, k) = acc[k];
 }
 FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e, int y);
 FB_DEV void kvel_p3(FB_PHASE_ARGS) {
-  float* part_ = sh_dyn(sh); float* bfs_ = part_ + FB_PARTF;
+  float* part_ = sh_dyn(sh);
   if (y < m.nroot) {
     int r = y, b = m.root_body[r];
-    for (int k = 0; k < 12; k++) {
-      float a1 = 0;
-      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) a1 += PART(l, k);
-      BFS(b, k) += a1;
+    for (int k = 0; k < 6; k++) {
+      float a1 = 0, a2 = 0;
+      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) { a1 += PART(l, k); a2 += PART(l, 6 + k); }
+      AT(d.bfrc, S6I(b, k)) += a1; AT(d.bfl, S6I(b, k)) += a2;
     }
   }
   sensors_vel(m, d, e, y);
 }
 // all lanes over dofs: qfrc_bias = S . f_subtree ; qfrc_passive = S . fluid_subtree + springs + dampers
 FB_DEV void kvel_p3b(FB_PHASE_ARGS) {
-  float* part_ = sh_dyn(sh); const float* bfs_ = part_ + FB_PARTF; (void)part_;
   for (int k = y; k < m.nv; k += FB_NY) {
     int b = m.dof_bodyid[k];
     V3 Sa = ld3(d.Sang, k, d, e), Sl = ld3(d.Slin, k, d, e);
-    S6 f, fl; f.a = v3(BFS(b, 0), BFS(b, 1), BFS(b, 2)); f.l = v3(BFS(b, 3), BFS(b, 4), BFS(b, 5));
-    fl.a = v3(BFS(b, 6), BFS(b, 7), BFS(b, 8)); fl.l = v3(BFS(b, 9), BFS(b, 10), BFS(b, 11));
+    S6 f = ld6(d.bfrc, b, d, e), fl = ld6(d.bfl, b, d, e);
     AT(d.qfrc_bias, k) = dot(Sa, f.a) + dot(Sl, f.l);
     float pas = dot(Sa, fl.a) + dot(Sl, fl.l) - m.dof_damping[k] * AT(d.qvel, k);
     int j = m.dof_jntid[k];

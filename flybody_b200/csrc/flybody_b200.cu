@@ -208,12 +208,15 @@ static void fb_launch(FbSim* s, int kind, size_t dyn_floats = 0, int nwarps = -1
   (void)kind;
   int e0 = 0;
   if (nwarps < 0) { e0 = s->cur_e0; nwarps = s->cur_n; }
-  static std::vector<unsigned char> buf;
-  size_t need = slice_bytes(sizeof(Sh), dyn_floats) + 64;
-  if (buf.size() < need) buf.resize(need);
+  // the slice is exactly as large as the GPU launch makes it, followed by a canary: a phase that writes past its shared-memory
+  // slice (on the GPU: into the next warp's slice or out of the block's allocation) aborts the CPU tests instead of passing
+  const size_t used = slice_bytes(sizeof(Sh), dyn_floats);
+  std::vector<unsigned char> buf(used + 256, 0);
+  memset(buf.data() + used, 0xAB, 256);
   Sh& sh = *reinterpret_cast<Sh*>(buf.data());
   (void)blob_words; set_prog(sh, s->m.tsolve_blob);        // host emulation: the program is read in place
   for (int e = e0; e < e0 + nwarps; e++) (St::emu(s->m, s->d, sh, e), ...);
+  for (size_t i = 0; i < 256; i++) if (buf[used + i] != 0xAB) { fprintf(stderr, "fb_emu: shared-memory slice overrun in a kernel of kind %d (slice %zu bytes)\n", kind, used); abort(); }
   s->launches++;
 }
 static void fb_launch_warp(FbSim* s, int kind) {
@@ -274,10 +277,10 @@ FB_DEV void ph_smooth_out(FB_PHASE_ARGS) {
 #define FB_ST_VEL Ph<kvel_p0>, Ph<kvel_p1>, Ph<kvel_p1b>, Ph<kvel_p2>, Ph<kvel_p3>, Ph<kvel_p3b>, Ph<kvel_p4>
 #define FB_ST_SMOOTH Ph<kact_p0>, Ph<kact_p1>, Ph<kact_p2>, Ph<kact_p2b>, Ph<kact_p3>, Wf<wf_smooth_solve>, Ph<ph_smooth_out>, Ph<kref>
 #define FB_ST_FINISH Ph<kfin_f1>, Wf<kfin_solve>, Ph<kfin_f5>, Ph<kfin_f6>, Ph<kfin_f7>, Wf<kfin_solve_euler>, Ph<kfin_f8>, Ph<kfin_f9>, Ph<kfin_f10>
-static size_t dyn_pos(const DevModel& m) { return (size_t)FB_PARTF + (size_t)m.nM; }
+static size_t dyn_pos(const DevModel& m) { return (size_t)FB_PARTF + std::max((size_t)m.nM, (size_t)10 * m.nbody); }   // LS region: inertia matrix rows, before that the composite inertias (CRBS)
 static size_t dyn_col(const DevModel& m) { return (size_t)FB_COL_DYN(m); }
 static size_t dyn_proj(const DevModel&) { return (size_t)FB_NY * FB_ZCAP; }
-static size_t dyn_vel(const DevModel& m) { return (size_t)FB_VEL_DYN(m); }
+static size_t dyn_vel(const DevModel&) { return (size_t)FB_PARTF; }
 static size_t dyn_tsolve(const DevModel& m) { return (size_t)(FB_NXS(m) + ((m.nM + 3) & ~3)); }
 
 static void launch_step1(FbSim* s) {

@@ -47,10 +47,10 @@ for rnd in range(a.rounds):                      # interleaved rounds: box drift
             sim.sync(); torch.cuda.synchronize()
             prof = {k: round(v[0] / a.steps, 3) for k, v in sim.profile_read().items() if v[1]}
             sim.profile(False)
-            nefc = sim.get(st.NEFC)[:, 0]
+            nefc = sim.get(st.NEFC)[:, 0]; nit = sim.get(st.SOLVER_NITER)[:, 0].astype(int)
             key = (os.path.basename(lib), N)
             res.setdefault(key, []).append(ms)
             print(json.dumps({'lib': key[0], 'envs': N, 'round': rnd, 'ms_per_step': round(ms, 3), 'env_steps_per_s': round(N / ms * 1e3), 'stages_ms': prof,
-                              'nefc_mean': float(nefc.mean()), 'share_nefc_gt32': float((nefc > 32).mean()), 'flags': int((sim.get(st.FLAGS) != 0).sum())}), flush=True)
+                              'nefc_mean': float(nefc.mean()), 'niter_hist': {str(b): int((nit == b).sum()) for b in range(0, 9)}, 'niter_gt8': int((nit > 8).sum()), 'niter_max': int(nit.max()), 'share_nefc_gt32': float((nefc > 32).mean()), 'flags': int((sim.get(st.FLAGS) != 0).sum())}), flush=True)
             sim.close()
 print('SUMMARY', {f'{k[0]}@{k[1]}': [round(x, 3) for x in v] for k, v in res.items()})
