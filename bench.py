@@ -93,12 +93,31 @@ def start_state(m, wl, rs):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def host_cores():
-    """cores this process may run on (cgroup / affinity aware; os.cpu_count() is the machine's)"""
+def cpu_quota():
+    """CPU time the container may use, in cores (cgroup v2 cpu.max / v1 cfs quota), or None if unlimited / unknown"""
     try:
-        return sorted(os.sched_getaffinity(0))
+        q, p = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        return None if q == 'max' else float(q) / float(p)
+    except Exception:
+        pass
+    try:
+        q = float(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read()); p = float(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+        return None if q <= 0 else q / p
+    except Exception:
+        return None
+
+
+def host_cores():
+    """cores this process may run on: the affinity mask, cut to the cgroup's CPU quota (os.cpu_count() is the machine's: a container
+    that is allowed 16 cores' worth of time on a 128-core host runs 128 workers at an eighth of their speed each)"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
     except AttributeError:
-        return list(range(os.cpu_count() or 1))
+        cores = list(range(os.cpu_count() or 1))
+    q = cpu_quota()
+    if q is not None and q >= 1 and int(q) < len(cores):
+        cores = cores[:int(q)]
+    return cores
 
 
 def cpu_oracle_worker(args):
@@ -145,7 +164,7 @@ def cpu_baseline(wl, budget_s=10.0, max_steps=100000):
                       f'gcc -O3 -mavx2, tree-sparse L^T D L + low-rank Newton Hessian as MuJoCo structures it; NOT MuJoCo itself (not installable '
                       f'here); {sum(n for n, _ in res)} env-steps total',
             'per_core': rate / len(cores), 'single_process_per_core': n1 / t1,
-            'machine_cpu_count': os.cpu_count()}
+            'machine_cpu_count': os.cpu_count(), 'cgroup_cpu_quota_cores': cpu_quota()}
 
 
 def run_reference(args, wl):

@@ -304,7 +304,8 @@ def load_mesh_cache(assets_dir=None, rebuild=False):
 
 
 def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mesh_cache=None,
-                    joint_filter=None, claw_friction=1.0, terminal=None, force_actuators=False, use_wings=None, use_legs=None):
+                    joint_filter=None, claw_friction=1.0, terminal=None, force_actuators=False, use_wings=None, use_legs=None,
+                    use_mouth=False, use_antennae=False, adhesion_filter=0.007, dyntype_filterexact=False):
     """`variant` picks the task's model surgery (reference tasks/base.py `Walking` / `Flying`); `force_actuators`, `use_wings`,
     `use_legs` and `joint_filter` are the `FruitFly` constructor switches the env factories expose (reference fly_envs.py:100-246:
     force_actuators, disable_wings, disable_legs, joint_filter); None keeps the task's default."""
@@ -320,6 +321,16 @@ def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mes
         timestep = float(fx.root.find('option').get('timestep'))
         spawn = np.zeros(3)
         prefix = ''
+    elif variant == 'walker':
+        # the `FruitFly` entity on its own, as the reference's tests/test_flywalker.py builds it (`mjcf.Physics.from_mjcf_model(
+        # fly.mjcf_model)`): the walker's MJCF surgery, no task, no arena, no ghost; the free joint is removed (fruitfly.py:187),
+        # so the thorax is welded to the world
+        fx = build_fly_xml(xml_path, name='walker', use_legs=True if use_legs is None else use_legs,
+                           use_wings=True if use_wings is None else use_wings, use_mouth=use_mouth, use_antennae=use_antennae,
+                           joint_filter=0.01 if joint_filter is None else joint_filter, adhesion_filter=adhesion_filter,
+                           force_actuators=force_actuators, dyntype_filterexact=dyntype_filterexact)
+        timestep = float(fx.root.find('option').get('timestep'))
+        spawn, prefix = np.zeros(3), ''
     elif variant == 'walk':
         jf = 0.01 if joint_filter is None else joint_filter
         fx = build_fly_xml(xml_path, name='walker', use_legs=True if use_legs is None else use_legs,
@@ -384,7 +395,7 @@ def compile_variant(variant='walk', assets_dir=None, inertia_mode='legacy2', mes
     classes = parse_defaults(fx.root)
     bodies = [Body('world', -1, np.zeros(3), np.array([1.0, 0, 0, 0]))]
     _extract_bodies(fx, classes, prefix, mesh_cache, inertia_mode, bodies, 0, spawn,
-                    root_free=(variant != 'bare'))
+                    root_free=(variant not in ('bare', 'walker')))
     n_walker_bodies = len(bodies)
 
     # excludes -> body-name pairs

@@ -711,8 +711,7 @@ FB_DEV void proj_chain(const DevModel& m, const DevData& d, int e, int r, int la
   if (L > FB_ZCAP) { FB_FLAG_OR(4); L = FB_ZCAP; }
   const int Lo = other_last >= 0 ? m.dof_chainlen[other_last] : 0, base = accumulate ? FB_ZCAP : 0;
   // chain b joins chain a at its first common ancestor: from there up the entries are added to chain a's slots
-  int join = L;
-  if (accumulate) for (int p = 0; p < L; p++) if (in_chain(m, m.dof_anc[adr0 + p], other_last)) { join = p; break; }
+  const int join = (accumulate && other_last >= 0) ? L - m.dof_lca[last * m.nv + other_last] : L;
   for (int p = 0; p < L; p++) {
     int k = m.dof_anc[adr0 + p];
     float v = contact ? sgn * contact_J(m, d, e, f, pos, k) : (p == 0 ? sgn : 0.0f);
@@ -752,17 +751,20 @@ FB_DEV void kproj_p0(FB_ROW_ARGS) {
   }
 }
 // A = Z Z^T (= J M^-1 J^T, the unregularised Delassus matrix), packed lower triangle; pairs dealt to all lanes
-// Z[r] . Z[c] restricted to one chain of row c (`cl` = its end dof, `cbase` = its slot base); chain b stops where it joins chain a
-FB_DEV float zdot_chain(const DevModel& m, const DevData& d, int e, int r, int rla, int rlb, int Lra, int Lrb, int c, int cl, int cbase, int stop_at) {
-  if (cl < 0) return 0.0f;
-  const int adr = m.dof_Madr[cl]; int L = m.dof_chainlen[cl]; if (L > FB_ZCAP) L = FB_ZCAP;
+// Z[r] . Z[c] over the dofs one chain of row r shares with one chain of row c.  Two ancestor chains share exactly their common TAIL
+// (from the lowest common ancestor up), m.dof_lca gives its length, and with the chain-sparse row layout (EJC) the shared dofs are
+// a CONTIGUOUS slot range in both rows: a plain dot product, no membership tests and no chain walk.  (x, y) in {a, b}: `base` is
+// the chain's slot base (0 / FB_ZCAP), `lim` how many of its leading slots the row stores (chain a: all of it; chain b: only the
+// part below its join with chain a -- the common ancestors carry the summed entry in their chain-a slot).
+FB_DEV float zdot_tail(const DevModel& m, const DevData& d, int e, int r, int lx, int Lx, int xbase, int xlim, int c, int ly, int Ly, int ybase, int ylim) {
+  if (lx < 0 || ly < 0) return 0.0f;
+  const int mlen = m.dof_lca[lx * m.nv + ly];
+  if (mlen == 0) return 0.0f;
+  const int sh = Lx - Ly;                                   // slot in chain x = slot in chain y + sh (both count from the chain's end dof upwards)
+  int p = Ly - mlen, p_hi = Ly < ylim ? Ly : ylim;
+  if (xlim - sh < p_hi) p_hi = xlim - sh;
   float s = 0;
-  for (int p = 0; p < L; p++) {
-    const int k = m.dof_anc[adr + p], ck = L - p;
-    if (stop_at >= 0 && in_chain(m, k, stop_at)) break;          // from here up the entries live in (and were counted with) chain a
-    if (in_chain(m, k, rla)) s += EJC(d.efc_Z, r, Lra - ck) * EJC(d.efc_Z, c, cbase + p);
-    else if (in_chain(m, k, rlb)) s += EJC(d.efc_Z, r, FB_ZCAP + Lrb - ck) * EJC(d.efc_Z, c, cbase + p);
-  }
+  for (; p < p_hi; p++) s += EJC(d.efc_Z, r, xbase + p + sh) * EJC(d.efc_Z, c, ybase + p);
   return s;
 }
 FB_DEV void kproj_p1(FB_ROW_ARGS) {
@@ -774,7 +776,11 @@ FB_DEV void kproj_p1(FB_ROW_ARGS) {
     int c = idx - r * (r + 1) / 2;
     const int rla = AT(d.efc_la, r), rlb = AT(d.efc_lb, r), cla = AT(d.efc_la, c), clb = AT(d.efc_lb, c);
     const int Lra = rla >= 0 ? m.dof_chainlen[rla] : 0, Lrb = rlb >= 0 ? m.dof_chainlen[rlb] : 0;
-    AT(d.efc_A, idx) = zdot_chain(m, d, e, r, rla, rlb, Lra, Lrb, c, cla, 0, -1) + zdot_chain(m, d, e, r, rla, rlb, Lra, Lrb, c, clb, FB_ZCAP, cla);
+    const int Lca = cla >= 0 ? m.dof_chainlen[cla] : 0, Lcb = clb >= 0 ? m.dof_chainlen[clb] : 0;
+    const int jr = (rlb >= 0 && rla >= 0) ? Lrb - m.dof_lca[rlb * m.nv + rla] : Lrb;      // slots of chain b below its join with chain a
+    const int jc = (clb >= 0 && cla >= 0) ? Lcb - m.dof_lca[clb * m.nv + cla] : Lcb;
+    AT(d.efc_A, idx) = zdot_tail(m, d, e, r, rla, Lra, 0, Lra, c, cla, Lca, 0, Lca) + zdot_tail(m, d, e, r, rla, Lra, 0, Lra, c, clb, Lcb, FB_ZCAP, jc)
+                     + zdot_tail(m, d, e, r, rlb, Lrb, FB_ZCAP, jr, c, cla, Lca, 0, Lca) + zdot_tail(m, d, e, r, rlb, Lrb, FB_ZCAP, jr, c, clb, Lcb, FB_ZCAP, jc);
   }
 }
 // aref and b = J qacc_smooth - aref for every row.  J qacc_smooth = Z (D^-1/2 L^-T qfrc_smooth); that vector is
@@ -792,10 +798,9 @@ FB_DEV void kref(FB_PHASE_ARGS) {
       for (int t = 0; t < len; t++) { int k = m.dof_anc[adr + t]; vel += EJC(d.efc_J, r, t) * AT(d.qvel, k); as += EJC(d.efc_Z, r, t) * XS(k); }
     }
     if (lb >= 0) {
-      int adr = m.dof_Madr[lb], len = m.dof_chainlen[lb];
+      int adr = m.dof_Madr[lb], len = m.dof_chainlen[lb] - (la >= 0 ? m.dof_lca[lb * m.nv + la] : 0);      // common ancestors were counted with chain a
       for (int t = 0; t < len; t++) {
         int k = m.dof_anc[adr + t];
-        if (la >= 0 && k <= la && la <= m.dof_subend[k]) break;      // common ancestors were counted with chain a
         vel += EJC(d.efc_J, r, FB_ZCAP + t) * AT(d.qvel, k); as += EJC(d.efc_Z, r, FB_ZCAP + t) * XS(k);
       }
     }

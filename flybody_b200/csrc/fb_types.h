@@ -80,6 +80,7 @@ struct DevModel {
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
   const float *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_solref, *jnt_solimp, *jnt_margin, *qpos0, *qpos_spring;
   const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subend, *dof_depth /* #non-root ancestors; local index for root dofs */, *dof_isroot, *dof_chainlen, *dof_anc /* [nM] t-th ancestor of the row's dof */, *dof_ancslot /* same, as shared-memory slot of tri_solve */;
+  const unsigned char* dof_lca;   // [nv][nv] number of common ancestors-or-self of two dofs (= chain length of their lowest common ancestor, 0: none)
   const int *dof_rootidx /* root (index into root_body) a list dof hangs off, -1 for root dofs */, *root_haslists;
   const unsigned *step_hdr_a, *step_hdr_c;   // [max_list_ndof][32] packed sweep headers, deepest-first / shallowest-first
   const unsigned* tsolve_blob; int ts_hdr_words, ts_nm_pad, ts_blob_words;    // sweep program copied per CTA into shared memory (fb_tree.h)

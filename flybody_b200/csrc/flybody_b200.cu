@@ -500,6 +500,15 @@ static int build_model(FbSim* s, const FbModel* h) {
     for (int i = 0; i < nv; i++) if (dof_list[i] >= 0) { rootidx[i] = lr[dof_list[i]]; haslists[lr[dof_list[i]]] = 1; }
     m.dof_rootidx = up(s, rootidx); m.root_haslists = up(s, haslists);
   }
+  { // common-ancestor counts of every dof pair (kproj_p1: the dofs two constraint rows share are the common TAIL of their chains)
+    if (nv > 255) { s->err = "too many dofs for the byte-sized common-ancestor table"; return -3; }
+    std::vector<unsigned char> lca((size_t)nv * nv, 0); std::vector<int> mark(nv, -1);
+    for (int a = 0; a < nv; a++) {
+      for (int j = a; j >= 0; j = h->dof_parentid[j]) mark[j] = a;
+      for (int b = 0; b < nv; b++) { int j = b; while (j >= 0 && mark[j] != a) j = h->dof_parentid[j]; lca[(size_t)a * nv + b] = (unsigned char)(j >= 0 ? chainlen[j] : 0); }
+    }
+    m.dof_lca = up(s, lca);
+  }
   { std::vector<int> adh(nb, -1); for (int i = 0; i < h->nu; i++) if (h->actuator_trntype[i] == FB_TRN_BODY) adh[h->actuator_trnid[i]] = i; m.body_adhesion = up(s, adh); }
   { // packed headers of the lock-step sweeps (see fb_tree.h) and the row address of every ancestor entry
     if (h->nM >= 4096 || nv >= 256) { s->err = "model too large for the packed sweep headers (nM < 4096, nv < 256)"; return -3; }

@@ -199,12 +199,12 @@ class BatchedFlyEnv:
 
     def __init__(self, variant, n_envs, device=0, terminal_com_dist=0.3, time_limit=10.0, future_steps=64,
                  lib_path=None, reset_noise=0.0, seed=0, traj_generator=None, wpg_pattern_path=None, inference_mode=True,
-                 max_reference_steps=None, device_task=False):
+                 max_reference_steps=None, device_task=False, model=None):
         assert variant in _VARIANTS
         self._variant = variant
         self._batched = n_envs is not None
         self.n_envs = int(n_envs) if self._batched else 1
-        self.model = load_model(variant)
+        self.model = model if model is not None else load_model(variant)      # `model`: a variant from flymodel.model_for
         m = self.model
         self._device = int(device)
         self._sim = st.BatchedStepper(m, self.n_envs, device=device, lib_path=lib_path)
@@ -269,13 +269,15 @@ class BatchedFlyEnv:
                 out.extend(range(m.sensor_adr[i], m.sensor_adr[i] + m.sensor_dim[i]))
             return np.array(out)
         self._sd = dict(accelerometer=sd(['accelerometer']), gyro=sd(['gyro']), velocimeter=sd(['velocimeter']))
-        if variant == 'walk':
+        self._has_legs = 'walker/force_tarsus_T1_left' in sens      # Walking always; Flying with disable_legs=False (base.py:360-364)
+        if self._has_legs:
             legs = [f'T{k}_{s}' for k in (1, 2, 3) for s in ('left', 'right')]
             self._sd.update(force=sd([f'force_tarsus_{l}' for l in legs]), touch=sd([f'touch_claw_{l}' for l in legs]))
             app = [f'walker/claw_T{k}_{s}' for k in (1, 2, 3) for s in ('left', 'right')] + ['walker/head']
             self._app_sites = np.array([sn.index(n) for n in app])
         else:
             self._app_sites = np.zeros(0, np.int64)
+        if variant != 'walk':
             # position of the wing joints inside the joints_pos observable (the host reads wing angles from there)
             self._wing_in_obs = np.array([m.meta['observable_joints'].index(n) for n in wing_names])
             self._wing_qpos_host = np.zeros((N, 6))
@@ -339,7 +341,11 @@ class BatchedFlyEnv:
         if 'force' in sd:
             full['force'] = (len(sd['force']), (len(sd['force']),), (st.OBS_SENSOR_MEAN, sd['force'][0], len(sd['force'])))
             full['touch'] = (len(sd['touch']), (len(sd['touch']),), (st.OBS_SENSOR_MEAN, sd['touch'][0], len(sd['touch'])))
-        rows = [('walker/' + k,) + full[k] for k in _VARIANTS[self._variant]['obs']]
+        names = list(_VARIANTS[self._variant]['obs'])
+        if self._has_legs and 'force' not in names:      # Flying with legs: appendages_pos, force, touch join the walker's observables,
+            walker = sorted(names[:-2] + ['appendages_pos', 'force', 'touch'])      # which dm_control lists alphabetically, task ones last
+            names = walker + names[-2:]
+        rows = [('walker/' + k,) + full[k] for k in names]
         rows += [('_velocimeter_now', 3, (3,), (st.OBS_SENSOR_NOW, sd['velocimeter'][0], 3)),
                  ('_gyro_now', 3, (3,), (st.OBS_SENSOR_NOW, sd['gyro'][0], 3)),
                  ('_scalars', 3, (3,), (st.OBS_SCALARS, 0, 3))]
@@ -775,15 +781,17 @@ def walk_imitation(ref_path=None, force_actuators=False, disable_wings=True, tra
     dataset, or its `.npz` conversion, see `trajectory_loaders`) every env tracks its own snippet, starts from the
     snippet's full-body pose and is rewarded with the DeepMimic factors; without it the task runs in inference mode on
     the synthetic straight walk, reward 1 (`fly_envs.py:127-135`)."""
+    model = None
     if force_actuators or not disable_wings or joint_filter != 0.01:
-        raise NotImplementedError('only the default walk_imitation model variant is compiled '
-                                  '(flybody_b200/assets/fly_walk.npz); recompile with compiler.compile_variant')
+        from .flymodel import model_for
+        model = model_for('walk', force_actuators=force_actuators, use_wings=True if not disable_wings else None,
+                          joint_filter=None if joint_filter == 0.01 else joint_filter)
     tg = None
     if ref_path is not None:
         tg = HDF5WalkingTrajectoryLoader(path=ref_path, random_state=random_state, traj_indices=traj_indices)
     return BatchedFlyEnv('walk', n_envs, device=device, terminal_com_dist=terminal_com_dist, time_limit=10.0,
                          future_steps=64, lib_path=lib_path, reset_noise=reset_noise, seed=seed, traj_generator=tg,
-                         inference_mode=ref_path is None, max_reference_steps=max_reference_steps, device_task=device_task)
+                         inference_mode=ref_path is None, max_reference_steps=max_reference_steps, device_task=device_task, model=model)
 
 
 def flight_imitation(ref_path=None, wpg_pattern_path=None, force_actuators=False, disable_legs=True, traj_indices=None,
@@ -792,16 +800,18 @@ def flight_imitation(ref_path=None, wpg_pattern_path=None, force_actuators=False
     """Batched `flybody.fly_envs.flight_imitation` (reference `fly_envs.py:30-97`): wing-beat-pattern-generator flight
     tracking, 4 substeps of 5e-5 s per control step, 12 actions (head 3, wings 6, abdomen 2, beat frequency 1).  With
     `ref_path` every env tracks its own (randomly cut) CoM trajectory of the flight dataset."""
-    if force_actuators or not disable_legs or joint_filter != 0.0:
-        raise NotImplementedError('only the default flight_imitation model variant is compiled '
-                                  '(flybody_b200/assets/fly_flight.npz); recompile with compiler.compile_variant')
+    model = None
+    if force_actuators or not disable_legs or joint_filter != 0.0:      # a non-default FruitFly: compiled on first use (flymodel.model_for)
+        from .flymodel import model_for
+        model = model_for('flight', force_actuators=force_actuators, use_legs=True if not disable_legs else None,
+                          joint_filter=None if joint_filter == 0.0 else joint_filter)
     tg = None
     if ref_path is not None:
         tg = HDF5FlightTrajectoryLoader(path=ref_path, traj_indices=traj_indices, randomize_start_step=randomize_start_step,
                                         random_state=random_state)
     return BatchedFlyEnv('flight', n_envs, device=device, terminal_com_dist=terminal_com_dist, time_limit=0.6,
                          future_steps=future_steps, lib_path=lib_path, seed=seed, wpg_pattern_path=wpg_pattern_path,
-                         traj_generator=tg, device_task=device_task)
+                         traj_generator=tg, device_task=device_task, model=model)
 
 
 def vision_guided_flight(wpg_pattern_path=None, bumps_or_trench='bumps', force_actuators=False, disable_legs=True, random_state=None,

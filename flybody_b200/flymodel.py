@@ -161,3 +161,62 @@ def from_compiled(m):
     arrays = {k: v for k, v in m.items() if isinstance(v, np.ndarray)}
     meta = {k: v for k, v in m.items() if not isinstance(v, np.ndarray) and not k.startswith('_')}
     return FlyModel(arrays, meta)
+
+
+# ------------------------------------------------------------------------------------------------ model variants on demand
+def reference_assets_dir():
+    """Directory holding the reference's `fruitfly.xml` + meshes: $FLYBODY_ASSETS, an installed `flybody` package, or the
+    reference checkout of the build container.  None if none is present (only the shipped, pre-compiled variants are available)."""
+    cand = [os.environ.get('FLYBODY_ASSETS')]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec('flybody')
+        if spec is not None and spec.submodule_search_locations:
+            cand.append(os.path.join(list(spec.submodule_search_locations)[0], 'fruitfly', 'assets'))
+    except Exception:
+        pass
+    cand.append('/root/reference/flybody/fruitfly/assets')
+    for c in cand:
+        if c and os.path.exists(os.path.join(c, 'fruitfly.xml')):
+            return c
+    return None
+
+
+def variant_name(variant, force_actuators=False, use_wings=None, use_legs=None, joint_filter=None):
+    name = f'fly_{variant}'
+    if force_actuators:
+        name += '_force'
+    if use_wings is not None:
+        name += '_wings' if use_wings else '_nowings'
+    if use_legs is not None:
+        name += '_legs' if use_legs else '_nolegs'
+    if joint_filter is not None:
+        name += f'_jf{joint_filter:g}'
+    return name
+
+
+def model_for(variant, force_actuators=False, use_wings=None, use_legs=None, joint_filter=None, cache_dir=None):
+    """The compiled model of a task (`variant` = walk / flight / vision) with the `FruitFly` switches the reference's env factories
+    expose (reference fly_envs.py:100-246: force_actuators, disable_wings, disable_legs, joint_filter; None = the task's default).
+    The default models ship pre-compiled (`assets/fly_*.npz`); any other combination is compiled from the reference's
+    `fruitfly.xml` on first use (`flybody_b200.compiler`, ~2 s) and cached."""
+    if not force_actuators and use_wings is None and use_legs is None and joint_filter is None:
+        return load_model(variant)
+    name = variant_name(variant, force_actuators, use_wings, use_legs, joint_filter)
+    cache_dir = cache_dir or os.environ.get('FLYBODY_B200_CACHE') or os.path.join(os.path.expanduser('~'), '.cache', 'flybody_b200')
+    for d in (ASSETS, cache_dir):
+        p = os.path.join(d, name + '.npz')
+        if os.path.exists(p):
+            return load_model(path=p)
+    src = reference_assets_dir()
+    if src is None:
+        raise NotImplementedError(
+            f'model variant {name} is not among the pre-compiled ones ({sorted(f for f in os.listdir(ASSETS) if f.endswith(".npz"))}) and the '
+            "reference's fruitfly.xml was not found to compile it: install flybody or set FLYBODY_ASSETS to its fruitfly/assets directory")
+    from .compiler import compile_model as cm
+    m = cm.compile_variant(variant, assets_dir=src, mesh_cache=cm.load_mesh_cache(src), force_actuators=force_actuators, use_wings=use_wings,
+                           use_legs=use_legs, joint_filter=joint_filter)
+    os.makedirs(cache_dir, exist_ok=True)
+    p = os.path.join(cache_dir, name + '.npz')
+    cm.save_model(m, p)
+    return load_model(path=p)
