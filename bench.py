@@ -371,6 +371,84 @@ def line_of(wl, args, world, r):
     }
 
 
+def measure_vision(args, world, rank, local, n_envs=1024):
+    """BASELINE.json configs[4] shape: `vision_guided_flight` (heightfield terrain contacts, two 32 x 32 x 3 eye cameras rendered on the
+    device every step, wing-beat pattern generator) + the reference's vision policy (VisNet + two-level controller,
+    flybody_b200/policy_torch.py, random weights) in the loop.  The env's task hooks are host code (flybody_b200/vision_env.py), so this
+    workload has no device-resident arm: the one number is end to end -- env.step(host actions) -> observations on the host -> policy
+    forward on the GPU of rank 0 (observations + eyes of all ranks gathered over NCCL, actions scattered back) -> actions on the host."""
+    import torch
+    import torch.distributed as dist
+    from flybody_b200 import fly_envs
+    from flybody_b200.policy_torch import vision_policy_for
+    dev = torch.device('cuda', local)
+    K, W, N = args.steps, args.warmup, n_envs
+    env = fly_envs.vision_guided_flight(n_envs=N, device=local, seed=1234 + rank, terrain_bank=64)
+    ts = env.reset()
+    vis, ctl, keys = vision_policy_for(env, device=dev)
+    spec = env.action_spec()
+    lo, hi = torch.tensor(spec.minimum, device=dev, dtype=torch.float32), torch.tensor(spec.maximum, device=dev, dtype=torch.float32)
+    A = spec.shape[0]
+    bufs = {}
+
+    def act(ts):
+        o = ts.observation
+        left, right = torch.from_numpy(o['walker/left_eye']).to(dev, non_blocking=True), torch.from_numpy(o['walker/right_eye']).to(dev, non_blocking=True)
+        task = torch.from_numpy(o['walker/task_input']).to(dev)
+        others = torch.from_numpy(np.concatenate([np.asarray(o[k], np.float32).reshape(N, -1) for k in keys], 1)).to(dev)
+        if world > 1:
+            if not bufs:
+                for name, t in (('left', left), ('right', right), ('task', task), ('others', others)):
+                    bufs[name] = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+                bufs['a_loc'] = torch.empty((N, A), device=dev)
+            for name, t in (('left', left), ('right', right), ('task', task), ('others', others)):
+                dist.gather(t.contiguous(), bufs[name], dst=0)
+            if rank == 0:
+                left, right, task, others = (torch.cat(bufs[n]) for n in ('left', 'right', 'task', 'others'))
+        a = None
+        if rank == 0:
+            with torch.no_grad():
+                a = torch.minimum(torch.maximum(ctl(vis(left, right, task, others)), lo), hi)
+        if world > 1:
+            dist.scatter(bufs['a_loc'], [a[r * N:(r + 1) * N].contiguous() for r in range(world)] if rank == 0 else None, src=0)
+            a = bufs['a_loc']
+        return a.cpu().numpy()
+
+    for k in range(W):
+        ts = env.step(act(ts))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0, r0 = env._sim.launch_count, env.n_resets
+    t0 = time.perf_counter()
+    for k in range(K):
+        ts = env.step(act(ts))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches, resets = env._sim.launch_count - l0, env.n_resets - r0
+    env._sim.profile(True)
+    for k in range(5):
+        ts = env.step(act(ts))
+    prof = {k: v[0] / 5 for k, v in env._sim.profile_read().items() if v[1]}
+    env._sim.profile(False)
+    if world > 1:
+        t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+    eyes_bytes = int(np.asarray(ts.observation['walker/left_eye']).nbytes * 2)
+    obs_bytes = int(sum(np.asarray(v).nbytes for k, v in ts.observation.items() if 'eye' not in k))
+    total = N * world
+    res = {'metric': 'env-steps/sec on vision_guided_flight + vision policy in the loop (control steps of 4 substeps)', 'value': total * K / dt, 'unit': 'env-steps/s',
+           'ms_per_step': dt / K * 1e3, 'n_gpus': world, 'gpu_launches': int(launches),
+           'config': {'workload': f'vision_guided_flight {N} envs per GPU (BASELINE.json configs[4]: 1024 per GPU), bumps terrain 401 x 401 per env from a bank of 64, '
+                                  'eyes 2 x 32 x 32 x 3 uint8 rendered every step, policy = VisNet + TwoLevelController (torch, random weights) on rank 0',
+                      'envs_per_gpu': N, 'total_envs': total, 'auto_resets_in_window': int(resets),
+                      'note': 'end-to-end only: the task hooks of this env are host code, so `value` IS the e2e number (no device-resident arm)'},
+           'e2e': {'value': total * K / dt, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(N * env.model.nu * 4 + eyes_bytes + obs_bytes), 'd2h_bytes_per_step': int(eyes_bytes + obs_bytes + N * A * 4),
+                   'api': 'flybody_b200.fly_envs.vision_guided_flight(n_envs).step(action) + policy_torch.VisNet / TwoLevelController'},
+           'stage_ms_per_step': prof}
+    env.close()
+    return res
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -383,6 +461,14 @@ def run_ours(args, wl):
     if world > 1:
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # stdout carries exactly one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if args.workload == 'vision':
+        res = measure_vision(args, world, rank, local, n_envs=args.envs if args.envs != ENVS_PER_GPU else 1024)
+        if rank == 0:
+            res.update({'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic'})
+            print(json.dumps(res))
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     r = measure(wl, args, world, rank, local, with_exchange=world > 1)
     if rank == 0:
         line = line_of(wl, args, world, r)
@@ -394,6 +480,10 @@ def run_ours(args, wl):
                 line['extra'] = {'flight_imitation': {k: lf[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'config', 'gpu_launches', 'e2e', 'roofline')}}
             except Exception as e:                                   # the headline must not depend on the extra block
                 line['extra'] = {'flight_imitation': {'error': repr(e)}}
+            try:
+                line['extra']['vision_guided_flight'] = measure_vision(args, 1, 0, local)
+            except Exception as e:
+                line['extra']['vision_guided_flight'] = {'error': repr(e)}
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline(wl, budget_s=args.cpu_seconds)
         print(json.dumps(line))
@@ -413,10 +503,10 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the nested flight_imitation block')
     ap.add_argument('--preroll', type=int, default=-1, help='control steps of staggered-reset pre-roll before the warm-up (-1: one episode length; 0: standing start)')
-    ap.add_argument('--workload', default='walk', choices=sorted(WORKLOADS), help='walk = the headline (BASELINE configs[1]); flight = configs[2]')
+    ap.add_argument('--workload', default='walk', choices=sorted(WORKLOADS) + ['vision'], help='walk = the headline (BASELINE configs[1]); flight = configs[2]')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS.get(args.workload, WORKLOADS['flight'])
     if args.impl == 'reference':
         run_reference(args, wl)
     else:

@@ -1161,6 +1161,9 @@ FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e, int y) {
       case FB_OBS_SCALARS: if (y == 0) { o[k] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; } o[k + 1] = s2; o[k + 2] = AT(d.time, 0); } break;
       case FB_OBS_ROOT_POSE: if (y < 3) o[k + y] = comp(rpos + ref, y); else if (y < 7) o[k + y] = AT(d.qpos, rq + y); break;
       case FB_OBS_SUBTREE_COM: if (y < 3) { float mass = AT(d.crb10, FB_I10S * a); o[k + y] = (mass > 0 ? AT(d.crb10, FB_I10S * a + 1 + y) / mass : 0.0f) + AT(d.ref, y); } break;
+      case FB_OBS_WORLD_CONTACT: if (y == 0) { int nc = AT(d.ncon, 0); float hit = 0.0f;
+          for (int ci = 0; ci < nc; ci++) if (AT(d.con_efcadr, ci) >= 0 && (m.geom_bodyid[AT(d.con_geom1, ci)] == 0 || m.geom_bodyid[AT(d.con_geom2, ci)] == 0)) hit = 1.0f;
+          o[k] = hit; } break;
       default: break;
     }
   }

@@ -1162,6 +1162,7 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
       case FB_OBS_REF_QUAT: dim += 4 * b; break;
       case FB_OBS_ROOT_ZAXIS: case FB_OBS_SCALARS: case FB_OBS_SUBTREE_COM: dim += 3; break;
       case FB_OBS_ROOT_POSE: dim += 7; break;
+      case FB_OBS_WORLD_CONTACT: dim += 1; break;
       default: s->err = "fb_obs_program: unknown item kind"; return -1;
     }
     if ((k == FB_OBS_REF_DISP || k == FB_OBS_REF_QUAT) && (!p->ref_qpos || p->ref_len <= 0)) { s->err = "fb_obs_program: reference table missing"; return -1; }

@@ -97,7 +97,8 @@ class BatchedVisionFlightEnv:
                 ('walker/joints_pos', nq, (st.OBS_QPOS, 0, nq)), ('walker/joints_vel', nq, (st.OBS_QVEL, nq, nq)),
                 ('walker/velocimeter', 3, (st.OBS_SENSOR_MEAN, sd('velocimeter'), 3)), ('walker/world_zaxis', 3, (st.OBS_ROOT_ZAXIS, 0, 3)),
                 ('_velocimeter_now', 3, (st.OBS_SENSOR_NOW, sd('velocimeter'), 3)), ('_root_pose', 7, (st.OBS_ROOT_POSE, 0, 7)),
-                ('_root_qvel', 6, (st.OBS_QVEL, 2 * nq, 6)), ('_scalars', 3, (st.OBS_SCALARS, 0, 3))]
+                ('_root_qvel', 6, (st.OBS_QVEL, 2 * nq, 6)), ('_scalars', 3, (st.OBS_SCALARS, 0, 3)),
+                ('_world_contact', 1, (st.OBS_WORLD_CONTACT, 0, 1))]
         lists = list(self._obs_qadr) + list(self._obs_vadr) + list(range(self._root_v, self._root_v + 6))
         dim = self._sim.obs_program([r[2] for r in rows], lists, m.body_id('walker/thorax'), self._n_sub, None)
         off = np.concatenate([[0], np.cumsum([r[1] for r in rows])])
@@ -115,6 +116,7 @@ class BatchedVisionFlightEnv:
         self._time = np.zeros(N)
         self._needs_reset = np.ones(N, bool)
         self._wing_qpos = np.zeros((N, 6))
+        self._has_trench = np.zeros(N, bool)
         self.n_resets = 0
 
     # ---------------------------------------------------------------------------------- specs
@@ -165,6 +167,7 @@ class BatchedVisionFlightEnv:
                 self._terrain[e] = self._arenas[e].generate(self._rs)
             else:
                 self._terrain[e], self._arenas[e].trench_specs = self._bank[self._rs.randint(len(self._bank))]
+            self._has_trench[e] = self._arenas[e].trench_specs is not None
             z = float(arenas.hfield_height(self._terrain[e], [x], [y], self._half)[0]) + self._target_height[e]
             qpos[k, self._root_q:self._root_q + 3] = (x, y, z)
             qpos[k, self._root_q + 3:self._root_q + 7] = self._hover_quat
@@ -242,12 +245,9 @@ class BatchedVisionFlightEnv:
 
     # -------------------------------------------------------------------------- task quantities
     def floor_contact(self):
-        """`check_floor_contact` (vision_flight.py:235-247): an active contact with a geom of the world body (ground plane, terrain)."""
-        ncon = self._sim.get(st.NCON)[:, 0].astype(np.int64)
-        c = self._sim.get(st.CONTACT).reshape(self.n_envs, -1, 16)
-        world = self.model.geom_bodyid[np.clip(c[..., 7].astype(np.int64), 0, self.model.ngeom - 1)] == 0
-        live = np.arange(c.shape[1])[None, :] < ncon[:, None]
-        return (live & world & (c[..., 0] < 0)).any(1)
+        """`check_floor_contact` (vision_flight.py:235-247): an active contact (efc_address >= 0) with a geom of the world body (ground
+        plane, terrain) -- evaluated on the device by the observation program (FB_OBS_WORLD_CONTACT), read from the record."""
+        return self._rec[:, self._sl['_world_contact']][:, 0] > 0.5
 
     def reward_factors(self, rec):
         """[N, 6] (vision_flight.py:157-233): height above the terrain, forward speed, speed, side speed, body axis, centre of
@@ -263,9 +263,9 @@ class BatchedVisionFlightEnv:
         ang = np.arccos(np.clip(zaxis @ self._target_zaxis, -1.0, 1.0))
         world_zaxis = _tolerance_linear(ang, 0.0, 0.0, np.pi)
         centre = np.ones(self.n_envs)
-        for e, a in enumerate(self._arenas):
-            spec = a.trench_specs
-            if spec is not None and spec['x_coords'][0] <= pose[e, 0] <= spec['x_coords'][-1]:
+        for e in np.nonzero(self._has_trench)[0]:                       # ('bumps' arenas have no trench: nothing to do)
+            spec = self._arenas[e].trench_specs
+            if spec['x_coords'][0] <= pose[e, 0] <= spec['x_coords'][-1]:
                 yc = spec['y_coords'][np.abs(spec['x_coords'] - pose[e, 0]).argmin()]
                 centre[e] = _tolerance_linear(pose[e, 1], yc, yc, 0.15)
         return np.stack([height, x_speed, speed, side, world_zaxis, centre], 1)

@@ -250,8 +250,10 @@ enum FbObsItem {
   FB_OBS_SCALARS = 9,     /* flags, |qacc|^2, time                                                           */
   FB_OBS_ROOT_POSE = 10,  /* root xpos[3] + quat[4]                                                          */
   FB_OBS_SUBTREE_COM = 11,/* a = body id : physics.data.subtree_com[body]                                    */
-  FB_OBS_DOF_AXIS_EGO = 12 /* a = offset into list (dof ids), b = count : world joint axis (physics.bind(joints).xaxis,
+  FB_OBS_DOF_AXIS_EGO = 12,/* a = offset into list (dof ids), b = count : world joint axis (physics.bind(joints).xaxis,
                               tasks/rewards.py:48-50) rotated into the root frame                                */
+  FB_OBS_WORLD_CONTACT = 13 /* 1 float: 1 if an active contact (efc_address >= 0) involves a geom of the world body (ground plane, terrain):
+                               the reference's check_floor_contact (tasks/vision_flight.py:235-247)                        */
 };
 typedef struct FbObsProgram {
   int32_t n_items; const int32_t* kind; const int32_t* a; const int32_t* b;
