@@ -209,25 +209,18 @@ def measure(wl, args, world, rank, local, with_exchange):
     P = args.preroll if args.preroll >= 0 else wl['episode']
     n_act_rows = 64                                                    # a ring of resident random action batches
     acts = (torch.rand((n_act_rows, N, A), device=dev, generator=gen) - 0.5) * (2 * wl['act_scale'])
-    # config 4 exchange buffers: rank 0 is the actor (policy side)
-    obs_dim = None
-    xb = {}
+    # config 4 exchange (flybody_b200.sharding.ActorExchange): rank 0 is the actor (policy side)
+    from flybody_b200.sharding import ActorExchange
+    xch = ActorExchange(world, rank, N, A, device=dev) if with_exchange else None
+    a_all = (torch.rand((world, N, A), device=dev, generator=gen) - 0.5) * (2 * wl['act_scale']) if (with_exchange and rank == 0) else None
 
     def exchange(obs, out, k):
         """actions for every rank leave rank 0, observations + (reward, discount, step_type) of every rank arrive on rank 0"""
         if not with_exchange:
             return acts[k % n_act_rows]
-        if 'a_loc' not in xb:
-            xb['a_loc'] = torch.empty((N, A), device=dev)
-            if rank == 0:
-                xb['a_all'] = (torch.rand((world, N, A), device=dev, generator=gen) - 0.5) * (2 * wl['act_scale'])
-                xb['obs_all'] = [torch.empty_like(obs) for _ in range(world)]
-                xb['out_all'] = [torch.empty_like(out) for _ in range(world)]
         if obs is not None:
-            dist.gather(obs, xb['obs_all'] if rank == 0 else None, dst=0)
-            dist.gather(out, xb['out_all'] if rank == 0 else None, dst=0)
-        dist.scatter(xb['a_loc'], [xb['a_all'][r] for r in range(world)] if rank == 0 else None, src=0)
-        return xb['a_loc']
+            xch.gather(obs, out)
+        return xch.scatter_actions(a_all)
 
     state = {'obs': None, 'out': None}
 

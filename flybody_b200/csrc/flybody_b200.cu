@@ -51,6 +51,9 @@ static void d2h(void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 #ifndef FB_FUSE_DEFAULT
 #define FB_FUSE_DEFAULT 0
 #endif
+#ifndef FB_OVERLAP_VEL_DEFAULT
+#define FB_OVERLAP_VEL_DEFAULT 0
+#endif
 enum { K_ACT = 0, K_SMOOTH, K_REF, K_SOLVE, K_FINISH, K_POS, K_COL, K_CON, K_PROJ, K_VEL, K_SENS, K_PACK, K_MISC, K_STEP2, K_STEP1, K_STEP, K_NKIND };
 static const char* const kKindNames[K_NKIND] = {"act", "smooth", "ref", "solve", "finish", "pos", "col", "con", "proj", "vel", "sens", "pack", "misc", "step2", "step1", "step"};
 #ifndef FB_EMU
@@ -84,6 +87,7 @@ struct FbSim {
   // FB_SPLIT: the batch is stepped as `split` env ranges ("chains") on their own streams, each chain started a few kernels
   // after the previous one, so that different stage kernels share the SMs and one chain's stragglers overlap the other's work
   int split, chain_stagger, chain_count, chain_idx; cudaStream_t cur_stream, aux[3]; cudaEvent_t chain_ev[4], join_ev[4];
+  int overlap_vel; cudaEvent_t fork_ev, vel_ev;       // FB_OVERLAP_VEL: velocity stage as a parallel branch of the step (launch_step1)
   struct StepGraph { cudaGraphExec_t exec; bool seen, failed; int n_sub; long long launches; DevData d; DevModel m; };
   StepGraph graph[2];          // [hold pending?]
   bool graphs_on;
@@ -285,6 +289,25 @@ static size_t dyn_tsolve(const DevModel& m) { return (size_t)(FB_NXS(m) + ((m.nM
 
 static void launch_step1(FbSim* s) {
   fb_launch<ShTree, FB_ST_POS>(s, K_POS, dyn_pos(s->m));
+#ifndef FB_EMU
+  // The velocity stage (comVel, RNE bias, passive forces, velocity sensors) needs the position stage only; collision and the
+  // constraint rows need it too but not each other's outputs: vel runs as a parallel branch next to col -> proj (second stream,
+  // captured into the step graph as a fork / join).  Every kernel is a single wave that fills the register file, so the branch's
+  // blocks start as the collision kernel's blocks drain -- they fill its barrier / MPR tail instead of waiting behind proj.
+  if (s->overlap_vel && s->split == 1 && !s->prof_on) {
+    cudaStream_t main_st = s->cur_stream, side = s->aux[2];
+    cudaEventRecord(s->fork_ev, main_st); cudaStreamWaitEvent(side, s->fork_ev, 0);
+    s->cur_stream = side;
+    fb_launch<ShTree, FB_ST_VEL>(s, K_VEL, dyn_vel(s->m));
+    cudaEventRecord(s->vel_ev, side);
+    s->cur_stream = main_st;
+    fb_launch<ShCol, FB_ST_COL>(s, K_COL, dyn_col(s->m));
+    if (s->hf_on) launch_hfield(s);
+    fb_launch<ShCon, FB_ST_PROJ>(s, K_PROJ, dyn_proj(s->m));
+    cudaStreamWaitEvent(main_st, s->vel_ev, 0);
+    return;
+  }
+#endif
   fb_launch<ShCol, FB_ST_COL>(s, K_COL, dyn_col(s->m));
   if (s->hf_on) launch_hfield(s);              // heightfield contacts join the contact list before the constraint rows are built
   fb_launch<ShCon, FB_ST_PROJ>(s, K_PROJ, dyn_proj(s->m));
@@ -738,6 +761,8 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   s->chain_count = -1; s->chain_idx = 0; s->cur_stream = s->stream;
   for (int i = 0; i < 3; i++) cudaStreamCreateWithFlags(&s->aux[i], cudaStreamNonBlocking);
   for (int i = 0; i < 4; i++) { cudaEventCreateWithFlags(&s->chain_ev[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&s->join_ev[i], cudaEventDisableTiming); }
+  cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming); cudaEventCreateWithFlags(&s->vel_ev, cudaEventDisableTiming);
+  s->overlap_vel = getenv("FB_OVERLAP_VEL") ? atoi(getenv("FB_OVERLAP_VEL")) : FB_OVERLAP_VEL_DEFAULT;
   // small batches are latency-bound (a per-CTA copy of the sweep program in shared memory halves the sweeps' latency);
   // at full occupancy the copy costs more than it saves and the compact program is read in place.  FB_BLOB=0/1 overrides.
   s->blob_in_smem = getenv("FB_BLOB") ? atoi(getenv("FB_BLOB")) : (n_envs <= 1024);

@@ -48,3 +48,38 @@ def scatter_actions(actions_all, n_local, nu, world, rank, src=0, device=None):
         chunks = [a[r].contiguous() for r in range(world)]
     dist.scatter(out, chunks, src=src)
     return out
+
+
+class ActorExchange:
+    """The per-control-step exchange of BASELINE.json configs[3] ("NCCL obs gather to rank 0 for the DMPO actor loop"): rank 0 is the
+    actor.  `scatter_actions` sends every rank its [n_local, n_action] rows of rank 0's [world, n_local, n_action] action tensor;
+    `gather` brings every rank's observation rows [n_local, obs_dim] and (reward, discount, step_type, 0) rows [n_local, 4] to rank 0.
+    Tensors live on the device (nccl) or the host (gloo, CPU tests); the receive buffers are allocated once.  With world == 1 both calls
+    are local no-ops.  bench.py times exactly these two calls inside its step loop; tests/test_multirank.py runs them under gloo."""
+
+    def __init__(self, world, rank, n_local, n_action, device=None):
+        import torch
+        self.world, self.rank, self.n_local, self.n_action = int(world), int(rank), int(n_local), int(n_action)
+        self.a_loc = torch.empty((n_local, n_action), dtype=torch.float32, device=device)
+        self.obs_all = self.out_all = None
+
+    def scatter_actions(self, actions_all):
+        """actions_all: [world, n_local, n_action] float32 on rank 0 (ignored elsewhere) -> this rank's [n_local, n_action]"""
+        import torch.distributed as dist
+        if self.world == 1:
+            return actions_all[0]
+        dist.scatter(self.a_loc, [actions_all[r] for r in range(self.world)] if self.rank == 0 else None, src=0)
+        return self.a_loc
+
+    def gather(self, obs, out):
+        """-> (list of [n_local, obs_dim], list of [n_local, 4]) on rank 0, (None, None) elsewhere"""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return [obs], [out]
+        if self.rank == 0 and self.obs_all is None:
+            self.obs_all = [torch.empty_like(obs) for _ in range(self.world)]
+            self.out_all = [torch.empty_like(out) for _ in range(self.world)]
+        dist.gather(obs, self.obs_all if self.rank == 0 else None, dst=0)
+        dist.gather(out, self.out_all if self.rank == 0 else None, dst=0)
+        return (self.obs_all, self.out_all) if self.rank == 0 else (None, None)

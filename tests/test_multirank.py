@@ -94,13 +94,13 @@ def _task_worker(rank, world, port, emu, out_path):
     rs = np.random.RandomState(9)
     acts = rs.uniform(-0.5, 0.5, (16, N_TOTAL, 59)).astype(np.float32)
     rows = []
+    xch = sharding.ActorExchange(world, rank, hi - lo, 59)             # the exchange bench.py times at N > 1 (there over nccl)
     for k in range(16):
-        a = sharding.scatter_actions(acts[k] if rank == 0 else None, hi - lo, 59, world, rank)
+        a = xch.scatter_actions(torch.from_numpy(acts[k]).reshape(world, hi - lo, 59) if rank == 0 else None)
         env.step(a.numpy())
-        blk = torch.from_numpy(np.concatenate([env._rec, env._out4], 1).copy())
-        got = sharding.gather_observations(blk, world, rank)
+        obs_all, out_all = xch.gather(torch.from_numpy(env._rec.copy()), torch.from_numpy(env._out4.copy()))
         if rank == 0:
-            rows.append(torch.cat(got).numpy())
+            rows.append(np.concatenate([torch.cat(obs_all).numpy(), torch.cat(out_all).numpy()], 1))
     if rank == 0:
         np.save(out_path, np.array(rows))
     dist.barrier()

@@ -15,9 +15,16 @@ m = load_model(a.model)
 n_sub, scale = (10, 0.5) if a.model == 'walk' else (4, 0.2)
 res = {}
 for rnd in range(a.rounds):                      # interleaved rounds: box drift shows up as a difference between the rounds
-    for lib in a.libs:
+    for spec in a.libs:                          # "path.so" or "path.so:VAR=val,VAR2=val2" (environment read by fb_create)
+        lib, _, envs = spec.partition(':')
+        sets = dict(kv.split('=') for kv in envs.split(',') if kv)
         for N in [int(x) for x in a.envs.split(',')]:
+            old = {k: os.environ.get(k) for k in sets}
+            os.environ.update(sets)
             sim = st.BatchedStepper(m, N, lib_path=lib)
+            for k, v in old.items():
+                if v is None: os.environ.pop(k, None)
+                else: os.environ[k] = v
             rs = np.random.RandomState(1)
             q = np.tile(m.qpos0, (N, 1))
             if a.model == 'walk':
@@ -48,7 +55,7 @@ for rnd in range(a.rounds):                      # interleaved rounds: box drift
             prof = {k: round(v[0] / a.steps, 3) for k, v in sim.profile_read().items() if v[1]}
             sim.profile(False)
             nefc = sim.get(st.NEFC)[:, 0]; nit = sim.get(st.SOLVER_NITER)[:, 0].astype(int)
-            key = (os.path.basename(lib), N)
+            key = (os.path.basename(spec), N)
             res.setdefault(key, []).append(ms)
             print(json.dumps({'lib': key[0], 'envs': N, 'round': rnd, 'ms_per_step': round(ms, 3), 'env_steps_per_s': round(N / ms * 1e3), 'stages_ms': prof,
                               'nefc_mean': float(nefc.mean()), 'niter_hist': {str(b): int((nit == b).sum()) for b in range(0, 9)}, 'niter_gt8': int((nit > 8).sum()), 'niter_max': int(nit.max()), 'share_nefc_gt32': float((nefc > 32).mean()), 'flags': int((sim.get(st.FLAGS) != 0).sum())}), flush=True)
