@@ -386,7 +386,8 @@ def measure_vision(args, world, rank, local, n_envs=1024):
 
     def act(ts):
         o = ts.observation
-        left, right = torch.from_numpy(o['walker/left_eye']).to(dev, non_blocking=True), torch.from_numpy(o['walker/right_eye']).to(dev, non_blocking=True)
+        eyes = env.eyes_device()                                        # the images of this step, still on the device (the host copy is in `o`)
+        left, right = eyes[:, 1], eyes[:, 0]
         task = torch.from_numpy(o['walker/task_input']).to(dev)
         others = torch.from_numpy(np.concatenate([np.asarray(o[k], np.float32).reshape(N, -1) for k in keys], 1)).to(dev)
         if world > 1:

@@ -132,6 +132,7 @@ class BatchedStepper:
     def __init__(self, model: FlyModel, n_envs: int, device: int = 0, lib_path: str | None = None):
         self.model = model
         self.n_envs = int(n_envs)
+        self.device = int(device)
         self._lib = load_library(lib_path)
         h = C.c_void_p()
         rc = self._lib.fb_create(C.byref(model.c), self.n_envs, int(device), C.byref(h))
@@ -350,6 +351,12 @@ class BatchedStepper:
         h = np.ascontiguousarray(heights, np.float32).reshape(len(ids), -1)
         assert h.shape[1] == self._hfield_cells, (h.shape, self._hfield_cells)
         self._check(self._lib.fb_hfield_write(self._h, ids.ctypes.data, len(ids), h.ctypes.data), 'fb_hfield_write')
+
+    def eyes_ptr(self):
+        """(device pointer, bytes per env) of the eye-camera images (valid after eye_program; rewritten by every render_eyes)"""
+        p, n = C.c_void_p(), C.c_int()
+        self._check(self._lib.fb_eyes_ptr(self._h, C.byref(p), C.byref(n)), 'fb_eyes_ptr')
+        return p.value, n.value
 
     def render_eyes(self, out=None):
         """-> uint8 [n_envs, n_cam, size, size, 3] rendered from the current body poses."""

@@ -104,13 +104,15 @@ class BatchedVisionFlightEnv:
         off = np.concatenate([[0], np.cumsum([r[1] for r in rows])])
         assert off[-1] == dim
         self._sl = {r[0]: slice(int(off[i]), int(off[i + 1])) for i, r in enumerate(rows)}
-        self._rec = np.empty((N, dim), np.float32)
+        self._rec = self._pinned((N, dim), np.float32)
         # eyes
         quats = [np.asarray(q, np.float64) / np.linalg.norm(q) for _, _, q in BatchedFlyEnv._EYE_CAMERAS]
         head = m.body_id('walker/head')
         self._sim.eye_program([head, head], [p for _, p, _ in BatchedFlyEnv._EYE_CAMERAS], quats, fovy_deg=eye_camera_fovy, size=eye_camera_size,
                               nrow=a0.nrow, ncol=a0.ncol, half_size=self._half, z_offset=float(m.geom_pos[m.meta['hf_geom']][2]))
         self._eye_size = eye_camera_size
+        self._eyes_host = self._pinned((N, 2, eye_camera_size, eye_camera_size, 3), np.uint8)      # D2H target of every step's render
+        self._eyes_dev = None
         # per-env episode state
         self._target_height, self._target_speed = np.zeros(N), np.zeros(N)
         self._time = np.zeros(N)
@@ -118,6 +120,30 @@ class BatchedVisionFlightEnv:
         self._wing_qpos = np.zeros((N, 6))
         self._has_trench = np.zeros(N, bool)
         self.n_resets = 0
+
+    @staticmethod
+    def _pinned(shape, dtype):
+        """page-locked host buffer where torch + CUDA are present (device -> host copies at full PCIe rate), plain numpy otherwise"""
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name)).pin_memory().numpy()
+        except Exception:
+            pass
+        return np.empty(shape, dtype)
+
+    def eyes_device(self):
+        """zero-copy torch view [n_envs, 2, size, size, 3] uint8 (index 0 right eye, 1 left eye) of the images the last step rendered,
+        on this env's device -- for a policy that lives on the GPU (the numpy observation holds the same images on the host)."""
+        import torch
+        if self._eyes_dev is None:
+            ptr, nbytes = self._sim.eyes_ptr()
+
+            class _View:
+                def __init__(self, ptr, shape):
+                    self.__cuda_array_interface__ = {'shape': shape, 'typestr': '|u1', 'data': (int(ptr), False), 'version': 2}
+            self._eyes_dev = torch.as_tensor(_View(ptr, (self.n_envs, 2, self._eye_size, self._eye_size, 3)), device=f'cuda:{self._sim.device}')
+        return self._eyes_dev
 
     # ---------------------------------------------------------------------------------- specs
     def action_spec(self):
@@ -185,7 +211,7 @@ class BatchedVisionFlightEnv:
 
     def _observation(self):
         rec, sl, N = self._rec, self._sl, self.n_envs
-        eyes = self._sim.render_eyes()
+        eyes = self._sim.render_eyes(self._eyes_host)
         obs = collections.OrderedDict()
         for k in self._OBS:
             name = 'walker/' + k
