@@ -70,11 +70,12 @@ def add_sine_trench(terrain, arena_size, wavelength=5, phase=0.0, amplitude=1.0,
 
 
 def hfield_height(terrain, x, y, half_size):
-    """height at the grid point nearest to (x, y) (reference `tasks/vision_flight.py:81-95`; x, y arrays broadcast)."""
+    """height at the grid point nearest to (x, y) (reference `tasks/vision_flight.py:81-95`: argmin of |axis - x| over the grid axis
+    `linspace(-half, half, n)`, first minimum on ties; x, y arrays broadcast) -- computed in closed form instead of an [N, n] table."""
     ncol = terrain.shape[-1]
-    axis = np.linspace(-half_size, half_size, ncol)
-    xi = np.abs(axis[None, :] - np.asarray(x, np.float64).reshape(-1, 1)).argmin(1)
-    yi = np.abs(axis[None, :] - np.asarray(y, np.float64).reshape(-1, 1)).argmin(1)
+    step = 2.0 * half_size / (ncol - 1)
+    nearest = lambda v: np.clip(np.ceil((np.asarray(v, np.float64).reshape(-1) + half_size) / step - 0.5), 0, ncol - 1).astype(np.int64)
+    xi, yi = nearest(x), nearest(y)
     return terrain[..., yi, xi] if terrain.ndim == 2 else terrain[np.arange(len(xi)), yi, xi]
 
 
