@@ -212,7 +212,8 @@ def measure(wl, args, world, rank, local, with_exchange):
     # config 4 exchange (flybody_b200.sharding.ActorExchange): rank 0 is the actor (policy side)
     from flybody_b200.sharding import ActorExchange
     xch = ActorExchange(world, rank, N, A, device=dev) if with_exchange else None
-    a_all = (torch.rand((world, N, A), device=dev, generator=gen) - 0.5) * (2 * wl['act_scale']) if (with_exchange and rank == 0) else None
+    # (a ring of action batches for all ranks: constant actions would drive every fly into its joint limits)
+    a_all = (torch.rand((16, world, N, A), device=dev, generator=gen) - 0.5) * (2 * wl['act_scale']) if (with_exchange and rank == 0) else None
 
     def exchange(obs, out, k):
         """actions for every rank leave rank 0, observations + (reward, discount, step_type) of every rank arrive on rank 0"""
@@ -220,7 +221,7 @@ def measure(wl, args, world, rank, local, with_exchange):
             return acts[k % n_act_rows]
         if obs is not None:
             xch.gather(obs, out)
-        return xch.scatter_actions(a_all)
+        return xch.scatter_actions(a_all[k % 16] if rank == 0 else None)
 
     state = {'obs': None, 'out': None}
 
@@ -294,13 +295,19 @@ def measure(wl, args, world, rank, local, with_exchange):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
+    t_step = t_x = 0.0
     for k in range(W, W + K):
+        ta = time.perf_counter()
         env.step(a_np[k])
+        tb = time.perf_counter()
         if with_exchange:
             with torch.cuda.stream(stream):
                 exchange(state['obs'], state['out'], k)
+        t_step += tb - ta; t_x += time.perf_counter() - tb
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get('FB_BENCH_DEBUG'):
+        print(f'[rank {rank}] e2e loop: env.step {t_step / K * 1e3:.2f} ms, exchange enqueue {t_x / K * 1e3:.2f} ms, total {e2e_s / K * 1e3:.2f} ms per step', file=sys.stderr, flush=True)
     sampler.stop_flag = True; sampler.join(timeout=2)
     if world > 1:
         t = torch.tensor([ms, e2e_s, xms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms, e2e_s, xms = [float(x) for x in t.tolist()]

@@ -31,12 +31,13 @@ enum { W_LAM = 0, W_JAR, W_F, W_R, W_U, W_DL, W_ADL, W_P, X_E0, X_E1, X_XQ, X_OU
 #define FB_SOLVE_WARP_FLOATS (S_NSLOT * FB_SOLVE_NCAP + 2 * TRI(FB_SOLVE_NCAP, 0) + 4 * 32)
 
 // memory of one env's problem: base pointers + element strides (1 in shared memory, Np in global memory)
-struct SolveMem { float* v; float* A; float* G; float* red; int st; };
-// SM == true: the env's slice of shared memory (row capacity FB_SOLVE_NCAP); false: the env's global record
-// (row capacity FB_MAXEFC)
-#define SV(slot, r) sm.v[SM ? ((slot) * FB_SOLVE_NCAP + (r)) : ((slot) * FB_MAXEFC + (r)) * sm.st]
-#define AM(r, c) sm.A[SM ? ((r) >= (c) ? TRI(r, c) : TRI(c, r)) : ((r) >= (c) ? TRI(r, c) : TRI(c, r)) * sm.st]
-#define GM(p, q) sm.G[SM ? TRI(p, q) : TRI(p, q) * sm.st]        // p >= q
+struct SolveMem { float* v; float* A; float* G; float* red; int cap; };
+// Work vectors v [S_NSLOT][cap], packed Delassus matrix A and packed Hessian factor G.  SM == true: all three in shared memory (A is
+// copied in from the record): the heavy-env kernel fb_run_solve_big, cap = FB_MAXEFC; false: in the env's global record.
+#define SV(slot, r) sm.v[(slot) * sm.cap + (r)]
+#define AM(r, c) sm.A[(r) >= (c) ? TRI(r, c) : TRI(c, r)]
+#define GM(p, q) sm.G[TRI(p, q)]        // p >= q
+#define FB_SOLVE_BIG_FLOATS (S_NSLOT * FB_MAXEFC + 2 * TRI(FB_MAXEFC, 0) + 4 * 32)
 #define RED(k, l) sm.red[(k) * 32 + (l)]
 
 #define NOUNROLL _Pragma("unroll 1")

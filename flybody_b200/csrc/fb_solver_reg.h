@@ -84,7 +84,7 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
   float* A = wsm; float* G = A + 32 * 33; float* P = G + TRI(32, 0); float* XQ = P + 32; float* XO = XQ + 32;
   float* E0s = XO + 32; float* E1s = E0s + 32; float* Us = E1s + 32;
   int* ECR = reinterpret_cast<int*>(Us + 32); int* ECK = ECR + 32;
-  SolveMem sm; sm.v = nullptr; sm.A = nullptr; sm.G = nullptr; sm.st = 1; sm.red = reinterpret_cast<float*>(ECK + 32);     // WSUM staging (host emulation)
+  SolveMem sm; sm.v = nullptr; sm.A = nullptr; sm.G = nullptr; sm.cap = 32; sm.red = reinterpret_cast<float*>(ECK + 32);     // WSUM staging (host emulation)
   float tot[4] = {0, 0, 0, 0}; (void)tot; (void)sm;
   LREG(float, D); LREG(float, D1); LREG(float, D2); LREG(float, b); LREG(float, Rr); LREG(float, mu); LREG(float, c1); LREG(float, c2);
   LREG(float, lam); LREG(float, jar); LREG(float, f); LREG(float, res); LREG(float, dl); LREG(float, adl); LREG(float, e0); LREG(float, e1);
@@ -294,13 +294,31 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
   WPAR_END
 }
 
+// Envs with more rows than the register path holds (nefc > 32: freshly reset flies, flies pressed against their joint limits --
+// 0.05 - 1 % of a batch) are NOT solved by the warp that finds them: on the record in global memory the generic code is several times
+// slower than a typical env, and a kernel is as slow as its slowest warp.  They are queued (d.heavy_list) and solved by
+// fb_run_solve_big right behind this kernel: one warp per heavy env, the whole problem (work vectors, A, G for up to FB_MAXEFC rows,
+// 117 KB) in shared memory, on as many SMs as there are heavy envs.
+FB_WARPFN void ksolve_big(const DevModel& m, const DevData& d, float* smem, int e) {
+  const int n = AT(d.nefc, 0);
+  SolveMem sm;
+  sm.v = smem; sm.A = sm.v + S_NSLOT * FB_MAXEFC; sm.G = sm.A + TRI(FB_MAXEFC, 0); sm.red = sm.G + TRI(FB_MAXEFC, 0); sm.cap = FB_MAXEFC;
+  ksolve_impl<true>(m, d, sm, e, n);
+}
 // one env; `wsm` = this warp's shared-memory slice (FB_SOLVE_WARP_FLOATS floats)
 FB_WARPFN void ksolve_warp(const DevModel& m, const DevData& d, float* wsm, int e) {
   const int n = AT(d.nefc, 0);
-  if (n <= m.solve_ncap) ksolve_reg(m, d, wsm, e, n);
-  else {   // more than 32 rows: the generic code on the env's global record (row capacity FB_MAXEFC)
-    SolveMem sm;
-    sm.red = wsm; sm.v = &AT(d.efc_w, 0); sm.A = &AT(d.efc_A, 0); sm.G = &AT(d.efc_G, 0); sm.st = 1;
-    ksolve_impl<false>(m, d, sm, e, n);
+  if (n <= m.solve_ncap) { ksolve_reg(m, d, wsm, e, n); return; }
+#ifdef __CUDACC__
+  if (d.heavy_list) {                      // queue it for fb_run_solve_big
+    if (threadIdx.x == 0) { int slot = atomicAdd(d.heavy_count, 1); d.heavy_list[slot] = e; }
+    return;
   }
+  { SolveMem sm;                           // fused launch groupings (FB_FUSE): no second kernel, the generic code on the env's global record
+    sm.red = wsm; sm.v = &AT(d.efc_w, 0); sm.A = &AT(d.efc_A, 0); sm.G = &AT(d.efc_G, 0); sm.cap = FB_MAXEFC;
+    ksolve_impl<false>(m, d, sm, e, n); }
+#else
+  { static float* big = nullptr; if (!big) big = (float*)malloc(sizeof(float) * FB_SOLVE_BIG_FLOATS);      // host emulation: the heavy-env kernel's code path, inline
+    ksolve_big(m, d, big, e); }
+#endif
 }

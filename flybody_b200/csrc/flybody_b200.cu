@@ -69,7 +69,7 @@ struct FbSim {
   std::vector<void*> allocs;
   std::vector<int> h_dof_parent, h_dof_Madr, h_body_lastdof, h_geom_bodyid;
   std::vector<double> h_qpos0;
-  int device; long long launches; float last_ms; std::string err;
+  int device, n_sm; long long launches; float last_ms; std::string err;
   int first_substep; int hold_pending;
   int* rst_ids_dev; float* rst_qpos_dev; float* rst_qvel_dev; int rst_cap;
   const int* act_map_dev; int n_action;
@@ -183,6 +183,12 @@ __global__ void __launch_bounds__(32 * FB_SOLVE_WPB, FB_MINB) fb_run_solve(DevMo
   if (e == 0 && threadIdx.x == 0) d.clk[32 * d.clk_launch + 1] = clock64();
 #endif
 }
+// heavy envs (nefc > 32) queued by fb_run_solve: one warp per env, the whole problem in shared memory; the blocks stride over the queue
+__global__ void __launch_bounds__(32, 1) fb_run_solve_big(DevModel m, DevData d) {
+  extern __shared__ __align__(16) float fb_smem_big[];
+  const int count = *d.heavy_count;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) { ksolve_big(m, d, fb_smem_big, d.heavy_list[i]); __syncwarp(); }
+}
 static void fb_launch_warp(FbSim* s, int kind) {
 #ifdef FB_CLK
   s->d.clk_launch = (int)(s->launches % 4096);
@@ -190,18 +196,21 @@ static void fb_launch_warp(FbSim* s, int kind) {
   dim3 block(32, FB_SOLVE_WPB), grid((s->cur_n + FB_SOLVE_WPB - 1) / FB_SOLVE_WPB);
   size_t bytes = sizeof(float) * FB_SOLVE_WARP_FLOATS * FB_SOLVE_WPB;
   static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(fb_run_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = true; }
+  if (!configured) { cudaFuncSetAttribute(fb_run_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaFuncSetAttribute(fb_run_solve_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * FB_SOLVE_BIG_FLOATS)); configured = true; }
   cudaStream_t st = s->cur_stream;
   if (s->prof_on) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, st);
     fb_run_solve<<<grid, block, bytes, st>>>(s->m, s->d, s->cur_e0, s->cur_n);
+    if (s->d.heavy_list) fb_run_solve_big<<<s->n_sm, 32, sizeof(float) * FB_SOLVE_BIG_FLOATS, st>>>(s->m, s->d);
     cudaEventRecord(b, st);
     s->prof_events.push_back({kind, a, b});
   } else {
     fb_run_solve<<<grid, block, bytes, st>>>(s->m, s->d, s->cur_e0, s->cur_n);
+    if (s->d.heavy_list) fb_run_solve_big<<<s->n_sm, 32, sizeof(float) * FB_SOLVE_BIG_FLOATS, st>>>(s->m, s->d);
   }
-  s->launches++;
+  s->launches += s->d.heavy_list ? 2 : 1;
   chain_mark(s);
 }
 #else
@@ -675,6 +684,10 @@ static int alloc_data(FbSim* s, int N) {
 #ifdef FB_CLK
   d.clk = (long long*)dalloc<long long>(s, 32 * 4096);
 #endif
+#ifndef FB_EMU
+  // queue of envs for the heavy-env solve kernel (one-kernel-per-stage launch sequence on a single chain only)
+  if (s->fuse == 0 && s->split == 1 && !getenv("FB_NO_HEAVY_KERNEL")) { d.heavy_count = dalloc<int>(s, 4); d.heavy_list = dalloc<int>(s, d.Np); }
+#endif
   d.obs_dim = m.nq + m.nv + m.na + 2 * m.nsensordata + 12 + 3 * m.nsite + 3;
   d.obs = dalloc<float>(s, (size_t)d.obs_dim * d.Np);
   s->stage_cap = 0; s->stage = nullptr; s->stage_i = nullptr;
@@ -754,6 +767,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  { int n_sm = 0; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device); s->n_sm = n_sm > 0 ? n_sm : 148; }
   cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
   s->graphs_on = getenv("FB_NO_GRAPH") == nullptr;
   s->split = getenv("FB_SPLIT") ? atoi(getenv("FB_SPLIT")) : FB_SPLIT_DEFAULT; if (s->split < 1 || s->split > 4) s->split = 1;
