@@ -295,10 +295,10 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
 }
 
 // Envs with more rows than the register path holds (nefc > 32: freshly reset flies, flies pressed against their joint limits --
-// 0.05 - 1 % of a batch) are NOT solved by the warp that finds them: on the record in global memory the generic code is several times
-// slower than a typical env, and a kernel is as slow as its slowest warp.  They are queued (d.heavy_list) and solved by
-// fb_run_solve_big right behind this kernel: one warp per heavy env, the whole problem (work vectors, A, G for up to FB_MAXEFC rows,
-// 117 KB) in shared memory, on as many SMs as there are heavy envs.
+// 0.05 - 1 % of a batch) run the generic code on their record in global memory, inline in this kernel (default), or -- FB_HEAVY_KERNEL=1,
+// measured slower, see alloc_data -- are queued (d.heavy_list) and solved by fb_run_solve_big right behind this kernel: one warp per
+// heavy env with the whole problem (work vectors, A, G for up to FB_MAXEFC rows, 117 KB) in shared memory.  The host emulation always
+// takes the shared-memory form, so that both instantiations of ksolve_impl are exercised by the CPU tests.
 FB_WARPFN void ksolve_big(const DevModel& m, const DevData& d, float* smem, int e) {
   const int n = AT(d.nefc, 0);
   SolveMem sm;

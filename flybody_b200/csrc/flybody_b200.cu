@@ -685,8 +685,11 @@ static int alloc_data(FbSim* s, int N) {
   d.clk = (long long*)dalloc<long long>(s, 32 * 4096);
 #endif
 #ifndef FB_EMU
-  // queue of envs for the heavy-env solve kernel (one-kernel-per-stage launch sequence on a single chain only)
-  if (s->fuse == 0 && s->split == 1 && !getenv("FB_NO_HEAVY_KERNEL")) { d.heavy_count = dalloc<int>(s, 4); d.heavy_list = dalloc<int>(s, d.Np); }
+  // FB_HEAVY_KERNEL=1: queue of envs for the heavy-env solve kernel (fb_run_solve_big).  Measured on the B200 and left OFF: with 2 of 4096
+  // envs above 32 rows the solve stage went from 2.77 to 4.04 ms per control step -- a single warp needs > 100 us for a 48-row problem even
+  // from shared memory, and behind the main kernel that time is serial, whereas inline (generic code on the env's global record) it
+  // overlaps with the other envs' solves and only stretches the kernel's tail by ~15 %.
+  if (s->fuse == 0 && s->split == 1 && getenv("FB_HEAVY_KERNEL") && atoi(getenv("FB_HEAVY_KERNEL"))) { d.heavy_count = dalloc<int>(s, 4); d.heavy_list = dalloc<int>(s, d.Np); }
 #endif
   d.obs_dim = m.nq + m.nv + m.na + 2 * m.nsensordata + 12 + 3 * m.nsite + 3;
   d.obs = dalloc<float>(s, (size_t)d.obs_dim * d.Np);
