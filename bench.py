@@ -202,7 +202,9 @@ def measure(wl, args, world, rank, local, with_exchange):
     dev = torch.device('cuda', local)
     N, K, W, A = args.envs, args.steps, args.warmup, wl['n_action']
     env = make_env(wl, N, local, 1234 + rank, device_task=True)
-    env.reset()
+    env.reset()                                      # the INITIAL states carry U(-0.05, 0.05) rad on the leg joints (decorrelation) ...
+    if wl['model'] == 'walk':
+        env.set_reset_noise(0.0)                     # ... the auto-resets go back to the task's exact start pose, as the reference's do
     sim = env.physics.stepper
     stream = torch.cuda.ExternalStream(sim.stream, device=dev)
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)

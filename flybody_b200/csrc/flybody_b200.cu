@@ -1297,6 +1297,13 @@ int fb_task_reset_all(FbHandle s) {
   h2d(s->task_host.needs_reset, ones.data(), sizeof(int) * ones.size());
   return 0;
 }
+int fb_task_set_reset_noise(FbHandle s, float amp) {
+  if (!s || !s->d.task || !(amp >= 0)) return -1;
+  if (sync_stream(s) != 0) return -2;
+  s->task_host.noise_amp = amp;
+  h2d((void*)s->d.task, &s->task_host, sizeof(DevTask));          // same pointers, new scalar
+  return 0;
+}
 int fb_task_request_reset(FbHandle s, const int32_t* env_ids, int n) {
   if (!s || !s->d.task || (n > 0 && !env_ids) || n < 0) return -1;
   if (n == 0) return 0;

@@ -563,6 +563,17 @@ class BatchedFlyEnv:
             self._sim.task_request_reset(ids)
         self._needs_reset[ids] = True
 
+    def set_reset_noise(self, amp):
+        """U(-amp, amp) rad added to the actuated leg joints of the start pose at the resets from now on (0: the reference's exact
+        start pose).  `reset_noise=` of the factory sets the initial value; a batch is typically started with noise once, so that the
+        envs decorrelate, and reset exactly afterwards."""
+        if self._device_task and amp > 0 and not self._reset_noise > 0:
+            raise ValueError('the device task program was uploaded without a noise joint list: create the env with reset_noise > 0')
+        if self._device_task:
+            self._sim.task_set_reset_noise(amp)
+        else:
+            self._reset_noise = float(amp)
+
     def device_reset_count(self):
         """episodes started so far, summed over the envs (device-side task logic: read from the device's episode counters)"""
         return int(self._sim.task_episodes().sum()) if self._device_task else int(self.n_resets)

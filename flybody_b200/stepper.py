@@ -22,7 +22,7 @@ MAXCON, MAXEFC = 64, 160
 
 EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_set_action_map', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_record_stride', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
-           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_request_reset', 'fb_task_episodes', 'fb_task_uniforms', 'fb_task_ptrs', 'fb_task_read', 'fb_eye_program', 'fb_hfield_collision', 'fb_hfield_write', 'fb_render_eyes', 'fb_eyes_ptr', 'fb_eyes_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_request_reset', 'fb_task_set_reset_noise', 'fb_task_episodes', 'fb_task_uniforms', 'fb_task_ptrs', 'fb_task_read', 'fb_eye_program', 'fb_hfield_collision', 'fb_hfield_write', 'fb_render_eyes', 'fb_eyes_ptr', 'fb_eyes_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
 
 # enum FbObsItem
@@ -94,6 +94,7 @@ def load_library(path=None):
     lib.fb_task_uniforms.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_task_request_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.fb_task_episodes.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fb_task_set_reset_noise.argtypes = [C.c_void_p, C.c_float]
     lib.fb_task_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
     lib.fb_task_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fb_eye_program.argtypes = [C.c_void_p, C.c_void_p]
@@ -303,6 +304,9 @@ class BatchedStepper:
     def task_request_reset(self, env_ids):
         ids = np.ascontiguousarray(env_ids, np.int32)
         self._check(self._lib.fb_task_request_reset(self._h, ids.ctypes.data, len(ids)), 'fb_task_request_reset')
+
+    def task_set_reset_noise(self, amp):
+        self._check(self._lib.fb_task_set_reset_noise(self._h, float(amp)), 'fb_task_set_reset_noise')
 
     def task_episodes(self):
         out = np.zeros(self.n_envs, np.int32)

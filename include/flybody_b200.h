@@ -314,6 +314,10 @@ int fb_task_program(FbHandle h, const FbTaskProgram* p);
 int fb_task_step(FbHandle h, const float* action, int is_device, int n_substeps);
 /* Mark every env for reset at the next fb_task_step (env.reset()).                                                    */
 int fb_task_reset_all(FbHandle h);
+/* Amplitude of the U(-a, a) joint noise the device-side reset adds to the listed start-pose joints (FbTaskProgram.noise_amp), changed
+ * without re-uploading the program: e.g. noise for the very first reset only (decorrelated start states), exact start pose at the
+ * auto-resets, as the reference's initialize_episode has it.                                                            */
+int fb_task_set_reset_noise(FbHandle h, float amp);
 /* Mark the listed envs for reset at the next fb_task_step, whatever their episode state (an actor restarting single
  * environments; bench.py's pre-roll uses it to spread the envs over the phases of an episode).                          */
 int fb_task_request_reset(FbHandle h, const int32_t* env_ids, int n);

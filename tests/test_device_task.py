@@ -152,3 +152,18 @@ def test_request_reset_restarts_single_envs(emu):
     assert np.allclose(q[1, :3], env._ref_qpos[0, :3], atol=1e-6) and not np.allclose(q[0, :3], env._ref_qpos[0, :3], atol=1e-6)
     assert env.device_reset_count() == int(env._sim.task_episodes().sum())
     env.close()
+
+
+def test_reset_noise_can_be_limited_to_the_first_reset(emu):
+    """fb_task_set_reset_noise: noisy initial states (decorrelation), exact start pose at later resets -- what bench.py does (SURVEY.md
+    8(d) config 2 asks for noise on the INITIAL state; the reference's auto-resets return to the task's start pose)."""
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=4, lib_path=emu, device_task=True, reset_noise=0.05, seed=3)
+    env.reset()
+    q = env._sim.get(st.QPOS)[:, env._leg_act_qadr].astype(np.float64) - env.model.qpos0[env._leg_act_qadr]
+    assert np.std(q) > 0.02
+    env.set_reset_noise(0.0)
+    env.request_reset([0, 2])
+    env.step(np.zeros((4, 59), np.float32))
+    q = env._sim.get(st.QPOS)[:, env._leg_act_qadr].astype(np.float64) - env.model.qpos0[env._leg_act_qadr]
+    assert np.abs(q[[0, 2]]).max() < 1e-6 and np.std(q[[1, 3]]) > 0.01       # reset envs: exact start pose; the others moved on from their noisy one
+    env.close()
