@@ -1163,6 +1163,7 @@ FB_DEV void ktaskobs(const DevModel& m, const DevData& d, int e, int y) {
       case FB_OBS_SCALARS: if (y == 0) { o[k] = (float)AT(d.flags, 0); float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; } o[k + 1] = s2; o[k + 2] = AT(d.time, 0); } break;
       case FB_OBS_ROOT_POSE: if (y < 3) o[k + y] = comp(rpos + ref, y); else if (y < 7) o[k + y] = AT(d.qpos, rq + y); break;
       case FB_OBS_SUBTREE_COM: if (y < 3) { float mass = AT(d.crb10, FB_I10S * a); o[k + y] = (mass > 0 ? AT(d.crb10, FB_I10S * a + 1 + y) / mass : 0.0f) + AT(d.ref, y); } break;
+      case FB_OBS_TASK_TARGET: if (d.task && d.task->target) for (int i = y; i < b; i += FB_NY) o[k + i] = d.task->target[2 * e + i]; break;
       case FB_OBS_WORLD_CONTACT: if (y == 0) { int nc = AT(d.ncon, 0); float hit = 0.0f;
           for (int ci = 0; ci < nc; ci++) if (AT(d.con_efcadr, ci) >= 0 && (m.geom_bodyid[AT(d.con_geom1, ci)] == 0 || m.geom_bodyid[AT(d.con_geom2, ci)] == 0)) hit = 1.0f;
           o[k] = hit; } break;
@@ -1196,6 +1197,42 @@ FB_DEV int wb_argmin_phase(const float* tab, int n, float target) {
   for (int i = 1; i < n; i++) { float dd = fabsf(target - tab[i]); if (dd < bd) { bd = dd; best = i; } }
   return best;
 }
+// kind 2 (vision_guided_flight).  Height of a heightfield at the grid point nearest to (x, y): VisionFlightImitationWBPG.get_hfield_height
+// (tasks/vision_flight.py:81-95: argmin of |axis - x| over linspace(-half, half, n); first minimum on ties)
+FB_DEV float tk_hf_nearest(const DevTask& t, const float* h, float x, float y) {
+  const float step = 2.0f * t.hf_half / (float)(t.hf_ncol - 1);
+  int xi = (int)ceilf((x + t.hf_half) / step - 0.5f), yi = (int)ceilf((y + t.hf_half) / step - 0.5f);
+  xi = xi < 0 ? 0 : (xi > t.hf_ncol - 1 ? t.hf_ncol - 1 : xi); yi = yi < 0 ? 0 : (yi > t.hf_nrow - 1 ? t.hf_nrow - 1 : yi);
+  return h[(size_t)yi * t.hf_ncol + xi];
+}
+FB_DEV float tk_draw(const DevTask& t, int e, int episode, int k) { return t.has_uniform[e] ? t.uniform[8 * e + k] : tk_u01(t, e, episode, 16 + k); }
+// initialize_episode_mjcf + initialize_episode of the vision task (vision_flight.py:97-139): targets, start point, wing-beat phase, a
+// terrain of the bank copied into the env's heightfield (all lanes), the fly in its hover pose `target_height` above the terrain at the
+// target speed.  Draw order: target height, target speed, x, y, wing-beat phase, terrain.
+FB_DEV void ktask_reset_vision(const DevModel& m, const DevData& d, const DevTask& t, int e, int y, int episode) {
+  int pick = (int)(tk_draw(t, e, episode, 5) * (float)t.n_bank); pick = pick < 0 ? 0 : (pick >= t.n_bank ? t.n_bank - 1 : pick);
+  const size_t cells = (size_t)t.hf_nrow * t.hf_ncol;
+  const float* src = t.bank + cells * pick;
+  float* dst = t.hf_data + cells * e;
+  for (size_t i = y; i < cells; i += FB_NY) dst[i] = src[i];
+  for (int i = y; i < t.hf_ncm; i += FB_NY) t.hf_cmax[(size_t)t.hf_ncm * e + i] = t.bank_cmax[(size_t)t.hf_ncm * pick + i];
+  if (y != 0) return;
+  t.hf_hmax[e] = t.bank_hmax[pick];
+  const float th = t.th_rng[0] + (t.th_rng[1] - t.th_rng[0]) * tk_draw(t, e, episode, 0), ts = t.ts_rng[0] + (t.ts_rng[1] - t.ts_rng[0]) * tk_draw(t, e, episode, 1);
+  const float x = t.x_rng[0] + (t.x_rng[1] - t.x_rng[0]) * tk_draw(t, e, episode, 2), yy = t.y_rng[0] + (t.y_rng[1] - t.y_rng[0]) * tk_draw(t, e, episode, 3);
+  t.target[2 * e] = th; t.target[2 * e + 1] = ts;
+  AT(d.qpos, t.root_qadr) = x; AT(d.qpos, t.root_qadr + 1) = yy; AT(d.qpos, t.root_qadr + 2) = tk_hf_nearest(t, src, x, yy) + th;
+  for (int i = 0; i < 4; i++) AT(d.qpos, t.root_qadr + 3 + i) = t.hover_quat[i];
+  const float phase = tk_draw(t, e, episode, 4);
+  int idx = wb_nearest(t, t.wb_base_freq), len = t.wb_len[idx];
+  int pos = wb_argmin_phase(t.wb_phase + (size_t)idx * t.tab_len, t.tab_len, phase);
+  const float* q0 = t.wb_traj + ((size_t)idx * t.tab_len + pos) * t.n_wing;
+  for (int i = 0; i < t.n_wing; i++) AT(d.qpos, t.wing_qadr[i]) = q0[i];        // (the vision task starts the wings at rest: vision_flight.py:131-134)
+  AT(d.qvel, t.root_vadr) = ts;
+  t.wb_freq[e] = t.wb_base_freq; t.wb_idx[e] = idx; t.wb_pos[e] = pos; (void)len;
+  AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = 1; AT(d.prev_n, 0) = 0;
+  t.step[e] = 0;          // (has_uniform is read by every lane above: ktask_commit clears it)
+}
 FB_DEV void ktask_reset(const DevModel& m, const DevData& d, int e, int y) {
   if (!d.task || e >= d.N) return;
   const DevTask& t = *d.task;
@@ -1211,11 +1248,12 @@ FB_DEV void ktask_reset2(const DevModel& m, const DevData& d, int e, int y) {   
   const DevTask& t = *d.task;
   if (!t.needs_reset[e]) return;
   const int episode = t.episode[e];
+  if (t.kind == 2) { ktask_reset_vision(m, d, t, e, y, episode); return; }
   if (y < 7) { float r = t.ref_qpos[y]; AT(d.qpos, t.root_qadr + y) = r; if (t.ghost_qadr >= 0) AT(d.qpos, t.ghost_qadr + y) = r + (y < 3 ? t.ghost_offset[y] : 0.0f); }
   for (int i = y; i < t.n_noise; i += FB_NY) AT(d.qpos, t.noise_qadr[i]) += t.noise_amp * (2.0f * tk_u01(t, e, episode, 1 + i) - 1.0f);
   if (y == 0) {
     if (t.kind == 1) {          // wings on the beat pattern of the base frequency at a random phase, root at the reference speed
-      float phase = t.has_uniform[e] ? t.uniform[e] : tk_u01(t, e, episode, 0);
+      float phase = t.has_uniform[e] ? t.uniform[8 * e] : tk_u01(t, e, episode, 0);
       int idx = wb_nearest(t, t.wb_base_freq), len = t.wb_len[idx];
       int pos = wb_argmin_phase(t.wb_phase + (size_t)idx * t.tab_len, t.tab_len, phase);
       int nxt = pos + 1 < len ? pos + 1 : len - 1;
@@ -1239,7 +1277,7 @@ FB_DEV void ktask_before(const DevModel& m, const DevData& d, int e, int y) {
     else if (y < 13) AT(d.qvel, t.ghost_vadr + y - 7) = resetting ? 0.0f : t.ref_qvel[6 * step + y - 7];
   }
   if (y == 0) {
-    if (t.kind == 1 && !resetting) {
+    if (t.kind >= 1 && !resetting) {
       float a = t.user_col >= 0 ? d.sc_vals[(size_t)e * d.sc_k + t.user_col] : 0.0f;
       if (!(a == a)) a = 0.0f;
       float ctrl_freq = t.wb_base_freq * (1.0f + t.wb_rel_range * a);
@@ -1263,7 +1301,7 @@ FB_DEV void ktask_commit(const DevModel& m, const DevData& d, int e, int y) {
   const DevTask& t = *d.task;
   const int resetting = t.needs_reset[e];
   t.resetting[e] = resetting;
-  if (resetting) t.episode[e] = t.episode[e] + 1; else t.step[e] = t.step[e] + 1;
+  if (resetting) { t.episode[e] = t.episode[e] + 1; t.has_uniform[e] = 0; } else t.step[e] = t.step[e] + 1;
   t.op_step[e] = t.step[e]; t.op_first[e] = (unsigned char)resetting;
 }
 FB_DEV float tk_lin_tol(float x, float margin) { float v = 1.0f - fabsf(x) / margin; return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
@@ -1278,6 +1316,27 @@ FB_DEV void ktask_after(const DevModel& m, const DevData& d, int e, int y) {
   float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; }
   const bool bad = (AT(d.flags, 0) & 1) != 0 || !(sqrtf(s2) <= t.term_qacc);      // bits 1, 2 are capacity overflows, not bad physics
   bool terminate; float reward;
+  if (t.kind == 2) {      // vision_flight.py:157-254: five reward factors (bumps arenas), fatal contacts with world geoms
+    const float th = t.target[2 * e], ts = t.target[2 * e + 1];
+    const float x = AT(d.qpos, t.root_qadr), yy = AT(d.qpos, t.root_qadr + 1), z = AT(d.qpos, t.root_qadr + 2);
+    const float vx = AT(d.qvel, t.root_vadr), vy = AT(d.qvel, t.root_vadr + 1), vz = AT(d.qvel, t.root_vadr + 2);
+    auto lin = [](float v, float lo, float hi, float margin) { float dd = v < lo ? lo - v : (v > hi ? v - hi : 0.0f); dd /= margin; return dd <= 0.0f ? 1.0f : (dd >= 1.0f ? 0.0f : 1.0f - dd); };
+    const float height = lin(z - tk_hf_nearest(t, t.hf_data + (size_t)t.hf_nrow * t.hf_ncol * e, x, yy), th, th, 0.15f);
+    const float x_speed = lin(vx, ts, 3.0e38f, 1.1f * ts), speed = lin(sqrtf(vx * vx + vy * vy + vz * vz), ts, ts, 1.1f * ts);
+    const float side = lin(AT(d.sensordata, t.velocimeter_adr + 1), 0.0f, 0.0f, 10.0f);
+    const M3 R = ld9(d.xmat, t.root_body, d, e);
+    float c = R.m[6] * t.target_zaxis[0] + R.m[7] * t.target_zaxis[1] + R.m[8] * t.target_zaxis[2]; c = c < -1.0f ? -1.0f : (c > 1.0f ? 1.0f : c);
+    const float zax = lin(acosf(c), 0.0f, 0.0f, 3.14159265358979f);
+    reward = height * x_speed * speed * side * zax;
+    bool contact = false;
+    if (t.fatal) { const int nc = AT(d.ncon, 0); for (int ci = 0; ci < nc; ci++) if (AT(d.con_efcadr, ci) >= 0 && (m.geom_bodyid[AT(d.con_geom1, ci)] == 0 || m.geom_bodyid[AT(d.con_geom2, ci)] == 0)) contact = true; }
+    terminate = bad || contact;
+    const bool last = terminate || (double)step_now * (double)t.dt >= (double)t.time_limit - 1e-9;
+    float* out = t.out + 4 * (size_t)e;
+    out[0] = resetting ? 0.0f : reward; out[1] = resetting ? 1.0f : (terminate ? 0.0f : 1.0f); out[2] = resetting ? 0.0f : (last ? 2.0f : 1.0f); out[3] = 0.0f;
+    t.needs_reset[e] = (last && !resetting) ? 1 : 0;
+    return;
+  }
   if (t.kind == 0) {
     const float* lv = &AT(d.sensordata, t.velocimeter_adr); const float* av = &AT(d.sensordata, t.gyro_adr);
     float linvel = sqrtf(lv[0] * lv[0] + lv[1] * lv[1] + lv[2] * lv[2]), angvel = sqrtf(av[0] * av[0] + av[1] * av[1] + av[2] * av[2]);

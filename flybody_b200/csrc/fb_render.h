@@ -19,8 +19,11 @@ struct DevEye {
   float sky_top[3], sky_horizon[3], ground[3], ambient, diffuse;
   const float* hfield;                              // [N][nrow * ncol] heights (world units), row = y, col = x
   const float* hmax;                                // [N] highest point of the env's terrain
+  const float* cmax;                                // [N][nbr * nbc] highest grid point of every FB_EYE_BLOCK x FB_EYE_BLOCK cell block (incl. its border points)
+  int nbr, nbc;
   unsigned char* out;                               // [N][n_cam][size][size][3]
 };
+#define FB_EYE_BLOCK 8
 
 FB_DEV float eye_height(const DevEye& p, const float* h, float x, float y) {      // bilinear terrain height inside the arena
   const float fx = (x + p.half_size) * (float)(p.ncol - 1) / (2.0f * p.half_size), fy = (y + p.half_size) * (float)(p.nrow - 1) / (2.0f * p.half_size);
@@ -33,7 +36,7 @@ FB_DEV float eye_height(const DevEye& p, const float* h, float x, float y) {    
 FB_DEV unsigned char eye_u8(float v) { v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); return (unsigned char)(v * 255.0f + 0.5f); }
 
 // colour of the ray from `o` along the unit vector `dir`
-FB_DEV void eye_cast(const DevEye& p, const float* h, float hmax, V3 o, V3 dir, float* rgb) {
+FB_DEV void eye_cast(const DevEye& p, const float* h, const float* cm, float hmax, V3 o, V3 dir, float* rgb) {
   float t_hit = -1.0f; V3 n = v3(0, 0, 1);
   if (p.nrow > 0) {
     const float S = p.half_size, cell = 2.0f * S / (float)(p.ncol - 1);
@@ -49,12 +52,31 @@ FB_DEV void eye_cast(const DevEye& p, const float* h, float hmax, V3 o, V3 dir, 
     else if (dir.z > 0.0f) t1 = fminf(t1, (ztop - o.z) / dir.z);
     if (t1 > t0) {
       const float hstep = 0.5f * cell / fmaxf(sqrtf(dir.x * dir.x + dir.y * dir.y), 0.05f);       // <= half a cell sideways per step
-      float tp = t0, t = t0; bool below = false;
-      for (int it = 0; it < 4096 && t <= t1; it++) {
+      // samples at t0 + k hstep.  The bilinear surface inside a block of FB_EYE_BLOCK^2 cells never exceeds the block's highest grid
+      // point, so while the ray is above that height from here to where it leaves the block, every sample on the way is above the
+      // surface and is skipped (conservative: the first sample found below the surface is the one plain marching finds).
+      const float bw = (float)FB_EYE_BLOCK * cell, inv_cell = 1.0f / cell;
+      int k = 0; bool below = false; float t = t0;
+      for (int it = 0; it < 8192; it++) {
+        t = t0 + (float)k * hstep;
+        if (t > t1) break;
         const V3 q = o + dir * t;
+        if (cm) {
+          int ix = (int)floorf((q.x + S) * inv_cell), iy = (int)floorf((q.y + S) * inv_cell);
+          ix = ix < 0 ? 0 : (ix > p.ncol - 2 ? p.ncol - 2 : ix); iy = iy < 0 ? 0 : (iy > p.nrow - 2 ? p.nrow - 2 : iy);
+          const int bx = ix / FB_EYE_BLOCK, by = iy / FB_EYE_BLOCK;
+          const float top = cm[by * p.nbc + bx] + p.z_offset;
+          if (q.z > top) {
+            float te = t1;                           // where the ray leaves the block's footprint
+            if (dir.x > 1e-9f) te = fminf(te, ((float)(bx + 1) * bw - S - o.x) / dir.x); else if (dir.x < -1e-9f) te = fminf(te, ((float)bx * bw - S - o.x) / dir.x);
+            if (dir.y > 1e-9f) te = fminf(te, ((float)(by + 1) * bw - S - o.y) / dir.y); else if (dir.y < -1e-9f) te = fminf(te, ((float)by * bw - S - o.y) / dir.y);
+            if (te > t && o.z + dir.z * te > top) { int kn = (int)floorf((te - t0) / hstep) + 1; k = kn > k ? kn : k + 1; continue; }
+          }
+        }
         if (q.z < eye_height(p, h, q.x, q.y)) { below = true; break; }
-        tp = t; t += hstep;
+        k++;
       }
+      const float tp = k > 0 ? t0 + (float)(k - 1) * hstep : t0;
       if (below) {
         float lo = tp, hi = t;
         for (int it = 0; it < 8; it++) { const float mid = 0.5f * (lo + hi); const V3 q = o + dir * mid; if (q.z < eye_height(p, h, q.x, q.y)) hi = mid; else lo = mid; }
@@ -86,7 +108,8 @@ FB_DEV void eye_pixel(const DevData& d, const DevEye& p, int e, int cam, int i, 
   const float u = (2.0f * ((float)j + 0.5f) / (float)p.size - 1.0f) * p.tan_half, v = (1.0f - 2.0f * ((float)i + 0.5f) / (float)p.size) * p.tan_half;
   const V3 dir = mul(Rb, mul(Rc, normalized(v3(u, v, -1.0f))));
   float rgb[3];
-  eye_cast(p, p.nrow > 0 ? p.hfield + (size_t)e * p.nrow * p.ncol : nullptr, p.nrow > 0 ? p.hmax[e] : 0.0f, o, dir, rgb);
+  eye_cast(p, p.nrow > 0 ? p.hfield + (size_t)e * p.nrow * p.ncol : nullptr, (p.nrow > 0 && p.cmax) ? p.cmax + (size_t)e * p.nbr * p.nbc : nullptr,
+           p.nrow > 0 ? p.hmax[e] : 0.0f, o, dir, rgb);
   unsigned char* px = p.out + ((((size_t)e * p.n_cam + cam) * p.size + i) * p.size + j) * 3;
   px[0] = eye_u8(rgb[0]); px[1] = eye_u8(rgb[1]); px[2] = eye_u8(rgb[2]);
 }

@@ -157,7 +157,7 @@ struct DevData {
 // ghost placement, wing-beat pattern generator, termination, reward, discount -- for the shared-reference (inference)
 // form of walk_imitation / flight_imitation.  Lives in device memory; DevData::task points at it.
 struct DevTask {
-  int kind;                                // 0 walk_imitation, 1 flight_imitation
+  int kind;                                // 0 walk_imitation, 1 flight_imitation, 2 vision_guided_flight
   int root_qadr, root_vadr, ghost_qadr, ghost_vadr, root_body, user_col /* action column of the beat-frequency action, -1: none */;
   float ghost_offset[3], dt, time_limit, term_com, term_linvel, term_angvel, term_qacc, term_height;
   int velocimeter_adr, gyro_adr, com_body, episode_steps, ref_len, obs_refdisp_off, obs_refquat_off;
@@ -166,8 +166,13 @@ struct DevTask {
   int n_wing; const int *wing_qadr, *wing_vadr, *wing_ctrl;
   int n_freq, tab_len; const float *wb_traj /*[n_freq][tab_len][n_wing]*/, *wb_phase, *wb_phase_mod /*[n_freq][tab_len], +inf padded*/, *wb_freqs; const int* wb_len;
   float wb_base_freq, wb_rel_range, wb_rate, com_offset[3];
+  // kind 2 (vision_guided_flight): ranges of the per-episode draws, hover pose, terrain bank and the env's own heightfield buffers
+  float th_rng[2], ts_rng[2], x_rng[2], y_rng[2], hover_quat[4], target_zaxis[3]; int fatal;
+  int n_bank, hf_nrow, hf_ncol, hf_ncm; float hf_half, hf_zoff;
+  const float *bank, *bank_hmax, *bank_cmax; float *hf_data, *hf_hmax, *hf_cmax;
+  float* target;                           // [N][2] target height, target speed of the running episode
   // per-env state
-  int *step, *needs_reset, *resetting, *episode, *wb_idx, *wb_pos, *has_uniform; float *uniform, *wb_freq;
+  int *step, *needs_reset, *resetting, *episode, *wb_idx, *wb_pos, *has_uniform; float *uniform /* [N][8] */, *wb_freq;
   int* op_step; unsigned char* op_first;   // the observation program's per-env inputs, maintained here instead of by fb_task_inputs
   float* out;                              // [N][4] reward, discount, step_type (0 FIRST, 1 MID, 2 LAST), 0
 };

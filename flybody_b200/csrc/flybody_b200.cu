@@ -79,7 +79,8 @@ struct FbSim {
   int* op_step_dev; unsigned char* op_first_dev;
   float* ref_slots; int ref_slot_len;      // per-env reference tables (fb_ref_slots)
   DevHf hf; bool hf_on; int hf_nrow, hf_ncol;      // heightfield collision (fb_hfield_collision)
-  DevEye eye; float* hfield_dev; float* hmax_dev; unsigned char* eye_out; size_t eye_bytes;   // eye cameras (fb_eye_program)
+  float *bank_dev, *bank_hmax_dev, *bank_cmax_dev; int bank_n;      // terrain bank of the device-side vision task (fb_hfield_bank)
+  DevEye eye; float* hfield_dev; float* hmax_dev; float* cmax_dev; int hf_nbr, hf_nbc; unsigned char* eye_out; size_t eye_bytes;   // eye cameras (fb_eye_program)
   DevTask task_host;                       // host copy of the device-side task program (its pointers are device pointers)
   float* stage; int* stage_i; size_t stage_cap, stage_icap; unsigned ws_slot;
 #ifndef FB_EMU
@@ -765,7 +766,7 @@ int fb_create(const FbModel* hm, int n_envs, int device, FbHandle* out) {
   FbSim* s = new FbSim();
   s->device = device; s->launches = 0; s->last_ms = 0; s->hm = *hm; s->first_substep = 1; s->hold_pending = 0; s->prof_on = 0; memset(s->prof_ms, 0, sizeof(s->prof_ms)); memset(s->prof_n, 0, sizeof(s->prof_n));
   s->fuse = getenv("FB_FUSE") ? atoi(getenv("FB_FUSE")) : FB_FUSE_DEFAULT; if (s->fuse < 0 || s->fuse > 6 || s->fuse == 5) s->fuse = FB_FUSE_DEFAULT;
-  s->ref_slots = nullptr; s->ref_slot_len = 0; s->eye_out = nullptr; s->hfield_dev = nullptr; s->hmax_dev = nullptr; s->eye_bytes = 0; s->hf_on = false; s->hf_nrow = s->hf_ncol = 0;
+  s->ref_slots = nullptr; s->ref_slot_len = 0; s->eye_out = nullptr; s->hfield_dev = nullptr; s->hmax_dev = nullptr; s->cmax_dev = nullptr; s->hf_nbr = s->hf_nbc = 0; s->bank_dev = s->bank_hmax_dev = s->bank_cmax_dev = nullptr; s->bank_n = 0; s->eye_bytes = 0; s->hf_on = false; s->hf_nrow = s->hf_ncol = 0;
   s->op_step_dev = nullptr; s->op_first_dev = nullptr; s->stage_cap = 0; s->stage_icap = 0; s->stage = nullptr; s->stage_i = nullptr;
 #ifndef FB_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete s; return -2; }
@@ -1199,7 +1200,7 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
     int k = p->kind[i], b = p->b[i];
     offs.push_back(dim);
     switch (k) {
-      case FB_OBS_SENSOR_MEAN: case FB_OBS_SENSOR_NOW: case FB_OBS_ACT: case FB_OBS_QPOS: case FB_OBS_QVEL: dim += b; break;
+      case FB_OBS_SENSOR_MEAN: case FB_OBS_SENSOR_NOW: case FB_OBS_ACT: case FB_OBS_QPOS: case FB_OBS_QVEL: case FB_OBS_TASK_TARGET: dim += b; break;
       case FB_OBS_SITES_EGO: case FB_OBS_REF_DISP: case FB_OBS_DOF_AXIS_EGO: dim += 3 * b; break;
       case FB_OBS_REF_QUAT: dim += 4 * b; break;
       case FB_OBS_ROOT_ZAXIS: case FB_OBS_SCALARS: case FB_OBS_SUBTREE_COM: dim += 3; break;
@@ -1259,7 +1260,8 @@ int fb_task_program(FbHandle s, const FbTaskProgram* p) {
   if (!s->d.tobs || !s->act_map_dev) { s->err = "fb_task_program: call fb_set_action_map and fb_obs_program first"; return -1; }
   if (s->d.op_ref_slot) { s->err = "fb_task_program: per-env reference slots keep the host-side task code"; return -1; }
   if (p->ref_len <= 0 || !p->ref_qpos || !p->ref_qvel || !p->reset_qpos) { s->err = "fb_task_program: reference / reset tables missing"; return -1; }
-  if (p->kind == 1 && (p->n_wing <= 0 || p->n_freq <= 0 || p->tab_len <= 0 || !p->wb_traj || !p->wb_phase || !p->wb_phase_mod || !p->wb_freqs || !p->wb_len)) { s->err = "fb_task_program: wing-beat tables missing"; return -1; }
+  if (p->kind == 2 && (!s->bank_dev || !s->hfield_dev || s->bank_n <= 0)) { s->err = "fb_task_program: kind 2 needs fb_hfield_collision / fb_eye_program and fb_hfield_bank first"; return -1; }
+  if (p->kind >= 1 && (p->n_wing <= 0 || p->n_freq <= 0 || p->tab_len <= 0 || !p->wb_traj || !p->wb_phase || !p->wb_phase_mod || !p->wb_freqs || !p->wb_len)) { s->err = "fb_task_program: wing-beat tables missing"; return -1; }
   if (sync_stream(s) != 0) return -2;
   const DevModel& m = s->m; const int Np = s->d.Np;
   DevTask t; memset(&t, 0, sizeof(t));
@@ -1274,7 +1276,7 @@ int fb_task_program(FbHandle s, const FbTaskProgram* p) {
   auto upi32 = [&](const int32_t* src, size_t n) { std::vector<int> v(src, src + n); return up(s, v); };
   t.reset_qpos = upf32(p->reset_qpos, m.nq); t.ref_qpos = upf32(p->ref_qpos, (size_t)7 * p->ref_len); t.ref_qvel = upf32(p->ref_qvel, (size_t)6 * p->ref_len);
   t.n_noise = p->noise_qadr ? p->n_noise : 0; t.noise_qadr = t.n_noise ? upi32(p->noise_qadr, t.n_noise) : nullptr; t.noise_amp = p->noise_amp; t.seed = p->seed;
-  if (p->kind == 1) {
+  if (p->kind >= 1) {
     t.n_wing = p->n_wing; t.wing_qadr = upi32(p->wing_qadr, p->n_wing); t.wing_vadr = upi32(p->wing_vadr, p->n_wing); t.wing_ctrl = upi32(p->wing_ctrl, p->n_wing);
     t.n_freq = p->n_freq; t.tab_len = p->tab_len; const size_t nt = (size_t)p->n_freq * p->tab_len;
     t.wb_traj = upf32(p->wb_traj, nt * p->n_wing); t.wb_phase = upf32(p->wb_phase, nt); t.wb_phase_mod = upf32(p->wb_phase_mod, nt);
@@ -1283,7 +1285,16 @@ int fb_task_program(FbHandle s, const FbTaskProgram* p) {
   }
   t.step = dalloc<int>(s, Np); t.needs_reset = dalloc<int>(s, Np); t.resetting = dalloc<int>(s, Np); t.episode = dalloc<int>(s, Np);
   t.wb_idx = dalloc<int>(s, Np); t.wb_pos = dalloc<int>(s, Np); t.has_uniform = dalloc<int>(s, Np);
-  t.uniform = dalloc<float>(s, Np); t.wb_freq = dalloc<float>(s, Np); t.out = dalloc<float>(s, (size_t)4 * Np);
+  t.uniform = dalloc<float>(s, (size_t)8 * Np); t.wb_freq = dalloc<float>(s, Np); t.out = dalloc<float>(s, (size_t)4 * Np);
+  if (p->kind == 2) {
+    for (int i = 0; i < 2; i++) { t.th_rng[i] = p->target_height_range[i]; t.ts_rng[i] = p->target_speed_range[i]; t.x_rng[i] = p->init_x_range[i]; t.y_rng[i] = p->init_y_range[i]; }
+    for (int i = 0; i < 4; i++) t.hover_quat[i] = p->hover_quat[i];
+    for (int i = 0; i < 3; i++) t.target_zaxis[i] = p->target_zaxis[i];
+    t.fatal = p->floor_contacts_fatal;
+    t.n_bank = s->bank_n; t.hf_nrow = s->hf_nrow; t.hf_ncol = s->hf_ncol; t.hf_ncm = s->hf_nbr * s->hf_nbc; t.hf_half = s->hf.size[0]; t.hf_zoff = 0.0f;
+    t.bank = s->bank_dev; t.bank_hmax = s->bank_hmax_dev; t.bank_cmax = s->bank_cmax_dev; t.hf_data = s->hfield_dev; t.hf_hmax = s->hmax_dev; t.hf_cmax = s->cmax_dev;
+    t.target = dalloc<float>(s, (size_t)2 * Np);
+  }
   t.op_step = s->op_step_dev; t.op_first = s->op_first_dev;
   DevTask* dev = (DevTask*)dalloc<unsigned char>(s, sizeof(DevTask));
   h2d(dev, &t, sizeof(t));
@@ -1327,8 +1338,40 @@ int fb_task_uniforms(FbHandle s, const int32_t* env_ids, int n, const float* u) 
   const int one = 1;
   for (int k = 0; k < n; k++) {
     if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_task_uniforms: env id out of range"; return -1; }
-    h2d(s->task_host.uniform + env_ids[k], u + k, sizeof(float)); h2d(s->task_host.has_uniform + env_ids[k], &one, sizeof(int));
+    h2d(s->task_host.uniform + (size_t)8 * env_ids[k], u + k, sizeof(float)); h2d(s->task_host.has_uniform + env_ids[k], &one, sizeof(int));
   }
+  return 0;
+}
+int fb_task_uniform_rows(FbHandle s, const int32_t* env_ids, int n, const float* u) {
+  if (!s || !s->d.task || !env_ids || !u || n < 0) return -1;
+  if (sync_stream(s) != 0) return -2;
+  const int one = 1;
+  for (int k = 0; k < n; k++) {
+    if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_task_uniform_rows: env id out of range"; return -1; }
+    h2d(s->task_host.uniform + (size_t)8 * env_ids[k], u + (size_t)8 * k, 8 * sizeof(float)); h2d(s->task_host.has_uniform + env_ids[k], &one, sizeof(int));
+  }
+  return 0;
+}
+int fb_hfield_bank(FbHandle s, int n_terrain, const float* heights) {
+  if (!s || !s->hfield_dev || n_terrain <= 0 || !heights) { if (s) s->err = "fb_hfield_bank: set up the heightfield grid first (fb_hfield_collision / fb_eye_program)"; return -1; }
+  if (sync_stream(s) != 0) return -2;
+  const size_t cells = (size_t)s->hf_nrow * s->hf_ncol, ncm = (size_t)s->hf_nbr * s->hf_nbc;
+  std::vector<float> hmax(n_terrain), cm(ncm * n_terrain);
+  for (int k = 0; k < n_terrain; k++) {
+    const float* hk = heights + cells * k;
+    float mx = hk[0]; for (size_t i = 1; i < cells; i++) mx = std::max(mx, hk[i]);
+    hmax[k] = mx;
+    for (int br = 0; br < s->hf_nbr; br++) for (int bc = 0; bc < s->hf_nbc; bc++) {
+      float v = -3.0e38f;
+      for (int iy = br * FB_EYE_BLOCK; iy <= std::min((br + 1) * FB_EYE_BLOCK, s->hf_nrow - 1); iy++)
+        for (int ix = bc * FB_EYE_BLOCK; ix <= std::min((bc + 1) * FB_EYE_BLOCK, s->hf_ncol - 1); ix++) v = std::max(v, hk[(size_t)iy * s->hf_ncol + ix]);
+      cm[ncm * k + (size_t)br * s->hf_nbc + bc] = v;
+    }
+  }
+  s->bank_dev = dalloc<float>(s, cells * n_terrain); s->bank_hmax_dev = dalloc<float>(s, n_terrain); s->bank_cmax_dev = dalloc<float>(s, ncm * n_terrain);
+  if (!s->bank_dev) { s->err = "out of device memory (terrain bank)"; return -4; }
+  h2d(s->bank_dev, heights, sizeof(float) * cells * n_terrain); h2d(s->bank_hmax_dev, hmax.data(), sizeof(float) * n_terrain); h2d(s->bank_cmax_dev, cm.data(), sizeof(float) * cm.size());
+  s->bank_n = n_terrain;
   return 0;
 }
 int fb_task_step(FbHandle s, const float* action, int is_device, int n_substeps) {
@@ -1379,6 +1422,9 @@ static int ensure_hfield(FbSim* s, int nrow, int ncol) {
   }
   s->hfield_dev = dalloc<float>(s, (size_t)nrow * ncol * s->d.Np); s->hmax_dev = dalloc<float>(s, s->d.Np);
   s->hf_nrow = nrow; s->hf_ncol = ncol;
+  // block maxima for the eye ray marcher (fb_render.h: FB_EYE_BLOCK)
+  s->hf_nbr = (nrow - 1 + FB_EYE_BLOCK - 1) / FB_EYE_BLOCK; s->hf_nbc = (ncol - 1 + FB_EYE_BLOCK - 1) / FB_EYE_BLOCK;
+  s->cmax_dev = dalloc<float>(s, (size_t)s->hf_nbr * s->hf_nbc * s->d.Np);
   return 0;
 }
 int fb_hfield_collision(FbHandle s, int geom, const float* size, int nrow, int ncol, const int32_t* pair_geom, int npair) {
@@ -1416,6 +1462,7 @@ int fb_eye_program(FbHandle s, const FbEyeProgram* p) {
   s->eye_bytes = (size_t)y.n_cam * y.size * y.size * 3;
   s->eye_out = dalloc<unsigned char>(s, s->eye_bytes * s->d.Np);
   y.hfield = s->hfield_dev; y.hmax = s->hmax_dev; y.out = s->eye_out;
+  y.cmax = (y.nrow > 0 && !getenv("FB_EYE_NO_SKIP")) ? s->cmax_dev : nullptr; y.nbr = s->hf_nbr; y.nbc = s->hf_nbc;
   return 0;
 }
 int fb_hfield_write(FbHandle s, const int32_t* env_ids, int n, const float* heights) {
@@ -1425,7 +1472,17 @@ int fb_hfield_write(FbHandle s, const int32_t* env_ids, int n, const float* heig
     if (env_ids[k] < 0 || env_ids[k] >= s->d.N) { s->err = "fb_hfield_write: env id out of range"; return -1; }
     float mx = heights[cells * k]; for (size_t i = 1; i < cells; i++) mx = std::max(mx, heights[cells * k + i]);
     upload_async(s, s->hfield_dev + cells * env_ids[k], heights + cells * k, sizeof(float) * cells);
+    // highest grid point of every block of FB_EYE_BLOCK x FB_EYE_BLOCK cells, border points included
+    std::vector<float> cm((size_t)s->hf_nbr * s->hf_nbc);
+    const float* hk = heights + cells * k;
+    for (int br = 0; br < s->hf_nbr; br++) for (int bc = 0; bc < s->hf_nbc; bc++) {
+      float v = -3.0e38f;
+      for (int iy = br * FB_EYE_BLOCK; iy <= std::min((br + 1) * FB_EYE_BLOCK, s->hf_nrow - 1); iy++)
+        for (int ix = bc * FB_EYE_BLOCK; ix <= std::min((bc + 1) * FB_EYE_BLOCK, s->hf_ncol - 1); ix++) v = std::max(v, hk[(size_t)iy * s->hf_ncol + ix]);
+      cm[(size_t)br * s->hf_nbc + bc] = v;
+    }
     if (sync_stream(s) != 0) return -2;
+    h2d(s->cmax_dev + cm.size() * env_ids[k], cm.data(), sizeof(float) * cm.size());
     h2d(s->hmax_dev + env_ids[k], &mx, sizeof(float));
   }
   return 0;

@@ -22,12 +22,12 @@ MAXCON, MAXEFC = 64, 160
 
 EXPORTS = ['fb_create', 'fb_destroy', 'fb_reset', 'fb_reset_hold', 'fb_set_ctrl', 'fb_set_action_map', 'fb_write_state', 'fb_step', 'fb_forward',
            'fb_get', 'fb_field_size', 'fb_record_stride', 'fb_set', 'fb_obs_ptr', 'fb_n_envs', 'fb_n_envs_padded', 'fb_stream',
-           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_request_reset', 'fb_task_set_reset_noise', 'fb_task_episodes', 'fb_task_uniforms', 'fb_task_ptrs', 'fb_task_read', 'fb_eye_program', 'fb_hfield_collision', 'fb_hfield_write', 'fb_render_eyes', 'fb_eyes_ptr', 'fb_eyes_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
+           'fb_sync', 'fb_pack_obs', 'fb_read_obs', 'fb_obs_program', 'fb_ref_slots', 'fb_ref_slot_write', 'fb_task_program', 'fb_task_step', 'fb_task_reset_all', 'fb_task_request_reset', 'fb_task_set_reset_noise', 'fb_task_episodes', 'fb_task_uniforms', 'fb_task_uniform_rows', 'fb_hfield_bank', 'fb_task_ptrs', 'fb_task_read', 'fb_eye_program', 'fb_hfield_collision', 'fb_hfield_write', 'fb_render_eyes', 'fb_eyes_ptr', 'fb_eyes_read', 'fb_task_inputs', 'fb_read_task_obs', 'fb_profile', 'fb_profile_read', 'fb_profile_name', 'fb_launch_count', 'fb_last_step_ms', 'fb_set_solver', 'fb_last_error', 'fb_version']
 
 
 # enum FbObsItem
 (OBS_SENSOR_MEAN, OBS_SENSOR_NOW, OBS_ACT, OBS_QPOS, OBS_QVEL, OBS_SITES_EGO, OBS_ROOT_ZAXIS, OBS_REF_DISP,
- OBS_REF_QUAT, OBS_SCALARS, OBS_ROOT_POSE, OBS_SUBTREE_COM, OBS_DOF_AXIS_EGO, OBS_WORLD_CONTACT) = range(14)
+ OBS_REF_QUAT, OBS_SCALARS, OBS_ROOT_POSE, OBS_SUBTREE_COM, OBS_DOF_AXIS_EGO, OBS_WORLD_CONTACT, OBS_TASK_TARGET) = range(15)
 
 
 class FbObsProgram(C.Structure):
@@ -49,7 +49,9 @@ class FbTaskProgram(C.Structure):
                 ('n_wing', C.c_int32), ('wing_qadr', C.POINTER(C.c_int32)), ('wing_vadr', C.POINTER(C.c_int32)), ('wing_ctrl', C.POINTER(C.c_int32)),
                 ('n_freq', C.c_int32), ('tab_len', C.c_int32), ('wb_traj', C.POINTER(C.c_float)), ('wb_phase', C.POINTER(C.c_float)),
                 ('wb_phase_mod', C.POINTER(C.c_float)), ('wb_freqs', C.POINTER(C.c_float)), ('wb_len', C.POINTER(C.c_int32)),
-                ('wb_base_freq', C.c_float), ('wb_rel_range', C.c_float), ('wb_rate', C.c_float), ('com_offset', C.c_float * 3)]
+                ('wb_base_freq', C.c_float), ('wb_rel_range', C.c_float), ('wb_rate', C.c_float), ('com_offset', C.c_float * 3),
+                ('target_height_range', C.c_float * 2), ('target_speed_range', C.c_float * 2), ('init_x_range', C.c_float * 2), ('init_y_range', C.c_float * 2),
+                ('hover_quat', C.c_float * 4), ('target_zaxis', C.c_float * 3), ('floor_contacts_fatal', C.c_int32)]
 
 
 class FbEyeProgram(C.Structure):
@@ -95,6 +97,8 @@ def load_library(path=None):
     lib.fb_task_request_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.fb_task_episodes.argtypes = [C.c_void_p, C.c_void_p]
     lib.fb_task_set_reset_noise.argtypes = [C.c_void_p, C.c_float]
+    lib.fb_task_uniform_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.fb_hfield_bank.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.fb_task_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
     lib.fb_task_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.fb_eye_program.argtypes = [C.c_void_p, C.c_void_p]
@@ -285,8 +289,8 @@ class BatchedStepper:
                 v = fp(v)
             elif ctype is C.POINTER(C.c_int32):
                 v = ip(v)
-            elif ctype is C.c_float * 3:
-                v = (C.c_float * 3)(*[float(x) for x in v])
+            elif ctype in (C.c_float * 2, C.c_float * 3, C.c_float * 4):
+                v = ctype(*[float(x) for x in v])
             setattr(p, name, v)
         self._check(self._lib.fb_task_program(self._h, C.byref(p)), 'fb_task_program')
 
@@ -304,6 +308,15 @@ class BatchedStepper:
     def task_request_reset(self, env_ids):
         ids = np.ascontiguousarray(env_ids, np.int32)
         self._check(self._lib.fb_task_request_reset(self._h, ids.ctypes.data, len(ids)), 'fb_task_request_reset')
+
+    def task_uniform_rows(self, env_ids, rows):
+        ids = np.ascontiguousarray(env_ids, np.int32); u = np.ascontiguousarray(rows, np.float32).reshape(len(ids), 8)
+        self._check(self._lib.fb_task_uniform_rows(self._h, ids.ctypes.data, len(ids), u.ctypes.data), 'fb_task_uniform_rows')
+
+    def hfield_bank(self, heights):
+        h = np.ascontiguousarray(heights, np.float32).reshape(len(heights), -1)
+        assert h.shape[1] == self._hfield_cells, (h.shape, self._hfield_cells)
+        self._check(self._lib.fb_hfield_bank(self._h, h.shape[0], h.ctypes.data), 'fb_hfield_bank')
 
     def task_set_reset_noise(self, amp):
         self._check(self._lib.fb_task_set_reset_noise(self._h, float(amp)), 'fb_task_set_reset_noise')
@@ -361,6 +374,10 @@ class BatchedStepper:
         p, n = C.c_void_p(), C.c_int()
         self._check(self._lib.fb_eyes_ptr(self._h, C.byref(p), C.byref(n)), 'fb_eyes_ptr')
         return p.value, n.value
+
+    def render_eyes_async(self):
+        """launch the eye renderer on the stepper's stream; the images stay on the device (eyes_ptr)"""
+        self._check(self._lib.fb_render_eyes(self._h), 'fb_render_eyes')
 
     def render_eyes(self, out=None):
         """-> uint8 [n_envs, n_cam, size, size, 3] rendered from the current body poses."""

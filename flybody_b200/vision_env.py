@@ -38,7 +38,7 @@ class BatchedVisionFlightEnv:
 
     def __init__(self, n_envs, bumps_or_trench='bumps', wpg_pattern_path=None, device=0, lib_path=None, seed=0, eye_camera_size=32,
                  eye_camera_fovy=150.0, target_height_range=(0.5, 0.8), target_speed_range=(20, 40), init_pos_x_range=(-5, -5),
-                 init_pos_y_range=(0, 0), time_limit=0.4, floor_contacts_fatal=True, terrain_bank=None, **kwargs_arena):
+                 init_pos_y_range=(0, 0), time_limit=0.4, floor_contacts_fatal=True, terrain_bank=None, device_task=False, **kwargs_arena):
         if bumps_or_trench not in ('bumps', 'trench'):
             raise ValueError("Only 'bumps' and 'trench' terrains are supported.")
         self._batched = n_envs is not None
@@ -98,7 +98,7 @@ class BatchedVisionFlightEnv:
                 ('walker/velocimeter', 3, (st.OBS_SENSOR_MEAN, sd('velocimeter'), 3)), ('walker/world_zaxis', 3, (st.OBS_ROOT_ZAXIS, 0, 3)),
                 ('_velocimeter_now', 3, (st.OBS_SENSOR_NOW, sd('velocimeter'), 3)), ('_root_pose', 7, (st.OBS_ROOT_POSE, 0, 7)),
                 ('_root_qvel', 6, (st.OBS_QVEL, 2 * nq, 6)), ('_scalars', 3, (st.OBS_SCALARS, 0, 3)),
-                ('_world_contact', 1, (st.OBS_WORLD_CONTACT, 0, 1))]
+                ('_world_contact', 1, (st.OBS_WORLD_CONTACT, 0, 1)), ('_task_target', 2, (st.OBS_TASK_TARGET, 0, 2))]
         lists = list(self._obs_qadr) + list(self._obs_vadr) + list(range(self._root_v, self._root_v + 6))
         dim = self._sim.obs_program([r[2] for r in rows], lists, m.body_id('walker/thorax'), self._n_sub, None)
         off = np.concatenate([[0], np.cumsum([r[1] for r in rows])])
@@ -119,7 +119,14 @@ class BatchedVisionFlightEnv:
         self._needs_reset = np.ones(N, bool)
         self._wing_qpos = np.zeros((N, 6))
         self._has_trench = np.zeros(N, bool)
+        self._last_draws = np.zeros((N, 8), np.float32)
         self.n_resets = 0
+        # task hooks on the device (fb_task_*, kind 2): needs the terrain bank (a resetting env copies one of its terrains on the device)
+        self._device_task = bool(device_task)
+        if self._device_task:
+            if self._bank is None or bumps_or_trench != 'bumps':
+                raise NotImplementedError("device_task=True needs terrain_bank=K and 'bumps' arenas (the trench-centre reward factor is host code)")
+            self._upload_task_program(seed)
 
     @staticmethod
     def _pinned(shape, dtype):
@@ -173,6 +180,77 @@ class BatchedVisionFlightEnv:
     def target_speed(self):
         return self._target_speed.copy()
 
+    def _upload_task_program(self, seed):
+        """fb_task_program kind 2: the hooks of this env as a device-side program (same constants as the host path)."""
+        m, wb, r = self.model, self._wbpg, self._ranges
+        self._sim.set_action_map(np.concatenate([self._ctrl_of_action, [-1]]))      # the user action (beat frequency) has no ctrl slot
+        self._sim.hfield_bank(np.stack([t for t, _ in self._bank]))
+        dummy = np.zeros((1, 7), np.float32); dummy[0, 3] = 1.0
+        self._sim.task_program(
+            kind=2, root_qadr=self._root_q, root_vadr=self._root_v, ghost_qadr=-1, ghost_vadr=-1, user_col=len(self._ctrl_of_action),
+            ghost_offset=(0, 0, 0), control_timestep=self._control_timestep, time_limit=self._time_limit, terminal_com_dist=3e38, terminal_linvel=3e38,
+            terminal_angvel=3e38, terminal_qacc=_TERMINAL_QACC, terminal_height=-3e38,
+            velocimeter_adr=int(m.sensor_adr[m.meta['sensor_names'].index('walker/velocimeter')]),
+            gyro_adr=int(m.sensor_adr[m.meta['sensor_names'].index('walker/gyro')]), com_body=m.body_id('walker/thorax'), episode_steps=1 << 30, ref_len=1,
+            ref_qpos=dummy, ref_qvel=np.zeros((1, 6), np.float32), obs_refdisp_off=0, obs_refquat_off=0, reset_qpos=m.qpos0, n_noise=0, noise_qadr=None,
+            noise_amp=0.0, seed=int(seed) & 0xffffffff, n_wing=6, wing_qadr=self._wing_qadr,
+            wing_vadr=np.array([m.jnt_dofadr_of(n) for n in [f'walker/wing_{a}_{s_}' for s_ in ('left', 'right') for a in ('yaw', 'roll', 'pitch')]]),
+            wing_ctrl=self._ctrl_of_action[self._action_indices['wings']], n_freq=wb.traj.shape[0], tab_len=wb.traj.shape[1], wb_traj=wb.traj,
+            wb_phase=np.where(np.isfinite(wb.phase), wb.phase, 3e38), wb_phase_mod=np.where(np.isfinite(wb.phase_mod), wb.phase_mod, 3e38),
+            wb_freqs=wb.beat_freqs, wb_len=wb.lengths, wb_base_freq=wb.base_beat_freq, wb_rel_range=wb.rel_freq_range, wb_rate=wb._rate,
+            com_offset=(0, 0, 0), target_height_range=r['h'], target_speed_range=r['v'], init_x_range=r['x'], init_y_range=r['y'],
+            hover_quat=self._hover_quat, target_zaxis=self._target_zaxis, floor_contacts_fatal=1 if self._fatal else 0)
+        self._out4 = self._pinned((self.n_envs, 4), np.float32)
+        self._dev_views = None
+
+    def _device_step(self, action, draws=None):
+        """one control step with the task hooks on the device: actions in, observation rows + (reward, discount, step_type) + eyes out"""
+        resetting = self._needs_reset.copy()
+        if draws is not None and resetting.any():               # (tests: the draws the host-side code would make at these resets)
+            ids = np.nonzero(resetting)[0]
+            self._sim.task_uniform_rows(ids, draws[ids])
+        self._sim.task_step(action, self._n_sub)
+        self._sim.task_read(self._rec, self._out4)
+        self._time = np.where(resetting, 0.0, self._time + self._control_timestep)
+        self.n_resets += int(resetting.sum())
+        tgt = self._rec[:, self._sl['_task_target']]
+        self._target_height, self._target_speed = tgt[:, 0].astype(np.float64), tgt[:, 1].astype(np.float64)
+        step_type = self._out4[:, 2].astype(np.int64)
+        self._needs_reset = step_type == int(StepType.LAST)
+        return TimeStep(step_type, self._out4[:, 0].astype(np.float64), self._out4[:, 1].astype(np.float64), self._observation())
+
+    def step_device(self, action):
+        """Device-resident control step (see `BatchedFlyEnv.step_device`): `action` a CUDA tensor [n_envs, 12]; returns zero-copy torch
+        views (observation rows, out [n_envs, 4] = reward, discount, step_type, 0, eyes uint8 [n_envs, 2, S, S, 3]); nothing is copied to
+        the host and the call does not synchronise.  Column slices of the rows: `observation_layout()`."""
+        if not self._device_task:
+            raise RuntimeError('step_device needs device_task=True')
+        import torch
+        cai = action.__cuda_array_interface__
+        assert tuple(cai['shape']) == (self.n_envs, self._action_spec.shape[0]) and cai['typestr'] == '<f4', cai
+        self._sim.task_step(cai['data'][0], self._n_sub, is_device=True)
+        self._sim.render_eyes_async()
+        self._needs_reset[:] = False
+        if self._dev_views is None:
+            obs_ptr, dim, out_ptr = self._sim.task_ptrs()
+
+            class _View:
+                def __init__(self, ptr, shape):
+                    self.__cuda_array_interface__ = {'shape': shape, 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+            dev = f'cuda:{self._sim.device}'
+            self._dev_views = (torch.as_tensor(_View(obs_ptr, (self.n_envs, dim)), device=dev), torch.as_tensor(_View(out_ptr, (self.n_envs, 4)), device=dev))
+        return self._dev_views + (self.eyes_device(),)
+
+    def observation_layout(self):
+        """{observable name: column slice} of the observation rows `step_device` returns (eyes come as their own tensor)"""
+        return {k: sl for k, sl in self._sl.items() if not k.startswith('_')} | {'walker/task_input': self._sl['_task_target']}
+
+    def request_reset(self, env_ids):
+        ids = np.asarray(env_ids, np.int64).reshape(-1)
+        if len(ids) and self._device_task:
+            self._sim.task_request_reset(ids)
+        self._needs_reset[ids] = True
+
     def hfield_height(self, x, y):
         """`VisionFlightImitationWBPG.get_hfield_height` per env: height at the grid point nearest to (x, y)."""
         return arenas.hfield_height(self._terrain, x, y, self._half)
@@ -185,14 +263,18 @@ class BatchedVisionFlightEnv:
         n = len(ids)
         qpos, qvel = np.tile(m.qpos0, (n, 1)), np.zeros((n, m.nv))
         for k, e in enumerate(ids):
-            self._target_height[e] = self._rs.uniform(*r['h'])
-            self._target_speed[e] = self._rs.uniform(*r['v'])
-            x, y = self._rs.uniform(*r['x']), self._rs.uniform(*r['y'])
-            wq, _ = self._wbpg.reset(np.array([e]), np.array([self._rs.uniform()]))
+            # one row of six uniforms per episode, in the order the device-side task program consumes them (fb_task_uniform_rows):
+            # target height, target speed, start x, start y, wing-beat phase, terrain pick
+            u = self._rs.uniform(size=6)
+            self._last_draws[e, :6] = u
+            self._target_height[e] = r['h'][0] + (r['h'][1] - r['h'][0]) * u[0]
+            self._target_speed[e] = r['v'][0] + (r['v'][1] - r['v'][0]) * u[1]
+            x, y = r['x'][0] + (r['x'][1] - r['x'][0]) * u[2], r['y'][0] + (r['y'][1] - r['y'][0]) * u[3]
+            wq, _ = self._wbpg.reset(np.array([e]), np.array([u[4]]))
             if self._bank is None:
                 self._terrain[e] = self._arenas[e].generate(self._rs)
             else:
-                self._terrain[e], self._arenas[e].trench_specs = self._bank[self._rs.randint(len(self._bank))]
+                self._terrain[e], self._arenas[e].trench_specs = self._bank[min(int(u[5] * len(self._bank)), len(self._bank) - 1)]
             self._has_trench[e] = self._arenas[e].trench_specs is not None
             z = float(arenas.hfield_height(self._terrain[e], [x], [y], self._half)[0]) + self._target_height[e]
             qpos[k, self._root_q:self._root_q + 3] = (x, y, z)
@@ -229,6 +311,11 @@ class BatchedVisionFlightEnv:
 
     def reset(self):
         N = self.n_envs
+        if self._device_task:
+            self._sim.task_reset_all()
+            self._needs_reset[:] = True
+            ts = self._device_step(np.zeros((N, self._action_spec.shape[0]), np.float32), draws=getattr(self, '_forced_draws', None))
+            return self._unbatch(ts, first=True)
         self._reset_envs(np.arange(N), hold=False)
         self._sim.task_inputs(np.zeros(N, np.int32), np.ones(N, np.uint8))
         self._sim.read_task_obs(self._rec)
@@ -236,6 +323,10 @@ class BatchedVisionFlightEnv:
 
     def step(self, action):
         m, N = self.model, self.n_envs
+        if self._device_task:
+            a = np.asarray(action, np.float32).reshape(N, -1)
+            assert a.shape[1] == self._action_spec.shape[0], f'action must have {self._action_spec.shape[0]} entries'
+            return self._unbatch(self._device_step(a, draws=getattr(self, '_forced_draws', None)))
         action = np.array(action, np.float64, copy=True).reshape(N, -1)
         assert action.shape[1] == self._action_spec.shape[0], f'action must have {self._action_spec.shape[0]} entries'
         resetting = self._needs_reset.copy()

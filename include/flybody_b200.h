@@ -252,6 +252,8 @@ enum FbObsItem {
   FB_OBS_SUBTREE_COM = 11,/* a = body id : physics.data.subtree_com[body]                                    */
   FB_OBS_DOF_AXIS_EGO = 12,/* a = offset into list (dof ids), b = count : world joint axis (physics.bind(joints).xaxis,
                               tasks/rewards.py:48-50) rotated into the root frame                                */
+  FB_OBS_TASK_TARGET = 14,   /* b floats of the device task's per-episode targets (kind 2: target height, target speed = the reference's
+                               `task_input` observable, tasks/vision_flight.py:56-76)                                     */
   FB_OBS_WORLD_CONTACT = 13 /* 1 float: 1 if an active contact (efc_address >= 0) involves a geom of the world body (ground plane, terrain):
                                the reference's check_floor_contact (tasks/vision_flight.py:235-247)                        */
 };
@@ -288,7 +290,7 @@ int fb_read_obs(FbHandle h, float* host_dst);
  * (host or device pointer), observation rows + (reward, discount, step_type) out.  Covers the shared-reference (inference-mode)
  * tasks; dataset mode keeps the host-side task code.  Requires fb_set_action_map and fb_obs_program first.          */
 typedef struct FbTaskProgram {
-  int32_t kind;                        /* 0 walk_imitation, 1 flight_imitation */
+  int32_t kind;                        /* 0 walk_imitation, 1 flight_imitation, 2 vision_guided_flight (fields at the end of the struct) */
   int32_t root_qadr, root_vadr, ghost_qadr, ghost_vadr;   /* free-joint slots of the walker root and of the ghost */
   int32_t user_col;                    /* column of the beat-frequency action in the action row, -1 if none */
   float ghost_offset[3];
@@ -307,6 +309,13 @@ typedef struct FbTaskProgram {
   const float* wb_freqs /* [n_freq] */; const int32_t* wb_len /* [n_freq] */;
   float wb_base_freq, wb_rel_range, wb_rate;
   float com_offset[3];                 /* root -> CoM offset in the root frame (tasks/task_utils.py:237) */
+  /* kind 2, vision_guided_flight (tasks/vision_flight.py:97-254): no ghost / reference; per episode a target height and speed, a start
+   * point, a wing-beat phase and a terrain of the device bank (fb_hfield_bank) are drawn; reward = product of the height / forward speed /
+   * speed / side speed / body axis factors (the trench-centre factor applies to 'trench' arenas, which keep the host-side task code);
+   * termination on a bad state or, if floor_contacts_fatal, an active contact with a world geom.                                */
+  float target_height_range[2], target_speed_range[2], init_x_range[2], init_y_range[2];
+  float hover_quat[4], target_zaxis[3];
+  int32_t floor_contacts_fatal;
 } FbTaskProgram;
 int fb_task_program(FbHandle h, const FbTaskProgram* p);
 /* One control step with the task logic on the device: [auto-reset] -> action -> ctrl -> before_step -> n_substeps x physics ->
@@ -323,6 +332,13 @@ int fb_task_set_reset_noise(FbHandle h, float amp);
 int fb_task_request_reset(FbHandle h, const int32_t* env_ids, int n);
 /* Per-env count of episodes started so far (resets done by the device-side task logic), int32 [n_envs] to the host.    */
 int fb_task_episodes(FbHandle h, int32_t* dst);
+/* Terrain bank for the device-side vision task: K heightfields [K][nrow * ncol] (world units, the grid of fb_hfield_collision /
+ * fb_eye_program); a resetting env copies one of them into its own heightfield (collision + eyes).                      */
+int fb_hfield_bank(FbHandle h, int n_terrain, const float* heights);
+/* Rows of 8 uniform numbers in [0,1) consumed by the listed envs' next reset instead of the device's counter hash (kind 2: target
+ * height, target speed, start x, start y, wing-beat phase, terrain pick; kind 1: wing-beat phase) -- lets a test feed the device the
+ * draws of the host-side task code.                                                                                    */
+int fb_task_uniform_rows(FbHandle h, const int32_t* env_ids, int n, const float* u);
 /* Uniform numbers in [0,1) consumed by the listed envs' next reset (flight: wing-beat phase); without them the device
  * draws from a counter hash of (seed, env, episode).                                                                 */
 int fb_task_uniforms(FbHandle h, const int32_t* env_ids, int n, const float* u);

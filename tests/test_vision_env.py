@@ -60,7 +60,7 @@ def test_reward_factors_follow_their_definitions(emu):
     assert np.allclose(f[:, 2], np.clip(1 - np.abs(np.linalg.norm(vel, axis=1) - ts) / (1.1 * ts), 0, 1))
     assert np.all(f[:, 5] == 1.0)                                      # no trench in the 'bumps' arena
     # one step after the start the fly is still close to its targets
-    assert np.all(f[:, 0] > 0.9) and np.all(f[:, 2] > 0.9) and np.all(f[:, 4] > 0.9)
+    assert np.all(f[:, 0] > 0.9) and np.all(f[:, 2] > 0.85) and np.all(f[:, 4] > 0.9)
     env.close()
 
 
@@ -115,3 +115,46 @@ def test_terrain_bank_option(emu):
     ts = env.step(np.zeros((4, 12)))
     assert np.all(np.isfinite(ts.reward))
     env.close()
+
+
+@pytest.mark.parametrize('low_start', [True, False])
+def test_device_task_matches_the_host_task_code(emu, low_start):
+    """fb_task_* kind 2: the vision task's hooks on the device (terrain pick from the device bank, targets, start pose, wing-beat
+    generator, five reward factors, fatal world contacts, time limit) against the host-side task code of this file's env, step by step
+    through terminations and auto-resets; the device is fed the host's random draws (fb_task_uniform_rows)."""
+    # low start: the flies begin within contact range of the terrain -> fatal contacts (discount 0); otherwise the time limit ends episodes
+    kw = dict(n_envs=3, lib_path=emu, seed=5, terrain_bank=2, time_limit=0.004, **(dict(target_height_range=(0.12, 0.2)) if low_start else {}))
+    host = fly_envs.vision_guided_flight(**kw)
+    dev = fly_envs.vision_guided_flight(device_task=True, **kw)
+    th = host.reset()
+    dev._forced_draws = host._last_draws.copy()
+    td = dev.reset()
+    for k in th.observation:
+        a, b = np.asarray(th.observation[k], np.float64), np.asarray(td.observation[k], np.float64)
+        if a.size == 0:
+            continue
+        if 'eye' in k:
+            assert (np.abs(a - b) <= 2).mean() > 0.99, k
+        else:
+            assert np.allclose(a, b, atol=2e-4 * (np.abs(a).max() + 1)), (k, np.abs(a - b).max())
+    assert np.allclose(host._sim.get(st.QPOS), dev._sim.get(st.QPOS), atol=1e-6)
+    rs = np.random.RandomState(0)
+    seen_last = seen_first = False
+    discounts = set()
+    for step in range(30):
+        a = rs.uniform(-0.2, 0.2, (3, 12)).astype(np.float32)
+        a[0, :] = 1.0 if step > 8 else a[0]                      # env 0 is driven off course -> terrain contact or time limit -> LAST -> auto-reset
+        th = host.step(a)
+        dev._forced_draws = host._last_draws.copy()
+        td = dev.step(a)
+        assert np.array_equal(np.asarray(th.step_type), np.asarray(td.step_type)), (step, th.step_type, td.step_type)
+        assert np.allclose(th.reward, td.reward, atol=2e-3), (step, th.reward, td.reward)
+        assert np.array_equal(th.discount, td.discount), step
+        assert np.allclose(host._sim.get(st.QPOS), dev._sim.get(st.QPOS), atol=2e-3), (step, np.abs(host._sim.get(st.QPOS) - dev._sim.get(st.QPOS)).max())
+        assert np.allclose(th.observation['walker/task_input'], td.observation['walker/task_input'], atol=1e-6)
+        discounts |= set(np.asarray(th.discount)[np.asarray(th.step_type) == int(StepType.LAST)].tolist())
+        seen_last |= bool((np.asarray(th.step_type) == int(StepType.LAST)).any())
+        seen_first |= step > 0 and bool((np.asarray(th.step_type) == int(StepType.FIRST)).any())
+    assert seen_last and seen_first
+    assert (0.0 in discounts) if low_start else (1.0 in discounts), discounts
+    host.close(); dev.close()
