@@ -375,30 +375,30 @@ def line_of(wl, args, world, r):
 
 def measure_vision(args, world, rank, local, n_envs=1024):
     """BASELINE.json configs[4] shape: `vision_guided_flight` (heightfield terrain contacts, two 32 x 32 x 3 eye cameras rendered on the
-    device every step, wing-beat pattern generator) + the reference's vision policy (VisNet + two-level controller,
-    flybody_b200/policy_torch.py, random weights) in the loop.  The env's task hooks are host code (flybody_b200/vision_env.py), so this
-    workload has no device-resident arm: the one number is end to end -- env.step(host actions) -> observations on the host -> policy
-    forward on the GPU of rank 0 (observations + eyes of all ranks gathered over NCCL, actions scattered back) -> actions on the host."""
+    device every step, wing-beat pattern generator, the task's hooks as device code: fb_task_* kind 2) + the reference's vision policy
+    (VisNet + two-level controller, flybody_b200/policy_torch.py, random weights) in the loop on rank 0 (observation rows + eyes of all
+    ranks gathered over NCCL, actions scattered back).  `value`: everything stays in HBM (`step_device`: torch views of the rows and the
+    eye images).  `e2e`: env.step(host actions) -> observations + eyes on the host -> policy input copied up -> actions copied down."""
     import torch
     import torch.distributed as dist
     from flybody_b200 import fly_envs
     from flybody_b200.policy_torch import vision_policy_for
     dev = torch.device('cuda', local)
     K, W, N = args.steps, args.warmup, n_envs
-    env = fly_envs.vision_guided_flight(n_envs=N, device=local, seed=1234 + rank, terrain_bank=64)
+    env = fly_envs.vision_guided_flight(n_envs=N, device=local, seed=1234 + rank, terrain_bank=64, device_task=True)
     ts = env.reset()
     vis, ctl, keys = vision_policy_for(env, device=dev)
     spec = env.action_spec()
     lo, hi = torch.tensor(spec.minimum, device=dev, dtype=torch.float32), torch.tensor(spec.maximum, device=dev, dtype=torch.float32)
     A = spec.shape[0]
+    layout = env.observation_layout()
+    keys = [k for k in keys if k in layout and layout[k].stop > layout[k].start]          # (actuator_activation is empty for this model)
+    col_task = torch.arange(layout['walker/task_input'].start, layout['walker/task_input'].stop, device=dev)
+    col_others = torch.cat([torch.arange(layout[k].start, layout[k].stop, device=dev) for k in keys])
     bufs = {}
 
-    def act(ts):
-        o = ts.observation
-        eyes = env.eyes_device()                                        # the images of this step, still on the device (the host copy is in `o`)
+    def policy(eyes, task, others):
         left, right = eyes[:, 1], eyes[:, 0]
-        task = torch.from_numpy(o['walker/task_input']).to(dev)
-        others = torch.from_numpy(np.concatenate([np.asarray(o[k], np.float32).reshape(N, -1) for k in keys], 1)).to(dev)
         if world > 1:
             if not bufs:
                 for name, t in (('left', left), ('right', right), ('task', task), ('others', others)):
@@ -415,38 +415,79 @@ def measure_vision(args, world, rank, local, n_envs=1024):
         if world > 1:
             dist.scatter(bufs['a_loc'], [a[r * N:(r + 1) * N].contiguous() for r in range(world)] if rank == 0 else None, src=0)
             a = bufs['a_loc']
-        return a.cpu().numpy()
+        return a.contiguous()
 
-    for k in range(W):
-        ts = env.step(act(ts))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    l0, r0 = env._sim.launch_count, env.n_resets
-    t0 = time.perf_counter()
-    for k in range(K):
-        ts = env.step(act(ts))
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    launches, resets = env._sim.launch_count - l0, env.n_resets - r0
-    env._sim.profile(True)
-    for k in range(5):
-        ts = env.step(act(ts))
+    def act_host(ts):                                       # observations on the host (the dm_env contract) -> policy input copied up
+        o = ts.observation
+        eyes = torch.from_numpy(np.stack([np.asarray(o['walker/right_eye']), np.asarray(o['walker/left_eye'])], 1)).to(dev)
+        task = torch.from_numpy(np.asarray(o['walker/task_input'], np.float32)).to(dev)
+        others = torch.from_numpy(np.concatenate([np.asarray(o[k], np.float32).reshape(N, -1) for k in keys], 1)).to(dev)
+        return policy(eyes, task, others).cpu().numpy()
+
+    def act_dev(rows, eyes):
+        return policy(eyes, rows[:, col_task], rows[:, col_others])
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def maxr(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+        return x
+
+    # ---- device-resident arm: the policy runs on the stepper's stream, ordered after the step and the eye render
+    stream = torch.cuda.ExternalStream(env._sim.stream, device=dev)
+    with torch.cuda.stream(stream):
+        a = torch.zeros((N, A), device=dev)
+        for k in range(max(W, 3)):
+            rows, out, eyes = env.step_device(a)
+            a = act_dev(rows, eyes)
+        sync()
+        l0 = env._sim.launch_count
+        e0 = env._sim.task_episodes().sum()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for k in range(K):
+            rows, out, eyes = env.step_device(a)
+            a = act_dev(rows, eyes)
+        ev1.record(stream)
+        sync()
+        dt_dev = maxr(ev0.elapsed_time(ev1) * 1e-3)
+        launches = env._sim.launch_count - l0
+        resets = int(env._sim.task_episodes().sum() - e0)
+        env._sim.profile(True)
+        for k in range(5):
+            rows, out, eyes = env.step_device(a)
+            a = act_dev(rows, eyes)
+        torch.cuda.synchronize()
     prof = {k: v[0] / 5 for k, v in env._sim.profile_read().items() if v[1]}
     env._sim.profile(False)
-    if world > 1:
-        t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+    # ---- end-to-end arm (host observations, host actions)
+    ts = env.reset()
+    for k in range(max(W, 3)):
+        ts = env.step(act_host(ts))
+    sync()
+    t0 = time.perf_counter()
+    for k in range(K):
+        ts = env.step(act_host(ts))
+    sync()
+    dt = maxr(time.perf_counter() - t0)
     eyes_bytes = int(np.asarray(ts.observation['walker/left_eye']).nbytes * 2)
-    obs_bytes = int(sum(np.asarray(v).nbytes for k, v in ts.observation.items() if 'eye' not in k))
+    obs_bytes = int(env._rec.nbytes + env._out4.nbytes)
+    pol_bytes = int(sum(np.asarray(ts.observation[k]).reshape(N, -1).shape[1] for k in keys) * N * 4 + N * 2 * 4)
     total = N * world
-    res = {'metric': 'env-steps/sec on vision_guided_flight + vision policy in the loop (control steps of 4 substeps)', 'value': total * K / dt, 'unit': 'env-steps/s',
-           'ms_per_step': dt / K * 1e3, 'n_gpus': world, 'gpu_launches': int(launches),
-           'config': {'workload': f'vision_guided_flight {N} envs per GPU (BASELINE.json configs[4]: 1024 per GPU), bumps terrain 401 x 401 per env from a bank of 64, '
-                                  'eyes 2 x 32 x 32 x 3 uint8 rendered every step, policy = VisNet + TwoLevelController (torch, random weights) on rank 0',
-                      'envs_per_gpu': N, 'total_envs': total, 'auto_resets_in_window': int(resets),
-                      'note': 'end-to-end only: the task hooks of this env are host code, so `value` IS the e2e number (no device-resident arm)'},
-           'e2e': {'value': total * K / dt, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(N * env.model.nu * 4 + eyes_bytes + obs_bytes), 'd2h_bytes_per_step': int(eyes_bytes + obs_bytes + N * A * 4),
-                   'api': 'flybody_b200.fly_envs.vision_guided_flight(n_envs).step(action) + policy_torch.VisNet / TwoLevelController'},
+    res = {'metric': 'env-steps/sec on vision_guided_flight + vision policy in the loop (control steps of 4 substeps)', 'value': total * K / dt_dev, 'unit': 'env-steps/s',
+           'ms_per_step': dt_dev / K * 1e3, 'n_gpus': world, 'gpu_launches': int(launches),
+           'config': {'workload': f'vision_guided_flight {N} envs per GPU (BASELINE.json configs[4]: 1024 per GPU), bumps terrain 401 x 401 per env from a device bank of 64, '
+                                  'task hooks on the device (fb_task_* kind 2), eyes 2 x 32 x 32 x 3 uint8 rendered every step, '
+                                  'policy = VisNet + TwoLevelController (torch, random weights) on rank 0',
+                      'envs_per_gpu': N, 'total_envs': total, 'auto_resets_in_window': resets,
+                      'note': '`value`: observation rows, eyes and actions stay in HBM (step_device); `e2e`: the dm_env-style env.step() with host buffers'},
+           'e2e': {'value': total * K / dt, 'unit': 'env-steps/s', 'ms_per_step': dt / K * 1e3,
+                   'h2d_bytes_per_step': int(N * A * 4 + eyes_bytes + pol_bytes), 'd2h_bytes_per_step': int(eyes_bytes + obs_bytes + N * A * 4),
+                   'api': 'flybody_b200.fly_envs.vision_guided_flight(n_envs, device_task=True).step(action) + policy_torch.VisNet / TwoLevelController'},
            'stage_ms_per_step': prof}
     env.close()
     return res

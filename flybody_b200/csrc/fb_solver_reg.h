@@ -16,6 +16,12 @@
 
 #define A_(r, c) A[(r) * 33 + (c)]
 #define GP(p, q) G[TRI(p, q)]                    // p >= q
+#define FB_CHOL_REG 24                           // Hessian blocks up to this size are factorised in registers (steady-state walk: 8 - 23 columns)
+#ifdef __CUDACC__
+#define FB_RSQRT(x) rsqrtf(x)
+#else
+#define FB_RSQRT(x) (1.0f / sqrtf(x))
+#endif
 
 // forces / cost / Hessian factors of the rows headed by one lane: a plain row (kind 0) or the normal row of an elliptic
 // contact (kind 1) with its two friction rows (values j1, j2, D1, D2 of lanes +1, +2)
@@ -170,23 +176,63 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
           GP(p, q) = s;
         }
       WPAR_END
-      // Cholesky G = L L^T, column by column (two warp barriers per column); the forward substitution L y = p rides
-      // along on lane 0
-      NOUNROLL for (int j = 0; j < nc; j++) {
-        WPAR_BEGIN NOUNROLL for (int i = j + lane; i < nc; i += 32) {
-            float t = GP(i, j); NOUNROLL for (int k = 0; k < j; k++) t -= GP(i, k) * GP(j, k);
-            GP(i, j) = (i == j) ? sqrtf(fmaxf(t, 1e-12f)) : t; }
-        WPAR_END
-        WPAR_BEGIN const float dg = GP(j, j);
-          NOUNROLL for (int i = j + 1 + lane; i < nc; i += 32) GP(i, j) = GP(i, j) / dg;
-          if (lane == 0) { float yv = P[j]; NOUNROLL for (int k = 0; k < j; k++) yv -= GP(j, k) * XQ[k]; XQ[j] = yv / dg; }
-        WPAR_END
-      }
-      NOUNROLL for (int j = nc - 1; j >= 0; j--) {     // backward: L^T out = y
-        WPAR_BEGIN float xj = XQ[j] / GP(j, j);
-          NOUNROLL for (int i = lane; i < j; i += 32) XQ[i] -= GP(j, i) * xj;
-          if (lane == 0) XO[j] = xj;
-        WPAR_END
+      if (nc <= FB_CHOL_REG) {
+        // Cholesky G = L L^T with ROW i OF G / L IN THE REGISTERS OF LANE i (right-looking: after step j every lane has subtracted
+        // column j's outer product from its row; L[k][j] travels by shuffle).  The loops are unrolled with uniform early exits, so
+        // every register index is static.  The forward substitution L y = p rides along (y in a lane register); L is written back
+        // to the packed triangle (triangular numbers mod 32 are a permutation: conflict-free) for the backward substitution,
+        // where lane i needs column i of L.  All lanes < nc work in every step -- the column-by-column shared-memory form below
+        // kept 2.4 - 4.6 lanes busy (profiles/r02_ncu_full_v9_summary.json).
+        LREGA(float, g, FB_CHOL_REG); LREG(float, yv); LREG(float, lcol); LREG(float, yjr); LREG(float, dinv);
+        WPAR_BEGIN {
+#pragma unroll
+          for (int k = 0; k < FB_CHOL_REG; k++) LA(g, k) = (k < nc && lane < nc && k <= lane) ? GP(lane, k) : 0.0f;
+          L(yv) = lane < nc ? P[lane] : 0.0f; L(dinv) = 0.0f;
+        } WPAR_END
+#pragma unroll
+        for (int j = 0; j < FB_CHOL_REG; j++) {
+          if (j >= nc) break;
+          WPAR_BEGIN {
+            const float inv = FB_RSQRT(fmaxf(SHFA(g, j, j), 1e-12f));
+            L(lcol) = LA(g, j) * inv;                      // lane j: L[j][j]; lanes above: L[i][j]; lanes below: 0
+            L(yjr) = SHF(yv, j) * inv;
+            if (lane == j) L(dinv) = inv;
+          } WPAR_END
+          WPAR_BEGIN {
+            const float l = L(lcol), yj = L(yjr);
+            if (lane >= j && lane < nc) GP(lane, j) = l;
+            if (lane == j) L(yv) = yj; else if (lane > j) L(yv) -= l * yj;
+#pragma unroll
+            for (int k = j + 1; k < FB_CHOL_REG; k++) {
+              if (k >= nc) break;
+              const float lk = SHF(lcol, k);
+              if (lane >= k) LA(g, k) -= l * lk;
+            }
+          } WPAR_END
+        }
+        NOUNROLL for (int i = nc - 1; i > 0; i--) {      // backward: L^T x = y; x_i = y_i / L[i][i] once the rows above are subtracted
+          WPAR_BEGIN { const float xi = SHF(yv, i) * SHF(dinv, i); if (lane < i) L(yv) -= GP(i, lane) * xi; } WPAR_END
+        }
+        WPAR_BEGIN { if (lane < nc) XO[lane] = L(yv) * L(dinv); } WPAR_END
+      } else {
+        // larger blocks: column by column in shared memory (two warp barriers per column); the forward substitution L y = p
+        // rides along on lane 0
+        NOUNROLL for (int j = 0; j < nc; j++) {
+          WPAR_BEGIN NOUNROLL for (int i = j + lane; i < nc; i += 32) {
+              float t = GP(i, j); NOUNROLL for (int k = 0; k < j; k++) t -= GP(i, k) * GP(j, k);
+              GP(i, j) = (i == j) ? sqrtf(fmaxf(t, 1e-12f)) : t; }
+          WPAR_END
+          WPAR_BEGIN const float dg = GP(j, j);
+            NOUNROLL for (int i = j + 1 + lane; i < nc; i += 32) GP(i, j) = GP(i, j) / dg;
+            if (lane == 0) { float yv = P[j]; NOUNROLL for (int k = 0; k < j; k++) yv -= GP(j, k) * XQ[k]; XQ[j] = yv / dg; }
+          WPAR_END
+        }
+        NOUNROLL for (int j = nc - 1; j >= 0; j--) {     // backward: L^T out = y
+          WPAR_BEGIN float xj = XQ[j] / GP(j, j);
+            NOUNROLL for (int i = lane; i < j; i += 32) XQ[i] -= GP(j, i) * xj;
+            if (lane == 0) XO[j] = xj;
+          WPAR_END
+        }
       }
       // dlam = -r + E q ; A dlam ; quadratic coefficients of the Gauss term along dlam
       WPAR_BEGIN { float v = -L(res); int stt = L(state), c0 = L(colx);

@@ -49,6 +49,9 @@
 #define LREG(type, name) type name
 #define L(name) name
 #define SHF(name, src) __shfl_sync(0xffffffffu, name, (src) & 31)
+#define LREGA(type, name, K) type name[K]             /* K registers per lane: every index must be a compile-time constant after unrolling */
+#define LA(name, k) name[k]
+#define SHFA(name, k, src) __shfl_sync(0xffffffffu, name[k], (src) & 31)
 #define BALLOT(out, name, cmp) out = __ballot_sync(0xffffffffu, (name)cmp)
 #define POPC(x) __popc(x)
 #define FFS(x) __ffs((int)(x))
@@ -56,6 +59,9 @@
 #define LREG(type, name) type name[32] = {}
 #define L(name) name[lane]
 #define SHF(name, src) name[(src) & 31]
+#define LREGA(type, name, K) type name[K][32] = {}
+#define LA(name, k) name[k][lane]
+#define SHFA(name, k, src) name[k][(src) & 31]
 #define BALLOT(out, name, cmp) { out = 0; for (int l_ = 0; l_ < 32; l_++) if ((name[l_])cmp) out |= 1u << l_; }
 #define POPC(x) __builtin_popcount(x)
 #define FFS(x) __builtin_ffs((int)(x))

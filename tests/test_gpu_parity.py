@@ -164,6 +164,44 @@ def test_vision_model_stage_parity_on_gpu():
     th.check_vision_free_flight(None)
 
 
+@pytest.mark.parametrize('low_start', [True, False])
+def test_vision_device_task_logic_on_gpu(low_start):
+    """fb_task_* kind 2 (terrain bank pick, targets, start pose, reward factors, fatal world contacts, time limit) on the CUDA build
+    against the host-side vision task code on the same stepper, through terminations and auto-resets (tests/test_vision_env.py)."""
+    import test_vision_env as tv
+    tv.test_device_task_matches_the_host_task_code(None, low_start)
+
+
+def test_vision_device_resident_rollout_matches_host_api():
+    """vision env step_device (CUDA actions in; observation rows, (reward, discount, step_type) and eye images as zero-copy views)
+    against step() on a twin env."""
+    import torch
+    from flybody_b200 import fly_envs
+    n = 32
+    kw = dict(n_envs=n, seed=3, terrain_bank=4, time_limit=0.001, device_task=True)      # 5 control steps per episode
+    a_env, b_env = fly_envs.vision_guided_flight(**kw), fly_envs.vision_guided_flight(**kw)
+    a_env.reset(); b_env.reset()
+    lay = a_env.observation_layout()
+    stream = torch.cuda.ExternalStream(a_env._sim.stream)
+    rs = np.random.RandomState(0)
+    saw_first = False
+    for k in range(12):
+        act = rs.uniform(-0.3, 0.3, (n, 12)).astype(np.float32)
+        ts = b_env.step(act)
+        with torch.cuda.stream(stream):
+            rows, out, eyes = a_env.step_device(torch.from_numpy(act).cuda(a_env._sim.device))
+            stream.synchronize()
+            rows_h, out_h, eyes_h = rows.cpu().numpy(), out.cpu().numpy(), eyes.cpu().numpy()
+        assert np.array_equal(out_h[:, 2].astype(np.int64), np.asarray(ts.step_type, np.int64)), k
+        assert np.array_equal(out_h[:, 0], np.asarray(ts.reward, np.float32)) and np.array_equal(out_h[:, 1], np.asarray(ts.discount, np.float32))
+        assert np.array_equal(rows_h[:, lay['walker/gyro']].reshape(n, -1), np.asarray(ts.observation['walker/gyro']).reshape(n, -1))
+        assert np.array_equal(rows_h[:, lay['walker/task_input']], np.asarray(ts.observation['walker/task_input']))
+        assert np.array_equal(eyes_h[:, 1], np.asarray(ts.observation['walker/left_eye'])) and np.array_equal(eyes_h[:, 0], np.asarray(ts.observation['walker/right_eye']))
+        saw_first |= bool((out_h[:, 2] == 0).any())
+    assert saw_first
+    a_env.close(); b_env.close()
+
+
 @pytest.mark.parametrize('device_task', [False, True])
 def test_sensor_observables_match_the_oracle_mean_on_gpu(device_task):
     """the buffered observables of env.reset() / env.step() against the oracle's per-substep mean, incl. the FIRST step"""
