@@ -16,7 +16,9 @@
 
 #define A_(r, c) A[(r) * 33 + (c)]
 #define GP(p, q) G[TRI(p, q)]                    // p >= q
+#ifndef FB_CHOL_REG
 #define FB_CHOL_REG 24                           // Hessian blocks up to this size are factorised in registers (steady-state walk: 8 - 23 columns)
+#endif
 #ifdef __CUDACC__
 #define FB_RSQRT(x) rsqrtf(x)
 #else
@@ -176,6 +178,7 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
           GP(p, q) = s;
         }
       WPAR_END
+#if FB_CHOL_REG > 0
       if (nc <= FB_CHOL_REG) {
         // Cholesky G = L L^T with ROW i OF G / L IN THE REGISTERS OF LANE i (right-looking: after step j every lane has subtracted
         // column j's outer product from its row; L[k][j] travels by shuffle).  The loops are unrolled with uniform early exits, so
@@ -214,7 +217,9 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
           WPAR_BEGIN { const float xi = SHF(yv, i) * SHF(dinv, i); if (lane < i) L(yv) -= GP(i, lane) * xi; } WPAR_END
         }
         WPAR_BEGIN { if (lane < nc) XO[lane] = L(yv) * L(dinv); } WPAR_END
-      } else {
+      } else
+#endif
+      {
         // larger blocks: column by column in shared memory (two warp barriers per column); the forward substitution L y = p
         // rides along on lane 0
         NOUNROLL for (int j = 0; j < nc; j++) {
