@@ -189,7 +189,7 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
         LREGA(float, g, FB_CHOL_REG); LREG(float, yv); LREG(float, lcol); LREG(float, yjr); LREG(float, dinv);
         WPAR_BEGIN {
 #pragma unroll
-          for (int k = 0; k < FB_CHOL_REG; k++) LA(g, k) = (k < nc && lane < nc && k <= lane) ? GP(lane, k) : 0.0f;
+          for (int k = 0; k < FB_CHOL_REG; k++) LA(g, k) = (k < nc && lane < nc && k <= lane) ? GP(lane, k) : 0.0f;      // (an early exit at k >= nc costs registers: measured 18 % slower)
           L(yv) = lane < nc ? P[lane] : 0.0f; L(dinv) = 0.0f;
         } WPAR_END
 #pragma unroll
@@ -322,26 +322,48 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
     }
     WPAR_BEGIN { const int r = lane; if (r < n) { EFC(d.efc_force, r) = L(f); AT(d.prev_lam, r) = L(lam); AT(d.prev_key, r) = AT(d.efc_key, r); } } WPAR_END
   }
-  // ---- qfrc_constraint = J^T f and Z^T f, per dof (see ksolve_impl); row data comes from the lane registers
+  // ---- qfrc_constraint = J^T f and Z^T f.  The rows are chain-sparse (fb_constraint.h: EJC): lane s takes slot s of a row's chain a
+  // (dof = s-th ancestor of the row's last dof, m.dof_anc) and adds its product to per-dof accumulators in shared memory (A is dead
+  // by now), row after row -- within a row the dofs are distinct, a warp barrier orders the rows, so every dof sums in row order.
+  // Loads of four rows are in flight together.  Chain b (the second body of a self-contact, below its join with chain a) follows
+  // for the few rows that have one.  (Before: every lane scanned every row for its four dofs -- 8 loads per row and lane, most of
+  // them masked; 25 % of the kernel's stall samples, profiles/r02_ncu_full_v10_summary.json.)
+  float* QJ = wsm; float* QZ = wsm + 128;
+  LREG(int, jb);
   WPAR_BEGIN
     if (lane == 0) { AT(d.niter, 0) = niter; if (d.do_integrate) AT(d.prev_n, 0) = n; }
-    float sj[4] = {0, 0, 0, 0}, sz[4] = {0, 0, 0, 0}; int se[4], ck[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; se[i] = k < m.nv ? m.dof_subend[k] : -1; ck[i] = k < m.nv ? m.dof_chainlen[k] : 0; }
-#pragma unroll 2
-    for (int r = 0; r < n; r++) {
-      const int la_ = SHF(la, r), lb_ = SHF(lb, r), La_ = SHF(cla, r), Lb_ = SHF(clb, r); const float fr = SHF(f, r);
+    for (int i = 0; i < 4; i++) { QJ[lane + 32 * i] = 0.0f; QZ[lane + 32 * i] = 0.0f; }
+    L(jb) = (n > 0 && lane < n && L(lb) >= 0) ? L(clb) - (L(la) >= 0 ? (int)m.dof_lca[L(lb) * m.nv + L(la)] : 0) : 0;
+  WPAR_END
+  NOUNROLL for (int r0 = 0; r0 < n; r0 += 4) {
+    LREGA(float, gj, 4); LREGA(float, gz, 4); LREGA(int, gd, 4);
+    WPAR_BEGIN
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int k = lane + 32 * i;
-        const bool ina = (k <= la_ && la_ <= se[i]), in = ina || (k <= lb_ && lb_ <= se[i]);
-        const int idx = in ? r * FB_JROW + (ina ? La_ - ck[i] : FB_ZCAP + Lb_ - ck[i]) : 0;      // chain-sparse rows (fb_constraint.h: EJC)
-        const float vj = AT(d.efc_J, idx), vz = AT(d.efc_Z, idx);
-        sj[i] += in ? vj * fr : 0.0f; sz[i] += in ? vz * fr : 0.0f;
+      for (int u = 0; u < 4; u++) {
+        const int r = r0 + u, la_ = SHF(la, r), La_ = SHF(cla, r);
+        const bool on = r < n && lane < La_;
+        LA(gd, u) = on ? m.dof_anc[m.dof_Madr[la_] + lane] : -1;
+        LA(gj, u) = on ? AT(d.efc_J, r * FB_JROW + lane) : 0.0f; LA(gz, u) = on ? AT(d.efc_Z, r * FB_JROW + lane) : 0.0f;
       }
-    }
+    WPAR_END
 #pragma unroll
-    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; if (k < m.nv) { AT(d.qfrc_constraint, k) = sj[i]; AT(d.qfrc_zf, k) = sz[i]; } }
+    for (int u = 0; u < 4; u++) {
+      WPAR_BEGIN { const int r = r0 + u, dd = LA(gd, u); const float fr = SHF(f, r);
+        if (r < n && dd >= 0) { QJ[dd] += LA(gj, u) * fr; QZ[dd] += LA(gz, u) * fr; } } WPAR_END
+    }
+  }
+  unsigned mb;
+  BALLOT(mb, jb, > 0);
+  while (mb) {
+    const int r = FFS(mb) - 1; mb &= mb - 1;
+    WPAR_BEGIN { const int lb_ = SHF(lb, r), J_ = SHF(jb, r); const float fr = SHF(f, r);
+      if (lane < J_) { const int dd = m.dof_anc[m.dof_Madr[lb_] + lane];
+        QJ[dd] += AT(d.efc_J, r * FB_JROW + FB_ZCAP + lane) * fr; QZ[dd] += AT(d.efc_Z, r * FB_JROW + FB_ZCAP + lane) * fr; } } WPAR_END
+  }
+  WPAR_BEGIN
+#pragma unroll
+    for (int i = 0; i < 4; i++) { int k = lane + 32 * i; if (k < m.nv) { AT(d.qfrc_constraint, k) = QJ[k]; AT(d.qfrc_zf, k) = QZ[k]; } }
   WPAR_END
 }
 

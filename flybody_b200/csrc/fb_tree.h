@@ -210,8 +210,8 @@ FB_DEV void ld_reinit_damped(const DevModel& m, const DevData& d, ShTree& sh, in
 }
 
 // sparse L^T D L factorisation (Featherstone; MuJoCo mj_factorM).  Row k of LD holds (k,k), (k,parent(k)), ...
-// at dof_Madr[k] + t.  The lists advance in lock-step, one dof per step (deepest first); FB_FSUB lanes share a
-// list and split the rank-1 update of the ancestor rows of that dof.  Updates that land in the root block are
+// at dof_Madr[k] + t.  The lists advance in lock-step, one dof per step (deepest first); the rank-1 updates of the
+// ancestor rows of the step's dofs are dealt to all 32 lanes (factor_step_sched).  Updates that land in the root block are
 // summed into sh.part (21 entries per lane) and applied by the root lane afterwards.
 #define FB_FSUB 3
 // packed per-(step, lane) header of the lock-step sweeps: one coalesced load instead of the dependent chain
@@ -222,17 +222,21 @@ FB_DEV void ld_reinit_damped(const DevModel& m, const DevData& d, ShTree& sh, in
 #define HDR_DEPTH(h) ((int)(((h) >> 18) & 63u))
 #define HDR_DOF(h) ((int)((h) >> 24))
 #define FB_ROOTD6 6            // dofs of a root body (free joint)
-FB_DEV void factor_step_update_h(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, unsigned hd) {
+// One step of the sweep: the dofs k of this step (one per list) subtract their rank-1 term from the rows of their non-root ancestors,
+// row(anc_t)[s] -= (r_k[t] / D_k) r_k[t + s]  (M_ancadr: row address of the t-th ancestor; the root's dofs are the tail of every chain
+// and are handled by factor_root_accum).  The (k, t) pairs of a step touch different rows, so they are independent work items; the
+// host deals them to the 32 lanes longest-first onto the least loaded lane (DevModel::fs_rng / fs_items, built in fb_create) --
+// round 1 gave every list 3 fixed lanes, which kept 12 of 32 busy.  The item after the current one is loaded while this one runs.
+FB_DEV void factor_step_sched(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, unsigned rng) {
   float* part_ = sh_dyn(sh); float* ldsh = part_ + FB_PARTF; (void)part_;
-  if (hd == FB_HDR_IDLE) return;
-  const int sub = y % FB_FSUB, adrk = HDR_ADR(hd), len = HDR_LEN(hd);
-  float invD = 1.0f / LS(adrk);
-  // non-root ancestor rows are dealt round-robin to the FB_FSUB lanes of the list (M_ancadr[adrk + t] = row address of
-  // the t-th ancestor; the root's dofs are the tail of every chain and are handled by factor_root_accum)
-  const int tend = 1 + HDR_DEPTH(hd);
-  for (int t = 1 + sub; t < tend; t += FB_FSUB) {
-    float a = LS(adrk + t) * invD;
-    int adri = m.M_ancadr[adrk + t], li = len - t;          // chain of the ancestor = tail of the chain of k
+  const int cnt = (int)(rng >> 16);
+  if (cnt == 0) return;
+  const FsItem* ip = m.fs_items + (rng & 0xffffu);
+  FsItem it = ip[0];
+  for (int q = 0; q < cnt; q++) {
+    const FsItem nx = q + 1 < cnt ? ip[q + 1] : it;
+    const int adrk = (int)(it.x & 4095u), t = (int)((it.x >> 12) & 63u), li = (int)(it.x >> 18), adri = (int)it.y;
+    const float a = LS(adrk + t) * (1.0f / LS(adrk));
     int s2 = 0;
     for (; s2 + 4 <= li; s2 += 4) {                          // batched so that the loads are in flight together
       float r0 = LS(adrk + t + s2), r1 = LS(adrk + t + s2 + 1), r2 = LS(adrk + t + s2 + 2), r3 = LS(adrk + t + s2 + 3);
@@ -240,10 +244,8 @@ FB_DEV void factor_step_update_h(const DevModel& m, const DevData& d, ShTree& sh
       LS(adri + s2) = x0 - a * r0; LS(adri + s2 + 1) = x1 - a * r1; LS(adri + s2 + 2) = x2 - a * r2; LS(adri + s2 + 3) = x3 - a * r3;
     }
     for (; s2 < li; s2++) LS(adri + s2) -= a * LS(adrk + t + s2);
+    it = nx;
   }
-}
-FB_DEV void factor_step_update(const DevModel& m, const DevData& d, ShTree& sh, int e, int lane, int y, int step) {
-  factor_step_update_h(m, d, sh, e, lane, y, m.step_hdr_a[step * FB_NY + y]);
 }
 // Root blocks.  Once the lists are eliminated, row k of a non-root dof holds its final (unscaled) coupling r_k to the
 // root's dofs and D_k; the Schur update of the root block is sum_k r_k r_k^T / D_k.  32 lanes split the dofs, each
@@ -299,18 +301,18 @@ FB_DEV void factor_root(const DevModel& m, const DevData& d, ShTree& sh, int e, 
 // warp function: the whole factorisation of the rows currently held in shared memory
 FB_WARPFN void kpos_factor(const DevModel& m, const DevData& d, ShTree& sh, int e) {
 #ifdef __CUDACC__
-  {   // the packed header of the NEXT step is loaded while this step's rank-1 updates run (one dependent global load less per step)
-    const int lane = threadIdx.x; const unsigned* hp = m.step_hdr_a + lane;
-    unsigned hd = m.max_list_ndof > 0 ? hp[0] : FB_HDR_IDLE;
+  {   // the schedule entry of the NEXT step is loaded while this step's rank-1 updates run (one dependent global load less per step)
+    const int lane = threadIdx.x; const unsigned* hp = m.fs_rng + lane;
+    unsigned hd = m.max_list_ndof > 0 ? hp[0] : 0u;
     for (int step = 0; step < m.max_list_ndof; step++) {
-      const unsigned nxt = step + 1 < m.max_list_ndof ? hp[(step + 1) * FB_NY] : FB_HDR_IDLE;
-      factor_step_update_h(m, d, sh, e, 0, lane, hd); __syncwarp();
+      const unsigned nxt = step + 1 < m.max_list_ndof ? hp[(step + 1) * FB_NY] : 0u;
+      factor_step_sched(m, d, sh, e, 0, lane, hd); __syncwarp();
       hd = nxt;
     }
   }
 #else
   for (int step = 0; step < m.max_list_ndof; step++) {
-    WPAR_BEGIN factor_step_update(m, d, sh, e, 0, lane, step); WPAR_END
+    WPAR_BEGIN factor_step_sched(m, d, sh, e, 0, lane, m.fs_rng[step * FB_NY + lane]); WPAR_END
   }
 #endif
   for (int r = 0; r < m.nroot; r++) {

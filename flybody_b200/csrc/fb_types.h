@@ -68,6 +68,7 @@
 #endif
 
 
+struct alignas(8) FsItem { unsigned x, y; };
 struct DevModel {
   // sizes / options
   int nq, nv, nu, na, nbody, njnt, ngeom, npair, nsite, ntendon, nwrap, nsensor, nsensordata, nM, nfluid;
@@ -91,6 +92,7 @@ struct DevModel {
   const unsigned *step_hdr_a, *step_hdr_c;   // [max_list_ndof][32] packed sweep headers, deepest-first / shallowest-first
   const unsigned* tsolve_blob; int ts_hdr_words, ts_nm_pad, ts_blob_words;    // sweep program copied per CTA into shared memory (fb_tree.h)
   const int* M_ancadr;         // [nM] row address (dof_Madr) of the ancestor an entry belongs to
+  const unsigned* fs_rng; const FsItem* fs_items;   // factorisation schedule: per (step, lane) first item | count << 16; item = (adr_k | t << 12 | update length << 18, adr of the ancestor row)
   const float* M_damp;         // per entry of the packed inertia: joint damping on the diagonals, 0 elsewhere
   const int* body_adhesion;    // adhesion actuator acting on the body, or -1
   const float *dof_armature, *dof_damping, *dof_invweight0;

@@ -535,6 +535,7 @@ static int build_model(FbSim* s, const FbModel* h) {
   }
   { // common-ancestor counts of every dof pair (kproj_p1: the dofs two constraint rows share are the common TAIL of their chains)
     if (nv > 255) { s->err = "too many dofs for the byte-sized common-ancestor table"; return -3; }
+    if (nv > 128) { s->err = "too many dofs for the register-path force gather (4 dofs per lane, fb_solver_reg.h)"; return -3; }
     std::vector<unsigned char> lca((size_t)nv * nv, 0); std::vector<int> mark(nv, -1);
     for (int a = 0; a < nv; a++) {
       for (int j = a; j >= 0; j = h->dof_parentid[j]) mark[j] = a;
@@ -575,6 +576,31 @@ static int build_model(FbSim* s, const FbModel* h) {
     std::vector<int> ancadr(h->nM, 0);
     for (int i = 0; i < nv; i++) { int t = 0; for (int j = i; j >= 0; j = h->dof_parentid[j], t++) ancadr[h->dof_Madr[i] + t] = h->dof_Madr[j]; }
     m.M_ancadr = up(s, ancadr);
+    { // balanced schedule of the factorisation sweeps (fb_tree.h: factor_step_sched): the rank-1 update of one ancestor row by the
+      // step's dof of one list is a work item (cost = its length + a constant); the items of a step touch different rows, so they
+      // are dealt to the 32 lanes longest-first onto the least loaded lane instead of 3 fixed lanes per list
+      const int nstep = std::max(m.max_list_ndof, 1);
+      std::vector<unsigned> rng((size_t)FB_NY * nstep, 0u); std::vector<unsigned> items;
+      for (int st = 0; st < nstep; st++) {
+        struct It { unsigned x, y; int cost; };
+        std::vector<It> its;
+        for (int l = 0; l < nlist; l++) {
+          if (st >= dnum_h[l]) continue;
+          const int k = dl_h[dadr_h[l] + st], adrk = h->dof_Madr[k], len = chainlen[k];
+          for (int t = 1; t < 1 + depth[k]; t++) its.push_back({(unsigned)adrk | ((unsigned)t << 12) | ((unsigned)(len - t) << 18), (unsigned)ancadr[adrk + t], len - t + 6});
+        }
+        std::stable_sort(its.begin(), its.end(), [](const It& a, const It& b) { return a.cost > b.cost; });
+        std::vector<std::vector<It>> lane_items(FB_NY); std::vector<int> load(FB_NY, 0);
+        for (const It& it : its) { int best = 0; for (int y = 1; y < FB_NY; y++) if (load[y] < load[best]) best = y; lane_items[best].push_back(it); load[best] += it.cost; }
+        for (int y = 0; y < FB_NY; y++) {
+          if (items.size() / 2 >= 65536 || lane_items[y].size() >= 65536) { s->err = "factorisation schedule too long"; return -3; }
+          rng[(size_t)st * FB_NY + y] = (unsigned)(items.size() / 2) | ((unsigned)lane_items[y].size() << 16);
+          for (const It& it : lane_items[y]) { items.push_back(it.x); items.push_back(it.y); }
+        }
+      }
+      if (items.empty()) { items.push_back(0); items.push_back(0); }
+      m.fs_rng = up(s, rng); m.fs_items = reinterpret_cast<const FsItem*>(up(s, items));
+    }
   }
   { std::vector<float> mdamp(h->nM, 0.0f); for (int i = 0; i < nv; i++) mdamp[h->dof_Madr[i]] = (float)h->dof_damping[i]; m.M_damp = up(s, mdamp); }
   m.dof_subend = up(s, subend); m.dof_depth = up(s, depth); m.dof_isroot = up(s, disroot); m.dof_chainlen = up(s, chainlen);

@@ -38,4 +38,10 @@ for k in range(3):
     ts = env.step(rs.uniform(-0.2, 0.2, (env.n_envs, 12)))
 print('vision ok', {k: v.shape for k, v in ts.observation.items() if 'eye' in k}, flush=True)
 env.close()
+env = fly_envs.vision_guided_flight(n_envs=min(N, 32), seed=1, terrain_bank=4, device_task=True, time_limit=0.0008, target_height_range=(0.12, 0.6))
+env.reset()
+for k in range(8):                                                   # device-side vision task: terrain bank copies, contact / time-limit resets
+    ts = env.step(rs.uniform(-0.2, 0.2, (env.n_envs, 12)))
+print('vision device task ok, resets', env.n_resets, flush=True)
+env.close()
 print('SANITIZE_TARGET_DONE')
