@@ -1217,7 +1217,7 @@ FB_DEV void ktask_reset_vision(const DevModel& m, const DevData& d, const DevTas
   for (size_t i = y; i < cells; i += FB_NY) dst[i] = src[i];
   for (int i = y; i < t.hf_ncm; i += FB_NY) t.hf_cmax[(size_t)t.hf_ncm * e + i] = t.bank_cmax[(size_t)t.hf_ncm * pick + i];
   if (y != 0) return;
-  t.hf_hmax[e] = t.bank_hmax[pick];
+  t.hf_hmax[e] = t.bank_hmax[pick]; t.pick[e] = pick;
   const float th = t.th_rng[0] + (t.th_rng[1] - t.th_rng[0]) * tk_draw(t, e, episode, 0), ts = t.ts_rng[0] + (t.ts_rng[1] - t.ts_rng[0]) * tk_draw(t, e, episode, 1);
   const float x = t.x_rng[0] + (t.x_rng[1] - t.x_rng[0]) * tk_draw(t, e, episode, 2), yy = t.y_rng[0] + (t.y_rng[1] - t.y_rng[0]) * tk_draw(t, e, episode, 3);
   t.target[2 * e] = th; t.target[2 * e + 1] = ts;
@@ -1316,7 +1316,7 @@ FB_DEV void ktask_after(const DevModel& m, const DevData& d, int e, int y) {
   float s2 = 0; for (int i = 0; i < m.nv; i++) { float x = AT(d.qacc, i); s2 += x * x; }
   const bool bad = (AT(d.flags, 0) & 1) != 0 || !(sqrtf(s2) <= t.term_qacc);      // bits 1, 2 are capacity overflows, not bad physics
   bool terminate; float reward;
-  if (t.kind == 2) {      // vision_flight.py:157-254: five reward factors (bumps arenas), fatal contacts with world geoms
+  if (t.kind == 2) {      // vision_flight.py:157-254: reward factors, fatal contacts with world geoms
     const float th = t.target[2 * e], ts = t.target[2 * e + 1];
     const float x = AT(d.qpos, t.root_qadr), yy = AT(d.qpos, t.root_qadr + 1), z = AT(d.qpos, t.root_qadr + 2);
     const float vx = AT(d.qvel, t.root_vadr), vy = AT(d.qvel, t.root_vadr + 1), vz = AT(d.qvel, t.root_vadr + 2);
@@ -1327,7 +1327,18 @@ FB_DEV void ktask_after(const DevModel& m, const DevData& d, int e, int y) {
     const M3 R = ld9(d.xmat, t.root_body, d, e);
     float c = R.m[6] * t.target_zaxis[0] + R.m[7] * t.target_zaxis[1] + R.m[8] * t.target_zaxis[2]; c = c < -1.0f ? -1.0f : (c > 1.0f ? 1.0f : c);
     const float zax = lin(acosf(c), 0.0f, 0.0f, 3.14159265358979f);
-    reward = height * x_speed * speed * side * zax;
+    float centre = 1.0f;      // 'trench' arenas: distance to the corridor's centre line at the nearest of its sample points (the lower one on ties)
+    if (t.trench_cap > 0) {
+      const int pk = t.pick[e], tn = t.trench_len[pk]; const float x0 = t.trench_x[2 * pk], x1 = t.trench_x[2 * pk + 1];
+      if (x >= x0 && x <= x1) {
+        const float u = (x - x0) / (x1 - x0) * (float)(tn - 1);
+        int idx = (int)floorf(u); if (u - (float)idx > 0.5f) idx++;
+        idx = idx < 0 ? 0 : (idx > tn - 1 ? tn - 1 : idx);
+        const float yc = t.trench_y[(size_t)pk * t.trench_cap + idx];
+        centre = lin(yy, yc, yc, 0.15f);
+      }
+    }
+    reward = height * x_speed * speed * side * zax * centre;
     bool contact = false;
     if (t.fatal) { const int nc = AT(d.ncon, 0); for (int ci = 0; ci < nc; ci++) if (AT(d.con_efcadr, ci) >= 0 && (m.geom_bodyid[AT(d.con_geom1, ci)] == 0 || m.geom_bodyid[AT(d.con_geom2, ci)] == 0)) contact = true; }
     terminate = bad || contact;

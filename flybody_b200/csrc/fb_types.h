@@ -179,6 +179,7 @@ struct DevTask {
   int n_bank, hf_nrow, hf_ncol, hf_ncm; float hf_half, hf_zoff;
   const float *bank, *bank_hmax, *bank_cmax; float *hf_data, *hf_hmax, *hf_cmax;
   float* target;                           // [N][2] target height, target speed of the running episode
+  int trench_cap; const float *trench_x, *trench_y; const int* trench_len; int* pick;   // 'trench' arenas: centre line per bank terrain; the env's terrain
   // per-env state
   int *step, *needs_reset, *resetting, *episode, *wb_idx, *wb_pos, *has_uniform; float *uniform /* [N][8] */, *wb_freq;
   int* op_step; unsigned char* op_first;   // the observation program's per-env inputs, maintained here instead of by fb_task_inputs

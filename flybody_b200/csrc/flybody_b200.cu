@@ -1319,7 +1319,16 @@ int fb_task_program(FbHandle s, const FbTaskProgram* p) {
     t.fatal = p->floor_contacts_fatal;
     t.n_bank = s->bank_n; t.hf_nrow = s->hf_nrow; t.hf_ncol = s->hf_ncol; t.hf_ncm = s->hf_nbr * s->hf_nbc; t.hf_half = s->hf.size[0]; t.hf_zoff = 0.0f;
     t.bank = s->bank_dev; t.bank_hmax = s->bank_hmax_dev; t.bank_cmax = s->bank_cmax_dev; t.hf_data = s->hfield_dev; t.hf_hmax = s->hmax_dev; t.hf_cmax = s->cmax_dev;
-    t.target = dalloc<float>(s, (size_t)2 * Np);
+    t.target = dalloc<float>(s, (size_t)2 * Np); t.pick = dalloc<int>(s, Np);
+    t.trench_cap = 0; t.trench_x = t.trench_y = nullptr; t.trench_len = nullptr;
+    if (p->trench_cap > 0) {
+      if (!p->trench_y || !p->trench_x || !p->trench_len) { s->err = "fb_task_program: trench centre lines missing"; return -1; }
+      for (int k = 0; k < s->bank_n; k++) if (p->trench_len[k] < 2 || p->trench_len[k] > p->trench_cap || !(p->trench_x[2 * k + 1] > p->trench_x[2 * k])) { s->err = "fb_task_program: bad trench centre line"; return -1; }
+      float* ty = dalloc<float>(s, (size_t)p->trench_cap * s->bank_n); h2d(ty, p->trench_y, sizeof(float) * (size_t)p->trench_cap * s->bank_n);
+      float* tx = dalloc<float>(s, (size_t)2 * s->bank_n); h2d(tx, p->trench_x, sizeof(float) * 2 * s->bank_n);
+      int* tl = dalloc<int>(s, s->bank_n); h2d(tl, p->trench_len, sizeof(int) * s->bank_n);
+      t.trench_cap = p->trench_cap; t.trench_x = tx; t.trench_y = ty; t.trench_len = tl;
+    }
   }
   t.op_step = s->op_step_dev; t.op_first = s->op_first_dev;
   DevTask* dev = (DevTask*)dalloc<unsigned char>(s, sizeof(DevTask));

@@ -828,9 +828,9 @@ def flight_imitation(ref_path=None, wpg_pattern_path=None, force_actuators=False
 def vision_guided_flight(wpg_pattern_path=None, bumps_or_trench='bumps', force_actuators=False, disable_legs=True, random_state=None,
                          joint_filter=0.0, n_envs=None, device=0, lib_path=None, seed=0, **kwargs_arena):
     """Batched `flybody.fly_envs.vision_guided_flight` (reference `fly_envs.py:194-246`): 'bumps' or 'trench' terrain, eye
-    cameras, wing-beat pattern generator, fatal ground contacts -- `flybody_b200.vision_env.BatchedVisionFlightEnv`.  A first
-    cut of SURVEY.md 8(f).1: verified under host emulation (terrain contacts against the fp64 oracle, eyes against the camera
-    model), the heightfield kernel has not been run or timed on a B200 yet."""
+    cameras, wing-beat pattern generator, fatal ground contacts -- `flybody_b200.vision_env.BatchedVisionFlightEnv` (SURVEY.md
+    8(f).1; terrain contacts against the fp64 oracle and eyes against the camera model in tests/test_hfield.py, test_eyes.py and on the
+    B200 in tests/test_gpu_parity.py).  `terrain_bank=K, device_task=True` run the task's hooks on the device (fb_task_* kind 2)."""
     if force_actuators or not disable_legs or joint_filter != 0.0:
         raise NotImplementedError('only the default vision_guided_flight model variant is compiled (flybody_b200/assets/fly_vision.npz)')
     from .vision_env import BatchedVisionFlightEnv

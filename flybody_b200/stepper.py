@@ -51,7 +51,8 @@ class FbTaskProgram(C.Structure):
                 ('wb_phase_mod', C.POINTER(C.c_float)), ('wb_freqs', C.POINTER(C.c_float)), ('wb_len', C.POINTER(C.c_int32)),
                 ('wb_base_freq', C.c_float), ('wb_rel_range', C.c_float), ('wb_rate', C.c_float), ('com_offset', C.c_float * 3),
                 ('target_height_range', C.c_float * 2), ('target_speed_range', C.c_float * 2), ('init_x_range', C.c_float * 2), ('init_y_range', C.c_float * 2),
-                ('hover_quat', C.c_float * 4), ('target_zaxis', C.c_float * 3), ('floor_contacts_fatal', C.c_int32)]
+                ('hover_quat', C.c_float * 4), ('target_zaxis', C.c_float * 3), ('floor_contacts_fatal', C.c_int32),
+                ('trench_cap', C.c_int32), ('trench_x', C.POINTER(C.c_float)), ('trench_len', C.POINTER(C.c_int32)), ('trench_y', C.POINTER(C.c_float))]
 
 
 class FbEyeProgram(C.Structure):

@@ -124,8 +124,8 @@ class BatchedVisionFlightEnv:
         # task hooks on the device (fb_task_*, kind 2): needs the terrain bank (a resetting env copies one of its terrains on the device)
         self._device_task = bool(device_task)
         if self._device_task:
-            if self._bank is None or bumps_or_trench != 'bumps':
-                raise NotImplementedError("device_task=True needs terrain_bank=K and 'bumps' arenas (the trench-centre reward factor is host code)")
+            if self._bank is None:
+                raise NotImplementedError('device_task=True needs terrain_bank=K (a resetting env copies one of the K terrains on the device)')
             self._upload_task_program(seed)
 
     @staticmethod
@@ -186,6 +186,14 @@ class BatchedVisionFlightEnv:
         self._sim.set_action_map(np.concatenate([self._ctrl_of_action, [-1]]))      # the user action (beat frequency) has no ctrl slot
         self._sim.hfield_bank(np.stack([t for t, _ in self._bank]))
         dummy = np.zeros((1, 7), np.float32); dummy[0, 3] = 1.0
+        trench = {}
+        if self._bank[0][1] is not None:                                 # 'trench' arenas: the corridor's centre line of every bank terrain
+            cap = max(len(sp['y_coords']) for _, sp in self._bank)
+            ty = np.zeros((len(self._bank), cap), np.float32)
+            for k, (_, sp) in enumerate(self._bank):
+                ty[k, :len(sp['y_coords'])] = sp['y_coords']
+            trench = dict(trench_cap=cap, trench_y=ty, trench_len=np.array([len(sp['y_coords']) for _, sp in self._bank], np.int32),
+                          trench_x=np.array([[sp['x_coords'][0], sp['x_coords'][-1]] for _, sp in self._bank], np.float32))
         self._sim.task_program(
             kind=2, root_qadr=self._root_q, root_vadr=self._root_v, ghost_qadr=-1, ghost_vadr=-1, user_col=len(self._ctrl_of_action),
             ghost_offset=(0, 0, 0), control_timestep=self._control_timestep, time_limit=self._time_limit, terminal_com_dist=3e38, terminal_linvel=3e38,
@@ -199,7 +207,7 @@ class BatchedVisionFlightEnv:
             wb_phase=np.where(np.isfinite(wb.phase), wb.phase, 3e38), wb_phase_mod=np.where(np.isfinite(wb.phase_mod), wb.phase_mod, 3e38),
             wb_freqs=wb.beat_freqs, wb_len=wb.lengths, wb_base_freq=wb.base_beat_freq, wb_rel_range=wb.rel_freq_range, wb_rate=wb._rate,
             com_offset=(0, 0, 0), target_height_range=r['h'], target_speed_range=r['v'], init_x_range=r['x'], init_y_range=r['y'],
-            hover_quat=self._hover_quat, target_zaxis=self._target_zaxis, floor_contacts_fatal=1 if self._fatal else 0)
+            hover_quat=self._hover_quat, target_zaxis=self._target_zaxis, floor_contacts_fatal=1 if self._fatal else 0, **trench)
         self._out4 = self._pinned((self.n_envs, 4), np.float32)
         self._dev_views = None
 

@@ -311,11 +311,14 @@ typedef struct FbTaskProgram {
   float com_offset[3];                 /* root -> CoM offset in the root frame (tasks/task_utils.py:237) */
   /* kind 2, vision_guided_flight (tasks/vision_flight.py:97-254): no ghost / reference; per episode a target height and speed, a start
    * point, a wing-beat phase and a terrain of the device bank (fb_hfield_bank) are drawn; reward = product of the height / forward speed /
-   * speed / side speed / body axis factors (the trench-centre factor applies to 'trench' arenas, which keep the host-side task code);
+   * speed / side speed / body axis factors and, for 'trench' arenas, the distance to the corridor's centre line (vision_flight.py:214-226:
+   * y of the centre line at trench_len[k] equally spaced x in [trench_x[k][0], trench_x[k][1]] for bank terrain k);
    * termination on a bad state or, if floor_contacts_fatal, an active contact with a world geom.                                */
   float target_height_range[2], target_speed_range[2], init_x_range[2], init_y_range[2];
   float hover_quat[4], target_zaxis[3];
   int32_t floor_contacts_fatal;
+  int32_t trench_cap;                  /* 0: no centre-line factor; else the row stride of trench_y */
+  const float* trench_x /* [n_terrain][2] first / last x */; const int32_t* trench_len /* [n_terrain] samples */; const float* trench_y /* [n_terrain][trench_cap] */;
 } FbTaskProgram;
 int fb_task_program(FbHandle h, const FbTaskProgram* p);
 /* One control step with the task logic on the device: [auto-reset] -> action -> ctrl -> before_step -> n_substeps x physics ->

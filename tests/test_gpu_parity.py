@@ -164,12 +164,12 @@ def test_vision_model_stage_parity_on_gpu():
     th.check_vision_free_flight(None)
 
 
-@pytest.mark.parametrize('low_start', [True, False])
-def test_vision_device_task_logic_on_gpu(low_start):
-    """fb_task_* kind 2 (terrain bank pick, targets, start pose, reward factors, fatal world contacts, time limit) on the CUDA build
+@pytest.mark.parametrize('low_start,arena', [(True, 'bumps'), (False, 'bumps'), (False, 'trench')])
+def test_vision_device_task_logic_on_gpu(low_start, arena):
+    """fb_task_* kind 2 (terrain bank pick, targets, start pose, reward factors incl. the trench centre line, fatal world contacts, time limit) on the CUDA build
     against the host-side vision task code on the same stepper, through terminations and auto-resets (tests/test_vision_env.py)."""
     import test_vision_env as tv
-    tv.test_device_task_matches_the_host_task_code(None, low_start)
+    tv.test_device_task_matches_the_host_task_code(None, low_start, arena)
 
 
 def test_vision_device_resident_rollout_matches_host_api():

@@ -117,13 +117,15 @@ def test_terrain_bank_option(emu):
     env.close()
 
 
-@pytest.mark.parametrize('low_start', [True, False])
-def test_device_task_matches_the_host_task_code(emu, low_start):
+@pytest.mark.parametrize('low_start,arena', [(True, 'bumps'), (False, 'bumps'), (False, 'trench')])
+def test_device_task_matches_the_host_task_code(emu, low_start, arena):
     """fb_task_* kind 2: the vision task's hooks on the device (terrain pick from the device bank, targets, start pose, wing-beat
     generator, five reward factors, fatal world contacts, time limit) against the host-side task code of this file's env, step by step
     through terminations and auto-resets; the device is fed the host's random draws (fb_task_uniform_rows)."""
     # low start: the flies begin within contact range of the terrain -> fatal contacts (discount 0); otherwise the time limit ends episodes
     kw = dict(n_envs=3, lib_path=emu, seed=5, terrain_bank=2, time_limit=0.004, **(dict(target_height_range=(0.12, 0.2)) if low_start else {}))
+    if arena == 'trench':           # start inside the corridor's x range, off its centre line: the sixth reward factor is < 1
+        kw.update(bumps_or_trench='trench', init_pos_x_range=(-2.0, -1.5), init_pos_y_range=(-0.12, 0.12))
     host = fly_envs.vision_guided_flight(**kw)
     dev = fly_envs.vision_guided_flight(device_task=True, **kw)
     th = host.reset()
@@ -141,6 +143,7 @@ def test_device_task_matches_the_host_task_code(emu, low_start):
     rs = np.random.RandomState(0)
     seen_last = seen_first = False
     discounts = set()
+    centre_min = 1.0
     for step in range(30):
         a = rs.uniform(-0.2, 0.2, (3, 12)).astype(np.float32)
         a[0, :] = 1.0 if step > 8 else a[0]                      # env 0 is driven off course -> terrain contact or time limit -> LAST -> auto-reset
@@ -152,9 +155,12 @@ def test_device_task_matches_the_host_task_code(emu, low_start):
         assert np.array_equal(th.discount, td.discount), step
         assert np.allclose(host._sim.get(st.QPOS), dev._sim.get(st.QPOS), atol=1e-2), (step, np.abs(host._sim.get(st.QPOS) - dev._sim.get(st.QPOS)).max())      # (env 0 is driven against its joint limits: the fp64-host / fp32-device wing residual difference grows chaotically)
         assert np.allclose(th.observation['walker/task_input'], td.observation['walker/task_input'], atol=1e-6)
+        centre_min = min(centre_min, float(host.reward_factors(host._rec)[:, 5].min()))
         discounts |= set(np.asarray(th.discount)[np.asarray(th.step_type) == int(StepType.LAST)].tolist())
         seen_last |= bool((np.asarray(th.step_type) == int(StepType.LAST)).any())
         seen_first |= step > 0 and bool((np.asarray(th.step_type) == int(StepType.FIRST)).any())
     assert seen_last and seen_first
     assert (0.0 in discounts) if low_start else (1.0 in discounts), discounts
+    if arena == 'trench':
+        assert centre_min < 0.999, centre_min
     host.close(); dev.close()
