@@ -67,6 +67,7 @@ struct FbSim {
 #endif
   FbModel hm;                       // host copy of scalar fields (pointers invalid after create)
   std::vector<void*> allocs;
+  std::vector<void*> obs_scope, task_scope;   // device buffers of the current observation / task program: freed when the program is replaced
   std::vector<int> h_dof_parent, h_dof_Madr, h_body_lastdof, h_geom_bodyid;
   std::vector<double> h_qpos0;
   int device, n_sm; long long launches; float last_ms; std::string err;
@@ -438,6 +439,11 @@ static const float* upf3(FbSim* s, const double* src, size_t n) {      // n 3-ve
 }
 static const int* upi(FbSim* s, const int32_t* src, size_t n) { std::vector<int> v(src, src + n); return up(s, v); }
 template <typename T> static T* dalloc(FbSim* s, size_t n) { void* p = dev_alloc(sizeof(T) * n); s->allocs.push_back(p); return (T*)p; }
+// free the buffers a replaced program owned (the stream is idle: the callers synchronise first)
+static void scope_free(FbSim* s, std::vector<void*>& scope) {
+  for (void* p : scope) { if (!p) continue; for (auto& a : s->allocs) if (a == p) { a = nullptr; break; } dev_free(p); }
+  scope.clear();
+}
 
 static int build_model(FbSim* s, const FbModel* h) {
   DevModel& m = s->m;
@@ -1247,6 +1253,11 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
     for (int j = 0; j < p->b[i]; j++) if (p->list[p->a[i] + j] < 0 || p->list[p->a[i] + j] >= lim) { s->err = "fb_obs_program: list entry out of range"; return -1; }
   }
   if (p->root_body <= 0 || p->root_body >= m.nbody) { s->err = "fb_obs_program: root body"; return -1; }
+  // a replaced program's buffers are freed; the task program points into them (observation rows, per-env step inputs), so it goes too
+  // and has to be uploaded again (fly_envs does: observation program, then task program)
+  scope_free(s, s->task_scope); s->d.task = nullptr;
+  scope_free(s, s->obs_scope);
+  const size_t obs_mark = s->allocs.size();
   std::vector<int> kind(p->kind, p->kind + p->n_items), a(p->a, p->a + p->n_items), b(p->b, p->b + p->n_items), list(p->list, p->list + std::max(p->n_list, 0));
   s->d.op_kind = up(s, kind); s->d.op_a = up(s, a); s->d.op_b = up(s, b); s->d.op_off = up(s, offs); s->d.op_list = up(s, list);
   s->d.op_n = p->n_items; s->d.op_root_body = p->root_body; s->d.op_nsub = p->n_sub; s->d.op_ref_len = p->ref_len; s->d.op_ref_slot = 0;
@@ -1254,6 +1265,7 @@ int fb_obs_program(FbHandle s, const FbObsProgram* p) {
   s->d.tobs_dim = dim; s->d.tobs = dalloc<float>(s, (size_t)dim * s->d.Np);
   s->op_step_dev = dalloc<int>(s, s->d.Np); s->op_first_dev = (unsigned char*)dalloc<int>(s, s->d.Np);
   s->d.op_step = s->op_step_dev; s->d.op_first = s->op_first_dev;
+  s->obs_scope.assign(s->allocs.begin() + obs_mark, s->allocs.end());
 #ifndef FB_EMU
   cudaDeviceSynchronize();
 #endif
@@ -1290,6 +1302,8 @@ int fb_task_program(FbHandle s, const FbTaskProgram* p) {
   if (p->kind >= 1 && (p->n_wing <= 0 || p->n_freq <= 0 || p->tab_len <= 0 || !p->wb_traj || !p->wb_phase || !p->wb_phase_mod || !p->wb_freqs || !p->wb_len)) { s->err = "fb_task_program: wing-beat tables missing"; return -1; }
   if (sync_stream(s) != 0) return -2;
   const DevModel& m = s->m; const int Np = s->d.Np;
+  scope_free(s, s->task_scope); s->d.task = nullptr;
+  const size_t task_mark = s->allocs.size();
   DevTask t; memset(&t, 0, sizeof(t));
   t.kind = p->kind; t.root_qadr = p->root_qadr; t.root_vadr = p->root_vadr; t.ghost_qadr = p->ghost_qadr; t.ghost_vadr = p->ghost_vadr;
   t.root_body = s->d.op_root_body; t.user_col = p->user_col;
@@ -1334,6 +1348,7 @@ int fb_task_program(FbHandle s, const FbTaskProgram* p) {
   DevTask* dev = (DevTask*)dalloc<unsigned char>(s, sizeof(DevTask));
   h2d(dev, &t, sizeof(t));
   s->task_host = t; s->d.task = dev;
+  s->task_scope.assign(s->allocs.begin() + task_mark, s->allocs.end());
   return fb_task_reset_all(s);
 }
 int fb_task_reset_all(FbHandle s) {

@@ -9,6 +9,7 @@ is returned (what the reference's tests construct).  The physics is the CUDA ste
 logic mirrors `flybody/tasks/walk_imitation.py` / `tasks/base.py` in vectorised numpy.
 """
 import collections
+import hashlib
 
 import numpy as np
 
@@ -287,6 +288,7 @@ class BatchedFlyEnv:
         self._future = future_steps + 1
         self._rec = None
         self._program_ref_id = None
+        self._program_switched = False
         # One reference per env (dataset loaders hand out a different snippet per episode) or one shared by all envs (the
         # Inference* loaders hold a single trajectory): the shared case keeps one device table, the per-env case one slot per env.
         tg = self.task._traj_generator
@@ -451,18 +453,23 @@ class BatchedFlyEnv:
 
     def _load_snippet(self, ids):
         """initialize_episode_mjcf: pick the reference of the episode that starts now (walk_imitation.py:93-110,
-        flight_imitation.py:88-111).  Shared mode: one trajectory for every env (re-uploaded only when the loader's arrays
-        change); per-env mode: each env of `ids` draws its own snippet and its device slot is rewritten."""
+        flight_imitation.py:88-111).  Shared mode: ONE trajectory for every env, re-uploaded when the loader returns different
+        values (content digest, so in-place edits count).  The switch is global: envs in mid-episode follow the new trajectory from
+        their current step on, and with the task hooks on the device the re-upload restarts every env (`_program_switched`) -- a
+        batch whose envs need independent references uses the per-env mode (`ref_path=` datasets), where each env of `ids` draws
+        its own snippet and only its device slot is rewritten."""
         t = self.task
         tg = t._traj_generator
         if not self._per_env_ref:
             snip = tg.get_trajectory(traj_idx=t._next_traj_idx)
             t._next_traj_idx = None
-            key = snip['qvel'] if self._variant == 'walk' else snip[1]     # identity of the loader's arrays
-            if self._program_ref_id is not key:
+            qpos, qvel = self._snippet_root(snip)
+            qpos, qvel = np.asarray(qpos, np.float64), np.asarray(qvel, np.float64)
+            key = (qpos.shape, hashlib.blake2b(qpos.tobytes() + qvel.tobytes(), digest_size=16).digest())
+            if self._program_ref_id != key:
+                self._program_switched = self._program_ref_id is not None
                 self._program_ref_id = key
-                qpos, qvel = self._snippet_root(snip)
-                self._ref_qpos, self._ref_qvel = np.asarray(qpos, np.float64), np.asarray(qvel, np.float64)
+                self._ref_qpos, self._ref_qvel = qpos, qvel
                 self._upload_program()
             self._ref_len[:] = self._ref_qpos.shape[0]
             self._episode_steps[:] = self._steps_of(self._ref_qpos.shape[0])
@@ -538,6 +545,9 @@ class BatchedFlyEnv:
         resetting = self._needs_reset.copy()
         if resetting.any():
             self._load_snippet(np.nonzero(resetting)[0])            # a trajectory set since the last reset re-uploads the programs
+            if self._program_switched:                              # ... which restarts every env on the device (fb_task_reset_all)
+                resetting[:] = True
+                self._program_switched = False
         if self._variant == 'flight' and resetting.any():           # the wing-beat phases the host path would draw at these resets
             ids = np.nonzero(resetting)[0]
             self._sim.task_uniforms(ids, self._rs.uniform(size=len(ids)))

@@ -102,6 +102,31 @@ def test_walk_device_task_episode_end_is_a_good_termination(emu):
     env.close()
 
 
+def test_switching_the_shared_trajectory_restarts_every_env(emu):
+    """shared-reference mode + device task: a trajectory set between episodes is uploaded when the next env resets; the device then
+    restarts all envs and the host's counters follow; an in-place edit of the loader's arrays counts as a change (content digest)"""
+    from flybody_b200.synthetic import constant_speed_trajectory
+    env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=3, lib_path=emu, device_task=True)
+    env.reset()
+    for k in range(3):
+        ts = env.step(np.zeros((3, 59), np.float32))
+    assert np.all(np.asarray(ts.step_type) == int(StepType.MID)) and np.all(env._step_counter == 3)
+    q, v = constant_speed_trajectory(n_steps=200, speed=1.0, init_pos=(0, 0, 0.1278), control_timestep=2e-3)
+    env.task._traj_generator.set_next_trajectory(q, v)
+    env.request_reset([1])
+    ts = env.step(np.zeros((3, 59), np.float32))
+    assert np.all(np.asarray(ts.step_type) == int(StepType.FIRST)) and np.all(env._step_counter == 0) and np.all(env._time == 0)
+    first_digest = env._program_ref_id
+    ts = env.step(np.zeros((3, 59), np.float32))
+    assert np.all(np.asarray(ts.step_type) == int(StepType.MID))
+    q[:, 0] += 0.01                                                        # same arrays, edited in place
+    env.task._traj_generator.set_next_trajectory(q, v)
+    env.request_reset([0])
+    ts = env.step(np.zeros((3, 59), np.float32))
+    assert env._program_ref_id != first_digest and np.all(np.asarray(ts.step_type) == int(StepType.FIRST))
+    env.close()
+
+
 def test_walk_device_task_reset_noise_is_bounded_and_varies(emu):
     env = fly_envs.walk_imitation(terminal_com_dist=float('inf'), n_envs=8, lib_path=emu, device_task=True, reset_noise=0.05, seed=3)
     env.reset()

@@ -149,6 +149,7 @@ def test_device_task_logic_on_gpu():
     dt.test_walk_device_task_matches_host_task_code(None)
     dt.test_walk_device_task_episode_end_is_a_good_termination(None)
     dt.test_walk_device_task_reset_noise_is_bounded_and_varies(None)
+    dt.test_switching_the_shared_trajectory_restarts_every_env(None)      # re-uploaded programs free the replaced device buffers
     dt.test_flight_device_task_matches_host_task_code(None)
 
 
