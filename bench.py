@@ -183,7 +183,7 @@ def run_reference(args, wl):
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0, 'wall_s': wall}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
@@ -509,7 +509,7 @@ def run_ours(args, wl):
         res = measure_vision(args, world, rank, local, n_envs=args.envs if args.envs != ENVS_PER_GPU else 1024)
         if rank == 0:
             res.update({'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic'})
-            print(json.dumps(res))
+            emit(res)
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
         return
@@ -530,13 +530,31 @@ def run_ours(args, wl):
                 line['extra']['vision_guided_flight'] = {'error': repr(e)}
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline(wl, budget_s=args.cpu_seconds)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the one JSON line of this run, on the process's ORIGINAL stdout (see main)"""
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (the NCCL version banner, library chatter of the
+    # worker processes) is sent to stderr for the whole run
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
