@@ -1418,6 +1418,11 @@ int fb_hfield_bank(FbHandle s, int n_terrain, const float* heights) {
       cm[ncm * k + (size_t)br * s->hf_nbc + bc] = v;
     }
   }
+  if (s->bank_dev) {      // a replaced bank is freed; a vision task program pointing at it has to be uploaded again
+    std::vector<void*> old = {s->bank_dev, s->bank_hmax_dev, s->bank_cmax_dev};
+    scope_free(s, old);
+    if (s->d.task && s->task_host.kind == 2) { scope_free(s, s->task_scope); s->d.task = nullptr; }
+  }
   s->bank_dev = dalloc<float>(s, cells * n_terrain); s->bank_hmax_dev = dalloc<float>(s, n_terrain); s->bank_cmax_dev = dalloc<float>(s, ncm * n_terrain);
   if (!s->bank_dev) { s->err = "out of device memory (terrain bank)"; return -4; }
   h2d(s->bank_dev, heights, sizeof(float) * cells * n_terrain); h2d(s->bank_hmax_dev, hmax.data(), sizeof(float) * n_terrain); h2d(s->bank_cmax_dev, cm.data(), sizeof(float) * cm.size());
