@@ -184,9 +184,20 @@ FB_DEV void mass_row(const DevModel& m, const DevData& d, int e, int lane, float
   I10 I = ld10(d.crb10, b, d, e);
   V3 L, p;
   inert_mul(I, ld3(d.Sang, i, d, e), ld3(d.Slin, i, d, e), L, p);
-  int adr = m.dof_Madr[i];
+  const int adr = m.dof_Madr[i], len = m.dof_chainlen[i];
   int t = 0;
-  for (int j = i; j >= 0; j = m.dof_parentid[j], t++) {
+  for (; t + 4 <= len; t += 4) {       // four ancestors at a time: their motion-axis loads are in flight together (a store to qM between
+    // two loads would otherwise order them: the compiler cannot rule out that the arrays overlap)
+    const int j0 = m.dof_anc[adr + t], j1 = m.dof_anc[adr + t + 1], j2 = m.dof_anc[adr + t + 2], j3 = m.dof_anc[adr + t + 3];
+    const V3 a0 = ld3(d.Sang, j0, d, e), l0 = ld3(d.Slin, j0, d, e), a1 = ld3(d.Sang, j1, d, e), l1 = ld3(d.Slin, j1, d, e);
+    const V3 a2 = ld3(d.Sang, j2, d, e), l2 = ld3(d.Slin, j2, d, e), a3 = ld3(d.Sang, j3, d, e), l3 = ld3(d.Slin, j3, d, e);
+    float v0 = dot(a0, L) + dot(l0, p), v1 = dot(a1, L) + dot(l1, p), v2 = dot(a2, L) + dot(l2, p), v3_ = dot(a3, L) + dot(l3, p);
+    if (t == 0) v0 += m.dof_armature[i];
+    AT(d.qM, adr + t) = v0; LS(adr + t) = v0; AT(d.qM, adr + t + 1) = v1; LS(adr + t + 1) = v1;
+    AT(d.qM, adr + t + 2) = v2; LS(adr + t + 2) = v2; AT(d.qM, adr + t + 3) = v3_; LS(adr + t + 3) = v3_;
+  }
+  for (; t < len; t++) {
+    const int j = m.dof_anc[adr + t];
     float v = dot(ld3(d.Sang, j, d, e), L) + dot(ld3(d.Slin, j, d, e), p);
     if (t == 0) v += m.dof_armature[i];
     AT(d.qM, adr + t) = v; LS(adr + t) = v;
