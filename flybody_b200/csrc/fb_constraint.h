@@ -817,22 +817,22 @@ FB_DEV void kact_p0(FB_PHASE_ARGS) {
 FB_DEV void kact_p1(FB_PHASE_ARGS) {
   for (int i = y; i < m.nu; i += FB_NY) {
     float ctrl = AT(d.ctrl, i);
-    if (m.actuator_ctrllimited[i]) ctrl = clampf(ctrl, m.actuator_ctrlrange[2 * i], m.actuator_ctrlrange[2 * i + 1]);
-    int id = m.actuator_trnid[i], tt = m.actuator_trntype[i];
+    if (MLD(m.actuator_ctrllimited[i])) ctrl = clampf(ctrl, MLD(m.actuator_ctrlrange[2 * i]), MLD(m.actuator_ctrlrange[2 * i + 1]));
+    int id = MLD(m.actuator_trnid[i]), tt = MLD(m.actuator_trntype[i]);
     float len = 0, vel = 0;
-    if (tt == FB_TRN_JOINT) { len = AT(d.qpos, m.jnt_qposadr[id]); vel = AT(d.qvel, m.jnt_dofadr[id]); }
+    if (tt == FB_TRN_JOINT) { len = AT(d.qpos, MLD(m.jnt_qposadr[id])); vel = AT(d.qvel, MLD(m.jnt_dofadr[id])); }
     else if (tt == FB_TRN_TENDON) {
-      for (int w = m.tendon_adr[id]; w < m.tendon_adr[id] + m.tendon_num[id]; w++) { len += m.wrap_coef[w] * AT(d.qpos, m.wrap_qposadr[w]); vel += m.wrap_coef[w] * AT(d.qvel, m.wrap_dofid[w]); }
+      for (int w = MLD(m.tendon_adr[id]); w < MLD(m.tendon_adr[id]) + MLD(m.tendon_num[id]); w++) { len += MLD(m.wrap_coef[w]) * AT(d.qpos, MLD(m.wrap_qposadr[w])); vel += MLD(m.wrap_coef[w]) * AT(d.qvel, MLD(m.wrap_dofid[w])); }
     }
-    float input = ctrl; int aa = m.actuator_actadr[i];
-    if (aa >= 0) { AT(d.act_dot, aa) = (ctrl - AT(d.act, aa)) / fmaxf(FB_MINVAL, m.actuator_dynprm[3 * i]); input = AT(d.act, aa); }
-    float force = m.actuator_gainprm[3 * i] * input;
-    if (m.actuator_biastype[i] == 1) force += m.actuator_biasprm[3 * i] + m.actuator_biasprm[3 * i + 1] * len + m.actuator_biasprm[3 * i + 2] * vel;
-    if (m.actuator_forcelimited[i]) force = clampf(force, m.actuator_forcerange[2 * i], m.actuator_forcerange[2 * i + 1]);
+    float input = ctrl; int aa = MLD(m.actuator_actadr[i]);
+    if (aa >= 0) { AT(d.act_dot, aa) = (ctrl - AT(d.act, aa)) / fmaxf(FB_MINVAL, MLD(m.actuator_dynprm[3 * i])); input = AT(d.act, aa); }
+    float force = MLD(m.actuator_gainprm[3 * i]) * input;
+    if (MLD(m.actuator_biastype[i]) == 1) force += MLD(m.actuator_biasprm[3 * i]) + MLD(m.actuator_biasprm[3 * i + 1]) * len + MLD(m.actuator_biasprm[3 * i + 2]) * vel;
+    if (MLD(m.actuator_forcelimited[i])) force = clampf(force, MLD(m.actuator_forcerange[2 * i]), MLD(m.actuator_forcerange[2 * i + 1]));
     AT(d.actuator_force, i) = force;
     // joint / tendon transmissions touch disjoint dofs (one actuator per joint or tendon in the fly model)
-    if (tt == FB_TRN_JOINT) AT(d.qfrc_actuator, m.jnt_dofadr[id]) += force;
-    else if (tt == FB_TRN_TENDON) { for (int w = m.tendon_adr[id]; w < m.tendon_adr[id] + m.tendon_num[id]; w++) AT(d.qfrc_actuator, m.wrap_dofid[w]) += m.wrap_coef[w] * force; }
+    if (tt == FB_TRN_JOINT) AT(d.qfrc_actuator, MLD(m.jnt_dofadr[id])) += force;
+    else if (tt == FB_TRN_TENDON) { for (int w = MLD(m.tendon_adr[id]); w < MLD(m.tendon_adr[id]) + MLD(m.tendon_num[id]); w++) AT(d.qfrc_actuator, MLD(m.wrap_dofid[w])) += MLD(m.wrap_coef[w]) * force; }
   }
 }
 // adhesion (body transmission): moment = - mean of the contact-normal Jacobians of all detected contacts of the
@@ -995,12 +995,17 @@ FB_DEV void kfin_f8(FB_PHASE_ARGS) {
   }
   if (!d.do_integrate) return;
   if (AT(d.hold, 0)) return;          // env staged for reset: recompute (forward) but do not integrate
-  if (y == 0) {
-    for (int r = 0; r < m.nroot; r++) integrate_body(m, d, e, lane, xs, m.root_body[r]);
-    AT(d.time, 0) += m.timestep;
+  // semi-implicit Euler: the free joints one lane per root (quaternion update), every other dof on its own lane -- walking the lists
+  // body by body put a chain of dependent read-modify-writes of qvel / qpos on one lane per list
+  if (y < m.nroot) integrate_body(m, d, e, lane, xs, m.root_body[y]);
+  if (y == 0) AT(d.time, 0) += m.timestep;
+  const float h = m.timestep;
+  for (int k = y; k < m.nv; k += FB_NY) {
+    const int j = m.dof_jntid[k];
+    if (m.jnt_type[j] == FB_JNT_FREE) continue;
+    const float v = AT(d.qvel, k) + h * XS(k);
+    AT(d.qvel, k) = v; AT(d.qpos, m.jnt_qposadr[j]) += h * v;
   }
-  if (y >= m.nlist) return;
-  FB_LIST_LOOP_FWD integrate_body(m, d, e, lane, xs, b);
 }
 FB_DEV float ray_quad(float a, float b, float c, float* x) {
   float det = b * b - a * c;

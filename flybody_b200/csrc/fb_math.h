@@ -90,8 +90,19 @@ FB_DEV void st9(float* arr, int i, const DevData& d, int e, const M3& R) {
   stf4(p, R.m[0], R.m[1], R.m[2], R.m[3]); stf4(p + 4, R.m[4], R.m[5], R.m[6], R.m[7]); stf4(p + 8, R.m[8], 0.0f, 0.0f, 0.0f);
 }
 // model tables of 3-vectors are uploaded padded to four floats (build_model: upf3), quaternion tables are four wide anyway
+// (no kernel writes a model table: the read-only path lets the compiler move these loads above stores to the record)
+#ifdef __CUDACC__
+#define MLD(x) __ldg(&(x))
+#else
+#define MLD(x) (x)
+#endif
+#ifdef __CUDACC__
+FB_DEV V3 mld3(const float* a, int i) { const float4 v = __ldg(reinterpret_cast<const float4*>(a + 4 * i)); return v3(v.x, v.y, v.z); }
+FB_DEV Q4 mld4(const float* a, int i) { const float4 v = __ldg(reinterpret_cast<const float4*>(a + 4 * i)); return q4(v.x, v.y, v.z, v.w); }
+#else
 FB_DEV V3 mld3(const float* a, int i) { F4 v = ldf4(a + 4 * i); return v3(v.x, v.y, v.z); }
 FB_DEV Q4 mld4(const float* a, int i) { F4 v = ldf4(a + 4 * i); return q4(v.x, v.y, v.z, v.w); }
+#endif
 
 // 10-parameter spatial inertia about the reference point: m, h[3], Ixx Iyy Izz Ixy Ixz Iyz
 struct I10 { float v[10]; };

@@ -37,10 +37,10 @@ FB_DEV void body_pose(const DevModel& m, const DevData& d, int e, int b, V3 ppos
   M3 pR = q2m(pq);
   pos = ppos + mul(pR, mld3(m.body_pos, b));
   quat = qmul(pq, mld4(m.body_quat, b));
-  int jn = m.body_jntnum[b];
+  int jn = MLD(m.body_jntnum[b]);
   for (int k = 0; k < jn; k++) {
-    int j = m.body_jntadr[b] + k, qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
-    if (m.jnt_type[j] == FB_JNT_FREE) {
+    int j = MLD(m.body_jntadr[b]) + k, qa = MLD(m.jnt_qposadr[j]), da = MLD(m.jnt_dofadr[j]);
+    if (MLD(m.jnt_type[j]) == FB_JNT_FREE) {
       pos = v3(AT(d.qpos, qa), AT(d.qpos, qa + 1), AT(d.qpos, qa + 2)) - ref;
       quat = qnormalize(q4(AT(d.qpos, qa + 3), AT(d.qpos, qa + 4), AT(d.qpos, qa + 5), AT(d.qpos, qa + 6)));
       M3 R = q2m(quat);
@@ -57,7 +57,7 @@ FB_DEV void body_pose(const DevModel& m, const DevData& d, int e, int b, V3 ppos
       V3 jp = mld3(m.jnt_pos, j), ja = mld3(m.jnt_axis, j);
       V3 anchor = pos + mul(R, jp);
       V3 axis = mul(R, ja);
-      quat = qmul(quat, axisangle(ja, AT(d.qpos, qa) - m.qpos0[qa]));
+      quat = qmul(quat, axisangle(ja, AT(d.qpos, qa) - MLD(m.qpos0[qa])));
       R = q2m(quat);
       pos = anchor - mul(R, jp);
       st3(d.Sang, da, d, e, axis);
@@ -118,7 +118,7 @@ FB_DEV void kpos_p1(FB_PHASE_ARGS) {
   V3 ref = v3(AT(d.ref, 0), AT(d.ref, 1), AT(d.ref, 2));
   int prev = -1; V3 cpos = v3(0, 0, 0); Q4 cq = q4(1, 0, 0, 0);
   FB_LIST_LOOP_FWD {
-    int p = m.body_parentid[b];
+    int p = MLD(m.body_parentid[b]);
     V3 ppos; Q4 pq;
     if (p == prev) { ppos = cpos; pq = cq; } else { ppos = ld3(d.xpos, p, d, e); pq = ld4(d.xquat, p, d, e); }
     body_pose(m, d, e, b, ppos, pq, ref, cpos, cq);
@@ -713,13 +713,11 @@ FB_DEV void kvel_p2(FB_PHASE_ARGS) {
 FB_DEV void sensors_vel(const DevModel& m, const DevData& d, int e, int y);
 FB_DEV void kvel_p3(FB_PHASE_ARGS) {
   float* part_ = sh_dyn(sh);
-  if (y < m.nroot) {
-    int r = y, b = m.root_body[r];
-    for (int k = 0; k < 6; k++) {
-      float a1 = 0, a2 = 0;
-      for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) { a1 += PART(l, k); a2 += PART(l, 6 + k); }
-      AT(d.bfrc, S6I(b, k)) += a1; AT(d.bfl, S6I(b, k)) += a2;
-    }
+  for (int t = y; t < 12 * m.nroot; t += FB_NY) {      // lanes over (root, component): the lists' partial sums onto the root bodies
+    const int r = t / 12, k = t - 12 * r, b = m.root_body[r];
+    float a = 0;
+    for (int l = 0; l < m.nlist; l++) if (m.list_root[l] == r) a += PART(l, k);
+    if (k < 6) AT(d.bfrc, S6I(b, k)) += a; else AT(d.bfl, S6I(b, k - 6)) += a;
   }
   sensors_vel(m, d, e, y);
 }
