@@ -207,7 +207,7 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
             if (lane == j) L(yv) = yj; else if (lane > j) L(yv) -= l * yj;
 #pragma unroll
             for (int k = j + 1; k < FB_CHOL_REG; k++) {
-              if (k >= nc) break;
+              if ((k - j - 1) % 4 == 0 && k >= nc) break;      // exit test once per four columns: columns >= nc hold zeros (lcol = 0 there), their updates are no-ops
               const float lk = SHF(lcol, k);
               if (lane >= k) LA(g, k) -= l * lk;
             }
