@@ -181,23 +181,27 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
 #if FB_CHOL_REG > 0
       if (nc <= FB_CHOL_REG) {
         // Cholesky G = L L^T with ROW i OF G / L IN THE REGISTERS OF LANE i (right-looking: after step j every lane has subtracted
-        // column j's outer product from its row; L[k][j] travels by shuffle).  The loops are unrolled with uniform early exits, so
-        // every register index is static.  The forward substitution L y = p rides along (y in a lane register); L is written back
-        // to the packed triangle (triangular numbers mod 32 are a permutation: conflict-free) for the backward substitution,
-        // where lane i needs column i of L.  All lanes < nc work in every step -- the column-by-column shared-memory form below
-        // kept 2.4 - 4.6 lanes busy (profiles/r02_ncu_full_v9_summary.json).
+        // column j's outer product from its row; L[k][j] travels by shuffle).  Register indices must be static, so the row lives
+        // in slots that shift by one per step (below).  The forward substitution L y = p rides along (y in a lane register); L is
+        // written back to the packed triangle (triangular numbers mod 32 are a permutation: conflict-free) for the backward
+        // substitution, where lane i needs column i of L.  All lanes < nc work in every step -- the column-by-column shared-memory
+        // form below kept 2.4 - 4.6 lanes busy (profiles/r02_ncu_full_v9_summary.json).
         LREGA(float, g, FB_CHOL_REG); LREG(float, yv); LREG(float, lcol); LREG(float, yjr); LREG(float, dinv);
         WPAR_BEGIN {
 #pragma unroll
           for (int k = 0; k < FB_CHOL_REG; k++) LA(g, k) = (k < nc && lane < nc && k <= lane) ? GP(lane, k) : 0.0f;      // (an early exit at k >= nc costs registers: measured 18 % slower)
           L(yv) = lane < nc ? P[lane] : 0.0f; L(dinv) = 0.0f;
         } WPAR_END
-#pragma unroll
-        for (int j = 0; j < FB_CHOL_REG; j++) {
-          if (j >= nc) break;
+        // slot s of the register row always holds column j + s: every step works on slot 0 and writes the updated column j + q into
+        // slot q - 1 (update and shift in one FMA), so the loop over the columns stays rolled -- one copy of the step in the
+        // instruction cache.  (First version: both loops unrolled, 24 copies; a third of the kernel's stall samples waited for
+        // instructions, profiles/r02_ncu_full_v13_summary.json.)  The exit test of the inner loop comes once per four columns: columns
+        // >= nc hold zeros, their updates are no-ops (per column: 1.94 ms per control step; per four: 1.73; rolled: 1.71).  Entries
+        // above the diagonal (slot index > row) carry values nobody reads.
+        NOUNROLL for (int j = 0; j < nc; j++) {
           WPAR_BEGIN {
-            const float inv = FB_RSQRT(fmaxf(SHFA(g, j, j), 1e-12f));
-            L(lcol) = LA(g, j) * inv;                      // lane j: L[j][j]; lanes above: L[i][j]; lanes below: 0
+            const float inv = FB_RSQRT(fmaxf(SHFA(g, 0, j), 1e-12f));
+            L(lcol) = LA(g, 0) * inv;                      // lane j: L[j][j]; lanes above: L[i][j]
             L(yjr) = SHF(yv, j) * inv;
             if (lane == j) L(dinv) = inv;
           } WPAR_END
@@ -205,11 +209,11 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
             const float l = L(lcol), yj = L(yjr);
             if (lane >= j && lane < nc) GP(lane, j) = l;
             if (lane == j) L(yv) = yj; else if (lane > j) L(yv) -= l * yj;
+            const int rem = nc - 1 - j;
 #pragma unroll
-            for (int k = j + 1; k < FB_CHOL_REG; k++) {
-              if ((k - j - 1) % 4 == 0 && k >= nc) break;      // exit test once per four columns: columns >= nc hold zeros (lcol = 0 there), their updates are no-ops
-              const float lk = SHF(lcol, k);
-              if (lane >= k) LA(g, k) -= l * lk;
+            for (int q = 1; q < FB_CHOL_REG; q++) {
+              if ((q - 1) % 4 == 0 && q > rem) break;          // (columns >= nc hold zeros: lanes >= nc have lcol = 0)
+              LA(g, q - 1) = LA(g, q) - l * SHF(lcol, j + q);
             }
           } WPAR_END
         }
