@@ -32,7 +32,6 @@ What is recorded, per task (`walk_imitation(terminal_com_dist=inf)` as `tests/te
 Field names follow mjData / mjModel.  Everything is float64 / int32.
 """
 import argparse
-import copy
 import json
 import os
 import sys

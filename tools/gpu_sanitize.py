@@ -7,7 +7,7 @@ CPU tests; this is the check that sees it."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.getcwd())
-from flybody_b200 import arenas, fly_envs, stepper as st
+from flybody_b200 import fly_envs, stepper as st
 from flybody_b200.flymodel import load_model
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
