@@ -1,5 +1,5 @@
 """MuJoCo pin kit, consumer side.  `tools/dump_mujoco_goldens.py` (run wherever the reference + mujoco exist) writes
-`tests/golden/mujoco_{walk,flight}.npz`; these tests then pin, against a REAL MuJoCo,
+`tests/golden/mujoco_{walk,flight,vision}.npz`; these tests then pin, against a REAL MuJoCo,
 
   (a) the model compiler                       test_compiler_matches_mjmodel           arrays by NAME, 1e-9 relative
   (b) the fp64 oracle, stage by stage          test_oracle_stage_fields                smooth 1e-8, constraint 1e-5 relative
@@ -99,6 +99,9 @@ class Maps:
         # the floor: our 'floor' <-> the recorded model's plane geom
         planes = [i for i, t in enumerate(g['model/geom_type']) if int(t) == 0]
         self.floor = (ours['geom_names'].index('floor') if 'floor' in ours['geom_names'] else -1, planes[0] if planes else -1)
+        # the terrain of vision_guided_flight: our heightfield geom <-> the recorded model's hfield geom (mjGEOM_HFIELD = 1)
+        hfs = [i for i, t in enumerate(g['model/geom_type']) if int(t) == 1]
+        self.terrain = (int(ours['hf_geom']) if 'hf_geom' in ours else -1, hfs[0] if hfs else -1)
 
     def to_ours(self, pair, their_vec, n_ours, fill=None):
         out = np.zeros(n_ours) if fill is None else np.array(fill, np.float64).copy()
@@ -166,6 +169,9 @@ class OracleBackend:
         self.o.set(fo.CTRL, ctrl); self.o.set(fo.QACC_WARMSTART, warm)
         self.o.forward()
 
+    def set_terrain(self, heights):
+        self.o.set_hfield(self.m.meta['hf_geom'], self.m.hf_size, heights, self.m.hf_pair_geom)
+
     def get(self, f):
         return self.o.get(f)
 
@@ -186,12 +192,31 @@ class StepperBackend:
             self.s.set(st.ACT, act)
         self.s.set_control(ctrl); self.s.forward()
 
+    def set_terrain(self, heights):
+        h = np.asarray(heights, np.float32)
+        self.s.hfield_collision(self.m.meta['hf_geom'], self.m.hf_size, h.shape[0], h.shape[1], self.m.hf_pair_geom)
+        self.s.hfield_write(np.arange(2), np.stack([h, h]))
+
     def get(self, f):
         return self.s.get(f)[1].astype(np.float64)
 
     def control_step(self, n_sub):
         self.s.step(n_sub)
         return self.get(st.QPOS), self.get(st.QVEL), self.get(st.SENSOR_MEAN)
+
+
+def dev_con_tol(variant):
+    """constraint-stage gate of the fp32 stepper: terrain contacts come from MPR against prisms of the heightfield (fp32 portal
+    refinement), their forces agree with the fp64 oracle to 5e-3 relative where primitive contacts reach 1e-3"""
+    return TOL['dev_constraint'] * (5 if variant == 'vision' else 1)
+
+
+def with_terrain(be, g):
+    """vision_guided_flight files carry the episode's heightfield (hfield/data: mjModel.hfield_data, normalised; hfield/size: radius x,
+    radius y, elevation z, base z): world heights = data * elevation"""
+    if 'hfield/data' in g:
+        be.set_terrain(np.asarray(g['hfield/data'], np.float64) * float(g['hfield/size'][2]))
+    return be
 
 
 def our_state(m, mp, g, prefix, row=None):
@@ -233,6 +258,8 @@ def check_stage_fields(m, g, mp, be, tol_smooth, tol_con):
         gmap = {int(b): int(a) for a, b in zip(*mp.geom)}
         if mp.floor[0] >= 0:
             gmap[mp.floor[1]] = mp.floor[0]
+        if mp.terrain[0] >= 0 and mp.terrain[1] >= 0:
+            gmap[mp.terrain[1]] = mp.terrain[0]
         theirs = sorted((gmap[int(a)], gmap[int(b)], float(dd)) for a, b, dd in zip(g[P + 'con_geom1'], g[P + 'con_geom2'], g[P + 'con_dist'])
                         if int(a) in gmap and int(b) in gmap)
         ncon = int(be.get(fo.NCON)[0])
@@ -296,49 +323,49 @@ def check_observations(m, g, mp):
 
 
 # ------------------------------------------------------------------------------------------------ tests on the real files
-@pytest.mark.parametrize('variant', ['walk', 'flight'])
+@pytest.mark.parametrize('variant', ['walk', 'flight', 'vision'])
 def test_compiler_matches_mjmodel(variant):
     g = golden(variant)
     check_compiler(load_model(variant), g)
 
 
-@pytest.mark.parametrize('variant', ['walk', 'flight'])
+@pytest.mark.parametrize('variant', ['walk', 'flight', 'vision'])
 def test_recorded_observations_follow_the_buffer_rules(variant):
     g = golden(variant)
     m = load_model(variant)
     check_observations(m, g, Maps(m, g))
 
 
-@pytest.mark.parametrize('variant', ['walk', 'flight'])
+@pytest.mark.parametrize('variant', ['walk', 'flight', 'vision'])
 def test_oracle_stage_fields(variant):
     g = golden(variant); m = load_model(variant); mp = Maps(m, g)
-    print(check_stage_fields(m, g, mp, OracleBackend(m), TOL['smooth'], TOL['constraint']))
+    print(check_stage_fields(m, g, mp, with_terrain(OracleBackend(m), g), TOL['smooth'], TOL['constraint']))
 
 
-@pytest.mark.parametrize('variant', ['walk', 'flight'])
+@pytest.mark.parametrize('variant', ['walk', 'flight', 'vision'])
 def test_oracle_teacher_forced_trajectory(variant):
     g = golden(variant); m = load_model(variant); mp = Maps(m, g)
-    print(check_teacher_forced(m, g, mp, OracleBackend(m), TOL['tf_q'], TOL['tf_v'], TOL['tf_s']))
+    print(check_teacher_forced(m, g, mp, with_terrain(OracleBackend(m), g), TOL['tf_q'], TOL['tf_v'], TOL['tf_s']))
 
 
-@pytest.mark.parametrize('variant', ['walk', 'flight'])
+@pytest.mark.parametrize('variant', ['walk', 'flight', 'vision'])
 def test_stepper_kernel_source_against_mujoco(variant):
     """the kernel source (host emulation) against MuJoCo: 20 control steps + every recorded stage"""
     g = golden(variant); m = load_model(variant); mp = Maps(m, g)
     ge.build()
-    be = StepperBackend(m, ge.EMU)
-    print(check_stage_fields(m, g, mp, be, TOL['dev_smooth'], TOL['dev_constraint']))
+    be = with_terrain(StepperBackend(m, ge.EMU), g)
+    print(check_stage_fields(m, g, mp, be, TOL['dev_smooth'], dev_con_tol(variant)))
     print(check_teacher_forced(m, g, mp, be, TOL['dev_q'], 4 * TOL['dev_v'], 5 * TOL['dev_s'], max_events=0.15, n_steps=20))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('variant', ['walk', 'flight'])
+@pytest.mark.parametrize('variant', ['walk', 'flight', 'vision'])
 def test_cuda_stepper_against_mujoco(variant):
     """BASELINE.json config 1 on the B200 against the recorded CPU MuJoCo trajectory (north_star: "outputs match the reference CPU
     MuJoCo qpos/qvel trajectories on identical action sequences within a stated fp32 tolerance")."""
     g = golden(variant); m = load_model(variant); mp = Maps(m, g)
-    be = StepperBackend(m, None)
-    print(check_stage_fields(m, g, mp, be, TOL['dev_smooth'], TOL['dev_constraint']))
+    be = with_terrain(StepperBackend(m, None), g)
+    print(check_stage_fields(m, g, mp, be, TOL['dev_smooth'], dev_con_tol(variant)))
     print(check_teacher_forced(m, g, mp, be, TOL['dev_q'], TOL['dev_v'], TOL['dev_s'], max_events=0.10))
 
 
@@ -355,7 +382,7 @@ def write_selftest_file(path, variant, n_steps=6, n_stage=3, seed=0):
     # within the walker but are shifted behind a foreign free joint (7 qpos / 6 dofs)
     def perm(names, n_foreign, tag):
         ours = list(range(len(names)))
-        keep = [i for i in ours if names[i].startswith('walker/') or names[i] == 'floor']
+        keep = [i for i in ours if names[i].startswith('walker/') or names[i] in ('floor', 'terrain')]
         order = keep[1:] + keep[:1]                                       # rotate
         their_names = [f'{tag}/foreign{i}' for i in range(n_foreign)] + [('groundplane' if names[i] == 'floor' else names[i]) for i in order]
         return order, their_names, n_foreign
@@ -430,6 +457,15 @@ def write_selftest_file(path, variant, n_steps=6, n_stage=3, seed=0):
                     qacc_warmstart=qspace(o.get(fo.QACC_WARMSTART), nv_w, DS, nv_t), sensordata=sens_t(o.get(fo.SENSORDATA)))
     n_sub = 10 if variant == 'walk' else 4
     q0 = m.qpos0.copy()
+    if variant == 'vision':          # an episode's terrain, the fly low enough over it that its body geoms meet the heightfield
+        from flybody_b200 import arenas
+        nrow, ncol = int(m.meta['hf_nrow']), int(m.meta['hf_ncol'])
+        terr = arenas.SineBumps(dim=int(m.hf_size[0]), grid_density=(nrow - 1) // (2 * int(m.hf_size[0]))).generate(rs)
+        assert terr.shape == (nrow, ncol), terr.shape
+        o.set_hfield(m.meta['hf_geom'], m.hf_size, terr, m.hf_pair_geom)
+        out['hfield/data'] = np.asarray(terr, np.float64) / float(m.hf_size[2]); out['hfield/size'] = np.asarray(m.hf_size, np.float64)
+        x, y = -5.0, 0.0
+        q0[0], q0[1], q0[2] = x, y, float(arenas.hfield_height(terr[None], [x], [y], float(m.hf_size[0]))[0]) + 0.1
     if variant == 'walk':
         for side in ('left', 'right'):
             for dof, val in (('yaw', 1.5), ('roll', 0.7), ('pitch', -1.0)):
@@ -437,6 +473,7 @@ def write_selftest_file(path, variant, n_steps=6, n_stage=3, seed=0):
     o.reset(q0)
     traj, sub, stages, stage_steps = [their_state()], [], {}, []
     scale = 0.5 if variant == 'walk' else 0.2
+    seen_terrain_contact = False
     for k in range(n_steps):
         ctrl = rs.uniform(-scale, scale, m.nu)
         if k % max(1, n_steps // n_stage) == 0 and len(stage_steps) < n_stage:
@@ -456,6 +493,7 @@ def write_selftest_file(path, variant, n_steps=6, n_stage=3, seed=0):
             gi = inv(g_order)
             stages[P + 'con_geom1'] = np.array([gi[int(c[7])] + g_sh for c in con], np.int32); stages[P + 'con_geom2'] = np.array([gi[int(c[8])] + g_sh for c in con], np.int32)
             stages[P + 'con_dist'] = np.array([c[0] for c in con])
+            seen_terrain_contact |= any(int(c[7]) == m.meta.get('hf_geom', -9) or int(c[8]) == m.meta.get('hf_geom', -9) for c in con)
         o.set(fo.CTRL, ctrl)
         ns = m.nsensordata
         o_sum = np.zeros(ns)
@@ -463,6 +501,7 @@ def write_selftest_file(path, variant, n_steps=6, n_stage=3, seed=0):
             o.step2(); o.step1()
             sub.append(their_state())
         traj.append(their_state())
+    assert variant != 'vision' or seen_terrain_contact, 'the self-test file should exercise heightfield contacts'
     for f in traj[0]:
         out['traj/' + f] = np.stack([r[f] for r in traj]); out['sub/' + f] = np.stack([r[f] for r in sub])
     # observations the way dm_control's buffers would report them
@@ -478,7 +517,7 @@ def write_selftest_file(path, variant, n_steps=6, n_stage=3, seed=0):
     np.savez_compressed(path, **out)
 
 
-@pytest.mark.parametrize('variant', ['walk', 'flight'])
+@pytest.mark.parametrize('variant', ['walk', 'flight', 'vision'])
 def test_consumer_plumbing_with_an_oracle_generated_file(variant, tmp_path):
     """every checker above, run on a file of the dump tool's layout that the oracle produced (permuted / shifted index spaces):
     proves the name maps, the teacher-forcing and the comparisons execute and close to round-off -- NOT a parity statement."""
@@ -489,11 +528,11 @@ def test_consumer_plumbing_with_an_oracle_generated_file(variant, tmp_path):
     m = load_model(variant)
     mp = check_compiler(m, g)
     check_observations(m, g, mp)
-    w = check_stage_fields(m, g, mp, OracleBackend(m), 1e-10, 1e-7)
+    w = check_stage_fields(m, g, mp, with_terrain(OracleBackend(m), g), 1e-10, 1e-7)
     assert 'qM' in w and 'xpos' in w
-    r = check_teacher_forced(m, g, mp, OracleBackend(m), 1e-10, 1e-8, 1e-8)
+    r = check_teacher_forced(m, g, mp, with_terrain(OracleBackend(m), g), 1e-10, 1e-8, 1e-8)
     assert r['steps'] == 6 and r['p90_s'] is not None
     ge.build()
-    be = StepperBackend(m, ge.EMU)
-    check_stage_fields(m, g, mp, be, TOL['dev_smooth'], TOL['dev_constraint'])
+    be = with_terrain(StepperBackend(m, ge.EMU), g)
+    check_stage_fields(m, g, mp, be, TOL['dev_smooth'], dev_con_tol(variant))
     check_teacher_forced(m, g, mp, be, TOL['dev_q'], 10 * TOL['dev_v'], 10 * TOL['dev_s'], max_events=0.34)

@@ -6,7 +6,8 @@ dependencies; no GPU needed):
 
     python tools/dump_mujoco_goldens.py [--reference /path/to/flybody/checkout] [--out tests/golden] [--steps 200]
 
-It writes `tests/golden/mujoco_walk.npz` and `tests/golden/mujoco_flight.npz` (a few MB each).  Commit them; from then on
+It writes `tests/golden/mujoco_walk.npz`, `mujoco_flight.npz` and `mujoco_vision.npz` (a few MB each; the vision file carries the
+episode's heightfield as hfield/data + hfield/size and needs an OpenGL backend for the eye cameras).  Commit them; from then on
 `pytest tests/test_mujoco_goldens.py` pins (a) the model compiler, (b) the fp64 oracle and (c, `-m gpu`) the CUDA stepper against a
 real MuJoCo, and DESIGN.md's "parity unpinned" caveat can go.  Nothing in this repository imports mujoco at test or run time: the
 `.npz` files are the only thing that travels.  (The build container and the GPU boxes have no mujoco / dm_control and no network:
@@ -191,6 +192,10 @@ def record_task(name, env, actions, n_substep_steps, stage_every, mujoco_mod):
     except Exception as e:                         # older dm_control: no extra hooks -> no per-substep rows
         print('  (no after_substep hook:', e, ')')
     ts = env.reset()
+    if int(model.nhfield) > 0:       # the episode's terrain (vision_guided_flight: regenerated by initialize_episode_mjcf at every reset)
+        nrow, ncol, adr = int(model.hfield_nrow[0]), int(model.hfield_ncol[0]), int(model.hfield_adr[0])
+        out['hfield/data'] = np.array(model.hfield_data[adr:adr + nrow * ncol], np.float64).reshape(nrow, ncol)      # normalised: x elevation = world
+        out['hfield/size'] = np.array(model.hfield_size[0], np.float64)                                           # radius x, radius y, elevation z, base z
     rows = [state_row(data)]
     obs_rows = [{k: np.array(v, np.float64) for k, v in ts.observation.items()}]
     rew, disc, stype = [0.0], [1.0], [int(ts.step_type)]
@@ -262,6 +267,18 @@ def main():
     out = record_task('flight', env, acts, args.substep_steps, max(1, len(acts) // args.stages), mujoco)
     np.savez_compressed(os.path.join(args.out, 'mujoco_flight.npz'), **out)
     print('wrote mujoco_flight.npz:', len(out), 'arrays,', out['traj/qpos'].shape[0] - 1, 'control steps')
+    # vision_guided_flight ('bumps' arena, synthetic wing-beat pattern): terrain contacts (mjc_ConvexHField) and the task's observables.
+    # The eye cameras render through MuJoCo's OpenGL context: on a headless machine set MUJOCO_GL=egl (or osmesa) first.
+    try:
+        from flybody.fly_envs import vision_guided_flight
+        env = vision_guided_flight(bumps_or_trench='bumps')
+        A = env.action_spec().shape[0]
+        acts = np.random.RandomState(0).uniform(-0.2, 0.2, (min(T, 100), A))
+        out = record_task('vision', env, acts, args.substep_steps, max(1, len(acts) // args.stages), mujoco)
+        np.savez_compressed(os.path.join(args.out, 'mujoco_vision.npz'), **out)
+        print('wrote mujoco_vision.npz:', len(out), 'arrays,', out['traj/qpos'].shape[0] - 1, 'control steps')
+    except Exception as e:
+        print('vision_guided_flight NOT recorded (the eye cameras need an OpenGL backend: MUJOCO_GL=egl or osmesa):', repr(e))
     print('now: git add tests/golden/mujoco_*.npz && python -m pytest tests/test_mujoco_goldens.py -q')
 
 
