@@ -164,3 +164,20 @@ def test_device_task_matches_the_host_task_code(emu, low_start, arena):
     if arena == 'trench':
         assert centre_min < 0.999, centre_min
     host.close(); dev.close()
+
+
+def test_replacing_the_terrain_bank_invalidates_the_vision_task_program(emu):
+    """fb_hfield_bank frees a replaced bank; the device task program pointed into it, so stepping needs a fresh fb_task_program"""
+    env = fly_envs.vision_guided_flight(n_envs=2, lib_path=emu, seed=1, terrain_bank=2, device_task=True)
+    env.reset()
+    env.step(np.zeros((2, 12), np.float32))
+    bank = np.stack([t for t, _ in env._bank])
+    env._sim.hfield_bank(bank[::-1].copy())
+    with pytest.raises(st.StepperError):
+        env._sim.task_step(np.zeros((2, 12), np.float32), env._n_sub)
+    env._upload_task_program(seed=1)
+    ts = env.reset()
+    assert np.all(np.asarray(ts.step_type) == int(StepType.FIRST))
+    ts = env.step(np.zeros((2, 12), np.float32))
+    assert np.all(np.isfinite(ts.reward))
+    env.close()
