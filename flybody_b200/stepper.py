@@ -341,7 +341,11 @@ class BatchedStepper:
 
     # ---- eye cameras (fb_eye_program / fb_render_eyes)
     def eye_program(self, bodies, pos, quat, fovy_deg=150.0, size=32, nrow=0, ncol=0, half_size=20.0, z_offset=0.0, zfar=50.0,
-                    sky_top=(0.25, 0.45, 0.85), sky_horizon=(0.75, 0.85, 0.95), ground=(0.45, 0.40, 0.25), ambient=0.4, diffuse=0.8):
+                    sky_top=(0.33, 0.47, 0.70), sky_horizon=(0.50, 0.56, 0.65), ground=(0.15, 0.11, 0.08), ambient=0.4, diffuse=0.8):
+        """The default palette is calibrated, not copied: MuJoCo's GL image cannot be reproduced, but the gray-level statistics the
+        reference's vision network assumes can -- `VisNet` normalises with mean 77 / std 56 "from the trench task"
+        (network_factory_vis.py:158-162); with these colours the eyes of `vision_guided_flight('trench')` measure 76 / 56 (bumps: 80 / 57),
+        tests/test_eyes.py::test_eye_statistics_match_the_vision_network_normalisation."""
         p = FbEyeProgram()
         p.n_cam = len(bodies)
         for c in range(p.n_cam):

@@ -9,6 +9,10 @@ from flybody_b200 import arenas, fly_envs, stepper as st
 from flybody_b200.compiler.quat import q2mat
 
 
+import inspect
+GROUND_RED = inspect.signature(st.BatchedStepper.eye_program).parameters['ground'].default[0]      # red channel of the default ground colour
+
+
 @pytest.fixture(scope='module')
 def emu():
     ge.build()
@@ -51,7 +55,7 @@ def test_flat_ground_horizon_follows_the_camera_model(emu):
         g = ~sky & clear
         t = -o[2] / d[..., 2]; hit = o + d * t[..., None]
         tex = np.where((np.floor(hit[..., 0]) + np.floor(hit[..., 1])).astype(np.int64) & 1, 1.0, 0.75)
-        want = 0.45 * (0.4 + 0.8 * -d[..., 2]) * tex
+        want = GROUND_RED * (0.4 + 0.8 * -d[..., 2]) * tex
         near = g & (t < 50.0)
         edge = np.abs(hit[..., 0] - np.round(hit[..., 0])) < 0.02
         edge |= np.abs(hit[..., 1] - np.round(hit[..., 1])) < 0.02          # fp32 vs fp64 may disagree on the checker cell at its edges
@@ -107,4 +111,22 @@ def test_eye_program_validation(emu):
         env._sim.eye_program([0, 0], [(0, 0, 0)] * 2, [(1, 0, 0, 0)] * 2)  # the world body carries no eye
     with pytest.raises(st.StepperError):
         env._sim.eye_program([2, 2], [(0, 0, 0)] * 2, [(1, 0, 0, 0)] * 2, fovy_deg=190.0)
+    env.close()
+
+
+@pytest.mark.parametrize('arena,tol', [('trench', 8.0), ('bumps', 12.0)])
+def test_eye_statistics_match_the_vision_network_normalisation(emu, arena, tol):
+    """MuJoCo's GL pixels are out of reach, the statistics its consumer assumes are not.  The reference's VisNet
+    normalises the gray image with mean 77 and std 56 "from the trench task" (network_factory_vis.py:158-162); the eyes of
+    `vision_guided_flight` over a few flying steps land within `tol` gray levels of both (the default palette of
+    stepper.eye_program is calibrated for this), so the network's first layer sees inputs of unit scale."""
+    env = fly_envs.vision_guided_flight(n_envs=8, lib_path=emu, seed=3, terrain_bank=4, bumps_or_trench=arena)
+    env.reset()
+    rs = np.random.RandomState(0)
+    imgs = []
+    for k in range(4):
+        ts = env.step(rs.uniform(-0.2, 0.2, (8, 12)))
+        imgs.append(np.stack([ts.observation['walker/left_eye'], ts.observation['walker/right_eye']]))
+    gray = np.stack(imgs).astype(np.float64).mean(-1)
+    assert abs(gray.mean() - 77.0) < tol and abs(gray.std() - 56.0) < tol, (gray.mean(), gray.std())
     env.close()
