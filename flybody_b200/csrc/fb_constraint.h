@@ -1229,12 +1229,12 @@ FB_DEV void ktask_reset_vision(const DevModel& m, const DevData& d, const DevTas
   AT(d.qpos, t.root_qadr) = x; AT(d.qpos, t.root_qadr + 1) = yy; AT(d.qpos, t.root_qadr + 2) = tk_hf_nearest(t, src, x, yy) + th;
   for (int i = 0; i < 4; i++) AT(d.qpos, t.root_qadr + 3 + i) = t.hover_quat[i];
   const float phase = tk_draw(t, e, episode, 4);
-  int idx = wb_nearest(t, t.wb_base_freq), len = t.wb_len[idx];
+  const int idx = wb_nearest(t, t.wb_base_freq);
   int pos = wb_argmin_phase(t.wb_phase + (size_t)idx * t.tab_len, t.tab_len, phase);
   const float* q0 = t.wb_traj + ((size_t)idx * t.tab_len + pos) * t.n_wing;
   for (int i = 0; i < t.n_wing; i++) AT(d.qpos, t.wing_qadr[i]) = q0[i];        // (the vision task starts the wings at rest: vision_flight.py:131-134)
   AT(d.qvel, t.root_vadr) = ts;
-  t.wb_freq[e] = t.wb_base_freq; t.wb_idx[e] = idx; t.wb_pos[e] = pos; (void)len;
+  t.wb_freq[e] = t.wb_base_freq; t.wb_idx[e] = idx; t.wb_pos[e] = pos;
   AT(d.time, 0) = 0; AT(d.flags, 0) = 0; AT(d.hold, 0) = 1; AT(d.prev_n, 0) = 0;
   t.step[e] = 0;          // (has_uniform is read by every lane above: ktask_commit clears it)
 }
@@ -1242,7 +1242,6 @@ FB_DEV void ktask_reset(const DevModel& m, const DevData& d, int e, int y) {
   if (!d.task || e >= d.N) return;
   const DevTask& t = *d.task;
   if (!t.needs_reset[e]) return;
-  const int episode = t.episode[e];
   for (int i = y; i < m.nq; i += FB_NY) AT(d.qpos, i) = t.reset_qpos[i];
   for (int i = y; i < m.nv; i += FB_NY) { AT(d.qvel, i) = 0.0f; AT(d.qacc, i) = 0.0f; }
   for (int i = y; i < m.na; i += FB_NY) AT(d.act, i) = 0.0f;

@@ -35,7 +35,7 @@
 // section ends in a warp barrier; the host emulation (tests only) runs the 32 lanes one after the other.
 // Code between sections is warp-uniform.
 #ifdef __CUDACC__
-#define WPAR_BEGIN { const int lane = threadIdx.x;
+#define WPAR_BEGIN { const int lane = threadIdx.x; (void)lane;
 #define WPAR_END } __syncwarp();
 #define FB_WARPFN __device__ __forceinline__
 #else

@@ -552,7 +552,6 @@ static int build_model(FbSim* s, const FbModel* h) {
   { std::vector<int> adh(nb, -1); for (int i = 0; i < h->nu; i++) if (h->actuator_trntype[i] == FB_TRN_BODY) adh[h->actuator_trnid[i]] = i; m.body_adhesion = up(s, adh); }
   { // packed headers of the lock-step sweeps (see fb_tree.h) and the row address of every ancestor entry
     if (h->nM >= 4096 || nv >= 256) { s->err = "model too large for the packed sweep headers (nM < 4096, nv < 256)"; return -3; }
-    const int* ldadr = nullptr; (void)ldadr;
     std::vector<unsigned> ha((size_t)FB_NY * std::max(m.max_list_ndof, 1), 0xffffffffu), hc(ha);
     std::vector<int> dadr_h, dnum_h, dl_h;      // rebuild the per-list dof order exactly as above
     for (int l = 0; l < nlist; l++) { dadr_h.push_back((int)dl_h.size()); int c = 0;
