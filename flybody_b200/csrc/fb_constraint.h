@@ -396,7 +396,7 @@ FB_DEV void kcol_stage(FB_COL_ARGS) {
 #define COL_NCON(j) ccnt[(j) * FB_LANES + lane]
 #define FB_COL_DYN(m) (6 * (m).ngeom + 3 * FB_MAXCAND)
 #define FB_COL_PTRS float* gx = sh_dyn(sh); float* gn = gx + 3 * m.ngeom * FB_LANES; int* flat = reinterpret_cast<int*>(gn + 3 * m.ngeom * FB_LANES); \
-  int* ccnt = flat + FB_MAXCAND * FB_LANES; int* jobs = ccnt + FB_MAXCAND * FB_LANES; (void)gx; (void)gn; (void)flat; (void)ccnt; (void)jobs;
+  int* ccnt = flat + FB_MAXCAND * FB_LANES; [[maybe_unused]] int* jobs = ccnt + FB_MAXCAND * FB_LANES; (void)gx; (void)gn; (void)flat; (void)ccnt;
 // 1. broadphase: lane l tests the pairs l, l + 32, ... of the static pair list (packed record: geoms, plane flag; margin +
 // bounding radii -- one coalesced line per step), four steps loaded ahead of the tests.  The hits are ranked with ballots,
 // so the candidate list comes out in pair order without per-lane lists.

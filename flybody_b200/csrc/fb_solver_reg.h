@@ -92,8 +92,8 @@ FB_WARPFN void ksolve_reg(const DevModel& m, const DevData& d, float* wsm, int e
   float* A = wsm; float* G = A + 32 * 33; float* P = G + TRI(32, 0); float* XQ = P + 32; float* XO = XQ + 32;
   float* E0s = XO + 32; float* E1s = E0s + 32; float* Us = E1s + 32;
   int* ECR = reinterpret_cast<int*>(Us + 32); int* ECK = ECR + 32;
-  SolveMem sm; sm.v = nullptr; sm.A = nullptr; sm.G = nullptr; sm.cap = 32; sm.red = reinterpret_cast<float*>(ECK + 32);     // WSUM staging (host emulation)
-  float tot[4] = {0, 0, 0, 0}; (void)tot; (void)sm;
+  [[maybe_unused]] SolveMem sm; sm.v = nullptr; sm.A = nullptr; sm.G = nullptr; sm.cap = 32; sm.red = reinterpret_cast<float*>(ECK + 32);     // WSUM staging (host emulation)
+  float tot[4] = {0, 0, 0, 0}; (void)tot;
   LREG(float, D); LREG(float, D1); LREG(float, D2); LREG(float, b); LREG(float, Rr); LREG(float, mu); LREG(float, c1); LREG(float, c2);
   LREG(float, lam); LREG(float, jar); LREG(float, f); LREG(float, res); LREG(float, dl); LREG(float, adl); LREG(float, e0); LREG(float, e1);
   LREG(float, j1); LREG(float, j2); LREG(float, hf1); LREG(float, hf2); LREG(float, he01); LREG(float, he02); LREG(float, he11); LREG(float, he12);
