@@ -289,6 +289,7 @@ class BatchedFlyEnv:
         self._rec = None
         self._program_ref_id = None
         self._program_switched = False
+        self.n_capacity_overflows = 0            # env-steps whose contact / constraint-row lists hit their capacity (FB_FLAGS bits 1, 2)
         # One reference per env (dataset loaders hand out a different snippet per episode) or one shared by all envs (the
         # Inference* loaders hold a single trajectory): the shared case keeps one device table, the per-env case one slot per env.
         tg = self.task._traj_generator
@@ -553,6 +554,8 @@ class BatchedFlyEnv:
             self._sim.task_uniforms(ids, self._rs.uniform(size=len(ids)))
         self._sim.task_step(action, self._n_sub)
         self._sim.task_read(self._rec, self._out4)
+        flags = self._rec[:, self._obs_slices['_scalars']][:, 0].astype(np.int64)      # bits 1, 2: capacity overflows (counted, not a termination)
+        self.n_capacity_overflows += int(((flags & 6) != 0).sum())
         self.h2d_bytes_per_step = action.nbytes
         self.d2h_bytes_per_step = self._rec.nbytes + self._out4.nbytes
         self._step_counter = np.where(resetting, 0, self._step_counter + 1)
@@ -726,7 +729,7 @@ class BatchedFlyEnv:
         # FB_FLAGS bit 0 = non-finite / diverged state (reference base.py:222-225 terminates on it); bits 1, 2 = contact /
         # constraint-row capacity overflows, which are counted, not treated as bad physics
         flags = scal[:, 0].astype(np.int64)
-        self.n_capacity_overflows = getattr(self, 'n_capacity_overflows', 0) + int(((flags & 6) != 0).sum())
+        self.n_capacity_overflows += int(((flags & 6) != 0).sum())
         bad = ((flags & 1) != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
         if self._variant == 'walk':
             linvel = np.linalg.norm(rec[:, sl['_velocimeter_now']], axis=1)

@@ -121,6 +121,7 @@ class BatchedVisionFlightEnv:
         self._has_trench = np.zeros(N, bool)
         self._last_draws = np.zeros((N, 8), np.float32)
         self.n_resets = 0
+        self.n_capacity_overflows = 0            # env-steps whose contact / constraint-row lists hit their capacity (FB_FLAGS bits 1, 2)
         # task hooks on the device (fb_task_*, kind 2): needs the terrain bank (a resetting env copies one of its terrains on the device)
         self._device_task = bool(device_task)
         if self._device_task:
@@ -219,6 +220,8 @@ class BatchedVisionFlightEnv:
             self._sim.task_uniform_rows(ids, draws[ids])
         self._sim.task_step(action, self._n_sub)
         self._sim.task_read(self._rec, self._out4)
+        flags = self._rec[:, self._sl['_scalars']][:, 0].astype(np.int64)        # bits 1, 2: capacity overflows (counted, not a termination)
+        self.n_capacity_overflows += int(((flags & 6) != 0).sum())
         self._time = np.where(resetting, 0.0, self._time + self._control_timestep)
         self.n_resets += int(resetting.sum())
         tgt = self._rec[:, self._sl['_task_target']]
@@ -359,7 +362,7 @@ class BatchedVisionFlightEnv:
         # FB_FLAGS bit 0 = non-finite / diverged state (reference base.py:222-225 terminates on it); bits 1, 2 = contact /
         # constraint-row capacity overflows, which are counted, not treated as bad physics
         flags = scal[:, 0].astype(np.int64)
-        self.n_capacity_overflows = getattr(self, 'n_capacity_overflows', 0) + int(((flags & 6) != 0).sum())
+        self.n_capacity_overflows += int(((flags & 6) != 0).sum())
         bad = ((flags & 1) != 0) | ~(np.sqrt(scal[:, 1].astype(np.float64)) <= _TERMINAL_QACC)
         terminate = bad | (self.floor_contact() if self._fatal else False)
         discount = np.where(terminate, 0.0, 1.0)                      # base.py:208-212

@@ -181,3 +181,18 @@ def test_replacing_the_terrain_bank_invalidates_the_vision_task_program(emu):
     ts = env.step(np.zeros((2, 12), np.float32))
     assert np.all(np.isfinite(ts.reward))
     env.close()
+
+
+@pytest.mark.parametrize('device_task', [False, True])
+def test_capacity_overflow_is_counted_not_a_termination(emu, device_task):
+    """FB_FLAGS bits 1 / 2 (contact list or constraint rows at capacity: FB_MAXCON = 64 contacts here) are not bad physics: the
+    reference terminates on |qacc| only (tasks/base.py:222-225), so the episode goes on and the env counts the event"""
+    env = fly_envs.vision_guided_flight(n_envs=2, lib_path=emu, seed=1, terrain_bank=2, target_height_range=(0.04, 0.05),
+                                        floor_contacts_fatal=False, device_task=device_task)
+    env.reset()
+    ts = env.step(np.zeros((2, 12), np.float32))                      # the fly starts half inside the terrain: > 64 candidate contacts
+    assert np.all(env._sim.get(st.NCON)[:, 0] == 64) and np.all(env._sim.get(st.FLAGS)[:, 0].astype(np.int64) & 6)
+    assert np.all(env._sim.get(st.FLAGS)[:, 0].astype(np.int64) & 1 == 0)
+    assert np.all(np.asarray(ts.step_type) == int(StepType.MID)) and np.all(np.asarray(ts.discount) == 1.0)
+    assert env.n_capacity_overflows >= 2
+    env.close()
