@@ -46,6 +46,21 @@ def test_solver_shared_and_global_memory_paths(emu, ncap, seed, monkeypatch):
     compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=emu), seed=seed, pos_scale=0.1 if seed == 0 else 0.0)
 
 
+@pytest.mark.parametrize('chol_reg', [0, 8])
+def test_hessian_block_fallback_path_matches_the_oracle(chol_reg, tmp_path):
+    """The register solver factors its Hessian block in registers for up to FB_CHOL_REG = 24 columns and column by column in shared
+    memory above that -- a path the steady-state walk (8 - 23 columns) rarely takes.  Built with FB_CHOL_REG = 0 (always the shared-memory
+    form) and 8 (both forms within one solve) the kernel source must give the same answers against the oracle."""
+    import subprocess
+    lib = str(tmp_path / f'libfb_emu_chol{chol_reg}.so')
+    subprocess.check_call(['g++', '-x', 'c++', '-DFB_EMU', f'-DFB_CHOL_REG={chol_reg}', '-O2', '-std=c++17', '-fPIC', '-shared', '-o', lib,
+                           os.path.join(ge.CSRC, 'flybody_b200.cu'), '-lm'])
+    m = load_model('walk')
+    compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=lib), seed=4, pos_scale=0.0)        # 18 rows: the register solver
+    r = summarize_tf(*teacher_forced_errors(m, st.BatchedStepper(m, 1, lib_path=lib), n_steps=3, n_sub=10))
+    assert r['p90_q'] < 2e-6 and r['p90_v'] < 2e-3, r
+
+
 def test_generic_convex_narrowphase_matches_the_oracle_on_shallow_contacts():
     """device MPR (double precision inside, fp32 inputs) vs the fp64 oracle on random sphere / capsule / ellipsoid /
     cylinder pairs brought to a 3e-4 cm overlap: same contact decision, depth within 2e-5 in >= 95 % of the cases (MPR is
