@@ -19,9 +19,11 @@ def emu():
     return ge.EMU
 
 
-def test_stage_parity_walk(emu):
+@pytest.mark.parametrize('seed', [0, 2])
+def test_stage_parity_walk(emu, seed):
+    """seed 0: 55 rows (generic solver path); seed 2: 31 rows with six self-contacts (register path, both dof chains of a row)"""
     m = load_model('walk')
-    compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=emu), seed=0)
+    compare_stage_fields(m, st.BatchedStepper(m, 2, lib_path=emu), seed=seed)
 
 
 def test_stage_parity_flight(emu):
